@@ -1,0 +1,154 @@
+/* vslam_b200.h — C-ABI of the B200-native PTAM tracking front-end.
+ *
+ * Drop-in boundary for the per-frame tracking path of ahcorde/visualSLAM_Android (jni/).  Plain
+ * pointers and sizes only; no C++/torch types.  One context per GPU; a context tracks `n_streams`
+ * independent cameras ("streams") of one image size against one shared, read-only map, and every
+ * batched entry point processes all streams in one set of kernel launches.
+ *
+ * Reference interface each entry point stands in for (file:line under /root/reference):
+ *   vslam_make_keyframe_lite[_dev]   KeyFrame::MakeKeyFrame_Lite           jni/KeyFrame.cc:5-51, jni/KeyFrame.h:89
+ *                                    (cv::resize 2:1 pyramid :20-23, cvCornerFast_10 jni/vision/cvfast.cpp:6088-9241,
+ *                                     row LUT :41-49)
+ *   vslam_upload_source_keyframe     the map keyframe a MapPoint's patch comes from (MapPoint::pPatchSourceKF,
+ *                                    jni/MapPoint.h:38); pyramid built like MakeKeyFrame_Lite
+ *   vslam_set_map                    Map::vpPoints / MapPoint fields read by the tracker (jni/Map.h:29, jni/MapPoint.h:33-54)
+ *   vslam_set_camera                 ATANCamera scalars after RefreshParams (jni/ATANCamera.cc:37-129)
+ *   vslam_project_all                first loop of Tracker::TrackMap       jni/Tracker.cc:369-392
+ *                                    (TrackerData::Project jni/TrackerData.h:69-86, GetDerivsUnsafe :92-95,
+ *                                     PatchFinder::CalcSearchLevelAndWarpMatrix jni/PatchFinder.cc:31-68)
+ *   vslam_search_for_points          Tracker::SearchForPoints              jni/Tracker.cc:629-674
+ *                                    (MakeTemplateCoarseCont jni/PatchFinder.cc:79-125, FindPatchCoarse :170-235,
+ *                                     ZMSSDAtPoint :352-380, MakeSubPixTemplate/IterateSubPixToConvergence :242-350)
+ *   vslam_calc_pose_update           Tracker::CalcPoseUpdate               jni/Tracker.cc:683-774 (+ Tukey, myWLS<6>)
+ *   vslam_track_map                  Tracker::TrackMap                     jni/Tracker.cc:358-626
+ *   vslam_track_frame[_dev]          Tracker::TrackFrame (good-map branch) jni/Tracker.cc:76-112
+ *                                    (ApplyMotionModel :781-798, UpdateMotionModel :802-820, AssessTrackingQuality :832-878)
+ *   vslam_create / vslam_destroy     JNI native_createTest / native_disposeTest   jni/jni_part.cpp:114-123
+ *   vslam_track_frame                JNI native_update                            jni/jni_part.cpp:132-145
+ *
+ * All functions return 0 on success and a negative VSLAM_E_* code on failure; vslam_last_error() gives the text.
+ * Nothing throws across this boundary.  Work is enqueued on the context's CUDA stream; the vslam_get_* readers and
+ * vslam_sync() wait for it.  Host input buffers are only read during the call that receives them.
+ * A context is not thread-safe; distinct contexts are independent (no globals).
+ */
+#ifndef VSLAM_B200_H
+#define VSLAM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VSLAM_LEVELS 4            /* jni/KeyFrame.h:31 */
+#define VSLAM_MAX_PATCH 11        /* int32 ZMSSD arithmetic of jni/PatchFinder.cc:379 overflows above 11 */
+
+#define VSLAM_OK 0
+#define VSLAM_E_INVALID (-1)      /* bad argument */
+#define VSLAM_E_CUDA (-2)         /* CUDA runtime error (text in vslam_last_error) */
+#define VSLAM_E_CAPACITY (-3)     /* more corners than max_corner_frac allows: reported, never silently truncated */
+#define VSLAM_E_NO_DEVICE (-4)    /* no usable CUDA device: there is no CPU fallback */
+
+typedef struct vslam_ctx vslam_ctx;
+
+typedef struct vslam_config {
+  int device;               /* CUDA device ordinal */
+  int width, height;        /* level-0 size; width % 32 == 0, height % 8 == 0 (every level keeps even dimensions) */
+  int n_streams;            /* independent cameras tracked by this context */
+  int max_points;           /* map capacity N */
+  int patch_size;           /* PatchFinder template side P: 8 or 11 (reference default 11, jni/PatchFinder.h:48) */
+  int max_source_keyframes; /* device-resident source pyramids */
+  float max_corner_frac;    /* corner-list capacity per level as a fraction of the level's pixels (0 => 0.5) */
+  void* cuda_stream;        /* cudaStream_t to enqueue on (NULL => the context creates its own) */
+  int truncate_error;       /* 1 = reproduce the (int) cast of jni/Tracker.cc:766-767 (reference behaviour) */
+  unsigned rand_seed;       /* per-stream glibc rand() state starts as srand(rand_seed) would leave it (reference: 1) */
+} vslam_config;
+
+/* Tunables the reference hard-codes (jni/Tracker.cc:405-410,495-497,518); vslam_default_params() gives its values. */
+typedef struct vslam_params {
+  unsigned coarse_min, coarse_max, coarse_range;
+  int coarse_subpix_its;
+  double coarse_min_vel;
+  int fine_range, fine_range_after_coarse, fine_subpix_its_top_level;
+  int max_patches_per_frame;
+  int use_sbi;              /* Tracker::mbUseSBIInit (jni/Tracker.cc:87-89): motion model takes rotation from sbi_rot */
+} vslam_params;
+
+void vslam_default_config(vslam_config* cfg);
+void vslam_default_params(vslam_params* p);
+
+int vslam_create(const vslam_config* cfg, vslam_ctx** out);
+void vslam_destroy(vslam_ctx* ctx);
+const char* vslam_last_error(const vslam_ctx* ctx);   /* ctx may be NULL: error of the last failed vslam_create */
+int vslam_sync(vslam_ctx* ctx);
+int vslam_set_params(vslam_ctx* ctx, const vslam_params* p);
+
+/* cam13: fx fy cx cy W Winv 2tan(W/2) 1/(2tan) distortionEnabled largestRadius maxR width height */
+int vslam_set_camera(vslam_ctx* ctx, const double* cam13);
+/* Host-side mirror of ATANCamera::RefreshParams: fills cam13 from the 5 normalised parameters and an image size.
+ * as_shipped_radius = 1 reproduces the int-temporary bug of jni/ATANCamera.cc:70-82 (largestRadius = maxR = 0). */
+void vslam_camera_from_params(const double* params5, int width, int height, int as_shipped_radius, double* cam13);
+
+int vslam_upload_source_keyframe(vslam_ctx* ctx, int kf_id, const uint8_t* gray_host, int stride);
+int vslam_set_map(vslam_ctx* ctx, int n, const double* world3, const double* pixel_right3, const double* pixel_down3,
+                  const int32_t* ir_center2, const int32_t* src_level, const int32_t* src_kf /* NULL => all 0 */);
+
+/* ---- KeyFrame::MakeKeyFrame_Lite for streams [first, first+count) -------------------------------------------- */
+/* gray_host: frame k at gray_host + k*frame_stride, rows `stride` bytes apart (pinned memory recommended). */
+int vslam_make_keyframe_lite(vslam_ctx* ctx, int first_stream, int count, const uint8_t* gray_host, int stride, size_t frame_stride);
+/* gray_dev: same layout in device memory (16-byte aligned, stride % 16 == 0).  Zero-copy: the buffer becomes level 0 of
+ * those streams' current keyframe and must stay unmodified until their next make_keyframe_lite / track_frame. */
+int vslam_make_keyframe_lite_dev(vslam_ctx* ctx, int first_stream, int count, const uint8_t* gray_dev, int stride, size_t frame_stride);
+int vslam_level_dims(const vslam_ctx* ctx, int level, int* width, int* height);
+int vslam_get_level(vslam_ctx* ctx, int stream, int level, uint8_t* out, int out_stride);
+int vslam_get_num_corners(vslam_ctx* ctx, int stream, int level, int* n);
+int vslam_get_corners(vslam_ctx* ctx, int stream, int level, int32_t* xy, int cap);     /* (x,y) pairs, raster order */
+int vslam_get_row_lut(vslam_ctx* ctx, int stream, int level, int32_t* lut);             /* H_level entries */
+
+/* ---- per-stream tracker state (Tracker members, jni/Tracker.h:105-133) ----------------------------------------- */
+int vslam_set_pose(vslam_ctx* ctx, int stream, const double* pose12);   /* row-major 3x4 [R|t], camera-from-world */
+int vslam_get_pose(vslam_ctx* ctx, int stream, double* pose12);
+int vslam_get_poses(vslam_ctx* ctx, double* pose12_per_stream);         /* all streams, one D2H copy */
+int vslam_set_motion(vslam_ctx* ctx, int stream, const double* velocity6, double msd_scaled_velocity, double scene_depth_mean,
+                     double scene_depth_sigma);
+int vslam_get_motion(vslam_ctx* ctx, int stream, double* velocity6, double* msd_scaled_velocity, double* scene_depth_mean,
+                     double* scene_depth_sigma);
+int vslam_set_sbi_rotation(vslam_ctx* ctx, int stream, const double* rot6);  /* Tracker::mv6SBIRot (computed by the caller) */
+/* attempted[4], found[4], quality (0 BAD,1 DODGY,2 GOOD), lost_frames, did_coarse */
+int vslam_get_counters(vslam_ctx* ctx, int stream, int32_t* attempted4, int32_t* found4, int* quality, int* lost_frames, int* did_coarse);
+/* Per-point TrackerData dump, layout of oracle/ref_harness.cc ref_tracker_point_state: ints[n][8], dbl[n][32]. */
+int vslam_get_point_states(vslam_ctx* ctx, int stream, int32_t* ints, double* dbl);
+int vslam_get_point_template(vslam_ctx* ctx, int stream, int point, uint8_t* tmpl /* P*P */, int* sum, int* sumsq);
+int vslam_get_point_counts(vslam_ctx* ctx, int stream, int32_t* outlier_inlier /* n*2 */);
+/* 6-vectors and sigma^2 of every CalcPoseUpdate of the last track_map (<= 20), in order. */
+int vslam_get_updates(vslam_ctx* ctx, int stream, double* upd6, double* sigma_sq, int cap, int* n);
+int vslam_get_zmssd_evals(vslam_ctx* ctx, unsigned long long* total);   /* candidates scored since create (all streams) */
+
+/* ---- stages, all streams at once ------------------------------------------------------------------------------- */
+int vslam_project_all(vslam_ctx* ctx);
+/* Stage isolation for parity tests: overwrite what vslam_project_all computed for `stream` with caller-supplied
+ * projected pixels (n*2), warp matrices mm2WarpInverse (n*4, row-major) and search levels (n), n = map size. */
+int vslam_set_point_projection(vslam_ctx* ctx, int stream, const double* v2image, const double* warp_inverse, const int32_t* level);
+/* idx: per-stream lists, stream s uses idx[s*idx_stride .. + n[s]); the same list is used by vslam_calc_pose_update. */
+int vslam_set_lists(vslam_ctx* ctx, const int32_t* idx, const int32_t* n, int idx_stride);
+int vslam_clear_counters(vslam_ctx* ctx);
+int vslam_search_for_points(vslam_ctx* ctx, int range, int subpix_its);
+int vslam_project_and_derivs(vslam_ctx* ctx, int only_found);
+int vslam_calc_jacobians(vslam_ctx* ctx);
+int vslam_calc_pose_update(vslam_ctx* ctx, double override_sigma, int mark_outliers, int apply, double* upd6_per_stream /* may be NULL */);
+int vslam_track_map(vslam_ctx* ctx);
+/* MakeKeyFrame_Lite + (if lost_frames < 3) ApplyMotionModel, TrackMap, UpdateMotionModel, AssessTrackingQuality. */
+int vslam_track_frame(vslam_ctx* ctx, const uint8_t* gray_host, int stride, size_t frame_stride);
+int vslam_track_frame_dev(vslam_ctx* ctx, const uint8_t* gray_dev, int stride, size_t frame_stride);
+
+/* Test hook: y[i] = the correctly-rounded device atan used by the camera model (csrc/atan_dd.cuh). */
+int vslam_debug_atan(const double* x_host, double* y_host, int n);
+
+/* Number of kernels this library has launched on the context since creation (bench.py's gpu_launches). */
+unsigned long long vslam_kernel_launches(const vslam_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -532,6 +532,7 @@ void make_subpix_template(Finder& f) {
   f.subPixPos[0] = f.coarsePos[0]; f.subPixPos[1] = f.coarsePos[1];
   f.meanDiff = 0.0;
 }
+static int g_dbg_point = -1; static bool g_dbg = false;
 // PatchFinder::IterateSubPix (jni/PatchFinder.cc:291-350)
 double iterate_subpix(Finder& f, const OKeyFrame& kf) {
   const int P = f.P, Q = P - 2;
@@ -561,6 +562,7 @@ double iterate_subpix(Finder& f, const OKeyFrame& kf) {
   f.subPixPos[0] -= upd[0] * sc; f.subPixPos[1] -= upd[1] * sc;
   f.meanDiff -= upd[2];
   double d = 0; d += upd[0] * upd[0]; d += upd[1] * upd[1];
+  if (g_dbg) fprintf(stderr, "orc it: acc %.17g %.17g %.17g upd %.17g %.17g %.17g pos %.17g %.17g d %.17g mix %.9g %.9g %.9g %.9g\n", acc[0], acc[1], acc[2], upd[0], upd[1], upd[2], f.subPixPos[0], f.subPixPos[1], d, fMixTL, fMixTR, fMixBL, fMixBR);
   return d;
 }
 // PatchFinder::IterateSubPixToConvergence (jni/PatchFinder.cc:272-285)
@@ -702,6 +704,7 @@ int search_for_points(OTracker& t, const std::vector<int>& v, int nRange, int nS
   int nFound = 0;
   for (size_t k = 0; k < v.size(); k++) {
     TData& TD = t.td[v[k]]; Finder& F = TD.finder;
+    g_dbg = (v[k] == g_dbg_point);
     make_template_coarse_cont(F, t.pts[v[k]], *t.srcKF);
     if (F.templateBad) { TD.inImage = TD.potentiallyVisible = TD.found = false; continue; }
     t.attempted[F.level]++;
@@ -880,6 +883,7 @@ void assess_tracking_quality(OTracker& t) {
 // =================================================================================================
 extern "C" {
 
+void orc_debug_point(int i) { g_dbg_point = i; }
 // ---- RNG
 void* orc_rand_create(unsigned seed) { GlibcRand* r = new GlibcRand(); r->seed(seed); return r; }
 int orc_rand_next(void* r) { return ((GlibcRand*)r)->next(); }

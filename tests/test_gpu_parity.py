@@ -1,0 +1,330 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the CPU oracle on the same seeded inputs.
+
+Bit-exact: pyramid pixels, corner lists + row LUT, search levels, template pixels and sums, ZMSSD argmin positions,
+found flags, counters.  Tolerance (written at each assert): FP64 geometry 1e-9 relative, pose / update 6-vectors 1e-6
+(the contract is 1e-4), sub-pixel positions 1e-6 px.
+"""
+import numpy as np
+import pytest
+
+import common
+from visualslam_android_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _ctx(cam, f0, smap, n_streams=1, **kw):
+    from visualslam_android_b200 import api
+    ctx = api.Context(cam.width, cam.height, n_streams=n_streams, max_points=smap.n, **kw)
+    ctx.set_camera(cam.scalars())
+    ctx.upload_source_keyframe(f0)
+    ctx.set_map(smap.world, smap.pix_right_w, smap.pix_down_w, smap.ir_center, smap.src_level)
+    return ctx
+
+
+def _orc(cam, f0, smap, **kw):
+    from oracle import oraclebind
+    return oraclebind.OrcWorld(cam, f0, smap, **kw)
+
+
+def _check_keyframe(ctx, s, okf):
+    for l in range(4):
+        assert np.array_equal(ctx.level(s, l), okf.pixels(l)), f"level {l} pixels"
+        assert np.array_equal(ctx.corners(s, l), okf.corners(l)), f"level {l} corners"
+        assert np.array_equal(ctx.row_lut(s, l), okf.row_lut(l)), f"level {l} row LUT"
+
+
+@pytest.mark.parametrize("size", [(640, 480), (320, 240), (1920, 1080), (96, 64)])
+def test_make_keyframe_lite_bit_exact(size):
+    from oracle import oraclebind
+    from visualslam_android_b200 import api
+    W, H = size
+    cam = synth.Camera(W, H)
+    tex = common.texture(4096 if W > 640 else 2048)
+    ctx = api.Context(W, H, n_streams=3, max_points=8)
+    frames = np.stack([synth.render_frame(tex, cam, synth.se3_exp(np.array(synth.CONFIG1_TWIST) * k)) for k in range(3)])
+    ctx.make_keyframe_lite(frames)
+    for s in range(3):
+        _check_keyframe(ctx, s, oraclebind.OrcKeyFrame().make_lite(frames[s]))
+    # a second call on the same context (look-back state / tickets are reset per call), different content per stream
+    frames2 = frames[::-1].copy()
+    ctx.make_keyframe_lite(frames2)
+    for s in range(3):
+        _check_keyframe(ctx, s, oraclebind.OrcKeyFrame().make_lite(frames2[s]))
+    ctx.close()
+
+
+def test_make_keyframe_lite_edge_images():
+    from oracle import oraclebind
+    from visualslam_android_b200 import api
+    W, H = 160, 120
+    rs = np.random.RandomState(3)
+    imgs = np.stack([
+        np.zeros((H, W), np.uint8),                                   # no corners at all
+        rs.randint(0, 256, (H, W)).astype(np.uint8),                  # noise: corners everywhere, including the x=3 / x=W-4 columns
+        np.full((H, W), 255, np.uint8),                               # saturated
+        ((np.indices((H, W)).sum(0) // 7 % 2) * 255).astype(np.uint8),  # diagonal stripes
+    ])
+    ctx = api.Context(W, H, n_streams=4, max_points=8, max_corner_frac=1.0)
+    ctx.make_keyframe_lite(imgs)
+    for s in range(4):
+        _check_keyframe(ctx, s, oraclebind.OrcKeyFrame().make_lite(imgs[s]))
+    ctx.close()
+
+
+def test_corner_capacity_overflow_is_reported():
+    from visualslam_android_b200 import api
+    W, H = 160, 120
+    img = np.random.RandomState(3).randint(0, 256, (1, H, W)).astype(np.uint8)
+    ctx = api.Context(W, H, n_streams=1, max_points=8, max_corner_frac=0.01)
+    ctx.make_keyframe_lite(img)
+    with pytest.raises(api.VslamError) as e:
+        ctx.sync()
+    assert e.value.code == api.E_CAPACITY
+    ctx.close()
+
+
+def test_make_keyframe_lite_device_input_zero_copy():
+    import torch
+    from oracle import oraclebind
+    from visualslam_android_b200 import api
+    W, H = 640, 480
+    cam = synth.Camera(W, H)
+    frames = np.stack([synth.render_frame(common.texture(), cam, synth.se3_exp(np.array(synth.CONFIG1_TWIST) * k)) for k in range(2)])
+    dev = torch.from_numpy(frames).cuda()
+    ctx = api.Context(W, H, n_streams=2, max_points=8, cuda_stream=torch.cuda.current_stream().cuda_stream)
+    ctx.make_keyframe_lite_ptr(dev.data_ptr(), 2, W, W * H, device=True)
+    for s in range(2):
+        _check_keyframe(ctx, s, oraclebind.OrcKeyFrame().make_lite(frames[s]))
+    ctx.close()
+
+
+def _compare_states(gi, gd, oi, od, geom_tol=1e-9):
+    assert np.array_equal(gi[:, 0], oi[:, 0]), "bInImage"
+    assert np.array_equal(gi[:, 1], oi[:, 1]), "nSearchLevel"
+    vis = oi[:, 0] == 1
+    # projected pixel, derivs, v3Cam, warp: 1e-9 relative (contract 1e-12 on v2Image is checked separately below)
+    for cols, name in (((0, 1), "v2Image"), ((4, 5, 6, 7), "derivs"), ((8, 9, 10), "v3Cam"), ((11, 12, 13, 14), "warpInverse")):
+        a, b = gd[vis][:, cols], od[vis][:, cols]
+        assert np.allclose(a, b, rtol=geom_tol, atol=1e-12), name
+
+
+def test_atan_cr_matches_host_libm():
+    """csrc/atan_dd.cuh against the host's atan (what the reference's ATANCamera calls): bit-equal for >= 99.9 %, never off by more than 1 ulp."""
+    import math
+    from visualslam_android_b200 import api
+    rs = np.random.RandomState(5)
+    x = np.concatenate([rs.uniform(0, 0.03, 200000), rs.uniform(0, 1, 100000), rs.uniform(1, 40, 50000), -rs.uniform(0, 2, 20000),
+                        np.array([0.0, 1e-12, 1e-9, 0.125, 0.0625, 1.0, 8.0, 1e19, -1e-3])])
+    y = api.debug_atan(x)
+    ref = np.array([math.atan(v) for v in x])
+    same = (y == ref)
+    assert same.mean() >= 0.999, same.mean()
+    ulp = np.abs(y - ref) / np.maximum(np.spacing(np.abs(ref)), 5e-324)
+    assert ulp.max() <= 1.0, ulp.max()
+
+
+def test_project_all_matches_oracle():
+    cam, f0, smap = common.scene()
+    ctx, ow = _ctx(cam, f0, smap), _orc(cam, f0, smap)
+    pose = synth.se3_exp(np.array(synth.CONFIG1_TWIST) * 0.5)
+    ctx.set_pose(0, pose); ow.set_pose(pose)
+    ctx.project_all(); ow.L.orc_tracker_project_all(ow.tracker)
+    gi, gd = ctx.point_states(0); oi, od = ow.point_states()
+    _compare_states(gi, gd, oi, od)
+    vis = oi[:, 0] == 1
+    rel = np.abs(gd[vis][:, :2] - od[vis][:, :2]) / np.maximum(np.abs(od[vis][:, :2]), 1.0)
+    assert rel.max() <= 1e-12, rel.max()      # SURVEY.md §8 contract for the projected pixel
+    # with the correctly-rounded device atan the whole projection is bit-identical for (almost) every point
+    ident = (gd[vis][:, [0, 1, 4, 5, 6, 7, 11, 12, 13, 14]] == od[vis][:, [0, 1, 4, 5, 6, 7, 11, 12, 13, 14]]).all(1)
+    assert ident.mean() >= 0.99, ident.mean()
+    ctx.close()
+
+
+@pytest.mark.parametrize("P", [11, 8])
+@pytest.mark.parametrize("rng,subpix", [(10, 0), (30, 8), (5, 8)])
+def test_search_for_points_bit_exact(P, rng, subpix):
+    cam, f0, smap = common.scene()
+    ctx, ow = _ctx(cam, f0, smap, patch_size=P), _orc(cam, f0, smap, P=P)
+    f1, pose1 = common.frame_at(cam, np.array(synth.CONFIG1_TWIST) * 0.6)
+    start = synth.se3_exp(np.array(synth.CONFIG1_TWIST) * 0.3)
+    ctx.make_keyframe_lite(f1); ow.make_current_kf(f1)
+    ctx.set_pose(0, start); ow.set_pose(start)
+    ctx.project_all(); ow.L.orc_tracker_project_all(ow.tracker)
+    oi, od = ow.point_states()
+    # stage isolation (SURVEY.md §8 parity contract): the search is fed the oracle's projected pixels / warp matrices
+    ctx.set_point_projection(0, od[:, 0:2], od[:, 11:15], oi[:, 1])
+    idx = np.nonzero(oi[:, 1] >= 0)[0].astype(np.int32)
+    ctx.set_lists([idx]); ctx.clear_counters(); ow.L.orc_tracker_clear_counters(ow.tracker)
+    ctx.search_for_points(rng, subpix)
+    nfound = ow.L.orc_tracker_search_for_points(ow.tracker, idx, len(idx), rng, subpix)
+    gi, gd = ctx.point_states(0); oi, od = ow.point_states()
+    assert np.array_equal(gi[idx][:, [2, 3, 5]], oi[idx][:, [2, 3, 5]]), "searched / found / templateBad flags"
+    a, f, *_ = ctx.counters(0); oa, of, *_ = ow.counters()
+    assert np.array_equal(a, oa) and np.array_equal(f, of) and f.sum() == nfound
+    assert ctx.zmssd_evals() == ow.L.orc_tracker_zmssd_evals(ow.tracker)
+    # templates of every searched point: bit-exact pixels and sums
+    for k in idx:
+        gt, gs, gq = ctx.point_template(0, int(k)); ot, os_, oq = ow.point_template(int(k))
+        assert np.array_equal(gt, ot) and (gs, gq) == (os_, oq), f"template of point {k}"
+    fnd = idx[oi[idx][:, 3] == 1]
+    assert len(fnd) > 100
+    if subpix == 0:
+        assert np.array_equal(gd[fnd][:, 2:4], od[fnd][:, 2:4]), "coarse positions must be identical"
+        assert np.array_equal(gi[fnd][:, 4], oi[fnd][:, 4])
+    else:
+        assert np.abs(gd[fnd][:, 2:4] - od[fnd][:, 2:4]).max() <= 1e-6, "sub-pixel position (px)"
+        assert np.array_equal(gd[fnd][:, 30:32], od[fnd][:, 30:32]), "coarse positions must be identical"
+    assert np.array_equal(gd[fnd][:, 15], od[fnd][:, 15])
+    ctx.close()
+
+
+def test_template_cache_and_second_frame():
+    """The per-point template reuse cache (jni/PatchFinder.cc:91-102) persists across frames."""
+    cam, f0, smap = common.scene()
+    ctx, ow = _ctx(cam, f0, smap), _orc(cam, f0, smap)
+    for k, sc in enumerate((0.2, 0.21, 0.6)):
+        f1, _ = common.frame_at(cam, np.array(synth.CONFIG1_TWIST) * sc)
+        start = synth.se3_exp(np.array(synth.CONFIG1_TWIST) * (sc - 0.05))
+        ctx.make_keyframe_lite(f1); ow.make_current_kf(f1)
+        ctx.set_pose(0, start); ow.set_pose(start)
+        ctx.project_all(); ow.L.orc_tracker_project_all(ow.tracker)
+        oi, _ = ow.point_states()
+        idx = np.nonzero(oi[:, 1] >= 0)[0].astype(np.int32)
+        ctx.set_lists([idx])
+        ctx.search_for_points(10, 0); ow.L.orc_tracker_search_for_points(ow.tracker, idx, len(idx), 10, 0)
+        gi, gd = ctx.point_states(0); oi, od = ow.point_states()
+        assert np.array_equal(gi[idx][:, [2, 3, 5]], oi[idx][:, [2, 3, 5]]), f"frame {k}"
+        fnd = idx[oi[idx][:, 3] == 1]
+        assert np.array_equal(gd[fnd][:, 2:4], od[fnd][:, 2:4])
+        for j in idx[::97]:
+            gt, gs, gq = ctx.point_template(0, int(j)); ot, os_, oq = ow.point_template(int(j))
+            assert np.array_equal(gt, ot) and (gs, gq) == (os_, oq)
+    ctx.close()
+
+
+@pytest.mark.parametrize("sigma,mark", [(0.0, False), (16.0, True), (1.0, False)])
+def test_calc_pose_update_matches_oracle(sigma, mark):
+    cam, f0, smap = common.scene()
+    ctx, ow = _ctx(cam, f0, smap), _orc(cam, f0, smap)
+    f1, _ = common.frame_at(cam, np.array(synth.CONFIG1_TWIST) * 0.6)
+    start = synth.se3_exp(np.array(synth.CONFIG1_TWIST) * 0.3)
+    ctx.make_keyframe_lite(f1); ow.make_current_kf(f1)
+    ctx.set_pose(0, start); ow.set_pose(start)
+    ctx.project_all(); ow.L.orc_tracker_project_all(ow.tracker)
+    oi, _ = ow.point_states()
+    idx = np.nonzero(oi[:, 1] >= 0)[0].astype(np.int32)
+    ctx.set_lists([idx])
+    ctx.search_for_points(10, 0); ow.L.orc_tracker_search_for_points(ow.tracker, idx, len(idx), 10, 0)
+    ctx.calc_jacobians(); ow.L.orc_tracker_calc_jacobians(ow.tracker, idx, len(idx))
+    gu = ctx.calc_pose_update(sigma, mark, apply=True)[0]
+    ou = np.zeros(6); ow.L.orc_tracker_calc_pose_update(ow.tracker, idx, len(idx), sigma, int(mark), 1, ou)
+    assert np.linalg.norm(gu - ou) <= 1e-6 * max(np.linalg.norm(ou), 1e-12), (gu, ou)   # contract: 1e-4 relative
+    assert np.abs(ctx.get_pose(0) - ow.get_pose()).max() <= 1e-9
+    gi, gd = ctx.point_states(0); oi, od = ow.point_states()
+    fnd = idx[oi[idx][:, 3] == 1]
+    assert np.allclose(gd[fnd][:, 16:28], od[fnd][:, 16:28], rtol=1e-9, atol=1e-12), "Jacobians"
+    if mark:
+        assert np.array_equal(ctx.point_counts(0), ow.point_counts()), "inlier / outlier counters"
+    _, gs = ctx.updates(0)
+    if sigma == 0.0:
+        e2 = ((od[fnd][:, 2:4] - od[fnd][:, 0:2]) * od[fnd][:, 15:16]) ** 2
+        s2 = ow.L.orc_tukey_sigma_squared(np.ascontiguousarray(e2.sum(1)), len(fnd))
+        assert abs(gs[-1] - s2) <= 1e-9 * s2, "Tukey sigma^2"
+    ctx.close()
+
+
+def test_calc_pose_update_degenerate_sets():
+    """Zero found points -> zero update (jni/Tracker.cc:712-716); < 4 points exercises the size_t wrap of MEstimator.h:73."""
+    cam, f0, smap = common.scene()
+    ctx, ow = _ctx(cam, f0, smap), _orc(cam, f0, smap)
+    f1, _ = common.frame_at(cam, np.array(synth.CONFIG1_TWIST) * 0.2)
+    ctx.make_keyframe_lite(f1); ow.make_current_kf(f1)
+    ctx.set_pose(0, synth.IDENTITY_POSE); ow.set_pose(synth.IDENTITY_POSE)
+    ctx.project_all(); ow.L.orc_tracker_project_all(ow.tracker)
+    oi, _ = ow.point_states()
+    allidx = np.nonzero(oi[:, 1] >= 0)[0].astype(np.int32)
+    for n in (0, 1, 2, 4):
+        idx = allidx[:n].copy()
+        ctx.set_lists([idx])
+        if n:
+            ctx.search_for_points(10, 0); ow.L.orc_tracker_search_for_points(ow.tracker, idx, n, 10, 0)
+            ctx.calc_jacobians(); ow.L.orc_tracker_calc_jacobians(ow.tracker, idx, n)
+        gu = ctx.calc_pose_update(0.0, False, apply=False)[0]
+        ou = np.zeros(6); ow.L.orc_tracker_calc_pose_update(ow.tracker, idx if n else np.zeros(1, np.int32), n, 0.0, 0, 0, ou)
+        assert np.allclose(gu, ou, rtol=1e-6, atol=1e-15), (n, gu, ou)
+    ctx.close()
+
+
+def _track_map_case(scale_start, scale_frame, velocity=None, P=11):
+    cam, f0, smap = common.scene()
+    ctx, ow = _ctx(cam, f0, smap, patch_size=P), _orc(cam, f0, smap, P=P)
+    f1, _ = common.frame_at(cam, np.array(synth.CONFIG1_TWIST) * scale_frame)
+    start = synth.se3_exp(np.array(synth.CONFIG1_TWIST) * scale_start)
+    ctx.make_keyframe_lite(f1); ow.make_current_kf(f1)
+    ctx.set_pose(0, start); ow.set_pose(start)
+    if velocity is not None:
+        ctx.set_motion(0, np.zeros(6), velocity); ow.L.orc_tracker_set_velocity(ow.tracker, np.zeros(6), velocity)
+    ctx.track_map(); ow.L.orc_tracker_track_map(ow.tracker)
+    return ctx, ow
+
+
+def _check_track_map(ctx, ow):
+    a, f, q, lost, dc = ctx.counters(0); oa, of, oq, olost, odc = ow.counters()
+    assert np.array_equal(a, oa) and np.array_equal(f, of), "manMeasAttempted / manMeasFound"
+    assert dc == odc, "mbDidCoarse"
+    gi, gd = ctx.point_states(0); oi, od = ow.point_states()
+    pvs = oi[:, 1] >= 0
+    assert np.array_equal(gi[:, :2], oi[:, :2])
+    assert np.array_equal(gi[pvs][:, [2, 3, 5]], oi[pvs][:, [2, 3, 5]]), "searched / found / templateBad per point"
+    fnd = oi[:, 3] == 1
+    assert np.abs(gd[fnd][:, 2:4] - od[fnd][:, 2:4]).max() <= 1e-6, "found positions (px)"
+    gu, gs = ctx.updates(0); ou, os_ = ow.updates()
+    assert len(gu) == len(ou)
+    for k in range(len(ou)):   # contract: 1e-4 relative on each twist; we hold 1e-6 (plus an absolute floor for ~0 updates)
+        assert np.linalg.norm(gu[k] - ou[k]) <= 1e-6 * np.linalg.norm(ou[k]) + 1e-12, (k, gu[k], ou[k])
+        assert abs(gs[k] - os_[k]) <= 1e-9 * abs(os_[k])
+    assert np.abs(ctx.get_pose(0) - ow.get_pose()).max() <= 1e-9, "final pose"
+    assert np.array_equal(ctx.point_counts(0), ow.point_counts()), "inlier / outlier counters"
+    # final reprojection residuals of the found points: 1e-4 relative contract, checked at 1e-6 px absolute
+    rg = (gd[fnd][:, 2:4] - gd[fnd][:, 0:2]); ro = (od[fnd][:, 2:4] - od[fnd][:, 0:2])
+    assert np.abs(rg - ro).max() <= 1e-6
+
+
+def test_track_map_fine_only_matches_oracle():
+    ctx, ow = _track_map_case(0.0, 1.0)     # start pose I, full twist
+    _check_track_map(ctx, ow)
+    ctx.close()
+
+
+def test_track_map_with_coarse_stage_matches_oracle():
+    ctx, ow = _track_map_case(0.0, 1.0, velocity=0.05)
+    assert ow.counters()[4] == 1, "coarse stage must have run in this case"
+    _check_track_map(ctx, ow)
+    ctx.close()
+
+
+def test_track_map_patch8():
+    ctx, ow = _track_map_case(0.2, 0.5, P=8)
+    _check_track_map(ctx, ow)
+    ctx.close()
+
+
+def test_track_frame_sequence_multi_stream():
+    """4 streams x 6 frames through vslam_track_frame (motion model + TrackMap + quality), each against its own oracle tracker."""
+    from visualslam_android_b200 import api
+    cam, f0, smap = common.scene()
+    S, K = 4, 6
+    ctx = _ctx(cam, f0, smap, n_streams=S)
+    ows = [_orc(cam, f0, smap) for _ in range(S)]
+    for k in range(1, K + 1):
+        frames = np.stack([synth.render_frame(common.texture(), cam, synth.stream_pose(4 * k, s)) for s in range(S)])
+        ctx.track_frame(frames)
+        for s, ow in enumerate(ows):
+            ow.L.orc_tracker_track_frame(ow.tracker, np.ascontiguousarray(frames[s]), cam.width, cam.height, cam.width)
+        poses = ctx.get_poses()
+        for s, ow in enumerate(ows):
+            assert np.abs(poses[s] - ow.get_pose()).max() <= 1e-8, (k, s)
+            a, f, q, lost, dc = ctx.counters(s); oa, of, oq, olost, odc = ow.counters()
+            assert np.array_equal(a, oa) and np.array_equal(f, of) and (q, lost, dc) == (oq, olost, odc), (k, s)
+    ctx.close()

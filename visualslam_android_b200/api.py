@@ -1,0 +1,357 @@
+"""ctypes binding of libvslam_b200.so — the C-ABI declared in include/vslam_b200.h.
+
+This is the only way Python reaches the CUDA path.  There is no CPU fallback: a missing library or a
+missing GPU raises.  (The reference's host language is C++; this module exists for tests and bench.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libvslam_b200.so")
+LEVELS = 4
+
+OK, E_INVALID, E_CUDA, E_CAPACITY, E_NO_DEVICE = 0, -1, -2, -3, -4
+
+
+class VslamError(RuntimeError):
+    def __init__(self, code, text):
+        super().__init__(f"vslam error {code}: {text}")
+        self.code = code
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int), ("width", C.c_int), ("height", C.c_int), ("n_streams", C.c_int), ("max_points", C.c_int),
+                ("patch_size", C.c_int), ("max_source_keyframes", C.c_int), ("max_corner_frac", C.c_float), ("cuda_stream", C.c_void_p),
+                ("truncate_error", C.c_int), ("rand_seed", C.c_uint)]
+
+
+class Params(C.Structure):
+    _fields_ = [("coarse_min", C.c_uint), ("coarse_max", C.c_uint), ("coarse_range", C.c_uint), ("coarse_subpix_its", C.c_int),
+                ("coarse_min_vel", C.c_double), ("fine_range", C.c_int), ("fine_range_after_coarse", C.c_int),
+                ("fine_subpix_its_top_level", C.c_int), ("max_patches_per_frame", C.c_int), ("use_sbi", C.c_int)]
+
+
+# every symbol include/vslam_b200.h declares (tests/test_abi_cpu.py checks the library exports all of them)
+ABI_SYMBOLS = [
+    "vslam_default_config", "vslam_default_params", "vslam_create", "vslam_destroy", "vslam_last_error", "vslam_sync", "vslam_set_params",
+    "vslam_set_camera", "vslam_camera_from_params", "vslam_upload_source_keyframe", "vslam_set_map", "vslam_make_keyframe_lite",
+    "vslam_make_keyframe_lite_dev", "vslam_level_dims", "vslam_get_level", "vslam_get_num_corners", "vslam_get_corners", "vslam_get_row_lut",
+    "vslam_set_pose", "vslam_get_pose", "vslam_get_poses", "vslam_set_motion", "vslam_get_motion", "vslam_set_sbi_rotation", "vslam_get_counters",
+    "vslam_get_point_states", "vslam_get_point_template", "vslam_get_point_counts", "vslam_get_updates", "vslam_get_zmssd_evals",
+    "vslam_project_all", "vslam_set_point_projection", "vslam_set_lists", "vslam_clear_counters", "vslam_search_for_points", "vslam_project_and_derivs", "vslam_calc_jacobians",
+    "vslam_calc_pose_update", "vslam_track_map", "vslam_track_frame", "vslam_track_frame_dev", "vslam_debug_atan", "vslam_kernel_launches",
+]
+
+_lib = None
+
+
+def load():
+    """Load the CUDA library; raise if it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(visualslam_android_b200 has no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, i, d = C.c_void_p, C.c_int, C.c_double
+    pi, pd = C.POINTER(C.c_int), C.POINTER(C.c_double)
+
+    def sig(name, res, *args):
+        f = getattr(L, name)
+        f.restype = res
+        f.argtypes = list(args)
+
+    sig("vslam_default_config", None, C.POINTER(Config))
+    sig("vslam_default_params", None, C.POINTER(Params))
+    sig("vslam_create", i, C.POINTER(Config), C.POINTER(vp))
+    sig("vslam_destroy", None, vp)
+    sig("vslam_last_error", C.c_char_p, vp)
+    sig("vslam_sync", i, vp)
+    sig("vslam_set_params", i, vp, C.POINTER(Params))
+    sig("vslam_set_camera", i, vp, vp)
+    sig("vslam_camera_from_params", None, vp, i, i, i, vp)
+    sig("vslam_upload_source_keyframe", i, vp, i, vp, i)
+    sig("vslam_set_map", i, vp, i, vp, vp, vp, vp, vp, vp)
+    sig("vslam_make_keyframe_lite", i, vp, i, i, vp, i, C.c_size_t)
+    sig("vslam_make_keyframe_lite_dev", i, vp, i, i, vp, i, C.c_size_t)
+    sig("vslam_level_dims", i, vp, i, pi, pi)
+    sig("vslam_get_level", i, vp, i, i, vp, i)
+    sig("vslam_get_num_corners", i, vp, i, i, pi)
+    sig("vslam_get_corners", i, vp, i, i, vp, i)
+    sig("vslam_get_row_lut", i, vp, i, i, vp)
+    sig("vslam_set_pose", i, vp, i, vp)
+    sig("vslam_get_pose", i, vp, i, vp)
+    sig("vslam_get_poses", i, vp, vp)
+    sig("vslam_set_motion", i, vp, i, vp, d, d, d)
+    sig("vslam_get_motion", i, vp, i, vp, pd, pd, pd)
+    sig("vslam_set_sbi_rotation", i, vp, i, vp)
+    sig("vslam_get_counters", i, vp, i, vp, vp, pi, pi, pi)
+    sig("vslam_get_point_states", i, vp, i, vp, vp)
+    sig("vslam_get_point_template", i, vp, i, i, vp, pi, pi)
+    sig("vslam_get_point_counts", i, vp, i, vp)
+    sig("vslam_get_updates", i, vp, i, vp, vp, i, pi)
+    sig("vslam_get_zmssd_evals", i, vp, C.POINTER(C.c_ulonglong))
+    sig("vslam_project_all", i, vp)
+    sig("vslam_set_point_projection", i, vp, i, vp, vp, vp)
+    sig("vslam_set_lists", i, vp, vp, vp, i)
+    sig("vslam_clear_counters", i, vp)
+    sig("vslam_search_for_points", i, vp, i, i)
+    sig("vslam_project_and_derivs", i, vp, i)
+    sig("vslam_calc_jacobians", i, vp)
+    sig("vslam_calc_pose_update", i, vp, d, i, i, vp)
+    sig("vslam_track_map", i, vp)
+    sig("vslam_track_frame", i, vp, vp, i, C.c_size_t)
+    sig("vslam_track_frame_dev", i, vp, vp, i, C.c_size_t)
+    sig("vslam_kernel_launches", C.c_ulonglong, vp)
+    sig("vslam_debug_atan", i, vp, vp, i)
+    _lib = L
+    return L
+
+
+def camera_from_params(params5, width, height, as_shipped_radius=False) -> np.ndarray:
+    L = load()
+    p = np.ascontiguousarray(params5, dtype=np.float64)
+    out = np.zeros(13)
+    L.vslam_camera_from_params(p.ctypes.data, int(width), int(height), int(as_shipped_radius), out.ctypes.data)
+    return out
+
+
+def debug_atan(x) -> np.ndarray:
+    L = load()
+    a = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.empty_like(a)
+    rc = L.vslam_debug_atan(a.ctypes.data, out.ctypes.data, a.size)
+    if rc != OK:
+        raise VslamError(rc, 'vslam_debug_atan')
+    return out
+
+
+def _ptr(a):
+    return a.ctypes.data if isinstance(a, np.ndarray) else int(a)
+
+
+class Context:
+    """One GPU context: `n_streams` cameras of one size tracked against one map (see include/vslam_b200.h)."""
+
+    def __init__(self, width, height, n_streams=1, max_points=1000, patch_size=11, device=0, cuda_stream=None, truncate_error=True,
+                 max_corner_frac=0.5, rand_seed=1, max_source_keyframes=1):
+        self.L = load()
+        cfg = Config()
+        self.L.vslam_default_config(C.byref(cfg))
+        cfg.device, cfg.width, cfg.height, cfg.n_streams, cfg.max_points = device, width, height, n_streams, max_points
+        cfg.patch_size, cfg.max_source_keyframes, cfg.max_corner_frac = patch_size, max_source_keyframes, max_corner_frac
+        cfg.cuda_stream = cuda_stream
+        cfg.truncate_error, cfg.rand_seed = int(truncate_error), rand_seed
+        h = C.c_void_p()
+        rc = self.L.vslam_create(C.byref(cfg), C.byref(h))
+        if rc != OK:
+            raise VslamError(rc, self.L.vslam_last_error(None).decode())
+        self.h = h
+        self.width, self.height, self.S, self.N, self.P = width, height, n_streams, max_points, patch_size
+        self.n_points = 0
+        self._keep = []
+
+    def close(self):
+        if self.h:
+            self.L.vslam_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != OK:
+            raise VslamError(rc, self.L.vslam_last_error(self.h).decode())
+
+    # -- setup
+    def set_params(self, **kw):
+        p = Params()
+        self.L.vslam_default_params(C.byref(p))
+        for k, v in kw.items():
+            setattr(p, k, v)
+        self._ck(self.L.vslam_set_params(self.h, C.byref(p)))
+
+    def set_camera(self, cam13):
+        a = np.ascontiguousarray(cam13, dtype=np.float64)
+        assert a.size == 13
+        self._ck(self.L.vslam_set_camera(self.h, a.ctypes.data))
+
+    def upload_source_keyframe(self, gray, kf_id=0):
+        g = np.ascontiguousarray(gray, dtype=np.uint8)
+        self._ck(self.L.vslam_upload_source_keyframe(self.h, kf_id, g.ctypes.data, g.shape[1]))
+
+    def set_map(self, world, right, down, ir_center, src_level, src_kf=None):
+        w = np.ascontiguousarray(world, dtype=np.float64)
+        r = np.ascontiguousarray(right, dtype=np.float64)
+        d = np.ascontiguousarray(down, dtype=np.float64)
+        c = np.ascontiguousarray(ir_center, dtype=np.int32)
+        lv = np.ascontiguousarray(src_level, dtype=np.int32)
+        kf = None if src_kf is None else np.ascontiguousarray(src_kf, dtype=np.int32)
+        n = w.shape[0]
+        self._ck(self.L.vslam_set_map(self.h, n, w.ctypes.data, r.ctypes.data, d.ctypes.data, c.ctypes.data, lv.ctypes.data,
+                                      None if kf is None else kf.ctypes.data))
+        self.n_points = n
+
+    # -- MakeKeyFrame_Lite
+    def make_keyframe_lite(self, frames, first_stream=0):
+        """frames: host uint8 array (count, H, W) or (H, W)."""
+        f = np.ascontiguousarray(frames, dtype=np.uint8)
+        if f.ndim == 2:
+            f = f[None]
+        self._ck(self.L.vslam_make_keyframe_lite(self.h, first_stream, f.shape[0], f.ctypes.data, f.shape[2], f.shape[1] * f.shape[2]))
+
+    def make_keyframe_lite_ptr(self, ptr, count, stride, frame_stride, first_stream=0, device=False):
+        fn = self.L.vslam_make_keyframe_lite_dev if device else self.L.vslam_make_keyframe_lite
+        self._ck(fn(self.h, first_stream, count, int(ptr), stride, frame_stride))
+
+    def level_dims(self, l):
+        w, h = C.c_int(), C.c_int()
+        self._ck(self.L.vslam_level_dims(self.h, l, C.byref(w), C.byref(h)))
+        return w.value, h.value
+
+    def level(self, s, l):
+        w, h = self.level_dims(l)
+        out = np.empty((h, w), dtype=np.uint8)
+        self._ck(self.L.vslam_get_level(self.h, s, l, out.ctypes.data, w))
+        return out
+
+    def corners(self, s, l):
+        n = C.c_int()
+        self._ck(self.L.vslam_get_num_corners(self.h, s, l, C.byref(n)))
+        out = np.empty((n.value, 2), dtype=np.int32)
+        self._ck(self.L.vslam_get_corners(self.h, s, l, out.ctypes.data, n.value))
+        return out
+
+    def row_lut(self, s, l):
+        _, h = self.level_dims(l)
+        out = np.empty(h, dtype=np.int32)
+        self._ck(self.L.vslam_get_row_lut(self.h, s, l, out.ctypes.data))
+        return out
+
+    # -- tracker state
+    def set_pose(self, s, pose):
+        p = np.ascontiguousarray(pose, dtype=np.float64).reshape(12)
+        self._ck(self.L.vslam_set_pose(self.h, s, p.ctypes.data))
+
+    def get_pose(self, s):
+        out = np.empty(12)
+        self._ck(self.L.vslam_get_pose(self.h, s, out.ctypes.data))
+        return out.reshape(3, 4)
+
+    def get_poses(self):
+        out = np.empty((self.S, 12))
+        self._ck(self.L.vslam_get_poses(self.h, out.ctypes.data))
+        return out.reshape(self.S, 3, 4)
+
+    def set_motion(self, s, velocity6, msd, depth_mean=1.0, depth_sigma=1.0):
+        v = np.ascontiguousarray(velocity6, dtype=np.float64)
+        self._ck(self.L.vslam_set_motion(self.h, s, v.ctypes.data, msd, depth_mean, depth_sigma))
+
+    def get_motion(self, s):
+        v = np.empty(6)
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        self._ck(self.L.vslam_get_motion(self.h, s, v.ctypes.data, C.byref(a), C.byref(b), C.byref(c)))
+        return v, a.value, b.value, c.value
+
+    def set_sbi_rotation(self, s, rot6):
+        v = np.ascontiguousarray(rot6, dtype=np.float64)
+        self._ck(self.L.vslam_set_sbi_rotation(self.h, s, v.ctypes.data))
+
+    def counters(self, s):
+        a = np.zeros(4, dtype=np.int32)
+        f = np.zeros(4, dtype=np.int32)
+        q, lost, dc = C.c_int(), C.c_int(), C.c_int()
+        self._ck(self.L.vslam_get_counters(self.h, s, a.ctypes.data, f.ctypes.data, C.byref(q), C.byref(lost), C.byref(dc)))
+        return a, f, q.value, lost.value, dc.value
+
+    def point_states(self, s):
+        ints = np.zeros((self.n_points, 8), dtype=np.int32)
+        dbl = np.zeros((self.n_points, 32), dtype=np.float64)
+        self._ck(self.L.vslam_get_point_states(self.h, s, ints.ctypes.data, dbl.ctypes.data))
+        return ints, dbl
+
+    def point_template(self, s, i):
+        t = np.zeros(self.P * self.P, dtype=np.uint8)
+        a, b = C.c_int(), C.c_int()
+        self._ck(self.L.vslam_get_point_template(self.h, s, i, t.ctypes.data, C.byref(a), C.byref(b)))
+        return t.reshape(self.P, self.P), a.value, b.value
+
+    def point_counts(self, s):
+        out = np.zeros((self.n_points, 2), dtype=np.int32)
+        self._ck(self.L.vslam_get_point_counts(self.h, s, out.ctypes.data))
+        return out
+
+    def updates(self, s):
+        u = np.zeros((20, 6))
+        sg = np.zeros(20)
+        n = C.c_int()
+        self._ck(self.L.vslam_get_updates(self.h, s, u.ctypes.data, sg.ctypes.data, 20, C.byref(n)))
+        return u[:n.value], sg[:n.value]
+
+    def zmssd_evals(self):
+        v = C.c_ulonglong()
+        self._ck(self.L.vslam_get_zmssd_evals(self.h, C.byref(v)))
+        return v.value
+
+    # -- stages
+    def project_all(self):
+        self._ck(self.L.vslam_project_all(self.h))
+
+    def set_point_projection(self, s, v2image, warp_inverse, level):
+        a = np.ascontiguousarray(v2image, dtype=np.float64)
+        b = np.ascontiguousarray(warp_inverse, dtype=np.float64)
+        c = np.ascontiguousarray(level, dtype=np.int32)
+        assert a.shape == (self.n_points, 2) and b.shape == (self.n_points, 4) and c.shape == (self.n_points,)
+        self._ck(self.L.vslam_set_point_projection(self.h, s, a.ctypes.data, b.ctypes.data, c.ctypes.data))
+
+    def set_lists(self, lists):
+        """lists: one index sequence per stream."""
+        n = np.array([len(x) for x in lists], dtype=np.int32)
+        stride = max(1, int(n.max()))
+        idx = np.zeros((self.S, stride), dtype=np.int32)
+        for s, x in enumerate(lists):
+            idx[s, :len(x)] = x
+        self._ck(self.L.vslam_set_lists(self.h, idx.ctypes.data, n.ctypes.data, stride))
+
+    def clear_counters(self):
+        self._ck(self.L.vslam_clear_counters(self.h))
+
+    def search_for_points(self, rng, subpix_its):
+        self._ck(self.L.vslam_search_for_points(self.h, rng, subpix_its))
+
+    def project_and_derivs(self, only_found=True):
+        self._ck(self.L.vslam_project_and_derivs(self.h, int(only_found)))
+
+    def calc_jacobians(self):
+        self._ck(self.L.vslam_calc_jacobians(self.h))
+
+    def calc_pose_update(self, override_sigma=0.0, mark_outliers=False, apply=False):
+        out = np.zeros((self.S, 6))
+        self._ck(self.L.vslam_calc_pose_update(self.h, float(override_sigma), int(mark_outliers), int(apply), out.ctypes.data))
+        return out
+
+    def track_map(self):
+        self._ck(self.L.vslam_track_map(self.h))
+
+    def track_frame(self, frames):
+        f = np.ascontiguousarray(frames, dtype=np.uint8)
+        assert f.shape[0] == self.S
+        self._ck(self.L.vslam_track_frame(self.h, f.ctypes.data, f.shape[2], f.shape[1] * f.shape[2]))
+
+    def track_frame_ptr(self, ptr, stride, frame_stride, device=False):
+        fn = self.L.vslam_track_frame_dev if device else self.L.vslam_track_frame
+        self._ck(fn(self.h, int(ptr), stride, frame_stride))
+
+    def sync(self):
+        self._ck(self.L.vslam_sync(self.h))
+
+    def kernel_launches(self):
+        return int(self.L.vslam_kernel_launches(self.h))

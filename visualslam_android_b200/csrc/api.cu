@@ -1,0 +1,514 @@
+// C-ABI of the B200 tracking front-end (include/vslam_b200.h): context, memory layout in HBM, readers.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+#include "vslam_internal.cuh"
+
+static std::string g_create_error;
+
+namespace {
+
+int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+template <class T> cudaError_t dalloc(T** p, size_t count) {
+  cudaError_t e = cudaMalloc((void**)p, count * sizeof(T) + 256);   // +256: aligned word reads may touch the tail
+  if (e == cudaSuccess) e = cudaMemset(*p, 0, count * sizeof(T) + 256);
+  return e;
+}
+
+// glibc srandom_r (TYPE_3) — state after srand(seed)
+void glibc_seed(unsigned seed, int* ring, int* f, int* b) {
+  if (seed == 0) seed = 1;
+  int st[31];
+  st[0] = (int)seed;
+  for (int i = 1; i < 31; i++) {
+    long hi = st[i - 1] / 127773, lo = st[i - 1] % 127773;
+    long w = 16807 * lo - 2836 * hi;
+    if (w < 0) w += 2147483647;
+    st[i] = (int)w;
+  }
+  int ff = 3, bb = 0;
+  for (int i = 0; i < 310; i++) {
+    st[ff] = (int)((unsigned)st[ff] + (unsigned)st[bb]);
+    if (++ff >= 31) ff = 0;
+    if (++bb >= 31) bb = 0;
+  }
+  memcpy(ring, st, sizeof(st)); *f = ff; *b = bb;
+}
+
+int check_stream(vslam_ctx* ctx, int s) {
+  if (!ctx) return VSLAM_E_INVALID;
+  if (s < 0 || s >= ctx->S) { ctx->err = "stream index out of range"; return VSLAM_E_INVALID; }
+  return VSLAM_OK;
+}
+
+int check_status(vslam_ctx* ctx) {   // after a sync: report corner-capacity overflow
+  int st[4];
+  VS_CUDA(cudaMemcpyAsync(st, ctx->status, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
+  VS_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (st[0]) {
+    VS_CUDA(cudaMemsetAsync(ctx->status, 0, sizeof(st), ctx->stream));
+    ctx->err = "corner list capacity exceeded (raise vslam_config.max_corner_frac)";
+    return VSLAM_E_CAPACITY;
+  }
+  return VSLAM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void vslam_default_config(vslam_config* c) {
+  memset(c, 0, sizeof(*c));
+  c->device = 0; c->width = 640; c->height = 480; c->n_streams = 1; c->max_points = 1000; c->patch_size = 11;
+  c->max_source_keyframes = 1; c->max_corner_frac = 0.5f; c->cuda_stream = nullptr; c->truncate_error = 1; c->rand_seed = 1;
+}
+
+void vslam_default_params(vslam_params* p) {   // jni/Tracker.cc:405-410,495-497,518
+  p->coarse_min = 20; p->coarse_max = 60; p->coarse_range = 30; p->coarse_subpix_its = 8; p->coarse_min_vel = 0.006;
+  p->fine_range = 10; p->fine_range_after_coarse = 5; p->fine_subpix_its_top_level = 8; p->max_patches_per_frame = 1000; p->use_sbi = 1;
+}
+
+const char* vslam_last_error(const vslam_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+unsigned long long vslam_kernel_launches(const vslam_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+void vslam_camera_from_params(const double* p, int width, int height, int as_shipped_radius, double* c) {   // jni/ATANCamera.cc:37-86
+  c[0] = width * p[0]; c[1] = height * p[1]; c[2] = width * p[2] - 0.5; c[3] = height * p[3] - 0.5;
+  c[4] = p[4];
+  if (p[4] != 0.0) { c[6] = 2.0 * tan(p[4] / 2.0); c[7] = 1.0 / c[6]; c[5] = 1.0 / p[4]; c[8] = 1.0; }
+  else { c[5] = 0.0; c[6] = 0.0; c[7] = 0.0; c[8] = 0.0; }
+  double v0, v1;
+  if (as_shipped_radius) { const int a = (int)p[2], b = (int)(1.0 - p[2]); v0 = (a > b ? a : b) / p[0]; const int c2 = (int)p[3], d = (int)(1.0 - p[3]); v1 = (c2 > d ? c2 : d) / p[1]; }
+  else { v0 = (p[2] > 1.0 - p[2] ? p[2] : 1.0 - p[2]) / p[0]; v1 = (p[3] > 1.0 - p[3] ? p[3] : 1.0 - p[3]) / p[1]; }
+  double d2 = 0; d2 += v0 * v0; d2 += v1 * v1;
+  const double r = sqrt(d2);
+  c[9] = (p[4] == 0.0) ? r : tan(r * p[4]) * c[7];
+  c[10] = 1.5 * c[9];
+  c[11] = width; c[12] = height;
+}
+
+int vslam_create(const vslam_config* cfg, vslam_ctx** out) {
+  if (!cfg || !out) { g_create_error = "null argument"; return VSLAM_E_INVALID; }
+  *out = nullptr;
+  if (cfg->width <= 0 || cfg->height <= 0 || cfg->width % 32 || cfg->height % 8 || cfg->width > 65535 || cfg->height > 65535) {
+    g_create_error = "width must be a positive multiple of 32 and height of 8 (every pyramid level keeps even dimensions)"; return VSLAM_E_INVALID; }
+  if (cfg->n_streams < 1 || cfg->max_points < 1 || cfg->max_source_keyframes < 1) { g_create_error = "n_streams, max_points, max_source_keyframes must be >= 1"; return VSLAM_E_INVALID; }
+  if (cfg->patch_size < 4 || cfg->patch_size > VSLAM_MAX_PATCH) { g_create_error = "patch_size must be in [4, 11]"; return VSLAM_E_INVALID; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= cfg->device) { g_create_error = "no CUDA device (this library has no CPU fallback)"; cudaGetLastError(); return VSLAM_E_NO_DEVICE; }
+  vslam_ctx* ctx = new (std::nothrow) vslam_ctx();
+  if (!ctx) { g_create_error = "out of host memory"; return VSLAM_E_INVALID; }
+  ctx->cfg = *cfg; vslam_default_params(&ctx->params);
+  ctx->S = cfg->n_streams; ctx->N = cfg->max_points; ctx->P = cfg->patch_size; ctx->launches = 0; ctx->n_src = cfg->max_source_keyframes;
+  ctx->scratch_host = nullptr; ctx->scratch_host_bytes = 0;
+  const float frac = cfg->max_corner_frac > 0 ? cfg->max_corner_frac : 0.5f;
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_create_error = std::string(#call) + ": " + cudaGetErrorString(e_); vslam_destroy(ctx); return VSLAM_E_CUDA; } } while (0)
+  CK(cudaSetDevice(cfg->device));
+  if (cfg->cuda_stream) { ctx->stream = (cudaStream_t)cfg->cuda_stream; ctx->own_stream = false; }
+  else { CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
+  const int S = ctx->S, N = ctx->N;
+  int w = cfg->width, h = cfg->height;
+  for (int l = 0; l < VS_LEVELS; l++) {
+    LevelDesc& L = ctx->lev[l];
+    L.w = w; L.h = h; L.pitch = round_up(w, 128);
+    L.cap = (int)((double)w * h * frac); if (L.cap < 64) L.cap = 64;
+    L.n_strips = (h + VS_STRIP_ROWS - 1) / VS_STRIP_ROWS;
+    CK(dalloc(&L.img, (size_t)S * h * L.pitch));
+    CK(dalloc(&L.corners, (size_t)S * L.cap));
+    CK(dalloc(&L.lut, (size_t)S * (h + 1)));
+    CK(dalloc(&L.strip_state, (size_t)S * L.n_strips));
+    ctx->src.w[l] = w; ctx->src.h[l] = h; ctx->src.pitch[l] = L.pitch;
+    CK(dalloc(&ctx->src.img[l], (size_t)ctx->n_src * h * L.pitch));
+    w /= 2; h /= 2;
+  }
+  CK(dalloc(&ctx->l0_ptr, (size_t)S)); CK(dalloc(&ctx->l0_stride, (size_t)S));
+  ctx->l0_ptr_host = new const uint8_t*[S]; ctx->l0_stride_host = new int[S];
+  for (int s = 0; s < S; s++) { ctx->l0_ptr_host[s] = ctx->lev[0].img + (size_t)s * ctx->lev[0].h * ctx->lev[0].pitch; ctx->l0_stride_host[s] = ctx->lev[0].pitch; }
+  CK(cudaMemcpy(ctx->l0_ptr, ctx->l0_ptr_host, sizeof(uint8_t*) * S, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->l0_stride, ctx->l0_stride_host, sizeof(int) * S, cudaMemcpyHostToDevice));
+  CK(dalloc(&ctx->tickets, (size_t)VS_LEVELS)); CK(dalloc(&ctx->status, (size_t)4)); CK(dalloc(&ctx->evals, (size_t)1));
+  // map
+  ctx->map.n = 0;
+  CK(dalloc(&ctx->map.world, (size_t)3 * N)); CK(dalloc(&ctx->map.right, (size_t)3 * N)); CK(dalloc(&ctx->map.down, (size_t)3 * N));
+  CK(dalloc(&ctx->map.ircenter, (size_t)2 * N)); CK(dalloc(&ctx->map.srclevel, (size_t)N)); CK(dalloc(&ctx->map.srckf, (size_t)N));
+  // per (stream, point) state
+  const size_t SN = (size_t)S * N;
+  PointState& ps = ctx->ps;
+  CK(dalloc(&ps.v3cam, 3 * SN)); CK(dalloc(&ps.v2image, 2 * SN)); CK(dalloc(&ps.derivs, 4 * SN)); CK(dalloc(&ps.warpinv, 4 * SN));
+  CK(dalloc(&ps.lastwarp, 4 * SN)); CK(dalloc(&ps.v2found, 2 * SN)); CK(dalloc(&ps.coarse, 2 * SN)); CK(dalloc(&ps.jac, 12 * SN));
+  CK(dalloc(&ps.err, 2 * SN)); CK(dalloc(&ps.sqrtinv, SN)); CK(dalloc(&ps.flags, SN)); CK(dalloc(&ps.level, SN));
+  CK(dalloc(&ps.tmpl, SN * VS_TMPL_BYTES)); CK(dalloc(&ps.tsum, 2 * SN)); CK(dalloc(&ps.counts, 2 * SN));
+  { std::vector<int> lv(SN, -1); CK(cudaMemcpy(ps.level, lv.data(), SN * sizeof(int), cudaMemcpyHostToDevice)); }
+  // per-stream state
+  CK(dalloc(&ctx->ss, (size_t)S));
+  {
+    std::vector<StreamState> h(S);
+    memset(h.data(), 0, sizeof(StreamState) * S);
+    for (int s = 0; s < S; s++) {
+      StreamState& st = h[s];
+      st.pose[0] = st.pose[5] = st.pose[10] = 1.0; memcpy(st.start_pose, st.pose, sizeof(st.pose));
+      st.depth_mean = 1.0; st.depth_sigma = 1.0; st.quality = 2;   // Tracker::Reset (jni/Tracker.cc:45-60)
+      glibc_seed(cfg->rand_seed, st.rng_ring, &st.rng_f, &st.rng_b);
+    }
+    CK(cudaMemcpy(ctx->ss, h.data(), sizeof(StreamState) * S, cudaMemcpyHostToDevice));
+  }
+  ctx->list_cap = N + 8;
+  CK(dalloc(&ctx->lists, (size_t)S * ctx->list_cap));
+  CK(dalloc(&ctx->pvs, (size_t)S * VS_LEVELS * N));
+  { int c = 1; while (c < ctx->list_cap) c <<= 1; ctx->sort_cap = c; }
+  CK(dalloc(&ctx->sort_scratch, (size_t)S * ctx->sort_cap));
+  memset(&ctx->cam, 0, sizeof(ctx->cam));
+#undef CK
+  *out = ctx;
+  return VSLAM_OK;
+}
+
+void vslam_destroy(vslam_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->cfg.device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  for (int l = 0; l < VS_LEVELS; l++) { cudaFree(ctx->lev[l].img); cudaFree(ctx->lev[l].corners); cudaFree(ctx->lev[l].lut); cudaFree(ctx->lev[l].strip_state); cudaFree(ctx->src.img[l]); }
+  cudaFree(ctx->l0_ptr); cudaFree(ctx->l0_stride); cudaFree(ctx->tickets); cudaFree(ctx->status); cudaFree(ctx->evals);
+  cudaFree(ctx->map.world); cudaFree(ctx->map.right); cudaFree(ctx->map.down); cudaFree(ctx->map.ircenter); cudaFree(ctx->map.srclevel); cudaFree(ctx->map.srckf);
+  PointState& ps = ctx->ps;
+  cudaFree(ps.v3cam); cudaFree(ps.v2image); cudaFree(ps.derivs); cudaFree(ps.warpinv); cudaFree(ps.lastwarp); cudaFree(ps.v2found); cudaFree(ps.coarse);
+  cudaFree(ps.jac); cudaFree(ps.err); cudaFree(ps.sqrtinv); cudaFree(ps.flags); cudaFree(ps.level); cudaFree(ps.tmpl); cudaFree(ps.tsum); cudaFree(ps.counts);
+  cudaFree(ctx->ss); cudaFree(ctx->lists); cudaFree(ctx->pvs); cudaFree(ctx->sort_scratch);
+  if (ctx->scratch_host) cudaFreeHost(ctx->scratch_host);
+  delete[] ctx->l0_ptr_host; delete[] ctx->l0_stride_host;
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int vslam_sync(vslam_ctx* ctx) {
+  if (!ctx) return VSLAM_E_INVALID;
+  VS_CUDA(cudaStreamSynchronize(ctx->stream));
+  return check_status(ctx);
+}
+
+int vslam_set_params(vslam_ctx* ctx, const vslam_params* p) {
+  if (!ctx || !p) return VSLAM_E_INVALID;
+  if (2 * p->coarse_max > (unsigned)ctx->list_cap) { ctx->err = "coarse_max too large"; return VSLAM_E_INVALID; }
+  ctx->params = *p;
+  return VSLAM_OK;
+}
+
+int vslam_set_camera(vslam_ctx* ctx, const double* c) {
+  if (!ctx || !c) return VSLAM_E_INVALID;
+  CamDev& d = ctx->cam;
+  d.fx = c[0]; d.fy = c[1]; d.cx = c[2]; d.cy = c[3]; d.W = c[4]; d.Winv = c[5]; d.twoTan = c[6]; d.oneOver2Tan = c[7]; d.distEnabled = c[8];
+  d.largestRadius = c[9]; d.maxR = c[10]; d.width = c[11]; d.height = c[12];
+  return VSLAM_OK;
+}
+
+int vslam_upload_source_keyframe(vslam_ctx* ctx, int kf, const uint8_t* gray, int stride) {
+  if (!ctx || !gray) return VSLAM_E_INVALID;
+  if (kf < 0 || kf >= ctx->n_src || stride < ctx->src.w[0]) { ctx->err = "bad source keyframe id or stride"; return VSLAM_E_INVALID; }
+  VS_CUDA(cudaMemcpy2DAsync(ctx->src.img[0] + (size_t)kf * ctx->src.h[0] * ctx->src.pitch[0], ctx->src.pitch[0], gray, stride, ctx->src.w[0], ctx->src.h[0],
+                            cudaMemcpyHostToDevice, ctx->stream));
+  int rc = vs_launch_source_pyramid(ctx, kf);
+  if (rc) return rc;
+  VS_CUDA(cudaStreamSynchronize(ctx->stream));   // the host buffer is only read during this call
+  return VSLAM_OK;
+}
+
+int vslam_set_map(vslam_ctx* ctx, int n, const double* world, const double* right, const double* down, const int32_t* irc, const int32_t* lvl, const int32_t* kf) {
+  if (!ctx || !world || !right || !down || !irc || !lvl) return VSLAM_E_INVALID;
+  if (n < 0 || n > ctx->N) { ctx->err = "map larger than max_points"; return VSLAM_E_INVALID; }
+  for (int i = 0; i < n; i++) if (lvl[i] < 0 || lvl[i] >= VS_LEVELS || (kf && (kf[i] < 0 || kf[i] >= ctx->n_src))) { ctx->err = "map point with bad source level / keyframe"; return VSLAM_E_INVALID; }
+  VS_CUDA(cudaStreamSynchronize(ctx->stream));
+  VS_CUDA(cudaMemcpy(ctx->map.world, world, sizeof(double) * 3 * n, cudaMemcpyHostToDevice));
+  VS_CUDA(cudaMemcpy(ctx->map.right, right, sizeof(double) * 3 * n, cudaMemcpyHostToDevice));
+  VS_CUDA(cudaMemcpy(ctx->map.down, down, sizeof(double) * 3 * n, cudaMemcpyHostToDevice));
+  VS_CUDA(cudaMemcpy(ctx->map.ircenter, irc, sizeof(int) * 2 * n, cudaMemcpyHostToDevice));
+  VS_CUDA(cudaMemcpy(ctx->map.srclevel, lvl, sizeof(int) * n, cudaMemcpyHostToDevice));
+  if (kf) VS_CUDA(cudaMemcpy(ctx->map.srckf, kf, sizeof(int) * n, cudaMemcpyHostToDevice));
+  else VS_CUDA(cudaMemset(ctx->map.srckf, 0, sizeof(int) * n));
+  // a new map invalidates every per-point tracker state (TrackerData is created lazily per MapPoint, jni/Tracker.cc:372)
+  const size_t SN = (size_t)ctx->S * ctx->N;
+  VS_CUDA(cudaMemset(ctx->ps.flags, 0, SN * sizeof(int)));
+  VS_CUDA(cudaMemset(ctx->ps.counts, 0, 2 * SN * sizeof(int)));
+  ctx->map.n = n;
+  return VSLAM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- MakeKeyFrame_Lite
+static int adopt_l0(vslam_ctx* ctx, int first, int count, const uint8_t* base, int stride, size_t frame_stride, bool own) {
+  for (int k = 0; k < count; k++) {
+    const int s = first + k;
+    ctx->l0_ptr_host[s] = own ? ctx->lev[0].img + (size_t)s * ctx->lev[0].h * ctx->lev[0].pitch : base + (size_t)k * frame_stride;
+    ctx->l0_stride_host[s] = own ? ctx->lev[0].pitch : stride;
+  }
+  VS_CUDA(cudaMemcpyAsync(ctx->l0_ptr + first, ctx->l0_ptr_host + first, sizeof(uint8_t*) * count, cudaMemcpyHostToDevice, ctx->stream));
+  VS_CUDA(cudaMemcpyAsync(ctx->l0_stride + first, ctx->l0_stride_host + first, sizeof(int) * count, cudaMemcpyHostToDevice, ctx->stream));
+  return VSLAM_OK;
+}
+
+static int upload_frames(vslam_ctx* ctx, int first, int count, const uint8_t* gray, int stride, size_t frame_stride) {
+  const LevelDesc& L = ctx->lev[0];
+  uint8_t* dst = L.img + (size_t)first * L.h * L.pitch;
+  if (stride == L.pitch && frame_stride == (size_t)L.h * L.pitch) {
+    VS_CUDA(cudaMemcpyAsync(dst, gray, (size_t)count * L.h * L.pitch, cudaMemcpyHostToDevice, ctx->stream));
+  } else {
+    for (int k = 0; k < count; k++)
+      VS_CUDA(cudaMemcpy2DAsync(dst + (size_t)k * L.h * L.pitch, L.pitch, gray + (size_t)k * frame_stride, stride, L.w, L.h, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  return VSLAM_OK;
+}
+
+static int check_range(vslam_ctx* ctx, int first, int count, const void* p, int stride) {
+  if (!ctx) return VSLAM_E_INVALID;
+  if (!p || first < 0 || count < 1 || first + count > ctx->S || stride < ctx->lev[0].w) { ctx->err = "bad stream range, pointer or stride"; return VSLAM_E_INVALID; }
+  return VSLAM_OK;
+}
+
+int vslam_make_keyframe_lite(vslam_ctx* ctx, int first, int count, const uint8_t* gray, int stride, size_t frame_stride) {
+  int rc = check_range(ctx, first, count, gray, stride); if (rc) return rc;
+  bool was_adopted = false;
+  for (int s = first; s < first + count; s++) was_adopted |= ctx->l0_stride_host[s] != ctx->lev[0].pitch || ctx->l0_ptr_host[s] != ctx->lev[0].img + (size_t)s * ctx->lev[0].h * ctx->lev[0].pitch;
+  if (was_adopted && (rc = adopt_l0(ctx, first, count, nullptr, 0, 0, true))) return rc;
+  if ((rc = upload_frames(ctx, first, count, gray, stride, frame_stride))) return rc;
+  return vs_launch_pyramid_fast(ctx, first, count);
+}
+
+int vslam_make_keyframe_lite_dev(vslam_ctx* ctx, int first, int count, const uint8_t* gray, int stride, size_t frame_stride) {
+  int rc = check_range(ctx, first, count, gray, stride); if (rc) return rc;
+  if (((uintptr_t)gray & 15) || (stride & 15) || (frame_stride & 15)) { ctx->err = "device frames must be 16-byte aligned with stride % 16 == 0"; return VSLAM_E_INVALID; }
+  bool same = true;
+  for (int k = 0; k < count; k++) same &= ctx->l0_ptr_host[first + k] == gray + (size_t)k * frame_stride && ctx->l0_stride_host[first + k] == stride;
+  if (!same && (rc = adopt_l0(ctx, first, count, gray, stride, frame_stride, false))) return rc;
+  return vs_launch_pyramid_fast(ctx, first, count);
+}
+
+int vslam_level_dims(const vslam_ctx* ctx, int level, int* w, int* h) {
+  if (!ctx || level < 0 || level >= VS_LEVELS) return VSLAM_E_INVALID;
+  *w = ctx->lev[level].w; *h = ctx->lev[level].h; return VSLAM_OK;
+}
+
+int vslam_get_level(vslam_ctx* ctx, int s, int l, uint8_t* out, int out_stride) {
+  int rc = check_stream(ctx, s); if (rc) return rc;
+  if (l < 0 || l >= VS_LEVELS || !out || out_stride < ctx->lev[l].w) { ctx->err = "bad level / stride"; return VSLAM_E_INVALID; }
+  const LevelDesc& L = ctx->lev[l];
+  if ((rc = vslam_sync(ctx))) return rc;
+  const uint8_t* src = l == 0 ? ctx->l0_ptr_host[s] : L.img + (size_t)s * L.h * L.pitch;
+  const int sp = l == 0 ? ctx->l0_stride_host[s] : L.pitch;
+  VS_CUDA(cudaMemcpy2D(out, out_stride, src, sp, L.w, L.h, cudaMemcpyDeviceToHost));
+  return VSLAM_OK;
+}
+
+int vslam_get_num_corners(vslam_ctx* ctx, int s, int l, int* n) {
+  int rc = check_stream(ctx, s); if (rc) return rc;
+  if (l < 0 || l >= VS_LEVELS || !n) return VSLAM_E_INVALID;
+  if ((rc = vslam_sync(ctx))) return rc;
+  const LevelDesc& L = ctx->lev[l];
+  VS_CUDA(cudaMemcpy(n, L.lut + (size_t)s * (L.h + 1) + L.h, sizeof(int), cudaMemcpyDeviceToHost));
+  return VSLAM_OK;
+}
+
+int vslam_get_corners(vslam_ctx* ctx, int s, int l, int32_t* xy, int cap) {
+  int n = 0; int rc = vslam_get_num_corners(ctx, s, l, &n); if (rc) return rc;
+  if (n > cap) { ctx->err = "output buffer too small"; return VSLAM_E_INVALID; }
+  std::vector<uint32_t> tmp(n);
+  const LevelDesc& L = ctx->lev[l];
+  if (n) VS_CUDA(cudaMemcpy(tmp.data(), L.corners + (size_t)s * L.cap, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < n; i++) { xy[2 * i] = tmp[i] & 0xffff; xy[2 * i + 1] = tmp[i] >> 16; }
+  return VSLAM_OK;
+}
+
+int vslam_get_row_lut(vslam_ctx* ctx, int s, int l, int32_t* lut) {
+  int rc = check_stream(ctx, s); if (rc) return rc;
+  if (l < 0 || l >= VS_LEVELS || !lut) return VSLAM_E_INVALID;
+  if ((rc = vslam_sync(ctx))) return rc;
+  const LevelDesc& L = ctx->lev[l];
+  VS_CUDA(cudaMemcpy(lut, L.lut + (size_t)s * (L.h + 1), sizeof(int) * L.h, cudaMemcpyDeviceToHost));
+  return VSLAM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- per-stream state
+static int read_ss(vslam_ctx* ctx, int s, StreamState* st) {
+  VS_CUDA(cudaStreamSynchronize(ctx->stream));
+  VS_CUDA(cudaMemcpy(st, ctx->ss + s, sizeof(StreamState), cudaMemcpyDeviceToHost));
+  return VSLAM_OK;
+}
+static int write_ss(vslam_ctx* ctx, int s, const StreamState* st) {
+  VS_CUDA(cudaMemcpy(ctx->ss + s, st, sizeof(StreamState), cudaMemcpyHostToDevice));
+  return VSLAM_OK;
+}
+
+int vslam_set_pose(vslam_ctx* ctx, int s, const double* p) {
+  int rc = check_stream(ctx, s); if (rc) return rc;
+  VS_CUDA(cudaStreamSynchronize(ctx->stream));
+  VS_CUDA(cudaMemcpy((char*)(ctx->ss + s) + offsetof(StreamState, pose), p, sizeof(double) * 12, cudaMemcpyHostToDevice));
+  return VSLAM_OK;
+}
+int vslam_get_pose(vslam_ctx* ctx, int s, double* p) {
+  int rc = check_stream(ctx, s); if (rc) return rc;
+  VS_CUDA(cudaStreamSynchronize(ctx->stream));
+  VS_CUDA(cudaMemcpy(p, (char*)(ctx->ss + s) + offsetof(StreamState, pose), sizeof(double) * 12, cudaMemcpyDeviceToHost));
+  return VSLAM_OK;
+}
+int vslam_get_poses(vslam_ctx* ctx, double* p) {
+  if (!ctx || !p) return VSLAM_E_INVALID;
+  VS_CUDA(cudaMemcpy2DAsync(p, sizeof(double) * 12, (char*)ctx->ss + offsetof(StreamState, pose), sizeof(StreamState), sizeof(double) * 12, ctx->S, cudaMemcpyDeviceToHost, ctx->stream));
+  VS_CUDA(cudaStreamSynchronize(ctx->stream));
+  return VSLAM_OK;
+}
+int vslam_set_motion(vslam_ctx* ctx, int s, const double* v6, double msd, double dmean, double dsigma) {
+  int rc = check_stream(ctx, s); if (rc) return rc;
+  StreamState st; if ((rc = read_ss(ctx, s, &st))) return rc;
+  memcpy(st.velocity, v6, sizeof(st.velocity)); st.msd_scaled_vel = msd; st.depth_mean = dmean; st.depth_sigma = dsigma;
+  return write_ss(ctx, s, &st);
+}
+int vslam_get_motion(vslam_ctx* ctx, int s, double* v6, double* msd, double* dmean, double* dsigma) {
+  int rc = check_stream(ctx, s); if (rc) return rc;
+  StreamState st; if ((rc = read_ss(ctx, s, &st))) return rc;
+  memcpy(v6, st.velocity, sizeof(st.velocity)); *msd = st.msd_scaled_vel; *dmean = st.depth_mean; *dsigma = st.depth_sigma;
+  return VSLAM_OK;
+}
+int vslam_set_sbi_rotation(vslam_ctx* ctx, int s, const double* r6) {
+  int rc = check_stream(ctx, s); if (rc) return rc;
+  VS_CUDA(cudaStreamSynchronize(ctx->stream));
+  VS_CUDA(cudaMemcpy((char*)(ctx->ss + s) + offsetof(StreamState, sbi_rot), r6, sizeof(double) * 6, cudaMemcpyHostToDevice));
+  return VSLAM_OK;
+}
+int vslam_get_counters(vslam_ctx* ctx, int s, int32_t* att, int32_t* fnd, int* quality, int* lost, int* did_coarse) {
+  int rc = check_stream(ctx, s); if (rc) return rc;
+  StreamState st; if ((rc = read_ss(ctx, s, &st))) return rc;
+  for (int l = 0; l < VS_LEVELS; l++) { att[l] = st.attempted[l]; fnd[l] = st.found[l]; }
+  *quality = st.quality; *lost = st.lost_frames; *did_coarse = st.did_coarse;
+  return VSLAM_OK;
+}
+int vslam_get_updates(vslam_ctx* ctx, int s, double* upd6, double* sig, int cap, int* n) {
+  int rc = check_stream(ctx, s); if (rc) return rc;
+  StreamState st; if ((rc = read_ss(ctx, s, &st))) return rc;
+  *n = st.n_updates;
+  for (int k = 0; k < st.n_updates && k < cap; k++) { memcpy(upd6 + 6 * k, st.updates + 6 * k, sizeof(double) * 6); sig[k] = st.sigmas[k]; }
+  return VSLAM_OK;
+}
+int vslam_get_zmssd_evals(vslam_ctx* ctx, unsigned long long* total) {
+  if (!ctx || !total) return VSLAM_E_INVALID;
+  VS_CUDA(cudaStreamSynchronize(ctx->stream));
+  VS_CUDA(cudaMemcpy(total, ctx->evals, sizeof(*total), cudaMemcpyDeviceToHost));
+  return VSLAM_OK;
+}
+
+int vslam_get_point_states(vslam_ctx* ctx, int s, int32_t* ints, double* dbl) {
+  int rc = check_stream(ctx, s); if (rc) return rc;
+  VS_CUDA(cudaStreamSynchronize(ctx->stream));
+  const int n = ctx->map.n, N = ctx->N; const size_t SN = (size_t)ctx->S * N, o = (size_t)s * N;
+  std::vector<double> buf((size_t)36 * n); std::vector<int> fl(n), lv(n);
+  auto grab = [&](const double* src, int comps, double* dst) -> cudaError_t {
+    for (int c = 0; c < comps; c++) { cudaError_t e = cudaMemcpy(dst + (size_t)c * n, src + c * SN + o, sizeof(double) * n, cudaMemcpyDeviceToHost); if (e != cudaSuccess) return e; }
+    return cudaSuccess;
+  };
+  double* b = buf.data();
+  const PointState& ps = ctx->ps;
+  VS_CUDA(grab(ps.v2image, 2, b)); VS_CUDA(grab(ps.v2found, 2, b + 2 * n)); VS_CUDA(grab(ps.derivs, 4, b + 4 * n)); VS_CUDA(grab(ps.v3cam, 3, b + 8 * n));
+  VS_CUDA(grab(ps.warpinv, 4, b + 11 * n)); VS_CUDA(grab(ps.sqrtinv, 1, b + 15 * n)); VS_CUDA(grab(ps.jac, 12, b + 16 * n)); VS_CUDA(grab(ps.err, 2, b + 28 * n));
+  VS_CUDA(grab(ps.coarse, 2, b + 30 * n));
+  VS_CUDA(cudaMemcpy(fl.data(), ps.flags + o, sizeof(int) * n, cudaMemcpyDeviceToHost));
+  VS_CUDA(cudaMemcpy(lv.data(), ps.level + o, sizeof(int) * n, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < n; i++) {
+    int32_t* I = ints + 8 * (size_t)i; double* Dd = dbl + 32 * (size_t)i;
+    const int f = fl[i];
+    I[0] = !!(f & F_INIMAGE); I[1] = lv[i]; I[2] = !!(f & F_SEARCHED); I[3] = !!(f & F_FOUND); I[4] = !!(f & F_SUBPIX); I[5] = !!(f & F_TBAD); I[6] = !!(f & F_HASTD); I[7] = 0;
+    for (int c = 0; c < 32; c++) Dd[c] = b[(size_t)c * n + i];
+  }
+  return VSLAM_OK;
+}
+
+int vslam_get_point_template(vslam_ctx* ctx, int s, int i, uint8_t* tmpl, int* sum, int* sumsq) {
+  int rc = check_stream(ctx, s); if (rc) return rc;
+  if (i < 0 || i >= ctx->map.n) return VSLAM_E_INVALID;
+  VS_CUDA(cudaStreamSynchronize(ctx->stream));
+  const size_t gi = (size_t)s * ctx->N + i, SN = (size_t)ctx->S * ctx->N;
+  VS_CUDA(cudaMemcpy(tmpl, ctx->ps.tmpl + gi * VS_TMPL_BYTES, ctx->P * ctx->P, cudaMemcpyDeviceToHost));
+  VS_CUDA(cudaMemcpy(sum, ctx->ps.tsum + gi, sizeof(int), cudaMemcpyDeviceToHost));
+  VS_CUDA(cudaMemcpy(sumsq, ctx->ps.tsum + SN + gi, sizeof(int), cudaMemcpyDeviceToHost));
+  return VSLAM_OK;
+}
+
+int vslam_get_point_counts(vslam_ctx* ctx, int s, int32_t* oi) {
+  int rc = check_stream(ctx, s); if (rc) return rc;
+  VS_CUDA(cudaStreamSynchronize(ctx->stream));
+  const int n = ctx->map.n; const size_t SN = (size_t)ctx->S * ctx->N, o = (size_t)s * ctx->N;
+  std::vector<int> a(n), b(n);
+  VS_CUDA(cudaMemcpy(a.data(), ctx->ps.counts + o, sizeof(int) * n, cudaMemcpyDeviceToHost));
+  VS_CUDA(cudaMemcpy(b.data(), ctx->ps.counts + SN + o, sizeof(int) * n, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < n; i++) { oi[2 * i] = a[i]; oi[2 * i + 1] = b[i]; }
+  return VSLAM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- stages
+int vslam_project_all(vslam_ctx* ctx) { if (!ctx) return VSLAM_E_INVALID; return vs_launch_project_all(ctx, 0); }
+
+int vslam_set_point_projection(vslam_ctx* ctx, int s, const double* v2image, const double* warp, const int32_t* level) {
+  int rc = check_stream(ctx, s); if (rc) return rc;
+  if (!v2image || !warp || !level) return VSLAM_E_INVALID;
+  VS_CUDA(cudaStreamSynchronize(ctx->stream));
+  const int n = ctx->map.n; const size_t SN = (size_t)ctx->S * ctx->N, o = (size_t)s * ctx->N;
+  std::vector<double> col(n);
+  for (int c = 0; c < 2; c++) { for (int i = 0; i < n; i++) col[i] = v2image[2 * i + c]; VS_CUDA(cudaMemcpy(ctx->ps.v2image + c * SN + o, col.data(), sizeof(double) * n, cudaMemcpyHostToDevice)); }
+  for (int c = 0; c < 4; c++) { for (int i = 0; i < n; i++) col[i] = warp[4 * i + c]; VS_CUDA(cudaMemcpy(ctx->ps.warpinv + c * SN + o, col.data(), sizeof(double) * n, cudaMemcpyHostToDevice)); }
+  VS_CUDA(cudaMemcpy(ctx->ps.level + o, level, sizeof(int) * n, cudaMemcpyHostToDevice));
+  return VSLAM_OK;
+}
+
+int vslam_set_lists(vslam_ctx* ctx, const int32_t* idx, const int32_t* n, int idx_stride) {
+  if (!ctx || !idx || !n) return VSLAM_E_INVALID;
+  VS_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::vector<StreamState> h(ctx->S);
+  VS_CUDA(cudaMemcpy(h.data(), ctx->ss, sizeof(StreamState) * ctx->S, cudaMemcpyDeviceToHost));
+  for (int s = 0; s < ctx->S; s++) {
+    if (n[s] < 0 || n[s] > ctx->list_cap) { ctx->err = "list longer than max_points"; return VSLAM_E_INVALID; }
+    for (int k = 0; k < n[s]; k++) if (idx[(size_t)s * idx_stride + k] < 0 || idx[(size_t)s * idx_stride + k] >= ctx->map.n) { ctx->err = "list entry is not a map point"; return VSLAM_E_INVALID; }
+    if (n[s]) VS_CUDA(cudaMemcpy(ctx->lists + (size_t)s * ctx->list_cap, idx + (size_t)s * idx_stride, sizeof(int) * n[s], cudaMemcpyHostToDevice));
+    h[s].nA = n[s]; h[s].nB = 0; h[s].nB_top = 0;
+  }
+  VS_CUDA(cudaMemcpy(ctx->ss, h.data(), sizeof(StreamState) * ctx->S, cudaMemcpyHostToDevice));
+  return VSLAM_OK;
+}
+
+int vslam_clear_counters(vslam_ctx* ctx) {
+  if (!ctx) return VSLAM_E_INVALID;
+  VS_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::vector<StreamState> h(ctx->S);
+  VS_CUDA(cudaMemcpy(h.data(), ctx->ss, sizeof(StreamState) * ctx->S, cudaMemcpyDeviceToHost));
+  for (int s = 0; s < ctx->S; s++) { for (int l = 0; l < VS_LEVELS; l++) h[s].attempted[l] = h[s].found[l] = 0; h[s].n_updates = 0; }
+  VS_CUDA(cudaMemcpy(ctx->ss, h.data(), sizeof(StreamState) * ctx->S, cudaMemcpyHostToDevice));
+  return VSLAM_OK;
+}
+
+int vslam_search_for_points(vslam_ctx* ctx, int range, int subpix) { if (!ctx) return VSLAM_E_INVALID; return vs_launch_search(ctx, 0, range, subpix); }
+int vslam_project_and_derivs(vslam_ctx* ctx, int only_found) { if (!ctx) return VSLAM_E_INVALID; return vs_launch_project_and_derivs(ctx, only_found); }
+int vslam_calc_jacobians(vslam_ctx* ctx) { if (!ctx) return VSLAM_E_INVALID; return vs_launch_calc_jacobians(ctx); }
+
+int vslam_calc_pose_update(vslam_ctx* ctx, double sigma, int mark, int apply, double* out) {
+  if (!ctx) return VSLAM_E_INVALID;
+  int rc = vs_launch_pose(ctx, 0, sigma, mark, apply); if (rc) return rc;
+  if (out) {
+    VS_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::vector<StreamState> h(ctx->S);
+    VS_CUDA(cudaMemcpy(h.data(), ctx->ss, sizeof(StreamState) * ctx->S, cudaMemcpyDeviceToHost));
+    for (int s = 0; s < ctx->S; s++) { const int u = h[s].n_updates - 1; for (int k = 0; k < 6; k++) out[6 * s + k] = u >= 0 ? h[s].updates[6 * u + k] : 0.0; }
+  }
+  return VSLAM_OK;
+}
+
+int vslam_track_map(vslam_ctx* ctx) { if (!ctx) return VSLAM_E_INVALID; return vs_launch_track_map(ctx, 0); }
+
+int vslam_track_frame(vslam_ctx* ctx, const uint8_t* gray, int stride, size_t frame_stride) {
+  if (!ctx) return VSLAM_E_INVALID;
+  int rc = vslam_make_keyframe_lite(ctx, 0, ctx->S, gray, stride, frame_stride); if (rc) return rc;
+  return vs_launch_track_map(ctx, 1);
+}
+int vslam_track_frame_dev(vslam_ctx* ctx, const uint8_t* gray, int stride, size_t frame_stride) {
+  if (!ctx) return VSLAM_E_INVALID;
+  int rc = vslam_make_keyframe_lite_dev(ctx, 0, ctx->S, gray, stride, frame_stride); if (rc) return rc;
+  return vs_launch_track_map(ctx, 1);
+}
+
+}  // extern "C"

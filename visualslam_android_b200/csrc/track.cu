@@ -1,0 +1,854 @@
+// Tracker::TrackMap on the GPU (reference: jni/Tracker.cc:358-626), batched over all streams of a context.
+//
+//   k_project_lists   one CTA per stream: TrackerData::Project + GetDerivsUnsafe + CalcSearchLevelAndWarpMatrix for
+//                     every map point, ordered per-level PVS lists, std::random_shuffle with the stream's glibc rand()
+//                     state, coarse / fine list selection (all of the reference's rand() use happens here).
+//   k_search          one warp per (stream, list entry): MakeTemplateCoarseCont, FindPatchCoarse (ZMSSD with dp4a over
+//                     the FAST corners of the row-LUT window), sub-pixel inverse-compositional refinement.
+//   k_pose            one CTA per stream: the ten Gauss-Newton iterations of a stage — re-projection / linear update,
+//                     Jacobians, Tukey sigma (bitonic sort + median), weights, the 27-term normal-equation reduction,
+//                     6x6 LU solve, pose = exp(mu) * pose — plus scene depth, motion model and quality assessment.
+// FP64 throughout, no FMA contraction (-fmad=false): integer results are bit-exact, poses agree to ~1e-12.
+#include "geometry.cuh"
+
+namespace {
+
+constexpr int kPT = 256;  // threads per CTA in per-stream kernels
+constexpr int kSearchWarps = 4;
+
+struct Dev {   // everything the kernels need, passed by value
+  LevelDesc lev[VS_LEVELS];
+  const uint8_t* const* l0_ptr; const int* l0_stride;
+  CamDev cam; MapDev map; SourceKF src; PointState ps;
+  StreamState* ss; int* lists; int list_cap; int* pvs; double* sort_scratch; int sort_cap;
+  unsigned long long* evals;
+  int S, N, P, truncate;
+  vslam_params prm;
+};
+
+__device__ __forceinline__ int LevelScale(int l) { return 1 << l; }
+
+// ------------------------------------------------------------------------------------------------
+// TrackerData::Project (jni/TrackerData.h:69-86).  Returns true if Cam.Project was reached (cache valid).
+__device__ inline bool td_project(const Dev& D, const double* pose, int i, size_t gi, size_t SN, CamCache& cc, int& flags) {
+  flags &= ~F_INIMAGE;
+  const double* w = D.map.world + 3 * (size_t)i;
+  const double wp[3] = {w[0], w[1], w[2]};
+  double c[3]; se3_apply(pose, wp, c);
+  D.ps.v3cam[gi] = c[0]; D.ps.v3cam[SN + gi] = c[1]; D.ps.v3cam[2 * SN + gi] = c[2];
+  if (c[2] < 0.001) return false;
+  const double px = c[0] / c[2], py = c[1] / c[2];
+  double d = 0; d += px * px; d += py * py;
+  if (d > D.cam.largestRadius * D.cam.largestRadius) return false;
+  double im[2]; cam_project(D.cam, px, py, im, cc);
+  D.ps.v2image[gi] = im[0]; D.ps.v2image[SN + gi] = im[1];
+  if (cc.invalid) return true;
+  if (im[0] < 0 || im[1] < 0 || im[0] > D.cam.width || im[1] > D.cam.height) return true;
+  flags |= F_INIMAGE;
+  return true;
+}
+
+// PatchFinder::CalcSearchLevelAndWarpMatrix (jni/PatchFinder.cc:31-68)
+__device__ inline int calc_level_warp(const Dev& D, const double* pose, int i, size_t gi, size_t SN, const double* dv, int& flags) {
+  const double c[3] = {D.ps.v3cam[gi], D.ps.v3cam[SN + gi], D.ps.v3cam[2 * SN + gi]};
+  const double invz = 1.0 / c[2];
+  const double* rp = D.map.right + 3 * (size_t)i; const double* dp = D.map.down + 3 * (size_t)i;
+  const double r3[3] = {rp[0], rp[1], rp[2]}, d3[3] = {dp[0], dp[1], dp[2]};
+  double mr[3], md[3]; rot_apply(pose, r3, mr); rot_apply(pose, d3, md);
+  double a[2], b[2];
+  for (int k = 0; k < 2; k++) { a[k] = mr[k] - c[k] * mr[2] * invz; b[k] = md[k] - c[k] * md[2] * invz; }
+  double aux1[2], aux2[2];
+  for (int r = 0; r < 2; r++) {
+    double s = dv[2 * r] * a[0]; s += dv[2 * r + 1] * a[1]; aux1[r] = s * invz;
+    double t = dv[2 * r] * b[0]; t += dv[2 * r + 1] * b[1]; aux2[r] = t * invz;
+  }
+  const double w00 = aux1[0], w01 = aux2[0], w10 = aux1[1], w11 = aux2[1];
+  D.ps.warpinv[gi] = w00; D.ps.warpinv[SN + gi] = w01; D.ps.warpinv[2 * SN + gi] = w10; D.ps.warpinv[3 * SN + gi] = w11;
+  double det = w00 * w11 - w01 * w10;
+  int level = 0;
+  while (det > 3 && level < VS_LEVELS - 1) { level++; det *= 0.25; }
+  if (det > 3 || det < 0.25) { flags |= F_TBAD; return -1; }
+  return level;
+}
+
+// ------------------------------------------------------------------------------------------------
+// First loop of TrackMap + list building.  mode 0: stage API (flags reset for every point, no lists); mode 1: TrackMap.
+__global__ void __launch_bounds__(kPT) k_project_lists(Dev D, int mode, int apply_motion) {
+  extern __shared__ int sh_i[];          // [N] packed level lists (L3|L2|L1|L0), [N] random draws
+  __shared__ double s_pose[12];
+  __shared__ int s_cnt[kPT / 32][VS_LEVELS], s_run[VS_LEVELS], s_off[VS_LEVELS + 1];
+  __shared__ int s_seg[8];
+  const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = D.map.n;
+  const size_t SN = (size_t)D.S * D.N;
+  StreamState* st = D.ss + s;
+  if (mode == 1 && st->lost_frames >= 3) return;   // lost streams wait for the (out-of-scope) relocaliser, jni/Tracker.cc:104,133
+  if (tid == 0 && apply_motion) {   // Tracker::ApplyMotionModel (jni/Tracker.cc:781-798)
+    double v[6]; for (int k = 0; k < 6; k++) v[k] = st->velocity[k];
+    for (int k = 0; k < 12; k++) st->start_pose[k] = st->pose[k];
+    if (D.prm.use_sbi) { v[0] = 0.0; v[1] = 0.0; v[3] = st->sbi_rot[3]; v[4] = st->sbi_rot[4]; v[5] = st->sbi_rot[5]; }
+    double e[12], np[12]; se3_exp(v, e); se3_mul(e, st->start_pose, np);
+    for (int k = 0; k < 12; k++) st->pose[k] = np[k];
+  }
+  __syncthreads();
+  if (tid < 12) s_pose[tid] = st->pose[tid];
+  if (tid < VS_LEVELS) s_run[tid] = 0;
+  if (mode == 1 && tid < VS_LEVELS) { st->attempted[tid] = 0; st->found[tid] = 0; }
+  __syncthreads();
+  int* pvs = D.pvs + (size_t)s * VS_LEVELS * D.N;
+
+  for (int base = 0; base < N; base += kPT) {
+    const int i = base + tid;
+    int level = -1; bool pv = false;
+    if (i < N) {
+      const size_t gi = (size_t)s * D.N + i;
+      int flags = D.ps.flags[gi] | F_HASTD;
+      if (mode == 0) { flags &= ~(F_SEARCHED | F_FOUND | F_SUBPIX); }
+      CamCache cc;
+      td_project(D, s_pose, i, gi, SN, cc, flags);
+      if (flags & F_INIMAGE) {
+        double dv[4]; cam_derivs(D.cam, cc, dv);
+        for (int k = 0; k < 4; k++) D.ps.derivs[k * SN + gi] = dv[k];
+        level = calc_level_warp(D, s_pose, i, gi, SN, dv, flags);
+        D.ps.level[gi] = level;
+        if (level >= 0) { pv = true; flags &= ~(F_SEARCHED | F_FOUND); }
+      } else if (mode == 0) D.ps.level[gi] = -1;
+      D.ps.flags[gi] = flags;
+    }
+    if (mode == 1) {   // ordered append to the per-level PVS lists (jni/Tracker.cc:391)
+      unsigned bal[VS_LEVELS];
+#pragma unroll
+      for (int l = 0; l < VS_LEVELS; l++) { bal[l] = __ballot_sync(0xffffffffu, pv && level == l); if (lane == 0) s_cnt[warp][l] = __popc(bal[l]); }
+      __syncthreads();
+      if (pv) {
+        int off = s_run[level];
+        for (int w = 0; w < warp; w++) off += s_cnt[w][level];
+        off += __popc(bal[level] & ((1u << lane) - 1u));
+        pvs[level * D.N + off] = i;
+      }
+      __syncthreads();
+      if (tid < VS_LEVELS) { int a = s_run[tid]; for (int w = 0; w < kPT / 32; w++) a += s_cnt[w][tid]; s_run[tid] = a; }
+      __syncthreads();
+    }
+  }
+  if (mode == 0) return;
+
+  // packed layout in shared memory: [L3][L2][L1][L0]
+  if (tid == 0) { s_off[0] = 0; s_off[1] = s_run[3]; s_off[2] = s_off[1] + s_run[2]; s_off[3] = s_off[2] + s_run[1]; s_off[4] = s_off[3] + s_run[0]; }
+  __syncthreads();
+  int* list = sh_i; int* rnd = sh_i + D.N;
+  for (int q = 0; q < VS_LEVELS; q++) {   // q-th packed segment holds level 3-q
+    const int l = 3 - q, n = s_run[l];
+    for (int k = tid; k < n; k += kPT) list[s_off[q] + k] = pvs[l * D.N + k];
+  }
+  const int total = s_off[4];
+  // random draws for the four level shuffles, in level order 0..3 (jni/Tracker.cc:396-397)
+  int ring_f = 0, ring_b = 0;
+  if (tid == 0) {
+    int ring[31]; for (int k = 0; k < 31; k++) ring[k] = st->rng_ring[k];
+    ring_f = st->rng_f; ring_b = st->rng_b;
+    int pos = 0;
+    for (int l = 0; l < VS_LEVELS; l++) for (int k = 1; k < s_run[l]; k++) rnd[pos++] = glibc_rand_next(ring, ring_f, ring_b);
+    for (int k = 0; k < 31; k++) st->rng_ring[k] = ring[k];
+    st->rng_f = ring_f; st->rng_b = ring_b;
+  }
+  __syncthreads();
+  if (lane == 0 && warp < VS_LEVELS) {   // std::random_shuffle of level `warp` (libstdc++ bits/stl_algo.h:4581-4597)
+    const int l = warp, n = s_run[l];
+    int roff = 0; for (int k = 0; k < l; k++) roff += max(s_run[k] - 1, 0);
+    int* v = list + s_off[3 - l];
+    for (int k = 1; k < n; k++) { const int j = rnd[roff + k - 1] % (k + 1); if (k != j) { const int t = v[k]; v[k] = v[j]; v[j] = t; } }
+  }
+  __syncthreads();
+  if (tid == 0) {   // coarse / fine selection (jni/Tracker.cc:399-527)
+    const int n3 = s_run[3], n2 = s_run[2];
+    unsigned nCoarseMax = D.prm.coarse_max, nCoarseRange = D.prm.coarse_range;
+    bool tryCoarse = !(st->msd_scaled_vel < D.prm.coarse_min_vel || nCoarseMax == 0);
+    if (st->just_recovered) { tryCoarse = true; nCoarseMax *= 2; nCoarseRange *= 2; st->just_recovered = 0; }
+    int a0 = 0, a1 = 0, t0 = 0, t1 = n3, f0 = n3;   // A = [a0,a1), top = [t0,t1), fine = [f0,total)
+    if (tryCoarse && (unsigned)(n3 + n2) > D.prm.coarse_min) {
+      if ((unsigned)n3 > nCoarseMax) { a0 = 0; a1 = (int)nCoarseMax; t0 = a1; t1 = n3; f0 = n3; }
+      else {
+        a0 = 0; a1 = n3; t0 = t1 = 0; f0 = n3;
+        if ((unsigned)n3 < nCoarseMax) {
+          const int more = (int)nCoarseMax - n3;
+          if (n2 <= more) { a0 = n3; a1 = n3 + n2; f0 = n3 + n2; }    // vNextToSearch overwritten by the L2 list (quirk, :454-456)
+          else { a1 = n3 + more; f0 = n3 + more; }
+        }
+      }
+    } else tryCoarse = false;
+    st->try_coarse = tryCoarse ? 1 : 0; st->coarse_range = (int)nCoarseRange; st->did_coarse = 0;
+    int nFine = total - f0;
+    int use = D.prm.max_patches_per_frame - ((a1 - a0) + (t1 - t0));
+    if (use < 0) use = 0;
+    if (nFine > use) {
+      int ring[31]; for (int k = 0; k < 31; k++) ring[k] = st->rng_ring[k];
+      int* v = list + f0;
+      for (int k = 1; k < nFine; k++) { const int j = glibc_rand_next(ring, ring_f, ring_b) % (k + 1); if (k != j) { const int t = v[k]; v[k] = v[j]; v[j] = t; } }
+      for (int k = 0; k < 31; k++) st->rng_ring[k] = ring[k];
+      st->rng_f = ring_f; st->rng_b = ring_b;
+      nFine = use;
+    }
+    s_seg[0] = a0; s_seg[1] = a1 - a0; s_seg[2] = t0; s_seg[3] = t1 - t0; s_seg[4] = f0; s_seg[5] = nFine;
+    st->nA = a1 - a0; st->nB_top = t1 - t0; st->nB = (t1 - t0) + nFine; st->n_updates = 0;
+  }
+  __syncthreads();
+  int* out = D.lists + (size_t)s * D.list_cap;
+  int dst = 0;
+  for (int g = 0; g < 3; g++) {
+    const int src0 = s_seg[2 * g], n = s_seg[2 * g + 1];
+    for (int k = tid; k < n; k += kPT) out[dst + k] = list[src0 + k];
+    dst += n;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SearchForPoints, one warp per list entry.
+struct SearchSmem {
+  double pos[VS_MAXP * VS_MAXP * 2];    // template sample positions / sub-pixel products
+  double jx[81], jy[81], prod2[81];
+  uint32_t tw[VS_MAXP * 3];            // template rows as 3 zero-padded words
+  uint8_t tmpl[VS_TMPL_BYTES];
+};
+
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+  for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+
+// mode 0: explicit list [0,nA) with (range, subpix) arguments; 1: coarse set A; 2: fine set B (re-projected first)
+__global__ void __launch_bounds__(kSearchWarps * 32) k_search(Dev D, int mode, int range_arg, int subpix_arg) {
+  __shared__ SearchSmem sm_all[kSearchWarps];
+  const int s = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int e = blockIdx.x * kSearchWarps + warp;
+  StreamState* st = D.ss + s;
+  if (mode != 0 && st->lost_frames >= 3) return;
+  int first, count, range, subpix;
+  if (mode == 0) { first = 0; count = st->nA; range = range_arg; subpix = subpix_arg; }
+  else if (mode == 1) { if (!st->try_coarse) return; first = 0; count = st->nA; range = st->coarse_range; subpix = D.prm.coarse_subpix_its; }
+  else { first = st->nA; count = st->nB; range = st->did_coarse ? D.prm.fine_range_after_coarse : D.prm.fine_range; subpix = (e < st->nB_top) ? D.prm.fine_subpix_its_top_level : 0; }
+  if (e >= count) return;
+  SearchSmem& sm = sm_all[warp];
+  const int i = D.lists[(size_t)s * D.list_cap + first + e];
+  const size_t SN = (size_t)D.S * D.N, gi = (size_t)s * D.N + i;
+  const int P = D.P, PP = P * P;
+  int flags = D.ps.flags[gi];
+  const int level = D.ps.level[gi];
+
+  if (mode == 2 && lane == 0) {   // ProjectAndDerivs with bFound == false: projection only (jni/TrackerData.h:98-102)
+    CamCache cc; td_project(D, st->pose, i, gi, SN, cc, flags);
+  }
+  flags = __shfl_sync(0xffffffffu, flags, 0);
+
+  // ---- MakeTemplateCoarseCont (jni/PatchFinder.cc:79-125)
+  double m2[4]; int refresh = 0, inside = 0, tsum = 0, tsumsq = 0;
+  if (lane == 0) {
+    const double w0 = D.ps.warpinv[gi], w1 = D.ps.warpinv[SN + gi], w2 = D.ps.warpinv[2 * SN + gi], w3 = D.ps.warpinv[3 * SN + gi];
+    const double invdet = 1.0 / (w0 * w3 - w1 * w2);
+    const int sc = LevelScale(level);
+    m2[0] = (w3 * invdet) * sc; m2[1] = (-w1 * invdet) * sc; m2[2] = (-w2 * invdet) * sc; m2[3] = (w0 * invdet) * sc;
+    refresh = !(flags & F_HAVELAST);
+    for (int c = 0; !refresh && c < 2; c++) {
+      const double d0 = m2[c] - D.ps.lastwarp[c * SN + gi], d1 = m2[2 + c] - D.ps.lastwarp[(2 + c) * SN + gi];
+      double dd = 0; dd += d0 * d0; dd += d1 * d1;
+      const double lim = 0.07;
+      if (dd > lim * lim) refresh = 1;
+    }
+  }
+  refresh = __shfl_sync(0xffffffffu, refresh, 0);
+  const int kf = D.map.srckf[i], sl = D.map.srclevel[i];
+  if (refresh) {
+    const uint8_t* simg = D.src.img[sl] + (size_t)kf * D.src.h[sl] * D.src.pitch[sl];
+    const int iw = D.src.w[sl], ih = D.src.h[sl], sp = D.src.pitch[sl];
+    if (lane == 0) {   // transform_image (jni/vision/ImageHandler.cpp:21-113): sample positions by sequential accumulation
+      const double across0 = m2[0], across1 = m2[2], down0 = m2[1], down1 = m2[3];
+      const double o = (double)(P / 2);
+      double a = m2[0] * o; a += m2[1] * o; double b = m2[2] * o; b += m2[3] * o;
+      const double p00 = (double)D.map.ircenter[2 * i] - a, p01 = (double)D.map.ircenter[2 * i + 1] - b;
+      double min_x = p00, min_y = p01, max_x = min_x, max_y = min_y;
+      if (across0 < 0) min_x += P * across0; else max_x += P * across0;
+      if (down0 < 0) min_x += P * down0; else max_x += P * down0;
+      if (across1 < 0) min_y += P * across1; else max_y += P * across1;
+      if (down1 < 0) min_y += P * down1; else max_y += P * down1;
+      const double cr0 = down0 - P * across0, cr1 = down1 - P * across1;
+      inside = (min_x >= 0 && min_y >= 0 && max_x < iw - 1 && max_y < ih - 1);
+      double px = p00, py = p01;
+      for (int r = 0; r < P; ++r, px += cr0, py += cr1)
+        for (int c = 0; c < P; ++c, px += across0, py += across1) { sm.pos[2 * (r * P + c)] = px; sm.pos[2 * (r * P + c) + 1] = py; }
+    }
+    inside = __shfl_sync(0xffffffffu, inside, 0);
+    __syncwarp();
+    const float x_bound = iw - 1, y_bound = ih - 1;
+    int outside = 0;
+    for (int k = lane; k < PP; k += 32) {
+      double x = sm.pos[2 * k], y = sm.pos[2 * k + 1];
+      uint8_t v = 0;
+      if (inside || (0 <= x && 0 <= y && x < x_bound && y < y_bound)) {   // sample(u8) (jni/vision/ImageHandler.cpp:12-19)
+        const int lx = (int)x, ly = (int)y;
+        x -= lx; y -= ly;
+        const uint8_t* r0 = simg + (size_t)ly * sp + lx; const uint8_t* r1 = r0 + sp;
+        v = (uint8_t)((1 - y) * ((1 - x) * r0[0] + x * r0[1]) + y * ((1 - x) * r1[0] + x * r1[1]));
+      } else outside++;
+      sm.tmpl[k] = v;
+    }
+    outside = warp_sum(outside);
+    __syncwarp();
+    int ts = 0, tq = 0;
+    for (int k = lane; k < PP; k += 32) { const int b = sm.tmpl[k]; ts += b; tq += b * b; D.ps.tmpl[gi * VS_TMPL_BYTES + k] = (uint8_t)b; }
+    ts = warp_sum(ts); tq = warp_sum(tq);
+    tsum = ts; tsumsq = tq;
+    flags = outside ? (flags | F_TBAD) : (flags & ~F_TBAD);
+    flags |= F_HAVELAST;
+    if (lane == 0) {
+      D.ps.tsum[gi] = ts; D.ps.tsum[SN + gi] = tq;
+      for (int c = 0; c < 4; c++) D.ps.lastwarp[c * SN + gi] = m2[c];
+    }
+  } else {
+    for (int k = lane; k < PP; k += 32) sm.tmpl[k] = D.ps.tmpl[gi * VS_TMPL_BYTES + k];
+    tsum = D.ps.tsum[gi]; tsumsq = D.ps.tsum[SN + gi];
+  }
+  __syncwarp();
+  if (flags & F_TBAD) {   // jni/Tracker.cc:637-640
+    if (lane == 0) D.ps.flags[gi] = flags & ~(F_INIMAGE | F_FOUND);
+    return;
+  }
+  // template rows as zero-padded words for dp4a
+  for (int k = lane; k < P * 3; k += 32) {
+    const int r = k / 3, w = k - 3 * r;
+    uint32_t v = 0;
+    for (int b = 0; b < 4; b++) { const int c = 4 * w + b; if (c < P) v |= (uint32_t)sm.tmpl[r * P + c] << (8 * b); }
+    sm.tw[k] = v;
+  }
+  __syncwarp();
+  if (lane == 0) atomicAdd(&st->attempted[level], 1);
+
+  // ---- FindPatchCoarse (jni/PatchFinder.cc:170-235)
+  const LevelDesc& L = D.lev[level];
+  const uint8_t* img; int pitch;
+  if (level == 0) { img = D.l0_ptr[s]; pitch = D.l0_stride[s]; } else { img = L.img + (size_t)s * L.h * L.pitch; pitch = L.pitch; }
+  const int maxSSD = PP * 500;
+  const int nLevelScale = LevelScale(level);
+  const double ix = D.ps.v2image[gi] / nLevelScale, iy = D.ps.v2image[SN + gi] / nLevelScale;
+  const unsigned nRange = ((unsigned)range + nLevelScale - 1) / nLevelScale;
+  int nTop = iy - nRange;
+  const int nBottomPlusOne = iy + nRange + 1;
+  const int nLeft = ix - nRange, nRight = ix + nRange;
+  unsigned long long best = ((unsigned long long)(unsigned)(maxSSD + 1) << 32) | 0xffffffffull;
+  flags |= F_SEARCHED;
+  bool searched_any = true;
+  if (nTop < 0) nTop = 0;
+  if (nTop >= L.h || nBottomPlusOne <= 0) searched_any = false;
+  int nevals = 0;
+  if (searched_any) {
+    const int* lut = L.lut + (size_t)s * (L.h + 1);
+    const int begin = lut[nTop], end = (nBottomPlusOne >= L.h) ? lut[L.h] : lut[nBottomPlusOne];
+    const uint32_t* corners = L.corners + (size_t)s * L.cap;
+    const int b = P / 2, nwords = (P + 3) >> 2;
+    const uint32_t lastmask = (P & 3) ? ((1u << (8 * (P & 3))) - 1u) : 0xffffffffu;
+    for (int c0 = begin; c0 < end; c0 += 32) {
+      const int ci = c0 + lane;
+      if (ci >= end) continue;
+      const uint32_t cw = corners[ci];
+      const int cx = cw & 0xffff, cy = cw >> 16;
+      if ((double)cx < nLeft || (double)cx > nRight) continue;
+      const double dx = ix - (double)cx, dy = iy - (double)cy;
+      double d2 = 0; d2 += dx * dx; d2 += dy * dy;
+      if (d2 > nRange * nRange) continue;
+      // ZMSSDAtPoint (jni/PatchFinder.cc:352-380)
+      int ssd;
+      nevals++;
+      if (!(cx >= b && cy >= b && cx < L.w - b && cy < L.h - b)) ssd = maxSSD + 1;
+      else {
+        unsigned sum = 0, sumsq = 0, cross = 0;
+        const uint8_t* rp = img + (size_t)(cy - b) * pitch + (cx - b);
+        for (int r = 0; r < P; r++, rp += pitch) {
+          const unsigned a = (unsigned)((uintptr_t)rp & 3u), sh = a * 8;
+          const uint32_t* wp = (const uint32_t*)(rp - a);
+          uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = 0, w3 = 0;
+          if (a + P > 8) w2 = __ldg(wp + 2);
+          if (a + P > 12) w3 = __ldg(wp + 3);
+          uint32_t n0 = __funnelshift_r(w0, w1, sh), n1 = __funnelshift_r(w1, w2, sh), n2 = __funnelshift_r(w2, w3, sh);
+          if (nwords == 3) n2 &= lastmask; else if (nwords == 2) { n1 &= lastmask; n2 = 0; } else { n0 &= lastmask; n1 = 0; n2 = 0; }
+          sum = __dp4a(n0, 0x01010101u, sum); sumsq = __dp4a(n0, n0, sumsq); cross = __dp4a(n0, sm.tw[3 * r], cross);
+          sum = __dp4a(n1, 0x01010101u, sum); sumsq = __dp4a(n1, n1, sumsq); cross = __dp4a(n1, sm.tw[3 * r + 1], cross);
+          sum = __dp4a(n2, 0x01010101u, sum); sumsq = __dp4a(n2, n2, sumsq); cross = __dp4a(n2, sm.tw[3 * r + 2], cross);
+        }
+        const int SA = tsum, SB = (int)sum;
+        ssd = ((2 * SA * SB - SA * SA - SB * SB) / PP + (int)sumsq + tsumsq - 2 * (int)cross);
+      }
+      const unsigned long long key = ((unsigned long long)(unsigned)ssd << 32) | (unsigned)ci;   // ssd >= 0; ties -> lowest corner index
+      best = key < best ? key : best;
+    }
+  }
+#pragma unroll
+  for (int d = 16; d; d >>= 1) { const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, d); best = o < best ? o : best; }
+  nevals = warp_sum(nevals);
+  if (lane == 0 && nevals) atomicAdd(D.evals, (unsigned long long)nevals);
+  const int bestSSD = (int)(best >> 32);
+  if (!(bestSSD < maxSSD)) {
+    if (lane == 0) D.ps.flags[gi] = flags & ~F_FOUND;
+    return;
+  }
+  const uint32_t bc = (L.corners + (size_t)s * L.cap)[(unsigned)best];
+  const double coarse0 = ((double)(bc & 0xffff) + 0.5) * nLevelScale - 0.5, coarse1 = ((double)(bc >> 16) + 0.5) * nLevelScale - 0.5;  // LevelZeroPos
+  flags |= F_FOUND;
+  double found0 = coarse0, found1 = coarse1;
+  int ok = 1;
+  if (subpix > 0) {
+    flags |= F_SUBPIX;
+    // ---- MakeSubPixTemplate (jni/PatchFinder.cc:242-267)
+    const int Q = P - 2, QQ = Q * Q;
+    for (int k = lane; k < QQ; k += 32) {
+      const int x = k / Q + 1, y = k - (x - 1) * Q + 1;   // stored index (x-1)*Q + (y-1)
+      sm.jx[k] = 0.5 * (sm.tmpl[y * P + x + 1] - sm.tmpl[y * P + x - 1]);
+      sm.jy[k] = 0.5 * (sm.tmpl[(y + 1) * P + x] - sm.tmpl[(y - 1) * P + x]);
+    }
+    __syncwarp();
+    double h = 0;   // lanes 0..8 each own one entry of JtJ (sums of multiples of 0.25: exact in any order)
+    if (lane < 9) {
+      const int a = lane / 3, b2 = lane - 3 * a;
+      for (int k = 0; k < QQ; k++) {
+        const double ga = a == 0 ? sm.jx[k] : (a == 1 ? sm.jy[k] : 1.0), gb = b2 == 0 ? sm.jx[k] : (b2 == 1 ? sm.jy[k] : 1.0);
+        h += ga * gb;
+      }
+    }
+    double H[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) H[k] = __shfl_sync(0xffffffffu, h, k);
+    double hinv[9];
+    {   // 3x3 inverse: adjugate * (1/det), evaluation order of the oracle (oracle/vslam_oracle.cc inverse3)
+      const double c00 = H[4] * H[8] - H[5] * H[7], c10 = H[5] * H[6] - H[3] * H[8], c20 = H[3] * H[7] - H[4] * H[6];
+      const double det = H[0] * c00 + H[1] * c10 + H[2] * c20, invdet = 1.0 / det;
+      hinv[0] = c00 * invdet; hinv[3] = c10 * invdet; hinv[6] = c20 * invdet;
+      hinv[1] = (H[2] * H[7] - H[1] * H[8]) * invdet; hinv[4] = (H[0] * H[8] - H[2] * H[6]) * invdet; hinv[7] = (H[1] * H[6] - H[0] * H[7]) * invdet;
+      hinv[2] = (H[1] * H[5] - H[2] * H[4]) * invdet; hinv[5] = (H[2] * H[3] - H[0] * H[5]) * invdet; hinv[8] = (H[0] * H[4] - H[1] * H[3]) * invdet;
+    }
+    double sp0 = coarse0, sp1 = coarse1, meanDiff = 0.0;
+    ok = 0;
+    // ---- IterateSubPixToConvergence / IterateSubPix (jni/PatchFinder.cc:272-350)
+    for (int it = 0; it < subpix; it++) {
+      const double c0 = (sp0 + 0.5) / nLevelScale - 0.5, c1 = (sp1 + 0.5) / nLevelScale - 0.5;   // LevelNPos
+      const int xb = (c0 > 0.0 ? c0 + 0.5 : c0 - 0.5), yb = (c1 > 0.0 ? c1 + 0.5 : c1 - 0.5);
+      const int bd = P / 2 + 1;
+      if (!(xb >= bd && yb >= bd && xb < L.w - bd && yb < L.h - bd)) break;   // off the image: not converged
+      const double b0 = c0 - (double)(P / 2), b1 = c1 - (double)(P / 2);
+      const double dX = b0 - floor(b0), dY = b1 - floor(b1);
+      const float fTL = (1.0 - dX) * (1.0 - dY), fTR = (dX) * (1.0 - dY), fBL = (1.0 - dX) * (dY), fBR = (dX) * (dY);
+      for (int k = lane; k < QQ; k += 32) {   // k = (y-1)*Q + (x-1): the reference's loop order
+        const int y = k / Q + 1, x = k - (y - 1) * Q + 1;
+        const uint8_t* tl = img + (size_t)((int)b1 + y) * pitch + ((int)b0 + x);
+        const float fPixel = fTL * tl[0] + fTR * tl[1] + fBL * tl[pitch] + fBR * tl[pitch + 1];
+        const double dDiff = fPixel - sm.tmpl[y * P + x] + meanDiff;
+        const int j = (x - 1) * Q + (y - 1);
+        sm.pos[k] = dDiff * sm.jx[j]; sm.pos[QQ + k] = dDiff * sm.jy[j]; sm.prod2[k] = dDiff;
+      }
+      __syncwarp();
+      double acc = 0;   // lanes 0,1,2 add their accumulator's terms in pixel order, like the reference's serial loop
+      if (lane < 3) { const double* p = lane == 0 ? sm.pos : (lane == 1 ? sm.pos + QQ : sm.prod2); for (int k = 0; k < QQ; k++) acc += p[k]; }
+      const double a0 = __shfl_sync(0xffffffffu, acc, 0), a1 = __shfl_sync(0xffffffffu, acc, 1), a2 = __shfl_sync(0xffffffffu, acc, 2);
+      __syncwarp();
+      double upd[3];
+#pragma unroll
+      for (int r = 0; r < 3; r++) { double sacc = hinv[3 * r] * a0; sacc += hinv[3 * r + 1] * a1; sacc += hinv[3 * r + 2] * a2; upd[r] = sacc; }
+      sp0 -= upd[0] * nLevelScale; sp1 -= upd[1] * nLevelScale;
+      meanDiff -= upd[2];
+      double d = 0; d += upd[0] * upd[0]; d += upd[1] * upd[1];
+#ifdef VS_DEBUG_POINT
+      if (i == VS_DEBUG_POINT && lane == 0) printf("gpu it: acc %.17g %.17g %.17g upd %.17g %.17g %.17g pos %.17g %.17g d %.17g mix %.9g %.9g %.9g %.9g\n", a0, a1, a2, upd[0], upd[1], upd[2], sp0, sp1, d, fTL, fTR, fBL, fBR);
+#endif
+      const double lim = 0.03;
+      if (d < lim * lim) { ok = 1; break; }
+    }
+    found0 = sp0; found1 = sp1;
+  }
+  if (lane == 0) {
+    D.ps.coarse[gi] = coarse0; D.ps.coarse[SN + gi] = coarse1;
+    D.ps.sqrtinv[gi] = (1.0 / nLevelScale);
+    if (ok) { D.ps.v2found[gi] = found0; D.ps.v2found[SN + gi] = found1; atomicAdd(&st->found[level], 1); if (subpix <= 0) flags &= ~F_SUBPIX; }
+    else flags &= ~F_FOUND;   // sub-pixel iteration did not converge (jni/Tracker.cc:660-666)
+    D.ps.flags[gi] = flags;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pose-update kernel, one CTA per stream.
+__device__ inline void block_bitonic_sort(double* a, int n2) {   // ascending, n2 = power of two
+  for (int k = 2; k <= n2; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < n2; t += blockDim.x) {
+        const int p = t ^ j;
+        if (p > t) {
+          const double x = a[t], y = a[p];
+          const bool up = (t & k) == 0;
+          if ((x > y) == up) { a[t] = y; a[p] = x; }
+        }
+      }
+      __syncthreads();
+    }
+}
+
+// dynamic inverse = partial-pivot LU, column by column; then mu = Cinv * b  (oracle/vslam_oracle.cc inverse_lu; jni/myWLS.h:53-62)
+__device__ inline void solve6(const double* Cin, const double* b, double* mu) {
+  double a[36], inv[36], x[6]; int piv[6];
+  for (int i = 0; i < 36; i++) a[i] = Cin[i];
+  for (int i = 0; i < 6; i++) piv[i] = i;
+  for (int k = 0; k < 6; k++) {
+    int p = k; double best = fabs(a[k * 6 + k]);
+    for (int i = k + 1; i < 6; i++) if (fabs(a[i * 6 + k]) > best) { best = fabs(a[i * 6 + k]); p = i; }
+    if (p != k) { for (int j = 0; j < 6; j++) { const double t = a[k * 6 + j]; a[k * 6 + j] = a[p * 6 + j]; a[p * 6 + j] = t; } const int t = piv[k]; piv[k] = piv[p]; piv[p] = t; }
+    for (int i = k + 1; i < 6; i++) { a[i * 6 + k] /= a[k * 6 + k]; for (int j = k + 1; j < 6; j++) a[i * 6 + j] -= a[i * 6 + k] * a[k * 6 + j]; }
+  }
+  for (int c = 0; c < 6; c++) {
+    for (int i = 0; i < 6; i++) x[i] = (piv[i] == c) ? 1.0 : 0.0;
+    for (int i = 0; i < 6; i++) for (int j = 0; j < i; j++) x[i] -= a[i * 6 + j] * x[j];
+    for (int i = 5; i >= 0; i--) { for (int j = i + 1; j < 6; j++) x[i] -= a[i * 6 + j] * x[j]; x[i] /= a[i * 6 + i]; }
+    for (int i = 0; i < 6; i++) inv[i * 6 + c] = x[i];
+  }
+  for (int i = 0; i < 6; i++) { double s = inv[6 * i] * b[0]; for (int j = 1; j < 6; j++) s += inv[6 * i + j] * b[j]; mu[i] = s; }
+}
+
+struct PoseSmem {
+  double pose[12];
+  double red[kPT / 32][28];
+  double sums[28];
+  double mu[6], last[6];
+  double sigma;
+  int nerr, cnt;
+};
+
+// One CalcPoseUpdate over list entries [0,n) (jni/Tracker.cc:683-774).  Leaves mu in sm.mu (zeros if nothing found).
+__device__ void calc_pose_update(const Dev& D, PoseSmem& sm, double* sortbuf, int sortcap, const int* list, int n, int s, double overrideSigma, bool mark) {
+  const size_t SN = (size_t)D.S * D.N;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) sm.nerr = 0;
+  __syncthreads();
+  // errors (:703-709); the squared errors only feed a sort, so their order in the buffer is irrelevant
+  for (int k = tid; k < n; k += kPT) {
+    const size_t gi = (size_t)s * D.N + list[k];
+    if (!(D.ps.flags[gi] & F_FOUND)) continue;
+    const double si = D.ps.sqrtinv[gi];
+    const double e0 = (D.ps.v2found[gi] - D.ps.v2image[gi]) * si, e1 = (D.ps.v2found[SN + gi] - D.ps.v2image[SN + gi]) * si;
+    D.ps.err[gi] = e0; D.ps.err[SN + gi] = e1;
+    double e2 = 0; e2 += e0 * e0; e2 += e1 * e1;
+    const int slot = atomicAdd(&sm.nerr, 1);
+    if (overrideSigma <= 0 && slot < sortcap) sortbuf[slot] = e2;
+  }
+  __syncthreads();
+  const int nerr = sm.nerr;
+  if (nerr == 0) { if (tid < 6) sm.mu[tid] = 0.0; if (tid == 0) sm.sigma = 0.0; __syncthreads(); return; }
+  if (overrideSigma > 0) { if (tid == 0) sm.sigma = overrideSigma; }
+  else {   // Tukey::FindSigmaSquared (jni/MEstimator.h:67-77)
+    int n2 = 1; while (n2 < nerr) n2 <<= 1;
+    for (int k = nerr + tid; k < n2; k += kPT) sortbuf[k] = __longlong_as_double(0x7ff0000000000000ll);
+    __syncthreads();
+    block_bitonic_sort(sortbuf, n2);
+    if (tid == 0) {
+      const double med = sortbuf[nerr / 2];
+      const unsigned long long den = (unsigned long long)nerr * 2ull - 6ull;   // size_t arithmetic of the reference
+      double sigma = 1.4826 * (1 + 5.0 / (double)den) * sqrt(med);
+      sigma = 4.6851 * sigma;
+      sm.sigma = sigma * sigma;
+    }
+  }
+  __syncthreads();
+  const double sig2 = sm.sigma;
+  // weighted normal equations: 21 upper-triangle terms + 6 right-hand sides (jni/myWLS.h:39-50)
+  double acc[27];
+#pragma unroll
+  for (int k = 0; k < 27; k++) acc[k] = 0.0;
+  for (int k = tid; k < n; k += kPT) {
+    const int i = list[k];
+    const size_t gi = (size_t)s * D.N + i;
+    if (!(D.ps.flags[gi] & F_FOUND)) continue;
+    const double e0 = D.ps.err[gi], e1 = D.ps.err[SN + gi];
+    double e2 = 0; e2 += e0 * e0; e2 += e1 * e1;
+    const double sq = (e2 > sig2) ? 0.0 : 1.0 - (e2 / sig2);
+    const double w = sq * sq;
+    if (w == 0.0) { if (mark) D.ps.counts[gi]++; continue; }
+    else if (mark) D.ps.counts[SN + gi]++;
+    const double si = D.ps.sqrtinv[gi];
+#pragma unroll
+    for (int row = 0; row < 2; row++) {
+      double J[6];
+#pragma unroll
+      for (int c = 0; c < 6; c++) J[c] = si * D.ps.jac[(size_t)(6 * row + c) * SN + gi];
+      const double e = row ? e1 : e0;
+      const double m = D.truncate ? (double)(int)e : e;   // (int) cast of jni/Tracker.cc:766-767
+      int q = 0;
+#pragma unroll
+      for (int r = 0; r < 6; r++) {
+        const double Jw = w * J[r];
+        acc[21 + r] += m * Jw;
+#pragma unroll
+        for (int c = r; c < 6; c++) acc[q++] += Jw * J[c];
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 27; k++) {
+    double v = acc[k];
+#pragma unroll
+    for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if (lane == 0) sm.red[warp][k] = v;
+  }
+  __syncthreads();
+  if (tid < 27) { double v = 0; for (int w = 0; w < kPT / 32; w++) v += sm.red[w][tid]; sm.sums[tid] = v; }
+  __syncthreads();
+  if (tid == 0) {
+    double C[36], b[6];
+    int q = 0;
+    for (int r = 0; r < 6; r++) for (int c = r; c < 6; c++) { C[6 * r + c] = sm.sums[q] + (r == c ? 100.0 : 0.0); C[6 * c + r] = C[6 * r + c]; q++; }   // prior 100*I (:734)
+    for (int r = 0; r < 6; r++) b[r] = sm.sums[21 + r];
+    solve6(C, b, sm.mu);
+  }
+  __syncthreads();
+}
+
+__device__ void reproject_found(const Dev& D, const double* pose, const int* list, int n, int s, int only_found, int* quirk) {
+  const size_t SN = (size_t)D.S * D.N;
+  for (int k = threadIdx.x; k < n; k += kPT) {
+    const int i = list[k];
+    const size_t gi = (size_t)s * D.N + i;
+    int flags = D.ps.flags[gi];
+    if (only_found && !(flags & F_FOUND)) continue;
+    CamCache cc;
+    const bool projected = td_project(D, pose, i, gi, SN, cc, flags);
+    if (flags & F_FOUND) {   // ProjectAndDerivs refreshes the derivatives `if(bFound)` (jni/TrackerData.h:98-102)
+      if (projected) { double dv[4]; cam_derivs(D.cam, cc, dv); for (int c = 0; c < 4; c++) D.ps.derivs[c * SN + gi] = dv[c]; }
+      else atomicAdd(quirk, 1);   // reference would read the camera's cache of another point here; we keep the old derivatives
+    }
+    D.ps.flags[gi] = flags;
+  }
+}
+// TrackerData::CalcJacobian (jni/TrackerData.h:107-123)
+__device__ void calc_jacobians(const Dev& D, const int* list, int n, int s) {
+  const size_t SN = (size_t)D.S * D.N;
+  for (int k = threadIdx.x; k < n; k += kPT) {
+    const size_t gi = (size_t)s * D.N + list[k];
+    if (!(D.ps.flags[gi] & F_FOUND)) continue;
+    const double c[3] = {D.ps.v3cam[gi], D.ps.v3cam[SN + gi], D.ps.v3cam[2 * SN + gi]};
+    const double dv[4] = {D.ps.derivs[gi], D.ps.derivs[SN + gi], D.ps.derivs[2 * SN + gi], D.ps.derivs[3 * SN + gi]};
+    const double invz = 1.0 / c[2];
+    const double pos[4] = {c[0], c[1], c[2], 1.0};
+#pragma unroll
+    for (int m = 0; m < 6; m++) {
+      double v4[3] = {0, 0, 0};
+      if (m < 3) v4[m] = pos[3];
+      else { v4[(m + 1) % 3] = -pos[(m + 2) % 3]; v4[(m + 2) % 3] = pos[(m + 1) % 3]; }
+      const double c0 = (v4[0] - c[0] * v4[2] * invz) * invz, c1 = (v4[1] - c[1] * v4[2] * invz) * invz;
+      double a0 = dv[0] * c0; a0 += dv[1] * c1;
+      double a1 = dv[2] * c0; a1 += dv[3] * c1;
+      D.ps.jac[(size_t)m * SN + gi] = a0; D.ps.jac[(size_t)(6 + m) * SN + gi] = a1;
+    }
+  }
+}
+// TrackerData::LinearUpdate (jni/TrackerData.h:126-132)
+__device__ void linear_update(const Dev& D, const int* list, int n, int s, const double* v6) {
+  const size_t SN = (size_t)D.S * D.N;
+  for (int k = threadIdx.x; k < n; k += kPT) {
+    const size_t gi = (size_t)s * D.N + list[k];
+    if (!(D.ps.flags[gi] & F_FOUND)) continue;
+    for (int r = 0; r < 2; r++) {
+      double sacc = D.ps.jac[(size_t)(6 * r) * SN + gi] * v6[0];
+      for (int c = 1; c < 6; c++) sacc += D.ps.jac[(size_t)(6 * r + c) * SN + gi] * v6[c];
+      D.ps.v2image[r * SN + gi] += sacc;
+    }
+  }
+}
+
+// mode 0: one CalcPoseUpdate over [0,nA) (stage API);  1: coarse stage;  2: fine stage (+ scene depth; + motion model / quality if tail)
+__global__ void __launch_bounds__(kPT) k_pose(Dev D, int mode, double sigma_arg, int mark_arg, int apply_arg, int tail) {
+  extern __shared__ double sh_sort[];
+  __shared__ PoseSmem sm;
+  const int s = blockIdx.x, tid = threadIdx.x;
+  StreamState* st = D.ss + s;
+  if (mode != 0 && st->lost_frames >= 3) return;
+  const int* list = D.lists + (size_t)s * D.list_cap;
+  double* sortbuf = sh_sort; int sortcap = 2048;
+  const int nA = st->nA, nAll = st->nA + st->nB;
+  { int need = 1; while (need < (mode == 2 ? nAll : nA)) need <<= 1; if (need > 2048) { sortbuf = D.sort_scratch + (size_t)s * D.sort_cap; sortcap = D.sort_cap; } }
+  if (tid < 12) sm.pose[tid] = st->pose[tid];
+  if (tid < 6) sm.last[tid] = 0.0;
+  __syncthreads();
+
+  if (mode == 0) {
+    calc_pose_update(D, sm, sortbuf, sortcap, list, nA, s, sigma_arg, mark_arg != 0);
+    if (tid == 0) {
+      const int u = st->n_updates < VS_MAX_UPDATES ? st->n_updates : VS_MAX_UPDATES - 1;
+      for (int k = 0; k < 6; k++) st->updates[6 * u + k] = sm.mu[k];
+      st->sigmas[u] = sm.sigma; st->n_updates = u + 1;
+      if (apply_arg) { double e[12], np[12]; se3_exp(sm.mu, e); se3_mul(e, sm.pose, np); for (int k = 0; k < 12; k++) st->pose[k] = np[k]; }
+    }
+    return;
+  }
+
+  int n; int iters = 10;
+  if (mode == 1) {   // coarse stage (jni/Tracker.cc:464-489)
+    if (!st->try_coarse) return;
+    n = nA;
+    if (tid == 0) sm.cnt = 0;
+    __syncthreads();
+    int c = 0;
+    for (int k = tid; k < n; k += kPT) c += (D.ps.flags[(size_t)s * D.N + list[k]] & F_FOUND) ? 1 : 0;
+    if (c) atomicAdd(&sm.cnt, c);
+    __syncthreads();
+    if ((unsigned)sm.cnt < D.prm.coarse_min) return;
+    if (tid == 0) st->did_coarse = 1;
+  } else n = nAll;
+
+  for (int iter = 0; iter < iters; iter++) {
+    bool nonlinear = true;
+    if (mode == 2) nonlinear = (iter == 0 || iter == 4 || iter == 9);
+    if (iter != 0) {
+      if (nonlinear) reproject_found(D, sm.pose, list, n, s, 1, &st->quirk_stale_cache);
+      else linear_update(D, list, n, s, sm.last);
+      __syncthreads();
+    }
+    if (nonlinear) { calc_jacobians(D, list, n, s); __syncthreads(); }
+    const double ov = (iter > 5) ? (mode == 1 ? 1.0 : 16.0) : 0.0;
+    calc_pose_update(D, sm, sortbuf, sortcap, list, n, s, ov, mode == 2 && iter == 9);
+    if (tid == 0) {
+      double e[12], np[12]; se3_exp(sm.mu, e); se3_mul(e, sm.pose, np);
+      for (int k = 0; k < 12; k++) sm.pose[k] = np[k];
+      for (int k = 0; k < 6; k++) sm.last[k] = sm.mu[k];
+      const int u = st->n_updates;
+      if (u < VS_MAX_UPDATES) { for (int k = 0; k < 6; k++) st->updates[6 * u + k] = sm.mu[k]; st->sigmas[u] = sm.sigma; st->n_updates = u + 1; }
+    }
+    __syncthreads();
+  }
+  if (tid < 12) st->pose[tid] = sm.pose[tid];
+  if (mode != 2) return;
+
+  // scene depth from the tracked features (jni/Tracker.cc:610-625); fixed-shape parallel sums
+  {
+    const size_t SN2 = 2 * (size_t)D.S * D.N;
+    double a0 = 0, a1 = 0, a2 = 0;
+    for (int k = tid; k < n; k += kPT) {
+      const size_t gi = (size_t)s * D.N + list[k];
+      if (D.ps.flags[gi] & F_FOUND) { const double z = D.ps.v3cam[SN2 + gi]; a0 += z; a1 += z * z; a2 += 1.0; }
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) { a0 += __shfl_xor_sync(0xffffffffu, a0, d); a1 += __shfl_xor_sync(0xffffffffu, a1, d); a2 += __shfl_xor_sync(0xffffffffu, a2, d); }
+    if ((tid & 31) == 0) { sm.red[tid >> 5][0] = a0; sm.red[tid >> 5][1] = a1; sm.red[tid >> 5][2] = a2; }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double dSum = 0, dSumSq = 0, dNum = 0;
+    for (int w = 0; w < kPT / 32; w++) { dSum += sm.red[w][0]; dSumSq += sm.red[w][1]; dNum += sm.red[w][2]; }
+    const int nNum = (int)dNum;
+    if (nNum > 20) { st->depth_mean = dSum / nNum; st->depth_sigma = sqrt((dSumSq / nNum) - (st->depth_mean) * (st->depth_mean)); }
+    if (tail) {
+      // Tracker::UpdateMotionModel (jni/Tracker.cc:802-820)
+      double inv[12], nfo[12], m[6];
+      se3_inverse(st->start_pose, inv); se3_mul(sm.pose, inv, nfo); se3_ln(nfo, m);
+      double sacc = 0;
+      for (int k = 0; k < 6; k++) { st->velocity[k] = 0.9 * (0.5 * m[k] + 0.5 * st->velocity[k]); }
+      for (int k = 0; k < 6; k++) sacc += st->velocity[k] * st->velocity[k];
+      st->vel_mag = sqrt(sacc);
+      double v[6]; for (int k = 0; k < 6; k++) v[k] = st->velocity[k];
+      for (int k = 0; k < 3; k++) v[k] *= 1.0 / st->depth_mean;
+      sacc = 0; for (int k = 0; k < 6; k++) sacc += v[k] * v[k];
+      st->msd_scaled_vel = sqrt(sacc);
+      // Tracker::AssessTrackingQuality (jni/Tracker.cc:832-878); the keyframe-distance test belongs to MapMaker (out of scope)
+      int nTA = 0, nTF = 0, nLA = 0, nLF = 0;
+      for (int l = 0; l < VS_LEVELS; l++) { nTA += st->attempted[l]; nTF += st->found[l]; if (l >= 2) { nLA += st->attempted[l]; nLF += st->found[l]; } }
+      int q;
+      if (nTF == 0 || nTA == 0) q = 0;
+      else {
+        const double tot = (double)nTF / nTA, lg = (nLA > 10) ? (double)nLF / nLA : tot;
+        q = (tot > 0.3) ? 2 : (lg < 0.13 ? 0 : 1);
+      }
+      st->quality = q;
+      if (q == 0) st->lost_frames++; else st->lost_frames = 0;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kPT) k_project_and_derivs(Dev D, int only_found) {
+  const int s = blockIdx.x;
+  StreamState* st = D.ss + s;
+  reproject_found(D, st->pose, D.lists + (size_t)s * D.list_cap, st->nA, s, only_found, &st->quirk_stale_cache);
+}
+__global__ void __launch_bounds__(kPT) k_calc_jacobians(Dev D) {
+  const int s = blockIdx.x;
+  calc_jacobians(D, D.lists + (size_t)s * D.list_cap, D.ss[s].nA, s);
+}
+
+__global__ void k_atan(const double* x, double* y, int n) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) y[i] = atan_cr(x[i]); }
+
+Dev make_dev(const vslam_ctx* ctx) {
+  Dev D;
+  for (int l = 0; l < VS_LEVELS; l++) D.lev[l] = ctx->lev[l];
+  D.l0_ptr = ctx->l0_ptr; D.l0_stride = ctx->l0_stride;
+  D.cam = ctx->cam; D.map = ctx->map; D.src = ctx->src; D.ps = ctx->ps; D.ss = ctx->ss; D.lists = ctx->lists; D.list_cap = ctx->list_cap;
+  D.pvs = ctx->pvs; D.sort_scratch = ctx->sort_scratch; D.sort_cap = ctx->sort_cap; D.evals = ctx->evals;
+  D.S = ctx->S; D.N = ctx->N; D.P = ctx->P; D.truncate = ctx->cfg.truncate_error; D.prm = ctx->params;
+  return D;
+}
+
+}  // namespace
+
+int vs_launch_project_all(vslam_ctx* ctx, int mode) {
+  const Dev D = make_dev(ctx);
+  const size_t smem = (size_t)2 * ctx->N * sizeof(int);
+  VS_CUDA(cudaFuncSetAttribute(k_project_lists, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_project_lists<<<ctx->S, kPT, smem, ctx->stream>>>(D, mode & 1, (mode >> 1) & 1);
+  VS_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return VSLAM_OK;
+}
+
+int vs_launch_search(vslam_ctx* ctx, int which, int range, int subpix) {
+  const Dev D = make_dev(ctx);
+  const int max_entries = which == 1 ? (int)(2 * ctx->params.coarse_max) : ctx->list_cap;
+  dim3 grid((max_entries + kSearchWarps - 1) / kSearchWarps, ctx->S);
+  k_search<<<grid, kSearchWarps * 32, 0, ctx->stream>>>(D, which, range, subpix);
+  VS_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return VSLAM_OK;
+}
+
+int vs_launch_pose(vslam_ctx* ctx, int mode, double sigma, int mark, int apply) {
+  const Dev D = make_dev(ctx);
+  const size_t smem = 2048 * sizeof(double);
+  k_pose<<<ctx->S, kPT, smem, ctx->stream>>>(D, mode & 3, sigma, mark, apply, (mode >> 2) & 1);
+  VS_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return VSLAM_OK;
+}
+
+int vs_launch_project_and_derivs(vslam_ctx* ctx, int only_found) {
+  k_project_and_derivs<<<ctx->S, kPT, 0, ctx->stream>>>(make_dev(ctx), only_found);
+  VS_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return VSLAM_OK;
+}
+int vs_launch_calc_jacobians(vslam_ctx* ctx) {
+  k_calc_jacobians<<<ctx->S, kPT, 0, ctx->stream>>>(make_dev(ctx));
+  VS_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return VSLAM_OK;
+}
+
+// Tracker::TrackMap for all streams: 5 launches, no host synchronisation in between.
+int vs_launch_track_map(vslam_ctx* ctx, int with_motion_model) {
+  int rc;
+  if ((rc = vs_launch_project_all(ctx, 1 | (with_motion_model ? 2 : 0)))) return rc;
+  if ((rc = vs_launch_search(ctx, 1, 0, 0))) return rc;
+  if ((rc = vs_launch_pose(ctx, 1, 0.0, 0, 0))) return rc;
+  if ((rc = vs_launch_search(ctx, 2, 0, 0))) return rc;
+  if ((rc = vs_launch_pose(ctx, 2 | (with_motion_model ? 4 : 0), 0.0, 0, 0))) return rc;
+  return VSLAM_OK;
+}
+
+// Test hook: atan_cr over a device-side copy of x (used to compare against the host libm).
+extern "C" int vslam_debug_atan(const double* x_host, double* y_host, int n) {
+  double *dx = nullptr, *dy = nullptr;
+  if (cudaMalloc(&dx, sizeof(double) * n) != cudaSuccess || cudaMalloc(&dy, sizeof(double) * n) != cudaSuccess) return VSLAM_E_CUDA;
+  cudaMemcpy(dx, x_host, sizeof(double) * n, cudaMemcpyHostToDevice);
+  k_atan<<<(n + 255) / 256, 256>>>(dx, dy, n);
+  const cudaError_t e = cudaMemcpy(y_host, dy, sizeof(double) * n, cudaMemcpyDeviceToHost);
+  cudaFree(dx); cudaFree(dy);
+  return e == cudaSuccess ? VSLAM_OK : VSLAM_E_CUDA;
+}

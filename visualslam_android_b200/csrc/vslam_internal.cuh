@@ -1,0 +1,122 @@
+// Internal layout of a vslam_ctx and device helpers shared by the kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include "vslam_b200.h"
+
+#define VS_LEVELS VSLAM_LEVELS
+#define VS_MAXP VSLAM_MAX_PATCH
+#define VS_TMPL_BYTES 128           // P*P <= 121 bytes, padded
+#define VS_STRIP_ROWS 16            // rows of a level handled by one CTA of the pyramid+FAST kernel
+#define VS_MAX_UPDATES 20           // 10 coarse + 10 fine CalcPoseUpdate calls per TrackMap
+
+// ------------------------------------------------------------------------------------------------
+// Device-visible description of one pyramid level of the per-stream "current keyframe".
+struct LevelDesc {
+  int w, h, pitch;            // pitch: bytes between rows of the ctx-owned level image (multiple of 128)
+  int cap;                    // corner capacity per stream
+  int n_strips;               // ceil(h / VS_STRIP_ROWS)
+  uint8_t* img;               // [S][h][pitch]      (level 0: only used by the host-input path, see l0_ptr)
+  uint32_t* corners;          // [S][cap]           packed (y << 16 | x), raster order
+  int* lut;                   // [S][h + 1]         lut[y] = #corners with row < y ; lut[h] = total
+  unsigned long long* strip_state;  // [S][n_strips] decoupled look-back words
+};
+
+struct CamDev { double fx, fy, cx, cy, W, Winv, twoTan, oneOver2Tan, distEnabled, largestRadius, maxR, width, height; };
+
+// Per (stream, point) tracker state, SoA with index s * N + i   (TrackerData + PatchFinder, jni/TrackerData.h, jni/PatchFinder.h)
+struct PointState {
+  double* v3cam;      // [3][S*N]
+  double* v2image;    // [2][S*N]
+  double* derivs;     // [4][S*N]  row-major 2x2
+  double* warpinv;    // [4][S*N]
+  double* lastwarp;   // [4][S*N]
+  double* v2found;    // [2][S*N]
+  double* coarse;     // [2][S*N]
+  double* jac;        // [12][S*N]
+  double* err;        // [2][S*N]
+  double* sqrtinv;    // [S*N]
+  int* flags;         // [S*N] bit0 inImage, bit1 searched, bit2 found, bit3 didSubPix, bit4 templateBad, bit5 haveLast, bit6 hasTData
+  int* level;         // [S*N] nSearchLevel (-1 = rejected)
+  uint8_t* tmpl;      // [S*N][VS_TMPL_BYTES]
+  int* tsum;          // [2][S*N] sum, sumsq
+  int* counts;        // [2][S*N] outlier, inlier
+};
+enum { F_INIMAGE = 1, F_SEARCHED = 2, F_FOUND = 4, F_SUBPIX = 8, F_TBAD = 16, F_HAVELAST = 32, F_HASTD = 64 };
+
+struct MapDev {
+  int n;
+  double* world;   // [n][3]
+  double* right;   // [n][3]
+  double* down;    // [n][3]
+  int* ircenter;   // [n][2]
+  int* srclevel;   // [n]
+  int* srckf;      // [n]
+};
+
+struct SourceKF {   // device pyramids of the map's source keyframes: level l of keyframe k at img[l] + k*h*pitch
+  int w[VS_LEVELS], h[VS_LEVELS], pitch[VS_LEVELS];
+  uint8_t* img[VS_LEVELS];
+};
+
+// Per-stream tracker scalars (Tracker members)
+struct StreamState {
+  double pose[12], start_pose[12];
+  double velocity[6], sbi_rot[6];
+  double msd_scaled_vel, vel_mag, depth_mean, depth_sigma;
+  int attempted[VS_LEVELS], found[VS_LEVELS];
+  int quality, lost_frames, did_coarse, just_recovered;
+  int rng_ring[31]; int rng_f, rng_b;
+  int nA, nB, nB_top;           // iteration list = [0,nA) coarse set, [nA, nA+nB) fine set (first nB_top entries: top level, sub-pixel)
+  int try_coarse, coarse_range, n_updates, quirk_stale_cache;
+  double updates[VS_MAX_UPDATES * 6], sigmas[VS_MAX_UPDATES];
+};
+
+struct vslam_ctx {
+  vslam_config cfg;
+  vslam_params params;
+  cudaStream_t stream;
+  bool own_stream;
+  int S, N, P;
+  LevelDesc lev[VS_LEVELS];
+  LevelDesc* lev_dev;            // [VS_LEVELS] copy on device
+  const uint8_t** l0_ptr;        // [S] device: level-0 image of each stream (ctx-owned or adopted user buffer)
+  int* l0_stride;                // [S] device
+  const uint8_t** l0_ptr_host; int* l0_stride_host;
+  unsigned* tickets;             // [VS_LEVELS] device
+  int* status;                   // [4] device: [0] capacity overflow flag
+  CamDev cam; CamDev* cam_dev;
+  MapDev map; MapDev* map_dev;
+  SourceKF src; SourceKF* src_dev; int n_src;
+  PointState ps; PointState* ps_dev;
+  StreamState* ss;               // [S] device
+  int* lists;                    // [S][list_cap] iteration / search lists
+  int list_cap;
+  int* pvs;                      // [S][N] scratch for the per-level potentially-visible sets
+  double* sort_scratch;          // [S][sort_cap]
+  int sort_cap;
+  unsigned long long* evals;     // device counter
+  unsigned long long launches;
+  void* scratch_host; size_t scratch_host_bytes;   // pinned staging
+  std::string err;
+};
+
+#define VS_CUDA(call)                                                                                 \
+  do {                                                                                                \
+    cudaError_t e_ = (call);                                                                          \
+    if (e_ != cudaSuccess) {                                                                          \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                  \
+      return VSLAM_E_CUDA;                                                                            \
+    }                                                                                                 \
+  } while (0)
+
+// kernels/launchers implemented in the .cu files
+int vs_launch_pyramid_fast(vslam_ctx* ctx, int first_stream, int count);
+int vs_launch_source_pyramid(vslam_ctx* ctx, int kf_id);
+int vs_launch_project_all(vslam_ctx* ctx, int build_lists);
+int vs_launch_search(vslam_ctx* ctx, int which /*0 explicit list,1 coarse A,2 fine B*/, int range, int subpix);
+int vs_launch_pose(vslam_ctx* ctx, int mode, double sigma, int mark, int apply);
+int vs_launch_track_map(vslam_ctx* ctx, int with_motion_model);
+int vs_launch_project_and_derivs(vslam_ctx* ctx, int only_found);
+int vs_launch_calc_jacobians(vslam_ctx* ctx);
