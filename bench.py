@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""Benchmark of the B200 tracking front-end.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[3]): S = 256 independent synthetic VGA camera streams per GPU, 1000 map points,
+one `step` = one frame of every stream through the TrackFrame-equivalent path (MakeKeyFrame_Lite: 4-level pyramid +
+FAST-10 + row LUT; ApplyMotionModel; TrackMap coarse+fine with 10 Tukey-WLS iterations each; UpdateMotionModel;
+AssessTrackingQuality).  Streams never exchange data: N GPUs = N independent contexts, no collective on the data path.
+
+  value  tracked frames/s with the frames already resident in HBM (vslam_track_frame_dev), CUDA-event timed
+  e2e    the same through the host-buffer C-ABI call (vslam_track_frame: pinned host frames copied in every step) plus a
+         device->host read of every stream's pose, every step
+  roofline      pyramid+FAST stage (k_pyramid_fast, 4 launches per step): algorithmic bytes / event-timed duration
+  cpu_baseline  the reference's own sources (oracle/_ref) — or the oracle port when that library is absent — tracking the
+                same kind of sequence on the host cores, one process per core
+
+`--impl reference` times only the CPU arm and prints the same JSON line with "impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, N_POINTS = 640, 480, 1000
+STREAMS_PER_GPU = 256
+FRAME_STEP = 2          # synthetic sequence index advance per step (≈ 1 px of image motion per frame)
+METRIC = "tracked_frames_per_sec"
+UNIT = "frames/s"
+WORKLOAD = ("configs[3]: 256 independent synthetic VGA (640x480) camera streams per GPU, 1000 map points, full TrackFrame-equivalent "
+            "per frame (4-level pyramid + FAST-10 + row LUT, coarse+fine PatchFinder search, 10+10 Tukey-WLS iterations), P=11")
+
+
+# ------------------------------------------------------------------------------------------------ synthetic data
+def stream_poses(n_streams, n_frames, first_stream=0):
+    from visualslam_android_b200 import synth
+    return np.stack([np.stack([synth.stream_pose(FRAME_STEP * k, first_stream + s) for k in range(n_frames)]) for s in range(n_streams)])
+
+
+def render_frames_torch(tex_t, cam, poses, device):
+    """Torch version of synth.render_frame for a batch of poses (B,3,4) -> uint8 (B,H,W).  Input generation only."""
+    import torch
+    B = poses.shape[0]
+    size = tex_t.shape[0]
+    v, u = torch.meshgrid(torch.arange(cam.height, device=device, dtype=torch.float64), torch.arange(cam.width, device=device, dtype=torch.float64), indexing="ij")
+    dx = (u - cam.cx) / cam.fx
+    dy = (v - cam.cy) / cam.fy
+    rd = torch.sqrt(dx * dx + dy * dy)
+    r = torch.tan(rd * cam.w) * cam.one_over_two_tan
+    f = torch.where(rd > 0.01, r / rd.clamp_min(1e-300), torch.ones_like(rd))
+    ray = torch.stack([dx * f, dy * f, torch.ones_like(dx)], dim=-1).to(torch.float32)          # (H,W,3)
+    P = torch.as_tensor(poses, device=device, dtype=torch.float64)
+    R, t = P[:, :, :3], P[:, :, 3]
+    o = -(R.transpose(1, 2) @ t[:, :, None])[:, :, 0]                                              # (B,3)
+    d = torch.einsum("hwc,bcd->bhwd", ray, R.to(torch.float32))                                    # R^T ray
+    s = ((1.0 - o[:, 2]).to(torch.float32))[:, None, None] / d[..., 2]
+    X = o[:, 0].to(torch.float32)[:, None, None] + s * d[..., 0]
+    Y = o[:, 1].to(torch.float32)[:, None, None] + s * d[..., 1]
+    tu = torch.remainder(X * float(cam.fx) + size / 2.0, size - 1.0)
+    tv = torch.remainder(Y * float(cam.fx) + size / 2.0, size - 1.0)
+    iu = tu.floor().long().clamp_(0, size - 2)
+    iv = tv.floor().long().clamp_(0, size - 2)
+    fu = tu - iu
+    fv = tv - iv
+    flat = tex_t.reshape(-1)
+    i00 = iv * size + iu
+    val = (1 - fv) * ((1 - fu) * flat[i00] + fu * flat[i00 + 1]) + fv * ((1 - fu) * flat[i00 + size] + fu * flat[i00 + size + 1])
+    return (val + 0.5).floor().clamp_(0, 255).to(torch.uint8)
+
+
+def build_scene():
+    """KF0 + map from the CPU oracle's MakeKeyFrame_Lite (input preparation, outside every timed region)."""
+    from oracle import oraclebind
+    from visualslam_android_b200 import synth
+    cam = synth.Camera(W, H)
+    tex = synth.make_texture(2048)
+    f0 = synth.render_frame(tex, cam, synth.IDENTITY_POSE)
+    kf = oraclebind.OrcKeyFrame().make_lite(f0)
+    smap = synth.build_map(cam, [kf.corners(l) for l in range(4)], [kf.dims(l) for l in range(4)], N_POINTS)
+    return cam, tex, f0, smap
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_worker(path, stream, n_warm, n_steps, frames_per_step, use_ref):
+    """One process = one camera stream tracked by the reference (oracle/_ref) or the oracle port.  Prints per-step seconds."""
+    from visualslam_android_b200 import synth
+    d = np.load(path, allow_pickle=False)
+    frames, f0 = d["frames"][stream], d["f0"]
+    smap = synth.SyntheticMap(world=d["world"], pix_right_w=d["right"], pix_down_w=d["down"], ir_center=d["irc"], src_level=d["lvl"],
+                              center_nc=d["cnc"], one_right_nc=d["rnc"], one_down_nc=d["dnc"])
+    cam = synth.Camera(W, H)
+    if use_ref:
+        from oracle import refbind
+        rw = refbind.RefWorld(W, H, f0, smap)
+        rw.L.ref_srand(1)
+        rw.L.ref_tracker_set_sbi_rot(rw.tracker, np.zeros(6), 1)
+        step = lambda fr: rw.L.ref_tracker_track_frame_nosbi(rw.tracker, fr, W, H, W)
+    else:
+        from oracle import oraclebind
+        ow = oraclebind.OrcWorld(cam, f0, smap)
+        step = lambda fr: ow.L.orc_tracker_track_frame(ow.tracker, fr, W, H, W)
+    k = 0
+    times = []
+    for s in range(n_warm + n_steps):
+        t0 = time.perf_counter()
+        for _ in range(frames_per_step):
+            step(np.ascontiguousarray(frames[k % len(frames)]))
+            k += 1
+        times.append(time.perf_counter() - t0)
+    print(json.dumps({"t_start": time.time() - sum(times[n_warm:]), "steps": times[n_warm:]}))
+
+
+def run_cpu_arm(cam, f0, smap, frames_by_stream, n_procs, n_warm, n_steps, frames_per_step):
+    """Launch n_procs tracker processes concurrently; returns (frames/s aggregate, seconds per step, kind)."""
+    from oracle import refbind
+    use_ref = refbind.available()
+    fd, path = tempfile.mkstemp(suffix=".npz", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    os.close(fd)
+    np.savez(path, frames=frames_by_stream, f0=f0, world=smap.world, right=smap.pix_right_w, down=smap.pix_down_w, irc=smap.ir_center,
+             lvl=smap.src_level, cnc=smap.center_nc, rnc=smap.one_right_nc, dnc=smap.one_down_nc)
+    try:
+        procs = [subprocess.Popen([sys.executable, os.path.abspath(__file__), "--cpu-worker", path, str(i % len(frames_by_stream)), str(n_warm),
+                                   str(n_steps), str(frames_per_step), str(int(use_ref))], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                                  env={**os.environ, "CUDA_VISIBLE_DEVICES": "", "OMP_NUM_THREADS": "1"}) for i in range(n_procs)]
+        outs = []
+        for p in procs:
+            o, e = p.communicate(timeout=900)
+            if p.returncode != 0:
+                raise RuntimeError("cpu worker failed: " + e[-2000:])
+            outs.append(json.loads(o.strip().splitlines()[-1]))
+    finally:
+        os.unlink(path)
+    per_step = np.array([o["steps"] for o in outs])          # (procs, steps) seconds
+    step_s = per_step.max(axis=0)                             # a step ends when the slowest worker finished it
+    total = float(step_s.sum())
+    fps = n_procs * n_steps * frames_per_step / total
+    return fps, total / n_steps, ("reference" if use_ref else "port")
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            self.fh = os.fdopen(fd, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=self.fh, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                p = [x.strip() for x in line.split(",")]
+                if len(p) < 9:
+                    continue
+                try:
+                    sm.append(float(p[1])); smax.append(float(p[2]))
+                except ValueError:
+                    continue
+                for nm, v in zip(names, p[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+        finally:
+            os.unlink(self.path)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------ main
+def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "--cpu-worker":
+        a = sys.argv[2:]
+        cpu_worker(a[0], int(a[1]), int(a[2]), int(a[3]), int(a[4]), bool(int(a[5])))
+        return
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--streams", type=int, default=STREAMS_PER_GPU, help="camera streams per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    K, Wm = args.steps, max(args.warmup, 3 if args.impl == "ours" else 1)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    config = {"workload": WORKLOAD, "streams_per_gpu": args.streams, "frame": [W, H], "map_points": N_POINTS, "patch": 11, "parallelism": f"streams sharded over {world} GPU(s), no collective",
+              "l2": "every step reads a frame set that was never touched since upload (78.6 MB per 256 streams) and the per-step working set "
+                    "(frames + pyramids + corner lists + per-point state, > 250 MB) exceeds the 126 MB L2; no explicit flush"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cam, tex, f0, smap = build_scene()
+        n_procs = os.cpu_count() or 1
+        fps_step = 10
+        n_seq = min(8, n_procs)
+        poses = stream_poses(n_seq, (Wm + K) * fps_step + 1)[:, 1:]
+        frames = render_cpu_or_gpu(tex, cam, poses)
+        fps, step_s, kind = run_cpu_arm(cam, f0, smap, frames, n_procs, Wm, K, fps_step)
+        sample = f"{n_procs} processes (one tracker each, {n_seq} distinct synthetic sequences), {fps_step} frames per process per step; SmallBlurryImage steps excluded (SURVEY §8 f1)"
+        line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": Wm, "ms_per_step": step_s * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32 + f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": fps, "unit": UNIT, "cores": n_procs, "kind": kind, "sample": sample},
+                "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from visualslam_android_b200 import api
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    S = args.streams
+    cam, tex, f0, smap = build_scene()
+    tex_t = torch.from_numpy(tex.astype(np.float32)).to(dev)
+    n_frames = 1 + 2 * (Wm + K) + Wm  # frame 0 = identity; then one set for the resident leg and one for the end-to-end leg
+    poses = stream_poses(S, n_frames, first_stream=rank * S)                    # (S, n_frames, 3, 4)
+    frames_dev = torch.empty((n_frames - 1, S, H, W), dtype=torch.uint8, device=dev)
+    for k in range(1, n_frames):
+        for s0 in range(0, S, 64):
+            frames_dev[k - 1, s0:s0 + 64] = render_frames_torch(tex_t, cam, poses[s0:s0 + 64, k], dev)
+    torch.cuda.synchronize()
+    frames_host = torch.empty((Wm + K + Wm, S, H, W), dtype=torch.uint8).pin_memory()
+    frames_host.copy_(frames_dev[Wm + K:])
+    torch.cuda.synchronize()
+
+    stream = torch.cuda.Stream(device=dev)       # an explicit stream: the library launches on it and the CUDA events below are recorded on it
+    torch.cuda.set_stream(stream)
+    ctx = api.Context(W, H, n_streams=S, max_points=smap.n, device=local_rank, cuda_stream=stream.cuda_stream)
+    ctx.set_camera(cam.scalars())
+    ctx.upload_source_keyframe(f0)
+    ctx.set_map(smap.world, smap.pix_right_w, smap.pix_down_w, smap.ir_center, smap.src_level)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    fs = H * W
+    # ---- leg 1: frames resident in HBM -------------------------------------------------------------------------
+    for k in range(Wm):
+        ctx.track_frame_ptr(frames_dev[k].data_ptr(), W, fs, device=True)
+    ctx.sync()
+    ctx.set_timing(True)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    launches0 = ctx.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for k in range(Wm, Wm + K):
+        ctx.track_frame_ptr(frames_dev[k].data_ptr(), W, fs, device=True)
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    launches = ctx.kernel_launches() - launches0
+    dev_ms = max_over_ranks(e0.elapsed_time(e1))
+    stage = ctx.stage_times()
+    ctx.set_timing(False)
+    ctx.sync()     # raises on corner-capacity overflow
+    probe = list(range(0, S, max(1, S // 8)))
+    corners_per_step = sum(int(ctx.corners(s, l).shape[0]) for l in range(4) for s in probe) * (S / len(probe))
+    found = np.array([ctx.counters(s)[1].sum() for s in range(0, S, max(1, S // 16))])
+    quality = np.array([ctx.counters(s)[2] for s in range(0, S, max(1, S // 16))])
+    value = world * S * K / (dev_ms * 1e-3)
+
+    # ---- leg 2: end to end through the host-buffer call, pose read-back every step ------------------------------
+    poses_out = np.empty((S, 12))
+    for k in range(Wm):
+        ctx.track_frame_ptr(frames_host[k].data_ptr(), W, fs, device=False)
+        ctx.get_poses()
+    barrier()
+    t0 = time.perf_counter()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record(stream)
+    for k in range(Wm, Wm + K):
+        ctx.track_frame_ptr(frames_host[k].data_ptr(), W, fs, device=False)
+        poses_out = ctx.get_poses()
+    e3.record(stream)
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max_over_ranks(max(e2.elapsed_time(e3), wall_ms))
+    e2e_value = world * S * K / (e2e_ms * 1e-3)
+    assert np.isfinite(poses_out).all()
+
+    # ---- roofline of the pyramid+FAST stage ----------------------------------------------------------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    pyr_ms = sum(stage[f"pyrfast_l{l}"][0] for l in range(4))
+    lut_bytes = 4 * sum((H >> l) for l in range(4))
+    alg_bytes_step = S * (1.328125 * W * H + lut_bytes) + 4.0 * corners_per_step
+    achieved = alg_bytes_step * K / (pyr_ms * 1e-3) / 1e9
+    roofline = {"kernel": "k_pyramid_fast (4 launches per step: levels 0-3)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_step": alg_bytes_step,
+                "ms_per_step": pyr_ms / K, "share_of_step": pyr_ms / dev_ms,
+                "note": "instruction-issue bound (FAST segment test), not HBM bound: see DESIGN.md §5 and profiles/"}
+    stages_ms = {k: round(v[0] / K, 4) for k, v in stage.items() if v[1]}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": dev_ms / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32 (pyramid, FAST, ZMSSD) + f64 (projection, WLS)", "data": "synthetic", "config": config,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": S * H * W, "d2h_bytes_per_step": S * 12 * 8, "ms_per_step": e2e_ms / K},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "stages_ms_per_step": stages_ms,
+            "tracking": {"found_per_frame_mean": float(found.mean()), "quality_good_frac": float((quality == 2).mean()),
+                         "zmssd_evals_total": int(ctx.zmssd_evals())}}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n_procs = os.cpu_count() or 1
+        n_seq = min(8, n_procs)
+        fps_step, cpu_steps = 10, 6
+        seq = render_cpu_or_gpu(tex, cam, stream_poses(n_seq, (1 + cpu_steps) * fps_step + 1)[:, 1:])
+        fps, step_s, kind = run_cpu_arm(cam, f0, smap, seq, n_procs, 1, cpu_steps, fps_step)
+        line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": n_procs, "kind": kind,
+                                "sample": f"{n_procs} processes x {cpu_steps * fps_step} frames of the same synthetic VGA sequences (1000 map points), "
+                                          f"{'reference jni/ sources compiled by oracle/build_ref.sh' if kind == 'reference' else 'oracle port'}, "
+                                          "SmallBlurryImage steps excluded on both sides (SURVEY §8 f1)"}
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line))
+
+
+def render_cpu_or_gpu(tex, cam, poses):
+    """(n_seq, n_frames, 3, 4) poses -> uint8 frames; GPU renderer if a device is visible, numpy otherwise."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            dev = torch.device("cuda", 0)
+            tex_t = torch.from_numpy(tex.astype(np.float32)).to(dev)
+            out = [torch.cat([render_frames_torch(tex_t, cam, poses[s, k0:k0 + 32], dev) for k0 in range(0, poses.shape[1], 32)]).cpu().numpy()
+                   for s in range(poses.shape[0])]
+            return np.stack(out)
+    except Exception:
+        pass
+    from visualslam_android_b200 import synth
+    return np.stack([np.stack([synth.render_frame(tex, cam, poses[s, k]) for k in range(poses.shape[1])]) for s in range(poses.shape[0])])
+
+
+if __name__ == "__main__":
+    main()

@@ -142,6 +142,14 @@ int vslam_track_map(vslam_ctx* ctx);
 int vslam_track_frame(vslam_ctx* ctx, const uint8_t* gray_host, int stride, size_t frame_stride);
 int vslam_track_frame_dev(vslam_ctx* ctx, const uint8_t* gray_dev, int stride, size_t frame_stride);
 
+/* Per-kernel device times measured with CUDA events on the context's stream.  Stages: 0-3 pyramid+FAST level 0-3,
+ * 4 project+lists, 5 coarse search, 6 coarse pose iterations, 7 fine search, 8 fine pose iterations, 9 host->device copy,
+ * 10 other.  vslam_get_stage_times synchronises, returns the milliseconds and launch counts accumulated since the last call
+ * and resets them. */
+#define VSLAM_N_STAGES 11
+int vslam_set_timing(vslam_ctx* ctx, int on);
+int vslam_get_stage_times(vslam_ctx* ctx, double* ms /* [VSLAM_N_STAGES] */, int* launches /* [VSLAM_N_STAGES] */);
+
 /* Test hook: y[i] = the correctly-rounded device atan used by the camera model (csrc/atan_dd.cuh). */
 int vslam_debug_atan(const double* x_host, double* y_host, int n);
 

@@ -364,6 +364,22 @@ void ref_tracker_track_frame(void* t, const uint8_t* gray, int w, int h, int str
   cv::Mat col(1, 1, CV_8UC4, g_dummy_rgba);
   tr->TrackFrame(im, col, false);
 }
+// Tracker::TrackFrame's good-map branch (jni/Tracker.cc:76-112) driven piece by piece WITHOUT the SmallBlurryImage steps
+// (jni/Tracker.cc:86-97,105-106: the f1 "next" row of SURVEY.md §8): the SBI rotation is whatever ref_tracker_set_sbi_rot set.
+void ref_tracker_track_frame_nosbi(void* t, const uint8_t* gray, int w, int h, int stride) {
+  Tracker* tr = ((RefTracker*)t)->tr;
+  cv::Mat im = wrap_gray(gray, w, h, stride);
+  cv::Mat col(1, 1, CV_8UC4, g_dummy_rgba);
+  tr->mCurrentKF.mMeasurements.clear();
+  tr->mCurrentKF.MakeKeyFrame_Lite(im, col);
+  tr->mnFrame++;
+  if (tr->mnLostFrames < 3) {
+    tr->ApplyMotionModel();
+    tr->TrackMap(col);
+    tr->UpdateMotionModel();
+    tr->AssessTrackingQuality();
+  }
+}
 void ref_tracker_motion_model(void* t, int apply_not_update) {
   Tracker* tr = ((RefTracker*)t)->tr;
   if (apply_not_update) tr->ApplyMotionModel(); else tr->UpdateMotionModel();

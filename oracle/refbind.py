@@ -100,6 +100,7 @@ def lib():
     sig("ref_tracker_track_map", None, vp)
     sig("ref_tracker_track_frame", None, vp, _u8p, i, i, i)
     sig("ref_tracker_motion_model", None, vp, i)
+    sig("ref_tracker_track_frame_nosbi", None, vp, _u8p, i, i, i)
     sig("ref_tracker_set_sbi_rot", None, vp, _f64p, i)
     sig("ref_tracker_get_sbi_rot", None, vp, _f64p)
     sig("ref_tracker_counters", None, vp, _i32p, _i32p, C.POINTER(i), C.POINTER(i), C.POINTER(i))

@@ -1,0 +1,92 @@
+#!/usr/bin/env python
+"""Generate tests/golden/ref_small.npz from the COMPILED REFERENCE (oracle/_ref/libvslam_ref.so, built from
+/root/reference/jni by oracle/build_ref.sh).  Run in the build container:  python tests/golden/make_golden.py
+
+The fixture pins the CPU restatement (oracle/vslam_oracle.cc) wherever oracle/_ref is not available (e.g. on the GPU box
+before build, or for readers without /root/reference): tests/test_oracle_golden.py replays the same inputs through the
+restatement and compares with what the reference produced here.
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import refbind  # noqa: E402
+from visualslam_android_b200 import synth  # noqa: E402
+
+W, H, N = 320, 240, 300
+
+
+def main():
+    cam = synth.Camera(W, H)
+    tex = synth.make_texture(1024)
+    f0 = synth.render_frame(tex, cam, synth.IDENTITY_POSE)
+    kf0 = refbind.RefKeyFrame().make_lite(f0)
+    smap = synth.build_map(cam, [kf0.corners(l) for l in range(4)], [kf0.dims(l) for l in range(4)], N)
+    out = {"f0": f0, "world": smap.world, "ir_center": smap.ir_center, "src_level": smap.src_level, "center_nc": smap.center_nc,
+           "one_right_nc": smap.one_right_nc, "one_down_nc": smap.one_down_nc, "cam13": cam.scalars()}
+    rw = refbind.RefWorld(W, H, f0, smap)
+    pr, pd = rw.pixel_vectors()
+    out["pix_right_w"], out["pix_down_w"] = pr, pd
+    sc = np.zeros(13); rw.L.ref_cam_scalars(rw.cam, sc); out["ref_cam_scalars"] = sc
+
+    # --- case A: MakeKeyFrame_Lite + MakeKeyFrame_Rest on frame 1
+    tw = np.array(synth.CONFIG1_TWIST) * 0.4
+    f1 = synth.render_frame(tex, cam, synth.se3_exp(tw))
+    out["f1"] = f1
+    rgba = np.repeat(f1[:, :, None], 4, axis=2).copy()
+    kf = refbind.RefKeyFrame().make_lite(f1, rgba)
+    kf.make_rest()
+    for l in range(4):
+        out[f"lvl{l}"] = kf.pixels(l); out[f"corners{l}"] = kf.corners(l); out[f"lut{l}"] = kf.row_lut(l)
+        out[f"max{l}"] = kf.max_corners(l)
+        xy, s = kf.candidates(l); out[f"cand{l}"] = xy; out[f"cand_score{l}"] = s
+
+    # --- case B: TrackMap, fine stage only (start pose = 0.2 twist), then a second TrackMap with a coarse stage on frame 2
+    rw.L.ref_srand(1)
+    rw.make_current_kf(f1)
+    start = synth.se3_exp(np.array(synth.CONFIG1_TWIST) * 0.2)
+    rw.set_pose(start); out["start_pose"] = start
+    rw.L.ref_tracker_track_map(rw.tracker)
+    ints, dbl = rw.point_states()
+    out["B_ints"], out["B_dbl"] = ints[:, [0, 1, 2, 3, 5]], dbl[:, [0, 1, 2, 3, 15]]
+    a, f, q, lost, dc = rw.counters()
+    out["B_counters"] = np.concatenate([a, f, [dc]]); out["B_pose"] = rw.get_pose()
+    f2 = synth.render_frame(tex, cam, synth.se3_exp(np.array(synth.CONFIG1_TWIST) * 0.9))
+    out["f2"] = f2
+    rw.make_current_kf(f2)
+    rw.L.ref_tracker_set_velocity(rw.tracker, np.zeros(6), 0.05)
+    rw.L.ref_tracker_track_map(rw.tracker)
+    ints, dbl = rw.point_states()
+    out["C_ints"], out["C_dbl"] = ints[:, [0, 1, 2, 3, 5]], dbl[:, [0, 1, 2, 3, 15]]
+    a, f, q, lost, dc = rw.counters()
+    out["C_counters"] = np.concatenate([a, f, [dc]]); out["C_pose"] = rw.get_pose()
+    cnt = np.zeros((smap.n, 2), dtype=np.int32)
+    for k in range(smap.n):
+        x, y = C.c_int(), C.c_int(); rw.L.ref_map_point_counts(rw.map, k, C.byref(x), C.byref(y)); cnt[k] = (x.value, y.value)
+    out["C_counts"] = cnt
+
+    # --- case D: SE3 exp / ln and Tukey known answers
+    rs = np.random.RandomState(11)
+    mus = np.concatenate([rs.uniform(-0.3, 0.3, (20, 6)), rs.uniform(-1e-4, 1e-4, (5, 6)), rs.uniform(-2.5, 2.5, (10, 6))])
+    exps = np.zeros((len(mus), 12)); lns = np.zeros((len(mus), 6))
+    for k, mu in enumerate(mus):
+        rw.L.ref_se3_exp(np.ascontiguousarray(mu), exps[k]); rw.L.ref_se3_ln(exps[k], lns[k])
+    out["D_mu"], out["D_exp"], out["D_ln"] = mus, exps, lns
+    errs = [rs.uniform(0, 9, n) for n in (1, 2, 4, 5, 100, 1001)]
+    out["D_tukey_in"] = np.concatenate(errs); out["D_tukey_n"] = np.array([len(e) for e in errs])
+    out["D_tukey_out"] = np.array([rw.L.ref_tukey_sigma_squared(np.ascontiguousarray(e), len(e)) for e in errs])
+    # libc rand() after srand(1): first draws
+    rw.L.ref_srand(1)
+    out["D_rand"] = np.array([rw.L.ref_rand() for _ in range(400)], dtype=np.int64)
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_small.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()

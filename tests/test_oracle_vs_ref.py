@@ -1,0 +1,210 @@
+"""CPU: the oracle restatement against the compiled reference itself (oracle/_ref, built from /root/reference/jni by
+oracle/build_ref.sh).  Skipped where that library does not exist; tests/test_oracle_golden.py covers that case."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import common
+from oracle import oraclebind, refbind
+from visualslam_android_b200 import synth
+
+pytestmark = pytest.mark.skipif(not refbind.available(), reason="oracle/_ref/libvslam_ref.so not built (needs /root/reference)")
+
+
+def _worlds(P=11, **kw):
+    cam, f0, smap = common.scene(**kw)
+    rw = refbind.RefWorld(cam.width, cam.height, f0, smap)
+    pr, pd = rw.pixel_vectors()
+    ow = oraclebind.OrcWorld(cam, f0, smap, P=P, pix_right=pr, pix_down=pd)
+    return cam, f0, smap, rw, ow
+
+
+@pytest.mark.parametrize("kind", ["synthetic", "noise", "flat", "gradient"])
+def test_make_keyframe_lite(kind):
+    rs = np.random.RandomState(4)
+    if kind == "synthetic":
+        cam, f0, _ = common.scene()
+        im, _ = common.frame_at(cam, np.array(synth.CONFIG1_TWIST))
+    elif kind == "noise":
+        im = rs.randint(0, 256, (120, 160)).astype(np.uint8)
+    elif kind == "flat":
+        im = np.full((64, 96), 77, np.uint8)
+    else:
+        im = (np.add.outer(np.arange(72) * 3, np.arange(96) * 2) % 256).astype(np.uint8)
+    rk, ok = refbind.RefKeyFrame().make_lite(im), oraclebind.OrcKeyFrame().make_lite(im)
+    for l in range(4):
+        assert np.array_equal(rk.pixels(l), ok.pixels(l))
+        assert np.array_equal(rk.corners(l), ok.corners(l))
+        assert np.array_equal(rk.row_lut(l), ok.row_lut(l))
+
+
+def test_make_keyframe_rest_nonmax_and_shi_tomasi():
+    cam, f0, _ = common.scene()
+    im, _ = common.frame_at(cam, np.array(synth.CONFIG1_TWIST) * 0.7)
+    rgba = np.repeat(im[:, :, None], 4, axis=2).copy()
+    rk = refbind.RefKeyFrame().make_lite(im, rgba); rk.make_rest()
+    ok = oraclebind.OrcKeyFrame().make_lite(im); ok.make_rest()
+    for l in range(4):
+        assert np.array_equal(rk.max_corners(l), ok.max_corners(l)), l
+        rxy, rs_ = rk.candidates(l); oxy, os_ = ok.candidates(l)
+        assert np.array_equal(rxy, oxy) and np.array_equal(rs_, os_), l
+
+
+def test_camera_project_unproject_derivs():
+    cam = synth.Camera(640, 480)
+    L, R = oraclebind.lib(), refbind.lib()
+    rc = R.ref_cam_create(640.0, 480.0, 1)
+    rs = np.random.RandomState(0)
+    for _ in range(300):
+        p = rs.uniform(-0.9, 0.9, 2)
+        ri, oi_, rd, od = np.zeros(2), np.zeros(2), np.zeros(4), np.zeros(4)
+        rinv, oinv = C.c_int(), C.c_int()
+        R.ref_cam_project(rc, p, ri, C.byref(rinv), rd); L.orc_cam_project(cam.scalars(), p, oi_, C.byref(oinv), od)
+        assert np.array_equal(ri, oi_) and np.array_equal(rd, od) and rinv.value == oinv.value
+        ru, ou = np.zeros(2), np.zeros(2)
+        R.ref_cam_unproject(rc, ri, ru); L.orc_cam_unproject(cam.scalars(), oi_, ou)
+        assert np.array_equal(ru, ou)
+
+
+@pytest.mark.parametrize("P", [11, 8])
+def test_stagewise_project_search_pose(P):
+    cam, f0, smap, rw, ow = _worlds(P=P) if P == 11 else _worlds_p8()
+    f1, _ = common.frame_at(cam, np.array(synth.CONFIG1_TWIST) * 0.6)
+    start = synth.se3_exp(np.array(synth.CONFIG1_TWIST) * 0.3)
+    rw.make_current_kf(f1); ow.make_current_kf(f1)
+    rw.set_pose(start); ow.set_pose(start)
+    rw.L.ref_tracker_project_all(rw.tracker); ow.L.orc_tracker_project_all(ow.tracker)
+    ri, rd = rw.point_states(); oi, od = ow.point_states()
+    assert np.array_equal(ri[:, :2], oi[:, :2])
+    vis = oi[:, 0] == 1
+    cols = [0, 1] + list(range(4, 15))     # (v2Found, columns 2-3, is uninitialised memory in the reference before a search)
+    assert np.array_equal(rd[vis][:, cols], od[vis][:, cols]), "projection, derivs, v3Cam, warp: bit for bit"
+    idx = np.nonzero(oi[:, 1] >= 0)[0].astype(np.int32)
+    for rng, sub in ((10, 0), (30, 8)):
+        rw.L.ref_tracker_clear_counters(rw.tracker); ow.L.orc_tracker_clear_counters(ow.tracker)
+        nr = rw.L.ref_tracker_search_for_points(rw.tracker, idx, len(idx), rng, sub)
+        no = ow.L.orc_tracker_search_for_points(ow.tracker, idx, len(idx), rng, sub)
+        assert nr == no
+        ri, rd = rw.point_states(); oi, od = ow.point_states()
+        assert np.array_equal(ri[idx][:, [2, 3, 5]], oi[idx][:, [2, 3, 5]])
+        fnd = idx[oi[idx][:, 3] == 1]
+        assert np.array_equal(rd[fnd][:, [2, 3, 15, 30, 31]], od[fnd][:, [2, 3, 15, 30, 31]]), "found / coarse positions: bit for bit"
+        assert np.array_equal(rw.counters()[0], ow.counters()[0]) and np.array_equal(rw.counters()[1], ow.counters()[1])
+        for k in idx[::37]:
+            t = np.zeros(P * P, np.uint8); s, q = C.c_int(), C.c_int()
+            rw.L.ref_tracker_point_template(rw.tracker, int(k), t, C.byref(s), C.byref(q))
+            ot, os_, oq = ow.point_template(int(k))
+            assert np.array_equal(t.reshape(P, P), ot) and (s.value, q.value) == (os_, oq)
+    rw.L.ref_tracker_calc_jacobians(rw.tracker, idx, len(idx)); ow.L.orc_tracker_calc_jacobians(ow.tracker, idx, len(idx))
+    for sigma, mark in ((0.0, 0), (16.0, 1)):
+        ru, ou = np.zeros(6), np.zeros(6)
+        rw.L.ref_tracker_calc_pose_update(rw.tracker, idx, len(idx), sigma, mark, 1, ru)
+        ow.L.orc_tracker_calc_pose_update(ow.tracker, idx, len(idx), sigma, mark, 1, ou)
+        assert np.array_equal(ru, ou), "CalcPoseUpdate 6-vector: bit for bit"
+        assert np.array_equal(rw.get_pose(), ow.get_pose())
+
+
+def _worlds_p8():
+    pytest.skip("the reference's Tracker hard-wires PatchFinder(11) (jni/TrackerData.h:44); P=8 is pinned per object in test_patchfinder_p8")
+
+
+def test_patchfinder_p8_object_level():
+    """PatchFinder(8) one object at a time (the 8x8 configuration of north_star) against the restatement's stand-alone entry points."""
+    cam, f0, smap, rw, ow = _worlds()
+    f1, _ = common.frame_at(cam, np.array(synth.CONFIG1_TWIST) * 0.5)
+    rk = rw.make_current_kf(f1); okf = ow.make_current_kf(f1)
+    rw.set_pose(synth.IDENTITY_POSE); ow.set_pose(synth.IDENTITY_POSE)
+    rw.L.ref_tracker_project_all(rw.tracker)
+    ri, rd = rw.point_states()
+    R, L = rw.L, ow.L
+    pf = R.ref_pf_create(8)
+    assert R.ref_pf_max_ssd(pf) == 32000
+    n_checked = 0
+    for k in np.nonzero(ri[:, 1] >= 0)[0][::9]:
+        level = int(ri[k, 1]); winv = np.ascontiguousarray(rd[k, 11:15])
+        R.ref_pf_set_level_warp(pf, level, winv)
+        t = np.zeros(64, np.uint8); s, q = C.c_int(), C.c_int()
+        bad = R.ref_pf_make_template(pf, rw.map, int(k), t, C.byref(s), C.byref(q))
+        det = winv[0] * winv[3] - winv[1] * winv[2]
+        m2 = np.array([winv[3] / det, -winv[1] / det, -winv[2] / det, winv[0] / det])
+        invdet = 1.0 / det
+        m2 = np.array([(winv[3] * invdet) * (1 << level), (-winv[1] * invdet) * (1 << level), (-winv[2] * invdet) * (1 << level), (winv[0] * invdet) * (1 << level)])
+        ot = np.zeros(64, np.uint8); os_, oq = C.c_int(), C.c_int()
+        nout = L.orc_make_template(ow.src_kf.h, int(smap.src_level[k]), np.ascontiguousarray(smap.ir_center[k]), 8, m2, ot, C.byref(os_), C.byref(oq))
+        assert (nout != 0) == bool(bad)
+        assert np.array_equal(t, ot) and (s.value, q.value) == (os_.value, oq.value)
+        if bad:
+            continue
+        pos_r, pos_o = np.zeros(2), np.zeros(2); best = C.c_int(); ev = C.c_long()
+        fr = R.ref_pf_find_coarse(pf, rd[k, 0], rd[k, 1], rk.h, 12, pos_r)
+        fo = L.orc_find_patch_coarse(okf.h, level, ot, 8, rd[k, 0], rd[k, 1], 12, pos_o, C.byref(best), C.byref(ev))
+        assert fr == fo and (not fr or np.array_equal(pos_r, pos_o))
+        if fr:
+            sp_r, sp_o = np.zeros(2), np.zeros(2)
+            cr = R.ref_pf_subpix(pf, rk.h, pos_r, 8, sp_r, None); co = L.orc_subpix(okf.h, level, ot, 8, pos_o, 8, sp_o, None)
+            assert cr == co and np.array_equal(sp_r, sp_o)
+            cx, cy = int((pos_r[0] + 0.5) / (1 << level)), int((pos_r[1] + 0.5) / (1 << level))
+            assert R.ref_pf_zmssd(pf, rk.h, level, cx, cy) == L.orc_zmssd(okf.h, level, ot, 8, cx, cy) == best.value
+        n_checked += 1
+    assert n_checked > 40
+    R.ref_pf_destroy(pf)
+
+
+@pytest.mark.parametrize("start,frame,vel", [(0.0, 1.0, None), (0.0, 1.0, 0.05), (0.2, 0.5, None), (0.5, 0.5, 0.02)])
+def test_track_map_whole(start, frame, vel):
+    cam, f0, smap, rw, ow = _worlds()
+    f1, _ = common.frame_at(cam, np.array(synth.CONFIG1_TWIST) * frame)
+    sp = synth.se3_exp(np.array(synth.CONFIG1_TWIST) * start)
+    rw.make_current_kf(f1); ow.make_current_kf(f1)
+    rw.set_pose(sp); ow.set_pose(sp)
+    if vel is not None:
+        rw.L.ref_tracker_set_velocity(rw.tracker, np.zeros(6), vel); ow.L.orc_tracker_set_velocity(ow.tracker, np.zeros(6), vel)
+    rw.L.ref_srand(1)
+    rw.L.ref_tracker_track_map(rw.tracker); ow.L.orc_tracker_track_map(ow.tracker)
+    assert np.array_equal(rw.get_pose(), ow.get_pose())
+    ra, rf, _, _, rdc = rw.counters(); oa, of, _, _, odc = ow.counters()
+    assert np.array_equal(ra, oa) and np.array_equal(rf, of) and rdc == odc
+    ri, rd = rw.point_states(); oi, od = ow.point_states()
+    pvs = oi[:, 1] >= 0
+    assert np.array_equal(ri[pvs][:, [0, 1, 2, 3, 5]], oi[pvs][:, [0, 1, 2, 3, 5]])
+    fnd = oi[:, 3] == 1
+    assert np.array_equal(rd[fnd][:, :4], od[fnd][:, :4])
+
+
+def test_track_frame_sequence_no_sbi():
+    cam, f0, smap, rw, ow = _worlds()
+    rw.L.ref_srand(1)
+    rw.L.ref_tracker_set_sbi_rot(rw.tracker, np.zeros(6), 1)
+    for k in range(1, 9):
+        fr = synth.render_frame(common.texture(), cam, synth.stream_pose(5 * k, 3))
+        rw.L.ref_tracker_track_frame_nosbi(rw.tracker, fr, cam.width, cam.height, cam.width)
+        ow.L.orc_tracker_track_frame(ow.tracker, fr, cam.width, cam.height, cam.width)
+        assert np.array_equal(rw.get_pose(), ow.get_pose()), k
+        assert all(np.array_equal(a, b) if isinstance(a, np.ndarray) else a == b for a, b in zip(rw.counters(), ow.counters())), k
+        rv, ov = np.zeros(6), np.zeros(6); rm, om = C.c_double(), C.c_double()
+        rw.L.ref_tracker_get_velocity(rw.tracker, rv, C.byref(rm)); ow.L.orc_tracker_get_velocity(ow.tracker, ov, C.byref(om))
+        assert np.array_equal(rv, ov) and rm.value == om.value
+
+
+def test_minipatch_find():
+    cam, f0, smap, rw, ow = _worlds()
+    f1, _ = common.frame_at(cam, np.array(synth.CONFIG1_TWIST) * 0.15)
+    rk0 = refbind.RefKeyFrame().make_lite(f0); rk1 = refbind.RefKeyFrame().make_lite(f1)
+    ok0 = oraclebind.OrcKeyFrame().make_lite(f0); ok1 = oraclebind.OrcKeyFrame().make_lite(f1)
+    R, L = rw.L, ow.L
+    R.ref_mp_set_max_ssd(100000)
+    mp = R.ref_mp_create()
+    c = ok0.corners(0)
+    c = c[(c[:, 0] > 10) & (c[:, 1] > 10) & (c[:, 0] < 630) & (c[:, 1] < 470)][::41]
+    nfound = 0
+    for x, y in c:
+        R.ref_mp_sample(mp, rk0.h, int(x), int(y), None)
+        for use_lut in (0, 1):
+            pr, po = np.array([x, y], float), np.array([x, y], float); best = C.c_int()
+            fr = R.ref_mp_find(mp, rk1.h, pr, 10, use_lut)
+            fo = L.orc_minipatch_find(ok0.h, int(x), int(y), ok1.h, po, 10, use_lut, 100000, C.byref(best))
+            assert fr == fo and np.array_equal(pr, po)
+            nfound += fr
+    assert nfound > 20
+    R.ref_mp_destroy(mp)

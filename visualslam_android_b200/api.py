@@ -43,7 +43,7 @@ ABI_SYMBOLS = [
     "vslam_set_pose", "vslam_get_pose", "vslam_get_poses", "vslam_set_motion", "vslam_get_motion", "vslam_set_sbi_rotation", "vslam_get_counters",
     "vslam_get_point_states", "vslam_get_point_template", "vslam_get_point_counts", "vslam_get_updates", "vslam_get_zmssd_evals",
     "vslam_project_all", "vslam_set_point_projection", "vslam_set_lists", "vslam_clear_counters", "vslam_search_for_points", "vslam_project_and_derivs", "vslam_calc_jacobians",
-    "vslam_calc_pose_update", "vslam_track_map", "vslam_track_frame", "vslam_track_frame_dev", "vslam_debug_atan", "vslam_kernel_launches",
+    "vslam_calc_pose_update", "vslam_track_map", "vslam_track_frame", "vslam_track_frame_dev", "vslam_debug_atan", "vslam_kernel_launches", "vslam_set_timing", "vslam_get_stage_times",
 ]
 
 _lib = None
@@ -109,6 +109,8 @@ def load():
     sig("vslam_track_frame_dev", i, vp, vp, i, C.c_size_t)
     sig("vslam_kernel_launches", C.c_ulonglong, vp)
     sig("vslam_debug_atan", i, vp, vp, i)
+    sig("vslam_set_timing", i, vp, i)
+    sig("vslam_get_stage_times", i, vp, vp, vp)
     _lib = L
     return L
 
@@ -352,6 +354,19 @@ class Context:
 
     def sync(self):
         self._ck(self.L.vslam_sync(self.h))
+
+    STAGES = ("pyrfast_l0", "pyrfast_l1", "pyrfast_l2", "pyrfast_l3", "project_lists", "search_coarse", "pose_coarse", "search_fine",
+              "pose_fine", "h2d", "other")
+
+    def set_timing(self, on=True):
+        self._ck(self.L.vslam_set_timing(self.h, int(on)))
+
+    def stage_times(self):
+        """{stage: (ms, launches)} accumulated since the last call (synchronises)."""
+        ms = np.zeros(len(self.STAGES))
+        n = np.zeros(len(self.STAGES), dtype=np.int32)
+        self._ck(self.L.vslam_get_stage_times(self.h, ms.ctypes.data, n.ctypes.data))
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(self.STAGES)}
 
     def kernel_launches(self):
         return int(self.L.vslam_kernel_launches(self.h))

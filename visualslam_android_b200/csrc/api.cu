@@ -103,7 +103,7 @@ int vslam_create(const vslam_config* cfg, vslam_ctx** out) {
   if (!ctx) { g_create_error = "out of host memory"; return VSLAM_E_INVALID; }
   ctx->cfg = *cfg; vslam_default_params(&ctx->params);
   ctx->S = cfg->n_streams; ctx->N = cfg->max_points; ctx->P = cfg->patch_size; ctx->launches = 0; ctx->n_src = cfg->max_source_keyframes;
-  ctx->scratch_host = nullptr; ctx->scratch_host_bytes = 0;
+  ctx->scratch_host = nullptr; ctx->scratch_host_bytes = 0; ctx->timing = false; ctx->ev_used = 0;
   const float frac = cfg->max_corner_frac > 0 ? cfg->max_corner_frac : 0.5f;
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_create_error = std::string(#call) + ": " + cudaGetErrorString(e_); vslam_destroy(ctx); return VSLAM_E_CUDA; } } while (0)
   CK(cudaSetDevice(cfg->device));
@@ -178,6 +178,7 @@ void vslam_destroy(vslam_ctx* ctx) {
   cudaFree(ps.jac); cudaFree(ps.err); cudaFree(ps.sqrtinv); cudaFree(ps.flags); cudaFree(ps.level); cudaFree(ps.tmpl); cudaFree(ps.tsum); cudaFree(ps.counts);
   cudaFree(ctx->ss); cudaFree(ctx->lists); cudaFree(ctx->pvs); cudaFree(ctx->sort_scratch);
   if (ctx->scratch_host) cudaFreeHost(ctx->scratch_host);
+  for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   delete[] ctx->l0_ptr_host; delete[] ctx->l0_stride_host;
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -187,6 +188,26 @@ int vslam_sync(vslam_ctx* ctx) {
   if (!ctx) return VSLAM_E_INVALID;
   VS_CUDA(cudaStreamSynchronize(ctx->stream));
   return check_status(ctx);
+}
+
+int vslam_set_timing(vslam_ctx* ctx, int on) {
+  if (!ctx) return VSLAM_E_INVALID;
+  VS_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->timing = on != 0; ctx->ev_used = 0; ctx->ev_stage.clear();
+  return VSLAM_OK;
+}
+
+int vslam_get_stage_times(vslam_ctx* ctx, double* ms, int* launches) {
+  if (!ctx || !ms || !launches) return VSLAM_E_INVALID;
+  VS_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int k = 0; k < VSLAM_N_STAGES; k++) { ms[k] = 0.0; launches[k] = 0; }
+  for (size_t k = 0; k < ctx->ev_stage.size(); k++) {
+    float t = 0.f;
+    VS_CUDA(cudaEventElapsedTime(&t, ctx->ev_pool[2 * k], ctx->ev_pool[2 * k + 1]));
+    ms[ctx->ev_stage[k]] += t; launches[ctx->ev_stage[k]]++;
+  }
+  ctx->ev_used = 0; ctx->ev_stage.clear();
+  return VSLAM_OK;
 }
 
 int vslam_set_params(vslam_ctx* ctx, const vslam_params* p) {
@@ -249,6 +270,7 @@ static int adopt_l0(vslam_ctx* ctx, int first, int count, const uint8_t* base, i
 
 static int upload_frames(vslam_ctx* ctx, int first, int count, const uint8_t* gray, int stride, size_t frame_stride) {
   const LevelDesc& L = ctx->lev[0];
+  vs_time_begin(ctx, VS_ST_H2D);
   uint8_t* dst = L.img + (size_t)first * L.h * L.pitch;
   if (stride == L.pitch && frame_stride == (size_t)L.h * L.pitch) {
     VS_CUDA(cudaMemcpyAsync(dst, gray, (size_t)count * L.h * L.pitch, cudaMemcpyHostToDevice, ctx->stream));
@@ -256,6 +278,7 @@ static int upload_frames(vslam_ctx* ctx, int first, int count, const uint8_t* gr
     for (int k = 0; k < count; k++)
       VS_CUDA(cudaMemcpy2DAsync(dst + (size_t)k * L.h * L.pitch, L.pitch, gray + (size_t)k * frame_stride, stride, L.w, L.h, cudaMemcpyHostToDevice, ctx->stream));
   }
+  vs_time_end(ctx);
   return VSLAM_OK;
 }
 

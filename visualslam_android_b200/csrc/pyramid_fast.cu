@@ -258,8 +258,10 @@ int vs_launch_pyramid_fast(vslam_ctx* ctx, int first_stream, int count) {
     if (smem > 227 * 1024) { ctx->err = "pyramid_fast: strip does not fit in shared memory (row stride too large)"; return VSLAM_E_INVALID; }
     VS_CUDA(cudaFuncSetAttribute(k_pyramid_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const bool has_next = l + 1 < VS_LEVELS;
+    vs_time_begin(ctx, VS_ST_PYR0 + l);
     k_pyramid_fast<<<count * L.n_strips, kThreads, smem, ctx->stream>>>(L, has_next ? ctx->lev[l + 1] : L, has_next ? 1 : 0, l, ctx->l0_ptr, ctx->l0_stride,
                                                                        first_stream, kFastThr[l], ctx->tickets + l, ctx->status);
+    vs_time_end(ctx);
     VS_CUDA(cudaGetLastError());
     ctx->launches++;
   }

@@ -793,7 +793,9 @@ int vs_launch_project_all(vslam_ctx* ctx, int mode) {
   const Dev D = make_dev(ctx);
   const size_t smem = (size_t)2 * ctx->N * sizeof(int);
   VS_CUDA(cudaFuncSetAttribute(k_project_lists, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  vs_time_begin(ctx, VS_ST_PROJECT);
   k_project_lists<<<ctx->S, kPT, smem, ctx->stream>>>(D, mode & 1, (mode >> 1) & 1);
+  vs_time_end(ctx);
   VS_CUDA(cudaGetLastError());
   ctx->launches++;
   return VSLAM_OK;
@@ -803,7 +805,9 @@ int vs_launch_search(vslam_ctx* ctx, int which, int range, int subpix) {
   const Dev D = make_dev(ctx);
   const int max_entries = which == 1 ? (int)(2 * ctx->params.coarse_max) : ctx->list_cap;
   dim3 grid((max_entries + kSearchWarps - 1) / kSearchWarps, ctx->S);
+  vs_time_begin(ctx, which == 2 ? VS_ST_SEARCH_FINE : VS_ST_SEARCH_COARSE);
   k_search<<<grid, kSearchWarps * 32, 0, ctx->stream>>>(D, which, range, subpix);
+  vs_time_end(ctx);
   VS_CUDA(cudaGetLastError());
   ctx->launches++;
   return VSLAM_OK;
@@ -812,7 +816,9 @@ int vs_launch_search(vslam_ctx* ctx, int which, int range, int subpix) {
 int vs_launch_pose(vslam_ctx* ctx, int mode, double sigma, int mark, int apply) {
   const Dev D = make_dev(ctx);
   const size_t smem = 2048 * sizeof(double);
+  vs_time_begin(ctx, (mode & 3) == 2 ? VS_ST_POSE_FINE : VS_ST_POSE_COARSE);
   k_pose<<<ctx->S, kPT, smem, ctx->stream>>>(D, mode & 3, sigma, mark, apply, (mode >> 2) & 1);
+  vs_time_end(ctx);
   VS_CUDA(cudaGetLastError());
   ctx->launches++;
   return VSLAM_OK;

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <vector>
 #include "vslam_b200.h"
 
 #define VS_LEVELS VSLAM_LEVELS
@@ -99,6 +100,8 @@ struct vslam_ctx {
   unsigned long long* evals;     // device counter
   unsigned long long launches;
   void* scratch_host; size_t scratch_host_bytes;   // pinned staging
+  // optional per-kernel timing with CUDA events on ctx->stream (vslam_set_timing)
+  bool timing; std::vector<cudaEvent_t> ev_pool; std::vector<int> ev_stage; size_t ev_used;
   std::string err;
 };
 
@@ -110,6 +113,16 @@ struct vslam_ctx {
       return VSLAM_E_CUDA;                                                                            \
     }                                                                                                 \
   } while (0)
+
+enum { VS_ST_PYR0 = 0, VS_ST_PYR1, VS_ST_PYR2, VS_ST_PYR3, VS_ST_PROJECT, VS_ST_SEARCH_COARSE, VS_ST_POSE_COARSE, VS_ST_SEARCH_FINE, VS_ST_POSE_FINE, VS_ST_H2D, VS_ST_OTHER };
+// Bracket one launch with two events of the pool (no-ops unless timing is on).
+inline void vs_time_begin(vslam_ctx* ctx, int stage) {
+  if (!ctx->timing) return;
+  if (ctx->ev_used + 2 > ctx->ev_pool.size()) { for (int k = 0; k < 64; k++) { cudaEvent_t e; cudaEventCreate(&e); ctx->ev_pool.push_back(e); } }
+  ctx->ev_stage.push_back(stage);
+  cudaEventRecord(ctx->ev_pool[ctx->ev_used++], ctx->stream);
+}
+inline void vs_time_end(vslam_ctx* ctx) { if (ctx->timing) cudaEventRecord(ctx->ev_pool[ctx->ev_used++], ctx->stream); }
 
 // kernels/launchers implemented in the .cu files
 int vs_launch_pyramid_fast(vslam_ctx* ctx, int first_stream, int count);
