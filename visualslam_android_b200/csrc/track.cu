@@ -6,7 +6,7 @@
 //   k_search          one warp per (stream, list entry): MakeTemplateCoarseCont, FindPatchCoarse (ZMSSD with dp4a over
 //                     the FAST corners of the row-LUT window), sub-pixel inverse-compositional refinement.
 //   k_pose            one CTA per stream: the ten Gauss-Newton iterations of a stage — re-projection / linear update,
-//                     Jacobians, Tukey sigma (bitonic sort + median), weights, the 27-term normal-equation reduction,
+//                     Jacobians, Tukey sigma (radix-select median), weights, the 27-term normal-equation reduction,
 //                     6x6 LU solve, pose = exp(mu) * pose — plus scene depth, motion model and quality assessment.
 // FP64 throughout, no FMA contraction (-fmad=false): integer results are bit-exact, poses agree to ~1e-12.
 #include "geometry.cuh"
@@ -204,11 +204,13 @@ __global__ void __launch_bounds__(kPT) k_project_lists(Dev D, int mode, int appl
 
 // ------------------------------------------------------------------------------------------------
 // SearchForPoints, one warp per list entry.
+constexpr int kCandCap = 96;           // ZMSSD candidates gathered per round of one warp
 struct SearchSmem {
   double pos[VS_MAXP * VS_MAXP * 2];    // template sample positions / sub-pixel products
   double jx[81], jy[81], prod2[81];
   uint32_t tw[VS_MAXP * 3];            // template rows as 3 zero-padded words
-  uint8_t tmpl[VS_TMPL_BYTES];
+  uint32_t tmpl_w[VS_TMPL_BYTES / 4];  // template bytes (row-major, P*P), word view for the coalesced load
+  uint32_t cand_cw[kCandCap]; int cand_idx[kCandCap]; int acc[kCandCap * 3];
 };
 
 __device__ __forceinline__ int warp_sum(int v) {
@@ -217,7 +219,9 @@ __device__ __forceinline__ int warp_sum(int v) {
   return v;
 }
 
-// mode 0: explicit list [0,nA) with (range, subpix) arguments; 1: coarse set A; 2: fine set B (re-projected first)
+// mode 0: explicit list [0,nA) with (range, subpix) arguments; 1: coarse set A; 2: fine set B
+// PT: compile-time template side (8 or 11), 0 = use the run-time D.P
+template <int PT>
 __global__ void __launch_bounds__(kSearchWarps * 32) k_search(Dev D, int mode, int range_arg, int subpix_arg) {
   __shared__ SearchSmem sm_all[kSearchWarps];
   const int s = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -232,14 +236,11 @@ __global__ void __launch_bounds__(kSearchWarps * 32) k_search(Dev D, int mode, i
   SearchSmem& sm = sm_all[warp];
   const int i = D.lists[(size_t)s * D.list_cap + first + e];
   const size_t SN = (size_t)D.S * D.N, gi = (size_t)s * D.N + i;
-  const int P = D.P, PP = P * P;
+  const int P = PT ? PT : D.P, PP = P * P;
+  uint8_t* const tmpl = (uint8_t*)sm.tmpl_w;
   int flags = D.ps.flags[gi];
   const int level = D.ps.level[gi];
-
-  if (mode == 2 && lane == 0) {   // ProjectAndDerivs with bFound == false: projection only (jni/TrackerData.h:98-102)
-    CamCache cc; td_project(D, st->pose, i, gi, SN, cc, flags);
-  }
-  flags = __shfl_sync(0xffffffffu, flags, 0);
+  // (the fine set was re-projected by k_reproject_fine if the coarse stage moved the pose)
 
   // ---- MakeTemplateCoarseCont (jni/PatchFinder.cc:79-125)
   double m2[4]; int refresh = 0, inside = 0, tsum = 0, tsumsq = 0;
@@ -290,12 +291,13 @@ __global__ void __launch_bounds__(kSearchWarps * 32) k_search(Dev D, int mode, i
         const uint8_t* r0 = simg + (size_t)ly * sp + lx; const uint8_t* r1 = r0 + sp;
         v = (uint8_t)((1 - y) * ((1 - x) * r0[0] + x * r0[1]) + y * ((1 - x) * r1[0] + x * r1[1]));
       } else outside++;
-      sm.tmpl[k] = v;
+      tmpl[k] = v;
     }
     outside = warp_sum(outside);
     __syncwarp();
     int ts = 0, tq = 0;
-    for (int k = lane; k < PP; k += 32) { const int b = sm.tmpl[k]; ts += b; tq += b * b; D.ps.tmpl[gi * VS_TMPL_BYTES + k] = (uint8_t)b; }
+    for (int k = lane; k < PP; k += 32) { const int b = tmpl[k]; ts += b; tq += b * b; }
+    if (lane * 4 < PP) ((uint32_t*)(D.ps.tmpl + gi * VS_TMPL_BYTES))[lane] = sm.tmpl_w[lane];   // bytes past P*P are never read
     ts = warp_sum(ts); tq = warp_sum(tq);
     tsum = ts; tsumsq = tq;
     flags = outside ? (flags | F_TBAD) : (flags & ~F_TBAD);
@@ -305,7 +307,7 @@ __global__ void __launch_bounds__(kSearchWarps * 32) k_search(Dev D, int mode, i
       for (int c = 0; c < 4; c++) D.ps.lastwarp[c * SN + gi] = m2[c];
     }
   } else {
-    for (int k = lane; k < PP; k += 32) sm.tmpl[k] = D.ps.tmpl[gi * VS_TMPL_BYTES + k];
+    sm.tmpl_w[lane] = ((const uint32_t*)(D.ps.tmpl + gi * VS_TMPL_BYTES))[lane];   // one coalesced 128-byte load
     tsum = D.ps.tsum[gi]; tsumsq = D.ps.tsum[SN + gi];
   }
   __syncwarp();
@@ -317,7 +319,7 @@ __global__ void __launch_bounds__(kSearchWarps * 32) k_search(Dev D, int mode, i
   for (int k = lane; k < P * 3; k += 32) {
     const int r = k / 3, w = k - 3 * r;
     uint32_t v = 0;
-    for (int b = 0; b < 4; b++) { const int c = 4 * w + b; if (c < P) v |= (uint32_t)sm.tmpl[r * P + c] << (8 * b); }
+    for (int b = 0; b < 4; b++) { const int c = 4 * w + b; if (c < P) v |= (uint32_t)tmpl[r * P + c] << (8 * b); }
     sm.tw[k] = v;
   }
   __syncwarp();
@@ -346,44 +348,59 @@ __global__ void __launch_bounds__(kSearchWarps * 32) k_search(Dev D, int mode, i
     const uint32_t* corners = L.corners + (size_t)s * L.cap;
     const int b = P / 2, nwords = (P + 3) >> 2;
     const uint32_t lastmask = (P & 3) ? ((1u << (8 * (P & 3))) - 1u) : 0xffffffffu;
-    for (int c0 = begin; c0 < end; c0 += 32) {
-      const int ci = c0 + lane;
-      if (ci >= end) continue;
-      const uint32_t cw = corners[ci];
-      const int cx = cw & 0xffff, cy = cw >> 16;
-      if ((double)cx < nLeft || (double)cx > nRight) continue;
-      const double dx = ix - (double)cx, dy = iy - (double)cy;
-      double d2 = 0; d2 += dx * dx; d2 += dy * dy;
-      if (d2 > nRange * nRange) continue;
-      // ZMSSDAtPoint (jni/PatchFinder.cc:352-380)
-      int ssd;
-      nevals++;
-      if (!(cx >= b && cy >= b && cx < L.w - b && cy < L.h - b)) ssd = maxSSD + 1;
-      else {
-        unsigned sum = 0, sumsq = 0, cross = 0;
-        const uint8_t* rp = img + (size_t)(cy - b) * pitch + (cx - b);
-        for (int r = 0; r < P; r++, rp += pitch) {
-          const unsigned a = (unsigned)((uintptr_t)rp & 3u), sh = a * 8;
-          const uint32_t* wp = (const uint32_t*)(rp - a);
-          uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = 0, w3 = 0;
-          if (a + P > 8) w2 = __ldg(wp + 2);
-          if (a + P > 12) w3 = __ldg(wp + 3);
-          uint32_t n0 = __funnelshift_r(w0, w1, sh), n1 = __funnelshift_r(w1, w2, sh), n2 = __funnelshift_r(w2, w3, sh);
-          if (nwords == 3) n2 &= lastmask; else if (nwords == 2) { n1 &= lastmask; n2 = 0; } else { n0 &= lastmask; n1 = 0; n2 = 0; }
-          sum = __dp4a(n0, 0x01010101u, sum); sumsq = __dp4a(n0, n0, sumsq); cross = __dp4a(n0, sm.tw[3 * r], cross);
-          sum = __dp4a(n1, 0x01010101u, sum); sumsq = __dp4a(n1, n1, sumsq); cross = __dp4a(n1, sm.tw[3 * r + 1], cross);
-          sum = __dp4a(n2, 0x01010101u, sum); sumsq = __dp4a(n2, n2, sumsq); cross = __dp4a(n2, sm.tw[3 * r + 2], cross);
+    int c0 = begin;
+    while (c0 < end) {   // rounds: gather up to kCandCap candidates, then score them with (candidate,row) work items
+      int ncand = 0;
+      for (; c0 < end && ncand <= kCandCap - 32; c0 += 32) {
+        const int ci = c0 + lane;
+        bool pass = false; uint32_t cw = 0;
+        if (ci < end) {
+          cw = corners[ci];
+          const int cx = cw & 0xffff, cy = cw >> 16;
+          pass = !((double)cx < nLeft || (double)cx > nRight);
+          if (pass) { const double dx = ix - (double)cx, dy = iy - (double)cy; double d2 = 0; d2 += dx * dx; d2 += dy * dy; pass = !(d2 > nRange * nRange); }
         }
-        const int SA = tsum, SB = (int)sum;
-        ssd = ((2 * SA * SB - SA * SA - SB * SB) / PP + (int)sumsq + tsumsq - 2 * (int)cross);
+        const unsigned bal = __ballot_sync(0xffffffffu, pass);
+        if (pass) { const int slot = ncand + __popc(bal & ((1u << lane) - 1u)); sm.cand_cw[slot] = cw; sm.cand_idx[slot] = ci; }
+        ncand += __popc(bal);
       }
-      const unsigned long long key = ((unsigned long long)(unsigned)ssd << 32) | (unsigned)ci;   // ssd >= 0; ties -> lowest corner index
-      best = key < best ? key : best;
+      nevals += ncand;   // (every lane holds the same count; reduced once below)
+      for (int k = lane; k < ncand * 3; k += 32) sm.acc[k] = 0;
+      __syncwarp();
+      // ZMSSDAtPoint (jni/PatchFinder.cc:352-380): one work item = one template row of one candidate
+      for (int item = lane; item < ncand * P; item += 32) {
+        const int c = item / P, r = item - c * P;
+        const uint32_t cw = sm.cand_cw[c];
+        const int cx = cw & 0xffff, cy = cw >> 16;
+        if (!(cx >= b && cy >= b && cx < L.w - b && cy < L.h - b)) continue;
+        const uint8_t* rp = img + (size_t)(cy - b + r) * pitch + (cx - b);
+        const unsigned a = (unsigned)((uintptr_t)rp & 3u), sh = a * 8;
+        const uint32_t* wp = (const uint32_t*)(rp - a);
+        uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = 0, w3 = 0;
+        if (a + P > 8) w2 = __ldg(wp + 2);
+        if (a + P > 12) w3 = __ldg(wp + 3);
+        uint32_t n0 = __funnelshift_r(w0, w1, sh), n1 = __funnelshift_r(w1, w2, sh), n2 = __funnelshift_r(w2, w3, sh);
+        if (nwords == 3) n2 &= lastmask; else if (nwords == 2) { n1 &= lastmask; n2 = 0; } else { n0 &= lastmask; n1 = 0; n2 = 0; }
+        unsigned sum = __dp4a(n0, 0x01010101u, 0u), sumsq = __dp4a(n0, n0, 0u), cross = __dp4a(n0, sm.tw[3 * r], 0u);
+        sum = __dp4a(n1, 0x01010101u, sum); sumsq = __dp4a(n1, n1, sumsq); cross = __dp4a(n1, sm.tw[3 * r + 1], cross);
+        sum = __dp4a(n2, 0x01010101u, sum); sumsq = __dp4a(n2, n2, sumsq); cross = __dp4a(n2, sm.tw[3 * r + 2], cross);
+        atomicAdd(&sm.acc[3 * c], (int)sum); atomicAdd(&sm.acc[3 * c + 1], (int)sumsq); atomicAdd(&sm.acc[3 * c + 2], (int)cross);
+      }
+      __syncwarp();
+      for (int c = lane; c < ncand; c += 32) {
+        const uint32_t cw = sm.cand_cw[c];
+        const int cx = cw & 0xffff, cy = cw >> 16;
+        int ssd;
+        if (!(cx >= b && cy >= b && cx < L.w - b && cy < L.h - b)) ssd = maxSSD + 1;
+        else { const int SA = tsum, SB = sm.acc[3 * c]; ssd = ((2 * SA * SB - SA * SA - SB * SB) / PP + sm.acc[3 * c + 1] + tsumsq - 2 * sm.acc[3 * c + 2]); }
+        const unsigned long long key = ((unsigned long long)(unsigned)ssd << 32) | (unsigned)sm.cand_idx[c];   // ssd >= 0; ties -> lowest corner index
+        best = key < best ? key : best;
+      }
+      __syncwarp();
     }
   }
 #pragma unroll
   for (int d = 16; d; d >>= 1) { const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, d); best = o < best ? o : best; }
-  nevals = warp_sum(nevals);
   if (lane == 0 && nevals) atomicAdd(D.evals, (unsigned long long)nevals);
   const int bestSSD = (int)(best >> 32);
   if (!(bestSSD < maxSSD)) {
@@ -401,21 +418,19 @@ __global__ void __launch_bounds__(kSearchWarps * 32) k_search(Dev D, int mode, i
     const int Q = P - 2, QQ = Q * Q;
     for (int k = lane; k < QQ; k += 32) {
       const int x = k / Q + 1, y = k - (x - 1) * Q + 1;   // stored index (x-1)*Q + (y-1)
-      sm.jx[k] = 0.5 * (sm.tmpl[y * P + x + 1] - sm.tmpl[y * P + x - 1]);
-      sm.jy[k] = 0.5 * (sm.tmpl[(y + 1) * P + x] - sm.tmpl[(y - 1) * P + x]);
+      sm.jx[k] = 0.5 * (tmpl[y * P + x + 1] - tmpl[y * P + x - 1]);
+      sm.jy[k] = 0.5 * (tmpl[(y + 1) * P + x] - tmpl[(y - 1) * P + x]);
     }
     __syncwarp();
-    double h = 0;   // lanes 0..8 each own one entry of JtJ (sums of multiples of 0.25: exact in any order)
-    if (lane < 9) {
-      const int a = lane / 3, b2 = lane - 3 * a;
-      for (int k = 0; k < QQ; k++) {
-        const double ga = a == 0 ? sm.jx[k] : (a == 1 ? sm.jy[k] : 1.0), gb = b2 == 0 ? sm.jx[k] : (b2 == 1 ? sm.jy[k] : 1.0);
-        h += ga * gb;
-      }
-    }
-    double H[9];
+    // JtJ of (gx, gy, 1): sums of multiples of 0.25 below 2^53 are exact in any order, so a warp reduction is bit-exact
+    double hxx = 0, hxy = 0, hyy = 0, hx = 0, hy = 0;
+    for (int k = lane; k < QQ; k += 32) { const double gx = sm.jx[k], gy = sm.jy[k]; hxx += gx * gx; hxy += gx * gy; hyy += gy * gy; hx += gx; hy += gy; }
 #pragma unroll
-    for (int k = 0; k < 9; k++) H[k] = __shfl_sync(0xffffffffu, h, k);
+    for (int d = 16; d; d >>= 1) {
+      hxx += __shfl_xor_sync(0xffffffffu, hxx, d); hxy += __shfl_xor_sync(0xffffffffu, hxy, d); hyy += __shfl_xor_sync(0xffffffffu, hyy, d);
+      hx += __shfl_xor_sync(0xffffffffu, hx, d); hy += __shfl_xor_sync(0xffffffffu, hy, d);
+    }
+    const double H[9] = {hxx, hxy, hx, hxy, hyy, hy, hx, hy, (double)QQ};
     double hinv[9];
     {   // 3x3 inverse: adjugate * (1/det), evaluation order of the oracle (oracle/vslam_oracle.cc inverse3)
       const double c00 = H[4] * H[8] - H[5] * H[7], c10 = H[5] * H[6] - H[3] * H[8], c20 = H[3] * H[7] - H[4] * H[6];
@@ -439,7 +454,7 @@ __global__ void __launch_bounds__(kSearchWarps * 32) k_search(Dev D, int mode, i
         const int y = k / Q + 1, x = k - (y - 1) * Q + 1;
         const uint8_t* tl = img + (size_t)((int)b1 + y) * pitch + ((int)b0 + x);
         const float fPixel = fTL * tl[0] + fTR * tl[1] + fBL * tl[pitch] + fBR * tl[pitch + 1];
-        const double dDiff = fPixel - sm.tmpl[y * P + x] + meanDiff;
+        const double dDiff = fPixel - tmpl[y * P + x] + meanDiff;
         const int j = (x - 1) * Q + (y - 1);
         sm.pos[k] = dDiff * sm.jx[j]; sm.pos[QQ + k] = dDiff * sm.jy[j]; sm.prod2[k] = dDiff;
       }
@@ -473,19 +488,40 @@ __global__ void __launch_bounds__(kSearchWarps * 32) k_search(Dev D, int mode, i
 
 // ------------------------------------------------------------------------------------------------
 // Pose-update kernel, one CTA per stream.
-__device__ inline void block_bitonic_sort(double* a, int n2) {   // ascending, n2 = power of two
-  for (int k = 2; k <= n2; k <<= 1)
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = threadIdx.x; t < n2; t += blockDim.x) {
-        const int p = t ^ j;
-        if (p > t) {
-          const double x = a[t], y = a[p];
-          const bool up = (t & k) == 0;
-          if ((x > y) == up) { a[t] = y; a[p] = x; }
-        }
-      }
-      __syncthreads();
+// k-th smallest (0-based) of n non-negative doubles: MSB-first 8-bit radix select on the IEEE bit patterns (monotonic
+// for values >= 0).  All threads of the CTA call it; `hist` is 256 ints of shared memory, `sel` two 64-bit words.
+__device__ inline double block_radix_select(const double* a, int n, int k, int* hist, unsigned long long* sel) {
+  const int tid = threadIdx.x;
+  unsigned long long prefix = 0;   // bits decided so far (upper bytes)
+  int rank = k;
+  for (int pass = 7; pass >= 0; pass--) {
+    for (int b = tid; b < 256; b += blockDim.x) hist[b] = 0;
+    __syncthreads();
+    const int sh = 8 * pass;
+    for (int t = tid; t < n; t += blockDim.x) {
+      const unsigned long long key = (unsigned long long)__double_as_longlong(a[t]);
+      if (pass == 7 || (key >> (sh + 8)) == (prefix >> (sh + 8))) atomicAdd(&hist[(int)((key >> sh) & 255ull)], 1);
     }
+    __syncthreads();
+    if (tid < 32) {   // warp 0: find the bin that holds rank `rank`
+      int c[8]; int mine = 0;
+#pragma unroll
+      for (int q = 0; q < 8; q++) { c[q] = hist[tid * 8 + q]; mine += c[q]; }
+      int incl = mine;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if (tid >= d) incl += v; }
+      const int excl = incl - mine;
+      if (rank >= excl && rank < incl) {
+        int r = rank - excl, q = 0;
+        while (r >= c[q]) { r -= c[q]; q++; }
+        sel[0] = prefix | ((unsigned long long)(tid * 8 + q) << sh); sel[1] = (unsigned long long)r;
+      }
+    }
+    __syncthreads();
+    prefix = sel[0]; rank = (int)sel[1];
+    __syncthreads();
+  }
+  return __longlong_as_double((long long)prefix);
 }
 
 // dynamic inverse = partial-pivot LU, column by column; then mu = Cinv * b  (oracle/vslam_oracle.cc inverse_lu; jni/myWLS.h:53-62)
@@ -515,6 +551,8 @@ struct PoseSmem {
   double mu[6], last[6];
   double sigma;
   int nerr, cnt;
+  int hist[256];
+  unsigned long long sel[2];
 };
 
 // One CalcPoseUpdate over list entries [0,n) (jni/Tracker.cc:683-774).  Leaves mu in sm.mu (zeros if nothing found).
@@ -538,13 +576,9 @@ __device__ void calc_pose_update(const Dev& D, PoseSmem& sm, double* sortbuf, in
   const int nerr = sm.nerr;
   if (nerr == 0) { if (tid < 6) sm.mu[tid] = 0.0; if (tid == 0) sm.sigma = 0.0; __syncthreads(); return; }
   if (overrideSigma > 0) { if (tid == 0) sm.sigma = overrideSigma; }
-  else {   // Tukey::FindSigmaSquared (jni/MEstimator.h:67-77)
-    int n2 = 1; while (n2 < nerr) n2 <<= 1;
-    for (int k = nerr + tid; k < n2; k += kPT) sortbuf[k] = __longlong_as_double(0x7ff0000000000000ll);
-    __syncthreads();
-    block_bitonic_sort(sortbuf, n2);
+  else {   // Tukey::FindSigmaSquared (jni/MEstimator.h:67-77): the sort there only serves to pick v[n/2]
+    const double med = block_radix_select(sortbuf, nerr, nerr / 2, sm.hist, sm.sel);
     if (tid == 0) {
-      const double med = sortbuf[nerr / 2];
       const unsigned long long den = (unsigned long long)nerr * 2ull - 6ull;   // size_t arithmetic of the reference
       double sigma = 1.4826 * (1 + 5.0 / (double)den) * sqrt(med);
       sigma = 4.6851 * sigma;
@@ -658,7 +692,7 @@ __device__ void linear_update(const Dev& D, const int* list, int n, int s, const
 }
 
 // mode 0: one CalcPoseUpdate over [0,nA) (stage API);  1: coarse stage;  2: fine stage (+ scene depth; + motion model / quality if tail)
-__global__ void __launch_bounds__(kPT) k_pose(Dev D, int mode, double sigma_arg, int mark_arg, int apply_arg, int tail) {
+__global__ void __launch_bounds__(kPT, 2) k_pose(Dev D, int mode, double sigma_arg, int mark_arg, int apply_arg, int tail) {
   extern __shared__ double sh_sort[];
   __shared__ PoseSmem sm;
   const int s = blockIdx.x, tid = threadIdx.x;
@@ -667,7 +701,7 @@ __global__ void __launch_bounds__(kPT) k_pose(Dev D, int mode, double sigma_arg,
   const int* list = D.lists + (size_t)s * D.list_cap;
   double* sortbuf = sh_sort; int sortcap = 2048;
   const int nA = st->nA, nAll = st->nA + st->nB;
-  { int need = 1; while (need < (mode == 2 ? nAll : nA)) need <<= 1; if (need > 2048) { sortbuf = D.sort_scratch + (size_t)s * D.sort_cap; sortcap = D.sort_cap; } }
+  if ((mode == 2 ? nAll : nA) > 2048) { sortbuf = D.sort_scratch + (size_t)s * D.sort_cap; sortcap = D.sort_cap; }
   if (tid < 12) sm.pose[tid] = st->pose[tid];
   if (tid < 6) sm.last[tid] = 0.0;
   __syncthreads();
@@ -765,6 +799,24 @@ __global__ void __launch_bounds__(kPT) k_pose(Dev D, int mode, double sigma_arg,
   }
 }
 
+// ProjectAndDerivs of the fine set [nA, nA+nB) before its search (jni/Tracker.cc:501-503,530-532).  Nothing in that set is
+// `found` yet, so only the projection is refreshed; when the coarse stage did not run the pose is unchanged and the
+// projection of k_project_lists is still exact, so the CTA returns at once.
+__global__ void __launch_bounds__(kPT) k_reproject_fine(Dev D) {
+  const int s = blockIdx.x;
+  StreamState* st = D.ss + s;
+  if (st->lost_frames >= 3 || !st->did_coarse) return;
+  const size_t SN = (size_t)D.S * D.N;
+  const int* list = D.lists + (size_t)s * D.list_cap + st->nA;
+  for (int k = threadIdx.x; k < st->nB; k += kPT) {
+    const int i = list[k];
+    const size_t gi = (size_t)s * D.N + i;
+    int flags = D.ps.flags[gi];
+    CamCache cc; td_project(D, st->pose, i, gi, SN, cc, flags);
+    D.ps.flags[gi] = flags;
+  }
+}
+
 __global__ void __launch_bounds__(kPT) k_project_and_derivs(Dev D, int only_found) {
   const int s = blockIdx.x;
   StreamState* st = D.ss + s;
@@ -806,7 +858,9 @@ int vs_launch_search(vslam_ctx* ctx, int which, int range, int subpix) {
   const int max_entries = which == 1 ? (int)(2 * ctx->params.coarse_max) : ctx->list_cap;
   dim3 grid((max_entries + kSearchWarps - 1) / kSearchWarps, ctx->S);
   vs_time_begin(ctx, which == 2 ? VS_ST_SEARCH_FINE : VS_ST_SEARCH_COARSE);
-  k_search<<<grid, kSearchWarps * 32, 0, ctx->stream>>>(D, which, range, subpix);
+  if (ctx->P == 11) k_search<11><<<grid, kSearchWarps * 32, 0, ctx->stream>>>(D, which, range, subpix);
+  else if (ctx->P == 8) k_search<8><<<grid, kSearchWarps * 32, 0, ctx->stream>>>(D, which, range, subpix);
+  else k_search<0><<<grid, kSearchWarps * 32, 0, ctx->stream>>>(D, which, range, subpix);
   vs_time_end(ctx);
   VS_CUDA(cudaGetLastError());
   ctx->launches++;
@@ -837,12 +891,17 @@ int vs_launch_calc_jacobians(vslam_ctx* ctx) {
   return VSLAM_OK;
 }
 
-// Tracker::TrackMap for all streams: 5 launches, no host synchronisation in between.
+// Tracker::TrackMap for all streams: 6 launches, no host synchronisation in between.
 int vs_launch_track_map(vslam_ctx* ctx, int with_motion_model) {
   int rc;
   if ((rc = vs_launch_project_all(ctx, 1 | (with_motion_model ? 2 : 0)))) return rc;
   if ((rc = vs_launch_search(ctx, 1, 0, 0))) return rc;
   if ((rc = vs_launch_pose(ctx, 1, 0.0, 0, 0))) return rc;
+  vs_time_begin(ctx, VS_ST_OTHER);
+  k_reproject_fine<<<ctx->S, kPT, 0, ctx->stream>>>(make_dev(ctx));
+  vs_time_end(ctx);
+  VS_CUDA(cudaGetLastError());
+  ctx->launches++;
   if ((rc = vs_launch_search(ctx, 2, 0, 0))) return rc;
   if ((rc = vs_launch_pose(ctx, 2 | (with_motion_model ? 4 : 0), 0.0, 0, 0))) return rc;
   return VSLAM_OK;
