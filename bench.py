@@ -311,24 +311,34 @@ def main():
     quality = np.array([ctx.counters(s)[2] for s in range(0, S, max(1, S // 16))])
     value = world * S * K / (dev_ms * 1e-3)
 
-    # ---- leg 2: end to end through the host-buffer call, pose read-back every step ------------------------------
-    poses_out = np.empty((S, 12))
+    # ---- leg 2: end to end through the host-buffer C-ABI call, pose read-back every step ------------------------------
+    # vslam_track_frame_async: pinned host frames -> (copy stream) -> kernels -> every stream's pose copied back to pinned host
+    # memory, each step; the copy of step k overlaps the kernels of step k-1 (two level-0 buffers).
+    poses_pin = torch.empty((2, S, 12), dtype=torch.float64).pin_memory()
+    prev = None
     for k in range(Wm):
-        ctx.track_frame_ptr(frames_host[k].data_ptr(), W, fs, device=False)
-        ctx.get_poses()
+        sid = ctx.track_frame_async(frames_host[k].data_ptr(), W, fs, poses_pin[k & 1].data_ptr())
+        if prev is not None:
+            ctx.wait_step(prev)
+        prev = sid
+    ctx.wait_step(prev)
     barrier()
+    acc = 0.0
+    prev = None
     t0 = time.perf_counter()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record(stream)
     for k in range(Wm, Wm + K):
-        ctx.track_frame_ptr(frames_host[k].data_ptr(), W, fs, device=False)
-        poses_out = ctx.get_poses()
-    e3.record(stream)
+        sid = ctx.track_frame_async(frames_host[k].data_ptr(), W, fs, poses_pin[k & 1].data_ptr())
+        if prev is not None:
+            ctx.wait_step(prev)
+            acc += float(poses_pin[(k - 1) & 1, :, 3].sum())      # the result of step k-1 is consumed on the host
+        prev = sid
+    ctx.wait_step(prev)
+    acc += float(poses_pin[(Wm + K - 1) & 1, :, 3].sum())
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
-    e2e_ms = max_over_ranks(max(e2.elapsed_time(e3), wall_ms))
+    e2e_ms = max_over_ranks(wall_ms)
     e2e_value = world * S * K / (e2e_ms * 1e-3)
-    assert np.isfinite(poses_out).all()
+    assert np.isfinite(acc)
 
     # ---- roofline of the pyramid+FAST stage ----------------------------------------------------------------------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")

@@ -28,7 +28,8 @@
  *
  * All functions return 0 on success and a negative VSLAM_E_* code on failure; vslam_last_error() gives the text.
  * Nothing throws across this boundary.  Work is enqueued on the context's CUDA stream; the vslam_get_* readers and
- * vslam_sync() wait for it.  Host input buffers are only read during the call that receives them.
+ * vslam_sync() wait for it.  Host frame buffers passed to the *_lite / track_frame calls are read asynchronously: keep them
+ * valid until the next vslam_sync / vslam_get_* / vslam_wait_step; all other host inputs are consumed during the call.
  * A context is not thread-safe; distinct contexts are independent (no globals).
  */
 #ifndef VSLAM_B200_H
@@ -141,6 +142,13 @@ int vslam_track_map(vslam_ctx* ctx);
 /* MakeKeyFrame_Lite + (if lost_frames < 3) ApplyMotionModel, TrackMap, UpdateMotionModel, AssessTrackingQuality. */
 int vslam_track_frame(vslam_ctx* ctx, const uint8_t* gray_host, int stride, size_t frame_stride);
 int vslam_track_frame_dev(vslam_ctx* ctx, const uint8_t* gray_dev, int stride, size_t frame_stride);
+/* Pipelined form of vslam_track_frame for a continuous feed: the host->device copy of this step runs on an internal copy
+ * stream into one of two level-0 buffers and overlaps the kernels of the previous step; if poses_out is not NULL every
+ * stream's pose (12 doubles each) is copied there when the step completes.  gray_host and poses_out (pinned memory) must
+ * stay valid until vslam_wait_step(id) returns.  Returns a step id >= 0 (or a negative error); at most two steps are in
+ * flight, a third call blocks until the oldest has finished. */
+int vslam_track_frame_async(vslam_ctx* ctx, const uint8_t* gray_host, int stride, size_t frame_stride, double* poses_out);
+int vslam_wait_step(vslam_ctx* ctx, int step_id);
 
 /* Per-kernel device times measured with CUDA events on the context's stream.  Stages: 0-3 pyramid+FAST level 0-3,
  * 4 project+lists, 5 coarse search, 6 coarse pose iterations, 7 fine search, 8 fine pose iterations, 9 host->device copy,

@@ -328,3 +328,29 @@ def test_track_frame_sequence_multi_stream():
             a, f, q, lost, dc = ctx.counters(s); oa, of, oq, olost, odc = ow.counters()
             assert np.array_equal(a, oa) and np.array_equal(f, of) and (q, lost, dc) == (oq, olost, odc), (k, s)
     ctx.close()
+
+
+def test_track_frame_async_pipeline_matches_oracle():
+    """vslam_track_frame_async (double-buffered level 0, copy stream, pose write-back) gives the same poses as the oracle."""
+    import torch
+    cam, f0, smap = common.scene()
+    S, K = 2, 5
+    ctx = _ctx(cam, f0, smap, n_streams=S)
+    ows = [_orc(cam, f0, smap) for _ in range(S)]
+    frames = torch.from_numpy(np.stack([np.stack([synth.render_frame(common.texture(), cam, synth.stream_pose(3 * k, s)) for s in range(S)])
+                                        for k in range(1, K + 1)])).pin_memory()
+    poses = torch.zeros((K, S, 12), dtype=torch.float64).pin_memory()
+    ids = [ctx.track_frame_async(frames[k].data_ptr(), cam.width, cam.width * cam.height, poses[k].data_ptr()) for k in range(K)]
+    for sid in ids:
+        ctx.wait_step(sid)
+    for k in range(K):
+        for s, ow in enumerate(ows):
+            ow.L.orc_tracker_track_frame(ow.tracker, np.ascontiguousarray(frames[k, s].numpy()), cam.width, cam.height, cam.width)
+            assert np.abs(poses[k, s].numpy().reshape(3, 4) - ow.get_pose()).max() <= 1e-8, (k, s)
+    # the synchronous entry point keeps working on the same context afterwards
+    nxt = np.stack([synth.render_frame(common.texture(), cam, synth.stream_pose(3 * (K + 1), s)) for s in range(S)])
+    ctx.track_frame(nxt)
+    for s, ow in enumerate(ows):
+        ow.L.orc_tracker_track_frame(ow.tracker, np.ascontiguousarray(nxt[s]), cam.width, cam.height, cam.width)
+        assert np.abs(ctx.get_pose(s) - ow.get_pose()).max() <= 1e-8
+    ctx.close()

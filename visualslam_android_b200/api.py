@@ -43,7 +43,7 @@ ABI_SYMBOLS = [
     "vslam_set_pose", "vslam_get_pose", "vslam_get_poses", "vslam_set_motion", "vslam_get_motion", "vslam_set_sbi_rotation", "vslam_get_counters",
     "vslam_get_point_states", "vslam_get_point_template", "vslam_get_point_counts", "vslam_get_updates", "vslam_get_zmssd_evals",
     "vslam_project_all", "vslam_set_point_projection", "vslam_set_lists", "vslam_clear_counters", "vslam_search_for_points", "vslam_project_and_derivs", "vslam_calc_jacobians",
-    "vslam_calc_pose_update", "vslam_track_map", "vslam_track_frame", "vslam_track_frame_dev", "vslam_debug_atan", "vslam_kernel_launches", "vslam_set_timing", "vslam_get_stage_times",
+    "vslam_calc_pose_update", "vslam_track_map", "vslam_track_frame", "vslam_track_frame_dev", "vslam_track_frame_async", "vslam_wait_step", "vslam_debug_atan", "vslam_kernel_launches", "vslam_set_timing", "vslam_get_stage_times",
 ]
 
 _lib = None
@@ -108,6 +108,8 @@ def load():
     sig("vslam_track_frame", i, vp, vp, i, C.c_size_t)
     sig("vslam_track_frame_dev", i, vp, vp, i, C.c_size_t)
     sig("vslam_kernel_launches", C.c_ulonglong, vp)
+    sig("vslam_track_frame_async", i, vp, vp, i, C.c_size_t, vp)
+    sig("vslam_wait_step", i, vp, i)
     sig("vslam_debug_atan", i, vp, vp, i)
     sig("vslam_set_timing", i, vp, i)
     sig("vslam_get_stage_times", i, vp, vp, vp)
@@ -351,6 +353,16 @@ class Context:
     def track_frame_ptr(self, ptr, stride, frame_stride, device=False):
         fn = self.L.vslam_track_frame_dev if device else self.L.vslam_track_frame
         self._ck(fn(self.h, int(ptr), stride, frame_stride))
+
+    def track_frame_async(self, ptr, stride, frame_stride, poses_out_ptr=None):
+        """Pipelined host-input step; returns the step id to pass to wait_step."""
+        rc = self.L.vslam_track_frame_async(self.h, int(ptr), stride, frame_stride, None if poses_out_ptr is None else int(poses_out_ptr))
+        if rc < 0:
+            self._ck(rc)
+        return rc
+
+    def wait_step(self, step):
+        self._ck(self.L.vslam_wait_step(self.h, step))
 
     def sync(self):
         self._ck(self.L.vslam_sync(self.h))

@@ -103,7 +103,7 @@ int vslam_create(const vslam_config* cfg, vslam_ctx** out) {
   if (!ctx) { g_create_error = "out of host memory"; return VSLAM_E_INVALID; }
   ctx->cfg = *cfg; vslam_default_params(&ctx->params);
   ctx->S = cfg->n_streams; ctx->N = cfg->max_points; ctx->P = cfg->patch_size; ctx->launches = 0; ctx->n_src = cfg->max_source_keyframes;
-  ctx->scratch_host = nullptr; ctx->scratch_host_bytes = 0; ctx->timing = false; ctx->ev_used = 0;
+  ctx->scratch_host = nullptr; ctx->scratch_host_bytes = 0; ctx->timing = false; ctx->ev_used = 0; ctx->l0_alt = nullptr; ctx->copy_stream = nullptr; ctx->step = 0; ctx->pipe_ready = false; ctx->status_pin = nullptr;
   const float frac = cfg->max_corner_frac > 0 ? cfg->max_corner_frac : 0.5f;
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_create_error = std::string(#call) + ": " + cudaGetErrorString(e_); vslam_destroy(ctx); return VSLAM_E_CUDA; } } while (0)
   CK(cudaSetDevice(cfg->device));
@@ -179,6 +179,9 @@ void vslam_destroy(vslam_ctx* ctx) {
   cudaFree(ctx->ss); cudaFree(ctx->lists); cudaFree(ctx->pvs); cudaFree(ctx->sort_scratch);
   if (ctx->scratch_host) cudaFreeHost(ctx->scratch_host);
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+  if (ctx->pipe_ready) { for (int k = 0; k < 2; k++) { cudaEventDestroy(ctx->ev_copied[k]); cudaEventDestroy(ctx->ev_computed[k]); cudaEventDestroy(ctx->ev_done[k]); } cudaStreamDestroy(ctx->copy_stream); }
+  cudaFree(ctx->l0_alt);
+  if (ctx->status_pin) cudaFreeHost(ctx->status_pin);
   delete[] ctx->l0_ptr_host; delete[] ctx->l0_stride_host;
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -268,18 +271,22 @@ static int adopt_l0(vslam_ctx* ctx, int first, int count, const uint8_t* base, i
   return VSLAM_OK;
 }
 
-static int upload_frames(vslam_ctx* ctx, int first, int count, const uint8_t* gray, int stride, size_t frame_stride) {
+static int upload_frames_to(vslam_ctx* ctx, uint8_t* base, cudaStream_t st, int first, int count, const uint8_t* gray, int stride, size_t frame_stride) {
   const LevelDesc& L = ctx->lev[0];
-  vs_time_begin(ctx, VS_ST_H2D);
-  uint8_t* dst = L.img + (size_t)first * L.h * L.pitch;
+  uint8_t* dst = base + (size_t)first * L.h * L.pitch;
   if (stride == L.pitch && frame_stride == (size_t)L.h * L.pitch) {
-    VS_CUDA(cudaMemcpyAsync(dst, gray, (size_t)count * L.h * L.pitch, cudaMemcpyHostToDevice, ctx->stream));
+    VS_CUDA(cudaMemcpyAsync(dst, gray, (size_t)count * L.h * L.pitch, cudaMemcpyHostToDevice, st));
   } else {
     for (int k = 0; k < count; k++)
-      VS_CUDA(cudaMemcpy2DAsync(dst + (size_t)k * L.h * L.pitch, L.pitch, gray + (size_t)k * frame_stride, stride, L.w, L.h, cudaMemcpyHostToDevice, ctx->stream));
+      VS_CUDA(cudaMemcpy2DAsync(dst + (size_t)k * L.h * L.pitch, L.pitch, gray + (size_t)k * frame_stride, stride, L.w, L.h, cudaMemcpyHostToDevice, st));
   }
-  vs_time_end(ctx);
   return VSLAM_OK;
+}
+static int upload_frames(vslam_ctx* ctx, int first, int count, const uint8_t* gray, int stride, size_t frame_stride) {
+  vs_time_begin(ctx, VS_ST_H2D);
+  int rc = upload_frames_to(ctx, ctx->lev[0].img, ctx->stream, first, count, gray, stride, frame_stride);
+  vs_time_end(ctx);
+  return rc;
 }
 
 static int check_range(vslam_ctx* ctx, int first, int count, const void* p, int stride) {
@@ -528,6 +535,56 @@ int vslam_track_frame(vslam_ctx* ctx, const uint8_t* gray, int stride, size_t fr
   int rc = vslam_make_keyframe_lite(ctx, 0, ctx->S, gray, stride, frame_stride); if (rc) return rc;
   return vs_launch_track_map(ctx, 1);
 }
+// Pipelined host-input path: the copy of step k (copy stream, level-0 buffer k&1) overlaps the kernels of step k-1.
+int vslam_track_frame_async(vslam_ctx* ctx, const uint8_t* gray, int stride, size_t frame_stride, double* poses_out) {
+  int rc = check_range(ctx, 0, ctx ? ctx->S : 0, gray, stride); if (rc) return rc;
+  const LevelDesc& L = ctx->lev[0];
+  if (!ctx->pipe_ready) {
+    VS_CUDA(dalloc(&ctx->l0_alt, (size_t)ctx->S * L.h * L.pitch));
+    VS_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    VS_CUDA(cudaHostAlloc((void**)&ctx->status_pin, sizeof(int) * 8, cudaHostAllocDefault));
+    memset(ctx->status_pin, 0, sizeof(int) * 8);
+    for (int k = 0; k < 2; k++) {
+      VS_CUDA(cudaEventCreateWithFlags(&ctx->ev_copied[k], cudaEventDisableTiming)); VS_CUDA(cudaEventCreateWithFlags(&ctx->ev_computed[k], cudaEventDisableTiming));
+      VS_CUDA(cudaEventCreateWithFlags(&ctx->ev_done[k], cudaEventDisableTiming));
+      VS_CUDA(cudaEventRecord(ctx->ev_computed[k], ctx->stream)); VS_CUDA(cudaEventRecord(ctx->ev_done[k], ctx->stream));
+    }
+    ctx->pipe_ready = true;
+  }
+  const int slot = (int)(ctx->step & 1);
+  VS_CUDA(cudaEventSynchronize(ctx->ev_done[slot]));                       // at most two steps in flight
+  uint8_t* buf = slot ? ctx->l0_alt : L.img;
+  VS_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_computed[slot], 0));   // the kernels that last read this buffer are done
+  if ((rc = upload_frames_to(ctx, buf, ctx->copy_stream, 0, ctx->S, gray, stride, frame_stride))) return rc;
+  VS_CUDA(cudaEventRecord(ctx->ev_copied[slot], ctx->copy_stream));
+  VS_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[slot], 0));
+  bool same = true;
+  for (int s = 0; s < ctx->S; s++) same &= ctx->l0_ptr_host[s] == buf + (size_t)s * L.h * L.pitch && ctx->l0_stride_host[s] == L.pitch;
+  if (!same && (rc = adopt_l0(ctx, 0, ctx->S, buf, L.pitch, (size_t)L.h * L.pitch, false))) return rc;
+  if ((rc = vs_launch_pyramid_fast(ctx, 0, ctx->S))) return rc;
+  if ((rc = vs_launch_track_map(ctx, 1))) return rc;
+  VS_CUDA(cudaEventRecord(ctx->ev_computed[slot], ctx->stream));
+  if (poses_out)
+    VS_CUDA(cudaMemcpy2DAsync(poses_out, sizeof(double) * 12, (char*)ctx->ss + offsetof(StreamState, pose), sizeof(StreamState), sizeof(double) * 12, ctx->S,
+                              cudaMemcpyDeviceToHost, ctx->stream));
+  VS_CUDA(cudaMemcpyAsync(ctx->status_pin + 4 * slot, ctx->status, sizeof(int) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  VS_CUDA(cudaEventRecord(ctx->ev_done[slot], ctx->stream));
+  const int id = (int)ctx->step;
+  ctx->step = (ctx->step + 1) & 0x3fffffff;   // ids wrap at 2^30 (even, so the slot parity is preserved)
+  return id;
+}
+
+int vslam_wait_step(vslam_ctx* ctx, int step) {
+  if (!ctx || !ctx->pipe_ready || step < 0 || step >= ctx->step) { if (ctx) ctx->err = "unknown step id"; return VSLAM_E_INVALID; }
+  if (ctx->step - step > 2) return VSLAM_OK;   // older steps completed before their slot was reused
+  VS_CUDA(cudaEventSynchronize(ctx->ev_done[step & 1]));
+  if (ctx->status_pin[4 * (step & 1)]) {       // corner-capacity overflow seen by that step (the flag is sticky until vslam_sync)
+    ctx->err = "corner list capacity exceeded (raise vslam_config.max_corner_frac)";
+    return VSLAM_E_CAPACITY;
+  }
+  return VSLAM_OK;
+}
+
 int vslam_track_frame_dev(vslam_ctx* ctx, const uint8_t* gray, int stride, size_t frame_stride) {
   if (!ctx) return VSLAM_E_INVALID;
   int rc = vslam_make_keyframe_lite_dev(ctx, 0, ctx->S, gray, stride, frame_stride); if (rc) return rc;

@@ -85,6 +85,8 @@ struct vslam_ctx {
   const uint8_t** l0_ptr;        // [S] device: level-0 image of each stream (ctx-owned or adopted user buffer)
   int* l0_stride;                // [S] device
   const uint8_t** l0_ptr_host; int* l0_stride_host;
+  // double-buffered host-input pipeline (vslam_track_frame_async): level-0 buffer 0 is lev[0].img, buffer 1 is l0_alt
+  uint8_t* l0_alt; cudaStream_t copy_stream; cudaEvent_t ev_copied[2], ev_computed[2], ev_done[2]; long long step; bool pipe_ready; int* status_pin;   // [2][4] pinned copy of `status` per slot
   unsigned* tickets;             // [VS_LEVELS] device
   int* status;                   // [4] device: [0] capacity overflow flag
   CamDev cam; CamDev* cam_dev;
