@@ -23,6 +23,9 @@
  *   vslam_track_map                  Tracker::TrackMap                     jni/Tracker.cc:358-626
  *   vslam_track_frame[_dev]          Tracker::TrackFrame (good-map branch) jni/Tracker.cc:76-112
  *                                    (ApplyMotionModel :781-798, UpdateMotionModel :802-820, AssessTrackingQuality :832-878)
+ *   vslam_make_keyframe_rest         KeyFrame::MakeKeyFrame_Rest           jni/KeyFrame.cc:53-95 (fast_nonmax jni/vision/cvfast.cpp:9243-9405,
+ *                                    FindShiTomasiScoreAtPoint jni/vision/ImageHandler.cpp:124-155)
+ *   vslam_minipatch_sample / _find   MiniPatch::SampleFromImage / FindPatch jni/MiniPatch.cc:32-83
  *   vslam_create / vslam_destroy     JNI native_createTest / native_disposeTest   jni/jni_part.cpp:114-123
  *   vslam_track_frame                JNI native_update                            jni/jni_part.cpp:132-145
  *
@@ -106,6 +109,20 @@ int vslam_get_level(vslam_ctx* ctx, int stream, int level, uint8_t* out, int out
 int vslam_get_num_corners(vslam_ctx* ctx, int stream, int level, int* n);
 int vslam_get_corners(vslam_ctx* ctx, int stream, int level, int32_t* xy, int cap);     /* (x,y) pairs, raster order */
 int vslam_get_row_lut(vslam_ctx* ctx, int stream, int level, int32_t* lut);             /* H_level entries */
+
+/* ---- KeyFrame::MakeKeyFrame_Rest (jni/KeyFrame.cc:53-95: fast_nonmax + Shi-Tomasi candidates; the SmallBlurryImage tail is not
+ * part of this path) for one stream's current keyframe.  Results stay readable until the next call. */
+int vslam_make_keyframe_rest(vslam_ctx* ctx, int stream);
+int vslam_get_max_corners(vslam_ctx* ctx, int stream, int level, int32_t* xy /* may be NULL: count only */, int cap, int* n);   /* Level::vMaxCorners */
+int vslam_get_candidates(vslam_ctx* ctx, int stream, int level, int32_t* xy, double* st_score, int cap, int* n);                /* Level::vCandidates */
+
+/* ---- MiniPatch (jni/MiniPatch.cc): trail tracking while the initial map is built (Tracker::TrailTracking_*, jni/Tracker.cc:264-346).
+ * `which` selects the searched image: 0 = the stream's current keyframe, 1 = its snapshot (the "previous frame" of the married-match
+ * check), taken with vslam_snapshot_keyframe.  Patches are 9x9 bytes each; positions are level-0 pixels (integer valued). */
+int vslam_snapshot_keyframe(vslam_ctx* ctx, int stream);
+int vslam_minipatch_sample(vslam_ctx* ctx, int stream, int which, int n, const int32_t* xy, uint8_t* patches81);            /* SampleFromImage */
+int vslam_minipatch_find(vslam_ctx* ctx, int stream, int which, int n, const uint8_t* patches81, double* pos2 /* in/out */,
+                         int32_t* found, int32_t* best_ssd /* may be NULL */, int range, int max_ssd);                      /* FindPatch */
 
 /* ---- per-stream tracker state (Tracker members, jni/Tracker.h:105-133) ----------------------------------------- */
 int vslam_set_pose(vslam_ctx* ctx, int stream, const double* pose12);   /* row-major 3x4 [R|t], camera-from-world */

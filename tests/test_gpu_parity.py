@@ -354,3 +354,112 @@ def test_track_frame_async_pipeline_matches_oracle():
         ow.L.orc_tracker_track_frame(ow.tracker, np.ascontiguousarray(nxt[s]), cam.width, cam.height, cam.width)
         assert np.abs(ctx.get_pose(s) - ow.get_pose()).max() <= 1e-8
     ctx.close()
+
+
+@pytest.mark.parametrize("kind", ["synthetic", "noise"])
+def test_make_keyframe_rest_bit_exact(kind):
+    """a13: FAST scores -> non-max -> Shi-Tomasi candidates on the device against the oracle (ints exact, ST score exact: integer sums)."""
+    from oracle import oraclebind
+    from visualslam_android_b200 import api
+    if kind == "synthetic":
+        cam = synth.Camera(640, 480)
+        im = synth.render_frame(common.texture(), cam, synth.se3_exp(np.array(synth.CONFIG1_TWIST) * 0.7))
+    else:
+        im = np.random.RandomState(9).randint(0, 256, (240, 320)).astype(np.uint8)
+    H, W = im.shape
+    ctx = api.Context(W, H, n_streams=2, max_points=8, max_corner_frac=1.0)
+    ctx.make_keyframe_lite(np.stack([np.zeros_like(im), im]))
+    ctx.make_keyframe_rest(1)
+    ok = oraclebind.OrcKeyFrame().make_lite(im); ok.make_rest()
+    for l in range(4):
+        assert np.array_equal(ctx.max_corners(1, l), ok.max_corners(l)), f"vMaxCorners level {l}"
+        gxy, gs = ctx.candidates(1, l); oxy, os_ = ok.candidates(l)
+        assert np.array_equal(gxy, oxy), f"vCandidates level {l}"
+        assert np.array_equal(gs, os_), f"Shi-Tomasi scores level {l}"
+    ctx.make_keyframe_rest(0)       # an image without corners
+    assert all(len(ctx.max_corners(0, l)) == 0 for l in range(4))
+    ctx.close()
+
+
+def test_minipatch_trail_tracking_bit_exact():
+    """a12: SampleFromImage + FindPatch forward (current frame) and backward (snapshot of the previous frame), as in
+    Tracker::TrailTracking_Advance (jni/Tracker.cc:294-346), against the oracle."""
+    import ctypes as C
+    from oracle import oraclebind
+    cam, f0, smap = common.scene()
+    f1, _ = common.frame_at(cam, np.array(synth.CONFIG1_TWIST) * 0.15)
+    ctx = _ctx(cam, f0, smap)
+    ok0 = oraclebind.OrcKeyFrame().make_lite(f0); ok1 = oraclebind.OrcKeyFrame().make_lite(f1)
+    L = oraclebind.lib()
+    ctx.make_keyframe_lite(f0)
+    ctx.snapshot_keyframe(0)                     # previous frame
+    c = ok0.corners(0)
+    c = c[(c[:, 0] > 10) & (c[:, 1] > 10) & (c[:, 0] < 630) & (c[:, 1] < 470)][::9]
+    patches = ctx.minipatch_sample(0, c)
+    for k in range(0, len(c), 17):
+        x, y = c[k]
+        assert np.array_equal(patches[k], f0[y - 4:y + 5, x - 4:x + 5])
+    ctx.make_keyframe_lite(f1)                   # current frame
+    for rng, max_ssd in ((10, 100000), (10, 2000), (3, 100000)):
+        pos, found, best = ctx.minipatch_find(0, patches, c.astype(np.float64), rng, max_ssd)
+        for k, (x, y) in enumerate(c):
+            po = np.array([x, y], float); b = C.c_int()
+            fo = L.orc_minipatch_find(ok0.h, int(x), int(y), ok1.h, po, rng, 1, max_ssd, C.byref(b))
+            assert fo == found[k] and b.value == best[k] and np.array_equal(po, pos[k]), (rng, max_ssd, k)
+        assert found.sum() > 20
+    # backward search in the snapshot (which = 1): patches sampled at the forward result in the current frame
+    pos, found, _ = ctx.minipatch_find(0, patches, c.astype(np.float64), 10, 100000)
+    fw = pos[found == 1].astype(np.int32)
+    fw = fw[(fw[:, 0] >= 4) & (fw[:, 1] >= 4) & (fw[:, 0] < 636) & (fw[:, 1] < 476)]
+    back_patches = ctx.minipatch_sample(0, fw)
+    bpos, bfound, bbest = ctx.minipatch_find(0, back_patches, fw.astype(np.float64), 10, 100000, which=1)
+    for k, (x, y) in enumerate(fw):
+        po = np.array([x, y], float); b = C.c_int()
+        fo = L.orc_minipatch_find(ok1.h, int(x), int(y), ok0.h, po, 10, 1, 100000, C.byref(b))
+        assert fo == bfound[k] and b.value == bbest[k] and np.array_equal(po, bpos[k])
+    ctx.close()
+
+
+@pytest.mark.parametrize("size,n_points", [((1920, 1080), 5000), ((3840, 2160), 20000)])
+def test_large_configs_keyframe_search_pose(size, n_points):
+    """BASELINE configs[2] and [4] at full size: 1080p / 5000 points and 4K / 20000 points.  MakeKeyFrame_Lite is compared with
+    the oracle bit for bit; SearchForPoints on every level (8 sub-pixel iterations, beyond the 1000-patch cap, so driven
+    directly) and one CalcPoseUpdate are compared with the oracle; plus size-independent properties of the corner list."""
+    W, H = size
+    cam, f0, smap = common.scene(W, H, n_points, 4096)
+    assert smap.n == n_points
+    ctx, ow = _ctx(cam, f0, smap), _orc(cam, f0, smap)
+    tw = np.array(synth.CONFIG1_TWIST) * 0.3
+    f1, _ = common.frame_at(cam, tw, 4096)
+    ctx.make_keyframe_lite(f1); okf = ow.make_current_kf(f1)
+    _check_keyframe(ctx, 0, okf)
+    for l in range(4):   # properties that do not need the oracle: raster order, LUT = exclusive row histogram, x/y ranges
+        c = ctx.corners(0, l); w, h = ctx.level_dims(l)
+        key = c[:, 1].astype(np.int64) * 65536 + c[:, 0]
+        assert np.all(np.diff(key) > 0) and c[:, 0].min() >= 3 and c[:, 0].max() <= w - 4 and c[:, 1].min() >= 3 and c[:, 1].max() <= h - 4
+        assert np.array_equal(ctx.row_lut(0, l), np.searchsorted(c[:, 1], np.arange(h), side="left"))
+    start = synth.se3_exp(tw * 0.6)
+    ctx.set_pose(0, start); ow.set_pose(start)
+    ctx.project_all(); ow.L.orc_tracker_project_all(ow.tracker)
+    oi, od = ow.point_states()
+    gi, gd = ctx.point_states(0)
+    assert np.array_equal(gi[:, :2], oi[:, :2])
+    ctx.set_point_projection(0, od[:, 0:2], od[:, 11:15], oi[:, 1])
+    idx = np.nonzero(oi[:, 1] >= 0)[0].astype(np.int32)
+    assert len(idx) > 0.9 * n_points
+    ctx.set_lists([idx]); ctx.clear_counters(); ow.L.orc_tracker_clear_counters(ow.tracker)
+    ctx.search_for_points(10, 8); ow.L.orc_tracker_search_for_points(ow.tracker, idx, len(idx), 10, 8)
+    gi, gd = ctx.point_states(0); oi, od = ow.point_states()
+    assert np.array_equal(gi[idx][:, [2, 3, 5]], oi[idx][:, [2, 3, 5]])
+    a, f, *_ = ctx.counters(0); oa, of, *_ = ow.counters()
+    assert np.array_equal(a, oa) and np.array_equal(f, of)
+    assert ctx.zmssd_evals() == ow.L.orc_tracker_zmssd_evals(ow.tracker)
+    fnd = idx[oi[idx][:, 3] == 1]
+    assert len(fnd) > 0.8 * len(idx)
+    assert np.array_equal(gd[fnd][:, 30:32], od[fnd][:, 30:32]) and np.abs(gd[fnd][:, 2:4] - od[fnd][:, 2:4]).max() <= 1e-6
+    ctx.calc_jacobians(); ow.L.orc_tracker_calc_jacobians(ow.tracker, idx, len(idx))
+    gu = ctx.calc_pose_update(0.0, True, apply=True)[0]
+    ou = np.zeros(6); ow.L.orc_tracker_calc_pose_update(ow.tracker, idx, len(idx), 0.0, 1, 1, ou)
+    assert np.linalg.norm(gu - ou) <= 1e-6 * np.linalg.norm(ou), (gu, ou)     # contract 1e-4
+    assert np.array_equal(ctx.point_counts(0), ow.point_counts())
+    ctx.close()

@@ -40,6 +40,7 @@ ABI_SYMBOLS = [
     "vslam_default_config", "vslam_default_params", "vslam_create", "vslam_destroy", "vslam_last_error", "vslam_sync", "vslam_set_params",
     "vslam_set_camera", "vslam_camera_from_params", "vslam_upload_source_keyframe", "vslam_set_map", "vslam_make_keyframe_lite",
     "vslam_make_keyframe_lite_dev", "vslam_level_dims", "vslam_get_level", "vslam_get_num_corners", "vslam_get_corners", "vslam_get_row_lut",
+    "vslam_make_keyframe_rest", "vslam_get_max_corners", "vslam_get_candidates", "vslam_snapshot_keyframe", "vslam_minipatch_sample", "vslam_minipatch_find",
     "vslam_set_pose", "vslam_get_pose", "vslam_get_poses", "vslam_set_motion", "vslam_get_motion", "vslam_set_sbi_rotation", "vslam_get_counters",
     "vslam_get_point_states", "vslam_get_point_template", "vslam_get_point_counts", "vslam_get_updates", "vslam_get_zmssd_evals",
     "vslam_project_all", "vslam_set_point_projection", "vslam_set_lists", "vslam_clear_counters", "vslam_search_for_points", "vslam_project_and_derivs", "vslam_calc_jacobians",
@@ -84,6 +85,12 @@ def load():
     sig("vslam_get_num_corners", i, vp, i, i, pi)
     sig("vslam_get_corners", i, vp, i, i, vp, i)
     sig("vslam_get_row_lut", i, vp, i, i, vp)
+    sig("vslam_make_keyframe_rest", i, vp, i)
+    sig("vslam_get_max_corners", i, vp, i, i, vp, i, pi)
+    sig("vslam_get_candidates", i, vp, i, i, vp, vp, i, pi)
+    sig("vslam_snapshot_keyframe", i, vp, i)
+    sig("vslam_minipatch_sample", i, vp, i, i, i, vp, vp)
+    sig("vslam_minipatch_find", i, vp, i, i, i, vp, vp, vp, vp, i, i)
     sig("vslam_set_pose", i, vp, i, vp)
     sig("vslam_get_pose", i, vp, i, vp)
     sig("vslam_get_poses", i, vp, vp)
@@ -239,6 +246,43 @@ class Context:
         out = np.empty(h, dtype=np.int32)
         self._ck(self.L.vslam_get_row_lut(self.h, s, l, out.ctypes.data))
         return out
+
+    # -- MakeKeyFrame_Rest / MiniPatch
+    def make_keyframe_rest(self, s):
+        self._ck(self.L.vslam_make_keyframe_rest(self.h, s))
+
+    def max_corners(self, s, l):
+        n = C.c_int()
+        self._ck(self.L.vslam_get_max_corners(self.h, s, l, None, 0, C.byref(n)))
+        out = np.empty((n.value, 2), dtype=np.int32)
+        self._ck(self.L.vslam_get_max_corners(self.h, s, l, out.ctypes.data, n.value, C.byref(n)))
+        return out
+
+    def candidates(self, s, l):
+        n = C.c_int()
+        self._ck(self.L.vslam_get_candidates(self.h, s, l, None, None, 0, C.byref(n)))
+        xy = np.empty((n.value, 2), dtype=np.int32)
+        sc = np.empty(n.value, dtype=np.float64)
+        self._ck(self.L.vslam_get_candidates(self.h, s, l, xy.ctypes.data, sc.ctypes.data, n.value, C.byref(n)))
+        return xy, sc
+
+    def snapshot_keyframe(self, s):
+        self._ck(self.L.vslam_snapshot_keyframe(self.h, s))
+
+    def minipatch_sample(self, s, xy, which=0):
+        xy = np.ascontiguousarray(xy, dtype=np.int32)
+        out = np.empty((xy.shape[0], 9, 9), dtype=np.uint8)
+        self._ck(self.L.vslam_minipatch_sample(self.h, s, which, xy.shape[0], xy.ctypes.data, out.ctypes.data))
+        return out
+
+    def minipatch_find(self, s, patches, pos, rng=10, max_ssd=100000, which=0):
+        p = np.ascontiguousarray(patches, dtype=np.uint8)
+        pos = np.ascontiguousarray(pos, dtype=np.float64).copy()
+        n = pos.shape[0]
+        found = np.zeros(n, dtype=np.int32)
+        best = np.zeros(n, dtype=np.int32)
+        self._ck(self.L.vslam_minipatch_find(self.h, s, which, n, p.ctypes.data, pos.ctypes.data, found.ctypes.data, best.ctypes.data, rng, max_ssd))
+        return pos, found, best
 
     # -- tracker state
     def set_pose(self, s, pose):

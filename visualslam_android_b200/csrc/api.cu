@@ -104,6 +104,8 @@ int vslam_create(const vslam_config* cfg, vslam_ctx** out) {
   ctx->cfg = *cfg; vslam_default_params(&ctx->params);
   ctx->S = cfg->n_streams; ctx->N = cfg->max_points; ctx->P = cfg->patch_size; ctx->launches = 0; ctx->n_src = cfg->max_source_keyframes;
   ctx->scratch_host = nullptr; ctx->scratch_host_bytes = 0; ctx->timing = false; ctx->ev_used = 0; ctx->l0_alt = nullptr; ctx->copy_stream = nullptr; ctx->step = 0; ctx->pipe_ready = false; ctx->status_pin = nullptr;
+  ctx->rest_scores = nullptr; ctx->rest_max = nullptr; ctx->rest_cand = nullptr; ctx->rest_cand_score = nullptr; ctx->rest_counts = nullptr; ctx->rest_stream = -1;
+  ctx->snap_img = nullptr; ctx->snap_corners = nullptr; ctx->snap_lut = nullptr;
   const float frac = cfg->max_corner_frac > 0 ? cfg->max_corner_frac : 0.5f;
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_create_error = std::string(#call) + ": " + cudaGetErrorString(e_); vslam_destroy(ctx); return VSLAM_E_CUDA; } } while (0)
   CK(cudaSetDevice(cfg->device));
@@ -181,6 +183,8 @@ void vslam_destroy(vslam_ctx* ctx) {
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   if (ctx->pipe_ready) { for (int k = 0; k < 2; k++) { cudaEventDestroy(ctx->ev_copied[k]); cudaEventDestroy(ctx->ev_computed[k]); cudaEventDestroy(ctx->ev_done[k]); } cudaStreamDestroy(ctx->copy_stream); }
   cudaFree(ctx->l0_alt);
+  cudaFree(ctx->rest_scores); cudaFree(ctx->rest_max); cudaFree(ctx->rest_cand); cudaFree(ctx->rest_cand_score); cudaFree(ctx->rest_counts);
+  cudaFree(ctx->snap_img); cudaFree(ctx->snap_corners); cudaFree(ctx->snap_lut);
   if (ctx->status_pin) cudaFreeHost(ctx->status_pin);
   delete[] ctx->l0_ptr_host; delete[] ctx->l0_stride_host;
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -355,6 +359,82 @@ int vslam_get_row_lut(vslam_ctx* ctx, int s, int l, int32_t* lut) {
   const LevelDesc& L = ctx->lev[l];
   VS_CUDA(cudaMemcpy(lut, L.lut + (size_t)s * (L.h + 1), sizeof(int) * L.h, cudaMemcpyDeviceToHost));
   return VSLAM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- MakeKeyFrame_Rest / MiniPatch
+int vslam_make_keyframe_rest(vslam_ctx* ctx, int s) {
+  int rc = check_stream(ctx, s); if (rc) return rc;
+  return vs_keyframe_rest(ctx, s);
+}
+
+static int rest_list(vslam_ctx* ctx, int s, int l, const uint32_t* src, int which, int32_t* xy, double* score, int cap, int* n) {
+  int rc = check_stream(ctx, s); if (rc) return rc;
+  if (l < 0 || l >= VS_LEVELS || !n || ctx->rest_stream != s) { ctx->err = "call vslam_make_keyframe_rest for this stream first"; return VSLAM_E_INVALID; }
+  VS_CUDA(cudaStreamSynchronize(ctx->stream));
+  int counts[2];
+  VS_CUDA(cudaMemcpy(counts, ctx->rest_counts + 2 * l, sizeof(counts), cudaMemcpyDeviceToHost));
+  *n = counts[which];
+  if (!xy) return VSLAM_OK;
+  if (*n > cap) { ctx->err = "output buffer too small"; return VSLAM_E_INVALID; }
+  std::vector<uint32_t> tmp(*n);
+  if (*n) VS_CUDA(cudaMemcpy(tmp.data(), src + ctx->rest_off[l], sizeof(uint32_t) * *n, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < *n; i++) { xy[2 * i] = tmp[i] & 0xffff; xy[2 * i + 1] = tmp[i] >> 16; }
+  if (score && *n) VS_CUDA(cudaMemcpy(score, ctx->rest_cand_score + ctx->rest_off[l], sizeof(double) * *n, cudaMemcpyDeviceToHost));
+  return VSLAM_OK;
+}
+int vslam_get_max_corners(vslam_ctx* ctx, int s, int l, int32_t* xy, int cap, int* n) { return ctx ? rest_list(ctx, s, l, ctx->rest_max, 0, xy, nullptr, cap, n) : VSLAM_E_INVALID; }
+int vslam_get_candidates(vslam_ctx* ctx, int s, int l, int32_t* xy, double* score, int cap, int* n) { return ctx ? rest_list(ctx, s, l, ctx->rest_cand, 1, xy, score, cap, n) : VSLAM_E_INVALID; }
+
+int vslam_snapshot_keyframe(vslam_ctx* ctx, int s) {
+  int rc = check_stream(ctx, s); if (rc) return rc;
+  const LevelDesc& L = ctx->lev[0];
+  if (!ctx->snap_img) {
+    VS_CUDA(dalloc(&ctx->snap_img, (size_t)ctx->S * L.h * L.pitch)); VS_CUDA(dalloc(&ctx->snap_corners, (size_t)ctx->S * L.cap));
+    VS_CUDA(dalloc(&ctx->snap_lut, (size_t)ctx->S * (L.h + 1)));
+  }
+  VS_CUDA(cudaMemcpy2DAsync(ctx->snap_img + (size_t)s * L.h * L.pitch, L.pitch, ctx->l0_ptr_host[s], ctx->l0_stride_host[s], L.w, L.h, cudaMemcpyDeviceToDevice, ctx->stream));
+  VS_CUDA(cudaMemcpyAsync(ctx->snap_corners + (size_t)s * L.cap, L.corners + (size_t)s * L.cap, sizeof(uint32_t) * L.cap, cudaMemcpyDeviceToDevice, ctx->stream));
+  VS_CUDA(cudaMemcpyAsync(ctx->snap_lut + (size_t)s * (L.h + 1), L.lut + (size_t)s * (L.h + 1), sizeof(int) * (L.h + 1), cudaMemcpyDeviceToDevice, ctx->stream));
+  return VSLAM_OK;
+}
+
+static int minipatch_common(vslam_ctx* ctx, int s, int which, int n) {
+  int rc = check_stream(ctx, s); if (rc) return rc;
+  if (n < 0 || (which != 0 && which != 1) || (which == 1 && !ctx->snap_img)) { ctx->err = "bad MiniPatch arguments (snapshot the keyframe first for which = 1)"; return VSLAM_E_INVALID; }
+  return VSLAM_OK;
+}
+
+int vslam_minipatch_sample(vslam_ctx* ctx, int s, int which, int n, const int32_t* xy, uint8_t* patches81) {
+  int rc = minipatch_common(ctx, s, which, n); if (rc) return rc;
+  if (n == 0) return VSLAM_OK;
+  const int W = ctx->lev[0].w, H = ctx->lev[0].h;
+  for (int i = 0; i < n; i++) if (!(xy[2 * i] >= 4 && xy[2 * i + 1] >= 4 && xy[2 * i] < W - 4 && xy[2 * i + 1] < H - 4)) { ctx->err = "MiniPatch centre within 4 px of the border (the reference asserts, jni/MiniPatch.cc:75)"; return VSLAM_E_INVALID; }
+  int* dxy = nullptr; uint8_t* dp = nullptr;
+  VS_CUDA(cudaMalloc(&dxy, sizeof(int) * 2 * n)); VS_CUDA(cudaMalloc(&dp, (size_t)81 * n));
+  VS_CUDA(cudaMemcpyAsync(dxy, xy, sizeof(int) * 2 * n, cudaMemcpyHostToDevice, ctx->stream));
+  rc = vs_minipatch_sample(ctx, s, which, dxy, n, dp);
+  if (!rc) { cudaError_t e = cudaMemcpyAsync(patches81, dp, (size_t)81 * n, cudaMemcpyDeviceToHost, ctx->stream); if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream); if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = VSLAM_E_CUDA; } }
+  cudaFree(dxy); cudaFree(dp);
+  return rc;
+}
+
+int vslam_minipatch_find(vslam_ctx* ctx, int s, int which, int n, const uint8_t* patches81, double* pos2, int32_t* found, int32_t* best_ssd, int range, int max_ssd) {
+  int rc = minipatch_common(ctx, s, which, n); if (rc) return rc;
+  if (n == 0) return VSLAM_OK;
+  uint8_t* dp = nullptr; double* dpos = nullptr; int* df = nullptr; int* db = nullptr;
+  VS_CUDA(cudaMalloc(&dp, (size_t)81 * n)); VS_CUDA(cudaMalloc(&dpos, sizeof(double) * 2 * n)); VS_CUDA(cudaMalloc(&df, sizeof(int) * n)); VS_CUDA(cudaMalloc(&db, sizeof(int) * n));
+  VS_CUDA(cudaMemcpyAsync(dp, patches81, (size_t)81 * n, cudaMemcpyHostToDevice, ctx->stream));
+  VS_CUDA(cudaMemcpyAsync(dpos, pos2, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, ctx->stream));
+  rc = vs_minipatch_find(ctx, s, which, dp, n, dpos, df, db, range, max_ssd);
+  if (!rc) {
+    cudaError_t e = cudaMemcpyAsync(pos2, dpos, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(found, df, sizeof(int) * n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && best_ssd) e = cudaMemcpyAsync(best_ssd, db, sizeof(int) * n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = VSLAM_E_CUDA; }
+  }
+  cudaFree(dp); cudaFree(dpos); cudaFree(df); cudaFree(db);
+  return rc;
 }
 
 // ---------------------------------------------------------------------------------------------- per-stream state

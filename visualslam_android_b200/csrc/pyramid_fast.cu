@@ -89,8 +89,9 @@ k_pyramid_fast(LevelDesc L, LevelDesc Ln, int has_next, int level, const uint8_t
   const int n_pairs = (y1 - y0 + 1) >> 1;
   uint8_t* next_img = has_next ? Ln.img + (size_t)s * Ln.h * Ln.pitch : nullptr;
 
-  for (int item = warp; item < n_pairs * n_chunks; item += kWarps) {
-    const int pr = item / n_chunks, ch = item - pr * n_chunks;
+  int pr = warp / n_chunks, ch = warp - pr * n_chunks;   // work item = (row pair, 128-pixel chunk); advanced incrementally below
+  for (int item = warp; item < n_pairs * n_chunks; item += kWarps, ch += kWarps) {
+    while (ch >= n_chunks) { ch -= n_chunks; pr++; }
     const int y = y0 + 2 * pr;           // rows y and y+1
     const int x0 = (ch << 7) + (lane << 2);
     const bool active = x0 < W;
@@ -144,14 +145,15 @@ k_pyramid_fast(LevelDesc L, LevelDesc Ln, int has_next, int level, const uint8_t
       const uint32_t e = queue[q];
       const int ry = e >> 16, x = e & 0xffff;
       const uint8_t* p = img + (size_t)ry * stride + x;
-      const int c = p[0];
+      const int cb = (int)p[0] + thr, c_b = (int)p[0] - thr;
       const int s1 = stride, s2 = 2 * stride, s3 = 3 * stride;
       uint32_t br = 0, dk = 0;
+      // sign bit of (cb - v) <=> v > cb ; sign bit of (v - c_b) <=> v < c_b : shifted into the masks with funnel shifts
 #define RING(off)                                                       \
   {                                                                     \
-    const int d = (int)p[(off)] - c;                                    \
-    br = __funnelshift_l((uint32_t)(thr - d), br, 1);                   \
-    dk = __funnelshift_l((uint32_t)(d + thr), dk, 1);                   \
+    const int v = (int)p[(off)];                                        \
+    br = __funnelshift_l((uint32_t)(cb - v), br, 1);                    \
+    dk = __funnelshift_l((uint32_t)(v - c_b), dk, 1);                   \
   }
       RING(s3) RING(1 + s3) RING(2 + s2) RING(3 + s1) RING(3) RING(3 - s1) RING(2 - s2) RING(1 - s3)
       RING(-s3) RING(-1 - s3) RING(-2 - s2) RING(-3 - s1) RING(-3) RING(-3 + s1) RING(-2 + s2) RING(-1 + s3)
