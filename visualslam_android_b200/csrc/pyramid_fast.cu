@@ -18,7 +18,7 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kQueue = 256;  // candidates per warp work item: 2 rows x 128 pixels
+constexpr int kQueue = 288;  // per-warp candidate queue: up to 31 carried over + 256 of one work item (2 rows x 128 pixels)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -45,6 +45,31 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 
 // per-byte (x > t) for 4 packed bytes, t < 128: flag in bit 7 of every byte (other bits are garbage)
 __device__ __forceinline__ uint32_t bytes_gt(uint32_t x, uint32_t k /* (127 - t) * 0x01010101 */) { return ((x & 0x7f7f7f7fu) + k) | x; }
+
+// Exact FAST-10 segment test of one candidate (queue entry = smem row << 16 | x); sets its bit in the strip's corner bitmask.
+__device__ __forceinline__ void ring_test(uint32_t e, const uint8_t* img, int stride, int thr, uint32_t* bitmask, int words_per_row, int row_bias) {
+  const int ry = e >> 16, x = e & 0xffff;
+  const uint8_t* p = img + (size_t)ry * stride + x;
+  const int cb = (int)p[0] + thr, c_b = (int)p[0] - thr;
+  const int s1 = stride, s2 = 2 * stride, s3 = 3 * stride;
+  uint32_t br = 0, dk = 0;
+  // sign bit of (cb - v) <=> v > cb ; sign bit of (v - c_b) <=> v < c_b : shifted into the masks with funnel shifts
+#define RING(off)                                                       \
+  {                                                                     \
+    const int v = (int)p[(off)];                                        \
+    br = __funnelshift_l((uint32_t)(cb - v), br, 1);                    \
+    dk = __funnelshift_l((uint32_t)(v - c_b), dk, 1);                   \
+  }
+  RING(s3) RING(1 + s3) RING(2 + s2) RING(3 + s1) RING(3) RING(3 - s1) RING(2 - s2) RING(1 - s3)
+  RING(-s3) RING(-1 - s3) RING(-2 - s2) RING(-3 - s1) RING(-3) RING(-3 + s1) RING(-2 + s2) RING(-1 + s3)
+#undef RING
+  br |= br << 16; dk |= dk << 16;
+  uint32_t b1 = br & (br >> 1), d1 = dk & (dk >> 1);
+  uint32_t b2 = b1 & (b1 >> 2), d2 = d1 & (d1 >> 2);
+  b2 &= b2 >> 4; d2 &= d2 >> 4;
+  b2 &= b1 >> 8; d2 &= d1 >> 8;
+  if ((b2 | d2) & 0xffffu) atomicOr(&bitmask[(ry + row_bias) * words_per_row + (x >> 5)], 1u << (x & 31));
+}
 
 constexpr unsigned long long kFlagAgg = 1ull << 32, kFlagInc = 2ull << 32;
 
@@ -89,6 +114,7 @@ k_pyramid_fast(LevelDesc L, LevelDesc Ln, int has_next, int level, const uint8_t
   const int n_pairs = (y1 - y0 + 1) >> 1;
   uint8_t* next_img = has_next ? Ln.img + (size_t)s * Ln.h * Ln.pitch : nullptr;
 
+  int qn = 0;   // candidates waiting in this warp's queue (warp-uniform)
   int pr = warp / n_chunks, ch = warp - pr * n_chunks;   // work item = (row pair, 128-pixel chunk); advanced incrementally below
   for (int item = warp; item < n_pairs * n_chunks; item += kWarps, ch += kWarps) {
     while (ch >= n_chunks) { ch -= n_chunks; pr++; }
@@ -124,49 +150,28 @@ k_pyramid_fast(LevelDesc L, LevelDesc Ln, int has_next, int level, const uint8_t
         cand[k] = m1 & m2 & vmask;
       }
     }
-    // compact the candidates of the warp into its queue, raster order not needed here
+    // append the candidates of this work item to the warp's queue (order is irrelevant: corners land in a bitmask)
     const int mine = __popc(cand[0]) + __popc(cand[1]);
     int incl = mine;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    int pos = incl - mine;
+    int pos = qn + incl - mine;
+    qn += __shfl_sync(0xffffffffu, incl, 31);
 #pragma unroll
     for (int k = 0; k < 2; k++) {
       uint32_t m = cand[k];
+      const uint32_t ebase = ((uint32_t)(y + k - ya) << 16) | (uint32_t)x0;
       while (m) {
         const int b = __ffs(m) - 1; m &= m - 1;
-        queue[pos++] = ((uint32_t)(y + k - ya) << 16) | (uint32_t)(x0 + (b >> 3));
+        queue[pos++] = ebase + (uint32_t)(b >> 3);
       }
     }
     __syncwarp();
-    // exact ring test, one lane per candidate
-    for (int q = lane; q < total; q += 32) {
-      const uint32_t e = queue[q];
-      const int ry = e >> 16, x = e & 0xffff;
-      const uint8_t* p = img + (size_t)ry * stride + x;
-      const int cb = (int)p[0] + thr, c_b = (int)p[0] - thr;
-      const int s1 = stride, s2 = 2 * stride, s3 = 3 * stride;
-      uint32_t br = 0, dk = 0;
-      // sign bit of (cb - v) <=> v > cb ; sign bit of (v - c_b) <=> v < c_b : shifted into the masks with funnel shifts
-#define RING(off)                                                       \
-  {                                                                     \
-    const int v = (int)p[(off)];                                        \
-    br = __funnelshift_l((uint32_t)(cb - v), br, 1);                    \
-    dk = __funnelshift_l((uint32_t)(v - c_b), dk, 1);                   \
-  }
-      RING(s3) RING(1 + s3) RING(2 + s2) RING(3 + s1) RING(3) RING(3 - s1) RING(2 - s2) RING(1 - s3)
-      RING(-s3) RING(-1 - s3) RING(-2 - s2) RING(-3 - s1) RING(-3) RING(-3 + s1) RING(-2 + s2) RING(-1 + s3)
-#undef RING
-      br |= br << 16; dk |= dk << 16;
-      uint32_t b1 = br & (br >> 1), d1 = dk & (dk >> 1);
-      uint32_t b2 = b1 & (b1 >> 2), d2 = d1 & (d1 >> 2);
-      b2 &= b2 >> 4; d2 &= d2 >> 4;
-      b2 &= b1 >> 8; d2 &= d1 >> 8;
-      if ((b2 | d2) & 0xffffu) atomicOr(&bitmask[(ry + ya - y0) * words_per_row + (x >> 5)], 1u << (x & 31));
-    }
+    // exact ring test on full groups of 32 queued candidates; the remainder waits for the next work item
+    while (qn >= 32) { qn -= 32; ring_test(queue[qn + lane], img, stride, thr, bitmask, words_per_row, ya - y0); }
     __syncwarp();
   }
+  if (lane < qn) ring_test(queue[lane], img, stride, thr, bitmask, words_per_row, ya - y0);
   __syncthreads();
 
   // per-row corner counts
