@@ -361,12 +361,21 @@ def main():
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     pyr_ms = sum(stage[f"pyrfast_l{l}"][0] for l in range(4))
     lut_bytes = 4 * sum((H >> l) for l in range(4))
-    alg_bytes_step = S * (1.328125 * W * H + lut_bytes) + 4.0 * corners_per_step
+    alg_bytes_step = S * (1.328125 * W * H + lut_bytes) + 4.0 * corners_per_step            # whole stage, per step
     achieved = alg_bytes_step * K / (pyr_ms * 1e-3) / 1e9
-    roofline = {"kernel": "k_pyramid_fast (4 launches per step: levels 0-3)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_step": alg_bytes_step,
-                "ms_per_step": pyr_ms / K, "share_of_step": pyr_ms / dev_ms,
-                "note": "instruction-issue bound (FAST segment test), not HBM bound: see DESIGN.md §5 and profiles/"}
+    # level-0 launch alone (75 % of the pixels): reads level 0, writes level 1 + its corner list + LUT
+    l0_corners = sum(int(ctx.corners(s, 0).shape[0]) for s in probe) * (S / len(probe))
+    l0_bytes = S * (1.25 * W * H + 4 * (H + 1)) + 4.0 * l0_corners
+    l0_ms = stage["pyrfast_l0"][0] / K
+    # DRAM bytes of that launch from the committed ncu --set full capture (profiles/r01_final_ncu_full_summary.json, S=256 VGA)
+    l0_traffic = 78.743296e6 + 10.982400e6 if (S == 256 and (W, H) == (640, 480)) else None
+    roofline = {"kernel": "k_pyramid_fast (pyramid + FAST-10 + raster compaction + row LUT; 4 launches per step, levels 0-3)", "bound": "hbm",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": l0_traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_step": alg_bytes_step, "ms_per_step": pyr_ms / K, "share_of_step": pyr_ms / dev_ms,
+                "level0_launch": {"algorithmic_bytes": l0_bytes, "ms": l0_ms, "achieved": l0_bytes / (l0_ms * 1e-3) / 1e9,
+                                  "frac": l0_bytes / (l0_ms * 1e-3) / 1e9 / peak, "traffic": l0_traffic},
+                "note": "traffic is the level-0 launch's dram read+write bytes (ncu); the stage is instruction-issue bound (85 % issue-slot "
+                        "utilisation, ~260 warp-instructions per 128 pixels), not HBM bound: DESIGN.md §4.1 and profiles/r01_final_*"}
     stages_ms = {k: round(v[0] / K, 4) for k, v in stage.items() if v[1]}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": dev_ms / K, "higher_is_better": True,

@@ -6,6 +6,6 @@ HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 if [ "$HERE/libvslam_oracle.so" -nt "$HERE/vslam_oracle.cc" ] && [ "$HERE/libvslam_oracle.so" -nt "$HERE/build_oracle.sh" ]; then
   echo "build_oracle: up to date"; exit 0
 fi
-${CXX:-g++} -std=gnu++11 -O3 -fPIC -ffp-contract=off -fno-fast-math -Wall -Wno-unused-function -shared \
+${VSLAM_CXX:-/usr/bin/g++} -std=gnu++11 -O3 -fPIC -ffp-contract=off -fno-fast-math -Wall -Wno-unused-function -shared \
   "$HERE/vslam_oracle.cc" -o "$HERE/libvslam_oracle.so"
 echo "build_oracle: wrote $HERE/libvslam_oracle.so"

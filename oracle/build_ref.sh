@@ -34,7 +34,7 @@ Tracker.h Tracker.cc TrackerData.h myWLS.h vision/ImageHandler.h vision/ImageHan
 for f in $FILES; do
   sed -E 's@#include "(/Users/ahcorde/Downloads/eigen|/opt/local/include/eigen3)/Eigen/Dense"@#include <Eigen/Dense>@' "$REF/$f" > "$TMP/$f"
 done
-CXX="${CXX:-g++}"
+CXX="${VSLAM_CXX:-/usr/bin/g++}"   # (the image exports CXX=/opt/gcc/bin/g++, which links libstdc++ statically: iostreams of a dlopen-ed library then crash)
 # -O3 as in jni/Application.mk; -ffp-contract=off: no FMA contraction (the reference's ARMv7/x86 builds have none);
 # gnu++11 keeps std::random_shuffle / std::binary_function; -Wno-narrowing for cvfast.cpp's size_t->int ring offsets.
 NDBG="-DNDEBUG"; [ -n "${VSLAM_REF_DEBUG:-}" ] && NDBG=""   # NDK release builds define NDEBUG

@@ -100,6 +100,14 @@ def lib():
     sig("orc_tracker_linear_update", None, vp, _i32p, i, _f64p)
     sig("orc_tracker_calc_pose_update", None, vp, _i32p, i, d, i, i, _f64p)
     sig("orc_tukey_sigma_squared", d, _f64p, i)
+    sig("orc_tracker_enable_sbi", None, vp, _f64p)
+    sig("orc_tracker_get_sbi_rot", None, vp, _f64p)
+    sig("orc_sbi_create", vp, vp, d)
+    sig("orc_sbi_destroy", None, vp)
+    sig("orc_sbi_dims", None, vp, pi, pi)
+    sig("orc_sbi_template", None, vp, np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS"))
+    sig("orc_sbi_small", None, vp, _u8p)
+    sig("orc_sbi_rotation", d, vp, vp, _f64p, i, C.c_void_p, _f64p)
     _lib = L
     return L
 

@@ -65,6 +65,7 @@ struct Cam {
   bool invalid;
 };
 
+Cam cam_from13(const double* s);
 // jni/ATANCamera.h:136-142
 double rtrans_factor(const Cam& c, double r) {
   if (r < 0.001 || c.W == 0.0) return 1.0;
@@ -672,6 +673,174 @@ void inverse_lu(const double* m, int n, double* r) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// SmallBlurryImage (jni/SmallBlurryImage.cc) — the f1 row of SURVEY.md §8: per-frame rotation estimate that seeds the motion model.
+struct SBI {
+  int w, h;
+  std::vector<uint8_t> small;        // mimSmall
+  std::vector<float> tmpl;           // mimTemplate (zero-mean, blurred)
+  std::vector<float> jac;            // mimImageJacs, 2 floats per pixel
+  bool madeJacs;
+};
+// cv::GaussianBlur(float, ksize 9x9, sigma, BORDER_REPLICATE) as restated by the OpenCV stand-in (oracle/shim/opencv2/core/core.hpp):
+// getGaussianKernel taps in float, row pass then column pass, float accumulation in tap order.
+void gaussian_blur_9(std::vector<float>& im, int W, int H, double sigma) {
+  const int n = 9; float k[9];
+  { const double scale2x = -0.5 / (sigma * sigma); double sum = 0;
+    for (int i = 0; i < n; i++) { const double x = i - (n - 1) * 0.5; const double t = std::exp(scale2x * x * x); k[i] = (float)t; sum += k[i]; }
+    sum = 1. / sum; for (int i = 0; i < n; i++) k[i] = (float)(k[i] * sum); }
+  std::vector<float> tmp((size_t)W * H), out((size_t)W * H);
+  for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) {
+    float s = 0; for (int i = 0; i < n; i++) { int xx = x + i - n / 2; xx = xx < 0 ? 0 : (xx >= W ? W - 1 : xx); s += k[i] * im[(size_t)y * W + xx]; }
+    tmp[(size_t)y * W + x] = s; }
+  for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) {
+    float s = 0; for (int i = 0; i < n; i++) { int yy = y + i - n / 2; yy = yy < 0 ? 0 : (yy >= H ? H - 1 : yy); s += k[i] * tmp[(size_t)yy * W + x]; }
+    out[(size_t)y * W + x] = s; }
+  im.swap(out);
+}
+// SmallBlurryImage::MakeFromKF (jni/SmallBlurryImage.cc:20-55), dBlur <= 2.0 branch (the tracker uses 0.75, jni/Tracker.cc:87)
+void sbi_make(SBI& s, const OKeyFrame& kf, double dBlur) {
+  const Image& l3 = kf.lev[3].im;
+  s.w = l3.w / 2; s.h = l3.h / 2; s.madeJacs = false;
+  Image sm; half_sample(l3, sm);   // cv::resize to exactly half: (a+b+c+d+2)>>2 (requires even level-3 dimensions)
+  s.small = sm.px;
+  unsigned nSum = 0; for (size_t i = 0; i < s.small.size(); i++) nSum += s.small[i];
+  const float fMean = ((float)nSum) / (s.h * s.w);
+  s.tmpl.resize((size_t)s.w * s.h);
+  for (size_t i = 0; i < s.small.size(); i++) s.tmpl[i] = s.small[i] - fMean;
+  gaussian_blur_9(s.tmpl, s.w, s.h, dBlur);
+}
+// SmallBlurryImage::MakeJacs (jni/SmallBlurryImage.cc:58-79)
+void sbi_make_jacs(SBI& s) {
+  s.jac.assign((size_t)2 * s.w * s.h, 0.f);
+  for (int x = 0; x < s.w; x++) for (int y = 0; y < s.h; y++)
+    if (x >= 1 && y >= 1 && x < s.w - 1 && y < s.h - 1) {
+      s.jac[2 * ((size_t)y * s.w + x)] = s.tmpl[(size_t)y * s.w + x + 1] - s.tmpl[(size_t)y * s.w + x - 1];
+      s.jac[2 * ((size_t)y * s.w + x) + 1] = s.tmpl[(size_t)(y + 1) * s.w + x] - s.tmpl[(size_t)(y - 1) * s.w + x];
+    }
+  s.madeJacs = true;
+}
+// transform_image, float source and destination (jni/vision/ImageHandler.cpp:3-10,21-113)
+void transform_image_f32(const std::vector<float>& in, int iw, int ih, std::vector<float>& out, int w, int h, const double* M, const double* inOrig, const double* outOrig, double def) {
+  const double across[2] = {M[0], M[2]}, down[2] = {M[1], M[3]};
+  double p0[2];
+  { double a = M[0] * outOrig[0]; a += M[1] * outOrig[1]; double b = M[2] * outOrig[0]; b += M[3] * outOrig[1]; p0[0] = inOrig[0] - a; p0[1] = inOrig[1] - b; }
+  double min_x = p0[0], min_y = p0[1], max_x = min_x, max_y = min_y;
+  if (across[0] < 0) min_x += w * across[0]; else max_x += w * across[0];
+  if (down[0] < 0) min_x += h * down[0]; else max_x += h * down[0];
+  if (across[1] < 0) min_y += w * across[1]; else max_y += w * across[1];
+  if (down[1] < 0) min_y += h * down[1]; else max_y += h * down[1];
+  const double cr[2] = {down[0] - w * across[0], down[1] - w * across[1]};
+  const bool inside = (min_x >= 0 && min_y >= 0 && max_x < iw - 1 && max_y < ih - 1);
+  const float x_bound = iw - 1, y_bound = ih - 1;
+  out.resize((size_t)w * h);
+  double p[2] = {p0[0], p0[1]};
+  for (int i = 0; i < h; ++i, p[0] += cr[0], p[1] += cr[1])
+    for (int j = 0; j < w; ++j, p[0] += across[0], p[1] += across[1]) {
+      if (inside || (0 <= p[0] && 0 <= p[1] && p[0] < x_bound && p[1] < y_bound)) {
+        double x = p[0], y = p[1];
+        const int lx = (int)x, ly = (int)y;
+        x -= lx; y -= ly;
+        const float* r0 = &in[(size_t)ly * iw]; const float* r1 = &in[(size_t)(ly + 1) * iw];
+        const double v = (double)((1 - y) * ((1 - x) * r0[lx] + x * r0[lx + 1]) + y * ((1 - x) * r1[lx] + x * r1[lx + 1]));
+        out[(size_t)i * w + j] = (float)v;
+      } else out[(size_t)i * w + j] = (float)def;
+    }
+}
+struct SE2 { double R[4]; double t[2]; };   // row-major rotation
+SE2 se2_identity() { SE2 s; s.R[0] = s.R[3] = 1; s.R[1] = s.R[2] = 0; s.t[0] = s.t[1] = 0; return s; }
+SE2 se2_mul(const SE2& a, const SE2& b) {   // jni/RT.h:512-520
+  SE2 r;
+  for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++) { double s = a.R[2 * i] * b.R[j]; s += a.R[2 * i + 1] * b.R[2 + j]; r.R[2 * i + j] = s; }
+  for (int i = 0; i < 2; i++) { double s = a.R[2 * i] * b.t[0]; s += a.R[2 * i + 1] * b.t[1]; r.t[i] = a.t[i] + s; }
+  return r;
+}
+SE2 se2_inverse(const SE2& a) {   // jni/RT.h:502-508
+  SE2 r; r.R[0] = a.R[0]; r.R[1] = a.R[2]; r.R[2] = a.R[1]; r.R[3] = a.R[3];
+  for (int i = 0; i < 2; i++) { double s = r.R[2 * i] * a.t[0]; s += r.R[2 * i + 1] * a.t[1]; r.t[i] = -s; }
+  return r;
+}
+// SmallBlurryImage::IteratePosRelToTarget (jni/SmallBlurryImage.cc:99-222)
+SE2 sbi_iterate(const SBI& cur, const SBI& other, int nIterations, double* finalScore) {
+  const int W = cur.w, H = cur.h;
+  SE2 CtoC = se2_identity(), WfromC = se2_identity();
+  const double cx = W / 2.0, cy = H / 2.0;   // irCenter = mirSize / 2
+  WfromC.t[0] = cx; WfromC.t[1] = cy;
+  double dMeanOffset = 0.0, dFinalScore = 0.0;
+  std::vector<float> warped;
+  for (int it = 0; it < nIterations; it++) {
+    dFinalScore = 0.0;
+    double acc[4] = {0, 0, 0, 0}, tri[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const SE2 X = se2_mul(se2_mul(WfromC, CtoC), se2_inverse(WfromC));
+    const double zero[2] = {0, 0};
+    transform_image_f32(cur.tmpl, W, H, warped, W, H, X.R, X.t, zero, -9e20f);
+    for (int i = 0; i < W; i++)
+      for (int j = 0; j < H; j++) {
+        if (!(i >= 1 && j >= 1 && i < W - 1 && j < H - 1)) continue;
+        const float l = warped[(size_t)j * W + i - 1], r = warped[(size_t)j * W + i + 1], u = warped[(size_t)(j - 1) * W + i], d = warped[(size_t)(j + 1) * W + i], here = warped[(size_t)j * W + i];
+        if (l + r + u + d + here < -9999.9) continue;
+        const double g0 = r - l, g1 = d - u;
+        const double s0 = 0.25 * (g0 + other.jac[2 * ((size_t)j * W + i)]), s1 = 0.25 * (g1 + other.jac[2 * ((size_t)j * W + i) + 1]);
+        const double J[4] = {s0, s1, -((double)j - cy) * s0 + ((double)i - cx) * s1, 1.0};
+        const double dDiff = warped[(size_t)j * W + i] - other.tmpl[(size_t)j * W + i] + dMeanOffset;
+        dFinalScore += dDiff * dDiff;
+        for (int k = 0; k < 4; k++) acc[k] += dDiff * J[k];
+        tri[0] += J[0] * J[0]; tri[1] += J[1] * J[0]; tri[2] += J[1] * J[1]; tri[3] += J[2] * J[0]; tri[4] += J[2] * J[1]; tri[5] += J[2] * J[2];
+        tri[6] += J[0]; tri[7] += J[1]; tri[8] += J[2]; tri[9] += 1.0;
+      }
+    double m4[16]; int v = 0;
+    for (int j = 0; j < 4; j++) for (int i = 0; i <= j; i++) { m4[4 * j + i] = m4[4 * i + j] = tri[v++]; }
+    double inv[16]; inverse_lu(m4, 4, inv);
+    double upd[4];
+    for (int i = 0; i < 4; i++) { double s = inv[4 * i] * acc[0]; for (int k = 1; k < 4; k++) s += inv[4 * i + k] * acc[k]; upd[i] = s; }
+    SE2 U; U.t[0] = -upd[0]; U.t[1] = -upd[1];
+    const double ang = -upd[2];
+    U.R[0] = U.R[3] = cos(ang); U.R[2] = sin(ang); U.R[1] = -U.R[2];   // mySO2::exp (jni/RT.h:461-467)
+    CtoC = se2_mul(CtoC, U);
+    dMeanOffset -= upd[3];
+  }
+  if (finalScore) *finalScore = dFinalScore;
+  return CtoC;
+}
+// SmallBlurryImage::SE3fromSE2 (jni/SmallBlurryImage.cc:245-333): rotation-only pose whose image motion matches the SE2; returns ln() (6-vector)
+void se3_from_se2(const SE2& se2, Cam cam /* at the SBI image size */, int W, int H, double* v6) {
+  double turned[2][2], orig[2][3];
+  const double c[2] = {W / 2.0, H / 2.0};
+  const double off[2][2] = {{5, 0}, {-5, 0}};
+  for (int k = 0; k < 2; k++) {
+    for (int i = 0; i < 2; i++) { double s = se2.R[2 * i] * off[k][0]; s += se2.R[2 * i + 1] * off[k][1]; turned[k][i] = c[i] + (se2.t[i] + s); }
+    const double im[2] = {c[0] + off[k][0], c[1] + off[k][1]}; double u[2];
+    cam_unproject(cam, im, u); orig[k][0] = u[0]; orig[k][1] = u[1]; orig[k][2] = 1.0;
+  }
+  double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  for (int it = 0; it < 3; it++) {
+    double C[9] = {10, 0, 0, 0, 10, 0, 0, 0, 10}, b[3] = {0, 0, 0};   // myWLS<3>, prior 10
+    for (int k = 0; k < 2; k++) {
+      double v3[3]; mat3_mul_vec(R, orig[k], v3);
+      double pix[2]; cam_project(cam, v3[0] / v3[2], v3[1] / v3[2], pix);
+      const double err[2] = {turned[k][0] - pix[0], turned[k][1] - pix[1]};
+      double dv[4]; cam_derivs(cam, dv);
+      double J[2][3];
+      const double invz = 1.0 / v3[2];
+      for (int m = 0; m < 3; m++) {
+        double mo[3]; mo[m] = 0; mo[(m + 1) % 3] = -v3[(m + 2) % 3]; mo[(m + 2) % 3] = v3[(m + 1) % 3];   // mySO3::generator_field (jni/RT.h:71-78)
+        const double c0 = (mo[0] - v3[0] * mo[2] * invz) * invz, c1 = (mo[1] - v3[1] * mo[2] * invz) * invz;
+        double a0 = dv[0] * c0; a0 += dv[1] * c1; double a1 = dv[2] * c0; a1 += dv[3] * c1;
+        J[0][m] = a0; J[1][m] = a1;
+      }
+      for (int row = 0; row < 2; row++)
+        for (int r = 0; r < 3; r++) { const double Jw = 1.0 * J[row][r]; b[r] += err[row] * Jw; for (int cc = r; cc < 3; cc++) C[3 * r + cc] += Jw * J[row][cc]; }
+    }
+    for (int r = 1; r < 3; r++) for (int cc = 0; cc < r; cc++) C[3 * r + cc] = C[3 * cc + r];
+    double Ci[9]; inverse3(C, Ci);
+    double mu[3]; for (int i = 0; i < 3; i++) { double s = Ci[3 * i] * b[0]; s += Ci[3 * i + 1] * b[1]; s += Ci[3 * i + 2] * b[2]; mu[i] = s; }
+    double E[9], Rn[9]; so3_exp(mu, E); mat3_mul(E, R, Rn); memcpy(R, Rn, sizeof(R));
+  }
+  SE3 s = se3_identity(); memcpy(s.R, R, sizeof(R));
+  se3_ln(s, v6);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Tracker (jni/Tracker.cc)
 struct OTracker {
@@ -690,6 +859,8 @@ struct OTracker {
   long zmssdEvals;
   std::vector<double> updates;  // 6-vectors of every CalcPoseUpdate of the last TrackMap, in order
   std::vector<double> sigmas;   // sigma^2 used by each of them
+  // SmallBlurryImage state (Tracker::mpSBIThisFrame / mpSBILastFrame, jni/Tracker.cc:86-97)
+  bool computeSBI, haveSBI; SBI sbiThis, sbiLast; Cam sbiCam; int nFrame;
 };
 
 TData& ensure_td(OTracker& t, int i) {
@@ -878,6 +1049,13 @@ void assess_tracking_quality(OTracker& t) {
   if (t.quality == 0) t.lostFrames++; else t.lostFrames = 0;
 }
 
+Cam cam_from13(const double* s) {
+  Cam c; memset(&c, 0, sizeof(c));
+  c.fx = s[0]; c.fy = s[1]; c.cx = s[2]; c.cy = s[3]; c.W = s[4]; c.Winv = s[5]; c.twoTan = s[6]; c.oneOver2Tan = s[7]; c.distEnabled = s[8];
+  c.largestRadius = s[9]; c.maxR = s[10]; c.width = s[11]; c.height = s[12];
+  return c;
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -913,12 +1091,6 @@ void orc_kf_fast_scores(void* k, int l, int barrier, int32_t* out) {
 double orc_shi_tomasi(void* k, int l, int nsize, int px, int py) { return shi_tomasi(((OKeyFrame*)k)->lev[l].im, nsize, px, py); }
 
 // ---- camera (13 scalars in, see synth.Camera.scalars)
-static Cam cam_from13(const double* s) {
-  Cam c; memset(&c, 0, sizeof(c));
-  c.fx = s[0]; c.fy = s[1]; c.cx = s[2]; c.cy = s[3]; c.W = s[4]; c.Winv = s[5]; c.twoTan = s[6]; c.oneOver2Tan = s[7]; c.distEnabled = s[8];
-  c.largestRadius = s[9]; c.maxR = s[10]; c.width = s[11]; c.height = s[12];
-  return c;
-}
 void orc_cam_project(const double* cam13, const double* cam2, double* im2, int* invalid, double* derivs4) {
   Cam c = cam_from13(cam13); cam_project(c, cam2[0], cam2[1], im2); if (invalid) *invalid = c.invalid; if (derivs4) cam_derivs(c, derivs4);
 }
@@ -976,6 +1148,7 @@ void* orc_tracker_create(const double* cam13, int P) {
   for (int i = 0; i < LEVELS; i++) t->attempted[i] = t->foundCnt[i] = 0;
   t->quality = 2; t->lostFrames = 0; t->didCoarse = false; t->justRecovered = false; t->truncateError = true; t->zmssdEvals = 0;
   t->rng.seed(1);
+  t->computeSBI = false; t->haveSBI = false; t->nFrame = 0; memset(&t->sbiCam, 0, sizeof(t->sbiCam));
   return t;
 }
 void orc_tracker_destroy(void* t) { delete (OTracker*)t; }
@@ -1007,7 +1180,36 @@ void orc_tracker_assess_quality(void* t) { assess_tracking_quality(*(OTracker*)t
 void orc_tracker_track_frame(void* t_, const uint8_t* gray, int w, int h, int stride) {
   OTracker* t = (OTracker*)t_;
   make_keyframe_lite(t->cur, gray, w, h, stride);
-  if (t->lostFrames < 3) { apply_motion_model(*t); track_map(*t); update_motion_model(*t); assess_tracking_quality(*t); }
+  if (t->computeSBI) {   // jni/Tracker.cc:86-97: rotate the two SmallBlurryImages; on the first frame both come from the same keyframe
+    if (!t->haveSBI) { sbi_make(t->sbiThis, t->cur, 0.75); t->sbiLast = t->sbiThis; t->haveSBI = true; }
+    else { t->sbiLast = t->sbiThis; sbi_make(t->sbiThis, t->cur, 0.75); }
+  }
+  t->nFrame++;
+  if (t->lostFrames < 3) {
+    if (t->computeSBI && t->useSBI) {   // Tracker::CalcSBIRotation (jni/Tracker.cc:885-893)
+      sbi_make_jacs(t->sbiLast);
+      const SE2 se2 = sbi_iterate(t->sbiThis, t->sbiLast, 6, 0);
+      se3_from_se2(se2, t->sbiCam, t->sbiThis.w, t->sbiThis.h, t->sbiRot);
+    }
+    apply_motion_model(*t); track_map(*t); update_motion_model(*t); assess_tracking_quality(*t);
+  }
+}
+// Turn the on-board SmallBlurryImage path on: cam13 = camera scalars at the SBI image size (level 3 halved)
+void orc_tracker_enable_sbi(void* t_, const double* sbi_cam13) { OTracker* t = (OTracker*)t_; t->computeSBI = true; t->useSBI = true; t->sbiCam = cam_from13(sbi_cam13); }
+void orc_tracker_get_sbi_rot(void* t_, double* v6) { memcpy(v6, ((OTracker*)t_)->sbiRot, sizeof(double) * 6); }
+// stand-alone SBI pieces for the tests
+void* orc_sbi_create(void* kf, double blur) { SBI* s = new SBI(); sbi_make(*s, *(OKeyFrame*)kf, blur); return s; }
+void orc_sbi_destroy(void* s) { delete (SBI*)s; }
+void orc_sbi_dims(void* s, int* w, int* h) { *w = ((SBI*)s)->w; *h = ((SBI*)s)->h; }
+void orc_sbi_template(void* s_, float* out) { SBI* s = (SBI*)s_; memcpy(out, s->tmpl.data(), s->tmpl.size() * sizeof(float)); }
+void orc_sbi_small(void* s_, uint8_t* out) { SBI* s = (SBI*)s_; memcpy(out, s->small.data(), s->small.size()); }
+double orc_sbi_rotation(void* this_, void* other_, const double* sbi_cam13, int its, double* se2_3, double* v6) {
+  SBI* a = (SBI*)this_; SBI* b = (SBI*)other_;
+  sbi_make_jacs(*b);
+  double score; const SE2 r = sbi_iterate(*a, *b, its, &score);
+  if (se2_3) { se2_3[0] = r.t[0]; se2_3[1] = r.t[1]; se2_3[2] = atan2(r.R[2], r.R[0]); }
+  se3_from_se2(r, cam_from13(sbi_cam13), a->w, a->h, v6);
+  return score;
 }
 void orc_tracker_counters(void* t_, int32_t* attempted4, int32_t* found4, int* quality, int* lost, int* did_coarse) {
   OTracker* t = (OTracker*)t_;

@@ -208,3 +208,62 @@ def test_minipatch_find():
             nfound += fr
     assert nfound > 20
     R.ref_mp_destroy(mp)
+
+
+def test_small_blurry_image_pieces():
+    """f1: SmallBlurryImage::MakeFromKF, IteratePosRelToTarget and SE3fromSE2 (jni/SmallBlurryImage.cc) — restatement vs compiled reference."""
+    cam, f0, smap = common.scene()
+    R, L = refbind.lib(), oraclebind.lib()
+    R.ref_sbi_reset_size()
+    sbi_cam = synth.Camera(cam.width // 16, cam.height // 16)
+    rc = R.ref_cam_create(float(cam.width), float(cam.height), 1)
+    fa, _ = common.frame_at(cam, np.array(synth.CONFIG1_TWIST) * 0.3)
+    fb, _ = common.frame_at(cam, np.array(synth.CONFIG1_TWIST) * 0.5)
+    rka, rkb = refbind.RefKeyFrame().make_lite(fa), refbind.RefKeyFrame().make_lite(fb)
+    oka, okb = oraclebind.OrcKeyFrame().make_lite(fa), oraclebind.OrcKeyFrame().make_lite(fb)
+    ra, rb = R.ref_sbi_create(rka.h, 0.75), R.ref_sbi_create(rkb.h, 0.75)
+    oa, ob = L.orc_sbi_create(oka.h, 0.75), L.orc_sbi_create(okb.h, 0.75)
+    w, h = C.c_int(), C.c_int(); L.orc_sbi_dims(oa, C.byref(w), C.byref(h))
+    assert (w.value, h.value) == (40, 30)
+    for r_, o_ in ((ra, oa), (rb, ob)):
+        rt, ot = np.zeros((30, 40), np.float32), np.zeros((30, 40), np.float32)
+        rs_, os_ = np.zeros((30, 40), np.uint8), np.zeros((30, 40), np.uint8)
+        R.ref_sbi_template(r_, rt); L.orc_sbi_template(o_, ot); R.ref_sbi_small(r_, rs_); L.orc_sbi_small(o_, os_)
+        assert np.array_equal(rs_, os_) and np.array_equal(rt, ot), "mimSmall / mimTemplate bit for bit"
+    rv, ov, rse2, ose2 = np.zeros(6), np.zeros(6), np.zeros(3), np.zeros(3)
+    rscore = R.ref_sbi_rotation(rb, ra, rc, 6, rse2.ctypes.data, rv)
+    oscore = L.orc_sbi_rotation(ob, oa, sbi_cam.scalars(), 6, ose2.ctypes.data, ov)
+    assert np.array_equal(rse2, ose2) and rscore == oscore, "ESM SE2 alignment: bit for bit"
+    assert np.array_equal(rv, ov), "SE3fromSE2(...).ln(): bit for bit"
+    assert np.abs(rv[3:]).max() > 1e-4       # a real rotation was estimated
+
+
+def test_gaussian_blur_stand_in_is_close_to_opencv():
+    """The float GaussianBlur of the OpenCV stand-in (third-party arithmetic of the SBI path) against cv2 4.13."""
+    cv2 = pytest.importorskip("cv2")
+    cam, f0, smap = common.scene()
+    L = oraclebind.lib()
+    ok = oraclebind.OrcKeyFrame().make_lite(f0)
+    o = L.orc_sbi_create(ok.h, 0.75)
+    ot, os_ = np.zeros((30, 40), np.float32), np.zeros((30, 40), np.uint8)
+    L.orc_sbi_template(o, ot); L.orc_sbi_small(o, os_)
+    src = os_.astype(np.float32) - np.float32(os_.sum(dtype=np.uint32)) / np.float32(1200)
+    want = cv2.GaussianBlur(src, (9, 9), 0.75, sigmaY=0.75, borderType=cv2.BORDER_REPLICATE)
+    assert np.abs(want - ot).max() < 2e-4, np.abs(want - ot).max()
+
+
+def test_track_frame_with_sbi_is_the_reference_trackframe():
+    """The unmodified Tracker::TrackFrame (SmallBlurryImage included) against the restatement with its on-board SBI."""
+    cam, f0, smap, rw, ow = _worlds()
+    rw.L.ref_sbi_reset_size()
+    rw.L.ref_srand(1)
+    ow.L.orc_tracker_enable_sbi(ow.tracker, synth.Camera(cam.width // 16, cam.height // 16).scalars())
+    for k in range(1, 9):
+        fr = synth.render_frame(common.texture(), cam, synth.stream_pose(5 * k, 2))
+        rw.L.ref_tracker_track_frame(rw.tracker, fr, cam.width, cam.height, cam.width)
+        ow.L.orc_tracker_track_frame(ow.tracker, fr, cam.width, cam.height, cam.width)
+        rv, ov = np.zeros(6), np.zeros(6)
+        rw.L.ref_tracker_get_sbi_rot(rw.tracker, rv); ow.L.orc_tracker_get_sbi_rot(ow.tracker, ov)
+        assert np.array_equal(rv, ov), k
+        assert np.array_equal(rw.get_pose(), ow.get_pose()), k
+        assert all(np.array_equal(a, b) if isinstance(a, np.ndarray) else a == b for a, b in zip(rw.counters(), ow.counters())), k
