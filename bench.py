@@ -4,9 +4,9 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 Workload (BASELINE.json configs[3]): S = 256 independent synthetic VGA camera streams per GPU, 1000 map points,
-one `step` = one frame of every stream through the TrackFrame-equivalent path (MakeKeyFrame_Lite: 4-level pyramid +
-FAST-10 + row LUT; ApplyMotionModel; TrackMap coarse+fine with 10 Tukey-WLS iterations each; UpdateMotionModel;
-AssessTrackingQuality).  Streams never exchange data: N GPUs = N independent contexts, no collective on the data path.
+one `step` = one frame of every stream through Tracker::TrackFrame's good-map branch (MakeKeyFrame_Lite: 4-level pyramid +
+FAST-10 + row LUT; SmallBlurryImage + CalcSBIRotation; ApplyMotionModel; TrackMap coarse+fine with 10 Tukey-WLS iterations
+each; UpdateMotionModel; AssessTrackingQuality).  Streams never exchange data: N GPUs = N independent contexts, no collective on the data path.
 
   value  tracked frames/s with the frames already resident in HBM (vslam_track_frame_dev), CUDA-event timed
   e2e    the same through the host-buffer C-ABI call (vslam_track_frame: pinned host frames copied in every step) plus a
@@ -39,7 +39,7 @@ FRAME_STEP = 2          # synthetic sequence index advance per step (≈ 1 px of
 METRIC = "tracked_frames_per_sec"
 UNIT = "frames/s"
 WORKLOAD = ("configs[3]: 256 independent synthetic VGA (640x480) camera streams per GPU, 1000 map points, full TrackFrame-equivalent "
-            "per frame (4-level pyramid + FAST-10 + row LUT, coarse+fine PatchFinder search, 10+10 Tukey-WLS iterations), P=11")
+            "per frame (4-level pyramid + FAST-10 + row LUT, SmallBlurryImage rotation estimate, coarse+fine PatchFinder search, 10+10 Tukey-WLS iterations), P=11")
 
 
 # ------------------------------------------------------------------------------------------------ synthetic data
@@ -104,11 +104,12 @@ def cpu_worker(path, stream, n_warm, n_steps, frames_per_step, use_ref):
         from oracle import refbind
         rw = refbind.RefWorld(W, H, f0, smap)
         rw.L.ref_srand(1)
-        rw.L.ref_tracker_set_sbi_rot(rw.tracker, np.zeros(6), 1)
-        step = lambda fr: rw.L.ref_tracker_track_frame_nosbi(rw.tracker, fr, W, H, W)
+        rw.L.ref_sbi_reset_size()
+        step = lambda fr: rw.L.ref_tracker_track_frame(rw.tracker, fr, W, H, W)      # the unmodified Tracker::TrackFrame, SmallBlurryImage included
     else:
         from oracle import oraclebind
         ow = oraclebind.OrcWorld(cam, f0, smap)
+        ow.L.orc_tracker_enable_sbi(ow.tracker, synth.Camera(W // 16, H // 16).scalars())
         step = lambda fr: ow.L.orc_tracker_track_frame(ow.tracker, fr, W, H, W)
     k = 0
     times = []
@@ -234,7 +235,7 @@ def main():
         poses = stream_poses(n_seq, (Wm + K) * fps_step + 1)[:, 1:]
         frames = render_cpu_or_gpu(tex, cam, poses)
         fps, step_s, kind = run_cpu_arm(cam, f0, smap, frames, n_procs, Wm, K, fps_step)
-        sample = f"{n_procs} processes (one tracker each, {n_seq} distinct synthetic sequences), {fps_step} frames per process per step; SmallBlurryImage steps excluded (SURVEY §8 f1)"
+        sample = f"{n_procs} processes (one tracker each, {n_seq} distinct synthetic sequences), {fps_step} frames per process per step; unmodified Tracker::TrackFrame (SmallBlurryImage included)"
         line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": Wm, "ms_per_step": step_s * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32 + f64", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": fps, "unit": UNIT, "cores": n_procs, "kind": kind, "sample": sample},
@@ -244,7 +245,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from visualslam_android_b200 import api
+    from visualslam_android_b200 import api, synth
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
@@ -279,6 +280,7 @@ def main():
     torch.cuda.set_stream(stream)
     ctx = api.Context(W, H, n_streams=S, max_points=smap.n, device=local_rank, cuda_stream=stream.cuda_stream)
     ctx.set_camera(cam.scalars())
+    ctx.enable_sbi(synth.Camera(W // 16, H // 16).scalars())       # SmallBlurryImage + CalcSBIRotation on the device, like the reference's TrackFrame
     ctx.upload_source_keyframe(f0)
     ctx.set_map(smap.world, smap.pix_right_w, smap.pix_down_w, smap.ir_center, smap.src_level)
 
@@ -394,7 +396,7 @@ def main():
         line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": n_procs, "kind": kind,
                                 "sample": f"{n_procs} processes x {cpu_steps * fps_step} frames of the same synthetic VGA sequences (1000 map points), "
                                           f"{'reference jni/ sources compiled by oracle/build_ref.sh' if kind == 'reference' else 'oracle port'}, "
-                                          "SmallBlurryImage steps excluded on both sides (SURVEY §8 f1)"}
+                                          "whole Tracker::TrackFrame (SmallBlurryImage included) on both sides"}
     ctx.close()
     if world > 1:
         dist.barrier()

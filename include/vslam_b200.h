@@ -26,6 +26,7 @@
  *   vslam_make_keyframe_rest         KeyFrame::MakeKeyFrame_Rest           jni/KeyFrame.cc:53-95 (fast_nonmax jni/vision/cvfast.cpp:9243-9405,
  *                                    FindShiTomasiScoreAtPoint jni/vision/ImageHandler.cpp:124-155)
  *   vslam_minipatch_sample / _find   MiniPatch::SampleFromImage / FindPatch jni/MiniPatch.cc:32-83
+ *   vslam_enable_sbi                 SmallBlurryImage + Tracker::CalcSBIRotation jni/SmallBlurryImage.cc, jni/Tracker.cc:86-97,885-893
  *   vslam_create / vslam_destroy     JNI native_createTest / native_disposeTest   jni/jni_part.cpp:114-123
  *   vslam_track_frame                JNI native_update                            jni/jni_part.cpp:132-145
  *
@@ -132,7 +133,12 @@ int vslam_set_motion(vslam_ctx* ctx, int stream, const double* velocity6, double
                      double scene_depth_sigma);
 int vslam_get_motion(vslam_ctx* ctx, int stream, double* velocity6, double* msd_scaled_velocity, double* scene_depth_mean,
                      double* scene_depth_sigma);
-int vslam_set_sbi_rotation(vslam_ctx* ctx, int stream, const double* rot6);  /* Tracker::mv6SBIRot (computed by the caller) */
+int vslam_set_sbi_rotation(vslam_ctx* ctx, int stream, const double* rot6);  /* Tracker::mv6SBIRot supplied by the caller (when the on-device SBI is off) */
+/* SmallBlurryImage on the device (jni/SmallBlurryImage.cc; Tracker::CalcSBIRotation jni/Tracker.cc:885-893): after this call every
+ * vslam_track_frame* builds the 1/16-size blurred thumbnail of each stream, aligns it to the previous frame's (6 ESM iterations) and
+ * writes the resulting rotation into mv6SBIRot before the motion model runs.  cam13_sbi = vslam_camera_from_params at (width/16, height/16). */
+int vslam_enable_sbi(vslam_ctx* ctx, const double* cam13_sbi);
+int vslam_get_sbi_rotation(vslam_ctx* ctx, int stream, double* rot6);
 /* attempted[4], found[4], quality (0 BAD,1 DODGY,2 GOOD), lost_frames, did_coarse */
 int vslam_get_counters(vslam_ctx* ctx, int stream, int32_t* attempted4, int32_t* found4, int* quality, int* lost_frames, int* did_coarse);
 /* Per-point TrackerData dump, layout of oracle/ref_harness.cc ref_tracker_point_state: ints[n][8], dbl[n][32]. */

@@ -484,3 +484,31 @@ def test_long_sequence_stays_consistent_with_oracle():
         assert abs(int(f.sum()) - int(of.sum())) <= 0.02 * of.sum(), k
     assert worst < 2e-3, worst
     ctx.close()
+
+
+def test_track_frame_with_on_device_sbi():
+    """f1: SmallBlurryImage + CalcSBIRotation on the device: vslam_track_frame is then the reference's whole TrackFrame (good-map
+    branch).  The oracle side is the restatement that tests/test_oracle_vs_ref.py pins bit-for-bit to the unmodified TrackFrame."""
+    cam, f0, smap = common.scene()
+    S, K = 3, 6
+    sbi_cam = synth.Camera(cam.width // 16, cam.height // 16)
+    ctx = _ctx(cam, f0, smap, n_streams=S)
+    ctx.enable_sbi(sbi_cam.scalars())
+    ows = [_orc(cam, f0, smap) for _ in range(S)]
+    for ow in ows:
+        ow.L.orc_tracker_enable_sbi(ow.tracker, sbi_cam.scalars())
+    big = 0.0
+    for k in range(1, K + 1):
+        frames = np.stack([synth.render_frame(common.texture(), cam, synth.stream_pose(5 * k, s + 1)) for s in range(S)])
+        ctx.track_frame(frames)
+        for s, ow in enumerate(ows):
+            ow.L.orc_tracker_track_frame(ow.tracker, np.ascontiguousarray(frames[s]), cam.width, cam.height, cam.width)
+            orot = np.zeros(6); ow.L.orc_tracker_get_sbi_rot(ow.tracker, orot)
+            grot = ctx.get_sbi_rotation(s)
+            assert np.abs(grot - orot).max() <= 1e-9, (k, s, grot, orot)     # rotation vector (rad)
+            big = max(big, np.abs(orot[3:]).max())
+            assert np.abs(ctx.get_pose(s) - ow.get_pose()).max() <= 1e-8, (k, s)
+            a, f, q, lost, dc = ctx.counters(s); oa, of, oq, olost, odc = ow.counters()
+            assert np.array_equal(a, oa) and np.array_equal(f, of) and (q, lost, dc) == (oq, olost, odc), (k, s)
+    assert big > 1e-4, "the sequences must contain a measurable inter-frame rotation"
+    ctx.close()

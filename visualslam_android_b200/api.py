@@ -41,7 +41,7 @@ ABI_SYMBOLS = [
     "vslam_set_camera", "vslam_camera_from_params", "vslam_upload_source_keyframe", "vslam_set_map", "vslam_make_keyframe_lite",
     "vslam_make_keyframe_lite_dev", "vslam_level_dims", "vslam_get_level", "vslam_get_num_corners", "vslam_get_corners", "vslam_get_row_lut",
     "vslam_make_keyframe_rest", "vslam_get_max_corners", "vslam_get_candidates", "vslam_snapshot_keyframe", "vslam_minipatch_sample", "vslam_minipatch_find",
-    "vslam_set_pose", "vslam_get_pose", "vslam_get_poses", "vslam_set_motion", "vslam_get_motion", "vslam_set_sbi_rotation", "vslam_get_counters",
+    "vslam_set_pose", "vslam_get_pose", "vslam_get_poses", "vslam_set_motion", "vslam_get_motion", "vslam_set_sbi_rotation", "vslam_enable_sbi", "vslam_get_sbi_rotation", "vslam_get_counters",
     "vslam_get_point_states", "vslam_get_point_template", "vslam_get_point_counts", "vslam_get_updates", "vslam_get_zmssd_evals",
     "vslam_project_all", "vslam_set_point_projection", "vslam_set_lists", "vslam_clear_counters", "vslam_search_for_points", "vslam_project_and_derivs", "vslam_calc_jacobians",
     "vslam_calc_pose_update", "vslam_track_map", "vslam_track_frame", "vslam_track_frame_dev", "vslam_track_frame_async", "vslam_wait_step", "vslam_debug_atan", "vslam_kernel_launches", "vslam_set_timing", "vslam_get_stage_times",
@@ -97,6 +97,8 @@ def load():
     sig("vslam_set_motion", i, vp, i, vp, d, d, d)
     sig("vslam_get_motion", i, vp, i, vp, pd, pd, pd)
     sig("vslam_set_sbi_rotation", i, vp, i, vp)
+    sig("vslam_enable_sbi", i, vp, vp)
+    sig("vslam_get_sbi_rotation", i, vp, i, vp)
     sig("vslam_get_counters", i, vp, i, vp, vp, pi, pi, pi)
     sig("vslam_get_point_states", i, vp, i, vp, vp)
     sig("vslam_get_point_template", i, vp, i, i, vp, pi, pi)
@@ -312,6 +314,16 @@ class Context:
     def set_sbi_rotation(self, s, rot6):
         v = np.ascontiguousarray(rot6, dtype=np.float64)
         self._ck(self.L.vslam_set_sbi_rotation(self.h, s, v.ctypes.data))
+
+    def enable_sbi(self, cam13_sbi):
+        a = np.ascontiguousarray(cam13_sbi, dtype=np.float64)
+        self._ck(self.L.vslam_enable_sbi(self.h, a.ctypes.data))
+
+    def get_sbi_rotation(self, s):
+        """mv6SBIRot of stream s (read from the stream state)."""
+        out = np.zeros(6)
+        self._ck(self.L.vslam_get_sbi_rotation(self.h, s, out.ctypes.data))
+        return out
 
     def counters(self, s):
         a = np.zeros(4, dtype=np.int32)

@@ -106,6 +106,7 @@ int vslam_create(const vslam_config* cfg, vslam_ctx** out) {
   ctx->scratch_host = nullptr; ctx->scratch_host_bytes = 0; ctx->timing = false; ctx->ev_used = 0; ctx->l0_alt = nullptr; ctx->copy_stream = nullptr; ctx->step = 0; ctx->pipe_ready = false; ctx->status_pin = nullptr;
   ctx->rest_scores = nullptr; ctx->rest_max = nullptr; ctx->rest_cand = nullptr; ctx->rest_cand_score = nullptr; ctx->rest_counts = nullptr; ctx->rest_stream = -1;
   ctx->snap_img = nullptr; ctx->snap_corners = nullptr; ctx->snap_lut = nullptr;
+  ctx->sbi_on = false; ctx->sbi_tmpl = nullptr; ctx->sbi_scratch = nullptr; ctx->sbi_jac = nullptr; ctx->sbi_small = nullptr; ctx->sbi_have = nullptr;
   const float frac = cfg->max_corner_frac > 0 ? cfg->max_corner_frac : 0.5f;
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_create_error = std::string(#call) + ": " + cudaGetErrorString(e_); vslam_destroy(ctx); return VSLAM_E_CUDA; } } while (0)
   CK(cudaSetDevice(cfg->device));
@@ -185,6 +186,7 @@ void vslam_destroy(vslam_ctx* ctx) {
   cudaFree(ctx->l0_alt);
   cudaFree(ctx->rest_scores); cudaFree(ctx->rest_max); cudaFree(ctx->rest_cand); cudaFree(ctx->rest_cand_score); cudaFree(ctx->rest_counts);
   cudaFree(ctx->snap_img); cudaFree(ctx->snap_corners); cudaFree(ctx->snap_lut);
+  cudaFree(ctx->sbi_tmpl); cudaFree(ctx->sbi_scratch); cudaFree(ctx->sbi_jac); cudaFree(ctx->sbi_small); cudaFree(ctx->sbi_have);
   if (ctx->status_pin) cudaFreeHost(ctx->status_pin);
   delete[] ctx->l0_ptr_host; delete[] ctx->l0_stride_host;
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -221,6 +223,36 @@ int vslam_set_params(vslam_ctx* ctx, const vslam_params* p) {
   if (!ctx || !p) return VSLAM_E_INVALID;
   if (2 * p->coarse_max > (unsigned)ctx->list_cap) { ctx->err = "coarse_max too large"; return VSLAM_E_INVALID; }
   ctx->params = *p;
+  return VSLAM_OK;
+}
+
+// SmallBlurryImage on the device: needs the camera at the SBI image size (level 3 halved = width/16 x height/16).
+int vslam_enable_sbi(vslam_ctx* ctx, const double* c) {
+  if (!ctx || !c) return VSLAM_E_INVALID;
+  const LevelDesc& L3 = ctx->lev[3];
+  if ((L3.w & 1) || (L3.h & 1)) { ctx->err = "SmallBlurryImage needs even level-3 dimensions (cv::resize to exactly half); height % 16 != 0 here"; return VSLAM_E_INVALID; }
+  CamDev& d = ctx->sbi_cam;
+  d.fx = c[0]; d.fy = c[1]; d.cx = c[2]; d.cy = c[3]; d.W = c[4]; d.Winv = c[5]; d.twoTan = c[6]; d.oneOver2Tan = c[7]; d.distEnabled = c[8];
+  d.largestRadius = c[9]; d.maxR = c[10]; d.width = c[11]; d.height = c[12];
+  const int w = L3.w / 2, h = L3.h / 2; const size_t n = (size_t)w * h;
+  {   // cv::getGaussianKernel(9, 0.75, CV_32F) as the stand-in computes it (host exp, float taps)
+    const double sigma = 0.75, scale2x = -0.5 / (sigma * sigma); double sum = 0;
+    for (int i = 0; i < 9; i++) { const double x = i - 4.0; ctx->sbi_taps[i] = (float)exp(scale2x * x * x); sum += ctx->sbi_taps[i]; }
+    sum = 1. / sum; for (int i = 0; i < 9; i++) ctx->sbi_taps[i] = (float)(ctx->sbi_taps[i] * sum);
+  }
+  for (int k = 0; k < 2; k++) {   // ATANCamera::UnProject of (w/2 +- 5, h/2) on the host (jni/ATANCamera.cc:149-164)
+    const double im[2] = {w / 2.0 + (k ? -5.0 : 5.0), h / 2.0};
+    const double dx = (im[0] - d.cx) * (1.0 / d.fx), dy = (im[1] - d.cy) * (1.0 / d.fy);
+    const double distR = sqrt(dx * dx + dy * dy);
+    const double r = (d.W == 0.0) ? distR : tan(distR * d.W) * d.oneOver2Tan;
+    const double factor = (distR > 0.01) ? r / distR : 1.0;
+    ctx->sbi_orig[k][0] = dx * factor; ctx->sbi_orig[k][1] = dy * factor; ctx->sbi_orig[k][2] = 1.0;
+  }
+  if (!ctx->sbi_tmpl) {
+    VS_CUDA(dalloc(&ctx->sbi_tmpl, (size_t)ctx->S * 2 * n)); VS_CUDA(dalloc(&ctx->sbi_scratch, (size_t)ctx->S * 3 * n));
+    VS_CUDA(dalloc(&ctx->sbi_jac, (size_t)ctx->S * 2 * n)); VS_CUDA(dalloc(&ctx->sbi_small, (size_t)ctx->S * n)); VS_CUDA(dalloc(&ctx->sbi_have, (size_t)2 * ctx->S));
+  }
+  ctx->sbi_on = true;
   return VSLAM_OK;
 }
 
@@ -484,6 +516,12 @@ int vslam_set_sbi_rotation(vslam_ctx* ctx, int s, const double* r6) {
   VS_CUDA(cudaMemcpy((char*)(ctx->ss + s) + offsetof(StreamState, sbi_rot), r6, sizeof(double) * 6, cudaMemcpyHostToDevice));
   return VSLAM_OK;
 }
+int vslam_get_sbi_rotation(vslam_ctx* ctx, int s, double* r6) {
+  int rc = check_stream(ctx, s); if (rc) return rc;
+  VS_CUDA(cudaStreamSynchronize(ctx->stream));
+  VS_CUDA(cudaMemcpy(r6, (char*)(ctx->ss + s) + offsetof(StreamState, sbi_rot), sizeof(double) * 6, cudaMemcpyDeviceToHost));
+  return VSLAM_OK;
+}
 int vslam_get_counters(vslam_ctx* ctx, int s, int32_t* att, int32_t* fnd, int* quality, int* lost, int* did_coarse) {
   int rc = check_stream(ctx, s); if (rc) return rc;
   StreamState st; if ((rc = read_ss(ctx, s, &st))) return rc;
@@ -613,6 +651,7 @@ int vslam_track_map(vslam_ctx* ctx) { if (!ctx) return VSLAM_E_INVALID; return v
 int vslam_track_frame(vslam_ctx* ctx, const uint8_t* gray, int stride, size_t frame_stride) {
   if (!ctx) return VSLAM_E_INVALID;
   int rc = vslam_make_keyframe_lite(ctx, 0, ctx->S, gray, stride, frame_stride); if (rc) return rc;
+  if ((rc = vs_launch_sbi(ctx))) return rc;
   return vs_launch_track_map(ctx, 1);
 }
 // Pipelined host-input path: the copy of step k (copy stream, level-0 buffer k&1) overlaps the kernels of step k-1.
@@ -642,6 +681,7 @@ int vslam_track_frame_async(vslam_ctx* ctx, const uint8_t* gray, int stride, siz
   for (int s = 0; s < ctx->S; s++) same &= ctx->l0_ptr_host[s] == buf + (size_t)s * L.h * L.pitch && ctx->l0_stride_host[s] == L.pitch;
   if (!same && (rc = adopt_l0(ctx, 0, ctx->S, buf, L.pitch, (size_t)L.h * L.pitch, false))) return rc;
   if ((rc = vs_launch_pyramid_fast(ctx, 0, ctx->S))) return rc;
+  if ((rc = vs_launch_sbi(ctx))) return rc;
   if ((rc = vs_launch_track_map(ctx, 1))) return rc;
   VS_CUDA(cudaEventRecord(ctx->ev_computed[slot], ctx->stream));
   if (poses_out)
@@ -668,6 +708,7 @@ int vslam_wait_step(vslam_ctx* ctx, int step) {
 int vslam_track_frame_dev(vslam_ctx* ctx, const uint8_t* gray, int stride, size_t frame_stride) {
   if (!ctx) return VSLAM_E_INVALID;
   int rc = vslam_make_keyframe_lite_dev(ctx, 0, ctx->S, gray, stride, frame_stride); if (rc) return rc;
+  if ((rc = vs_launch_sbi(ctx))) return rc;
   return vs_launch_track_map(ctx, 1);
 }
 

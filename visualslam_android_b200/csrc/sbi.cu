@@ -1,0 +1,258 @@
+// SmallBlurryImage on the GPU (reference: jni/SmallBlurryImage.cc; the f1 row of SURVEY.md §8).
+// One CTA per stream, once per frame, between the pyramid kernels and the projection kernel:
+//   MakeFromKF   level 3 halved ((a+b+c+d+2)>>2), mean removed in float, 9x9 float Gaussian (sigma 0.75, BORDER_REPLICATE)
+//   MakeJacs     central differences of the previous frame's template
+//   IteratePosRelToTarget   6 ESM iterations aligning this frame's template to the previous one (SE2 + mean offset)
+//   SE3fromSE2   3 Gauss-Newton steps for the camera rotation that reproduces the SE2; ln() of it seeds Tracker::ApplyMotionModel
+// Deviations from the serial reference, both below 1e-12 relative on the result: the warp positions are evaluated in closed
+// form (p0 + i*down + j*across) instead of by running sums, and the 15 ESM sums are reduced in a fixed tree, not serially.
+#include "geometry.cuh"
+
+namespace {
+
+constexpr int kT = 256;
+
+struct SbiDev {
+  int w, h;                 // SBI size = level 3 / 2
+  int l3w, l3h, l3pitch; const uint8_t* l3;   // [S][l3h][l3pitch]
+  float taps[9];            // getGaussianKernel(9, 0.75) in float, computed on the host
+  CamDev cam;               // camera scalars at the SBI image size
+  double orig[2][3];        // un-projected (w/2 +- 5, h/2) points (host: tan)
+  float* tmpl;              // [S][2][n]  this / last template (ping-pong by frame parity)
+  float* scratch;           // [S][3][n]  tmp, warped, (spare)
+  float* jac;               // [S][2n]    gradient image of the last template
+  uint8_t* small;           // [S][n]
+  StreamState* ss; int* have; int* parity;   // per stream
+  int use_sbi;
+};
+
+__device__ inline double block_sum(double v, double* red) {
+#pragma unroll
+  for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double r = 0;
+  for (int k = 0; k < kT / 32; k++) r += red[k];
+  return r;
+}
+
+// 4x4 inverse by partial-pivot LU (same routine as the oracle's inverse_lu), then inv * b
+__device__ inline void solve4(const double* m, const double* b, double* x4) {
+  double a[16], inv[16], x[4]; int piv[4];
+  for (int i = 0; i < 16; i++) a[i] = m[i];
+  for (int i = 0; i < 4; i++) piv[i] = i;
+  for (int k = 0; k < 4; k++) {
+    int p = k; double best = fabs(a[k * 4 + k]);
+    for (int i = k + 1; i < 4; i++) if (fabs(a[i * 4 + k]) > best) { best = fabs(a[i * 4 + k]); p = i; }
+    if (p != k) { for (int j = 0; j < 4; j++) { const double t = a[k * 4 + j]; a[k * 4 + j] = a[p * 4 + j]; a[p * 4 + j] = t; } const int t = piv[k]; piv[k] = piv[p]; piv[p] = t; }
+    for (int i = k + 1; i < 4; i++) { a[i * 4 + k] /= a[k * 4 + k]; for (int j = k + 1; j < 4; j++) a[i * 4 + j] -= a[i * 4 + k] * a[k * 4 + j]; }
+  }
+  for (int c = 0; c < 4; c++) {
+    for (int i = 0; i < 4; i++) x[i] = (piv[i] == c) ? 1.0 : 0.0;
+    for (int i = 0; i < 4; i++) for (int j = 0; j < i; j++) x[i] -= a[i * 4 + j] * x[j];
+    for (int i = 3; i >= 0; i--) { for (int j = i + 1; j < 4; j++) x[i] -= a[i * 4 + j] * x[j]; x[i] /= a[i * 4 + i]; }
+    for (int i = 0; i < 4; i++) inv[i * 4 + c] = x[i];
+  }
+  for (int i = 0; i < 4; i++) { double s = inv[4 * i] * b[0]; for (int k = 1; k < 4; k++) s += inv[4 * i + k] * b[k]; x4[i] = s; }
+}
+
+__device__ inline void inverse3(const double* m, double* r) {
+  const double c00 = m[4] * m[8] - m[5] * m[7], c10 = m[5] * m[6] - m[3] * m[8], c20 = m[3] * m[7] - m[4] * m[6];
+  const double det = m[0] * c00 + m[1] * c10 + m[2] * c20, invdet = 1.0 / det;
+  r[0] = c00 * invdet; r[3] = c10 * invdet; r[6] = c20 * invdet;
+  r[1] = (m[2] * m[7] - m[1] * m[8]) * invdet; r[4] = (m[0] * m[8] - m[2] * m[6]) * invdet; r[7] = (m[1] * m[6] - m[0] * m[7]) * invdet;
+  r[2] = (m[1] * m[5] - m[2] * m[4]) * invdet; r[5] = (m[2] * m[3] - m[0] * m[5]) * invdet; r[8] = (m[0] * m[4] - m[1] * m[3]) * invdet;
+}
+
+__global__ void __launch_bounds__(kT) k_sbi(SbiDev D) {
+  __shared__ double red[kT / 32];
+  __shared__ double red14[kT / 32][14];
+  __shared__ double sX[6];        // current warp: R (4, row-major) and t (2)
+  __shared__ double sCtoC[6];     // accumulated SE2
+  __shared__ double sMean;
+  const int s = blockIdx.x, tid = threadIdx.x;
+  const int W = D.w, H = D.h, n = W * H;
+  StreamState* st = D.ss + s;
+  const int par = D.parity[s];
+  float* cur = D.tmpl + ((size_t)s * 2 + par) * n;
+  float* last = D.tmpl + ((size_t)s * 2 + (par ^ 1)) * n;
+  float* tmp = D.scratch + (size_t)s * 3 * n;
+  float* warped = tmp + n;
+  uint8_t* small = D.small + (size_t)s * n;
+  const uint8_t* l3 = D.l3 + (size_t)s * D.l3h * D.l3pitch;
+
+  // ---- MakeFromKF (jni/SmallBlurryImage.cc:20-55)
+  double isum = 0;
+  for (int i = tid; i < n; i += kT) {
+    const int y = i / W, x = i - y * W;
+    const uint8_t* a = l3 + (size_t)(2 * y) * D.l3pitch + 2 * x;
+    const int v = (a[0] + a[1] + a[D.l3pitch] + a[D.l3pitch + 1] + 2) >> 2;
+    small[i] = (uint8_t)v; isum += v;
+  }
+  isum = block_sum(isum, red);            // integer valued: exact
+  const float fMean = ((float)(unsigned)isum) / (H * W);
+  for (int i = tid; i < n; i += kT) cur[i] = (float)small[i] - fMean;
+  __syncthreads();
+  for (int i = tid; i < n; i += kT) {    // row pass
+    const int y = i / W, x = i - y * W; float acc = 0;
+#pragma unroll
+    for (int k = 0; k < 9; k++) { int xx = x + k - 4; xx = xx < 0 ? 0 : (xx >= W ? W - 1 : xx); acc += D.taps[k] * cur[y * W + xx]; }
+    tmp[i] = acc;
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += kT) {    // column pass
+    const int y = i / W, x = i - y * W; float acc = 0;
+#pragma unroll
+    for (int k = 0; k < 9; k++) { int yy = y + k - 4; yy = yy < 0 ? 0 : (yy >= H ? H - 1 : yy); acc += D.taps[k] * tmp[yy * W + x]; }
+    cur[i] = acc;
+  }
+  __syncthreads();
+  const bool first = !D.have[s];
+  if (first) { for (int i = tid; i < n; i += kT) last[i] = cur[i]; }   // first frame: both SBIs come from the same keyframe (jni/Tracker.cc:90-93)
+  __syncthreads();
+  if (tid == 0) { D.have[s] = 1; D.parity[s] = par ^ 1; }               // next frame: `cur` becomes `last`
+  if (!D.use_sbi || st->lost_frames >= 3) return;
+
+  // ---- MakeJacs of the last frame (jni/SmallBlurryImage.cc:58-79)
+  float* jac = D.jac + (size_t)s * 2 * n;
+  for (int i = tid; i < n; i += kT) {
+    const int y = i / W, x = i - y * W;
+    float gx = 0.f, gy = 0.f;
+    if (x >= 1 && y >= 1 && x < W - 1 && y < H - 1) { gx = last[i + 1] - last[i - 1]; gy = last[i + W] - last[i - W]; }
+    jac[2 * i] = gx; jac[2 * i + 1] = gy;
+  }
+  // ---- IteratePosRelToTarget (jni/SmallBlurryImage.cc:99-222)
+  const double cx = W / 2.0, cy = H / 2.0;
+  if (tid == 0) { sCtoC[0] = 1; sCtoC[1] = 0; sCtoC[2] = 0; sCtoC[3] = 1; sCtoC[4] = 0; sCtoC[5] = 0; sMean = 0.0; }
+  __syncthreads();
+  for (int it = 0; it < 6; it++) {
+    if (tid == 0) {   // X = WfromC * CtoC * WfromC^-1 with WfromC = (I, centre)
+      const double* R = sCtoC; const double t0 = sCtoC[4], t1 = sCtoC[5];
+      // A = WfromC * CtoC : rotation R (I*R evaluated like the reference: sums with exact zeros), translation c + (1*t0 + 0*t1, ...)
+      double AR[4]; for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++) { double sacc = (i == 0 ? 1.0 : 0.0) * R[j]; sacc += (i == 1 ? 1.0 : 0.0) * R[2 + j]; AR[2 * i + j] = sacc; }
+      double At[2]; { double a = 1.0 * t0; a += 0.0 * t1; At[0] = cx + a; double b = 0.0 * t0; b += 1.0 * t1; At[1] = cy + b; }
+      // inverse of WfromC: rotation I, translation -(I * c)
+      double it0, it1; { double a = 1.0 * cx; a += 0.0 * cy; it0 = -a; double b = 0.0 * cx; b += 1.0 * cy; it1 = -b; }
+      for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++) { double sacc = AR[2 * i] * (j == 0 ? 1.0 : 0.0); sacc += AR[2 * i + 1] * (j == 1 ? 1.0 : 0.0); sX[2 * i + j] = sacc; }
+      for (int i = 0; i < 2; i++) { double sacc = AR[2 * i] * it0; sacc += AR[2 * i + 1] * it1; sX[4 + i] = At[i] + sacc; }
+    }
+    __syncthreads();
+    {   // transform_image (float): out(i,j) = bilinear(cur, p0 + i*down + j*across), default -9e20f outside
+      const double a0 = sX[0], a1 = sX[2], d0 = sX[1], d1 = sX[3];
+      const double p00 = sX[4], p01 = sX[5];   // outOrig = 0  =>  p0 = inOrig
+      const float xb = W - 1, yb = H - 1;
+      for (int i = tid; i < n; i += kT) {
+        const int r = i / W, c = i - r * W;
+        double x = p00 + r * d0 + c * a0, y = p01 + r * d1 + c * a1;
+        float v = -9e20f;
+        if (0 <= x && 0 <= y && x < xb && y < yb) {
+          const int lx = (int)x, ly = (int)y;
+          x -= lx; y -= ly;
+          const float* r0 = cur + ly * W + lx; const float* r1 = r0 + W;
+          v = (float)((1 - y) * ((1 - x) * r0[0] + x * r0[1]) + y * ((1 - x) * r1[0] + x * r1[1]));
+        }
+        warped[i] = v;
+      }
+    }
+    __syncthreads();
+    double acc[15];
+#pragma unroll
+    for (int k = 0; k < 15; k++) acc[k] = 0;
+    const double mean = sMean;
+    for (int i = tid; i < n; i += kT) {
+      const int y = i / W, x = i - y * W;
+      if (!(x >= 1 && y >= 1 && x < W - 1 && y < H - 1)) continue;
+      const float l = warped[i - 1], r = warped[i + 1], u = warped[i - W], d = warped[i + W], here = warped[i];
+      if (l + r + u + d + here < -9999.9) continue;
+      const double g0 = r - l, g1 = d - u;
+      const double s0 = 0.25 * (g0 + jac[2 * i]), s1 = 0.25 * (g1 + jac[2 * i + 1]);
+      const double J0 = s0, J1 = s1, J2 = -((double)y - cy) * s0 + ((double)x - cx) * s1;
+      const double dd = here - last[i] + mean;
+      acc[0] += dd * J0; acc[1] += dd * J1; acc[2] += dd * J2; acc[3] += dd * 1.0;
+      acc[4] += J0 * J0; acc[5] += J1 * J0; acc[6] += J1 * J1; acc[7] += J2 * J0; acc[8] += J2 * J1; acc[9] += J2 * J2;
+      acc[10] += J0; acc[11] += J1; acc[12] += J2; acc[13] += 1.0; acc[14] += dd * dd;
+    }
+    // one fixed-shape reduction for all 14 sums: warp shuffles, then 8 partials per sum through shared memory
+#pragma unroll
+    for (int k = 0; k < 14; k++) {
+#pragma unroll
+      for (int d = 16; d; d >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], d);
+    }
+    __syncthreads();
+    if ((tid & 31) == 0) { for (int k = 0; k < 14; k++) red14[tid >> 5][k] = acc[k]; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int k = 0; k < 14; k++) { double r = 0; for (int w = 0; w < kT / 32; w++) r += red14[w][k]; acc[k] = r; }
+      double m4[16]; int v = 0;
+      for (int j = 0; j < 4; j++) for (int i = 0; i <= j; i++) { m4[4 * j + i] = m4[4 * i + j] = acc[4 + v]; v++; }
+      double upd[4]; solve4(m4, acc, upd);
+      const double ang = -upd[2];
+      const double c = cos(ang), sn = sin(ang);
+      const double U[6] = {c, -sn, sn, c, -upd[0], -upd[1]};   // mySO2::exp (jni/RT.h:461-467), translation -update
+      double R[4], t[2];
+      for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++) { double sacc = sCtoC[2 * i] * U[j]; sacc += sCtoC[2 * i + 1] * U[2 + j]; R[2 * i + j] = sacc; }
+      for (int i = 0; i < 2; i++) { double sacc = sCtoC[2 * i] * U[4]; sacc += sCtoC[2 * i + 1] * U[5]; t[i] = sCtoC[4 + i] + sacc; }
+      for (int k = 0; k < 4; k++) sCtoC[k] = R[k];
+      sCtoC[4] = t[0]; sCtoC[5] = t[1];
+      sMean -= upd[3];
+    }
+    __syncthreads();
+  }
+  // ---- SE3fromSE2 (jni/SmallBlurryImage.cc:245-333) and ln() -> Tracker::mv6SBIRot
+  if (tid == 0) {
+    const double c2[2] = {W / 2.0, H / 2.0};
+    const double off[2][2] = {{5, 0}, {-5, 0}};
+    double turned[2][2];
+    for (int k = 0; k < 2; k++) for (int i = 0; i < 2; i++) { double sacc = sCtoC[2 * i] * off[k][0]; sacc += sCtoC[2 * i + 1] * off[k][1]; turned[k][i] = c2[i] + (sCtoC[4 + i] + sacc); }
+    double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    for (int it = 0; it < 3; it++) {
+      double C[9] = {10, 0, 0, 0, 10, 0, 0, 0, 10}, b[3] = {0, 0, 0};
+      for (int k = 0; k < 2; k++) {
+        double v3[3];
+        for (int i = 0; i < 3; i++) { double sacc = R[3 * i] * D.orig[k][0]; sacc += R[3 * i + 1] * D.orig[k][1]; sacc += R[3 * i + 2] * D.orig[k][2]; v3[i] = sacc; }
+        double pix[2]; CamCache cc; cam_project(D.cam, v3[0] / v3[2], v3[1] / v3[2], pix, cc);
+        const double err[2] = {turned[k][0] - pix[0], turned[k][1] - pix[1]};
+        double dv[4]; cam_derivs(D.cam, cc, dv);
+        double J[2][3];
+        const double invz = 1.0 / v3[2];
+        for (int m = 0; m < 3; m++) {
+          double mo[3]; mo[m] = 0; mo[(m + 1) % 3] = -v3[(m + 2) % 3]; mo[(m + 2) % 3] = v3[(m + 1) % 3];
+          const double c0 = (mo[0] - v3[0] * mo[2] * invz) * invz, c1 = (mo[1] - v3[1] * mo[2] * invz) * invz;
+          double a0 = dv[0] * c0; a0 += dv[1] * c1; double a1 = dv[2] * c0; a1 += dv[3] * c1;
+          J[0][m] = a0; J[1][m] = a1;
+        }
+        for (int row = 0; row < 2; row++)
+          for (int r = 0; r < 3; r++) { const double Jw = 1.0 * J[row][r]; b[r] += err[row] * Jw; for (int q = r; q < 3; q++) C[3 * r + q] += Jw * J[row][q]; }
+      }
+      for (int r = 1; r < 3; r++) for (int q = 0; q < r; q++) C[3 * r + q] = C[3 * q + r];
+      double Ci[9]; inverse3(C, Ci);
+      double mu[3]; for (int i = 0; i < 3; i++) { double sacc = Ci[3 * i] * b[0]; sacc += Ci[3 * i + 1] * b[1]; sacc += Ci[3 * i + 2] * b[2]; mu[i] = sacc; }
+      double E[9], Rn[9]; so3_exp(mu, E);
+      for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { double sacc = E[3 * i] * R[j]; sacc += E[3 * i + 1] * R[3 + j]; sacc += E[3 * i + 2] * R[6 + j]; Rn[3 * i + j] = sacc; }
+      for (int i = 0; i < 9; i++) R[i] = Rn[i];
+    }
+    double P[12]; for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) P[4 * i + j] = R[3 * i + j]; P[4 * i + 3] = 0.0; }
+    double v6[6]; se3_ln(P, v6);
+    for (int k = 0; k < 6; k++) st->sbi_rot[k] = v6[k];
+  }
+}
+
+}  // namespace
+
+int vs_launch_sbi(vslam_ctx* ctx) {
+  if (!ctx->sbi_on) return VSLAM_OK;
+  SbiDev D;
+  const LevelDesc& L3 = ctx->lev[3];
+  D.w = L3.w / 2; D.h = L3.h / 2; D.l3w = L3.w; D.l3h = L3.h; D.l3pitch = L3.pitch; D.l3 = L3.img;
+  for (int k = 0; k < 9; k++) D.taps[k] = ctx->sbi_taps[k];
+  D.cam = ctx->sbi_cam; memcpy(D.orig, ctx->sbi_orig, sizeof(D.orig));
+  D.tmpl = ctx->sbi_tmpl; D.scratch = ctx->sbi_scratch; D.jac = ctx->sbi_jac; D.small = ctx->sbi_small; D.ss = ctx->ss; D.have = ctx->sbi_have; D.parity = ctx->sbi_have + ctx->S;
+  D.use_sbi = ctx->params.use_sbi;
+  vs_time_begin(ctx, VS_ST_OTHER);
+  k_sbi<<<ctx->S, kT, 0, ctx->stream>>>(D);
+  vs_time_end(ctx);
+  VS_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return VSLAM_OK;
+}

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <cstring>
 #include <vector>
 #include "vslam_b200.h"
 
@@ -105,6 +106,8 @@ struct vslam_ctx {
   // MakeKeyFrame_Rest results of one stream (lazy scratch) and the per-stream keyframe snapshot used by MiniPatch trail tracking
   int* rest_scores; uint32_t* rest_max; uint32_t* rest_cand; double* rest_cand_score; int* rest_counts; size_t rest_off[VS_LEVELS]; int rest_stream;
   uint8_t* snap_img; uint32_t* snap_corners; int* snap_lut;
+  // on-device SmallBlurryImage (vslam_enable_sbi)
+  bool sbi_on; float sbi_taps[9]; CamDev sbi_cam; double sbi_orig[2][3]; float* sbi_tmpl; float* sbi_scratch; float* sbi_jac; uint8_t* sbi_small; int* sbi_have;
   // optional per-kernel timing with CUDA events on ctx->stream (vslam_set_timing)
   bool timing; std::vector<cudaEvent_t> ev_pool; std::vector<int> ev_stage; size_t ev_used;
   std::string err;
@@ -138,6 +141,7 @@ int vs_launch_pose(vslam_ctx* ctx, int mode, double sigma, int mark, int apply);
 int vs_launch_track_map(vslam_ctx* ctx, int with_motion_model);
 int vs_launch_project_and_derivs(vslam_ctx* ctx, int only_found);
 int vs_launch_calc_jacobians(vslam_ctx* ctx);
+int vs_launch_sbi(vslam_ctx* ctx);
 int vs_keyframe_rest(vslam_ctx* ctx, int stream);
 int vs_minipatch_sample(vslam_ctx* ctx, int stream, int which, const int* xy_dev, int n, uint8_t* patches_dev);
 int vs_minipatch_find(vslam_ctx* ctx, int stream, int which, const uint8_t* patches_dev, int n, double* pos_dev, int* found_dev, int* best_dev, int range, int max_ssd);
