@@ -251,6 +251,16 @@ def main():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if os.environ.get("VSLAM_BENCH_AFFINITY", "1") == "1":
+        # bind this rank to the CPUs NVML reports as local to its GPU, BEFORE the pinned frame pool is allocated (first touch => local NUMA node)
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[local_rank]) if vis and vis.split(",")[0].isdigit() else local_rank
+            nv.nvmlDeviceSetCpuAffinity(nv.nvmlDeviceGetHandleByIndex(idx))
+        except Exception:
+            pass
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -308,6 +318,7 @@ def main():
     sampler.start()
     barrier()
     launches0 = ctx.kernel_launches()
+    evals0 = ctx.zmssd_evals()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for k in range(K):
@@ -315,6 +326,7 @@ def main():
     e1.record(stream)
     barrier()
     launches = ctx.kernel_launches() - launches0
+    evals1 = ctx.zmssd_evals()
     dev_ms = max_over_ranks(e0.elapsed_time(e1))
     stage = ctx.stage_times()
     ctx.set_timing(False)
@@ -378,12 +390,21 @@ def main():
                                   "frac": l0_bytes / (l0_ms * 1e-3) / 1e9 / peak, "traffic": l0_traffic},
                 "note": "traffic is the level-0 launch's dram read+write bytes (ncu); the stage is instruction-issue bound (85 % issue-slot "
                         "utilisation, ~260 warp-instructions per 128 pixels), not HBM bound: DESIGN.md §4.1 and profiles/r01_final_*"}
+    # ZMSSD: 3*P^2 integer MACs per scored candidate over the time of the two search kernels, against a measured dp4a peak
+    evals_timed = evals1 - evals0
+    search_ms = stage["search_fine"][0] + stage["search_coarse"][0]
+    dp4a_peak = api.dp4a_peak_tmacs()
+    zm_achieved = 3.0 * 11 * 11 * evals_timed / (search_ms * 1e-3) / 1e12
+    zmssd = {"kernel": "k_search (template generation + FindPatchCoarse/ZMSSD + sub-pixel refinement)", "bound": "integer pipe", "achieved": zm_achieved,
+             "peak": dp4a_peak, "unit": "TMAC/s", "frac": zm_achieved / dp4a_peak, "candidates_scored_per_step": evals_timed / K,
+             "peak_source": "dp4a micro-benchmark of this run (vslam_debug_dp4a_peak)",
+             "note": "ZMSSD is a small part of k_search (about 6 candidates per point); the kernel is latency / issue bound, see profiles/"}
     stages_ms = {k: round(v[0] / K, 4) for k, v in stage.items() if v[1]}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": dev_ms / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32 (pyramid, FAST, ZMSSD) + f64 (projection, WLS)", "data": "synthetic", "config": config,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": S * H * W, "d2h_bytes_per_step": S * 12 * 8, "ms_per_step": e2e_ms / K},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "stages_ms_per_step": stages_ms,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "zmssd_roofline": zmssd, "stages_ms_per_step": stages_ms,
             "tracking": {"found_per_frame_mean": float(found.mean()), "quality_good_frac": float((quality == 2).mean()),
                          "zmssd_evals_total": int(ctx.zmssd_evals())}}
 

@@ -184,6 +184,9 @@ int vslam_get_stage_times(vslam_ctx* ctx, double* ms /* [VSLAM_N_STAGES] */, int
 /* Test hook: y[i] = the correctly-rounded device atan used by the camera model (csrc/atan_dd.cuh). */
 int vslam_debug_atan(const double* x_host, double* y_host, int n);
 
+/* Integer-pipe micro-benchmark: measured dp4a throughput of the current device in tera-MACs/s (the ZMSSD roofline denominator). */
+int vslam_debug_dp4a_peak(double* tmacs_per_s);
+
 /* Number of kernels this library has launched on the context since creation (bench.py's gpu_launches). */
 unsigned long long vslam_kernel_launches(const vslam_ctx* ctx);
 

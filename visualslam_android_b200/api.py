@@ -44,7 +44,7 @@ ABI_SYMBOLS = [
     "vslam_set_pose", "vslam_get_pose", "vslam_get_poses", "vslam_set_motion", "vslam_get_motion", "vslam_set_sbi_rotation", "vslam_enable_sbi", "vslam_get_sbi_rotation", "vslam_get_counters",
     "vslam_get_point_states", "vslam_get_point_template", "vslam_get_point_counts", "vslam_get_updates", "vslam_get_zmssd_evals",
     "vslam_project_all", "vslam_set_point_projection", "vslam_set_lists", "vslam_clear_counters", "vslam_search_for_points", "vslam_project_and_derivs", "vslam_calc_jacobians",
-    "vslam_calc_pose_update", "vslam_track_map", "vslam_track_frame", "vslam_track_frame_dev", "vslam_track_frame_async", "vslam_wait_step", "vslam_debug_atan", "vslam_kernel_launches", "vslam_set_timing", "vslam_get_stage_times",
+    "vslam_calc_pose_update", "vslam_track_map", "vslam_track_frame", "vslam_track_frame_dev", "vslam_track_frame_async", "vslam_wait_step", "vslam_debug_atan", "vslam_debug_dp4a_peak", "vslam_kernel_launches", "vslam_set_timing", "vslam_get_stage_times",
 ]
 
 _lib = None
@@ -120,6 +120,7 @@ def load():
     sig("vslam_track_frame_async", i, vp, vp, i, C.c_size_t, vp)
     sig("vslam_wait_step", i, vp, i)
     sig("vslam_debug_atan", i, vp, vp, i)
+    sig("vslam_debug_dp4a_peak", i, pd)
     sig("vslam_set_timing", i, vp, i)
     sig("vslam_get_stage_times", i, vp, vp, vp)
     _lib = L
@@ -142,6 +143,16 @@ def debug_atan(x) -> np.ndarray:
     if rc != OK:
         raise VslamError(rc, 'vslam_debug_atan')
     return out
+
+
+def dp4a_peak_tmacs() -> float:
+    """Measured dp4a throughput (tera-MACs/s) of the current CUDA device."""
+    L = load()
+    v = C.c_double()
+    rc = L.vslam_debug_dp4a_peak(C.byref(v))
+    if rc != OK:
+        raise VslamError(rc, 'vslam_debug_dp4a_peak')
+    return v.value
 
 
 def _ptr(a):

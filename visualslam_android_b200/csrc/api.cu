@@ -95,6 +95,7 @@ int vslam_create(const vslam_config* cfg, vslam_ctx** out) {
   *out = nullptr;
   if (cfg->width <= 0 || cfg->height <= 0 || cfg->width % 32 || cfg->height % 8 || cfg->width > 65535 || cfg->height > 65535) {
     g_create_error = "width must be a positive multiple of 32 and height of 8 (every pyramid level keeps even dimensions)"; return VSLAM_E_INVALID; }
+  if (cfg->max_points > 65536) { g_create_error = "max_points must be <= 65536"; return VSLAM_E_INVALID; }
   if (cfg->n_streams < 1 || cfg->max_points < 1 || cfg->max_source_keyframes < 1) { g_create_error = "n_streams, max_points, max_source_keyframes must be >= 1"; return VSLAM_E_INVALID; }
   if (cfg->patch_size < 4 || cfg->patch_size > VSLAM_MAX_PATCH) { g_create_error = "patch_size must be in [4, 11]"; return VSLAM_E_INVALID; }
   int ndev = 0;

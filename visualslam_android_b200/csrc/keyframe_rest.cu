@@ -202,3 +202,46 @@ int vs_minipatch_find(vslam_ctx* ctx, int s, int which, const uint8_t* patches_d
   ctx->launches++;
   return VSLAM_OK;
 }
+
+// Integer-pipe micro-benchmark (the ZMSSD roofline denominator): back-to-back independent dp4a chains, 8 per thread.
+namespace {
+__global__ void __launch_bounds__(256) k_dp4a_peak(unsigned* out, int iters, unsigned seed) {
+  unsigned a[8], b = seed + threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < 8; k++) a[k] = seed * (k + 1) + blockIdx.x;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] = __dp4a(a[k], b, a[k]);
+    b += 0x01010101u;
+  }
+  unsigned r = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) r ^= a[k];
+  if (r == 0x12345678u) out[0] = r;   // keeps the chains alive
+}
+}  // namespace
+
+// Returns measured dp4a throughput in tera-MACs per second (4 MACs per dp4a lane-instruction) on the current device.
+extern "C" int vslam_debug_dp4a_peak(double* tmacs_per_s) {
+  if (!tmacs_per_s) return VSLAM_E_INVALID;
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return VSLAM_E_CUDA;
+  unsigned* out = nullptr;
+  if (cudaMalloc(&out, 4) != cudaSuccess) return VSLAM_E_CUDA;
+  const int blocks = sms * 8, iters = 4096;
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  k_dp4a_peak<<<blocks, 256>>>(out, 64, 1u);   // warm-up
+  double best = 0;
+  for (int rep = 0; rep < 5; rep++) {
+    cudaEventRecord(e0);
+    k_dp4a_peak<<<blocks, 256>>>(out, iters, 7u + rep);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    const double macs = (double)blocks * 256 * iters * 8 * 4;
+    const double t = macs / (ms * 1e-3) / 1e12;
+    if (t > best) best = t;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+  *tmacs_per_s = best;
+  return cudaGetLastError() == cudaSuccess ? VSLAM_OK : VSLAM_E_CUDA;
+}

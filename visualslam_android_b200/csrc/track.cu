@@ -488,96 +488,96 @@ __global__ void __launch_bounds__(kSearchWarps * 32) k_search(Dev D, int mode, i
 
 // ------------------------------------------------------------------------------------------------
 // Pose-update kernel, one CTA per stream.
-// k-th smallest (0-based) of n non-negative doubles: MSB-first 8-bit radix select on the IEEE bit patterns (monotonic
-// for values >= 0).  All threads of the CTA call it; `hist` is 256 ints of shared memory, `sel` two 64-bit words.
+// k-th smallest (0-based) of n non-negative doubles: MSB-first 11-bit radix select on the IEEE bit patterns (monotonic for
+// values >= 0), stopping as soon as the selected bin holds a single element.  All threads of the CTA call it;
+// `hist` is 2048 ints of shared memory, `sel` three 64-bit words.
 __device__ inline double block_radix_select(const double* a, int n, int k, int* hist, unsigned long long* sel) {
   const int tid = threadIdx.x;
-  unsigned long long prefix = 0;   // bits decided so far (upper bytes)
-  int rank = k;
-  for (int pass = 7; pass >= 0; pass--) {
-    for (int b = tid; b < 256; b += blockDim.x) hist[b] = 0;
+  unsigned long long prefix = 0;   // bits decided so far
+  int rank = k, sh = 64;
+  while (sh > 0) {
+    const int bits = sh >= 11 ? 11 : sh, nsh = sh - bits, nb = 1 << bits;
+    for (int b = tid; b < nb; b += blockDim.x) hist[b] = 0;
     __syncthreads();
-    const int sh = 8 * pass;
     for (int t = tid; t < n; t += blockDim.x) {
       const unsigned long long key = (unsigned long long)__double_as_longlong(a[t]);
-      if (pass == 7 || (key >> (sh + 8)) == (prefix >> (sh + 8))) atomicAdd(&hist[(int)((key >> sh) & 255ull)], 1);
+      if (sh == 64 || (key >> sh) == (prefix >> sh)) atomicAdd(&hist[(int)((key >> nsh) & (unsigned long long)(nb - 1))], 1);
     }
     __syncthreads();
     if (tid < 32) {   // warp 0: find the bin that holds rank `rank`
-      int c[8]; int mine = 0;
-#pragma unroll
-      for (int q = 0; q < 8; q++) { c[q] = hist[tid * 8 + q]; mine += c[q]; }
+      const int per = nb >> 5;
+      int mine = 0;
+      for (int q = 0; q < per; q++) mine += hist[tid * per + ((q + tid) & (per - 1))];   // rotated start per lane: no bank conflicts
       int incl = mine;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if (tid >= d) incl += v; }
       const int excl = incl - mine;
       if (rank >= excl && rank < incl) {
         int r = rank - excl, q = 0;
-        while (r >= c[q]) { r -= c[q]; q++; }
-        sel[0] = prefix | ((unsigned long long)(tid * 8 + q) << sh); sel[1] = (unsigned long long)r;
+        while (r >= hist[tid * per + q]) { r -= hist[tid * per + q]; q++; }
+        sel[0] = prefix | ((unsigned long long)(tid * per + q) << nsh); sel[1] = (unsigned long long)r; sel[2] = (unsigned long long)hist[tid * per + q];
       }
     }
     __syncthreads();
     prefix = sel[0]; rank = (int)sel[1];
+    const bool single = sel[2] == 1ull;
+    sh = nsh;
     __syncthreads();
+    if (single && sh > 0) {   // exactly one element carries this prefix: fetch it
+      for (int t = tid; t < n; t += blockDim.x) {
+        const unsigned long long key = (unsigned long long)__double_as_longlong(a[t]);
+        if ((key >> sh) == (prefix >> sh)) sel[0] = key;
+      }
+      __syncthreads();
+      prefix = sel[0];
+      __syncthreads();
+      break;
+    }
   }
   return __longlong_as_double((long long)prefix);
 }
 
-// dynamic inverse = partial-pivot LU, column by column; then mu = Cinv * b  (oracle/vslam_oracle.cc inverse_lu; jni/myWLS.h:53-62)
-__device__ inline void solve6(const double* Cin, const double* b, double* mu) {
-  double a[36], inv[36], x[6]; int piv[6];
-  for (int i = 0; i < 36; i++) a[i] = Cin[i];
-  for (int i = 0; i < 6; i++) piv[i] = i;
-  for (int k = 0; k < 6; k++) {
-    int p = k; double best = fabs(a[k * 6 + k]);
-    for (int i = k + 1; i < 6; i++) if (fabs(a[i * 6 + k]) > best) { best = fabs(a[i * 6 + k]); p = i; }
-    if (p != k) { for (int j = 0; j < 6; j++) { const double t = a[k * 6 + j]; a[k * 6 + j] = a[p * 6 + j]; a[p * 6 + j] = t; } const int t = piv[k]; piv[k] = piv[p]; piv[p] = t; }
-    for (int i = k + 1; i < 6; i++) { a[i * 6 + k] /= a[k * 6 + k]; for (int j = k + 1; j < 6; j++) a[i * 6 + j] -= a[i * 6 + k] * a[k * 6 + j]; }
-  }
-  for (int c = 0; c < 6; c++) {
-    for (int i = 0; i < 6; i++) x[i] = (piv[i] == c) ? 1.0 : 0.0;
-    for (int i = 0; i < 6; i++) for (int j = 0; j < i; j++) x[i] -= a[i * 6 + j] * x[j];
-    for (int i = 5; i >= 0; i--) { for (int j = i + 1; j < 6; j++) x[i] -= a[i * 6 + j] * x[j]; x[i] /= a[i * 6 + i]; }
-    for (int i = 0; i < 6; i++) inv[i * 6 + c] = x[i];
-  }
-  for (int i = 0; i < 6; i++) { double s = inv[6 * i] * b[0]; for (int j = 1; j < 6; j++) s += inv[6 * i + j] * b[j]; mu[i] = s; }
-}
-
+#ifdef VS_POSE_TIMING
+#define PT_MARK(k) do { __syncthreads(); const long long t_ = clock64(); const int z_ = threadIdx.x == 0 ? 0 : 16; const long long d_ = t_ - sm.tlast[z_ ? 1 : 0]; sm.tacc[(k) + z_] += d_; __syncthreads(); sm.tlast[z_ ? 1 : 0] = t_; } while (0)
+#else
+#define PT_MARK(k) do { } while (0)
+#endif
 struct PoseSmem {
+#ifdef VS_POSE_TIMING
+  long long tacc[32], tlast[2];   // [0..15]: thread 0's phase counters, [16..31] and tlast[1]: dummy slots for the other threads (branch-free marks)
+#endif
   double pose[12];
   double red[kPT / 32][28];
   double sums[28];
   double mu[6], last[6];
   double sigma;
   int nerr, cnt;
-  int hist[256];
-  unsigned long long sel[2];
+  unsigned long long sel[3];
+  int warpcnt[kPT / 32];
+  double lu[36], inv[36]; int piv[6];
 };
 
 // One CalcPoseUpdate over list entries [0,n) (jni/Tracker.cc:683-774).  Leaves mu in sm.mu (zeros if nothing found).
-__device__ void calc_pose_update(const Dev& D, PoseSmem& sm, double* sortbuf, int sortcap, const int* list, int n, int s, double overrideSigma, bool mark) {
+__device__ void calc_pose_update(const Dev& D, PoseSmem& sm, double* sortbuf, int sortcap, int* hist, double* part, const int* list, int n, int s, double overrideSigma, bool mark) {
   const size_t SN = (size_t)D.S * D.N;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) sm.nerr = 0;
-  __syncthreads();
   // errors (:703-709); the squared errors only feed a sort, so their order in the buffer is irrelevant
+  // `list` holds found points only (built once per kernel by build_found_list)
   for (int k = tid; k < n; k += kPT) {
     const size_t gi = (size_t)s * D.N + list[k];
-    if (!(D.ps.flags[gi] & F_FOUND)) continue;
     const double si = D.ps.sqrtinv[gi];
     const double e0 = (D.ps.v2found[gi] - D.ps.v2image[gi]) * si, e1 = (D.ps.v2found[SN + gi] - D.ps.v2image[SN + gi]) * si;
     D.ps.err[gi] = e0; D.ps.err[SN + gi] = e1;
     double e2 = 0; e2 += e0 * e0; e2 += e1 * e1;
-    const int slot = atomicAdd(&sm.nerr, 1);
-    if (overrideSigma <= 0 && slot < sortcap) sortbuf[slot] = e2;
+    if (overrideSigma <= 0 && k < sortcap) sortbuf[k] = e2;
   }
   __syncthreads();
-  const int nerr = sm.nerr;
+  PT_MARK(4);
+  const int nerr = n;
   if (nerr == 0) { if (tid < 6) sm.mu[tid] = 0.0; if (tid == 0) sm.sigma = 0.0; __syncthreads(); return; }
   if (overrideSigma > 0) { if (tid == 0) sm.sigma = overrideSigma; }
   else {   // Tukey::FindSigmaSquared (jni/MEstimator.h:67-77): the sort there only serves to pick v[n/2]
-    const double med = block_radix_select(sortbuf, nerr, nerr / 2, sm.hist, sm.sel);
+    const double med = block_radix_select(sortbuf, nerr, nerr / 2, hist, sm.sel);
     if (tid == 0) {
       const unsigned long long den = (unsigned long long)nerr * 2ull - 6ull;   // size_t arithmetic of the reference
       double sigma = 1.4826 * (1 + 5.0 / (double)den) * sqrt(med);
@@ -586,6 +586,7 @@ __device__ void calc_pose_update(const Dev& D, PoseSmem& sm, double* sortbuf, in
     }
   }
   __syncthreads();
+  PT_MARK(5);
   const double sig2 = sm.sigma;
   // weighted normal equations: 21 upper-triangle terms + 6 right-hand sides (jni/myWLS.h:39-50)
   double acc[27];
@@ -594,7 +595,6 @@ __device__ void calc_pose_update(const Dev& D, PoseSmem& sm, double* sortbuf, in
   for (int k = tid; k < n; k += kPT) {
     const int i = list[k];
     const size_t gi = (size_t)s * D.N + i;
-    if (!(D.ps.flags[gi] & F_FOUND)) continue;
     const double e0 = D.ps.err[gi], e1 = D.ps.err[SN + gi];
     double e2 = 0; e2 += e0 * e0; e2 += e1 * e1;
     const double sq = (e2 > sig2) ? 0.0 : 1.0 - (e2 / sig2);
@@ -619,24 +619,87 @@ __device__ void calc_pose_update(const Dev& D, PoseSmem& sm, double* sortbuf, in
       }
     }
   }
+  // fixed-shape reduction: partials transposed through shared memory ([27][256]), then one warp-row per sum
 #pragma unroll
-  for (int k = 0; k < 27; k++) {
-    double v = acc[k];
+  for (int k = 0; k < 27; k++) part[k * kPT + tid] = acc[k];
+  __syncthreads();
+  for (int k = warp; k < 27; k += kPT / 32) {
+    double v = 0;
+#pragma unroll
+    for (int q = 0; q < kPT / 32; q++) v += part[k * kPT + q * 32 + lane];
 #pragma unroll
     for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-    if (lane == 0) sm.red[warp][k] = v;
+    if (lane == 0) sm.sums[k] = v;
   }
   __syncthreads();
-  if (tid < 27) { double v = 0; for (int w = 0; w < kPT / 32; w++) v += sm.red[w][tid]; sm.sums[tid] = v; }
-  __syncthreads();
-  if (tid == 0) {
-    double C[36], b[6];
-    int q = 0;
-    for (int r = 0; r < 6; r++) for (int c = r; c < 6; c++) { C[6 * r + c] = sm.sums[q] + (r == c ? 100.0 : 0.0); C[6 * c + r] = C[6 * r + c]; q++; }   // prior 100*I (:734)
-    for (int r = 0; r < 6; r++) b[r] = sm.sums[21 + r];
-    solve6(C, b, sm.mu);
+  PT_MARK(6);
+  // mu = inverse(C) * b with inverse = partial-pivot LU, column by column (jni/myWLS.h:53-62; oracle inverse_lu): same operations per
+  // element as the serial routine, spread over six lanes of warp 0 (rows during elimination, columns during substitution).
+  if (warp == 0) {
+    __syncwarp();   // reconverge first: with diverged lanes every shuffle below takes the slow WARPSYNC.COLLECTIVE path (~300 cycles each)
+    // lane r (< 6) keeps row r of C in registers; pivot search, row swap and the pivot-row broadcast go through shuffles
+    const int r6 = lane < 6 ? lane : 5;
+    double row[6];
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+      const int lo = r6 < c ? r6 : c, hi = r6 < c ? c : r6;
+      const int q = lo * 6 - (lo * (lo - 1)) / 2 + (hi - lo);          // index of (lo,hi) in the packed upper triangle
+      row[c] = sm.sums[q] + (lo == hi ? 100.0 : 0.0);                    // prior 100*I (:734)
+    }
+    int mypiv = r6;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      // partial pivoting: first row i >= k with the largest |a[i][k]| (strict >, as the serial routine)
+      double best = (lane >= k && lane < 6) ? fabs(row[k]) : -1.0; int bi = lane;
+#pragma unroll
+      for (int d = 4; d; d >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, d); const int oi = __shfl_xor_sync(0xffffffffu, bi, d);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+      }
+      const int p = __shfl_sync(0xffffffffu, bi, 0);
+      // swap rows k and p (and their pivot labels)
+      const int src = lane == k ? p : (lane == p ? k : lane);
+#pragma unroll
+      for (int c = 0; c < 6; c++) row[c] = __shfl_sync(0xffffffffu, row[c], src);
+      mypiv = __shfl_sync(0xffffffffu, mypiv, src);
+      double prow[6];
+#pragma unroll
+      for (int c = 0; c < 6; c++) prow[c] = __shfl_sync(0xffffffffu, row[c], k);
+      if (lane > k && lane < 6) {
+        const double f = row[k] / prow[k];
+        row[k] = f;
+#pragma unroll
+        for (int j = k + 1; j < 6; j++) row[j] -= f * prow[j];
+      }
+    }
+    if (lane < 6) {
+#pragma unroll
+      for (int c = 0; c < 6; c++) sm.lu[lane * 6 + c] = row[c];
+      sm.piv[lane] = mypiv;
+    }
+    __syncwarp();
+    if (lane < 6) {   // column `lane` of the inverse
+      const int c = lane; double x[6];
+#pragma unroll
+      for (int i = 0; i < 6; i++) x[i] = (sm.piv[i] == c) ? 1.0 : 0.0;
+#pragma unroll
+      for (int i = 0; i < 6; i++)
+#pragma unroll
+        for (int j = 0; j < i; j++) x[i] -= sm.lu[i * 6 + j] * x[j];
+#pragma unroll
+      for (int i = 5; i >= 0; i--) {
+#pragma unroll
+        for (int j = i + 1; j < 6; j++) x[i] -= sm.lu[i * 6 + j] * x[j];
+        x[i] /= sm.lu[i * 6 + i];
+      }
+#pragma unroll
+      for (int i = 0; i < 6; i++) sm.inv[i * 6 + c] = x[i];
+    }
+    __syncwarp();
+    if (lane < 6) { const int i = lane; double sacc = sm.inv[6 * i] * sm.sums[21]; for (int j = 1; j < 6; j++) sacc += sm.inv[6 * i + j] * sm.sums[21 + j]; sm.mu[i] = sacc; }
   }
   __syncthreads();
+  PT_MARK(7);
 }
 
 __device__ void reproject_found(const Dev& D, const double* pose, const int* list, int n, int s, int only_found, int* quirk) {
@@ -656,11 +719,11 @@ __device__ void reproject_found(const Dev& D, const double* pose, const int* lis
   }
 }
 // TrackerData::CalcJacobian (jni/TrackerData.h:107-123)
-__device__ void calc_jacobians(const Dev& D, const int* list, int n, int s) {
+__device__ void calc_jacobians(const Dev& D, const int* list, int n, int s, bool all_found) {
   const size_t SN = (size_t)D.S * D.N;
   for (int k = threadIdx.x; k < n; k += kPT) {
     const size_t gi = (size_t)s * D.N + list[k];
-    if (!(D.ps.flags[gi] & F_FOUND)) continue;
+    if (!all_found && !(D.ps.flags[gi] & F_FOUND)) continue;
     const double c[3] = {D.ps.v3cam[gi], D.ps.v3cam[SN + gi], D.ps.v3cam[2 * SN + gi]};
     const double dv[4] = {D.ps.derivs[gi], D.ps.derivs[SN + gi], D.ps.derivs[2 * SN + gi], D.ps.derivs[3 * SN + gi]};
     const double invz = 1.0 / c[2];
@@ -678,17 +741,49 @@ __device__ void calc_jacobians(const Dev& D, const int* list, int n, int s) {
   }
 }
 // TrackerData::LinearUpdate (jni/TrackerData.h:126-132)
-__device__ void linear_update(const Dev& D, const int* list, int n, int s, const double* v6) {
+__device__ void linear_update(const Dev& D, const int* list, int n, int s, const double* v6) {   // `list`: found points only
   const size_t SN = (size_t)D.S * D.N;
   for (int k = threadIdx.x; k < n; k += kPT) {
     const size_t gi = (size_t)s * D.N + list[k];
-    if (!(D.ps.flags[gi] & F_FOUND)) continue;
     for (int r = 0; r < 2; r++) {
       double sacc = D.ps.jac[(size_t)(6 * r) * SN + gi] * v6[0];
       for (int c = 1; c < 6; c++) sacc += D.ps.jac[(size_t)(6 * r + c) * SN + gi] * v6[c];
       D.ps.v2image[r * SN + gi] += sacc;
     }
   }
+}
+
+// Found entries of list[0,n), written to flist in ASCENDING POINT INDEX (a bitmap of the set, then an ordered expansion): the
+// per-point SoA arrays are then read with consecutive addresses by consecutive threads.  The order of the set does not matter
+// to the algorithm (sums, median).  `bitmap` needs (N+31)/32 words.  Returns the number of found entries (all threads).
+__device__ int build_found_list(const Dev& D, PoseSmem& sm, const int* list, int n, int s, int* flist, unsigned* bitmap) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int words = (D.map.n + 31) >> 5;
+  for (int w = tid; w < words; w += kPT) bitmap[w] = 0u;
+  __syncthreads();
+  for (int k = tid; k < n; k += kPT) {
+    const int idx = list[k];
+    if (D.ps.flags[(size_t)s * D.N + idx] & F_FOUND) atomicOr(&bitmap[idx >> 5], 1u << (idx & 31));
+  }
+  __syncthreads();
+  int base = 0;
+  for (int w0 = 0; w0 < words; w0 += kPT) {
+    const int w = w0 + tid;
+    unsigned m = w < words ? bitmap[w] : 0u;
+    const int mine = __popc(m);
+    int incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+    if (lane == 31) sm.warpcnt[warp] = incl;
+    __syncthreads();
+    int off = base, tot = 0;
+    for (int q = 0; q < kPT / 32; q++) { if (q < warp) off += sm.warpcnt[q]; tot += sm.warpcnt[q]; }
+    int pos = off + incl - mine;
+    while (m) { const int b = __ffs(m) - 1; m &= m - 1; flist[pos++] = (w << 5) + b; }
+    base += tot;
+    __syncthreads();
+  }
+  return base;
 }
 
 // mode 0: one CalcPoseUpdate over [0,nA) (stage API);  1: coarse stage;  2: fine stage (+ scene depth; + motion model / quality if tail)
@@ -699,15 +794,29 @@ __global__ void __launch_bounds__(kPT, 2) k_pose(Dev D, int mode, double sigma_a
   StreamState* st = D.ss + s;
   if (mode != 0 && st->lost_frames >= 3) return;
   const int* list = D.lists + (size_t)s * D.list_cap;
+  // dynamic shared memory: [2048 doubles sort keys][2048 ints found list][2048 ints radix histogram][27*256 doubles partial sums]
   double* sortbuf = sh_sort; int sortcap = 2048;
+  int* flist = (int*)(sh_sort + 2048);
+  int* hist = flist + 2048;
+  double* part = sh_sort + 2048 + 2048;          // [27][kPT] partial sums of the normal equations
   const int nA = st->nA, nAll = st->nA + st->nB;
-  if ((mode == 2 ? nAll : nA) > 2048) { sortbuf = D.sort_scratch + (size_t)s * D.sort_cap; sortcap = D.sort_cap; }
+  const int nlist = (mode == 2) ? nAll : nA;
+  if (nlist > 2048) { sortbuf = D.sort_scratch + (size_t)s * D.sort_cap; sortcap = D.sort_cap; flist = D.pvs + (size_t)s * VS_LEVELS * D.N; }
   if (tid < 12) sm.pose[tid] = st->pose[tid];
   if (tid < 6) sm.last[tid] = 0.0;
   __syncthreads();
+  if (mode == 1 && !st->try_coarse) return;
+  // every point that enters the iterations was searched before this kernel: the found set is fixed from here on
+#ifdef VS_POSE_TIMING
+  if (tid < 32) sm.tacc[tid] = 0;
+  if (tid < 2) sm.tlast[tid] = clock64();
+  __syncthreads();
+#endif
+  const int n = build_found_list(D, sm, list, nlist, s, flist, (unsigned*)hist);   // (the histogram buffer doubles as the bitmap: N <= 65536)
+  PT_MARK(0);
 
   if (mode == 0) {
-    calc_pose_update(D, sm, sortbuf, sortcap, list, nA, s, sigma_arg, mark_arg != 0);
+    calc_pose_update(D, sm, sortbuf, sortcap, hist, part, flist, n, s, sigma_arg, mark_arg != 0);
     if (tid == 0) {
       const int u = st->n_updates < VS_MAX_UPDATES ? st->n_updates : VS_MAX_UPDATES - 1;
       for (int k = 0; k < 6; k++) st->updates[6 * u + k] = sm.mu[k];
@@ -717,31 +826,23 @@ __global__ void __launch_bounds__(kPT, 2) k_pose(Dev D, int mode, double sigma_a
     return;
   }
 
-  int n; int iters = 10;
-  if (mode == 1) {   // coarse stage (jni/Tracker.cc:464-489)
-    if (!st->try_coarse) return;
-    n = nA;
-    if (tid == 0) sm.cnt = 0;
-    __syncthreads();
-    int c = 0;
-    for (int k = tid; k < n; k += kPT) c += (D.ps.flags[(size_t)s * D.N + list[k]] & F_FOUND) ? 1 : 0;
-    if (c) atomicAdd(&sm.cnt, c);
-    __syncthreads();
-    if ((unsigned)sm.cnt < D.prm.coarse_min) return;
+  const int iters = 10;
+  if (mode == 1) {   // coarse stage (jni/Tracker.cc:464-489): needs nFound >= CoarseMin
+    if ((unsigned)n < D.prm.coarse_min) return;
     if (tid == 0) st->did_coarse = 1;
-  } else n = nAll;
+  }
 
   for (int iter = 0; iter < iters; iter++) {
     bool nonlinear = true;
     if (mode == 2) nonlinear = (iter == 0 || iter == 4 || iter == 9);
     if (iter != 0) {
-      if (nonlinear) reproject_found(D, sm.pose, list, n, s, 1, &st->quirk_stale_cache);
-      else linear_update(D, list, n, s, sm.last);
+      if (nonlinear) { reproject_found(D, sm.pose, flist, n, s, 1, &st->quirk_stale_cache); PT_MARK(1); }
+      else { linear_update(D, flist, n, s, sm.last); PT_MARK(2); }
       __syncthreads();
     }
-    if (nonlinear) { calc_jacobians(D, list, n, s); __syncthreads(); }
+    if (nonlinear) { calc_jacobians(D, flist, n, s, true); __syncthreads(); PT_MARK(3); }
     const double ov = (iter > 5) ? (mode == 1 ? 1.0 : 16.0) : 0.0;
-    calc_pose_update(D, sm, sortbuf, sortcap, list, n, s, ov, mode == 2 && iter == 9);
+    calc_pose_update(D, sm, sortbuf, sortcap, hist, part, flist, n, s, ov, mode == 2 && iter == 9);
     if (tid == 0) {
       double e[12], np[12]; se3_exp(sm.mu, e); se3_mul(e, sm.pose, np);
       for (int k = 0; k < 12; k++) sm.pose[k] = np[k];
@@ -750,7 +851,11 @@ __global__ void __launch_bounds__(kPT, 2) k_pose(Dev D, int mode, double sigma_a
       if (u < VS_MAX_UPDATES) { for (int k = 0; k < 6; k++) st->updates[6 * u + k] = sm.mu[k]; st->sigmas[u] = sm.sigma; st->n_updates = u + 1; }
     }
     __syncthreads();
+    PT_MARK(8);
   }
+#ifdef VS_POSE_TIMING
+  if (tid == 0 && s == 7 && mode == 2) printf("k_pose cycles: found_list %lld reproject %lld linear %lld jac %lld err %lld median %lld accum %lld solve %lld exp %lld (n=%d)\n", sm.tacc[0], sm.tacc[1], sm.tacc[2], sm.tacc[3], sm.tacc[4], sm.tacc[5], sm.tacc[6], sm.tacc[7], sm.tacc[8], n);
+#endif
   if (tid < 12) st->pose[tid] = sm.pose[tid];
   if (mode != 2) return;
 
@@ -759,8 +864,8 @@ __global__ void __launch_bounds__(kPT, 2) k_pose(Dev D, int mode, double sigma_a
     const size_t SN2 = 2 * (size_t)D.S * D.N;
     double a0 = 0, a1 = 0, a2 = 0;
     for (int k = tid; k < n; k += kPT) {
-      const size_t gi = (size_t)s * D.N + list[k];
-      if (D.ps.flags[gi] & F_FOUND) { const double z = D.ps.v3cam[SN2 + gi]; a0 += z; a1 += z * z; a2 += 1.0; }
+      const size_t gi = (size_t)s * D.N + flist[k];
+      const double z = D.ps.v3cam[SN2 + gi]; a0 += z; a1 += z * z; a2 += 1.0;
     }
 #pragma unroll
     for (int d = 16; d; d >>= 1) { a0 += __shfl_xor_sync(0xffffffffu, a0, d); a1 += __shfl_xor_sync(0xffffffffu, a1, d); a2 += __shfl_xor_sync(0xffffffffu, a2, d); }
@@ -824,7 +929,7 @@ __global__ void __launch_bounds__(kPT) k_project_and_derivs(Dev D, int only_foun
 }
 __global__ void __launch_bounds__(kPT) k_calc_jacobians(Dev D) {
   const int s = blockIdx.x;
-  calc_jacobians(D, D.lists + (size_t)s * D.list_cap, D.ss[s].nA, s);
+  calc_jacobians(D, D.lists + (size_t)s * D.list_cap, D.ss[s].nA, s, false);
 }
 
 __global__ void k_atan(const double* x, double* y, int n) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) y[i] = atan_cr(x[i]); }
@@ -869,7 +974,8 @@ int vs_launch_search(vslam_ctx* ctx, int which, int range, int subpix) {
 
 int vs_launch_pose(vslam_ctx* ctx, int mode, double sigma, int mark, int apply) {
   const Dev D = make_dev(ctx);
-  const size_t smem = 2048 * sizeof(double);
+  const size_t smem = 2048 * sizeof(double) + 2 * 2048 * sizeof(int) + 27 * kPT * sizeof(double);   // sort keys + found list + radix histogram + partial sums
+  VS_CUDA(cudaFuncSetAttribute(k_pose, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   vs_time_begin(ctx, (mode & 3) == 2 ? VS_ST_POSE_FINE : VS_ST_POSE_COARSE);
   k_pose<<<ctx->S, kPT, smem, ctx->stream>>>(D, mode & 3, sigma, mark, apply, (mode >> 2) & 1);
   vs_time_end(ctx);
