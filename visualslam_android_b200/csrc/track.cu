@@ -244,14 +244,19 @@ __global__ void __launch_bounds__(kSearchWarps * 32) k_search(Dev D, int mode, i
 
   // ---- MakeTemplateCoarseCont (jni/PatchFinder.cc:79-125)
   double m2[4]; int refresh = 0, inside = 0, tsum = 0, tsumsq = 0;
+  // every per-point scalar this warp will need, loaded up front (uniform addresses: one transaction each) so the misses overlap
+  const double w0 = D.ps.warpinv[gi], w1 = D.ps.warpinv[SN + gi], w2 = D.ps.warpinv[2 * SN + gi], w3 = D.ps.warpinv[3 * SN + gi];
+  const double lw0 = D.ps.lastwarp[gi], lw1 = D.ps.lastwarp[SN + gi], lw2 = D.ps.lastwarp[2 * SN + gi], lw3 = D.ps.lastwarp[3 * SN + gi];
+  const double v2i0 = D.ps.v2image[gi], v2i1 = D.ps.v2image[SN + gi];
+  const int tsum_old = D.ps.tsum[gi], tsumsq_old = D.ps.tsum[SN + gi];
+  const uint32_t tmpl_old = ((const uint32_t*)(D.ps.tmpl + gi * VS_TMPL_BYTES))[lane];   // one coalesced 128-byte load
   if (lane == 0) {
-    const double w0 = D.ps.warpinv[gi], w1 = D.ps.warpinv[SN + gi], w2 = D.ps.warpinv[2 * SN + gi], w3 = D.ps.warpinv[3 * SN + gi];
     const double invdet = 1.0 / (w0 * w3 - w1 * w2);
     const int sc = LevelScale(level);
     m2[0] = (w3 * invdet) * sc; m2[1] = (-w1 * invdet) * sc; m2[2] = (-w2 * invdet) * sc; m2[3] = (w0 * invdet) * sc;
     refresh = !(flags & F_HAVELAST);
     for (int c = 0; !refresh && c < 2; c++) {
-      const double d0 = m2[c] - D.ps.lastwarp[c * SN + gi], d1 = m2[2 + c] - D.ps.lastwarp[(2 + c) * SN + gi];
+      const double d0 = m2[c] - (c ? lw1 : lw0), d1 = m2[2 + c] - (c ? lw3 : lw2);
       double dd = 0; dd += d0 * d0; dd += d1 * d1;
       const double lim = 0.07;
       if (dd > lim * lim) refresh = 1;
@@ -307,8 +312,8 @@ __global__ void __launch_bounds__(kSearchWarps * 32) k_search(Dev D, int mode, i
       for (int c = 0; c < 4; c++) D.ps.lastwarp[c * SN + gi] = m2[c];
     }
   } else {
-    sm.tmpl_w[lane] = ((const uint32_t*)(D.ps.tmpl + gi * VS_TMPL_BYTES))[lane];   // one coalesced 128-byte load
-    tsum = D.ps.tsum[gi]; tsumsq = D.ps.tsum[SN + gi];
+    sm.tmpl_w[lane] = tmpl_old;
+    tsum = tsum_old; tsumsq = tsumsq_old;
   }
   __syncwarp();
   if (flags & F_TBAD) {   // jni/Tracker.cc:637-640
@@ -318,8 +323,12 @@ __global__ void __launch_bounds__(kSearchWarps * 32) k_search(Dev D, int mode, i
   // template rows as zero-padded words for dp4a
   for (int k = lane; k < P * 3; k += 32) {
     const int r = k / 3, w = k - 3 * r;
+    const int off = r * P + 4 * w, rem = P - 4 * w;              // bytes [off, off+4) of the packed template, `rem` of them inside row r
     uint32_t v = 0;
-    for (int b = 0; b < 4; b++) { const int c = 4 * w + b; if (c < P) v |= (uint32_t)tmpl[r * P + c] << (8 * b); }
+    if (rem > 0) {
+      v = __funnelshift_r(sm.tmpl_w[off >> 2], sm.tmpl_w[(off >> 2) + 1 < VS_TMPL_BYTES / 4 ? (off >> 2) + 1 : off >> 2], 8 * (off & 3));
+      if (rem < 4) v &= (1u << (8 * rem)) - 1u;
+    }
     sm.tw[k] = v;
   }
   __syncwarp();
@@ -331,7 +340,7 @@ __global__ void __launch_bounds__(kSearchWarps * 32) k_search(Dev D, int mode, i
   if (level == 0) { img = D.l0_ptr[s]; pitch = D.l0_stride[s]; } else { img = L.img + (size_t)s * L.h * L.pitch; pitch = L.pitch; }
   const int maxSSD = PP * 500;
   const int nLevelScale = LevelScale(level);
-  const double ix = D.ps.v2image[gi] / nLevelScale, iy = D.ps.v2image[SN + gi] / nLevelScale;
+  const double ix = v2i0 / nLevelScale, iy = v2i1 / nLevelScale;
   const unsigned nRange = ((unsigned)range + nLevelScale - 1) / nLevelScale;
   int nTop = iy - nRange;
   const int nBottomPlusOne = iy + nRange + 1;
