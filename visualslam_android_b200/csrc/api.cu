@@ -104,7 +104,7 @@ int vslam_create(const vslam_config* cfg, vslam_ctx** out) {
   if (!ctx) { g_create_error = "out of host memory"; return VSLAM_E_INVALID; }
   ctx->cfg = *cfg; vslam_default_params(&ctx->params);
   ctx->S = cfg->n_streams; ctx->N = cfg->max_points; ctx->P = cfg->patch_size; ctx->launches = 0; ctx->n_src = cfg->max_source_keyframes;
-  ctx->scratch_host = nullptr; ctx->scratch_host_bytes = 0; ctx->timing = false; ctx->ev_used = 0; ctx->l0_alt = nullptr; ctx->copy_stream = nullptr; ctx->step = 0; ctx->pipe_ready = false; ctx->status_pin = nullptr;
+  ctx->side_stream = nullptr; ctx->ev_fork = nullptr; ctx->ev_join = nullptr; ctx->scratch_host = nullptr; ctx->scratch_host_bytes = 0; ctx->timing = false; ctx->ev_used = 0; ctx->l0_alt = nullptr; ctx->copy_stream = nullptr; ctx->step = 0; ctx->pipe_ready = false; ctx->status_pin = nullptr;
   ctx->rest_scores = nullptr; ctx->rest_max = nullptr; ctx->rest_cand = nullptr; ctx->rest_cand_score = nullptr; ctx->rest_counts = nullptr; ctx->rest_stream = -1;
   ctx->snap_img = nullptr; ctx->snap_corners = nullptr; ctx->snap_lut = nullptr;
   ctx->sbi_on = false; ctx->sbi_tmpl = nullptr; ctx->sbi_scratch = nullptr; ctx->sbi_jac = nullptr; ctx->sbi_small = nullptr; ctx->sbi_have = nullptr;
@@ -113,13 +113,16 @@ int vslam_create(const vslam_config* cfg, vslam_ctx** out) {
   CK(cudaSetDevice(cfg->device));
   if (cfg->cuda_stream) { ctx->stream = (cudaStream_t)cfg->cuda_stream; ctx->own_stream = false; }
   else { CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
+  CK(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
   const int S = ctx->S, N = ctx->N;
   int w = cfg->width, h = cfg->height;
   for (int l = 0; l < VS_LEVELS; l++) {
     LevelDesc& L = ctx->lev[l];
     L.w = w; L.h = h; L.pitch = round_up(w, 128);
     L.cap = (int)((double)w * h * frac); if (L.cap < 64) L.cap = 64;
-    L.n_strips = (h + VS_STRIP_ROWS - 1) / VS_STRIP_ROWS;
+    L.strip_rows = vs_strip_rows(l, w, L.pitch);
+    L.n_strips = (h + L.strip_rows - 1) / L.strip_rows;
     CK(dalloc(&L.img, (size_t)S * h * L.pitch));
     CK(dalloc(&L.corners, (size_t)S * L.cap));
     CK(dalloc(&L.lut, (size_t)S * (h + 1)));
@@ -191,6 +194,9 @@ void vslam_destroy(vslam_ctx* ctx) {
   if (ctx->status_pin) cudaFreeHost(ctx->status_pin);
   delete[] ctx->l0_ptr_host; delete[] ctx->l0_stride_host;
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   delete ctx;
 }
 
@@ -332,22 +338,32 @@ static int check_range(vslam_ctx* ctx, int first, int count, const void* p, int 
   return VSLAM_OK;
 }
 
-int vslam_make_keyframe_lite(vslam_ctx* ctx, int first, int count, const uint8_t* gray, int stride, size_t frame_stride) {
+// Host frames: copy into the ctx-owned level-0 images (re-adopting them if a device buffer had been adopted).
+static int stage_host_frames(vslam_ctx* ctx, int first, int count, const uint8_t* gray, int stride, size_t frame_stride) {
   int rc = check_range(ctx, first, count, gray, stride); if (rc) return rc;
   bool was_adopted = false;
   for (int s = first; s < first + count; s++) was_adopted |= ctx->l0_stride_host[s] != ctx->lev[0].pitch || ctx->l0_ptr_host[s] != ctx->lev[0].img + (size_t)s * ctx->lev[0].h * ctx->lev[0].pitch;
   if (was_adopted && (rc = adopt_l0(ctx, first, count, nullptr, 0, 0, true))) return rc;
-  if ((rc = upload_frames(ctx, first, count, gray, stride, frame_stride))) return rc;
-  return vs_launch_pyramid_fast(ctx, first, count);
+  return upload_frames(ctx, first, count, gray, stride, frame_stride);
 }
-
-int vslam_make_keyframe_lite_dev(vslam_ctx* ctx, int first, int count, const uint8_t* gray, int stride, size_t frame_stride) {
+// Device frames: adopt the caller's buffer as level 0 (zero copy).
+static int adopt_device_frames(vslam_ctx* ctx, int first, int count, const uint8_t* gray, int stride, size_t frame_stride) {
   int rc = check_range(ctx, first, count, gray, stride); if (rc) return rc;
   if (((uintptr_t)gray & 15) || (stride & 15) || (frame_stride & 15)) { ctx->err = "device frames must be 16-byte aligned with stride % 16 == 0"; return VSLAM_E_INVALID; }
   bool same = true;
   for (int k = 0; k < count; k++) same &= ctx->l0_ptr_host[first + k] == gray + (size_t)k * frame_stride && ctx->l0_stride_host[first + k] == stride;
   if (!same && (rc = adopt_l0(ctx, first, count, gray, stride, frame_stride, false))) return rc;
-  return vs_launch_pyramid_fast(ctx, first, count);
+  return VSLAM_OK;
+}
+
+int vslam_make_keyframe_lite(vslam_ctx* ctx, int first, int count, const uint8_t* gray, int stride, size_t frame_stride) {
+  const int rc = stage_host_frames(ctx, first, count, gray, stride, frame_stride);
+  return rc ? rc : vs_launch_pyramid_fast(ctx, first, count);
+}
+
+int vslam_make_keyframe_lite_dev(vslam_ctx* ctx, int first, int count, const uint8_t* gray, int stride, size_t frame_stride) {
+  const int rc = adopt_device_frames(ctx, first, count, gray, stride, frame_stride);
+  return rc ? rc : vs_launch_pyramid_fast(ctx, first, count);
 }
 
 int vslam_level_dims(const vslam_ctx* ctx, int level, int* w, int* h) {
@@ -651,9 +667,8 @@ int vslam_track_map(vslam_ctx* ctx) { if (!ctx) return VSLAM_E_INVALID; return v
 
 int vslam_track_frame(vslam_ctx* ctx, const uint8_t* gray, int stride, size_t frame_stride) {
   if (!ctx) return VSLAM_E_INVALID;
-  int rc = vslam_make_keyframe_lite(ctx, 0, ctx->S, gray, stride, frame_stride); if (rc) return rc;
-  if ((rc = vs_launch_sbi(ctx))) return rc;
-  return vs_launch_track_map(ctx, 1);
+  const int rc = stage_host_frames(ctx, 0, ctx->S, gray, stride, frame_stride);
+  return rc ? rc : vs_launch_frame(ctx);
 }
 // Pipelined host-input path: the copy of step k (copy stream, level-0 buffer k&1) overlaps the kernels of step k-1.
 int vslam_track_frame_async(vslam_ctx* ctx, const uint8_t* gray, int stride, size_t frame_stride, double* poses_out) {
@@ -681,9 +696,7 @@ int vslam_track_frame_async(vslam_ctx* ctx, const uint8_t* gray, int stride, siz
   bool same = true;
   for (int s = 0; s < ctx->S; s++) same &= ctx->l0_ptr_host[s] == buf + (size_t)s * L.h * L.pitch && ctx->l0_stride_host[s] == L.pitch;
   if (!same && (rc = adopt_l0(ctx, 0, ctx->S, buf, L.pitch, (size_t)L.h * L.pitch, false))) return rc;
-  if ((rc = vs_launch_pyramid_fast(ctx, 0, ctx->S))) return rc;
-  if ((rc = vs_launch_sbi(ctx))) return rc;
-  if ((rc = vs_launch_track_map(ctx, 1))) return rc;
+  if ((rc = vs_launch_frame(ctx))) return rc;
   VS_CUDA(cudaEventRecord(ctx->ev_computed[slot], ctx->stream));
   if (poses_out)
     VS_CUDA(cudaMemcpy2DAsync(poses_out, sizeof(double) * 12, (char*)ctx->ss + offsetof(StreamState, pose), sizeof(StreamState), sizeof(double) * 12, ctx->S,
@@ -708,9 +721,8 @@ int vslam_wait_step(vslam_ctx* ctx, int step) {
 
 int vslam_track_frame_dev(vslam_ctx* ctx, const uint8_t* gray, int stride, size_t frame_stride) {
   if (!ctx) return VSLAM_E_INVALID;
-  int rc = vslam_make_keyframe_lite_dev(ctx, 0, ctx->S, gray, stride, frame_stride); if (rc) return rc;
-  if ((rc = vs_launch_sbi(ctx))) return rc;
-  return vs_launch_track_map(ctx, 1);
+  const int rc = adopt_device_frames(ctx, 0, ctx->S, gray, stride, frame_stride);
+  return rc ? rc : vs_launch_frame(ctx);
 }
 
 }  // extern "C"

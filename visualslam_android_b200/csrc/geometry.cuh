@@ -148,3 +148,23 @@ __device__ __forceinline__ int glibc_rand_next(int* ring, int& f, int& b) {
   if (++b >= 31) b = 0;
   return (int)(v >> 1);
 }
+// n consecutive draws of the same generator into out[0..n) (shared memory), with the 31-word ring held in registers:
+// the ring is read rotated so that the rear index is 0, one draw is r[(j+3)%31] += r[j] (front = rear + 3, glibc
+// random_r.c), and after 31 draws the rear index is back at 0.  Updates ring / f / b exactly as n calls of glibc_rand_next.
+__device__ inline void glibc_rand_fill(int* ring, int& f, int& b, int* out, int n) {
+  uint32_t r[31];
+  const int b0 = b;
+#pragma unroll
+  for (int j = 0; j < 31; j++) { int q = b0 + j; if (q >= 31) q -= 31; r[j] = (uint32_t)ring[q]; }
+  int k = 0;
+  for (; n - k >= 31; k += 31) {
+#pragma unroll
+    for (int j = 0; j < 31; j++) { r[(j + 3) % 31] += r[j]; out[k + j] = (int)(r[(j + 3) % 31] >> 1); }
+  }
+  const int rem = n - k;
+#pragma unroll
+  for (int j = 0; j < 31; j++) if (j < rem) { r[(j + 3) % 31] += r[j]; out[k + j] = (int)(r[(j + 3) % 31] >> 1); }
+#pragma unroll
+  for (int j = 0; j < 31; j++) { int q = b0 + j; if (q >= 31) q -= 31; ring[q] = (int)r[j]; }
+  b = (b0 + n) % 31; f = (b + 3) % 31;
+}

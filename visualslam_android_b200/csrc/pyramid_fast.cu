@@ -1,9 +1,10 @@
 // KeyFrame::MakeKeyFrame_Lite on the GPU (reference: jni/KeyFrame.cc:5-51).
 //
-// One kernel per pyramid level l, batched over all streams:  a CTA owns a strip of VS_STRIP_ROWS rows of level l
-// of one stream.  It
+// Two launches, batched over all streams.  k_pyramid_fast handles level 0 (and writes levels 1..3), k_fast_levels
+// handles levels 1..3.  A CTA owns a strip of LevelDesc::strip_rows rows of one level of one stream.  It
 //   1. stages the strip plus a 3-row halo into shared memory with ONE bulk async copy (cp.async.bulk, TMA engine);
-//   2. writes the matching rows of level l+1:  (a+b+c+d+2)>>2  (cv::resize 2:1, jni/KeyFrame.cc:20-23);
+//   2. (level 0) writes the matching rows of level 1:  (a+b+c+d+2)>>2  (cv::resize 2:1, jni/KeyFrame.cc:20-23; SURVEY.md
+//      F2), and, from the same staged rows, the matching rows of levels 2 and 3;
 //   3. runs FAST-10 (jni/vision/cvfast.cpp:6088-9241 == segment test):
 //        a byte-SIMD rejection test on 4 pixels per lane (VABSDIFF4 + SWAR compares): a 10-arc contains at least one
 //        pixel of every opposite ring pair, so both (0,8) and (4,12) must hold a pixel differing by more than t;
@@ -73,64 +74,93 @@ __device__ __forceinline__ void ring_test(uint32_t e, const uint8_t* img, int st
 
 constexpr unsigned long long kFlagAgg = 1ull << 32, kFlagInc = 2ull << 32;
 
-__global__ void __launch_bounds__(kThreads)
-k_pyramid_fast(LevelDesc L, LevelDesc Ln, int has_next, int level, const uint8_t* const* __restrict__ l0_ptr, const int* __restrict__ l0_stride,
-               int first_stream, int thr, unsigned* __restrict__ ticket, int* __restrict__ status) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t bar;
-  __shared__ int s_ticket;
-  __shared__ int s_rowcnt[VS_STRIP_ROWS], s_rowoff[VS_STRIP_ROWS + 1];
-  __shared__ int s_base;
+struct StripShared {
+  uint64_t bar;
+  int ticket, base;
+  int qcnt[kWarps];   // level 0: fill level of every warp's candidate queue
+  int rowcnt[VS_MAX_STRIP_ROWS], rowoff[VS_MAX_STRIP_ROWS + 1];
+};
 
+// n / d for small n (n * d < 2^32) with m = magic_div(d): one IMAD.HI instead of an integer division
+__device__ __forceinline__ uint32_t magic_div(uint32_t d) { return 0xffffffffu / d + 1u; }
+
+// Levels 2 and 3 of a strip from its level-1 rows kept in shared memory (l1s: rows1 rows of w1 bytes, rows1 % 4 == 0 or
+// rows1 == 4): cv::resize 2:1 once / twice more, every intermediate pixel rounded as the level-by-level computation
+// rounds it, (a+b+c+d+2)>>2 (jni/KeyFrame.cc:20-23).  Threads t of nt.
+__device__ __forceinline__ void emit_levels_2_3(const uint8_t* l1s, int w1, int rows1, const LevelDesc& L2, const LevelDesc& L3, int s, int y0, int t, int nt) {
+  uint8_t* d2 = L2.img + ((size_t)s * L2.h + (y0 >> 2)) * L2.pitch;
+  uint8_t* d3 = L3.img + ((size_t)s * L3.h + (y0 >> 3)) * L3.pitch;
+  const int p2 = L2.w >> 1, n2 = (rows1 >> 1) * p2;       // level 2: two pixels per step
+  const uint32_t m2 = magic_div((uint32_t)p2);
+  for (int i = t; i < n2; i += nt) {
+    const int r = (int)__umulhi((uint32_t)i, m2), xp = i - r * p2;
+    const uint32_t c0 = *(const uint32_t*)(l1s + (2 * r) * w1 + 4 * xp), c1 = *(const uint32_t*)(l1s + (2 * r + 1) * w1 + 4 * xp);
+    const unsigned o0 = __dp4a(c0, 0x00000101u, __dp4a(c1, 0x00000101u, 2u)) >> 2;
+    const unsigned o1 = __dp4a(c0, 0x01010000u, __dp4a(c1, 0x01010000u, 2u)) >> 2;
+    *(uint16_t*)(d2 + (size_t)r * L2.pitch + 2 * xp) = (uint16_t)(o0 | (o1 << 8));
+  }
+  const int w3 = L3.w, n3 = (rows1 >> 2) * w3;            // level 3: one pixel (a 4x4 block of level 1) per step
+  const uint32_t m3 = magic_div((uint32_t)w3);
+  for (int i = t; i < n3; i += nt) {
+    const int r = (int)__umulhi((uint32_t)i, m3), x = i - r * w3;
+    const uint8_t* p = l1s + (4 * r) * w1 + 4 * x;
+    const uint32_t q0 = *(const uint32_t*)p, q1 = *(const uint32_t*)(p + w1), q2 = *(const uint32_t*)(p + 2 * w1), q3 = *(const uint32_t*)(p + 3 * w1);
+    const unsigned a = __dp4a(q0, 0x00000101u, __dp4a(q1, 0x00000101u, 2u)) >> 2, b = __dp4a(q0, 0x01010000u, __dp4a(q1, 0x01010000u, 2u)) >> 2;
+    const unsigned c = __dp4a(q2, 0x00000101u, __dp4a(q3, 0x00000101u, 2u)) >> 2, d = __dp4a(q2, 0x01010000u, __dp4a(q3, 0x01010000u, 2u)) >> 2;
+    d3[(size_t)r * L3.pitch + x] = (uint8_t)((a + b + c + d + 2u) >> 2);
+  }
+}
+
+// One strip (rows [strip*R, +R) of level L of stream s): stage, [level 0: write levels 1..3], FAST-10, raster-ordered append.
+template <bool kLevel0>
+__device__ __forceinline__ void fast_strip(const LevelDesc& L, const uint8_t* __restrict__ src, const int stride, const int s, const int strip, const int thr,
+                                           const LevelDesc* Lchild /* [3] levels 1..3, level 0 only */, int* __restrict__ status, StripShared& sh, uint8_t* smem) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) { s_ticket = (int)atomicAdd(ticket, 1u); mbar_init(&bar, 1); }
-  __syncthreads();
-  const int t = s_ticket;
-  const int s = first_stream + t / L.n_strips, strip = t % L.n_strips;
-
-  const uint8_t* src; int stride;
-  if (level == 0) { src = l0_ptr[s]; stride = l0_stride[s]; }
-  else { src = L.img + (size_t)s * L.h * L.pitch; stride = L.pitch; }
-
-  const int W = L.w, H = L.h;
-  const int y0 = strip * VS_STRIP_ROWS, y1 = min(y0 + VS_STRIP_ROWS, H);
+  const int W = L.w, H = L.h, R = L.strip_rows;
+  const int y0 = strip * R, y1 = min(y0 + R, H);
   const int ya = max(y0 - 3, 0), yb = min(y1 + 3, H);
   const int words_per_row = (W + 31) >> 5;
   uint8_t* img = smem;                                                  // rows ya..yb-1, `stride` bytes apart
-  uint32_t* bitmask = (uint32_t*)(smem + (size_t)(VS_STRIP_ROWS + 6) * stride);   // [VS_STRIP_ROWS][words_per_row]
-  uint32_t* queue = bitmask + VS_STRIP_ROWS * words_per_row + warp * kQueue;
+  uint32_t* bitmask = (uint32_t*)(smem + (size_t)(R + 6) * stride);     // [R][words_per_row]
+  uint32_t* queue = bitmask + R * words_per_row + warp * kQueue;
 
   if (tid == 0) {
     const uint32_t bytes = (uint32_t)(yb - ya) * (uint32_t)stride;
-    mbar_expect_tx(&bar, bytes);
-    bulk_g2s(img, src + (size_t)ya * stride, bytes, &bar);
+    mbar_expect_tx(&sh.bar, bytes);
+    bulk_g2s(img, src + (size_t)ya * stride, bytes, &sh.bar);
   }
-  for (int i = tid; i < VS_STRIP_ROWS * words_per_row; i += kThreads) bitmask[i] = 0;
+  for (int i = tid; i < R * words_per_row; i += kThreads) bitmask[i] = 0;
+  if (tid < kWarps) sh.qcnt[tid] = 0;
   __syncthreads();
-  mbar_wait(&bar, 0);
+  mbar_wait(&sh.bar, 0);
 
   const uint32_t kcmp = (uint32_t)(127 - thr) * 0x01010101u;
-  const int n_chunks = (W + 127) >> 7;
   const int n_pairs = (y1 - y0 + 1) >> 1;
-  uint8_t* next_img = has_next ? Ln.img + (size_t)s * Ln.h * Ln.pitch : nullptr;
+  const int wq = W >> 2, n_slots = n_pairs * wq;      // a lane slot = 4 pixels x 2 rows; slots of the strip in raster order, 32 per work item
+  const uint32_t mq = magic_div((uint32_t)wq);
+  uint8_t* next_img = nullptr; int next_pitch = 0;
+  uint8_t* l1s = (uint8_t*)(bitmask + R * words_per_row + kWarps * kQueue);   // level 0 only: the strip's level-1 rows, W/2 bytes apart
+  if (kLevel0) { next_pitch = Lchild[0].pitch; next_img = Lchild[0].img + ((size_t)s * Lchild[0].h + (y0 >> 1)) * next_pitch; }   // level-1 row of y0
 
   int qn = 0;   // candidates waiting in this warp's queue (warp-uniform)
-  int pr = warp / n_chunks, ch = warp - pr * n_chunks;   // work item = (row pair, 128-pixel chunk); advanced incrementally below
-  for (int item = warp; item < n_pairs * n_chunks; item += kWarps, ch += kWarps) {
-    while (ch >= n_chunks) { ch -= n_chunks; pr++; }
+  for (int item = warp; item * 32 < n_slots; item += kWarps) {
+    const int slot = item * 32 + lane;
+    const int pr = (int)__umulhi((uint32_t)slot, mq);
     const int y = y0 + 2 * pr;           // rows y and y+1
-    const int x0 = (ch << 7) + (lane << 2);
-    const bool active = x0 < W;
+    const int x0 = (slot - pr * wq) << 2;
+    const bool active = slot < n_slots;
     uint32_t cand[2] = {0u, 0u};
     if (active) {
       const uint8_t* r0 = img + (size_t)(y - ya) * stride + x0;
       const uint32_t c0 = *(const uint32_t*)r0;
       const bool have1 = (y + 1) < y1;
       const uint32_t c1 = have1 ? *(const uint32_t*)(r0 + stride) : 0u;
-      if (has_next && have1) {   // half-sample: two output pixels per lane
+      if (kLevel0 && have1) {   // half-sample: two pixels of level 1 per lane
         const unsigned o0 = __dp4a(c0, 0x00000101u, __dp4a(c1, 0x00000101u, 2u)) >> 2;
         const unsigned o1 = __dp4a(c0, 0x01010000u, __dp4a(c1, 0x01010000u, 2u)) >> 2;
-        *(uint16_t*)(next_img + (size_t)(y >> 1) * Ln.pitch + (x0 >> 1)) = (uint16_t)(o0 | (o1 << 8));
+        const uint16_t o = (uint16_t)(o0 | (o1 << 8));
+        *(uint16_t*)(next_img + (uint32_t)(pr * next_pitch + (x0 >> 1))) = o;
+        *(uint16_t*)(l1s + pr * (W >> 1) + (x0 >> 1)) = o;
       }
       // x in [3, W-4] only (jni/vision/cvfast.cpp:6115-6119)
       uint32_t vmask = 0x80808080u;
@@ -144,7 +174,9 @@ k_pyramid_fast(LevelDesc L, LevelDesc Ln, int has_next, int level, const uint8_t
         const uint32_t c = k ? c1 : c0;
         const uint32_t up = *(const uint32_t*)(r - 3 * stride), dn = *(const uint32_t*)(r + 3 * stride);
         const uint32_t m1 = bytes_gt(__vabsdiffu4(up, c), kcmp) | bytes_gt(__vabsdiffu4(dn, c), kcmp);
-        const uint32_t lw = (x0 > 0) ? *(const uint32_t*)(r - 4) : 0u, rw = (x0 + 4 < W) ? *(const uint32_t*)(r + 4) : 0u;
+        // unconditional: at x0 == 0 / W-4 the neighbour word lies in the adjacent staged row (rows < 3 and >= H-3 are never
+        // tested, so it is inside the buffer) and only feeds the pixels x < 3 / x > W-4 that vmask clears
+        const uint32_t lw = *(const uint32_t*)(r - 4), rw = *(const uint32_t*)(r + 4);
         const uint32_t lf = __byte_perm(lw, c, 0x4321), rt = __byte_perm(c, rw, 0x6543);
         const uint32_t m2 = bytes_gt(__vabsdiffu4(lf, c), kcmp) | bytes_gt(__vabsdiffu4(rt, c), kcmp);
         cand[k] = m1 & m2 & vmask;
@@ -152,11 +184,19 @@ k_pyramid_fast(LevelDesc L, LevelDesc Ln, int has_next, int level, const uint8_t
     }
     // append the candidates of this work item to the warp's queue (order is irrelevant: corners land in a bitmask)
     const int mine = __popc(cand[0]) + __popc(cand[1]);
-    int incl = mine;
+    int pos;
+    if (kLevel0) {   // sparse candidates (about one lane in three has any): one shared-memory atomic per such lane beats the 5-step scan
+      pos = 0;
+      if (mine) pos = atomicAdd(&sh.qcnt[warp], mine);
+      __syncwarp();
+      qn = *(volatile int*)&sh.qcnt[warp];
+    } else {
+      int incl = mine;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
-    int pos = qn + incl - mine;
-    qn += __shfl_sync(0xffffffffu, incl, 31);
+      for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+      pos = qn + incl - mine;
+      qn += __shfl_sync(0xffffffffu, incl, 31);
+    }
 #pragma unroll
     for (int k = 0; k < 2; k++) {
       uint32_t m = cand[k];
@@ -168,7 +208,10 @@ k_pyramid_fast(LevelDesc L, LevelDesc Ln, int has_next, int level, const uint8_t
     }
     __syncwarp();
     // exact ring test on full groups of 32 queued candidates; the remainder waits for the next work item
-    while (qn >= 32) { qn -= 32; ring_test(queue[qn + lane], img, stride, thr, bitmask, words_per_row, ya - y0); }
+    if (qn >= 32) {
+      while (qn >= 32) { qn -= 32; ring_test(queue[qn + lane], img, stride, thr, bitmask, words_per_row, ya - y0); }
+      if (kLevel0 && lane == 0) sh.qcnt[warp] = qn;
+    }
     __syncwarp();
   }
   if (lane < qn) ring_test(queue[lane], img, stride, thr, bitmask, words_per_row, ya - y0);
@@ -181,13 +224,13 @@ k_pyramid_fast(LevelDesc L, LevelDesc Ln, int has_next, int level, const uint8_t
     for (int w = lane; w < words_per_row; w += 32) c += __popc(bitmask[r * words_per_row + w]);
 #pragma unroll
     for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
-    if (lane == 0) s_rowcnt[r] = c;
+    if (lane == 0) sh.rowcnt[r] = c;
   }
   __syncthreads();
   if (tid == 0) {
     int acc = 0;
-    for (int r = 0; r < rows; r++) { s_rowoff[r] = acc; acc += s_rowcnt[r]; }
-    s_rowoff[rows] = acc;
+    for (int r = 0; r < rows; r++) { sh.rowoff[r] = acc; acc += sh.rowcnt[r]; }
+    sh.rowoff[rows] = acc;
     // decoupled look-back over the strips of this image (predecessors hold lower tickets, hence are resident or done)
     unsigned long long* st = L.strip_state + (size_t)s * L.n_strips;
     unsigned long long excl = 0;
@@ -203,17 +246,19 @@ k_pyramid_fast(LevelDesc L, LevelDesc Ln, int has_next, int level, const uint8_t
       }
       atomicExch(&st[strip], kFlagInc | (unsigned)(excl + acc));
     }
-    s_base = (int)excl;
+    sh.base = (int)excl;
     if ((long long)excl + acc > L.cap) atomicExch(&status[0], 1);
   }
+  if (kLevel0 && warp > 0)   // levels 2 and 3 of this strip while thread 0 looks back
+    emit_levels_2_3(l1s, W >> 1, (y1 - y0) >> 1, Lchild[1], Lchild[2], s, y0, tid - 32, kThreads - 32);
   __syncthreads();
-  const int base = s_base;
+  const int base = sh.base;
   int* lut = L.lut + (size_t)s * (H + 1);
-  if (tid < rows) lut[y0 + tid] = base + s_rowoff[tid];
-  if (tid == 0 && y1 == H) lut[H] = base + s_rowoff[rows];
+  if (tid < rows) lut[y0 + tid] = base + sh.rowoff[tid];
+  if (tid == 0 && y1 == H) lut[H] = base + sh.rowoff[rows];
   uint32_t* out = L.corners + (size_t)s * L.cap;
   for (int r = warp; r < rows; r += kWarps) {
-    int run = base + s_rowoff[r];
+    int run = base + sh.rowoff[r];
     const uint32_t yy = (uint32_t)(y0 + r) << 16;
     for (int w0 = 0; w0 < words_per_row; w0 += 32) {
       const int w = w0 + lane;
@@ -233,6 +278,36 @@ k_pyramid_fast(LevelDesc L, LevelDesc Ln, int has_next, int level, const uint8_t
   }
 }
 
+// Level 0 of every stream: pyramid levels 1..3 + FAST-10 of level 0.
+__global__ void __launch_bounds__(kThreads)   // 40 registers / 6 CTAs per SM measured faster than 32 / 8
+k_pyramid_fast(LevelDesc L, LevelDesc L1, LevelDesc L2, LevelDesc L3, const uint8_t* const* __restrict__ l0_ptr, const int* __restrict__ l0_stride,
+               int first_stream, int thr, unsigned* __restrict__ ticket, int* __restrict__ status) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ StripShared sh;
+  __shared__ LevelDesc child[3];
+  if (threadIdx.x == 0) { sh.ticket = (int)atomicAdd(ticket, 1u); mbar_init(&sh.bar, 1); child[0] = L1; child[1] = L2; child[2] = L3; }
+  __syncthreads();
+  const int t = sh.ticket;
+  const int s = first_stream + t / L.n_strips, strip = t % L.n_strips;
+  fast_strip<true>(L, l0_ptr[s], l0_stride[s], s, strip, thr, child, status, sh, smem);
+}
+
+// FAST-10 of levels 1..3 of every stream in one launch: tickets run over level 1's strips, then level 2's, then level 3's.
+__global__ void __launch_bounds__(kThreads, 8)
+k_fast_levels(LevelDesc L1, LevelDesc L2, LevelDesc L3, int first_stream, int count, int thr1, int thr2, int thr3, unsigned* __restrict__ ticket,
+              int* __restrict__ status) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ StripShared sh;
+  if (threadIdx.x == 0) { sh.ticket = (int)atomicAdd(ticket, 1u); mbar_init(&sh.bar, 1); }
+  __syncthreads();
+  int t = sh.ticket, thr = thr1;
+  const int n1 = count * L1.n_strips, n2 = count * L2.n_strips;
+  LevelDesc L = L1;
+  if (t >= n1) { t -= n1; L = L2; thr = thr2; if (t >= n2) { t -= n2; L = L3; thr = thr3; } }
+  const int s = first_stream + t / L.n_strips, strip = t % L.n_strips;
+  fast_strip<false>(L, L.img + (size_t)s * L.h * L.pitch, L.pitch, s, strip, thr, nullptr, status, sh, smem);
+}
+
 // plain 2:1 half-sample for the (rare) source-keyframe uploads
 __global__ void k_half_sample(const uint8_t* __restrict__ src, int sw, int sh, int spitch, uint8_t* __restrict__ dst, int dpitch) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
@@ -241,38 +316,68 @@ __global__ void k_half_sample(const uint8_t* __restrict__ src, int sw, int sh, i
   dst[(size_t)y * dpitch + x] = (uint8_t)((a[0] + a[1] + a[spitch] + a[spitch + 1] + 2) >> 2);
 }
 
-size_t pyrfast_smem_bytes(int stride, int w) {
+size_t pyrfast_smem_bytes(int stride, int w, int rows, bool level0) {
   const int words_per_row = (w + 31) >> 5;
-  return (size_t)(VS_STRIP_ROWS + 6) * stride + (size_t)VS_STRIP_ROWS * words_per_row * 4 + (size_t)kWarps * kQueue * 4;
+  return (size_t)(rows + 6) * stride + (size_t)rows * words_per_row * 4 + (size_t)kWarps * kQueue * 4 + (level0 ? (size_t)(rows / 2) * (w / 2) : 0);
 }
 
 }  // namespace
 
+// Rows per CTA for level l.  16 everywhere: at level 0 the level-1..3 rows a CTA emits stay whole (16 -> 8, 4, 2), and at
+// the small levels taller strips (32 / 64 rows) measured slower on B200 (fewer CTAs to balance, longer look-back chain).
+int vs_strip_rows(int level, int w, int pitch) {
+  (void)level; (void)w; (void)pitch;
+  return 16;
+}
+
 // FAST thresholds per level (jni/KeyFrame.cc:32-39)
 static const int kFastThr[VS_LEVELS] = {10, 15, 15, 10};
 
-int vs_launch_pyramid_fast(vslam_ctx* ctx, int first_stream, int count) {
+// Level 0: pyramid levels 1..3 + FAST-10 of level 0 (one launch).
+int vs_launch_pyramid_l0(vslam_ctx* ctx, int first_stream, int count) {
   VS_CUDA(cudaMemsetAsync(ctx->tickets, 0, sizeof(unsigned) * VS_LEVELS, ctx->stream));
   for (int l = 0; l < VS_LEVELS; l++) {
     LevelDesc& L = ctx->lev[l];
     VS_CUDA(cudaMemsetAsync(L.strip_state + (size_t)first_stream * L.n_strips, 0, sizeof(unsigned long long) * (size_t)count * L.n_strips, ctx->stream));
   }
-  for (int l = 0; l < VS_LEVELS; l++) {
-    LevelDesc& L = ctx->lev[l];
-    int stride = L.pitch;
-    if (l == 0) { stride = 0; for (int s = first_stream; s < first_stream + count; s++) stride = ctx->l0_stride_host[s] > stride ? ctx->l0_stride_host[s] : stride; }
-    const size_t smem = pyrfast_smem_bytes(stride, L.w);
-    if (smem > 227 * 1024) { ctx->err = "pyramid_fast: strip does not fit in shared memory (row stride too large)"; return VSLAM_E_INVALID; }
-    VS_CUDA(cudaFuncSetAttribute(k_pyramid_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const bool has_next = l + 1 < VS_LEVELS;
-    vs_time_begin(ctx, VS_ST_PYR0 + l);
-    k_pyramid_fast<<<count * L.n_strips, kThreads, smem, ctx->stream>>>(L, has_next ? ctx->lev[l + 1] : L, has_next ? 1 : 0, l, ctx->l0_ptr, ctx->l0_stride,
-                                                                       first_stream, kFastThr[l], ctx->tickets + l, ctx->status);
-    vs_time_end(ctx);
-    VS_CUDA(cudaGetLastError());
-    ctx->launches++;
-  }
+  LevelDesc& L = ctx->lev[0];
+  int stride = 0;
+  for (int s = first_stream; s < first_stream + count; s++) stride = ctx->l0_stride_host[s] > stride ? ctx->l0_stride_host[s] : stride;
+  const size_t smem = pyrfast_smem_bytes(stride, L.w, L.strip_rows, true);
+  if (smem > 227 * 1024) { ctx->err = "pyramid_fast: strip does not fit in shared memory (row stride too large)"; return VSLAM_E_INVALID; }
+  VS_CUDA(cudaFuncSetAttribute(k_pyramid_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  vs_time_begin(ctx, VS_ST_PYR0);
+  k_pyramid_fast<<<count * L.n_strips, kThreads, smem, ctx->stream>>>(L, ctx->lev[1], ctx->lev[2], ctx->lev[3], ctx->l0_ptr, ctx->l0_stride, first_stream, kFastThr[0],
+                                                                     ctx->tickets, ctx->status);
+  vs_time_end(ctx);
+  VS_CUDA(cudaGetLastError());
+  ctx->launches++;
   return VSLAM_OK;
+}
+
+// Levels 1..3: FAST-10 (one launch).  Needs the level images written by vs_launch_pyramid_l0.
+int vs_launch_fast_levels(vslam_ctx* ctx, int first_stream, int count) {
+  size_t smem = 0; int blocks = 0;
+  for (int l = 1; l < VS_LEVELS; l++) {
+    const LevelDesc& L = ctx->lev[l];
+    const size_t b = pyrfast_smem_bytes(L.pitch, L.w, L.strip_rows, false);
+    smem = b > smem ? b : smem;
+    blocks += count * L.n_strips;
+  }
+  if (smem > 227 * 1024) { ctx->err = "fast_levels: strip does not fit in shared memory"; return VSLAM_E_INVALID; }
+  VS_CUDA(cudaFuncSetAttribute(k_fast_levels, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  vs_time_begin(ctx, VS_ST_PYR1);
+  k_fast_levels<<<blocks, kThreads, smem, ctx->stream>>>(ctx->lev[1], ctx->lev[2], ctx->lev[3], first_stream, count, kFastThr[1], kFastThr[2], kFastThr[3],
+                                                        ctx->tickets + 1, ctx->status);
+  vs_time_end(ctx);
+  VS_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return VSLAM_OK;
+}
+
+int vs_launch_pyramid_fast(vslam_ctx* ctx, int first_stream, int count) {
+  const int rc = vs_launch_pyramid_l0(ctx, first_stream, count);
+  return rc ? rc : vs_launch_fast_levels(ctx, first_stream, count);
 }
 
 int vs_launch_source_pyramid(vslam_ctx* ctx, int kf) {

@@ -144,20 +144,36 @@ __global__ void __launch_bounds__(kPT) k_project_lists(Dev D, int mode, int appl
   const int total = s_off[4];
   // random draws for the four level shuffles, in level order 0..3 (jni/Tracker.cc:396-397)
   int ring_f = 0, ring_b = 0;
+  int n_draws = 0;
+#pragma unroll
+  for (int l = 0; l < VS_LEVELS; l++) n_draws += max(s_run[l] - 1, 0);
   if (tid == 0) {
-    int ring[31]; for (int k = 0; k < 31; k++) ring[k] = st->rng_ring[k];
+    glibc_rand_fill(st->rng_ring, st->rng_f, st->rng_b, rnd, n_draws);
     ring_f = st->rng_f; ring_b = st->rng_b;
-    int pos = 0;
-    for (int l = 0; l < VS_LEVELS; l++) for (int k = 1; k < s_run[l]; k++) rnd[pos++] = glibc_rand_next(ring, ring_f, ring_b);
-    for (int k = 0; k < 31; k++) st->rng_ring[k] = ring[k];
-    st->rng_f = ring_f; st->rng_b = ring_b;
   }
   __syncthreads();
-  if (lane == 0 && warp < VS_LEVELS) {   // std::random_shuffle of level `warp` (libstdc++ bits/stl_algo.h:4581-4597)
+  // draw -> swap partner of std::random_shuffle (libstdc++ bits/stl_algo.h:4581-4597: i-th element swaps with rand() % (i+1)), all threads
+  for (int d = tid; d < n_draws; d += kPT) {
+    int k = d;
+#pragma unroll
+    for (int l = 0; l < VS_LEVELS - 1; l++) { const int m = max(s_run[l] - 1, 0); if (k >= 0 && k >= m) k -= m; else break; }
+    rnd[d] = rnd[d] % (k + 2);
+  }
+  __syncthreads();
+  if (lane == 0 && warp < VS_LEVELS) {   // the swaps of level `warp`, in order
     const int l = warp, n = s_run[l];
     int roff = 0; for (int k = 0; k < l; k++) roff += max(s_run[k] - 1, 0);
     int* v = list + s_off[3 - l];
-    for (int k = 1; k < n; k++) { const int j = rnd[roff + k - 1] % (k + 1); if (k != j) { const int t = v[k]; v[k] = v[j]; v[j] = t; } }
+    const int* jv = rnd + roff - 1;
+    if (n > 1) {
+      int jn = jv[1], vkn = v[1];
+      for (int k = 1; k < n; k++) {
+        const int j = jn, vk = vkn;
+        if (k + 1 < n) { jn = jv[k + 1]; vkn = v[k + 1]; }   // v[k+1] is untouched until step k+1
+        const int vj = v[j];
+        v[k] = vj; v[j] = vk;
+      }
+    }
   }
   __syncthreads();
   if (tid == 0) {   // coarse / fine selection (jni/Tracker.cc:399-527)
@@ -1007,9 +1023,8 @@ int vs_launch_calc_jacobians(vslam_ctx* ctx) {
 }
 
 // Tracker::TrackMap for all streams: 6 launches, no host synchronisation in between.
-int vs_launch_track_map(vslam_ctx* ctx, int with_motion_model) {
+int vs_launch_track_map_rest(vslam_ctx* ctx, int with_motion_model) {
   int rc;
-  if ((rc = vs_launch_project_all(ctx, 1 | (with_motion_model ? 2 : 0)))) return rc;
   if ((rc = vs_launch_search(ctx, 1, 0, 0))) return rc;
   if ((rc = vs_launch_pose(ctx, 1, 0.0, 0, 0))) return rc;
   vs_time_begin(ctx, VS_ST_OTHER);
@@ -1020,6 +1035,34 @@ int vs_launch_track_map(vslam_ctx* ctx, int with_motion_model) {
   if ((rc = vs_launch_search(ctx, 2, 0, 0))) return rc;
   if ((rc = vs_launch_pose(ctx, 2 | (with_motion_model ? 4 : 0), 0.0, 0, 0))) return rc;
   return VSLAM_OK;
+}
+int vs_launch_track_map(vslam_ctx* ctx, int with_motion_model) {
+  const int rc = vs_launch_project_all(ctx, 1 | (with_motion_model ? 2 : 0));
+  return rc ? rc : vs_launch_track_map_rest(ctx, with_motion_model);
+}
+
+// Tracker::TrackFrame for all streams (jni/Tracker.cc:68-160, map-good branch).  The level images exist once the level-0
+// launch is done, so SmallBlurryImage + motion model + projection (side stream; small grids, latency-bound) run beside
+// the FAST pass of levels 1..3 (main stream) and join before the first patch search, which needs the corner lists.
+// With per-stage timing on, the two branches are serialised so that every stage is timed alone.
+int vs_launch_frame(vslam_ctx* ctx) {
+  int rc;
+  if ((rc = vs_launch_pyramid_l0(ctx, 0, ctx->S))) return rc;
+  const bool fork = !ctx->timing;
+  cudaStream_t main_stream = ctx->stream;
+  if (fork) {
+    VS_CUDA(cudaEventRecord(ctx->ev_fork, main_stream));
+    VS_CUDA(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+    ctx->stream = ctx->side_stream;
+  }
+  rc = vs_launch_sbi(ctx);
+  if (!rc) rc = vs_launch_project_all(ctx, 3);
+  ctx->stream = main_stream;
+  if (fork) VS_CUDA(cudaEventRecord(ctx->ev_join, ctx->side_stream));
+  if (rc) return rc;
+  if ((rc = vs_launch_fast_levels(ctx, 0, ctx->S))) return rc;
+  if (fork) VS_CUDA(cudaStreamWaitEvent(main_stream, ctx->ev_join, 0));
+  return vs_launch_track_map_rest(ctx, 1);
 }
 
 // Test hook: atan_cr over a device-side copy of x (used to compare against the host libm).

@@ -10,7 +10,7 @@
 #define VS_LEVELS VSLAM_LEVELS
 #define VS_MAXP VSLAM_MAX_PATCH
 #define VS_TMPL_BYTES 128           // P*P <= 121 bytes, padded
-#define VS_STRIP_ROWS 16            // rows of a level handled by one CTA of the pyramid+FAST kernel
+#define VS_MAX_STRIP_ROWS 64        // upper bound of LevelDesc::strip_rows
 #define VS_MAX_UPDATES 20           // 10 coarse + 10 fine CalcPoseUpdate calls per TrackMap
 
 // ------------------------------------------------------------------------------------------------
@@ -18,7 +18,8 @@
 struct LevelDesc {
   int w, h, pitch;            // pitch: bytes between rows of the ctx-owned level image (multiple of 128)
   int cap;                    // corner capacity per stream
-  int n_strips;               // ceil(h / VS_STRIP_ROWS)
+  int strip_rows;             // rows of this level handled by one CTA of the pyramid / FAST kernels (vs_strip_rows)
+  int n_strips;               // ceil(h / strip_rows)
   uint8_t* img;               // [S][h][pitch]      (level 0: only used by the host-input path, see l0_ptr)
   uint32_t* corners;          // [S][cap]           packed (y << 16 | x), raster order
   int* lut;                   // [S][h + 1]         lut[y] = #corners with row < y ; lut[h] = total
@@ -88,6 +89,7 @@ struct vslam_ctx {
   const uint8_t** l0_ptr_host; int* l0_stride_host;
   // double-buffered host-input pipeline (vslam_track_frame_async): level-0 buffer 0 is lev[0].img, buffer 1 is l0_alt
   uint8_t* l0_alt; cudaStream_t copy_stream; cudaEvent_t ev_copied[2], ev_computed[2], ev_done[2]; long long step; bool pipe_ready; int* status_pin;   // [2][4] pinned copy of `status` per slot
+  cudaStream_t side_stream; cudaEvent_t ev_fork, ev_join;   // SmallBlurryImage + projection run beside the FAST pass of levels 1..3
   unsigned* tickets;             // [VS_LEVELS] device
   int* status;                   // [4] device: [0] capacity overflow flag
   CamDev cam; CamDev* cam_dev;
@@ -133,12 +135,17 @@ inline void vs_time_begin(vslam_ctx* ctx, int stage) {
 inline void vs_time_end(vslam_ctx* ctx) { if (ctx->timing) cudaEventRecord(ctx->ev_pool[ctx->ev_used++], ctx->stream); }
 
 // kernels/launchers implemented in the .cu files
-int vs_launch_pyramid_fast(vslam_ctx* ctx, int first_stream, int count);
+int vs_strip_rows(int level, int w, int pitch);
+int vs_launch_pyramid_fast(vslam_ctx* ctx, int first_stream, int count);   // = vs_launch_pyramid_l0 + vs_launch_fast_levels
+int vs_launch_pyramid_l0(vslam_ctx* ctx, int first_stream, int count);
+int vs_launch_fast_levels(vslam_ctx* ctx, int first_stream, int count);
 int vs_launch_source_pyramid(vslam_ctx* ctx, int kf_id);
 int vs_launch_project_all(vslam_ctx* ctx, int build_lists);
 int vs_launch_search(vslam_ctx* ctx, int which /*0 explicit list,1 coarse A,2 fine B*/, int range, int subpix);
 int vs_launch_pose(vslam_ctx* ctx, int mode, double sigma, int mark, int apply);
 int vs_launch_track_map(vslam_ctx* ctx, int with_motion_model);
+int vs_launch_track_map_rest(vslam_ctx* ctx, int with_motion_model);   // everything after vs_launch_project_all
+int vs_launch_frame(vslam_ctx* ctx);                                   // pyramid + FAST, SmallBlurryImage, TrackMap of all streams
 int vs_launch_project_and_derivs(vslam_ctx* ctx, int only_found);
 int vs_launch_calc_jacobians(vslam_ctx* ctx);
 int vs_launch_sbi(vslam_ctx* ctx);
