@@ -316,15 +316,19 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
-    launches0 = ctx.kernel_launches()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for k in range(K):
-        ctx.track_frame_ptr(frames_dev[tri(step_no)].data_ptr(), W, fs, device=True); step_no += 1
-    e1.record(stream)
-    barrier()
-    launches = ctx.kernel_launches() - launches0
-    dev_ms = max_over_ranks(e0.elapsed_time(e1))
+    def value_leg(first_step):
+        step = first_step
+        launches0 = ctx.kernel_launches()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for k in range(K):
+            ctx.track_frame_ptr(frames_dev[tri(step)].data_ptr(), W, fs, device=True); step += 1
+        e1.record(stream)
+        barrier()
+        return step, ctx.kernel_launches() - launches0, max_over_ranks(e0.elapsed_time(e1))
+
+    step_no, launches, dev_ms = value_leg(step_no)
+    remeasured = None
     # per-stage pass (not part of `value`): CUDA events around every launch; the library serialises the side-stream branch
     # (SmallBlurryImage + projection) behind the level-0 launch in this mode, so every stage is timed alone
     Ks = min(K, 25)
@@ -336,6 +340,11 @@ def main():
     evals1 = ctx.zmssd_evals()
     stage = ctx.stage_times()
     ctx.set_timing(False)
+    # a timed region several times longer than the sum of its own kernels means the box stalled (seen once on a cold box: 40 s inside
+    # a 2-step region); such a run is re-measured once, and the line says so
+    if max_over_ranks(1.0 if dev_ms / K > 3.0 * sum(v[0] for v in stage.values()) / Ks else 0.0) > 0:   # same decision on every rank
+        remeasured = dev_ms / K
+        step_no, launches, dev_ms = value_leg(step_no)
     ctx.sync()     # raises on corner-capacity overflow
     probe = list(range(0, S, max(1, S // 8)))
     corners_per_step = sum(int(ctx.corners(s, l).shape[0]) for l in range(4) for s in probe) * (S / len(probe))
@@ -413,7 +422,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": dev_ms / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32 (pyramid, FAST, ZMSSD) + f64 (projection, WLS)", "data": "synthetic", "config": config,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": S * H * W, "d2h_bytes_per_step": S * 12 * 8, "ms_per_step": e2e_ms / K},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "zmssd_roofline": zmssd, "stages_ms_per_step": stages_ms,
+            "gpu_launches": int(launches), "clocks": clocks, **({"remeasured_after_stall_ms_per_step": remeasured} if remeasured else {}), "roofline": roofline, "zmssd_roofline": zmssd, "stages_ms_per_step": stages_ms,
             "tracking": {"found_per_frame_mean": float(found.mean()), "quality_good_frac": float((quality == 2).mean()),
                          "zmssd_evals_total": int(ctx.zmssd_evals())}}
 
