@@ -144,7 +144,7 @@ int vslam_create(const vslam_config* cfg, vslam_ctx** out) {
   // per (stream, point) state
   const size_t SN = (size_t)S * N;
   PointState& ps = ctx->ps;
-  CK(dalloc(&ps.v3cam, 3 * SN)); CK(dalloc(&ps.v2image, 2 * SN)); CK(dalloc(&ps.derivs, 4 * SN)); CK(dalloc(&ps.warpinv, 4 * SN));
+  CK(dalloc(&ps.v3cam, 3 * SN)); CK(dalloc(&ps.v2image, 2 * SN)); CK(dalloc(&ps.derivs, 4 * SN)); CK(dalloc(&ps.warpinv, 4 * SN)); CK(dalloc(&ps.m2, 4 * SN));
   CK(dalloc(&ps.lastwarp, 4 * SN)); CK(dalloc(&ps.v2found, 2 * SN)); CK(dalloc(&ps.coarse, 2 * SN)); CK(dalloc(&ps.jac, 12 * SN));
   CK(dalloc(&ps.err, 2 * SN)); CK(dalloc(&ps.sqrtinv, SN)); CK(dalloc(&ps.flags, SN)); CK(dalloc(&ps.level, SN));
   CK(dalloc(&ps.tmpl, SN * VS_TMPL_BYTES)); CK(dalloc(&ps.tsum, 2 * SN)); CK(dalloc(&ps.counts, 2 * SN));
@@ -181,7 +181,7 @@ void vslam_destroy(vslam_ctx* ctx) {
   cudaFree(ctx->l0_ptr); cudaFree(ctx->l0_stride); cudaFree(ctx->tickets); cudaFree(ctx->status); cudaFree(ctx->evals);
   cudaFree(ctx->map.world); cudaFree(ctx->map.right); cudaFree(ctx->map.down); cudaFree(ctx->map.ircenter); cudaFree(ctx->map.srclevel); cudaFree(ctx->map.srckf);
   PointState& ps = ctx->ps;
-  cudaFree(ps.v3cam); cudaFree(ps.v2image); cudaFree(ps.derivs); cudaFree(ps.warpinv); cudaFree(ps.lastwarp); cudaFree(ps.v2found); cudaFree(ps.coarse);
+  cudaFree(ps.v3cam); cudaFree(ps.v2image); cudaFree(ps.derivs); cudaFree(ps.warpinv); cudaFree(ps.m2); cudaFree(ps.lastwarp); cudaFree(ps.v2found); cudaFree(ps.coarse);
   cudaFree(ps.jac); cudaFree(ps.err); cudaFree(ps.sqrtinv); cudaFree(ps.flags); cudaFree(ps.level); cudaFree(ps.tmpl); cudaFree(ps.tsum); cudaFree(ps.counts);
   cudaFree(ctx->ss); cudaFree(ctx->lists); cudaFree(ctx->pvs); cudaFree(ctx->sort_scratch);
   if (ctx->scratch_host) cudaFreeHost(ctx->scratch_host);
@@ -590,7 +590,9 @@ int vslam_get_point_template(vslam_ctx* ctx, int s, int i, uint8_t* tmpl, int* s
   if (i < 0 || i >= ctx->map.n) return VSLAM_E_INVALID;
   VS_CUDA(cudaStreamSynchronize(ctx->stream));
   const size_t gi = (size_t)s * ctx->N + i, SN = (size_t)ctx->S * ctx->N;
-  VS_CUDA(cudaMemcpy(tmpl, ctx->ps.tmpl + gi * VS_TMPL_BYTES, ctx->P * ctx->P, cudaMemcpyDeviceToHost));
+  uint8_t rows[VS_TMPL_BYTES];   // device layout: one row per 12 bytes
+  VS_CUDA(cudaMemcpy(rows, ctx->ps.tmpl + gi * VS_TMPL_BYTES, VS_TMPL_BYTES, cudaMemcpyDeviceToHost));
+  for (int r = 0; r < ctx->P; r++) memcpy(tmpl + r * ctx->P, rows + 12 * r, ctx->P);
   VS_CUDA(cudaMemcpy(sum, ctx->ps.tsum + gi, sizeof(int), cudaMemcpyDeviceToHost));
   VS_CUDA(cudaMemcpy(sumsq, ctx->ps.tsum + SN + gi, sizeof(int), cudaMemcpyDeviceToHost));
   return VSLAM_OK;
@@ -619,6 +621,17 @@ int vslam_set_point_projection(vslam_ctx* ctx, int s, const double* v2image, con
   for (int c = 0; c < 2; c++) { for (int i = 0; i < n; i++) col[i] = v2image[2 * i + c]; VS_CUDA(cudaMemcpy(ctx->ps.v2image + c * SN + o, col.data(), sizeof(double) * n, cudaMemcpyHostToDevice)); }
   for (int c = 0; c < 4; c++) { for (int i = 0; i < n; i++) col[i] = warp[4 * i + c]; VS_CUDA(cudaMemcpy(ctx->ps.warpinv + c * SN + o, col.data(), sizeof(double) * n, cudaMemcpyHostToDevice)); }
   VS_CUDA(cudaMemcpy(ctx->ps.level + o, level, sizeof(int) * n, cudaMemcpyHostToDevice));
+  // m2 = inverse(warp) * 2^level, the same IEEE operations as calc_level_warp (track.cu)
+  for (int c = 0; c < 4; c++) {
+    for (int i = 0; i < n; i++) {
+      const double w00 = warp[4 * i], w01 = warp[4 * i + 1], w10 = warp[4 * i + 2], w11 = warp[4 * i + 3];
+      const double invdet = 1.0 / (w00 * w11 - w01 * w10);
+      const int sc = level[i] >= 0 ? 1 << level[i] : 1;
+      const double a = c == 0 ? w11 : (c == 1 ? -w01 : (c == 2 ? -w10 : w00));
+      col[i] = (a * invdet) * sc;
+    }
+    VS_CUDA(cudaMemcpy(ctx->ps.m2 + c * SN + o, col.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
+  }
   return VSLAM_OK;
 }
 

@@ -68,6 +68,11 @@ __device__ inline int calc_level_warp(const Dev& D, const double* pose, int i, s
   int level = 0;
   while (det > 3 && level < VS_LEVELS - 1) { level++; det *= 0.25; }
   if (det > 3 || det < 0.25) { flags |= F_TBAD; return -1; }
+  // m2 = inverse(mm2WarpInverse) * LevelScale (jni/PatchFinder.cc:82-83, 2x2 adjugate inverse as frozen in the oracle), here
+  // instead of on a single lane of k_search
+  const double invdet = 1.0 / (w00 * w11 - w01 * w10);
+  const int sc = LevelScale(level);
+  D.ps.m2[gi] = (w11 * invdet) * sc; D.ps.m2[SN + gi] = (-w01 * invdet) * sc; D.ps.m2[2 * SN + gi] = (-w10 * invdet) * sc; D.ps.m2[3 * SN + gi] = (w00 * invdet) * sc;
   return level;
 }
 
@@ -224,8 +229,7 @@ constexpr int kCandCap = 96;           // ZMSSD candidates gathered per round of
 struct SearchSmem {
   double pos[VS_MAXP * VS_MAXP * 2];    // template sample positions / sub-pixel products
   double jx[81], jy[81], prod2[81];
-  uint32_t tw[VS_MAXP * 3];            // template rows as 3 zero-padded words
-  uint32_t tmpl_w[VS_TMPL_BYTES / 4];  // template bytes (row-major, P*P), word view for the coalesced load
+  uint32_t tmpl_w[VS_TMPL_BYTES / 4];  // template, one row = 3 zero-padded words (12 bytes): the dp4a operand layout
   uint32_t cand_cw[kCandCap]; int cand_idx[kCandCap]; int acc[kCandCap * 3];
 };
 
@@ -261,15 +265,13 @@ __global__ void __launch_bounds__(kSearchWarps * 32) k_search(Dev D, int mode, i
   // ---- MakeTemplateCoarseCont (jni/PatchFinder.cc:79-125)
   double m2[4]; int refresh = 0, inside = 0, tsum = 0, tsumsq = 0;
   // every per-point scalar this warp will need, loaded up front (uniform addresses: one transaction each) so the misses overlap
-  const double w0 = D.ps.warpinv[gi], w1 = D.ps.warpinv[SN + gi], w2 = D.ps.warpinv[2 * SN + gi], w3 = D.ps.warpinv[3 * SN + gi];
+  m2[0] = D.ps.m2[gi]; m2[1] = D.ps.m2[SN + gi]; m2[2] = D.ps.m2[2 * SN + gi]; m2[3] = D.ps.m2[3 * SN + gi];
   const double lw0 = D.ps.lastwarp[gi], lw1 = D.ps.lastwarp[SN + gi], lw2 = D.ps.lastwarp[2 * SN + gi], lw3 = D.ps.lastwarp[3 * SN + gi];
   const double v2i0 = D.ps.v2image[gi], v2i1 = D.ps.v2image[SN + gi];
   const int tsum_old = D.ps.tsum[gi], tsumsq_old = D.ps.tsum[SN + gi];
-  const uint32_t tmpl_old = ((const uint32_t*)(D.ps.tmpl + gi * VS_TMPL_BYTES))[lane];   // one coalesced 128-byte load
+  const uint32_t* tmpl_g = (const uint32_t*)(D.ps.tmpl + gi * VS_TMPL_BYTES);
+  const uint32_t tmpl_old = tmpl_g[lane], tmpl_old2 = lane < VS_TMPL_BYTES / 4 - 32 ? tmpl_g[32 + lane] : 0u;   // coalesced
   if (lane == 0) {
-    const double invdet = 1.0 / (w0 * w3 - w1 * w2);
-    const int sc = LevelScale(level);
-    m2[0] = (w3 * invdet) * sc; m2[1] = (-w1 * invdet) * sc; m2[2] = (-w2 * invdet) * sc; m2[3] = (w0 * invdet) * sc;
     refresh = !(flags & F_HAVELAST);
     for (int c = 0; !refresh && c < 2; c++) {
       const double d0 = m2[c] - (c ? lw1 : lw0), d1 = m2[2 + c] - (c ? lw3 : lw2);
@@ -303,6 +305,8 @@ __global__ void __launch_bounds__(kSearchWarps * 32) k_search(Dev D, int mode, i
     __syncwarp();
     const float x_bound = iw - 1, y_bound = ih - 1;
     int outside = 0;
+    sm.tmpl_w[lane] = 0u; if (lane < VS_TMPL_BYTES / 4 - 32) sm.tmpl_w[32 + lane] = 0u;   // row padding must be zero
+    __syncwarp();
     for (int k = lane; k < PP; k += 32) {
       double x = sm.pos[2 * k], y = sm.pos[2 * k + 1];
       uint8_t v = 0;
@@ -312,13 +316,14 @@ __global__ void __launch_bounds__(kSearchWarps * 32) k_search(Dev D, int mode, i
         const uint8_t* r0 = simg + (size_t)ly * sp + lx; const uint8_t* r1 = r0 + sp;
         v = (uint8_t)((1 - y) * ((1 - x) * r0[0] + x * r0[1]) + y * ((1 - x) * r1[0] + x * r1[1]));
       } else outside++;
-      tmpl[k] = v;
+      const int r = k / P;
+      tmpl[k + r * (12 - P)] = v;
     }
     outside = warp_sum(outside);
     __syncwarp();
     int ts = 0, tq = 0;
-    for (int k = lane; k < PP; k += 32) { const int b = tmpl[k]; ts += b; tq += b * b; }
-    if (lane * 4 < PP) ((uint32_t*)(D.ps.tmpl + gi * VS_TMPL_BYTES))[lane] = sm.tmpl_w[lane];   // bytes past P*P are never read
+    for (int k = lane; k < 3 * P; k += 32) { const uint32_t w = sm.tmpl_w[k]; ts += (int)__dp4a(w, 0x01010101u, 0u); tq += (int)__dp4a(w, w, 0u); }   // padding is zero
+    { uint32_t* g = (uint32_t*)(D.ps.tmpl + gi * VS_TMPL_BYTES); g[lane] = sm.tmpl_w[lane]; if (lane < VS_TMPL_BYTES / 4 - 32) g[32 + lane] = sm.tmpl_w[32 + lane]; }
     ts = warp_sum(ts); tq = warp_sum(tq);
     tsum = ts; tsumsq = tq;
     flags = outside ? (flags | F_TBAD) : (flags & ~F_TBAD);
@@ -328,7 +333,7 @@ __global__ void __launch_bounds__(kSearchWarps * 32) k_search(Dev D, int mode, i
       for (int c = 0; c < 4; c++) D.ps.lastwarp[c * SN + gi] = m2[c];
     }
   } else {
-    sm.tmpl_w[lane] = tmpl_old;
+    sm.tmpl_w[lane] = tmpl_old; if (lane < VS_TMPL_BYTES / 4 - 32) sm.tmpl_w[32 + lane] = tmpl_old2;
     tsum = tsum_old; tsumsq = tsumsq_old;
   }
   __syncwarp();
@@ -336,18 +341,6 @@ __global__ void __launch_bounds__(kSearchWarps * 32) k_search(Dev D, int mode, i
     if (lane == 0) D.ps.flags[gi] = flags & ~(F_INIMAGE | F_FOUND);
     return;
   }
-  // template rows as zero-padded words for dp4a
-  for (int k = lane; k < P * 3; k += 32) {
-    const int r = k / 3, w = k - 3 * r;
-    const int off = r * P + 4 * w, rem = P - 4 * w;              // bytes [off, off+4) of the packed template, `rem` of them inside row r
-    uint32_t v = 0;
-    if (rem > 0) {
-      v = __funnelshift_r(sm.tmpl_w[off >> 2], sm.tmpl_w[(off >> 2) + 1 < VS_TMPL_BYTES / 4 ? (off >> 2) + 1 : off >> 2], 8 * (off & 3));
-      if (rem < 4) v &= (1u << (8 * rem)) - 1u;
-    }
-    sm.tw[k] = v;
-  }
-  __syncwarp();
   if (lane == 0) atomicAdd(&st->attempted[level], 1);
 
   // ---- FindPatchCoarse (jni/PatchFinder.cc:170-235)
@@ -356,7 +349,8 @@ __global__ void __launch_bounds__(kSearchWarps * 32) k_search(Dev D, int mode, i
   if (level == 0) { img = D.l0_ptr[s]; pitch = D.l0_stride[s]; } else { img = L.img + (size_t)s * L.h * L.pitch; pitch = L.pitch; }
   const int maxSSD = PP * 500;
   const int nLevelScale = LevelScale(level);
-  const double ix = v2i0 / nLevelScale, iy = v2i1 / nLevelScale;
+  const double invScale = 1.0 / nLevelScale;                    // 2^-level: x / 2^l == x * 2^-l exactly
+  const double ix = v2i0 * invScale, iy = v2i1 * invScale;
   const unsigned nRange = ((unsigned)range + nLevelScale - 1) / nLevelScale;
   int nTop = iy - nRange;
   const int nBottomPlusOne = iy + nRange + 1;
@@ -386,11 +380,10 @@ __global__ void __launch_bounds__(kSearchWarps * 32) k_search(Dev D, int mode, i
           if (pass) { const double dx = ix - (double)cx, dy = iy - (double)cy; double d2 = 0; d2 += dx * dx; d2 += dy * dy; pass = !(d2 > nRange * nRange); }
         }
         const unsigned bal = __ballot_sync(0xffffffffu, pass);
-        if (pass) { const int slot = ncand + __popc(bal & ((1u << lane) - 1u)); sm.cand_cw[slot] = cw; sm.cand_idx[slot] = ci; }
+        if (pass) { const int slot = ncand + __popc(bal & ((1u << lane) - 1u)); sm.cand_cw[slot] = cw; sm.cand_idx[slot] = ci; sm.acc[3 * slot] = 0; sm.acc[3 * slot + 1] = 0; sm.acc[3 * slot + 2] = 0; }
         ncand += __popc(bal);
       }
       nevals += ncand;   // (every lane holds the same count; reduced once below)
-      for (int k = lane; k < ncand * 3; k += 32) sm.acc[k] = 0;
       __syncwarp();
       // ZMSSDAtPoint (jni/PatchFinder.cc:352-380): one work item = one template row of one candidate
       for (int item = lane; item < ncand * P; item += 32) {
@@ -406,9 +399,9 @@ __global__ void __launch_bounds__(kSearchWarps * 32) k_search(Dev D, int mode, i
         if (a + P > 12) w3 = __ldg(wp + 3);
         uint32_t n0 = __funnelshift_r(w0, w1, sh), n1 = __funnelshift_r(w1, w2, sh), n2 = __funnelshift_r(w2, w3, sh);
         if (nwords == 3) n2 &= lastmask; else if (nwords == 2) { n1 &= lastmask; n2 = 0; } else { n0 &= lastmask; n1 = 0; n2 = 0; }
-        unsigned sum = __dp4a(n0, 0x01010101u, 0u), sumsq = __dp4a(n0, n0, 0u), cross = __dp4a(n0, sm.tw[3 * r], 0u);
-        sum = __dp4a(n1, 0x01010101u, sum); sumsq = __dp4a(n1, n1, sumsq); cross = __dp4a(n1, sm.tw[3 * r + 1], cross);
-        sum = __dp4a(n2, 0x01010101u, sum); sumsq = __dp4a(n2, n2, sumsq); cross = __dp4a(n2, sm.tw[3 * r + 2], cross);
+        unsigned sum = __dp4a(n0, 0x01010101u, 0u), sumsq = __dp4a(n0, n0, 0u), cross = __dp4a(n0, sm.tmpl_w[3 * r], 0u);
+        sum = __dp4a(n1, 0x01010101u, sum); sumsq = __dp4a(n1, n1, sumsq); cross = __dp4a(n1, sm.tmpl_w[3 * r + 1], cross);
+        sum = __dp4a(n2, 0x01010101u, sum); sumsq = __dp4a(n2, n2, sumsq); cross = __dp4a(n2, sm.tmpl_w[3 * r + 2], cross);
         atomicAdd(&sm.acc[3 * c], (int)sum); atomicAdd(&sm.acc[3 * c + 1], (int)sumsq); atomicAdd(&sm.acc[3 * c + 2], (int)cross);
       }
       __syncwarp();
@@ -443,8 +436,8 @@ __global__ void __launch_bounds__(kSearchWarps * 32) k_search(Dev D, int mode, i
     const int Q = P - 2, QQ = Q * Q;
     for (int k = lane; k < QQ; k += 32) {
       const int x = k / Q + 1, y = k - (x - 1) * Q + 1;   // stored index (x-1)*Q + (y-1)
-      sm.jx[k] = 0.5 * (tmpl[y * P + x + 1] - tmpl[y * P + x - 1]);
-      sm.jy[k] = 0.5 * (tmpl[(y + 1) * P + x] - tmpl[(y - 1) * P + x]);
+      sm.jx[k] = 0.5 * (tmpl[y * 12 + x + 1] - tmpl[y * 12 + x - 1]);
+      sm.jy[k] = 0.5 * (tmpl[(y + 1) * 12 + x] - tmpl[(y - 1) * 12 + x]);
     }
     __syncwarp();
     // JtJ of (gx, gy, 1): sums of multiples of 0.25 below 2^53 are exact in any order, so a warp reduction is bit-exact
@@ -468,7 +461,7 @@ __global__ void __launch_bounds__(kSearchWarps * 32) k_search(Dev D, int mode, i
     ok = 0;
     // ---- IterateSubPixToConvergence / IterateSubPix (jni/PatchFinder.cc:272-350)
     for (int it = 0; it < subpix; it++) {
-      const double c0 = (sp0 + 0.5) / nLevelScale - 0.5, c1 = (sp1 + 0.5) / nLevelScale - 0.5;   // LevelNPos
+      const double c0 = (sp0 + 0.5) * invScale - 0.5, c1 = (sp1 + 0.5) * invScale - 0.5;   // LevelNPos
       const int xb = (c0 > 0.0 ? c0 + 0.5 : c0 - 0.5), yb = (c1 > 0.0 ? c1 + 0.5 : c1 - 0.5);
       const int bd = P / 2 + 1;
       if (!(xb >= bd && yb >= bd && xb < L.w - bd && yb < L.h - bd)) break;   // off the image: not converged
@@ -479,7 +472,7 @@ __global__ void __launch_bounds__(kSearchWarps * 32) k_search(Dev D, int mode, i
         const int y = k / Q + 1, x = k - (y - 1) * Q + 1;
         const uint8_t* tl = img + (size_t)((int)b1 + y) * pitch + ((int)b0 + x);
         const float fPixel = fTL * tl[0] + fTR * tl[1] + fBL * tl[pitch] + fBR * tl[pitch + 1];
-        const double dDiff = fPixel - tmpl[y * P + x] + meanDiff;
+        const double dDiff = fPixel - tmpl[y * 12 + x] + meanDiff;
         const int j = (x - 1) * Q + (y - 1);
         sm.pos[k] = dDiff * sm.jx[j]; sm.pos[QQ + k] = dDiff * sm.jy[j]; sm.prod2[k] = dDiff;
       }
@@ -504,7 +497,7 @@ __global__ void __launch_bounds__(kSearchWarps * 32) k_search(Dev D, int mode, i
   }
   if (lane == 0) {
     D.ps.coarse[gi] = coarse0; D.ps.coarse[SN + gi] = coarse1;
-    D.ps.sqrtinv[gi] = (1.0 / nLevelScale);
+    D.ps.sqrtinv[gi] = invScale;
     if (ok) { D.ps.v2found[gi] = found0; D.ps.v2found[SN + gi] = found1; atomicAdd(&st->found[level], 1); if (subpix <= 0) flags &= ~F_SUBPIX; }
     else flags &= ~F_FOUND;   // sub-pixel iteration did not converge (jni/Tracker.cc:660-666)
     D.ps.flags[gi] = flags;
@@ -586,18 +579,7 @@ struct PoseSmem {
 __device__ void calc_pose_update(const Dev& D, PoseSmem& sm, double* sortbuf, int sortcap, int* hist, double* part, const int* list, int n, int s, double overrideSigma, bool mark) {
   const size_t SN = (size_t)D.S * D.N;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // errors (:703-709); the squared errors only feed a sort, so their order in the buffer is irrelevant
-  // `list` holds found points only (built once per kernel by build_found_list)
-  for (int k = tid; k < n; k += kPT) {
-    const size_t gi = (size_t)s * D.N + list[k];
-    const double si = D.ps.sqrtinv[gi];
-    const double e0 = (D.ps.v2found[gi] - D.ps.v2image[gi]) * si, e1 = (D.ps.v2found[SN + gi] - D.ps.v2image[SN + gi]) * si;
-    D.ps.err[gi] = e0; D.ps.err[SN + gi] = e1;
-    double e2 = 0; e2 += e0 * e0; e2 += e1 * e1;
-    if (overrideSigma <= 0 && k < sortcap) sortbuf[k] = e2;
-  }
-  __syncthreads();
-  PT_MARK(4);
+  // the errors (:703-709) and the squared errors for the median were written by pose_points_pass
   const int nerr = n;
   if (nerr == 0) { if (tid < 6) sm.mu[tid] = 0.0; if (tid == 0) sm.sigma = 0.0; __syncthreads(); return; }
   if (overrideSigma > 0) { if (tid == 0) sm.sigma = overrideSigma; }
@@ -638,9 +620,11 @@ __device__ void calc_pose_update(const Dev& D, PoseSmem& sm, double* sortbuf, in
 #pragma unroll
       for (int r = 0; r < 6; r++) {
         const double Jw = w * J[r];
-        acc[21 + r] += m * Jw;
+        // fused multiply-add: the sums over points are a parallel reduction (order differs from the reference's serial loop
+        // anyway), so contracting here costs no parity and halves the FP64 instructions of the phase
+        acc[21 + r] = __fma_rn(m, Jw, acc[21 + r]);
 #pragma unroll
-        for (int c = r; c < 6; c++) acc[q++] += Jw * J[c];
+        for (int c = r; c < 6; c++) { acc[q] = __fma_rn(Jw, J[c], acc[q]); q++; }
       }
     }
   }
@@ -765,16 +749,65 @@ __device__ void calc_jacobians(const Dev& D, const int* list, int n, int s, bool
     }
   }
 }
-// TrackerData::LinearUpdate (jni/TrackerData.h:126-132)
-__device__ void linear_update(const Dev& D, const int* list, int n, int s, const double* v6) {   // `list`: found points only
+// One pass over the found points of a Gauss-Newton iteration, everything a point needs before the median in one go and in
+// registers (no barrier, no reload between the steps):
+//   action 1: TrackerData::ProjectAndDerivs (jni/TrackerData.h:91-103) with the current pose      (non-linear iterations > 0)
+//   action 2: TrackerData::LinearUpdate (jni/TrackerData.h:126-132) with the last update `v6`     (linear iterations)
+//   action 0: nothing (iteration 0: the projection of k_project_lists / k_reproject_fine stands)
+//   jacobian: TrackerData::CalcJacobian (jni/TrackerData.h:107-123)                               (non-linear iterations)
+//   then the error of jni/Tracker.cc:703-709 and its square (for the Tukey median, order irrelevant).
+__device__ void pose_points_pass(const Dev& D, const double* pose, const int* flist, int n, int s, int action, bool jacobian, const double* v6,
+                                 double* sortbuf, int sortcap, bool want_sort, int* quirk) {
   const size_t SN = (size_t)D.S * D.N;
   for (int k = threadIdx.x; k < n; k += kPT) {
-    const size_t gi = (size_t)s * D.N + list[k];
-    for (int r = 0; r < 2; r++) {
-      double sacc = D.ps.jac[(size_t)(6 * r) * SN + gi] * v6[0];
-      for (int c = 1; c < 6; c++) sacc += D.ps.jac[(size_t)(6 * r + c) * SN + gi] * v6[c];
-      D.ps.v2image[r * SN + gi] += sacc;
+    const int i = flist[k];
+    const size_t gi = (size_t)s * D.N + i;
+    const double si = D.ps.sqrtinv[gi], f0 = D.ps.v2found[gi], f1 = D.ps.v2found[SN + gi];
+    double im0, im1, c[3], dv[4];
+    bool have_cd = false;
+    if (action == 1) {
+      int flags = D.ps.flags[gi];
+      CamCache cc;
+      const bool projected = td_project(D, pose, i, gi, SN, cc, flags);
+      // (flist holds found points only; ProjectAndDerivs refreshes the derivatives `if(bFound)`)
+      if (projected) { cam_derivs(D.cam, cc, dv); for (int q = 0; q < 4; q++) D.ps.derivs[q * SN + gi] = dv[q]; }
+      else { atomicAdd(quirk, 1); for (int q = 0; q < 4; q++) dv[q] = D.ps.derivs[q * SN + gi]; }   // reference reads another point's cache here; we keep the old derivatives
+      D.ps.flags[gi] = flags;
+      c[0] = D.ps.v3cam[gi]; c[1] = D.ps.v3cam[SN + gi]; c[2] = D.ps.v3cam[2 * SN + gi];
+      im0 = D.ps.v2image[gi]; im1 = D.ps.v2image[SN + gi];
+      have_cd = true;
+    } else if (action == 2) {
+      im0 = D.ps.v2image[gi]; im1 = D.ps.v2image[SN + gi];
+      double a0 = D.ps.jac[gi] * v6[0], a1 = D.ps.jac[(size_t)6 * SN + gi] * v6[0];
+#pragma unroll
+      for (int q = 1; q < 6; q++) { a0 += D.ps.jac[(size_t)q * SN + gi] * v6[q]; a1 += D.ps.jac[(size_t)(6 + q) * SN + gi] * v6[q]; }
+      im0 += a0; im1 += a1;
+      D.ps.v2image[gi] = im0; D.ps.v2image[SN + gi] = im1;
+    } else {
+      im0 = D.ps.v2image[gi]; im1 = D.ps.v2image[SN + gi];
     }
+    if (jacobian) {
+      if (!have_cd) {
+        c[0] = D.ps.v3cam[gi]; c[1] = D.ps.v3cam[SN + gi]; c[2] = D.ps.v3cam[2 * SN + gi];
+        for (int q = 0; q < 4; q++) dv[q] = D.ps.derivs[q * SN + gi];
+      }
+      const double invz = 1.0 / c[2];
+      const double pos[4] = {c[0], c[1], c[2], 1.0};
+#pragma unroll
+      for (int m = 0; m < 6; m++) {
+        double v4[3] = {0, 0, 0};
+        if (m < 3) v4[m] = pos[3];
+        else { v4[(m + 1) % 3] = -pos[(m + 2) % 3]; v4[(m + 2) % 3] = pos[(m + 1) % 3]; }
+        const double c0 = (v4[0] - c[0] * v4[2] * invz) * invz, c1 = (v4[1] - c[1] * v4[2] * invz) * invz;
+        double a0 = dv[0] * c0; a0 += dv[1] * c1;
+        double a1 = dv[2] * c0; a1 += dv[3] * c1;
+        D.ps.jac[(size_t)m * SN + gi] = a0; D.ps.jac[(size_t)(6 + m) * SN + gi] = a1;
+      }
+    }
+    const double e0 = (f0 - im0) * si, e1 = (f1 - im1) * si;
+    D.ps.err[gi] = e0; D.ps.err[SN + gi] = e1;
+    double e2 = 0; e2 += e0 * e0; e2 += e1 * e1;
+    if (want_sort && k < sortcap) sortbuf[k] = e2;
   }
 }
 
@@ -841,6 +874,8 @@ __global__ void __launch_bounds__(kPT, 2) k_pose(Dev D, int mode, double sigma_a
   PT_MARK(0);
 
   if (mode == 0) {
+    pose_points_pass(D, sm.pose, flist, n, s, 0, false, sm.last, sortbuf, sortcap, sigma_arg <= 0, &st->quirk_stale_cache);
+    __syncthreads();
     calc_pose_update(D, sm, sortbuf, sortcap, hist, part, flist, n, s, sigma_arg, mark_arg != 0);
     if (tid == 0) {
       const int u = st->n_updates < VS_MAX_UPDATES ? st->n_updates : VS_MAX_UPDATES - 1;
@@ -860,13 +895,10 @@ __global__ void __launch_bounds__(kPT, 2) k_pose(Dev D, int mode, double sigma_a
   for (int iter = 0; iter < iters; iter++) {
     bool nonlinear = true;
     if (mode == 2) nonlinear = (iter == 0 || iter == 4 || iter == 9);
-    if (iter != 0) {
-      if (nonlinear) { reproject_found(D, sm.pose, flist, n, s, 1, &st->quirk_stale_cache); PT_MARK(1); }
-      else { linear_update(D, flist, n, s, sm.last); PT_MARK(2); }
-      __syncthreads();
-    }
-    if (nonlinear) { calc_jacobians(D, flist, n, s, true); __syncthreads(); PT_MARK(3); }
     const double ov = (iter > 5) ? (mode == 1 ? 1.0 : 16.0) : 0.0;
+    pose_points_pass(D, sm.pose, flist, n, s, iter == 0 ? 0 : (nonlinear ? 1 : 2), nonlinear, sm.last, sortbuf, sortcap, ov <= 0, &st->quirk_stale_cache);
+    __syncthreads();
+    PT_MARK(1);
     calc_pose_update(D, sm, sortbuf, sortcap, hist, part, flist, n, s, ov, mode == 2 && iter == 9);
     if (tid == 0) {
       double e[12], np[12]; se3_exp(sm.mu, e); se3_mul(e, sm.pose, np);

@@ -9,7 +9,7 @@
 
 #define VS_LEVELS VSLAM_LEVELS
 #define VS_MAXP VSLAM_MAX_PATCH
-#define VS_TMPL_BYTES 128           // P*P <= 121 bytes, padded
+#define VS_TMPL_BYTES 144           // template rows padded to 12 bytes (3 words, the dp4a operand layout): 11 * 12 = 132, rounded to 16
 #define VS_MAX_STRIP_ROWS 64        // upper bound of LevelDesc::strip_rows
 #define VS_MAX_UPDATES 20           // 10 coarse + 10 fine CalcPoseUpdate calls per TrackMap
 
@@ -34,6 +34,7 @@ struct PointState {
   double* v2image;    // [2][S*N]
   double* derivs;     // [4][S*N]  row-major 2x2
   double* warpinv;    // [4][S*N]
+  double* m2;         // [4][S*N]  inverse(warpinv) * 2^level (valid when level >= 0)
   double* lastwarp;   // [4][S*N]
   double* v2found;    // [2][S*N]
   double* coarse;     // [2][S*N]
