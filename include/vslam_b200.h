@@ -133,6 +133,10 @@ int vslam_set_motion(vslam_ctx* ctx, int stream, const double* velocity6, double
                      double scene_depth_sigma);
 int vslam_get_motion(vslam_ctx* ctx, int stream, double* velocity6, double* msd_scaled_velocity, double* scene_depth_mean,
                      double* scene_depth_sigma);
+/* Tracker::Reset (jni/Tracker.cc:45-60), the tracker's own state of one stream: quality GOOD, lost-frame and coarse flags cleared,
+ * velocity and scaled speed zero, scene depth 1 +- 1, counters zero.  The pose is left as it is (the reference's Reset does not
+ * touch mse3CamFromWorld); the map is replaced with vslam_set_map (MapMaker's part of the reset is out of scope). */
+int vslam_reset_stream(vslam_ctx* ctx, int stream);
 int vslam_set_sbi_rotation(vslam_ctx* ctx, int stream, const double* rot6);  /* Tracker::mv6SBIRot supplied by the caller (when the on-device SBI is off) */
 /* SmallBlurryImage on the device (jni/SmallBlurryImage.cc; Tracker::CalcSBIRotation jni/Tracker.cc:885-893): after this call every
  * vslam_track_frame* builds the 1/16-size blurred thumbnail of each stream, aligns it to the previous frame's (6 ESM iterations) and

@@ -8,13 +8,26 @@
 //   Tracker::TrackFrame(cv::Mat&, cv::Mat&, bool)         vslam_b200::Tracker::TrackFrame            (jni/Tracker.h:55)
 //   Tracker::GetCurrentPose()                             vslam_b200::Tracker::GetCurrentPose        (jni/Tracker.h:58)
 //   Tracker::GetMessageForUser()                          same text format                           (jni/Tracker.cc:113-125)
+//   Tracker::Reset()                                      vslam_reset_stream                         (jni/Tracker.cc:45-60)
+//   Tracker::TrackMap()                                   vslam_track_map                            (jni/Tracker.cc:358-626)
+//   Tracker::SearchForPoints(vTD, nRange, nSubPixIts)     vslam_set_lists + vslam_search_for_points  (jni/Tracker.cc:629-674)
+//   Tracker::CalcPoseUpdate(vTD, dOverrideSigma, bMark)   vslam_set_lists + vslam_calc_pose_update   (jni/Tracker.cc:683-774)
+//   Tracker::TrackForInitialMap / TrailTracking_Start /   vslam_make_keyframe_rest, vslam_minipatch_*, vslam_snapshot_keyframe
+//            TrailTracking_Advance                        (jni/Tracker.cc:203-346); InitFromStereo is MapMaker's: a hook
+//   KeyFrame::MakeKeyFrame_Rest()                         vslam_make_keyframe_rest                   (jni/KeyFrame.cc:53-95)
+//   MiniPatch::SampleFromImage / FindPatch                vslam_minipatch_sample / _find, one patch   (jni/MiniPatch.cc:6-83)
+//   PatchFinder (per-object, slow path)                   stage calls on a one-entry list            (jni/PatchFinder.h:45-121)
+// Map points are addressed by their index in the arrays given to SetMap (the reference passes MapPoint& / TrackerData*).
 // The colour image argument is accepted and ignored (it is only used for drawing / map-point colouring, off the hot path).
 #ifndef VSLAM_B200_SHELL_HPP
 #define VSLAM_B200_SHELL_HPP
 
+#include <algorithm>
+#include <list>
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include <Eigen/Dense>
@@ -30,10 +43,13 @@ namespace vslam_b200 {
 
 inline void check(vslam_ctx* c, int rc) { if (rc != VSLAM_OK) throw std::runtime_error(std::string("vslam_b200: ") + vslam_last_error(c)); }
 
+struct Candidate { Eigen::Vector2d irLevelPos; double dSTScore; };   // jni/KeyFrame.h:33-38
 struct Level {
   cv::Mat im;
-  std::vector<Eigen::Vector2d> vCorners;   // all FAST corners on this level, raster order
-  std::vector<int> vCornerRowLUT;          // row index into vCorners
+  std::vector<Eigen::Vector2d> vCorners;     // all FAST corners on this level, raster order
+  std::vector<int> vCornerRowLUT;            // row index into vCorners
+  std::vector<Eigen::Vector2d> vMaxCorners;  // maximal FAST corners (MakeKeyFrame_Rest)
+  std::vector<Candidate> vCandidates;        // Shi-Tomasi thresholded maximal corners (MakeKeyFrame_Rest)
 };
 
 // One camera stream of a context.  Several KeyFrame/Tracker objects may share one context (one per GPU).
@@ -43,10 +59,15 @@ class Context {
     vslam_config cfg; vslam_default_config(&cfg);
     cfg.width = width; cfg.height = height; cfg.n_streams = n_streams; cfg.max_points = max_points; cfg.patch_size = patch_size; cfg.device = device;
     if (vslam_create(&cfg, &c_) != VSLAM_OK) throw std::runtime_error(std::string("vslam_b200: ") + vslam_last_error(0));
+    n_streams_ = n_streams;
   }
   ~Context() { vslam_destroy(c_); }
   vslam_ctx* get() const { return c_; }
+  int Streams() const { return n_streams_; }
+  int MapSize() const { return n_points_; }
+  void SetMapSize(int n) { n_points_ = n; }
  private:
+  int n_points_ = 0, n_streams_ = 0;
   Context(const Context&); Context& operator=(const Context&);
   vslam_ctx* c_;
 };
@@ -77,33 +98,94 @@ struct KeyFrame {
       aLevels[l].vCornerRowLUT.assign(lut.begin(), lut.end());
     }
   }
+  // jni/KeyFrame.cc:53-95 — FAST score + non-max suppression + Shi-Tomasi candidates of the stream's current keyframe.
+  void MakeKeyFrame_Rest() {
+    vslam_ctx* c = ctx_.get();
+    check(c, vslam_make_keyframe_rest(c, stream_));
+    for (int l = 0; l < LEVELS; l++) {
+      int n = 0; check(c, vslam_get_max_corners(c, stream_, l, 0, 0, &n));
+      std::vector<int32_t> xy(2 * (size_t)n + 2); std::vector<double> sc((size_t)n + 1);
+      check(c, vslam_get_max_corners(c, stream_, l, &xy[0], n, &n));
+      aLevels[l].vMaxCorners.resize(n);
+      for (int i = 0; i < n; i++) aLevels[l].vMaxCorners[i] = Eigen::Vector2d(xy[2 * i], xy[2 * i + 1]);
+      int m = 0; check(c, vslam_get_candidates(c, stream_, l, &xy[0], &sc[0], n, &m));
+      aLevels[l].vCandidates.resize(m);
+      for (int i = 0; i < m; i++) { aLevels[l].vCandidates[i].irLevelPos = Eigen::Vector2d(xy[2 * i], xy[2 * i + 1]); aLevels[l].vCandidates[i].dSTScore = sc[i]; }
+    }
+  }
+  int stream() const { return stream_; }
+  Context& context() const { return ctx_; }
  private:
   Context& ctx_; int stream_;
+};
+
+// jni/MiniPatch.h:16-26.  The searched image is a device-resident level-0 image of the stream: which = 0 the current keyframe,
+// 1 its snapshot (vslam_snapshot_keyframe; Tracker::mPreviousFrameKF).  One patch per call: the slow path; the trail tracker
+// below batches all trails into one call.
+struct MiniPatch {
+  static int& mnHalfPatchSize() { static int v = 4; return v; }       // jni/MiniPatch.cc:86-88
+  static int& mnRange() { static int v = 10; return v; }
+  static int& mnMaxSSD() { static int v = 9999; return v; }
+  unsigned char im[81];
+  void SampleFromImage(const Eigen::Vector2d& irPos, KeyFrame& kf, int which = 0) {
+    const int32_t xy[2] = {(int32_t)irPos(0), (int32_t)irPos(1)};
+    check(kf.context().get(), vslam_minipatch_sample(kf.context().get(), kf.stream(), which, 1, xy, im));
+  }
+  bool FindPatch(Eigen::Vector2d& irPos, KeyFrame& kf, int nRange, int which = 0) {
+    double pos[2] = {irPos(0), irPos(1)}; int32_t found = 0;
+    check(kf.context().get(), vslam_minipatch_find(kf.context().get(), kf.stream(), which, 1, im, pos, &found, 0, nRange, mnMaxSSD()));
+    if (found) irPos = Eigen::Vector2d(pos[0], pos[1]);
+    return found != 0;
+  }
 };
 
 // Pose as the reference's mySE3 stores it: rotation matrix + translation (camera-from-world).
 struct SE3 { Eigen::Matrix3d R; Eigen::Vector3d t; };
 
+// Initial-map trail (jni/Tracker.h:37-41)
+struct Trail { MiniPatch mPatch; Eigen::Vector2d irCurrentPos, irInitialPos; };
+
 class Tracker {
  public:
   // cam13: see vslam_set_camera; the map is set once with SetMap (the reference reads Map::vpPoints directly).
-  Tracker(Context& ctx, int stream, const double* cam13) : ctx_(ctx), stream_(stream) { check(ctx_.get(), vslam_set_camera(ctx_.get(), cam13)); }
+  Tracker(Context& ctx, int stream, const double* cam13) : mCurrentKF(ctx, stream), ctx_(ctx), stream_(stream) {
+    check(ctx_.get(), vslam_set_camera(ctx_.get(), cam13)); Reset();
+  }
 
   void SetMap(int n, const double* world3, const double* right3, const double* down3, const int32_t* irCenter2, const int32_t* srcLevel, const int32_t* srcKF) {
-    check(ctx_.get(), vslam_set_map(ctx_.get(), n, world3, right3, down3, irCenter2, srcLevel, srcKF)); n_points_ = n;
+    check(ctx_.get(), vslam_set_map(ctx_.get(), n, world3, right3, down3, irCenter2, srcLevel, srcKF)); ctx_.SetMapSize(n); mbMapGood = n > 0;
   }
+  // SmallBlurryImage rotation estimate inside TrackFrame, as the reference always does (jni/Tracker.cc:87-97); cam13_small = the
+  // camera scalars for the thumbnail size (width/16 x height/16), see vslam_camera_from_params
+  void EnableSBI(const double* cam13_small) { check(ctx_.get(), vslam_enable_sbi(ctx_.get(), cam13_small)); }
   void SetSourceKeyFrame(int id, cv::Mat& gray) { check(ctx_.get(), vslam_upload_source_keyframe(ctx_.get(), id, gray.data, (int)gray.step)); }
 
-  // jni/Tracker.cc:76-146, good-map branch.  With several streams per context use vslam_track_frame directly (one call tracks all streams).
+  // jni/Tracker.cc:45-60 (the tracker's part; MapMaker::RequestReset is the caller's)
+  void Reset() {
+    check(ctx_.get(), vslam_reset_stream(ctx_.get(), stream_));
+    mbUserPressedSpacebar = false; mnInitialStage = TRAIL_TRACKING_NOT_STARTED; mlTrails.clear(); mnFrame = 0; mbMapGood = false;
+  }
+  // jni/Tracker.cc:349-353 (the reference's GUI handler sets the flag)
+  void PressSpacebar() { mbUserPressedSpacebar = true; }
+
+  // jni/Tracker.cc:76-146.  Good map: MakeKeyFrame_Lite, SmallBlurryImage, motion model, TrackMap, quality — one call, all on the
+  // device.  No map yet: MakeKeyFrame_Lite + TrackForInitialMap.  With several streams per context use vslam_track_frame
+  // directly (one call tracks all streams).
   void TrackFrame(cv::Mat& imFrame, cv::Mat& /*imageColor*/, bool /*bDraw*/) {
     vslam_ctx* c = ctx_.get();
+    msg_.str("");
+    mnFrame++;
+    if (!mbMapGood) {
+      check(c, vslam_make_keyframe_lite(c, stream_, 1, imFrame.data, (int)imFrame.step, 0));
+      TrackForInitialMap();
+      return;
+    }
     check(c, vslam_track_frame(c, imFrame.data, (int)imFrame.step, 0));
     int32_t att[LEVELS], fnd[LEVELS]; int q, lost, coarse;
     check(c, vslam_get_counters(c, stream_, att, fnd, &q, &lost, &coarse));
-    msg_.str("");
     msg_ << "Tracking Map, quality " << (q == 2 ? "good." : (q == 1 ? "poor." : "bad.")) << " Found:";
     for (int l = 0; l < LEVELS; l++) msg_ << " " << fnd[l] << "/" << att[l];
-    msg_ << " Map: " << n_points_ << "P";
+    msg_ << " Map: " << ctx_.MapSize() << "P";
   }
   SE3 GetCurrentPose() {
     double p[12]; check(ctx_.get(), vslam_get_pose(ctx_.get(), stream_, p));
@@ -117,8 +199,217 @@ class Tracker {
     check(ctx_.get(), vslam_set_pose(ctx_.get(), stream_, p));
   }
   std::string GetMessageForUser() { return msg_.str(); }
+
+  // ---- the reference's protected stage functions, usable one at a time on this stream (other streams' lists are left empty)
+  void TrackMap() { check(ctx_.get(), vslam_track_map(ctx_.get())); }
+  // vTD: indices of the map points to search (the reference passes vector<TrackerData*>); the points must have been projected
+  // (TrackMap / vslam_project_all).  Returns the number found.
+  int SearchForPoints(const std::vector<int>& vTD, int nRange, int nSubPixIts) {
+    vslam_ctx* c = ctx_.get();
+    SetList(vTD);
+    check(c, vslam_clear_counters(c));
+    check(c, vslam_search_for_points(c, nRange, nSubPixIts));
+    int32_t att[LEVELS], fnd[LEVELS]; int q, lost, coarse, n = 0;
+    check(c, vslam_get_counters(c, stream_, att, fnd, &q, &lost, &coarse));
+    for (int l = 0; l < LEVELS; l++) n += fnd[l];
+    return n;
+  }
+  // TrackerData::CalcJacobian for the found points of the list (jni/TrackerData.h:107-123)
+  void CalcJacobians(const std::vector<int>& vTD) { SetList(vTD); check(ctx_.get(), vslam_calc_jacobians(ctx_.get())); }
+  // Jacobians of the listed points must be current (CalcJacobians, or TrackMap's own iterations).
+  Eigen::VectorXd CalcPoseUpdate(const std::vector<int>& vTD, double dOverrideSigma = 0.0, bool bMarkOutliers = false) {
+    vslam_ctx* c = ctx_.get();
+    SetList(vTD);
+    std::vector<double> upd(6 * (size_t)ctx_.Streams());
+    check(c, vslam_calc_pose_update(c, dOverrideSigma, bMarkOutliers ? 1 : 0, 0, &upd[0]));
+    Eigen::VectorXd v(6);
+    for (int k = 0; k < 6; k++) v(k) = upd[6 * (size_t)stream_ + k];
+    return v;
+  }
+
+  // ---- initial map: trails between the first two keyframes (jni/Tracker.cc:203-346) -------------------------------------------
+  enum { TRAIL_TRACKING_NOT_STARTED, TRAIL_TRACKING_STARTED, TRAIL_TRACKING_COMPLETE };
+  int mnInitialStage;
+  std::list<Trail> mlTrails;
+  KeyFrame mCurrentKF;
+  // Matches handed to MapMaker::InitFromStereo at the second spacebar press (MapMaker is outside this library)
+  std::vector<std::pair<Eigen::Vector2d, Eigen::Vector2d> > vInitMatches;
+
+  void TrackForInitialMap() {
+    MiniPatch::mnMaxSSD() = 100000;   // "Tracker.MiniPatchMaxSSD" (jni/Tracker.cc:226-227)
+    if (mnInitialStage == TRAIL_TRACKING_NOT_STARTED) {
+      if (mbUserPressedSpacebar) { mbUserPressedSpacebar = false; TrailTracking_Start(); mnInitialStage = TRAIL_TRACKING_STARTED; }
+      else msg_ << "Point camera at planar scene and press spacebar to start tracking for initial map." << std::endl;
+      return;
+    }
+    if (mnInitialStage == TRAIL_TRACKING_STARTED) {
+      const int nGoodTrails = TrailTracking_Advance();
+      if (nGoodTrails < 10) { Reset(); return; }
+      if (mbUserPressedSpacebar) {
+        mbUserPressedSpacebar = false;
+        vInitMatches.clear();
+        for (std::list<Trail>::iterator i = mlTrails.begin(); i != mlTrails.end(); ++i) vInitMatches.push_back(std::make_pair(i->irInitialPos, i->irCurrentPos));
+        mnInitialStage = TRAIL_TRACKING_COMPLETE;   // the caller runs InitFromStereo on vInitMatches and then SetMap
+      } else msg_ << "Translate the camera slowly sideways, and press spacebar again to perform stereo init." << std::endl;
+    }
+  }
+
+  // The current frame is to be the first keyframe (jni/Tracker.cc:264-292)
+  void TrailTracking_Start() {
+    vslam_ctx* c = ctx_.get();
+    mCurrentKF.MakeKeyFrame_Rest();
+    int w, h; check(c, vslam_level_dims(c, 0, &w, &h));
+    const int b = MiniPatch::mnHalfPatchSize();
+    std::vector<std::pair<double, Eigen::Vector2d> > v;
+    const std::vector<Candidate>& cand = mCurrentKF.aLevels[0].vCandidates;
+    for (size_t i = 0; i < cand.size(); i++) {
+      const int x = (int)cand[i].irLevelPos(0), y = (int)cand[i].irLevelPos(1);
+      if (!(x >= b && y >= b && x < w - b && y < h - b)) continue;      // in_image_with_border
+      v.push_back(std::make_pair(-1.0 * cand[i].dSTScore, cand[i].irLevelPos));
+    }
+    std::sort(v.begin(), v.end(), CompareFirst());   // the reference's comparator and std::sort: as shipped, the LOWEST scores come first
+    int nToAdd = 1000;                               // "MaxInitialTrails"
+    std::vector<int32_t> xy;
+    for (size_t i = 0; i < v.size() && nToAdd > 0; i++, nToAdd--) { xy.push_back((int32_t)v[i].second(0)); xy.push_back((int32_t)v[i].second(1)); }
+    const int n = (int)(xy.size() / 2);
+    std::vector<unsigned char> patches(81 * (size_t)n + 1);
+    if (n) check(c, vslam_minipatch_sample(c, stream_, 0, n, &xy[0], &patches[0]));    // all trails in one call
+    mlTrails.clear();
+    for (int i = 0; i < n; i++) {
+      Trail t;
+      std::copy(patches.begin() + 81 * (size_t)i, patches.begin() + 81 * (size_t)(i + 1), t.mPatch.im);
+      t.irInitialPos = Eigen::Vector2d(xy[2 * i], xy[2 * i + 1]); t.irCurrentPos = t.irInitialPos;
+      mlTrails.push_back(t);
+    }
+    check(c, vslam_snapshot_keyframe(c, stream_));   // mPreviousFrameKF = mFirstKF
+  }
+
+  // Steady-state trail tracking: advance from the previous frame, remove duds (jni/Tracker.cc:294-346).  Forward search of every
+  // trail in the current frame, patches re-sampled at the hits, backward search in the previous frame: three batched calls.
+  int TrailTracking_Advance() {
+    vslam_ctx* c = ctx_.get();
+    const int n = (int)mlTrails.size();
+    int nGoodTrails = 0;
+    if (n) {
+      std::vector<unsigned char> patches(81 * (size_t)n);
+      std::vector<double> pos(2 * (size_t)n), bpos;
+      std::vector<int32_t> found(n), bfound, fxy;
+      int k = 0;
+      for (std::list<Trail>::iterator i = mlTrails.begin(); i != mlTrails.end(); ++i, ++k) {
+        std::copy(i->mPatch.im, i->mPatch.im + 81, patches.begin() + 81 * (size_t)k);
+        pos[2 * k] = i->irCurrentPos(0); pos[2 * k + 1] = i->irCurrentPos(1);
+      }
+      const std::vector<double> start(pos);
+      check(c, vslam_minipatch_find(c, stream_, 0, n, &patches[0], &pos[0], &found[0], 0, 10, MiniPatch::mnMaxSSD()));
+      std::vector<int> idx;
+      for (k = 0; k < n; k++) if (found[k]) { idx.push_back(k); fxy.push_back((int32_t)pos[2 * k]); fxy.push_back((int32_t)pos[2 * k + 1]); bpos.push_back(pos[2 * k]); bpos.push_back(pos[2 * k + 1]); }
+      const int m = (int)idx.size();
+      std::vector<unsigned char> back(81 * (size_t)m + 1);
+      bfound.assign(m + 1, 0);
+      if (m) {
+        check(c, vslam_minipatch_sample(c, stream_, 0, m, &fxy[0], &back[0]));                                            // BackwardsPatch.SampleFromImage
+        check(c, vslam_minipatch_find(c, stream_, 1, m, &back[0], &bpos[0], &bfound[0], 0, 10, MiniPatch::mnMaxSSD()));   // married-match check
+      }
+      std::vector<char> keep(n, 0);
+      for (int j = 0; j < m; j++) {
+        k = idx[j];
+        const double dx = bpos[2 * j] - start[2 * k], dy = bpos[2 * j + 1] - start[2 * k + 1];
+        bool bFound = bfound[j] != 0;
+        if (dx * dx + dy * dy > 2) bFound = false;
+        keep[k] = bFound ? 1 : 0;
+        nGoodTrails++;                                  // counted before the married-match verdict, as the reference does (:317-318)
+      }
+      k = 0;
+      for (std::list<Trail>::iterator i = mlTrails.begin(); i != mlTrails.end(); ++k) {
+        if (found[k]) i->irCurrentPos = Eigen::Vector2d(pos[2 * k], pos[2 * k + 1]);
+        if (!keep[k]) i = mlTrails.erase(i); else ++i;
+      }
+    }
+    check(c, vslam_snapshot_keyframe(c, stream_));   // mPreviousFrameKF = mCurrentKF
+    return nGoodTrails;
+  }
+
  private:
-  Context& ctx_; int stream_; int n_points_ = 0; std::ostringstream msg_;
+  struct CompareFirst { bool operator()(const std::pair<double, Eigen::Vector2d>& a, const std::pair<double, Eigen::Vector2d>& b) const { return a.first > b.first; } };   // jni/Tracker.h:47-52 (`>` on -dSTScore)
+  void SetList(const std::vector<int>& vTD) {
+    vslam_ctx* c = ctx_.get();
+    const int stride = (int)vTD.size() > 0 ? (int)vTD.size() : 1;
+    std::vector<int32_t> idx((size_t)ctx_.Streams() * stride, 0), n(ctx_.Streams(), 0);
+    for (size_t k = 0; k < vTD.size(); k++) idx[(size_t)stream_ * stride + k] = vTD[k];
+    n[stream_] = (int32_t)vTD.size();
+    check(c, vslam_set_lists(c, &idx[0], &n[0], stride));
+  }
+  Context& ctx_; int stream_; int mnFrame = 0; bool mbUserPressedSpacebar = false; bool mbMapGood = false; std::ostringstream msg_;
+};
+
+// jni/PatchFinder.h:45-121, per object, for one map point of one stream at a time: the slow path (every call moves the whole
+// stream's point state across PCIe).  The batched fast path is Tracker::SearchForPoints / vslam_track_frame.
+class PatchFinder {
+ public:
+  PatchFinder(Context& ctx, int stream, int nPatchSize = 11) : mnMaxSSD(nPatchSize * nPatchSize * 500), ctx_(ctx), stream_(stream), point_(-1), mnSearchLevel(-1), mbFound(false), mbTemplateBad(false) {}
+  // Projects the map with se3CFromW as the stream's pose and returns the search level of `point` (negative: inappropriate warp)
+  int CalcSearchLevelAndWarpMatrix(int point, const SE3& se3CFromW) {
+    vslam_ctx* c = ctx_.get();
+    double p[12];
+    for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) p[4 * i + j] = se3CFromW.R(i, j); p[4 * i + 3] = se3CFromW.t(i); }
+    check(c, vslam_set_pose(c, stream_, p));
+    check(c, vslam_project_all(c));
+    point_ = point;
+    Pull();
+    mnSearchLevel = ints_[8 * (size_t)point + 1];
+    for (int r = 0; r < 2; r++) for (int q = 0; q < 2; q++) mm2WarpInverse(r, q) = dbl_[32 * (size_t)point + 11 + 2 * r + q];
+    mbTemplateBad = mnSearchLevel < 0;
+    return mnSearchLevel;
+  }
+  int GetLevel() { return mnSearchLevel; }
+  int GetLevelScale() { return 1 << mnSearchLevel; }
+  Eigen::Matrix2d GetWarpInverse() { return mm2WarpInverse; }
+  // TrackerData::v2Image of the point at that pose (what the reference's callers pass to FindPatchCoarse), and any point's level
+  Eigen::Vector2d GetProjection() { return Eigen::Vector2d(dbl_[32 * (size_t)point_], dbl_[32 * (size_t)point_ + 1]); }
+  int LevelOf(int point) { return ints_[8 * (size_t)point + 1]; }
+  // The template is (re)generated on the device by the next FindPatchCoarse under the reference's reuse rule (jni/PatchFinder.cc:91-102)
+  void MakeTemplateCoarseCont(int point) { point_ = point; }
+  bool TemplateBad() { return mbTemplateBad; }
+  // Search around v2Pos (level-0 pixels) in the stream's current keyframe (kf must be that keyframe)
+  bool FindPatchCoarse(const Eigen::Vector2d& v2Pos, KeyFrame& /*kf*/, unsigned int nRange) { return Search(v2Pos, (int)nRange, 0); }
+  Eigen::Vector2d GetCoarsePosAsVector() { return mv2CoarsePos; }
+  void MakeSubPixTemplate() {}
+  // Coarse search + inverse-compositional refinement in one device call (the reference splits them; the result is the same)
+  bool FindPatchCoarseAndSubPix(const Eigen::Vector2d& v2Pos, KeyFrame& /*kf*/, unsigned int nRange, int nMaxIts) { return Search(v2Pos, (int)nRange, nMaxIts); }
+  Eigen::Vector2d GetSubPixPos() { return mv2SubPixPos; }
+  int mnMaxSSD;
+
+ private:
+  void Pull() {
+    vslam_ctx* c = ctx_.get();
+    const int n = ctx_.MapSize();
+    ints_.resize(8 * (size_t)n); dbl_.resize(32 * (size_t)n);
+    check(c, vslam_get_point_states(c, stream_, &ints_[0], &dbl_[0]));
+  }
+  bool Search(const Eigen::Vector2d& v2Pos, int nRange, int nSubPix) {
+    vslam_ctx* c = ctx_.get();
+    const int n = ctx_.MapSize();
+    Pull();
+    std::vector<double> v2(2 * (size_t)n), warp(4 * (size_t)n); std::vector<int32_t> lev(n);
+    for (int i = 0; i < n; i++) { v2[2 * i] = dbl_[32 * (size_t)i]; v2[2 * i + 1] = dbl_[32 * (size_t)i + 1]; for (int q = 0; q < 4; q++) warp[4 * i + q] = dbl_[32 * (size_t)i + 11 + q]; lev[i] = ints_[8 * (size_t)i + 1]; }
+    v2[2 * point_] = v2Pos(0); v2[2 * point_ + 1] = v2Pos(1);
+    check(c, vslam_set_point_projection(c, stream_, &v2[0], &warp[0], &lev[0]));
+    const int ns = ctx_.Streams();
+    std::vector<int32_t> idx(ns, 0), cnt(ns, 0);
+    idx[stream_] = point_; cnt[stream_] = 1;
+    check(c, vslam_set_lists(c, &idx[0], &cnt[0], 1));
+    check(c, vslam_search_for_points(c, nRange, nSubPix));
+    Pull();
+    const int32_t* I = &ints_[8 * (size_t)point_]; const double* Dd = &dbl_[32 * (size_t)point_];
+    mbTemplateBad = I[5] != 0;
+    mbFound = I[3] != 0;
+    mv2CoarsePos = Eigen::Vector2d(Dd[30], Dd[31]);
+    mv2SubPixPos = Eigen::Vector2d(Dd[2], Dd[3]);
+    return mbFound;
+  }
+  Context& ctx_; int stream_, point_, mnSearchLevel; bool mbFound, mbTemplateBad;
+  Eigen::Matrix2d mm2WarpInverse; Eigen::Vector2d mv2CoarsePos, mv2SubPixPos;
+  std::vector<int32_t> ints_; std::vector<double> dbl_;
 };
 
 }  // namespace vslam_b200

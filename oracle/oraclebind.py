@@ -67,6 +67,12 @@ def lib():
     sig("orc_find_patch_coarse", i, vp, i, _u8p, i, d, d, u, _f64p, pi, C.POINTER(C.c_long))
     sig("orc_subpix", i, vp, i, _u8p, i, _f64p, i, _f64p, C.c_void_p)
     sig("orc_minipatch_find", i, vp, i, i, vp, _f64p, i, i, i, pi)
+    sig("orc_trails_create", vp)
+    sig("orc_trails_destroy", None, vp)
+    sig("orc_trails_start", i, vp, vp)
+    sig("orc_trails_advance", i, vp, vp, i)
+    sig("orc_trails_count", i, vp)
+    sig("orc_trails_get", None, vp, _f64p)
     sig("orc_tracker_create", vp, _f64p, i)
     sig("orc_tracker_destroy", None, vp)
     sig("orc_tracker_seed", None, vp, u)
@@ -172,6 +178,27 @@ class OrcKeyFrame:
         out = np.empty(n, dtype=np.int32)
         if n:
             self.L.orc_kf_fast_scores(self.h, l, barrier, out)
+        return out
+
+
+class OrcTrails:
+    """Trail list of the restatement (Tracker::TrailTracking_Start / _Advance)."""
+
+    def __init__(self):
+        self.L = lib()
+        self.h = self.L.orc_trails_create()
+
+    def start(self, kf: "OrcKeyFrame"):
+        return self.L.orc_trails_start(self.h, kf.h)
+
+    def advance(self, kf: "OrcKeyFrame", max_ssd=100000):
+        return self.L.orc_trails_advance(self.h, kf.h, max_ssd)
+
+    def trails(self):
+        n = self.L.orc_trails_count(self.h)
+        out = np.zeros((n, 4))
+        if n:
+            self.L.orc_trails_get(self.h, out)
         return out
 
 

@@ -364,6 +364,27 @@ void ref_tracker_track_frame(void* t, const uint8_t* gray, int w, int h, int str
   cv::Mat col(1, 1, CV_8UC4, g_dummy_rgba);
   tr->TrackFrame(im, col, false);
 }
+// Trail tracking for the initial map (jni/Tracker.cc:264-346) on the tracker's current keyframe (ref_tracker_make_current_kf first)
+int ref_tracker_trail_start(void* t) {
+  Tracker* tr = ((RefTracker*)t)->tr;
+  tr->mlTrails.clear();
+  tr->TrailTracking_Start();
+  return (int)tr->mlTrails.size();
+}
+int ref_tracker_trail_advance(void* t, int max_ssd) {
+  Tracker* tr = ((RefTracker*)t)->tr;
+  MiniPatch::mnMaxSSD = max_ssd;
+  cv::Mat col(1, 1, CV_8UC4, g_dummy_rgba);
+  return tr->TrailTracking_Advance(col);
+}
+int ref_tracker_trail_count(void* t) { return (int)((RefTracker*)t)->tr->mlTrails.size(); }
+void ref_tracker_trails(void* t, double* init_cur4) {
+  Tracker* tr = ((RefTracker*)t)->tr;
+  int k = 0;
+  for (std::list<Trail>::iterator i = tr->mlTrails.begin(); i != tr->mlTrails.end(); ++i, ++k) {
+    init_cur4[4 * k] = i->irInitialPos(0); init_cur4[4 * k + 1] = i->irInitialPos(1); init_cur4[4 * k + 2] = i->irCurrentPos(0); init_cur4[4 * k + 3] = i->irCurrentPos(1);
+  }
+}
 // Tracker::TrackFrame's good-map branch (jni/Tracker.cc:76-112) driven piece by piece WITHOUT the SmallBlurryImage steps
 // (jni/Tracker.cc:86-97,105-106: the f1 "next" row of SURVEY.md §8): the SBI rotation is whatever ref_tracker_set_sbi_rot set.
 void ref_tracker_track_frame_nosbi(void* t, const uint8_t* gray, int w, int h, int stride) {

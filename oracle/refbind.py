@@ -99,6 +99,10 @@ def lib():
     sig("ref_tracker_make_current_kf", None, vp, _u8p, i, i, i)
     sig("ref_tracker_track_map", None, vp)
     sig("ref_tracker_track_frame", None, vp, _u8p, i, i, i)
+    sig("ref_tracker_trail_start", i, vp)
+    sig("ref_tracker_trail_advance", i, vp, i)
+    sig("ref_tracker_trail_count", i, vp)
+    sig("ref_tracker_trails", None, vp, _f64p)
     sig("ref_tracker_motion_model", None, vp, i)
     sig("ref_tracker_track_frame_nosbi", None, vp, _u8p, i, i, i)
     sig("ref_tracker_set_sbi_rot", None, vp, _f64p, i)

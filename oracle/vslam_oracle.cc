@@ -17,6 +17,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <list>
+#include <utility>
 #include <vector>
 
 namespace {
@@ -1137,6 +1139,80 @@ int orc_minipatch_find(void* src, int sx, int sy, void* kf, double* pos2, int ra
   const Image& s = ((OKeyFrame*)src)->lev[0].im;
   for (int r = 0; r < n; r++) memcpy(patch + r * n, s.row(sy - half + r) + (sx - half), n);
   return minipatch_find(patch, half, max_ssd, pos2, ((OKeyFrame*)kf)->lev[0], range, use_lut != 0, best);
+}
+
+// ---- Trail tracking for the initial map (Tracker::TrailTracking_Start / _Advance, jni/Tracker.cc:264-346)
+struct OTrail { uint8_t patch[81]; double cur[2], init[2]; };
+struct OTrails { std::list<OTrail> trails; OKeyFrame prev; };
+// jni/Tracker.h:47-52: `lhs.first > rhs.first` on first = -dSTScore, i.e. the LOWEST Shi-Tomasi scores come first (the comment at
+// jni/Tracker.cc:275 says the opposite; reproduced as shipped — it only matters when there are more than 1000 candidates)
+struct CompareFirstO { bool operator()(const std::pair<double, Corner>& a, const std::pair<double, Corner>& b) const { return a.first > b.first; } };
+void* orc_trails_create() { return new OTrails(); }
+void orc_trails_destroy(void* t) { delete (OTrails*)t; }
+// jni/Tracker.cc:264-292: MakeKeyFrame_Rest, level-0 candidates inside the MiniPatch border sorted by -dSTScore (std::sort, the
+// reference's comparator), at most 1000 trails, patches sampled from the frame, previous frame = this frame.
+int orc_trails_start(void* t_, void* kf_) {
+  OTrails* t = (OTrails*)t_; OKeyFrame* kf = (OKeyFrame*)kf_;
+  make_keyframe_rest(*kf);
+  const OLevel& L = kf->lev[0];
+  const int half = 4;
+  std::vector<std::pair<double, Corner> > v;
+  for (size_t i = 0; i < L.candidates.size(); i++) {
+    const Corner c = L.candidates[i];
+    if (!(c.x >= half && c.y >= half && c.x < L.im.w - half && c.y < L.im.h - half)) continue;
+    v.push_back(std::make_pair(-1.0 * L.candScores[i], c));
+  }
+  std::sort(v.begin(), v.end(), CompareFirstO());
+  int nToAdd = 1000;
+  t->trails.clear();
+  for (size_t i = 0; i < v.size() && nToAdd > 0; i++) {
+    const Corner c = v[i].second;
+    if (!(c.x >= half && c.y >= half && c.x < L.im.w - half && c.y < L.im.h - half)) continue;
+    OTrail tr;
+    for (int r = 0; r < 9; r++) memcpy(tr.patch + r * 9, L.im.row(c.y - half + r) + (c.x - half), 9);
+    tr.init[0] = tr.cur[0] = c.x; tr.init[1] = tr.cur[1] = c.y;
+    t->trails.push_back(tr);
+    nToAdd--;
+  }
+  t->prev = *kf;
+  return (int)t->trails.size();
+}
+// jni/Tracker.cc:294-346: forward FindPatch (range 10, no LUT argument => linear corner scan), married-match check backwards into
+// the previous frame, erase trails that fail; nGoodTrails counts the forward hits.
+int orc_trails_advance(void* t_, void* kf_, int max_ssd) {
+  OTrails* t = (OTrails*)t_; OKeyFrame* kf = (OKeyFrame*)kf_;
+  const OLevel& cur = kf->lev[0]; const OLevel& prev = t->prev.lev[0];
+  const int half = 4;
+  int nGood = 0;
+  for (std::list<OTrail>::iterator i = t->trails.begin(); i != t->trails.end();) {
+    std::list<OTrail>::iterator next = i; ++next;
+    OTrail& tr = *i;
+    const double start[2] = {tr.cur[0], tr.cur[1]};
+    double end[2] = {start[0], start[1]};
+    bool bFound = minipatch_find(tr.patch, half, max_ssd, end, cur, 10, false, 0);
+    if (bFound) {
+      uint8_t back[81];
+      const int ex = (int)end[0], ey = (int)end[1];
+      for (int r = 0; r < 9; r++) memcpy(back + r * 9, cur.im.row(ey - half + r) + (ex - half), 9);
+      double bw[2] = {end[0], end[1]};
+      bFound = minipatch_find(back, half, max_ssd, bw, prev, 10, false, 0);
+      const double dx = bw[0] - start[0], dy = bw[1] - start[1];
+      if (dx * dx + dy * dy > 2) bFound = false;
+      tr.cur[0] = end[0]; tr.cur[1] = end[1];
+      nGood++;
+    }
+    if (!bFound) t->trails.erase(i);
+    i = next;
+  }
+  t->prev = *kf;
+  return nGood;
+}
+int orc_trails_count(void* t) { return (int)((OTrails*)t)->trails.size(); }
+void orc_trails_get(void* t, double* init_cur4) {
+  int k = 0;
+  for (std::list<OTrail>::iterator i = ((OTrails*)t)->trails.begin(); i != ((OTrails*)t)->trails.end(); ++i, ++k) {
+    init_cur4[4 * k] = i->init[0]; init_cur4[4 * k + 1] = i->init[1]; init_cur4[4 * k + 2] = i->cur[0]; init_cur4[4 * k + 3] = i->cur[1];
+  }
 }
 
 // ---- Tracker

@@ -1,0 +1,109 @@
+// Test driver for include/vslam_b200_shell.hpp: runs the reference-shaped C++ API (KeyFrame, Tracker, MiniPatch, PatchFinder) on a
+// scene file written by tests/test_gpu_shell.py and prints the results as text; the Python side compares them with the oracle.
+//   shell_driver <scene.bin> trails|track|stages
+// scene.bin: int32 W,H,N,F; double params5[5]; u8 src[W*H]; double world[3N], right[3N], down[3N]; int32 irCenter[2N]; int32 level[N];
+//            double pose0[12]; u8 frames[F][W*H]
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include "vslam_b200_shell.hpp"
+
+using namespace vslam_b200;
+
+template <class T> static void rd(std::ifstream& f, T* p, size_t n) { f.read((char*)p, sizeof(T) * n); if (!f) { fprintf(stderr, "short scene file\n"); exit(2); } }
+
+int main(int argc, char** argv) {
+  if (argc < 3) return 2;
+  std::ifstream f(argv[1], std::ios::binary);
+  int32_t hdr[4]; rd(f, hdr, 4);
+  const int W = hdr[0], H = hdr[1], N = hdr[2], F = hdr[3];
+  double p5[5]; rd(f, p5, 5);
+  std::vector<unsigned char> src((size_t)W * H); rd(f, &src[0], src.size());
+  std::vector<double> world(3 * (size_t)N), right(3 * (size_t)N), down(3 * (size_t)N); rd(f, &world[0], world.size()); rd(f, &right[0], right.size()); rd(f, &down[0], down.size());
+  std::vector<int32_t> irc(2 * (size_t)N), lvl(N), kf0(N, 0); rd(f, &irc[0], irc.size()); rd(f, &lvl[0], lvl.size());
+  double pose0[12]; rd(f, pose0, 12);
+  std::vector<std::vector<unsigned char> > frames(F, std::vector<unsigned char>((size_t)W * H));
+  for (int k = 0; k < F; k++) rd(f, &frames[k][0], frames[k].size());
+  const std::string mode = argv[2];
+  double cam[13], cam_sbi[13];
+  vslam_camera_from_params(p5, W, H, 0, cam);
+  vslam_camera_from_params(p5, W / 16, H / 16, 0, cam_sbi);
+  cv::Mat colour(1, 1, CV_8UC4);
+  try {
+    Context ctx(W, H, 1, N > 0 ? N : 1);
+    Tracker tracker(ctx, 0, cam);
+    SE3 start; for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) start.R(i, j) = pose0[4 * i + j]; start.t(i) = pose0[4 * i + 3]; }
+
+    if (mode == "trails") {   // Tracker::TrackForInitialMap over the frames: spacebar on frame 0
+      for (int k = 0; k < F; k++) {
+        cv::Mat g(H, W, CV_8UC1, &frames[k][0]);
+        if (k == 0) { tracker.TrackFrame(g, colour, false); printf("msg %s", tracker.GetMessageForUser().c_str()); tracker.PressSpacebar(); }
+        if (k == F - 1) tracker.PressSpacebar();
+        tracker.TrackFrame(g, colour, false);
+        printf("frame %d stage %d trails %d\n", k, tracker.mnInitialStage, (int)tracker.mlTrails.size());
+        for (std::list<Trail>::iterator i = tracker.mlTrails.begin(); i != tracker.mlTrails.end(); ++i)
+          printf("t %.17g %.17g %.17g %.17g\n", i->irInitialPos(0), i->irInitialPos(1), i->irCurrentPos(0), i->irCurrentPos(1));
+      }
+      printf("matches %d\n", (int)tracker.vInitMatches.size());
+      // the per-object MiniPatch path on the first surviving trail: sample in the current frame, find it again in the same frame
+      if (!tracker.mlTrails.empty()) {
+        MiniPatch mp; Eigen::Vector2d pos = tracker.mlTrails.front().irCurrentPos;
+        mp.SampleFromImage(pos, tracker.mCurrentKF);
+        Eigen::Vector2d q = pos; const bool ok = mp.FindPatch(q, tracker.mCurrentKF, 10);
+        printf("minipatch %d %.17g %.17g %.17g %.17g\n", ok ? 1 : 0, pos(0), pos(1), q(0), q(1));
+      }
+      return 0;
+    }
+
+    cv::Mat s(H, W, CV_8UC1, &src[0]);
+    tracker.SetSourceKeyFrame(0, s);
+    tracker.SetMap(N, &world[0], &right[0], &down[0], &irc[0], &lvl[0], &kf0[0]);
+    tracker.SetCurrentPose(start);
+
+    if (mode == "track") {    // Tracker::TrackFrame with the map good (SmallBlurryImage on, like the reference)
+      tracker.EnableSBI(cam_sbi);
+      for (int k = 0; k < F; k++) {
+        cv::Mat g(H, W, CV_8UC1, &frames[k][0]);
+        tracker.TrackFrame(g, colour, false);
+        const SE3 p = tracker.GetCurrentPose();
+        printf("pose");
+        for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) printf(" %.17g", p.R(i, j)); printf(" %.17g", p.t(i)); }
+        printf("\nmsg %s\n", tracker.GetMessageForUser().c_str());
+      }
+      return 0;
+    }
+
+    if (mode == "stages") {   // the protected stage functions and the per-object PatchFinder on frame 0
+      cv::Mat g(H, W, CV_8UC1, &frames[0][0]);
+      tracker.mCurrentKF.MakeKeyFrame_Lite(g, colour);
+      PatchFinder finder(ctx, 0);
+      for (int pt = 0; pt < N; pt += N / 12 > 0 ? N / 12 : 1) {
+        const int level = finder.CalcSearchLevelAndWarpMatrix(pt, start);
+        const Eigen::Vector2d v2 = finder.GetProjection();
+        const Eigen::Matrix2d wi = finder.GetWarpInverse();
+        printf("pf %d level %d v2 %.17g %.17g warp %.17g %.17g %.17g %.17g", pt, level, v2(0), v2(1), wi(0, 0), wi(0, 1), wi(1, 0), wi(1, 1));
+        if (level >= 0) {
+          finder.MakeTemplateCoarseCont(pt);
+          const bool found = finder.FindPatchCoarseAndSubPix(v2, tracker.mCurrentKF, 10, 8);
+          const Eigen::Vector2d c = finder.GetCoarsePosAsVector(), sp = finder.GetSubPixPos();
+          printf(" bad %d found %d coarse %.17g %.17g subpix %.17g %.17g", finder.TemplateBad() ? 1 : 0, found ? 1 : 0, c(0), c(1), sp(0), sp(1));
+        }
+        printf("\n");
+      }
+      // SearchForPoints + CalcPoseUpdate on every third point
+      finder.CalcSearchLevelAndWarpMatrix(0, start);   // (re-project the whole map at the start pose)
+      std::vector<int> list;
+      for (int pt = 0; pt < N; pt += 3) if (finder.LevelOf(pt) >= 0) list.push_back(pt);
+      const int nfound = tracker.SearchForPoints(list, 12, 4);
+      printf("search %d of %d\n", nfound, (int)list.size());
+      tracker.CalcJacobians(list);
+      const Eigen::VectorXd mu = tracker.CalcPoseUpdate(list);
+      printf("update %.17g %.17g %.17g %.17g %.17g %.17g\n", mu(0), mu(1), mu(2), mu(3), mu(4), mu(5));
+      const Eigen::VectorXd mu2 = tracker.CalcPoseUpdate(list, 16.0, true);
+      printf("update16 %.17g %.17g %.17g %.17g %.17g %.17g\n", mu2(0), mu2(1), mu2(2), mu2(3), mu2(4), mu2(5));
+      return 0;
+    }
+  } catch (const std::exception& e) { fprintf(stderr, "%s\n", e.what()); return 3; }
+  return 2;
+}

@@ -210,6 +210,38 @@ def test_minipatch_find():
     R.ref_mp_destroy(mp)
 
 
+def test_trail_tracking_start_and_advance():
+    """f2 host logic: Tracker::TrailTracking_Start / _Advance (jni/Tracker.cc:264-346) of the compiled reference against the
+    restatement, over a short sideways motion: same trails (initial and current positions, list order) after every frame."""
+    cam, f0, smap, rw, ow = _worlds()
+    R = rw.L
+    tw = np.array([0.02, 0.004, 0.0, 0.0, 0.0, 0.003])
+    rw.make_current_kf(f0)
+    n_ref = R.ref_tracker_trail_start(rw.tracker)
+    ot = oraclebind.OrcTrails()
+    n_orc = ot.start(oraclebind.OrcKeyFrame().make_lite(f0))
+    assert n_ref == n_orc and n_ref > 100
+
+    def ref_trails():
+        out = np.zeros((R.ref_tracker_trail_count(rw.tracker), 4))
+        if len(out):
+            R.ref_tracker_trails(rw.tracker, out)
+        return out
+    assert np.array_equal(ref_trails(), ot.trails())
+    counts = []
+    for k in range(1, 5):
+        f, _ = common.frame_at(cam, tw * k)
+        rw.make_current_kf(f)
+        g_ref = R.ref_tracker_trail_advance(rw.tracker, 100000)
+        g_orc = ot.advance(oraclebind.OrcKeyFrame().make_lite(f), 100000)
+        assert g_ref == g_orc
+        tr, to = ref_trails(), ot.trails()
+        assert np.array_equal(tr, to)
+        counts.append(len(tr))
+    assert counts[-1] > 30 and counts[-1] < n_ref      # some trails die, many survive
+    assert np.abs(to[:, 2:] - to[:, :2]).max() > 3      # and they moved
+
+
 def test_small_blurry_image_pieces():
     """f1: SmallBlurryImage::MakeFromKF, IteratePosRelToTarget and SE3fromSE2 (jni/SmallBlurryImage.cc) — restatement vs compiled reference."""
     cam, f0, smap = common.scene()

@@ -41,7 +41,7 @@ ABI_SYMBOLS = [
     "vslam_set_camera", "vslam_camera_from_params", "vslam_upload_source_keyframe", "vslam_set_map", "vslam_make_keyframe_lite",
     "vslam_make_keyframe_lite_dev", "vslam_level_dims", "vslam_get_level", "vslam_get_num_corners", "vslam_get_corners", "vslam_get_row_lut",
     "vslam_make_keyframe_rest", "vslam_get_max_corners", "vslam_get_candidates", "vslam_snapshot_keyframe", "vslam_minipatch_sample", "vslam_minipatch_find",
-    "vslam_set_pose", "vslam_get_pose", "vslam_get_poses", "vslam_set_motion", "vslam_get_motion", "vslam_set_sbi_rotation", "vslam_enable_sbi", "vslam_get_sbi_rotation", "vslam_get_counters",
+    "vslam_set_pose", "vslam_get_pose", "vslam_get_poses", "vslam_set_motion", "vslam_get_motion", "vslam_reset_stream", "vslam_set_sbi_rotation", "vslam_enable_sbi", "vslam_get_sbi_rotation", "vslam_get_counters",
     "vslam_get_point_states", "vslam_get_point_template", "vslam_get_point_counts", "vslam_get_updates", "vslam_get_zmssd_evals",
     "vslam_project_all", "vslam_set_point_projection", "vslam_set_lists", "vslam_clear_counters", "vslam_search_for_points", "vslam_project_and_derivs", "vslam_calc_jacobians",
     "vslam_calc_pose_update", "vslam_track_map", "vslam_track_frame", "vslam_track_frame_dev", "vslam_track_frame_async", "vslam_wait_step", "vslam_debug_atan", "vslam_debug_dp4a_peak", "vslam_kernel_launches", "vslam_set_timing", "vslam_get_stage_times",
@@ -95,6 +95,7 @@ def load():
     sig("vslam_get_pose", i, vp, i, vp)
     sig("vslam_get_poses", i, vp, vp)
     sig("vslam_set_motion", i, vp, i, vp, d, d, d)
+    sig("vslam_reset_stream", i, vp, i)
     sig("vslam_get_motion", i, vp, i, vp, pd, pd, pd)
     sig("vslam_set_sbi_rotation", i, vp, i, vp)
     sig("vslam_enable_sbi", i, vp, vp)
@@ -315,6 +316,10 @@ class Context:
     def set_motion(self, s, velocity6, msd, depth_mean=1.0, depth_sigma=1.0):
         v = np.ascontiguousarray(velocity6, dtype=np.float64)
         self._ck(self.L.vslam_set_motion(self.h, s, v.ctypes.data, msd, depth_mean, depth_sigma))
+
+    def reset_stream(self, s):
+        """Tracker::Reset (jni/Tracker.cc:45-60) for the tracker state of stream s."""
+        self._ck(self.L.vslam_reset_stream(self.h, s))
 
     def get_motion(self, s):
         v = np.empty(6)

@@ -527,6 +527,15 @@ int vslam_get_motion(vslam_ctx* ctx, int s, double* v6, double* msd, double* dme
   memcpy(v6, st.velocity, sizeof(st.velocity)); *msd = st.msd_scaled_vel; *dmean = st.depth_mean; *dsigma = st.depth_sigma;
   return VSLAM_OK;
 }
+int vslam_reset_stream(vslam_ctx* ctx, int s) {
+  int rc = check_stream(ctx, s); if (rc) return rc;
+  StreamState st; if ((rc = read_ss(ctx, s, &st))) return rc;
+  st.did_coarse = 0; st.quality = 2; st.lost_frames = 0; st.msd_scaled_vel = 0.0; st.vel_mag = 0.0; st.depth_mean = 1.0; st.depth_sigma = 1.0;
+  st.just_recovered = 0; st.n_updates = 0; st.try_coarse = 0;
+  for (int k = 0; k < 6; k++) st.velocity[k] = 0.0;
+  for (int l = 0; l < VS_LEVELS; l++) st.attempted[l] = st.found[l] = 0;
+  return write_ss(ctx, s, &st);
+}
 int vslam_set_sbi_rotation(vslam_ctx* ctx, int s, const double* r6) {
   int rc = check_stream(ctx, s); if (rc) return rc;
   VS_CUDA(cudaStreamSynchronize(ctx->stream));
