@@ -83,6 +83,23 @@ def main():
     rw.L.ref_srand(1)
     out["D_rand"] = np.array([rw.L.ref_rand() for _ in range(400)], dtype=np.int64)
 
+    # --- case E: initial-map trail tracking (Tracker::TrailTracking_Start on f0, _Advance on three frames of a sideways motion)
+    rw.make_current_kf(f0)
+    out["E_start_n"] = np.array([rw.L.ref_tracker_trail_start(rw.tracker)])
+
+    def trails():
+        t = np.zeros((rw.L.ref_tracker_trail_count(rw.tracker), 4))
+        if len(t):
+            rw.L.ref_tracker_trails(rw.tracker, t)
+        return t
+    out["E_trails0"] = trails()
+    for k in range(1, 4):
+        fk = synth.render_frame(tex, cam, synth.se3_exp(np.array([0.02, 0.004, 0.0, 0.0, 0.0, 0.003]) * k))
+        out[f"E_f{k}"] = fk
+        rw.make_current_kf(fk)
+        out[f"E_good{k}"] = np.array([rw.L.ref_tracker_trail_advance(rw.tracker, 100000)])
+        out[f"E_trails{k}"] = trails()
+
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_small.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")

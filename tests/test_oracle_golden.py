@@ -72,6 +72,17 @@ def test_track_map_golden_fine_then_coarse():
     assert np.array_equal(ow.point_counts(), G["C_counts"]), "M-estimator inlier / outlier counters"
 
 
+def test_trail_tracking_golden():
+    """Tracker::TrailTracking_Start / _Advance (jni/Tracker.cc:264-346): trail lists of the compiled reference, frame by frame."""
+    ot = oraclebind.OrcTrails()
+    assert ot.start(oraclebind.OrcKeyFrame().make_lite(G["f0"])) == int(G["E_start_n"][0])
+    assert np.array_equal(ot.trails(), G["E_trails0"])
+    for k in range(1, 4):
+        assert ot.advance(oraclebind.OrcKeyFrame().make_lite(G[f"E_f{k}"]), 100000) == int(G[f"E_good{k}"][0])
+        assert np.array_equal(ot.trails(), G[f"E_trails{k}"]), k
+    assert 10 < len(G["E_trails3"]) < int(G["E_start_n"][0])
+
+
 def test_se3_exp_ln_golden():
     L = oraclebind.lib()
     for mu, e, l in zip(G["D_mu"], G["D_exp"], G["D_ln"]):
