@@ -149,6 +149,58 @@ def run_cpu_arm(cam, f0, smap, frames_by_stream, n_procs, n_warm, n_steps, frame
     return fps, total / n_steps, ("reference" if use_ref else "port")
 
 
+def cpu_stage_times(reps=20, warm=5):
+    """per-stage times of BASELINE config 1 (one VGA frame, 1000 map points, start pose I, frame at CONFIG1_TWIST) on
+    one host core: the reference's own sources (oracle/_ref, P = 11 as shipped) and the oracle port at P = 11 and P = 8.
+    Median of `reps` repetitions after `warm` warm-ups, milliseconds."""
+    from oracle import oraclebind, refbind
+    from visualslam_android_b200 import synth
+    cam, tex, f0, smap = build_scene()
+    f1 = synth.render_frame(tex, cam, synth.se3_exp(np.array(synth.CONFIG1_TWIST)))
+    eye = synth.IDENTITY_POSE
+
+    def med(fn, setup=None):
+        ts = []
+        for r in range(warm + reps):
+            if setup:
+                setup()
+            t0 = time.perf_counter(); fn(); ts.append((time.perf_counter() - t0) * 1e3)
+        return float(np.median(ts[warm:]))
+
+    def stages(kind, w, L, pre):
+        t = w.tracker
+        g = lambda name: getattr(L, pre + name)
+        out = {}
+        kf_make = (lambda: refbind.RefKeyFrame().make_lite(f1)) if kind == "reference" else (lambda: oraclebind.OrcKeyFrame().make_lite(f1))
+        out["make_keyframe_lite"] = med(kf_make)
+        w.make_current_kf(f1)
+        reset = lambda: (w.set_pose(eye), g("tracker_set_velocity")(t, np.zeros(6), 0.0))
+        out["track_map_fine_only"] = med(lambda: g("tracker_track_map")(t), reset)
+        reset_c = lambda: (w.set_pose(eye), g("tracker_set_velocity")(t, np.zeros(6), 0.05))
+        out["track_map_coarse_and_fine"] = med(lambda: g("tracker_track_map")(t), reset_c)
+        w.set_pose(eye)
+        out["project_all"] = med(lambda: g("tracker_project_all")(t))
+        ints, _ = w.point_states()
+        lst = np.ascontiguousarray(np.nonzero((ints[:, 0] == 1) & (ints[:, 1] >= 0))[0].astype(np.int32))
+        out["search_for_points_range10"] = med(lambda: g("tracker_search_for_points")(t, lst, len(lst), 10, 0))
+        out["search_for_points_range10_subpix8"] = med(lambda: g("tracker_search_for_points")(t, lst, len(lst), 10, 8))
+        g("tracker_calc_jacobians")(t, lst, len(lst))
+        mu = np.zeros(6)
+        out["calc_pose_update"] = med(lambda: g("tracker_calc_pose_update")(t, lst, len(lst), 0.0, 0, 0, mu))
+        out["points_searched"] = int(len(lst))
+        return out
+
+    res = {}
+    if refbind.available():
+        rw = refbind.RefWorld(W, H, f0, smap)
+        res["reference_P11"] = stages("reference", rw, rw.L, "ref_")
+    for P in (11, 8):
+        ow = oraclebind.OrcWorld(cam, f0, smap, P=P)
+        res[f"port_P{P}"] = stages("port", ow, ow.L, "orc_")
+    return {"what": "per-stage CPU times, BASELINE config 1, one core, ms (median of %d after %d warm-ups); the stand-in cv::Mat / cv::resize of the "
+                    "reference build are plain scalar C++, not OpenCV's SIMD paths" % (reps, warm), "cores": 1, "stages_ms": res}
+
+
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
     """SM clock / throttle reasons sampled DURING the timed region by a background thread through NVML (pynvml)."""
@@ -214,6 +266,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--streams", type=int, default=STREAMS_PER_GPU, help="camera streams per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-stages", action="store_true", help="SURVEY §8(d)(i): per-stage CPU times of config 1 (reference build and oracle port), no GPU work")
     args = ap.parse_args()
     K, Wm = args.steps, max(args.warmup, 3 if args.impl == "ours" else 1)
     rank = int(os.environ.get("RANK", "0"))
@@ -241,6 +294,10 @@ def main():
                 "cpu_baseline": {"value": fps, "unit": UNIT, "cores": n_procs, "kind": kind, "sample": sample},
                 "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
         print(json.dumps(line))
+        return
+
+    if args.cpu_stages:
+        print(json.dumps(cpu_stage_times()))
         return
 
     import torch
