@@ -162,6 +162,14 @@ int vslam_set_point_projection(vslam_ctx* ctx, int stream, const double* v2image
 int vslam_set_lists(vslam_ctx* ctx, const int32_t* idx, const int32_t* n, int idx_stride);
 int vslam_clear_counters(vslam_ctx* ctx);
 int vslam_search_for_points(vslam_ctx* ctx, int range, int subpix_its);
+/* MapMaker::ReFind_Common (jni/MapMaker.cc:967-1036), batched: every stream stands for one keyframe (its current keyframe image and
+ * pose), its list (vslam_set_lists) for the map points to re-find in it.  Per pair: projection and in-image tests, a cold-finder
+ * MakeTemplateCoarse (always regenerated; the reference's static PatchFinder does the same whenever consecutive calls name different
+ * points), FindPatchCoarse with `range` (reference: 4), then on levels > 0 MakeSubPixTemplate + IterateSubPixToConvergence
+ * (`subpix_its`, reference: 8) whose position is kept whether or not it converged.  The Measurement / sNeverRetryKFs bookkeeping
+ * is the caller's.  vslam_get_refind_results: list order, flags3 = {found, level, bSubPix}, pos2 = Measurement::v2RootPos. */
+int vslam_refind(vslam_ctx* ctx, int range, int subpix_its);
+int vslam_get_refind_results(vslam_ctx* ctx, int stream, int32_t* flags3, double* pos2, int cap, int* n);
 int vslam_project_and_derivs(vslam_ctx* ctx, int only_found);
 int vslam_calc_jacobians(vslam_ctx* ctx);
 int vslam_calc_pose_update(vslam_ctx* ctx, double override_sigma, int mark_outliers, int apply, double* upd6_per_stream /* may be NULL */);

@@ -364,6 +364,42 @@ void ref_tracker_track_frame(void* t, const uint8_t* gray, int w, int h, int str
   cv::Mat col(1, 1, CV_8UC4, g_dummy_rgba);
   tr->TrackFrame(im, col, false);
 }
+// MapMaker::ReFind_Common (jni/MapMaker.cc:967-1036).  MapMaker.cc itself is not part of this build (it needs Eigen's JacobiSVD /
+// EigenSolver and the Bundle / HomographyInit link surface), so the function's call sequence is transcribed here on the REFERENCE'S
+// OWN objects: the arithmetic below is all reference code (mySE3, ATANCamera::Project / GetProjectionDerivs_Eigen,
+// PatchFinder::MakeTemplateCoarse / FindPatchCoarse / MakeSubPixTemplate / IterateSubPixToConvergence), only the control flow of
+// ReFind_Common is restated; the Measurement / sNeverRetryKFs bookkeeping is left out.  k = the tracker's current keyframe with
+// se3CfromW = the tracker's pose.
+void ref_refind(void* t, const int32_t* idx, int n, int range, int subpix_its, int32_t* out3, double* pos2) {
+  Tracker* tr = ((RefTracker*)t)->tr;
+  Map* map = ((RefTracker*)t)->map;
+  KeyFrame& k = tr->mCurrentKF;
+  k.se3CfromW = tr->mse3CamFromWorld;
+  ATANCamera& cam = tr->mCamera;
+  static PatchFinder Finder;
+  for (int q = 0; q < n; q++) {
+    MapPoint& p = *map->vpPoints[idx[q]];
+    out3[3 * q] = 0; out3[3 * q + 1] = -1; out3[3 * q + 2] = 0; pos2[2 * q] = pos2[2 * q + 1] = 0.0;
+    Eigen::Vector3d v3Cam = k.se3CfromW * p.v3WorldPos;
+    if (v3Cam(2) < 0.001) continue;
+    Eigen::Vector2d v2ImPlane; v2ImPlane(0) = v3Cam(0) / v3Cam(2); v2ImPlane(1) = v3Cam(1) / v3Cam(2);
+    if (v2ImPlane.dot(v2ImPlane) > cam.LargestRadiusInImage() * cam.LargestRadiusInImage()) continue;
+    Eigen::Vector2d v2Image = cam.Project(v2ImPlane);
+    if (cam.Invalid()) continue;
+    if (v2Image[0] < 0 || v2Image[1] < 0 || v2Image[0] > k.aLevels[0].im.cols || v2Image[1] > k.aLevels[0].im.rows) continue;
+    Eigen::Matrix2d m2CamDerivs = cam.GetProjectionDerivs_Eigen();
+    Finder.MakeTemplateCoarse(p, k.se3CfromW, m2CamDerivs);
+    out3[3 * q + 1] = Finder.GetLevel();
+    if (Finder.TemplateBad()) continue;
+    if (!Finder.FindPatchCoarse(Eigen::Vector2d(v2Image[0], v2Image[1]), k, range)) continue;
+    out3[3 * q] = 1;
+    Eigen::Vector2d r;
+    if (Finder.GetLevel() > 0) { Finder.MakeSubPixTemplate(); Finder.IterateSubPixToConvergence(k, subpix_its); r = Finder.GetSubPixPos(); out3[3 * q + 2] = 1; }
+    else r = Finder.GetCoarsePosAsVector();
+    pos2[2 * q] = r(0); pos2[2 * q + 1] = r(1);
+  }
+}
+
 // Trail tracking for the initial map (jni/Tracker.cc:264-346) on the tracker's current keyframe (ref_tracker_make_current_kf first)
 int ref_tracker_trail_start(void* t) {
   Tracker* tr = ((RefTracker*)t)->tr;

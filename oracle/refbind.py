@@ -99,6 +99,7 @@ def lib():
     sig("ref_tracker_make_current_kf", None, vp, _u8p, i, i, i)
     sig("ref_tracker_track_map", None, vp)
     sig("ref_tracker_track_frame", None, vp, _u8p, i, i, i)
+    sig("ref_refind", None, vp, _i32p, i, i, i, _i32p, _f64p)
     sig("ref_tracker_trail_start", i, vp)
     sig("ref_tracker_trail_advance", i, vp, i)
     sig("ref_tracker_trail_count", i, vp)

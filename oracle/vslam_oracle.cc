@@ -1331,6 +1331,42 @@ void orc_tracker_point_counts(void* t_, int i, int* outlier, int* inlier) { cons
 int orc_tracker_search_for_points(void* t_, const int32_t* idx, int n, int range, int subpix) {
   std::vector<int> v(idx, idx + n); return search_for_points(*(OTracker*)t_, v, range, subpix);
 }
+// MapMaker::ReFind_Common (jni/MapMaker.cc:967-1036) for the listed points in the tracker's current keyframe at the tracker's pose
+// (k.se3CfromW), without the Measurement / sNeverRetryKFs bookkeeping.  ONE PatchFinder for the whole list, like the function's
+// `static PatchFinder Finder` (so the template reuse rule sees consecutive calls); cold != 0 forgets it between points.
+// out3[k] = {found, Finder.GetLevel(), bSubPix}, pos2[k] = m.v2RootPos.
+void orc_tracker_refind(void* t_, const int32_t* idx, int n, int range, int subpix_its, int cold, int32_t* out3, double* pos2) {
+  OTracker* t = (OTracker*)t_;
+  Finder F; F.init(t->P);
+  int last = -1;
+  for (int k = 0; k < n; k++) {
+    const MapPointO& p = t->pts[idx[k]];
+    out3[3 * k] = 0; out3[3 * k + 1] = -1; out3[3 * k + 2] = 0; pos2[2 * k] = pos2[2 * k + 1] = 0.0;
+    double v3Cam[3]; se3_apply(t->pose, p.world, v3Cam);
+    if (v3Cam[2] < 0.001) continue;
+    const double ipx = v3Cam[0] / v3Cam[2], ipy = v3Cam[1] / v3Cam[2];
+    double d = 0; d += ipx * ipx; d += ipy * ipy;
+    if (d > t->cam.largestRadius * t->cam.largestRadius) continue;
+    double v2Image[2]; cam_project(t->cam, ipx, ipy, v2Image);
+    if (t->cam.invalid) continue;
+    if (v2Image[0] < 0 || v2Image[1] < 0 || v2Image[0] > t->cur.lev[0].im.w || v2Image[1] > t->cur.lev[0].im.h) continue;
+    double derivs[4]; cam_derivs(t->cam, derivs);
+    // Finder.MakeTemplateCoarse(p, k.se3CfromW, m2CamDerivs)
+    if (cold || last != idx[k]) F.haveLast = false;          // &p != mpLastTemplateMapPoint
+    calc_search_level_and_warp(F, p, t->pose, derivs);       // may set templateBad; MakeTemplateCoarseCont runs regardless
+    make_template_coarse_cont(F, p, *t->srcKF);
+    last = idx[k];
+    out3[3 * k + 1] = F.level;
+    if (F.templateBad) continue;
+    if (!find_patch_coarse(F, v2Image[0], v2Image[1], t->cur, (unsigned)range, &t->zmssdEvals, 0)) continue;
+    out3[3 * k] = 1;
+    if (F.level > 0) {
+      make_subpix_template(F);
+      iterate_subpix_to_convergence(F, t->cur, subpix_its);
+      pos2[2 * k] = F.subPixPos[0]; pos2[2 * k + 1] = F.subPixPos[1]; out3[3 * k + 2] = 1;
+    } else { pos2[2 * k] = F.coarsePos[0]; pos2[2 * k + 1] = F.coarsePos[1]; }
+  }
+}
 void orc_tracker_clear_counters(void* t_) { OTracker* t = (OTracker*)t_; for (int i = 0; i < LEVELS; i++) t->attempted[i] = t->foundCnt[i] = 0; }
 void orc_tracker_calc_jacobians(void* t_, const int32_t* idx, int n) { OTracker* t = (OTracker*)t_; for (int i = 0; i < n; i++) if (t->td[idx[i]].found) td_calc_jacobian(t->td[idx[i]]); }
 void orc_tracker_project_and_derivs(void* t_, const int32_t* idx, int n, int only_found) {

@@ -100,6 +100,17 @@ def main():
         out[f"E_good{k}"] = np.array([rw.L.ref_tracker_trail_advance(rw.tracker, 100000)])
         out[f"E_trails{k}"] = trails()
 
+    # --- case F: MapMaker::ReFind_Common's call sequence (oracle/ref_harness.cc ref_refind) on frame 2 with a slightly wrong pose
+    rw.make_current_kf(f2)
+    off = synth.se3_exp(np.array([0.0008, -0.0006, 0.0005, 0.0006, -0.0004, 0.0007]))
+    true = synth.se3_exp(np.array(synth.CONFIG1_TWIST) * 0.9)
+    kf_pose = (np.vstack([off, [0, 0, 0, 1]]) @ np.vstack([true, [0, 0, 0, 1]]))[:3]
+    rw.set_pose(kf_pose); out["F_pose"] = kf_pose
+    idx = np.arange(smap.n, dtype=np.int32)
+    ro, rp = np.zeros((smap.n, 3), dtype=np.int32), np.zeros((smap.n, 2))
+    rw.L.ref_refind(rw.tracker, idx, smap.n, 4, 8, ro, rp)
+    out["F_flags"], out["F_pos"] = ro, rp
+
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_small.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")

@@ -512,3 +512,44 @@ def test_track_frame_with_on_device_sbi():
             assert np.array_equal(a, oa) and np.array_equal(f, of) and (q, lost, dc) == (oq, olost, odc), (k, s)
     assert big > 1e-4, "the sequences must contain a measurable inter-frame rotation"
     ctx.close()
+
+
+def test_refind_common_batched_over_keyframes():
+    """f3: MapMaker::ReFind_Common (jni/MapMaker.cc:967-1036) batched — every stream is one keyframe (own image, own pose), the list
+    names the map points to re-find; level, found flag, bSubPix and v2RootPos against the oracle (pinned to the reference's calls in
+    tests/test_oracle_vs_ref.py::test_refind_common).  The third keyframe is so close to the plane that warps are rejected."""
+    cam, f0, smap = common.scene()
+    twists = [np.array(synth.CONFIG1_TWIST), np.array([0.05, -0.03, 0.45, 0.02, -0.03, 0.3]), np.array([0.0, 0.0, -0.935, 0.0, 0.0, 0.0])]
+    off = synth.se3_exp(np.array([0.0008, -0.0006, 0.0005, 0.0006, -0.0004, 0.0007]))
+    S = len(twists)
+    ctx = _ctx(cam, f0, smap, n_streams=S)
+    frames, poses = [], []
+    for tw in twists:
+        fr, pose = common.frame_at(cam, tw)
+        frames.append(fr); poses.append((np.vstack([off, [0, 0, 0, 1]]) @ np.vstack([pose, [0, 0, 0, 1]]))[:3])
+    ctx.make_keyframe_lite(np.stack(frames))
+    idx = np.arange(smap.n, dtype=np.int32)
+    for s in range(S):
+        ctx.set_pose(s, poses[s])
+    ctx.set_lists([idx] * S)
+    ctx.refind(4, 8)
+    for s in range(S):
+        ow = _orc(cam, f0, smap)
+        ow.make_current_kf(frames[s]); ow.set_pose(poses[s])
+        oo, op = np.zeros((smap.n, 3), dtype=np.int32), np.zeros((smap.n, 2))
+        ow.L.orc_tracker_refind(ow.tracker, idx, smap.n, 4, 8, 1, oo, op)
+        fl, pos = ctx.refind_results(s, smap.n)
+        searched = oo[:, 1] >= 0                      # (level is only reported for points that reach the template step)
+        assert np.array_equal(fl[searched], oo[searched]), s
+        assert np.array_equal(fl[~searched, 0], oo[~searched, 0]) and fl[~searched, 0].sum() == 0
+        f = oo[:, 0] == 1
+        coarse = f & (oo[:, 2] == 0)
+        assert np.array_equal(pos[coarse], op[coarse]), s
+        sub = f & (oo[:, 2] == 1)
+        if sub.any():
+            assert np.abs(pos[sub] - op[sub]).max() <= 1e-6, s
+        if s < 2:
+            assert f.sum() > 300 and sub.sum() > 50 and coarse.sum() > 50
+        else:
+            assert (oo[:, 1] == 3).sum() > 5
+    ctx.close()

@@ -83,6 +83,19 @@ def test_trail_tracking_golden():
     assert 10 < len(G["E_trails3"]) < int(G["E_start_n"][0])
 
 
+def test_refind_common_golden():
+    """MapMaker::ReFind_Common's PatchFinder / camera call sequence on the reference's objects (jni/MapMaker.cc:967-1036)."""
+    cam = synth.Camera(W, H)
+    smap = _smap()
+    ow = oraclebind.OrcWorld(cam, G["f0"], smap)
+    ow.make_current_kf(G["f2"]); ow.set_pose(G["F_pose"])
+    idx = np.arange(smap.n, dtype=np.int32)
+    oo, op = np.zeros((smap.n, 3), dtype=np.int32), np.zeros((smap.n, 2))
+    ow.L.orc_tracker_refind(ow.tracker, idx, smap.n, 4, 8, 0, oo, op)
+    assert np.array_equal(oo, G["F_flags"]) and np.array_equal(op, G["F_pos"])
+    assert oo[:, 0].sum() > 100 and oo[:, 2].sum() > 20
+
+
 def test_se3_exp_ln_golden():
     L = oraclebind.lib()
     for mu, e, l in zip(G["D_mu"], G["D_exp"], G["D_ln"]):

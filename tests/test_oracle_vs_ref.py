@@ -242,6 +242,36 @@ def test_trail_tracking_start_and_advance():
     assert np.abs(to[:, 2:] - to[:, :2]).max() > 3      # and they moved
 
 
+@pytest.mark.parametrize("case", ["near", "far_from_keyframe", "very_close"])
+def test_refind_common(case):
+    """f3: MapMaker::ReFind_Common (jni/MapMaker.cc:967-1036) — the reference's PatchFinder / camera calls in that function's order
+    (oracle/ref_harness.cc ref_refind) against the restatement, for every map point in a keyframe whose pose is slightly off.
+    `very_close` puts the camera so near the plane that warps are rejected (det > 3 at level 3): the function then still builds the
+    template at the level the loop reached, which the restatement reproduces."""
+    cam, f0, smap, rw, ow = _worlds()
+    tw = {"near": np.array(synth.CONFIG1_TWIST), "far_from_keyframe": np.array([0.05, -0.03, 0.45, 0.02, -0.03, 0.3]),
+          "very_close": np.array([0.0, 0.0, -0.935, 0.0, 0.0, 0.0])}[case]
+    frame, pose = common.frame_at(cam, tw)
+    off = synth.se3_exp(np.array([0.0008, -0.0006, 0.0005, 0.0006, -0.0004, 0.0007]))
+    kf_pose = (np.vstack([off, [0, 0, 0, 1]]) @ np.vstack([pose, [0, 0, 0, 1]]))[:3]
+    rw.make_current_kf(frame); ow.make_current_kf(frame)
+    rw.set_pose(kf_pose); ow.set_pose(kf_pose)
+    idx = np.arange(smap.n, dtype=np.int32)
+    ro, rp = np.zeros((smap.n, 3), dtype=np.int32), np.zeros((smap.n, 2))
+    oo, op = np.zeros((smap.n, 3), dtype=np.int32), np.zeros((smap.n, 2))
+    rw.L.ref_refind(rw.tracker, idx, smap.n, 4, 8, ro, rp)
+    ow.L.orc_tracker_refind(ow.tracker, idx, smap.n, 4, 8, 0, oo, op)
+    assert np.array_equal(ro, oo)
+    assert np.array_equal(rp, op)
+    if case == "very_close":
+        assert (ro[:, 1] == 3).sum() > 5                  # points whose warp was rejected at level 3 still went through the template step
+    else:
+        assert ro[:, 0].sum() > 300 and (ro[:, 2] == 1).sum() > 50 and ((ro[:, 0] == 1) & (ro[:, 2] == 0)).sum() > 50
+    # a cold finder per point gives the same answers when consecutive points differ (the batched GPU semantics)
+    ow.L.orc_tracker_refind(ow.tracker, idx, smap.n, 4, 8, 1, oo, op)
+    assert np.array_equal(ro, oo) and np.array_equal(rp, op)
+
+
 def test_small_blurry_image_pieces():
     """f1: SmallBlurryImage::MakeFromKF, IteratePosRelToTarget and SE3fromSE2 (jni/SmallBlurryImage.cc) — restatement vs compiled reference."""
     cam, f0, smap = common.scene()

@@ -43,7 +43,7 @@ ABI_SYMBOLS = [
     "vslam_make_keyframe_rest", "vslam_get_max_corners", "vslam_get_candidates", "vslam_snapshot_keyframe", "vslam_minipatch_sample", "vslam_minipatch_find",
     "vslam_set_pose", "vslam_get_pose", "vslam_get_poses", "vslam_set_motion", "vslam_get_motion", "vslam_reset_stream", "vslam_set_sbi_rotation", "vslam_enable_sbi", "vslam_get_sbi_rotation", "vslam_get_counters",
     "vslam_get_point_states", "vslam_get_point_template", "vslam_get_point_counts", "vslam_get_updates", "vslam_get_zmssd_evals",
-    "vslam_project_all", "vslam_set_point_projection", "vslam_set_lists", "vslam_clear_counters", "vslam_search_for_points", "vslam_project_and_derivs", "vslam_calc_jacobians",
+    "vslam_project_all", "vslam_set_point_projection", "vslam_set_lists", "vslam_clear_counters", "vslam_search_for_points", "vslam_refind", "vslam_get_refind_results", "vslam_project_and_derivs", "vslam_calc_jacobians",
     "vslam_calc_pose_update", "vslam_track_map", "vslam_track_frame", "vslam_track_frame_dev", "vslam_track_frame_async", "vslam_wait_step", "vslam_debug_atan", "vslam_debug_dp4a_peak", "vslam_kernel_launches", "vslam_set_timing", "vslam_get_stage_times",
 ]
 
@@ -111,6 +111,8 @@ def load():
     sig("vslam_set_lists", i, vp, vp, vp, i)
     sig("vslam_clear_counters", i, vp)
     sig("vslam_search_for_points", i, vp, i, i)
+    sig("vslam_refind", i, vp, i, i)
+    sig("vslam_get_refind_results", i, vp, i, vp, vp, i, pi)
     sig("vslam_project_and_derivs", i, vp, i)
     sig("vslam_calc_jacobians", i, vp)
     sig("vslam_calc_pose_update", i, vp, d, i, i, vp)
@@ -402,6 +404,15 @@ class Context:
 
     def search_for_points(self, rng, subpix_its):
         self._ck(self.L.vslam_search_for_points(self.h, rng, subpix_its))
+
+    def refind(self, rng=4, subpix_its=8):
+        """MapMaker::ReFind_Common for every (stream, listed point) pair (set_lists first)."""
+        self._ck(self.L.vslam_refind(self.h, rng, subpix_its))
+
+    def refind_results(self, s, cap):
+        fl = np.zeros((max(cap, 1), 3), dtype=np.int32); pos = np.zeros((max(cap, 1), 2)); n = C.c_int()
+        self._ck(self.L.vslam_get_refind_results(self.h, s, fl.ctypes.data, pos.ctypes.data, cap, C.byref(n)))
+        return fl[:min(cap, n.value)], pos[:min(cap, n.value)]
 
     def project_and_derivs(self, only_found=True):
         self._ck(self.L.vslam_project_and_derivs(self.h, int(only_found)))

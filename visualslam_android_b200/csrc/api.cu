@@ -146,7 +146,7 @@ int vslam_create(const vslam_config* cfg, vslam_ctx** out) {
   PointState& ps = ctx->ps;
   CK(dalloc(&ps.v3cam, 3 * SN)); CK(dalloc(&ps.v2image, 2 * SN)); CK(dalloc(&ps.derivs, 4 * SN)); CK(dalloc(&ps.warpinv, 4 * SN)); CK(dalloc(&ps.m2, 4 * SN));
   CK(dalloc(&ps.lastwarp, 4 * SN)); CK(dalloc(&ps.v2found, 2 * SN)); CK(dalloc(&ps.coarse, 2 * SN)); CK(dalloc(&ps.jac, 12 * SN));
-  CK(dalloc(&ps.err, 2 * SN)); CK(dalloc(&ps.sqrtinv, SN)); CK(dalloc(&ps.flags, SN)); CK(dalloc(&ps.level, SN));
+  CK(dalloc(&ps.err, 2 * SN)); CK(dalloc(&ps.sqrtinv, SN)); CK(dalloc(&ps.flags, SN)); CK(dalloc(&ps.level, SN)); CK(dalloc(&ps.rlevel, SN));
   CK(dalloc(&ps.tmpl, SN * VS_TMPL_BYTES)); CK(dalloc(&ps.tsum, 2 * SN)); CK(dalloc(&ps.counts, 2 * SN));
   { std::vector<int> lv(SN, -1); CK(cudaMemcpy(ps.level, lv.data(), SN * sizeof(int), cudaMemcpyHostToDevice)); }
   // per-stream state
@@ -182,7 +182,7 @@ void vslam_destroy(vslam_ctx* ctx) {
   cudaFree(ctx->map.world); cudaFree(ctx->map.right); cudaFree(ctx->map.down); cudaFree(ctx->map.ircenter); cudaFree(ctx->map.srclevel); cudaFree(ctx->map.srckf);
   PointState& ps = ctx->ps;
   cudaFree(ps.v3cam); cudaFree(ps.v2image); cudaFree(ps.derivs); cudaFree(ps.warpinv); cudaFree(ps.m2); cudaFree(ps.lastwarp); cudaFree(ps.v2found); cudaFree(ps.coarse);
-  cudaFree(ps.jac); cudaFree(ps.err); cudaFree(ps.sqrtinv); cudaFree(ps.flags); cudaFree(ps.level); cudaFree(ps.tmpl); cudaFree(ps.tsum); cudaFree(ps.counts);
+  cudaFree(ps.jac); cudaFree(ps.err); cudaFree(ps.sqrtinv); cudaFree(ps.flags); cudaFree(ps.level); cudaFree(ps.rlevel); cudaFree(ps.tmpl); cudaFree(ps.tsum); cudaFree(ps.counts);
   cudaFree(ctx->ss); cudaFree(ctx->lists); cudaFree(ctx->pvs); cudaFree(ctx->sort_scratch);
   if (ctx->scratch_host) cudaFreeHost(ctx->scratch_host);
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
@@ -669,7 +669,36 @@ int vslam_clear_counters(vslam_ctx* ctx) {
   return VSLAM_OK;
 }
 
-int vslam_search_for_points(vslam_ctx* ctx, int range, int subpix) { if (!ctx) return VSLAM_E_INVALID; return vs_launch_search(ctx, 0, range, subpix); }
+int vslam_search_for_points(vslam_ctx* ctx, int range, int subpix) { if (!ctx) return VSLAM_E_INVALID; return vs_launch_search(ctx, 0, range, subpix, 0); }
+
+// MapMaker::ReFind_Common (jni/MapMaker.cc:967-1036) for every (stream = keyframe, listed point) pair: projection with the stream's
+// pose, cold-finder template, FindPatchCoarse with `range` (the reference uses 4), sub-pixel refinement (8 iterations) on levels > 0.
+int vslam_refind(vslam_ctx* ctx, int range, int subpix_its) {
+  if (!ctx) return VSLAM_E_INVALID;
+  int rc = vs_launch_project_all(ctx, 0); if (rc) return rc;
+  return vs_launch_search(ctx, 0, range, subpix_its, 1);
+}
+// Results of vslam_refind for the current list of `stream`, in list order: flags3[k] = {found, level, bSubPix}, pos2[k] = v2RootPos
+int vslam_get_refind_results(vslam_ctx* ctx, int s, int32_t* flags3, double* pos2, int cap, int* n_out) {
+  int rc = check_stream(ctx, s); if (rc) return rc;
+  if (!flags3 || !pos2 || !n_out) return VSLAM_E_INVALID;
+  StreamState st; if ((rc = read_ss(ctx, s, &st))) return rc;
+  const int n = st.nA < cap ? st.nA : cap;
+  *n_out = st.nA;
+  const int N = ctx->N; const size_t SN = (size_t)ctx->S * N, o = (size_t)s * N;
+  std::vector<int> list(n > 0 ? n : 1), fl(ctx->map.n), lv(ctx->map.n); std::vector<double> f0(ctx->map.n), f1(ctx->map.n);
+  if (n > 0) VS_CUDA(cudaMemcpy(list.data(), ctx->lists + (size_t)s * ctx->list_cap, sizeof(int) * n, cudaMemcpyDeviceToHost));
+  VS_CUDA(cudaMemcpy(fl.data(), ctx->ps.flags + o, sizeof(int) * ctx->map.n, cudaMemcpyDeviceToHost));
+  VS_CUDA(cudaMemcpy(lv.data(), ctx->ps.rlevel + o, sizeof(int) * ctx->map.n, cudaMemcpyDeviceToHost));
+  VS_CUDA(cudaMemcpy(f0.data(), ctx->ps.v2found + o, sizeof(double) * ctx->map.n, cudaMemcpyDeviceToHost));
+  VS_CUDA(cudaMemcpy(f1.data(), ctx->ps.v2found + SN + o, sizeof(double) * ctx->map.n, cudaMemcpyDeviceToHost));
+  for (int k = 0; k < n; k++) {
+    const int i = list[k];
+    flags3[3 * k] = !!(fl[i] & F_FOUND); flags3[3 * k + 1] = lv[i]; flags3[3 * k + 2] = !!(fl[i] & F_SUBPIX);
+    pos2[2 * k] = f0[i]; pos2[2 * k + 1] = f1[i];
+  }
+  return VSLAM_OK;
+}
 int vslam_project_and_derivs(vslam_ctx* ctx, int only_found) { if (!ctx) return VSLAM_E_INVALID; return vs_launch_project_and_derivs(ctx, only_found); }
 int vslam_calc_jacobians(vslam_ctx* ctx) { if (!ctx) return VSLAM_E_INVALID; return vs_launch_calc_jacobians(ctx); }
 

@@ -67,12 +67,14 @@ __device__ inline int calc_level_warp(const Dev& D, const double* pose, int i, s
   double det = w00 * w11 - w01 * w10;
   int level = 0;
   while (det > 3 && level < VS_LEVELS - 1) { level++; det *= 0.25; }
-  if (det > 3 || det < 0.25) { flags |= F_TBAD; return -1; }
   // m2 = inverse(mm2WarpInverse) * LevelScale (jni/PatchFinder.cc:82-83, 2x2 adjugate inverse as frozen in the oracle), here
-  // instead of on a single lane of k_search
+  // instead of on a single lane of k_search.  Also for rejected warps, with the level the loop reached (mnSearchLevel keeps that
+  // value): MapMaker::ReFind_Common goes on to MakeTemplateCoarseCont after a rejection (jni/PatchFinder.cc:72-76).
   const double invdet = 1.0 / (w00 * w11 - w01 * w10);
   const int sc = LevelScale(level);
   D.ps.m2[gi] = (w11 * invdet) * sc; D.ps.m2[SN + gi] = (-w01 * invdet) * sc; D.ps.m2[2 * SN + gi] = (-w10 * invdet) * sc; D.ps.m2[3 * SN + gi] = (w00 * invdet) * sc;
+  D.ps.rlevel[gi] = level;
+  if (det > 3 || det < 0.25) { flags |= F_TBAD; return -1; }
   return level;
 }
 
@@ -240,9 +242,13 @@ __device__ __forceinline__ int warp_sum(int v) {
 }
 
 // mode 0: explicit list [0,nA) with (range, subpix) arguments; 1: coarse set A; 2: fine set B
+// sflags (mode 0): kSearchRefind = MapMaker::ReFind_Common's variant (jni/MapMaker.cc:967-1036): a cold PatchFinder per point (the
+// template is always regenerated and its bad flag comes from the warp alone), the level the warp loop reached even for rejected
+// warps, sub-pixel refinement only on levels > 0 and its position kept whether or not it converged.
 // PT: compile-time template side (8 or 11), 0 = use the run-time D.P
+constexpr int kSearchRefind = 1;
 template <int PT>
-__global__ void __launch_bounds__(kSearchWarps * 32) k_search(Dev D, int mode, int range_arg, int subpix_arg) {
+__global__ void __launch_bounds__(kSearchWarps * 32) k_search(Dev D, int mode, int range_arg, int subpix_arg, int sflags) {
   __shared__ SearchSmem sm_all[kSearchWarps];
   const int s = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int e = blockIdx.x * kSearchWarps + warp;
@@ -259,7 +265,13 @@ __global__ void __launch_bounds__(kSearchWarps * 32) k_search(Dev D, int mode, i
   const int P = PT ? PT : D.P, PP = P * P;
   uint8_t* const tmpl = (uint8_t*)sm.tmpl_w;
   int flags = D.ps.flags[gi];
-  const int level = D.ps.level[gi];
+  const bool refind = (sflags & kSearchRefind) != 0;
+  const int level = refind ? D.ps.rlevel[gi] : D.ps.level[gi];
+  if (refind) {
+    flags &= ~(F_SEARCHED | F_FOUND | F_SUBPIX);
+    if (!(flags & F_INIMAGE)) { if (lane == 0) D.ps.flags[gi] = flags; return; }   // not in this keyframe's image: "never retry"
+    if (level == 0) subpix = 0;
+  }
   // (the fine set was re-projected by k_reproject_fine if the coarse stage moved the pose)
 
   // ---- MakeTemplateCoarseCont (jni/PatchFinder.cc:79-125)
@@ -272,7 +284,7 @@ __global__ void __launch_bounds__(kSearchWarps * 32) k_search(Dev D, int mode, i
   const uint32_t* tmpl_g = (const uint32_t*)(D.ps.tmpl + gi * VS_TMPL_BYTES);
   const uint32_t tmpl_old = tmpl_g[lane], tmpl_old2 = lane < VS_TMPL_BYTES / 4 - 32 ? tmpl_g[32 + lane] : 0u;   // coalesced
   if (lane == 0) {
-    refresh = !(flags & F_HAVELAST);
+    refresh = refind || !(flags & F_HAVELAST);
     for (int c = 0; !refresh && c < 2; c++) {
       const double d0 = m2[c] - (c ? lw1 : lw0), d1 = m2[2 + c] - (c ? lw3 : lw2);
       double dd = 0; dd += d0 * d0; dd += d1 * d1;
@@ -498,7 +510,7 @@ __global__ void __launch_bounds__(kSearchWarps * 32) k_search(Dev D, int mode, i
   if (lane == 0) {
     D.ps.coarse[gi] = coarse0; D.ps.coarse[SN + gi] = coarse1;
     D.ps.sqrtinv[gi] = invScale;
-    if (ok) { D.ps.v2found[gi] = found0; D.ps.v2found[SN + gi] = found1; atomicAdd(&st->found[level], 1); if (subpix <= 0) flags &= ~F_SUBPIX; }
+    if (ok || refind) { D.ps.v2found[gi] = found0; D.ps.v2found[SN + gi] = found1; atomicAdd(&st->found[level], 1); if (subpix <= 0) flags &= ~F_SUBPIX; }
     else flags &= ~F_FOUND;   // sub-pixel iteration did not converge (jni/Tracker.cc:660-666)
     D.ps.flags[gi] = flags;
   }
@@ -1015,14 +1027,14 @@ int vs_launch_project_all(vslam_ctx* ctx, int mode) {
   return VSLAM_OK;
 }
 
-int vs_launch_search(vslam_ctx* ctx, int which, int range, int subpix) {
+int vs_launch_search(vslam_ctx* ctx, int which, int range, int subpix, int sflags) {
   const Dev D = make_dev(ctx);
   const int max_entries = which == 1 ? (int)(2 * ctx->params.coarse_max) : ctx->list_cap;
   dim3 grid((max_entries + kSearchWarps - 1) / kSearchWarps, ctx->S);
   vs_time_begin(ctx, which == 2 ? VS_ST_SEARCH_FINE : VS_ST_SEARCH_COARSE);
-  if (ctx->P == 11) k_search<11><<<grid, kSearchWarps * 32, 0, ctx->stream>>>(D, which, range, subpix);
-  else if (ctx->P == 8) k_search<8><<<grid, kSearchWarps * 32, 0, ctx->stream>>>(D, which, range, subpix);
-  else k_search<0><<<grid, kSearchWarps * 32, 0, ctx->stream>>>(D, which, range, subpix);
+  if (ctx->P == 11) k_search<11><<<grid, kSearchWarps * 32, 0, ctx->stream>>>(D, which, range, subpix, sflags);
+  else if (ctx->P == 8) k_search<8><<<grid, kSearchWarps * 32, 0, ctx->stream>>>(D, which, range, subpix, sflags);
+  else k_search<0><<<grid, kSearchWarps * 32, 0, ctx->stream>>>(D, which, range, subpix, sflags);
   vs_time_end(ctx);
   VS_CUDA(cudaGetLastError());
   ctx->launches++;
@@ -1057,14 +1069,14 @@ int vs_launch_calc_jacobians(vslam_ctx* ctx) {
 // Tracker::TrackMap for all streams: 6 launches, no host synchronisation in between.
 int vs_launch_track_map_rest(vslam_ctx* ctx, int with_motion_model) {
   int rc;
-  if ((rc = vs_launch_search(ctx, 1, 0, 0))) return rc;
+  if ((rc = vs_launch_search(ctx, 1, 0, 0, 0))) return rc;
   if ((rc = vs_launch_pose(ctx, 1, 0.0, 0, 0))) return rc;
   vs_time_begin(ctx, VS_ST_OTHER);
   k_reproject_fine<<<ctx->S, kPT, 0, ctx->stream>>>(make_dev(ctx));
   vs_time_end(ctx);
   VS_CUDA(cudaGetLastError());
   ctx->launches++;
-  if ((rc = vs_launch_search(ctx, 2, 0, 0))) return rc;
+  if ((rc = vs_launch_search(ctx, 2, 0, 0, 0))) return rc;
   if ((rc = vs_launch_pose(ctx, 2 | (with_motion_model ? 4 : 0), 0.0, 0, 0))) return rc;
   return VSLAM_OK;
 }

@@ -43,6 +43,7 @@ struct PointState {
   double* sqrtinv;    // [S*N]
   int* flags;         // [S*N] bit0 inImage, bit1 searched, bit2 found, bit3 didSubPix, bit4 templateBad, bit5 haveLast, bit6 hasTData
   int* level;         // [S*N] nSearchLevel (-1 = rejected)
+  int* rlevel;        // [S*N] the level the warp loop reached (PatchFinder::mnSearchLevel, also for rejected warps)
   uint8_t* tmpl;      // [S*N][VS_TMPL_BYTES]
   int* tsum;          // [2][S*N] sum, sumsq
   int* counts;        // [2][S*N] outlier, inlier
@@ -142,7 +143,7 @@ int vs_launch_pyramid_l0(vslam_ctx* ctx, int first_stream, int count);
 int vs_launch_fast_levels(vslam_ctx* ctx, int first_stream, int count);
 int vs_launch_source_pyramid(vslam_ctx* ctx, int kf_id);
 int vs_launch_project_all(vslam_ctx* ctx, int build_lists);
-int vs_launch_search(vslam_ctx* ctx, int which /*0 explicit list,1 coarse A,2 fine B*/, int range, int subpix);
+int vs_launch_search(vslam_ctx* ctx, int which /*0 explicit list,1 coarse A,2 fine B*/, int range, int subpix, int sflags /*1: ReFind_Common variant*/);
 int vs_launch_pose(vslam_ctx* ctx, int mode, double sigma, int mark, int apply);
 int vs_launch_track_map(vslam_ctx* ctx, int with_motion_model);
 int vs_launch_track_map_rest(vslam_ctx* ctx, int with_motion_model);   // everything after vs_launch_project_all
