@@ -170,6 +170,17 @@ int vslam_search_for_points(vslam_ctx* ctx, int range, int subpix_its);
  * is the caller's.  vslam_get_refind_results: list order, flags3 = {found, level, bSubPix}, pos2 = Measurement::v2RootPos. */
 int vslam_refind(vslam_ctx* ctx, int range, int subpix_its);
 int vslam_get_refind_results(vslam_ctx* ctx, int stream, int32_t* flags3, double* pos2, int cap, int* n);
+/* The search of MapMaker::AddPointEpipolar (jni/MapMaker.cc:525-640) for n candidates of level `level` of source keyframe `src_kf`
+ * (vslam_upload_source_keyframe; positions cand_xy in level pixels, e.g. Level::vCandidates) in the CURRENT keyframe of `stream`
+ * (the target): epipolar line from the two keyframe poses (row-major 3x4, camera-from-world) and the source keyframe's scene depth
+ * (dSceneDepthMean +- dSceneDepthSigma, clamped by mdWiggleScale as the reference does), un-warped template, ZMSSD over the target
+ * level's FAST corners inside the epipolar band, sub-pixel refinement (10 iterations).  found[k] = 1 iff a match was found and the
+ * refinement converged; pos2[k] = the refined level-0 position (Measurement::v2RootPos in the target); best_corner / best_zmssd (may be
+ * NULL): index into the target level's corner list and its score (-1 / mnMaxSSD+1 if no corner qualified).  Triangulation and the
+ * new MapPoint are the caller's (MapMaker).  Synchronous. */
+int vslam_epipolar_search(vslam_ctx* ctx, int stream, int src_kf, int level, int n, const int32_t* cand_xy, const double* src_pose12,
+                          const double* target_pose12, double depth_mean, double depth_sigma, double wiggle_scale, int32_t* found, double* pos2,
+                          int32_t* best_corner, int32_t* best_zmssd);
 int vslam_project_and_derivs(vslam_ctx* ctx, int only_found);
 int vslam_calc_jacobians(vslam_ctx* ctx);
 int vslam_calc_pose_update(vslam_ctx* ctx, double override_sigma, int mark_outliers, int apply, double* upd6_per_stream /* may be NULL */);

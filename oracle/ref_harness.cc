@@ -400,6 +400,86 @@ void ref_refind(void* t, const int32_t* idx, int n, int range, int subpix_its, i
   }
 }
 
+// The search of MapMaker::AddPointEpipolar (jni/MapMaker.cc:525-640), same arrangement as ref_refind: the function's call sequence
+// transcribed on the reference's own objects (ATANCamera::UnProject / LargestRadiusInImage / OnePixelDist, mySE3 / mySO3 operators,
+// PatchFinder::MakeTemplateCoarseNoWarp / ZMSSDAtPoint / MakeSubPixTemplate / IterateSubPixToConvergence, LevelZeroPos), stopping
+// where the triangulation starts.  kSrc / kTarget: KeyFrame handles (ref_kf_*), kSrc after MakeKeyFrame_Rest; poses row-major 3x4.
+// out3 = {converged match found, index of the best corner in kTarget's level (-1: none), its ZMSSD}; pos2 = Finder.GetSubPixPos().
+void ref_epipolar_search(void* t, void* ksrc, void* ktgt, const double* src_pose12, const double* tgt_pose12, double depth_mean, double depth_sigma,
+                         double wiggle, int nLevel, int nCandidate, int32_t* out3, double* pos2) {
+  Tracker* tr = ((RefTracker*)t)->tr;
+  ATANCamera& cam = tr->mCamera;
+  KeyFrame& kSrc = *(KeyFrame*)ksrc; KeyFrame& kTarget = *(KeyFrame*)ktgt;
+  kSrc.se3CfromW = pose_from12(src_pose12); kTarget.se3CfromW = pose_from12(tgt_pose12);
+  kSrc.dSceneDepthMean = depth_mean; kSrc.dSceneDepthSigma = depth_sigma;
+  out3[0] = 0; out3[1] = -1; out3[2] = 0; pos2[0] = pos2[1] = 0.0;
+  static Eigen::MatrixXd imUnProj[2];
+  static int cw = 0, ch = 0;
+  if (cw != kSrc.aLevels[0].im.cols || ch != kSrc.aLevels[0].im.rows) {
+    cw = kSrc.aLevels[0].im.cols; ch = kSrc.aLevels[0].im.rows;
+    imUnProj[0].resize(ch, cw); imUnProj[1].resize(ch, cw);
+    for (int i = 0; i < cw; i++) for (int j = 0; j < ch; j++) { Eigen::Vector2d p2d = cam.UnProject(Eigen::Vector2d(i, j)); imUnProj[0](j, i) = p2d(0); imUnProj[1](j, i) = p2d(1); }
+  }
+  int nLevelScale = LevelScale(nLevel);
+  Candidate& candidate = kSrc.aLevels[nLevel].vCandidates[nCandidate];
+  Eigen::Vector2d irLevelPos = candidate.irLevelPos;
+  Eigen::Vector2d v2RootPos = LevelZeroPos(irLevelPos, nLevel);
+  Eigen::Vector2d un = cam.UnProject(v2RootPos);
+  Eigen::Vector3d v3Ray_SC; v3Ray_SC(0) = un(0); v3Ray_SC(1) = un(1); v3Ray_SC(2) = 1.0;
+  v3Ray_SC.normalize();
+  Eigen::Vector3d v3LineDirn_TC = kTarget.se3CfromW.get_rotation() * (kSrc.se3CfromW.get_rotation().inverse() * v3Ray_SC);
+  double dStartDepth = std::max(wiggle, depth_mean - depth_sigma);
+  double dEndDepth = std::min(40 * wiggle, depth_mean + depth_sigma);
+  Eigen::Vector3d v3CamCenter_TC = kTarget.se3CfromW * kSrc.se3CfromW.inverse().get_translation();
+  Eigen::Vector3d v3RayStart_TC = v3CamCenter_TC + dStartDepth * v3LineDirn_TC;
+  Eigen::Vector3d v3RayEnd_TC = v3CamCenter_TC + dEndDepth * v3LineDirn_TC;
+  if (v3RayEnd_TC(2) <= v3RayStart_TC(2)) return;
+  if (v3RayEnd_TC(2) <= 0.0) return;
+  if (v3RayStart_TC(2) <= 0.0) v3RayStart_TC += v3LineDirn_TC * (0.001 - v3RayStart_TC(2) / v3LineDirn_TC(2));
+  Eigen::Vector2d v2A; v2A(0) = v3RayStart_TC(0) / v3RayStart_TC(2); v2A(1) = v3RayStart_TC(1) / v3RayStart_TC(2);
+  Eigen::Vector2d v2B; v2B(0) = v3RayEnd_TC(0) / v3RayEnd_TC(2); v2B(1) = v3RayEnd_TC(1) / v3RayEnd_TC(2);
+  Eigen::Vector2d v2AlongProjectedLine = v2A - v2B;
+  if (v2AlongProjectedLine.dot(v2AlongProjectedLine) < 0.00000001) return;
+  v2AlongProjectedLine.normalize();
+  Eigen::Vector2d v2Normal; v2Normal(0) = v2AlongProjectedLine(1); v2Normal(1) = -v2AlongProjectedLine(0);
+  double dNormDist = v2A.dot(v2Normal);
+  if (fabs(dNormDist) > cam.LargestRadiusInImage()) return;
+  double dMinLen = std::min(v2AlongProjectedLine.dot(v2A), v2AlongProjectedLine.dot(v2B)) - 0.05;
+  double dMaxLen = std::max(v2AlongProjectedLine.dot(v2A), v2AlongProjectedLine.dot(v2B)) + 0.05;
+  if (dMinLen < -2.0) dMinLen = -2.0;
+  if (dMaxLen < -2.0) dMaxLen = -2.0;
+  if (dMinLen > 2.0) dMinLen = 2.0;
+  if (dMaxLen > 2.0) dMaxLen = 2.0;
+  PatchFinder Finder;
+  int a = irLevelPos(0), b = irLevelPos(1);
+  Finder.MakeTemplateCoarseNoWarp(kSrc, nLevel, a, b);
+  if (Finder.TemplateBad()) return;
+  std::vector<Eigen::Vector2d>& vIR = kTarget.aLevels[nLevel].vCorners;
+  int nBest = -1;
+  int nBestZMSSD = Finder.mnMaxSSD + 1;
+  double dMaxDistDiff = cam.OnePixelDist() * (4.0 + 1.0 * nLevelScale);
+  double dMaxDistSq = dMaxDistDiff * dMaxDistDiff;
+  for (unsigned int i = 0; i < vIR.size(); i++) {
+    Eigen::Vector2d zpos = LevelZeroPos(vIR[i], nLevel);
+    Eigen::Vector2d v2Im(imUnProj[0](zpos(1), zpos(0)), imUnProj[1](zpos(1), zpos(0)));
+    double dDistDiff = dNormDist - v2Im.dot(v2Normal);
+    if (dDistDiff * dDistDiff > dMaxDistSq) continue;
+    if (v2Im.dot(v2AlongProjectedLine) < dMinLen) continue;
+    if (v2Im.dot(v2AlongProjectedLine) > dMaxLen) continue;
+    int nZMSSD = Finder.ZMSSDAtPoint(kTarget.aLevels[nLevel].im, (int)vIR[i](0), (int)vIR[i](1));
+    if (nZMSSD < nBestZMSSD) { nBest = i; nBestZMSSD = nZMSSD; }
+  }
+  out3[1] = nBest; out3[2] = nBestZMSSD;
+  if (nBest == -1) return;
+  Finder.MakeSubPixTemplate();
+  Finder.SetSubPixPos(LevelZeroPos(vIR[nBest], nLevel));
+  bool bSubPixConverges = Finder.IterateSubPixToConvergence(kTarget, 10);
+  Eigen::Vector2d r = Finder.GetSubPixPos();
+  pos2[0] = r(0); pos2[1] = r(1);
+  out3[0] = bSubPixConverges ? 1 : 0;
+}
+int ref_kf_num_candidates_l(void* kf, int l) { return (int)((KeyFrame*)kf)->aLevels[l].vCandidates.size(); }
+
 // Trail tracking for the initial map (jni/Tracker.cc:264-346) on the tracker's current keyframe (ref_tracker_make_current_kf first)
 int ref_tracker_trail_start(void* t) {
   Tracker* tr = ((RefTracker*)t)->tr;

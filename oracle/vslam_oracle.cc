@@ -1367,6 +1367,85 @@ void orc_tracker_refind(void* t_, const int32_t* idx, int n, int range, int subp
     } else { pos2[2 * k] = F.coarsePos[0]; pos2[2 * k + 1] = F.coarsePos[1]; }
   }
 }
+// The search of MapMaker::AddPointEpipolar (jni/MapMaker.cc:525-640) for candidate `cand` (level pixels) of level `level` of kSrc in
+// kTarget; the tracker only lends its camera and patch size.  out3 = {converged match, best corner index (-1 none), its ZMSSD};
+// pos2 = Finder.GetSubPixPos().  geom8 (may be NULL): v2Normal, v2Along, dNormDist, dMinLen, dMaxLen, dMaxDistSq.
+void orc_epipolar_search(void* t_, void* ksrc, void* ktgt, const double* src12, const double* tgt12, double depth_mean, double depth_sigma, double wiggle,
+                         int level, int cx_, int cy_, int32_t* out3, double* pos2, double* geom8) {
+  OTracker* t = (OTracker*)t_;
+  Cam cam = t->cam;
+  const OKeyFrame& kSrc = *(OKeyFrame*)ksrc; const OKeyFrame& kTarget = *(OKeyFrame*)ktgt;
+  const SE3 S = se3_from12(src12), T = se3_from12(tgt12);
+  out3[0] = 0; out3[1] = -1; out3[2] = 0; pos2[0] = pos2[1] = 0.0;
+  const int nLevelScale = LevelScale(level);
+  const double root[2] = {LevelZeroPos(cx_, level), LevelZeroPos(cy_, level)};
+  double un[2]; cam_unproject(cam, root, un);
+  double ray[3] = {un[0], un[1], 1.0};
+  { double nn = 0; nn += ray[0] * ray[0]; nn += ray[1] * ray[1]; nn += ray[2] * ray[2]; const double n = sqrt(nn); for (int i = 0; i < 3; i++) ray[i] /= n; }
+  // v3LineDirn_TC = R_T * (R_S^-1 * ray)
+  double St[9]; for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) St[3 * i + j] = S.R[3 * j + i];
+  double tmp[3], dirn[3]; mat3_mul_vec(St, ray, tmp); mat3_mul_vec(T.R, tmp, dirn);
+  const double dStart = std::max(wiggle, depth_mean - depth_sigma), dEnd = std::min(40 * wiggle, depth_mean + depth_sigma);
+  const SE3 Sinv = se3_inverse(S);
+  double center[3]; se3_apply(T, Sinv.t, center);
+  double start[3], end[3];
+  for (int i = 0; i < 3; i++) { start[i] = center[i] + dStart * dirn[i]; end[i] = center[i] + dEnd * dirn[i]; }
+  if (end[2] <= start[2]) return;
+  if (end[2] <= 0.0) return;
+  if (start[2] <= 0.0) { const double f = 0.001 - start[2] / dirn[2]; for (int i = 0; i < 3; i++) start[i] += dirn[i] * f; }
+  const double A[2] = {start[0] / start[2], start[1] / start[2]}, B[2] = {end[0] / end[2], end[1] / end[2]};
+  double al[2] = {A[0] - B[0], A[1] - B[1]};
+  double aa = 0; aa += al[0] * al[0]; aa += al[1] * al[1];
+  if (aa < 0.00000001) return;
+  { const double n = sqrt(aa); al[0] /= n; al[1] /= n; }
+  const double nr[2] = {al[1], -al[0]};
+  double dNormDist = 0; dNormDist += A[0] * nr[0]; dNormDist += A[1] * nr[1];
+  if (fabs(dNormDist) > cam.largestRadius) return;
+  double aA = 0; aA += al[0] * A[0]; aA += al[1] * A[1];
+  double aB = 0; aB += al[0] * B[0]; aB += al[1] * B[1];
+  double dMinLen = std::min(aA, aB) - 0.05, dMaxLen = std::max(aA, aB) + 0.05;
+  if (dMinLen < -2.0) dMinLen = -2.0;
+  if (dMaxLen < -2.0) dMaxLen = -2.0;
+  if (dMinLen > 2.0) dMinLen = 2.0;
+  if (dMaxLen > 2.0) dMaxLen = 2.0;
+  // mdOnePixelDist (jni/ATANCamera.cc:86-91)
+  double uc[2], ur[2]; const double c0[2] = {cam.width / 2, cam.height / 2}, c1[2] = {cam.width / 2 + 1.0, cam.height / 2 + 1.0};
+  cam_unproject(cam, c0, uc); cam_unproject(cam, c1, ur);
+  double dd = 0; dd += (uc[0] - ur[0]) * (uc[0] - ur[0]); dd += (uc[1] - ur[1]) * (uc[1] - ur[1]);
+  const double onePixelDist = sqrt(dd) / sqrt(2.0);
+  const double dMaxDistDiff = onePixelDist * (4.0 + 1.0 * nLevelScale), dMaxDistSq = dMaxDistDiff * dMaxDistDiff;
+  if (geom8) { geom8[0] = nr[0]; geom8[1] = nr[1]; geom8[2] = al[0]; geom8[3] = al[1]; geom8[4] = dNormDist; geom8[5] = dMinLen; geom8[6] = dMaxLen; geom8[7] = dMaxDistSq; }
+  // Finder.MakeTemplateCoarseNoWarp(kSrc, nLevel, a, b) (jni/PatchFinder.cc:130-143)
+  Finder F; F.init(t->P); F.level = level;
+  const Image& sim = kSrc.lev[level].im;
+  if (!in_image_with_border(sim, cx_, cy_, F.P / 2 + 1)) return;
+  for (int r = 0; r < F.P; r++) memcpy(&F.tmpl[r * F.P], sim.row(cy_ - F.P / 2 + r) + (cx_ - F.P / 2), F.P);
+  make_template_sums(F);
+  const OLevel& TL = kTarget.lev[level];
+  const int W0 = kTarget.lev[0].im.w;
+  int nBest = -1, nBestZMSSD = F.maxSSD + 1;
+  for (size_t i = 0; i < TL.corners.size(); i++) {
+    // vv2Corners[i] = imUnProj(zpos(1), zpos(0)): the table holds UnProject of integer pixels and is indexed with the truncated position
+    const int zx = (int)LevelZeroPos(TL.corners[i].x, level), zy = (int)LevelZeroPos(TL.corners[i].y, level);
+    (void)W0;
+    const double px[2] = {(double)zx, (double)zy}; double v2Im[2]; cam_unproject(cam, px, v2Im);
+    double dn = 0; dn += v2Im[0] * nr[0]; dn += v2Im[1] * nr[1];
+    const double dDistDiff = dNormDist - dn;
+    if (dDistDiff * dDistDiff > dMaxDistSq) continue;
+    double da = 0; da += v2Im[0] * al[0]; da += v2Im[1] * al[1];
+    if (da < dMinLen) continue;
+    if (da > dMaxLen) continue;
+    const int z = zmssd_at_point(F, TL.im, TL.corners[i].x, TL.corners[i].y);
+    if (z < nBestZMSSD) { nBest = (int)i; nBestZMSSD = z; }
+  }
+  out3[1] = nBest; out3[2] = nBestZMSSD;
+  if (nBest == -1) return;
+  make_subpix_template(F);
+  F.subPixPos[0] = LevelZeroPos(TL.corners[nBest].x, level); F.subPixPos[1] = LevelZeroPos(TL.corners[nBest].y, level);
+  const bool ok = iterate_subpix_to_convergence(F, kTarget, 10);
+  pos2[0] = F.subPixPos[0]; pos2[1] = F.subPixPos[1];
+  out3[0] = ok ? 1 : 0;
+}
 void orc_tracker_clear_counters(void* t_) { OTracker* t = (OTracker*)t_; for (int i = 0; i < LEVELS; i++) t->attempted[i] = t->foundCnt[i] = 0; }
 void orc_tracker_calc_jacobians(void* t_, const int32_t* idx, int n) { OTracker* t = (OTracker*)t_; for (int i = 0; i < n; i++) if (t->td[idx[i]].found) td_calc_jacobian(t->td[idx[i]]); }
 void orc_tracker_project_and_derivs(void* t_, const int32_t* idx, int n, int only_found) {

@@ -111,6 +111,23 @@ def main():
     rw.L.ref_refind(rw.tracker, idx, smap.n, 4, 8, ro, rp)
     out["F_flags"], out["F_pos"] = ro, rp
 
+    # --- case G: the search of MapMaker::AddPointEpipolar (oracle/ref_harness.cc ref_epipolar_search): candidates of f0 searched in f3
+    tw3 = np.array([0.12, 0.03, 0.02, 0.01, -0.03, 0.02])
+    pose3 = synth.se3_exp(tw3)
+    f3 = synth.render_frame(tex, cam, pose3)
+    out["G_f3"], out["G_pose"] = f3, pose3
+    rk0 = refbind.RefKeyFrame().make_lite(f0); rk0.make_rest()
+    rk3 = refbind.RefKeyFrame().make_lite(f3)
+    eye = np.ascontiguousarray(synth.IDENTITY_POSE, dtype=np.float64).reshape(12); p3 = np.ascontiguousarray(pose3, dtype=np.float64).reshape(12)
+    rows = []
+    for level in range(4):
+        xy, _ = rk0.candidates(level)
+        for k in range(0, len(xy), max(1, len(xy) // 40)):
+            ro, rp = np.zeros(3, dtype=np.int32), np.zeros(2)
+            rw.L.ref_epipolar_search(rw.tracker, rk0.h, rk3.h, eye, p3, 1.0, 0.3, 0.1, level, k, ro, rp)
+            rows.append([level, xy[k, 0], xy[k, 1], ro[0], ro[1], ro[2], rp[0], rp[1]])
+    out["G_rows"] = np.array(rows, dtype=np.float64)
+
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_small.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")

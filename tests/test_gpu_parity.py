@@ -553,3 +553,39 @@ def test_refind_common_batched_over_keyframes():
         else:
             assert (oo[:, 1] == 3).sum() > 5
     ctx.close()
+
+
+def test_epipolar_search_matches_the_oracle():
+    """f3: the search of MapMaker::AddPointEpipolar (jni/MapMaker.cc:525-640): every Shi-Tomasi candidate of every level of source
+    keyframe 0 searched along its epipolar line in the stream's current keyframe; found flag, best corner and its ZMSSD exact,
+    refined position to 1e-6 px, against the oracle (pinned in tests/test_oracle_vs_ref.py::test_epipolar_search)."""
+    from oracle import oraclebind
+    cam, f0, smap = common.scene()
+    tw = np.array([0.12, 0.03, 0.02, 0.01, -0.03, 0.02])
+    f1, pose1 = common.frame_at(cam, tw)
+    ctx = _ctx(cam, f0, smap)
+    ctx.make_keyframe_lite(f0)
+    ctx.make_keyframe_rest(0)
+    cands = [ctx.candidates(0, l)[0] for l in range(4)]
+    ok0 = oraclebind.OrcKeyFrame().make_lite(f0); ok0.make_rest()
+    ok1 = oraclebind.OrcKeyFrame().make_lite(f1)
+    ctx.make_keyframe_lite(f1)
+    ow = _orc(cam, f0, smap)
+    eye = np.ascontiguousarray(synth.IDENTITY_POSE, dtype=np.float64).reshape(12); p1 = np.ascontiguousarray(pose1, dtype=np.float64).reshape(12)
+    total_found = 0
+    for level in range(4):
+        xy = cands[level]
+        assert np.array_equal(xy, ok0.candidates(level)[0])
+        for mean, sigma, wig in ((1.0, 0.3, 0.1), (1.4, 0.2, 0.1)):
+            found, pos, bi, bs = ctx.epipolar_search(0, 0, level, xy, eye, p1, mean, sigma, wig)
+            step = max(1, len(xy) // 150)
+            for k in range(0, len(xy), step):
+                oo, op = np.zeros(3, dtype=np.int32), np.zeros(2)
+                ow.L.orc_epipolar_search(ow.tracker, ok0.h, ok1.h, eye, p1, mean, sigma, wig, level, int(xy[k, 0]), int(xy[k, 1]), oo, op, None)
+                assert (found[k], bi[k]) == (oo[0], oo[1]), (level, k, found[k], bi[k], bs[k], oo)
+                if oo[1] >= 0:
+                    assert bs[k] == oo[2]
+                    assert np.abs(pos[k] - op).max() <= 1e-6, (level, k)
+            total_found += int(found.sum())
+    assert total_found > 200
+    ctx.close()

@@ -96,6 +96,22 @@ def test_refind_common_golden():
     assert oo[:, 0].sum() > 100 and oo[:, 2].sum() > 20
 
 
+def test_epipolar_search_golden():
+    """The search of MapMaker::AddPointEpipolar (jni/MapMaker.cc:525-640) on the reference's objects: found flag, best corner, ZMSSD
+    and refined position for candidates of every level."""
+    cam = synth.Camera(W, H)
+    ow = oraclebind.OrcWorld(cam, G["f0"], _smap())
+    k0 = oraclebind.OrcKeyFrame().make_lite(G["f0"]); k3 = oraclebind.OrcKeyFrame().make_lite(G["G_f3"])
+    eye = np.ascontiguousarray(synth.IDENTITY_POSE, dtype=np.float64).reshape(12); p3 = np.ascontiguousarray(G["G_pose"], dtype=np.float64).reshape(12)
+    nfound = 0
+    for row in G["G_rows"]:
+        oo, op = np.zeros(3, dtype=np.int32), np.zeros(2)
+        ow.L.orc_epipolar_search(ow.tracker, k0.h, k3.h, eye, p3, 1.0, 0.3, 0.1, int(row[0]), int(row[1]), int(row[2]), oo, op, None)
+        assert np.array_equal(oo, row[3:6].astype(np.int32)) and np.array_equal(op, row[6:8]), row
+        nfound += int(oo[0])
+    assert nfound > 20
+
+
 def test_se3_exp_ln_golden():
     L = oraclebind.lib()
     for mu, e, l in zip(G["D_mu"], G["D_exp"], G["D_ln"]):

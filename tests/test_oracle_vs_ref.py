@@ -272,6 +272,33 @@ def test_refind_common(case):
     assert np.array_equal(ro, oo) and np.array_equal(rp, op)
 
 
+def test_epipolar_search():
+    """f3: the search of MapMaker::AddPointEpipolar (jni/MapMaker.cc:525-640) — call sequence on the reference's objects
+    (ref_epipolar_search) against the restatement, for the Shi-Tomasi candidates of every level of one keyframe searched in a
+    second keyframe taken after a sideways motion."""
+    cam, f0, smap, rw, ow = _worlds()
+    tw = np.array([0.12, 0.03, 0.02, 0.01, -0.03, 0.02])
+    f1, pose1 = common.frame_at(cam, tw)
+    rk0 = refbind.RefKeyFrame().make_lite(f0); rk0.make_rest()
+    rk1 = refbind.RefKeyFrame().make_lite(f1)
+    ok0 = oraclebind.OrcKeyFrame().make_lite(f0); ok0.make_rest()
+    ok1 = oraclebind.OrcKeyFrame().make_lite(f1)
+    eye = np.ascontiguousarray(synth.IDENTITY_POSE, dtype=np.float64).reshape(12); p1 = np.ascontiguousarray(pose1, dtype=np.float64).reshape(12)
+    nfound = nbest = 0
+    for level in range(4):
+        xy, _ = ok0.candidates(level)
+        assert rw.L.ref_kf_num_candidates_l(rk0.h, level) == len(xy)
+        for k in range(0, len(xy), max(1, len(xy) // 60)):
+            ro, rp = np.zeros(3, dtype=np.int32), np.zeros(2)
+            oo, op = np.zeros(3, dtype=np.int32), np.zeros(2)
+            for mean, sigma, wig in ((1.0, 0.3, 0.1), (1.4, 0.2, 0.1)):
+                rw.L.ref_epipolar_search(rw.tracker, rk0.h, rk1.h, eye, p1, mean, sigma, wig, level, k, ro, rp)
+                ow.L.orc_epipolar_search(ow.tracker, ok0.h, ok1.h, eye, p1, mean, sigma, wig, level, int(xy[k, 0]), int(xy[k, 1]), oo, op, None)
+                assert np.array_equal(ro, oo) and np.array_equal(rp, op), (level, k, ro, oo, rp, op)
+                nfound += int(ro[0]); nbest += int(ro[1] >= 0)
+    assert nfound > 40 and nbest > nfound
+
+
 def test_small_blurry_image_pieces():
     """f1: SmallBlurryImage::MakeFromKF, IteratePosRelToTarget and SE3fromSE2 (jni/SmallBlurryImage.cc) — restatement vs compiled reference."""
     cam, f0, smap = common.scene()

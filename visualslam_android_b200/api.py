@@ -43,7 +43,7 @@ ABI_SYMBOLS = [
     "vslam_make_keyframe_rest", "vslam_get_max_corners", "vslam_get_candidates", "vslam_snapshot_keyframe", "vslam_minipatch_sample", "vslam_minipatch_find",
     "vslam_set_pose", "vslam_get_pose", "vslam_get_poses", "vslam_set_motion", "vslam_get_motion", "vslam_reset_stream", "vslam_set_sbi_rotation", "vslam_enable_sbi", "vslam_get_sbi_rotation", "vslam_get_counters",
     "vslam_get_point_states", "vslam_get_point_template", "vslam_get_point_counts", "vslam_get_updates", "vslam_get_zmssd_evals",
-    "vslam_project_all", "vslam_set_point_projection", "vslam_set_lists", "vslam_clear_counters", "vslam_search_for_points", "vslam_refind", "vslam_get_refind_results", "vslam_project_and_derivs", "vslam_calc_jacobians",
+    "vslam_project_all", "vslam_set_point_projection", "vslam_set_lists", "vslam_clear_counters", "vslam_search_for_points", "vslam_refind", "vslam_get_refind_results", "vslam_epipolar_search", "vslam_project_and_derivs", "vslam_calc_jacobians",
     "vslam_calc_pose_update", "vslam_track_map", "vslam_track_frame", "vslam_track_frame_dev", "vslam_track_frame_async", "vslam_wait_step", "vslam_debug_atan", "vslam_debug_dp4a_peak", "vslam_kernel_launches", "vslam_set_timing", "vslam_get_stage_times",
 ]
 
@@ -112,6 +112,7 @@ def load():
     sig("vslam_clear_counters", i, vp)
     sig("vslam_search_for_points", i, vp, i, i)
     sig("vslam_refind", i, vp, i, i)
+    sig("vslam_epipolar_search", i, vp, i, i, i, i, vp, vp, vp, d, d, d, vp, vp, vp, vp)
     sig("vslam_get_refind_results", i, vp, i, vp, vp, i, pi)
     sig("vslam_project_and_derivs", i, vp, i)
     sig("vslam_calc_jacobians", i, vp)
@@ -413,6 +414,15 @@ class Context:
         fl = np.zeros((max(cap, 1), 3), dtype=np.int32); pos = np.zeros((max(cap, 1), 2)); n = C.c_int()
         self._ck(self.L.vslam_get_refind_results(self.h, s, fl.ctypes.data, pos.ctypes.data, cap, C.byref(n)))
         return fl[:min(cap, n.value)], pos[:min(cap, n.value)]
+
+    def epipolar_search(self, s, src_kf, level, cand_xy, src_pose, tgt_pose, depth_mean, depth_sigma, wiggle_scale):
+        """The search of MapMaker::AddPointEpipolar for candidates of a source keyframe level in stream s's current keyframe."""
+        xy = np.ascontiguousarray(cand_xy, dtype=np.int32).reshape(-1, 2); n = len(xy)
+        sp = np.ascontiguousarray(src_pose, dtype=np.float64).reshape(12); tp = np.ascontiguousarray(tgt_pose, dtype=np.float64).reshape(12)
+        found = np.zeros(max(n, 1), dtype=np.int32); pos = np.zeros((max(n, 1), 2)); bi = np.zeros(max(n, 1), dtype=np.int32); bs = np.zeros(max(n, 1), dtype=np.int32)
+        self._ck(self.L.vslam_epipolar_search(self.h, s, src_kf, level, n, xy.ctypes.data, sp.ctypes.data, tp.ctypes.data, depth_mean, depth_sigma, wiggle_scale,
+                                              found.ctypes.data, pos.ctypes.data, bi.ctypes.data, bs.ctypes.data))
+        return found[:n], pos[:n], bi[:n], bs[:n]
 
     def project_and_derivs(self, only_found=True):
         self._ck(self.L.vslam_project_and_derivs(self.h, int(only_found)))

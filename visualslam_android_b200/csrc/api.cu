@@ -104,7 +104,7 @@ int vslam_create(const vslam_config* cfg, vslam_ctx** out) {
   if (!ctx) { g_create_error = "out of host memory"; return VSLAM_E_INVALID; }
   ctx->cfg = *cfg; vslam_default_params(&ctx->params);
   ctx->S = cfg->n_streams; ctx->N = cfg->max_points; ctx->P = cfg->patch_size; ctx->launches = 0; ctx->n_src = cfg->max_source_keyframes;
-  ctx->side_stream = nullptr; ctx->ev_fork = nullptr; ctx->ev_join = nullptr; ctx->scratch_host = nullptr; ctx->scratch_host_bytes = 0; ctx->timing = false; ctx->ev_used = 0; ctx->l0_alt = nullptr; ctx->copy_stream = nullptr; ctx->step = 0; ctx->pipe_ready = false; ctx->status_pin = nullptr;
+  ctx->unproj_lut = nullptr; ctx->unproj_ok = false; ctx->side_stream = nullptr; ctx->ev_fork = nullptr; ctx->ev_join = nullptr; ctx->scratch_host = nullptr; ctx->scratch_host_bytes = 0; ctx->timing = false; ctx->ev_used = 0; ctx->l0_alt = nullptr; ctx->copy_stream = nullptr; ctx->step = 0; ctx->pipe_ready = false; ctx->status_pin = nullptr;
   ctx->rest_scores = nullptr; ctx->rest_max = nullptr; ctx->rest_cand = nullptr; ctx->rest_cand_score = nullptr; ctx->rest_counts = nullptr; ctx->rest_stream = -1;
   ctx->snap_img = nullptr; ctx->snap_corners = nullptr; ctx->snap_lut = nullptr;
   ctx->sbi_on = false; ctx->sbi_tmpl = nullptr; ctx->sbi_scratch = nullptr; ctx->sbi_jac = nullptr; ctx->sbi_small = nullptr; ctx->sbi_have = nullptr;
@@ -194,6 +194,7 @@ void vslam_destroy(vslam_ctx* ctx) {
   if (ctx->status_pin) cudaFreeHost(ctx->status_pin);
   delete[] ctx->l0_ptr_host; delete[] ctx->l0_stride_host;
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  cudaFree(ctx->unproj_lut);
   if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
@@ -268,6 +269,7 @@ int vslam_set_camera(vslam_ctx* ctx, const double* c) {
   CamDev& d = ctx->cam;
   d.fx = c[0]; d.fy = c[1]; d.cx = c[2]; d.cy = c[3]; d.W = c[4]; d.Winv = c[5]; d.twoTan = c[6]; d.oneOver2Tan = c[7]; d.distEnabled = c[8];
   d.largestRadius = c[9]; d.maxR = c[10]; d.width = c[11]; d.height = c[12];
+  ctx->unproj_ok = false;
   return VSLAM_OK;
 }
 
@@ -699,6 +701,95 @@ int vslam_get_refind_results(vslam_ctx* ctx, int s, int32_t* flags3, double* pos
   }
   return VSLAM_OK;
 }
+// ---- MapMaker::AddPointEpipolar, the search (jni/MapMaker.cc:525-640) ------------------------------------------------------------
+namespace {
+// ATANCamera::UnProject (jni/ATANCamera.cc:149-164) with invrtrans (jni/ATANCamera.h:145-150); host libm, like the reference
+void host_unproject(const CamDev& c, double x, double y, double* out) {
+  const double dx = (x - c.cx) * (1.0 / c.fx), dy = (y - c.cy) * (1.0 / c.fy);
+  const double distR = sqrt(dx * dx + dy * dy);
+  const double R = (c.W == 0.0) ? distR : (tan(distR * c.W) * c.oneOver2Tan);
+  const double factor = (distR > 0.01) ? R / distR : 1.0;
+  out[0] = dx * factor; out[1] = dy * factor;
+}
+void rot_vec(const double* P, const double* v, double* o) { for (int i = 0; i < 3; i++) { double s = P[4 * i] * v[0]; s += P[4 * i + 1] * v[1]; s += P[4 * i + 2] * v[2]; o[i] = s; } }
+void rot_t_vec(const double* P, const double* v, double* o) { for (int i = 0; i < 3; i++) { double s = P[i] * v[0]; s += P[4 + i] * v[1]; s += P[8 + i] * v[2]; o[i] = s; } }
+}  // namespace
+
+int vslam_epipolar_search(vslam_ctx* ctx, int stream, int src_kf, int level, int n, const int32_t* cand_xy, const double* src_pose, const double* tgt_pose,
+                          double depth_mean, double depth_sigma, double wiggle_scale, int32_t* found, double* pos2, int32_t* best_corner, int32_t* best_zmssd) {
+  int rc = check_stream(ctx, stream); if (rc) return rc;
+  if (!cand_xy || !src_pose || !tgt_pose || !found || !pos2 || n < 0 || level < 0 || level >= VS_LEVELS || src_kf < 0 || src_kf >= ctx->n_src) { ctx->err = "bad argument"; return VSLAM_E_INVALID; }
+  const CamDev& cam = ctx->cam;
+  const int W = ctx->lev[0].w, H = ctx->lev[0].h;
+  if (!ctx->unproj_ok) {   // imUnProj: UnProject of every integer pixel (jni/MapMaker.cc:530-540)
+    std::vector<double> lut((size_t)2 * W * H);
+    for (int j = 0; j < H; j++) for (int i = 0; i < W; i++) host_unproject(cam, (double)i, (double)j, &lut[2 * ((size_t)j * W + i)]);
+    if (!ctx->unproj_lut) VS_CUDA(dalloc(&ctx->unproj_lut, lut.size()));
+    VS_CUDA(cudaMemcpy(ctx->unproj_lut, lut.data(), sizeof(double) * lut.size(), cudaMemcpyHostToDevice));
+    ctx->unproj_ok = true;
+  }
+  // mdOnePixelDist (jni/ATANCamera.cc:86-91)
+  double uc[2], ur[2]; host_unproject(cam, cam.width / 2, cam.height / 2, uc); host_unproject(cam, cam.width / 2 + 1.0, cam.height / 2 + 1.0, ur);
+  const double ddx = uc[0] - ur[0], ddy = uc[1] - ur[1];
+  double dd = ddx * ddx; dd += ddy * ddy;
+  const double onePixelDist = sqrt(dd) / sqrt(2.0);
+  const int nLevelScale = 1 << level;
+  const double dMaxDistDiff = onePixelDist * (4.0 + 1.0 * nLevelScale), dMaxDistSq = dMaxDistDiff * dMaxDistDiff;
+  // v3CamCenter_TC = kTarget.se3CfromW * kSrc.se3CfromW.inverse().get_translation()
+  const double ts[3] = {src_pose[3], src_pose[7], src_pose[11]};
+  double rts[3]; rot_t_vec(src_pose, ts, rts);
+  const double sinv_t[3] = {-rts[0], -rts[1], -rts[2]};
+  double center[3]; rot_vec(tgt_pose, sinv_t, center); center[0] = center[0] + tgt_pose[3]; center[1] = center[1] + tgt_pose[7]; center[2] = center[2] + tgt_pose[11];
+  const double dStartDepth = std::max(wiggle_scale, depth_mean - depth_sigma), dEndDepth = std::min(40 * wiggle_scale, depth_mean + depth_sigma);
+  std::vector<EpiCand> cands(n > 0 ? n : 1);
+  for (int k = 0; k < n; k++) {
+    EpiCand& C = cands[k];
+    memset(&C, 0, sizeof(C));
+    C.x = cand_xy[2 * k]; C.y = cand_xy[2 * k + 1];
+    const double root0 = ((double)C.x + 0.5) * nLevelScale - 0.5, root1 = ((double)C.y + 0.5) * nLevelScale - 0.5;   // LevelZeroPos
+    double u[2]; host_unproject(cam, root0, root1, u);
+    double ray[3] = {u[0], u[1], 1.0};
+    { double nn = ray[0] * ray[0]; nn += ray[1] * ray[1]; nn += ray[2] * ray[2]; const double nrm = sqrt(nn); ray[0] /= nrm; ray[1] /= nrm; ray[2] /= nrm; }
+    double tmp[3], dirn[3]; rot_t_vec(src_pose, ray, tmp); rot_vec(tgt_pose, tmp, dirn);
+    double start[3], end[3];
+    for (int q = 0; q < 3; q++) { start[q] = center[q] + dStartDepth * dirn[q]; end[q] = center[q] + dEndDepth * dirn[q]; }
+    if (end[2] <= start[2]) continue;
+    if (end[2] <= 0.0) continue;
+    if (start[2] <= 0.0) { const double f = 0.001 - start[2] / dirn[2]; for (int q = 0; q < 3; q++) start[q] += dirn[q] * f; }
+    const double A[2] = {start[0] / start[2], start[1] / start[2]}, B[2] = {end[0] / end[2], end[1] / end[2]};
+    double al[2] = {A[0] - B[0], A[1] - B[1]};
+    double aa = al[0] * al[0]; aa += al[1] * al[1];
+    if (aa < 0.00000001) continue;
+    { const double nrm = sqrt(aa); al[0] /= nrm; al[1] /= nrm; }
+    const double nrml[2] = {al[1], -al[0]};
+    double dNormDist = A[0] * nrml[0]; dNormDist += A[1] * nrml[1];
+    if (fabs(dNormDist) > cam.largestRadius) continue;
+    double aA = al[0] * A[0]; aA += al[1] * A[1];
+    double aB = al[0] * B[0]; aB += al[1] * B[1];
+    double dMinLen = std::min(aA, aB) - 0.05, dMaxLen = std::max(aA, aB) + 0.05;
+    if (dMinLen < -2.0) dMinLen = -2.0;
+    if (dMaxLen < -2.0) dMaxLen = -2.0;
+    if (dMinLen > 2.0) dMinLen = 2.0;
+    if (dMaxLen > 2.0) dMaxLen = 2.0;
+    C.nx = nrml[0]; C.ny = nrml[1]; C.ax = al[0]; C.ay = al[1]; C.normDist = dNormDist; C.minLen = dMinLen; C.maxLen = dMaxLen; C.maxDistSq = dMaxDistSq; C.valid = 1;
+  }
+  if (n == 0) return VSLAM_OK;
+  EpiCand* cd = nullptr; int* oi = nullptr; double* op = nullptr;
+  cudaError_t e = cudaMalloc(&cd, sizeof(EpiCand) * n);
+  if (e == cudaSuccess) e = cudaMalloc(&oi, sizeof(int) * 3 * n);
+  if (e == cudaSuccess) e = cudaMalloc(&op, sizeof(double) * 2 * n);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(cd, cands.data(), sizeof(EpiCand) * n, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) { rc = vs_launch_epipolar(ctx, stream, src_kf, level, n, cd, ctx->unproj_lut, 10, oi, op); if (rc) { cudaFree(cd); cudaFree(oi); cudaFree(op); return rc; } }
+  std::vector<int> hi(3 * (size_t)n);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(hi.data(), oi, sizeof(int) * 3 * n, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(pos2, op, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(cd); cudaFree(oi); cudaFree(op);
+  if (e != cudaSuccess) { ctx->err = std::string("vslam_epipolar_search: ") + cudaGetErrorString(e); return VSLAM_E_CUDA; }
+  for (int k = 0; k < n; k++) { found[k] = hi[3 * k]; if (best_corner) best_corner[k] = hi[3 * k + 1]; if (best_zmssd) best_zmssd[k] = hi[3 * k + 2]; }
+  return VSLAM_OK;
+}
+
 int vslam_project_and_derivs(vslam_ctx* ctx, int only_found) { if (!ctx) return VSLAM_E_INVALID; return vs_launch_project_and_derivs(ctx, only_found); }
 int vslam_calc_jacobians(vslam_ctx* ctx) { if (!ctx) return VSLAM_E_INVALID; return vs_launch_calc_jacobians(ctx); }
 

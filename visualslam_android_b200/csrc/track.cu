@@ -229,16 +229,126 @@ __global__ void __launch_bounds__(kPT) k_project_lists(Dev D, int mode, int appl
 // SearchForPoints, one warp per list entry.
 constexpr int kCandCap = 96;           // ZMSSD candidates gathered per round of one warp
 struct SearchSmem {
-  double pos[VS_MAXP * VS_MAXP * 2];    // template sample positions / sub-pixel products
-  double jx[81], jy[81], prod2[81];
+  union {   // the three phases of a warp never overlap: template generation (pos), candidate scoring (cand_*, acc), sub-pixel (pos, jx, jy, prod2)
+    struct { double pos[VS_MAXP * VS_MAXP * 2]; double jx[81], jy[81], prod2[81]; };   // template sample positions / sub-pixel products and gradients
+    struct { uint32_t cand_cw[kCandCap]; int cand_idx[kCandCap]; int acc[kCandCap * 3]; };
+  };
   uint32_t tmpl_w[VS_TMPL_BYTES / 4];  // template, one row = 3 zero-padded words (12 bytes): the dp4a operand layout
-  uint32_t cand_cw[kCandCap]; int cand_idx[kCandCap]; int acc[kCandCap * 3];
 };
 
 __device__ __forceinline__ int warp_sum(int v) {
 #pragma unroll
   for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
   return v;
+}
+
+// ZMSSDAtPoint (jni/PatchFinder.cc:352-380) of the `ncand` candidates filed in sm.cand_cw / cand_idx (accumulators zeroed by the
+// filer): one work item = one template row of one candidate; returns min(best, keys) with key = ssd << 32 | cand_idx (ties: lowest index).
+template <int PT>
+__device__ __forceinline__ unsigned long long score_candidates(SearchSmem& sm, int ncand, const uint8_t* __restrict__ img, int pitch, int lw, int lh, int P,
+                                                                int tsum, int tsumsq, int maxSSD, unsigned long long best) {
+  const int lane = threadIdx.x & 31, PP = P * P;
+  const int b = P / 2, nwords = (P + 3) >> 2;
+  const uint32_t lastmask = (P & 3) ? ((1u << (8 * (P & 3))) - 1u) : 0xffffffffu;
+  // ZMSSDAtPoint (jni/PatchFinder.cc:352-380): one work item = one template row of one candidate
+  for (int item = lane; item < ncand * P; item += 32) {
+    const int c = item / P, r = item - c * P;
+    const uint32_t cw = sm.cand_cw[c];
+    const int cx = cw & 0xffff, cy = cw >> 16;
+    if (!(cx >= b && cy >= b && cx < lw - b && cy < lh - b)) continue;
+    const uint8_t* rp = img + (size_t)(cy - b + r) * pitch + (cx - b);
+    const unsigned a = (unsigned)((uintptr_t)rp & 3u), sh = a * 8;
+    const uint32_t* wp = (const uint32_t*)(rp - a);
+    uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = 0, w3 = 0;
+    if (a + P > 8) w2 = __ldg(wp + 2);
+    if (a + P > 12) w3 = __ldg(wp + 3);
+    uint32_t n0 = __funnelshift_r(w0, w1, sh), n1 = __funnelshift_r(w1, w2, sh), n2 = __funnelshift_r(w2, w3, sh);
+    if (nwords == 3) n2 &= lastmask; else if (nwords == 2) { n1 &= lastmask; n2 = 0; } else { n0 &= lastmask; n1 = 0; n2 = 0; }
+    unsigned sum = __dp4a(n0, 0x01010101u, 0u), sumsq = __dp4a(n0, n0, 0u), cross = __dp4a(n0, sm.tmpl_w[3 * r], 0u);
+    sum = __dp4a(n1, 0x01010101u, sum); sumsq = __dp4a(n1, n1, sumsq); cross = __dp4a(n1, sm.tmpl_w[3 * r + 1], cross);
+    sum = __dp4a(n2, 0x01010101u, sum); sumsq = __dp4a(n2, n2, sumsq); cross = __dp4a(n2, sm.tmpl_w[3 * r + 2], cross);
+    atomicAdd(&sm.acc[3 * c], (int)sum); atomicAdd(&sm.acc[3 * c + 1], (int)sumsq); atomicAdd(&sm.acc[3 * c + 2], (int)cross);
+  }
+  __syncwarp();
+  for (int c = lane; c < ncand; c += 32) {
+    const uint32_t cw = sm.cand_cw[c];
+    const int cx = cw & 0xffff, cy = cw >> 16;
+    int ssd;
+    if (!(cx >= b && cy >= b && cx < lw - b && cy < lh - b)) ssd = maxSSD + 1;
+    else { const int SA = tsum, SB = sm.acc[3 * c]; ssd = ((2 * SA * SB - SA * SA - SB * SB) / PP + sm.acc[3 * c + 1] + tsumsq - 2 * sm.acc[3 * c + 2]); }
+    const unsigned long long key = ((unsigned long long)(unsigned)ssd << 32) | (unsigned)sm.cand_idx[c];   // ssd >= 0; ties -> lowest corner index
+    best = key < best ? key : best;
+  }
+  return best;
+}
+
+// MakeSubPixTemplate + IterateSubPixToConvergence (jni/PatchFinder.cc:242-350) around (coarse0, coarse1) (level-0 pixels) in the
+// level image `img`; tmpl: the template in 12-byte rows.  Returns 1 if converged; (out0, out1) = mv2SubPixPos in any case.
+__device__ __forceinline__ int subpix_refine(SearchSmem& sm, const uint8_t* tmpl, const uint8_t* __restrict__ img, int pitch, int lw, int lh, int level, int P,
+                                             int subpix, double coarse0, double coarse1, double& out0, double& out1) {
+  const int lane = threadIdx.x & 31;
+  const int nLevelScale = LevelScale(level);
+  const double invScale = 1.0 / nLevelScale;
+  // ---- MakeSubPixTemplate (jni/PatchFinder.cc:242-267)
+  const int Q = P - 2, QQ = Q * Q;
+  for (int k = lane; k < QQ; k += 32) {
+    const int x = k / Q + 1, y = k - (x - 1) * Q + 1;   // stored index (x-1)*Q + (y-1)
+    sm.jx[k] = 0.5 * (tmpl[y * 12 + x + 1] - tmpl[y * 12 + x - 1]);
+    sm.jy[k] = 0.5 * (tmpl[(y + 1) * 12 + x] - tmpl[(y - 1) * 12 + x]);
+  }
+  __syncwarp();
+  // JtJ of (gx, gy, 1): sums of multiples of 0.25 below 2^53 are exact in any order, so a warp reduction is bit-exact
+  double hxx = 0, hxy = 0, hyy = 0, hx = 0, hy = 0;
+  for (int k = lane; k < QQ; k += 32) { const double gx = sm.jx[k], gy = sm.jy[k]; hxx += gx * gx; hxy += gx * gy; hyy += gy * gy; hx += gx; hy += gy; }
+#pragma unroll
+  for (int d = 16; d; d >>= 1) {
+    hxx += __shfl_xor_sync(0xffffffffu, hxx, d); hxy += __shfl_xor_sync(0xffffffffu, hxy, d); hyy += __shfl_xor_sync(0xffffffffu, hyy, d);
+    hx += __shfl_xor_sync(0xffffffffu, hx, d); hy += __shfl_xor_sync(0xffffffffu, hy, d);
+  }
+  const double H[9] = {hxx, hxy, hx, hxy, hyy, hy, hx, hy, (double)QQ};
+  double hinv[9];
+  {   // 3x3 inverse: adjugate * (1/det), evaluation order of the oracle (oracle/vslam_oracle.cc inverse3)
+    const double c00 = H[4] * H[8] - H[5] * H[7], c10 = H[5] * H[6] - H[3] * H[8], c20 = H[3] * H[7] - H[4] * H[6];
+    const double det = H[0] * c00 + H[1] * c10 + H[2] * c20, invdet = 1.0 / det;
+    hinv[0] = c00 * invdet; hinv[3] = c10 * invdet; hinv[6] = c20 * invdet;
+    hinv[1] = (H[2] * H[7] - H[1] * H[8]) * invdet; hinv[4] = (H[0] * H[8] - H[2] * H[6]) * invdet; hinv[7] = (H[1] * H[6] - H[0] * H[7]) * invdet;
+    hinv[2] = (H[1] * H[5] - H[2] * H[4]) * invdet; hinv[5] = (H[2] * H[3] - H[0] * H[5]) * invdet; hinv[8] = (H[0] * H[4] - H[1] * H[3]) * invdet;
+  }
+  double sp0 = coarse0, sp1 = coarse1, meanDiff = 0.0;
+  int ok = 0;
+  // ---- IterateSubPixToConvergence / IterateSubPix (jni/PatchFinder.cc:272-350)
+  for (int it = 0; it < subpix; it++) {
+    const double c0 = (sp0 + 0.5) * invScale - 0.5, c1 = (sp1 + 0.5) * invScale - 0.5;   // LevelNPos
+    const int xb = (c0 > 0.0 ? c0 + 0.5 : c0 - 0.5), yb = (c1 > 0.0 ? c1 + 0.5 : c1 - 0.5);
+    const int bd = P / 2 + 1;
+    if (!(xb >= bd && yb >= bd && xb < lw - bd && yb < lh - bd)) break;   // off the image: not converged
+    const double b0 = c0 - (double)(P / 2), b1 = c1 - (double)(P / 2);
+    const double dX = b0 - floor(b0), dY = b1 - floor(b1);
+    const float fTL = (1.0 - dX) * (1.0 - dY), fTR = (dX) * (1.0 - dY), fBL = (1.0 - dX) * (dY), fBR = (dX) * (dY);
+    for (int k = lane; k < QQ; k += 32) {   // k = (y-1)*Q + (x-1): the reference's loop order
+      const int y = k / Q + 1, x = k - (y - 1) * Q + 1;
+      const uint8_t* tl = img + (size_t)((int)b1 + y) * pitch + ((int)b0 + x);
+      const float fPixel = fTL * tl[0] + fTR * tl[1] + fBL * tl[pitch] + fBR * tl[pitch + 1];
+      const double dDiff = fPixel - tmpl[y * 12 + x] + meanDiff;
+      const int j = (x - 1) * Q + (y - 1);
+      sm.pos[k] = dDiff * sm.jx[j]; sm.pos[QQ + k] = dDiff * sm.jy[j]; sm.prod2[k] = dDiff;
+    }
+    __syncwarp();
+    double acc = 0;   // lanes 0,1,2 add their accumulator's terms in pixel order, like the reference's serial loop
+    if (lane < 3) { const double* p = lane == 0 ? sm.pos : (lane == 1 ? sm.pos + QQ : sm.prod2); for (int k = 0; k < QQ; k++) acc += p[k]; }
+    const double a0 = __shfl_sync(0xffffffffu, acc, 0), a1 = __shfl_sync(0xffffffffu, acc, 1), a2 = __shfl_sync(0xffffffffu, acc, 2);
+    __syncwarp();
+    double upd[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) { double sacc = hinv[3 * r] * a0; sacc += hinv[3 * r + 1] * a1; sacc += hinv[3 * r + 2] * a2; upd[r] = sacc; }
+    sp0 -= upd[0] * nLevelScale; sp1 -= upd[1] * nLevelScale;
+    meanDiff -= upd[2];
+    double d = 0; d += upd[0] * upd[0]; d += upd[1] * upd[1];
+    const double lim = 0.03;
+    if (d < lim * lim) { ok = 1; break; }
+  }
+  out0 = sp0; out1 = sp1;
+  return ok;
 }
 
 // mode 0: explicit list [0,nA) with (range, subpix) arguments; 1: coarse set A; 2: fine set B
@@ -248,7 +358,7 @@ __device__ __forceinline__ int warp_sum(int v) {
 // PT: compile-time template side (8 or 11), 0 = use the run-time D.P
 constexpr int kSearchRefind = 1;
 template <int PT>
-__global__ void __launch_bounds__(kSearchWarps * 32) k_search(Dev D, int mode, int range_arg, int subpix_arg, int sflags) {
+__global__ void __launch_bounds__(kSearchWarps * 32, 10) k_search(Dev D, int mode, int range_arg, int subpix_arg, int sflags) {
   __shared__ SearchSmem sm_all[kSearchWarps];
   const int s = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int e = blockIdx.x * kSearchWarps + warp;
@@ -377,8 +487,6 @@ __global__ void __launch_bounds__(kSearchWarps * 32) k_search(Dev D, int mode, i
     const int* lut = L.lut + (size_t)s * (L.h + 1);
     const int begin = lut[nTop], end = (nBottomPlusOne >= L.h) ? lut[L.h] : lut[nBottomPlusOne];
     const uint32_t* corners = L.corners + (size_t)s * L.cap;
-    const int b = P / 2, nwords = (P + 3) >> 2;
-    const uint32_t lastmask = (P & 3) ? ((1u << (8 * (P & 3))) - 1u) : 0xffffffffu;
     int c0 = begin;
     while (c0 < end) {   // rounds: gather up to kCandCap candidates, then score them with (candidate,row) work items
       int ncand = 0;
@@ -397,35 +505,7 @@ __global__ void __launch_bounds__(kSearchWarps * 32) k_search(Dev D, int mode, i
       }
       nevals += ncand;   // (every lane holds the same count; reduced once below)
       __syncwarp();
-      // ZMSSDAtPoint (jni/PatchFinder.cc:352-380): one work item = one template row of one candidate
-      for (int item = lane; item < ncand * P; item += 32) {
-        const int c = item / P, r = item - c * P;
-        const uint32_t cw = sm.cand_cw[c];
-        const int cx = cw & 0xffff, cy = cw >> 16;
-        if (!(cx >= b && cy >= b && cx < L.w - b && cy < L.h - b)) continue;
-        const uint8_t* rp = img + (size_t)(cy - b + r) * pitch + (cx - b);
-        const unsigned a = (unsigned)((uintptr_t)rp & 3u), sh = a * 8;
-        const uint32_t* wp = (const uint32_t*)(rp - a);
-        uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = 0, w3 = 0;
-        if (a + P > 8) w2 = __ldg(wp + 2);
-        if (a + P > 12) w3 = __ldg(wp + 3);
-        uint32_t n0 = __funnelshift_r(w0, w1, sh), n1 = __funnelshift_r(w1, w2, sh), n2 = __funnelshift_r(w2, w3, sh);
-        if (nwords == 3) n2 &= lastmask; else if (nwords == 2) { n1 &= lastmask; n2 = 0; } else { n0 &= lastmask; n1 = 0; n2 = 0; }
-        unsigned sum = __dp4a(n0, 0x01010101u, 0u), sumsq = __dp4a(n0, n0, 0u), cross = __dp4a(n0, sm.tmpl_w[3 * r], 0u);
-        sum = __dp4a(n1, 0x01010101u, sum); sumsq = __dp4a(n1, n1, sumsq); cross = __dp4a(n1, sm.tmpl_w[3 * r + 1], cross);
-        sum = __dp4a(n2, 0x01010101u, sum); sumsq = __dp4a(n2, n2, sumsq); cross = __dp4a(n2, sm.tmpl_w[3 * r + 2], cross);
-        atomicAdd(&sm.acc[3 * c], (int)sum); atomicAdd(&sm.acc[3 * c + 1], (int)sumsq); atomicAdd(&sm.acc[3 * c + 2], (int)cross);
-      }
-      __syncwarp();
-      for (int c = lane; c < ncand; c += 32) {
-        const uint32_t cw = sm.cand_cw[c];
-        const int cx = cw & 0xffff, cy = cw >> 16;
-        int ssd;
-        if (!(cx >= b && cy >= b && cx < L.w - b && cy < L.h - b)) ssd = maxSSD + 1;
-        else { const int SA = tsum, SB = sm.acc[3 * c]; ssd = ((2 * SA * SB - SA * SA - SB * SB) / PP + sm.acc[3 * c + 1] + tsumsq - 2 * sm.acc[3 * c + 2]); }
-        const unsigned long long key = ((unsigned long long)(unsigned)ssd << 32) | (unsigned)sm.cand_idx[c];   // ssd >= 0; ties -> lowest corner index
-        best = key < best ? key : best;
-      }
+      best = score_candidates<PT>(sm, ncand, img, pitch, L.w, L.h, P, tsum, tsumsq, maxSSD, best);
       __syncwarp();
     }
   }
@@ -444,68 +524,7 @@ __global__ void __launch_bounds__(kSearchWarps * 32) k_search(Dev D, int mode, i
   int ok = 1;
   if (subpix > 0) {
     flags |= F_SUBPIX;
-    // ---- MakeSubPixTemplate (jni/PatchFinder.cc:242-267)
-    const int Q = P - 2, QQ = Q * Q;
-    for (int k = lane; k < QQ; k += 32) {
-      const int x = k / Q + 1, y = k - (x - 1) * Q + 1;   // stored index (x-1)*Q + (y-1)
-      sm.jx[k] = 0.5 * (tmpl[y * 12 + x + 1] - tmpl[y * 12 + x - 1]);
-      sm.jy[k] = 0.5 * (tmpl[(y + 1) * 12 + x] - tmpl[(y - 1) * 12 + x]);
-    }
-    __syncwarp();
-    // JtJ of (gx, gy, 1): sums of multiples of 0.25 below 2^53 are exact in any order, so a warp reduction is bit-exact
-    double hxx = 0, hxy = 0, hyy = 0, hx = 0, hy = 0;
-    for (int k = lane; k < QQ; k += 32) { const double gx = sm.jx[k], gy = sm.jy[k]; hxx += gx * gx; hxy += gx * gy; hyy += gy * gy; hx += gx; hy += gy; }
-#pragma unroll
-    for (int d = 16; d; d >>= 1) {
-      hxx += __shfl_xor_sync(0xffffffffu, hxx, d); hxy += __shfl_xor_sync(0xffffffffu, hxy, d); hyy += __shfl_xor_sync(0xffffffffu, hyy, d);
-      hx += __shfl_xor_sync(0xffffffffu, hx, d); hy += __shfl_xor_sync(0xffffffffu, hy, d);
-    }
-    const double H[9] = {hxx, hxy, hx, hxy, hyy, hy, hx, hy, (double)QQ};
-    double hinv[9];
-    {   // 3x3 inverse: adjugate * (1/det), evaluation order of the oracle (oracle/vslam_oracle.cc inverse3)
-      const double c00 = H[4] * H[8] - H[5] * H[7], c10 = H[5] * H[6] - H[3] * H[8], c20 = H[3] * H[7] - H[4] * H[6];
-      const double det = H[0] * c00 + H[1] * c10 + H[2] * c20, invdet = 1.0 / det;
-      hinv[0] = c00 * invdet; hinv[3] = c10 * invdet; hinv[6] = c20 * invdet;
-      hinv[1] = (H[2] * H[7] - H[1] * H[8]) * invdet; hinv[4] = (H[0] * H[8] - H[2] * H[6]) * invdet; hinv[7] = (H[1] * H[6] - H[0] * H[7]) * invdet;
-      hinv[2] = (H[1] * H[5] - H[2] * H[4]) * invdet; hinv[5] = (H[2] * H[3] - H[0] * H[5]) * invdet; hinv[8] = (H[0] * H[4] - H[1] * H[3]) * invdet;
-    }
-    double sp0 = coarse0, sp1 = coarse1, meanDiff = 0.0;
-    ok = 0;
-    // ---- IterateSubPixToConvergence / IterateSubPix (jni/PatchFinder.cc:272-350)
-    for (int it = 0; it < subpix; it++) {
-      const double c0 = (sp0 + 0.5) * invScale - 0.5, c1 = (sp1 + 0.5) * invScale - 0.5;   // LevelNPos
-      const int xb = (c0 > 0.0 ? c0 + 0.5 : c0 - 0.5), yb = (c1 > 0.0 ? c1 + 0.5 : c1 - 0.5);
-      const int bd = P / 2 + 1;
-      if (!(xb >= bd && yb >= bd && xb < L.w - bd && yb < L.h - bd)) break;   // off the image: not converged
-      const double b0 = c0 - (double)(P / 2), b1 = c1 - (double)(P / 2);
-      const double dX = b0 - floor(b0), dY = b1 - floor(b1);
-      const float fTL = (1.0 - dX) * (1.0 - dY), fTR = (dX) * (1.0 - dY), fBL = (1.0 - dX) * (dY), fBR = (dX) * (dY);
-      for (int k = lane; k < QQ; k += 32) {   // k = (y-1)*Q + (x-1): the reference's loop order
-        const int y = k / Q + 1, x = k - (y - 1) * Q + 1;
-        const uint8_t* tl = img + (size_t)((int)b1 + y) * pitch + ((int)b0 + x);
-        const float fPixel = fTL * tl[0] + fTR * tl[1] + fBL * tl[pitch] + fBR * tl[pitch + 1];
-        const double dDiff = fPixel - tmpl[y * 12 + x] + meanDiff;
-        const int j = (x - 1) * Q + (y - 1);
-        sm.pos[k] = dDiff * sm.jx[j]; sm.pos[QQ + k] = dDiff * sm.jy[j]; sm.prod2[k] = dDiff;
-      }
-      __syncwarp();
-      double acc = 0;   // lanes 0,1,2 add their accumulator's terms in pixel order, like the reference's serial loop
-      if (lane < 3) { const double* p = lane == 0 ? sm.pos : (lane == 1 ? sm.pos + QQ : sm.prod2); for (int k = 0; k < QQ; k++) acc += p[k]; }
-      const double a0 = __shfl_sync(0xffffffffu, acc, 0), a1 = __shfl_sync(0xffffffffu, acc, 1), a2 = __shfl_sync(0xffffffffu, acc, 2);
-      __syncwarp();
-      double upd[3];
-#pragma unroll
-      for (int r = 0; r < 3; r++) { double sacc = hinv[3 * r] * a0; sacc += hinv[3 * r + 1] * a1; sacc += hinv[3 * r + 2] * a2; upd[r] = sacc; }
-      sp0 -= upd[0] * nLevelScale; sp1 -= upd[1] * nLevelScale;
-      meanDiff -= upd[2];
-      double d = 0; d += upd[0] * upd[0]; d += upd[1] * upd[1];
-#ifdef VS_DEBUG_POINT
-      if (i == VS_DEBUG_POINT && lane == 0) printf("gpu it: acc %.17g %.17g %.17g upd %.17g %.17g %.17g pos %.17g %.17g d %.17g mix %.9g %.9g %.9g %.9g\n", a0, a1, a2, upd[0], upd[1], upd[2], sp0, sp1, d, fTL, fTR, fBL, fBR);
-#endif
-      const double lim = 0.03;
-      if (d < lim * lim) { ok = 1; break; }
-    }
-    found0 = sp0; found1 = sp1;
+    ok = subpix_refine(sm, tmpl, img, pitch, L.w, L.h, level, P, subpix, coarse0, coarse1, found0, found1);
   }
   if (lane == 0) {
     D.ps.coarse[gi] = coarse0; D.ps.coarse[SN + gi] = coarse1;
@@ -514,6 +533,79 @@ __global__ void __launch_bounds__(kSearchWarps * 32) k_search(Dev D, int mode, i
     else flags &= ~F_FOUND;   // sub-pixel iteration did not converge (jni/Tracker.cc:660-666)
     D.ps.flags[gi] = flags;
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The search of MapMaker::AddPointEpipolar (jni/MapMaker.cc:525-640), one warp per candidate of the source keyframe: un-warped
+// template (PatchFinder::MakeTemplateCoarseNoWarp, jni/PatchFinder.cc:130-143), every FAST corner of the target level whose
+// image-plane position (the reference's per-pixel UnProject table, index = truncated level-zero position) lies in the epipolar
+// band, ZMSSD, best candidate (first wins ties; accepted up to and including mnMaxSSD), then MakeSubPixTemplate +
+// IterateSubPixToConvergence(10).  The per-candidate line geometry is computed on the host (vslam_epipolar_search, api.cu).
+__global__ void __launch_bounds__(kSearchWarps * 32) k_epipolar(Dev D, int s, int src_kf, int level, int n, const EpiCand* __restrict__ cand,
+                                                                const double* __restrict__ unproj, int subpix_its, int* __restrict__ out_int, double* __restrict__ out_pos) {
+  __shared__ SearchSmem sm_all[kSearchWarps];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int e = blockIdx.x * kSearchWarps + warp;
+  if (e >= n) return;
+  SearchSmem& sm = sm_all[warp];
+  const EpiCand C = cand[e];
+  const int P = D.P, PP = P * P, maxSSD = PP * 500;
+  int found = 0, best_idx = -1, best_ssd = maxSSD + 1; double pos0 = 0, pos1 = 0;
+  const int sw = D.src.w[level], sh = D.src.h[level], sp = D.src.pitch[level];
+  const int bd = P / 2 + 1;
+  const bool tmpl_ok = C.valid && C.x >= bd && C.y >= bd && C.x < sw - bd && C.y < sh - bd;
+  if (tmpl_ok) {
+    const uint8_t* simg = D.src.img[level] + (size_t)src_kf * sh * sp;
+    uint8_t* const tmpl = (uint8_t*)sm.tmpl_w;
+    sm.tmpl_w[lane] = 0u; if (lane < VS_TMPL_BYTES / 4 - 32) sm.tmpl_w[32 + lane] = 0u;
+    __syncwarp();
+    for (int k = lane; k < PP; k += 32) { const int r = k / P, c = k - r * P; tmpl[r * 12 + c] = simg[(size_t)(C.y - P / 2 + r) * sp + (C.x - P / 2 + c)]; }
+    __syncwarp();
+    int ts = 0, tq = 0;
+    for (int k = lane; k < 3 * P; k += 32) { const uint32_t w = sm.tmpl_w[k]; ts += (int)__dp4a(w, 0x01010101u, 0u); tq += (int)__dp4a(w, w, 0u); }
+    ts = warp_sum(ts); tq = warp_sum(tq);
+    const LevelDesc& L = D.lev[level];
+    const uint8_t* img; int pitch;
+    if (level == 0) { img = D.l0_ptr[s]; pitch = D.l0_stride[s]; } else { img = L.img + (size_t)s * L.h * L.pitch; pitch = L.pitch; }
+    const int* lut = L.lut + (size_t)s * (L.h + 1);
+    const uint32_t* corners = L.corners + (size_t)s * L.cap;
+    const int end = lut[L.h], W0 = D.lev[0].w, scale = LevelScale(level);
+    unsigned long long best = ((unsigned long long)(unsigned)(maxSSD + 1) << 32) | 0xffffffffull;
+    int c0 = 0;
+    while (c0 < end) {
+      int ncand = 0;
+      for (; c0 < end && ncand <= kCandCap - 32; c0 += 32) {
+        const int ci = c0 + lane;
+        bool pass = false; uint32_t cw = 0;
+        if (ci < end) {
+          cw = corners[ci];
+          const int cx = cw & 0xffff, cy = cw >> 16;
+          const int zx = (int)(((double)cx + 0.5) * scale - 0.5), zy = (int)(((double)cy + 0.5) * scale - 0.5);   // LevelZeroPos, truncated by the table index
+          const double ux = unproj[2 * ((size_t)zy * W0 + zx)], uy = unproj[2 * ((size_t)zy * W0 + zx) + 1];
+          double dn = ux * C.nx; dn += uy * C.ny;
+          const double dDistDiff = C.normDist - dn;
+          double da = ux * C.ax; da += uy * C.ay;
+          pass = !(dDistDiff * dDistDiff > C.maxDistSq) && !(da < C.minLen) && !(da > C.maxLen);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, pass);
+        if (pass) { const int slot = ncand + __popc(bal & ((1u << lane) - 1u)); sm.cand_cw[slot] = cw; sm.cand_idx[slot] = ci; sm.acc[3 * slot] = 0; sm.acc[3 * slot + 1] = 0; sm.acc[3 * slot + 2] = 0; }
+        ncand += __popc(bal);
+      }
+      __syncwarp();
+      best = score_candidates<0>(sm, ncand, img, pitch, L.w, L.h, P, ts, tq, maxSSD, best);
+      __syncwarp();
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) { const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, d); best = o < best ? o : best; }
+    best_ssd = (int)(best >> 32);
+    if (best_ssd < maxSSD + 1) {   // nBest != -1
+      best_idx = (int)(unsigned)best;
+      const uint32_t bc = corners[best_idx];
+      const double c0d = ((double)(bc & 0xffff) + 0.5) * scale - 0.5, c1d = ((double)(bc >> 16) + 0.5) * scale - 0.5;
+      found = subpix_refine(sm, tmpl, img, pitch, L.w, L.h, level, P, subpix_its, c0d, c1d, pos0, pos1);
+    }
+  }
+  if (lane == 0) { out_int[3 * e] = found; out_int[3 * e + 1] = best_idx; out_int[3 * e + 2] = best_ssd; out_pos[2 * e] = pos0; out_pos[2 * e + 1] = pos1; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1118,4 +1210,12 @@ extern "C" int vslam_debug_atan(const double* x_host, double* y_host, int n) {
   const cudaError_t e = cudaMemcpy(y_host, dy, sizeof(double) * n, cudaMemcpyDeviceToHost);
   cudaFree(dx); cudaFree(dy);
   return e == cudaSuccess ? VSLAM_OK : VSLAM_E_CUDA;
+}
+
+int vs_launch_epipolar(vslam_ctx* ctx, int stream, int src_kf, int level, int n, const EpiCand* cand_dev, const double* unproj_dev, int subpix_its, int* out_int_dev, double* out_pos_dev) {
+  if (n <= 0) return VSLAM_OK;
+  k_epipolar<<<(n + kSearchWarps - 1) / kSearchWarps, kSearchWarps * 32, 0, ctx->stream>>>(make_dev(ctx), stream, src_kf, level, n, cand_dev, unproj_dev, subpix_its, out_int_dev, out_pos_dev);
+  VS_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return VSLAM_OK;
 }

@@ -65,6 +65,13 @@ struct SourceKF {   // device pyramids of the map's source keyframes: level l of
   uint8_t* img[VS_LEVELS];
 };
 
+// One candidate of MapMaker::AddPointEpipolar, line geometry resolved on the host (api.cu vslam_epipolar_search)
+struct EpiCand {
+  double nx, ny, ax, ay;        // v2Normal, v2AlongProjectedLine
+  double normDist, minLen, maxLen, maxDistSq;
+  int x, y, valid, pad;         // candidate position in the source level; valid = 0: rejected before the search
+};
+
 // Per-stream tracker scalars (Tracker members)
 struct StreamState {
   double pose[12], start_pose[12];
@@ -110,6 +117,7 @@ struct vslam_ctx {
   // MakeKeyFrame_Rest results of one stream (lazy scratch) and the per-stream keyframe snapshot used by MiniPatch trail tracking
   int* rest_scores; uint32_t* rest_max; uint32_t* rest_cand; double* rest_cand_score; int* rest_counts; size_t rest_off[VS_LEVELS]; int rest_stream;
   uint8_t* snap_img; uint32_t* snap_corners; int* snap_lut;
+  double* unproj_lut; bool unproj_ok;   // [H][W][2] ATANCamera::UnProject of every integer level-0 pixel (MapMaker::AddPointEpipolar's imUnProj), built on the host
   // on-device SmallBlurryImage (vslam_enable_sbi)
   bool sbi_on; float sbi_taps[9]; CamDev sbi_cam; double sbi_orig[2][3]; float* sbi_tmpl; float* sbi_scratch; float* sbi_jac; uint8_t* sbi_small; int* sbi_have;
   // optional per-kernel timing with CUDA events on ctx->stream (vslam_set_timing)
@@ -151,6 +159,7 @@ int vs_launch_frame(vslam_ctx* ctx);                                   // pyrami
 int vs_launch_project_and_derivs(vslam_ctx* ctx, int only_found);
 int vs_launch_calc_jacobians(vslam_ctx* ctx);
 int vs_launch_sbi(vslam_ctx* ctx);
+int vs_launch_epipolar(vslam_ctx* ctx, int stream, int src_kf, int level, int n, const EpiCand* cand_dev, const double* unproj_dev, int subpix_its, int* out_int_dev, double* out_pos_dev);
 int vs_keyframe_rest(vslam_ctx* ctx, int stream);
 int vs_minipatch_sample(vslam_ctx* ctx, int stream, int which, const int* xy_dev, int n, uint8_t* patches_dev);
 int vs_minipatch_find(vslam_ctx* ctx, int stream, int which, const uint8_t* patches_dev, int n, double* pos_dev, int* found_dev, int* best_dev, int range, int max_ssd);
