@@ -143,6 +143,15 @@ int vslam_set_sbi_rotation(vslam_ctx* ctx, int stream, const double* rot6);  /* 
  * writes the resulting rotation into mv6SBIRot before the motion model runs.  cam13_sbi = vslam_camera_from_params at (width/16, height/16). */
 int vslam_enable_sbi(vslam_ctx* ctx, const double* cam13_sbi);
 int vslam_get_sbi_rotation(vslam_ctx* ctx, int stream, double* rot6);
+/* Relocaliser (jni/Relocaliser.cc:17-58 + Tracker::AttemptRecovery, jni/Tracker.cc:167-180): register the map's keyframes (ids of
+ * uploaded source keyframes + their poses; needs vslam_enable_sbi).  From then on vslam_track_frame* runs the lost branch of
+ * Tracker::TrackFrame (jni/Tracker.cc:134-140) on the device for every stream with lost_frames >= 3: SmallBlurryImage of the frame
+ * (blur 2.5), SSD against every keyframe's, ESM alignment to the best, SE3fromSE2 * keyframe pose; if the score < 9e6 the stream
+ * continues from that pose (velocity zero, doubled coarse stage) with TrackMap + AssessTrackingQuality in the same frame.  Without
+ * registered keyframes a lost stream waits (vslam_set_pose / vslam_reset_stream / vslam_set_lost). */
+int vslam_set_reloc_keyframes(vslam_ctx* ctx, int n, const int32_t* src_kf_ids, const double* poses12);
+int vslam_get_reloc_info(vslam_ctx* ctx, int stream, int* best_keyframe, double* score, int* n_recoveries, int* recovered_last_frame);
+int vslam_set_lost(vslam_ctx* ctx, int stream, int lost_frames, int quality);
 /* attempted[4], found[4], quality (0 BAD,1 DODGY,2 GOOD), lost_frames, did_coarse */
 int vslam_get_counters(vslam_ctx* ctx, int stream, int32_t* attempted4, int32_t* found4, int* quality, int* lost_frames, int* did_coarse);
 /* Per-point TrackerData dump, layout of oracle/ref_harness.cc ref_tracker_point_state: ints[n][8], dbl[n][32]. */
@@ -185,7 +194,9 @@ int vslam_project_and_derivs(vslam_ctx* ctx, int only_found);
 int vslam_calc_jacobians(vslam_ctx* ctx);
 int vslam_calc_pose_update(vslam_ctx* ctx, double override_sigma, int mark_outliers, int apply, double* upd6_per_stream /* may be NULL */);
 int vslam_track_map(vslam_ctx* ctx);
-/* MakeKeyFrame_Lite + (if lost_frames < 3) ApplyMotionModel, TrackMap, UpdateMotionModel, AssessTrackingQuality. */
+/* Tracker::TrackFrame, map-good branch (jni/Tracker.cc:76-140): MakeKeyFrame_Lite, SmallBlurryImage (vslam_enable_sbi), then per stream
+ * either (lost_frames < 3) CalcSBIRotation, ApplyMotionModel, TrackMap, UpdateMotionModel, AssessTrackingQuality, or (lost, with
+ * vslam_set_reloc_keyframes) AttemptRecovery and on success TrackMap + AssessTrackingQuality. */
 int vslam_track_frame(vslam_ctx* ctx, const uint8_t* gray_host, int stride, size_t frame_stride);
 int vslam_track_frame_dev(vslam_ctx* ctx, const uint8_t* gray_dev, int stride, size_t frame_stride);
 /* Pipelined form of vslam_track_frame for a continuous feed: the host->device copy of this step runs on an internal copy

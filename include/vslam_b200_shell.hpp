@@ -180,13 +180,18 @@ class Tracker {
       TrackForInitialMap();
       return;
     }
-    check(c, vslam_track_frame(c, imFrame.data, (int)imFrame.step, 0));
     int32_t att[LEVELS], fnd[LEVELS]; int q, lost, coarse;
+    check(c, vslam_get_counters(c, stream_, att, fnd, &q, &lost, &coarse));
+    const bool was_lost = lost >= 3;
+    check(c, vslam_track_frame(c, imFrame.data, (int)imFrame.step, 0));
+    if (was_lost) { msg_ << "** Attempting recovery **."; return; }   // jni/Tracker.cc:134-140 (the relocaliser runs inside vslam_track_frame)
     check(c, vslam_get_counters(c, stream_, att, fnd, &q, &lost, &coarse));
     msg_ << "Tracking Map, quality " << (q == 2 ? "good." : (q == 1 ? "poor." : "bad.")) << " Found:";
     for (int l = 0; l < LEVELS; l++) msg_ << " " << fnd[l] << "/" << att[l];
     msg_ << " Map: " << ctx_.MapSize() << "P";
   }
+  // Relocaliser keyframes (Map::vpKeyFrames with their SmallBlurryImages, jni/Relocaliser.cc): ids of uploaded source keyframes + poses (n x 12)
+  void SetRelocKeyFrames(int n, const int32_t* src_kf_ids, const double* poses12) { check(ctx_.get(), vslam_set_reloc_keyframes(ctx_.get(), n, src_kf_ids, poses12)); }
   SE3 GetCurrentPose() {
     double p[12]; check(ctx_.get(), vslam_get_pose(ctx_.get(), stream_, p));
     SE3 s;

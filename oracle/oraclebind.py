@@ -109,6 +109,9 @@ def lib():
     sig("orc_tracker_calc_pose_update", None, vp, _i32p, i, d, i, i, _f64p)
     sig("orc_tukey_sigma_squared", d, _f64p, i)
     sig("orc_tracker_enable_sbi", None, vp, _f64p)
+    sig("orc_tracker_add_reloc_keyframe", None, vp, vp, _f64p)
+    sig("orc_tracker_reloc_info", None, vp, pi, pd, pi)
+    sig("orc_tracker_set_lost", None, vp, i, i)
     sig("orc_tracker_get_sbi_rot", None, vp, _f64p)
     sig("orc_sbi_create", vp, vp, d)
     sig("orc_sbi_destroy", None, vp)

@@ -480,6 +480,16 @@ void ref_epipolar_search(void* t, void* ksrc, void* ktgt, const double* src_pose
 }
 int ref_kf_num_candidates_l(void* kf, int l) { return (int)((KeyFrame*)kf)->aLevels[l].vCandidates.size(); }
 
+// Relocaliser support: a map keyframe gets its SmallBlurryImage the way KeyFrame::MakeKeyFrame_Rest (jni/KeyFrame.cc:98) and the
+// map maker (MakeJacs before the keyframe is used as an alignment target) leave it
+void ref_kf_make_sbi(void* kf_) {
+  KeyFrame* kf = (KeyFrame*)kf_;
+  if (kf->pSBI) delete kf->pSBI;
+  kf->pSBI = new SmallBlurryImage(*kf);
+  kf->pSBI->MakeJacs();
+}
+void ref_tracker_set_lost(void* t, int lost_frames, int quality) { Tracker* tr = ((RefTracker*)t)->tr; tr->mnLostFrames = lost_frames; tr->mTrackingQuality = (decltype(tr->mTrackingQuality))quality; }
+
 // Trail tracking for the initial map (jni/Tracker.cc:264-346) on the tracker's current keyframe (ref_tracker_make_current_kf first)
 int ref_tracker_trail_start(void* t) {
   Tracker* tr = ((RefTracker*)t)->tr;

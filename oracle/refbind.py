@@ -102,6 +102,8 @@ def lib():
     sig("ref_refind", None, vp, _i32p, i, i, i, _i32p, _f64p)
     sig("ref_epipolar_search", None, vp, vp, vp, _f64p, _f64p, d, d, d, i, i, _i32p, _f64p)
     sig("ref_kf_num_candidates_l", i, vp, i)
+    sig("ref_kf_make_sbi", None, vp)
+    sig("ref_tracker_set_lost", None, vp, i, i)
     sig("ref_tracker_trail_start", i, vp)
     sig("ref_tracker_trail_advance", i, vp, i)
     sig("ref_tracker_trail_count", i, vp)

@@ -687,8 +687,8 @@ struct SBI {
 };
 // cv::GaussianBlur(float, ksize 9x9, sigma, BORDER_REPLICATE) as restated by the OpenCV stand-in (oracle/shim/opencv2/core/core.hpp):
 // getGaussianKernel taps in float, row pass then column pass, float accumulation in tap order.
-void gaussian_blur_9(std::vector<float>& im, int W, int H, double sigma) {
-  const int n = 9; float k[9];
+void gaussian_blur(std::vector<float>& im, int W, int H, int n /* taps: 9 or 17 */, double sigma) {
+  float k[17];
   { const double scale2x = -0.5 / (sigma * sigma); double sum = 0;
     for (int i = 0; i < n; i++) { const double x = i - (n - 1) * 0.5; const double t = std::exp(scale2x * x * x); k[i] = (float)t; sum += k[i]; }
     sum = 1. / sum; for (int i = 0; i < n; i++) k[i] = (float)(k[i] * sum); }
@@ -701,7 +701,8 @@ void gaussian_blur_9(std::vector<float>& im, int W, int H, double sigma) {
     out[(size_t)y * W + x] = s; }
   im.swap(out);
 }
-// SmallBlurryImage::MakeFromKF (jni/SmallBlurryImage.cc:20-55), dBlur <= 2.0 branch (the tracker uses 0.75, jni/Tracker.cc:87)
+// SmallBlurryImage::MakeFromKF (jni/SmallBlurryImage.cc:20-55); the tracker uses dBlur 0.75 (jni/Tracker.cc:87), the relocaliser
+// and MakeKeyFrame_Rest the default 2.5 (jni/SmallBlurryImage.h:19)
 void sbi_make(SBI& s, const OKeyFrame& kf, double dBlur) {
   const Image& l3 = kf.lev[3].im;
   s.w = l3.w / 2; s.h = l3.h / 2; s.madeJacs = false;
@@ -711,7 +712,7 @@ void sbi_make(SBI& s, const OKeyFrame& kf, double dBlur) {
   const float fMean = ((float)nSum) / (s.h * s.w);
   s.tmpl.resize((size_t)s.w * s.h);
   for (size_t i = 0; i < s.small.size(); i++) s.tmpl[i] = s.small[i] - fMean;
-  gaussian_blur_9(s.tmpl, s.w, s.h, dBlur);
+  gaussian_blur(s.tmpl, s.w, s.h, dBlur <= 2.0 ? 9 : 17, dBlur);   // cv::Size(9,9) / cv::Size(17,17) (jni/SmallBlurryImage.cc:50-54)
 }
 // SmallBlurryImage::MakeJacs (jni/SmallBlurryImage.cc:58-79)
 void sbi_make_jacs(SBI& s) {
@@ -806,7 +807,7 @@ SE2 sbi_iterate(const SBI& cur, const SBI& other, int nIterations, double* final
   return CtoC;
 }
 // SmallBlurryImage::SE3fromSE2 (jni/SmallBlurryImage.cc:245-333): rotation-only pose whose image motion matches the SE2; returns ln() (6-vector)
-void se3_from_se2(const SE2& se2, Cam cam /* at the SBI image size */, int W, int H, double* v6) {
+SE3 se3_from_se2_pose(const SE2& se2, Cam cam /* at the SBI image size */, int W, int H) {
   double turned[2][2], orig[2][3];
   const double c[2] = {W / 2.0, H / 2.0};
   const double off[2][2] = {{5, 0}, {-5, 0}};
@@ -840,8 +841,9 @@ void se3_from_se2(const SE2& se2, Cam cam /* at the SBI image size */, int W, in
     double E[9], Rn[9]; so3_exp(mu, E); mat3_mul(E, R, Rn); memcpy(R, Rn, sizeof(R));
   }
   SE3 s = se3_identity(); memcpy(s.R, R, sizeof(R));
-  se3_ln(s, v6);
+  return s;
 }
+void se3_from_se2(const SE2& se2, Cam cam, int W, int H, double* v6) { se3_ln(se3_from_se2_pose(se2, cam, W, H), v6); }
 
 // ------------------------------------------------------------------------------------------------
 // Tracker (jni/Tracker.cc)
@@ -863,6 +865,8 @@ struct OTracker {
   std::vector<double> sigmas;   // sigma^2 used by each of them
   // SmallBlurryImage state (Tracker::mpSBIThisFrame / mpSBILastFrame, jni/Tracker.cc:86-97)
   bool computeSBI, haveSBI; SBI sbiThis, sbiLast; Cam sbiCam; int nFrame;
+  // Relocaliser (jni/Relocaliser.cc): the map keyframes' SmallBlurryImages (blur 2.5, with gradient images) and poses
+  std::vector<SBI> relocSBI; std::vector<SE3> relocPose; int relocBest; double relocScore; int nRecoveries;
 };
 
 TData& ensure_td(OTracker& t, int i) {
@@ -1061,6 +1065,29 @@ Cam cam_from13(const double* s) {
 }  // namespace
 
 // =================================================================================================
+// SmallBlurryImage::ZMSSD (jni/SmallBlurryImage.cc:82-94): plain SSD of the two zero-mean templates, x outer / y inner, float difference
+double sbi_zmssd(const SBI& a, const SBI& b) {
+  double dSSD = 0.0;
+  for (int x = 0; x < a.w; x++) for (int y = 0; y < a.h; y++) { const double dDiff = a.tmpl[(size_t)y * a.w + x] - b.tmpl[(size_t)y * a.w + x]; dSSD += dDiff * dDiff; }
+  return dSSD;
+}
+// Relocaliser::AttemptRecovery + ScoreKFs (jni/Relocaliser.cc:17-58) and Tracker::AttemptRecovery (jni/Tracker.cc:167-180)
+bool attempt_recovery(OTracker& t) {
+  SBI cur; sbi_make(cur, t.cur, 2.5);
+  double best = 99999999999999.9; int nBest = -1;
+  for (size_t i = 0; i < t.relocSBI.size(); i++) { const double d = sbi_zmssd(cur, t.relocSBI[i]); if (d < best) { best = d; nBest = (int)i; } }
+  double dScore = 0;
+  const SE2 se2 = sbi_iterate(cur, t.relocSBI[nBest], 6, &dScore);
+  const SE3 se3Best = se3_mul(se3_from_se2_pose(se2, t.sbiCam, cur.w, cur.h), t.relocPose[nBest]);
+  t.relocBest = nBest; t.relocScore = dScore;
+  if (!(dScore < 9e6)) return false;
+  t.pose = t.startPose = se3Best;
+  memset(t.velocity, 0, sizeof(t.velocity));
+  t.justRecovered = true;
+  t.nRecoveries++;
+  return true;
+}
+
 extern "C" {
 
 void orc_debug_point(int i) { g_dbg_point = i; }
@@ -1225,6 +1252,7 @@ void* orc_tracker_create(const double* cam13, int P) {
   t->quality = 2; t->lostFrames = 0; t->didCoarse = false; t->justRecovered = false; t->truncateError = true; t->zmssdEvals = 0;
   t->rng.seed(1);
   t->computeSBI = false; t->haveSBI = false; t->nFrame = 0; memset(&t->sbiCam, 0, sizeof(t->sbiCam));
+  t->relocBest = -1; t->relocScore = 0; t->nRecoveries = 0;
   return t;
 }
 void orc_tracker_destroy(void* t) { delete (OTracker*)t; }
@@ -1268,8 +1296,18 @@ void orc_tracker_track_frame(void* t_, const uint8_t* gray, int w, int h, int st
       se3_from_se2(se2, t->sbiCam, t->sbiThis.w, t->sbiThis.h, t->sbiRot);
     }
     apply_motion_model(*t); track_map(*t); update_motion_model(*t); assess_tracking_quality(*t);
+  } else if (!t->relocSBI.empty()) {   // jni/Tracker.cc:134-140: tracking lost -> relocalise against the map keyframes
+    if (attempt_recovery(*t)) { track_map(*t); assess_tracking_quality(*t); }
   }
 }
+// Relocaliser keyframe: SmallBlurryImage(kf) with the default blur 2.5 (KeyFrame::MakeKeyFrame_Rest, jni/KeyFrame.cc:98) + MakeJacs
+void orc_tracker_add_reloc_keyframe(void* t_, void* kf, const double* pose12) {
+  OTracker* t = (OTracker*)t_;
+  SBI s; sbi_make(s, *(OKeyFrame*)kf, 2.5); sbi_make_jacs(s);
+  t->relocSBI.push_back(s); t->relocPose.push_back(se3_from12(pose12));
+}
+void orc_tracker_reloc_info(void* t_, int* best, double* score, int* n_recoveries) { OTracker* t = (OTracker*)t_; *best = t->relocBest; *score = t->relocScore; *n_recoveries = t->nRecoveries; }
+void orc_tracker_set_lost(void* t_, int lost_frames, int quality) { OTracker* t = (OTracker*)t_; t->lostFrames = lost_frames; t->quality = quality; }
 // Turn the on-board SmallBlurryImage path on: cam13 = camera scalars at the SBI image size (level 3 halved)
 void orc_tracker_enable_sbi(void* t_, const double* sbi_cam13) { OTracker* t = (OTracker*)t_; t->computeSBI = true; t->useSBI = true; t->sbiCam = cam_from13(sbi_cam13); }
 void orc_tracker_get_sbi_rot(void* t_, double* v6) { memcpy(v6, ((OTracker*)t_)->sbiRot, sizeof(double) * 6); }

@@ -128,6 +128,36 @@ def main():
             rows.append([level, xy[k, 0], xy[k, 1], ro[0], ro[1], ro[2], rp[0], rp[1]])
     out["G_rows"] = np.array(rows, dtype=np.float64)
 
+    # --- case H: the unmodified Tracker::TrackFrame through a loss of tracking and two relocalisations (three map keyframes).
+    # Noise frames are regenerated by the test from RandomState(5); rendered frames are stored.
+    rw2 = refbind.RefWorld(W, H, f0, smap)
+    kf_tw = [np.zeros(6), np.array([0.10, 0.02, 0.01, 0.01, -0.04, 0.05]), np.array([-0.08, -0.05, 0.02, -0.02, 0.03, -0.06])]
+    keep = []
+    for k, tw in enumerate(kf_tw):
+        pose = synth.se3_exp(tw); fr = synth.render_frame(tex, cam, pose)
+        out[f"H_kf{k}"], out[f"H_kfpose{k}"] = fr, pose
+        if k == 0:
+            rk = rw2.src_kf
+        else:
+            rk = refbind.RefKeyFrame().make_lite(fr); rk.set_pose(pose); rw2.L.ref_map_add_keyframe(rw2.map, rk.h)
+        rw2.L.ref_kf_make_sbi(rk.h); keep.append(rk)
+    rw2.set_pose(synth.IDENTITY_POSE)
+    rw2.L.ref_srand(1)
+    rs5 = np.random.RandomState(5)
+    rend = lambda tw: synth.render_frame(tex, cam, synth.se3_exp(np.asarray(tw)))
+    plan = [("r", np.array(synth.CONFIG1_TWIST) * 0.2)] + [("n", None)] * 4 + [("r", kf_tw[1] + np.array([0.004, -0.003, 0.002, 0.01, 0.008, -0.012])),
+            ("r", kf_tw[1] + np.array([0.006, -0.002, 0.002, 0.012, 0.006, -0.01]))] + [("n", None)] * 4 + [("r", kf_tw[2] + np.array([-0.003, 0.004, 0.001, -0.008, 0.01, 0.009]))]
+    poses, cnts, kinds, nr = [], [], [], 0
+    for kind, tw in plan:
+        if kind == "n":
+            fr = rs5.randint(0, 255, (H, W)).astype(np.uint8)
+        else:
+            fr = rend(tw); out[f"H_r{nr}"] = fr; nr += 1
+        kinds.append(0 if kind == "n" else 1)
+        rw2.L.ref_tracker_track_frame(rw2.tracker, np.ascontiguousarray(fr), W, H, W)
+        poses.append(rw2.get_pose()); a, f, q, lost, dc = rw2.counters(); cnts.append(np.concatenate([a, f, [q, lost, dc]]))
+    out["H_kinds"], out["H_poses"], out["H_counters"] = np.array(kinds), np.stack(poses), np.stack(cnts)
+
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_small.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")

@@ -4,6 +4,8 @@ Bit-exact: pyramid pixels, corner lists + row LUT, search levels, template pixel
 found flags, counters.  Tolerance (written at each assert): FP64 geometry 1e-9 relative, pose / update 6-vectors 1e-6
 (the contract is 1e-4), sub-pixel positions 1e-6 px.
 """
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -588,4 +590,60 @@ def test_epipolar_search_matches_the_oracle():
                     assert np.abs(pos[k] - op).max() <= 1e-6, (level, k)
             total_found += int(found.sum())
     assert total_found > 200
+    ctx.close()
+
+
+def test_track_frame_relocalises_lost_streams():
+    """f4: the lost branch of Tracker::TrackFrame on the device (k_relocalise: Relocaliser::AttemptRecovery + Tracker::AttemptRecovery,
+    then TrackMap with the doubled coarse stage and AssessTrackingQuality in the same frame).  Two streams see different sequences
+    (noise frames that make them lose track at different times, then frames near different map keyframes); poses, counters, quality
+    and the chosen keyframe against the oracle, which tests/test_oracle_vs_ref.py pins bit-for-bit to the unmodified TrackFrame."""
+    from oracle import oraclebind
+    cam, f0, smap = common.scene()
+    sbi_cam = synth.Camera(cam.width // 16, cam.height // 16).scalars()
+    kf_twists = [np.zeros(6), np.array([0.10, 0.02, 0.01, 0.01, -0.04, 0.05]), np.array([-0.08, -0.05, 0.02, -0.02, 0.03, -0.06])]
+    kf_frames, kf_poses = zip(*[common.frame_at(cam, tw) for tw in kf_twists])
+    S = 2
+    ctx = _ctx(cam, f0, smap, n_streams=S, max_source_keyframes=3)
+    ctx.enable_sbi(sbi_cam)
+    for k in (1, 2):
+        ctx.upload_source_keyframe(kf_frames[k], k)
+    ctx.set_reloc_keyframes([0, 1, 2], np.stack(kf_poses))
+    ows = []
+    for s in range(S):
+        ow = _orc(cam, f0, smap)
+        ow.L.orc_tracker_enable_sbi(ow.tracker, sbi_cam)
+        keep = []
+        for k in range(3):
+            okf = oraclebind.OrcKeyFrame().make_lite(kf_frames[k]); keep.append(okf)
+            ow.L.orc_tracker_add_reloc_keyframe(ow.tracker, okf.h, np.ascontiguousarray(kf_poses[k], dtype=np.float64).reshape(12))
+        ow._kfs = keep
+        ows.append(ow)
+    rs = np.random.RandomState(5)
+    noise = lambda: rs.randint(0, 255, f0.shape).astype(np.uint8)
+    near = lambda k, d: common.frame_at(cam, kf_twists[k] + np.array(d))[0]
+    first = common.frame_at(cam, np.array(synth.CONFIG1_TWIST) * 0.2)[0]
+    seqs = [[first] + [noise() for _ in range(4)] + [near(1, [0.004, -0.003, 0.002, 0.01, 0.008, -0.012]), near(1, [0.006, -0.002, 0.002, 0.012, 0.006, -0.01])]
+            + [noise() for _ in range(4)] + [near(2, [-0.003, 0.004, 0.001, -0.008, 0.01, 0.009])],
+            [first, near(0, [0.01, 0.0, 0.0, 0.0, 0.0, 0.01])] + [noise() for _ in range(5)] + [near(2, [0.002, 0.001, -0.002, 0.006, -0.004, 0.008])]
+            + [near(2, [0.004, 0.002, -0.002, 0.008, -0.002, 0.006]), near(2, [0.006, 0.002, -0.001, 0.009, 0.0, 0.004]), near(2, [0.008, 0.003, 0.0, 0.01, 0.002, 0.002]), near(2, [0.009, 0.003, 0.0, 0.011, 0.003, 0.001])]]
+    assert len(seqs[0]) == len(seqs[1])
+    recovered = [0, 0]
+    for k in range(len(seqs[0])):
+        frames = np.stack([np.ascontiguousarray(seqs[s][k]) for s in range(S)])
+        ctx.track_frame(frames)
+        for s, ow in enumerate(ows):
+            ow.L.orc_tracker_track_frame(ow.tracker, frames[s], cam.width, cam.height, cam.width)
+            assert np.abs(ctx.get_pose(s) - ow.get_pose()).max() <= 1e-8, (k, s)
+            a, f, q, lost, dc = ctx.counters(s); oa, of, oq, olost, odc = ow.counters()
+            assert np.array_equal(a, oa) and np.array_equal(f, of) and (q, lost, dc) == (oq, olost, odc), (k, s)
+            best, score, nrec = C.c_int(), C.c_double(), C.c_int()
+            ow.L.orc_tracker_reloc_info(ow.tracker, C.byref(best), C.byref(score), C.byref(nrec))
+            gb, gs, gn, gr = ctx.reloc_info(s)
+            assert gn == nrec.value, (k, s)
+            if nrec.value:
+                assert gb == best.value and abs(gs - score.value) <= 1e-6 * max(1.0, abs(score.value)), (k, s)
+            recovered[s] = gn
+    assert recovered[0] >= 2 and recovered[1] >= 1
+    assert ctx.counters(0)[2] == 2 and ctx.counters(1)[2] == 2       # both streams end with quality GOOD
     ctx.close()

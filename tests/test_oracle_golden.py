@@ -112,6 +112,32 @@ def test_epipolar_search_golden():
     assert nfound > 20
 
 
+def test_track_frame_loss_and_relocalisation_golden():
+    """The unmodified Tracker::TrackFrame of the reference through a loss of tracking and two relocalisations (Relocaliser over three
+    map keyframes): pose and counters after every frame, bit for bit."""
+    cam = synth.Camera(W, H)
+    smap = _smap()
+    ow = oraclebind.OrcWorld(cam, G["f0"], smap)
+    ow.L.orc_tracker_enable_sbi(ow.tracker, synth.Camera(W // 16, H // 16).scalars())
+    keep = []
+    for k in range(3):
+        okf = oraclebind.OrcKeyFrame().make_lite(G[f"H_kf{k}"]); keep.append(okf)
+        ow.L.orc_tracker_add_reloc_keyframe(ow.tracker, okf.h, np.ascontiguousarray(G[f"H_kfpose{k}"], dtype=np.float64).reshape(12))
+    ow.set_pose(synth.IDENTITY_POSE)
+    rs5 = np.random.RandomState(5)
+    nr = 0
+    for k, kind in enumerate(G["H_kinds"]):
+        if kind == 0:
+            fr = rs5.randint(0, 255, (H, W)).astype(np.uint8)
+        else:
+            fr = G[f"H_r{nr}"]; nr += 1
+        ow.L.orc_tracker_track_frame(ow.tracker, np.ascontiguousarray(fr), W, H, W)
+        assert np.array_equal(ow.get_pose(), G["H_poses"][k]), k
+        a, f, q, lost, dc = ow.counters()
+        assert np.array_equal(np.concatenate([a, f, [q, lost, dc]]), G["H_counters"][k]), k
+    assert G["H_counters"][:, 9].max() >= 3 and G["H_counters"][-1, 8] == 2     # tracking was lost, and it ends GOOD
+
+
 def test_se3_exp_ln_golden():
     L = oraclebind.lib()
     for mu, e, l in zip(G["D_mu"], G["D_exp"], G["D_ln"]):

@@ -299,6 +299,50 @@ def test_epipolar_search():
     assert nfound > 40 and nbest > nfound
 
 
+def test_track_frame_recovers_a_lost_tracker():
+    """f4: the lost branch of Tracker::TrackFrame (jni/Tracker.cc:134-140) — Relocaliser::AttemptRecovery (ScoreKFs over the map
+    keyframes' SmallBlurryImages, ESM alignment to the best one, SE3fromSE2), then TrackMap with the doubled coarse stage and
+    AssessTrackingQuality — of the UNMODIFIED reference TrackFrame against the restatement, bit for bit.  Three map keyframes;
+    the tracker is blinded for three frames, then shown frames near the second and the third keyframe."""
+    cam, f0, smap, rw, ow = _worlds()
+    sbi_cam = synth.Camera(cam.width // 16, cam.height // 16).scalars()
+    ow.L.orc_tracker_enable_sbi(ow.tracker, sbi_cam)
+    kf_twists = [np.zeros(6), np.array([0.10, 0.02, 0.01, 0.01, -0.04, 0.05]), np.array([-0.08, -0.05, 0.02, -0.02, 0.03, -0.06])]
+    keep = []
+    for k, tw in enumerate(kf_twists):
+        fr, pose = common.frame_at(cam, tw)
+        if k == 0:
+            rk = rw.src_kf
+        else:
+            rk = refbind.RefKeyFrame().make_lite(fr); rk.set_pose(pose); rw.L.ref_map_add_keyframe(rw.map, rk.h)
+        rw.L.ref_kf_make_sbi(rk.h)
+        okf = oraclebind.OrcKeyFrame().make_lite(fr)
+        ow.L.orc_tracker_add_reloc_keyframe(ow.tracker, okf.h, np.ascontiguousarray(pose, dtype=np.float64).reshape(12))
+        keep += [rk, okf]
+    rw.set_pose(synth.IDENTITY_POSE); ow.set_pose(synth.IDENTITY_POSE)
+    rw.L.ref_srand(1)            # the reference shuffles with the process-wide rand(); the restatement's copy starts at seed 1
+    rs = np.random.RandomState(5)
+    seq = [common.frame_at(cam, np.array(synth.CONFIG1_TWIST) * 0.2)[0]]
+    seq += [rs.randint(0, 255, f0.shape).astype(np.uint8) for _ in range(4)]                                   # noise: quality BAD, then lost
+    seq += [common.frame_at(cam, kf_twists[1] + np.array([0.004, -0.003, 0.002, 0.01, 0.008, -0.012]))[0]]     # near keyframe 1
+    seq += [common.frame_at(cam, kf_twists[1] + np.array([0.006, -0.002, 0.002, 0.012, 0.006, -0.01]))[0]]
+    seq += [rs.randint(0, 255, f0.shape).astype(np.uint8) for _ in range(4)]
+    seq += [common.frame_at(cam, kf_twists[2] + np.array([-0.003, 0.004, 0.001, -0.008, 0.01, 0.009]))[0]]     # near keyframe 2
+    lost_seen = recovered = 0
+    for k, fr in enumerate(seq):
+        fr = np.ascontiguousarray(fr)
+        rw.L.ref_tracker_track_frame(rw.tracker, fr, cam.width, cam.height, cam.width)
+        ow.L.orc_tracker_track_frame(ow.tracker, fr, cam.width, cam.height, cam.width)
+        assert np.array_equal(rw.get_pose(), ow.get_pose()), k
+        a, f, q, lost, dc = rw.counters(); oa, of, oq, olost, odc = ow.counters()
+        assert np.array_equal(a, oa) and np.array_equal(f, of) and (q, lost, dc) == (oq, olost, odc), k
+        lost_seen += lost >= 3
+        recovered += (k in (5, 11)) and q == 2 and lost == 0
+    best, score, nrec = C.c_int(), C.c_double(), C.c_int()
+    ow.L.orc_tracker_reloc_info(ow.tracker, C.byref(best), C.byref(score), C.byref(nrec))
+    assert lost_seen >= 2 and recovered == 2 and nrec.value >= 2 and best.value == 2
+
+
 def test_small_blurry_image_pieces():
     """f1: SmallBlurryImage::MakeFromKF, IteratePosRelToTarget and SE3fromSE2 (jni/SmallBlurryImage.cc) — restatement vs compiled reference."""
     cam, f0, smap = common.scene()

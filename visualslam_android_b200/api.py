@@ -41,7 +41,7 @@ ABI_SYMBOLS = [
     "vslam_set_camera", "vslam_camera_from_params", "vslam_upload_source_keyframe", "vslam_set_map", "vslam_make_keyframe_lite",
     "vslam_make_keyframe_lite_dev", "vslam_level_dims", "vslam_get_level", "vslam_get_num_corners", "vslam_get_corners", "vslam_get_row_lut",
     "vslam_make_keyframe_rest", "vslam_get_max_corners", "vslam_get_candidates", "vslam_snapshot_keyframe", "vslam_minipatch_sample", "vslam_minipatch_find",
-    "vslam_set_pose", "vslam_get_pose", "vslam_get_poses", "vslam_set_motion", "vslam_get_motion", "vslam_reset_stream", "vslam_set_sbi_rotation", "vslam_enable_sbi", "vslam_get_sbi_rotation", "vslam_get_counters",
+    "vslam_set_pose", "vslam_get_pose", "vslam_get_poses", "vslam_set_motion", "vslam_get_motion", "vslam_reset_stream", "vslam_set_sbi_rotation", "vslam_enable_sbi", "vslam_get_sbi_rotation", "vslam_set_reloc_keyframes", "vslam_get_reloc_info", "vslam_set_lost", "vslam_get_counters",
     "vslam_get_point_states", "vslam_get_point_template", "vslam_get_point_counts", "vslam_get_updates", "vslam_get_zmssd_evals",
     "vslam_project_all", "vslam_set_point_projection", "vslam_set_lists", "vslam_clear_counters", "vslam_search_for_points", "vslam_refind", "vslam_get_refind_results", "vslam_epipolar_search", "vslam_project_and_derivs", "vslam_calc_jacobians",
     "vslam_calc_pose_update", "vslam_track_map", "vslam_track_frame", "vslam_track_frame_dev", "vslam_track_frame_async", "vslam_wait_step", "vslam_debug_atan", "vslam_debug_dp4a_peak", "vslam_kernel_launches", "vslam_set_timing", "vslam_get_stage_times",
@@ -96,6 +96,9 @@ def load():
     sig("vslam_get_poses", i, vp, vp)
     sig("vslam_set_motion", i, vp, i, vp, d, d, d)
     sig("vslam_reset_stream", i, vp, i)
+    sig("vslam_set_reloc_keyframes", i, vp, i, vp, vp)
+    sig("vslam_get_reloc_info", i, vp, i, pi, pd, pi, pi)
+    sig("vslam_set_lost", i, vp, i, i, i)
     sig("vslam_get_motion", i, vp, i, vp, pd, pd, pd)
     sig("vslam_set_sbi_rotation", i, vp, i, vp)
     sig("vslam_enable_sbi", i, vp, vp)
@@ -319,6 +322,19 @@ class Context:
     def set_motion(self, s, velocity6, msd, depth_mean=1.0, depth_sigma=1.0):
         v = np.ascontiguousarray(velocity6, dtype=np.float64)
         self._ck(self.L.vslam_set_motion(self.h, s, v.ctypes.data, msd, depth_mean, depth_sigma))
+
+    def set_reloc_keyframes(self, src_kf_ids, poses):
+        """Relocaliser keyframes: ids of uploaded source keyframes and their poses (n x 3 x 4)."""
+        ids = np.ascontiguousarray(src_kf_ids, dtype=np.int32); p = np.ascontiguousarray(poses, dtype=np.float64).reshape(len(ids), 12)
+        self._ck(self.L.vslam_set_reloc_keyframes(self.h, len(ids), ids.ctypes.data, p.ctypes.data))
+
+    def reloc_info(self, s):
+        b, sc, n, r = C.c_int(), C.c_double(), C.c_int(), C.c_int()
+        self._ck(self.L.vslam_get_reloc_info(self.h, s, C.byref(b), C.byref(sc), C.byref(n), C.byref(r)))
+        return b.value, sc.value, n.value, r.value
+
+    def set_lost(self, s, lost_frames, quality=0):
+        self._ck(self.L.vslam_set_lost(self.h, s, lost_frames, quality))
 
     def reset_stream(self, s):
         """Tracker::Reset (jni/Tracker.cc:45-60) for the tracker state of stream s."""

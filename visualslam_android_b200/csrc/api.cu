@@ -104,6 +104,7 @@ int vslam_create(const vslam_config* cfg, vslam_ctx** out) {
   if (!ctx) { g_create_error = "out of host memory"; return VSLAM_E_INVALID; }
   ctx->cfg = *cfg; vslam_default_params(&ctx->params);
   ctx->S = cfg->n_streams; ctx->N = cfg->max_points; ctx->P = cfg->patch_size; ctx->launches = 0; ctx->n_src = cfg->max_source_keyframes;
+  ctx->reloc_n = 0; ctx->reloc_tmpl = nullptr; ctx->reloc_jac = nullptr; ctx->reloc_tmp = nullptr; ctx->reloc_small = nullptr; ctx->reloc_pose = nullptr; ctx->reloc_scores = nullptr;
   ctx->unproj_lut = nullptr; ctx->unproj_ok = false; ctx->side_stream = nullptr; ctx->ev_fork = nullptr; ctx->ev_join = nullptr; ctx->scratch_host = nullptr; ctx->scratch_host_bytes = 0; ctx->timing = false; ctx->ev_used = 0; ctx->l0_alt = nullptr; ctx->copy_stream = nullptr; ctx->step = 0; ctx->pipe_ready = false; ctx->status_pin = nullptr;
   ctx->rest_scores = nullptr; ctx->rest_max = nullptr; ctx->rest_cand = nullptr; ctx->rest_cand_score = nullptr; ctx->rest_counts = nullptr; ctx->rest_stream = -1;
   ctx->snap_img = nullptr; ctx->snap_corners = nullptr; ctx->snap_lut = nullptr;
@@ -194,7 +195,7 @@ void vslam_destroy(vslam_ctx* ctx) {
   if (ctx->status_pin) cudaFreeHost(ctx->status_pin);
   delete[] ctx->l0_ptr_host; delete[] ctx->l0_stride_host;
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
-  cudaFree(ctx->unproj_lut);
+  cudaFree(ctx->unproj_lut); cudaFree(ctx->reloc_tmpl); cudaFree(ctx->reloc_jac); cudaFree(ctx->reloc_tmp); cudaFree(ctx->reloc_small); cudaFree(ctx->reloc_pose); cudaFree(ctx->reloc_scores);
   if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
@@ -264,6 +265,34 @@ int vslam_enable_sbi(vslam_ctx* ctx, const double* c) {
   return VSLAM_OK;
 }
 
+// Relocaliser keyframes (jni/Relocaliser.cc): n map keyframes given as source-keyframe ids (their pyramids are on the device) and poses.
+int vslam_set_reloc_keyframes(vslam_ctx* ctx, int n, const int32_t* src_kf_ids, const double* poses12) {
+  if (!ctx || n < 0 || (n > 0 && (!src_kf_ids || !poses12))) return VSLAM_E_INVALID;
+  if (!ctx->sbi_on) { ctx->err = "vslam_set_reloc_keyframes needs vslam_enable_sbi first (SmallBlurryImage size and camera)"; return VSLAM_E_INVALID; }
+  for (int k = 0; k < n; k++) if (src_kf_ids[k] < 0 || src_kf_ids[k] >= ctx->n_src) { ctx->err = "relocaliser keyframe is not a source keyframe id"; return VSLAM_E_INVALID; }
+  VS_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaFree(ctx->reloc_tmpl); cudaFree(ctx->reloc_jac); cudaFree(ctx->reloc_tmp); cudaFree(ctx->reloc_small); cudaFree(ctx->reloc_pose); cudaFree(ctx->reloc_scores);
+  ctx->reloc_tmpl = nullptr; ctx->reloc_jac = nullptr; ctx->reloc_tmp = nullptr; ctx->reloc_small = nullptr; ctx->reloc_pose = nullptr; ctx->reloc_scores = nullptr;
+  ctx->reloc_n = 0;
+  if (n == 0) return VSLAM_OK;
+  const size_t px = (size_t)(ctx->lev[3].w / 2) * (ctx->lev[3].h / 2);
+  {   // cv::getGaussianKernel(17, 2.5, CV_32F) as the stand-in computes it (host exp, float taps)
+    const double sigma = 2.5, scale2x = -0.5 / (sigma * sigma); double sum = 0;
+    for (int i = 0; i < 17; i++) { const double x = i - 8.0; ctx->reloc_taps[i] = (float)exp(scale2x * x * x); sum += ctx->reloc_taps[i]; }
+    sum = 1. / sum; for (int i = 0; i < 17; i++) ctx->reloc_taps[i] = (float)(ctx->reloc_taps[i] * sum);
+  }
+  VS_CUDA(dalloc(&ctx->reloc_tmpl, (size_t)n * px)); VS_CUDA(dalloc(&ctx->reloc_jac, (size_t)n * 2 * px)); VS_CUDA(dalloc(&ctx->reloc_tmp, (size_t)n * px));
+  VS_CUDA(dalloc(&ctx->reloc_small, (size_t)n * px)); VS_CUDA(dalloc(&ctx->reloc_pose, (size_t)n * 12)); VS_CUDA(dalloc(&ctx->reloc_scores, (size_t)ctx->S * n));
+  VS_CUDA(cudaMemcpy(ctx->reloc_pose, poses12, sizeof(double) * 12 * n, cudaMemcpyHostToDevice));
+  int* ids = nullptr; VS_CUDA(cudaMalloc(&ids, sizeof(int) * n));
+  cudaError_t e = cudaMemcpy(ids, src_kf_ids, sizeof(int) * n, cudaMemcpyHostToDevice);
+  ctx->reloc_n = n;
+  int rc = e == cudaSuccess ? vs_launch_reloc_make(ctx, ids) : VSLAM_E_CUDA;
+  if (!rc && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = VSLAM_E_CUDA;
+  cudaFree(ids);
+  if (rc) { ctx->reloc_n = 0; ctx->err = "vslam_set_reloc_keyframes: CUDA error"; }
+  return rc;
+}
 int vslam_set_camera(vslam_ctx* ctx, const double* c) {
   if (!ctx || !c) return VSLAM_E_INVALID;
   CamDev& d = ctx->cam;
@@ -533,11 +562,26 @@ int vslam_reset_stream(vslam_ctx* ctx, int s) {
   int rc = check_stream(ctx, s); if (rc) return rc;
   StreamState st; if ((rc = read_ss(ctx, s, &st))) return rc;
   st.did_coarse = 0; st.quality = 2; st.lost_frames = 0; st.msd_scaled_vel = 0.0; st.vel_mag = 0.0; st.depth_mean = 1.0; st.depth_sigma = 1.0;
-  st.just_recovered = 0; st.n_updates = 0; st.try_coarse = 0;
+  st.just_recovered = 0; st.n_updates = 0; st.try_coarse = 0; st.recovered = 0;
   for (int k = 0; k < 6; k++) st.velocity[k] = 0.0;
   for (int l = 0; l < VS_LEVELS; l++) st.attempted[l] = st.found[l] = 0;
   return write_ss(ctx, s, &st);
 }
+// best keyframe and final alignment score of the stream's last relocalisation attempt, recoveries so far, and whether the last frame recovered it
+int vslam_get_reloc_info(vslam_ctx* ctx, int s, int* best, double* score, int* n_recoveries, int* recovered_last_frame) {
+  int rc = check_stream(ctx, s); if (rc) return rc;
+  StreamState st; if ((rc = read_ss(ctx, s, &st))) return rc;
+  if (best) *best = st.reloc_best; if (score) *score = st.reloc_score; if (n_recoveries) *n_recoveries = st.n_recoveries; if (recovered_last_frame) *recovered_last_frame = st.recovered;
+  return VSLAM_OK;
+}
+// Test / hand-off hook: Tracker::mnLostFrames and mTrackingQuality of a stream
+int vslam_set_lost(vslam_ctx* ctx, int s, int lost_frames, int quality) {
+  int rc = check_stream(ctx, s); if (rc) return rc;
+  StreamState st; if ((rc = read_ss(ctx, s, &st))) return rc;
+  st.lost_frames = lost_frames; st.quality = quality;
+  return write_ss(ctx, s, &st);
+}
+
 int vslam_set_sbi_rotation(vslam_ctx* ctx, int s, const double* r6) {
   int rc = check_stream(ctx, s); if (rc) return rc;
   VS_CUDA(cudaStreamSynchronize(ctx->stream));

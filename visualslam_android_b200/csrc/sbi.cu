@@ -26,6 +26,15 @@ struct SbiDev {
   int use_sbi;
 };
 
+struct RelocDev {
+  int n_kf, w, h, l3h, l3pitch;
+  const uint8_t* src_l3;    // level 3 of the source keyframes [K_src][l3h][l3pitch]
+  float taps17[17];         // getGaussianKernel(17, 2.5) in float
+  float* kf_tmpl; float* kf_jac; float* kf_tmp; uint8_t* kf_small;   // [n_kf][n], [n_kf][2n], scratch
+  const double* kf_pose;    // [n_kf][12]
+  double* scores;           // [S][n_kf]
+};
+
 __device__ inline double block_sum(double v, double* red) {
 #pragma unroll
   for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
@@ -65,82 +74,79 @@ __device__ inline void inverse3(const double* m, double* r) {
   r[2] = (m[1] * m[5] - m[2] * m[4]) * invdet; r[5] = (m[2] * m[3] - m[0] * m[5]) * invdet; r[8] = (m[0] * m[4] - m[1] * m[3]) * invdet;
 }
 
-__global__ void __launch_bounds__(kT) k_sbi(SbiDev D) {
-  __shared__ double red[kT / 32];
-  __shared__ double red14[kT / 32][14];
-  __shared__ double sX[6];        // current warp: R (4, row-major) and t (2)
-  __shared__ double sCtoC[6];     // accumulated SE2
-  __shared__ double sMean;
-  const int s = blockIdx.x, tid = threadIdx.x;
-  const int W = D.w, H = D.h, n = W * H;
-  StreamState* st = D.ss + s;
-  const int par = D.parity[s];
-  float* cur = D.tmpl + ((size_t)s * 2 + par) * n;
-  float* last = D.tmpl + ((size_t)s * 2 + (par ^ 1)) * n;
-  float* tmp = D.scratch + (size_t)s * 3 * n;
-  float* warped = tmp + n;
-  uint8_t* small = D.small + (size_t)s * n;
-  const uint8_t* l3 = D.l3 + (size_t)s * D.l3h * D.l3pitch;
+// ---- building blocks (called by every thread of a kT-thread CTA) -----------------------------------------------------------------
+struct SbiShared {
+  double red[kT / 32];
+  double red15[kT / 32][15];
+  double X[6];        // current warp: R (4, row-major) and t (2)
+  double CtoC[6];     // accumulated SE2
+  double mean, score;
+  int best;
+};
 
-  // ---- MakeFromKF (jni/SmallBlurryImage.cc:20-55)
+// SmallBlurryImage::MakeFromKF (jni/SmallBlurryImage.cc:20-55): level 3 halved, mean removed, separable float Gaussian (ntaps = 9 for
+// dBlur <= 2, else 17), BORDER_REPLICATE.  `out` receives the template; `small` the u8 thumbnail; `tmp` is scratch.
+__device__ void sbi_make(const uint8_t* __restrict__ l3, int l3pitch, int W, int H, const float* taps, int ntaps, uint8_t* small, float* tmp, float* out, SbiShared& sh) {
+  const int tid = threadIdx.x, n = W * H, half = ntaps / 2;
   double isum = 0;
   for (int i = tid; i < n; i += kT) {
     const int y = i / W, x = i - y * W;
-    const uint8_t* a = l3 + (size_t)(2 * y) * D.l3pitch + 2 * x;
-    const int v = (a[0] + a[1] + a[D.l3pitch] + a[D.l3pitch + 1] + 2) >> 2;
+    const uint8_t* a = l3 + (size_t)(2 * y) * l3pitch + 2 * x;
+    const int v = (a[0] + a[1] + a[l3pitch] + a[l3pitch + 1] + 2) >> 2;
     small[i] = (uint8_t)v; isum += v;
   }
-  isum = block_sum(isum, red);            // integer valued: exact
+  isum = block_sum(isum, sh.red);            // integer valued: exact
   const float fMean = ((float)(unsigned)isum) / (H * W);
-  for (int i = tid; i < n; i += kT) cur[i] = (float)small[i] - fMean;
+  for (int i = tid; i < n; i += kT) out[i] = (float)small[i] - fMean;
   __syncthreads();
   for (int i = tid; i < n; i += kT) {    // row pass
     const int y = i / W, x = i - y * W; float acc = 0;
-#pragma unroll
-    for (int k = 0; k < 9; k++) { int xx = x + k - 4; xx = xx < 0 ? 0 : (xx >= W ? W - 1 : xx); acc += D.taps[k] * cur[y * W + xx]; }
+    for (int k = 0; k < ntaps; k++) { int xx = x + k - half; xx = xx < 0 ? 0 : (xx >= W ? W - 1 : xx); acc += taps[k] * out[y * W + xx]; }
     tmp[i] = acc;
   }
   __syncthreads();
   for (int i = tid; i < n; i += kT) {    // column pass
     const int y = i / W, x = i - y * W; float acc = 0;
-#pragma unroll
-    for (int k = 0; k < 9; k++) { int yy = y + k - 4; yy = yy < 0 ? 0 : (yy >= H ? H - 1 : yy); acc += D.taps[k] * tmp[yy * W + x]; }
-    cur[i] = acc;
+    for (int k = 0; k < ntaps; k++) { int yy = y + k - half; yy = yy < 0 ? 0 : (yy >= H ? H - 1 : yy); acc += taps[k] * tmp[yy * W + x]; }
+    out[i] = acc;
   }
   __syncthreads();
-  const bool first = !D.have[s];
-  if (first) { for (int i = tid; i < n; i += kT) last[i] = cur[i]; }   // first frame: both SBIs come from the same keyframe (jni/Tracker.cc:90-93)
-  __syncthreads();
-  if (tid == 0) { D.have[s] = 1; D.parity[s] = par ^ 1; }               // next frame: `cur` becomes `last`
-  if (!D.use_sbi || st->lost_frames >= 3) return;
+}
 
-  // ---- MakeJacs of the last frame (jni/SmallBlurryImage.cc:58-79)
-  float* jac = D.jac + (size_t)s * 2 * n;
-  for (int i = tid; i < n; i += kT) {
+// SmallBlurryImage::MakeJacs (jni/SmallBlurryImage.cc:58-79)
+__device__ void sbi_make_jacs(const float* __restrict__ t, float* jac, int W, int H) {
+  const int n = W * H;
+  for (int i = threadIdx.x; i < n; i += kT) {
     const int y = i / W, x = i - y * W;
     float gx = 0.f, gy = 0.f;
-    if (x >= 1 && y >= 1 && x < W - 1 && y < H - 1) { gx = last[i + 1] - last[i - 1]; gy = last[i + W] - last[i - W]; }
+    if (x >= 1 && y >= 1 && x < W - 1 && y < H - 1) { gx = t[i + 1] - t[i - 1]; gy = t[i + W] - t[i - W]; }
     jac[2 * i] = gx; jac[2 * i + 1] = gy;
   }
-  // ---- IteratePosRelToTarget (jni/SmallBlurryImage.cc:99-222)
+}
+
+// SmallBlurryImage::IteratePosRelToTarget (jni/SmallBlurryImage.cc:99-222): `its` ESM iterations aligning `cur` to the target `last`
+// (gradient image `jac`).  Leaves the SE2 in sh.CtoC and the final score (sum of squared differences of the last iteration) in sh.score.
+__device__ void sbi_esm(const float* __restrict__ cur, const float* __restrict__ last, const float* __restrict__ jac, float* warped, int W, int H, int its, SbiShared& sh) {
+  const int tid = threadIdx.x, n = W * H;
   const double cx = W / 2.0, cy = H / 2.0;
-  if (tid == 0) { sCtoC[0] = 1; sCtoC[1] = 0; sCtoC[2] = 0; sCtoC[3] = 1; sCtoC[4] = 0; sCtoC[5] = 0; sMean = 0.0; }
   __syncthreads();
-  for (int it = 0; it < 6; it++) {
+  if (tid == 0) { sh.CtoC[0] = 1; sh.CtoC[1] = 0; sh.CtoC[2] = 0; sh.CtoC[3] = 1; sh.CtoC[4] = 0; sh.CtoC[5] = 0; sh.mean = 0.0; sh.score = 0.0; }
+  __syncthreads();
+  for (int it = 0; it < its; it++) {
     if (tid == 0) {   // X = WfromC * CtoC * WfromC^-1 with WfromC = (I, centre)
-      const double* R = sCtoC; const double t0 = sCtoC[4], t1 = sCtoC[5];
+      const double* R = sh.CtoC; const double t0 = sh.CtoC[4], t1 = sh.CtoC[5];
       // A = WfromC * CtoC : rotation R (I*R evaluated like the reference: sums with exact zeros), translation c + (1*t0 + 0*t1, ...)
       double AR[4]; for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++) { double sacc = (i == 0 ? 1.0 : 0.0) * R[j]; sacc += (i == 1 ? 1.0 : 0.0) * R[2 + j]; AR[2 * i + j] = sacc; }
       double At[2]; { double a = 1.0 * t0; a += 0.0 * t1; At[0] = cx + a; double b = 0.0 * t0; b += 1.0 * t1; At[1] = cy + b; }
       // inverse of WfromC: rotation I, translation -(I * c)
       double it0, it1; { double a = 1.0 * cx; a += 0.0 * cy; it0 = -a; double b = 0.0 * cx; b += 1.0 * cy; it1 = -b; }
-      for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++) { double sacc = AR[2 * i] * (j == 0 ? 1.0 : 0.0); sacc += AR[2 * i + 1] * (j == 1 ? 1.0 : 0.0); sX[2 * i + j] = sacc; }
-      for (int i = 0; i < 2; i++) { double sacc = AR[2 * i] * it0; sacc += AR[2 * i + 1] * it1; sX[4 + i] = At[i] + sacc; }
+      for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++) { double sacc = AR[2 * i] * (j == 0 ? 1.0 : 0.0); sacc += AR[2 * i + 1] * (j == 1 ? 1.0 : 0.0); sh.X[2 * i + j] = sacc; }
+      for (int i = 0; i < 2; i++) { double sacc = AR[2 * i] * it0; sacc += AR[2 * i + 1] * it1; sh.X[4 + i] = At[i] + sacc; }
     }
     __syncthreads();
     {   // transform_image (float): out(i,j) = bilinear(cur, p0 + i*down + j*across), default -9e20f outside
-      const double a0 = sX[0], a1 = sX[2], d0 = sX[1], d1 = sX[3];
-      const double p00 = sX[4], p01 = sX[5];   // outOrig = 0  =>  p0 = inOrig
+      const double a0 = sh.X[0], a1 = sh.X[2], d0 = sh.X[1], d1 = sh.X[3];
+      const double p00 = sh.X[4], p01 = sh.X[5];   // outOrig = 0  =>  p0 = inOrig
       const float xb = W - 1, yb = H - 1;
       for (int i = tid; i < n; i += kT) {
         const int r = i / W, c = i - r * W;
@@ -159,7 +165,7 @@ __global__ void __launch_bounds__(kT) k_sbi(SbiDev D) {
     double acc[15];
 #pragma unroll
     for (int k = 0; k < 15; k++) acc[k] = 0;
-    const double mean = sMean;
+    const double mean = sh.mean;
     for (int i = tid; i < n; i += kT) {
       const int y = i / W, x = i - y * W;
       if (!(x >= 1 && y >= 1 && x < W - 1 && y < H - 1)) continue;
@@ -173,17 +179,18 @@ __global__ void __launch_bounds__(kT) k_sbi(SbiDev D) {
       acc[4] += J0 * J0; acc[5] += J1 * J0; acc[6] += J1 * J1; acc[7] += J2 * J0; acc[8] += J2 * J1; acc[9] += J2 * J2;
       acc[10] += J0; acc[11] += J1; acc[12] += J2; acc[13] += 1.0; acc[14] += dd * dd;
     }
-    // one fixed-shape reduction for all 14 sums: warp shuffles, then 8 partials per sum through shared memory
+    // one fixed-shape reduction for all 15 sums: warp shuffles, then 8 partials per sum through shared memory
 #pragma unroll
-    for (int k = 0; k < 14; k++) {
+    for (int k = 0; k < 15; k++) {
 #pragma unroll
       for (int d = 16; d; d >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], d);
     }
     __syncthreads();
-    if ((tid & 31) == 0) { for (int k = 0; k < 14; k++) red14[tid >> 5][k] = acc[k]; }
+    if ((tid & 31) == 0) { for (int k = 0; k < 15; k++) sh.red15[tid >> 5][k] = acc[k]; }
     __syncthreads();
     if (tid == 0) {
-      for (int k = 0; k < 14; k++) { double r = 0; for (int w = 0; w < kT / 32; w++) r += red14[w][k]; acc[k] = r; }
+      for (int k = 0; k < 15; k++) { double r = 0; for (int w = 0; w < kT / 32; w++) r += sh.red15[w][k]; acc[k] = r; }
+      sh.score = acc[14];
       double m4[16]; int v = 0;
       for (int j = 0; j < 4; j++) for (int i = 0; i <= j; i++) { m4[4 * j + i] = m4[4 * i + j] = acc[4 + v]; v++; }
       double upd[4]; solve4(m4, acc, upd);
@@ -191,57 +198,140 @@ __global__ void __launch_bounds__(kT) k_sbi(SbiDev D) {
       const double c = cos(ang), sn = sin(ang);
       const double U[6] = {c, -sn, sn, c, -upd[0], -upd[1]};   // mySO2::exp (jni/RT.h:461-467), translation -update
       double R[4], t[2];
-      for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++) { double sacc = sCtoC[2 * i] * U[j]; sacc += sCtoC[2 * i + 1] * U[2 + j]; R[2 * i + j] = sacc; }
-      for (int i = 0; i < 2; i++) { double sacc = sCtoC[2 * i] * U[4]; sacc += sCtoC[2 * i + 1] * U[5]; t[i] = sCtoC[4 + i] + sacc; }
-      for (int k = 0; k < 4; k++) sCtoC[k] = R[k];
-      sCtoC[4] = t[0]; sCtoC[5] = t[1];
-      sMean -= upd[3];
+      for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++) { double sacc = sh.CtoC[2 * i] * U[j]; sacc += sh.CtoC[2 * i + 1] * U[2 + j]; R[2 * i + j] = sacc; }
+      for (int i = 0; i < 2; i++) { double sacc = sh.CtoC[2 * i] * U[4]; sacc += sh.CtoC[2 * i + 1] * U[5]; t[i] = sh.CtoC[4 + i] + sacc; }
+      for (int k = 0; k < 4; k++) sh.CtoC[k] = R[k];
+      sh.CtoC[4] = t[0]; sh.CtoC[5] = t[1];
+      sh.mean -= upd[3];
     }
     __syncthreads();
   }
-  // ---- SE3fromSE2 (jni/SmallBlurryImage.cc:245-333) and ln() -> Tracker::mv6SBIRot
-  if (tid == 0) {
-    const double c2[2] = {W / 2.0, H / 2.0};
-    const double off[2][2] = {{5, 0}, {-5, 0}};
-    double turned[2][2];
-    for (int k = 0; k < 2; k++) for (int i = 0; i < 2; i++) { double sacc = sCtoC[2 * i] * off[k][0]; sacc += sCtoC[2 * i + 1] * off[k][1]; turned[k][i] = c2[i] + (sCtoC[4 + i] + sacc); }
-    double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-    for (int it = 0; it < 3; it++) {
-      double C[9] = {10, 0, 0, 0, 10, 0, 0, 0, 10}, b[3] = {0, 0, 0};
-      for (int k = 0; k < 2; k++) {
-        double v3[3];
-        for (int i = 0; i < 3; i++) { double sacc = R[3 * i] * D.orig[k][0]; sacc += R[3 * i + 1] * D.orig[k][1]; sacc += R[3 * i + 2] * D.orig[k][2]; v3[i] = sacc; }
-        double pix[2]; CamCache cc; cam_project(D.cam, v3[0] / v3[2], v3[1] / v3[2], pix, cc);
-        const double err[2] = {turned[k][0] - pix[0], turned[k][1] - pix[1]};
-        double dv[4]; cam_derivs(D.cam, cc, dv);
-        double J[2][3];
-        const double invz = 1.0 / v3[2];
-        for (int m = 0; m < 3; m++) {
-          double mo[3]; mo[m] = 0; mo[(m + 1) % 3] = -v3[(m + 2) % 3]; mo[(m + 2) % 3] = v3[(m + 1) % 3];
-          const double c0 = (mo[0] - v3[0] * mo[2] * invz) * invz, c1 = (mo[1] - v3[1] * mo[2] * invz) * invz;
-          double a0 = dv[0] * c0; a0 += dv[1] * c1; double a1 = dv[2] * c0; a1 += dv[3] * c1;
-          J[0][m] = a0; J[1][m] = a1;
-        }
-        for (int row = 0; row < 2; row++)
-          for (int r = 0; r < 3; r++) { const double Jw = 1.0 * J[row][r]; b[r] += err[row] * Jw; for (int q = r; q < 3; q++) C[3 * r + q] += Jw * J[row][q]; }
+}
+
+// SmallBlurryImage::SE3fromSE2 (jni/SmallBlurryImage.cc:245-333), one thread: the rotation (row-major 3x3) that reproduces the SE2
+__device__ void sbi_se3_from_se2(const double* CtoC, const CamDev& cam, const double (*orig)[3], int W, int H, double* R) {
+  const double c2[2] = {W / 2.0, H / 2.0};
+  const double off[2][2] = {{5, 0}, {-5, 0}};
+  double turned[2][2];
+  for (int k = 0; k < 2; k++) for (int i = 0; i < 2; i++) { double sacc = CtoC[2 * i] * off[k][0]; sacc += CtoC[2 * i + 1] * off[k][1]; turned[k][i] = c2[i] + (CtoC[4 + i] + sacc); }
+  for (int i = 0; i < 9; i++) R[i] = (i % 4 == 0) ? 1.0 : 0.0;
+  for (int it = 0; it < 3; it++) {
+    double C[9] = {10, 0, 0, 0, 10, 0, 0, 0, 10}, b[3] = {0, 0, 0};
+    for (int k = 0; k < 2; k++) {
+      double v3[3];
+      for (int i = 0; i < 3; i++) { double sacc = R[3 * i] * orig[k][0]; sacc += R[3 * i + 1] * orig[k][1]; sacc += R[3 * i + 2] * orig[k][2]; v3[i] = sacc; }
+      double pix[2]; CamCache cc; cam_project(cam, v3[0] / v3[2], v3[1] / v3[2], pix, cc);
+      const double err[2] = {turned[k][0] - pix[0], turned[k][1] - pix[1]};
+      double dv[4]; cam_derivs(cam, cc, dv);
+      double J[2][3];
+      const double invz = 1.0 / v3[2];
+      for (int m = 0; m < 3; m++) {
+        double mo[3]; mo[m] = 0; mo[(m + 1) % 3] = -v3[(m + 2) % 3]; mo[(m + 2) % 3] = v3[(m + 1) % 3];
+        const double c0 = (mo[0] - v3[0] * mo[2] * invz) * invz, c1 = (mo[1] - v3[1] * mo[2] * invz) * invz;
+        double a0 = dv[0] * c0; a0 += dv[1] * c1; double a1 = dv[2] * c0; a1 += dv[3] * c1;
+        J[0][m] = a0; J[1][m] = a1;
       }
-      for (int r = 1; r < 3; r++) for (int q = 0; q < r; q++) C[3 * r + q] = C[3 * q + r];
-      double Ci[9]; inverse3(C, Ci);
-      double mu[3]; for (int i = 0; i < 3; i++) { double sacc = Ci[3 * i] * b[0]; sacc += Ci[3 * i + 1] * b[1]; sacc += Ci[3 * i + 2] * b[2]; mu[i] = sacc; }
-      double E[9], Rn[9]; so3_exp(mu, E);
-      for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { double sacc = E[3 * i] * R[j]; sacc += E[3 * i + 1] * R[3 + j]; sacc += E[3 * i + 2] * R[6 + j]; Rn[3 * i + j] = sacc; }
-      for (int i = 0; i < 9; i++) R[i] = Rn[i];
+      for (int row = 0; row < 2; row++)
+        for (int r = 0; r < 3; r++) { const double Jw = 1.0 * J[row][r]; b[r] += err[row] * Jw; for (int q = r; q < 3; q++) C[3 * r + q] += Jw * J[row][q]; }
     }
+    for (int r = 1; r < 3; r++) for (int q = 0; q < r; q++) C[3 * r + q] = C[3 * q + r];
+    double Ci[9]; inverse3(C, Ci);
+    double mu[3]; for (int i = 0; i < 3; i++) { double sacc = Ci[3 * i] * b[0]; sacc += Ci[3 * i + 1] * b[1]; sacc += Ci[3 * i + 2] * b[2]; mu[i] = sacc; }
+    double E[9], Rn[9]; so3_exp(mu, E);
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { double sacc = E[3 * i] * R[j]; sacc += E[3 * i + 1] * R[3 + j]; sacc += E[3 * i + 2] * R[6 + j]; Rn[3 * i + j] = sacc; }
+    for (int i = 0; i < 9; i++) R[i] = Rn[i];
+  }
+}
+
+// Per frame and stream: the tracker's SmallBlurryImage pair (blur 0.75) and Tracker::CalcSBIRotation (jni/Tracker.cc:86-97,885-893)
+__global__ void __launch_bounds__(kT) k_sbi(SbiDev D) {
+  __shared__ SbiShared sh;
+  const int s = blockIdx.x, tid = threadIdx.x;
+  const int W = D.w, H = D.h, n = W * H;
+  StreamState* st = D.ss + s;
+  const int par = D.parity[s];
+  float* cur = D.tmpl + ((size_t)s * 2 + par) * n;
+  float* last = D.tmpl + ((size_t)s * 2 + (par ^ 1)) * n;
+  float* tmp = D.scratch + (size_t)s * 3 * n;
+  float* warped = tmp + n;
+  if (tid == 0) st->recovered = 0;      // set again by k_relocalise if this frame relocalises the stream
+  sbi_make(D.l3 + (size_t)s * D.l3h * D.l3pitch, D.l3pitch, W, H, D.taps, 9, D.small + (size_t)s * n, tmp, cur, sh);
+  const bool first = !D.have[s];
+  if (first) { for (int i = tid; i < n; i += kT) last[i] = cur[i]; }   // first frame: both SBIs come from the same keyframe (jni/Tracker.cc:90-93)
+  __syncthreads();
+  if (tid == 0) { D.have[s] = 1; D.parity[s] = par ^ 1; }               // next frame: `cur` becomes `last`
+  if (!D.use_sbi || st->lost_frames >= 3) return;
+  float* jac = D.jac + (size_t)s * 2 * n;
+  sbi_make_jacs(last, jac, W, H);
+  sbi_esm(cur, last, jac, warped, W, H, 6, sh);
+  if (tid == 0) {   // SE3fromSE2 and ln() -> Tracker::mv6SBIRot
+    double R[9]; sbi_se3_from_se2(sh.CtoC, D.cam, D.orig, W, H, R);
     double P[12]; for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) P[4 * i + j] = R[3 * i + j]; P[4 * i + 3] = 0.0; }
     double v6[6]; se3_ln(P, v6);
     for (int k = 0; k < 6; k++) st->sbi_rot[k] = v6[k];
   }
 }
 
+// Relocaliser keyframe k: SmallBlurryImage(kf) with the default blur 2.5 (jni/KeyFrame.cc:98) + MakeJacs, from the level-3 image of a
+// source keyframe.  One CTA per keyframe.
+__global__ void __launch_bounds__(kT) k_reloc_make(RelocDev Rd, const int* __restrict__ src_ids) {
+  __shared__ SbiShared sh;
+  const int k = blockIdx.x, n = Rd.w * Rd.h;
+  const uint8_t* l3 = Rd.src_l3 + (size_t)src_ids[k] * Rd.l3h * Rd.l3pitch;
+  float* out = Rd.kf_tmpl + (size_t)k * n;
+  sbi_make(l3, Rd.l3pitch, Rd.w, Rd.h, Rd.taps17, 17, Rd.kf_small + (size_t)k * n, Rd.kf_tmp + (size_t)k * n, out, sh);
+  sbi_make_jacs(out, Rd.kf_jac + (size_t)k * 2 * n, Rd.w, Rd.h);
+}
+
+// The lost branch of Tracker::TrackFrame (jni/Tracker.cc:134-140), one CTA per lost stream: Relocaliser::AttemptRecovery
+// (jni/Relocaliser.cc:17-58: SmallBlurryImage of the frame with blur 2.5, ScoreKFs = SSD against every map keyframe's, six ESM
+// iterations against the best, SE3fromSE2 * keyframe pose, accepted if the final score < 9e6) and Tracker::AttemptRecovery
+// (jni/Tracker.cc:167-180: pose = start pose = best, velocity zero, coarse stage forced).  TrackMap + AssessTrackingQuality follow in
+// the usual kernels, which treat a stream with `recovered` set as alive (no motion model before, no UpdateMotionModel after).
+__global__ void __launch_bounds__(kT) k_relocalise(SbiDev D, RelocDev Rd) {
+  __shared__ SbiShared sh;
+  const int s = blockIdx.x, tid = threadIdx.x;
+  StreamState* st = D.ss + s;
+  if (st->lost_frames < 3 || Rd.n_kf <= 0) return;
+  const int W = D.w, H = D.h, n = W * H;
+  float* tmp = D.scratch + (size_t)s * 3 * n;
+  float* warped = tmp + n;
+  float* cur = tmp + 2 * n;
+  sbi_make(D.l3 + (size_t)s * D.l3h * D.l3pitch, D.l3pitch, W, H, Rd.taps17, 17, D.small + (size_t)s * n, tmp, cur, sh);
+  // ScoreKFs: SmallBlurryImage::ZMSSD (jni/SmallBlurryImage.cc:82-94), serial sum in the reference's order (x outer, y inner), one thread per keyframe
+  double* scores = Rd.scores + (size_t)s * Rd.n_kf;
+  for (int k = tid; k < Rd.n_kf; k += kT) {
+    const float* o = Rd.kf_tmpl + (size_t)k * n;
+    double d = 0.0;
+    for (int x = 0; x < W; x++) for (int y = 0; y < H; y++) { const double df = cur[y * W + x] - o[y * W + x]; d += df * df; }
+    scores[k] = d;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double best = 99999999999999.9; int nb = -1;
+    for (int k = 0; k < Rd.n_kf; k++) if (scores[k] < best) { best = scores[k]; nb = k; }
+    sh.best = nb;
+  }
+  __syncthreads();
+  const int nb = sh.best;
+  if (nb < 0) return;
+  sbi_esm(cur, Rd.kf_tmpl + (size_t)nb * n, Rd.kf_jac + (size_t)nb * 2 * n, warped, W, H, 6, sh);
+  if (tid == 0) {
+    double R[9]; sbi_se3_from_se2(sh.CtoC, D.cam, D.orig, W, H, R);
+    double P[12]; for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) P[4 * i + j] = R[3 * i + j]; P[4 * i + 3] = 0.0; }
+    double bestp[12]; se3_mul(P, Rd.kf_pose + 12 * (size_t)nb, bestp);
+    st->reloc_best = nb; st->reloc_score = sh.score;
+    if (sh.score < 9e6) {
+      for (int k = 0; k < 12; k++) { st->pose[k] = bestp[k]; st->start_pose[k] = bestp[k]; }
+      for (int k = 0; k < 6; k++) st->velocity[k] = 0.0;
+      st->just_recovered = 1; st->recovered = 1; st->n_recoveries++;
+    }
+  }
+}
+
 }  // namespace
 
-int vs_launch_sbi(vslam_ctx* ctx) {
-  if (!ctx->sbi_on) return VSLAM_OK;
+static SbiDev make_sbi_dev(vslam_ctx* ctx) {
   SbiDev D;
   const LevelDesc& L3 = ctx->lev[3];
   D.w = L3.w / 2; D.h = L3.h / 2; D.l3w = L3.w; D.l3h = L3.h; D.l3pitch = L3.pitch; D.l3 = L3.img;
@@ -249,9 +339,38 @@ int vs_launch_sbi(vslam_ctx* ctx) {
   D.cam = ctx->sbi_cam; memcpy(D.orig, ctx->sbi_orig, sizeof(D.orig));
   D.tmpl = ctx->sbi_tmpl; D.scratch = ctx->sbi_scratch; D.jac = ctx->sbi_jac; D.small = ctx->sbi_small; D.ss = ctx->ss; D.have = ctx->sbi_have; D.parity = ctx->sbi_have + ctx->S;
   D.use_sbi = ctx->params.use_sbi;
+  return D;
+}
+static RelocDev make_reloc_dev(vslam_ctx* ctx) {
+  RelocDev R;
+  const LevelDesc& L3 = ctx->lev[3];
+  R.n_kf = ctx->reloc_n; R.w = L3.w / 2; R.h = L3.h / 2; R.l3h = ctx->src.h[3]; R.l3pitch = ctx->src.pitch[3]; R.src_l3 = ctx->src.img[3];
+  for (int k = 0; k < 17; k++) R.taps17[k] = ctx->reloc_taps[k];
+  R.kf_tmpl = ctx->reloc_tmpl; R.kf_jac = ctx->reloc_jac; R.kf_tmp = ctx->reloc_tmp; R.kf_small = ctx->reloc_small; R.kf_pose = ctx->reloc_pose; R.scores = ctx->reloc_scores;
+  return R;
+}
+
+int vs_launch_sbi(vslam_ctx* ctx) {
+  if (!ctx->sbi_on) return VSLAM_OK;
+  const SbiDev D = make_sbi_dev(ctx);
   vs_time_begin(ctx, VS_ST_OTHER);
   k_sbi<<<ctx->S, kT, 0, ctx->stream>>>(D);
   vs_time_end(ctx);
+  VS_CUDA(cudaGetLastError());
+  ctx->launches++;
+  if (ctx->reloc_n > 0) {   // lost streams try to relocalise; CTAs of streams that are not lost return at once
+    vs_time_begin(ctx, VS_ST_OTHER);
+    k_relocalise<<<ctx->S, kT, 0, ctx->stream>>>(D, make_reloc_dev(ctx));
+    vs_time_end(ctx);
+    VS_CUDA(cudaGetLastError());
+    ctx->launches++;
+  }
+  return VSLAM_OK;
+}
+
+// SmallBlurryImages (blur 2.5) + gradient images of ctx->reloc_n relocaliser keyframes from the source-keyframe pyramids
+int vs_launch_reloc_make(vslam_ctx* ctx, const int* src_ids_dev) {
+  k_reloc_make<<<ctx->reloc_n, kT, 0, ctx->stream>>>(make_reloc_dev(ctx), src_ids_dev);
   VS_CUDA(cudaGetLastError());
   ctx->launches++;
   return VSLAM_OK;

@@ -89,8 +89,8 @@ __global__ void __launch_bounds__(kPT) k_project_lists(Dev D, int mode, int appl
   const int N = D.map.n;
   const size_t SN = (size_t)D.S * D.N;
   StreamState* st = D.ss + s;
-  if (mode == 1 && st->lost_frames >= 3) return;   // lost streams wait for the (out-of-scope) relocaliser, jni/Tracker.cc:104,133
-  if (tid == 0 && apply_motion) {   // Tracker::ApplyMotionModel (jni/Tracker.cc:781-798)
+  if (mode == 1 && st->lost_frames >= 3 && !st->recovered) return;   // lost and not relocalised this frame (k_relocalise): nothing to do, jni/Tracker.cc:104,134-140
+  if (tid == 0 && apply_motion && !st->recovered) {   // Tracker::ApplyMotionModel (jni/Tracker.cc:781-798); a relocalised stream starts from the recovered pose
     double v[6]; for (int k = 0; k < 6; k++) v[k] = st->velocity[k];
     for (int k = 0; k < 12; k++) st->start_pose[k] = st->pose[k];
     if (D.prm.use_sbi) { v[0] = 0.0; v[1] = 0.0; v[3] = st->sbi_rot[3]; v[4] = st->sbi_rot[4]; v[5] = st->sbi_rot[5]; }
@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(kSearchWarps * 32, 10) k_search(Dev D, int mod
   const int s = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int e = blockIdx.x * kSearchWarps + warp;
   StreamState* st = D.ss + s;
-  if (mode != 0 && st->lost_frames >= 3) return;
+  if (mode != 0 && st->lost_frames >= 3 && !st->recovered) return;
   int first, count, range, subpix;
   if (mode == 0) { first = 0; count = st->nA; range = range_arg; subpix = subpix_arg; }
   else if (mode == 1) { if (!st->try_coarse) return; first = 0; count = st->nA; range = st->coarse_range; subpix = D.prm.coarse_subpix_its; }
@@ -954,7 +954,7 @@ __global__ void __launch_bounds__(kPT, 2) k_pose(Dev D, int mode, double sigma_a
   __shared__ PoseSmem sm;
   const int s = blockIdx.x, tid = threadIdx.x;
   StreamState* st = D.ss + s;
-  if (mode != 0 && st->lost_frames >= 3) return;
+  if (mode != 0 && st->lost_frames >= 3 && !st->recovered) return;
   const int* list = D.lists + (size_t)s * D.list_cap;
   // dynamic shared memory: [2048 doubles sort keys][2048 ints found list][2048 ints radix histogram][27*256 doubles partial sums]
   double* sortbuf = sh_sort; int sortcap = 2048;
@@ -1039,7 +1039,8 @@ __global__ void __launch_bounds__(kPT, 2) k_pose(Dev D, int mode, double sigma_a
     const int nNum = (int)dNum;
     if (nNum > 20) { st->depth_mean = dSum / nNum; st->depth_sigma = sqrt((dSumSq / nNum) - (st->depth_mean) * (st->depth_mean)); }
     if (tail) {
-      // Tracker::UpdateMotionModel (jni/Tracker.cc:802-820)
+      if (!st->recovered) {
+      // Tracker::UpdateMotionModel (jni/Tracker.cc:802-820); not after a relocalisation (jni/Tracker.cc:136-139)
       double inv[12], nfo[12], m[6];
       se3_inverse(st->start_pose, inv); se3_mul(sm.pose, inv, nfo); se3_ln(nfo, m);
       double sacc = 0;
@@ -1050,6 +1051,7 @@ __global__ void __launch_bounds__(kPT, 2) k_pose(Dev D, int mode, double sigma_a
       for (int k = 0; k < 3; k++) v[k] *= 1.0 / st->depth_mean;
       sacc = 0; for (int k = 0; k < 6; k++) sacc += v[k] * v[k];
       st->msd_scaled_vel = sqrt(sacc);
+      }
       // Tracker::AssessTrackingQuality (jni/Tracker.cc:832-878); the keyframe-distance test belongs to MapMaker (out of scope)
       int nTA = 0, nTF = 0, nLA = 0, nLF = 0;
       for (int l = 0; l < VS_LEVELS; l++) { nTA += st->attempted[l]; nTF += st->found[l]; if (l >= 2) { nLA += st->attempted[l]; nLF += st->found[l]; } }
@@ -1071,7 +1073,7 @@ __global__ void __launch_bounds__(kPT, 2) k_pose(Dev D, int mode, double sigma_a
 __global__ void __launch_bounds__(kPT) k_reproject_fine(Dev D) {
   const int s = blockIdx.x;
   StreamState* st = D.ss + s;
-  if (st->lost_frames >= 3 || !st->did_coarse) return;
+  if ((st->lost_frames >= 3 && !st->recovered) || !st->did_coarse) return;
   const size_t SN = (size_t)D.S * D.N;
   const int* list = D.lists + (size_t)s * D.list_cap + st->nA;
   for (int k = threadIdx.x; k < st->nB; k += kPT) {

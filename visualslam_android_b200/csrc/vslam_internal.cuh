@@ -83,6 +83,8 @@ struct StreamState {
   int nA, nB, nB_top;           // iteration list = [0,nA) coarse set, [nA, nA+nB) fine set (first nB_top entries: top level, sub-pixel)
   int try_coarse, coarse_range, n_updates, quirk_stale_cache;
   double updates[VS_MAX_UPDATES * 6], sigmas[VS_MAX_UPDATES];
+  // relocalisation (k_relocalise): set for the frame in which the stream was recovered; best keyframe / final ESM score of the last attempt
+  int recovered, reloc_best, n_recoveries, pad_; double reloc_score;
 };
 
 struct vslam_ctx {
@@ -117,6 +119,8 @@ struct vslam_ctx {
   // MakeKeyFrame_Rest results of one stream (lazy scratch) and the per-stream keyframe snapshot used by MiniPatch trail tracking
   int* rest_scores; uint32_t* rest_max; uint32_t* rest_cand; double* rest_cand_score; int* rest_counts; size_t rest_off[VS_LEVELS]; int rest_stream;
   uint8_t* snap_img; uint32_t* snap_corners; int* snap_lut;
+  // relocaliser keyframes (vslam_set_reloc_keyframes): SmallBlurryImages with blur 2.5, their gradient images and poses
+  int reloc_n; float reloc_taps[17]; float* reloc_tmpl; float* reloc_jac; float* reloc_tmp; uint8_t* reloc_small; double* reloc_pose; double* reloc_scores;
   double* unproj_lut; bool unproj_ok;   // [H][W][2] ATANCamera::UnProject of every integer level-0 pixel (MapMaker::AddPointEpipolar's imUnProj), built on the host
   // on-device SmallBlurryImage (vslam_enable_sbi)
   bool sbi_on; float sbi_taps[9]; CamDev sbi_cam; double sbi_orig[2][3]; float* sbi_tmpl; float* sbi_scratch; float* sbi_jac; uint8_t* sbi_small; int* sbi_have;
@@ -158,7 +162,8 @@ int vs_launch_track_map_rest(vslam_ctx* ctx, int with_motion_model);   // everyt
 int vs_launch_frame(vslam_ctx* ctx);                                   // pyramid + FAST, SmallBlurryImage, TrackMap of all streams
 int vs_launch_project_and_derivs(vslam_ctx* ctx, int only_found);
 int vs_launch_calc_jacobians(vslam_ctx* ctx);
-int vs_launch_sbi(vslam_ctx* ctx);
+int vs_launch_sbi(vslam_ctx* ctx);          // + k_relocalise when relocaliser keyframes are registered
+int vs_launch_reloc_make(vslam_ctx* ctx, const int* src_ids_dev);
 int vs_launch_epipolar(vslam_ctx* ctx, int stream, int src_kf, int level, int n, const EpiCand* cand_dev, const double* unproj_dev, int subpix_its, int* out_int_dev, double* out_pos_dev);
 int vs_keyframe_rest(vslam_ctx* ctx, int stream);
 int vs_minipatch_sample(vslam_ctx* ctx, int stream, int which, const int* xy_dev, int n, uint8_t* patches_dev);
