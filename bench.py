@@ -149,6 +149,79 @@ def run_cpu_arm(cam, f0, smap, frames_by_stream, n_procs, n_warm, n_steps, frame
     return fps, total / n_steps, ("reference" if use_ref else "port")
 
 
+def sweep_config5(device=0):
+    """SURVEY.md §8(d) config 5 on one GPU: 3840x2160 frames and a 20000-point map.
+    (1) pyramid + FAST-10 + row LUT for batches of 1..64 frames per launch pair: ms, frames/s, algorithmic GB/s and the fraction of the
+        measured HBM peak.  Every timed launch reads a frame set that was not touched by the previous launches worth > 126 MB (L2).
+    (2) SearchForPoints (no sub-pixel) for N points x search range: ms, candidates scored (identical on CPU and GPU), integer TMAC/s."""
+    import torch
+    from oracle import oraclebind
+    from visualslam_android_b200 import api, synth
+    W4, H4 = 3840, 2160
+    dev = torch.device("cuda", device)
+    torch.cuda.set_device(dev)
+    cam = synth.Camera(W4, H4)
+    tex = synth.make_texture(4096)
+    tex_t = torch.from_numpy(tex.astype(np.float32)).to(dev)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
+    stream = torch.cuda.Stream(device=dev); torch.cuda.set_stream(stream)
+    out = {"what": "config 5 sweep (3840x2160)", "hbm_peak_gbs": peak, "pyramid_fast": [], "search": []}
+    n_pool = 20                                              # 20 x 8.3 MB = 166 MB > L2
+    poses = np.stack([synth.stream_pose(3 * k, 1) for k in range(1, 65 + n_pool)])
+    frames = torch.empty((64 + n_pool, H4, W4), dtype=torch.uint8, device=dev)
+    for k in range(0, len(frames), 4):
+        frames[k:k + 4] = render_frames_torch(tex_t, cam, poses[k:k + 4], dev)
+    torch.cuda.synchronize()
+    for S in (1, 2, 4, 8, 16, 32, 64):
+        ctx = api.Context(W4, H4, n_streams=S, max_points=16, cuda_stream=stream.cuda_stream)
+        reps, t = 12, []
+        for r in range(3 + reps):
+            off = (r * max(S, n_pool)) % (len(frames) - S + 1) if S < n_pool else (r % 2) * (len(frames) - S)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            ctx.make_keyframe_lite_ptr(frames[off].data_ptr(), S, W4, H4 * W4, device=True)
+            e1.record(stream); ctx.sync()
+            if r >= 3:
+                t.append(e0.elapsed_time(e1))
+        ms = float(np.median(t))
+        corners = sum(int(ctx.corners(0, l).shape[0]) for l in range(4))
+        alg = S * (1.328125 * W4 * H4 + 4 * sum((H4 >> l) for l in range(4)) + 4.0 * corners)
+        out["pyramid_fast"].append({"frames_per_launch": S, "ms": ms, "frames_per_s": S / (ms * 1e-3), "algorithmic_gbs": alg / (ms * 1e-3) / 1e9,
+                                    "frac_of_hbm_peak": alg / (ms * 1e-3) / 1e9 / peak, "corners_per_frame": corners})
+        ctx.close()
+    # (2) patch search: one 4K stream, N map points, range sweep
+    f0 = synth.render_frame(tex, cam, synth.IDENTITY_POSE)
+    kf = oraclebind.OrcKeyFrame().make_lite(f0)
+    f1 = synth.render_frame(tex, cam, synth.se3_exp(np.array(synth.CONFIG1_TWIST)))
+    dp4a_peak = api.dp4a_peak_tmacs()
+    for N in (1000, 5000, 20000):
+        smap = synth.build_map(cam, [kf.corners(l) for l in range(4)], [kf.dims(l) for l in range(4)], N)
+        ctx = api.Context(W4, H4, n_streams=1, max_points=smap.n, cuda_stream=stream.cuda_stream)
+        ctx.set_camera(cam.scalars()); ctx.upload_source_keyframe(f0)
+        ctx.set_map(smap.world, smap.pix_right_w, smap.pix_down_w, smap.ir_center, smap.src_level)
+        ctx.set_pose(0, synth.IDENTITY_POSE)
+        ctx.make_keyframe_lite(f1[None])
+        ctx.project_all()
+        ints, _ = ctx.point_states(0)
+        lst = np.nonzero((ints[:, 0] == 1) & (ints[:, 1] >= 0))[0].astype(np.int32)
+        ctx.set_lists([lst])
+        for rng in (5, 10, 20, 40):
+            t = []; ev = 0
+            for r in range(2 + 6):
+                ev0 = ctx.zmssd_evals()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream); ctx.search_for_points(rng, 0); e1.record(stream); ctx.sync()
+                ev = ctx.zmssd_evals() - ev0
+                if r >= 2:
+                    t.append(e0.elapsed_time(e1))
+            ms = float(np.median(t))
+            out["search"].append({"points": int(len(lst)), "range": rng, "ms": ms, "points_per_s": len(lst) / (ms * 1e-3), "candidates_scored": int(ev),
+                                  "tmacs": 3.0 * 121 * ev / (ms * 1e-3) / 1e12, "dp4a_peak_tmacs": dp4a_peak})
+        ctx.close()
+    return out
+
+
 def cpu_stage_times(reps=20, warm=5):
     """per-stage times of BASELINE config 1 (one VGA frame, 1000 map points, start pose I, frame at CONFIG1_TWIST) on
     one host core: the reference's own sources (oracle/_ref, P = 11 as shipped) and the oracle port at P = 11 and P = 8.
@@ -266,6 +339,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--streams", type=int, default=STREAMS_PER_GPU, help="camera streams per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sweep", action="store_true", help="SURVEY §8(d) config 5: 4K frames, batch-size sweep of pyramid+FAST and points x range sweep of the patch search (one GPU)")
     ap.add_argument("--cpu-stages", action="store_true", help="SURVEY §8(d)(i): per-stage CPU times of config 1 (reference build and oracle port), no GPU work")
     args = ap.parse_args()
     K, Wm = args.steps, max(args.warmup, 3 if args.impl == "ours" else 1)
@@ -296,6 +370,9 @@ def main():
         print(json.dumps(line))
         return
 
+    if args.sweep:
+        print(json.dumps(sweep_config5(local_rank)))
+        return
     if args.cpu_stages:
         print(json.dumps(cpu_stage_times()))
         return

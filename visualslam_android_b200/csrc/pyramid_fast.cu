@@ -323,10 +323,13 @@ size_t pyrfast_smem_bytes(int stride, int w, int rows, bool level0) {
 
 }  // namespace
 
-// Rows per CTA for level l.  16 everywhere: at level 0 the level-1..3 rows a CTA emits stay whole (16 -> 8, 4, 2), and at
+// Rows per CTA for level l.  16 by default: at level 0 the level-1..3 rows a CTA emits stay whole (16 -> 8, 4, 2), and at
 // the small levels taller strips (32 / 64 rows) measured slower on B200 (fewer CTAs to balance, longer look-back chain).
 int vs_strip_rows(int level, int w, int pitch) {
-  (void)level; (void)w; (void)pitch;
+  // wide images (1080p, 4K): 16 rows of level 0 no longer leave room for several CTAs per SM (4K: 116 KB per CTA, one CTA per SM,
+  // measured 3.6 % of the HBM peak against 5.8 % at VGA); 8-row strips keep 3-5 CTAs resident.  8 is the floor at level 0: a strip
+  // must cover whole rows of level 3.
+  if (pyrfast_smem_bytes(pitch, w, 16, level == 0) > 48 * 1024) return 8;
   return 16;
 }
 
