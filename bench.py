@@ -339,6 +339,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--streams", type=int, default=STREAMS_PER_GPU, help="camera streams per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--groups", type=int, default=0, help="vslam_params.stream_groups (0 = library default)")
     ap.add_argument("--sweep", action="store_true", help="SURVEY §8(d) config 5: 4K frames, batch-size sweep of pyramid+FAST and points x range sweep of the patch search (one GPU)")
     ap.add_argument("--cpu-stages", action="store_true", help="SURVEY §8(d)(i): per-stage CPU times of config 1 (reference build and oracle port), no GPU work")
     args = ap.parse_args()
@@ -423,6 +424,8 @@ def main():
     stream = torch.cuda.Stream(device=dev)       # an explicit stream: the library launches on it and the CUDA events below are recorded on it
     torch.cuda.set_stream(stream)
     ctx = api.Context(W, H, n_streams=S, max_points=smap.n, device=local_rank, cuda_stream=stream.cuda_stream)
+    if args.groups:
+        ctx.set_params(stream_groups=args.groups)
     ctx.set_camera(cam.scalars())
     ctx.enable_sbi(synth.Camera(W // 16, H // 16).scalars())       # SmallBlurryImage + CalcSBIRotation on the device, like the reference's TrackFrame
     ctx.upload_source_keyframe(f0)

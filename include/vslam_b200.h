@@ -78,6 +78,10 @@ typedef struct vslam_params {
   int fine_range, fine_range_after_coarse, fine_subpix_its_top_level;
   int max_patches_per_frame;
   int use_sbi;              /* Tracker::mbUseSBIInit (jni/Tracker.cc:87-89): motion model takes rotation from sbi_rot */
+  int stream_groups;        /* execution only, no effect on results: vslam_track_frame* can split the streams into 1..4 groups whose
+                               kernels run on separate CUDA streams.  Default 1: on B200 with 256 VGA streams, 2-4 groups measured 5 %
+                               SLOWER (1.16 vs 1.10 ms per step) — the smaller grids cost more in tails than the overlap of one
+                               group's latency-bound kernels with another's throughput-bound ones gives back */
 } vslam_params;
 
 void vslam_default_config(vslam_config* cfg);

@@ -312,12 +312,15 @@ def test_track_map_patch8():
     ctx.close()
 
 
-def test_track_frame_sequence_multi_stream():
-    """4 streams x 6 frames through vslam_track_frame (motion model + TrackMap + quality), each against its own oracle tracker."""
+@pytest.mark.parametrize("groups", [1, 3])
+def test_track_frame_sequence_multi_stream(groups):
+    """4 streams x 6 frames through vslam_track_frame (motion model + TrackMap + quality), each against its own oracle tracker; also
+    with the streams split into 3 groups on separate CUDA streams (vslam_params.stream_groups), which must not change any result."""
     from visualslam_android_b200 import api
     cam, f0, smap = common.scene()
     S, K = 4, 6
     ctx = _ctx(cam, f0, smap, n_streams=S)
+    ctx.set_params(stream_groups=groups)
     ows = [_orc(cam, f0, smap) for _ in range(S)]
     for k in range(1, K + 1):
         frames = np.stack([synth.render_frame(common.texture(), cam, synth.stream_pose(4 * k, s)) for s in range(S)])

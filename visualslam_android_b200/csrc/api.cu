@@ -68,7 +68,7 @@ void vslam_default_config(vslam_config* c) {
 
 void vslam_default_params(vslam_params* p) {   // jni/Tracker.cc:405-410,495-497,518
   p->coarse_min = 20; p->coarse_max = 60; p->coarse_range = 30; p->coarse_subpix_its = 8; p->coarse_min_vel = 0.006;
-  p->fine_range = 10; p->fine_range_after_coarse = 5; p->fine_subpix_its_top_level = 8; p->max_patches_per_frame = 1000; p->use_sbi = 1;
+  p->fine_range = 10; p->fine_range_after_coarse = 5; p->fine_subpix_its_top_level = 8; p->max_patches_per_frame = 1000; p->use_sbi = 1; p->stream_groups = 1;
 }
 
 const char* vslam_last_error(const vslam_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
@@ -105,7 +105,8 @@ int vslam_create(const vslam_config* cfg, vslam_ctx** out) {
   ctx->cfg = *cfg; vslam_default_params(&ctx->params);
   ctx->S = cfg->n_streams; ctx->N = cfg->max_points; ctx->P = cfg->patch_size; ctx->launches = 0; ctx->n_src = cfg->max_source_keyframes;
   ctx->reloc_n = 0; ctx->reloc_tmpl = nullptr; ctx->reloc_jac = nullptr; ctx->reloc_tmp = nullptr; ctx->reloc_small = nullptr; ctx->reloc_pose = nullptr; ctx->reloc_scores = nullptr;
-  ctx->unproj_lut = nullptr; ctx->unproj_ok = false; ctx->side_stream = nullptr; ctx->ev_fork = nullptr; ctx->ev_join = nullptr; ctx->scratch_host = nullptr; ctx->scratch_host_bytes = 0; ctx->timing = false; ctx->ev_used = 0; ctx->l0_alt = nullptr; ctx->copy_stream = nullptr; ctx->step = 0; ctx->pipe_ready = false; ctx->status_pin = nullptr;
+  ctx->unproj_lut = nullptr; ctx->unproj_ok = false; for (int g = 0; g < VS_MAX_GROUPS; g++) { ctx->side_stream[g] = nullptr; ctx->group_stream[g] = nullptr; ctx->ev_fork[g] = nullptr; ctx->ev_join[g] = nullptr; ctx->ev_end[g] = nullptr; }
+  ctx->ev_begin = nullptr; ctx->cur_s0 = 0; ctx->cur_cnt = cfg->n_streams; ctx->cur_group = 0; ctx->scratch_host = nullptr; ctx->scratch_host_bytes = 0; ctx->timing = false; ctx->ev_used = 0; ctx->l0_alt = nullptr; ctx->copy_stream = nullptr; ctx->step = 0; ctx->pipe_ready = false; ctx->status_pin = nullptr;
   ctx->rest_scores = nullptr; ctx->rest_max = nullptr; ctx->rest_cand = nullptr; ctx->rest_cand_score = nullptr; ctx->rest_counts = nullptr; ctx->rest_stream = -1;
   ctx->snap_img = nullptr; ctx->snap_corners = nullptr; ctx->snap_lut = nullptr;
   ctx->sbi_on = false; ctx->sbi_tmpl = nullptr; ctx->sbi_scratch = nullptr; ctx->sbi_jac = nullptr; ctx->sbi_small = nullptr; ctx->sbi_have = nullptr;
@@ -114,8 +115,13 @@ int vslam_create(const vslam_config* cfg, vslam_ctx** out) {
   CK(cudaSetDevice(cfg->device));
   if (cfg->cuda_stream) { ctx->stream = (cudaStream_t)cfg->cuda_stream; ctx->own_stream = false; }
   else { CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
-  CK(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
-  CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+  for (int g = 0; g < VS_MAX_GROUPS; g++) {
+    CK(cudaStreamCreateWithFlags(&ctx->side_stream[g], cudaStreamNonBlocking));
+    if (g > 0) CK(cudaStreamCreateWithFlags(&ctx->group_stream[g], cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ctx->ev_fork[g], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->ev_join[g], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->ev_end[g], cudaEventDisableTiming));
+  }
+  CK(cudaEventCreateWithFlags(&ctx->ev_begin, cudaEventDisableTiming));
   const int S = ctx->S, N = ctx->N;
   int w = cfg->width, h = cfg->height;
   for (int l = 0; l < VS_LEVELS; l++) {
@@ -137,7 +143,7 @@ int vslam_create(const vslam_config* cfg, vslam_ctx** out) {
   for (int s = 0; s < S; s++) { ctx->l0_ptr_host[s] = ctx->lev[0].img + (size_t)s * ctx->lev[0].h * ctx->lev[0].pitch; ctx->l0_stride_host[s] = ctx->lev[0].pitch; }
   CK(cudaMemcpy(ctx->l0_ptr, ctx->l0_ptr_host, sizeof(uint8_t*) * S, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(ctx->l0_stride, ctx->l0_stride_host, sizeof(int) * S, cudaMemcpyHostToDevice));
-  CK(dalloc(&ctx->tickets, (size_t)VS_LEVELS)); CK(dalloc(&ctx->status, (size_t)4)); CK(dalloc(&ctx->evals, (size_t)1));
+  CK(dalloc(&ctx->tickets, (size_t)2 * VS_MAX_GROUPS)); CK(dalloc(&ctx->status, (size_t)4)); CK(dalloc(&ctx->evals, (size_t)1));
   // map
   ctx->map.n = 0;
   CK(dalloc(&ctx->map.world, (size_t)3 * N)); CK(dalloc(&ctx->map.right, (size_t)3 * N)); CK(dalloc(&ctx->map.down, (size_t)3 * N));
@@ -196,9 +202,14 @@ void vslam_destroy(vslam_ctx* ctx) {
   delete[] ctx->l0_ptr_host; delete[] ctx->l0_stride_host;
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   cudaFree(ctx->unproj_lut); cudaFree(ctx->reloc_tmpl); cudaFree(ctx->reloc_jac); cudaFree(ctx->reloc_tmp); cudaFree(ctx->reloc_small); cudaFree(ctx->reloc_pose); cudaFree(ctx->reloc_scores);
-  if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
-  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
-  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  for (int g = 0; g < VS_MAX_GROUPS; g++) {
+    if (ctx->side_stream[g]) cudaStreamDestroy(ctx->side_stream[g]);
+    if (ctx->group_stream[g]) cudaStreamDestroy(ctx->group_stream[g]);
+    if (ctx->ev_fork[g]) cudaEventDestroy(ctx->ev_fork[g]);
+    if (ctx->ev_join[g]) cudaEventDestroy(ctx->ev_join[g]);
+    if (ctx->ev_end[g]) cudaEventDestroy(ctx->ev_end[g]);
+  }
+  if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
   delete ctx;
 }
 

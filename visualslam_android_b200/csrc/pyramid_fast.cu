@@ -338,7 +338,8 @@ static const int kFastThr[VS_LEVELS] = {10, 15, 15, 10};
 
 // Level 0: pyramid levels 1..3 + FAST-10 of level 0 (one launch).
 int vs_launch_pyramid_l0(vslam_ctx* ctx, int first_stream, int count) {
-  VS_CUDA(cudaMemsetAsync(ctx->tickets, 0, sizeof(unsigned) * VS_LEVELS, ctx->stream));
+  unsigned* tickets = ctx->tickets + 2 * ctx->cur_group;   // [0]: level-0 launch, [1]: levels 1-3 launch; one pair per stream group
+  VS_CUDA(cudaMemsetAsync(tickets, 0, sizeof(unsigned) * 2, ctx->stream));
   for (int l = 0; l < VS_LEVELS; l++) {
     LevelDesc& L = ctx->lev[l];
     VS_CUDA(cudaMemsetAsync(L.strip_state + (size_t)first_stream * L.n_strips, 0, sizeof(unsigned long long) * (size_t)count * L.n_strips, ctx->stream));
@@ -351,7 +352,7 @@ int vs_launch_pyramid_l0(vslam_ctx* ctx, int first_stream, int count) {
   VS_CUDA(cudaFuncSetAttribute(k_pyramid_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   vs_time_begin(ctx, VS_ST_PYR0);
   k_pyramid_fast<<<count * L.n_strips, kThreads, smem, ctx->stream>>>(L, ctx->lev[1], ctx->lev[2], ctx->lev[3], ctx->l0_ptr, ctx->l0_stride, first_stream, kFastThr[0],
-                                                                     ctx->tickets, ctx->status);
+                                                                     tickets, ctx->status);
   vs_time_end(ctx);
   VS_CUDA(cudaGetLastError());
   ctx->launches++;
@@ -371,7 +372,7 @@ int vs_launch_fast_levels(vslam_ctx* ctx, int first_stream, int count) {
   VS_CUDA(cudaFuncSetAttribute(k_fast_levels, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   vs_time_begin(ctx, VS_ST_PYR1);
   k_fast_levels<<<blocks, kThreads, smem, ctx->stream>>>(ctx->lev[1], ctx->lev[2], ctx->lev[3], first_stream, count, kFastThr[1], kFastThr[2], kFastThr[3],
-                                                        ctx->tickets + 1, ctx->status);
+                                                        ctx->tickets + 2 * ctx->cur_group + 1, ctx->status);
   vs_time_end(ctx);
   VS_CUDA(cudaGetLastError());
   ctx->launches++;

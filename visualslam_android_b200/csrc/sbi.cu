@@ -23,7 +23,7 @@ struct SbiDev {
   float* jac;               // [S][2n]    gradient image of the last template
   uint8_t* small;           // [S][n]
   StreamState* ss; int* have; int* parity;   // per stream
-  int use_sbi;
+  int use_sbi, s0;
 };
 
 struct RelocDev {
@@ -246,7 +246,7 @@ __device__ void sbi_se3_from_se2(const double* CtoC, const CamDev& cam, const do
 // Per frame and stream: the tracker's SmallBlurryImage pair (blur 0.75) and Tracker::CalcSBIRotation (jni/Tracker.cc:86-97,885-893)
 __global__ void __launch_bounds__(kT) k_sbi(SbiDev D) {
   __shared__ SbiShared sh;
-  const int s = blockIdx.x, tid = threadIdx.x;
+  const int s = blockIdx.x + D.s0, tid = threadIdx.x;
   const int W = D.w, H = D.h, n = W * H;
   StreamState* st = D.ss + s;
   const int par = D.parity[s];
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(kT) k_reloc_make(RelocDev Rd, const int* __res
 // the usual kernels, which treat a stream with `recovered` set as alive (no motion model before, no UpdateMotionModel after).
 __global__ void __launch_bounds__(kT) k_relocalise(SbiDev D, RelocDev Rd) {
   __shared__ SbiShared sh;
-  const int s = blockIdx.x, tid = threadIdx.x;
+  const int s = blockIdx.x + D.s0, tid = threadIdx.x;
   StreamState* st = D.ss + s;
   if (st->lost_frames < 3 || Rd.n_kf <= 0) return;
   const int W = D.w, H = D.h, n = W * H;
@@ -338,7 +338,7 @@ static SbiDev make_sbi_dev(vslam_ctx* ctx) {
   for (int k = 0; k < 9; k++) D.taps[k] = ctx->sbi_taps[k];
   D.cam = ctx->sbi_cam; memcpy(D.orig, ctx->sbi_orig, sizeof(D.orig));
   D.tmpl = ctx->sbi_tmpl; D.scratch = ctx->sbi_scratch; D.jac = ctx->sbi_jac; D.small = ctx->sbi_small; D.ss = ctx->ss; D.have = ctx->sbi_have; D.parity = ctx->sbi_have + ctx->S;
-  D.use_sbi = ctx->params.use_sbi;
+  D.use_sbi = ctx->params.use_sbi; D.s0 = ctx->cur_s0;
   return D;
 }
 static RelocDev make_reloc_dev(vslam_ctx* ctx) {
@@ -354,13 +354,13 @@ int vs_launch_sbi(vslam_ctx* ctx) {
   if (!ctx->sbi_on) return VSLAM_OK;
   const SbiDev D = make_sbi_dev(ctx);
   vs_time_begin(ctx, VS_ST_OTHER);
-  k_sbi<<<ctx->S, kT, 0, ctx->stream>>>(D);
+  k_sbi<<<ctx->cur_cnt, kT, 0, ctx->stream>>>(D);
   vs_time_end(ctx);
   VS_CUDA(cudaGetLastError());
   ctx->launches++;
   if (ctx->reloc_n > 0) {   // lost streams try to relocalise; CTAs of streams that are not lost return at once
     vs_time_begin(ctx, VS_ST_OTHER);
-    k_relocalise<<<ctx->S, kT, 0, ctx->stream>>>(D, make_reloc_dev(ctx));
+    k_relocalise<<<ctx->cur_cnt, kT, 0, ctx->stream>>>(D, make_reloc_dev(ctx));
     vs_time_end(ctx);
     VS_CUDA(cudaGetLastError());
     ctx->launches++;

@@ -23,6 +23,7 @@ struct Dev {   // everything the kernels need, passed by value
   StreamState* ss; int* lists; int list_cap; int* pvs; double* sort_scratch; int sort_cap;
   unsigned long long* evals;
   int S, N, P, truncate;
+  int s0;                  // first stream of this launch (stream groups of vs_launch_frame; 0 otherwise)
   vslam_params prm;
 };
 
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(kPT) k_project_lists(Dev D, int mode, int appl
   __shared__ double s_pose[12];
   __shared__ int s_cnt[kPT / 32][VS_LEVELS], s_run[VS_LEVELS], s_off[VS_LEVELS + 1];
   __shared__ int s_seg[8];
-  const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int s = blockIdx.x + D.s0, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = D.map.n;
   const size_t SN = (size_t)D.S * D.N;
   StreamState* st = D.ss + s;
@@ -360,7 +361,7 @@ constexpr int kSearchRefind = 1;
 template <int PT>
 __global__ void __launch_bounds__(kSearchWarps * 32, 10) k_search(Dev D, int mode, int range_arg, int subpix_arg, int sflags) {
   __shared__ SearchSmem sm_all[kSearchWarps];
-  const int s = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int s = blockIdx.y + D.s0, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int e = blockIdx.x * kSearchWarps + warp;
   StreamState* st = D.ss + s;
   if (mode != 0 && st->lost_frames >= 3 && !st->recovered) return;
@@ -952,7 +953,7 @@ __device__ int build_found_list(const Dev& D, PoseSmem& sm, const int* list, int
 __global__ void __launch_bounds__(kPT, 2) k_pose(Dev D, int mode, double sigma_arg, int mark_arg, int apply_arg, int tail) {
   extern __shared__ double sh_sort[];
   __shared__ PoseSmem sm;
-  const int s = blockIdx.x, tid = threadIdx.x;
+  const int s = blockIdx.x + D.s0, tid = threadIdx.x;
   StreamState* st = D.ss + s;
   if (mode != 0 && st->lost_frames >= 3 && !st->recovered) return;
   const int* list = D.lists + (size_t)s * D.list_cap;
@@ -1071,7 +1072,7 @@ __global__ void __launch_bounds__(kPT, 2) k_pose(Dev D, int mode, double sigma_a
 // `found` yet, so only the projection is refreshed; when the coarse stage did not run the pose is unchanged and the
 // projection of k_project_lists is still exact, so the CTA returns at once.
 __global__ void __launch_bounds__(kPT) k_reproject_fine(Dev D) {
-  const int s = blockIdx.x;
+  const int s = blockIdx.x + D.s0;
   StreamState* st = D.ss + s;
   if ((st->lost_frames >= 3 && !st->recovered) || !st->did_coarse) return;
   const size_t SN = (size_t)D.S * D.N;
@@ -1086,12 +1087,12 @@ __global__ void __launch_bounds__(kPT) k_reproject_fine(Dev D) {
 }
 
 __global__ void __launch_bounds__(kPT) k_project_and_derivs(Dev D, int only_found) {
-  const int s = blockIdx.x;
+  const int s = blockIdx.x + D.s0;
   StreamState* st = D.ss + s;
   reproject_found(D, st->pose, D.lists + (size_t)s * D.list_cap, st->nA, s, only_found, &st->quirk_stale_cache);
 }
 __global__ void __launch_bounds__(kPT) k_calc_jacobians(Dev D) {
-  const int s = blockIdx.x;
+  const int s = blockIdx.x + D.s0;
   calc_jacobians(D, D.lists + (size_t)s * D.list_cap, D.ss[s].nA, s, false);
 }
 
@@ -1103,7 +1104,7 @@ Dev make_dev(const vslam_ctx* ctx) {
   D.l0_ptr = ctx->l0_ptr; D.l0_stride = ctx->l0_stride;
   D.cam = ctx->cam; D.map = ctx->map; D.src = ctx->src; D.ps = ctx->ps; D.ss = ctx->ss; D.lists = ctx->lists; D.list_cap = ctx->list_cap;
   D.pvs = ctx->pvs; D.sort_scratch = ctx->sort_scratch; D.sort_cap = ctx->sort_cap; D.evals = ctx->evals;
-  D.S = ctx->S; D.N = ctx->N; D.P = ctx->P; D.truncate = ctx->cfg.truncate_error; D.prm = ctx->params;
+  D.S = ctx->S; D.N = ctx->N; D.P = ctx->P; D.truncate = ctx->cfg.truncate_error; D.prm = ctx->params; D.s0 = ctx->cur_s0;
   return D;
 }
 
@@ -1114,7 +1115,7 @@ int vs_launch_project_all(vslam_ctx* ctx, int mode) {
   const size_t smem = (size_t)2 * ctx->N * sizeof(int);
   VS_CUDA(cudaFuncSetAttribute(k_project_lists, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   vs_time_begin(ctx, VS_ST_PROJECT);
-  k_project_lists<<<ctx->S, kPT, smem, ctx->stream>>>(D, mode & 1, (mode >> 1) & 1);
+  k_project_lists<<<ctx->cur_cnt, kPT, smem, ctx->stream>>>(D, mode & 1, (mode >> 1) & 1);
   vs_time_end(ctx);
   VS_CUDA(cudaGetLastError());
   ctx->launches++;
@@ -1124,7 +1125,7 @@ int vs_launch_project_all(vslam_ctx* ctx, int mode) {
 int vs_launch_search(vslam_ctx* ctx, int which, int range, int subpix, int sflags) {
   const Dev D = make_dev(ctx);
   const int max_entries = which == 1 ? (int)(2 * ctx->params.coarse_max) : ctx->list_cap;
-  dim3 grid((max_entries + kSearchWarps - 1) / kSearchWarps, ctx->S);
+  dim3 grid((max_entries + kSearchWarps - 1) / kSearchWarps, ctx->cur_cnt);
   vs_time_begin(ctx, which == 2 ? VS_ST_SEARCH_FINE : VS_ST_SEARCH_COARSE);
   if (ctx->P == 11) k_search<11><<<grid, kSearchWarps * 32, 0, ctx->stream>>>(D, which, range, subpix, sflags);
   else if (ctx->P == 8) k_search<8><<<grid, kSearchWarps * 32, 0, ctx->stream>>>(D, which, range, subpix, sflags);
@@ -1140,7 +1141,7 @@ int vs_launch_pose(vslam_ctx* ctx, int mode, double sigma, int mark, int apply) 
   const size_t smem = 2048 * sizeof(double) + 2 * 2048 * sizeof(int) + 27 * kPT * sizeof(double);   // sort keys + found list + radix histogram + partial sums
   VS_CUDA(cudaFuncSetAttribute(k_pose, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   vs_time_begin(ctx, (mode & 3) == 2 ? VS_ST_POSE_FINE : VS_ST_POSE_COARSE);
-  k_pose<<<ctx->S, kPT, smem, ctx->stream>>>(D, mode & 3, sigma, mark, apply, (mode >> 2) & 1);
+  k_pose<<<ctx->cur_cnt, kPT, smem, ctx->stream>>>(D, mode & 3, sigma, mark, apply, (mode >> 2) & 1);
   vs_time_end(ctx);
   VS_CUDA(cudaGetLastError());
   ctx->launches++;
@@ -1148,13 +1149,13 @@ int vs_launch_pose(vslam_ctx* ctx, int mode, double sigma, int mark, int apply) 
 }
 
 int vs_launch_project_and_derivs(vslam_ctx* ctx, int only_found) {
-  k_project_and_derivs<<<ctx->S, kPT, 0, ctx->stream>>>(make_dev(ctx), only_found);
+  k_project_and_derivs<<<ctx->cur_cnt, kPT, 0, ctx->stream>>>(make_dev(ctx), only_found);
   VS_CUDA(cudaGetLastError());
   ctx->launches++;
   return VSLAM_OK;
 }
 int vs_launch_calc_jacobians(vslam_ctx* ctx) {
-  k_calc_jacobians<<<ctx->S, kPT, 0, ctx->stream>>>(make_dev(ctx));
+  k_calc_jacobians<<<ctx->cur_cnt, kPT, 0, ctx->stream>>>(make_dev(ctx));
   VS_CUDA(cudaGetLastError());
   ctx->launches++;
   return VSLAM_OK;
@@ -1166,7 +1167,7 @@ int vs_launch_track_map_rest(vslam_ctx* ctx, int with_motion_model) {
   if ((rc = vs_launch_search(ctx, 1, 0, 0, 0))) return rc;
   if ((rc = vs_launch_pose(ctx, 1, 0.0, 0, 0))) return rc;
   vs_time_begin(ctx, VS_ST_OTHER);
-  k_reproject_fine<<<ctx->S, kPT, 0, ctx->stream>>>(make_dev(ctx));
+  k_reproject_fine<<<ctx->cur_cnt, kPT, 0, ctx->stream>>>(make_dev(ctx));
   vs_time_end(ctx);
   VS_CUDA(cudaGetLastError());
   ctx->launches++;
@@ -1179,28 +1180,55 @@ int vs_launch_track_map(vslam_ctx* ctx, int with_motion_model) {
   return rc ? rc : vs_launch_track_map_rest(ctx, with_motion_model);
 }
 
-// Tracker::TrackFrame for all streams (jni/Tracker.cc:68-160, map-good branch).  The level images exist once the level-0
-// launch is done, so SmallBlurryImage + motion model + projection (side stream; small grids, latency-bound) run beside
-// the FAST pass of levels 1..3 (main stream) and join before the first patch search, which needs the corner lists.
-// With per-stage timing on, the two branches are serialised so that every stage is timed alone.
-int vs_launch_frame(vslam_ctx* ctx) {
+// Tracker::TrackFrame for all streams (jni/Tracker.cc:68-160, map-good branch).
+// Launch graph of one stream group: the level images exist once the level-0 launch is done, so SmallBlurryImage + relocaliser +
+// motion model + projection (side stream; one CTA per stream, latency-bound) run beside the FAST pass of levels 1..3 (main stream)
+// and join before the first patch search, which needs the corner lists.
+static int launch_frame_group(vslam_ctx* ctx, int g, bool fork) {
   int rc;
-  if ((rc = vs_launch_pyramid_l0(ctx, 0, ctx->S))) return rc;
-  const bool fork = !ctx->timing;
   cudaStream_t main_stream = ctx->stream;
+  if ((rc = vs_launch_pyramid_l0(ctx, ctx->cur_s0, ctx->cur_cnt))) return rc;
   if (fork) {
-    VS_CUDA(cudaEventRecord(ctx->ev_fork, main_stream));
-    VS_CUDA(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
-    ctx->stream = ctx->side_stream;
+    VS_CUDA(cudaEventRecord(ctx->ev_fork[g], main_stream));
+    VS_CUDA(cudaStreamWaitEvent(ctx->side_stream[g], ctx->ev_fork[g], 0));
+    ctx->stream = ctx->side_stream[g];
   }
   rc = vs_launch_sbi(ctx);
   if (!rc) rc = vs_launch_project_all(ctx, 3);
   ctx->stream = main_stream;
-  if (fork) VS_CUDA(cudaEventRecord(ctx->ev_join, ctx->side_stream));
+  if (fork) VS_CUDA(cudaEventRecord(ctx->ev_join[g], ctx->side_stream[g]));
   if (rc) return rc;
-  if ((rc = vs_launch_fast_levels(ctx, 0, ctx->S))) return rc;
-  if (fork) VS_CUDA(cudaStreamWaitEvent(main_stream, ctx->ev_join, 0));
+  if ((rc = vs_launch_fast_levels(ctx, ctx->cur_s0, ctx->cur_cnt))) return rc;
+  if (fork) VS_CUDA(cudaStreamWaitEvent(main_stream, ctx->ev_join[g], 0));
   return vs_launch_track_map_rest(ctx, 1);
+}
+// Optionally (vslam_params.stream_groups > 1) the streams of a context are split into groups whose launch graphs run on separate
+// CUDA streams between one fork and one join on ctx->stream.  Streams are independent, so the split changes no result.  Measured on
+// B200 (256 VGA streams): 2-4 groups are 5 % slower than one (smaller grids, more tails; the hoped-for overlap of one group's
+// latency-bound k_pose with another group's k_search does not materialise because k_pose CTAs hold half an SM's registers each),
+// hence the default of 1.  With per-stage timing on (vslam_set_timing) everything is serialised on ctx->stream.
+int vs_launch_frame(vslam_ctx* ctx) {
+  int G = ctx->params.stream_groups;
+  if (G < 1) G = 1;
+  if (G > VS_MAX_GROUPS) G = VS_MAX_GROUPS;
+  if (G > ctx->S) G = ctx->S;
+  if (ctx->timing) { ctx->cur_s0 = 0; ctx->cur_cnt = ctx->S; ctx->cur_group = 0; return launch_frame_group(ctx, 0, false); }
+  cudaStream_t user_stream = ctx->stream;
+  int rc = VSLAM_OK;
+  if (G > 1) VS_CUDA(cudaEventRecord(ctx->ev_begin, user_stream));
+  for (int g = 0; g < G && !rc; g++) {
+    const int s0 = (int)((long long)ctx->S * g / G), s1 = (int)((long long)ctx->S * (g + 1) / G);
+    ctx->cur_s0 = s0; ctx->cur_cnt = s1 - s0; ctx->cur_group = g;
+    if (g > 0) { if (cudaStreamWaitEvent(ctx->group_stream[g], ctx->ev_begin, 0) != cudaSuccess) rc = VSLAM_E_CUDA; ctx->stream = ctx->group_stream[g]; }
+    if (!rc) rc = launch_frame_group(ctx, g, true);
+    ctx->stream = user_stream;
+    if (g > 0 && !rc) {
+      if (cudaEventRecord(ctx->ev_end[g], ctx->group_stream[g]) != cudaSuccess || cudaStreamWaitEvent(user_stream, ctx->ev_end[g], 0) != cudaSuccess) rc = VSLAM_E_CUDA;
+    }
+  }
+  ctx->cur_s0 = 0; ctx->cur_cnt = ctx->S; ctx->cur_group = 0;
+  if (rc == VSLAM_E_CUDA && ctx->err.empty()) ctx->err = "vs_launch_frame: CUDA stream/event error";
+  return rc;
 }
 
 // Test hook: atan_cr over a device-side copy of x (used to compare against the host libm).

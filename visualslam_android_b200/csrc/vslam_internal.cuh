@@ -11,6 +11,7 @@
 #define VS_MAXP VSLAM_MAX_PATCH
 #define VS_TMPL_BYTES 144           // template rows padded to 12 bytes (3 words, the dp4a operand layout): 11 * 12 = 132, rounded to 16
 #define VS_MAX_STRIP_ROWS 64        // upper bound of LevelDesc::strip_rows
+#define VS_MAX_GROUPS 4             // stream groups of vs_launch_frame
 #define VS_MAX_UPDATES 20           // 10 coarse + 10 fine CalcPoseUpdate calls per TrackMap
 
 // ------------------------------------------------------------------------------------------------
@@ -100,8 +101,11 @@ struct vslam_ctx {
   const uint8_t** l0_ptr_host; int* l0_stride_host;
   // double-buffered host-input pipeline (vslam_track_frame_async): level-0 buffer 0 is lev[0].img, buffer 1 is l0_alt
   uint8_t* l0_alt; cudaStream_t copy_stream; cudaEvent_t ev_copied[2], ev_computed[2], ev_done[2]; long long step; bool pipe_ready; int* status_pin;   // [2][4] pinned copy of `status` per slot
-  cudaStream_t side_stream; cudaEvent_t ev_fork, ev_join;   // SmallBlurryImage + projection run beside the FAST pass of levels 1..3
-  unsigned* tickets;             // [VS_LEVELS] device
+  // vs_launch_frame: stream groups (group 0 runs on ctx->stream) and, per group, a side stream on which SmallBlurryImage +
+  // projection run beside the FAST pass of levels 1..3
+  cudaStream_t group_stream[VS_MAX_GROUPS], side_stream[VS_MAX_GROUPS]; cudaEvent_t ev_fork[VS_MAX_GROUPS], ev_join[VS_MAX_GROUPS], ev_end[VS_MAX_GROUPS], ev_begin;
+  int cur_s0, cur_cnt, cur_group;   // stream range / group the launchers act on (0, S, 0 outside vs_launch_frame)
+  unsigned* tickets;             // [2 * VS_MAX_GROUPS] device
   int* status;                   // [4] device: [0] capacity overflow flag
   CamDev cam; CamDev* cam_dev;
   MapDev map; MapDev* map_dev;
