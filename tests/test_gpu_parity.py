@@ -650,3 +650,28 @@ def test_track_frame_relocalises_lost_streams():
     assert recovered[0] >= 2 and recovered[1] >= 1
     assert ctx.counters(0)[2] == 2 and ctx.counters(1)[2] == 2       # both streams end with quality GOOD
     ctx.close()
+
+
+@pytest.mark.parametrize("n_points", [1, 3, 25])
+def test_track_frame_tiny_maps_and_blank_frames(n_points):
+    """Edge cases of the whole TrackFrame: maps of 1 / 3 / 25 points (Tukey's `n*2-6` wraps or divides by zero, jni/MEstimator.h:73;
+    no coarse stage; quality falls to BAD), a blank frame (no FAST corner on any level) and a saturated one, against the oracle."""
+    cam, f0, smap_full = common.scene()
+    keep = np.arange(smap_full.n)[:: max(1, smap_full.n // n_points)][:n_points]
+    smap = synth.SyntheticMap(**{k: getattr(smap_full, k)[keep] for k in ("world", "pix_right_w", "pix_down_w", "ir_center", "src_level", "center_nc", "one_right_nc", "one_down_nc")})
+    ctx = _ctx(cam, f0, smap)
+    ow = _orc(cam, f0, smap)
+    frames = [common.frame_at(cam, np.array(synth.CONFIG1_TWIST) * 0.3)[0], np.zeros_like(f0), common.frame_at(cam, np.array(synth.CONFIG1_TWIST) * 0.5)[0],
+              np.full_like(f0, 255), common.frame_at(cam, np.array(synth.CONFIG1_TWIST) * 0.6)[0]]
+    for k, fr in enumerate(frames):
+        ctx.track_frame(fr[None])
+        ow.L.orc_tracker_track_frame(ow.tracker, np.ascontiguousarray(fr), cam.width, cam.height, cam.width)
+        gp, op = ctx.get_pose(0), ow.get_pose()
+        assert np.array_equal(np.isfinite(gp), np.isfinite(op)), k
+        fin = np.isfinite(op)
+        assert np.abs(gp[fin] - op[fin]).max() <= 1e-8 if fin.any() else True, (k, gp, op)
+        a, f, q, lost, dc = ctx.counters(0); oa, of, oq, olost, odc = ow.counters()
+        assert np.array_equal(a, oa) and np.array_equal(f, of) and (q, lost, dc) == (oq, olost, odc), (k, n_points)
+        if k in (1, 3):
+            assert sum(int(ctx.corners(0, l).shape[0]) for l in range(4)) == 0
+    ctx.close()
