@@ -489,13 +489,16 @@ __global__ void __launch_bounds__(kSearchWarps * 32, 10) k_search(Dev D, int mod
     const int begin = lut[nTop], end = (nBottomPlusOne >= L.h) ? lut[L.h] : lut[nBottomPlusOne];
     const uint32_t* corners = L.corners + (size_t)s * L.cap;
     int c0 = begin;
+    // the corner words of the next two 32-corner steps are requested before the current step is examined (the kernel is bound by
+    // the latency of these dependent-looking, in fact independent, loads)
+    uint32_t cw1 = (c0 + lane < end) ? __ldg(corners + c0 + lane) : 0u, cw2 = (c0 + 32 + lane < end) ? __ldg(corners + c0 + 32 + lane) : 0u;
     while (c0 < end) {   // rounds: gather up to kCandCap candidates, then score them with (candidate,row) work items
       int ncand = 0;
       for (; c0 < end && ncand <= kCandCap - 32; c0 += 32) {
         const int ci = c0 + lane;
-        bool pass = false; uint32_t cw = 0;
+        bool pass = false; const uint32_t cw = cw1;
+        cw1 = cw2; cw2 = (c0 + 64 + lane < end) ? __ldg(corners + c0 + 64 + lane) : 0u;
         if (ci < end) {
-          cw = corners[ci];
           const int cx = cw & 0xffff, cy = cw >> 16;
           pass = !((double)cx < nLeft || (double)cx > nRight);
           if (pass) { const double dx = ix - (double)cx, dy = iy - (double)cy; double d2 = 0; d2 += dx * dx; d2 += dy * dy; pass = !(d2 > nRange * nRange); }
