@@ -251,24 +251,42 @@ __device__ __forceinline__ unsigned long long score_candidates(SearchSmem& sm, i
   const int lane = threadIdx.x & 31, PP = P * P;
   const int b = P / 2, nwords = (P + 3) >> 2;
   const uint32_t lastmask = (P & 3) ? ((1u << (8 * (P & 3))) - 1u) : 0xffffffffu;
-  // ZMSSDAtPoint (jni/PatchFinder.cc:352-380): one work item = one template row of one candidate
-  for (int item = lane; item < ncand * P; item += 32) {
-    const int c = item / P, r = item - c * P;
-    const uint32_t cw = sm.cand_cw[c];
-    const int cx = cw & 0xffff, cy = cw >> 16;
-    if (!(cx >= b && cy >= b && cx < lw - b && cy < lh - b)) continue;
-    const uint8_t* rp = img + (size_t)(cy - b + r) * pitch + (cx - b);
-    const unsigned a = (unsigned)((uintptr_t)rp & 3u), sh = a * 8;
-    const uint32_t* wp = (const uint32_t*)(rp - a);
-    uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = 0, w3 = 0;
-    if (a + P > 8) w2 = __ldg(wp + 2);
-    if (a + P > 12) w3 = __ldg(wp + 3);
-    uint32_t n0 = __funnelshift_r(w0, w1, sh), n1 = __funnelshift_r(w1, w2, sh), n2 = __funnelshift_r(w2, w3, sh);
-    if (nwords == 3) n2 &= lastmask; else if (nwords == 2) { n1 &= lastmask; n2 = 0; } else { n0 &= lastmask; n1 = 0; n2 = 0; }
-    unsigned sum = __dp4a(n0, 0x01010101u, 0u), sumsq = __dp4a(n0, n0, 0u), cross = __dp4a(n0, sm.tmpl_w[3 * r], 0u);
-    sum = __dp4a(n1, 0x01010101u, sum); sumsq = __dp4a(n1, n1, sumsq); cross = __dp4a(n1, sm.tmpl_w[3 * r + 1], cross);
-    sum = __dp4a(n2, 0x01010101u, sum); sumsq = __dp4a(n2, n2, sumsq); cross = __dp4a(n2, sm.tmpl_w[3 * r + 2], cross);
-    atomicAdd(&sm.acc[3 * c], (int)sum); atomicAdd(&sm.acc[3 * c + 1], (int)sumsq); atomicAdd(&sm.acc[3 * c + 2], (int)cross);
+  // ZMSSDAtPoint (jni/PatchFinder.cc:352-380): one work item = one template row of one candidate; two items per lane and step so
+  // that eight image words are in flight per lane (the kernel waits on these loads, not on the dp4a pipe)
+  const int nitems = ncand * P;
+  for (int item0 = lane; item0 < nitems; item0 += 64) {
+    uint32_t w[2][4]; int cc[2], rr[2]; unsigned shf[2]; bool ok[2];
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const int item = item0 + 32 * u;
+      ok[u] = item < nitems;
+      const int c = ok[u] ? item / P : 0, r = item - c * P;
+      cc[u] = c; rr[u] = r;
+      const uint32_t cw = sm.cand_cw[c];
+      const int cx = cw & 0xffff, cy = cw >> 16;
+      ok[u] = ok[u] && (cx >= b && cy >= b && cx < lw - b && cy < lh - b);
+      w[u][0] = w[u][1] = w[u][2] = w[u][3] = 0u; shf[u] = 0;
+      if (ok[u]) {
+        const uint8_t* rp = img + (size_t)(cy - b + r) * pitch + (cx - b);
+        const unsigned a = (unsigned)((uintptr_t)rp & 3u);
+        shf[u] = a * 8;
+        const uint32_t* wp = (const uint32_t*)(rp - a);
+        w[u][0] = __ldg(wp); w[u][1] = __ldg(wp + 1);
+        if (a + P > 8) w[u][2] = __ldg(wp + 2);
+        if (a + P > 12) w[u][3] = __ldg(wp + 3);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      if (!ok[u]) continue;
+      uint32_t n0 = __funnelshift_r(w[u][0], w[u][1], shf[u]), n1 = __funnelshift_r(w[u][1], w[u][2], shf[u]), n2 = __funnelshift_r(w[u][2], w[u][3], shf[u]);
+      if (nwords == 3) n2 &= lastmask; else if (nwords == 2) { n1 &= lastmask; n2 = 0; } else { n0 &= lastmask; n1 = 0; n2 = 0; }
+      const int r = rr[u], c = cc[u];
+      unsigned sum = __dp4a(n0, 0x01010101u, 0u), sumsq = __dp4a(n0, n0, 0u), cross = __dp4a(n0, sm.tmpl_w[3 * r], 0u);
+      sum = __dp4a(n1, 0x01010101u, sum); sumsq = __dp4a(n1, n1, sumsq); cross = __dp4a(n1, sm.tmpl_w[3 * r + 1], cross);
+      sum = __dp4a(n2, 0x01010101u, sum); sumsq = __dp4a(n2, n2, sumsq); cross = __dp4a(n2, sm.tmpl_w[3 * r + 2], cross);
+      atomicAdd(&sm.acc[3 * c], (int)sum); atomicAdd(&sm.acc[3 * c + 1], (int)sumsq); atomicAdd(&sm.acc[3 * c + 2], (int)cross);
+    }
   }
   __syncwarp();
   for (int c = lane; c < ncand; c += 32) {
