@@ -534,15 +534,15 @@ def main():
     l0_corners = sum(int(ctx.corners(s, 0).shape[0]) for s in probe) * (S / len(probe))
     l0_bytes = S * (1.328125 * W * H + 4 * (H + 1)) + 4.0 * l0_corners
     l0_ms = stage["pyrfast_l0"][0] / Ks
-    # DRAM bytes of that launch from the committed ncu --set full capture (profiles/r01b_ncu_full_summary.json, S=256 VGA)
-    l0_traffic = 78.851584e6 + 12.374528e6 if (S == 256 and (W, H) == (640, 480)) else None
+    # DRAM bytes of that launch from the committed ncu --set full capture (profiles/r01c_ncu_full_summary.json, S=256 VGA)
+    l0_traffic = 78.845696e6 + 11.888128e6 if (S == 256 and (W, H) == (640, 480)) else None
     roofline = {"kernel": "k_pyramid_fast + k_fast_levels (pyramid + FAST-10 + raster compaction + row LUT; 2 launches per step: level 0 (+ level 1-3 images), levels 1-3)", "bound": "hbm",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": l0_traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_step": alg_bytes_step, "ms_per_step": pyr_ms / Ks, "share_of_step": (pyr_ms / Ks) / stage_sum_ms,
                 "level0_launch": {"algorithmic_bytes": l0_bytes, "ms": l0_ms, "achieved": l0_bytes / (l0_ms * 1e-3) / 1e9,
                                   "frac": l0_bytes / (l0_ms * 1e-3) / 1e9 / peak, "traffic": l0_traffic},
                 "note": "traffic is the level-0 launch's dram read+write bytes (ncu); the stage is instruction-issue bound (81-85 % issue-slot "
-                        "utilisation, ~270 warp-instructions per 256 pixels of level 0), not HBM bound: DESIGN.md §4.1 and profiles/r01b_*"}
+                        "utilisation, ~270 warp-instructions per 256 pixels of level 0), not HBM bound: DESIGN.md §4.1 and profiles/r01c_*"}
     # ZMSSD: 3*P^2 integer MACs per scored candidate over the time of the two search kernels, against a measured dp4a peak
     evals_timed = evals1 - evals0
     search_ms = stage["search_fine"][0] + stage["search_coarse"][0]
