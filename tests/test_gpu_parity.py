@@ -675,3 +675,40 @@ def test_track_frame_tiny_maps_and_blank_frames(n_points):
         if k in (1, 3):
             assert sum(int(ctx.corners(0, l).shape[0]) for l in range(4)) == 0
     ctx.close()
+
+
+def test_full_bench_size_256_streams_replicas_and_oracle():
+    """BASELINE configs[3] at full size: 256 VGA streams x 1000 points through vslam_track_frame_dev (device-resident frames, SBI on),
+    three frames.  Eight distinct camera sequences are replicated 32 times across the streams (interleaved), so that (a) every replica
+    must agree with the others BIT FOR BIT — poses, counters, corner lists — whatever SM it ran on and whatever its neighbours did,
+    and (b) one replica of each sequence is compared with the oracle."""
+    import torch
+    cam, f0, smap = common.scene()
+    S, D, K = 256, 8, 3
+    sbi_cam = synth.Camera(cam.width // 16, cam.height // 16).scalars()
+    ctx = _ctx(cam, f0, smap, n_streams=S)
+    ctx.enable_sbi(sbi_cam)
+    ows = []
+    for d in range(D):
+        ow = _orc(cam, f0, smap); ow.L.orc_tracker_enable_sbi(ow.tracker, sbi_cam); ows.append(ow)
+    for k in range(1, K + 1):
+        distinct = np.stack([synth.render_frame(common.texture(), cam, synth.stream_pose(5 * k, d + 1)) for d in range(D)])
+        frames = torch.from_numpy(distinct[np.arange(S) % D].copy()).cuda()
+        ctx.track_frame_ptr(frames.data_ptr(), cam.width, cam.width * cam.height, device=True)
+        poses = ctx.get_poses()
+        for d in range(D):
+            reps = poses[d::D]
+            assert np.array_equal(reps, np.broadcast_to(reps[0], reps.shape)), (k, d)       # bitwise identical replicas
+            ows[d].L.orc_tracker_track_frame(ows[d].tracker, np.ascontiguousarray(distinct[d]), cam.width, cam.height, cam.width)
+            assert np.abs(poses[d] - ows[d].get_pose()).max() <= 1e-8, (k, d)
+            a, f, q, lost, dc = ctx.counters(d); oa, of, oq, olost, odc = ows[d].counters()
+            assert np.array_equal(a, oa) and np.array_equal(f, of) and (q, lost, dc) == (oq, olost, odc), (k, d)
+            for s in (d + D * 7, d + D * 31):
+                assert ctx.counters(s)[0].tolist() == a.tolist() and ctx.counters(s)[1].tolist() == f.tolist()
+        if k == K:
+            for l in range(4):
+                c0 = ctx.corners(3, l)
+                assert np.array_equal(c0, ctx.corners(3 + D * 17, l)) and np.array_equal(ctx.row_lut(3, l), ctx.row_lut(3 + D * 30, l))
+                order = c0[:, 1].astype(np.int64) * 65536 + c0[:, 0]
+                assert np.all(np.diff(order) > 0)                                            # raster order, no duplicates
+    ctx.close()
