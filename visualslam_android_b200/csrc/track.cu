@@ -728,18 +728,23 @@ __device__ void calc_pose_update(const Dev& D, PoseSmem& sm, double* sortbuf, in
   for (int k = tid; k < n; k += kPT) {
     const int i = list[k];
     const size_t gi = (size_t)s * D.N + i;
-    const double e0 = D.ps.err[gi], e1 = D.ps.err[SN + gi];
+    // everything the point needs is requested before the weight is known (one round trip to L2 instead of two or three; a point
+    // whose weight turns out to be zero wastes its 12 Jacobian loads, which is rare after the first iterations).  Requesting the
+    // NEXT point's values as well was measured slower (register spills at the 128-register limit).
+    const double e0 = D.ps.err[gi], e1 = D.ps.err[SN + gi], si = D.ps.sqrtinv[gi];
+    double Jraw[12];
+#pragma unroll
+    for (int c = 0; c < 12; c++) Jraw[c] = D.ps.jac[(size_t)c * SN + gi];
     double e2 = 0; e2 += e0 * e0; e2 += e1 * e1;
     const double sq = (e2 > sig2) ? 0.0 : 1.0 - (e2 / sig2);
     const double w = sq * sq;
     if (w == 0.0) { if (mark) D.ps.counts[gi]++; continue; }
     else if (mark) D.ps.counts[SN + gi]++;
-    const double si = D.ps.sqrtinv[gi];
 #pragma unroll
     for (int row = 0; row < 2; row++) {
       double J[6];
 #pragma unroll
-      for (int c = 0; c < 6; c++) J[c] = si * D.ps.jac[(size_t)(6 * row + c) * SN + gi];
+      for (int c = 0; c < 6; c++) J[c] = si * Jraw[6 * row + c];
       const double e = row ? e1 : e0;
       const double m = D.truncate ? (double)(int)e : e;   // (int) cast of jni/Tracker.cc:766-767
       int q = 0;
