@@ -890,6 +890,38 @@ __device__ void calc_jacobians(const Dev& D, const int* list, int n, int s, bool
 __device__ void pose_points_pass(const Dev& D, const double* pose, const int* flist, int n, int s, int action, bool jacobian, const double* v6,
                                  double* sortbuf, int sortcap, bool want_sort, int* quirk) {
   const size_t SN = (size_t)D.S * D.N;
+  if (action == 2 && !jacobian) {
+    // linear iteration (7 of the 10 of a fine stage): two points per thread and step, both points' 17 values requested before either
+    // is used, so that a thread exposes one round trip to L2 per two points
+    for (int k0 = threadIdx.x; k0 < n; k0 += 2 * kPT) {
+      double si[2], f0[2], f1[2], im0[2], im1[2], J[2][12]; size_t gi[2]; bool ok[2];
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        const int k = k0 + u * kPT;
+        ok[u] = k < n;
+        gi[u] = (size_t)s * D.N + flist[ok[u] ? k : k0];
+        si[u] = D.ps.sqrtinv[gi[u]]; f0[u] = D.ps.v2found[gi[u]]; f1[u] = D.ps.v2found[SN + gi[u]];
+        im0[u] = D.ps.v2image[gi[u]]; im1[u] = D.ps.v2image[SN + gi[u]];
+#pragma unroll
+        for (int q = 0; q < 12; q++) J[u][q] = D.ps.jac[(size_t)q * SN + gi[u]];
+      }
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        if (!ok[u]) continue;
+        double a0 = J[u][0] * v6[0], a1 = J[u][6] * v6[0];
+#pragma unroll
+        for (int q = 1; q < 6; q++) { a0 += J[u][q] * v6[q]; a1 += J[u][6 + q] * v6[q]; }
+        const double n0 = im0[u] + a0, n1 = im1[u] + a1;
+        D.ps.v2image[gi[u]] = n0; D.ps.v2image[SN + gi[u]] = n1;
+        const double e0 = (f0[u] - n0) * si[u], e1 = (f1[u] - n1) * si[u];
+        D.ps.err[gi[u]] = e0; D.ps.err[SN + gi[u]] = e1;
+        double e2 = 0; e2 += e0 * e0; e2 += e1 * e1;
+        const int k = k0 + u * kPT;
+        if (want_sort && k < sortcap) sortbuf[k] = e2;
+      }
+    }
+    return;
+  }
   for (int k = threadIdx.x; k < n; k += kPT) {
     const int i = flist[k];
     const size_t gi = (size_t)s * D.N + i;
