@@ -17,6 +17,9 @@
 //   KeyFrame::MakeKeyFrame_Rest()                         vslam_make_keyframe_rest                   (jni/KeyFrame.cc:53-95)
 //   MiniPatch::SampleFromImage / FindPatch                vslam_minipatch_sample / _find, one patch   (jni/MiniPatch.cc:6-83)
 //   PatchFinder (per-object, slow path)                   stage calls on a one-entry list            (jni/PatchFinder.h:45-121)
+//   MapMaker::ReFindInSingleKeyFrame / ReFind_Common,     vslam_b200::MapSearch (vslam_refind, vslam_epipolar_search)
+//            the search of AddPointEpipolar               (jni/MapMaker.cc:525-640, 967-1056)
+//   Relocaliser (inside Tracker::TrackFrame when lost)    Tracker::SetRelocKeyFrames                 (jni/Relocaliser.cc:17-58)
 // Map points are addressed by their index in the arrays given to SetMap (the reference passes MapPoint& / TrackerData*).
 // The colour image argument is accepted and ignored (it is only used for drawing / map-point colouring, off the hot path).
 #ifndef VSLAM_B200_SHELL_HPP
@@ -415,6 +418,70 @@ class PatchFinder {
   Context& ctx_; int stream_, point_, mnSearchLevel; bool mbFound, mbTemplateBad;
   Eigen::Matrix2d mm2WarpInverse; Eigen::Vector2d mv2CoarsePos, mv2SubPixPos;
   std::vector<int32_t> ints_; std::vector<double> dbl_;
+};
+
+// jni/KeyFrame.h:45-50
+struct Measurement {
+  int nLevel; bool bSubPix; Eigen::Vector2d v2RootPos;
+  enum { SRC_TRACKER, SRC_REFIND, SRC_ROOT, SRC_TRAIL, SRC_EPIPOLAR } Source;
+};
+
+// The two searches MapMaker runs on keyframes (jni/MapMaker.cc), over the device kernels of the tracker.  A keyframe is a stream of
+// the context: its image must be that stream's current keyframe (KeyFrame::MakeKeyFrame_Lite) and `se3CfromW` its pose.  MapMaker's
+// bookkeeping (sMeasurementKFs, sNeverRetryKFs, the new MapPoint and its triangulation) stays with the caller.
+class MapSearch {
+ public:
+  explicit MapSearch(Context& ctx) : ctx_(ctx), mdWiggleScale(0.1) {}
+  double mdWiggleScale;   // MapMaker::mdWiggleScale (jni/MapMaker.cc:206)
+
+  // MapMaker::ReFindInSingleKeyFrame / ReFind_Common (jni/MapMaker.cc:967-1056) for the listed map points in keyframe `k`.
+  // Returns the number found; out[i] is valid where found[i] != 0.
+  int ReFindInSingleKeyFrame(KeyFrame& k, const SE3& se3CfromW, const std::vector<int>& points, std::vector<Measurement>& out, std::vector<char>& found) {
+    vslam_ctx* c = ctx_.get();
+    double p[12];
+    for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) p[4 * i + j] = se3CfromW.R(i, j); p[4 * i + 3] = se3CfromW.t(i); }
+    check(c, vslam_set_pose(c, k.stream(), p));
+    const int ns = ctx_.Streams(), n = (int)points.size(), stride = n > 0 ? n : 1;
+    std::vector<int32_t> idx((size_t)ns * stride, 0), cnt(ns, 0);
+    for (int i = 0; i < n; i++) idx[(size_t)k.stream() * stride + i] = points[i];
+    cnt[k.stream()] = n;
+    check(c, vslam_set_lists(c, &idx[0], &cnt[0], stride));
+    check(c, vslam_refind(c, 4, 8));                                   // "Very tight search radius!" (jni/MapMaker.cc:1007), 8 sub-pixel iterations (:1018)
+    std::vector<int32_t> fl(3 * (size_t)stride); std::vector<double> pos(2 * (size_t)stride); int got = 0;
+    check(c, vslam_get_refind_results(c, k.stream(), &fl[0], &pos[0], n, &got));
+    out.assign(n, Measurement()); found.assign(n, 0);
+    int nFoundNow = 0;
+    for (int i = 0; i < n; i++) {
+      if (!fl[3 * i]) continue;
+      found[i] = 1; nFoundNow++;
+      out[i].nLevel = fl[3 * i + 1]; out[i].bSubPix = fl[3 * i + 2] != 0; out[i].v2RootPos = Eigen::Vector2d(pos[2 * i], pos[2 * i + 1]); out[i].Source = Measurement::SRC_REFIND;
+    }
+    return nFoundNow;
+  }
+
+  // The search of MapMaker::AddPointEpipolar (jni/MapMaker.cc:525-640) for candidates (level pixels, e.g. Level::vCandidates of kSrc)
+  // of level nLevel of source keyframe `src_kf_id` (uploaded with Tracker::SetSourceKeyFrame) in the target keyframe kTarget.
+  // found[i] != 0: a match converged; out[i] = the SRC_EPIPOLAR measurement in the target (v2RootPos refined to sub-pixel).
+  int AddPointsEpipolar(int src_kf_id, const SE3& srcCfromW, double dSceneDepthMean, double dSceneDepthSigma, KeyFrame& kTarget, const SE3& targetCfromW, int nLevel,
+                        const std::vector<Eigen::Vector2d>& candidates, std::vector<Measurement>& out, std::vector<char>& found) {
+    vslam_ctx* c = ctx_.get();
+    double ps[12], pt[12];
+    for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) { ps[4 * i + j] = srcCfromW.R(i, j); pt[4 * i + j] = targetCfromW.R(i, j); } ps[4 * i + 3] = srcCfromW.t(i); pt[4 * i + 3] = targetCfromW.t(i); }
+    const int n = (int)candidates.size();
+    std::vector<int32_t> xy(2 * (size_t)n + 2), f(n + 1); std::vector<double> pos(2 * (size_t)n + 2);
+    for (int i = 0; i < n; i++) { xy[2 * i] = (int32_t)candidates[i](0); xy[2 * i + 1] = (int32_t)candidates[i](1); }
+    check(c, vslam_epipolar_search(c, kTarget.stream(), src_kf_id, nLevel, n, &xy[0], ps, pt, dSceneDepthMean, dSceneDepthSigma, mdWiggleScale, &f[0], &pos[0], 0, 0));
+    out.assign(n, Measurement()); found.assign(n, 0);
+    int nAdded = 0;
+    for (int i = 0; i < n; i++) {
+      if (!f[i]) continue;
+      found[i] = 1; nAdded++;
+      out[i].nLevel = nLevel; out[i].bSubPix = true; out[i].v2RootPos = Eigen::Vector2d(pos[2 * i], pos[2 * i + 1]); out[i].Source = Measurement::SRC_EPIPOLAR;
+    }
+    return nAdded;
+  }
+ private:
+  Context& ctx_;
 };
 
 }  // namespace vslam_b200

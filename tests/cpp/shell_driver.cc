@@ -1,6 +1,6 @@
 // Test driver for include/vslam_b200_shell.hpp: runs the reference-shaped C++ API (KeyFrame, Tracker, MiniPatch, PatchFinder) on a
 // scene file written by tests/test_gpu_shell.py and prints the results as text; the Python side compares them with the oracle.
-//   shell_driver <scene.bin> trails|track|stages
+//   shell_driver <scene.bin> trails|track|stages|mapsearch
 // scene.bin: int32 W,H,N,F; double params5[5]; u8 src[W*H]; double world[3N], right[3N], down[3N]; int32 irCenter[2N]; int32 level[N];
 //            double pose0[12]; u8 frames[F][W*H]
 #include <cstdio>
@@ -70,6 +70,29 @@ int main(int argc, char** argv) {
         printf("pose");
         for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) printf(" %.17g", p.R(i, j)); printf(" %.17g", p.t(i)); }
         printf("\nmsg %s\n", tracker.GetMessageForUser().c_str());
+      }
+      return 0;
+    }
+
+    if (mode == "mapsearch") {   // MapMaker's searches: frames[0] is the target keyframe at pose0; the source keyframe is keyframe 0 (identity pose)
+      cv::Mat g(H, W, CV_8UC1, &frames[0][0]);
+      MapSearch ms(ctx);
+      // candidates of the source keyframe: make it the stream's keyframe once to run MakeKeyFrame_Rest on it
+      tracker.mCurrentKF.MakeKeyFrame_Lite(s, colour);
+      tracker.mCurrentKF.MakeKeyFrame_Rest();
+      std::vector<std::vector<Eigen::Vector2d> > cands(LEVELS);
+      for (int l = 0; l < LEVELS; l++) for (size_t i = 0; i < tracker.mCurrentKF.aLevels[l].vCandidates.size(); i++) cands[l].push_back(tracker.mCurrentKF.aLevels[l].vCandidates[i].irLevelPos);
+      tracker.mCurrentKF.MakeKeyFrame_Lite(g, colour);
+      SE3 eye; for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) eye.R(i, j) = i == j ? 1.0 : 0.0; eye.t(i) = 0.0; }
+      std::vector<int> pts; for (int pt = 0; pt < N; pt++) pts.push_back(pt);
+      std::vector<Measurement> meas; std::vector<char> found;
+      const int nf = ms.ReFindInSingleKeyFrame(tracker.mCurrentKF, start, pts, meas, found);
+      printf("refind %d\n", nf);
+      for (int pt = 0; pt < N; pt++) if (found[pt]) printf("m %d %d %d %.17g %.17g\n", pt, meas[pt].nLevel, meas[pt].bSubPix ? 1 : 0, meas[pt].v2RootPos(0), meas[pt].v2RootPos(1));
+      for (int l = 0; l < LEVELS; l++) {
+        const int na = ms.AddPointsEpipolar(0, eye, 1.0, 0.3, tracker.mCurrentKF, start, l, cands[l], meas, found);
+        printf("epipolar %d %d of %d\n", l, na, (int)cands[l].size());
+        for (size_t i = 0; i < cands[l].size(); i++) if (found[i]) printf("e %d %d %d %.17g %.17g\n", l, (int)cands[l][i](0), (int)cands[l][i](1), meas[i].v2RootPos(0), meas[i].v2RootPos(1));
       }
       return 0;
     }

@@ -159,3 +159,45 @@ def test_shell_stage_functions_and_patchfinder_match_the_oracle(driver, tmp_path
     mu2 = np.zeros(6); ow2.L.orc_tracker_calc_pose_update(ow2.tracker, lst, len(lst), 16.0, 1, 0, mu2)
     got2 = np.array([float(x) for x in [l for l in out if l.startswith("update16")][0].split()[1:]])
     assert np.abs(got2 - mu2).max() <= 1e-9 * max(1.0, np.abs(mu2).max())
+
+
+def test_shell_mapmaker_searches_match_the_oracle(driver, tmp_path):
+    """MapSearch::ReFindInSingleKeyFrame (MapMaker::ReFind_Common for every map point) and MapSearch::AddPointsEpipolar (the search of
+    MapMaker::AddPointEpipolar for every Shi-Tomasi candidate of every level) through the shell, against the oracle."""
+    from oracle import oraclebind
+    cam, f0, smap = common.scene(n_points=600)
+    tw = np.array([0.12, 0.03, 0.02, 0.01, -0.03, 0.02])
+    f1, pose1 = common.frame_at(cam, tw)
+    scene = str(tmp_path / "mapsearch.bin")
+    _write_scene(scene, cam, f0, smap, pose1, [f1])
+    out = _run(driver, scene, "mapsearch")
+    ow = oraclebind.OrcWorld(cam, f0, smap)
+    ow.make_current_kf(f1); ow.set_pose(pose1)
+    idx = np.arange(smap.n, dtype=np.int32)
+    oo, op = np.zeros((smap.n, 3), dtype=np.int32), np.zeros((smap.n, 2))
+    ow.L.orc_tracker_refind(ow.tracker, idx, smap.n, 4, 8, 1, oo, op)
+    got = {int(l.split()[1]): l.split()[2:] for l in out if l.startswith("m ")}
+    assert int([l for l in out if l.startswith("refind")][0].split()[1]) == int(oo[:, 0].sum()) == len(got) and len(got) > 100
+    for pt, w in got.items():
+        assert oo[pt, 0] == 1 and int(w[0]) == oo[pt, 1] and int(w[1]) == oo[pt, 2]
+        assert np.abs(np.array([float(w[2]), float(w[3])]) - op[pt]).max() <= (1e-6 if oo[pt, 2] else 0.0)
+    ok0 = oraclebind.OrcKeyFrame().make_lite(f0); ok0.make_rest()
+    ok1 = oraclebind.OrcKeyFrame().make_lite(f1)
+    eye = np.ascontiguousarray(synth.IDENTITY_POSE, dtype=np.float64).reshape(12); p1 = np.ascontiguousarray(pose1, dtype=np.float64).reshape(12)
+    e_lines = [l.split() for l in out if l.startswith("e ")]
+    total = 0
+    for level in range(4):
+        xy, _ = ok0.candidates(level)
+        gl = {(int(w[2]), int(w[3])): (float(w[4]), float(w[5])) for w in e_lines if int(w[1]) == level}
+        nf = 0
+        for k in range(len(xy)):
+            o3, o2 = np.zeros(3, dtype=np.int32), np.zeros(2)
+            ow.L.orc_epipolar_search(ow.tracker, ok0.h, ok1.h, eye, p1, 1.0, 0.3, 0.1, level, int(xy[k, 0]), int(xy[k, 1]), o3, o2, None)
+            key = (int(xy[k, 0]), int(xy[k, 1]))
+            assert (key in gl) == bool(o3[0]), (level, k)
+            if o3[0]:
+                assert np.abs(np.array(gl[key]) - o2).max() <= 1e-6; nf += 1
+        hdr = [l.split() for l in out if l.startswith(f"epipolar {level} ")][0]
+        assert int(hdr[2]) == nf and int(hdr[4]) == len(xy)
+        total += nf
+    assert total > 100
