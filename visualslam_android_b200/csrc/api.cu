@@ -124,6 +124,7 @@ int vslam_create(const vslam_config* cfg, vslam_ctx** out) {
   CK(cudaEventCreateWithFlags(&ctx->ev_begin, cudaEventDisableTiming));
   const int S = ctx->S, N = ctx->N;
   int w = cfg->width, h = cfg->height;
+  size_t strip_words = 0;
   for (int l = 0; l < VS_LEVELS; l++) {
     LevelDesc& L = ctx->lev[l];
     L.w = w; L.h = h; L.pitch = round_up(w, 128);
@@ -133,17 +134,21 @@ int vslam_create(const vslam_config* cfg, vslam_ctx** out) {
     CK(dalloc(&L.img, (size_t)S * h * L.pitch));
     CK(dalloc(&L.corners, (size_t)S * L.cap));
     CK(dalloc(&L.lut, (size_t)S * (h + 1)));
-    CK(dalloc(&L.strip_state, (size_t)S * L.n_strips));
+    strip_words += (size_t)S * L.n_strips;
     ctx->src.w[l] = w; ctx->src.h[l] = h; ctx->src.pitch[l] = L.pitch;
     CK(dalloc(&ctx->src.img[l], (size_t)ctx->n_src * h * L.pitch));
     w /= 2; h /= 2;
   }
+  // one allocation for the look-back words of all levels and the tickets, so that a whole-context frame clears them with one memset
+  CK(dalloc(&ctx->sync_words, strip_words + VS_MAX_GROUPS)); ctx->sync_words_n = strip_words + VS_MAX_GROUPS;
+  { size_t off = 0; for (int l = 0; l < VS_LEVELS; l++) { ctx->lev[l].strip_state = ctx->sync_words + off; off += (size_t)S * ctx->lev[l].n_strips; }
+    ctx->tickets = (unsigned*)(ctx->sync_words + off); }
   CK(dalloc(&ctx->l0_ptr, (size_t)S)); CK(dalloc(&ctx->l0_stride, (size_t)S));
   ctx->l0_ptr_host = new const uint8_t*[S]; ctx->l0_stride_host = new int[S];
   for (int s = 0; s < S; s++) { ctx->l0_ptr_host[s] = ctx->lev[0].img + (size_t)s * ctx->lev[0].h * ctx->lev[0].pitch; ctx->l0_stride_host[s] = ctx->lev[0].pitch; }
   CK(cudaMemcpy(ctx->l0_ptr, ctx->l0_ptr_host, sizeof(uint8_t*) * S, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(ctx->l0_stride, ctx->l0_stride_host, sizeof(int) * S, cudaMemcpyHostToDevice));
-  CK(dalloc(&ctx->tickets, (size_t)2 * VS_MAX_GROUPS)); CK(dalloc(&ctx->status, (size_t)4)); CK(dalloc(&ctx->evals, (size_t)1));
+  CK(dalloc(&ctx->status, (size_t)4)); CK(dalloc(&ctx->evals, (size_t)1));
   // map
   ctx->map.n = 0;
   CK(dalloc(&ctx->map.world, (size_t)3 * N)); CK(dalloc(&ctx->map.right, (size_t)3 * N)); CK(dalloc(&ctx->map.down, (size_t)3 * N));
@@ -184,8 +189,8 @@ void vslam_destroy(vslam_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->cfg.device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  for (int l = 0; l < VS_LEVELS; l++) { cudaFree(ctx->lev[l].img); cudaFree(ctx->lev[l].corners); cudaFree(ctx->lev[l].lut); cudaFree(ctx->lev[l].strip_state); cudaFree(ctx->src.img[l]); }
-  cudaFree(ctx->l0_ptr); cudaFree(ctx->l0_stride); cudaFree(ctx->tickets); cudaFree(ctx->status); cudaFree(ctx->evals);
+  for (int l = 0; l < VS_LEVELS; l++) { cudaFree(ctx->lev[l].img); cudaFree(ctx->lev[l].corners); cudaFree(ctx->lev[l].lut); cudaFree(ctx->src.img[l]); }
+  cudaFree(ctx->l0_ptr); cudaFree(ctx->l0_stride); cudaFree(ctx->sync_words); cudaFree(ctx->status); cudaFree(ctx->evals);
   cudaFree(ctx->map.world); cudaFree(ctx->map.right); cudaFree(ctx->map.down); cudaFree(ctx->map.ircenter); cudaFree(ctx->map.srclevel); cudaFree(ctx->map.srckf);
   PointState& ps = ctx->ps;
   cudaFree(ps.v3cam); cudaFree(ps.v2image); cudaFree(ps.derivs); cudaFree(ps.warpinv); cudaFree(ps.m2); cudaFree(ps.lastwarp); cudaFree(ps.v2found); cudaFree(ps.coarse);

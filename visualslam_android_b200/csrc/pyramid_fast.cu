@@ -339,10 +339,14 @@ static const int kFastThr[VS_LEVELS] = {10, 15, 15, 10};
 // Level 0: pyramid levels 1..3 + FAST-10 of level 0 (one launch).
 int vs_launch_pyramid_l0(vslam_ctx* ctx, int first_stream, int count) {
   unsigned* tickets = ctx->tickets + 2 * ctx->cur_group;   // [0]: level-0 launch, [1]: levels 1-3 launch; one pair per stream group
-  VS_CUDA(cudaMemsetAsync(tickets, 0, sizeof(unsigned) * 2, ctx->stream));
-  for (int l = 0; l < VS_LEVELS; l++) {
-    LevelDesc& L = ctx->lev[l];
-    VS_CUDA(cudaMemsetAsync(L.strip_state + (size_t)first_stream * L.n_strips, 0, sizeof(unsigned long long) * (size_t)count * L.n_strips, ctx->stream));
+  if (first_stream == 0 && count == ctx->S && ctx->cur_group == 0) {
+    VS_CUDA(cudaMemsetAsync(ctx->sync_words, 0, sizeof(unsigned long long) * ctx->sync_words_n, ctx->stream));   // all look-back words + tickets at once
+  } else {
+    VS_CUDA(cudaMemsetAsync(tickets, 0, sizeof(unsigned) * 2, ctx->stream));
+    for (int l = 0; l < VS_LEVELS; l++) {
+      LevelDesc& L = ctx->lev[l];
+      VS_CUDA(cudaMemsetAsync(L.strip_state + (size_t)first_stream * L.n_strips, 0, sizeof(unsigned long long) * (size_t)count * L.n_strips, ctx->stream));
+    }
   }
   LevelDesc& L = ctx->lev[0];
   int stride = 0;

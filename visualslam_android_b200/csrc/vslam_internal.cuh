@@ -105,7 +105,8 @@ struct vslam_ctx {
   // projection run beside the FAST pass of levels 1..3
   cudaStream_t group_stream[VS_MAX_GROUPS], side_stream[VS_MAX_GROUPS]; cudaEvent_t ev_fork[VS_MAX_GROUPS], ev_join[VS_MAX_GROUPS], ev_end[VS_MAX_GROUPS], ev_begin;
   int cur_s0, cur_cnt, cur_group;   // stream range / group the launchers act on (0, S, 0 outside vs_launch_frame)
-  unsigned* tickets;             // [2 * VS_MAX_GROUPS] device
+  unsigned long long* sync_words; size_t sync_words_n;   // strip_state of levels 0..3, then the tickets: one allocation, one memset per frame
+  unsigned* tickets;             // [2 * VS_MAX_GROUPS] device (inside sync_words)
   int* status;                   // [4] device: [0] capacity overflow flag
   CamDev cam; CamDev* cam_dev;
   MapDev map; MapDev* map_dev;
