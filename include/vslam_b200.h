@@ -21,8 +21,13 @@
  *                                     ZMSSDAtPoint :352-380, MakeSubPixTemplate/IterateSubPixToConvergence :242-350)
  *   vslam_calc_pose_update           Tracker::CalcPoseUpdate               jni/Tracker.cc:683-774 (+ Tukey, myWLS<6>)
  *   vslam_track_map                  Tracker::TrackMap                     jni/Tracker.cc:358-626
- *   vslam_track_frame[_dev]          Tracker::TrackFrame (good-map branch) jni/Tracker.cc:76-112
- *                                    (ApplyMotionModel :781-798, UpdateMotionModel :802-820, AssessTrackingQuality :832-878)
+ *   vslam_track_frame[_dev|_async]   Tracker::TrackFrame (good-map branch) jni/Tracker.cc:76-140
+ *                                    (ApplyMotionModel :781-798, UpdateMotionModel :802-820, AssessTrackingQuality :832-878;
+ *                                     lost streams: AttemptRecovery :167-180 with vslam_set_reloc_keyframes)
+ *   vslam_set_reloc_keyframes        Relocaliser::AttemptRecovery / ScoreKFs       jni/Relocaliser.cc:17-58
+ *   vslam_reset_stream               Tracker::Reset                               jni/Tracker.cc:45-60
+ *   vslam_refind                     MapMaker::ReFind_Common                      jni/MapMaker.cc:967-1036
+ *   vslam_epipolar_search            MapMaker::AddPointEpipolar (the search)      jni/MapMaker.cc:525-640
  *   vslam_make_keyframe_rest         KeyFrame::MakeKeyFrame_Rest           jni/KeyFrame.cc:53-95 (fast_nonmax jni/vision/cvfast.cpp:9243-9405,
  *                                    FindShiTomasiScoreAtPoint jni/vision/ImageHandler.cpp:124-155)
  *   vslam_minipatch_sample / _find   MiniPatch::SampleFromImage / FindPatch jni/MiniPatch.cc:32-83
