@@ -263,13 +263,31 @@ def cpu_stage_times(reps=20, warm=5):
         out["points_searched"] = int(len(lst))
         return out
 
+    def sequence_fps(kind, w, L, pre, n=40):
+        """whole TrackFrame (SBI included) over a short config-2 style sequence on ONE core."""
+        frames = [np.ascontiguousarray(synth.render_frame(tex, cam, synth.stream_pose(FRAME_STEP * k, 1))) for k in range(1, n + 6)]
+        w.set_pose(eye)
+        getattr(L, pre + "tracker_set_velocity")(w.tracker, np.zeros(6), 0.0)
+        for fr in frames[:5]:
+            getattr(L, pre + "tracker_track_frame")(w.tracker, fr, W, H, W)
+        t0 = time.perf_counter()
+        for fr in frames[5:]:
+            getattr(L, pre + "tracker_track_frame")(w.tracker, fr, W, H, W)
+        return n / (time.perf_counter() - t0)
+
     res = {}
     if refbind.available():
         rw = refbind.RefWorld(W, H, f0, smap)
         res["reference_P11"] = stages("reference", rw, rw.L, "ref_")
+        rw2 = refbind.RefWorld(W, H, f0, smap)
+        rw2.L.ref_srand(1); rw2.L.ref_sbi_reset_size()
+        res["reference_P11"]["track_frame_sequence_fps_one_core"] = sequence_fps("reference", rw2, rw2.L, "ref_")
     for P in (11, 8):
         ow = oraclebind.OrcWorld(cam, f0, smap, P=P)
         res[f"port_P{P}"] = stages("port", ow, ow.L, "orc_")
+        ow2 = oraclebind.OrcWorld(cam, f0, smap, P=P)
+        ow2.L.orc_tracker_enable_sbi(ow2.tracker, synth.Camera(W // 16, H // 16).scalars())
+        res[f"port_P{P}"]["track_frame_sequence_fps_one_core"] = sequence_fps("port", ow2, ow2.L, "orc_")
     return {"what": "per-stage CPU times, BASELINE config 1, one core, ms (median of %d after %d warm-ups); the stand-in cv::Mat / cv::resize of the "
                     "reference build are plain scalar C++, not OpenCV's SIMD paths" % (reps, warm), "cores": 1, "stages_ms": res}
 
