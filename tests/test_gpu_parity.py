@@ -519,7 +519,8 @@ def test_track_frame_with_on_device_sbi():
     ctx.close()
 
 
-def test_refind_common_batched_over_keyframes():
+@pytest.mark.parametrize("P", [11, 8])
+def test_refind_common_batched_over_keyframes(P):
     """f3: MapMaker::ReFind_Common (jni/MapMaker.cc:967-1036) batched — every stream is one keyframe (own image, own pose), the list
     names the map points to re-find; level, found flag, bSubPix and v2RootPos against the oracle (pinned to the reference's calls in
     tests/test_oracle_vs_ref.py::test_refind_common).  The third keyframe is so close to the plane that warps are rejected."""
@@ -527,7 +528,7 @@ def test_refind_common_batched_over_keyframes():
     twists = [np.array(synth.CONFIG1_TWIST), np.array([0.05, -0.03, 0.45, 0.02, -0.03, 0.3]), np.array([0.0, 0.0, -0.935, 0.0, 0.0, 0.0])]
     off = synth.se3_exp(np.array([0.0008, -0.0006, 0.0005, 0.0006, -0.0004, 0.0007]))
     S = len(twists)
-    ctx = _ctx(cam, f0, smap, n_streams=S)
+    ctx = _ctx(cam, f0, smap, n_streams=S, patch_size=P)
     frames, poses = [], []
     for tw in twists:
         fr, pose = common.frame_at(cam, tw)
@@ -539,7 +540,7 @@ def test_refind_common_batched_over_keyframes():
     ctx.set_lists([idx] * S)
     ctx.refind(4, 8)
     for s in range(S):
-        ow = _orc(cam, f0, smap)
+        ow = _orc(cam, f0, smap, P=P)
         ow.make_current_kf(frames[s]); ow.set_pose(poses[s])
         oo, op = np.zeros((smap.n, 3), dtype=np.int32), np.zeros((smap.n, 2))
         ow.L.orc_tracker_refind(ow.tracker, idx, smap.n, 4, 8, 1, oo, op)
@@ -560,7 +561,8 @@ def test_refind_common_batched_over_keyframes():
     ctx.close()
 
 
-def test_epipolar_search_matches_the_oracle():
+@pytest.mark.parametrize("P", [11, 8])
+def test_epipolar_search_matches_the_oracle(P):
     """f3: the search of MapMaker::AddPointEpipolar (jni/MapMaker.cc:525-640): every Shi-Tomasi candidate of every level of source
     keyframe 0 searched along its epipolar line in the stream's current keyframe; found flag, best corner and its ZMSSD exact,
     refined position to 1e-6 px, against the oracle (pinned in tests/test_oracle_vs_ref.py::test_epipolar_search)."""
@@ -568,14 +570,14 @@ def test_epipolar_search_matches_the_oracle():
     cam, f0, smap = common.scene()
     tw = np.array([0.12, 0.03, 0.02, 0.01, -0.03, 0.02])
     f1, pose1 = common.frame_at(cam, tw)
-    ctx = _ctx(cam, f0, smap)
+    ctx = _ctx(cam, f0, smap, patch_size=P)
     ctx.make_keyframe_lite(f0)
     ctx.make_keyframe_rest(0)
     cands = [ctx.candidates(0, l)[0] for l in range(4)]
     ok0 = oraclebind.OrcKeyFrame().make_lite(f0); ok0.make_rest()
     ok1 = oraclebind.OrcKeyFrame().make_lite(f1)
     ctx.make_keyframe_lite(f1)
-    ow = _orc(cam, f0, smap)
+    ow = _orc(cam, f0, smap, P=P)
     eye = np.ascontiguousarray(synth.IDENTITY_POSE, dtype=np.float64).reshape(12); p1 = np.ascontiguousarray(pose1, dtype=np.float64).reshape(12)
     total_found = 0
     for level in range(4):
