@@ -74,6 +74,29 @@ def test_make_keyframe_lite_edge_images():
     ctx.close()
 
 
+@pytest.mark.parametrize("size", [(64, 48), (96, 72), (224, 104), (640, 8), (32, 200)])
+def test_make_keyframe_lite_threshold_boundaries_and_odd_sizes(size):
+    """FAST's comparisons are strict (`>` cb, `<` c_b, jni/vision/cvfast.cpp): images whose pixels sit exactly ON the thresholds of
+    their neighbours (values drawn from {c, c +- t, c +- (t+1)} for t = 10 and 15), few-valued noise, and plateaus with single
+    outliers, at sizes whose strips, row pairs and 128-pixel chunks are ragged (height 8, widths 32..224, odd level-3 heights)."""
+    from oracle import oraclebind
+    from visualslam_android_b200 import api
+    W, H = size
+    rs = np.random.RandomState(W * 1000 + H)
+    imgs = []
+    for base, t in ((100, 10), (100, 15), (20, 10), (240, 15)):
+        vals = np.clip(np.array([base, base + t, base - t, base + t + 1, base - t - 1]), 0, 255)
+        imgs.append(vals[rs.randint(0, 5, (H, W))].astype(np.uint8))
+    imgs.append(np.where(rs.rand(H, W) < 0.03, 200, 90).astype(np.uint8))          # plateau with isolated bright pixels
+    imgs.append((rs.randint(0, 3, (H, W)) * 11 + 60).astype(np.uint8))            # three grey values 11 apart (t = 10 passes, 15 does not)
+    imgs = np.stack(imgs)
+    ctx = api.Context(W, H, n_streams=len(imgs), max_points=8, max_corner_frac=1.0)
+    ctx.make_keyframe_lite(imgs)
+    for s in range(len(imgs)):
+        _check_keyframe(ctx, s, oraclebind.OrcKeyFrame().make_lite(imgs[s]))
+    ctx.close()
+
+
 def test_corner_capacity_overflow_is_reported():
     from visualslam_android_b200 import api
     W, H = 160, 120
