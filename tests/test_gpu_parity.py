@@ -281,8 +281,8 @@ def test_calc_pose_update_degenerate_sets():
     ctx.close()
 
 
-def _track_map_case(scale_start, scale_frame, velocity=None, P=11):
-    cam, f0, smap = common.scene()
+def _track_map_case(scale_start, scale_frame, velocity=None, P=11, n_points=1000):
+    cam, f0, smap = common.scene(n_points=n_points)
     ctx, ow = _ctx(cam, f0, smap, patch_size=P), _orc(cam, f0, smap, P=P)
     f1, _ = common.frame_at(cam, np.array(synth.CONFIG1_TWIST) * scale_frame)
     start = synth.se3_exp(np.array(synth.CONFIG1_TWIST) * scale_start)
@@ -325,6 +325,16 @@ def test_track_map_fine_only_matches_oracle():
 def test_track_map_with_coarse_stage_matches_oracle():
     ctx, ow = _track_map_case(0.0, 1.0, velocity=0.05)
     assert ow.counters()[4] == 1, "coarse stage must have run in this case"
+    _check_track_map(ctx, ow)
+    ctx.close()
+
+
+def test_track_map_more_points_than_the_patch_cap():
+    """2500 map points: the potentially-visible set exceeds MaxPatchesPerFrame = 1000, so TrackMap shuffles the remaining fine list
+    once more and truncates it (jni/Tracker.cc:518-527) — the fifth std::random_shuffle of the frame."""
+    ctx, ow = _track_map_case(0.0, 0.6, n_points=2500)
+    a = ow.counters()[0]
+    assert a.sum() <= 1000 and a.sum() > 900
     _check_track_map(ctx, ow)
     ctx.close()
 

@@ -151,9 +151,10 @@ def test_patchfinder_p8_object_level():
     R.ref_pf_destroy(pf)
 
 
-@pytest.mark.parametrize("start,frame,vel", [(0.0, 1.0, None), (0.0, 1.0, 0.05), (0.2, 0.5, None), (0.5, 0.5, 0.02)])
-def test_track_map_whole(start, frame, vel):
-    cam, f0, smap, rw, ow = _worlds()
+@pytest.mark.parametrize("start,frame,vel,n_points", [(0.0, 1.0, None, 1000), (0.0, 1.0, 0.05, 1000), (0.2, 0.5, None, 1000), (0.5, 0.5, 0.02, 1000),
+                                                      (0.0, 0.6, None, 2500), (0.0, 0.6, 0.05, 2500)])   # 2500: beyond the 1000-patch cap (jni/Tracker.cc:518-527)
+def test_track_map_whole(start, frame, vel, n_points):
+    cam, f0, smap, rw, ow = _worlds(n_points=n_points)
     f1, _ = common.frame_at(cam, np.array(synth.CONFIG1_TWIST) * frame)
     sp = synth.se3_exp(np.array(synth.CONFIG1_TWIST) * start)
     rw.make_current_kf(f1); ow.make_current_kf(f1)
@@ -167,7 +168,11 @@ def test_track_map_whole(start, frame, vel):
     assert np.array_equal(ra, oa) and np.array_equal(rf, of) and rdc == odc
     ri, rd = rw.point_states(); oi, od = ow.point_states()
     pvs = oi[:, 1] >= 0
-    assert np.array_equal(ri[pvs][:, [0, 1, 2, 3, 5]], oi[pvs][:, [0, 1, 2, 3, 5]])
+    assert np.array_equal(ri[pvs][:, [0, 1, 2, 3]], oi[pvs][:, [0, 1, 2, 3]])
+    srch = oi[:, 2] == 1     # PatchFinder::mbTemplateBad is uninitialised in the reference until the point is searched for the first time
+    assert np.array_equal(ri[srch][:, 5], oi[srch][:, 5])
+    if n_points > 1000:
+        assert srch.sum() == 1000 and pvs.sum() > 1000       # the cap was hit
     fnd = oi[:, 3] == 1
     assert np.array_equal(rd[fnd][:, :4], od[fnd][:, :4])
 
