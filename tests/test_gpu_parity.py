@@ -339,6 +339,16 @@ def test_track_map_more_points_than_the_patch_cap():
     ctx.close()
 
 
+@pytest.mark.parametrize("n_points", [90, 150, 300])
+def test_track_map_small_maps_coarse_set_branches(n_points):
+    """Coarse-stage list selection when level 3 has fewer points than CoarseMax (jni/Tracker.cc:425-462): level 2 tops the set up, or —
+    the reference's quirk — REPLACES it when it fits entirely (150 and 90 points); after the search fewer than CoarseMin points may be found,
+    in which case the coarse pose update is skipped."""
+    ctx, ow = _track_map_case(0.0, 0.6, velocity=0.05, n_points=n_points)
+    _check_track_map(ctx, ow)
+    ctx.close()
+
+
 def test_track_map_patch8():
     ctx, ow = _track_map_case(0.2, 0.5, P=8)
     _check_track_map(ctx, ow)

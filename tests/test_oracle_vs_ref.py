@@ -152,7 +152,8 @@ def test_patchfinder_p8_object_level():
 
 
 @pytest.mark.parametrize("start,frame,vel,n_points", [(0.0, 1.0, None, 1000), (0.0, 1.0, 0.05, 1000), (0.2, 0.5, None, 1000), (0.5, 0.5, 0.02, 1000),
-                                                      (0.0, 0.6, None, 2500), (0.0, 0.6, 0.05, 2500)])   # 2500: beyond the 1000-patch cap (jni/Tracker.cc:518-527)
+                                                      (0.0, 0.6, None, 2500), (0.0, 0.6, 0.05, 2500),    # 2500: beyond the 1000-patch cap (jni/Tracker.cc:518-527)
+                                                      (0.0, 0.6, 0.05, 150), (0.0, 0.6, 0.05, 300), (0.0, 0.6, 0.05, 90)])   # small maps: the coarse-set branches of :425-462, incl. the vNextToSearch overwrite
 def test_track_map_whole(start, frame, vel, n_points):
     cam, f0, smap, rw, ow = _worlds(n_points=n_points)
     f1, _ = common.frame_at(cam, np.array(synth.CONFIG1_TWIST) * frame)
