@@ -78,6 +78,7 @@ def lib():
     sig("orc_tracker_seed", None, vp, u)
     sig("orc_tracker_set_truncate", None, vp, i)
     sig("orc_tracker_set_map", None, vp, vp, i, _f64p, _f64p, _f64p, _i32p, _i32p)
+    sig("orc_tracker_set_point_source_kf", None, vp, i, vp)
     sig("orc_tracker_set_pose", None, vp, _f64p)
     sig("orc_tracker_get_pose", None, vp, _f64p)
     sig("orc_tracker_set_velocity", None, vp, _f64p, d)

@@ -418,6 +418,7 @@ struct MapPointO {
   double world[3], right[3], down[3];  // v3WorldPos, v3PixelRight_W, v3PixelDown_W
   int irCenter[2], srcLevel;
   int outlierCount, inlierCount;
+  const struct OKeyFrame* srcKF;   // MapPoint::pPatchSourceKF (jni/MapPoint.h:38)
 };
 
 // PatchFinder::CalcSearchLevelAndWarpMatrix (jni/PatchFinder.cc:31-68)
@@ -882,7 +883,7 @@ int search_for_points(OTracker& t, const std::vector<int>& v, int nRange, int nS
   for (size_t k = 0; k < v.size(); k++) {
     TData& TD = t.td[v[k]]; Finder& F = TD.finder;
     g_dbg = (v[k] == g_dbg_point);
-    make_template_coarse_cont(F, t.pts[v[k]], *t.srcKF);
+    make_template_coarse_cont(F, t.pts[v[k]], *t.pts[v[k]].srcKF);
     if (F.templateBad) { TD.inImage = TD.potentiallyVisible = TD.found = false; continue; }
     t.attempted[F.level]++;
     const bool bFound = find_patch_coarse(F, TD.v2Image[0], TD.v2Image[1], t.cur, nRange, &t.zmssdEvals, 0);
@@ -1265,8 +1266,11 @@ void orc_tracker_set_map(void* t_, void* srckf, int n, const double* world, cons
     MapPointO& p = t->pts[i];
     for (int k = 0; k < 3; k++) { p.world[k] = world[3 * i + k]; p.right[k] = right[3 * i + k]; p.down[k] = down[3 * i + k]; }
     p.irCenter[0] = irCenter[2 * i]; p.irCenter[1] = irCenter[2 * i + 1]; p.srcLevel = srcLevel[i]; p.outlierCount = p.inlierCount = 0;
+    p.srcKF = t->srcKF;
   }
 }
+// a map point whose patch comes from another keyframe of the map (MapPoint::pPatchSourceKF)
+void orc_tracker_set_point_source_kf(void* t_, int i, void* kf) { ((OTracker*)t_)->pts[i].srcKF = (OKeyFrame*)kf; }
 void orc_tracker_set_pose(void* t, const double* p12) { ((OTracker*)t)->pose = se3_from12(p12); }
 void orc_tracker_get_pose(void* t, double* p12) { se3_to12(((OTracker*)t)->pose, p12); }
 void orc_tracker_set_velocity(void* t_, const double* v6, double msd) { OTracker* t = (OTracker*)t_; memcpy(t->velocity, v6, sizeof(t->velocity)); t->msdScaledVel = msd; }
@@ -1392,7 +1396,7 @@ void orc_tracker_refind(void* t_, const int32_t* idx, int n, int range, int subp
     // Finder.MakeTemplateCoarse(p, k.se3CfromW, m2CamDerivs)
     if (cold || last != idx[k]) F.haveLast = false;          // &p != mpLastTemplateMapPoint
     calc_search_level_and_warp(F, p, t->pose, derivs);       // may set templateBad; MakeTemplateCoarseCont runs regardless
-    make_template_coarse_cont(F, p, *t->srcKF);
+    make_template_coarse_cont(F, p, *p.srcKF);
     last = idx[k];
     out3[3 * k + 1] = F.level;
     if (F.templateBad) continue;

@@ -757,3 +757,33 @@ def test_full_bench_size_256_streams_replicas_and_oracle():
                 order = c0[:, 1].astype(np.int64) * 65536 + c0[:, 0]
                 assert np.all(np.diff(order) > 0)                                            # raster order, no duplicates
     ctx.close()
+
+
+def test_track_map_with_two_source_keyframes():
+    """vslam_set_map's src_kf: map points whose patches come from different source keyframes (MapPoint::pPatchSourceKF), templates
+    sampled from the right keyframe pyramid; TrackMap against the oracle (pinned to the reference in tests/test_oracle_vs_ref.py)."""
+    from oracle import oraclebind
+    from visualslam_android_b200 import api
+    cam, kf_frames, kf_poses, smap, src_kf = common.two_keyframe_scene()
+    ctx = api.Context(cam.width, cam.height, n_streams=1, max_points=smap.n, max_source_keyframes=2)
+    ctx.set_camera(cam.scalars())
+    ctx.upload_source_keyframe(kf_frames[0], 0); ctx.upload_source_keyframe(kf_frames[1], 1)
+    ctx.set_map(smap.world, smap.pix_right_w, smap.pix_down_w, smap.ir_center, smap.src_level, src_kf)
+    ow = oraclebind.OrcWorld(cam, kf_frames[0], smap)
+    okf1 = oraclebind.OrcKeyFrame().make_lite(kf_frames[1])
+    for k in np.nonzero(src_kf == 1)[0]:
+        ow.L.orc_tracker_set_point_source_kf(ow.tracker, int(k), okf1.h)
+    tw = np.array([0.05, 0.01, 0.01, 0.005, -0.02, 0.03])
+    fr, pose = common.frame_at(cam, tw)
+    sp = synth.se3_exp(tw * 0.8)
+    ctx.make_keyframe_lite(fr); ow.make_current_kf(fr)
+    ctx.set_pose(0, sp); ow.set_pose(sp)
+    ctx.track_map(); ow.L.orc_tracker_track_map(ow.tracker)
+    _check_track_map(ctx, ow)
+    gi, _ = ctx.point_states(0)
+    assert gi[src_kf == 0, 3].sum() > 200 and gi[src_kf == 1, 3].sum() > 200
+    for k in (0, int(np.nonzero(src_kf == 1)[0][5])):          # a template of each keyframe, byte for byte
+        if gi[k, 2]:
+            gt, gs, gq = ctx.point_template(0, k); ot, os_, oq = ow.point_template(k)
+            assert np.array_equal(gt, ot) and (gs, gq) == (os_, oq)
+    ctx.close()

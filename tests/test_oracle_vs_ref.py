@@ -178,6 +178,50 @@ def test_track_map_whole(start, frame, vel, n_points):
     assert np.array_equal(rd[fnd][:, :4], od[fnd][:, :4])
 
 
+def _two_kf_worlds():
+    """Reference and restatement worlds for a map with two source keyframes (MapPoint::pPatchSourceKF differs between points)."""
+    cam, kf_frames, kf_poses, smap, src_kf = common.two_keyframe_scene()
+    n0 = int((src_kf == 0).sum())
+    first = synth.SyntheticMap(**{k: getattr(smap, k)[:n0] for k in ("world", "pix_right_w", "pix_down_w", "ir_center", "src_level", "center_nc", "one_right_nc", "one_down_nc")})
+    rw = refbind.RefWorld(cam.width, cam.height, kf_frames[0], first)
+    rk1 = refbind.RefKeyFrame().make_lite(kf_frames[1]); rk1.set_pose(kf_poses[1])
+    rw.L.ref_map_add_keyframe(rw.map, rk1.h)
+    normal = np.array([0.0, 0.0, -1.0])
+    for k in range(n0, smap.n):
+        rw.L.ref_map_add_point(rw.map, rk1.h, int(smap.src_level[k]), smap.ir_center[k].astype(np.float64), np.ascontiguousarray(smap.world[k]),
+                               np.ascontiguousarray(smap.center_nc[k]), np.ascontiguousarray(smap.one_right_nc[k]), np.ascontiguousarray(smap.one_down_nc[k]), normal)
+    rw.n = smap.n
+    pr, pd = rw.pixel_vectors()
+    assert np.abs(pr - smap.pix_right_w).max() < 1e-9 and np.abs(pd - smap.pix_down_w).max() < 1e-9     # RefreshPixelVectors with a keyframe pose
+    ow = oraclebind.OrcWorld(cam, kf_frames[0], smap, pix_right=pr, pix_down=pd)
+    okf1 = oraclebind.OrcKeyFrame().make_lite(kf_frames[1])
+    for k in range(n0, smap.n):
+        ow.L.orc_tracker_set_point_source_kf(ow.tracker, k, okf1.h)
+    ow._kf1, rw._kf1 = okf1, rk1
+    return cam, rw, ow, smap, src_kf, pr, pd
+
+
+def test_track_map_with_two_source_keyframes():
+    """Templates come from the keyframe a point was made in (MapPoint::pPatchSourceKF): a map with points from two keyframes,
+    tracked from a third viewpoint, reference against restatement, bit for bit."""
+    cam, rw, ow, smap, src_kf, _, _ = _two_kf_worlds()
+    tw = np.array([0.05, 0.01, 0.01, 0.005, -0.02, 0.03])
+    fr, pose = common.frame_at(cam, tw)
+    sp = synth.se3_exp(tw * 0.8)
+    rw.make_current_kf(fr); ow.make_current_kf(fr)
+    rw.set_pose(sp); ow.set_pose(sp)
+    rw.L.ref_srand(1)
+    rw.L.ref_tracker_track_map(rw.tracker); ow.L.orc_tracker_track_map(ow.tracker)
+    assert np.array_equal(rw.get_pose(), ow.get_pose())
+    ra, rf, _, _, _ = rw.counters(); oa, of, _, _, _ = ow.counters()
+    assert np.array_equal(ra, oa) and np.array_equal(rf, of)
+    ri, rd = rw.point_states(); oi, od = ow.point_states()
+    fnd = oi[:, 3] == 1
+    assert np.array_equal(ri[:, 3], oi[:, 3]) and np.array_equal(rd[fnd][:, :4], od[fnd][:, :4])
+    assert fnd[src_kf == 0].sum() > 200 and fnd[src_kf == 1].sum() > 200        # points of both keyframes are found
+    assert np.abs(ow.get_pose() - pose).max() < 5e-3
+
+
 def test_track_frame_sequence_no_sbi():
     cam, f0, smap, rw, ow = _worlds()
     rw.L.ref_srand(1)

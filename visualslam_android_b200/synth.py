@@ -221,6 +221,35 @@ def build_map(cam: Camera, corners_per_level, level_dims, n_points: int, seed: i
                         center_nc=center, one_right_nc=right, one_down_nc=down)
 
 
+def build_map_at_pose(cam: Camera, corners_per_level, level_dims, n_points: int, pose, seed: int = MAP_SEED + 1) -> SyntheticMap:
+    """Like build_map for a source keyframe at `pose` (3x4 camera-from-world): the *_nc rays are in that keyframe's camera frame,
+    world points are the rays' intersections with the scene plane z = 1 (world frame = frame of KF0).  pix_right_w / pix_down_w are
+    left zero: MapPoint::RefreshPixelVectors needs the keyframe pose, so the tests take them from the compiled reference or from
+    refresh_pixel_vectors_at_pose."""
+    m = build_map(cam, corners_per_level, level_dims, n_points, seed=seed)
+    R, t = np.asarray(pose)[:, :3], np.asarray(pose)[:, 3]
+    o = -R.T @ t                                   # camera centre in the world
+    d = m.center_nc @ R                            # R^T ray, row-wise
+    lam = (1.0 - o[2]) / d[:, 2]
+    world = o[None, :] + lam[:, None] * d
+    pr, pd = refresh_pixel_vectors_at_pose(m.center_nc, m.one_right_nc, m.one_down_nc, world, pose)
+    return SyntheticMap(world=world, pix_right_w=pr, pix_down_w=pd, ir_center=m.ir_center, src_level=m.src_level,
+                        center_nc=m.center_nc, one_right_nc=m.one_right_nc, one_down_nc=m.one_down_nc)
+
+
+def refresh_pixel_vectors_at_pose(center_nc, one_right_nc, one_down_nc, world, pose, normal=(0.0, 0.0, -1.0)):
+    """MapPoint::RefreshPixelVectors (jni/MapPoint.cc:4-29) for a source keyframe at `pose` (synthetic-input helper; parity tests use
+    the vectors computed by the compiled reference)."""
+    R, t = np.asarray(pose)[:, :3], np.asarray(pose)[:, 3]
+    nrm = np.asarray(normal, dtype=np.float64)
+    cam_pts = world @ R.T + t[None, :]
+    cam_height = np.abs(cam_pts @ nrm)
+    c_on = center_nc * (cam_height / np.abs(center_nc @ nrm))[:, None]
+    r_on = one_right_nc * (cam_height / np.abs(one_right_nc @ nrm))[:, None]
+    d_on = one_down_nc * (cam_height / np.abs(one_down_nc @ nrm))[:, None]
+    return (r_on - c_on) @ R, (d_on - c_on) @ R    # rotated into the world frame (R^T v, row-wise)
+
+
 def stream_pose(k: int, stream: int = 0, twist=CONFIG1_TWIST) -> np.ndarray:
     """Camera pose of frame k of a synthetic sequence."""
     xi = np.asarray(twist, dtype=np.float64)
