@@ -787,3 +787,37 @@ def test_track_map_with_two_source_keyframes():
             gt, gs, gq = ctx.point_template(0, k); ot, os_, oq = ow.point_template(k)
             assert np.array_equal(gt, ot) and (gs, gq) == (os_, oq)
     ctx.close()
+
+
+def test_api_housekeeping_timing_reset_and_forced_relocalisation():
+    """vslam_set_timing / vslam_get_stage_times (per-launch CUDA events), vslam_reset_stream (Tracker::Reset) and vslam_set_lost (a caller
+    declaring a stream lost: the next frame must go through the relocaliser and continue tracking)."""
+    cam, f0, smap = common.scene()
+    ctx = _ctx(cam, f0, smap, n_streams=2)
+    ctx.enable_sbi(synth.Camera(cam.width // 16, cam.height // 16).scalars())
+    ctx.set_reloc_keyframes([0], synth.IDENTITY_POSE[None])
+    fr = [common.frame_at(cam, np.array(synth.CONFIG1_TWIST) * k)[0] for k in (0.1, 0.2, 0.3)]
+    ctx.set_timing(True)
+    ctx.track_frame(np.stack([fr[0], fr[0]]))
+    st = ctx.stage_times()
+    for name in ("pyrfast_l0", "pyrfast_l1", "project_lists", "search_fine", "pose_fine", "other"):
+        assert st[name][0] > 0 and st[name][1] >= 1, name
+    ctx.set_timing(False)
+    assert ctx.counters(0)[2] == 2 and ctx.counters(1)[2] == 2
+    # stream 1 is declared lost by the caller: the next frame relocalises it against keyframe 0 and tracks on
+    ctx.set_lost(1, 3, 0)
+    ctx.track_frame(np.stack([fr[1], fr[1]]))
+    best, score, nrec, rec = ctx.reloc_info(1)
+    assert (best, nrec, rec) == (0, 1, 1) and score < 9e6
+    assert ctx.reloc_info(0)[2] == 0
+    a, f, q, lost, dc = ctx.counters(1)
+    assert q == 2 and lost == 0 and dc == 1            # quality GOOD again; the recovery forces the coarse stage
+    assert np.abs(ctx.get_pose(1) - ctx.get_pose(0)).max() < 5e-3
+    # Tracker::Reset
+    ctx.reset_stream(0)
+    a, f, q, lost, dc = ctx.counters(0)
+    v, msd, dm, ds = ctx.get_motion(0)
+    assert a.sum() == 0 and f.sum() == 0 and (q, lost, dc) == (2, 0, 0) and np.all(v == 0) and (msd, dm, ds) == (0.0, 1.0, 1.0)
+    ctx.track_frame(np.stack([fr[2], fr[2]]))
+    assert ctx.counters(0)[2] == 2
+    ctx.close()
