@@ -821,3 +821,30 @@ def test_api_housekeeping_timing_reset_and_forced_relocalisation():
     ctx.track_frame(np.stack([fr[2], fr[2]]))
     assert ctx.counters(0)[2] == 2
     ctx.close()
+
+
+def test_c_abi_rejects_bad_arguments_with_error_codes():
+    """Nothing throws or crashes across the C-ABI: bad arguments come back as VSLAM_E_INVALID with a message."""
+    from visualslam_android_b200 import api
+    cam, f0, smap = common.scene(n_points=200)
+    for bad in (dict(width=100, height=480), dict(width=640, height=100), dict(width=640, height=480, patch_size=12), dict(width=640, height=480, n_streams=0)):
+        with pytest.raises(api.VslamError) as e:
+            api.Context(**{"width": 640, "height": 480, **bad})
+        assert e.value.code == api.E_INVALID
+    ctx = _ctx(cam, f0, smap, n_streams=2)
+    L, h = ctx.L, ctx.h
+    assert L.vslam_get_pose(h, 2, np.zeros(12).ctypes.data) == api.E_INVALID                  # stream out of range
+    assert L.vslam_get_pose(None, 0, np.zeros(12).ctypes.data) == api.E_INVALID               # null context
+    assert L.vslam_upload_source_keyframe(h, 5, f0.ctypes.data, cam.width) == api.E_INVALID    # unknown source keyframe
+    assert L.vslam_make_keyframe_lite(h, 1, 2, f0.ctypes.data, cam.width, 0) == api.E_INVALID  # stream range past the end
+    assert L.vslam_make_keyframe_lite(h, 0, 1, f0.ctypes.data, cam.width - 1, 0) == api.E_INVALID   # stride smaller than the width
+    with pytest.raises(api.VslamError):
+        ctx.set_lists([[0, 1, smap.n], []])                                                    # list entry that is not a map point
+    with pytest.raises(api.VslamError):
+        ctx.set_reloc_keyframes([0], synth.IDENTITY_POSE[None])                               # needs vslam_enable_sbi first
+    assert b"enable_sbi" in L.vslam_last_error(h)
+    assert L.vslam_minipatch_find(h, 0, 1, 0, None, None, None, None, 10, 100) == api.E_INVALID   # snapshot not taken
+    ctx.make_keyframe_lite(np.stack([f0, f0]))                                                 # the context still works afterwards
+    ctx.sync()
+    assert ctx.corners(1, 0).shape[0] > 100
+    ctx.close()
