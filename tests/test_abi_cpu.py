@@ -83,3 +83,31 @@ def test_cpp_shell_compiles_against_the_reference_type_surface(tmp_path):
     import torch
     rc = subprocess.run([str(exe)]).returncode
     assert rc == (0 if torch.cuda.is_available() else 3)
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/vslam_b200.h is a C header (the boundary a cgo / JNI / ctypes binding sees): it compiles as C99 and a C translation unit
+    that drives the multi-camera loop of INTEGRATION.md links against the library."""
+    import subprocess
+    src = tmp_path / "abi_check.c"
+    src.write_text('#include "vslam_b200.h"\n'
+                   '#include <stdio.h>\n'
+                   'int main(void) {\n'
+                   '  vslam_config cfg; vslam_params prm; vslam_ctx* ctx = 0; double cam[13], p5[5] = {0.841906, 1.10893, 0.505171, 0.470265, -0.0133843};\n'
+                   '  vslam_default_config(&cfg); vslam_default_params(&prm);\n'
+                   '  cfg.n_streams = 4; cfg.max_points = 100;\n'
+                   '  vslam_camera_from_params(p5, cfg.width, cfg.height, 0, cam);\n'
+                   '  if (vslam_create(&cfg, &ctx) != VSLAM_OK) { printf("%s\\n", vslam_last_error(0)); return 3; }\n'
+                   '  vslam_set_camera(ctx, cam); vslam_set_params(ctx, &prm);\n'
+                   '  vslam_destroy(ctx);\n'
+                   '  return 0; }\n')
+    exe = tmp_path / "abi_check"
+    libdir = os.path.join(ROOT, "visualslam_android_b200")
+    r = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), "-L", libdir, "-lvslam_b200",
+                        f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    import torch
+    run = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert run.returncode == (0 if torch.cuda.is_available() else 3), run.stdout
+    if run.returncode == 3:
+        assert "no CUDA device" in run.stdout
