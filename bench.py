@@ -357,6 +357,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--streams", type=int, default=STREAMS_PER_GPU, help="camera streams per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--host-alloc", default="pinned", choices=["pinned", "wc"], help="how the e2e leg's host frame pool is allocated")
     ap.add_argument("--groups", type=int, default=0, help="vslam_params.stream_groups (0 = library default)")
     ap.add_argument("--sweep", action="store_true", help="SURVEY §8(d) config 5: 4K frames, batch-size sweep of pyramid+FAST and points x range sweep of the patch search (one GPU)")
     ap.add_argument("--cpu-stages", action="store_true", help="SURVEY §8(d)(i): per-stage CPU times of config 1 (reference build and oracle port), no GPU work")
@@ -369,7 +370,8 @@ def main():
     config = {"workload": WORKLOAD, "streams_per_gpu": args.streams, "frame": [W, H], "map_points": N_POINTS, "patch": 11, "parallelism": f"streams sharded over {world} GPU(s), no collective",
               "l2": "inputs larger than L2: each step reads a different 78.6 MB frame set out of a pool of 24 (1.9 GB, triangle-wave order: a set is "
                     "re-read at the earliest two steps later) and the per-step working set (frames + pyramids + corner lists + per-point state, "
-                    "> 250 MB) exceeds the 126 MB L2; no explicit flush"}
+                    "> 250 MB) exceeds the 126 MB L2; no explicit flush",
+              "e2e_host_frames": "pinned (cudaHostAlloc default)" if args.host_alloc == "pinned" else "pinned, write-combined"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -429,8 +431,23 @@ def main():
         for s0 in range(0, S, 64):
             frames_dev[k - 1, s0:s0 + 64] = render_frames_torch(tex_t, cam, poses[s0:s0 + 64, k], dev)
     torch.cuda.synchronize()
-    frames_host = torch.empty((M, S, H, W), dtype=torch.uint8).pin_memory()
-    frames_host.copy_(frames_dev)
+    if args.host_alloc == "wc":
+        # write-combined pinned memory (cudaHostAllocWriteCombined | Portable): the CPU never reads the frame pool, and on a multi-socket
+        # host the PCIe reads of WC memory are not snooped
+        import ctypes
+        rt = ctypes.CDLL("libcudart.so.12")
+        ptr = ctypes.c_void_p()
+        nbytes = M * S * H * W
+        rc = rt.cudaHostAlloc(ctypes.byref(ptr), ctypes.c_size_t(nbytes), ctypes.c_uint(0x04 | 0x01))
+        if rc != 0:
+            raise SystemExit(f"cudaHostAlloc(write-combined) failed: {rc}")
+        buf = (ctypes.c_uint8 * nbytes).from_address(ptr.value)
+        frames_host = torch.frombuffer(buf, dtype=torch.uint8).view(M, S, H, W)
+        rt.cudaMemcpy(ctypes.c_void_p(ptr.value), ctypes.c_void_p(frames_dev.data_ptr()), ctypes.c_size_t(nbytes), ctypes.c_int(2))   # device -> host
+        _keep_alive = (rt, buf)
+    else:
+        frames_host = torch.empty((M, S, H, W), dtype=torch.uint8).pin_memory()
+        frames_host.copy_(frames_dev)
     torch.cuda.synchronize()
 
     def tri(j):      # j-th step of the whole run -> index into the pool
