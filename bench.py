@@ -571,11 +571,21 @@ def main():
     l0_ms = stage["pyrfast_l0"][0] / Ks
     # DRAM bytes of that launch from the committed ncu --set full capture (profiles/r01c_ncu_full_summary.json, S=256 VGA)
     l0_traffic = 78.845696e6 + 11.888128e6 if (S == 256 and (W, H) == (640, 480)) else None
+    # the roofline that actually binds the level-0 launch: instruction issue.  Warp-instructions of the launch from the committed ncu
+    # capture (smsp__inst_executed.sum, profiles/r01c_ncu_full_summary.json; a property of the workload, not of the run) over the live
+    # launch time, against 4 issue slots per SM and clock
+    l0_inst = 166989951.0 if (S == 256 and (W, H) == (640, 480)) else None
+    sm_clock_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
+    issue = None
+    if l0_inst:
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        issue = {"bound": "instruction issue", "warp_instructions_per_launch": l0_inst, "achieved": l0_inst / (l0_ms * 1e-3) / 1e9,
+                 "peak": sms * 4 * sm_clock_hz / 1e9, "unit": "G warp-instr/s", "frac": l0_inst / (l0_ms * 1e-3) / (sms * 4 * sm_clock_hz)}
     roofline = {"kernel": "k_pyramid_fast + k_fast_levels (pyramid + FAST-10 + raster compaction + row LUT; 2 launches per step: level 0 (+ level 1-3 images), levels 1-3)", "bound": "hbm",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": l0_traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_step": alg_bytes_step, "ms_per_step": pyr_ms / Ks, "share_of_step": (pyr_ms / Ks) / stage_sum_ms,
                 "level0_launch": {"algorithmic_bytes": l0_bytes, "ms": l0_ms, "achieved": l0_bytes / (l0_ms * 1e-3) / 1e9,
-                                  "frac": l0_bytes / (l0_ms * 1e-3) / 1e9 / peak, "traffic": l0_traffic},
+                                  "frac": l0_bytes / (l0_ms * 1e-3) / 1e9 / peak, "traffic": l0_traffic, "issue_roofline": issue},
                 "note": "traffic is the level-0 launch's dram read+write bytes (ncu); the stage is instruction-issue bound (81-85 % issue-slot "
                         "utilisation, ~270 warp-instructions per 256 pixels of level 0), not HBM bound: DESIGN.md §4.1 and profiles/r01c_*"}
     # ZMSSD: 3*P^2 integer MACs per scored candidate over the time of the two search kernels, against a measured dp4a peak
