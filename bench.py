@@ -79,15 +79,31 @@ def render_frames_torch(tex_t, cam, poses, device):
     return (val + 0.5).floor().clamp_(0, 255).to(torch.uint8)
 
 
-def build_scene():
-    """KF0 + map from the CPU oracle's MakeKeyFrame_Lite (input preparation, outside every timed region)."""
+def keyframe_corners(f0, on_gpu, device=0):
+    """FAST corners and level sizes of one keyframe, for choosing the synthetic map's points (input preparation, outside every timed
+    region).  The GPU arm uses the library itself; only the CPU arms (cpu_baseline, --impl reference, --cpu-stages) use the oracle —
+    both give the same corners bit for bit (tests/test_gpu_parity.py), so every arm tracks the same map."""
+    h, w = f0.shape
+    if on_gpu:
+        from visualslam_android_b200 import api
+        ctx = api.Context(w, h, n_streams=1, max_points=8, device=device)
+        ctx.make_keyframe_lite(f0[None])
+        out = [ctx.corners(0, l) for l in range(4)], [ctx.level_dims(l) for l in range(4)]
+        ctx.close()
+        return out
     from oracle import oraclebind
+    kf = oraclebind.OrcKeyFrame().make_lite(f0)
+    return [kf.corners(l) for l in range(4)], [kf.dims(l) for l in range(4)]
+
+
+def build_scene(on_gpu=False, device=0):
+    """KF0 + map of N_POINTS points chosen among KF0's FAST corners."""
     from visualslam_android_b200 import synth
     cam = synth.Camera(W, H)
     tex = synth.make_texture(2048)
     f0 = synth.render_frame(tex, cam, synth.IDENTITY_POSE)
-    kf = oraclebind.OrcKeyFrame().make_lite(f0)
-    smap = synth.build_map(cam, [kf.corners(l) for l in range(4)], [kf.dims(l) for l in range(4)], N_POINTS)
+    corners, dims = keyframe_corners(f0, on_gpu, device)
+    smap = synth.build_map(cam, corners, dims, N_POINTS)
     return cam, tex, f0, smap
 
 
@@ -155,7 +171,6 @@ def sweep_config5(device=0):
         measured HBM peak.  Every timed launch reads a frame set that was not touched by the previous launches worth > 126 MB (L2).
     (2) SearchForPoints (no sub-pixel) for N points x search range: ms, candidates scored (identical on CPU and GPU), integer TMAC/s."""
     import torch
-    from oracle import oraclebind
     from visualslam_android_b200 import api, synth
     W4, H4 = 3840, 2160
     dev = torch.device("cuda", device)
@@ -192,11 +207,11 @@ def sweep_config5(device=0):
         ctx.close()
     # (2) patch search: one 4K stream, N map points, range sweep
     f0 = synth.render_frame(tex, cam, synth.IDENTITY_POSE)
-    kf = oraclebind.OrcKeyFrame().make_lite(f0)
+    kf_corners, kf_dims = keyframe_corners(f0, True, device)
     f1 = synth.render_frame(tex, cam, synth.se3_exp(np.array(synth.CONFIG1_TWIST)))
     dp4a_peak = api.dp4a_peak_tmacs()
     for N in (1000, 5000, 20000):
-        smap = synth.build_map(cam, [kf.corners(l) for l in range(4)], [kf.dims(l) for l in range(4)], N)
+        smap = synth.build_map(cam, kf_corners, kf_dims, N)
         ctx = api.Context(W4, H4, n_streams=1, max_points=smap.n, cuda_stream=stream.cuda_stream)
         ctx.set_camera(cam.scalars()); ctx.upload_source_keyframe(f0)
         ctx.set_map(smap.world, smap.pix_right_w, smap.pix_down_w, smap.ir_center, smap.src_level)
@@ -420,7 +435,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     S = args.streams
-    cam, tex, f0, smap = build_scene()
+    cam, tex, f0, smap = build_scene(on_gpu=True, device=local_rank)
     tex_t = torch.from_numpy(tex.astype(np.float32)).to(dev)
     # A pool of M consecutive frame sets per stream, traversed as a triangle wave (1,2,..,M,M-1,..,1,2,..) so that any number of
     # steps sees a continuous camera motion.  A set is re-read at the earliest two steps later, after > 126 MB of other traffic.
