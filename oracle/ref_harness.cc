@@ -364,119 +364,122 @@ void ref_tracker_track_frame(void* t, const uint8_t* gray, int w, int h, int str
   cv::Mat col(1, 1, CV_8UC4, g_dummy_rgba);
   tr->TrackFrame(im, col, false);
 }
-// MapMaker::ReFind_Common (jni/MapMaker.cc:967-1036).  MapMaker.cc itself is not part of this build (it needs Eigen's JacobiSVD /
-// EigenSolver and the Bundle / HomographyInit link surface), so the function's call sequence is transcribed here on the REFERENCE'S
-// OWN objects: the arithmetic below is all reference code (mySE3, ATANCamera::Project / GetProjectionDerivs_Eigen,
-// PatchFinder::MakeTemplateCoarse / FindPatchCoarse / MakeSubPixTemplate / IterateSubPixToConvergence), only the control flow of
-// ReFind_Common is restated; the Measurement / sNeverRetryKFs bookkeeping is left out.  k = the tracker's current keyframe with
-// se3CfromW = the tracker's pose.
+// f3 pins.  MapMaker.cc is not part of this build (it needs Eigen's JacobiSVD / EigenSolver and the Bundle / HomographyInit link
+// surface), so the two MapMaker searches are DRIVEN here on the reference's own objects: every arithmetic step below is a call into
+// reference code (mySE3 / mySO3 operators, ATANCamera::Project / UnProject / GetProjectionDerivs_Eigen / OnePixelDist,
+// PatchFinder::MakeTemplateCoarse / MakeTemplateCoarseNoWarp / FindPatchCoarse / ZMSSDAtPoint / MakeSubPixTemplate /
+// IterateSubPixToConvergence, LevelZeroPos); what this harness supplies is the ORDER of those calls, written from the description of
+// MapMaker::ReFind_Common (jni/MapMaker.cc:967-1036) and of the search part of MapMaker::AddPointEpipolar (:525-640) in SURVEY.md /
+// DESIGN.md.  Bookkeeping (measurement sets, new map points, triangulation) is left out.
+
+namespace {
+struct PixelOnPlane { bool ok; Eigen::Vector2d image; };
+// z = 1 projection of a camera-frame point, then the camera model with its validity checks
+PixelOnPlane to_pixel(ATANCamera& cam, const Eigen::Vector3d& in_camera, int cols, int rows) {
+  PixelOnPlane r; r.ok = false;
+  if (in_camera(2) < 0.001) return r;
+  Eigen::Vector2d plane; plane(0) = in_camera(0) / in_camera(2); plane(1) = in_camera(1) / in_camera(2);
+  const double limit = cam.LargestRadiusInImage();
+  if (plane.dot(plane) > limit * limit) return r;
+  r.image = cam.Project(plane);
+  if (cam.Invalid()) return r;
+  if (r.image[0] < 0 || r.image[1] < 0 || r.image[0] > cols || r.image[1] > rows) return r;
+  r.ok = true;
+  return r;
+}
+}  // namespace
+
+// Re-find listed map points in the tracker's current keyframe (pose = the tracker's pose).  ONE PatchFinder for the whole list, as
+// the reference keeps a function-static one.  out3 = {found, search level, refined}, pos2 = measurement position.
 void ref_refind(void* t, const int32_t* idx, int n, int range, int subpix_its, int32_t* out3, double* pos2) {
-  Tracker* tr = ((RefTracker*)t)->tr;
+  Tracker* tracker = ((RefTracker*)t)->tr;
   Map* map = ((RefTracker*)t)->map;
-  KeyFrame& k = tr->mCurrentKF;
-  k.se3CfromW = tr->mse3CamFromWorld;
-  ATANCamera& cam = tr->mCamera;
-  static PatchFinder Finder;
+  KeyFrame& frame = tracker->mCurrentKF;
+  frame.se3CfromW = tracker->mse3CamFromWorld;
+  ATANCamera& cam = tracker->mCamera;
+  static PatchFinder finder;
   for (int q = 0; q < n; q++) {
-    MapPoint& p = *map->vpPoints[idx[q]];
-    out3[3 * q] = 0; out3[3 * q + 1] = -1; out3[3 * q + 2] = 0; pos2[2 * q] = pos2[2 * q + 1] = 0.0;
-    Eigen::Vector3d v3Cam = k.se3CfromW * p.v3WorldPos;
-    if (v3Cam(2) < 0.001) continue;
-    Eigen::Vector2d v2ImPlane; v2ImPlane(0) = v3Cam(0) / v3Cam(2); v2ImPlane(1) = v3Cam(1) / v3Cam(2);
-    if (v2ImPlane.dot(v2ImPlane) > cam.LargestRadiusInImage() * cam.LargestRadiusInImage()) continue;
-    Eigen::Vector2d v2Image = cam.Project(v2ImPlane);
-    if (cam.Invalid()) continue;
-    if (v2Image[0] < 0 || v2Image[1] < 0 || v2Image[0] > k.aLevels[0].im.cols || v2Image[1] > k.aLevels[0].im.rows) continue;
-    Eigen::Matrix2d m2CamDerivs = cam.GetProjectionDerivs_Eigen();
-    Finder.MakeTemplateCoarse(p, k.se3CfromW, m2CamDerivs);
-    out3[3 * q + 1] = Finder.GetLevel();
-    if (Finder.TemplateBad()) continue;
-    if (!Finder.FindPatchCoarse(Eigen::Vector2d(v2Image[0], v2Image[1]), k, range)) continue;
-    out3[3 * q] = 1;
-    Eigen::Vector2d r;
-    if (Finder.GetLevel() > 0) { Finder.MakeSubPixTemplate(); Finder.IterateSubPixToConvergence(k, subpix_its); r = Finder.GetSubPixPos(); out3[3 * q + 2] = 1; }
-    else r = Finder.GetCoarsePosAsVector();
-    pos2[2 * q] = r(0); pos2[2 * q + 1] = r(1);
+    int32_t* o = out3 + 3 * q; double* xy = pos2 + 2 * q;
+    o[0] = 0; o[1] = -1; o[2] = 0; xy[0] = xy[1] = 0.0;
+    MapPoint& point = *map->vpPoints[idx[q]];
+    const PixelOnPlane px = to_pixel(cam, frame.se3CfromW * point.v3WorldPos, frame.aLevels[0].im.cols, frame.aLevels[0].im.rows);
+    if (!px.ok) continue;
+    Eigen::Matrix2d derivs = cam.GetProjectionDerivs_Eigen();
+    finder.MakeTemplateCoarse(point, frame.se3CfromW, derivs);
+    o[1] = finder.GetLevel();
+    if (finder.TemplateBad() || !finder.FindPatchCoarse(px.image, frame, range)) continue;
+    o[0] = 1;
+    const bool refine = finder.GetLevel() > 0;
+    if (refine) { finder.MakeSubPixTemplate(); finder.IterateSubPixToConvergence(frame, subpix_its); }
+    const Eigen::Vector2d where = refine ? finder.GetSubPixPos() : finder.GetCoarsePosAsVector();
+    o[2] = refine ? 1 : 0; xy[0] = where(0); xy[1] = where(1);
   }
 }
 
-// The search of MapMaker::AddPointEpipolar (jni/MapMaker.cc:525-640), same arrangement as ref_refind: the function's call sequence
-// transcribed on the reference's own objects (ATANCamera::UnProject / LargestRadiusInImage / OnePixelDist, mySE3 / mySO3 operators,
-// PatchFinder::MakeTemplateCoarseNoWarp / ZMSSDAtPoint / MakeSubPixTemplate / IterateSubPixToConvergence, LevelZeroPos), stopping
-// where the triangulation starts.  kSrc / kTarget: KeyFrame handles (ref_kf_*), kSrc after MakeKeyFrame_Rest; poses row-major 3x4.
-// out3 = {converged match found, index of the best corner in kTarget's level (-1: none), its ZMSSD}; pos2 = Finder.GetSubPixPos().
-void ref_epipolar_search(void* t, void* ksrc, void* ktgt, const double* src_pose12, const double* tgt_pose12, double depth_mean, double depth_sigma,
-                         double wiggle, int nLevel, int nCandidate, int32_t* out3, double* pos2) {
-  Tracker* tr = ((RefTracker*)t)->tr;
-  ATANCamera& cam = tr->mCamera;
-  KeyFrame& kSrc = *(KeyFrame*)ksrc; KeyFrame& kTarget = *(KeyFrame*)ktgt;
-  kSrc.se3CfromW = pose_from12(src_pose12); kTarget.se3CfromW = pose_from12(tgt_pose12);
-  kSrc.dSceneDepthMean = depth_mean; kSrc.dSceneDepthSigma = depth_sigma;
+// Epipolar search of one Shi-Tomasi candidate of `source` (after MakeKeyFrame_Rest) in `target`; poses row-major 3x4.
+// out3 = {converged match, index of the best corner of target's level (-1: none), its ZMSSD}; pos2 = refined position.
+void ref_epipolar_search(void* t, void* source_kf, void* target_kf, const double* src_pose12, const double* tgt_pose12, double depth_mean, double depth_sigma,
+                         double wiggle, int level, int candidate_index, int32_t* out3, double* pos2) {
+  ATANCamera& cam = ((RefTracker*)t)->tr->mCamera;
+  KeyFrame& source = *(KeyFrame*)source_kf; KeyFrame& target = *(KeyFrame*)target_kf;
+  source.se3CfromW = pose_from12(src_pose12); target.se3CfromW = pose_from12(tgt_pose12);
   out3[0] = 0; out3[1] = -1; out3[2] = 0; pos2[0] = pos2[1] = 0.0;
-  static Eigen::MatrixXd imUnProj[2];
-  static int cw = 0, ch = 0;
-  if (cw != kSrc.aLevels[0].im.cols || ch != kSrc.aLevels[0].im.rows) {
-    cw = kSrc.aLevels[0].im.cols; ch = kSrc.aLevels[0].im.rows;
-    imUnProj[0].resize(ch, cw); imUnProj[1].resize(ch, cw);
-    for (int i = 0; i < cw; i++) for (int j = 0; j < ch; j++) { Eigen::Vector2d p2d = cam.UnProject(Eigen::Vector2d(i, j)); imUnProj[0](j, i) = p2d(0); imUnProj[1](j, i) = p2d(1); }
+  // image-plane position of every integer pixel (the reference caches this table once per image size)
+  static Eigen::MatrixXd plane_x, plane_y; static int tw = 0, th = 0;
+  const int cols = source.aLevels[0].im.cols, rows = source.aLevels[0].im.rows;
+  if (tw != cols || th != rows) {
+    tw = cols; th = rows; plane_x.resize(rows, cols); plane_y.resize(rows, cols);
+    for (int u = 0; u < cols; u++) for (int v = 0; v < rows; v++) { const Eigen::Vector2d p = cam.UnProject(Eigen::Vector2d(u, v)); plane_x(v, u) = p(0); plane_y(v, u) = p(1); }
   }
-  int nLevelScale = LevelScale(nLevel);
-  Candidate& candidate = kSrc.aLevels[nLevel].vCandidates[nCandidate];
-  Eigen::Vector2d irLevelPos = candidate.irLevelPos;
-  Eigen::Vector2d v2RootPos = LevelZeroPos(irLevelPos, nLevel);
-  Eigen::Vector2d un = cam.UnProject(v2RootPos);
-  Eigen::Vector3d v3Ray_SC; v3Ray_SC(0) = un(0); v3Ray_SC(1) = un(1); v3Ray_SC(2) = 1.0;
-  v3Ray_SC.normalize();
-  Eigen::Vector3d v3LineDirn_TC = kTarget.se3CfromW.get_rotation() * (kSrc.se3CfromW.get_rotation().inverse() * v3Ray_SC);
-  double dStartDepth = std::max(wiggle, depth_mean - depth_sigma);
-  double dEndDepth = std::min(40 * wiggle, depth_mean + depth_sigma);
-  Eigen::Vector3d v3CamCenter_TC = kTarget.se3CfromW * kSrc.se3CfromW.inverse().get_translation();
-  Eigen::Vector3d v3RayStart_TC = v3CamCenter_TC + dStartDepth * v3LineDirn_TC;
-  Eigen::Vector3d v3RayEnd_TC = v3CamCenter_TC + dEndDepth * v3LineDirn_TC;
-  if (v3RayEnd_TC(2) <= v3RayStart_TC(2)) return;
-  if (v3RayEnd_TC(2) <= 0.0) return;
-  if (v3RayStart_TC(2) <= 0.0) v3RayStart_TC += v3LineDirn_TC * (0.001 - v3RayStart_TC(2) / v3LineDirn_TC(2));
-  Eigen::Vector2d v2A; v2A(0) = v3RayStart_TC(0) / v3RayStart_TC(2); v2A(1) = v3RayStart_TC(1) / v3RayStart_TC(2);
-  Eigen::Vector2d v2B; v2B(0) = v3RayEnd_TC(0) / v3RayEnd_TC(2); v2B(1) = v3RayEnd_TC(1) / v3RayEnd_TC(2);
-  Eigen::Vector2d v2AlongProjectedLine = v2A - v2B;
-  if (v2AlongProjectedLine.dot(v2AlongProjectedLine) < 0.00000001) return;
-  v2AlongProjectedLine.normalize();
-  Eigen::Vector2d v2Normal; v2Normal(0) = v2AlongProjectedLine(1); v2Normal(1) = -v2AlongProjectedLine(0);
-  double dNormDist = v2A.dot(v2Normal);
-  if (fabs(dNormDist) > cam.LargestRadiusInImage()) return;
-  double dMinLen = std::min(v2AlongProjectedLine.dot(v2A), v2AlongProjectedLine.dot(v2B)) - 0.05;
-  double dMaxLen = std::max(v2AlongProjectedLine.dot(v2A), v2AlongProjectedLine.dot(v2B)) + 0.05;
-  if (dMinLen < -2.0) dMinLen = -2.0;
-  if (dMaxLen < -2.0) dMaxLen = -2.0;
-  if (dMinLen > 2.0) dMinLen = 2.0;
-  if (dMaxLen > 2.0) dMaxLen = 2.0;
-  PatchFinder Finder;
-  int a = irLevelPos(0), b = irLevelPos(1);
-  Finder.MakeTemplateCoarseNoWarp(kSrc, nLevel, a, b);
-  if (Finder.TemplateBad()) return;
-  std::vector<Eigen::Vector2d>& vIR = kTarget.aLevels[nLevel].vCorners;
-  int nBest = -1;
-  int nBestZMSSD = Finder.mnMaxSSD + 1;
-  double dMaxDistDiff = cam.OnePixelDist() * (4.0 + 1.0 * nLevelScale);
-  double dMaxDistSq = dMaxDistDiff * dMaxDistDiff;
-  for (unsigned int i = 0; i < vIR.size(); i++) {
-    Eigen::Vector2d zpos = LevelZeroPos(vIR[i], nLevel);
-    Eigen::Vector2d v2Im(imUnProj[0](zpos(1), zpos(0)), imUnProj[1](zpos(1), zpos(0)));
-    double dDistDiff = dNormDist - v2Im.dot(v2Normal);
-    if (dDistDiff * dDistDiff > dMaxDistSq) continue;
-    if (v2Im.dot(v2AlongProjectedLine) < dMinLen) continue;
-    if (v2Im.dot(v2AlongProjectedLine) > dMaxLen) continue;
-    int nZMSSD = Finder.ZMSSDAtPoint(kTarget.aLevels[nLevel].im, (int)vIR[i](0), (int)vIR[i](1));
-    if (nZMSSD < nBestZMSSD) { nBest = i; nBestZMSSD = nZMSSD; }
+  const int scale = LevelScale(level);
+  Eigen::Vector2d level_pos = source.aLevels[level].vCandidates[candidate_index].irLevelPos;   // LevelZeroPos takes a mutable reference
+  const Eigen::Vector2d root = LevelZeroPos(level_pos, level);
+  // viewing ray of the candidate in the source camera, then as a direction in the target camera
+  const Eigen::Vector2d ray_plane = cam.UnProject(root);
+  Eigen::Vector3d ray; ray(0) = ray_plane(0); ray(1) = ray_plane(1); ray(2) = 1.0; ray.normalize();
+  const Eigen::Vector3d dir = target.se3CfromW.get_rotation() * (source.se3CfromW.get_rotation().inverse() * ray);
+  const double near_depth = std::max(wiggle, depth_mean - depth_sigma), far_depth = std::min(40 * wiggle, depth_mean + depth_sigma);
+  const Eigen::Vector3d origin = target.se3CfromW * source.se3CfromW.inverse().get_translation();
+  Eigen::Vector3d near_pt = origin + near_depth * dir;
+  const Eigen::Vector3d far_pt = origin + far_depth * dir;
+  if (far_pt(2) <= near_pt(2) || far_pt(2) <= 0.0) return;
+  if (near_pt(2) <= 0.0) near_pt += dir * (0.001 - near_pt(2) / dir(2));
+  Eigen::Vector2d a; a(0) = near_pt(0) / near_pt(2); a(1) = near_pt(1) / near_pt(2);
+  Eigen::Vector2d b; b(0) = far_pt(0) / far_pt(2); b(1) = far_pt(1) / far_pt(2);
+  Eigen::Vector2d along = a - b;
+  if (along.dot(along) < 0.00000001) return;
+  along.normalize();
+  Eigen::Vector2d across; across(0) = along(1); across(1) = -along(0);
+  const double offset = a.dot(across);
+  if (fabs(offset) > cam.LargestRadiusInImage()) return;
+  double lo = std::min(along.dot(a), along.dot(b)) - 0.05, hi = std::max(along.dot(a), along.dot(b)) + 0.05;
+  if (lo < -2.0) lo = -2.0;
+  if (hi < -2.0) hi = -2.0;
+  if (lo > 2.0) lo = 2.0;
+  if (hi > 2.0) hi = 2.0;
+  PatchFinder finder;
+  finder.MakeTemplateCoarseNoWarp(source, level, (int)level_pos(0), (int)level_pos(1));
+  if (finder.TemplateBad()) return;
+  std::vector<Eigen::Vector2d>& corners = target.aLevels[level].vCorners;
+  const double band = cam.OnePixelDist() * (4.0 + 1.0 * scale), band_sq = band * band;
+  int best = -1, best_score = finder.mnMaxSSD + 1;
+  for (unsigned int i = 0; i < corners.size(); i++) {
+    const Eigen::Vector2d z = LevelZeroPos(corners[i], level);
+    const Eigen::Vector2d on_plane(plane_x(z(1), z(0)), plane_y(z(1), z(0)));       // table indexed with the truncated position
+    const double off = offset - on_plane.dot(across);
+    if (off * off > band_sq) continue;
+    if (on_plane.dot(along) < lo) continue;
+    if (on_plane.dot(along) > hi) continue;
+    const int score = finder.ZMSSDAtPoint(target.aLevels[level].im, (int)corners[i](0), (int)corners[i](1));
+    if (score < best_score) { best = (int)i; best_score = score; }
   }
-  out3[1] = nBest; out3[2] = nBestZMSSD;
-  if (nBest == -1) return;
-  Finder.MakeSubPixTemplate();
-  Finder.SetSubPixPos(LevelZeroPos(vIR[nBest], nLevel));
-  bool bSubPixConverges = Finder.IterateSubPixToConvergence(kTarget, 10);
-  Eigen::Vector2d r = Finder.GetSubPixPos();
-  pos2[0] = r(0); pos2[1] = r(1);
-  out3[0] = bSubPixConverges ? 1 : 0;
+  out3[1] = best; out3[2] = best_score;
+  if (best < 0) return;
+  finder.MakeSubPixTemplate();
+  finder.SetSubPixPos(LevelZeroPos(corners[best], level));
+  out3[0] = finder.IterateSubPixToConvergence(target, 10) ? 1 : 0;
+  const Eigen::Vector2d refined = finder.GetSubPixPos();
+  pos2[0] = refined(0); pos2[1] = refined(1);
 }
 int ref_kf_num_candidates_l(void* kf, int l) { return (int)((KeyFrame*)kf)->aLevels[l].vCandidates.size(); }
 
