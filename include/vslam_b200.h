@@ -26,8 +26,11 @@
  *                                     lost streams: AttemptRecovery :167-180 with vslam_set_reloc_keyframes)
  *   vslam_set_reloc_keyframes        Relocaliser::AttemptRecovery / ScoreKFs       jni/Relocaliser.cc:17-58
  *   vslam_reset_stream               Tracker::Reset                               jni/Tracker.cc:45-60
+ *   vslam_save_map_file / _load_     (no reference counterpart: the reference keeps its map in memory only)
+ *   vslam_export_map_text            MapMaker::GUICommandHandler("SaveMap") dump  jni/MapMaker.cc:1254-1297
  *   vslam_refind                     MapMaker::ReFind_Common                      jni/MapMaker.cc:967-1036
  *   vslam_epipolar_search            MapMaker::AddPointEpipolar (the search)      jni/MapMaker.cc:525-640
+ *   vslam_epipolar_make_points       MapMaker::AddPointEpipolar (the new point)   jni/MapMaker.cc:646-690 (ReprojectPoint :176-200, MapPoint::RefreshPixelVectors)
  *   vslam_make_keyframe_rest         KeyFrame::MakeKeyFrame_Rest           jni/KeyFrame.cc:53-95 (fast_nonmax jni/vision/cvfast.cpp:9243-9405,
  *                                    FindShiTomasiScoreAtPoint jni/vision/ImageHandler.cpp:124-155)
  *   vslam_minipatch_sample / _find   MiniPatch::SampleFromImage / FindPatch jni/MiniPatch.cc:32-83
@@ -59,6 +62,7 @@ extern "C" {
 #define VSLAM_E_CUDA (-2)         /* CUDA runtime error (text in vslam_last_error) */
 #define VSLAM_E_CAPACITY (-3)     /* more corners than max_corner_frac allows: reported, never silently truncated */
 #define VSLAM_E_NO_DEVICE (-4)    /* no usable CUDA device: there is no CPU fallback */
+#define VSLAM_E_IO (-5)           /* map file cannot be opened / is truncated / fails its checksum */
 
 typedef struct vslam_ctx vslam_ctx;
 
@@ -161,6 +165,22 @@ int vslam_get_sbi_rotation(vslam_ctx* ctx, int stream, double* rot6);
 int vslam_set_reloc_keyframes(vslam_ctx* ctx, int n, const int32_t* src_kf_ids, const double* poses12);
 int vslam_get_reloc_info(vslam_ctx* ctx, int stream, int* best_keyframe, double* score, int* n_recoveries, int* recovered_last_frame);
 int vslam_set_lost(vslam_ctx* ctx, int stream, int lost_frames, int quality);
+
+/* ---- Map files: camera + source keyframes (level-0 images) + map points + relocaliser registration in one checksummed binary file
+ * (layout in csrc/mapfile.cu), so a service can restart or several processes / GPUs can serve streams of one map.
+ * vslam_save_map_file writes what this context currently holds.  vslam_load_map_file verifies the whole file first (size, version,
+ * checksum, capacity: the context is untouched on any error), then uploads the keyframes (pyramids are rebuilt on the device) and the
+ * points like vslam_upload_source_keyframe / vslam_set_map would; VSLAM_MAP_LOAD_CAMERA also installs the file's camera,
+ * VSLAM_MAP_LOAD_RELOC also re-registers the relocaliser keyframes (needs vslam_enable_sbi).  vslam_map_file_info reads only the
+ * header and needs no GPU.  vslam_export_map_text writes the reference's debug dump layout (jni/MapMaker.cc:1254-1297): <dir>/map.dump
+ * with world position + source level per point and <dir>/keyframes/<i>.info with the pose of the i-th relocaliser keyframe. */
+#define VSLAM_MAP_LOAD_CAMERA 1
+#define VSLAM_MAP_LOAD_RELOC 2
+typedef struct vslam_map_file_info_t { int width, height, n_points, n_keyframes, n_reloc_keyframes; double cam13[13]; } vslam_map_file_info_t;
+int vslam_map_file_info(const char* path, vslam_map_file_info_t* out);
+int vslam_save_map_file(vslam_ctx* ctx, const char* path);
+int vslam_load_map_file(vslam_ctx* ctx, const char* path, int flags);
+int vslam_export_map_text(vslam_ctx* ctx, const char* dir);
 /* attempted[4], found[4], quality (0 BAD,1 DODGY,2 GOOD), lost_frames, did_coarse */
 int vslam_get_counters(vslam_ctx* ctx, int stream, int32_t* attempted4, int32_t* found4, int* quality, int* lost_frames, int* did_coarse);
 /* Per-point TrackerData dump, layout of oracle/ref_harness.cc ref_tracker_point_state: ints[n][8], dbl[n][32]. */
@@ -199,6 +219,13 @@ int vslam_get_refind_results(vslam_ctx* ctx, int stream, int32_t* flags3, double
 int vslam_epipolar_search(vslam_ctx* ctx, int stream, int src_kf, int level, int n, const int32_t* cand_xy, const double* src_pose12,
                           const double* target_pose12, double depth_mean, double depth_sigma, double wiggle_scale, int32_t* found, double* pos2,
                           int32_t* best_corner, int32_t* best_zmssd);
+/* The rest of MapMaker::AddPointEpipolar for candidates whose search converged (jni/MapMaker.cc:646-690): triangulate the new point
+ * from the candidate's level-zero position in the source keyframe and the refined position in the target (MapMaker::ReprojectPoint,
+ * jni/MapMaker.cc:176-200, smallest right singular vector of the 4x4 two-view system), then derive the patch-source fields and
+ * MapPoint::RefreshPixelVectors (jni/MapPoint.cc:4-29).  Host arithmetic (one 4x4 SVD per new point).  The outputs are the
+ * vslam_set_map arrays of the new points; their source keyframe is the one `src_pose12` belongs to. */
+int vslam_epipolar_make_points(vslam_ctx* ctx, int level, int n, const int32_t* cand_xy, const double* found_pos2, const double* src_pose12, const double* tgt_pose12,
+                               double* world3, double* pixel_right3, double* pixel_down3, int32_t* ir_center2, int32_t* src_level);
 int vslam_project_and_derivs(vslam_ctx* ctx, int only_found);
 int vslam_calc_jacobians(vslam_ctx* ctx);
 int vslam_calc_pose_update(vslam_ctx* ctx, double override_sigma, int mark_outliers, int apply, double* upd6_per_stream /* may be NULL */);

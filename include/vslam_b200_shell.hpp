@@ -69,6 +69,14 @@ class Context {
   int Streams() const { return n_streams_; }
   int MapSize() const { return n_points_; }
   void SetMapSize(int n) { n_points_ = n; }
+  // Map files (no reference counterpart; layout in csrc/mapfile.cu): what this context holds of the map -> disk and back.
+  void SaveMap(const std::string& path) { if (vslam_save_map_file(c_, path.c_str()) != VSLAM_OK) throw std::runtime_error(std::string("vslam_b200: ") + vslam_last_error(c_)); }
+  void LoadMap(const std::string& path, int flags = VSLAM_MAP_LOAD_CAMERA) {
+    if (vslam_load_map_file(c_, path.c_str(), flags) != VSLAM_OK) throw std::runtime_error(std::string("vslam_b200: ") + vslam_last_error(c_));
+    vslam_map_file_info_t info; vslam_map_file_info(path.c_str(), &info); n_points_ = info.n_points;
+  }
+  // MapMaker::GUICommandHandler("SaveMap") (jni/MapMaker.cc:1254-1297): map.dump + keyframes/<i>.info under `dir`
+  void SaveMapText(const std::string& dir) { if (vslam_export_map_text(c_, dir.c_str()) != VSLAM_OK) throw std::runtime_error(std::string("vslam_b200: ") + vslam_last_error(c_)); }
  private:
   int n_points_ = 0, n_streams_ = 0;
   Context(const Context&); Context& operator=(const Context&);
@@ -479,6 +487,40 @@ class MapSearch {
       out[i].nLevel = nLevel; out[i].bSubPix = true; out[i].v2RootPos = Eigen::Vector2d(pos[2 * i], pos[2 * i + 1]); out[i].Source = Measurement::SRC_EPIPOLAR;
     }
     return nAdded;
+  }
+
+  // The MapPoint that MapMaker::AddPointEpipolar creates for a converged candidate (jni/MapMaker.cc:646-690): fields the tracker reads.
+  struct NewMapPoint {
+    Eigen::Vector3d v3WorldPos, v3PixelRight_W, v3PixelDown_W;
+    Eigen::Vector2d irCenter;   // level pixels in the source keyframe
+    int nSourceLevel;
+    Measurement root;           // SRC_ROOT measurement in the source keyframe
+  };
+  // Triangulate (MapMaker::ReprojectPoint, jni/MapMaker.cc:176-200) every candidate with found[i] != 0 of an AddPointsEpipolar call
+  // and fill its patch-source fields + RefreshPixelVectors; indices[k] = which candidate points[k] came from.
+  void MakeEpipolarPoints(const SE3& srcCfromW, const SE3& targetCfromW, int nLevel, const std::vector<Eigen::Vector2d>& candidates, const std::vector<Measurement>& meas,
+                          const std::vector<char>& found, std::vector<NewMapPoint>& points, std::vector<int>& indices) {
+    vslam_ctx* c = ctx_.get();
+    double ps[12], pt[12];
+    for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) { ps[4 * i + j] = srcCfromW.R(i, j); pt[4 * i + j] = targetCfromW.R(i, j); } ps[4 * i + 3] = srcCfromW.t(i); pt[4 * i + 3] = targetCfromW.t(i); }
+    indices.clear();
+    for (size_t i = 0; i < candidates.size(); i++) if (found[i]) indices.push_back((int)i);
+    const size_t n = indices.size();
+    std::vector<int32_t> xy(2 * n + 2), irc(2 * n + 2), lvl(n + 1); std::vector<double> pos(2 * n + 2), w(3 * n + 3), r(3 * n + 3), d(3 * n + 3);
+    for (size_t k = 0; k < n; k++) {
+      const int i = indices[k];
+      xy[2 * k] = (int32_t)candidates[i](0); xy[2 * k + 1] = (int32_t)candidates[i](1); pos[2 * k] = meas[i].v2RootPos(0); pos[2 * k + 1] = meas[i].v2RootPos(1);
+    }
+    check(c, vslam_epipolar_make_points(c, nLevel, (int)n, &xy[0], &pos[0], ps, pt, &w[0], &r[0], &d[0], &irc[0], &lvl[0]));
+    points.assign(n, NewMapPoint());
+    for (size_t k = 0; k < n; k++) {
+      NewMapPoint& p = points[k];
+      p.v3WorldPos = Eigen::Vector3d(w[3 * k], w[3 * k + 1], w[3 * k + 2]); p.v3PixelRight_W = Eigen::Vector3d(r[3 * k], r[3 * k + 1], r[3 * k + 2]);
+      p.v3PixelDown_W = Eigen::Vector3d(d[3 * k], d[3 * k + 1], d[3 * k + 2]);
+      p.irCenter = Eigen::Vector2d(irc[2 * k], irc[2 * k + 1]); p.nSourceLevel = lvl[k];
+      p.root.Source = Measurement::SRC_ROOT; p.root.nLevel = nLevel; p.root.bSubPix = true;
+      p.root.v2RootPos = Eigen::Vector2d((irc[2 * k] + 0.5) * (1 << nLevel) - 0.5, (irc[2 * k + 1] + 0.5) * (1 << nLevel) - 0.5);
+    }
   }
  private:
   Context& ctx_;

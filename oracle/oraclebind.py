@@ -103,6 +103,7 @@ def lib():
     sig("orc_tracker_search_for_points", i, vp, _i32p, i, i, i)
     sig("orc_tracker_clear_counters", None, vp)
     sig("orc_epipolar_search", None, vp, vp, vp, _f64p, _f64p, d, d, d, i, i, i, _i32p, _f64p, C.c_void_p)
+    sig("orc_epipolar_point_fields", None, _f64p, _f64p, i, i, i, _f64p, _f64p)
     sig("orc_tracker_refind", None, vp, _i32p, i, i, i, i, _i32p, _f64p)
     sig("orc_tracker_calc_jacobians", None, vp, _i32p, i)
     sig("orc_tracker_project_and_derivs", None, vp, _i32p, i, i)
@@ -122,6 +123,33 @@ def lib():
     sig("orc_sbi_rotation", d, vp, vp, _f64p, i, C.c_void_p, _f64p)
     _lib = L
     return L
+
+
+def triangulate(cam13, src_pose, tgt_pose, root_pos, found_pos):
+    """MapMaker::ReprojectPoint (jni/MapMaker.cc:176-200) as AddPointEpipolar calls it (:648): the homogeneous two-view system of the
+    source ray A = UnProject(root) and the target ray B = UnProject(found), solved by the right singular vector of the smallest
+    singular value (the reference uses Eigen::JacobiSVD -- Eigen is not under /root/reference, so LAPACK's SVD stands in: the vector
+    is unique up to sign and the sign cancels), then moved from the target camera's frame to the world.  Parity unpinned (no Eigen)."""
+    L = lib()
+    cam13 = np.ascontiguousarray(cam13, dtype=np.float64)
+    S = np.vstack([np.asarray(src_pose, dtype=np.float64).reshape(3, 4), [0, 0, 0, 1]])
+    T = np.vstack([np.asarray(tgt_pose, dtype=np.float64).reshape(3, 4), [0, 0, 0, 1]])
+    a, b = np.zeros(2), np.zeros(2)
+    L.orc_cam_unproject(cam13, np.ascontiguousarray(root_pos, dtype=np.float64), a)
+    L.orc_cam_unproject(cam13, np.ascontiguousarray(found_pos, dtype=np.float64), b)
+    P = (S @ np.linalg.inv(T))[:3]                    # se3AfromB, A = source, B = target
+    A = np.array([[-1.0, 0.0, b[0], 0.0], [0.0, -1.0, b[1], 0.0], a[0] * P[2] - P[0], a[1] * P[2] - P[1]])
+    v = np.linalg.svd(A)[2][3].copy()
+    if v[3] == 0.0:
+        v[3] = 0.00001
+    return (np.linalg.inv(T) @ np.append(v[:3] / v[3], 1.0))[:3]
+
+
+def epipolar_point_fields(cam13, src_pose, level, cx, cy, world):
+    out = np.zeros(15)
+    lib().orc_epipolar_point_fields(np.ascontiguousarray(cam13, dtype=np.float64), np.ascontiguousarray(src_pose, dtype=np.float64).reshape(12), level, int(cx), int(cy),
+                                    np.ascontiguousarray(world, dtype=np.float64), out)
+    return out.reshape(5, 3)
 
 
 class OrcKeyFrame:

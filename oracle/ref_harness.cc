@@ -481,6 +481,27 @@ void ref_epipolar_search(void* t, void* source_kf, void* target_kf, const double
   const Eigen::Vector2d refined = finder.GetSubPixPos();
   pos2[0] = refined(0); pos2[1] = refined(1);
 }
+// Patch-source fields of a map point created from a candidate of `source` (as the tail of MapMaker::AddPointEpipolar fills them,
+// jni/MapMaker.cc:655-684), then the reference's own MapPoint::RefreshPixelVectors.  out15 = centre ray, one-right ray, one-down
+// ray (source camera frame, unit length), pixel-right and pixel-down vectors (world frame).
+void ref_epipolar_point_fields(void* t, void* source_kf, const double* src_pose12, int level, int candidate_index, const double* world3, double* out15) {
+  ATANCamera& cam = ((RefTracker*)t)->tr->mCamera;
+  KeyFrame& source = *(KeyFrame*)source_kf;
+  source.se3CfromW = pose_from12(src_pose12);
+  Eigen::Vector2d level_pos = source.aLevels[level].vCandidates[candidate_index].irLevelPos;
+  const Eigen::Vector2d root = LevelZeroPos(level_pos, level);
+  const double step = LevelScale(level);
+  MapPoint point;
+  point.pPatchSourceKF = &source; point.nSourceLevel = level;
+  point.v3WorldPos = Eigen::Vector3d(world3[0], world3[1], world3[2]);
+  point.v3Normal_NC = Eigen::Vector3d(0, 0, -1);
+  Eigen::Vector3d* rays[3] = {&point.v3Center_NC, &point.v3OneRightFromCenter_NC, &point.v3OneDownFromCenter_NC};
+  const Eigen::Vector2d at[3] = {root, root + Eigen::Vector2d(step, 0), root + Eigen::Vector2d(0, step)};
+  for (int k = 0; k < 3; k++) { const Eigen::Vector2d p = cam.UnProject(at[k]); (*rays[k])(0) = p(0); (*rays[k])(1) = p(1); (*rays[k])(2) = 1.0; rays[k]->normalize(); }
+  point.RefreshPixelVectors();
+  for (int k = 0; k < 3; k++) for (int q = 0; q < 3; q++) out15[3 * k + q] = (*rays[k])(q);
+  for (int q = 0; q < 3; q++) { out15[9 + q] = point.v3PixelRight_W(q); out15[12 + q] = point.v3PixelDown_W(q); }
+}
 int ref_kf_num_candidates_l(void* kf, int l) { return (int)((KeyFrame*)kf)->aLevels[l].vCandidates.size(); }
 
 // Relocaliser support: a map keyframe gets its SmallBlurryImage the way KeyFrame::MakeKeyFrame_Rest (jni/KeyFrame.cc:98) and the

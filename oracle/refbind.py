@@ -101,6 +101,7 @@ def lib():
     sig("ref_tracker_track_frame", None, vp, _u8p, i, i, i)
     sig("ref_refind", None, vp, _i32p, i, i, i, _i32p, _f64p)
     sig("ref_epipolar_search", None, vp, vp, vp, _f64p, _f64p, d, d, d, i, i, _i32p, _f64p)
+    sig("ref_epipolar_point_fields", None, vp, vp, _f64p, i, i, _f64p, _f64p)
     sig("ref_kf_num_candidates_l", i, vp, i)
     sig("ref_kf_make_sbi", None, vp)
     sig("ref_tracker_set_lost", None, vp, i, i)

@@ -1126,6 +1126,32 @@ void orc_cam_project(const double* cam13, const double* cam2, double* im2, int* 
 }
 void orc_cam_unproject(const double* cam13, const double* im2, double* cam2) { Cam c = cam_from13(cam13); cam_unproject(c, im2, cam2); }
 
+// Patch-source fields of a new map point (tail of MapMaker::AddPointEpipolar, jni/MapMaker.cc:655-684) + MapPoint::RefreshPixelVectors
+// (jni/MapPoint.cc:4-29) with v3Normal_NC = (0,0,-1).  out15 = Center_NC, OneRightFromCenter_NC, OneDownFromCenter_NC, PixelRight_W, PixelDown_W.
+void orc_epipolar_point_fields(const double* cam13, const double* src12, int level, int cx, int cy, const double* world3, double* out15) {
+  Cam cam = cam_from13(cam13);
+  const SE3 S = se3_from12(src12);
+  const int nLevelScale = 1 << level;
+  const double root[2] = {(cx + 0.5) * nLevelScale - 0.5, (cy + 0.5) * nLevelScale - 0.5};
+  const double at[3][2] = {{root[0], root[1]}, {root[0] + nLevelScale, root[1]}, {root[0], root[1] + nLevelScale}};
+  double ray[3][3];
+  for (int k = 0; k < 3; k++) {
+    double u[2]; cam_unproject(cam, at[k], u);
+    ray[k][0] = u[0]; ray[k][1] = u[1]; ray[k][2] = 1.0;
+    double nn = ray[k][0] * ray[k][0]; nn += ray[k][1] * ray[k][1]; nn += ray[k][2] * ray[k][2];
+    const double nrm = sqrt(nn); for (int q = 0; q < 3; q++) ray[k][q] /= nrm;
+  }
+  double pc[3]; se3_apply(S, world3, pc);
+  const double nrmz[3] = {0, 0, -1};
+  auto dot3 = [](const double* a, const double* b) { double s = a[0] * b[0]; s += a[1] * b[1]; s += a[2] * b[2]; return s; };
+  const double dCamHeight = fabs(dot3(pc, nrmz));
+  double on[3][3];
+  for (int k = 0; k < 3; k++) { const double rate = fabs(dot3(ray[k], nrmz)); for (int q = 0; q < 3; q++) on[k][q] = ray[k][q] * dCamHeight / rate; }
+  const SE3 Sinv = se3_inverse(S);
+  for (int k = 1; k < 3; k++) { double d[3]; for (int q = 0; q < 3; q++) d[q] = on[k][q] - on[0][q]; mat3_mul_vec(Sinv.R, d, out15 + 6 + 3 * k); }
+  for (int k = 0; k < 3; k++) for (int q = 0; q < 3; q++) out15[3 * k + q] = ray[k][q];
+}
+
 // ---- SE3
 void orc_se3_exp(const double* mu6, double* pose12) { se3_to12(se3_exp(mu6), pose12); }
 void orc_se3_ln(const double* pose12, double* mu6) { se3_ln(se3_from12(pose12), mu6); }

@@ -46,3 +46,74 @@ def two_keyframe_scene(n0=500, n1=400):
     merged = synth.SyntheticMap(**{k: np.concatenate([getattr(smap0, k), getattr(smap1, k)]) for k in names})
     src_kf = np.concatenate([np.zeros(smap0.n, dtype=np.int32), np.ones(smap1.n, dtype=np.int32)])
     return cam, [f0, f1], [synth.IDENTITY_POSE, pose1], merged, src_kf
+
+
+# ---- map files: an independent restatement of the layout documented in visualslam_android_b200/csrc/mapfile.cu --------------------
+MAPFILE_MAGIC = b"VSLMAP\x00\x01"
+
+
+def _fnv1a64(data: bytes) -> int:
+    # FNV-1a is byte-serial; vectorise with the closed form over 8-bit lanes is not possible, so keep the files in the tests small.
+    h = 1469598103934665603
+    for b in data:
+        h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+def _pad8(buf: bytearray):
+    while len(buf) % 8:
+        buf.append(0)
+
+
+def mapfile_pack(width, height, cam13, keyframes, points, reloc):
+    """keyframes: list of (id, registered_index, HxW uint8); points: dict world/right/down (n,3) f64, ircenter (n,2), srclevel, srckf i32;
+    reloc: (ids int32[n], poses f64[n,12])."""
+    import struct
+    n = len(points["srclevel"])
+    out = bytearray()
+    out += MAPFILE_MAGIC + struct.pack("<IIiiiiii", 1, 168, width, height, n, len(keyframes), len(reloc[0]), 0)
+    out += np.asarray(cam13, dtype="<f8").tobytes() + bytes(24)
+    assert len(out) == 168
+    for kid, reg, img in keyframes:
+        out += struct.pack("<ii", kid, reg) + np.ascontiguousarray(img, dtype=np.uint8).tobytes()
+        _pad8(out)
+    if n:
+        for k in ("world", "right", "down"):
+            out += np.ascontiguousarray(points[k], dtype="<f8").tobytes()
+        for k in ("ircenter", "srclevel", "srckf"):
+            out += np.ascontiguousarray(points[k], dtype="<i4").tobytes()
+        _pad8(out)
+    out += np.ascontiguousarray(reloc[0], dtype="<i4").tobytes()
+    _pad8(out)
+    out += np.ascontiguousarray(reloc[1], dtype="<f8").tobytes()
+    out += struct.pack("<Q", _fnv1a64(bytes(out)))
+    return bytes(out)
+
+
+def mapfile_unpack(data: bytes):
+    import struct
+    assert data[:8] == MAPFILE_MAGIC
+    ver, hb, w, h, n, nkf, nrel, _ = struct.unpack_from("<IIiiiiii", data, 8)
+    assert (ver, hb) == (1, 168)
+    cam13 = np.frombuffer(data, dtype="<f8", count=13, offset=40)
+    pos = 168
+    kfs = []
+    for _k in range(nkf):
+        kid, reg = struct.unpack_from("<ii", data, pos); pos += 8
+        kfs.append((kid, reg, np.frombuffer(data, dtype=np.uint8, count=w * h, offset=pos).reshape(h, w))); pos += w * h
+        pos += -pos % 8
+    pts = {}
+    if n:
+        for k in ("world", "right", "down"):
+            pts[k] = np.frombuffer(data, dtype="<f8", count=3 * n, offset=pos).reshape(n, 3); pos += 24 * n
+        pts["ircenter"] = np.frombuffer(data, dtype="<i4", count=2 * n, offset=pos).reshape(n, 2); pos += 8 * n
+        for k in ("srclevel", "srckf"):
+            pts[k] = np.frombuffer(data, dtype="<i4", count=n, offset=pos); pos += 4 * n
+        pos += -pos % 8
+    rid = np.frombuffer(data, dtype="<i4", count=nrel, offset=pos); pos += 4 * nrel
+    pos += -pos % 8
+    rpose = np.frombuffer(data, dtype="<f8", count=12 * nrel, offset=pos).reshape(nrel, 12); pos += 96 * nrel
+    (chk,) = struct.unpack_from("<Q", data, pos)
+    assert pos + 8 == len(data), "trailing bytes"
+    assert chk == _fnv1a64(data[:pos]), "checksum"
+    return dict(width=w, height=h, cam13=cam13, keyframes=kfs, points=pts, reloc=(rid, rpose))

@@ -1,6 +1,6 @@
 // Test driver for include/vslam_b200_shell.hpp: runs the reference-shaped C++ API (KeyFrame, Tracker, MiniPatch, PatchFinder) on a
 // scene file written by tests/test_gpu_shell.py and prints the results as text; the Python side compares them with the oracle.
-//   shell_driver <scene.bin> trails|track|stages|mapsearch
+//   shell_driver <scene.bin> trails|track|stages|mapsearch [map file to write, mapsearch only]
 // scene.bin: int32 W,H,N,F; double params5[5]; u8 src[W*H]; double world[3N], right[3N], down[3N]; int32 irCenter[2N]; int32 level[N];
 //            double pose0[12]; u8 frames[F][W*H]
 #include <cstdio>
@@ -93,6 +93,19 @@ int main(int argc, char** argv) {
         const int na = ms.AddPointsEpipolar(0, eye, 1.0, 0.3, tracker.mCurrentKF, start, l, cands[l], meas, found);
         printf("epipolar %d %d of %d\n", l, na, (int)cands[l].size());
         for (size_t i = 0; i < cands[l].size(); i++) if (found[i]) printf("e %d %d %d %.17g %.17g\n", l, (int)cands[l][i](0), (int)cands[l][i](1), meas[i].v2RootPos(0), meas[i].v2RootPos(1));
+        std::vector<MapSearch::NewMapPoint> np; std::vector<int> from;
+        ms.MakeEpipolarPoints(eye, start, l, cands[l], meas, found, np, from);
+        for (size_t k = 0; k < np.size(); k++)
+          printf("p %d %d %d %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n", l, (int)np[k].irCenter(0), (int)np[k].irCenter(1), np[k].v3WorldPos(0), np[k].v3WorldPos(1), np[k].v3WorldPos(2),
+                 np[k].v3PixelRight_W(0), np[k].v3PixelRight_W(1), np[k].v3PixelRight_W(2), np[k].v3PixelDown_W(0), np[k].v3PixelDown_W(1), np[k].v3PixelDown_W(2));
+      }
+      if (argc > 3) {   // map file round trip through the shell: save, load into a second context, compare what it reports
+        ctx.SaveMap(argv[3]);
+        vslam_map_file_info_t info;
+        if (vslam_map_file_info(argv[3], &info) != VSLAM_OK) return 4;
+        Context other(W, H, 1, N > 0 ? N : 1);
+        other.LoadMap(argv[3]);
+        printf("mapfile %d %d %d %d\n", info.n_points, info.n_keyframes, info.n_reloc_keyframes, other.MapSize());
       }
       return 0;
     }

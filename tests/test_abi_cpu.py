@@ -111,3 +111,31 @@ def test_header_is_plain_c(tmp_path):
     assert run.returncode == (0 if torch.cuda.is_available() else 3), run.stdout
     if run.returncode == 3:
         assert "no CUDA device" in run.stdout
+
+
+def test_map_file_header_is_readable_without_a_gpu(tmp_path):
+    """vslam_map_file_info is host-only: it parses a file written by the tests' independent restatement of the layout
+    (tests/common.py mapfile_pack) and rejects files with a wrong magic / version or a short header."""
+    import common
+    from visualslam_android_b200 import api
+    rs = np.random.RandomState(3)
+    W, H, n = 64, 32, 5
+    cam13 = rs.rand(13)
+    pts = dict(world=rs.randn(n, 3), right=rs.randn(n, 3), down=rs.randn(n, 3), ircenter=rs.randint(0, 30, (n, 2)), srclevel=rs.randint(0, 4, n), srckf=np.zeros(n, dtype=np.int32))
+    kfs = [(0, 0, rs.randint(0, 255, (H, W)).astype(np.uint8)), (2, -1, rs.randint(0, 255, (H, W)).astype(np.uint8))]
+    blob = common.mapfile_pack(W, H, cam13, kfs, pts, (np.array([0], dtype=np.int32), rs.randn(1, 12)))
+    back = common.mapfile_unpack(blob)
+    assert np.array_equal(back["points"]["world"], pts["world"]) and back["keyframes"][1][0] == 2 and np.array_equal(back["keyframes"][1][2], kfs[1][2])
+    path = tmp_path / "m.vsmap"
+    path.write_bytes(blob)
+    info = api.map_file_info(path)
+    assert (info["width"], info["height"], info["n_points"], info["n_keyframes"], info["n_reloc_keyframes"]) == (W, H, n, 2, 1)
+    assert np.array_equal(info["cam13"], cam13)
+    for bad in (b"NOTAMAP!" + blob[8:], blob[:8] + b"\x02\x00\x00\x00" + blob[12:], blob[:100]):
+        path.write_bytes(bad)
+        with pytest.raises(api.VslamError) as e:
+            api.map_file_info(path)
+        assert e.value.code == api.E_INVALID
+    with pytest.raises(api.VslamError) as e:
+        api.map_file_info(tmp_path / "does_not_exist")
+    assert e.value.code == api.E_IO

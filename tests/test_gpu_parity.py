@@ -641,6 +641,58 @@ def test_epipolar_search_matches_the_oracle(P):
     ctx.close()
 
 
+def test_epipolar_new_points_are_triangulated_and_trackable():
+    """f3 tail (jni/MapMaker.cc:646-690): candidates found by the epipolar search become map points -- world position by
+    MapMaker::ReprojectPoint (restated with LAPACK's SVD in oracle/oraclebind.py; 1e-9 relative, the 4x4 SVD being third-party
+    arithmetic), patch-source fields + RefreshPixelVectors against the restatement that tests/test_oracle_vs_ref.py pins bit for bit
+    (1e-12: host arithmetic, same operations) -- and a map made ONLY of those new points tracks a third frame."""
+    from oracle import oraclebind
+    cam, f0, smap = common.scene()
+    src_pose = synth.se3_exp(np.array([0.02, -0.01, 0.03, 0.01, 0.02, -0.01]))
+    rel = synth.se3_exp(np.array([0.12, 0.03, 0.02, 0.01, -0.03, 0.02]))
+    f0s = synth.render_frame(common.texture(), cam, src_pose)
+    tgt_pose = rel @ np.vstack([src_pose, [0, 0, 0, 1]])
+    f1 = synth.render_frame(common.texture(), cam, tgt_pose)
+    ctx = _ctx(cam, f0s, smap)
+    ctx.make_keyframe_lite(f0s); ctx.make_keyframe_rest(0)
+    cands = [ctx.candidates(0, l)[0] for l in range(4)]
+    ctx.make_keyframe_lite(f1)
+    cam13 = np.ascontiguousarray(cam.scalars(), dtype=np.float64)
+    new = [[] for _ in range(5)]
+    for level in range(4):
+        xy = cands[level]
+        found, pos, _, _ = ctx.epipolar_search(0, 0, level, xy, src_pose, tgt_pose, 1.0, 0.3, 0.1)
+        sel = np.nonzero(found)[0]
+        world, right, down, irc, lvl = ctx.epipolar_make_points(level, xy[sel], pos[sel], src_pose, tgt_pose)
+        assert np.array_equal(irc, xy[sel]) and np.all(lvl == level)
+        for j in range(0, len(sel), max(1, len(sel) // 40)):
+            k = sel[j]
+            root = (xy[k] + 0.5) * (1 << level) - 0.5
+            ow_ = oraclebind.triangulate(cam13, src_pose, tgt_pose, root, pos[k])
+            assert np.abs(world[j] - ow_).max() <= 1e-9 * max(1.0, np.abs(ow_).max()), (level, k, world[j], ow_)
+            fields = oraclebind.epipolar_point_fields(cam13, src_pose, level, xy[k, 0], xy[k, 1], world[j])
+            assert np.abs(right[j] - fields[3]).max() <= 1e-12 and np.abs(down[j] - fields[4]).max() <= 1e-12, (level, k)
+        in_src = world @ src_pose[:, :3].T + src_pose[:, 3]
+        good = np.abs(in_src[:, 2] - np.median(in_src[:, 2])) < 0.1      # drop gross mismatches, as the bundle adjuster's outlier handling would
+        for a, v in zip(new, (world[good], right[good], down[good], irc[good], lvl[good])):
+            a.append(v)
+    world, right, down, irc, lvl = [np.concatenate(a) for a in new]
+    assert len(world) > 150
+    ctx.close()
+    # a fresh tracker whose whole map is the new points (source keyframe = f0s at src_pose) follows the camera to a third view
+    from visualslam_android_b200 import api
+    ctx = api.Context(cam.width, cam.height, n_streams=1, max_points=len(world))
+    ctx.set_camera(cam.scalars()); ctx.upload_source_keyframe(f0s)
+    ctx.set_map(world, right, down, irc, lvl)
+    third = synth.se3_exp(np.array([0.02, 0.01, 0.005, 0.003, -0.008, 0.005])) @ np.vstack([src_pose, [0, 0, 0, 1]])
+    ctx.set_pose(0, src_pose)
+    ctx.track_frame(synth.render_frame(common.texture(), cam, third)[None])
+    att, fnd, q, lost, dc = ctx.counters(0)
+    assert q == 2 and fnd.sum() > 0.6 * att.sum() and att.sum() > 100, (att, fnd, q)
+    assert np.abs(ctx.get_pose(0) - third).max() < 0.01, ctx.get_pose(0) - third
+    ctx.close()
+
+
 def test_track_frame_relocalises_lost_streams():
     """f4: the lost branch of Tracker::TrackFrame on the device (k_relocalise: Relocaliser::AttemptRecovery + Tracker::AttemptRecovery,
     then TrackMap with the doubled coarse stage and AssessTrackingQuality in the same frame).  Two streams see different sequences
@@ -879,3 +931,107 @@ def test_track_frame_random_configurations_from_identical_state(seed):
             assert np.array_equal(a, oa) and np.array_equal(f, of) and (q, lost, dc) == (oq, olost, odc), (seed, case, k, n_points, P, sbi, speed)
             assert np.abs(ctx.get_pose(0) - ow.get_pose()).max() <= 1e-7, (seed, case, k, n_points, P, sbi, speed)
         ctx.close()
+
+
+def test_map_file_round_trip_restart_and_text_export(tmp_path):
+    """f4 on-disk format: a context saves its map (camera, two source keyframes, points, relocaliser registration); the file matches the
+    documented layout byte for byte (tests/common.py restates it independently, checksum included); a fresh context that loads it
+    tracks the same frames to bit-identical poses and relocalises identically; corrupt / truncated / mismatching files are refused
+    with the context untouched; a file produced by the independent writer loads too; the text export has the reference's dump layout."""
+    from visualslam_android_b200 import api
+    cam, kf_frames, kf_poses, smap, src_kf = common.two_keyframe_scene()
+    sbi_cam = synth.Camera(cam.width // 16, cam.height // 16).scalars()
+
+    def fresh(**kw):
+        c = api.Context(cam.width, cam.height, n_streams=2, max_points=kw.pop("max_points", smap.n), max_source_keyframes=kw.pop("max_source_keyframes", 3), **kw)
+        return c
+    a = fresh()
+    a.set_camera(cam.scalars()); a.enable_sbi(sbi_cam)
+    a.upload_source_keyframe(kf_frames[0], 0); a.upload_source_keyframe(kf_frames[1], 2)          # ids need not be dense
+    kf_ids = np.where(src_kf == 0, 0, 2).astype(np.int32)
+    a.set_map(smap.world, smap.pix_right_w, smap.pix_down_w, smap.ir_center, smap.src_level, kf_ids)
+    a.set_reloc_keyframes([2, 0], np.stack([kf_poses[1], kf_poses[0]]))
+    path = tmp_path / "scene.vsmap"
+    a.save_map_file(path)
+    info = api.map_file_info(path)
+    assert (info["n_points"], info["n_keyframes"], info["n_reloc_keyframes"]) == (smap.n, 2, 2)
+    blob = path.read_bytes()
+    got = common.mapfile_unpack(blob)                                                              # asserts the checksum and the exact length
+    assert np.array_equal(got["cam13"], np.asarray(cam.scalars(), dtype=np.float64))
+    assert [(k, r) for k, r, _ in got["keyframes"]] == [(0, 1), (2, 0)]
+    assert np.array_equal(got["keyframes"][0][2], kf_frames[0]) and np.array_equal(got["keyframes"][1][2], kf_frames[1])
+    p = got["points"]
+    assert np.array_equal(p["world"], smap.world) and np.array_equal(p["right"], smap.pix_right_w) and np.array_equal(p["down"], smap.pix_down_w)
+    assert np.array_equal(p["ircenter"], smap.ir_center) and np.array_equal(p["srclevel"], smap.src_level) and np.array_equal(p["srckf"], kf_ids)
+    assert np.array_equal(got["reloc"][0], [2, 0]) and np.array_equal(got["reloc"][1], np.stack([kf_poses[1], kf_poses[0]]).reshape(2, 12))
+    # the independent writer produces the same bytes from the same content
+    again = common.mapfile_pack(cam.width, cam.height, cam.scalars(), got["keyframes"], p, got["reloc"])
+    assert again == blob
+
+    # refused files leave the target context untouched: b has no map yet and must still have none afterwards
+    b = fresh(); b.enable_sbi(sbi_cam)
+    bad = tmp_path / "bad.vsmap"
+    for data, code in ((blob[:200000] + bytes([blob[200000] ^ 1]) + blob[200001:], api.E_IO), (blob[:-9], api.E_IO), (blob[:len(blob) // 2], api.E_IO), (blob + b"\0", api.E_IO)):
+        bad.write_bytes(data)
+        with pytest.raises(api.VslamError) as e:
+            b.load_map_file(bad, api.MAP_LOAD_CAMERA | api.MAP_LOAD_RELOC)
+        assert e.value.code == code
+    small = api.Context(320, 240, n_streams=1, max_points=smap.n, max_source_keyframes=3)
+    with pytest.raises(api.VslamError) as e:
+        small.load_map_file(path)
+    assert e.value.code == api.E_INVALID and "image size" in str(e.value)
+    small.close()
+    for kw in (dict(max_points=smap.n - 1), dict(max_source_keyframes=2)):                         # keyframe id 2 needs 3 slots
+        c = fresh(**kw)
+        with pytest.raises(api.VslamError) as e:
+            c.load_map_file(path)
+        assert e.value.code == api.E_CAPACITY
+        c.close()
+    nosbi = fresh()
+    with pytest.raises(api.VslamError) as e:
+        nosbi.load_map_file(path, api.MAP_LOAD_RELOC)
+    assert e.value.code == api.E_INVALID
+    nosbi.close()
+    b.set_camera(cam.scalars())
+    first = common.frame_at(cam, np.array(synth.CONFIG1_TWIST) * 0.2)[0]
+    b.track_frame(np.stack([first, first]))
+    assert b.counters(0)[0].sum() == 0                                                             # nothing attempted: still no map
+
+    # restart: load into b (and the independent writer's file into c), then the same frames give the same bits
+    b.close(); b = fresh(); b.enable_sbi(sbi_cam)
+    b.load_map_file(path, api.MAP_LOAD_CAMERA | api.MAP_LOAD_RELOC)
+    other = tmp_path / "other.vsmap"; other.write_bytes(again)
+    c = fresh(); c.enable_sbi(sbi_cam); c.load_map_file(other, api.MAP_LOAD_CAMERA | api.MAP_LOAD_RELOC)
+    rs = np.random.RandomState(11)
+    noise = lambda: rs.randint(0, 255, kf_frames[0].shape).astype(np.uint8)
+    tw1 = np.array([0.10, 0.02, 0.01, 0.01, -0.04, 0.05])
+    seq = [first, common.frame_at(cam, np.array(synth.CONFIG1_TWIST) * 0.4)[0]] + [noise() for _ in range(4)] + [common.frame_at(cam, tw1 + np.array([0.004, -0.003, 0.002, 0.01, 0.008, -0.012]))[0],
+                                                                                                   common.frame_at(cam, tw1 + np.array([0.006, -0.002, 0.002, 0.012, 0.006, -0.01]))[0]]
+    for k, fr in enumerate(seq):
+        frames = np.stack([fr, seq[0] if k % 2 else fr])
+        for x in (a, b, c):
+            x.track_frame(frames)
+        for s in range(2):
+            assert np.array_equal(a.get_pose(s), b.get_pose(s)) and np.array_equal(a.get_pose(s), c.get_pose(s)), (k, s)
+            ca, cb = a.counters(s), b.counters(s)
+            assert np.array_equal(ca[0], cb[0]) and np.array_equal(ca[1], cb[1]) and ca[2:] == cb[2:], (k, s)
+            assert a.reloc_info(s) == b.reloc_info(s) == c.reloc_info(s), (k, s)
+    assert a.reloc_info(0)[2] >= 1 and a.reloc_info(0)[0] == 0                                     # recovered against registration index 0 = keyframe id 2
+    assert a.counters(0)[1].sum() > 100
+
+    # text export in the layout of the reference's SaveMap dump
+    out = tmp_path / "dump"
+    b.export_map_text(out)
+    lines = (out / "map.dump").read_text().split("\n")
+    assert lines[-1] == "" and len(lines) == 3 * smap.n + 1
+    for i in (0, 1, smap.n // 2, smap.n - 1):
+        x, y, zl = lines[3 * i], lines[3 * i + 1], lines[3 * i + 2]
+        z, lvl = zl.rsplit("  ", 1)
+        assert len(x) == len(y) == len(z)                                                          # Eigen aligns the column
+        assert [float(x), float(y), float(z)] == [float("%g" % v) for v in smap.world[i]] and int(lvl) == smap.src_level[i]
+    for k, pose in enumerate([kf_poses[1], kf_poses[0]]):
+        rows = (out / "keyframes" / f"{k}.info").read_text().split("\n")
+        assert rows[3:] == ["", ""]
+        assert np.array_equal(np.array([[float(v) for v in r.split(" ")] for r in rows[:3]]), np.array([[float("%g" % v) for v in r] for r in np.asarray(pose).reshape(3, 4)]))
+    for x in (a, b, c):
+        x.close()

@@ -43,8 +43,8 @@ def _write_scene(path, cam, f0, smap, pose0, frames):
             f.write(np.ascontiguousarray(fr, dtype=np.uint8).tobytes())
 
 
-def _run(driver, scene, mode):
-    r = subprocess.run([driver, scene, mode], capture_output=True, text=True, timeout=600)
+def _run(driver, scene, mode, *extra):
+    r = subprocess.run([driver, scene, mode, *extra], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, (r.returncode, r.stderr[-2000:])
     return r.stdout.splitlines()
 
@@ -170,7 +170,7 @@ def test_shell_mapmaker_searches_match_the_oracle(driver, tmp_path):
     f1, pose1 = common.frame_at(cam, tw)
     scene = str(tmp_path / "mapsearch.bin")
     _write_scene(scene, cam, f0, smap, pose1, [f1])
-    out = _run(driver, scene, "mapsearch")
+    out = _run(driver, scene, "mapsearch", str(tmp_path / "shell.vsmap"))
     ow = oraclebind.OrcWorld(cam, f0, smap)
     ow.make_current_kf(f1); ow.set_pose(pose1)
     idx = np.arange(smap.n, dtype=np.int32)
@@ -201,3 +201,20 @@ def test_shell_mapmaker_searches_match_the_oracle(driver, tmp_path):
         assert int(hdr[2]) == nf and int(hdr[4]) == len(xy)
         total += nf
     assert total > 100
+    # the new map points of the converged candidates (MapMaker::AddPointEpipolar's tail) and the map file round trip
+    cam13 = np.ascontiguousarray(cam.scalars(), dtype=np.float64)
+    found_at = {(int(w[1]), int(w[2]), int(w[3])): (float(w[4]), float(w[5])) for w in e_lines}
+    p_lines = [l.split() for l in out if l.startswith("p ")]
+    assert len(p_lines) == total
+    for w in p_lines[::7]:
+        level, cx, cy = int(w[1]), int(w[2]), int(w[3])
+        vals = np.array([float(v) for v in w[4:]]).reshape(3, 3)
+        root = (np.array([cx, cy]) + 0.5) * (1 << level) - 0.5
+        world = oraclebind.triangulate(cam13, synth.IDENTITY_POSE, pose1, root, np.array(found_at[(level, cx, cy)]))
+        assert np.abs(vals[0] - world).max() <= 1e-9 * max(1.0, np.abs(world).max())
+        fields = oraclebind.epipolar_point_fields(cam13, synth.IDENTITY_POSE, level, cx, cy, vals[0])
+        assert np.abs(vals[1] - fields[3]).max() <= 1e-12 and np.abs(vals[2] - fields[4]).max() <= 1e-12
+    mf = [l.split() for l in out if l.startswith("mapfile")][0]
+    assert [int(v) for v in mf[1:]] == [smap.n, 1, 0, smap.n]
+    back = common.mapfile_unpack((tmp_path / "shell.vsmap").read_bytes())
+    assert np.array_equal(back["keyframes"][0][2], f0) and np.array_equal(back["points"]["world"], smap.world)

@@ -451,3 +451,39 @@ def test_track_frame_with_sbi_is_the_reference_trackframe():
         assert np.array_equal(rv, ov), k
         assert np.array_equal(rw.get_pose(), ow.get_pose()), k
         assert all(np.array_equal(a, b) if isinstance(a, np.ndarray) else a == b for a, b in zip(rw.counters(), ow.counters())), k
+
+
+def test_epipolar_new_point_fields_and_triangulation():
+    """f3 tail: the patch-source fields + MapPoint::RefreshPixelVectors of a point created by AddPointEpipolar (jni/MapMaker.cc:655-684),
+    computed by the reference's MapPoint / ATANCamera objects, against the restatement, bit for bit; and the restated triangulation
+    (MapMaker::ReprojectPoint; Eigen's SVD is absent, LAPACK's stands in) recovers the synthetic scene's plane within noise."""
+    cam, f0, smap, rw, ow = _worlds()
+    tw = np.array([0.12, 0.03, 0.02, 0.01, -0.03, 0.02])
+    f1, pose1 = common.frame_at(cam, tw)
+    rk0 = refbind.RefKeyFrame().make_lite(f0); rk0.make_rest()
+    rk1 = refbind.RefKeyFrame().make_lite(f1)
+    ok0 = oraclebind.OrcKeyFrame().make_lite(f0); ok0.make_rest()
+    cam13 = np.ascontiguousarray(cam.scalars(), dtype=np.float64)
+    src_pose = synth.se3_exp(np.array([0.02, -0.01, 0.03, 0.01, 0.02, -0.01]))       # a non-identity source pose exercises the rotations
+    tgt_pose = pose1 @ np.vstack([src_pose, [0, 0, 0, 1]])
+    sp = np.ascontiguousarray(src_pose, dtype=np.float64).reshape(12); tp = np.ascontiguousarray(tgt_pose, dtype=np.float64).reshape(12)
+    rs = np.random.RandomState(2)
+    checked = depth_ok = 0
+    for level in range(4):
+        xy, _ = ok0.candidates(level)
+        for k in range(0, len(xy), max(1, len(xy) // 25)):
+            ro, rp = np.zeros(3, dtype=np.int32), np.zeros(2)
+            rw.L.ref_epipolar_search(rw.tracker, rk0.h, rk1.h, sp, tp, 1.0, 0.3, 0.1, level, k, ro, rp)
+            if not ro[0]:
+                continue
+            root = (xy[k] + 0.5) * (1 << level) - 0.5
+            world = oraclebind.triangulate(cam13, src_pose, tgt_pose, root, rp)
+            in_src = src_pose[:, :3] @ world + src_pose[:, 3]
+            depth_ok += abs(in_src[2] - 1.0) < 0.05                                     # the synthetic scene is the plane z = 1 of the first camera
+            for w in (world, rs.randn(3) + np.array([0, 0, 3.0])):
+                ref15 = np.zeros(15)
+                rw.L.ref_epipolar_point_fields(rw.tracker, rk0.h, sp, level, k, np.ascontiguousarray(w), ref15)
+                got = oraclebind.epipolar_point_fields(cam13, src_pose, level, xy[k, 0], xy[k, 1], w)
+                assert np.array_equal(got.reshape(15), ref15), (level, k)
+            checked += 1
+    assert checked > 30 and depth_ok > 0.9 * checked

@@ -14,7 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libvslam_b200.so")
 LEVELS = 4
 
-OK, E_INVALID, E_CUDA, E_CAPACITY, E_NO_DEVICE = 0, -1, -2, -3, -4
+OK, E_INVALID, E_CUDA, E_CAPACITY, E_NO_DEVICE, E_IO = 0, -1, -2, -3, -4, -5
+MAP_LOAD_CAMERA, MAP_LOAD_RELOC = 1, 2
 
 
 class VslamError(RuntimeError):
@@ -27,6 +28,11 @@ class Config(C.Structure):
     _fields_ = [("device", C.c_int), ("width", C.c_int), ("height", C.c_int), ("n_streams", C.c_int), ("max_points", C.c_int),
                 ("patch_size", C.c_int), ("max_source_keyframes", C.c_int), ("max_corner_frac", C.c_float), ("cuda_stream", C.c_void_p),
                 ("truncate_error", C.c_int), ("rand_seed", C.c_uint)]
+
+
+class MapFileInfo(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("n_points", C.c_int), ("n_keyframes", C.c_int), ("n_reloc_keyframes", C.c_int),
+                ("cam13", C.c_double * 13)]
 
 
 class Params(C.Structure):
@@ -45,9 +51,20 @@ ABI_SYMBOLS = [
     "vslam_get_point_states", "vslam_get_point_template", "vslam_get_point_counts", "vslam_get_updates", "vslam_get_zmssd_evals",
     "vslam_project_all", "vslam_set_point_projection", "vslam_set_lists", "vslam_clear_counters", "vslam_search_for_points", "vslam_refind", "vslam_get_refind_results", "vslam_epipolar_search", "vslam_project_and_derivs", "vslam_calc_jacobians",
     "vslam_calc_pose_update", "vslam_track_map", "vslam_track_frame", "vslam_track_frame_dev", "vslam_track_frame_async", "vslam_wait_step", "vslam_debug_atan", "vslam_debug_dp4a_peak", "vslam_kernel_launches", "vslam_set_timing", "vslam_get_stage_times",
+    "vslam_epipolar_make_points", "vslam_map_file_info", "vslam_save_map_file", "vslam_load_map_file", "vslam_export_map_text",
 ]
 
 _lib = None
+
+
+def map_file_info(path):
+    """Header of a map file (needs no GPU): dict with width, height, n_points, n_keyframes, n_reloc_keyframes, cam13."""
+    info = MapFileInfo()
+    rc = load().vslam_map_file_info(os.fsencode(path), C.byref(info))
+    if rc:
+        raise VslamError(rc, "not a readable vslam map file: " + str(path))
+    return dict(width=info.width, height=info.height, n_points=info.n_points, n_keyframes=info.n_keyframes,
+                n_reloc_keyframes=info.n_reloc_keyframes, cam13=np.array(info.cam13[:], dtype=np.float64))
 
 
 def load():
@@ -97,6 +114,11 @@ def load():
     sig("vslam_set_motion", i, vp, i, vp, d, d, d)
     sig("vslam_reset_stream", i, vp, i)
     sig("vslam_set_reloc_keyframes", i, vp, i, vp, vp)
+    sig("vslam_epipolar_make_points", i, vp, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp)
+    sig("vslam_map_file_info", i, C.c_char_p, C.POINTER(MapFileInfo))
+    sig("vslam_save_map_file", i, vp, C.c_char_p)
+    sig("vslam_load_map_file", i, vp, C.c_char_p, i)
+    sig("vslam_export_map_text", i, vp, C.c_char_p)
     sig("vslam_get_reloc_info", i, vp, i, pi, pd, pi, pi)
     sig("vslam_set_lost", i, vp, i, i, i)
     sig("vslam_get_motion", i, vp, i, vp, pd, pd, pd)
@@ -328,6 +350,18 @@ class Context:
         ids = np.ascontiguousarray(src_kf_ids, dtype=np.int32); p = np.ascontiguousarray(poses, dtype=np.float64).reshape(len(ids), 12)
         self._ck(self.L.vslam_set_reloc_keyframes(self.h, len(ids), ids.ctypes.data, p.ctypes.data))
 
+    def save_map_file(self, path):
+        """Camera + source keyframes + map points + relocaliser registration of this context -> one checksummed file."""
+        self._ck(self.L.vslam_save_map_file(self.h, os.fsencode(path)))
+
+    def load_map_file(self, path, flags=0):
+        """Load a map file (verified before anything is touched); flags: MAP_LOAD_CAMERA | MAP_LOAD_RELOC."""
+        self._ck(self.L.vslam_load_map_file(self.h, os.fsencode(path), flags))
+
+    def export_map_text(self, directory):
+        """The reference's SaveMap debug dump layout (jni/MapMaker.cc:1254-1297): map.dump + keyframes/<i>.info."""
+        self._ck(self.L.vslam_export_map_text(self.h, os.fsencode(directory)))
+
     def reloc_info(self, s):
         b, sc, n, r = C.c_int(), C.c_double(), C.c_int(), C.c_int()
         self._ck(self.L.vslam_get_reloc_info(self.h, s, C.byref(b), C.byref(sc), C.byref(n), C.byref(r)))
@@ -439,6 +473,18 @@ class Context:
         self._ck(self.L.vslam_epipolar_search(self.h, s, src_kf, level, n, xy.ctypes.data, sp.ctypes.data, tp.ctypes.data, depth_mean, depth_sigma, wiggle_scale,
                                               found.ctypes.data, pos.ctypes.data, bi.ctypes.data, bs.ctypes.data))
         return found[:n], pos[:n], bi[:n], bs[:n]
+
+    def epipolar_make_points(self, level, cand_xy, found_pos, src_pose, tgt_pose):
+        """Tail of MapMaker::AddPointEpipolar for converged candidates: triangulated world points and the vslam_set_map fields."""
+        xy = np.ascontiguousarray(cand_xy, dtype=np.int32).reshape(-1, 2); n = len(xy)
+        fp = np.ascontiguousarray(found_pos, dtype=np.float64).reshape(-1, 2)
+        assert len(fp) == n
+        sp = np.ascontiguousarray(src_pose, dtype=np.float64).reshape(12); tp = np.ascontiguousarray(tgt_pose, dtype=np.float64).reshape(12)
+        m = max(n, 1)
+        world = np.zeros((m, 3)); right = np.zeros((m, 3)); down = np.zeros((m, 3)); irc = np.zeros((m, 2), dtype=np.int32); lvl = np.zeros(m, dtype=np.int32)
+        self._ck(self.L.vslam_epipolar_make_points(self.h, level, n, xy.ctypes.data, fp.ctypes.data, sp.ctypes.data, tp.ctypes.data,
+                                                   world.ctypes.data, right.ctypes.data, down.ctypes.data, irc.ctypes.data, lvl.ctypes.data))
+        return world[:n], right[:n], down[:n], irc[:n], lvl[:n]
 
     def project_and_derivs(self, only_found=True):
         self._ck(self.L.vslam_project_and_derivs(self.h, int(only_found)))

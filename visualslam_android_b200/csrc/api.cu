@@ -103,7 +103,7 @@ int vslam_create(const vslam_config* cfg, vslam_ctx** out) {
   vslam_ctx* ctx = new (std::nothrow) vslam_ctx();
   if (!ctx) { g_create_error = "out of host memory"; return VSLAM_E_INVALID; }
   ctx->cfg = *cfg; vslam_default_params(&ctx->params);
-  ctx->S = cfg->n_streams; ctx->N = cfg->max_points; ctx->P = cfg->patch_size; ctx->launches = 0; ctx->n_src = cfg->max_source_keyframes;
+  ctx->S = cfg->n_streams; ctx->N = cfg->max_points; ctx->P = cfg->patch_size; ctx->launches = 0; ctx->n_src = cfg->max_source_keyframes; ctx->src_have.assign(ctx->n_src, 0);
   ctx->reloc_n = 0; ctx->reloc_tmpl = nullptr; ctx->reloc_jac = nullptr; ctx->reloc_tmp = nullptr; ctx->reloc_small = nullptr; ctx->reloc_pose = nullptr; ctx->reloc_scores = nullptr;
   ctx->unproj_lut = nullptr; ctx->unproj_ok = false; for (int g = 0; g < VS_MAX_GROUPS; g++) { ctx->side_stream[g] = nullptr; ctx->group_stream[g] = nullptr; ctx->ev_fork[g] = nullptr; ctx->ev_join[g] = nullptr; ctx->ev_end[g] = nullptr; }
   ctx->ev_begin = nullptr; ctx->cur_s0 = 0; ctx->cur_cnt = cfg->n_streams; ctx->cur_group = 0; ctx->scratch_host = nullptr; ctx->scratch_host_bytes = 0; ctx->timing = false; ctx->ev_used = 0; ctx->l0_alt = nullptr; ctx->copy_stream = nullptr; ctx->step = 0; ctx->pipe_ready = false; ctx->status_pin = nullptr;
@@ -289,7 +289,7 @@ int vslam_set_reloc_keyframes(vslam_ctx* ctx, int n, const int32_t* src_kf_ids, 
   VS_CUDA(cudaStreamSynchronize(ctx->stream));
   cudaFree(ctx->reloc_tmpl); cudaFree(ctx->reloc_jac); cudaFree(ctx->reloc_tmp); cudaFree(ctx->reloc_small); cudaFree(ctx->reloc_pose); cudaFree(ctx->reloc_scores);
   ctx->reloc_tmpl = nullptr; ctx->reloc_jac = nullptr; ctx->reloc_tmp = nullptr; ctx->reloc_small = nullptr; ctx->reloc_pose = nullptr; ctx->reloc_scores = nullptr;
-  ctx->reloc_n = 0;
+  ctx->reloc_n = 0; ctx->reloc_ids.clear(); ctx->reloc_poses_host.clear();
   if (n == 0) return VSLAM_OK;
   const size_t px = (size_t)(ctx->lev[3].w / 2) * (ctx->lev[3].h / 2);
   {   // cv::getGaussianKernel(17, 2.5, CV_32F) as the stand-in computes it (host exp, float taps)
@@ -307,6 +307,7 @@ int vslam_set_reloc_keyframes(vslam_ctx* ctx, int n, const int32_t* src_kf_ids, 
   if (!rc && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = VSLAM_E_CUDA;
   cudaFree(ids);
   if (rc) { ctx->reloc_n = 0; ctx->err = "vslam_set_reloc_keyframes: CUDA error"; }
+  else { ctx->reloc_ids.assign(src_kf_ids, src_kf_ids + n); ctx->reloc_poses_host.assign(poses12, poses12 + 12 * (size_t)n); }
   return rc;
 }
 int vslam_set_camera(vslam_ctx* ctx, const double* c) {
@@ -326,6 +327,7 @@ int vslam_upload_source_keyframe(vslam_ctx* ctx, int kf, const uint8_t* gray, in
   int rc = vs_launch_source_pyramid(ctx, kf);
   if (rc) return rc;
   VS_CUDA(cudaStreamSynchronize(ctx->stream));   // the host buffer is only read during this call
+  ctx->src_have[kf] = 1;
   return VSLAM_OK;
 }
 
@@ -847,6 +849,76 @@ int vslam_epipolar_search(vslam_ctx* ctx, int stream, int src_kf, int level, int
   cudaFree(cd); cudaFree(oi); cudaFree(op);
   if (e != cudaSuccess) { ctx->err = std::string("vslam_epipolar_search: ") + cudaGetErrorString(e); return VSLAM_E_CUDA; }
   for (int k = 0; k < n; k++) { found[k] = hi[3 * k]; if (best_corner) best_corner[k] = hi[3 * k + 1]; if (best_zmssd) best_zmssd[k] = hi[3 * k + 2]; }
+  return VSLAM_OK;
+}
+
+// ---- MapMaker::AddPointEpipolar, the new map point (jni/MapMaker.cc:646-690) -------------------------------------------------------
+namespace {
+// Right singular vector of the smallest singular value of a 4x4 matrix, by one-sided (Hestenes) Jacobi rotations of its columns.
+// The reference asks Eigen's JacobiSVD for the same vector (jni/MapMaker.cc:191-192); Eigen is not part of the reference tree, the
+// vector is unique up to sign, and the sign cancels in the dehomogenisation that follows.
+void smallest_right_singular_vector4(const double A[4][4], double v[4]) {
+  double U[4][4], V[4][4];
+  for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) { U[i][j] = A[i][j]; V[i][j] = i == j ? 1.0 : 0.0; }
+  for (int sweep = 0; sweep < 60; sweep++) {
+    double off = 0.0;
+    for (int p = 0; p < 3; p++) for (int q = p + 1; q < 4; q++) {
+      double alpha = 0, beta = 0, gamma = 0;
+      for (int i = 0; i < 4; i++) { alpha += U[i][p] * U[i][p]; beta += U[i][q] * U[i][q]; gamma += U[i][p] * U[i][q]; }
+      if (gamma == 0.0) continue;
+      off = std::max(off, fabs(gamma) / sqrt(alpha * beta));
+      const double zeta = (beta - alpha) / (2.0 * gamma);
+      const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+      const double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
+      for (int i = 0; i < 4; i++) {
+        const double up = U[i][p], uq = U[i][q]; U[i][p] = c * up - sn * uq; U[i][q] = sn * up + c * uq;
+        const double vp = V[i][p], vq = V[i][q]; V[i][p] = c * vp - sn * vq; V[i][q] = sn * vp + c * vq;
+      }
+    }
+    if (off < 1e-15) break;
+  }
+  int best = 0; double bn = -1;
+  for (int j = 0; j < 4; j++) { double nn = 0; for (int i = 0; i < 4; i++) nn += U[i][j] * U[i][j]; if (bn < 0 || nn < bn) { bn = nn; best = j; } }
+  for (int i = 0; i < 4; i++) v[i] = V[i][best];
+}
+void unit3(double* v) { double nn = v[0] * v[0]; nn += v[1] * v[1]; nn += v[2] * v[2]; const double nrm = sqrt(nn); v[0] /= nrm; v[1] /= nrm; v[2] /= nrm; }
+}  // namespace
+
+int vslam_epipolar_make_points(vslam_ctx* ctx, int level, int n, const int32_t* cand_xy, const double* found_pos2, const double* src_pose, const double* tgt_pose,
+                               double* world3, double* pixel_right3, double* pixel_down3, int32_t* ir_center2, int32_t* src_level) {
+  if (!ctx || n < 0 || level < 0 || level >= VS_LEVELS || !cand_xy || !found_pos2 || !src_pose || !tgt_pose || !world3 || !pixel_right3 || !pixel_down3 || !ir_center2 || !src_level) {
+    if (ctx) ctx->err = "bad argument"; return VSLAM_E_INVALID; }
+  const CamDev& cam = ctx->cam;
+  const int scale = 1 << level;
+  // se3AfromB = kSrc.se3CfromW * kTarget.se3CfromW.inverse(): R = Rs Rt^T, t = ts - R tt
+  double P[12];
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { double a = src_pose[4 * i] * tgt_pose[4 * j]; a += src_pose[4 * i + 1] * tgt_pose[4 * j + 1]; a += src_pose[4 * i + 2] * tgt_pose[4 * j + 2]; P[4 * i + j] = a; }
+  for (int i = 0; i < 3; i++) { double a = P[4 * i] * tgt_pose[3]; a += P[4 * i + 1] * tgt_pose[7]; a += P[4 * i + 2] * tgt_pose[11]; P[4 * i + 3] = src_pose[4 * i + 3] - a; }
+  for (int k = 0; k < n; k++) {
+    const double root[2] = {((double)cand_xy[2 * k] + 0.5) * scale - 0.5, ((double)cand_xy[2 * k + 1] + 0.5) * scale - 0.5};   // LevelZeroPos
+    double a2[2], b2[2]; host_unproject(cam, root[0], root[1], a2); host_unproject(cam, found_pos2[2 * k], found_pos2[2 * k + 1], b2);
+    // MapMaker::ReprojectPoint (jni/MapMaker.cc:176-200): the point, in the target camera's frame, that best satisfies both viewing rays
+    double A[4][4] = {{-1.0, 0.0, b2[0], 0.0}, {0.0, -1.0, b2[1], 0.0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
+    for (int j = 0; j < 4; j++) { A[2][j] = a2[0] * P[8 + j] - P[j]; A[3][j] = a2[1] * P[8 + j] - P[4 + j]; }
+    double v4[4]; smallest_right_singular_vector4(A, v4);
+    if (v4[3] == 0.0) v4[3] = 0.00001;
+    const double in_target[3] = {v4[0] / v4[3], v4[1] / v4[3], v4[2] / v4[3]};
+    // v3New = kTarget.se3CfromW.inverse() * point = Rt^T (point - tt)
+    const double d[3] = {in_target[0] - tgt_pose[3], in_target[1] - tgt_pose[7], in_target[2] - tgt_pose[11]};
+    double* w = world3 + 3 * k; rot_t_vec(tgt_pose, d, w);
+    // patch source fields (jni/MapMaker.cc:655-684) and MapPoint::RefreshPixelVectors (jni/MapPoint.cc:4-29) with the plane normal (0,0,-1)
+    double uc[2], ur[2], ud[2];
+    host_unproject(cam, root[0], root[1], uc); host_unproject(cam, root[0] + scale, root[1], ur); host_unproject(cam, root[0], root[1] + scale, ud);
+    double c3[3] = {uc[0], uc[1], 1.0}, r3[3] = {ur[0], ur[1], 1.0}, d3[3] = {ud[0], ud[1], 1.0};
+    unit3(c3); unit3(d3); unit3(r3);
+    double pc[3]; rot_vec(src_pose, w, pc); pc[0] += src_pose[3]; pc[1] += src_pose[7]; pc[2] += src_pose[11];
+    const double height = fabs(pc[2]);                       // |v3PlanePoint_C . (0,0,-1)|
+    double con[3], ron[3], don[3];
+    for (int q = 0; q < 3; q++) { con[q] = c3[q] * height / fabs(c3[2]); ron[q] = r3[q] * height / fabs(r3[2]); don[q] = d3[q] * height / fabs(d3[2]); }
+    const double dr[3] = {ron[0] - con[0], ron[1] - con[1], ron[2] - con[2]}, dd[3] = {don[0] - con[0], don[1] - con[1], don[2] - con[2]};
+    rot_t_vec(src_pose, dr, pixel_right3 + 3 * k); rot_t_vec(src_pose, dd, pixel_down3 + 3 * k);
+    ir_center2[2 * k] = cand_xy[2 * k]; ir_center2[2 * k + 1] = cand_xy[2 * k + 1]; src_level[k] = level;
+  }
   return VSLAM_OK;
 }
 

@@ -111,6 +111,8 @@ struct vslam_ctx {
   CamDev cam; CamDev* cam_dev;
   MapDev map; MapDev* map_dev;
   SourceKF src; SourceKF* src_dev; int n_src;
+  std::vector<char> src_have;    // [n_src] which source keyframes have been uploaded (map files, mapfile.cu)
+  std::vector<int> reloc_ids; std::vector<double> reloc_poses_host;   // host copy of the vslam_set_reloc_keyframes registration
   PointState ps; PointState* ps_dev;
   StreamState* ss;               // [S] device
   int* lists;                    // [S][list_cap] iteration / search lists
