@@ -1035,3 +1035,9 @@ def test_map_file_round_trip_restart_and_text_export(tmp_path):
         assert np.array_equal(np.array([[float(v) for v in r.split(" ")] for r in rows[:3]]), np.array([[float("%g" % v) for v in r] for r in np.asarray(pose).reshape(3, 4)]))
     for x in (a, b, c):
         x.close()
+
+
+def test_every_kernel_on_a_ragged_configuration():
+    """tests/sanitizer_case.py (352x272, 3 streams: every kernel and entry point once, with plausibility checks) as a plain test."""
+    import sanitizer_case
+    sanitizer_case.main()
