@@ -20,6 +20,16 @@ from visualslam_android_b200 import synth  # noqa: E402
 W, H, N = 320, 240, 300
 
 
+def _initialised_only(ints, dbl):
+    """The reference leaves TrackerData fields of points outside the potentially-visible set (and v2Found of points not found)
+    uninitialised: zero them so that the fixture is reproducible byte for byte.  The test compares the initialised entries only."""
+    ints, dbl = ints.copy(), dbl.copy()
+    pvs = ints[:, 1] >= 0
+    ints[~pvs, 2:] = 0
+    dbl[~(pvs & (ints[:, 3] == 1))] = 0.0
+    return ints, dbl
+
+
 def main():
     cam = synth.Camera(W, H)
     tex = synth.make_texture(1024)
@@ -52,7 +62,7 @@ def main():
     rw.set_pose(start); out["start_pose"] = start
     rw.L.ref_tracker_track_map(rw.tracker)
     ints, dbl = rw.point_states()
-    out["B_ints"], out["B_dbl"] = ints[:, [0, 1, 2, 3, 5]], dbl[:, [0, 1, 2, 3, 15]]
+    out["B_ints"], out["B_dbl"] = _initialised_only(ints[:, [0, 1, 2, 3, 5]], dbl[:, [0, 1, 2, 3, 15]])
     a, f, q, lost, dc = rw.counters()
     out["B_counters"] = np.concatenate([a, f, [dc]]); out["B_pose"] = rw.get_pose()
     f2 = synth.render_frame(tex, cam, synth.se3_exp(np.array(synth.CONFIG1_TWIST) * 0.9))
@@ -61,7 +71,7 @@ def main():
     rw.L.ref_tracker_set_velocity(rw.tracker, np.zeros(6), 0.05)
     rw.L.ref_tracker_track_map(rw.tracker)
     ints, dbl = rw.point_states()
-    out["C_ints"], out["C_dbl"] = ints[:, [0, 1, 2, 3, 5]], dbl[:, [0, 1, 2, 3, 15]]
+    out["C_ints"], out["C_dbl"] = _initialised_only(ints[:, [0, 1, 2, 3, 5]], dbl[:, [0, 1, 2, 3, 15]])
     a, f, q, lost, dc = rw.counters()
     out["C_counters"] = np.concatenate([a, f, [dc]]); out["C_pose"] = rw.get_pose()
     cnt = np.zeros((smap.n, 2), dtype=np.int32)
@@ -127,6 +137,26 @@ def main():
             rw.L.ref_epipolar_search(rw.tracker, rk0.h, rk3.h, eye, p3, 1.0, 0.3, 0.1, level, k, ro, rp)
             rows.append([level, xy[k, 0], xy[k, 1], ro[0], ro[1], ro[2], rp[0], rp[1]])
     out["G_rows"] = np.array(rows, dtype=np.float64)
+    # new-point fields of the converged candidates' source pixels (oracle/ref_harness.cc ref_epipolar_point_fields: the reference's MapPoint / ATANCamera
+    # objects), for the triangulated position and, to exercise the rotations, with the source keyframe at a non-identity pose
+    src_pose = synth.se3_exp(np.array([0.02, -0.01, 0.03, 0.01, 0.02, -0.01]))
+    sp = np.ascontiguousarray(src_pose, dtype=np.float64).reshape(12)
+    cam13 = np.ascontiguousarray(cam.scalars(), dtype=np.float64)
+    frows = []
+    for level in range(4):
+        xy, _ = rk0.candidates(level)
+        for k in range(0, len(xy), max(1, len(xy) // 40)):
+            r = [q for q in rows if q[0] == level and q[1] == xy[k, 0] and q[2] == xy[k, 1]][0]
+            if not r[3]:
+                continue
+            root = (xy[k] + 0.5) * (1 << level) - 0.5
+            ux, uy = cam.unproject(root[0], root[1])
+            world = np.array([float(ux), float(uy), 1.0]) * (1.0 + 0.01 * level)       # about where the synthetic plane is
+            for pose12, w in ((eye, world), (sp, world + np.array([0.05, -0.02, 0.4]))):
+                ref15 = np.zeros(15)
+                rw.L.ref_epipolar_point_fields(rw.tracker, rk0.h, pose12, level, k, np.ascontiguousarray(w), ref15)
+                frows.append(np.concatenate([[level, xy[k, 0], xy[k, 1]], pose12, w, ref15]))
+    out["G_fields"] = np.array(frows, dtype=np.float64)
 
     # --- case H: the unmodified Tracker::TrackFrame through a loss of tracking and two relocalisations (three map keyframes).
     # Noise frames are regenerated by the test from RandomState(5); rendered frames are stored.

@@ -112,6 +112,17 @@ def test_epipolar_search_golden():
     assert nfound > 20
 
 
+def test_epipolar_new_point_fields_golden():
+    """Patch-source rays and MapPoint::RefreshPixelVectors of points created from converged epipolar matches (tail of
+    MapMaker::AddPointEpipolar, jni/MapMaker.cc:655-684; jni/MapPoint.cc:4-29) as the reference's objects computed them."""
+    cam13 = np.ascontiguousarray(synth.Camera(W, H).scalars(), dtype=np.float64)
+    rows = G["G_fields"]
+    assert len(rows) > 40
+    for row in rows:
+        got = oraclebind.epipolar_point_fields(cam13, row[3:15], int(row[0]), int(row[1]), int(row[2]), row[15:18])
+        assert np.array_equal(got.reshape(15), row[18:33]), row[:3]
+
+
 def test_track_frame_loss_and_relocalisation_golden():
     """The unmodified Tracker::TrackFrame of the reference through a loss of tracking and two relocalisations (Relocaliser over three
     map keyframes): pose and counters after every frame, bit for bit."""
