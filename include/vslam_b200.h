@@ -26,6 +26,9 @@
  *                                     lost streams: AttemptRecovery :167-180 with vslam_set_reloc_keyframes)
  *   vslam_set_reloc_keyframes        Relocaliser::AttemptRecovery / ScoreKFs       jni/Relocaliser.cc:17-58
  *   vslam_reset_stream               Tracker::Reset                               jni/Tracker.cc:45-60
+ *   vslam_set_keyframe_policy        MapMaker::NeedNewKeyFrame / IsDistanceToNearestKeyFrameExcessive as called from TrackFrame
+ *                                    jni/Tracker.cc:127-132,869-871; jni/MapMaker.cc:705-773,1098-1101
+ *   vslam_add_keyframe_from_stream   Tracker::AddNewKeyFrame + MapMaker::AddKeyFrame jni/Tracker.cc:823-827, jni/MapMaker.cc:470-478
  *   vslam_save_map_file / _load_     (no reference counterpart: the reference keeps its map in memory only)
  *   vslam_export_map_text            MapMaker::GUICommandHandler("SaveMap") dump  jni/MapMaker.cc:1254-1297
  *   vslam_refind                     MapMaker::ReFind_Common                      jni/MapMaker.cc:967-1036
@@ -165,6 +168,20 @@ int vslam_get_sbi_rotation(vslam_ctx* ctx, int stream, double* rot6);
 int vslam_set_reloc_keyframes(vslam_ctx* ctx, int n, const int32_t* src_kf_ids, const double* poses12);
 int vslam_get_reloc_info(vslam_ctx* ctx, int stream, int* best_keyframe, double* score, int* n_recoveries, int* recovered_last_frame);
 int vslam_set_lost(vslam_ctx* ctx, int stream, int lost_frames, int quality);
+
+/* ---- Keyframe hand-off: the two MapMaker heuristics Tracker::TrackFrame consults, evaluated on the device over the registered
+ * keyframes' poses (vslam_set_reloc_keyframes / vslam_add_keyframe_from_stream), so that a host MapMaker only hears about streams
+ * that need a keyframe.  With the policy enabled every vslam_track_frame* also (1) turns quality DODGY into BAD when the camera is
+ * further than 10 x wiggle_scale from the nearest keyframe (MapMaker::IsDistanceToNearestKeyFrameExcessive, jni/MapMaker.cc:1098-1101,
+ * called at jni/Tracker.cc:869-871) and (2) raises a keyframe request when quality is GOOD, the distance to the nearest keyframe
+ * divided by the scene depth exceeds max_kf_dist_wiggle_mult x wiggle_scale_depth_normalized (MapMaker::NeedNewKeyFrame,
+ * jni/MapMaker.cc:763-773; the reference's values: 0.2, mdWiggleScaleDepthNormalized) and more than min_frames_between (20) frames
+ * passed since the stream's last keyframe (jni/Tracker.cc:127-129).  The remaining term, QueueSize() < 3, is the caller's.
+ * vslam_add_keyframe_from_stream = Tracker::AddNewKeyFrame + MapMaker::AddKeyFrame (jni/Tracker.cc:823-827, jni/MapMaker.cc:470-478):
+ * the stream's current keyframe is copied device-to-device into source keyframe slot kf_id at the stream's pose and registered. */
+int vslam_set_keyframe_policy(vslam_ctx* ctx, int enable, double wiggle_scale, double wiggle_scale_depth_normalized, double max_kf_dist_wiggle_mult, int min_frames_between);
+int vslam_get_keyframe_requests(vslam_ctx* ctx, int32_t* request /* [n_streams] */, int32_t* closest_keyframe /* may be NULL */, double* distance /* may be NULL */);
+int vslam_add_keyframe_from_stream(vslam_ctx* ctx, int stream, int kf_id);
 
 /* ---- Map files: camera + source keyframes (level-0 images) + map points + relocaliser registration in one checksummed binary file
  * (layout in csrc/mapfile.cu), so a service can restart or several processes / GPUs can serve streams of one map.

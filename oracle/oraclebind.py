@@ -103,6 +103,8 @@ def lib():
     sig("orc_tracker_search_for_points", i, vp, _i32p, i, i, i)
     sig("orc_tracker_clear_counters", None, vp)
     sig("orc_epipolar_search", None, vp, vp, vp, _f64p, _f64p, d, d, d, i, i, i, _i32p, _f64p, C.c_void_p)
+    sig("orc_tracker_set_keyframe_policy", None, vp, i, d, d, d, i)
+    sig("orc_tracker_keyframe_info", None, vp, pi, pi, pi, pi)
     sig("orc_epipolar_point_fields", None, _f64p, _f64p, i, i, i, _f64p, _f64p)
     sig("orc_tracker_refind", None, vp, _i32p, i, i, i, i, _i32p, _f64p)
     sig("orc_tracker_calc_jacobians", None, vp, _i32p, i)

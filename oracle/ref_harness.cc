@@ -55,9 +55,46 @@ MapMaker::MapMaker(Map& m, const ATANCamera& cam) : mMap(m), mCamera(cam) {
 MapMaker::~MapMaker() {}
 void MapMaker::RequestReset() { mbResetDone = true; mbResetRequested = false; }  // map is filled by the harness after construction
 bool MapMaker::ResetDone() { return mbResetDone; }
-bool MapMaker::NeedNewKeyFrame(KeyFrame&) { return false; }
-void MapMaker::AddKeyFrame(KeyFrame&) {}
-bool MapMaker::IsDistanceToNearestKeyFrameExcessive(KeyFrame&) { return false; }
+// The three MapMaker heuristics Tracker::TrackFrame consults.  Off (the default) they answer like an idle MapMaker and the pins of the
+// tracking path see no keyframe traffic.  Switched on by ref_set_keyframe_policy they are driven on the reference's objects: camera
+// positions through mySE3::inverse / get_translation, distances through Eigen-shim dot products, thresholds from the MapMaker members
+// the reference compares against (written from the description of jni/MapMaker.cc:705-773,1098-1101 in SURVEY.md / DESIGN.md).
+// A keyframe the tracker hands over joins the map at once, as if the MapMaker thread had emptied its queue before the next frame:
+// KeyFrame::operator= copy, then the relocaliser's SmallBlurryImage as KeyFrame::MakeKeyFrame_Rest would build it.
+namespace {
+bool g_keyframe_policy = false; double g_need_mult = 0.2; int g_keyframes_added = 0;
+double nearest_keyframe_distance(Map& map, KeyFrame& current) {
+  const Eigen::Vector3d here = current.se3CfromW.inverse().get_translation();
+  double best = 9999999999.9;
+  for (unsigned int i = 0; i < map.vpKeyFrames.size(); i++) {
+    if (map.vpKeyFrames[i] == &current) continue;
+    const Eigen::Vector3d there = map.vpKeyFrames[i]->se3CfromW.inverse().get_translation();
+    const Eigen::Vector3d step = there - here;
+    const double d = sqrt(step.dot(step));
+    if (d < best) best = d;
+  }
+  return best;
+}
+}  // namespace
+bool MapMaker::NeedNewKeyFrame(KeyFrame& current) {
+  if (!g_keyframe_policy) return false;
+  double d = nearest_keyframe_distance(mMap, current);
+  d *= (1.0 / current.dSceneDepthMean);
+  return d > g_need_mult * mdWiggleScaleDepthNormalized;
+}
+void MapMaker::AddKeyFrame(KeyFrame& k) {
+  if (!g_keyframe_policy) return;
+  KeyFrame* copy = new KeyFrame;
+  *copy = k;
+  copy->pSBI = new SmallBlurryImage(*copy);
+  copy->pSBI->MakeJacs();
+  mMap.vpKeyFrames.push_back(copy);
+  g_keyframes_added++;
+}
+bool MapMaker::IsDistanceToNearestKeyFrameExcessive(KeyFrame& current) {
+  if (!g_keyframe_policy) return false;
+  return nearest_keyframe_distance(mMap, current) > mdWiggleScale * 10.0;
+}
 bool MapMaker::InitFromStereo(KeyFrame&, KeyFrame&, vector<pair<Eigen::Vector2d, Eigen::Vector2d> >&, mySE3&) { return false; }
 void MapMaker::run() {}
 
@@ -501,6 +538,15 @@ void ref_epipolar_point_fields(void* t, void* source_kf, const double* src_pose1
   point.RefreshPixelVectors();
   for (int k = 0; k < 3; k++) for (int q = 0; q < 3; q++) out15[3 * k + q] = (*rays[k])(q);
   for (int q = 0; q < 3; q++) { out15[9 + q] = point.v3PixelRight_W(q); out15[12 + q] = point.v3PixelDown_W(q); }
+}
+void ref_set_keyframe_policy(void* t, int enable, double wiggle, double wiggle_dn, double mult) {
+  MapMaker* mm = ((RefTracker*)t)->mm;
+  g_keyframe_policy = enable != 0; g_need_mult = mult;
+  mm->mdWiggleScale = wiggle; mm->mdWiggleScaleDepthNormalized = enable ? wiggle_dn : 1e30;
+}
+void ref_keyframe_info(void* t, int* n_keyframes, int* added_total, int* n_frame, int* last_dropped) {
+  RefTracker* r = (RefTracker*)t;
+  *n_keyframes = (int)r->map->vpKeyFrames.size(); *added_total = g_keyframes_added; *n_frame = r->tr->mnFrame; *last_dropped = r->tr->mnLastKeyFrameDropped;
 }
 int ref_kf_num_candidates_l(void* kf, int l) { return (int)((KeyFrame*)kf)->aLevels[l].vCandidates.size(); }
 

@@ -101,6 +101,8 @@ def lib():
     sig("ref_tracker_track_frame", None, vp, _u8p, i, i, i)
     sig("ref_refind", None, vp, _i32p, i, i, i, _i32p, _f64p)
     sig("ref_epipolar_search", None, vp, vp, vp, _f64p, _f64p, d, d, d, i, i, _i32p, _f64p)
+    sig("ref_set_keyframe_policy", None, vp, i, d, d, d)
+    sig("ref_keyframe_info", None, vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int))
     sig("ref_epipolar_point_fields", None, vp, vp, _f64p, i, i, _f64p, _f64p)
     sig("ref_kf_num_candidates_l", i, vp, i)
     sig("ref_kf_make_sbi", None, vp)
@@ -248,6 +250,12 @@ class RefWorld:
         q, lost, dc = C.c_int(), C.c_int(), C.c_int()
         self.L.ref_tracker_counters(self.tracker, a, f, C.byref(q), C.byref(lost), C.byref(dc))
         return a, f, q.value, lost.value, dc.value
+
+    def message(self):
+        """Tracker::GetMessageForUser of the last frame."""
+        buf = C.create_string_buffer(1024)
+        self.L.ref_tracker_message(self.tracker, buf, 1024)
+        return buf.value.decode(errors="replace")
 
     def pixel_vectors(self):
         r = np.empty((self.n, 3))

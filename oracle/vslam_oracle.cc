@@ -868,6 +868,8 @@ struct OTracker {
   bool computeSBI, haveSBI; SBI sbiThis, sbiLast; Cam sbiCam; int nFrame;
   // Relocaliser (jni/Relocaliser.cc): the map keyframes' SmallBlurryImages (blur 2.5, with gradient images) and poses
   std::vector<SBI> relocSBI; std::vector<SE3> relocPose; int relocBest; double relocScore; int nRecoveries;
+  // keyframe hand-off (jni/Tracker.cc:127-132, :866-872): MapMaker's heuristics over the map keyframes (= relocPose), off by default
+  bool kfPolicy = false; double kfWiggle = 0.1, kfWiggleDN = 0.1, kfMult = 0.2; int kfMinFrames = 20, lastKeyFrameDropped = -20, kfAddedThisFrame = 0;
 };
 
 TData& ensure_td(OTracker& t, int i) {
@@ -1044,6 +1046,22 @@ void update_motion_model(OTracker& t) {
   t.msdScaledVel = sqrt(s);
 }
 // Tracker::AssessTrackingQuality (jni/Tracker.cc:832-878); MapMaker::IsDistanceToNearestKeyFrameExcessive is out of scope (false)
+// MapMaker::KeyFrameLinearDist (jni/MapMaker.cc:705-712) of the current keyframe (pose = the tracker's, jni/Tracker.cc:594) to each
+// map keyframe, minimum as MapMaker::ClosestKeyFrame takes it (jni/MapMaker.cc:736-754: strict <, first wins).
+double dist_to_nearest_keyframe(OTracker& t, int* closest) {
+  double dClosestDist = 9999999999.9; int nClosest = -1;
+  const SE3 cur = se3_inverse(t.pose);
+  for (size_t i = 0; i < t.relocPose.size(); i++) {
+    const SE3 kf = se3_inverse(t.relocPose[i]);
+    const double d[3] = {kf.t[0] - cur.t[0], kf.t[1] - cur.t[1], kf.t[2] - cur.t[2]};
+    double dd = d[0] * d[0]; dd += d[1] * d[1]; dd += d[2] * d[2];
+    const double dDist = sqrt(dd);
+    if (dDist < dClosestDist) { dClosestDist = dDist; nClosest = (int)i; }
+  }
+  if (closest) *closest = nClosest;
+  return dClosestDist;
+}
+
 void assess_tracking_quality(OTracker& t) {
   int nTotalAttempted = 0, nTotalFound = 0, nLargeAttempted = 0, nLargeFound = 0;
   for (int i = 0; i < LEVELS; i++) { nTotalAttempted += t.attempted[i]; nTotalFound += t.foundCnt[i]; if (i >= 2) { nLargeAttempted += t.attempted[i]; nLargeFound += t.foundCnt[i]; } }
@@ -1053,6 +1071,9 @@ void assess_tracking_quality(OTracker& t) {
     const double dLargeFracFound = (nLargeAttempted > 10) ? (double)nLargeFound / nLargeAttempted : dTotalFracFound;
     if (dTotalFracFound > 0.3) t.quality = 2; else if (dLargeFracFound < 0.13) t.quality = 0; else t.quality = 1;
   }
+  // jni/Tracker.cc:866-872: a DODGY tracker whose pose ran far away from every keyframe is BAD
+  // (MapMaker::IsDistanceToNearestKeyFrameExcessive, jni/MapMaker.cc:1098-1101: DistToNearestKeyFrame > mdWiggleScale * 10)
+  if (t.quality == 1 && t.kfPolicy && !t.relocPose.empty()) { if (dist_to_nearest_keyframe(t, 0) > t.kfWiggle * 10.0) t.quality = 0; }
   if (t.quality == 0) t.lostFrames++; else t.lostFrames = 0;
 }
 
@@ -1326,6 +1347,19 @@ void orc_tracker_track_frame(void* t_, const uint8_t* gray, int w, int h, int st
       se3_from_se2(se2, t->sbiCam, t->sbiThis.w, t->sbiThis.h, t->sbiRot);
     }
     apply_motion_model(*t); track_map(*t); update_motion_model(*t); assess_tracking_quality(*t);
+    // jni/Tracker.cc:127-132: heuristics to add a keyframe (MapMaker::NeedNewKeyFrame, jni/MapMaker.cc:763-773; the queue is always
+    // empty here: the keyframe joins the map at once)
+    t->kfAddedThisFrame = 0;
+    if (t->kfPolicy && !t->relocPose.empty() && t->quality == 2) {
+      double dDist = dist_to_nearest_keyframe(*t, 0);
+      dDist *= (1.0 / t->sceneDepthMean);
+      if (dDist > t->kfMult * t->kfWiggleDN && t->nFrame - t->lastKeyFrameDropped > t->kfMinFrames) {
+        // Tracker::AddNewKeyFrame (jni/Tracker.cc:823-827) -> MapMaker::AddKeyFrame copies mCurrentKF
+        SBI sb; sbi_make(sb, t->cur, 2.5); sbi_make_jacs(sb);
+        t->relocSBI.push_back(sb); t->relocPose.push_back(t->pose);
+        t->lastKeyFrameDropped = t->nFrame; t->kfAddedThisFrame = 1;
+      }
+    }
   } else if (!t->relocSBI.empty()) {   // jni/Tracker.cc:134-140: tracking lost -> relocalise against the map keyframes
     if (attempt_recovery(*t)) { track_map(*t); assess_tracking_quality(*t); }
   }
@@ -1335,6 +1369,12 @@ void orc_tracker_add_reloc_keyframe(void* t_, void* kf, const double* pose12) {
   OTracker* t = (OTracker*)t_;
   SBI s; sbi_make(s, *(OKeyFrame*)kf, 2.5); sbi_make_jacs(s);
   t->relocSBI.push_back(s); t->relocPose.push_back(se3_from12(pose12));
+}
+void orc_tracker_set_keyframe_policy(void* t_, int enable, double wiggle, double wiggle_dn, double mult, int min_frames) {
+  OTracker* t = (OTracker*)t_; t->kfPolicy = enable != 0; t->kfWiggle = wiggle; t->kfWiggleDN = wiggle_dn; t->kfMult = mult; t->kfMinFrames = min_frames;
+}
+void orc_tracker_keyframe_info(void* t_, int* n_keyframes, int* added_this_frame, int* n_frame, int* last_dropped) {
+  OTracker* t = (OTracker*)t_; *n_keyframes = (int)t->relocPose.size(); *added_this_frame = t->kfAddedThisFrame; *n_frame = t->nFrame; *last_dropped = t->lastKeyFrameDropped;
 }
 void orc_tracker_reloc_info(void* t_, int* best, double* score, int* n_recoveries) { OTracker* t = (OTracker*)t_; *best = t->relocBest; *score = t->relocScore; *n_recoveries = t->nRecoveries; }
 void orc_tracker_set_lost(void* t_, int lost_frames, int quality) { OTracker* t = (OTracker*)t_; t->lostFrames = lost_frames; t->quality = quality; }

@@ -5,6 +5,8 @@ found flags, counters.  Tolerance (written at each assert): FP64 geometry 1e-9 r
 (the contract is 1e-4), sub-pixel positions 1e-6 px.
 """
 import ctypes as C
+import os
+import tempfile
 
 import numpy as np
 import pytest
@@ -1041,3 +1043,88 @@ def test_every_kernel_on_a_ragged_configuration():
     """tests/sanitizer_case.py (352x272, 3 streams: every kernel and entry point once, with plausibility checks) as a plain test."""
     import sanitizer_case
     sanitizer_case.main()
+
+
+def test_track_frame_keyframe_handoff_on_device():
+    """jni/Tracker.cc:127-132,866-872 with the keyframe policy on: requests raised by the k_pose tail at the frames where the
+    restatement (pinned to the unmodified TrackFrame in tests/test_oracle_vs_ref.py) adds keyframes; vslam_add_keyframe_from_stream
+    (device-to-device copy of the stream's pyramid + relocaliser registration) makes a keyframe the stream later relocalises
+    against; DODGY -> BAD far away from every keyframe, DODGY kept with a roomy scale."""
+    from oracle import oraclebind
+    cam, f0, smap = common.scene()
+    sbi_cam = synth.Camera(cam.width // 16, cam.height // 16).scalars()
+    okf0 = oraclebind.OrcKeyFrame().make_lite(f0)
+
+    def pair(wiggle, wiggle_dn):
+        c = _ctx(cam, f0, smap, n_streams=1, max_source_keyframes=4)
+        c.enable_sbi(sbi_cam)
+        c.set_reloc_keyframes([0], synth.IDENTITY_POSE[None])
+        c.set_keyframe_policy(True, wiggle, wiggle_dn, 0.2, 20)
+        o = _orc(cam, f0, smap)
+        o.L.orc_tracker_enable_sbi(o.tracker, sbi_cam)
+        o.L.orc_tracker_add_reloc_keyframe(o.tracker, okf0.h, np.ascontiguousarray(synth.IDENTITY_POSE, dtype=np.float64).reshape(12))
+        o.L.orc_tracker_set_keyframe_policy(o.tracker, 1, wiggle, wiggle_dn, 0.2, 20)
+        return c, o
+    ctx, ow = pair(0.1, 0.1)
+    ctx0, ow0 = ctx, ow
+
+    def info():
+        v = [C.c_int() for _ in range(4)]
+        ow.L.orc_tracker_keyframe_info(ow.tracker, *[C.byref(x) for x in v])
+        return [x.value for x in v]
+
+    def both(fr, tag, noise=False, tol=1e-8, ctx=None, ow=None):
+        ctx = ctx or ctx0; ow = ow or ow0
+        fr = np.ascontiguousarray(fr)
+        ctx.track_frame(fr[None])
+        ow.L.orc_tracker_track_frame(ow.tracker, fr, cam.width, cam.height, cam.width)
+        a, f, q, lost, dc = ctx.counters(0); oa, of, oq, olost, odc = ow.counters()
+        assert (q, lost) == (oq, olost), (tag, q, oq, lost, olost)
+        if noise:      # a handful of chance matches on white noise: the (int) casts of the reference amplify 1e-13 differences; only BAD / lost must agree
+            return
+        assert np.abs(ctx.get_pose(0) - ow.get_pose()).max() <= tol, tag
+        assert np.array_equal(a, oa) and np.array_equal(f, of) and dc == odc, tag
+
+    step = np.array([0.004, 0.001, 0.0005, 0.0004, -0.0012, 0.0008])
+    rs = np.random.RandomState(9)
+    frames = [common.frame_at(cam, step * k)[0] for k in range(1, 31)]
+    frames += [rs.randint(0, 255, f0.shape).astype(np.uint8) for _ in range(4)]
+    frames += [common.frame_at(cam, step * 27.5)[0], common.frame_at(cam, step * 28.5)[0]]
+    added_at, next_id = [], 1
+    for k, fr in enumerate(frames):
+        both(fr, k, noise=30 <= k < 34)
+        req, closest, dist = ctx.keyframe_requests()
+        n_kf, oadd, oframe, olast = info()
+        assert bool(req[0]) == bool(oadd), (k, req, oadd, dist)
+        if req[0]:
+            ctx.add_keyframe_from_stream(0, next_id); next_id += 1; added_at.append(k + 1)
+            assert np.array_equal(ctx.keyframe_requests()[0], [0])
+    assert added_at == [6, 27]
+    best, score, nrec = C.c_int(), C.c_double(), C.c_int()
+    ow.L.orc_tracker_reloc_info(ow.tracker, C.byref(best), C.byref(score), C.byref(nrec))
+    gb, gs, gn, gr = ctx.reloc_info(0)
+    assert gn == nrec.value >= 1 and gb == best.value == 2 and abs(gs - score.value) <= 1e-6 * max(1.0, abs(score.value))
+    # the keyframe copied on the device is the frame the stream saw (frame 27), pyramid included
+    okf = oraclebind.OrcKeyFrame().make_lite(frames[26])
+    path = os.path.join(tempfile.mkdtemp(), "handoff.vsmap")
+    ctx.save_map_file(path)
+    saved = common.mapfile_unpack(open(path, "rb").read())
+    assert [k for k, _, _ in saved["keyframes"]] == [0, 1, 2] and np.array_equal(saved["keyframes"][2][2], frames[26])
+    assert np.array_equal(saved["reloc"][0], [0, 1, 2])
+    ctx.close()
+    # DODGY -> BAD far from every keyframe (tiny wiggle scale), DODGY stays DODGY with a roomy one; fresh trackers per case (a frame
+    # that is mostly noise leaves the two implementations in states that differ in the last bits, see `both`)
+    seen = kept = 0
+    for frac in (0.55, 0.65, 0.72, 0.8):
+        occ = common.frame_at(cam, step * 2.0)[0].copy()
+        occ[:int(cam.height * frac)] = rs.randint(0, 255, (int(cam.height * frac), cam.width))
+        for wiggle in (0.1, 1e-5):
+            c, o = pair(wiggle, 1e30)
+            both(common.frame_at(cam, step * 1.0)[0], ("good", frac, wiggle), ctx=c, ow=o)
+            both(occ, ("occluded", frac, wiggle), noise=True, ctx=c, ow=o)
+            a, f, q, lost, dc = c.counters(0)
+            dodgy_by_counts = f.sum() <= 0.3 * a.sum() and (f[2:].sum() >= 0.13 * a[2:].sum() if a[2:].sum() > 10 else f.sum() >= 0.13 * a.sum())
+            seen += bool(dodgy_by_counts and wiggle < 1e-3 and q == 0 and lost == 1)
+            kept += bool(dodgy_by_counts and wiggle > 1e-3 and q == 1 and lost == 0)
+            c.close()
+    assert seen >= 1 and kept >= 1

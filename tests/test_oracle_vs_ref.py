@@ -487,3 +487,77 @@ def test_epipolar_new_point_fields_and_triangulation():
                 assert np.array_equal(got.reshape(15), ref15), (level, k)
             checked += 1
     assert checked > 30 and depth_ok > 0.9 * checked
+
+
+def _kf_info(L, fn, tracker):
+    v = [C.c_int() for _ in range(4)]
+    getattr(L, fn)(tracker, *[C.byref(x) for x in v])
+    return [x.value for x in v]
+
+
+def test_track_frame_keyframe_handoff_heuristics():
+    """jni/Tracker.cc:127-132 and :866-872 of the UNMODIFIED Tracker::TrackFrame -- 'add a keyframe when tracking is GOOD, the camera
+    moved far enough from the nearest keyframe (relative to scene depth) and 20 frames passed', 'DODGY is BAD when the pose ran away
+    from every keyframe', mnFrame / mnLastKeyFrameDropped bookkeeping -- with the MapMaker side (NeedNewKeyFrame, AddKeyFrame,
+    IsDistanceToNearestKeyFrameExcessive) driven on the reference's objects, against the restatement: poses, counters, quality, the
+    frames at which keyframes are added, and a relocalisation against a keyframe added that way."""
+    cam, f0, smap, rw, ow = _worlds()
+    rw.L.ref_sbi_reset_size()
+    sbi_cam = synth.Camera(cam.width // 16, cam.height // 16).scalars()
+    ow.L.orc_tracker_enable_sbi(ow.tracker, sbi_cam)
+    rw.L.ref_kf_make_sbi(rw.src_kf.h)
+    okf0 = oraclebind.OrcKeyFrame().make_lite(f0)
+    ow.L.orc_tracker_add_reloc_keyframe(ow.tracker, okf0.h, np.ascontiguousarray(synth.IDENTITY_POSE, dtype=np.float64).reshape(12))
+    rw.set_pose(synth.IDENTITY_POSE); ow.set_pose(synth.IDENTITY_POSE)
+    rw.L.ref_srand(1)
+    try:
+        rw.L.ref_set_keyframe_policy(rw.tracker, 1, 0.1, 0.1, 0.2)
+        ow.L.orc_tracker_set_keyframe_policy(ow.tracker, 1, 0.1, 0.1, 0.2, 20)
+        base_added = _kf_info(rw.L, "ref_keyframe_info", rw.tracker)[1]
+        added_at = []
+        step = np.array([0.004, 0.001, 0.0005, 0.0004, -0.0012, 0.0008])
+        rs = np.random.RandomState(9)
+        frames = [common.frame_at(cam, step * k)[0] for k in range(1, 31)]
+        frames += [rs.randint(0, 255, f0.shape).astype(np.uint8) for _ in range(4)]                 # lose tracking ...
+        frames += [common.frame_at(cam, step * 27.5)[0], common.frame_at(cam, step * 28.5)[0]]       # ... and come back next to the last keyframe added
+        for k, fr in enumerate(frames):
+            fr = np.ascontiguousarray(fr)
+            rw.L.ref_tracker_track_frame(rw.tracker, fr, cam.width, cam.height, cam.width)
+            ow.L.orc_tracker_track_frame(ow.tracker, fr, cam.width, cam.height, cam.width)
+            assert np.array_equal(rw.get_pose(), ow.get_pose()), k
+            a, f, q, lost, dc = rw.counters(); oa, of, oq, olost, odc = ow.counters()
+            assert np.array_equal(a, oa) and np.array_equal(f, of) and (q, lost, dc) == (oq, olost, odc), k
+            rn, radd, rframe, rlast = _kf_info(rw.L, "ref_keyframe_info", rw.tracker)
+            on, oadd, oframe, olast = _kf_info(ow.L, "orc_tracker_keyframe_info", ow.tracker)
+            assert (rn, rframe, rlast) == (on, oframe, olast), (k, rn, on, rframe, oframe, rlast, olast)
+            if oadd:
+                added_at.append(k + 1)
+                assert "Adding key-frame" in rw.message()
+        assert added_at == [6, 27], added_at                     # 0.004/frame: first beyond 0.2 * 0.1 * depth at frame 6, then 21 frames later
+        assert _kf_info(rw.L, "ref_keyframe_info", rw.tracker)[1] - base_added == 2
+        best, score, nrec = C.c_int(), C.c_double(), C.c_int()
+        ow.L.orc_tracker_reloc_info(ow.tracker, C.byref(best), C.byref(score), C.byref(nrec))
+        assert nrec.value >= 1 and best.value == 2 and ow.counters()[2] == 2        # recovered against the keyframe added at frame 27
+        # DODGY -> BAD when the pose is far from every keyframe: the same partly occluded frame with a roomy and with a tiny wiggle scale
+        seen = 0
+        for frac in (0.55, 0.65, 0.72, 0.8):
+            occ = common.frame_at(cam, step * 29.0)[0].copy()
+            occ[:int(cam.height * frac)] = rs.randint(0, 255, (int(cam.height * frac), cam.width))
+            for wiggle in (0.1, 1e-5):
+                rw.L.ref_set_keyframe_policy(rw.tracker, 1, wiggle, 1e30, 0.2)
+                ow.L.orc_tracker_set_keyframe_policy(ow.tracker, 1, wiggle, 1e30, 0.2, 20)
+                good = common.frame_at(cam, step * 28.8)[0]
+                for fr in (good, occ):
+                    rw.L.ref_tracker_set_lost(rw.tracker, 0, 2); ow.L.orc_tracker_set_lost(ow.tracker, 0, 2) if fr is good else None
+                    fr = np.ascontiguousarray(fr)
+                    rw.L.ref_tracker_track_frame(rw.tracker, fr, cam.width, cam.height, cam.width)
+                    ow.L.orc_tracker_track_frame(ow.tracker, fr, cam.width, cam.height, cam.width)
+                    assert np.array_equal(rw.get_pose(), ow.get_pose()), (frac, wiggle)
+                    assert rw.counters()[2:4] == ow.counters()[2:4], (frac, wiggle, rw.counters(), ow.counters())
+                a, f, q, lost, dc = ow.counters()
+                tot = f.sum() / max(1, a.sum())
+                if tot <= 0.3 and wiggle < 1e-3 and q == 0 and lost == 1:
+                    seen += 1
+        assert seen >= 1, "no DODGY frame in the occlusion sweep"
+    finally:
+        rw.L.ref_set_keyframe_policy(rw.tracker, 0, 0.1, 0.1, 0.2)

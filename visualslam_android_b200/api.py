@@ -51,7 +51,7 @@ ABI_SYMBOLS = [
     "vslam_get_point_states", "vslam_get_point_template", "vslam_get_point_counts", "vslam_get_updates", "vslam_get_zmssd_evals",
     "vslam_project_all", "vslam_set_point_projection", "vslam_set_lists", "vslam_clear_counters", "vslam_search_for_points", "vslam_refind", "vslam_get_refind_results", "vslam_epipolar_search", "vslam_project_and_derivs", "vslam_calc_jacobians",
     "vslam_calc_pose_update", "vslam_track_map", "vslam_track_frame", "vslam_track_frame_dev", "vslam_track_frame_async", "vslam_wait_step", "vslam_debug_atan", "vslam_debug_dp4a_peak", "vslam_kernel_launches", "vslam_set_timing", "vslam_get_stage_times",
-    "vslam_epipolar_make_points", "vslam_map_file_info", "vslam_save_map_file", "vslam_load_map_file", "vslam_export_map_text",
+    "vslam_set_keyframe_policy", "vslam_get_keyframe_requests", "vslam_add_keyframe_from_stream", "vslam_epipolar_make_points", "vslam_map_file_info", "vslam_save_map_file", "vslam_load_map_file", "vslam_export_map_text",
 ]
 
 _lib = None
@@ -114,6 +114,9 @@ def load():
     sig("vslam_set_motion", i, vp, i, vp, d, d, d)
     sig("vslam_reset_stream", i, vp, i)
     sig("vslam_set_reloc_keyframes", i, vp, i, vp, vp)
+    sig("vslam_set_keyframe_policy", i, vp, i, d, d, d, i)
+    sig("vslam_get_keyframe_requests", i, vp, vp, vp, vp)
+    sig("vslam_add_keyframe_from_stream", i, vp, i, i)
     sig("vslam_epipolar_make_points", i, vp, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp)
     sig("vslam_map_file_info", i, C.c_char_p, C.POINTER(MapFileInfo))
     sig("vslam_save_map_file", i, vp, C.c_char_p)
@@ -349,6 +352,20 @@ class Context:
         """Relocaliser keyframes: ids of uploaded source keyframes and their poses (n x 3 x 4)."""
         ids = np.ascontiguousarray(src_kf_ids, dtype=np.int32); p = np.ascontiguousarray(poses, dtype=np.float64).reshape(len(ids), 12)
         self._ck(self.L.vslam_set_reloc_keyframes(self.h, len(ids), ids.ctypes.data, p.ctypes.data))
+
+    def set_keyframe_policy(self, enable=True, wiggle_scale=0.1, wiggle_scale_depth_normalized=0.1, max_kf_dist_wiggle_mult=0.2, min_frames_between=20):
+        """MapMaker::NeedNewKeyFrame / IsDistanceToNearestKeyFrameExcessive as Tracker::TrackFrame consults them, on the device."""
+        self._ck(self.L.vslam_set_keyframe_policy(self.h, int(enable), wiggle_scale, wiggle_scale_depth_normalized, max_kf_dist_wiggle_mult, min_frames_between))
+
+    def keyframe_requests(self):
+        """(request flag, index of the closest registered keyframe, distance to it) per stream after the last track_frame."""
+        r = np.zeros(self.S, dtype=np.int32); c = np.zeros(self.S, dtype=np.int32); dist = np.zeros(self.S)
+        self._ck(self.L.vslam_get_keyframe_requests(self.h, r.ctypes.data, c.ctypes.data, dist.ctypes.data))
+        return r, c, dist
+
+    def add_keyframe_from_stream(self, s, kf_id):
+        """Tracker::AddNewKeyFrame: the stream's current keyframe becomes source keyframe kf_id at the stream's pose (device copy)."""
+        self._ck(self.L.vslam_add_keyframe_from_stream(self.h, s, kf_id))
 
     def save_map_file(self, path):
         """Camera + source keyframes + map points + relocaliser registration of this context -> one checksummed file."""

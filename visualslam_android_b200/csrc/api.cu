@@ -105,6 +105,7 @@ int vslam_create(const vslam_config* cfg, vslam_ctx** out) {
   ctx->cfg = *cfg; vslam_default_params(&ctx->params);
   ctx->S = cfg->n_streams; ctx->N = cfg->max_points; ctx->P = cfg->patch_size; ctx->launches = 0; ctx->n_src = cfg->max_source_keyframes; ctx->src_have.assign(ctx->n_src, 0);
   ctx->reloc_n = 0; ctx->reloc_tmpl = nullptr; ctx->reloc_jac = nullptr; ctx->reloc_tmp = nullptr; ctx->reloc_small = nullptr; ctx->reloc_pose = nullptr; ctx->reloc_scores = nullptr;
+  ctx->kf_policy = false; ctx->kf_wiggle = 0.1; ctx->kf_wiggle_dn = 0.1; ctx->kf_mult = 0.2; ctx->kf_min_frames = 20;
   ctx->unproj_lut = nullptr; ctx->unproj_ok = false; for (int g = 0; g < VS_MAX_GROUPS; g++) { ctx->side_stream[g] = nullptr; ctx->group_stream[g] = nullptr; ctx->ev_fork[g] = nullptr; ctx->ev_join[g] = nullptr; ctx->ev_end[g] = nullptr; }
   ctx->ev_begin = nullptr; ctx->cur_s0 = 0; ctx->cur_cnt = cfg->n_streams; ctx->cur_group = 0; ctx->scratch_host = nullptr; ctx->scratch_host_bytes = 0; ctx->timing = false; ctx->ev_used = 0; ctx->l0_alt = nullptr; ctx->copy_stream = nullptr; ctx->step = 0; ctx->pipe_ready = false; ctx->status_pin = nullptr;
   ctx->rest_scores = nullptr; ctx->rest_max = nullptr; ctx->rest_cand = nullptr; ctx->rest_cand_score = nullptr; ctx->rest_counts = nullptr; ctx->rest_stream = -1;
@@ -170,6 +171,7 @@ int vslam_create(const vslam_config* cfg, vslam_ctx** out) {
       StreamState& st = h[s];
       st.pose[0] = st.pose[5] = st.pose[10] = 1.0; memcpy(st.start_pose, st.pose, sizeof(st.pose));
       st.depth_mean = 1.0; st.depth_sigma = 1.0; st.quality = 2;   // Tracker::Reset (jni/Tracker.cc:45-60)
+      st.frame_no = 0; st.last_kf_dropped = -20; st.kf_closest = -1;
       glibc_seed(cfg->rand_seed, st.rng_ring, &st.rng_f, &st.rng_b);
     }
     CK(cudaMemcpy(ctx->ss, h.data(), sizeof(StreamState) * S, cudaMemcpyHostToDevice));
@@ -581,6 +583,7 @@ int vslam_reset_stream(vslam_ctx* ctx, int s) {
   StreamState st; if ((rc = read_ss(ctx, s, &st))) return rc;
   st.did_coarse = 0; st.quality = 2; st.lost_frames = 0; st.msd_scaled_vel = 0.0; st.vel_mag = 0.0; st.depth_mean = 1.0; st.depth_sigma = 1.0;
   st.just_recovered = 0; st.n_updates = 0; st.try_coarse = 0; st.recovered = 0;
+  st.frame_no = 0; st.last_kf_dropped = -20; st.kf_request = 0; st.kf_closest = -1; st.kf_dist = 0.0;
   for (int k = 0; k < 6; k++) st.velocity[k] = 0.0;
   for (int l = 0; l < VS_LEVELS; l++) st.attempted[l] = st.found[l] = 0;
   return write_ss(ctx, s, &st);
@@ -592,6 +595,48 @@ int vslam_get_reloc_info(vslam_ctx* ctx, int s, int* best, double* score, int* n
   if (best) *best = st.reloc_best; if (score) *score = st.reloc_score; if (n_recoveries) *n_recoveries = st.n_recoveries; if (recovered_last_frame) *recovered_last_frame = st.recovered;
   return VSLAM_OK;
 }
+// ---- keyframe hand-off: the MapMaker heuristics Tracker::TrackFrame consults (jni/Tracker.cc:127-132, :869-871) ----------------------
+int vslam_set_keyframe_policy(vslam_ctx* ctx, int enable, double wiggle_scale, double wiggle_scale_depth_normalized, double max_kf_dist_wiggle_mult, int min_frames_between) {
+  if (!ctx) return VSLAM_E_INVALID;
+  if (enable && !(wiggle_scale > 0.0 && wiggle_scale_depth_normalized > 0.0 && max_kf_dist_wiggle_mult > 0.0 && min_frames_between >= 0)) { ctx->err = "keyframe policy: scales must be positive"; return VSLAM_E_INVALID; }
+  ctx->kf_policy = enable != 0;
+  if (enable) { ctx->kf_wiggle = wiggle_scale; ctx->kf_wiggle_dn = wiggle_scale_depth_normalized; ctx->kf_mult = max_kf_dist_wiggle_mult; ctx->kf_min_frames = min_frames_between; }
+  return VSLAM_OK;
+}
+int vslam_get_keyframe_requests(vslam_ctx* ctx, int32_t* request, int32_t* closest, double* dist) {
+  if (!ctx || !request) return VSLAM_E_INVALID;
+  int rc = vslam_sync(ctx); if (rc) return rc;
+  std::vector<StreamState> h(ctx->S);
+  VS_CUDA(cudaMemcpy(h.data(), ctx->ss, sizeof(StreamState) * ctx->S, cudaMemcpyDeviceToHost));
+  for (int s = 0; s < ctx->S; s++) { request[s] = h[s].kf_request; if (closest) closest[s] = h[s].kf_closest; if (dist) dist[s] = h[s].kf_dist; }
+  return VSLAM_OK;
+}
+// Tracker::AddNewKeyFrame (jni/Tracker.cc:823-827) + MapMaker::AddKeyFrame (jni/MapMaker.cc:470-478: `*pK = k`): the stream's current
+// keyframe (all four levels, device to device) becomes source keyframe `kf_id` at the stream's pose, joins the registered keyframes
+// (relocaliser + keyframe policy) and the stream's mnLastKeyFrameDropped is set.
+int vslam_add_keyframe_from_stream(vslam_ctx* ctx, int s, int kf_id) {
+  int rc = check_stream(ctx, s); if (rc) return rc;
+  if (kf_id < 0 || kf_id >= ctx->n_src) { ctx->err = "keyframe id exceeds max_source_keyframes"; return VSLAM_E_CAPACITY; }
+  if (!ctx->sbi_on) { ctx->err = "vslam_add_keyframe_from_stream needs vslam_enable_sbi first (the keyframe's SmallBlurryImage is built for the relocaliser)"; return VSLAM_E_INVALID; }
+  StreamState st; if ((rc = read_ss(ctx, s, &st))) return rc;
+  for (int l = 0; l < VS_LEVELS; l++) {
+    const LevelDesc& L = ctx->lev[l];
+    const uint8_t* from = l == 0 ? ctx->l0_ptr_host[s] : L.img + (size_t)s * L.h * L.pitch;
+    const int fp = l == 0 ? ctx->l0_stride_host[s] : L.pitch;
+    if (!from) { ctx->err = "stream has no current keyframe"; return VSLAM_E_INVALID; }
+    VS_CUDA(cudaMemcpy2DAsync(ctx->src.img[l] + (size_t)kf_id * ctx->src.h[l] * ctx->src.pitch[l], ctx->src.pitch[l], from, fp, L.w, L.h, cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  ctx->src_have[kf_id] = 1;
+  std::vector<int> ids = ctx->reloc_ids; std::vector<double> poses = ctx->reloc_poses_host;
+  size_t at = 0; while (at < ids.size() && ids[at] != kf_id) at++;
+  if (at == ids.size()) { ids.push_back(kf_id); poses.resize(12 * ids.size()); }
+  memcpy(&poses[12 * at], st.pose, sizeof(double) * 12);
+  if ((rc = vslam_set_reloc_keyframes(ctx, (int)ids.size(), ids.data(), poses.data()))) return rc;
+  if ((rc = read_ss(ctx, s, &st))) return rc;
+  st.last_kf_dropped = st.frame_no; st.kf_request = 0;
+  return write_ss(ctx, s, &st);
+}
+
 // Test / hand-off hook: Tracker::mnLostFrames and mTrackingQuality of a stream
 int vslam_set_lost(vslam_ctx* ctx, int s, int lost_frames, int quality) {
   int rc = check_stream(ctx, s); if (rc) return rc;

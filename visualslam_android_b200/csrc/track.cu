@@ -25,6 +25,8 @@ struct Dev {   // everything the kernels need, passed by value
   int S, N, P, truncate;
   int s0;                  // first stream of this launch (stream groups of vs_launch_frame; 0 otherwise)
   vslam_params prm;
+  // keyframe policy: poses of the map's keyframes (the relocaliser registration), 0 keyframes = policy off
+  const double* kf_pose; int kf_n, kf_min_frames; double kf_excess_dist, kf_need_dist;
 };
 
 __device__ __forceinline__ int LevelScale(int l) { return 1 << l; }
@@ -90,6 +92,7 @@ __global__ void __launch_bounds__(kPT) k_project_lists(Dev D, int mode, int appl
   const int N = D.map.n;
   const size_t SN = (size_t)D.S * D.N;
   StreamState* st = D.ss + s;
+  if (tid == 0 && apply_motion) { st->frame_no++; st->kf_request = 0; }   // mnFrame++ (jni/Tracker.cc:100): every TrackFrame, lost or not
   if (mode == 1 && st->lost_frames >= 3 && !st->recovered) return;   // lost and not relocalised this frame (k_relocalise): nothing to do, jni/Tracker.cc:104,134-140
   if (tid == 0 && apply_motion && !st->recovered) {   // Tracker::ApplyMotionModel (jni/Tracker.cc:781-798); a relocalised stream starts from the recovered pose
     double v[6]; for (int k = 0; k < 6; k++) v[k] = st->velocity[k];
@@ -1111,7 +1114,7 @@ __global__ void __launch_bounds__(kPT, 2) k_pose(Dev D, int mode, double sigma_a
       sacc = 0; for (int k = 0; k < 6; k++) sacc += v[k] * v[k];
       st->msd_scaled_vel = sqrt(sacc);
       }
-      // Tracker::AssessTrackingQuality (jni/Tracker.cc:832-878); the keyframe-distance test belongs to MapMaker (out of scope)
+      // Tracker::AssessTrackingQuality (jni/Tracker.cc:832-878)
       int nTA = 0, nTF = 0, nLA = 0, nLF = 0;
       for (int l = 0; l < VS_LEVELS; l++) { nTA += st->attempted[l]; nTF += st->found[l]; if (l >= 2) { nLA += st->attempted[l]; nLF += st->found[l]; } }
       int q;
@@ -1120,8 +1123,29 @@ __global__ void __launch_bounds__(kPT, 2) k_pose(Dev D, int mode, double sigma_a
         const double tot = (double)nTF / nTA, lg = (nLA > 10) ? (double)nLF / nLA : tot;
         q = (tot > 0.3) ? 2 : (lg < 0.13 ? 0 : 1);
       }
+      // MapMaker::ClosestKeyFrame / KeyFrameLinearDist (jni/MapMaker.cc:705-712,736-754) over the registered keyframes: only the two
+      // callers below need it (DODGY: "has the pose run miles away", GOOD: "is a new keyframe due")
+      double kfd = 9999999999.9; int kfc = -1;
+      if (D.kf_n > 0 && q != 0) {
+        double inv[12]; se3_inverse(sm.pose, inv);
+        for (int k = 0; k < D.kf_n; k++) {
+          double ki[12]; se3_inverse(D.kf_pose + 12 * k, ki);
+          const double d0 = ki[3] - inv[3], d1 = ki[7] - inv[7], d2 = ki[11] - inv[11];
+          double dd = d0 * d0; dd += d1 * d1; dd += d2 * d2;
+          const double dist = sqrt(dd);
+          if (dist < kfd) { kfd = dist; kfc = k; }
+        }
+        st->kf_dist = kfd; st->kf_closest = kfc;
+        if (q == 1 && kfd > D.kf_excess_dist) q = 0;          // IsDistanceToNearestKeyFrameExcessive (jni/MapMaker.cc:1098-1101)
+      }
       st->quality = q;
       if (q == 0) st->lost_frames++; else st->lost_frames = 0;
+      // jni/Tracker.cc:127-132 (not in the recovery branch): GOOD && MapMaker::NeedNewKeyFrame (jni/MapMaker.cc:763-773) && enough
+      // frames since the last one.  The queue-length term (QueueSize() < 3) is the caller's: it owns the queue.
+      if (kfc >= 0 && q == 2 && !st->recovered) {
+        double dDist = kfd; dDist *= (1.0 / st->depth_mean);
+        if (dDist > D.kf_need_dist && st->frame_no - st->last_kf_dropped > D.kf_min_frames) st->kf_request = 1;
+      }
     }
   }
 }
@@ -1163,6 +1187,9 @@ Dev make_dev(const vslam_ctx* ctx) {
   D.cam = ctx->cam; D.map = ctx->map; D.src = ctx->src; D.ps = ctx->ps; D.ss = ctx->ss; D.lists = ctx->lists; D.list_cap = ctx->list_cap;
   D.pvs = ctx->pvs; D.sort_scratch = ctx->sort_scratch; D.sort_cap = ctx->sort_cap; D.evals = ctx->evals;
   D.S = ctx->S; D.N = ctx->N; D.P = ctx->P; D.truncate = ctx->cfg.truncate_error; D.prm = ctx->params; D.s0 = ctx->cur_s0;
+  const bool kf = ctx->kf_policy && ctx->reloc_n > 0;
+  D.kf_pose = ctx->reloc_pose; D.kf_n = kf ? ctx->reloc_n : 0; D.kf_min_frames = ctx->kf_min_frames;
+  D.kf_excess_dist = ctx->kf_wiggle * 10.0; D.kf_need_dist = ctx->kf_mult * ctx->kf_wiggle_dn;
   return D;
 }
 

@@ -86,6 +86,8 @@ struct StreamState {
   double updates[VS_MAX_UPDATES * 6], sigmas[VS_MAX_UPDATES];
   // relocalisation (k_relocalise): set for the frame in which the stream was recovered; best keyframe / final ESM score of the last attempt
   int recovered, reloc_best, n_recoveries, pad_; double reloc_score;
+  // keyframe hand-off (vslam_set_keyframe_policy): Tracker::mnFrame / mnLastKeyFrameDropped, and what the last frame decided
+  int frame_no, last_kf_dropped, kf_request, kf_closest; double kf_dist;
 };
 
 struct vslam_ctx {
@@ -128,6 +130,8 @@ struct vslam_ctx {
   uint8_t* snap_img; uint32_t* snap_corners; int* snap_lut;
   // relocaliser keyframes (vslam_set_reloc_keyframes): SmallBlurryImages with blur 2.5, their gradient images and poses
   int reloc_n; float reloc_taps[17]; float* reloc_tmpl; float* reloc_jac; float* reloc_tmp; uint8_t* reloc_small; double* reloc_pose; double* reloc_scores;
+  // keyframe policy (vslam_set_keyframe_policy): the MapMaker heuristics the tracker consults, over the registered keyframes' poses
+  bool kf_policy; double kf_wiggle, kf_wiggle_dn, kf_mult; int kf_min_frames;
   double* unproj_lut; bool unproj_ok;   // [H][W][2] ATANCamera::UnProject of every integer level-0 pixel (MapMaker::AddPointEpipolar's imUnProj), built on the host
   // on-device SmallBlurryImage (vslam_enable_sbi)
   bool sbi_on; float sbi_taps[9]; CamDev sbi_cam; double sbi_orig[2][3]; float* sbi_tmpl; float* sbi_scratch; float* sbi_jac; uint8_t* sbi_small; int* sbi_have;
