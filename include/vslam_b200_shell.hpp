@@ -58,9 +58,10 @@ struct Level {
 // One camera stream of a context.  Several KeyFrame/Tracker objects may share one context (one per GPU).
 class Context {
  public:
-  Context(int width, int height, int n_streams, int max_points, int patch_size = 11, int device = 0) {
+  Context(int width, int height, int n_streams, int max_points, int patch_size = 11, int device = 0, int max_source_keyframes = 0 /* 0: library default */) {
     vslam_config cfg; vslam_default_config(&cfg);
     cfg.width = width; cfg.height = height; cfg.n_streams = n_streams; cfg.max_points = max_points; cfg.patch_size = patch_size; cfg.device = device;
+    if (max_source_keyframes > 0) cfg.max_source_keyframes = max_source_keyframes;
     if (vslam_create(&cfg, &c_) != VSLAM_OK) throw std::runtime_error(std::string("vslam_b200: ") + vslam_last_error(0));
     n_streams_ = n_streams;
   }
@@ -174,7 +175,7 @@ class Tracker {
   // jni/Tracker.cc:45-60 (the tracker's part; MapMaker::RequestReset is the caller's)
   void Reset() {
     check(ctx_.get(), vslam_reset_stream(ctx_.get(), stream_));
-    mbUserPressedSpacebar = false; mnInitialStage = TRAIL_TRACKING_NOT_STARTED; mlTrails.clear(); mnFrame = 0; mbMapGood = false;
+    mbUserPressedSpacebar = false; mnInitialStage = TRAIL_TRACKING_NOT_STARTED; mlTrails.clear(); mnFrame = 0; mnLastKeyFrameDropped = -20; mbMapGood = false;
   }
   // jni/Tracker.cc:349-353 (the reference's GUI handler sets the flag)
   void PressSpacebar() { mbUserPressedSpacebar = true; }
@@ -200,7 +201,28 @@ class Tracker {
     msg_ << "Tracking Map, quality " << (q == 2 ? "good." : (q == 1 ? "poor." : "bad.")) << " Found:";
     for (int l = 0; l < LEVELS; l++) msg_ << " " << fnd[l] << "/" << att[l];
     msg_ << " Map: " << ctx_.MapSize() << "P";
+    if (mnKeyFrames >= 0) msg_ << ", " << mnKeyFrames << "KF";
+    // jni/Tracker.cc:127-132: the first three terms are evaluated on the device (vslam_set_keyframe_policy); the queue length is ours
+    if (mnKeyFrames >= 0) {
+      std::vector<int32_t> req(ctx_.Streams());
+      check(c, vslam_get_keyframe_requests(c, &req[0], 0, 0));
+      if (req[stream_] && mnQueueSize < 3) { msg_ << " Adding key-frame."; AddNewKeyFrame(); }
+    }
   }
+  // The MapMaker heuristics TrackFrame consults (MapMaker::NeedNewKeyFrame, IsDistanceToNearestKeyFrameExcessive).  nKeyFrames = how
+  // many source-keyframe slots the map already uses: keyframes added by this tracker take the following ids.
+  void SetKeyFramePolicy(int nKeyFrames, double dWiggleScale, double dWiggleScaleDepthNormalized, double dMaxKFDistWiggleMult = 0.2, int nMinFrames = 20) {
+    check(ctx_.get(), vslam_set_keyframe_policy(ctx_.get(), 1, dWiggleScale, dWiggleScaleDepthNormalized, dMaxKFDistWiggleMult, nMinFrames));
+    mnKeyFrames = nKeyFrames;
+  }
+  // Tracker::AddNewKeyFrame (jni/Tracker.cc:823-827) + MapMaker::AddKeyFrame: device-to-device copy of mCurrentKF into the next slot
+  void AddNewKeyFrame() {
+    check(ctx_.get(), vslam_add_keyframe_from_stream(ctx_.get(), stream_, mnKeyFrames));
+    mnLastKeyFrameDropped = mnFrame; mnKeyFrames++;
+  }
+  int mnQueueSize = 0;           // MapMaker::QueueSize(): set by the host map maker while it digests keyframes
+  int mnKeyFrames = -1;          // -1: keyframe policy off
+  int mnLastKeyFrameDropped = -20;
   // Relocaliser keyframes (Map::vpKeyFrames with their SmallBlurryImages, jni/Relocaliser.cc): ids of uploaded source keyframes + poses (n x 12)
   void SetRelocKeyFrames(int n, const int32_t* src_kf_ids, const double* poses12) { check(ctx_.get(), vslam_set_reloc_keyframes(ctx_.get(), n, src_kf_ids, poses12)); }
   SE3 GetCurrentPose() {

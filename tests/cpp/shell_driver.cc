@@ -1,6 +1,6 @@
 // Test driver for include/vslam_b200_shell.hpp: runs the reference-shaped C++ API (KeyFrame, Tracker, MiniPatch, PatchFinder) on a
 // scene file written by tests/test_gpu_shell.py and prints the results as text; the Python side compares them with the oracle.
-//   shell_driver <scene.bin> trails|track|stages|mapsearch [map file to write, mapsearch only]
+//   shell_driver <scene.bin> trails|track|handoff|stages|mapsearch [map file to write, mapsearch only]
 // scene.bin: int32 W,H,N,F; double params5[5]; u8 src[W*H]; double world[3N], right[3N], down[3N]; int32 irCenter[2N]; int32 level[N];
 //            double pose0[12]; u8 frames[F][W*H]
 #include <cstdio>
@@ -31,7 +31,7 @@ int main(int argc, char** argv) {
   vslam_camera_from_params(p5, W / 16, H / 16, 0, cam_sbi);
   cv::Mat colour(1, 1, CV_8UC4);
   try {
-    Context ctx(W, H, 1, N > 0 ? N : 1);
+    Context ctx(W, H, 1, N > 0 ? N : 1, 11, 0, 4);
     Tracker tracker(ctx, 0, cam);
     SE3 start; for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) start.R(i, j) = pose0[4 * i + j]; start.t(i) = pose0[4 * i + 3]; }
 
@@ -70,6 +70,20 @@ int main(int argc, char** argv) {
         printf("pose");
         for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) printf(" %.17g", p.R(i, j)); printf(" %.17g", p.t(i)); }
         printf("\nmsg %s\n", tracker.GetMessageForUser().c_str());
+      }
+      return 0;
+    }
+
+    if (mode == "handoff") {  // TrackFrame with the keyframe policy: the shell adds keyframes when the device asks for one (jni/Tracker.cc:127-132)
+      tracker.EnableSBI(cam_sbi);
+      const int32_t id0 = 0; double eye12[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+      tracker.SetRelocKeyFrames(1, &id0, eye12);
+      tracker.SetKeyFramePolicy(1, 0.1, 0.1);
+      for (int k = 0; k < F; k++) {
+        cv::Mat g(H, W, CV_8UC1, &frames[k][0]);
+        tracker.TrackFrame(g, colour, false);
+        printf("msg %s\n", tracker.GetMessageForUser().c_str());
+        printf("kf %d %d\n", tracker.mnKeyFrames, tracker.mnLastKeyFrameDropped);
       }
       return 0;
     }

@@ -104,6 +104,38 @@ def test_shell_track_frame_matches_the_oracle(driver, tmp_path):
         assert msgs[k] == exp, (msgs[k], exp)
 
 
+def test_shell_adds_keyframes_when_the_device_asks(driver, tmp_path):
+    """Tracker::TrackFrame's keyframe heuristics through the shell (jni/Tracker.cc:127-132): messages, ' Adding key-frame.' on the frame
+    where the restatement adds one, mnLastKeyFrameDropped."""
+    from oracle import oraclebind
+    cam, f0, smap = common.scene(n_points=600)
+    step = np.array([0.004, 0.001, 0.0005, 0.0004, -0.0012, 0.0008])
+    frames = [common.frame_at(cam, step * k)[0] for k in range(1, 9)]
+    scene = str(tmp_path / "handoff.bin")
+    _write_scene(scene, cam, f0, smap, synth.IDENTITY_POSE, frames)
+    out = _run(driver, scene, "handoff")
+    msgs = [l[4:] for l in out if l.startswith("msg ")]
+    kfs = [[int(v) for v in l.split()[1:]] for l in out if l.startswith("kf ")]
+    ow = oraclebind.OrcWorld(cam, f0, smap)
+    ow.set_pose(synth.IDENTITY_POSE)
+    ow.L.orc_tracker_enable_sbi(ow.tracker, synth.Camera(cam.width // 16, cam.height // 16).scalars())
+    okf0 = oraclebind.OrcKeyFrame().make_lite(f0)
+    ow.L.orc_tracker_add_reloc_keyframe(ow.tracker, okf0.h, np.ascontiguousarray(synth.IDENTITY_POSE, dtype=np.float64).reshape(12))
+    ow.L.orc_tracker_set_keyframe_policy(ow.tracker, 1, 0.1, 0.1, 0.2, 20)
+    n_kf, added = 1, []
+    for k, fr in enumerate(frames):
+        ow.L.orc_tracker_track_frame(ow.tracker, np.ascontiguousarray(fr), cam.width, cam.height, cam.width)
+        a, f, q, lost, dc = ow.counters()
+        v = [C.c_int() for _ in range(4)]
+        ow.L.orc_tracker_keyframe_info(ow.tracker, *[C.byref(x) for x in v])
+        exp = "Tracking Map, quality " + {2: "good.", 1: "poor.", 0: "bad."}[q] + " Found:" + "".join(f" {f[l]}/{a[l]}" for l in range(4)) + f" Map: {smap.n}P, {n_kf}KF"
+        if v[1].value:
+            exp += " Adding key-frame."; n_kf += 1; added.append(k + 1)
+        assert msgs[k] == exp, (k, msgs[k], exp)
+        assert kfs[k] == [v[0].value, v[3].value], (k, kfs[k])
+    assert len(added) == 1 and added[0] in (5, 6)      # 0.004 per frame against 0.2 * 0.1 * scene depth; one keyframe, then the 20-frame gap
+
+
 def test_shell_stage_functions_and_patchfinder_match_the_oracle(driver, tmp_path):
     """PatchFinder per object (CalcSearchLevelAndWarpMatrix, FindPatchCoarse + sub-pixel) and Tracker::SearchForPoints / CalcPoseUpdate
     on explicit point lists, through the shell."""
