@@ -12,6 +12,7 @@
  *   vslam_upload_source_keyframe     the map keyframe a MapPoint's patch comes from (MapPoint::pPatchSourceKF,
  *                                    jni/MapPoint.h:38); pyramid built like MakeKeyFrame_Lite
  *   vslam_set_map                    Map::vpPoints / MapPoint fields read by the tracker (jni/Map.h:29, jni/MapPoint.h:33-54)
+ *   vslam_append_map_points          Map::vpPoints.push_back of new points during tracking (jni/MapMaker.cc:685, jni/Tracker.cc:372)
  *   vslam_set_camera                 ATANCamera scalars after RefreshParams (jni/ATANCamera.cc:37-129)
  *   vslam_project_all                first loop of Tracker::TrackMap       jni/Tracker.cc:369-392
  *                                    (TrackerData::Project jni/TrackerData.h:69-86, GetDerivsUnsafe :92-95,
@@ -114,6 +115,11 @@ void vslam_camera_from_params(const double* params5, int width, int height, int 
 int vslam_upload_source_keyframe(vslam_ctx* ctx, int kf_id, const uint8_t* gray_host, int stride);
 int vslam_set_map(vslam_ctx* ctx, int n, const double* world3, const double* pixel_right3, const double* pixel_down3,
                   const int32_t* ir_center2, const int32_t* src_level, const int32_t* src_kf /* NULL => all 0 */);
+/* Map::vpPoints.push_back while streams run (what MapMaker::AddPointEpipolar does from its thread, jni/MapMaker.cc:685): new points are
+ * appended behind the existing ones.  Unlike vslam_set_map the existing points keep their per-stream tracker state (template cache,
+ * found flags, M-estimator counters); the new points start without, like a MapPoint whose TrackerData is created on first use. */
+int vslam_append_map_points(vslam_ctx* ctx, int n_new, const double* world3, const double* pixel_right3, const double* pixel_down3,
+                            const int32_t* ir_center2, const int32_t* src_level, const int32_t* src_kf /* NULL => all 0 */);
 
 /* ---- KeyFrame::MakeKeyFrame_Lite for streams [first, first+count) -------------------------------------------- */
 /* gray_host: frame k at gray_host + k*frame_stride, rows `stride` bytes apart (pinned memory recommended). */

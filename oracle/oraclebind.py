@@ -103,6 +103,7 @@ def lib():
     sig("orc_tracker_search_for_points", i, vp, _i32p, i, i, i)
     sig("orc_tracker_clear_counters", None, vp)
     sig("orc_epipolar_search", None, vp, vp, vp, _f64p, _f64p, d, d, d, i, i, i, _i32p, _f64p, C.c_void_p)
+    sig("orc_tracker_append_points", None, vp, vp, i, _f64p, _f64p, _f64p, _i32p, _i32p)
     sig("orc_tracker_set_keyframe_policy", None, vp, i, d, d, d, i)
     sig("orc_tracker_keyframe_info", None, vp, pi, pi, pi, pi)
     sig("orc_epipolar_point_fields", None, _f64p, _f64p, i, i, i, _f64p, _f64p)
@@ -252,6 +253,15 @@ class OrcWorld:
         down = smap.pix_down_w if pix_down is None else pix_down
         self._keep = [np.ascontiguousarray(a) for a in (smap.world, right, down, smap.ir_center.astype(np.int32), smap.src_level.astype(np.int32))]
         L.orc_tracker_set_map(self.tracker, self.src_kf.h, self.n, *self._keep)
+
+    def append_points(self, smap, pix_right=None, pix_down=None, src_kf=None):
+        """New map points while tracking runs (existing points keep their TrackerData)."""
+        right = smap.pix_right_w if pix_right is None else pix_right
+        down = smap.pix_down_w if pix_down is None else pix_down
+        arrs = [np.ascontiguousarray(a) for a in (smap.world, right, down, smap.ir_center.astype(np.int32), smap.src_level.astype(np.int32))]
+        self._keep += arrs
+        self.L.orc_tracker_append_points(self.tracker, (src_kf or self.src_kf).h, smap.n, *arrs)
+        self.n += smap.n
 
     def set_pose(self, pose):
         self.L.orc_tracker_set_pose(self.tracker, np.ascontiguousarray(pose, dtype=np.float64).reshape(12))

@@ -221,6 +221,15 @@ class RefWorld:
         self.tracker = L.ref_tracker_create(int(width), int(height), self.cam, self.map, int(fix_radius))
         self.width, self.height = width, height
 
+    def append_points(self, smap):
+        """Map::vpPoints.push_back of new points while the tracker runs."""
+        normal = np.array([0.0, 0.0, -1.0])
+        for k in range(smap.n):
+            self.L.ref_map_add_point(self.map, self.src_kf.h, int(smap.src_level[k]), smap.ir_center[k].astype(np.float64),
+                                     np.ascontiguousarray(smap.world[k]), np.ascontiguousarray(smap.center_nc[k]),
+                                     np.ascontiguousarray(smap.one_right_nc[k]), np.ascontiguousarray(smap.one_down_nc[k]), normal)
+        self.n += smap.n
+
     # -- tracker state
     def set_pose(self, pose):
         self.L.ref_tracker_set_pose(self.tracker, np.ascontiguousarray(pose, dtype=np.float64).reshape(12))

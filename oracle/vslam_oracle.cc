@@ -1316,6 +1316,19 @@ void orc_tracker_set_map(void* t_, void* srckf, int n, const double* world, cons
     p.srcKF = t->srcKF;
   }
 }
+// Map::vpPoints.push_back of new points while the tracker runs (MapMaker::AddPointEpipolar, jni/MapMaker.cc:685): existing points keep
+// their TrackerData, the new ones get theirs on first use (jni/Tracker.cc:372)
+void orc_tracker_append_points(void* t_, void* srckf, int n, const double* world, const double* right, const double* down, const int32_t* irCenter, const int32_t* srcLevel) {
+  OTracker* t = (OTracker*)t_;
+  const size_t base = t->pts.size();
+  t->pts.resize(base + n); t->td.resize(base + n); t->hasTD.resize(base + n, 0);
+  for (int i = 0; i < n; i++) {
+    MapPointO& p = t->pts[base + i];
+    for (int k = 0; k < 3; k++) { p.world[k] = world[3 * i + k]; p.right[k] = right[3 * i + k]; p.down[k] = down[3 * i + k]; }
+    p.irCenter[0] = irCenter[2 * i]; p.irCenter[1] = irCenter[2 * i + 1]; p.srcLevel = srcLevel[i]; p.outlierCount = p.inlierCount = 0;
+    p.srcKF = (OKeyFrame*)srckf;
+  }
+}
 // a map point whose patch comes from another keyframe of the map (MapPoint::pPatchSourceKF)
 void orc_tracker_set_point_source_kf(void* t_, int i, void* kf) { ((OTracker*)t_)->pts[i].srcKF = (OKeyFrame*)kf; }
 void orc_tracker_set_pose(void* t, const double* p12) { ((OTracker*)t)->pose = se3_from12(p12); }

@@ -1128,3 +1128,43 @@ def test_track_frame_keyframe_handoff_on_device():
             kept += bool(dodgy_by_counts and wiggle > 1e-3 and q == 1 and lost == 0)
             c.close()
     assert seen >= 1 and kept >= 1
+
+
+def test_map_grows_while_streams_run():
+    """vslam_append_map_points: the map grows twice during a sequence; old points keep their per-stream state (template cache and
+    M-estimator counters carry over, which the second frame after an append depends on), new ones start fresh -- against the
+    restatement, which tests/test_oracle_vs_ref.py::test_map_grows_while_tracking pins to the unmodified TrackFrame.  Two streams
+    with different motions share the growing map."""
+    from visualslam_android_b200 import api
+    cam, f0, smap = common.scene()
+    names = ("world", "pix_right_w", "pix_down_w", "ir_center", "src_level", "center_nc", "one_right_nc", "one_down_nc")
+    parts = [synth.SyntheticMap(**{k: getattr(smap, k)[sl] for k in names}) for sl in (slice(0, 500), slice(500, 800), slice(800, 1000))]
+    S = 2
+    ctx = api.Context(cam.width, cam.height, n_streams=S, max_points=1000)
+    ctx.set_camera(cam.scalars()); ctx.upload_source_keyframe(f0)
+    ctx.set_map(parts[0].world, parts[0].pix_right_w, parts[0].pix_down_w, parts[0].ir_center, parts[0].src_level)
+    sbi_cam = synth.Camera(cam.width // 16, cam.height // 16).scalars()
+    ctx.enable_sbi(sbi_cam)
+    ows = [_orc(cam, f0, parts[0]) for _ in range(S)]
+    for ow in ows:
+        ow.L.orc_tracker_enable_sbi(ow.tracker, sbi_cam)
+    nxt = 1
+    for k in range(1, 10):
+        if k in (4, 7):
+            p = parts[nxt]; nxt += 1
+            ctx.append_map_points(p.world, p.pix_right_w, p.pix_down_w, p.ir_center, p.src_level)
+            for ow in ows:
+                ow.append_points(p)
+        frames = np.stack([synth.render_frame(common.texture(), cam, synth.stream_pose(4 * k, 2 + s)) for s in range(S)])
+        ctx.track_frame(frames)
+        for s, ow in enumerate(ows):
+            ow.L.orc_tracker_track_frame(ow.tracker, np.ascontiguousarray(frames[s]), cam.width, cam.height, cam.width)
+            assert np.abs(ctx.get_pose(s) - ow.get_pose()).max() <= 1e-8, (k, s)
+            a, f, q, lost, dc = ctx.counters(s); oa, of, oq, olost, odc = ow.counters()
+            assert np.array_equal(a, oa) and np.array_equal(f, of) and (q, lost, dc) == (oq, olost, odc), (k, s)
+            assert np.array_equal(ctx.point_counts(s), ow.point_counts()), (k, s)
+    assert ctx.counters(0)[0].sum() > 600
+    with pytest.raises(api.VslamError) as e:
+        ctx.append_map_points(parts[1].world, parts[1].pix_right_w, parts[1].pix_down_w, parts[1].ir_center, parts[1].src_level)
+    assert e.value.code == api.E_CAPACITY
+    ctx.close()

@@ -561,3 +561,34 @@ def test_track_frame_keyframe_handoff_heuristics():
         assert seen >= 1, "no DODGY frame in the occlusion sweep"
     finally:
         rw.L.ref_set_keyframe_policy(rw.tracker, 0, 0.1, 0.1, 0.2)
+
+
+def _submap(smap, sl):
+    return synth.SyntheticMap(**{k: getattr(smap, k)[sl] for k in ("world", "pix_right_w", "pix_down_w", "ir_center", "src_level", "center_nc", "one_right_nc", "one_down_nc")})
+
+
+def test_map_grows_while_tracking():
+    """Map::vpPoints.push_back during tracking (what MapMaker::AddPointEpipolar does from its thread): old points keep their
+    TrackerData (template cache, M-estimator counters), new ones get theirs on first use (jni/Tracker.cc:372) -- unmodified
+    TrackFrame vs restatement across two appends."""
+    cam, f0, smap = common.scene()
+    parts = [_submap(smap, slice(0, 500)), _submap(smap, slice(500, 800)), _submap(smap, slice(800, 1000))]
+    rw = refbind.RefWorld(cam.width, cam.height, f0, parts[0])
+    pr, pd = rw.pixel_vectors()
+    ow = oraclebind.OrcWorld(cam, f0, parts[0], pix_right=pr, pix_down=pd)
+    rw.L.ref_sbi_reset_size()
+    rw.L.ref_srand(1)
+    ow.L.orc_tracker_enable_sbi(ow.tracker, synth.Camera(cam.width // 16, cam.height // 16).scalars())
+    nxt = 1
+    for k in range(1, 10):
+        if k in (4, 7):
+            rw.append_points(parts[nxt])
+            pr, pd = rw.pixel_vectors()
+            ow.append_points(parts[nxt], pix_right=pr[-parts[nxt].n:], pix_down=pd[-parts[nxt].n:])
+            nxt += 1
+        fr = synth.render_frame(common.texture(), cam, synth.stream_pose(4 * k, 2))
+        rw.L.ref_tracker_track_frame(rw.tracker, fr, cam.width, cam.height, cam.width)
+        ow.L.orc_tracker_track_frame(ow.tracker, fr, cam.width, cam.height, cam.width)
+        assert np.array_equal(rw.get_pose(), ow.get_pose()), k
+        assert all(np.array_equal(a, b) if isinstance(a, np.ndarray) else a == b for a, b in zip(rw.counters(), ow.counters())), k
+    assert rw.n == ow.n == 1000 and ow.counters()[0].sum() > 600

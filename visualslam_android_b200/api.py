@@ -51,7 +51,7 @@ ABI_SYMBOLS = [
     "vslam_get_point_states", "vslam_get_point_template", "vslam_get_point_counts", "vslam_get_updates", "vslam_get_zmssd_evals",
     "vslam_project_all", "vslam_set_point_projection", "vslam_set_lists", "vslam_clear_counters", "vslam_search_for_points", "vslam_refind", "vslam_get_refind_results", "vslam_epipolar_search", "vslam_project_and_derivs", "vslam_calc_jacobians",
     "vslam_calc_pose_update", "vslam_track_map", "vslam_track_frame", "vslam_track_frame_dev", "vslam_track_frame_async", "vslam_wait_step", "vslam_debug_atan", "vslam_debug_dp4a_peak", "vslam_kernel_launches", "vslam_set_timing", "vslam_get_stage_times",
-    "vslam_set_keyframe_policy", "vslam_get_keyframe_requests", "vslam_add_keyframe_from_stream", "vslam_epipolar_make_points", "vslam_map_file_info", "vslam_save_map_file", "vslam_load_map_file", "vslam_export_map_text",
+    "vslam_append_map_points", "vslam_set_keyframe_policy", "vslam_get_keyframe_requests", "vslam_add_keyframe_from_stream", "vslam_epipolar_make_points", "vslam_map_file_info", "vslam_save_map_file", "vslam_load_map_file", "vslam_export_map_text",
 ]
 
 _lib = None
@@ -114,6 +114,7 @@ def load():
     sig("vslam_set_motion", i, vp, i, vp, d, d, d)
     sig("vslam_reset_stream", i, vp, i)
     sig("vslam_set_reloc_keyframes", i, vp, i, vp, vp)
+    sig("vslam_append_map_points", i, vp, i, vp, vp, vp, vp, vp, vp)
     sig("vslam_set_keyframe_policy", i, vp, i, d, d, d, i)
     sig("vslam_get_keyframe_requests", i, vp, vp, vp, vp)
     sig("vslam_add_keyframe_from_stream", i, vp, i, i)
@@ -257,6 +258,15 @@ class Context:
         self.n_points = n
 
     # -- MakeKeyFrame_Lite
+    def append_map_points(self, world, right, down, ir_center, src_level, src_kf=None):
+        """New map points behind the existing ones; existing points keep their per-stream tracker state."""
+        w = np.ascontiguousarray(world, dtype=np.float64); r = np.ascontiguousarray(right, dtype=np.float64); d = np.ascontiguousarray(down, dtype=np.float64)
+        c = np.ascontiguousarray(ir_center, dtype=np.int32); lv = np.ascontiguousarray(src_level, dtype=np.int32)
+        kf = None if src_kf is None else np.ascontiguousarray(src_kf, dtype=np.int32)
+        self._ck(self.L.vslam_append_map_points(self.h, w.shape[0], w.ctypes.data, r.ctypes.data, d.ctypes.data, c.ctypes.data, lv.ctypes.data,
+                                                None if kf is None else kf.ctypes.data))
+        self.n_points += w.shape[0]
+
     def make_keyframe_lite(self, frames, first_stream=0):
         """frames: host uint8 array (count, H, W) or (H, W)."""
         f = np.ascontiguousarray(frames, dtype=np.uint8)

@@ -353,6 +353,30 @@ int vslam_set_map(vslam_ctx* ctx, int n, const double* world, const double* righ
   return VSLAM_OK;
 }
 
+// Map::vpPoints.push_back while streams run (MapMaker::AddPointEpipolar from its thread, jni/MapMaker.cc:685): the new points go behind
+// the existing ones; existing points keep their per-stream tracker state (TrackerData: template cache, found flags, M-estimator counters),
+// the new ones start without (created on first use, jni/Tracker.cc:372).
+int vslam_append_map_points(vslam_ctx* ctx, int n_new, const double* world, const double* right, const double* down, const int32_t* irc, const int32_t* lvl, const int32_t* kf) {
+  if (!ctx || n_new < 0 || (n_new > 0 && (!world || !right || !down || !irc || !lvl))) return VSLAM_E_INVALID;
+  const int n0 = ctx->map.n;
+  if (n0 + n_new > ctx->N) { ctx->err = "map would exceed max_points"; return VSLAM_E_CAPACITY; }
+  for (int i = 0; i < n_new; i++) if (lvl[i] < 0 || lvl[i] >= VS_LEVELS || (kf && (kf[i] < 0 || kf[i] >= ctx->n_src))) { ctx->err = "map point with bad source level / keyframe"; return VSLAM_E_INVALID; }
+  if (n_new == 0) return VSLAM_OK;
+  int rc = vslam_sync(ctx); if (rc) return rc;
+  VS_CUDA(cudaMemcpy(ctx->map.world + 3 * (size_t)n0, world, sizeof(double) * 3 * n_new, cudaMemcpyHostToDevice));
+  VS_CUDA(cudaMemcpy(ctx->map.right + 3 * (size_t)n0, right, sizeof(double) * 3 * n_new, cudaMemcpyHostToDevice));
+  VS_CUDA(cudaMemcpy(ctx->map.down + 3 * (size_t)n0, down, sizeof(double) * 3 * n_new, cudaMemcpyHostToDevice));
+  VS_CUDA(cudaMemcpy(ctx->map.ircenter + 2 * (size_t)n0, irc, sizeof(int) * 2 * n_new, cudaMemcpyHostToDevice));
+  VS_CUDA(cudaMemcpy(ctx->map.srclevel + n0, lvl, sizeof(int) * n_new, cudaMemcpyHostToDevice));
+  if (kf) VS_CUDA(cudaMemcpy(ctx->map.srckf + n0, kf, sizeof(int) * n_new, cudaMemcpyHostToDevice));
+  else VS_CUDA(cudaMemset(ctx->map.srckf + n0, 0, sizeof(int) * n_new));
+  // per-stream state of the new points only: rows of [S][N] (flags) and [2][S][N] (counters)
+  VS_CUDA(cudaMemset2D(ctx->ps.flags + n0, sizeof(int) * ctx->N, 0, sizeof(int) * n_new, ctx->S));
+  VS_CUDA(cudaMemset2D(ctx->ps.counts + n0, sizeof(int) * ctx->N, 0, sizeof(int) * n_new, 2 * (size_t)ctx->S));
+  ctx->map.n = n0 + n_new;
+  return VSLAM_OK;
+}
+
 // ---------------------------------------------------------------------------------------------- MakeKeyFrame_Lite
 static int adopt_l0(vslam_ctx* ctx, int first, int count, const uint8_t* base, int stride, size_t frame_stride, bool own) {
   for (int k = 0; k < count; k++) {
