@@ -127,6 +127,9 @@ int vslam_make_keyframe_lite(vslam_ctx* ctx, int first_stream, int count, const 
 /* gray_dev: same layout in device memory (16-byte aligned, stride % 16 == 0).  Zero-copy: the buffer becomes level 0 of
  * those streams' current keyframe and must stay unmodified until their next make_keyframe_lite / track_frame. */
 int vslam_make_keyframe_lite_dev(vslam_ctx* ctx, int first_stream, int count, const uint8_t* gray_dev, int stride, size_t frame_stride);
+/* Source keyframe kf_id as stream `stream`'s current keyframe (zero copy of its level-0 image, then pyramid + FAST): what a host
+ * MapMaker does to make an OLD keyframe the target of vslam_epipolar_search / vslam_refind, which need the target's corners. */
+int vslam_make_keyframe_from_source(vslam_ctx* ctx, int stream, int kf_id);
 int vslam_level_dims(const vslam_ctx* ctx, int level, int* width, int* height);
 int vslam_get_level(vslam_ctx* ctx, int stream, int level, uint8_t* out, int out_stride);
 int vslam_get_num_corners(vslam_ctx* ctx, int stream, int level, int* n);

@@ -1168,3 +1168,54 @@ def test_map_grows_while_streams_run():
         ctx.append_map_points(parts[1].world, parts[1].pix_right_w, parts[1].pix_down_w, parts[1].ir_center, parts[1].src_level)
     assert e.value.code == api.E_CAPACITY
     ctx.close()
+
+
+def test_host_mapmaker_loop_grows_the_map_on_the_device():
+    """The loop a host MapMaker runs around the library, with no image crossing PCIe after the camera frame itself: the device raises
+    a keyframe request -> vslam_add_keyframe_from_stream -> MakeKeyFrame_Rest on the new keyframe -> the closest OLD keyframe becomes
+    a scratch stream's keyframe (vslam_make_keyframe_from_source) -> epipolar search of the new keyframe's candidates in it ->
+    triangulated points -> vslam_append_map_points.  The grown map is then tracked: the new points are found in later frames and
+    the pose stays on the ground truth.  (Functional test: each step has its own parity test above.)"""
+    from visualslam_android_b200 import api
+    cam, f0, smap = common.scene(n_points=500)
+    ctx = api.Context(cam.width, cam.height, n_streams=2, max_points=2000, max_source_keyframes=3)    # stream 0 tracks, stream 1 is MapMaker's scratch
+    ctx.set_camera(cam.scalars()); ctx.upload_source_keyframe(f0)
+    ctx.set_map(smap.world, smap.pix_right_w, smap.pix_down_w, smap.ir_center, smap.src_level)
+    ctx.enable_sbi(synth.Camera(cam.width // 16, cam.height // 16).scalars())
+    ctx.set_reloc_keyframes([0], synth.IDENTITY_POSE[None])
+    ctx.set_keyframe_policy(True, 0.1, 0.1, 0.2, 20)
+    step = np.array([0.008, 0.002, 0.001, 0.0008, -0.0024, 0.0016])
+    truth = lambda k: synth.se3_exp(step * k)
+    n_before = smap.n
+    grown_at = None
+    for k in range(1, 16):
+        fr = synth.render_frame(common.texture(), cam, truth(k))
+        ctx.track_frame(np.stack([fr, fr]))
+        assert np.abs(ctx.get_pose(0) - truth(k)).max() < 5e-3, k
+        req, closest, dist = ctx.keyframe_requests()
+        if req[0] and grown_at is None:
+            pose_new = ctx.get_pose(0)
+            ctx.add_keyframe_from_stream(0, 1)                                    # Tracker::AddNewKeyFrame
+            ctx.make_keyframe_rest(0)                                             # MapMaker::AddKeyFrameFromTopOfQueue: candidates of the new keyframe
+            cands = [ctx.candidates(0, l)[0] for l in range(4)]
+            _, _, depth_mean, depth_sigma = ctx.get_motion(0)
+            ctx.make_keyframe_from_source(1, int(closest[0]))                     # target = the closest old keyframe (keyframe 0, identity pose)
+            new = [[] for _ in range(5)]
+            for level in range(4):
+                found, pos, _, _ = ctx.epipolar_search(1, 1, level, cands[level], pose_new, synth.IDENTITY_POSE, depth_mean, depth_sigma, 0.1)
+                sel = np.nonzero(found)[0]
+                world, right, down, irc, lvl = ctx.epipolar_make_points(level, cands[level][sel], pos[sel], pose_new, synth.IDENTITY_POSE)
+                keep = np.abs(world[:, 2] - 1.0) < 0.1                             # the scene is the plane z = 1; the bundle adjuster would weed out the rest
+                for a, v in zip(new, (world[keep], right[keep], down[keep], irc[keep], lvl[keep])):
+                    a.append(v)
+            world, right, down, irc, lvl = [np.concatenate(a) for a in new]
+            assert len(world) > 100, len(world)
+            ctx.append_map_points(world, right, down, irc, lvl, np.ones(len(world), dtype=np.int32))
+            grown_at = k
+    assert grown_at is not None and ctx.n_points > n_before + 100
+    ints, dbl = ctx.point_states(0)
+    new_pts = ints[n_before:]
+    searched = new_pts[:, 2] == 1
+    assert searched.sum() > 50 and (new_pts[searched, 3] == 1).mean() > 0.6, (searched.sum(), (new_pts[searched, 3] == 1).mean())
+    assert ctx.counters(0)[2] == 2
+    ctx.close()

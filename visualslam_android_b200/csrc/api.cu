@@ -441,6 +441,15 @@ int vslam_make_keyframe_lite_dev(vslam_ctx* ctx, int first, int count, const uin
   return rc ? rc : vs_launch_pyramid_fast(ctx, first, count);
 }
 
+// A map keyframe as a stream's current keyframe (corners + row LUT are needed of a search TARGET, and only streams carry them):
+// zero-copy adoption of the source slot's level-0 image, then the usual pyramid + FAST pass.
+int vslam_make_keyframe_from_source(vslam_ctx* ctx, int s, int kf_id) {
+  int rc = check_stream(ctx, s); if (rc) return rc;
+  if (kf_id < 0 || kf_id >= ctx->n_src || !ctx->src_have[kf_id]) { ctx->err = "source keyframe was never uploaded"; return VSLAM_E_INVALID; }
+  const size_t fs = (size_t)ctx->src.h[0] * ctx->src.pitch[0];
+  return vslam_make_keyframe_lite_dev(ctx, s, 1, ctx->src.img[0] + (size_t)kf_id * fs, ctx->src.pitch[0], fs);
+}
+
 int vslam_level_dims(const vslam_ctx* ctx, int level, int* w, int* h) {
   if (!ctx || level < 0 || level >= VS_LEVELS) return VSLAM_E_INVALID;
   *w = ctx->lev[level].w; *h = ctx->lev[level].h; return VSLAM_OK;
