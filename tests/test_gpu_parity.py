@@ -1219,3 +1219,25 @@ def test_host_mapmaker_loop_grows_the_map_on_the_device():
     assert searched.sum() > 50 and (new_pts[searched, 3] == 1).mean() > 0.6, (searched.sum(), (new_pts[searched, 3] == 1).mean())
     assert ctx.counters(0)[2] == 2
     ctx.close()
+
+
+def test_track_map_config_switches_no_truncation_and_other_seed():
+    """vslam_config.truncate_error = 0 (the WLS takes the residual as a double instead of the reference's (int) cast) and
+    rand_seed != 1 (the per-stream copy of glibc rand() that std::random_shuffle draws from): 2500 points so that every shuffle of
+    TrackMap matters, coarse stage on."""
+    cam, f0, smap = common.scene(n_points=2500)
+    ctx = _ctx(cam, f0, smap, truncate_error=False, rand_seed=7)
+    ow = _orc(cam, f0, smap)
+    ow.L.orc_tracker_set_truncate(ow.tracker, 0); ow.L.orc_tracker_seed(ow.tracker, 7)
+    f1, _ = common.frame_at(cam, np.array(synth.CONFIG1_TWIST) * 0.8)
+    ctx.make_keyframe_lite(f1); ow.make_current_kf(f1)
+    ctx.set_pose(0, synth.IDENTITY_POSE); ow.set_pose(synth.IDENTITY_POSE)
+    ctx.set_motion(0, np.zeros(6), 0.05); ow.L.orc_tracker_set_velocity(ow.tracker, np.zeros(6), 0.05)
+    ctx.track_map(); ow.L.orc_tracker_track_map(ow.tracker)
+    assert ow.counters()[4] == 1
+    _check_track_map(ctx, ow)
+    # and the default seed really gives another selection of points (the switch is not a no-op)
+    ctx1 = _ctx(cam, f0, smap, truncate_error=False)
+    ctx1.make_keyframe_lite(f1); ctx1.set_pose(0, synth.IDENTITY_POSE); ctx1.set_motion(0, np.zeros(6), 0.05); ctx1.track_map()
+    assert not np.array_equal(ctx1.point_states(0)[0][:, 2], ctx.point_states(0)[0][:, 2])
+    ctx.close(); ctx1.close()
