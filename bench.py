@@ -365,6 +365,13 @@ def main():
         a = sys.argv[2:]
         cpu_worker(a[0], int(a[1]), int(a[2]), int(a[3]), int(a[4]), bool(int(a[5])))
         return
+    # stdout carries exactly ONE JSON line: whatever a library writes to fd 1 (NCCL prints its version banner there) goes to stderr
+    sys.stdout.flush()
+    real_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+    def emit(obj):
+        real_out.write(json.dumps(obj) + "\n"); real_out.flush()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
@@ -403,14 +410,14 @@ def main():
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32 + f64", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": fps, "unit": UNIT, "cores": n_procs, "kind": kind, "sample": sample},
                 "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return
 
     if args.sweep:
-        print(json.dumps(sweep_config5(local_rank)))
+        emit(sweep_config5(local_rank))
         return
     if args.cpu_stages:
-        print(json.dumps(cpu_stage_times()))
+        emit(cpu_stage_times())
         return
 
     import torch
@@ -638,7 +645,7 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
 
 
 def render_cpu_or_gpu(tex, cam, poses):
