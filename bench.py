@@ -619,6 +619,22 @@ def main():
              "peak": dp4a_peak, "unit": "TMAC/s", "frac": zm_achieved / dp4a_peak, "candidates_scored_per_step": evals_timed / Ks,
              "peak_source": "dp4a micro-benchmark of this run (vslam_debug_dp4a_peak)",
              "note": "ZMSSD is a small part of k_search (about 6 candidates per point); the kernel is latency / issue bound, see profiles/"}
+    # SURVEY.md §8(d) per-stage rates: templates/s, sub-pixel points/s (counted on a sample of streams from the per-point flags the last
+    # step left behind, scaled to all streams) over the search kernels' time; Gauss-Newton iterations/s per stream over the pose kernels' time
+    sample_streams = list(range(0, S, max(1, S // 8)))
+    n_tmpl = n_subpix = n_searched = 0
+    for s_ in sample_streams:
+        ints, _ = ctx.point_states(s_)
+        n_searched += int(ints[:, 2].sum()); n_subpix += int((ints[:, 2] & ints[:, 4]).sum()); n_tmpl += int((ints[:, 2] & ints[:, 7]).sum())
+    scale = S / len(sample_streams)
+    pose_ms = (stage["pose_fine"][0] + stage["pose_coarse"][0]) / Ks
+    its_per_frame = float(np.mean([len(ctx.updates(s_)[0]) for s_ in sample_streams]))
+    stage_rates = {"templates_generated_per_sec": n_tmpl * scale / (search_ms / Ks * 1e-3), "subpix_points_per_sec": n_subpix * scale / (search_ms / Ks * 1e-3),
+                   "points_searched_per_sec": n_searched * scale / (search_ms / Ks * 1e-3),
+                   "wls_iterations_per_sec_per_stream": its_per_frame / (pose_ms * 1e-3), "wls_iterations_per_frame": its_per_frame,
+                   "per_step": {"points_searched": n_searched * scale, "templates_generated": n_tmpl * scale, "subpix_points": n_subpix * scale},
+                   "note": f"counts from the last step of {len(sample_streams)} sampled streams (fine stage; the flags of a point describe its last search), "
+                           "times from the serialised stage pass"}
     stages_ms = {k: round(v[0] / Ks, 4) for k, v in stage.items() if v[1]}
     stages_ms["note"] = ("timed in a separate serialised pass; in the `value` leg SmallBlurryImage + projection (`other`, `project_lists`) run on a side "
                          "stream beside `pyrfast_l1` (= levels 1-3), so the stages sum to more than ms_per_step")
@@ -626,7 +642,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": dev_ms / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32 (pyramid, FAST, ZMSSD) + f64 (projection, WLS)", "data": "synthetic", "config": config,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": S * H * W, "d2h_bytes_per_step": S * 12 * 8, "ms_per_step": e2e_ms / K},
-            "gpu_launches": int(launches), "clocks": clocks, **({"remeasured_after_stall_ms_per_step": remeasured} if remeasured else {}), "roofline": roofline, "zmssd_roofline": zmssd, "stages_ms_per_step": stages_ms,
+            "gpu_launches": int(launches), "clocks": clocks, **({"remeasured_after_stall_ms_per_step": remeasured} if remeasured else {}), "roofline": roofline, "zmssd_roofline": zmssd, "stages_ms_per_step": stages_ms, "stage_rates": stage_rates,
             "tracking": {"found_per_frame_mean": float(found.mean()), "quality_good_frac": float((quality == 2).mean()),
                          "zmssd_evals_total": int(ctx.zmssd_evals())}}
 

@@ -730,7 +730,7 @@ int vslam_get_point_states(vslam_ctx* ctx, int s, int32_t* ints, double* dbl) {
   for (int i = 0; i < n; i++) {
     int32_t* I = ints + 8 * (size_t)i; double* Dd = dbl + 32 * (size_t)i;
     const int f = fl[i];
-    I[0] = !!(f & F_INIMAGE); I[1] = lv[i]; I[2] = !!(f & F_SEARCHED); I[3] = !!(f & F_FOUND); I[4] = !!(f & F_SUBPIX); I[5] = !!(f & F_TBAD); I[6] = !!(f & F_HASTD); I[7] = 0;
+    I[0] = !!(f & F_INIMAGE); I[1] = lv[i]; I[2] = !!(f & F_SEARCHED); I[3] = !!(f & F_FOUND); I[4] = !!(f & F_SUBPIX); I[5] = !!(f & F_TBAD); I[6] = !!(f & F_HASTD); I[7] = !!(f & F_NEWTMPL);
     for (int c = 0; c < 32; c++) Dd[c] = b[(size_t)c * n + i];
   }
   return VSLAM_OK;

@@ -471,12 +471,13 @@ __global__ void __launch_bounds__(kSearchWarps * 32, 10) k_search(Dev D, int mod
     ts = warp_sum(ts); tq = warp_sum(tq);
     tsum = ts; tsumsq = tq;
     flags = outside ? (flags | F_TBAD) : (flags & ~F_TBAD);
-    flags |= F_HAVELAST;
+    flags |= F_HAVELAST | F_NEWTMPL;
     if (lane == 0) {
       D.ps.tsum[gi] = ts; D.ps.tsum[SN + gi] = tq;
       for (int c = 0; c < 4; c++) D.ps.lastwarp[c * SN + gi] = m2[c];
     }
   } else {
+    flags &= ~F_NEWTMPL;
     sm.tmpl_w[lane] = tmpl_old; if (lane < VS_TMPL_BYTES / 4 - 32) sm.tmpl_w[32 + lane] = tmpl_old2;
     tsum = tsum_old; tsumsq = tsumsq_old;
   }

@@ -49,7 +49,8 @@ struct PointState {
   int* tsum;          // [2][S*N] sum, sumsq
   int* counts;        // [2][S*N] outlier, inlier
 };
-enum { F_INIMAGE = 1, F_SEARCHED = 2, F_FOUND = 4, F_SUBPIX = 8, F_TBAD = 16, F_HAVELAST = 32, F_HASTD = 64 };
+enum { F_INIMAGE = 1, F_SEARCHED = 2, F_FOUND = 4, F_SUBPIX = 8, F_TBAD = 16, F_HAVELAST = 32, F_HASTD = 64,
+       F_NEWTMPL = 128 /* the last search regenerated the template (statistics only) */ };
 
 struct MapDev {
   int n;
