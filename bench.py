@@ -33,6 +33,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 W, H, N_POINTS = 640, 480, 1000
+TEX_SIZE = 2048
+# --frame: the other frame sizes north_star asks throughput for: (W, H, map points, streams per GPU)
+FRAME_CONFIGS = {"1080p": (1920, 1080, 5000, 148), "4k": (3840, 2160, 20000, 148)}   # one CTA of the per-stream kernels per SM
 STREAMS_PER_GPU = 256
 POOL = 24               # distinct frame sets kept resident per leg (78.6 MB each at 256 VGA streams)
 FRAME_STEP = 2          # synthetic sequence index advance per step (≈ 1 px of image motion per frame)
@@ -100,7 +103,7 @@ def build_scene(on_gpu=False, device=0):
     """KF0 + map of N_POINTS points chosen among KF0's FAST corners."""
     from visualslam_android_b200 import synth
     cam = synth.Camera(W, H)
-    tex = synth.make_texture(2048)
+    tex = synth.make_texture(TEX_SIZE)
     f0 = synth.render_frame(tex, cam, synth.IDENTITY_POSE)
     corners, dims = keyframe_corners(f0, on_gpu, device)
     smap = synth.build_map(cam, corners, dims, N_POINTS)
@@ -381,16 +384,29 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--host-alloc", default="pinned", choices=["pinned", "wc"], help="how the e2e leg's host frame pool is allocated")
     ap.add_argument("--groups", type=int, default=0, help="vslam_params.stream_groups (0 = library default)")
+    ap.add_argument("--frame", default="vga", choices=["vga"] + sorted(FRAME_CONFIGS), help="frame size of the whole-TrackFrame workload: vga (the headline "
+                    "config), 1080p (5000 map points, 148 streams per GPU; no SmallBlurryImage: 1080 is not a multiple of 16) or 4k (20000 points, 148 streams)")
     ap.add_argument("--sweep", action="store_true", help="SURVEY §8(d) config 5: 4K frames, batch-size sweep of pyramid+FAST and points x range sweep of the patch search (one GPU)")
     ap.add_argument("--cpu-stages", action="store_true", help="SURVEY §8(d)(i): per-stage CPU times of config 1 (reference build and oracle port), no GPU work")
     args = ap.parse_args()
     K, Wm = args.steps, max(args.warmup, 3 if args.impl == "ours" else 1)
+    if args.frame != "vga":
+        global W, H, N_POINTS, TEX_SIZE, WORKLOAD
+        W, H, N_POINTS, s_default = FRAME_CONFIGS[args.frame]
+        TEX_SIZE = 4096
+        if args.streams == STREAMS_PER_GPU:
+            args.streams = s_default
+        args.no_cpu_baseline = True
+        global POOL
+        POOL = int(max(4, min(24, 6e9 // (args.streams * W * H))))      # keep the resident pool (and its pinned host copy) under ~6 GB
+        WORKLOAD = (f"{args.frame}: {args.streams} independent synthetic {W}x{H} camera streams per GPU, {N_POINTS} map points, full TrackFrame-equivalent per frame "
+                    f"(MaxPatchesPerFrame = 1000 as in the reference{'' if H % 16 == 0 else '; SmallBlurryImage off: the height is not a multiple of 16'}), P=11")
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     config = {"workload": WORKLOAD, "streams_per_gpu": args.streams, "frame": [W, H], "map_points": N_POINTS, "patch": 11, "parallelism": f"streams sharded over {world} GPU(s), no collective",
-              "l2": "inputs larger than L2: each step reads a different 78.6 MB frame set out of a pool of 24 (1.9 GB, triangle-wave order: a set is "
+              "l2": f"inputs larger than L2: each step reads a different {args.streams * W * H / 1e6:.1f} MB frame set out of a pool of {POOL} ({POOL * args.streams * W * H / 1e9:.1f} GB, triangle-wave order: a set is "
                     "re-read at the earliest two steps later) and the per-step working set (frames + pyramids + corner lists + per-point state, "
                     "> 250 MB) exceeds the 126 MB L2; no explicit flush",
               "e2e_host_frames": "pinned (cudaHostAlloc default)" if args.host_alloc == "pinned" else "pinned, write-combined"}
@@ -450,8 +466,9 @@ def main():
     poses = stream_poses(S, M + 1, first_stream=rank * S)                       # (S, M+1, 3, 4); index 0 = identity (the source keyframe)
     frames_dev = torch.empty((M, S, H, W), dtype=torch.uint8, device=dev)
     for k in range(1, M + 1):
-        for s0 in range(0, S, 64):
-            frames_dev[k - 1, s0:s0 + 64] = render_frames_torch(tex_t, cam, poses[s0:s0 + 64, k], dev)
+        rb = 64 if W * H <= 640 * 480 else 8          # render batch (float64 temporaries of B x H x W)
+        for s0 in range(0, S, rb):
+            frames_dev[k - 1, s0:s0 + rb] = render_frames_torch(tex_t, cam, poses[s0:s0 + rb, k], dev)
     torch.cuda.synchronize()
     if args.host_alloc == "wc":
         # write-combined pinned memory (cudaHostAllocWriteCombined | Portable): the CPU never reads the frame pool, and on a multi-socket
@@ -481,10 +498,16 @@ def main():
     stream = torch.cuda.Stream(device=dev)       # an explicit stream: the library launches on it and the CUDA events below are recorded on it
     torch.cuda.set_stream(stream)
     ctx = api.Context(W, H, n_streams=S, max_points=smap.n, device=local_rank, cuda_stream=stream.cuda_stream)
+    prm = {}
     if args.groups:
-        ctx.set_params(stream_groups=args.groups)
+        prm["stream_groups"] = args.groups
+    if H % 16:
+        prm["use_sbi"] = 0                                         # 1080p: cv::resize of level 3 is not an exact 2:1, the motion model runs without the SBI rotation
+    if prm:
+        ctx.set_params(**prm)
     ctx.set_camera(cam.scalars())
-    ctx.enable_sbi(synth.Camera(W // 16, H // 16).scalars())       # SmallBlurryImage + CalcSBIRotation on the device, like the reference's TrackFrame
+    if H % 16 == 0:
+        ctx.enable_sbi(synth.Camera(W // 16, H // 16).scalars())   # SmallBlurryImage + CalcSBIRotation on the device, like the reference's TrackFrame
     ctx.upload_source_keyframe(f0)
     ctx.set_map(smap.world, smap.pix_right_w, smap.pix_down_w, smap.ir_center, smap.src_level)
 

@@ -83,6 +83,19 @@ __device__ inline int calc_level_warp(const Dev& D, const double* pose, int i, s
 
 // ------------------------------------------------------------------------------------------------
 // First loop of TrackMap + list building.  mode 0: stage API (flags reset for every point, no lists); mode 1: TrackMap.
+// The swaps of one std::random_shuffle over v[0..n) (libstdc++ bits/stl_algo.h:4581-4597: element k swaps with element jv[k] = rand() % (k+1),
+// k = 1..n-1), in order: a serial chain through shared memory, with the next partner index and v[k+1] (untouched until step k+1) fetched ahead.
+__device__ __forceinline__ void shuffle_swaps(int* v, const int* jv, int n) {
+  if (n <= 1) return;
+  int jn = jv[1], vkn = v[1];
+  for (int k = 1; k < n; k++) {
+    const int j = jn, vk = vkn;
+    if (k + 1 < n) { jn = jv[k + 1]; vkn = v[k + 1]; }
+    const int vj = v[j];
+    v[k] = vj; v[j] = vk;
+  }
+}
+
 __global__ void __launch_bounds__(kPT) k_project_lists(Dev D, int mode, int apply_motion) {
   extern __shared__ int sh_i[];          // [N] packed level lists (L3|L2|L1|L0), [N] random draws
   __shared__ double s_pose[12];
@@ -154,14 +167,10 @@ __global__ void __launch_bounds__(kPT) k_project_lists(Dev D, int mode, int appl
   }
   const int total = s_off[4];
   // random draws for the four level shuffles, in level order 0..3 (jni/Tracker.cc:396-397)
-  int ring_f = 0, ring_b = 0;
   int n_draws = 0;
 #pragma unroll
   for (int l = 0; l < VS_LEVELS; l++) n_draws += max(s_run[l] - 1, 0);
-  if (tid == 0) {
-    glibc_rand_fill(st->rng_ring, st->rng_f, st->rng_b, rnd, n_draws);
-    ring_f = st->rng_f; ring_b = st->rng_b;
-  }
+  if (tid == 0) glibc_rand_fill(st->rng_ring, st->rng_f, st->rng_b, rnd, n_draws);
   __syncthreads();
   // draw -> swap partner of std::random_shuffle (libstdc++ bits/stl_algo.h:4581-4597: i-th element swaps with rand() % (i+1)), all threads
   for (int d = tid; d < n_draws; d += kPT) {
@@ -176,15 +185,7 @@ __global__ void __launch_bounds__(kPT) k_project_lists(Dev D, int mode, int appl
     int roff = 0; for (int k = 0; k < l; k++) roff += max(s_run[k] - 1, 0);
     int* v = list + s_off[3 - l];
     const int* jv = rnd + roff - 1;
-    if (n > 1) {
-      int jn = jv[1], vkn = v[1];
-      for (int k = 1; k < n; k++) {
-        const int j = jn, vk = vkn;
-        if (k + 1 < n) { jn = jv[k + 1]; vkn = v[k + 1]; }   // v[k+1] is untouched until step k+1
-        const int vj = v[j];
-        v[k] = vj; v[j] = vk;
-      }
-    }
+    shuffle_swaps(v, jv, n);
   }
   __syncthreads();
   if (tid == 0) {   // coarse / fine selection (jni/Tracker.cc:399-527)
@@ -205,19 +206,29 @@ __global__ void __launch_bounds__(kPT) k_project_lists(Dev D, int mode, int appl
       }
     } else tryCoarse = false;
     st->try_coarse = tryCoarse ? 1 : 0; st->coarse_range = (int)nCoarseRange; st->did_coarse = 0;
-    int nFine = total - f0;
+    const int nFine = total - f0;
     int use = D.prm.max_patches_per_frame - ((a1 - a0) + (t1 - t0));
     if (use < 0) use = 0;
-    if (nFine > use) {
-      int ring[31]; for (int k = 0; k < 31; k++) ring[k] = st->rng_ring[k];
-      int* v = list + f0;
-      for (int k = 1; k < nFine; k++) { const int j = glibc_rand_next(ring, ring_f, ring_b) % (k + 1); if (k != j) { const int t = v[k]; v[k] = v[j]; v[j] = t; } }
-      for (int k = 0; k < 31; k++) st->rng_ring[k] = ring[k];
-      st->rng_f = ring_f; st->rng_b = ring_b;
-      nFine = use;
-    }
     s_seg[0] = a0; s_seg[1] = a1 - a0; s_seg[2] = t0; s_seg[3] = t1 - t0; s_seg[4] = f0; s_seg[5] = nFine;
-    st->nA = a1 - a0; st->nB_top = t1 - t0; st->nB = (t1 - t0) + nFine; st->n_updates = 0;
+    s_seg[6] = nFine > use ? 1 : 0; s_seg[7] = use;
+  }
+  __syncthreads();
+  if (s_seg[6]) {
+    // more fine candidates than MaxPatchesPerFrame allows: the fifth std::random_shuffle of the frame, over the whole fine list, then
+    // truncation (jni/Tracker.cc:518-527).  Same three steps as the level shuffles: draws in bulk (one thread, ring in registers),
+    // `% (k+1)` by all threads, then the swap chain -- the only serial part -- with the next partner fetched ahead.
+    const int nF = s_seg[5];
+    if (tid == 0) glibc_rand_fill(st->rng_ring, st->rng_f, st->rng_b, rnd, nF - 1);
+    __syncthreads();
+    for (int d = tid; d < nF - 1; d += kPT) rnd[d] = rnd[d] % (d + 2);
+    __syncthreads();
+    if (tid == 0) shuffle_swaps(list + s_seg[4], rnd - 1, nF);
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const int nFine = s_seg[6] ? s_seg[7] : s_seg[5];
+    s_seg[5] = nFine;
+    st->nA = s_seg[1]; st->nB_top = s_seg[3]; st->nB = s_seg[3] + nFine; st->n_updates = 0;
   }
   __syncthreads();
   int* out = D.lists + (size_t)s * D.list_cap;
