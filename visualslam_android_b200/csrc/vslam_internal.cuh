@@ -98,7 +98,6 @@ struct vslam_ctx {
   bool own_stream;
   int S, N, P;
   LevelDesc lev[VS_LEVELS];
-  LevelDesc* lev_dev;            // [VS_LEVELS] copy on device
   const uint8_t** l0_ptr;        // [S] device: level-0 image of each stream (ctx-owned or adopted user buffer)
   int* l0_stride;                // [S] device
   const uint8_t** l0_ptr_host; int* l0_stride_host;
@@ -111,12 +110,12 @@ struct vslam_ctx {
   unsigned long long* sync_words; size_t sync_words_n;   // strip_state of levels 0..3, then the tickets: one allocation, one memset per frame
   unsigned* tickets;             // [2 * VS_MAX_GROUPS] device (inside sync_words)
   int* status;                   // [4] device: [0] capacity overflow flag
-  CamDev cam; CamDev* cam_dev;
-  MapDev map; MapDev* map_dev;
-  SourceKF src; SourceKF* src_dev; int n_src;
+  CamDev cam;
+  MapDev map;
+  SourceKF src; int n_src;
   std::vector<char> src_have;    // [n_src] which source keyframes have been uploaded (map files, mapfile.cu)
   std::vector<int> reloc_ids; std::vector<double> reloc_poses_host;   // host copy of the vslam_set_reloc_keyframes registration
-  PointState ps; PointState* ps_dev;
+  PointState ps;
   StreamState* ss;               // [S] device
   int* lists;                    // [S][list_cap] iteration / search lists
   int list_cap;
