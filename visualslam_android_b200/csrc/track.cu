@@ -244,9 +244,9 @@ __global__ void __launch_bounds__(kPT) k_project_lists(Dev D, int mode, int appl
 // SearchForPoints, one warp per list entry.
 constexpr int kCandCap = 96;           // ZMSSD candidates gathered per round of one warp
 struct SearchSmem {
-  union {   // the three phases of a warp never overlap: template generation (pos), candidate scoring (cand_*, acc), sub-pixel (pos, jx, jy, prod2)
+  union {   // the three phases of a warp never overlap: template generation (pos), candidate scoring (cand_*), sub-pixel (pos, jx, jy, prod2)
     struct { double pos[VS_MAXP * VS_MAXP * 2]; double jx[81], jy[81], prod2[81]; };   // template sample positions / sub-pixel products and gradients
-    struct { uint32_t cand_cw[kCandCap]; int cand_idx[kCandCap]; int acc[kCandCap * 3]; };
+    struct { uint32_t cand_cw[kCandCap]; int cand_idx[kCandCap]; };
   };
   uint32_t tmpl_w[VS_TMPL_BYTES / 4];  // template, one row = 3 zero-padded words (12 bytes): the dp4a operand layout
 };
@@ -257,28 +257,31 @@ __device__ __forceinline__ int warp_sum(int v) {
   return v;
 }
 
-// ZMSSDAtPoint (jni/PatchFinder.cc:352-380) of the `ncand` candidates filed in sm.cand_cw / cand_idx (accumulators zeroed by the
-// filer): one work item = one template row of one candidate; returns min(best, keys) with key = ssd << 32 | cand_idx (ties: lowest index).
+// ZMSSDAtPoint (jni/PatchFinder.cc:352-380) of the `ncand` candidates filed in sm.cand_cw / cand_idx; returns min(best, keys) with
+// key = ssd << 32 | cand_idx (ties: lowest index).  Eight lanes per candidate, four candidates per step: lane slot r works on template
+// rows r and r + 8 (eight image words in flight per lane: the kernel waits on these loads, not on the dp4a pipe), adds its two rows in
+// registers and the group's three sums -- packed into one 64-bit word, 23 + 23 + 15 bits hold the totals of an 11x11 patch -- are
+// combined by a three-step shuffle butterfly.  (The first version accumulated the rows with shared-memory atomics: up to 11 lanes on one
+// address, ten LSU wavefronts per instruction, a fifth of all LSU wavefronts of the kernel, whose LSU data pipe is 77 % busy.)
+static_assert(VSLAM_MAX_PATCH <= 16 && VSLAM_MAX_PATCH * VSLAM_MAX_PATCH * 255 * 255 < (1 << 23), "score_candidates: two rows per lane slot, 23-bit packed sums");
 template <int PT>
 __device__ __forceinline__ unsigned long long score_candidates(SearchSmem& sm, int ncand, const uint8_t* __restrict__ img, int pitch, int lw, int lh, int P,
                                                                 int tsum, int tsumsq, int maxSSD, unsigned long long best) {
   const int lane = threadIdx.x & 31, PP = P * P;
   const int b = P / 2, nwords = (P + 3) >> 2;
   const uint32_t lastmask = (P & 3) ? ((1u << (8 * (P & 3))) - 1u) : 0xffffffffu;
-  // ZMSSDAtPoint (jni/PatchFinder.cc:352-380): one work item = one template row of one candidate; two items per lane and step so
-  // that eight image words are in flight per lane (the kernel waits on these loads, not on the dp4a pipe)
-  const int nitems = ncand * P;
-  for (int item0 = lane; item0 < nitems; item0 += 64) {
-    uint32_t w[2][4]; int cc[2], rr[2]; unsigned shf[2]; bool ok[2];
+  const int slot = lane & 7, grp = lane >> 3;
+  for (int c0 = 0; c0 < ncand; c0 += 4) {
+    const int c = c0 + grp;
+    const bool have = c < ncand;
+    const uint32_t cw = sm.cand_cw[have ? c : 0];
+    const int cx = cw & 0xffff, cy = cw >> 16;
+    const bool inb = have && (cx >= b && cy >= b && cx < lw - b && cy < lh - b);
+    uint32_t w[2][4]; unsigned shf[2]; bool ok[2];
 #pragma unroll
     for (int u = 0; u < 2; u++) {
-      const int item = item0 + 32 * u;
-      ok[u] = item < nitems;
-      const int c = ok[u] ? item / P : 0, r = item - c * P;
-      cc[u] = c; rr[u] = r;
-      const uint32_t cw = sm.cand_cw[c];
-      const int cx = cw & 0xffff, cy = cw >> 16;
-      ok[u] = ok[u] && (cx >= b && cy >= b && cx < lw - b && cy < lh - b);
+      const int r = slot + 8 * u;
+      ok[u] = inb && r < P;
       w[u][0] = w[u][1] = w[u][2] = w[u][3] = 0u; shf[u] = 0;
       if (ok[u]) {
         const uint8_t* rp = img + (size_t)(cy - b + r) * pitch + (cx - b);
@@ -290,27 +293,30 @@ __device__ __forceinline__ unsigned long long score_candidates(SearchSmem& sm, i
         if (a + P > 12) w[u][3] = __ldg(wp + 3);
       }
     }
+    unsigned long long acc = 0ull;
 #pragma unroll
     for (int u = 0; u < 2; u++) {
       if (!ok[u]) continue;
       uint32_t n0 = __funnelshift_r(w[u][0], w[u][1], shf[u]), n1 = __funnelshift_r(w[u][1], w[u][2], shf[u]), n2 = __funnelshift_r(w[u][2], w[u][3], shf[u]);
       if (nwords == 3) n2 &= lastmask; else if (nwords == 2) { n1 &= lastmask; n2 = 0; } else { n0 &= lastmask; n1 = 0; n2 = 0; }
-      const int r = rr[u], c = cc[u];
+      const int r = slot + 8 * u;
       unsigned sum = __dp4a(n0, 0x01010101u, 0u), sumsq = __dp4a(n0, n0, 0u), cross = __dp4a(n0, sm.tmpl_w[3 * r], 0u);
       sum = __dp4a(n1, 0x01010101u, sum); sumsq = __dp4a(n1, n1, sumsq); cross = __dp4a(n1, sm.tmpl_w[3 * r + 1], cross);
       sum = __dp4a(n2, 0x01010101u, sum); sumsq = __dp4a(n2, n2, sumsq); cross = __dp4a(n2, sm.tmpl_w[3 * r + 2], cross);
-      atomicAdd(&sm.acc[3 * c], (int)sum); atomicAdd(&sm.acc[3 * c + 1], (int)sumsq); atomicAdd(&sm.acc[3 * c + 2], (int)cross);
+      acc += (unsigned long long)cross | ((unsigned long long)sumsq << 23) | ((unsigned long long)sum << 46);
     }
-  }
-  __syncwarp();
-  for (int c = lane; c < ncand; c += 32) {
-    const uint32_t cw = sm.cand_cw[c];
-    const int cx = cw & 0xffff, cy = cw >> 16;
-    int ssd;
-    if (!(cx >= b && cy >= b && cx < lw - b && cy < lh - b)) ssd = maxSSD + 1;
-    else { const int SA = tsum, SB = sm.acc[3 * c]; ssd = ((2 * SA * SB - SA * SA - SB * SB) / PP + sm.acc[3 * c + 1] + tsumsq - 2 * sm.acc[3 * c + 2]); }
-    const unsigned long long key = ((unsigned long long)(unsigned)ssd << 32) | (unsigned)sm.cand_idx[c];   // ssd >= 0; ties -> lowest corner index
-    best = key < best ? key : best;
+#pragma unroll
+    for (int d = 4; d; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if (slot == 0 && have) {
+      int ssd;
+      if (!inb) ssd = maxSSD + 1;
+      else {
+        const int SA = tsum, SB = (int)(acc >> 46), sq = (int)((acc >> 23) & 0x7fffffull), cr = (int)(acc & 0x7fffffull);
+        ssd = ((2 * SA * SB - SA * SA - SB * SB) / PP + sq + tsumsq - 2 * cr);
+      }
+      const unsigned long long key = ((unsigned long long)(unsigned)ssd << 32) | (unsigned)sm.cand_idx[c];   // ssd >= 0; ties -> lowest corner index
+      best = key < best ? key : best;
+    }
   }
   return best;
 }
@@ -537,7 +543,7 @@ __global__ void __launch_bounds__(kSearchWarps * 32, 10) k_search(Dev D, int mod
           if (pass) { const double dx = ix - (double)cx, dy = iy - (double)cy; double d2 = 0; d2 += dx * dx; d2 += dy * dy; pass = !(d2 > nRange * nRange); }
         }
         const unsigned bal = __ballot_sync(0xffffffffu, pass);
-        if (pass) { const int slot = ncand + __popc(bal & ((1u << lane) - 1u)); sm.cand_cw[slot] = cw; sm.cand_idx[slot] = ci; sm.acc[3 * slot] = 0; sm.acc[3 * slot + 1] = 0; sm.acc[3 * slot + 2] = 0; }
+        if (pass) { const int slot = ncand + __popc(bal & ((1u << lane) - 1u)); sm.cand_cw[slot] = cw; sm.cand_idx[slot] = ci; }
         ncand += __popc(bal);
       }
       nevals += ncand;   // (every lane holds the same count; reduced once below)
@@ -625,7 +631,7 @@ __global__ void __launch_bounds__(kSearchWarps * 32) k_epipolar(Dev D, int s, in
           pass = !(dDistDiff * dDistDiff > C.maxDistSq) && !(da < C.minLen) && !(da > C.maxLen);
         }
         const unsigned bal = __ballot_sync(0xffffffffu, pass);
-        if (pass) { const int slot = ncand + __popc(bal & ((1u << lane) - 1u)); sm.cand_cw[slot] = cw; sm.cand_idx[slot] = ci; sm.acc[3 * slot] = 0; sm.acc[3 * slot + 1] = 0; sm.acc[3 * slot + 2] = 0; }
+        if (pass) { const int slot = ncand + __popc(bal & ((1u << lane) - 1u)); sm.cand_cw[slot] = cw; sm.cand_idx[slot] = ci; }
         ncand += __popc(bal);
       }
       __syncwarp();
