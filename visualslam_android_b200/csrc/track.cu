@@ -434,12 +434,9 @@ __global__ void __launch_bounds__(kSearchWarps * 32, 10) k_search(Dev D, int mod
   const uint32_t tmpl_old = tmpl_g[lane], tmpl_old2 = lane < VS_TMPL_BYTES / 4 - 32 ? tmpl_g[32 + lane] : 0u;   // coalesced
   if (lane == 0) {
     refresh = refind || !(flags & F_HAVELAST);
-    for (int c = 0; !refresh && c < 2; c++) {
-      const double d0 = m2[c] - (c ? lw1 : lw0), d1 = m2[2 + c] - (c ? lw3 : lw2);
-      double dd = 0; dd += d0 * d0; dd += d1 * d1;
-      const double lim = 0.07;
-      if (dd > lim * lim) refresh = 1;
-    }
+    // (the two columns written out: indexing m2 with a loop variable would put it in local memory -- 28 sectors of stores per warp)
+    if (!refresh) { const double d0 = m2[0] - lw0, d1 = m2[2] - lw2; double dd = 0; dd += d0 * d0; dd += d1 * d1; if (dd > 0.07 * 0.07) refresh = 1; }
+    if (!refresh) { const double d0 = m2[1] - lw1, d1 = m2[3] - lw3; double dd = 0; dd += d0 * d0; dd += d1 * d1; if (dd > 0.07 * 0.07) refresh = 1; }
   }
   refresh = __shfl_sync(0xffffffffu, refresh, 0);
   const int kf = D.map.srckf[i], sl = D.map.srclevel[i];
@@ -491,7 +488,7 @@ __global__ void __launch_bounds__(kSearchWarps * 32, 10) k_search(Dev D, int mod
     flags |= F_HAVELAST | F_NEWTMPL;
     if (lane == 0) {
       D.ps.tsum[gi] = ts; D.ps.tsum[SN + gi] = tq;
-      for (int c = 0; c < 4; c++) D.ps.lastwarp[c * SN + gi] = m2[c];
+      D.ps.lastwarp[gi] = m2[0]; D.ps.lastwarp[SN + gi] = m2[1]; D.ps.lastwarp[2 * SN + gi] = m2[2]; D.ps.lastwarp[3 * SN + gi] = m2[3];
     }
   } else {
     flags &= ~F_NEWTMPL;
