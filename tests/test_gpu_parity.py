@@ -1094,11 +1094,12 @@ def test_track_frame_keyframe_handoff_on_device():
     for k, fr in enumerate(frames):
         both(fr, k, noise=30 <= k < 34)
         req, closest, dist = ctx.keyframe_requests()
+        assert np.array_equal(req, ctx.keyframe_requests(flags_only=True))           # the compact per-frame poll agrees with the full read-out
         n_kf, oadd, oframe, olast = info()
         assert bool(req[0]) == bool(oadd), (k, req, oadd, dist)
         if req[0]:
             ctx.add_keyframe_from_stream(0, next_id); next_id += 1; added_at.append(k + 1)
-            assert np.array_equal(ctx.keyframe_requests()[0], [0])
+            assert np.array_equal(ctx.keyframe_requests()[0], [0]) and np.array_equal(ctx.keyframe_requests(flags_only=True), [0])
     assert added_at == [6, 27]
     best, score, nrec = C.c_int(), C.c_double(), C.c_int()
     ow.L.orc_tracker_reloc_info(ow.tracker, C.byref(best), C.byref(score), C.byref(nrec))

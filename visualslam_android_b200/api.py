@@ -372,9 +372,13 @@ class Context:
         """MapMaker::NeedNewKeyFrame / IsDistanceToNearestKeyFrameExcessive as Tracker::TrackFrame consults them, on the device."""
         self._ck(self.L.vslam_set_keyframe_policy(self.h, int(enable), wiggle_scale, wiggle_scale_depth_normalized, max_kf_dist_wiggle_mult, min_frames_between))
 
-    def keyframe_requests(self):
-        """(request flag, index of the closest registered keyframe, distance to it) per stream after the last track_frame."""
+    def keyframe_requests(self, flags_only=False):
+        """(request flag, index of the closest registered keyframe, distance to it) per stream after the last track_frame;
+        flags_only: just the flags (the cheap per-frame poll: one copy of n_streams ints)."""
         r = np.zeros(self.S, dtype=np.int32); c = np.zeros(self.S, dtype=np.int32); dist = np.zeros(self.S)
+        if flags_only:
+            self._ck(self.L.vslam_get_keyframe_requests(self.h, r.ctypes.data, None, None))
+            return r
         self._ck(self.L.vslam_get_keyframe_requests(self.h, r.ctypes.data, c.ctypes.data, dist.ctypes.data))
         return r, c, dist
 

@@ -105,7 +105,7 @@ int vslam_create(const vslam_config* cfg, vslam_ctx** out) {
   ctx->cfg = *cfg; vslam_default_params(&ctx->params);
   ctx->S = cfg->n_streams; ctx->N = cfg->max_points; ctx->P = cfg->patch_size; ctx->launches = 0; ctx->n_src = cfg->max_source_keyframes; ctx->src_have.assign(ctx->n_src, 0);
   ctx->reloc_n = 0; ctx->reloc_tmpl = nullptr; ctx->reloc_jac = nullptr; ctx->reloc_tmp = nullptr; ctx->reloc_small = nullptr; ctx->reloc_pose = nullptr; ctx->reloc_scores = nullptr;
-  ctx->kf_policy = false; ctx->kf_wiggle = 0.1; ctx->kf_wiggle_dn = 0.1; ctx->kf_mult = 0.2; ctx->kf_min_frames = 20;
+  ctx->kf_req = nullptr; ctx->kf_policy = false; ctx->kf_wiggle = 0.1; ctx->kf_wiggle_dn = 0.1; ctx->kf_mult = 0.2; ctx->kf_min_frames = 20;
   ctx->unproj_lut = nullptr; ctx->unproj_ok = false; for (int g = 0; g < VS_MAX_GROUPS; g++) { ctx->side_stream[g] = nullptr; ctx->group_stream[g] = nullptr; ctx->ev_fork[g] = nullptr; ctx->ev_join[g] = nullptr; ctx->ev_end[g] = nullptr; }
   ctx->ev_begin = nullptr; ctx->cur_s0 = 0; ctx->cur_cnt = cfg->n_streams; ctx->cur_group = 0; ctx->scratch_host = nullptr; ctx->scratch_host_bytes = 0; ctx->timing = false; ctx->ev_used = 0; ctx->l0_alt = nullptr; ctx->copy_stream = nullptr; ctx->step = 0; ctx->pipe_ready = false; ctx->status_pin = nullptr;
   ctx->rest_scores = nullptr; ctx->rest_max = nullptr; ctx->rest_cand = nullptr; ctx->rest_cand_score = nullptr; ctx->rest_counts = nullptr; ctx->rest_stream = -1;
@@ -163,7 +163,7 @@ int vslam_create(const vslam_config* cfg, vslam_ctx** out) {
   CK(dalloc(&ps.tmpl, SN * VS_TMPL_BYTES)); CK(dalloc(&ps.tsum, 2 * SN)); CK(dalloc(&ps.counts, 2 * SN));
   { std::vector<int> lv(SN, -1); CK(cudaMemcpy(ps.level, lv.data(), SN * sizeof(int), cudaMemcpyHostToDevice)); }
   // per-stream state
-  CK(dalloc(&ctx->ss, (size_t)S));
+  CK(dalloc(&ctx->ss, (size_t)S)); CK(dalloc(&ctx->kf_req, (size_t)S));
   {
     std::vector<StreamState> h(S);
     memset(h.data(), 0, sizeof(StreamState) * S);
@@ -197,7 +197,7 @@ void vslam_destroy(vslam_ctx* ctx) {
   PointState& ps = ctx->ps;
   cudaFree(ps.v3cam); cudaFree(ps.v2image); cudaFree(ps.derivs); cudaFree(ps.warpinv); cudaFree(ps.m2); cudaFree(ps.lastwarp); cudaFree(ps.v2found); cudaFree(ps.coarse);
   cudaFree(ps.jac); cudaFree(ps.err); cudaFree(ps.sqrtinv); cudaFree(ps.flags); cudaFree(ps.level); cudaFree(ps.rlevel); cudaFree(ps.tmpl); cudaFree(ps.tsum); cudaFree(ps.counts);
-  cudaFree(ctx->ss); cudaFree(ctx->lists); cudaFree(ctx->pvs); cudaFree(ctx->sort_scratch);
+  cudaFree(ctx->ss); cudaFree(ctx->kf_req); cudaFree(ctx->lists); cudaFree(ctx->pvs); cudaFree(ctx->sort_scratch);
   if (ctx->scratch_host) cudaFreeHost(ctx->scratch_host);
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   if (ctx->pipe_ready) { for (int k = 0; k < 2; k++) { cudaEventDestroy(ctx->ev_copied[k]); cudaEventDestroy(ctx->ev_computed[k]); cudaEventDestroy(ctx->ev_done[k]); } cudaStreamDestroy(ctx->copy_stream); }
@@ -639,6 +639,10 @@ int vslam_set_keyframe_policy(vslam_ctx* ctx, int enable, double wiggle_scale, d
 int vslam_get_keyframe_requests(vslam_ctx* ctx, int32_t* request, int32_t* closest, double* dist) {
   if (!ctx || !request) return VSLAM_E_INVALID;
   int rc = vslam_sync(ctx); if (rc) return rc;
+  if (!closest && !dist) {   // the per-frame poll: S ints
+    VS_CUDA(cudaMemcpy(request, ctx->kf_req, sizeof(int) * ctx->S, cudaMemcpyDeviceToHost));
+    return VSLAM_OK;
+  }
   std::vector<StreamState> h(ctx->S);
   VS_CUDA(cudaMemcpy(h.data(), ctx->ss, sizeof(StreamState) * ctx->S, cudaMemcpyDeviceToHost));
   for (int s = 0; s < ctx->S; s++) { request[s] = h[s].kf_request; if (closest) closest[s] = h[s].kf_closest; if (dist) dist[s] = h[s].kf_dist; }
@@ -667,6 +671,7 @@ int vslam_add_keyframe_from_stream(vslam_ctx* ctx, int s, int kf_id) {
   if ((rc = vslam_set_reloc_keyframes(ctx, (int)ids.size(), ids.data(), poses.data()))) return rc;
   if ((rc = read_ss(ctx, s, &st))) return rc;
   st.last_kf_dropped = st.frame_no; st.kf_request = 0;
+  VS_CUDA(cudaMemset(ctx->kf_req + s, 0, sizeof(int)));
   return write_ss(ctx, s, &st);
 }
 

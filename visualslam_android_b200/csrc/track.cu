@@ -26,7 +26,7 @@ struct Dev {   // everything the kernels need, passed by value
   int s0;                  // first stream of this launch (stream groups of vs_launch_frame; 0 otherwise)
   vslam_params prm;
   // keyframe policy: poses of the map's keyframes (the relocaliser registration), 0 keyframes = policy off
-  const double* kf_pose; int kf_n, kf_min_frames; double kf_excess_dist, kf_need_dist;
+  const double* kf_pose; int kf_n, kf_min_frames; double kf_excess_dist, kf_need_dist; int* kf_req;
 };
 
 __device__ __forceinline__ int LevelScale(int l) { return 1 << l; }
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(kPT) k_project_lists(Dev D, int mode, int appl
   const int N = D.map.n;
   const size_t SN = (size_t)D.S * D.N;
   StreamState* st = D.ss + s;
-  if (tid == 0 && apply_motion) { st->frame_no++; st->kf_request = 0; }   // mnFrame++ (jni/Tracker.cc:100): every TrackFrame, lost or not
+  if (tid == 0 && apply_motion) { st->frame_no++; st->kf_request = 0; D.kf_req[s] = 0; }   // mnFrame++ (jni/Tracker.cc:100): every TrackFrame, lost or not
   if (mode == 1 && st->lost_frames >= 3 && !st->recovered) return;   // lost and not relocalised this frame (k_relocalise): nothing to do, jni/Tracker.cc:104,134-140
   if (tid == 0 && apply_motion && !st->recovered) {   // Tracker::ApplyMotionModel (jni/Tracker.cc:781-798); a relocalised stream starts from the recovered pose
     double v[6]; for (int k = 0; k < 6; k++) v[k] = st->velocity[k];
@@ -1159,7 +1159,7 @@ __global__ void __launch_bounds__(kPT, 2) k_pose(Dev D, int mode, double sigma_a
       // frames since the last one.  The queue-length term (QueueSize() < 3) is the caller's: it owns the queue.
       if (kfc >= 0 && q == 2 && !st->recovered) {
         double dDist = kfd; dDist *= (1.0 / st->depth_mean);
-        if (dDist > D.kf_need_dist && st->frame_no - st->last_kf_dropped > D.kf_min_frames) st->kf_request = 1;
+        if (dDist > D.kf_need_dist && st->frame_no - st->last_kf_dropped > D.kf_min_frames) { st->kf_request = 1; D.kf_req[s] = 1; }
       }
     }
   }
@@ -1204,7 +1204,7 @@ Dev make_dev(const vslam_ctx* ctx) {
   D.S = ctx->S; D.N = ctx->N; D.P = ctx->P; D.truncate = ctx->cfg.truncate_error; D.prm = ctx->params; D.s0 = ctx->cur_s0;
   const bool kf = ctx->kf_policy && ctx->reloc_n > 0;
   D.kf_pose = ctx->reloc_pose; D.kf_n = kf ? ctx->reloc_n : 0; D.kf_min_frames = ctx->kf_min_frames;
-  D.kf_excess_dist = ctx->kf_wiggle * 10.0; D.kf_need_dist = ctx->kf_mult * ctx->kf_wiggle_dn;
+  D.kf_excess_dist = ctx->kf_wiggle * 10.0; D.kf_need_dist = ctx->kf_mult * ctx->kf_wiggle_dn; D.kf_req = ctx->kf_req;
   return D;
 }
 

@@ -132,6 +132,7 @@ struct vslam_ctx {
   int reloc_n; float reloc_taps[17]; float* reloc_tmpl; float* reloc_jac; float* reloc_tmp; uint8_t* reloc_small; double* reloc_pose; double* reloc_scores;
   // keyframe policy (vslam_set_keyframe_policy): the MapMaker heuristics the tracker consults, over the registered keyframes' poses
   bool kf_policy; double kf_wiggle, kf_wiggle_dn, kf_mult; int kf_min_frames;
+  int* kf_req;                   // [S] device: compact mirror of StreamState::kf_request (one small D2H copy per poll)
   double* unproj_lut; bool unproj_ok;   // [H][W][2] ATANCamera::UnProject of every integer level-0 pixel (MapMaker::AddPointEpipolar's imUnProj), built on the host
   // on-device SmallBlurryImage (vslam_enable_sbi)
   bool sbi_on; float sbi_taps[9]; CamDev sbi_cam; double sbi_orig[2][3]; float* sbi_tmpl; float* sbi_scratch; float* sbi_jac; uint8_t* sbi_small; int* sbi_have;
