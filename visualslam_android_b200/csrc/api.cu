@@ -661,7 +661,9 @@ int vslam_add_keyframe_from_stream(vslam_ctx* ctx, int s, int kf_id) {
     const uint8_t* from = l == 0 ? ctx->l0_ptr_host[s] : L.img + (size_t)s * L.h * L.pitch;
     const int fp = l == 0 ? ctx->l0_stride_host[s] : L.pitch;
     if (!from) { ctx->err = "stream has no current keyframe"; return VSLAM_E_INVALID; }
-    VS_CUDA(cudaMemcpy2DAsync(ctx->src.img[l] + (size_t)kf_id * ctx->src.h[l] * ctx->src.pitch[l], ctx->src.pitch[l], from, fp, L.w, L.h, cudaMemcpyDeviceToDevice, ctx->stream));
+    uint8_t* to = ctx->src.img[l] + (size_t)kf_id * ctx->src.h[l] * ctx->src.pitch[l];
+    if (to == from) continue;   // the stream's level 0 IS this slot (vslam_make_keyframe_from_source of the same keyframe): nothing to copy
+    VS_CUDA(cudaMemcpy2DAsync(to, ctx->src.pitch[l], from, fp, L.w, L.h, cudaMemcpyDeviceToDevice, ctx->stream));
   }
   ctx->src_have[kf_id] = 1;
   std::vector<int> ids = ctx->reloc_ids; std::vector<double> poses = ctx->reloc_poses_host;
