@@ -124,26 +124,27 @@ __device__ void sbi_make_jacs(const float* __restrict__ t, float* jac, int W, in
   }
 }
 
+// X = WfromC * CtoC * WfromC^-1 with WfromC = (I, centre): the image-space transform of the current SE2 estimate (one thread)
+__device__ __forceinline__ void sbi_esm_transform(SbiShared& sh, double cx, double cy) {
+  const double* R = sh.CtoC; const double t0 = sh.CtoC[4], t1 = sh.CtoC[5];
+  // A = WfromC * CtoC : rotation R (I*R evaluated like the reference: sums with exact zeros), translation c + (1*t0 + 0*t1, ...)
+  double AR[4]; for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++) { double sacc = (i == 0 ? 1.0 : 0.0) * R[j]; sacc += (i == 1 ? 1.0 : 0.0) * R[2 + j]; AR[2 * i + j] = sacc; }
+  double At[2]; { double a = 1.0 * t0; a += 0.0 * t1; At[0] = cx + a; double b = 0.0 * t0; b += 1.0 * t1; At[1] = cy + b; }
+  // inverse of WfromC: rotation I, translation -(I * c)
+  double it0, it1; { double a = 1.0 * cx; a += 0.0 * cy; it0 = -a; double b = 0.0 * cx; b += 1.0 * cy; it1 = -b; }
+  for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++) { double sacc = AR[2 * i] * (j == 0 ? 1.0 : 0.0); sacc += AR[2 * i + 1] * (j == 1 ? 1.0 : 0.0); sh.X[2 * i + j] = sacc; }
+  for (int i = 0; i < 2; i++) { double sacc = AR[2 * i] * it0; sacc += AR[2 * i + 1] * it1; sh.X[4 + i] = At[i] + sacc; }
+}
+
 // SmallBlurryImage::IteratePosRelToTarget (jni/SmallBlurryImage.cc:99-222): `its` ESM iterations aligning `cur` to the target `last`
 // (gradient image `jac`).  Leaves the SE2 in sh.CtoC and the final score (sum of squared differences of the last iteration) in sh.score.
 __device__ void sbi_esm(const float* __restrict__ cur, const float* __restrict__ last, const float* __restrict__ jac, float* warped, int W, int H, int its, SbiShared& sh) {
   const int tid = threadIdx.x, n = W * H;
   const double cx = W / 2.0, cy = H / 2.0;
   __syncthreads();
-  if (tid == 0) { sh.CtoC[0] = 1; sh.CtoC[1] = 0; sh.CtoC[2] = 0; sh.CtoC[3] = 1; sh.CtoC[4] = 0; sh.CtoC[5] = 0; sh.mean = 0.0; sh.score = 0.0; }
+  if (tid == 0) { sh.CtoC[0] = 1; sh.CtoC[1] = 0; sh.CtoC[2] = 0; sh.CtoC[3] = 1; sh.CtoC[4] = 0; sh.CtoC[5] = 0; sh.mean = 0.0; sh.score = 0.0; sbi_esm_transform(sh, cx, cy); }
   __syncthreads();
   for (int it = 0; it < its; it++) {
-    if (tid == 0) {   // X = WfromC * CtoC * WfromC^-1 with WfromC = (I, centre)
-      const double* R = sh.CtoC; const double t0 = sh.CtoC[4], t1 = sh.CtoC[5];
-      // A = WfromC * CtoC : rotation R (I*R evaluated like the reference: sums with exact zeros), translation c + (1*t0 + 0*t1, ...)
-      double AR[4]; for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++) { double sacc = (i == 0 ? 1.0 : 0.0) * R[j]; sacc += (i == 1 ? 1.0 : 0.0) * R[2 + j]; AR[2 * i + j] = sacc; }
-      double At[2]; { double a = 1.0 * t0; a += 0.0 * t1; At[0] = cx + a; double b = 0.0 * t0; b += 1.0 * t1; At[1] = cy + b; }
-      // inverse of WfromC: rotation I, translation -(I * c)
-      double it0, it1; { double a = 1.0 * cx; a += 0.0 * cy; it0 = -a; double b = 0.0 * cx; b += 1.0 * cy; it1 = -b; }
-      for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++) { double sacc = AR[2 * i] * (j == 0 ? 1.0 : 0.0); sacc += AR[2 * i + 1] * (j == 1 ? 1.0 : 0.0); sh.X[2 * i + j] = sacc; }
-      for (int i = 0; i < 2; i++) { double sacc = AR[2 * i] * it0; sacc += AR[2 * i + 1] * it1; sh.X[4 + i] = At[i] + sacc; }
-    }
-    __syncthreads();
     {   // transform_image (float): out(i,j) = bilinear(cur, p0 + i*down + j*across), default -9e20f outside
       const double a0 = sh.X[0], a1 = sh.X[2], d0 = sh.X[1], d1 = sh.X[3];
       const double p00 = sh.X[4], p01 = sh.X[5];   // outOrig = 0  =>  p0 = inOrig
@@ -188,8 +189,13 @@ __device__ void sbi_esm(const float* __restrict__ cur, const float* __restrict__
     __syncthreads();
     if ((tid & 31) == 0) { for (int k = 0; k < 15; k++) sh.red15[tid >> 5][k] = acc[k]; }
     __syncthreads();
+    if (tid < 15) {   // lane k adds the eight partials of sum k (same order as a serial loop), lane 0 collects them
+      double r = 0; for (int w = 0; w < kT / 32; w++) r += sh.red15[w][tid];
+      sh.red15[0][tid] = r;
+    }
+    if (tid < 32) __syncwarp();
     if (tid == 0) {
-      for (int k = 0; k < 15; k++) { double r = 0; for (int w = 0; w < kT / 32; w++) r += sh.red15[w][k]; acc[k] = r; }
+      for (int k = 0; k < 15; k++) acc[k] = sh.red15[0][k];
       sh.score = acc[14];
       double m4[16]; int v = 0;
       for (int j = 0; j < 4; j++) for (int i = 0; i <= j; i++) { m4[4 * j + i] = m4[4 * i + j] = acc[4 + v]; v++; }
@@ -203,6 +209,7 @@ __device__ void sbi_esm(const float* __restrict__ cur, const float* __restrict__
       for (int k = 0; k < 4; k++) sh.CtoC[k] = R[k];
       sh.CtoC[4] = t[0]; sh.CtoC[5] = t[1];
       sh.mean -= upd[3];
+      if (it + 1 < its) sbi_esm_transform(sh, cx, cy);   // for the next iteration, in the same single-thread section (one barrier less per iteration)
     }
     __syncthreads();
   }
