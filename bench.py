@@ -551,10 +551,12 @@ def main():
     Ks = min(K, 25)
     ctx.set_timing(True)
     evals0 = ctx.zmssd_evals()
+    stats0 = ctx.search_stats()
     for k in range(Ks):
         ctx.track_frame_ptr(frames_dev[tri(step_no)].data_ptr(), W, fs, device=True); step_no += 1
     barrier()
     evals1 = ctx.zmssd_evals()
+    stats1 = ctx.search_stats()
     stage = ctx.stage_times()
     ctx.set_timing(False)
     # a timed region several times longer than the sum of its own kernels means the box stalled (seen once on a cold box: 40 s inside
@@ -645,19 +647,19 @@ def main():
     # SURVEY.md §8(d) per-stage rates: templates/s, sub-pixel points/s (counted on a sample of streams from the per-point flags the last
     # step left behind, scaled to all streams) over the search kernels' time; Gauss-Newton iterations/s per stream over the pose kernels' time
     sample_streams = list(range(0, S, max(1, S // 8)))
-    n_tmpl = n_subpix = n_searched = 0
-    for s_ in sample_streams:
-        ints, _ = ctx.point_states(s_)
-        n_searched += int(ints[:, 2].sum()); n_subpix += int((ints[:, 2] & ints[:, 4]).sum()); n_tmpl += int((ints[:, 2] & ints[:, 7]).sum())
-    scale = S / len(sample_streams)
+    attempted_per_frame = float(np.mean([ctx.counters(s_)[0].sum() for s_ in sample_streams]))
+    n_tmpl = (stats1["templates_generated"] - stats0["templates_generated"]) / Ks       # device counters over the Ks steps of the stage pass
+    n_subpix = (stats1["subpix_refinements"] - stats0["subpix_refinements"]) / Ks
+    n_searched = attempted_per_frame * S
     pose_ms = (stage["pose_fine"][0] + stage["pose_coarse"][0]) / Ks
     its_per_frame = float(np.mean([len(ctx.updates(s_)[0]) for s_ in sample_streams]))
-    stage_rates = {"templates_generated_per_sec": n_tmpl * scale / (search_ms / Ks * 1e-3), "subpix_points_per_sec": n_subpix * scale / (search_ms / Ks * 1e-3),
-                   "points_searched_per_sec": n_searched * scale / (search_ms / Ks * 1e-3),
+    stage_rates = {"templates_generated_per_sec": n_tmpl / (search_ms / Ks * 1e-3), "subpix_points_per_sec": n_subpix / (search_ms / Ks * 1e-3),
+                   "points_searched_per_sec": n_searched / (search_ms / Ks * 1e-3),
                    "wls_iterations_per_sec_per_stream": its_per_frame / (pose_ms * 1e-3), "wls_iterations_per_frame": its_per_frame,
-                   "per_step": {"points_searched": n_searched * scale, "templates_generated": n_tmpl * scale, "subpix_points": n_subpix * scale},
-                   "note": f"counts from the last step of {len(sample_streams)} sampled streams (fine stage; the flags of a point describe its last search), "
-                           "times from the serialised stage pass"}
+                   "per_step": {"points_searched": n_searched, "templates_generated": n_tmpl, "subpix_points": n_subpix},
+                   "note": f"templates / sub-pixel refinements: device counters over the {Ks} steps of the stage pass (template regeneration is bursty: the 0.07 "
+                           "reuse test of MakeTemplateCoarseCont trips for many points in the same frame); points searched: attempted counters of the last "
+                           f"frame on {len(sample_streams)} sampled streams; times from the serialised stage pass"}
     stages_ms = {k: round(v[0] / Ks, 4) for k, v in stage.items() if v[1]}
     stages_ms["note"] = ("timed in a separate serialised pass; in the `value` leg SmallBlurryImage + projection (`other`, `project_lists`) run on a side "
                          "stream beside `pyrfast_l1` (= levels 1-3), so the stages sum to more than ms_per_step")

@@ -216,6 +216,9 @@ int vslam_get_point_counts(vslam_ctx* ctx, int stream, int32_t* outlier_inlier /
 /* 6-vectors and sigma^2 of every CalcPoseUpdate of the last track_map (<= 20), in order. */
 int vslam_get_updates(vslam_ctx* ctx, int stream, double* upd6, double* sigma_sq, int cap, int* n);
 int vslam_get_zmssd_evals(vslam_ctx* ctx, unsigned long long* total);   /* candidates scored since create (all streams) */
+/* search counters since create (all streams): [0] ZMSSD candidates scored, [1] reserved (0), [2] templates generated
+ * (MakeTemplateCoarseCont calls that did not reuse the cached template), [3] sub-pixel refinements run */
+int vslam_get_search_stats(vslam_ctx* ctx, unsigned long long* stats4);
 
 /* ---- stages, all streams at once ------------------------------------------------------------------------------- */
 int vslam_project_all(vslam_ctx* ctx);

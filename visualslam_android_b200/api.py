@@ -51,7 +51,7 @@ ABI_SYMBOLS = [
     "vslam_get_point_states", "vslam_get_point_template", "vslam_get_point_counts", "vslam_get_updates", "vslam_get_zmssd_evals",
     "vslam_project_all", "vslam_set_point_projection", "vslam_set_lists", "vslam_clear_counters", "vslam_search_for_points", "vslam_refind", "vslam_get_refind_results", "vslam_epipolar_search", "vslam_project_and_derivs", "vslam_calc_jacobians",
     "vslam_calc_pose_update", "vslam_track_map", "vslam_track_frame", "vslam_track_frame_dev", "vslam_track_frame_async", "vslam_wait_step", "vslam_debug_atan", "vslam_debug_dp4a_peak", "vslam_kernel_launches", "vslam_set_timing", "vslam_get_stage_times",
-    "vslam_make_keyframe_from_source", "vslam_append_map_points", "vslam_set_keyframe_policy", "vslam_get_keyframe_requests", "vslam_add_keyframe_from_stream", "vslam_epipolar_make_points", "vslam_map_file_info", "vslam_save_map_file", "vslam_load_map_file", "vslam_export_map_text",
+    "vslam_get_search_stats", "vslam_make_keyframe_from_source", "vslam_append_map_points", "vslam_set_keyframe_policy", "vslam_get_keyframe_requests", "vslam_add_keyframe_from_stream", "vslam_epipolar_make_points", "vslam_map_file_info", "vslam_save_map_file", "vslam_load_map_file", "vslam_export_map_text",
 ]
 
 _lib = None
@@ -114,6 +114,7 @@ def load():
     sig("vslam_set_motion", i, vp, i, vp, d, d, d)
     sig("vslam_reset_stream", i, vp, i)
     sig("vslam_set_reloc_keyframes", i, vp, i, vp, vp)
+    sig("vslam_get_search_stats", i, vp, vp)
     sig("vslam_make_keyframe_from_source", i, vp, i, i)
     sig("vslam_append_map_points", i, vp, i, vp, vp, vp, vp, vp, vp)
     sig("vslam_set_keyframe_policy", i, vp, i, d, d, d, i)
@@ -460,6 +461,12 @@ class Context:
         n = C.c_int()
         self._ck(self.L.vslam_get_updates(self.h, s, u.ctypes.data, sg.ctypes.data, 20, C.byref(n)))
         return u[:n.value], sg[:n.value]
+
+    def search_stats(self):
+        """Counters since create, all streams: ZMSSD candidates scored, templates generated, sub-pixel refinements."""
+        v = (C.c_ulonglong * 4)()
+        self._ck(self.L.vslam_get_search_stats(self.h, v))
+        return dict(zmssd_candidates=int(v[0]), templates_generated=int(v[2]), subpix_refinements=int(v[3]))
 
     def zmssd_evals(self):
         v = C.c_ulonglong()

@@ -149,7 +149,7 @@ int vslam_create(const vslam_config* cfg, vslam_ctx** out) {
   for (int s = 0; s < S; s++) { ctx->l0_ptr_host[s] = ctx->lev[0].img + (size_t)s * ctx->lev[0].h * ctx->lev[0].pitch; ctx->l0_stride_host[s] = ctx->lev[0].pitch; }
   CK(cudaMemcpy(ctx->l0_ptr, ctx->l0_ptr_host, sizeof(uint8_t*) * S, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(ctx->l0_stride, ctx->l0_stride_host, sizeof(int) * S, cudaMemcpyHostToDevice));
-  CK(dalloc(&ctx->status, (size_t)4)); CK(dalloc(&ctx->evals, (size_t)1));
+  CK(dalloc(&ctx->status, (size_t)4)); CK(dalloc(&ctx->evals, (size_t)4));   // [0] ZMSSD candidates scored, [1] unused, [2] templates generated, [3] sub-pixel refinements
   // map
   ctx->map.n = 0;
   CK(dalloc(&ctx->map.world, (size_t)3 * N)); CK(dalloc(&ctx->map.right, (size_t)3 * N)); CK(dalloc(&ctx->map.down, (size_t)3 * N));
@@ -715,6 +715,13 @@ int vslam_get_zmssd_evals(vslam_ctx* ctx, unsigned long long* total) {
   if (!ctx || !total) return VSLAM_E_INVALID;
   VS_CUDA(cudaStreamSynchronize(ctx->stream));
   VS_CUDA(cudaMemcpy(total, ctx->evals, sizeof(*total), cudaMemcpyDeviceToHost));
+  return VSLAM_OK;
+}
+
+int vslam_get_search_stats(vslam_ctx* ctx, unsigned long long* stats4) {
+  if (!ctx || !stats4) return VSLAM_E_INVALID;
+  VS_CUDA(cudaStreamSynchronize(ctx->stream));
+  VS_CUDA(cudaMemcpy(stats4, ctx->evals, 4 * sizeof(*stats4), cudaMemcpyDeviceToHost));
   return VSLAM_OK;
 }
 

@@ -487,6 +487,7 @@ __global__ void __launch_bounds__(kSearchWarps * 32, 10) k_search(Dev D, int mod
     flags = outside ? (flags | F_TBAD) : (flags & ~F_TBAD);
     flags |= F_HAVELAST | F_NEWTMPL;
     if (lane == 0) {
+      atomicAdd(D.evals + 2, 1ull);
       D.ps.tsum[gi] = ts; D.ps.tsum[SN + gi] = tq;
       D.ps.lastwarp[gi] = m2[0]; D.ps.lastwarp[SN + gi] = m2[1]; D.ps.lastwarp[2 * SN + gi] = m2[2]; D.ps.lastwarp[3 * SN + gi] = m2[3];
     }
@@ -564,6 +565,7 @@ __global__ void __launch_bounds__(kSearchWarps * 32, 10) k_search(Dev D, int mod
   int ok = 1;
   if (subpix > 0) {
     flags |= F_SUBPIX;
+    if (lane == 0) atomicAdd(D.evals + 3, 1ull);
     ok = subpix_refine(sm, tmpl, img, pitch, L.w, L.h, level, P, subpix, coarse0, coarse1, found0, found1);
   }
   if (lane == 0) {
