@@ -41,6 +41,8 @@ POOL = 24               # distinct frame sets kept resident per leg (78.6 MB eac
 FRAME_STEP = 2          # synthetic sequence index advance per step (≈ 1 px of image motion per frame)
 METRIC = "tracked_frames_per_sec"
 UNIT = "frames/s"
+CPU_FRAMES_PER_STEP = 25   # frames per process per step in the CPU arms (a bounded sample of the same workload)
+SCALING = "weak"
 WORKLOAD = ("configs[3]: 256 independent synthetic VGA (640x480) camera streams per GPU, 1000 map points, full TrackFrame-equivalent "
             "per frame (4-level pyramid + FAST-10 + row LUT, SmallBlurryImage rotation estimate, coarse+fine PatchFinder search, 10+10 Tukey-WLS iterations), P=11")
 
@@ -111,61 +113,107 @@ def build_scene(on_gpu=False, device=0):
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_worker(path, stream, n_warm, n_steps, frames_per_step, use_ref):
+def tri(j, M):
+    """j-th step of a run -> index into a pool of M consecutive frame sets, traversed as a triangle wave (0,1,..,M-1,M-2,..,0,1,..): any
+    number of steps sees a continuous camera motion that stays over the mapped region.  The GPU arm and both CPU arms use this schedule."""
+    if M == 1:
+        return 0
+    p = j % (2 * M - 2)
+    return p if p < M else 2 * M - 2 - p
+
+
+def pool_size(K, Wm):
+    """Frame sets kept per stream; the same on every arm for the same --steps / --warmup."""
+    Wm = max(Wm, 3)
+    return min(POOL, 2 * (Wm + K) + Wm)
+
+
+def cpu_worker(path, shape, stream, n_warm, n_steps, frames_per_step, use_ref):
     """One process = one camera stream tracked by the reference (oracle/_ref) or the oracle port.  Prints per-step seconds."""
     from visualslam_android_b200 import synth
-    d = np.load(path, allow_pickle=False)
-    frames, f0 = d["frames"][stream], d["f0"]
+    n_seq, M = shape
+    frames = np.load(path + ".frames.npy", mmap_mode="r")[stream]           # (M, H, W): only this stream's pages are touched
+    d = np.load(path + ".scene.npz", allow_pickle=False)
+    f0 = d["f0"]
     smap = synth.SyntheticMap(world=d["world"], pix_right_w=d["right"], pix_down_w=d["down"], ir_center=d["irc"], src_level=d["lvl"],
                               center_nc=d["cnc"], one_right_nc=d["rnc"], one_down_nc=d["dnc"])
     cam = synth.Camera(W, H)
+    a4, f4 = np.zeros(4, dtype=np.int32), np.zeros(4, dtype=np.int32)
     if use_ref:
+        import ctypes as C
         from oracle import refbind
         rw = refbind.RefWorld(W, H, f0, smap)
         rw.L.ref_srand(1)
         rw.L.ref_sbi_reset_size()
+        # keyframe 0 joins the relocaliser (KeyFrame::MakeKeyFrame_Rest leaves pSBI behind, jni/KeyFrame.cc:98): a tracker that gets lost
+        # then recovers through Relocaliser::AttemptRecovery (jni/Relocaliser.cc:17-42) instead of dereferencing a null pSBI
+        rw.L.ref_kf_make_sbi(rw.src_kf.h)
         step = lambda fr: rw.L.ref_tracker_track_frame(rw.tracker, fr, W, H, W)      # the unmodified Tracker::TrackFrame, SmallBlurryImage included
+        q, lost, dc = C.c_int(), C.c_int(), C.c_int()
+        counters = lambda: rw.L.ref_tracker_counters(rw.tracker, a4, f4, C.byref(q), C.byref(lost), C.byref(dc))
     else:
         from oracle import oraclebind
         ow = oraclebind.OrcWorld(cam, f0, smap)
         ow.L.orc_tracker_enable_sbi(ow.tracker, synth.Camera(W // 16, H // 16).scalars())
         step = lambda fr: ow.L.orc_tracker_track_frame(ow.tracker, fr, W, H, W)
+        def counters():
+            a, f, *_ = ow.counters()
+            a4[:] = a; f4[:] = f
     k = 0
-    times = []
+    times, found, attempted = [], 0, 0
     for s in range(n_warm + n_steps):
         t0 = time.perf_counter()
         for _ in range(frames_per_step):
-            step(np.ascontiguousarray(frames[k % len(frames)]))
+            step(np.ascontiguousarray(frames[tri(k, M)]))
             k += 1
         times.append(time.perf_counter() - t0)
-    print(json.dumps({"t_start": time.time() - sum(times[n_warm:]), "steps": times[n_warm:]}))
+        if s >= n_warm:                      # counters of the step's last frame (outside the timed part)
+            counters()
+            found += int(f4.sum()); attempted += int(a4.sum())
+    print(json.dumps({"steps": times[n_warm:], "found_per_frame": found / max(n_steps, 1), "attempted_per_frame": attempted / max(n_steps, 1)}))
 
 
-def run_cpu_arm(cam, f0, smap, frames_by_stream, n_procs, n_warm, n_steps, frames_per_step):
-    """Launch n_procs tracker processes concurrently; returns (frames/s aggregate, seconds per step, kind)."""
+def run_cpu_arm(cam, tex, f0, smap, n_procs, n_warm, n_steps, frames_per_step, M):
+    """Launch n_procs tracker processes concurrently, process i on the GPU arm's stream i (same seeds, same triangle-wave pool of M frame
+    sets, same FRAME_STEP); returns (frames/s aggregate, seconds per step, kind, tracking stats)."""
     from oracle import refbind
     use_ref = refbind.available()
-    fd, path = tempfile.mkstemp(suffix=".npz", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    n_seq = n_procs
+    frames = render_cpu_or_gpu(tex, cam, stream_poses(n_seq, M + 1)[:, 1:])          # (n_seq, M, H, W): what GPU rank 0 feeds streams 0..n_seq-1
+    fd, path = tempfile.mkstemp(prefix="vslam_bench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
     os.close(fd)
-    np.savez(path, frames=frames_by_stream, f0=f0, world=smap.world, right=smap.pix_right_w, down=smap.pix_down_w, irc=smap.ir_center,
+    np.save(path + ".frames.npy", frames)
+    np.savez(path + ".scene.npz", f0=f0, world=smap.world, right=smap.pix_right_w, down=smap.pix_down_w, irc=smap.ir_center,
              lvl=smap.src_level, cnc=smap.center_nc, rnc=smap.one_right_nc, dnc=smap.one_down_nc)
     try:
-        procs = [subprocess.Popen([sys.executable, os.path.abspath(__file__), "--cpu-worker", path, str(i % len(frames_by_stream)), str(n_warm),
+        procs = [subprocess.Popen([sys.executable, os.path.abspath(__file__), "--cpu-worker", path, f"{n_seq},{M}", str(i % n_seq), str(n_warm),
                                    str(n_steps), str(frames_per_step), str(int(use_ref))], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
                                   env={**os.environ, "CUDA_VISIBLE_DEVICES": "", "OMP_NUM_THREADS": "1"}) for i in range(n_procs)]
-        outs = []
-        for p in procs:
-            o, e = p.communicate(timeout=900)
+        outs, failed = [], []
+        for i, p in enumerate(procs):
+            try:
+                o, e = p.communicate(timeout=900)
+            except subprocess.TimeoutExpired:
+                p.kill(); o, e = p.communicate()
+                failed.append(f"worker {i}: timed out"); continue
             if p.returncode != 0:
-                raise RuntimeError("cpu worker failed: " + e[-2000:])
+                why = f"signal {-p.returncode}" if p.returncode < 0 else f"exit code {p.returncode}"
+                failed.append(f"worker {i} (stream {i % n_seq}): {why}; stderr tail: {e[-1500:]!r}")
+                continue
             outs.append(json.loads(o.strip().splitlines()[-1]))
+        if failed:
+            raise RuntimeError("cpu worker(s) failed: " + " | ".join(failed))
     finally:
-        os.unlink(path)
+        for suffix in ("", ".frames.npy", ".scene.npz"):
+            if os.path.exists(path + suffix):
+                os.unlink(path + suffix)
     per_step = np.array([o["steps"] for o in outs])          # (procs, steps) seconds
     step_s = per_step.max(axis=0)                             # a step ends when the slowest worker finished it
     total = float(step_s.sum())
     fps = n_procs * n_steps * frames_per_step / total
-    return fps, total / n_steps, ("reference" if use_ref else "port")
+    stats = {"found_per_frame_mean": float(np.mean([o["found_per_frame"] for o in outs])),
+             "attempted_per_frame_mean": float(np.mean([o["attempted_per_frame"] for o in outs]))}
+    return fps, total / n_steps, ("reference" if use_ref else "port"), stats
 
 
 def sweep_config5(device=0):
@@ -366,7 +414,7 @@ class ClockSampler:
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "--cpu-worker":
         a = sys.argv[2:]
-        cpu_worker(a[0], int(a[1]), int(a[2]), int(a[3]), int(a[4]), bool(int(a[5])))
+        cpu_worker(a[0], tuple(int(x) for x in a[1].split(",")), int(a[2]), int(a[3]), int(a[4]), int(a[5]), bool(int(a[6])))
         return
     # stdout carries exactly ONE JSON line: whatever a library writes to fd 1 (NCCL prints its version banner there) goes to stderr
     sys.stdout.flush()
@@ -415,17 +463,17 @@ def main():
         if rank != 0:
             return
         cam, tex, f0, smap = build_scene()
-        n_procs = os.cpu_count() or 1
-        fps_step = 10
-        n_seq = min(8, n_procs)
-        poses = stream_poses(n_seq, (Wm + K) * fps_step + 1)[:, 1:]
-        frames = render_cpu_or_gpu(tex, cam, poses)
-        fps, step_s, kind = run_cpu_arm(cam, f0, smap, frames, n_procs, Wm, K, fps_step)
-        sample = f"{n_procs} processes (one tracker each, {n_seq} distinct synthetic sequences), {fps_step} frames per process per step; unmodified Tracker::TrackFrame (SmallBlurryImage included)"
+        n_procs = int(os.environ.get("VSLAM_BENCH_CPU_PROCS", 0)) or os.cpu_count() or 1
+        fps_step = CPU_FRAMES_PER_STEP
+        M = pool_size(K, Wm)
+        fps, step_s, kind, stats = run_cpu_arm(cam, tex, f0, smap, n_procs, Wm, K, fps_step, M)
+        sample = (f"{n_procs} processes = the GPU arm's streams 0..{n_procs - 1} (one tracker each, same seeds, same triangle-wave pool of {M} frame sets, "
+                  f"FRAME_STEP {FRAME_STEP}), {fps_step} frames per process per step; unmodified Tracker::TrackFrame (SmallBlurryImage included), "
+                  "keyframe 0 registered with the relocaliser")
         line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": Wm, "ms_per_step": step_s * 1e3,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32 + f64", "data": "synthetic", "config": config,
+                "higher_is_better": True, "scaling": SCALING, "vs_baseline": None, "dtype": "u8/i32 + f64", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": fps, "unit": UNIT, "cores": n_procs, "kind": kind, "sample": sample},
-                "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+                "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0, "tracking": stats}
         emit(line)
         return
 
@@ -462,7 +510,7 @@ def main():
     tex_t = torch.from_numpy(tex.astype(np.float32)).to(dev)
     # A pool of M consecutive frame sets per stream, traversed as a triangle wave (1,2,..,M,M-1,..,1,2,..) so that any number of
     # steps sees a continuous camera motion.  A set is re-read at the earliest two steps later, after > 126 MB of other traffic.
-    M = min(POOL, 2 * (Wm + K) + Wm)
+    M = pool_size(K, Wm)
     poses = stream_poses(S, M + 1, first_stream=rank * S)                       # (S, M+1, 3, 4); index 0 = identity (the source keyframe)
     frames_dev = torch.empty((M, S, H, W), dtype=torch.uint8, device=dev)
     for k in range(1, M + 1):
@@ -489,11 +537,9 @@ def main():
         frames_host.copy_(frames_dev)
     torch.cuda.synchronize()
 
-    def tri(j):      # j-th step of the whole run -> index into the pool
-        if M == 1:
-            return 0
-        p = j % (2 * M - 2)
-        return p if p < M else 2 * M - 2 - p
+    _tri = globals()["tri"]
+    def tri(j):      # j-th step of the whole run -> index into the pool (module-level tri: the schedule shared with the CPU arms)
+        return _tri(j, M)
 
     stream = torch.cuda.Stream(device=dev)       # an explicit stream: the library launches on it and the CUDA events below are recorded on it
     torch.cuda.set_stream(stream)
@@ -673,14 +719,16 @@ def main():
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n_procs = os.cpu_count() or 1
-        n_seq = min(8, n_procs)
-        fps_step, cpu_steps = 10, 6
-        seq = render_cpu_or_gpu(tex, cam, stream_poses(n_seq, (1 + cpu_steps) * fps_step + 1)[:, 1:])
-        fps, step_s, kind = run_cpu_arm(cam, f0, smap, seq, n_procs, 1, cpu_steps, fps_step)
+        fps_step, cpu_steps = CPU_FRAMES_PER_STEP, 6
+        fps, step_s, kind, stats = run_cpu_arm(cam, tex, f0, smap, n_procs, 1, cpu_steps, fps_step, M)
         line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": n_procs, "kind": kind,
-                                "sample": f"{n_procs} processes x {cpu_steps * fps_step} frames of the same synthetic VGA sequences (1000 map points), "
+                                "sample": f"{n_procs} processes = streams 0..{n_procs - 1} of this run x {cpu_steps * fps_step} frames of the same triangle-wave pool "
+                                          f"({M} frame sets, 1000 map points), "
                                           f"{'reference jni/ sources compiled by oracle/build_ref.sh' if kind == 'reference' else 'oracle port'}, "
-                                          "whole Tracker::TrackFrame (SmallBlurryImage included) on both sides"}
+                                          "whole Tracker::TrackFrame (SmallBlurryImage included) on both sides",
+                                "tracking": stats}
+        gf, cf = line["tracking"]["found_per_frame_mean"], stats["found_per_frame_mean"]
+        line["cpu_baseline"]["same_workload"] = bool(abs(gf - cf) <= 0.02 * max(gf, cf))      # found points per frame agree within 2 %
     ctx.close()
     if world > 1:
         dist.barrier()

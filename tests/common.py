@@ -117,3 +117,19 @@ def mapfile_unpack(data: bytes):
     assert pos + 8 == len(data), "trailing bytes"
     assert chk == _fnv1a64(data[:pos]), "checksum"
     return dict(width=w, height=h, cam13=cam13, keyframes=kfs, points=pts, reloc=(rid, rpose))
+
+
+def render_sequence(cam, poses, tex_size=2048):
+    """uint8 frames (len(poses), H, W) of the textured plane.  Input generation only: on a GPU box the torch renderer of bench.py is used
+    (float32 ray arithmetic, so the bytes differ slightly from synth.render_frame -- every arm of a test gets the same bytes either way)."""
+    poses = np.asarray(poses)
+    try:
+        import torch
+        if torch.cuda.is_available():
+            import bench
+            dev = torch.device("cuda", 0)
+            tex_t = torch.from_numpy(texture(tex_size).astype(np.float32)).to(dev)
+            return np.concatenate([bench.render_frames_torch(tex_t, cam, poses[k0:k0 + 32], dev).cpu().numpy() for k0 in range(0, len(poses), 32)])
+    except ImportError:
+        pass
+    return np.stack([synth.render_frame(texture(tex_size), cam, p) for p in poses])

@@ -63,3 +63,49 @@ def test_two_rank_gloo_aggregation():
     assert [v[0] for v in vals] == [5, 5]
     # 10 streams x 4 frames over max(5, 7.5) ms on both ranks
     assert all(abs(v[1] - 40 / 7.5e-3) < 1e-6 for v in vals)
+
+
+def test_reference_algorithm_amplifies_a_one_ulp_perturbation():
+    """Why long free-running sequences cannot be held to a fixed tolerance (tests/test_gpu_config2.py): the ORACLE against
+    ITSELF, one copy with t_x of its pose nudged by 1e-15 after frame 10.  Same code, same libm, same frames — and the two runs drift
+    apart by roughly x1.3 per frame (the motion model feeds the pose difference back), i.e. by many orders of magnitude within 60 frames.
+    Any implementation that is not bit-identical in every floating-point operation meets the same fate."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import common
+    from oracle import oraclebind
+    cam, f0, smap = common.scene()
+    W, H = cam.width, cam.height
+    sbi = synth.Camera(W // 16, H // 16).scalars()
+    a, b = oraclebind.OrcWorld(cam, f0, smap), oraclebind.OrcWorld(cam, f0, smap)
+    for o in (a, b):
+        o.L.orc_tracker_enable_sbi(o.tracker, sbi)
+    diff = []
+    for k in range(1, 71):
+        fr = synth.render_frame(common.texture(), cam, synth.stream_pose(k, 0))
+        for o in (a, b):
+            o.L.orc_tracker_track_frame(o.tracker, fr, W, H, W)
+        if k == 10:
+            assert np.array_equal(a.get_pose(), b.get_pose())          # identical until the nudge
+            p = b.get_pose().copy(); p[0, 3] += 1e-15; b.set_pose(p)
+        diff.append(np.abs(a.get_pose() - b.get_pose()).max())
+    assert diff[11] < 1e-14
+    assert diff[69] > 1e4 * diff[11], (diff[11], diff[69])                # > 4 orders of magnitude in 58 frames
+    growth = (diff[59] / diff[11]) ** (1.0 / 48)
+    assert 1.1 < growth < 1.8, growth
+
+
+def test_reference_arm_runs_on_the_gpu_arms_workload():
+    """`bench.py --impl reference` (the driver's reference arm) on a tiny budget: exits 0, one JSON line, tracks the triangle-wave pool the
+    GPU arm uses (about 950 of the 1000 map points found per frame) and registers keyframe 0 with the relocaliser."""
+    import json
+    from oracle import refbind
+    env = {**os.environ, "VSLAM_BENCH_CPU_PROCS": "2"}
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=600, env=env)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["e2e"]["value"] == line["value"]
+    assert line["cpu_baseline"]["kind"] == ("reference" if refbind.available() else "port")
+    assert line["tracking"]["found_per_frame_mean"] > 900

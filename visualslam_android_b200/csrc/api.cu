@@ -249,6 +249,8 @@ int vslam_get_stage_times(vslam_ctx* ctx, double* ms, int* launches) {
 int vslam_set_params(vslam_ctx* ctx, const vslam_params* p) {
   if (!ctx || !p) return VSLAM_E_INVALID;
   if (2 * p->coarse_max > (unsigned)ctx->list_cap) { ctx->err = "coarse_max too large"; return VSLAM_E_INVALID; }
+  if (p->stream_groups < 0 || p->stream_groups > VS_MAX_GROUPS) { ctx->err = "stream_groups must be 0 (default) .. 4"; return VSLAM_E_INVALID; }
+  if (p->max_patches_per_frame < 0) { ctx->err = "max_patches_per_frame must be >= 0"; return VSLAM_E_INVALID; }
   ctx->params = *p;
   return VSLAM_OK;
 }
@@ -288,6 +290,7 @@ int vslam_set_reloc_keyframes(vslam_ctx* ctx, int n, const int32_t* src_kf_ids, 
   if (!ctx || n < 0 || (n > 0 && (!src_kf_ids || !poses12))) return VSLAM_E_INVALID;
   if (!ctx->sbi_on) { ctx->err = "vslam_set_reloc_keyframes needs vslam_enable_sbi first (SmallBlurryImage size and camera)"; return VSLAM_E_INVALID; }
   for (int k = 0; k < n; k++) if (src_kf_ids[k] < 0 || src_kf_ids[k] >= ctx->n_src) { ctx->err = "relocaliser keyframe is not a source keyframe id"; return VSLAM_E_INVALID; }
+  for (int k = 0; k < n; k++) if (!ctx->src_have[src_kf_ids[k]]) { ctx->err = "relocaliser keyframe slot holds no image (vslam_upload_source_keyframe / vslam_add_keyframe_from_stream first)"; return VSLAM_E_INVALID; }
   VS_CUDA(cudaStreamSynchronize(ctx->stream));
   cudaFree(ctx->reloc_tmpl); cudaFree(ctx->reloc_jac); cudaFree(ctx->reloc_tmp); cudaFree(ctx->reloc_small); cudaFree(ctx->reloc_pose); cudaFree(ctx->reloc_scores);
   ctx->reloc_tmpl = nullptr; ctx->reloc_jac = nullptr; ctx->reloc_tmp = nullptr; ctx->reloc_small = nullptr; ctx->reloc_pose = nullptr; ctx->reloc_scores = nullptr;

@@ -15,6 +15,7 @@
 //
 // Host code only (file I/O + the existing upload entry points); nothing here is on the per-frame path.
 #include "vslam_internal.cuh"
+#include <exception>
 #include <cstdio>
 #include <cerrno>
 #include <sys/stat.h>
@@ -144,7 +145,11 @@ int vslam_load_map_file(vslam_ctx* ctx, const char* path, int flags) {
   if (rc) { fclose(f); return rc; }
   const int W = ctx->src.w[0], H = ctx->src.h[0];
   if (h.width != W || h.height != H) { fclose(f); ctx->err = "map file was written for another image size"; return VSLAM_E_INVALID; }
+  if (h.n_points < 0 || h.n_keyframes < 0 || h.n_reloc < 0) { fclose(f); ctx->err = "map file header holds negative counts"; return VSLAM_E_IO; }
   if (h.n_points > ctx->N || h.n_keyframes > ctx->n_src) { fclose(f); ctx->err = "map file exceeds this context's max_points / max_source_keyframes"; return VSLAM_E_CAPACITY; }
+  // relocaliser keyframes are source keyframes: a count beyond the slots is a corrupt header (sizes below come from the header, before the checksum)
+  if (h.n_reloc > ctx->n_src) { fclose(f); ctx->err = "map file registers more relocaliser keyframes than max_source_keyframes"; return VSLAM_E_CAPACITY; }
+  try {
   if ((flags & VSLAM_MAP_LOAD_RELOC) && h.n_reloc > 0 && !ctx->sbi_on) { fclose(f); ctx->err = "VSLAM_MAP_LOAD_RELOC needs vslam_enable_sbi first"; return VSLAM_E_INVALID; }
   // read and verify the whole file before touching the context: a truncated or corrupt file must leave the loaded map as it was
   const size_t n = (size_t)h.n_points, px = (size_t)W * H;
@@ -159,7 +164,7 @@ int vslam_load_map_file(vslam_ctx* ctx, const char* path, int flags) {
   in.get(rid.data(), 4 * (size_t)h.n_reloc); in.pad8(); in.get(rpose.data(), 96 * (size_t)h.n_reloc);
   uint64_t sum = 0; const bool have_sum = fread(&sum, 1, 8, f) == 8;
   const bool at_end = fgetc(f) == EOF;
-  fclose(f);
+  fclose(f); f = nullptr;
   if (!in.ok || !have_sum) { ctx->err = "map file is truncated"; return VSLAM_E_IO; }
   if (sum != in.sum.h || !at_end) { ctx->err = "map file checksum mismatch"; return VSLAM_E_IO; }
   for (int k = 0; k < h.n_keyframes; k++) if (kf_rec[2 * k] < 0 || kf_rec[2 * k] >= ctx->n_src) { ctx->err = "map file keyframe id exceeds max_source_keyframes"; return VSLAM_E_CAPACITY; }
@@ -170,6 +175,10 @@ int vslam_load_map_file(vslam_ctx* ctx, const char* path, int flags) {
   if ((rc = vslam_set_map(ctx, (int)n, n ? world.data() : &dz, n ? right.data() : &dz, n ? down.data() : &dz, n ? irc.data() : &iz, n ? lvl.data() : &iz, n ? kf.data() : &iz))) return rc;
   if (flags & VSLAM_MAP_LOAD_RELOC) { if ((rc = vslam_set_reloc_keyframes(ctx, h.n_reloc, rid.data(), rpose.data()))) return rc; }
   return VSLAM_OK;
+  } catch (const std::exception& e) {   // nothing may unwind across the C ABI (std::bad_alloc from the staging vectors)
+    if (f) fclose(f);
+    ctx->err = std::string("vslam_load_map_file: ") + e.what(); return VSLAM_E_IO;
+  }
 }
 
 int vslam_export_map_text(vslam_ctx* ctx, const char* dir) {

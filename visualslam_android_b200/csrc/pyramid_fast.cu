@@ -254,8 +254,9 @@ __device__ __forceinline__ void fast_strip(const LevelDesc& L, const uint8_t* __
   __syncthreads();
   const int base = sh.base;
   int* lut = L.lut + (size_t)s * (H + 1);
-  if (tid < rows) lut[y0 + tid] = base + sh.rowoff[tid];
-  if (tid == 0 && y1 == H) lut[H] = base + sh.rowoff[rows];
+  // (clamped to the capacity: on overflow -- reported through status[0] -- the readers of the LUT must not index past the list)
+  if (tid < rows) lut[y0 + tid] = min(base + sh.rowoff[tid], L.cap);
+  if (tid == 0 && y1 == H) lut[H] = min(base + sh.rowoff[rows], L.cap);
   uint32_t* out = L.corners + (size_t)s * L.cap;
   for (int r = warp; r < rows; r += kWarps) {
     int run = base + sh.rowoff[r];

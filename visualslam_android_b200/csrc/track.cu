@@ -96,7 +96,7 @@ __device__ __forceinline__ void shuffle_swaps(int* v, const int* jv, int n) {
   }
 }
 
-__global__ void __launch_bounds__(kPT) k_project_lists(Dev D, int mode, int apply_motion) {
+__global__ void __launch_bounds__(kPT) k_project_lists(Dev D, int mode, int apply_motion, int use_smem) {
   extern __shared__ int sh_i[];          // [N] packed level lists (L3|L2|L1|L0), [N] random draws
   __shared__ double s_pose[12];
   __shared__ int s_cnt[kPT / 32][VS_LEVELS], s_run[VS_LEVELS], s_off[VS_LEVELS + 1];
@@ -160,7 +160,8 @@ __global__ void __launch_bounds__(kPT) k_project_lists(Dev D, int mode, int appl
   // packed layout in shared memory: [L3][L2][L1][L0]
   if (tid == 0) { s_off[0] = 0; s_off[1] = s_run[3]; s_off[2] = s_off[1] + s_run[2]; s_off[3] = s_off[2] + s_run[1]; s_off[4] = s_off[3] + s_run[0]; }
   __syncthreads();
-  int* list = sh_i; int* rnd = sh_i + D.N;
+  // (maps too large for 2 x N ints of shared memory keep the two arrays in the stream's global sort scratch: sort_cap doubles >= 2 N ints)
+  int* list = use_smem ? sh_i : (int*)(D.sort_scratch + (size_t)s * D.sort_cap); int* rnd = list + D.N;
   for (int q = 0; q < VS_LEVELS; q++) {   // q-th packed segment holds level 3-q
     const int l = 3 - q, n = s_run[l];
     for (int k = tid; k < n; k += kPT) list[s_off[q] + k] = pvs[l * D.N + k];
@@ -1214,10 +1215,13 @@ Dev make_dev(const vslam_ctx* ctx) {
 
 int vs_launch_project_all(vslam_ctx* ctx, int mode) {
   const Dev D = make_dev(ctx);
-  const size_t smem = (size_t)2 * ctx->N * sizeof(int);
-  VS_CUDA(cudaFuncSetAttribute(k_project_lists, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // packed level lists + random draws: 2 x N ints of shared memory when that fits beside the static part, the stream's global scratch otherwise
+  size_t smem = (size_t)2 * ctx->N * sizeof(int);
+  const int use_smem = smem <= 200 * 1024;
+  if (!use_smem) smem = 0;
+  if (smem > ctx->smem_attr[0]) { VS_CUDA(cudaFuncSetAttribute(k_project_lists, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); ctx->smem_attr[0] = smem; }
   vs_time_begin(ctx, VS_ST_PROJECT);
-  k_project_lists<<<ctx->cur_cnt, kPT, smem, ctx->stream>>>(D, mode & 1, (mode >> 1) & 1);
+  k_project_lists<<<ctx->cur_cnt, kPT, smem, ctx->stream>>>(D, mode & 1, (mode >> 1) & 1, use_smem);
   vs_time_end(ctx);
   VS_CUDA(cudaGetLastError());
   ctx->launches++;
@@ -1227,6 +1231,7 @@ int vs_launch_project_all(vslam_ctx* ctx, int mode) {
 int vs_launch_search(vslam_ctx* ctx, int which, int range, int subpix, int sflags) {
   const Dev D = make_dev(ctx);
   const int max_entries = which == 1 ? (int)(2 * ctx->params.coarse_max) : ctx->list_cap;
+  if (max_entries <= 0) return VSLAM_OK;   // nCoarseMax == 0: the reference skips the coarse stage (jni/Tracker.cc:425)
   dim3 grid((max_entries + kSearchWarps - 1) / kSearchWarps, ctx->cur_cnt);
   vs_time_begin(ctx, which == 2 ? VS_ST_SEARCH_FINE : VS_ST_SEARCH_COARSE);
   if (ctx->P == 11) k_search<11><<<grid, kSearchWarps * 32, 0, ctx->stream>>>(D, which, range, subpix, sflags);
@@ -1241,7 +1246,7 @@ int vs_launch_search(vslam_ctx* ctx, int which, int range, int subpix, int sflag
 int vs_launch_pose(vslam_ctx* ctx, int mode, double sigma, int mark, int apply) {
   const Dev D = make_dev(ctx);
   const size_t smem = 2048 * sizeof(double) + 2 * 2048 * sizeof(int) + 27 * kPT * sizeof(double);   // sort keys + found list + radix histogram + partial sums
-  VS_CUDA(cudaFuncSetAttribute(k_pose, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem > ctx->smem_attr[1]) { VS_CUDA(cudaFuncSetAttribute(k_pose, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); ctx->smem_attr[1] = smem; }
   vs_time_begin(ctx, (mode & 3) == 2 ? VS_ST_POSE_FINE : VS_ST_POSE_COARSE);
   k_pose<<<ctx->cur_cnt, kPT, smem, ctx->stream>>>(D, mode & 3, sigma, mark, apply, (mode >> 2) & 1);
   vs_time_end(ctx);

@@ -138,6 +138,7 @@ struct vslam_ctx {
   bool sbi_on; float sbi_taps[9]; CamDev sbi_cam; double sbi_orig[2][3]; float* sbi_tmpl; float* sbi_scratch; float* sbi_jac; uint8_t* sbi_small; int* sbi_have;
   // optional per-kernel timing with CUDA events on ctx->stream (vslam_set_timing)
   bool timing; std::vector<cudaEvent_t> ev_pool; std::vector<int> ev_stage; size_t ev_used;
+  size_t smem_attr[4] = {0, 0, 0, 0};   // dynamic shared memory already opted into, per kernel (cudaFuncSetAttribute once, not per frame)
   std::string err;
 };
 
