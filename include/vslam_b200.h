@@ -95,6 +95,12 @@ typedef struct vslam_params {
                                kernels run on separate CUDA streams.  Default 1: on B200 with 256 VGA streams, 2-4 groups measured 5 %
                                SLOWER (1.16 vs 1.10 ms per step) — the smaller grids cost more in tails than the overlap of one
                                group's latency-bound kernels with another's throughput-bound ones gives back */
+  int serial_normal_equations; /* 0 (default): the 27 sums of CalcPoseUpdate's normal equations (jni/myWLS.h:39-50) are a fixed-shape parallel
+                               reduction with fused multiply-add.  1: accumulated serially in the reference's own order (list order, row 0
+                               then row 1, no contraction): bit-identical sums given identical inputs, and a chain of 2 n dependent
+                               additions per iteration (measured cost: DESIGN.md section 4.4) */
+  int pose_kernel;          /* execution only: 0 (default) = k_pose_fast (found points resident on the SM), 1 = k_pose (the round-1 kernel) */
+  int search_kernel;        /* execution only: 0 (default) = k_search_fast + k_subpix (eight lanes per map point), 1 = k_search (one warp per point, round 1) */
 } vslam_params;
 
 void vslam_default_config(vslam_config* cfg);
@@ -282,6 +288,7 @@ int vslam_get_stage_times(vslam_ctx* ctx, double* ms /* [VSLAM_N_STAGES] */, int
 
 /* Test hook: y[i] = the correctly-rounded device atan used by the camera model (csrc/atan_dd.cuh). */
 int vslam_debug_atan(const double* x_host, double* y_host, int n);
+int vslam_debug_atan_dd(const double* x_host, double* y_host, int n);   /* the slow double-double evaluation alone (test hook for the fast path's rounding test) */
 
 /* Integer-pipe micro-benchmark: measured dp4a throughput of the current device in tera-MACs/s (the ZMSSD roofline denominator). */
 int vslam_debug_dp4a_peak(double* tmacs_per_s);

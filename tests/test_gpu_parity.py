@@ -151,6 +151,16 @@ def test_atan_cr_matches_host_libm():
     assert ulp.max() <= 1.0, ulp.max()
 
 
+def test_atan_fast_path_is_the_correctly_rounded_value():
+    """|x| <= 1/16 takes a ~45-flop path (cubic term in double-double + Ziv's rounding test, csrc/atan_dd.cuh) that must return exactly what
+    the double-double routine returns: 2 M arguments in the range the camera model produces, plus the range ends."""
+    from visualslam_android_b200 import api
+    rs = np.random.RandomState(11)
+    x = np.concatenate([rs.uniform(-0.0625, 0.0625, 1200000), rs.uniform(-0.03, 0.03, 800000), 10.0 ** rs.uniform(-9.2, -1.2, 200000),
+                        np.array([0.0625, -0.0625, 1e-9, 0.06250000000000001, 0.9999999e-9, 0.0])])
+    assert np.array_equal(api.debug_atan(x), api.debug_atan(x, dd_only=True))
+
+
 def test_project_all_matches_oracle():
     cam, f0, smap = common.scene()
     ctx, ow = _ctx(cam, f0, smap), _orc(cam, f0, smap)

@@ -38,7 +38,8 @@ class MapFileInfo(C.Structure):
 class Params(C.Structure):
     _fields_ = [("coarse_min", C.c_uint), ("coarse_max", C.c_uint), ("coarse_range", C.c_uint), ("coarse_subpix_its", C.c_int),
                 ("coarse_min_vel", C.c_double), ("fine_range", C.c_int), ("fine_range_after_coarse", C.c_int),
-                ("fine_subpix_its_top_level", C.c_int), ("max_patches_per_frame", C.c_int), ("use_sbi", C.c_int), ("stream_groups", C.c_int)]
+                ("fine_subpix_its_top_level", C.c_int), ("max_patches_per_frame", C.c_int), ("use_sbi", C.c_int), ("stream_groups", C.c_int),
+                ("serial_normal_equations", C.c_int), ("pose_kernel", C.c_int), ("search_kernel", C.c_int)]
 
 
 # every symbol include/vslam_b200.h declares (tests/test_abi_cpu.py checks the library exports all of them)
@@ -50,7 +51,7 @@ ABI_SYMBOLS = [
     "vslam_set_pose", "vslam_get_pose", "vslam_get_poses", "vslam_set_motion", "vslam_get_motion", "vslam_reset_stream", "vslam_set_sbi_rotation", "vslam_enable_sbi", "vslam_get_sbi_rotation", "vslam_set_reloc_keyframes", "vslam_get_reloc_info", "vslam_set_lost", "vslam_get_counters",
     "vslam_get_point_states", "vslam_get_point_template", "vslam_get_point_counts", "vslam_get_updates", "vslam_get_zmssd_evals",
     "vslam_project_all", "vslam_set_point_projection", "vslam_set_lists", "vslam_clear_counters", "vslam_search_for_points", "vslam_refind", "vslam_get_refind_results", "vslam_epipolar_search", "vslam_project_and_derivs", "vslam_calc_jacobians",
-    "vslam_calc_pose_update", "vslam_track_map", "vslam_track_frame", "vslam_track_frame_dev", "vslam_track_frame_async", "vslam_wait_step", "vslam_debug_atan", "vslam_debug_dp4a_peak", "vslam_kernel_launches", "vslam_set_timing", "vslam_get_stage_times",
+    "vslam_calc_pose_update", "vslam_track_map", "vslam_track_frame", "vslam_track_frame_dev", "vslam_track_frame_async", "vslam_wait_step", "vslam_debug_atan", "vslam_debug_atan_dd", "vslam_debug_dp4a_peak", "vslam_kernel_launches", "vslam_set_timing", "vslam_get_stage_times",
     "vslam_get_search_stats", "vslam_make_keyframe_from_source", "vslam_append_map_points", "vslam_set_keyframe_policy", "vslam_get_keyframe_requests", "vslam_add_keyframe_from_stream", "vslam_epipolar_make_points", "vslam_map_file_info", "vslam_save_map_file", "vslam_load_map_file", "vslam_export_map_text",
 ]
 
@@ -155,6 +156,7 @@ def load():
     sig("vslam_track_frame_async", i, vp, vp, i, C.c_size_t, vp)
     sig("vslam_wait_step", i, vp, i)
     sig("vslam_debug_atan", i, vp, vp, i)
+    sig("vslam_debug_atan_dd", i, vp, vp, i)
     sig("vslam_debug_dp4a_peak", i, pd)
     sig("vslam_set_timing", i, vp, i)
     sig("vslam_get_stage_times", i, vp, vp, vp)
@@ -170,11 +172,12 @@ def camera_from_params(params5, width, height, as_shipped_radius=False) -> np.nd
     return out
 
 
-def debug_atan(x) -> np.ndarray:
+def debug_atan(x, dd_only=False) -> np.ndarray:
+    """The device atan of the camera model; dd_only: the double-double evaluation alone (without the fast path and its rounding test)."""
     L = load()
     a = np.ascontiguousarray(x, dtype=np.float64)
     out = np.empty_like(a)
-    rc = L.vslam_debug_atan(a.ctypes.data, out.ctypes.data, a.size)
+    rc = (L.vslam_debug_atan_dd if dd_only else L.vslam_debug_atan)(a.ctypes.data, out.ctypes.data, a.size)
     if rc != OK:
         raise VslamError(rc, 'vslam_debug_atan')
     return out
@@ -214,6 +217,10 @@ class Context:
         self.width, self.height, self.S, self.N, self.P = width, height, n_streams, max_points, patch_size
         self.n_points = 0
         self._keep = []
+        # debugging aid: VSLAM_PARAMS="pose_kernel=1,serial_normal_equations=1" overrides vslam_params of every context of the process (A/B runs of the tests)
+        env = os.environ.get("VSLAM_PARAMS")
+        if env:
+            self.set_params()
 
     def close(self):
         if self.h:
@@ -236,6 +243,10 @@ class Context:
         self.L.vslam_default_params(C.byref(p))
         for k, v in kw.items():
             setattr(p, k, v)
+        env = os.environ.get("VSLAM_PARAMS")       # debugging aid, see __init__
+        if env:
+            for k, v in (kv.split("=") for kv in env.split(",") if kv):
+                setattr(p, k, int(v))
         self._ck(self.L.vslam_set_params(self.h, C.byref(p)))
 
     def set_camera(self, cam13):
@@ -394,6 +405,7 @@ class Context:
     def load_map_file(self, path, flags=0):
         """Load a map file (verified before anything is touched); flags: MAP_LOAD_CAMERA | MAP_LOAD_RELOC."""
         self._ck(self.L.vslam_load_map_file(self.h, os.fsencode(path), flags))
+        self.n_points = int(map_file_info(path)["n_points"])     # point_states() / point_counts() size their buffers from it
 
     def export_map_text(self, directory):
         """The reference's SaveMap debug dump layout (jni/MapMaker.cc:1254-1297): map.dump + keyframes/<i>.info."""

@@ -68,7 +68,7 @@ void vslam_default_config(vslam_config* c) {
 
 void vslam_default_params(vslam_params* p) {   // jni/Tracker.cc:405-410,495-497,518
   p->coarse_min = 20; p->coarse_max = 60; p->coarse_range = 30; p->coarse_subpix_its = 8; p->coarse_min_vel = 0.006;
-  p->fine_range = 10; p->fine_range_after_coarse = 5; p->fine_subpix_its_top_level = 8; p->max_patches_per_frame = 1000; p->use_sbi = 1; p->stream_groups = 1;
+  p->fine_range = 10; p->fine_range_after_coarse = 5; p->fine_subpix_its_top_level = 8; p->max_patches_per_frame = 1000; p->use_sbi = 1; p->stream_groups = 1; p->serial_normal_equations = 0; p->pose_kernel = 0; p->search_kernel = 0;
 }
 
 const char* vslam_last_error(const vslam_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
@@ -135,6 +135,8 @@ int vslam_create(const vslam_config* cfg, vslam_ctx** out) {
     CK(dalloc(&L.img, (size_t)S * h * L.pitch));
     CK(dalloc(&L.corners, (size_t)S * L.cap));
     CK(dalloc(&L.lut, (size_t)S * (h + 1)));
+    L.xw = (w + 31) / 32 + 1;
+    CK(dalloc(&L.xlut, (size_t)S * h * L.xw));
     strip_words += (size_t)S * L.n_strips;
     ctx->src.w[l] = w; ctx->src.h[l] = h; ctx->src.pitch[l] = L.pitch;
     CK(dalloc(&ctx->src.img[l], (size_t)ctx->n_src * h * L.pitch));
@@ -191,7 +193,7 @@ void vslam_destroy(vslam_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->cfg.device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  for (int l = 0; l < VS_LEVELS; l++) { cudaFree(ctx->lev[l].img); cudaFree(ctx->lev[l].corners); cudaFree(ctx->lev[l].lut); cudaFree(ctx->src.img[l]); }
+  for (int l = 0; l < VS_LEVELS; l++) { cudaFree(ctx->lev[l].img); cudaFree(ctx->lev[l].corners); cudaFree(ctx->lev[l].lut); cudaFree(ctx->lev[l].xlut); cudaFree(ctx->src.img[l]); }
   cudaFree(ctx->l0_ptr); cudaFree(ctx->l0_stride); cudaFree(ctx->sync_words); cudaFree(ctx->status); cudaFree(ctx->evals);
   cudaFree(ctx->map.world); cudaFree(ctx->map.right); cudaFree(ctx->map.down); cudaFree(ctx->map.ircenter); cudaFree(ctx->map.srclevel); cudaFree(ctx->map.srckf);
   PointState& ps = ctx->ps;

@@ -261,6 +261,7 @@ __device__ __forceinline__ void fast_strip(const LevelDesc& L, const uint8_t* __
   for (int r = warp; r < rows; r += kWarps) {
     int run = base + sh.rowoff[r];
     const uint32_t yy = (uint32_t)(y0 + r) << 16;
+    int* xl = L.xlut + ((size_t)s * H + (y0 + r)) * L.xw;   // column index of the row (32-pixel buckets): the running positions below ARE its entries
     for (int w0 = 0; w0 < words_per_row; w0 += 32) {
       const int w = w0 + lane;
       uint32_t m = (w < words_per_row) ? bitmask[r * words_per_row + w] : 0u;
@@ -269,6 +270,7 @@ __device__ __forceinline__ void fast_strip(const LevelDesc& L, const uint8_t* __
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
       int pos = run + incl - mine;
+      if (w < words_per_row) xl[w] = min(pos, L.cap);
       while (m) {
         const int b = __ffs(m) - 1; m &= m - 1;
         if (pos < L.cap) out[pos] = yy | (uint32_t)((w << 5) + b);
@@ -276,6 +278,7 @@ __device__ __forceinline__ void fast_strip(const LevelDesc& L, const uint8_t* __
       }
       run += __shfl_sync(0xffffffffu, incl, 31);
     }
+    if (lane == 0) xl[words_per_row] = min(run, L.cap);
   }
 }
 

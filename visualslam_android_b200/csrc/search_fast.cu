@@ -1,0 +1,421 @@
+// Tracker::SearchForPoints (jni/Tracker.cc:629-674) with EIGHT LANES PER MAP POINT, four points per warp.
+//
+// k_search (track.cu) spends one warp per list entry: about 1200 warp-instructions per point at the tracker's workload (a 21 x 21
+// search window, about 130 FAST corners in its rows, about 6 of them inside the circle), most of them uniform bookkeeping executed by
+// 32 lanes for one point, and the kernel is bound by instruction issue (71 % of the issue slots).  Here a point gets a quarter warp:
+//   * per-point state, the re-use test of MakeTemplateCoarseCont (jni/PatchFinder.cc:79-125) and the search window (:170-209) cost one
+//     instruction stream per FOUR points;
+//   * the FAST corners of the window's rows are scanned eight at a time per point (x range first, as integers; the FP64 circle test of
+//     :216-219 only for the ~3 % that pass it), survivors go to a per-point queue in shared memory;
+//   * ZMSSD (jni/PatchFinder.cc:352-380): ONE LANE PER CANDIDATE walks all P rows -- unaligned P-byte rows through aligned 32-bit loads
+//     and a funnel shift, dp4a for sum I, sum I^2, sum I.T -- so the three sums stay in registers (no cross-lane reduction), and a round of up to
+//     eight candidates per point costs one instruction stream for four points;
+//   * argmin over the 64-bit key (ssd << 32 | corner index) = "first in raster order wins ties" (:223-226) by three shuffle steps.
+// A template that has to be regenerated (rare: the 0.07 re-use test keeps > 99 % of them at tracking speed) is produced by the whole warp
+// for that point, exactly like k_search does it (serial position accumulation of transform_image, jni/vision/ImageHandler.cpp:21-113).
+// The sub-pixel refinement (jni/PatchFinder.cc:242-350) of the entries that ask for it runs in a second kernel, k_subpix, one warp per
+// entry, on the coarse result this kernel leaves behind.
+#include "search_common.cuh"
+#include <algorithm>
+
+namespace {
+
+constexpr int kFW = 4;            // warps per CTA
+constexpr int kGL = 8;            // lanes per list entry
+constexpr int kGW = 32 / kGL;     // entries per warp
+constexpr int kQ = 48;            // candidate queue per entry
+#ifndef VS_SEARCH_NB
+#define VS_SEARCH_NB 4
+#endif
+constexpr int kNB = VS_SEARCH_NB; // template rows whose image words are requested together by the ZMSSD (registers: 4 per row)
+constexpr int kR = 3;             // window rows per lane and block
+constexpr int kRows = kGL * kR;   // window rows per block (a 21 x 21 window has 22)
+
+struct FastWarp {
+  union {
+    struct { uint32_t cw[kGW][kQ]; int idx[kGW][kQ]; } q;      // candidates waiting for their ZMSSD: corner word, corner index
+    double pos[VS_MAXP * VS_MAXP * 2];                         // template regeneration: sample positions
+  };
+  uint32_t tmpl[kGW][VS_TMPL_BYTES / 4];                       // the entries' templates, rows of 3 zero-padded words (the dp4a operand layout)
+  int rows[kGW][2][kRows];                                     // the current block of window rows: first item and first corner index of every row
+};
+
+struct Plan { int first, count, range, subpix_all, n_top, subpix_top; };
+// which entries a launch covers and with what range / sub-pixel iterations (jni/Tracker.cc:464-532); false: nothing to do for this stream
+__device__ __forceinline__ bool search_plan(const Dev& D, const StreamState* st, int mode, int range_arg, int subpix_arg, Plan& p) {
+  if (mode != 0 && st->lost_frames >= 3 && !st->recovered) return false;
+  p.n_top = 0; p.subpix_top = 0;
+  if (mode == 0) { p.first = 0; p.count = st->nA; p.range = range_arg; p.subpix_all = subpix_arg; }
+  else if (mode == 1) { if (!st->try_coarse) return false; p.first = 0; p.count = st->nA; p.range = st->coarse_range; p.subpix_all = D.prm.coarse_subpix_its; }
+  else { p.first = st->nA; p.count = st->nB; p.range = st->did_coarse ? D.prm.fine_range_after_coarse : D.prm.fine_range; p.subpix_all = 0; p.n_top = st->nB_top; p.subpix_top = D.prm.fine_subpix_its_top_level; }
+  return true;
+}
+
+// read-only load that keeps its place among its siblings (volatile asm): ptxas otherwise sinks the loads of a window between the dp4a
+// of the previous rows to save registers, which turns eleven rows into eleven dependent round trips
+__device__ __forceinline__ uint32_t ldg_ordered(const uint32_t* p) { uint32_t v; asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+
+constexpr int kSearchRefindF = 1;   // sflags: MapMaker::ReFind_Common's variant (jni/MapMaker.cc:967-1036), see k_search
+
+template <int PT>
+__global__ void __launch_bounds__(kFW * 32) k_search_fast(Dev D, int mode, int range_arg, int subpix_arg, int sflags) {
+  __shared__ FastWarp sm_all[kFW];
+  const int s = blockIdx.y + D.s0, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane / kGL, j = lane % kGL;
+  StreamState* st = D.ss + s;
+  Plan pl;
+  if (!search_plan(D, st, mode, range_arg, subpix_arg, pl)) return;
+  const int e0 = (blockIdx.x * kFW + warp) * kGW;
+  if (e0 >= pl.count) return;                                   // (warp-uniform)
+  FastWarp& W = sm_all[warp];
+  const int e = e0 + g;
+  bool alive = e < pl.count;
+  const int i = D.lists[(size_t)s * D.list_cap + pl.first + (alive ? e : e0)];
+  const size_t SN = (size_t)D.S * D.N, gi = (size_t)s * D.N + i;
+  const int P = PT ? PT : D.P, PP = P * P;
+  const bool refind = (sflags & kSearchRefindF) != 0;
+  int subpix = e < pl.n_top ? pl.subpix_top : pl.subpix_all;
+  int flags = D.ps.flags[gi];
+  const int level = refind ? D.ps.rlevel[gi] : D.ps.level[gi];
+  if (refind) {
+    flags &= ~(F_SEARCHED | F_FOUND | F_SUBPIX);
+    if (alive && !(flags & F_INIMAGE)) { if (j == 0) D.ps.flags[gi] = flags; alive = false; }   // not in this keyframe's image: "never retry"
+    if (level == 0) subpix = 0;
+  }
+
+  // ---- MakeTemplateCoarseCont (jni/PatchFinder.cc:79-125): the re-use test, per entry
+  double m2[4];
+  m2[0] = D.ps.m2[gi]; m2[1] = D.ps.m2[SN + gi]; m2[2] = D.ps.m2[2 * SN + gi]; m2[3] = D.ps.m2[3 * SN + gi];
+  const double lw0 = D.ps.lastwarp[gi], lw1 = D.ps.lastwarp[SN + gi], lw2 = D.ps.lastwarp[2 * SN + gi], lw3 = D.ps.lastwarp[3 * SN + gi];
+  const double v2i0 = D.ps.v2image[gi], v2i1 = D.ps.v2image[SN + gi];
+  int tsum = D.ps.tsum[gi], tsumsq = D.ps.tsum[SN + gi];
+  const uint32_t* tmpl_g = (const uint32_t*)(D.ps.tmpl + gi * VS_TMPL_BYTES);
+  uint32_t told[5];
+#pragma unroll
+  for (int q = 0; q < 5; q++) told[q] = (j + kGL * q < VS_TMPL_BYTES / 4) ? tmpl_g[j + kGL * q] : 0u;
+  bool refresh = refind || !(flags & F_HAVELAST);
+  if (!refresh) { const double d0 = m2[0] - lw0, d1 = m2[2] - lw2; double dd = 0; dd += d0 * d0; dd += d1 * d1; if (dd > 0.07 * 0.07) refresh = true; }
+  if (!refresh) { const double d0 = m2[1] - lw1, d1 = m2[3] - lw3; double dd = 0; dd += d0 * d0; dd += d1 * d1; if (dd > 0.07 * 0.07) refresh = true; }
+  uint32_t* const tw = W.tmpl[g];
+  if (!refresh) {
+    flags &= ~F_NEWTMPL;
+#pragma unroll
+    for (int q = 0; q < 5; q++) if (j + kGL * q < VS_TMPL_BYTES / 4) tw[j + kGL * q] = told[q];
+  }
+  __syncwarp();
+  // ---- templates that have to be regenerated: the whole warp, one entry after the other (transform_image, jni/vision/ImageHandler.cpp:21-113)
+  unsigned need = __ballot_sync(0xffffffffu, alive && refresh && j == 0);
+  while (need) {
+    const int gl = __ffs(need) - 1, gq = gl / kGL; need &= need - 1;
+    const double b0 = __shfl_sync(0xffffffffu, m2[0], gl), b1 = __shfl_sync(0xffffffffu, m2[1], gl), b2 = __shfl_sync(0xffffffffu, m2[2], gl), b3 = __shfl_sync(0xffffffffu, m2[3], gl);
+    const int bi = __shfl_sync(0xffffffffu, i, gl);
+    const size_t bgi = (size_t)s * D.N + bi;
+    const int kf = D.map.srckf[bi], sl = D.map.srclevel[bi];
+    const uint8_t* simg = D.src.img[sl] + (size_t)kf * D.src.h[sl] * D.src.pitch[sl];
+    const int iw = D.src.w[sl], ih = D.src.h[sl], sp = D.src.pitch[sl];
+    int inside = 0;
+    if (lane == 0) {   // sample positions by sequential accumulation, like the reference
+      const double across0 = b0, across1 = b2, down0 = b1, down1 = b3;
+      const double o = (double)(P / 2);
+      double a = b0 * o; a += b1 * o; double b = b2 * o; b += b3 * o;
+      const double p00 = (double)D.map.ircenter[2 * bi] - a, p01 = (double)D.map.ircenter[2 * bi + 1] - b;
+      double min_x = p00, min_y = p01, max_x = min_x, max_y = min_y;
+      if (across0 < 0) min_x += P * across0; else max_x += P * across0;
+      if (down0 < 0) min_x += P * down0; else max_x += P * down0;
+      if (across1 < 0) min_y += P * across1; else max_y += P * across1;
+      if (down1 < 0) min_y += P * down1; else max_y += P * down1;
+      const double cr0 = down0 - P * across0, cr1 = down1 - P * across1;
+      inside = (min_x >= 0 && min_y >= 0 && max_x < iw - 1 && max_y < ih - 1);
+      double px = p00, py = p01;
+      for (int r = 0; r < P; ++r, px += cr0, py += cr1)
+        for (int c = 0; c < P; ++c, px += across0, py += across1) { W.pos[2 * (r * P + c)] = px; W.pos[2 * (r * P + c) + 1] = py; }
+    }
+    inside = __shfl_sync(0xffffffffu, inside, 0);
+    uint32_t* const bw = W.tmpl[gq]; uint8_t* const bt = (uint8_t*)bw;
+    bw[lane] = 0u; if (lane < VS_TMPL_BYTES / 4 - 32) bw[32 + lane] = 0u;   // row padding must be zero
+    __syncwarp();
+    const float x_bound = iw - 1, y_bound = ih - 1;
+    int outside = 0;
+    for (int k = lane; k < PP; k += 32) {
+      double x = W.pos[2 * k], y = W.pos[2 * k + 1];
+      uint8_t v = 0;
+      if (inside || (0 <= x && 0 <= y && x < x_bound && y < y_bound)) {   // sample(u8) (jni/vision/ImageHandler.cpp:12-19)
+        const int lx = (int)x, ly = (int)y;
+        x -= lx; y -= ly;
+        const uint8_t* r0 = simg + (size_t)ly * sp + lx; const uint8_t* r1 = r0 + sp;
+        v = (uint8_t)((1 - y) * ((1 - x) * r0[0] + x * r0[1]) + y * ((1 - x) * r1[0] + x * r1[1]));
+      } else outside++;
+      const int r = k / P;
+      bt[k + r * (12 - P)] = v;
+    }
+    outside = warp_sum(outside);
+    __syncwarp();
+    int ts = 0, tq = 0;
+    for (int k = lane; k < 3 * P; k += 32) { const uint32_t w = bw[k]; ts += (int)__dp4a(w, 0x01010101u, 0u); tq += (int)__dp4a(w, w, 0u); }   // padding is zero
+    { uint32_t* gt = (uint32_t*)(D.ps.tmpl + bgi * VS_TMPL_BYTES); gt[lane] = bw[lane]; if (lane < VS_TMPL_BYTES / 4 - 32) gt[32 + lane] = bw[32 + lane]; }
+    ts = warp_sum(ts); tq = warp_sum(tq);
+    if (g == gq) {
+      tsum = ts; tsumsq = tq;
+      flags = outside ? (flags | F_TBAD) : (flags & ~F_TBAD);
+      flags |= F_HAVELAST | F_NEWTMPL;
+    }
+    if (lane == 0) {
+      atomicAdd(D.evals + 2, 1ull);
+      D.ps.tsum[bgi] = ts; D.ps.tsum[SN + bgi] = tq;
+      D.ps.lastwarp[bgi] = b0; D.ps.lastwarp[SN + bgi] = b1; D.ps.lastwarp[2 * SN + bgi] = b2; D.ps.lastwarp[3 * SN + bgi] = b3;
+    }
+    __syncwarp();
+  }
+  if (alive && (flags & F_TBAD)) {   // jni/Tracker.cc:637-640
+    if (j == 0) D.ps.flags[gi] = flags & ~(F_INIMAGE | F_FOUND);
+    alive = false;
+  }
+  if (alive && j == 0) atomicAdd(&st->attempted[level], 1);
+  __syncwarp();
+
+  // ---- FindPatchCoarse (jni/PatchFinder.cc:170-235)
+  const int lv = alive ? level : 0;
+  const LevelDesc& L = D.lev[lv];
+  const uint8_t* img; int pitch;
+  if (lv == 0) { img = D.l0_ptr[s]; pitch = D.l0_stride[s]; } else { img = L.img + (size_t)s * L.h * L.pitch; pitch = L.pitch; }
+  const int lw = L.w, lh = L.h;
+  const int maxSSD = PP * 500;
+  const int nLevelScale = LevelScale(lv);
+  const double invScale = 1.0 / nLevelScale;                    // 2^-level: x / 2^l == x * 2^-l exactly
+  const double ix = v2i0 * invScale, iy = v2i1 * invScale;
+  const unsigned nRange = ((unsigned)pl.range + nLevelScale - 1) / nLevelScale;
+  int nTop = iy - nRange;
+  const int nBottomPlusOne = iy + nRange + 1;
+  const int nLeft = ix - nRange, nRight = ix + nRange;
+  const double r2 = (double)(nRange * nRange);
+  unsigned long long best = ((unsigned long long)(unsigned)(maxSSD + 1) << 32) | 0xffffffffull;
+  flags |= F_SEARCHED;
+  if (nTop < 0) nTop = 0;
+  const uint32_t* corners = L.corners + (size_t)s * L.cap;
+  // The window's corners through the column index of the row LUT (LevelDesc::xlut, 32-pixel buckets, written by the FAST kernels):
+  // rows [nTop, nBot), buckets [wl, wr1) -- a superset of the x range of jni/PatchFinder.cc:214-215, which is then applied exactly.
+  const int nBot = nBottomPlusOne < lh ? nBottomPlusOne : lh;
+  const bool x_empty = nRight < 0 || nLeft > lw - 1;
+  const int wl = (nLeft > 0 ? nLeft : 0) >> 5, wr1 = ((nRight < lw - 1 ? nRight : lw - 1) >> 5) + 1;
+  const int* xl = L.xlut + (size_t)s * lh * L.xw;
+  const int xw = L.xw;
+  bool rows_left = alive && !x_empty && nTop < nBot;   // (nTop >= rows or nBottomPlusOne <= 0: nothing to search, jni/PatchFinder.cc:189-195)
+  int blk = 0, T = 0, t0 = 0;
+  int* const rs = W.rows[g][0]; int* const rl = W.rows[g][1];
+  const int b = P / 2, nwords = (P + 3) >> 2;
+  const uint32_t lastmask = (P & 3) ? ((1u << (8 * (P & 3))) - 1u) : 0xffffffffu;
+  int nevals = 0, qn = 0;
+  while (true) {
+    // -- scan: until the warp's entries have run out of corners or one of the queues could overflow in the next step
+    while (!__any_sync(0xffffffffu, qn > kQ - 2 * kGL)) {
+      if (!__any_sync(0xffffffffu, t0 < T)) {
+        if (!__any_sync(0xffffffffu, rows_left)) break;
+        // next block of kRows rows per entry: lane j takes rows j * kR .. j * kR + kR - 1 of the block; corner ranges from the column index
+        int lo[kR], cnt[kR], mine = 0;
+#pragma unroll
+        for (int r = 0; r < kR; r++) {
+          const int y = nTop + blk * kRows + j * kR + r;
+          lo[r] = 0; cnt[r] = 0;
+          if (rows_left && y < nBot) { const int* row = xl + (size_t)y * xw; lo[r] = __ldg(row + wl); cnt[r] = __ldg(row + wr1) - lo[r]; }
+          mine += cnt[r];
+        }
+        int incl = mine;
+#pragma unroll
+        for (int d = 1; d < kGL; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d, kGL); if (j >= d) incl += v; }
+        int start = incl - mine;
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < kR; r++) { rs[j * kR + r] = start; rl[j * kR + r] = lo[r]; start += cnt[r]; }
+        T = __shfl_sync(0xffffffffu, incl, kGL - 1, kGL); t0 = 0;
+        blk++;
+        rows_left = rows_left && (nTop + blk * kRows < nBot);
+        __syncwarp();
+        continue;
+      }
+      // two steps of eight corners per entry: item t of the block's concatenated row ranges -> (row q, offset) by binary search over the row starts
+      uint32_t cwv[2]; int civ[2]; bool hv[2];
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        const int t = t0 + u * kGL + j;
+        hv[u] = t < T;
+        int q = 0;
+#pragma unroll
+        for (int step = 16; step; step >>= 1) { const int q2 = q + step; if (q2 < kRows && rs[q2] <= t) q = q2; }
+        civ[u] = rl[q] + (t - rs[q]);
+        cwv[u] = hv[u] ? __ldg(corners + civ[u]) : 0u;
+      }
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        bool pass = false;
+        if (hv[u]) {
+          const int cx = cwv[u] & 0xffff, cy = cwv[u] >> 16;
+          pass = !(cx < nLeft || cx > nRight);                      // (the reference compares as doubles: same result for integers)
+          if (pass) { const double dx = ix - (double)cx, dy = iy - (double)cy; double d2 = 0; d2 += dx * dx; d2 += dy * dy; pass = !(d2 > r2); }
+        }
+        const unsigned gb = (__ballot_sync(0xffffffffu, pass) >> (kGL * g)) & ((1u << kGL) - 1u);
+        if (pass) { const int slot = qn + __popc(gb & ((1u << j) - 1u)); W.q.cw[g][slot] = cwv[u]; W.q.idx[g][slot] = civ[u]; }
+        qn += __popc(gb);
+      }
+      t0 += 2 * kGL;
+    }
+    if (!__any_sync(0xffffffffu, qn > 0)) break;
+    __syncwarp();
+    // -- ZMSSDAtPoint (jni/PatchFinder.cc:352-380) of the queued candidates: one lane per candidate, rounds of eight per entry
+    for (int q0 = 0; __any_sync(0xffffffffu, q0 < qn); q0 += kGL) {
+      const bool have = q0 + j < qn;
+      const uint32_t cw = W.q.cw[g][have ? q0 + j : 0];
+      const int cidx = W.q.idx[g][have ? q0 + j : 0];
+      const int cx = cw & 0xffff, cy = cw >> 16;
+      const bool inb = have && (cx >= b && cy >= b && cx < lw - b && cy < lh - b);
+      int ssd = maxSSD + 1;
+      if ((pitch & 3) == 0) {
+        // Rows a multiple of 4 bytes apart (every level image of the context; caller-owned level-0 frames with such a stride): one alignment
+        // for the whole window.  The words of kNB rows are requested back to back, with a warp barrier between the requests and their first
+        // use: left alone, ptxas sinks each row's loads between the dp4a of the previous row (fewer live registers), which turns a window
+        // into P dependent round trips to L1 / L2.  Lanes without a (valid) candidate read the image origin and discard the result.
+        const uint8_t* rp = inb ? img + (size_t)(cy - b) * pitch + (cx - b) : img;
+        const unsigned a = (unsigned)((uintptr_t)rp & 3u), shf = a * 8;
+        const uint32_t* wp = (const uint32_t*)(rp - a);
+        const int pw = inb ? pitch >> 2 : 0;
+        const bool need2 = a + P > 8, need3 = a + P > 12;
+        constexpr int NR = PT ? PT : VS_MAXP;
+        unsigned sum = 0, sumsq = 0, cross = 0;
+#pragma unroll
+        for (int r0 = 0; r0 < NR; r0 += kNB) {
+          uint32_t w[kNB][4];
+#pragma unroll
+          for (int u = 0; u < kNB; u++) {
+            const int r = r0 + u;
+            w[u][0] = w[u][1] = w[u][2] = w[u][3] = 0u;
+            if (r < NR && (PT != 0 || r < P)) {
+              const uint32_t* q = wp + r * pw;
+              w[u][0] = ldg_ordered(q); w[u][1] = ldg_ordered(q + 1);
+              if (need2) w[u][2] = ldg_ordered(q + 2);
+              if (need3) w[u][3] = ldg_ordered(q + 3);
+            }
+          }
+          __syncwarp();
+#pragma unroll
+          for (int u = 0; u < kNB; u++) {
+            const int r = r0 + u;
+            if (r < NR && (PT != 0 || r < P)) {
+              uint32_t n0 = __funnelshift_r(w[u][0], w[u][1], shf), n1 = __funnelshift_r(w[u][1], w[u][2], shf), n2 = __funnelshift_r(w[u][2], w[u][3], shf);
+              if (nwords == 3) n2 &= lastmask; else if (nwords == 2) { n1 &= lastmask; n2 = 0; } else { n0 &= lastmask; n1 = 0; n2 = 0; }
+              sum = __dp4a(n0, 0x01010101u, sum); sumsq = __dp4a(n0, n0, sumsq); cross = __dp4a(n0, tw[3 * r], cross);
+              if (nwords > 1) { sum = __dp4a(n1, 0x01010101u, sum); sumsq = __dp4a(n1, n1, sumsq); cross = __dp4a(n1, tw[3 * r + 1], cross); }
+              if (nwords > 2) { sum = __dp4a(n2, 0x01010101u, sum); sumsq = __dp4a(n2, n2, sumsq); cross = __dp4a(n2, tw[3 * r + 2], cross); }
+            }
+          }
+        }
+        if (inb) { const int SA = tsum, SB = (int)sum; ssd = ((2 * SA * SB - SA * SA - SB * SB) / PP + (int)sumsq + tsumsq - 2 * (int)cross); }
+      } else if (inb) {
+        unsigned sum = 0, sumsq = 0, cross = 0;
+        const uint8_t* rp = img + (size_t)(cy - b) * pitch + (cx - b);
+#pragma unroll 1
+        for (int r = 0; r < P; r++) {
+          const unsigned a = (unsigned)((uintptr_t)rp & 3u), shf = a * 8;
+          const uint32_t* wp = (const uint32_t*)(rp - a);
+          const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1);
+          const uint32_t w2 = (a + P > 8) ? __ldg(wp + 2) : 0u, w3 = (a + P > 12) ? __ldg(wp + 3) : 0u;
+          uint32_t n0 = __funnelshift_r(w0, w1, shf), n1 = __funnelshift_r(w1, w2, shf), n2 = __funnelshift_r(w2, w3, shf);
+          if (nwords == 3) n2 &= lastmask; else if (nwords == 2) { n1 &= lastmask; n2 = 0; } else { n0 &= lastmask; n1 = 0; n2 = 0; }
+          sum = __dp4a(n0, 0x01010101u, sum); sumsq = __dp4a(n0, n0, sumsq); cross = __dp4a(n0, tw[3 * r], cross);
+          if (nwords > 1) { sum = __dp4a(n1, 0x01010101u, sum); sumsq = __dp4a(n1, n1, sumsq); cross = __dp4a(n1, tw[3 * r + 1], cross); }
+          if (nwords > 2) { sum = __dp4a(n2, 0x01010101u, sum); sumsq = __dp4a(n2, n2, sumsq); cross = __dp4a(n2, tw[3 * r + 2], cross); }
+          rp += pitch;
+        }
+        const int SA = tsum, SB = (int)sum;
+        ssd = ((2 * SA * SB - SA * SA - SB * SB) / PP + (int)sumsq + tsumsq - 2 * (int)cross);
+      }
+      if (have) {
+        const unsigned long long key = ((unsigned long long)(unsigned)ssd << 32) | (unsigned)cidx;   // ssd >= 0; ties -> lowest corner index
+        best = key < best ? key : best;
+      }
+      __syncwarp();
+    }
+    nevals += qn; qn = 0;
+    __syncwarp();
+  }
+#pragma unroll
+  for (int d = kGL / 2; d; d >>= 1) { const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, d); best = o < best ? o : best; }
+  if (!alive) return;
+  if (j == 0 && nevals) atomicAdd(D.evals, (unsigned long long)nevals);
+  const int bestSSD = (int)(best >> 32);
+  if (!(bestSSD < maxSSD)) {
+    if (j == 0) D.ps.flags[gi] = flags & ~F_FOUND;
+    return;
+  }
+  if (j == 0) {
+    const uint32_t bc = corners[(unsigned)best];
+    const double coarse0 = ((double)(bc & 0xffff) + 0.5) * nLevelScale - 0.5, coarse1 = ((double)(bc >> 16) + 0.5) * nLevelScale - 0.5;  // LevelZeroPos
+    flags |= F_FOUND;
+    D.ps.coarse[gi] = coarse0; D.ps.coarse[SN + gi] = coarse1;
+    D.ps.sqrtinv[gi] = invScale;
+    if (subpix > 0) flags |= F_SUBPIX;          // k_subpix refines it, counts it as found if the iteration converges and un-finds it otherwise
+    else { flags &= ~F_SUBPIX; D.ps.v2found[gi] = coarse0; D.ps.v2found[SN + gi] = coarse1; atomicAdd(&st->found[level], 1); }
+    D.ps.flags[gi] = flags;
+  }
+}
+
+// MakeSubPixTemplate + IterateSubPixToConvergence (jni/PatchFinder.cc:242-350; jni/Tracker.cc:657-667) of the entries that k_search_fast
+// found and marked for refinement, one warp per entry.
+__global__ void __launch_bounds__(kFW * 32) k_subpix(Dev D, int mode, int range_arg, int subpix_arg, int sflags) {
+  __shared__ SearchSmem sm_all[kFW];
+  const int s = blockIdx.y + D.s0, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  StreamState* st = D.ss + s;
+  Plan pl;
+  if (!search_plan(D, st, mode, range_arg, subpix_arg, pl)) return;
+  const int n_sub = pl.subpix_all > 0 ? pl.count : (pl.subpix_top > 0 ? min(pl.n_top, pl.count) : 0);
+  const bool refind = (sflags & kSearchRefindF) != 0;
+  const size_t SN = (size_t)D.S * D.N;
+  SearchSmem& sm = sm_all[warp];
+  for (int e = blockIdx.x * kFW + warp; e < n_sub; e += gridDim.x * kFW) {   // (the grid is a few CTAs per stream: the fine stage refines only its top-level entries)
+  const int i = D.lists[(size_t)s * D.list_cap + pl.first + e];
+  const size_t gi = (size_t)s * D.N + i;
+  int flags = D.ps.flags[gi];
+  if ((flags & (F_FOUND | F_SUBPIX | F_SEARCHED)) != (F_FOUND | F_SUBPIX | F_SEARCHED)) continue;
+  const int subpix = e < pl.n_top ? pl.subpix_top : pl.subpix_all;
+  const int level = refind ? D.ps.rlevel[gi] : D.ps.level[gi];
+  if (subpix <= 0 || (refind && level == 0)) continue;
+  __syncwarp();
+  const uint32_t* tmpl_g = (const uint32_t*)(D.ps.tmpl + gi * VS_TMPL_BYTES);
+  sm.tmpl_w[lane] = tmpl_g[lane]; if (lane < VS_TMPL_BYTES / 4 - 32) sm.tmpl_w[32 + lane] = tmpl_g[32 + lane];
+  const double coarse0 = D.ps.coarse[gi], coarse1 = D.ps.coarse[SN + gi];
+  const LevelDesc& L = D.lev[level];
+  const uint8_t* img; int pitch;
+  if (level == 0) { img = D.l0_ptr[s]; pitch = D.l0_stride[s]; } else { img = L.img + (size_t)s * L.h * L.pitch; pitch = L.pitch; }
+  __syncwarp();
+  if (lane == 0) atomicAdd(D.evals + 3, 1ull);
+  double found0 = coarse0, found1 = coarse1;
+  const int ok = subpix_refine(sm, (const uint8_t*)sm.tmpl_w, img, pitch, L.w, L.h, level, D.P, subpix, coarse0, coarse1, found0, found1);
+  if (lane == 0) {
+    if (ok || refind) { D.ps.v2found[gi] = found0; D.ps.v2found[SN + gi] = found1; atomicAdd(&st->found[level], 1); }
+    else { flags &= ~F_FOUND; D.ps.flags[gi] = flags; }   // sub-pixel iteration did not converge (jni/Tracker.cc:660-666)
+  }
+  __syncwarp();
+  }
+}
+
+}  // namespace
+
+int vs_launch_search_fast(vslam_ctx* ctx, int which, int range, int subpix, int sflags) {
+  const Dev D = make_dev(ctx);
+  const int max_entries = which == 1 ? (int)(2 * ctx->params.coarse_max) : ctx->list_cap;
+  if (max_entries <= 0) return VSLAM_OK;   // nCoarseMax == 0: the reference skips the coarse stage (jni/Tracker.cc:425)
+  const int per_cta = kFW * kGW;
+  dim3 grid((max_entries + per_cta - 1) / per_cta, ctx->cur_cnt);
+  vs_time_begin(ctx, which == 2 ? VS_ST_SEARCH_FINE : VS_ST_SEARCH_COARSE);
+  if (ctx->P == 11) k_search_fast<11><<<grid, kFW * 32, 0, ctx->stream>>>(D, which, range, subpix, sflags);
+  else if (ctx->P == 8) k_search_fast<8><<<grid, kFW * 32, 0, ctx->stream>>>(D, which, range, subpix, sflags);
+  else k_search_fast<0><<<grid, kFW * 32, 0, ctx->stream>>>(D, which, range, subpix, sflags);
+  ctx->launches++;
+  // sub-pixel refinement: every entry of the coarse stage / of an explicit list with subpix > 0, the top-level entries of the fine stage
+  const bool any_subpix = which == 0 ? subpix > 0 : (which == 1 ? ctx->params.coarse_subpix_its > 0 : ctx->params.fine_subpix_its_top_level > 0);
+  if (any_subpix) {
+    dim3 g2(std::min((max_entries + kFW - 1) / kFW, 32), ctx->cur_cnt);
+    k_subpix<<<g2, kFW * 32, 0, ctx->stream>>>(D, which, range, subpix, sflags);
+    ctx->launches++;
+  }
+  vs_time_end(ctx);
+  VS_CUDA(cudaGetLastError());
+  return VSLAM_OK;
+}

@@ -9,77 +9,11 @@
 //                     Jacobians, Tukey sigma (radix-select median), weights, the 27-term normal-equation reduction,
 //                     6x6 LU solve, pose = exp(mu) * pose — plus scene depth, motion model and quality assessment.
 // FP64 throughout, no FMA contraction (-fmad=false): integer results are bit-exact, poses agree to ~1e-12.
-#include "geometry.cuh"
+#include "track_dev.cuh"
+#include "pose_common.cuh"
+#include "search_common.cuh"
 
 namespace {
-
-constexpr int kPT = 256;  // threads per CTA in per-stream kernels
-constexpr int kSearchWarps = 4;
-
-struct Dev {   // everything the kernels need, passed by value
-  LevelDesc lev[VS_LEVELS];
-  const uint8_t* const* l0_ptr; const int* l0_stride;
-  CamDev cam; MapDev map; SourceKF src; PointState ps;
-  StreamState* ss; int* lists; int list_cap; int* pvs; double* sort_scratch; int sort_cap;
-  unsigned long long* evals;
-  int S, N, P, truncate;
-  int s0;                  // first stream of this launch (stream groups of vs_launch_frame; 0 otherwise)
-  vslam_params prm;
-  // keyframe policy: poses of the map's keyframes (the relocaliser registration), 0 keyframes = policy off
-  const double* kf_pose; int kf_n, kf_min_frames; double kf_excess_dist, kf_need_dist; int* kf_req;
-};
-
-__device__ __forceinline__ int LevelScale(int l) { return 1 << l; }
-
-// ------------------------------------------------------------------------------------------------
-// TrackerData::Project (jni/TrackerData.h:69-86).  Returns true if Cam.Project was reached (cache valid).
-__device__ inline bool td_project(const Dev& D, const double* pose, int i, size_t gi, size_t SN, CamCache& cc, int& flags) {
-  flags &= ~F_INIMAGE;
-  const double* w = D.map.world + 3 * (size_t)i;
-  const double wp[3] = {w[0], w[1], w[2]};
-  double c[3]; se3_apply(pose, wp, c);
-  D.ps.v3cam[gi] = c[0]; D.ps.v3cam[SN + gi] = c[1]; D.ps.v3cam[2 * SN + gi] = c[2];
-  if (c[2] < 0.001) return false;
-  const double px = c[0] / c[2], py = c[1] / c[2];
-  double d = 0; d += px * px; d += py * py;
-  if (d > D.cam.largestRadius * D.cam.largestRadius) return false;
-  double im[2]; cam_project(D.cam, px, py, im, cc);
-  D.ps.v2image[gi] = im[0]; D.ps.v2image[SN + gi] = im[1];
-  if (cc.invalid) return true;
-  if (im[0] < 0 || im[1] < 0 || im[0] > D.cam.width || im[1] > D.cam.height) return true;
-  flags |= F_INIMAGE;
-  return true;
-}
-
-// PatchFinder::CalcSearchLevelAndWarpMatrix (jni/PatchFinder.cc:31-68)
-__device__ inline int calc_level_warp(const Dev& D, const double* pose, int i, size_t gi, size_t SN, const double* dv, int& flags) {
-  const double c[3] = {D.ps.v3cam[gi], D.ps.v3cam[SN + gi], D.ps.v3cam[2 * SN + gi]};
-  const double invz = 1.0 / c[2];
-  const double* rp = D.map.right + 3 * (size_t)i; const double* dp = D.map.down + 3 * (size_t)i;
-  const double r3[3] = {rp[0], rp[1], rp[2]}, d3[3] = {dp[0], dp[1], dp[2]};
-  double mr[3], md[3]; rot_apply(pose, r3, mr); rot_apply(pose, d3, md);
-  double a[2], b[2];
-  for (int k = 0; k < 2; k++) { a[k] = mr[k] - c[k] * mr[2] * invz; b[k] = md[k] - c[k] * md[2] * invz; }
-  double aux1[2], aux2[2];
-  for (int r = 0; r < 2; r++) {
-    double s = dv[2 * r] * a[0]; s += dv[2 * r + 1] * a[1]; aux1[r] = s * invz;
-    double t = dv[2 * r] * b[0]; t += dv[2 * r + 1] * b[1]; aux2[r] = t * invz;
-  }
-  const double w00 = aux1[0], w01 = aux2[0], w10 = aux1[1], w11 = aux2[1];
-  D.ps.warpinv[gi] = w00; D.ps.warpinv[SN + gi] = w01; D.ps.warpinv[2 * SN + gi] = w10; D.ps.warpinv[3 * SN + gi] = w11;
-  double det = w00 * w11 - w01 * w10;
-  int level = 0;
-  while (det > 3 && level < VS_LEVELS - 1) { level++; det *= 0.25; }
-  // m2 = inverse(mm2WarpInverse) * LevelScale (jni/PatchFinder.cc:82-83, 2x2 adjugate inverse as frozen in the oracle), here
-  // instead of on a single lane of k_search.  Also for rejected warps, with the level the loop reached (mnSearchLevel keeps that
-  // value): MapMaker::ReFind_Common goes on to MakeTemplateCoarseCont after a rejection (jni/PatchFinder.cc:72-76).
-  const double invdet = 1.0 / (w00 * w11 - w01 * w10);
-  const int sc = LevelScale(level);
-  D.ps.m2[gi] = (w11 * invdet) * sc; D.ps.m2[SN + gi] = (-w01 * invdet) * sc; D.ps.m2[2 * SN + gi] = (-w10 * invdet) * sc; D.ps.m2[3 * SN + gi] = (w00 * invdet) * sc;
-  D.ps.rlevel[gi] = level;
-  if (det > 3 || det < 0.25) { flags |= F_TBAD; return -1; }
-  return level;
-}
 
 // ------------------------------------------------------------------------------------------------
 // First loop of TrackMap + list building.  mode 0: stage API (flags reset for every point, no lists); mode 1: TrackMap.
@@ -239,156 +173,6 @@ __global__ void __launch_bounds__(kPT) k_project_lists(Dev D, int mode, int appl
     for (int k = tid; k < n; k += kPT) out[dst + k] = list[src0 + k];
     dst += n;
   }
-}
-
-// ------------------------------------------------------------------------------------------------
-// SearchForPoints, one warp per list entry.
-constexpr int kCandCap = 96;           // ZMSSD candidates gathered per round of one warp
-struct SearchSmem {
-  union {   // the three phases of a warp never overlap: template generation (pos), candidate scoring (cand_*), sub-pixel (pos, jx, jy, prod2)
-    struct { double pos[VS_MAXP * VS_MAXP * 2]; double jx[81], jy[81], prod2[81]; };   // template sample positions / sub-pixel products and gradients
-    struct { uint32_t cand_cw[kCandCap]; int cand_idx[kCandCap]; };
-  };
-  uint32_t tmpl_w[VS_TMPL_BYTES / 4];  // template, one row = 3 zero-padded words (12 bytes): the dp4a operand layout
-};
-
-__device__ __forceinline__ int warp_sum(int v) {
-#pragma unroll
-  for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-  return v;
-}
-
-// ZMSSDAtPoint (jni/PatchFinder.cc:352-380) of the `ncand` candidates filed in sm.cand_cw / cand_idx; returns min(best, keys) with
-// key = ssd << 32 | cand_idx (ties: lowest index).  Eight lanes per candidate, four candidates per step: lane slot r works on template
-// rows r and r + 8 (eight image words in flight per lane: the kernel waits on these loads, not on the dp4a pipe), adds its two rows in
-// registers and the group's three sums -- packed into one 64-bit word, 23 + 23 + 15 bits hold the totals of an 11x11 patch -- are
-// combined by a three-step shuffle butterfly.  (The first version accumulated the rows with shared-memory atomics: up to 11 lanes on one
-// address, ten LSU wavefronts per instruction, a fifth of all LSU wavefronts of the kernel, whose LSU data pipe is 77 % busy.)
-static_assert(VSLAM_MAX_PATCH <= 16 && VSLAM_MAX_PATCH * VSLAM_MAX_PATCH * 255 * 255 < (1 << 23), "score_candidates: two rows per lane slot, 23-bit packed sums");
-template <int PT>
-__device__ __forceinline__ unsigned long long score_candidates(SearchSmem& sm, int ncand, const uint8_t* __restrict__ img, int pitch, int lw, int lh, int P,
-                                                                int tsum, int tsumsq, int maxSSD, unsigned long long best) {
-  const int lane = threadIdx.x & 31, PP = P * P;
-  const int b = P / 2, nwords = (P + 3) >> 2;
-  const uint32_t lastmask = (P & 3) ? ((1u << (8 * (P & 3))) - 1u) : 0xffffffffu;
-  const int slot = lane & 7, grp = lane >> 3;
-  for (int c0 = 0; c0 < ncand; c0 += 4) {
-    const int c = c0 + grp;
-    const bool have = c < ncand;
-    const uint32_t cw = sm.cand_cw[have ? c : 0];
-    const int cx = cw & 0xffff, cy = cw >> 16;
-    const bool inb = have && (cx >= b && cy >= b && cx < lw - b && cy < lh - b);
-    uint32_t w[2][4]; unsigned shf[2]; bool ok[2];
-#pragma unroll
-    for (int u = 0; u < 2; u++) {
-      const int r = slot + 8 * u;
-      ok[u] = inb && r < P;
-      w[u][0] = w[u][1] = w[u][2] = w[u][3] = 0u; shf[u] = 0;
-      if (ok[u]) {
-        const uint8_t* rp = img + (size_t)(cy - b + r) * pitch + (cx - b);
-        const unsigned a = (unsigned)((uintptr_t)rp & 3u);
-        shf[u] = a * 8;
-        const uint32_t* wp = (const uint32_t*)(rp - a);
-        w[u][0] = __ldg(wp); w[u][1] = __ldg(wp + 1);
-        if (a + P > 8) w[u][2] = __ldg(wp + 2);
-        if (a + P > 12) w[u][3] = __ldg(wp + 3);
-      }
-    }
-    unsigned long long acc = 0ull;
-#pragma unroll
-    for (int u = 0; u < 2; u++) {
-      if (!ok[u]) continue;
-      uint32_t n0 = __funnelshift_r(w[u][0], w[u][1], shf[u]), n1 = __funnelshift_r(w[u][1], w[u][2], shf[u]), n2 = __funnelshift_r(w[u][2], w[u][3], shf[u]);
-      if (nwords == 3) n2 &= lastmask; else if (nwords == 2) { n1 &= lastmask; n2 = 0; } else { n0 &= lastmask; n1 = 0; n2 = 0; }
-      const int r = slot + 8 * u;
-      unsigned sum = __dp4a(n0, 0x01010101u, 0u), sumsq = __dp4a(n0, n0, 0u), cross = __dp4a(n0, sm.tmpl_w[3 * r], 0u);
-      sum = __dp4a(n1, 0x01010101u, sum); sumsq = __dp4a(n1, n1, sumsq); cross = __dp4a(n1, sm.tmpl_w[3 * r + 1], cross);
-      sum = __dp4a(n2, 0x01010101u, sum); sumsq = __dp4a(n2, n2, sumsq); cross = __dp4a(n2, sm.tmpl_w[3 * r + 2], cross);
-      acc += (unsigned long long)cross | ((unsigned long long)sumsq << 23) | ((unsigned long long)sum << 46);
-    }
-#pragma unroll
-    for (int d = 4; d; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
-    if (slot == 0 && have) {
-      int ssd;
-      if (!inb) ssd = maxSSD + 1;
-      else {
-        const int SA = tsum, SB = (int)(acc >> 46), sq = (int)((acc >> 23) & 0x7fffffull), cr = (int)(acc & 0x7fffffull);
-        ssd = ((2 * SA * SB - SA * SA - SB * SB) / PP + sq + tsumsq - 2 * cr);
-      }
-      const unsigned long long key = ((unsigned long long)(unsigned)ssd << 32) | (unsigned)sm.cand_idx[c];   // ssd >= 0; ties -> lowest corner index
-      best = key < best ? key : best;
-    }
-  }
-  return best;
-}
-
-// MakeSubPixTemplate + IterateSubPixToConvergence (jni/PatchFinder.cc:242-350) around (coarse0, coarse1) (level-0 pixels) in the
-// level image `img`; tmpl: the template in 12-byte rows.  Returns 1 if converged; (out0, out1) = mv2SubPixPos in any case.
-__device__ __forceinline__ int subpix_refine(SearchSmem& sm, const uint8_t* tmpl, const uint8_t* __restrict__ img, int pitch, int lw, int lh, int level, int P,
-                                             int subpix, double coarse0, double coarse1, double& out0, double& out1) {
-  const int lane = threadIdx.x & 31;
-  const int nLevelScale = LevelScale(level);
-  const double invScale = 1.0 / nLevelScale;
-  // ---- MakeSubPixTemplate (jni/PatchFinder.cc:242-267)
-  const int Q = P - 2, QQ = Q * Q;
-  for (int k = lane; k < QQ; k += 32) {
-    const int x = k / Q + 1, y = k - (x - 1) * Q + 1;   // stored index (x-1)*Q + (y-1)
-    sm.jx[k] = 0.5 * (tmpl[y * 12 + x + 1] - tmpl[y * 12 + x - 1]);
-    sm.jy[k] = 0.5 * (tmpl[(y + 1) * 12 + x] - tmpl[(y - 1) * 12 + x]);
-  }
-  __syncwarp();
-  // JtJ of (gx, gy, 1): sums of multiples of 0.25 below 2^53 are exact in any order, so a warp reduction is bit-exact
-  double hxx = 0, hxy = 0, hyy = 0, hx = 0, hy = 0;
-  for (int k = lane; k < QQ; k += 32) { const double gx = sm.jx[k], gy = sm.jy[k]; hxx += gx * gx; hxy += gx * gy; hyy += gy * gy; hx += gx; hy += gy; }
-#pragma unroll
-  for (int d = 16; d; d >>= 1) {
-    hxx += __shfl_xor_sync(0xffffffffu, hxx, d); hxy += __shfl_xor_sync(0xffffffffu, hxy, d); hyy += __shfl_xor_sync(0xffffffffu, hyy, d);
-    hx += __shfl_xor_sync(0xffffffffu, hx, d); hy += __shfl_xor_sync(0xffffffffu, hy, d);
-  }
-  const double H[9] = {hxx, hxy, hx, hxy, hyy, hy, hx, hy, (double)QQ};
-  double hinv[9];
-  {   // 3x3 inverse: adjugate * (1/det), evaluation order of the oracle (oracle/vslam_oracle.cc inverse3)
-    const double c00 = H[4] * H[8] - H[5] * H[7], c10 = H[5] * H[6] - H[3] * H[8], c20 = H[3] * H[7] - H[4] * H[6];
-    const double det = H[0] * c00 + H[1] * c10 + H[2] * c20, invdet = 1.0 / det;
-    hinv[0] = c00 * invdet; hinv[3] = c10 * invdet; hinv[6] = c20 * invdet;
-    hinv[1] = (H[2] * H[7] - H[1] * H[8]) * invdet; hinv[4] = (H[0] * H[8] - H[2] * H[6]) * invdet; hinv[7] = (H[1] * H[6] - H[0] * H[7]) * invdet;
-    hinv[2] = (H[1] * H[5] - H[2] * H[4]) * invdet; hinv[5] = (H[2] * H[3] - H[0] * H[5]) * invdet; hinv[8] = (H[0] * H[4] - H[1] * H[3]) * invdet;
-  }
-  double sp0 = coarse0, sp1 = coarse1, meanDiff = 0.0;
-  int ok = 0;
-  // ---- IterateSubPixToConvergence / IterateSubPix (jni/PatchFinder.cc:272-350)
-  for (int it = 0; it < subpix; it++) {
-    const double c0 = (sp0 + 0.5) * invScale - 0.5, c1 = (sp1 + 0.5) * invScale - 0.5;   // LevelNPos
-    const int xb = (c0 > 0.0 ? c0 + 0.5 : c0 - 0.5), yb = (c1 > 0.0 ? c1 + 0.5 : c1 - 0.5);
-    const int bd = P / 2 + 1;
-    if (!(xb >= bd && yb >= bd && xb < lw - bd && yb < lh - bd)) break;   // off the image: not converged
-    const double b0 = c0 - (double)(P / 2), b1 = c1 - (double)(P / 2);
-    const double dX = b0 - floor(b0), dY = b1 - floor(b1);
-    const float fTL = (1.0 - dX) * (1.0 - dY), fTR = (dX) * (1.0 - dY), fBL = (1.0 - dX) * (dY), fBR = (dX) * (dY);
-    for (int k = lane; k < QQ; k += 32) {   // k = (y-1)*Q + (x-1): the reference's loop order
-      const int y = k / Q + 1, x = k - (y - 1) * Q + 1;
-      const uint8_t* tl = img + (size_t)((int)b1 + y) * pitch + ((int)b0 + x);
-      const float fPixel = fTL * tl[0] + fTR * tl[1] + fBL * tl[pitch] + fBR * tl[pitch + 1];
-      const double dDiff = fPixel - tmpl[y * 12 + x] + meanDiff;
-      const int j = (x - 1) * Q + (y - 1);
-      sm.pos[k] = dDiff * sm.jx[j]; sm.pos[QQ + k] = dDiff * sm.jy[j]; sm.prod2[k] = dDiff;
-    }
-    __syncwarp();
-    double acc = 0;   // lanes 0,1,2 add their accumulator's terms in pixel order, like the reference's serial loop
-    if (lane < 3) { const double* p = lane == 0 ? sm.pos : (lane == 1 ? sm.pos + QQ : sm.prod2); for (int k = 0; k < QQ; k++) acc += p[k]; }
-    const double a0 = __shfl_sync(0xffffffffu, acc, 0), a1 = __shfl_sync(0xffffffffu, acc, 1), a2 = __shfl_sync(0xffffffffu, acc, 2);
-    __syncwarp();
-    double upd[3];
-#pragma unroll
-    for (int r = 0; r < 3; r++) { double sacc = hinv[3 * r] * a0; sacc += hinv[3 * r + 1] * a1; sacc += hinv[3 * r + 2] * a2; upd[r] = sacc; }
-    sp0 -= upd[0] * nLevelScale; sp1 -= upd[1] * nLevelScale;
-    meanDiff -= upd[2];
-    double d = 0; d += upd[0] * upd[0]; d += upd[1] * upd[1];
-    const double lim = 0.03;
-    if (d < lim * lim) { ok = 1; break; }
-  }
-  out0 = sp0; out1 = sp1;
-  return ok;
 }
 
 // mode 0: explicit list [0,nA) with (range, subpix) arguments; 1: coarse set A; 2: fine set B
@@ -796,69 +580,7 @@ __device__ void calc_pose_update(const Dev& D, PoseSmem& sm, double* sortbuf, in
   PT_MARK(6);
   // mu = inverse(C) * b with inverse = partial-pivot LU, column by column (jni/myWLS.h:53-62; oracle inverse_lu): same operations per
   // element as the serial routine, spread over six lanes of warp 0 (rows during elimination, columns during substitution).
-  if (warp == 0) {
-    __syncwarp();   // reconverge first: with diverged lanes every shuffle below takes the slow WARPSYNC.COLLECTIVE path (~300 cycles each)
-    // lane r (< 6) keeps row r of C in registers; pivot search, row swap and the pivot-row broadcast go through shuffles
-    const int r6 = lane < 6 ? lane : 5;
-    double row[6];
-#pragma unroll
-    for (int c = 0; c < 6; c++) {
-      const int lo = r6 < c ? r6 : c, hi = r6 < c ? c : r6;
-      const int q = lo * 6 - (lo * (lo - 1)) / 2 + (hi - lo);          // index of (lo,hi) in the packed upper triangle
-      row[c] = sm.sums[q] + (lo == hi ? 100.0 : 0.0);                    // prior 100*I (:734)
-    }
-    int mypiv = r6;
-#pragma unroll
-    for (int k = 0; k < 6; k++) {
-      // partial pivoting: first row i >= k with the largest |a[i][k]| (strict >, as the serial routine)
-      double best = (lane >= k && lane < 6) ? fabs(row[k]) : -1.0; int bi = lane;
-#pragma unroll
-      for (int d = 4; d; d >>= 1) {
-        const double ob = __shfl_xor_sync(0xffffffffu, best, d); const int oi = __shfl_xor_sync(0xffffffffu, bi, d);
-        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-      }
-      const int p = __shfl_sync(0xffffffffu, bi, 0);
-      // swap rows k and p (and their pivot labels)
-      const int src = lane == k ? p : (lane == p ? k : lane);
-#pragma unroll
-      for (int c = 0; c < 6; c++) row[c] = __shfl_sync(0xffffffffu, row[c], src);
-      mypiv = __shfl_sync(0xffffffffu, mypiv, src);
-      double prow[6];
-#pragma unroll
-      for (int c = 0; c < 6; c++) prow[c] = __shfl_sync(0xffffffffu, row[c], k);
-      if (lane > k && lane < 6) {
-        const double f = row[k] / prow[k];
-        row[k] = f;
-#pragma unroll
-        for (int j = k + 1; j < 6; j++) row[j] -= f * prow[j];
-      }
-    }
-    if (lane < 6) {
-#pragma unroll
-      for (int c = 0; c < 6; c++) sm.lu[lane * 6 + c] = row[c];
-      sm.piv[lane] = mypiv;
-    }
-    __syncwarp();
-    if (lane < 6) {   // column `lane` of the inverse
-      const int c = lane; double x[6];
-#pragma unroll
-      for (int i = 0; i < 6; i++) x[i] = (sm.piv[i] == c) ? 1.0 : 0.0;
-#pragma unroll
-      for (int i = 0; i < 6; i++)
-#pragma unroll
-        for (int j = 0; j < i; j++) x[i] -= sm.lu[i * 6 + j] * x[j];
-#pragma unroll
-      for (int i = 5; i >= 0; i--) {
-#pragma unroll
-        for (int j = i + 1; j < 6; j++) x[i] -= sm.lu[i * 6 + j] * x[j];
-        x[i] /= sm.lu[i * 6 + i];
-      }
-#pragma unroll
-      for (int i = 0; i < 6; i++) sm.inv[i * 6 + c] = x[i];
-    }
-    __syncwarp();
-    if (lane < 6) { const int i = lane; double sacc = sm.inv[6 * i] * sm.sums[21]; for (int j = 1; j < 6; j++) sacc += sm.inv[6 * i + j] * sm.sums[21 + j]; sm.mu[i] = sacc; }
-  }
+  if (warp == 0) wls_solve_warp(sm.sums, sm.lu, sm.inv, sm.piv, sm.mu);
   __syncthreads();
   PT_MARK(7);
 }
@@ -1116,55 +838,7 @@ __global__ void __launch_bounds__(kPT, 2) k_pose(Dev D, int mode, double sigma_a
   if (tid == 0) {
     double dSum = 0, dSumSq = 0, dNum = 0;
     for (int w = 0; w < kPT / 32; w++) { dSum += sm.red[w][0]; dSumSq += sm.red[w][1]; dNum += sm.red[w][2]; }
-    const int nNum = (int)dNum;
-    if (nNum > 20) { st->depth_mean = dSum / nNum; st->depth_sigma = sqrt((dSumSq / nNum) - (st->depth_mean) * (st->depth_mean)); }
-    if (tail) {
-      if (!st->recovered) {
-      // Tracker::UpdateMotionModel (jni/Tracker.cc:802-820); not after a relocalisation (jni/Tracker.cc:136-139)
-      double inv[12], nfo[12], m[6];
-      se3_inverse(st->start_pose, inv); se3_mul(sm.pose, inv, nfo); se3_ln(nfo, m);
-      double sacc = 0;
-      for (int k = 0; k < 6; k++) { st->velocity[k] = 0.9 * (0.5 * m[k] + 0.5 * st->velocity[k]); }
-      for (int k = 0; k < 6; k++) sacc += st->velocity[k] * st->velocity[k];
-      st->vel_mag = sqrt(sacc);
-      double v[6]; for (int k = 0; k < 6; k++) v[k] = st->velocity[k];
-      for (int k = 0; k < 3; k++) v[k] *= 1.0 / st->depth_mean;
-      sacc = 0; for (int k = 0; k < 6; k++) sacc += v[k] * v[k];
-      st->msd_scaled_vel = sqrt(sacc);
-      }
-      // Tracker::AssessTrackingQuality (jni/Tracker.cc:832-878)
-      int nTA = 0, nTF = 0, nLA = 0, nLF = 0;
-      for (int l = 0; l < VS_LEVELS; l++) { nTA += st->attempted[l]; nTF += st->found[l]; if (l >= 2) { nLA += st->attempted[l]; nLF += st->found[l]; } }
-      int q;
-      if (nTF == 0 || nTA == 0) q = 0;
-      else {
-        const double tot = (double)nTF / nTA, lg = (nLA > 10) ? (double)nLF / nLA : tot;
-        q = (tot > 0.3) ? 2 : (lg < 0.13 ? 0 : 1);
-      }
-      // MapMaker::ClosestKeyFrame / KeyFrameLinearDist (jni/MapMaker.cc:705-712,736-754) over the registered keyframes: only the two
-      // callers below need it (DODGY: "has the pose run miles away", GOOD: "is a new keyframe due")
-      double kfd = 9999999999.9; int kfc = -1;
-      if (D.kf_n > 0 && q != 0) {
-        double inv[12]; se3_inverse(sm.pose, inv);
-        for (int k = 0; k < D.kf_n; k++) {
-          double ki[12]; se3_inverse(D.kf_pose + 12 * k, ki);
-          const double d0 = ki[3] - inv[3], d1 = ki[7] - inv[7], d2 = ki[11] - inv[11];
-          double dd = d0 * d0; dd += d1 * d1; dd += d2 * d2;
-          const double dist = sqrt(dd);
-          if (dist < kfd) { kfd = dist; kfc = k; }
-        }
-        st->kf_dist = kfd; st->kf_closest = kfc;
-        if (q == 1 && kfd > D.kf_excess_dist) q = 0;          // IsDistanceToNearestKeyFrameExcessive (jni/MapMaker.cc:1098-1101)
-      }
-      st->quality = q;
-      if (q == 0) st->lost_frames++; else st->lost_frames = 0;
-      // jni/Tracker.cc:127-132 (not in the recovery branch): GOOD && MapMaker::NeedNewKeyFrame (jni/MapMaker.cc:763-773) && enough
-      // frames since the last one.  The queue-length term (QueueSize() < 3) is the caller's: it owns the queue.
-      if (kfc >= 0 && q == 2 && !st->recovered) {
-        double dDist = kfd; dDist *= (1.0 / st->depth_mean);
-        if (dDist > D.kf_need_dist && st->frame_no - st->last_kf_dropped > D.kf_min_frames) { st->kf_request = 1; D.kf_req[s] = 1; }
-      }
-    }
+    pose_stage_tail(D, st, s, sm.pose, dSum, dSumSq, dNum, tail);
   }
 }
 
@@ -1196,20 +870,7 @@ __global__ void __launch_bounds__(kPT) k_calc_jacobians(Dev D) {
   calc_jacobians(D, D.lists + (size_t)s * D.list_cap, D.ss[s].nA, s, false);
 }
 
-__global__ void k_atan(const double* x, double* y, int n) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) y[i] = atan_cr(x[i]); }
-
-Dev make_dev(const vslam_ctx* ctx) {
-  Dev D;
-  for (int l = 0; l < VS_LEVELS; l++) D.lev[l] = ctx->lev[l];
-  D.l0_ptr = ctx->l0_ptr; D.l0_stride = ctx->l0_stride;
-  D.cam = ctx->cam; D.map = ctx->map; D.src = ctx->src; D.ps = ctx->ps; D.ss = ctx->ss; D.lists = ctx->lists; D.list_cap = ctx->list_cap;
-  D.pvs = ctx->pvs; D.sort_scratch = ctx->sort_scratch; D.sort_cap = ctx->sort_cap; D.evals = ctx->evals;
-  D.S = ctx->S; D.N = ctx->N; D.P = ctx->P; D.truncate = ctx->cfg.truncate_error; D.prm = ctx->params; D.s0 = ctx->cur_s0;
-  const bool kf = ctx->kf_policy && ctx->reloc_n > 0;
-  D.kf_pose = ctx->reloc_pose; D.kf_n = kf ? ctx->reloc_n : 0; D.kf_min_frames = ctx->kf_min_frames;
-  D.kf_excess_dist = ctx->kf_wiggle * 10.0; D.kf_need_dist = ctx->kf_mult * ctx->kf_wiggle_dn; D.kf_req = ctx->kf_req;
-  return D;
-}
+__global__ void k_atan(const double* x, double* y, int n, int dd_only) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) y[i] = dd_only ? atan_cr_dd(x[i]) : atan_cr(x[i]); }
 
 }  // namespace
 
@@ -1229,6 +890,7 @@ int vs_launch_project_all(vslam_ctx* ctx, int mode) {
 }
 
 int vs_launch_search(vslam_ctx* ctx, int which, int range, int subpix, int sflags) {
+  if (ctx->params.search_kernel == 0) return vs_launch_search_fast(ctx, which, range, subpix, sflags);
   const Dev D = make_dev(ctx);
   const int max_entries = which == 1 ? (int)(2 * ctx->params.coarse_max) : ctx->list_cap;
   if (max_entries <= 0) return VSLAM_OK;   // nCoarseMax == 0: the reference skips the coarse stage (jni/Tracker.cc:425)
@@ -1244,6 +906,7 @@ int vs_launch_search(vslam_ctx* ctx, int which, int range, int subpix, int sflag
 }
 
 int vs_launch_pose(vslam_ctx* ctx, int mode, double sigma, int mark, int apply) {
+  if ((mode & 3) != 0 && ctx->params.pose_kernel == 0) return vs_launch_pose_fast(ctx, mode);   // the TrackMap stages; mode 0 (one CalcPoseUpdate, stage API) stays here
   const Dev D = make_dev(ctx);
   const size_t smem = 2048 * sizeof(double) + 2 * 2048 * sizeof(int) + 27 * kPT * sizeof(double);   // sort keys + found list + radix histogram + partial sums
   if (smem > ctx->smem_attr[1]) { VS_CUDA(cudaFuncSetAttribute(k_pose, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); ctx->smem_attr[1] = smem; }
@@ -1339,11 +1002,14 @@ int vs_launch_frame(vslam_ctx* ctx) {
 }
 
 // Test hook: atan_cr over a device-side copy of x (used to compare against the host libm).
-extern "C" int vslam_debug_atan(const double* x_host, double* y_host, int n) {
+static int debug_atan(const double* x_host, double* y_host, int n, int dd_only);
+extern "C" int vslam_debug_atan(const double* x_host, double* y_host, int n) { return debug_atan(x_host, y_host, n, 0); }
+extern "C" int vslam_debug_atan_dd(const double* x_host, double* y_host, int n) { return debug_atan(x_host, y_host, n, 1); }   // the double-double routine alone
+static int debug_atan(const double* x_host, double* y_host, int n, int dd_only) {
   double *dx = nullptr, *dy = nullptr;
   if (cudaMalloc(&dx, sizeof(double) * n) != cudaSuccess || cudaMalloc(&dy, sizeof(double) * n) != cudaSuccess) return VSLAM_E_CUDA;
   cudaMemcpy(dx, x_host, sizeof(double) * n, cudaMemcpyHostToDevice);
-  k_atan<<<(n + 255) / 256, 256>>>(dx, dy, n);
+  k_atan<<<(n + 255) / 256, 256>>>(dx, dy, n, dd_only);
   const cudaError_t e = cudaMemcpy(y_host, dy, sizeof(double) * n, cudaMemcpyDeviceToHost);
   cudaFree(dx); cudaFree(dy);
   return e == cudaSuccess ? VSLAM_OK : VSLAM_E_CUDA;

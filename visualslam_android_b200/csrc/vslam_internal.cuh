@@ -24,6 +24,7 @@ struct LevelDesc {
   uint8_t* img;               // [S][h][pitch]      (level 0: only used by the host-input path, see l0_ptr)
   uint32_t* corners;          // [S][cap]           packed (y << 16 | x), raster order
   int* lut;                   // [S][h + 1]         lut[y] = #corners with row < y ; lut[h] = total
+  int* xlut; int xw;          // [S][h][xw]         xw = ceil(w / 32) + 1: xlut[y][b] = #corners before (row y, column 32 b) in raster order; xlut[y][xw - 1] = end of row y
   unsigned long long* strip_state;  // [S][n_strips] decoupled look-back words
 };
 
@@ -170,6 +171,8 @@ int vs_launch_source_pyramid(vslam_ctx* ctx, int kf_id);
 int vs_launch_project_all(vslam_ctx* ctx, int build_lists);
 int vs_launch_search(vslam_ctx* ctx, int which /*0 explicit list,1 coarse A,2 fine B*/, int range, int subpix, int sflags /*1: ReFind_Common variant*/);
 int vs_launch_pose(vslam_ctx* ctx, int mode, double sigma, int mark, int apply);
+int vs_launch_search_fast(vslam_ctx* ctx, int which, int range, int subpix, int sflags);   // search_fast.cu: eight lanes per map point + k_subpix
+int vs_launch_pose_fast(vslam_ctx* ctx, int mode);   // pose_fast.cu: stages 1 / 2 with the found points resident on the SM
 int vs_launch_track_map(vslam_ctx* ctx, int with_motion_model);
 int vs_launch_track_map_rest(vslam_ctx* ctx, int with_motion_model);   // everything after vs_launch_project_all
 int vs_launch_frame(vslam_ctx* ctx);                                   // pyramid + FAST, SmallBlurryImage, TrackMap of all streams
