@@ -283,7 +283,7 @@ __device__ __forceinline__ void fast_strip(const LevelDesc& L, const uint8_t* __
 }
 
 // Level 0 of every stream: pyramid levels 1..3 + FAST-10 of level 0.
-__global__ void __launch_bounds__(kThreads)   // 40 registers / 6 CTAs per SM measured faster than 32 / 8
+__global__ void __launch_bounds__(kThreads, 6)   // 40 registers / 6 CTAs per SM measured faster than 32 / 8 (and than 48 / 5: registers are granted in blocks of 8)
 k_pyramid_fast(LevelDesc L, LevelDesc L1, LevelDesc L2, LevelDesc L3, const uint8_t* const* __restrict__ l0_ptr, const int* __restrict__ l0_stride,
                int first_stream, int thr, unsigned* __restrict__ ticket, int* __restrict__ status) {
   extern __shared__ __align__(128) uint8_t smem[];

@@ -24,6 +24,9 @@ constexpr int kFW = 4;            // warps per CTA
 constexpr int kGL = 8;            // lanes per list entry
 constexpr int kGW = 32 / kGL;     // entries per warp
 constexpr int kQ = 48;            // candidate queue per entry
+#ifndef VS_SEARCH_MINB
+#define VS_SEARCH_MINB 5
+#endif
 #ifndef VS_SEARCH_NB
 #define VS_SEARCH_NB 4
 #endif
@@ -58,7 +61,7 @@ __device__ __forceinline__ uint32_t ldg_ordered(const uint32_t* p) { uint32_t v;
 constexpr int kSearchRefindF = 1;   // sflags: MapMaker::ReFind_Common's variant (jni/MapMaker.cc:967-1036), see k_search
 
 template <int PT>
-__global__ void __launch_bounds__(kFW * 32) k_search_fast(Dev D, int mode, int range_arg, int subpix_arg, int sflags) {
+__global__ void __launch_bounds__(kFW * 32, VS_SEARCH_MINB) k_search_fast(Dev D, int mode, int range_arg, int subpix_arg, int sflags) {
   __shared__ FastWarp sm_all[kFW];
   const int s = blockIdx.y + D.s0, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane / kGL, j = lane % kGL;
   StreamState* st = D.ss + s;
@@ -188,6 +191,7 @@ __global__ void __launch_bounds__(kFW * 32) k_search_fast(Dev D, int mode, int r
   const int nLeft = ix - nRange, nRight = ix + nRange;
   const double r2 = (double)(nRange * nRange);
   unsigned long long best = ((unsigned long long)(unsigned)(maxSSD + 1) << 32) | 0xffffffffull;
+  uint32_t bestcw = 0u;                                         // the corner word of `best` (saves the dependent re-read of the corner list at the end)
   flags |= F_SEARCHED;
   if (nTop < 0) nTop = 0;
   const uint32_t* corners = L.corners + (size_t)s * L.cap;
@@ -328,7 +332,7 @@ __global__ void __launch_bounds__(kFW * 32) k_search_fast(Dev D, int mode, int r
       }
       if (have) {
         const unsigned long long key = ((unsigned long long)(unsigned)ssd << 32) | (unsigned)cidx;   // ssd >= 0; ties -> lowest corner index
-        best = key < best ? key : best;
+        if (key < best) { best = key; bestcw = cw; }
       }
       __syncwarp();
     }
@@ -336,7 +340,10 @@ __global__ void __launch_bounds__(kFW * 32) k_search_fast(Dev D, int mode, int r
     __syncwarp();
   }
 #pragma unroll
-  for (int d = kGL / 2; d; d >>= 1) { const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, d); best = o < best ? o : best; }
+  for (int d = kGL / 2; d; d >>= 1) {
+    const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, d); const uint32_t oc = __shfl_xor_sync(0xffffffffu, bestcw, d);
+    if (o < best) { best = o; bestcw = oc; }
+  }
   if (!alive) return;
   if (j == 0 && nevals) atomicAdd(D.evals, (unsigned long long)nevals);
   const int bestSSD = (int)(best >> 32);
@@ -345,7 +352,7 @@ __global__ void __launch_bounds__(kFW * 32) k_search_fast(Dev D, int mode, int r
     return;
   }
   if (j == 0) {
-    const uint32_t bc = corners[(unsigned)best];
+    const uint32_t bc = bestcw;
     const double coarse0 = ((double)(bc & 0xffff) + 0.5) * nLevelScale - 0.5, coarse1 = ((double)(bc >> 16) + 0.5) * nLevelScale - 0.5;  // LevelZeroPos
     flags |= F_FOUND;
     D.ps.coarse[gi] = coarse0; D.ps.coarse[SN + gi] = coarse1;
@@ -357,41 +364,129 @@ __global__ void __launch_bounds__(kFW * 32) k_search_fast(Dev D, int mode, int r
 }
 
 // MakeSubPixTemplate + IterateSubPixToConvergence (jni/PatchFinder.cc:242-350; jni/Tracker.cc:657-667) of the entries that k_search_fast
-// found and marked for refinement, one warp per entry.
+// found and marked for refinement: EIGHT LANES PER ENTRY, four entries per warp.  The iteration is a chain -- the three sums of an
+// iteration are added in pixel order like the reference's serial loop, 81 dependent additions each, by three lanes -- so what a warp can
+// do is run four such chains side by side; the bilinear samples and products of an iteration are spread over the entry's eight lanes.
+// The template gradients are recomputed from the template bytes where they are needed (exact: multiples of 0.5).
+struct SubpixEntry { double prod[3][(VS_MAXP - 2) * (VS_MAXP - 2)]; uint32_t tmpl_w[VS_TMPL_BYTES / 4]; };   // dDiff*gx, dDiff*gy, dDiff per interior pixel; the template
+
 __global__ void __launch_bounds__(kFW * 32) k_subpix(Dev D, int mode, int range_arg, int subpix_arg, int sflags) {
-  __shared__ SearchSmem sm_all[kFW];
-  const int s = blockIdx.y + D.s0, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ SubpixEntry sm_all[kFW][kGW];
+  const int s = blockIdx.y + D.s0, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane / kGL, j = lane % kGL;
   StreamState* st = D.ss + s;
   Plan pl;
   if (!search_plan(D, st, mode, range_arg, subpix_arg, pl)) return;
   const int n_sub = pl.subpix_all > 0 ? pl.count : (pl.subpix_top > 0 ? min(pl.n_top, pl.count) : 0);
   const bool refind = (sflags & kSearchRefindF) != 0;
   const size_t SN = (size_t)D.S * D.N;
-  SearchSmem& sm = sm_all[warp];
-  for (int e = blockIdx.x * kFW + warp; e < n_sub; e += gridDim.x * kFW) {   // (the grid is a few CTAs per stream: the fine stage refines only its top-level entries)
-  const int i = D.lists[(size_t)s * D.list_cap + pl.first + e];
-  const size_t gi = (size_t)s * D.N + i;
-  int flags = D.ps.flags[gi];
-  if ((flags & (F_FOUND | F_SUBPIX | F_SEARCHED)) != (F_FOUND | F_SUBPIX | F_SEARCHED)) continue;
-  const int subpix = e < pl.n_top ? pl.subpix_top : pl.subpix_all;
-  const int level = refind ? D.ps.rlevel[gi] : D.ps.level[gi];
-  if (subpix <= 0 || (refind && level == 0)) continue;
-  __syncwarp();
-  const uint32_t* tmpl_g = (const uint32_t*)(D.ps.tmpl + gi * VS_TMPL_BYTES);
-  sm.tmpl_w[lane] = tmpl_g[lane]; if (lane < VS_TMPL_BYTES / 4 - 32) sm.tmpl_w[32 + lane] = tmpl_g[32 + lane];
-  const double coarse0 = D.ps.coarse[gi], coarse1 = D.ps.coarse[SN + gi];
-  const LevelDesc& L = D.lev[level];
-  const uint8_t* img; int pitch;
-  if (level == 0) { img = D.l0_ptr[s]; pitch = D.l0_stride[s]; } else { img = L.img + (size_t)s * L.h * L.pitch; pitch = L.pitch; }
-  __syncwarp();
-  if (lane == 0) atomicAdd(D.evals + 3, 1ull);
-  double found0 = coarse0, found1 = coarse1;
-  const int ok = subpix_refine(sm, (const uint8_t*)sm.tmpl_w, img, pitch, L.w, L.h, level, D.P, subpix, coarse0, coarse1, found0, found1);
-  if (lane == 0) {
-    if (ok || refind) { D.ps.v2found[gi] = found0; D.ps.v2found[SN + gi] = found1; atomicAdd(&st->found[level], 1); }
-    else { flags &= ~F_FOUND; D.ps.flags[gi] = flags; }   // sub-pixel iteration did not converge (jni/Tracker.cc:660-666)
-  }
-  __syncwarp();
+  const int P = D.P, Q = P - 2, QQ = Q * Q;
+  SubpixEntry& E = sm_all[warp][g];
+  const uint8_t* const tmpl = (const uint8_t*)E.tmpl_w;
+  for (int e0 = (blockIdx.x * kFW + warp) * kGW; e0 < n_sub; e0 += gridDim.x * kFW * kGW) {   // (the grid is a few CTAs per stream: the fine stage refines only its top-level entries)
+    const int e = e0 + g;
+    bool active = e < n_sub;
+    const int i = D.lists[(size_t)s * D.list_cap + pl.first + (active ? e : e0)];
+    const size_t gi = (size_t)s * D.N + i;
+    int flags = D.ps.flags[gi];
+    const int subpix = e < pl.n_top ? pl.subpix_top : pl.subpix_all;
+    const int level = refind ? D.ps.rlevel[gi] : D.ps.level[gi];
+    active = active && (flags & (F_FOUND | F_SUBPIX | F_SEARCHED)) == (F_FOUND | F_SUBPIX | F_SEARCHED) && subpix > 0 && !(refind && level == 0);
+    const bool entry = active;                                   // this group has an entry to finish
+    const int lv = active ? level : 0;
+    const uint32_t* tmpl_g = (const uint32_t*)(D.ps.tmpl + gi * VS_TMPL_BYTES);
+#pragma unroll
+    for (int q = 0; q < 5; q++) if (j + kGL * q < VS_TMPL_BYTES / 4) E.tmpl_w[j + kGL * q] = tmpl_g[j + kGL * q];
+    const double coarse0 = D.ps.coarse[gi], coarse1 = D.ps.coarse[SN + gi];
+    const LevelDesc& L = D.lev[lv];
+    const uint8_t* img; int pitch;
+    if (lv == 0) { img = D.l0_ptr[s]; pitch = D.l0_stride[s]; } else { img = L.img + (size_t)s * L.h * L.pitch; pitch = L.pitch; }
+    const int lw = L.w, lh = L.h;
+    const int nLevelScale = LevelScale(lv);
+    const double invScale = 1.0 / nLevelScale;
+    __syncwarp();
+    if (entry && j == 0) atomicAdd(D.evals + 3, 1ull);
+    // ---- MakeSubPixTemplate (jni/PatchFinder.cc:242-267): JtJ of (gx, gy, 1); sums of multiples of 0.25 below 2^53 are exact in any order
+    double hxx = 0, hxy = 0, hyy = 0, hx = 0, hy = 0;
+    for (int k = j; k < QQ; k += kGL) {
+      const int x = k / Q + 1, y = k - (x - 1) * Q + 1;
+      const double gx = 0.5 * (tmpl[y * 12 + x + 1] - tmpl[y * 12 + x - 1]), gy = 0.5 * (tmpl[(y + 1) * 12 + x] - tmpl[(y - 1) * 12 + x]);
+      hxx += gx * gx; hxy += gx * gy; hyy += gy * gy; hx += gx; hy += gy;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int d = kGL / 2; d; d >>= 1) {
+      hxx += __shfl_xor_sync(0xffffffffu, hxx, d); hxy += __shfl_xor_sync(0xffffffffu, hxy, d); hyy += __shfl_xor_sync(0xffffffffu, hyy, d);
+      hx += __shfl_xor_sync(0xffffffffu, hx, d); hy += __shfl_xor_sync(0xffffffffu, hy, d);
+    }
+    const double H[9] = {hxx, hxy, hx, hxy, hyy, hy, hx, hy, (double)QQ};
+    double hinv[9];
+    {   // 3x3 inverse: adjugate * (1/det), evaluation order of the oracle (oracle/vslam_oracle.cc inverse3)
+      const double c00 = H[4] * H[8] - H[5] * H[7], c10 = H[5] * H[6] - H[3] * H[8], c20 = H[3] * H[7] - H[4] * H[6];
+      const double det = H[0] * c00 + H[1] * c10 + H[2] * c20, invdet = 1.0 / det;
+      hinv[0] = c00 * invdet; hinv[3] = c10 * invdet; hinv[6] = c20 * invdet;
+      hinv[1] = (H[2] * H[7] - H[1] * H[8]) * invdet; hinv[4] = (H[0] * H[8] - H[2] * H[6]) * invdet; hinv[7] = (H[1] * H[6] - H[0] * H[7]) * invdet;
+      hinv[2] = (H[1] * H[5] - H[2] * H[4]) * invdet; hinv[5] = (H[2] * H[3] - H[0] * H[5]) * invdet; hinv[8] = (H[0] * H[4] - H[1] * H[3]) * invdet;
+    }
+    double sp0 = coarse0, sp1 = coarse1, meanDiff = 0.0;
+    int ok = 0, it = 0;
+    // ---- IterateSubPixToConvergence / IterateSubPix (jni/PatchFinder.cc:272-350); the four entries of the warp iterate in step
+    while (__any_sync(0xffffffffu, active)) {
+      if (active && it >= subpix) active = false;                  // iteration budget used up: not converged
+      double b0 = 0, b1 = 0; float fTL = 0, fTR = 0, fBL = 0, fBR = 0;
+      if (active) {
+        const double c0 = (sp0 + 0.5) * invScale - 0.5, c1 = (sp1 + 0.5) * invScale - 0.5;   // LevelNPos
+        const int xb = (c0 > 0.0 ? c0 + 0.5 : c0 - 0.5), yb = (c1 > 0.0 ? c1 + 0.5 : c1 - 0.5);
+        const int bd = P / 2 + 1;
+        if (!(xb >= bd && yb >= bd && xb < lw - bd && yb < lh - bd)) active = false;   // off the image: not converged
+        else {
+          b0 = c0 - (double)(P / 2); b1 = c1 - (double)(P / 2);
+          const double dX = b0 - floor(b0), dY = b1 - floor(b1);
+          fTL = (1.0 - dX) * (1.0 - dY); fTR = (dX) * (1.0 - dY); fBL = (1.0 - dX) * (dY); fBR = (dX) * (dY);
+        }
+      }
+      if (active) {
+        for (int k = j; k < QQ; k += kGL) {   // k = (y-1)*Q + (x-1): the reference's loop order
+          const int y = k / Q + 1, x = k - (y - 1) * Q + 1;
+          const uint8_t* tl = img + (size_t)((int)b1 + y) * pitch + ((int)b0 + x);
+          const float fPixel = fTL * tl[0] + fTR * tl[1] + fBL * tl[pitch] + fBR * tl[pitch + 1];
+          const double dDiff = fPixel - tmpl[y * 12 + x] + meanDiff;
+          const double gx = 0.5 * (tmpl[y * 12 + x + 1] - tmpl[y * 12 + x - 1]), gy = 0.5 * (tmpl[(y + 1) * 12 + x] - tmpl[(y - 1) * 12 + x]);
+          E.prod[0][k] = dDiff * gx; E.prod[1][k] = dDiff * gy; E.prod[2][k] = dDiff;
+        }
+      }
+      __syncwarp();
+      double acc = 0;   // lanes 0,1,2 of the entry add their accumulator's terms in pixel order, like the reference's serial loop
+      if (active && j < 3) {   // (nine terms are fetched before they are added: the chain is 81 additions, not 81 x (shared-memory load + addition))
+        const double* p = E.prod[j];
+        int k = 0;
+        for (; k + 9 <= QQ; k += 9) {
+          double t[9];
+#pragma unroll
+          for (int u = 0; u < 9; u++) t[u] = p[k + u];
+#pragma unroll
+          for (int u = 0; u < 9; u++) acc += t[u];
+        }
+        for (; k < QQ; k++) acc += p[k];
+      }
+      __syncwarp();
+      const double a0 = __shfl_sync(0xffffffffu, acc, 0, kGL), a1 = __shfl_sync(0xffffffffu, acc, 1, kGL), a2 = __shfl_sync(0xffffffffu, acc, 2, kGL);
+      if (active) {
+        double upd[3];
+#pragma unroll
+        for (int r = 0; r < 3; r++) { double sacc = hinv[3 * r] * a0; sacc += hinv[3 * r + 1] * a1; sacc += hinv[3 * r + 2] * a2; upd[r] = sacc; }
+        sp0 -= upd[0] * nLevelScale; sp1 -= upd[1] * nLevelScale;
+        meanDiff -= upd[2];
+        double d = 0; d += upd[0] * upd[0]; d += upd[1] * upd[1];
+        const double lim = 0.03;
+        if (d < lim * lim) { ok = 1; active = false; }
+        it++;
+      }
+    }
+    if (entry && j == 0) {
+      if (ok || refind) { D.ps.v2found[gi] = sp0; D.ps.v2found[SN + gi] = sp1; atomicAdd(&st->found[level], 1); }
+      else { flags &= ~F_FOUND; D.ps.flags[gi] = flags; }   // sub-pixel iteration did not converge (jni/Tracker.cc:660-666)
+    }
+    __syncwarp();
   }
 }
 
@@ -411,7 +506,7 @@ int vs_launch_search_fast(vslam_ctx* ctx, int which, int range, int subpix, int 
   // sub-pixel refinement: every entry of the coarse stage / of an explicit list with subpix > 0, the top-level entries of the fine stage
   const bool any_subpix = which == 0 ? subpix > 0 : (which == 1 ? ctx->params.coarse_subpix_its > 0 : ctx->params.fine_subpix_its_top_level > 0);
   if (any_subpix) {
-    dim3 g2(std::min((max_entries + kFW - 1) / kFW, 32), ctx->cur_cnt);
+    dim3 g2(std::min((max_entries + kFW * kGW - 1) / (kFW * kGW), 16), ctx->cur_cnt);
     k_subpix<<<g2, kFW * 32, 0, ctx->stream>>>(D, which, range, subpix, sflags);
     ctx->launches++;
   }
