@@ -36,21 +36,25 @@ W, H, N_POINTS = 640, 480, 1000
 TEX_SIZE = 2048
 # --frame: the other frame sizes north_star asks throughput for: (W, H, map points, streams per GPU)
 FRAME_CONFIGS = {"1080p": (1920, 1080, 5000, 148), "4k": (3840, 2160, 20000, 148)}   # one CTA of the per-stream kernels per SM
-STREAMS_PER_GPU = 256
+STREAMS_PER_GPU = 256   # --scaling weak: streams per GPU; --scaling strong (default, BASELINE configs[3]): streams in TOTAL, stream s on GPU s mod G
 POOL = 24               # distinct frame sets kept resident per leg (78.6 MB each at 256 VGA streams)
 FRAME_STEP = 2          # synthetic sequence index advance per step (≈ 1 px of image motion per frame)
 METRIC = "tracked_frames_per_sec"
 UNIT = "frames/s"
 CPU_FRAMES_PER_STEP = 25   # frames per process per step in the CPU arms (a bounded sample of the same workload)
-SCALING = "weak"
-WORKLOAD = ("configs[3]: 256 independent synthetic VGA (640x480) camera streams per GPU, 1000 map points, full TrackFrame-equivalent "
-            "per frame (4-level pyramid + FAST-10 + row LUT, SmallBlurryImage rotation estimate, coarse+fine PatchFinder search, 10+10 Tukey-WLS iterations), P=11")
+SCALING = "strong"
+WORKLOAD = ("configs[3]: 256 independent synthetic VGA (640x480) camera streams, 1000 map points, full TrackFrame-equivalent per frame (4-level pyramid + "
+            "FAST-10 + row LUT, SmallBlurryImage rotation estimate, motion model, fine PatchFinder search + 10 Tukey-WLS iterations; the coarse stage with its "
+            "10 further iterations runs when the motion model asks for it -- not at this camera speed, see the `fast_motion` leg), P=11")
 
 
 # ------------------------------------------------------------------------------------------------ synthetic data
-def stream_poses(n_streams, n_frames, first_stream=0):
+def stream_poses(streams, n_frames, frame_step=None):
+    """(len(streams), n_frames, 3, 4) camera poses; `streams`: a count (streams 0..n-1) or the list of stream ids (= sequence seeds)."""
     from visualslam_android_b200 import synth
-    return np.stack([np.stack([synth.stream_pose(FRAME_STEP * k, first_stream + s) for k in range(n_frames)]) for s in range(n_streams)])
+    ids = range(streams) if isinstance(streams, int) else streams
+    step = FRAME_STEP if frame_step is None else frame_step
+    return np.stack([np.stack([synth.stream_pose(step * k, s) for k in range(n_frames)]) for s in ids])
 
 
 def render_frames_torch(tex_t, cam, poses, device):
@@ -101,15 +105,72 @@ def keyframe_corners(f0, on_gpu, device=0):
     return [kf.corners(l) for l in range(4)], [kf.dims(l) for l in range(4)]
 
 
-def build_scene(on_gpu=False, device=0):
-    """KF0 + map of N_POINTS points chosen among KF0's FAST corners."""
+def build_scene(on_gpu=False, device=0, size=None):
+    """KF0 + map of N_POINTS points chosen among KF0's FAST corners.  size: (W, H, map points, texture size), default = the module's workload."""
     from visualslam_android_b200 import synth
-    cam = synth.Camera(W, H)
-    tex = synth.make_texture(TEX_SIZE)
+    w, h, n_points, tex_size = size or (W, H, N_POINTS, TEX_SIZE)
+    cam = synth.Camera(w, h)
+    tex = synth.make_texture(tex_size)
     f0 = synth.render_frame(tex, cam, synth.IDENTITY_POSE)
     corners, dims = keyframe_corners(f0, on_gpu, device)
-    smap = synth.build_map(cam, corners, dims, N_POINTS)
+    smap = synth.build_map(cam, corners, dims, n_points)
     return cam, tex, f0, smap
+
+
+def short_leg(name, size, stream_ids, K, Wm, device, stream, frame_step=None, pool=6, barrier=None, scene=None):
+    """An extra, shorter leg of the GPU arm on its own context: whole TrackFrame of len(stream_ids) streams of `size` = (W, H, map points, texture
+    size), frames resident in HBM, CUDA-event timed over K steps after Wm warm-up steps.  Returns (ms per step of THIS rank, info dict)."""
+    import torch
+    from visualslam_android_b200 import api, synth
+    w, h, n_points, tex_size = size
+    dev = torch.device("cuda", device)
+    cam, tex, f0, smap = scene or build_scene(on_gpu=True, device=device, size=size)
+    tex_t = torch.from_numpy(tex.astype(np.float32)).to(dev)
+    S = len(stream_ids)
+    M = int(max(3, min(pool, 5e9 // (S * w * h))))
+    poses = stream_poses(stream_ids, M + 1, frame_step)
+    frames = torch.empty((M, S, h, w), dtype=torch.uint8, device=dev)
+    rb = 64 if w * h <= 640 * 480 else 8
+    for k in range(1, M + 1):
+        for s0 in range(0, S, rb):
+            frames[k - 1, s0:s0 + rb] = render_frames_torch(tex_t, cam, poses[s0:s0 + rb, k], dev)
+    ctx = api.Context(w, h, n_streams=S, max_points=smap.n, device=device, cuda_stream=stream.cuda_stream)
+    ctx.set_camera(cam.scalars())
+    sbi = (h % 16 == 0)
+    if sbi:
+        ctx.enable_sbi(synth.Camera(w // 16, h // 16).scalars())
+    else:
+        ctx.set_params(use_sbi=0)
+    ctx.upload_source_keyframe(f0)
+    ctx.set_map(smap.world, smap.pix_right_w, smap.pix_down_w, smap.ir_center, smap.src_level)
+    step = 0
+    for k in range(Wm):
+        ctx.track_frame_ptr(frames[tri(step, M)].data_ptr(), w, h * w, device=True); step += 1
+    ctx.sync()
+    if barrier:
+        barrier()
+    stats0 = ctx.search_stats()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for k in range(K):
+        ctx.track_frame_ptr(frames[tri(step, M)].data_ptr(), w, h * w, device=True); step += 1
+    e1.record(stream)
+    ctx.sync()
+    ms = e0.elapsed_time(e1) / K
+    stats1 = ctx.search_stats()
+    probe = list(range(0, S, max(1, S // 8)))
+    info = {"leg": name, "frame": [w, h], "map_points": n_points, "streams_this_gpu": S, "pool_sets": M, "frame_step": FRAME_STEP if frame_step is None else frame_step,
+            "small_blurry_image": sbi,
+            "found_per_frame_mean": float(np.mean([ctx.counters(s_)[1].sum() for s_ in probe])),
+            "quality_good_frac": float(np.mean([ctx.counters(s_)[2] == 2 for s_ in probe])),
+            "coarse_stage_frac": float(np.mean([ctx.counters(s_)[4] for s_ in probe])),
+            "wls_iterations_per_frame": float(np.mean([len(ctx.updates(s_)[0]) for s_ in probe])),
+            "templates_generated_per_step": (stats1["templates_generated"] - stats0["templates_generated"]) / K,
+            "subpix_refinements_per_step": (stats1["subpix_refinements"] - stats0["subpix_refinements"]) / K}
+    ctx.close()
+    del frames
+    torch.cuda.empty_cache()
+    return ms, info
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
@@ -428,7 +489,10 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--streams", type=int, default=STREAMS_PER_GPU, help="camera streams per GPU")
+    ap.add_argument("--streams", type=int, default=STREAMS_PER_GPU, help="camera streams: in total (--scaling strong) or per GPU (--scaling weak)")
+    ap.add_argument("--scaling", default=SCALING, choices=["strong", "weak"], help="strong (default, BASELINE configs[3]): --streams in total, stream s tracked by GPU s mod G; "
+                    "weak: --streams per GPU")
+    ap.add_argument("--no-extra-legs", action="store_true", help="skip the fast-motion, weak-scaling, 1080p and 4K legs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--host-alloc", default="pinned", choices=["pinned", "wc"], help="how the e2e leg's host frame pool is allocated")
     ap.add_argument("--groups", type=int, default=0, help="vslam_params.stream_groups (0 = library default)")
@@ -447,16 +511,21 @@ def main():
         args.no_cpu_baseline = True
         global POOL
         POOL = int(max(4, min(24, 6e9 // (args.streams * W * H))))      # keep the resident pool (and its pinned host copy) under ~6 GB
+        args.scaling = "weak"; args.no_extra_legs = True
         WORKLOAD = (f"{args.frame}: {args.streams} independent synthetic {W}x{H} camera streams per GPU, {N_POINTS} map points, full TrackFrame-equivalent per frame "
                     f"(MaxPatchesPerFrame = 1000 as in the reference{'' if H % 16 == 0 else '; SmallBlurryImage off: the height is not a multiple of 16'}), P=11")
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
-    config = {"workload": WORKLOAD, "streams_per_gpu": args.streams, "frame": [W, H], "map_points": N_POINTS, "patch": 11, "parallelism": f"streams sharded over {world} GPU(s), no collective",
-              "l2": f"inputs larger than L2: each step reads a different {args.streams * W * H / 1e6:.1f} MB frame set out of a pool of {POOL} ({POOL * args.streams * W * H / 1e9:.1f} GB, triangle-wave order: a set is "
-                    "re-read at the earliest two steps later) and the per-step working set (frames + pyramids + corner lists + per-point state, "
-                    "> 250 MB) exceeds the 126 MB L2; no explicit flush",
+    from visualslam_android_b200 import sharding
+    stream_ids = sharding.streams_for_rank(args.streams, rank, world) if args.scaling == "strong" else sharding.weak_streams(args.streams, rank)
+    streams_total = args.streams if args.scaling == "strong" else args.streams * world
+    spg = len(sharding.streams_for_rank(args.streams, 0, world)) if args.scaling == "strong" else args.streams
+    config = {"workload": WORKLOAD, "streams_total": streams_total, "streams_per_gpu": spg, "frame": [W, H], "map_points": N_POINTS, "patch": 11,
+              "parallelism": (f"{streams_total} streams in total, stream s on GPU s mod {world}, no collective" if args.scaling == "strong" else f"{args.streams} streams on each of {world} GPU(s), no collective"),
+              "l2": f"inputs larger than L2: each step reads a different {spg * W * H / 1e6:.1f} MB frame set out of a pool of {POOL} sets = {POOL * spg * W * H / 1e6:.0f} MB per GPU (> 126 MB L2; "
+                    "triangle-wave order, a set comes round again after up to 46 steps); no explicit flush",
               "e2e_host_frames": "pinned (cudaHostAlloc default)" if args.host_alloc == "pinned" else "pinned, write-combined"}
 
     if args.impl == "reference":
@@ -471,7 +540,7 @@ def main():
                   f"FRAME_STEP {FRAME_STEP}), {fps_step} frames per process per step; unmodified Tracker::TrackFrame (SmallBlurryImage included), "
                   "keyframe 0 registered with the relocaliser")
         line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": Wm, "ms_per_step": step_s * 1e3,
-                "higher_is_better": True, "scaling": SCALING, "vs_baseline": None, "dtype": "u8/i32 + f64", "data": "synthetic", "config": config,
+                "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "u8/i32 + f64", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": fps, "unit": UNIT, "cores": n_procs, "kind": kind, "sample": sample},
                 "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0, "tracking": stats}
         emit(line)
@@ -505,13 +574,13 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    S = args.streams
+    S = len(stream_ids)
     cam, tex, f0, smap = build_scene(on_gpu=True, device=local_rank)
     tex_t = torch.from_numpy(tex.astype(np.float32)).to(dev)
     # A pool of M consecutive frame sets per stream, traversed as a triangle wave (1,2,..,M,M-1,..,1,2,..) so that any number of
     # steps sees a continuous camera motion.  A set is re-read at the earliest two steps later, after > 126 MB of other traffic.
     M = pool_size(K, Wm)
-    poses = stream_poses(S, M + 1, first_stream=rank * S)                       # (S, M+1, 3, 4); index 0 = identity (the source keyframe)
+    poses = stream_poses(stream_ids, M + 1)                                     # (S, M+1, 3, 4); index 0 = identity (the source keyframe)
     frames_dev = torch.empty((M, S, H, W), dtype=torch.uint8, device=dev)
     for k in range(1, M + 1):
         rb = 64 if W * H <= 640 * 480 else 8          # render batch (float64 temporaries of B x H x W)
@@ -615,7 +684,7 @@ def main():
     corners_per_step = sum(int(ctx.corners(s, l).shape[0]) for l in range(4) for s in probe) * (S / len(probe))
     found = np.array([ctx.counters(s)[1].sum() for s in range(0, S, max(1, S // 16))])
     quality = np.array([ctx.counters(s)[2] for s in range(0, S, max(1, S // 16))])
-    value = world * S * K / (dev_ms * 1e-3)
+    value = streams_total * K / (dev_ms * 1e-3)
 
     # ---- leg 2: end to end through the host-buffer C-ABI call, pose read-back every step ------------------------------
     # vslam_track_frame_async: pinned host frames -> (copy stream) -> kernels -> every stream's pose copied back to pinned host
@@ -644,8 +713,30 @@ def main():
     wall_ms = (time.perf_counter() - t0) * 1e3
     clocks = sampler.stop()
     e2e_ms = max_over_ranks(wall_ms)
-    e2e_value = world * S * K / (e2e_ms * 1e-3)
+    e2e_value = streams_total * K / (e2e_ms * 1e-3)
     assert np.isfinite(acc)
+
+    # ---- what bounds e2e: the host-to-device copy of a step's frames.  Peak of this box, measured here: pinned cudaMemcpyAsync of the same
+    # frame sets on the library's copy path alone (no kernels), all ranks copying at the same time.
+    h2d_bytes = S * fs
+    stage_buf = torch.empty((S, H, W), dtype=torch.uint8, device=dev)
+    for k in range(2):
+        stage_buf.copy_(frames_host[tri(k)], non_blocking=True)
+    barrier()
+    nh = max(8, min(K, 40))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for k in range(nh):
+        stage_buf.copy_(frames_host[tri(step_no + k)], non_blocking=True)
+    e1.record(stream)
+    barrier()
+    h2d_ms = max_over_ranks(e0.elapsed_time(e1)) / nh
+    h2d_peak = h2d_bytes / (h2d_ms * 1e-3) / 1e9                       # GB/s per GPU with all ranks copying
+    h2d_achieved = h2d_bytes / (e2e_ms / K * 1e-3) / 1e9
+    h2d_roofline = {"bound": "host-to-device copy (PCIe / host memory)", "achieved": h2d_achieved, "peak": h2d_peak, "unit": "GB/s per GPU", "frac": h2d_achieved / h2d_peak,
+                    "aggregate_peak_gbs": h2d_peak * world, "bytes_per_step_per_gpu": h2d_bytes,
+                    "how": f"pinned cudaMemcpyAsync of {nh} frame sets per rank, all {world} rank(s) at once, CUDA events, max over ranks; achieved = the e2e leg's bytes over its step time"}
+    del stage_buf
 
     # ---- roofline of the pyramid+FAST stage ----------------------------------------------------------------------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -662,12 +753,16 @@ def main():
     l0_corners = sum(int(ctx.corners(s, 0).shape[0]) for s in probe) * (S / len(probe))
     l0_bytes = S * (1.328125 * W * H + 4 * (H + 1)) + 4.0 * l0_corners
     l0_ms = stage["pyrfast_l0"][0] / Ks
-    # DRAM bytes of that launch from the committed ncu --set full capture (profiles/r01c_ncu_full_summary.json, S=256 VGA)
-    l0_traffic = 78.845696e6 + 11.888128e6 if (S == 256 and (W, H) == (640, 480)) else None
-    # the roofline that actually binds the level-0 launch: instruction issue.  Warp-instructions of the launch from the committed ncu
-    # capture (smsp__inst_executed.sum, profiles/r01c_ncu_full_summary.json; a property of the workload, not of the run) over the live
-    # launch time, against 4 issue slots per SM and clock
-    l0_inst = 166989951.0 if (S == 256 and (W, H) == (640, 480)) else None
+    # DRAM bytes and executed warp-instructions of that launch: read from the committed ncu --set full capture of the CURRENT kernels
+    # (profiles/r02_ncu_counters.json, written by scratch/mkprofiles from the .ncu-rep of `bench.py --steps 2`; a property of the workload, not of
+    # the run).  null when the capture does not cover this configuration.
+    l0_traffic = l0_inst = None; counters_src = None
+    cpath = os.path.join(ROOT, "profiles", "r02_ncu_counters.json")
+    if os.path.exists(cpath):
+        cj = json.load(open(cpath))
+        kk = cj.get("kernels", {}).get("k_pyramid_fast")
+        if kk and cj.get("streams") == S and cj.get("frame") == [W, H]:
+            l0_traffic = kk["dram_bytes_read"] + kk["dram_bytes_write"]; l0_inst = kk["warp_instructions"]; counters_src = "profiles/r02_ncu_counters.json"
     sm_clock_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
     issue = None
     if l0_inst:
@@ -679,8 +774,8 @@ def main():
                 "algorithmic_bytes_per_step": alg_bytes_step, "ms_per_step": pyr_ms / Ks, "share_of_step": (pyr_ms / Ks) / stage_sum_ms,
                 "level0_launch": {"algorithmic_bytes": l0_bytes, "ms": l0_ms, "achieved": l0_bytes / (l0_ms * 1e-3) / 1e9,
                                   "frac": l0_bytes / (l0_ms * 1e-3) / 1e9 / peak, "traffic": l0_traffic, "issue_roofline": issue},
-                "note": "traffic is the level-0 launch's dram read+write bytes (ncu); the stage is instruction-issue bound (81-85 % issue-slot "
-                        "utilisation, ~270 warp-instructions per 256 pixels of level 0), not HBM bound: DESIGN.md §4.1 and profiles/r01c_*"}
+                "counters_source": counters_src,
+                "note": "traffic is the level-0 launch's dram read+write bytes (ncu --set full); the stage is instruction-issue bound, not HBM bound: DESIGN.md §4.1 and profiles/"}
     # ZMSSD: 3*P^2 integer MACs per scored candidate over the time of the two search kernels, against a measured dp4a peak
     evals_timed = evals1 - evals0
     search_ms = stage["search_fine"][0] + stage["search_coarse"][0]
@@ -711,11 +806,44 @@ def main():
                          "stream beside `pyrfast_l1` (= levels 1-3), so the stages sum to more than ms_per_step")
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": dev_ms / K, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32 (pyramid, FAST, ZMSSD) + f64 (projection, WLS)", "data": "synthetic", "config": config,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": S * H * W, "d2h_bytes_per_step": S * 12 * 8, "ms_per_step": e2e_ms / K},
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "u8/i32 (pyramid, FAST, ZMSSD) + f64 (projection, WLS)", "data": "synthetic", "config": config,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": S * H * W * world, "d2h_bytes_per_step": S * 12 * 8 * world, "ms_per_step": e2e_ms / K,
+                    "limiter": "host-to-device copy" if h2d_achieved > 0.8 * h2d_peak else "kernels (copy overlapped)"},
+            "h2d_roofline": h2d_roofline,
             "gpu_launches": int(launches), "clocks": clocks, **({"remeasured_after_stall_ms_per_step": remeasured} if remeasured else {}), "roofline": roofline, "zmssd_roofline": zmssd, "stages_ms_per_step": stages_ms, "stage_rates": stage_rates,
             "tracking": {"found_per_frame_mean": float(found.mean()), "quality_good_frac": float((quality == 2).mean()),
                          "zmssd_evals_total": int(ctx.zmssd_evals())}}
+
+    top_stage = max(((k, v) for k, v in stages_ms.items() if k != "note"), key=lambda kv: kv[1])[0]
+    line["limiter"] = {"value": f"kernel time, largest stage: {top_stage}", "e2e": line["e2e"]["limiter"]}
+    ctx.close()
+    del frames_dev, frames_host
+    torch.cuda.empty_cache()
+
+    # ---- extra legs (own contexts, frames resident, CUDA events, max over ranks): every rank takes part
+    if not args.no_extra_legs:
+        Ke, We = max(5, min(K, 20)), 3
+        vga = (W, H, N_POINTS, TEX_SIZE)
+        scene_vga = (cam, tex, f0, smap)
+        # (1) fast camera: the motion model's speed gate (jni/Tracker.cc:815-819,425) switches the coarse stage on in every frame -- 10 + 10
+        #     Gauss-Newton iterations -- and templates are regenerated as the warp moves past the 0.07 re-use test
+        ms, info = short_leg("fast_motion", vga, stream_ids, Ke, We, local_rank, stream, frame_step=6 * FRAME_STEP, pool=10, barrier=barrier, scene=scene_vga)
+        ms = max_over_ranks(ms)
+        line["fast_motion"] = {"value": streams_total / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, **info}
+        # (2) the other scaling mode, so that one line carries both
+        if world > 1:
+            other = "weak" if args.scaling == "strong" else "strong"
+            ids2 = sharding.weak_streams(args.streams, rank) if other == "weak" else sharding.streams_for_rank(args.streams, rank, world)
+            ms, info = short_leg(other, vga, ids2, Ke, We, local_rank, stream, pool=12, barrier=barrier, scene=scene_vga)
+            ms = max_over_ranks(ms)
+            tot2 = args.streams * world if other == "weak" else args.streams
+            line[other + "_scaling"] = {"value": tot2 / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "streams_total": tot2, **info}
+        # (3) the other frame sizes of north_star, 148 streams per GPU = one CTA of the per-stream kernels per SM
+        line["other_sizes"] = {}
+        for nm, (w2, h2, np2, s2) in FRAME_CONFIGS.items():
+            ms, info = short_leg(nm, (w2, h2, np2, 4096), sharding.weak_streams(s2, rank), max(4, Ke // 2), 3, local_rank, stream, pool=4, barrier=barrier)
+            ms = max_over_ranks(ms)
+            line["other_sizes"][nm] = {"value": s2 * world / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "scaling": "weak", **info}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n_procs = os.cpu_count() or 1
@@ -729,7 +857,6 @@ def main():
                                 "tracking": stats}
         gf, cf = line["tracking"]["found_per_frame_mean"], stats["found_per_frame_mean"]
         line["cpu_baseline"]["same_workload"] = bool(abs(gf - cf) <= 0.02 * max(gf, cf))      # found points per frame agree within 2 %
-    ctx.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
