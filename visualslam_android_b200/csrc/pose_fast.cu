@@ -150,9 +150,67 @@ __device__ __forceinline__ void radix_count(FastSmem& sm, bool part, int bin, in
   __syncwarp();   // reconverge before the next warp collective (a diverged warp takes the slow WARPSYNC.COLLECTIVE path, ~300 cycles per collective)
 }
 __device__ __forceinline__ double radix_select(FastSmem& sm, const double (&key)[kPP], int n, const double* spill, int k) {
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   unsigned long long prefix = 0;
   int rank = k, sh = 63;
+  {
+    // First level: 64 buckets by exponent (2^-63 .. 2^0, both ends clamped -- a monotone map, so bucket order is key order), counted in
+    // WARP-PRIVATE histograms: the squared errors of a frame span a few dozen binades, i.e. a few dozen heavily shared counters, and
+    // shared-memory atomics of different warps on one address serialise.  An interior bucket is one exponent = an 11-bit prefix, and the
+    // select continues on the mantissa below; a clamped end bucket (median < 2^-63 or >= 1 px^2) restarts with the generic loop.
+    constexpr int kEB = 64, kE0 = 1023 - 63;
+    for (int b = tid; b < (kFT / 32) * kEB; b += kFT) sm.hist[b] = 0;
+    __syncthreads();
+    int* wh = sm.hist + warp * kEB;
+#pragma unroll
+    for (int p = 0; p < kPP; p++) {
+      const int ex = (int)((unsigned long long)__double_as_longlong(key[p]) >> 52) - kE0;
+      const int bkt = ex < 0 ? 0 : (ex > kEB - 1 ? kEB - 1 : ex);
+      const bool part = tid + p * kFT < n;
+      const unsigned peers = __match_any_sync(0xffffffffu, part ? bkt : kEB + lane);
+      if (part && lane == __ffs(peers) - 1) wh[bkt] += __popc(peers);          // (one lane per distinct bucket of the warp: no atomic needed)
+      __syncwarp();
+    }
+    for (int t0 = kCap; t0 < n; t0 += kFT) {
+      const int t = t0 + tid;
+      const int ex = t < n ? (int)((unsigned long long)__double_as_longlong(spill[t - kCap]) >> 52) - kE0 : 0;
+      const int bkt = ex < 0 ? 0 : (ex > kEB - 1 ? kEB - 1 : ex);
+      const unsigned peers = __match_any_sync(0xffffffffu, t < n ? bkt : kEB + lane);
+      if (t < n && lane == __ffs(peers) - 1) wh[bkt] += __popc(peers);
+      __syncwarp();
+    }
+    __syncthreads();
+    if (tid < 32) {
+      int v0 = 0, v1 = 0;
+#pragma unroll
+      for (int w = 0; w < kFT / 32; w++) { v0 += sm.hist[w * kEB + 2 * lane]; v1 += sm.hist[w * kEB + 2 * lane + 1]; }
+      const int two = v0 + v1;
+      int incl = two;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+      const int excl = incl - two;
+      if (rank >= excl && rank < incl) {
+        int r = rank - excl, bkt = 2 * lane, cnt = v0;
+        if (r >= v0) { r -= v0; bkt++; cnt = v1; }
+        sm.sel[0] = (unsigned long long)bkt; sm.sel[1] = (unsigned long long)r; sm.sel[2] = (unsigned long long)cnt;
+      }
+    }
+    __syncthreads();
+    const int bkt = (int)sm.sel[0];
+    if (bkt > 0 && bkt < kEB - 1) {
+      prefix = (unsigned long long)(bkt + kE0) << 52; rank = (int)sm.sel[1]; sh = 52;
+      if (sm.sel[2] == 1ull) {   // a single key with this exponent: its owner publishes it
+        __syncthreads();
+#pragma unroll
+        for (int p = 0; p < kPP; p++)
+          if (tid + p * kFT < n) { const unsigned long long kk = (unsigned long long)__double_as_longlong(key[p]); if ((kk >> 52) == (prefix >> 52)) sm.sel[0] = kk; }
+        for (int t = kCap + tid; t < n; t += kFT) { const unsigned long long kk = (unsigned long long)__double_as_longlong(spill[t - kCap]); if ((kk >> 52) == (prefix >> 52)) sm.sel[0] = kk; }
+        __syncthreads();
+        prefix = sm.sel[0]; sh = 0;
+      }
+    }
+    __syncthreads();
+  }
   while (sh > 0) {
     const int bits = sh >= kRadixBits ? kRadixBits : sh, nsh = sh - bits, nb = 1 << bits;
     PF_SUB0();
@@ -163,13 +221,15 @@ __device__ __forceinline__ double radix_select(FastSmem& sm, const double (&key)
     for (int p = 0; p < kPP; p++) {
       const unsigned long long kk = (unsigned long long)__double_as_longlong(key[p]);
       const bool part = (tid + p * kFT < n) && (sh == 63 || (kk >> sh) == (prefix >> sh));
-      radix_count(sm, part, (int)((kk >> nsh) & (unsigned long long)(nb - 1)), lane);
+      if (sh == 63) radix_count(sm, part, (int)((kk >> nsh) & (unsigned long long)(nb - 1)), lane);   // every key takes part, few distinct digits: combine equal ones first
+      else if (part) atomicAdd(&sm.hist[(int)((kk >> nsh) & (unsigned long long)(nb - 1))], 1);          // one exponent's keys over 2048 bins: hardly any sharing
     }
     for (int t0 = kCap; t0 < n; t0 += kFT) {
       const int t = t0 + tid;
       const unsigned long long kk = t < n ? (unsigned long long)__double_as_longlong(spill[t - kCap]) : 0ull;
       const bool part = t < n && (sh == 63 || (kk >> sh) == (prefix >> sh));
-      radix_count(sm, part, (int)((kk >> nsh) & (unsigned long long)(nb - 1)), lane);
+      if (sh == 63) radix_count(sm, part, (int)((kk >> nsh) & (unsigned long long)(nb - 1)), lane);
+      else if (part) atomicAdd(&sm.hist[(int)((kk >> nsh) & (unsigned long long)(nb - 1))], 1);
     }
     __syncthreads();
     PF_SUB(1);
