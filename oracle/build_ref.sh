@@ -9,8 +9,8 @@
 #      those absolute paths are rewritten to <Eigen/Dense>) into a throw-away directory under
 #      $TMPDIR -- nothing from /root/reference is ever written into the repository;
 #   2. compiles them against oracle/shim/{Eigen,opencv2,opencv} (value-semantics stand-ins);
-#   3. links with oracle/ref_harness.cc, which stubs only MapMaker (its thread is disabled in
-#      the reference as shipped) and exports ref_* entry points;
+#   3. links with oracle/ref_harness.cc, which exports ref_* entry points (MapMaker.cc, Bundle.cc and HomographyInit.cc are the
+#      reference's; only the never-started map-maker THREAD is stood in for);
 #   4. writes ONLY the shared object into oracle/_ref/ (git-ignored, travels with gpurun).
 # Without /root/reference (e.g. on the GPU box) the script is a no-op that keeps a prebuilt .so.
 set -euo pipefail
@@ -28,7 +28,7 @@ fi
 TMP="$(mktemp -d "${TMPDIR:-/tmp}/vslam_ref.XXXXXX")"
 trap 'rm -rf "$TMP"' EXIT
 mkdir -p "$TMP/vision"
-FILES="ATANCamera.h ATANCamera.cc KeyFrame.h KeyFrame.cc LevelHelpers.h MEstimator.h Map.h Map.cc MapMaker.h MapPoint.h MapPoint.cc
+FILES="ATANCamera.h ATANCamera.cc Bundle.h Bundle.cc HomographyInit.h HomographyInit.cc KeyFrame.h KeyFrame.cc LevelHelpers.h MEstimator.h Map.h Map.cc MapMaker.h MapMaker.cc MapPoint.h MapPoint.cc
 MiniPatch.h MiniPatch.cc PatchFinder.h PatchFinder.cc RT.h Relocaliser.h Relocaliser.cc SmallBlurryImage.h SmallBlurryImage.cc
 Tracker.h Tracker.cc TrackerData.h myWLS.h vision/ImageHandler.h vision/ImageHandler.cpp vision/cvfast.h vision/cvfast.cpp"
 for f in $FILES; do
@@ -49,5 +49,5 @@ for f in $FILES; do
 done
 $CXX $FLAGS -c "$HERE/ref_harness.cc" -o "$TMP/ref_harness.o" &
 FAIL=0; for p in $(jobs -p); do wait "$p" || FAIL=1; done; [ "$FAIL" = 0 ] || { echo "build_ref: compile failed"; exit 1; }
-$CXX -shared -o "$OUT/libvslam_ref.so" $OBJS "$TMP/ref_harness.o"
+$CXX -shared -o "$OUT/libvslam_ref.so" $OBJS "$TMP/ref_harness.o" -lpthread
 echo "build_ref: wrote $OUT/libvslam_ref.so"

@@ -4,10 +4,12 @@
 // the product library.
 //
 // What is NOT the reference here (and why):
-//   * MapMaker member functions: stubs.  The reference's map-maker thread is commented out
-//     (jni/MapMaker.cc:55-56); the tracker only needs the reset handshake
-//     (jni/Tracker.cc:67-69) and "no new keyframe wanted".  Bundle/HomographyInit need
-//     Eigen::JacobiSVD and are out of scope.
+//   * MapMaker's THREAD.  jni/MapMaker.cc, Bundle.cc and HomographyInit.cc are compiled as they are (the Eigen stand-in provides a
+//     JacobiSVD / EigenSolver, oracle/shim/Eigen/Dense), but the reference never starts the map-maker thread
+//     (jni/MapMaker.cc:55-56), so (a) the reset handshake of Tracker::Reset (jni/Tracker.cc:67-69) is answered by a
+//     short-lived helper thread that does what MapMaker::run does on a reset request, and (b) keyframes the tracker queues with
+//     MapMaker::AddKeyFrame are taken off the queue after every frame and appended to the map with their SmallBlurryImage -- the
+//     map-building work of AddKeyFrameFromTopOfQueue (new points, bundle adjustment) is out of scope.
 //   * ref_cam_fix_radius(): optional run-time overwrite of ATANCamera::mdLargestRadius/mdMaxR
 //     with the value the code at jni/ATANCamera.cc:70-82 evidently intended (double, not int,
 //     temporaries).  As shipped both are 0 and TrackerData::Project rejects every point
@@ -46,57 +48,11 @@
 #undef protected
 #undef private
 
-// ------------------------------------------------------------------ MapMaker stubs (see header comment)
-MapMaker::MapMaker(Map& m, const ATANCamera& cam) : mMap(m), mCamera(cam) {
-  mbResetRequested = false; mbResetDone = true; mbBundleAbortRequested = false; mbBundleRunning = false;
-  mbBundleRunningIsRecent = false; mbBundleConverged_Full = true; mbBundleConverged_Recent = true;
-  mdWiggleScale = 0.1; mgvdWiggleScale = 0.1; mdWiggleScaleDepthNormalized = 1e30;
-}
-MapMaker::~MapMaker() {}
-void MapMaker::RequestReset() { mbResetDone = true; mbResetRequested = false; }  // map is filled by the harness after construction
-bool MapMaker::ResetDone() { return mbResetDone; }
-// The three MapMaker heuristics Tracker::TrackFrame consults.  Off (the default) they answer like an idle MapMaker and the pins of the
-// tracking path see no keyframe traffic.  Switched on by ref_set_keyframe_policy they are driven on the reference's objects: camera
-// positions through mySE3::inverse / get_translation, distances through Eigen-shim dot products, thresholds from the MapMaker members
-// the reference compares against (written from the description of jni/MapMaker.cc:705-773,1098-1101 in SURVEY.md / DESIGN.md).
-// A keyframe the tracker hands over joins the map at once, as if the MapMaker thread had emptied its queue before the next frame:
-// KeyFrame::operator= copy, then the relocaliser's SmallBlurryImage as KeyFrame::MakeKeyFrame_Rest would build it.
-namespace {
-bool g_keyframe_policy = false; double g_need_mult = 0.2; int g_keyframes_added = 0;
-double nearest_keyframe_distance(Map& map, KeyFrame& current) {
-  const Eigen::Vector3d here = current.se3CfromW.inverse().get_translation();
-  double best = 9999999999.9;
-  for (unsigned int i = 0; i < map.vpKeyFrames.size(); i++) {
-    if (map.vpKeyFrames[i] == &current) continue;
-    const Eigen::Vector3d there = map.vpKeyFrames[i]->se3CfromW.inverse().get_translation();
-    const Eigen::Vector3d step = there - here;
-    const double d = sqrt(step.dot(step));
-    if (d < best) best = d;
-  }
-  return best;
-}
-}  // namespace
-bool MapMaker::NeedNewKeyFrame(KeyFrame& current) {
-  if (!g_keyframe_policy) return false;
-  double d = nearest_keyframe_distance(mMap, current);
-  d *= (1.0 / current.dSceneDepthMean);
-  return d > g_need_mult * mdWiggleScaleDepthNormalized;
-}
-void MapMaker::AddKeyFrame(KeyFrame& k) {
-  if (!g_keyframe_policy) return;
-  KeyFrame* copy = new KeyFrame;
-  *copy = k;
-  copy->pSBI = new SmallBlurryImage(*copy);
-  copy->pSBI->MakeJacs();
-  mMap.vpKeyFrames.push_back(copy);
-  g_keyframes_added++;
-}
-bool MapMaker::IsDistanceToNearestKeyFrameExcessive(KeyFrame& current) {
-  if (!g_keyframe_policy) return false;
-  return nearest_keyframe_distance(mMap, current) > mdWiggleScale * 10.0;
-}
-bool MapMaker::InitFromStereo(KeyFrame&, KeyFrame&, vector<pair<Eigen::Vector2d, Eigen::Vector2d> >&, mySE3&) { return false; }
-void MapMaker::run() {}
+#include "MapMaker.h"
+#include <atomic>
+#include <thread>
+
+namespace { int g_keyframes_added = 0; }
 
 namespace {
 
@@ -118,6 +74,20 @@ void pose_to12(const mySE3& s, double* p) {
 struct RefTracker {
   Map* map; MapMaker* mm; Tracker* tr;
 };
+// Keyframes queued by the real MapMaker::AddKeyFrame (jni/MapMaker.cc: a copy with pSBI = NULL) join the map at once, as if the
+// map-maker thread had taken them off its queue before the next frame, with the relocaliser's SmallBlurryImage as
+// KeyFrame::MakeKeyFrame_Rest (jni/KeyFrame.cc:98) and the map maker's MakeJacs leave it.
+void drain_keyframe_queue(RefTracker* t) {
+  std::vector<KeyFrame*>& q = t->mm->mvpKeyFrameQueue;
+  for (size_t i = 0; i < q.size(); i++) {
+    KeyFrame* kf = q[i];
+    kf->pSBI = new SmallBlurryImage(*kf);
+    kf->pSBI->MakeJacs();
+    t->map->vpKeyFrames.push_back(kf);
+    g_keyframes_added++;
+  }
+  q.clear();
+}
 
 cv::Mat wrap_gray(const uint8_t* g, int w, int h, int stride) { return cv::Mat(h, w, CV_8UC1, (void*)g, (size_t)stride); }
 
@@ -356,10 +326,23 @@ int ref_mp_find(void* mp, void* kf, double* pos2, int range, int use_lut) {
 void* ref_tracker_create(int w, int h, void* cam, void* map_, int fix) {
   RefTracker* t = new RefTracker();
   t->map = (Map*)map_;
-  // Tracker::Tracker -> Reset() -> MapMaker::RequestReset (stub: done immediately; the map is filled by the caller afterwards,
-  // or was filled before: the stub does not wipe it).
+  // MapMaker::MapMaker -> Reset() and Tracker::Tracker -> Reset() -> MapMaker::RequestReset both wipe the map (Map::Reset deletes the
+  // points): the caller's map is set aside for the duration and put back afterwards.  The reset request is answered by a helper
+  // thread the way MapMaker::run answers it (CHECK_RESET, jni/MapMaker.cc:80), because the reference's own thread is never started.
+  std::vector<MapPoint*> points; points.swap(t->map->vpPoints);
+  std::vector<KeyFrame*> keyframes; keyframes.swap(t->map->vpKeyFrames);
+  const bool good = t->map->bGood;
   t->mm = new MapMaker(*t->map, *(ATANCamera*)cam);
-  t->tr = new Tracker(w, h, *(ATANCamera*)cam, *t->map, *t->mm);
+  {
+    std::atomic<bool> stop(false);
+    MapMaker* mm = t->mm;
+    std::thread helper([&stop, mm] { while (!stop.load()) { if (mm->mbResetRequested) mm->Reset(); usleep(20); } });
+    t->tr = new Tracker(w, h, *(ATANCamera*)cam, *t->map, *t->mm);
+    stop.store(true);
+    helper.join();
+  }
+  t->map->vpPoints.swap(points); t->map->vpKeyFrames.swap(keyframes); t->map->bGood = good;
+  t->mm->mdWiggleScale = 1e30; t->mm->mdWiggleScaleDepthNormalized = 1e30;   // keyframe heuristics off until ref_set_keyframe_policy (both members are uninitialised before InitFromStereo)
   fix_radius(t->tr->mCamera, fix);
   t->tr->mbDraw = false;
   return t;
@@ -400,6 +383,7 @@ void ref_tracker_track_frame(void* t, const uint8_t* gray, int w, int h, int str
   cv::Mat im = wrap_gray(gray, w, h, stride);
   cv::Mat col(1, 1, CV_8UC4, g_dummy_rgba);
   tr->TrackFrame(im, col, false);
+  drain_keyframe_queue((RefTracker*)t);
 }
 // f3 pins.  MapMaker.cc is not part of this build (it needs Eigen's JacobiSVD / EigenSolver and the Bundle / HomographyInit link
 // surface), so the two MapMaker searches are DRIVEN here on the reference's own objects: every arithmetic step below is a call into
@@ -540,9 +524,76 @@ void ref_epipolar_point_fields(void* t, void* source_kf, const double* src_pose1
   for (int q = 0; q < 3; q++) { out15[9 + q] = point.v3PixelRight_W(q); out15[12 + q] = point.v3PixelDown_W(q); }
 }
 void ref_set_keyframe_policy(void* t, int enable, double wiggle, double wiggle_dn, double mult) {
+  // the reference's own MapMaker::NeedNewKeyFrame / IsDistanceToNearestKeyFrameExcessive (jni/MapMaker.cc:763-773,1098-1101) compare against
+  // these two members; MaxKFDistWiggleMult is the constant 0.2 of :768 (`mult` must be that value)
   MapMaker* mm = ((RefTracker*)t)->mm;
-  g_keyframe_policy = enable != 0; g_need_mult = mult;
-  mm->mdWiggleScale = wiggle; mm->mdWiggleScaleDepthNormalized = enable ? wiggle_dn : 1e30;
+  assert(!enable || mult == 0.2); (void)mult;
+  mm->mdWiggleScale = enable ? wiggle : 1e30; mm->mdWiggleScaleDepthNormalized = enable ? wiggle_dn : 1e30;
+}
+
+// ------------------------------------------------------------------ the reference's own MapMaker functions (jni/MapMaker.cc), called directly
+static void ensure_mm_data(MapPoint& p) { if (!p.pMMData) p.pMMData = new MapMakerData(); }
+// MapMaker::ReFind_Common (jni/MapMaker.cc:967-1036) of the listed map points in the tracker's current keyframe (pose = the tracker's pose).
+// out4 = {found, measurement level, sub-pixel, never-retry}; pos2 = Measurement::v2RootPos.  The bookkeeping the call leaves behind is undone.
+void ref_mm_refind(void* t, const int32_t* idx, int n, int32_t* out4, double* pos2) {
+  RefTracker* r = (RefTracker*)t;
+  KeyFrame& frame = r->tr->mCurrentKF;
+  frame.se3CfromW = r->tr->mse3CamFromWorld;
+  for (int q = 0; q < n; q++) {
+    MapPoint& p = *r->map->vpPoints[idx[q]];
+    ensure_mm_data(p);
+    p.pMMData->sMeasurementKFs.erase(&frame); p.pMMData->sNeverRetryKFs.erase(&frame); frame.mMeasurements.erase(&p);
+    const bool found = r->mm->ReFind_Common(frame, p);
+    int32_t* o = out4 + 4 * q; o[0] = found; o[1] = -1; o[2] = 0; o[3] = (int)p.pMMData->sNeverRetryKFs.count(&frame);
+    pos2[2 * q] = pos2[2 * q + 1] = 0.0;
+    if (found) {
+      const Measurement& m = frame.mMeasurements[&p];
+      o[1] = m.nLevel; o[2] = m.bSubPix; pos2[2 * q] = m.v2RootPos(0); pos2[2 * q + 1] = m.v2RootPos(1);
+    }
+    p.pMMData->sMeasurementKFs.erase(&frame); p.pMMData->sNeverRetryKFs.erase(&frame); frame.mMeasurements.erase(&p);
+  }
+}
+// MapMaker::AddPointEpipolar (jni/MapMaker.cc:525-703) for candidate `candidate_index` of `source`'s level (after MakeKeyFrame_Rest) against
+// `target`.  Returns its result; on success out27 = the new MapPoint: world position, centre / one-right / one-down rays, pixel-right /
+// pixel-down vectors (6 x 3), irCenter (2), source level, the two measurements' root positions (source, target: 2 + 2), 2 spare.  The
+// point is taken out of the map again (the caller's map stays as it was).
+int ref_mm_add_point_epipolar(void* t, void* source_kf, void* target_kf, const double* src_pose12, const double* tgt_pose12, double depth_mean, double depth_sigma,
+                              double wiggle, int level, int candidate_index, double* out27) {
+  RefTracker* r = (RefTracker*)t;
+  KeyFrame& source = *(KeyFrame*)source_kf; KeyFrame& target = *(KeyFrame*)target_kf;
+  source.se3CfromW = pose_from12(src_pose12); target.se3CfromW = pose_from12(tgt_pose12);
+  source.dSceneDepthMean = depth_mean; source.dSceneDepthSigma = depth_sigma;
+  const double saved = r->mm->mdWiggleScale; r->mm->mdWiggleScale = wiggle;
+  const size_t before = r->map->vpPoints.size();
+  const bool ok = r->mm->AddPointEpipolar(source, target, level, candidate_index);
+  r->mm->mdWiggleScale = saved;
+  for (int k = 0; k < 27; k++) out27[k] = 0.0;
+  if (!ok) return 0;
+  assert(r->map->vpPoints.size() == before + 1);
+  MapPoint* p = r->map->vpPoints.back();
+  const Eigen::Vector3d* v[6] = {&p->v3WorldPos, &p->v3Center_NC, &p->v3OneRightFromCenter_NC, &p->v3OneDownFromCenter_NC, &p->v3PixelRight_W, &p->v3PixelDown_W};
+  for (int k = 0; k < 6; k++) for (int c = 0; c < 3; c++) out27[3 * k + c] = (*v[k])(c);
+  out27[18] = p->irCenter(0); out27[19] = p->irCenter(1); out27[20] = p->nSourceLevel;
+  out27[21] = source.mMeasurements[p].v2RootPos(0); out27[22] = source.mMeasurements[p].v2RootPos(1);
+  out27[23] = target.mMeasurements[p].v2RootPos(0); out27[24] = target.mMeasurements[p].v2RootPos(1);
+  source.mMeasurements.erase(p); target.mMeasurements.erase(p);
+  r->map->vpPoints.pop_back();
+  while (!r->mm->mqNewQueue.empty()) r->mm->mqNewQueue.pop();
+  delete p->pMMData; delete p;
+  return 1;
+}
+// MapMaker::ReprojectPoint (jni/MapMaker.cc:176-200): point in frame B from the two z = 1 projections
+void ref_mm_reproject_point(void* t, const double* a_from_b12, const double* plane_a2, const double* plane_b2, double* out3) {
+  RefTracker* r = (RefTracker*)t;
+  const Eigen::Vector3d p = r->mm->ReprojectPoint(pose_from12(a_from_b12), Eigen::Vector2d(plane_a2[0], plane_a2[1]), Eigen::Vector2d(plane_b2[0], plane_b2[1]));
+  for (int c = 0; c < 3; c++) out3[c] = p(c);
+}
+// MapMaker::NeedNewKeyFrame / IsDistanceToNearestKeyFrameExcessive / DistToNearestKeyFrame on the tracker's current keyframe and pose
+void ref_mm_keyframe_heuristics(void* t, int* need_new, int* excessive, double* dist) {
+  RefTracker* r = (RefTracker*)t;
+  KeyFrame& frame = r->tr->mCurrentKF;
+  frame.se3CfromW = r->tr->mse3CamFromWorld;
+  *need_new = r->mm->NeedNewKeyFrame(frame); *excessive = r->mm->IsDistanceToNearestKeyFrameExcessive(frame); *dist = r->mm->DistToNearestKeyFrame(frame);
 }
 void ref_keyframe_info(void* t, int* n_keyframes, int* added_total, int* n_frame, int* last_dropped) {
   RefTracker* r = (RefTracker*)t;

@@ -104,6 +104,11 @@ def lib():
     sig("ref_set_keyframe_policy", None, vp, i, d, d, d)
     sig("ref_keyframe_info", None, vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int))
     sig("ref_epipolar_point_fields", None, vp, vp, _f64p, i, i, _f64p, _f64p)
+    # the reference's own MapMaker functions (jni/MapMaker.cc is part of the build)
+    sig("ref_mm_refind", None, vp, _i32p, i, _i32p, _f64p)
+    sig("ref_mm_add_point_epipolar", i, vp, vp, vp, _f64p, _f64p, d, d, d, i, i, _f64p)
+    sig("ref_mm_reproject_point", None, vp, _f64p, _f64p, _f64p, _f64p)
+    sig("ref_mm_keyframe_heuristics", None, vp, C.POINTER(i), C.POINTER(i), C.POINTER(d))
     sig("ref_kf_num_candidates_l", i, vp, i)
     sig("ref_kf_make_sbi", None, vp)
     sig("ref_tracker_set_lost", None, vp, i, i)

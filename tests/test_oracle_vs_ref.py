@@ -321,6 +321,14 @@ def test_refind_common(case):
     # a cold finder per point gives the same answers when consecutive points differ (the batched GPU semantics)
     ow.L.orc_tracker_refind(ow.tracker, idx, smap.n, 4, 8, 1, oo, op)
     assert np.array_equal(ro, oo) and np.array_equal(rp, op)
+    # ... and the reference's OWN MapMaker::ReFind_Common (jni/MapMaker.cc is compiled into oracle/_ref), called point by point: what it
+    # returns and the Measurement it files (level, sub-pixel flag, root position) are the restatement's, bit for bit
+    mo, mp = np.zeros((smap.n, 4), dtype=np.int32), np.zeros((smap.n, 2))
+    rw.L.ref_mm_refind(rw.tracker, idx, smap.n, mo, mp)
+    assert np.array_equal(mo[:, 0], oo[:, 0])
+    f = oo[:, 0] == 1
+    assert np.array_equal(mo[f][:, 1:3], oo[f][:, 1:3]) and np.array_equal(mp[f], op[f])
+    assert np.all(mo[~f][:, 3] == 1)                     # everything it did not find is filed under "never retry"
 
 
 def test_epipolar_search():
@@ -335,7 +343,8 @@ def test_epipolar_search():
     ok0 = oraclebind.OrcKeyFrame().make_lite(f0); ok0.make_rest()
     ok1 = oraclebind.OrcKeyFrame().make_lite(f1)
     eye = np.ascontiguousarray(synth.IDENTITY_POSE, dtype=np.float64).reshape(12); p1 = np.ascontiguousarray(pose1, dtype=np.float64).reshape(12)
-    nfound = nbest = 0
+    cam13 = np.ascontiguousarray(cam.scalars(), dtype=np.float64)
+    nfound = nbest = n_points = 0
     for level in range(4):
         xy, _ = ok0.candidates(level)
         assert rw.L.ref_kf_num_candidates_l(rk0.h, level) == len(xy)
@@ -347,7 +356,22 @@ def test_epipolar_search():
                 ow.L.orc_epipolar_search(ow.tracker, ok0.h, ok1.h, eye, p1, mean, sigma, wig, level, int(xy[k, 0]), int(xy[k, 1]), oo, op, None)
                 assert np.array_equal(ro, oo) and np.array_equal(rp, op), (level, k, ro, oo, rp, op)
                 nfound += int(ro[0]); nbest += int(ro[1] >= 0)
-    assert nfound > 40 and nbest > nfound
+                # the reference's OWN MapMaker::AddPointEpipolar (jni/MapMaker.cc:525-703): succeeds exactly when the search converges, files
+                # the refined position as the target measurement, and builds the new MapPoint the restatement builds -- source rays and
+                # pixel vectors bit for bit, the triangulated position (MapMaker::ReprojectPoint through the stand-in JacobiSVD) to 1e-9
+                out = np.zeros(27)
+                ok = rw.L.ref_mm_add_point_epipolar(rw.tracker, rk0.h, rk1.h, eye, p1, mean, sigma, wig, level, k, out)
+                assert ok == int(oo[0]), (level, k)
+                if ok:
+                    assert np.array_equal(out[23:25], op) and np.array_equal(out[18:21], [xy[k, 0], xy[k, 1], level])
+                    root = (xy[k] + 0.5) * (1 << level) - 0.5
+                    assert np.array_equal(out[21:23], root)
+                    world = oraclebind.triangulate(cam13, synth.IDENTITY_POSE, pose1, root, op)
+                    assert np.abs(out[0:3] - world).max() <= 1e-9 * max(1.0, np.abs(world).max()), (level, k, out[0:3], world)
+                    got = oraclebind.epipolar_point_fields(cam13, synth.IDENTITY_POSE, level, xy[k, 0], xy[k, 1], out[0:3])
+                    assert np.array_equal(got.reshape(15), out[3:18]), (level, k)
+                    n_points += 1
+    assert nfound > 40 and nbest > nfound and n_points > 40
 
 
 def test_track_frame_recovers_a_lost_tracker():

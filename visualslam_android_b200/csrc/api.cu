@@ -106,7 +106,7 @@ int vslam_create(const vslam_config* cfg, vslam_ctx** out) {
   ctx->S = cfg->n_streams; ctx->N = cfg->max_points; ctx->P = cfg->patch_size; ctx->launches = 0; ctx->n_src = cfg->max_source_keyframes; ctx->src_have.assign(ctx->n_src, 0);
   ctx->reloc_n = 0; ctx->reloc_tmpl = nullptr; ctx->reloc_jac = nullptr; ctx->reloc_tmp = nullptr; ctx->reloc_small = nullptr; ctx->reloc_pose = nullptr; ctx->reloc_scores = nullptr;
   ctx->kf_req = nullptr; ctx->kf_policy = false; ctx->kf_wiggle = 0.1; ctx->kf_wiggle_dn = 0.1; ctx->kf_mult = 0.2; ctx->kf_min_frames = 20;
-  ctx->unproj_lut = nullptr; ctx->unproj_ok = false; for (int g = 0; g < VS_MAX_GROUPS; g++) { ctx->side_stream[g] = nullptr; ctx->group_stream[g] = nullptr; ctx->ev_fork[g] = nullptr; ctx->ev_join[g] = nullptr; ctx->ev_end[g] = nullptr; }
+  ctx->unproj_lut = nullptr; ctx->unproj_ok = false; ctx->epi_buf = nullptr; ctx->epi_cap = 0; for (int g = 0; g < VS_MAX_GROUPS; g++) { ctx->side_stream[g] = nullptr; ctx->group_stream[g] = nullptr; ctx->ev_fork[g] = nullptr; ctx->ev_join[g] = nullptr; ctx->ev_end[g] = nullptr; }
   ctx->ev_begin = nullptr; ctx->cur_s0 = 0; ctx->cur_cnt = cfg->n_streams; ctx->cur_group = 0; ctx->scratch_host = nullptr; ctx->scratch_host_bytes = 0; ctx->timing = false; ctx->ev_used = 0; ctx->l0_alt = nullptr; ctx->copy_stream = nullptr; ctx->step = 0; ctx->pipe_ready = false; ctx->status_pin = nullptr;
   ctx->rest_scores = nullptr; ctx->rest_max = nullptr; ctx->rest_cand = nullptr; ctx->rest_cand_score = nullptr; ctx->rest_counts = nullptr; ctx->rest_stream = -1;
   ctx->snap_img = nullptr; ctx->snap_corners = nullptr; ctx->snap_lut = nullptr;
@@ -194,7 +194,7 @@ void vslam_destroy(vslam_ctx* ctx) {
   cudaSetDevice(ctx->cfg.device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (int l = 0; l < VS_LEVELS; l++) { cudaFree(ctx->lev[l].img); cudaFree(ctx->lev[l].corners); cudaFree(ctx->lev[l].lut); cudaFree(ctx->lev[l].xlut); cudaFree(ctx->src.img[l]); }
-  cudaFree(ctx->l0_ptr); cudaFree(ctx->l0_stride); cudaFree(ctx->sync_words); cudaFree(ctx->status); cudaFree(ctx->evals);
+  cudaFree(ctx->epi_buf); cudaFree(ctx->l0_ptr); cudaFree(ctx->l0_stride); cudaFree(ctx->sync_words); cudaFree(ctx->status); cudaFree(ctx->evals);
   cudaFree(ctx->map.world); cudaFree(ctx->map.right); cudaFree(ctx->map.down); cudaFree(ctx->map.ircenter); cudaFree(ctx->map.srclevel); cudaFree(ctx->map.srckf);
   PointState& ps = ctx->ps;
   cudaFree(ps.v3cam); cudaFree(ps.v2image); cudaFree(ps.derivs); cudaFree(ps.warpinv); cudaFree(ps.m2); cudaFree(ps.lastwarp); cudaFree(ps.v2found); cudaFree(ps.coarse);
@@ -894,57 +894,38 @@ int vslam_epipolar_search(vslam_ctx* ctx, int stream, int src_kf, int level, int
   const double onePixelDist = sqrt(dd) / sqrt(2.0);
   const int nLevelScale = 1 << level;
   const double dMaxDistDiff = onePixelDist * (4.0 + 1.0 * nLevelScale), dMaxDistSq = dMaxDistDiff * dMaxDistDiff;
-  // v3CamCenter_TC = kTarget.se3CfromW * kSrc.se3CfromW.inverse().get_translation()
-  const double ts[3] = {src_pose[3], src_pose[7], src_pose[11]};
-  double rts[3]; rot_t_vec(src_pose, ts, rts);
-  const double sinv_t[3] = {-rts[0], -rts[1], -rts[2]};
-  double center[3]; rot_vec(tgt_pose, sinv_t, center); center[0] = center[0] + tgt_pose[3]; center[1] = center[1] + tgt_pose[7]; center[2] = center[2] + tgt_pose[11];
-  const double dStartDepth = std::max(wiggle_scale, depth_mean - depth_sigma), dEndDepth = std::min(40 * wiggle_scale, depth_mean + depth_sigma);
-  std::vector<EpiCand> cands(n > 0 ? n : 1);
-  for (int k = 0; k < n; k++) {
-    EpiCand& C = cands[k];
-    memset(&C, 0, sizeof(C));
-    C.x = cand_xy[2 * k]; C.y = cand_xy[2 * k + 1];
-    const double root0 = ((double)C.x + 0.5) * nLevelScale - 0.5, root1 = ((double)C.y + 0.5) * nLevelScale - 0.5;   // LevelZeroPos
-    double u[2]; host_unproject(cam, root0, root1, u);
-    double ray[3] = {u[0], u[1], 1.0};
-    { double nn = ray[0] * ray[0]; nn += ray[1] * ray[1]; nn += ray[2] * ray[2]; const double nrm = sqrt(nn); ray[0] /= nrm; ray[1] /= nrm; ray[2] /= nrm; }
-    double tmp[3], dirn[3]; rot_t_vec(src_pose, ray, tmp); rot_vec(tgt_pose, tmp, dirn);
-    double start[3], end[3];
-    for (int q = 0; q < 3; q++) { start[q] = center[q] + dStartDepth * dirn[q]; end[q] = center[q] + dEndDepth * dirn[q]; }
-    if (end[2] <= start[2]) continue;
-    if (end[2] <= 0.0) continue;
-    if (start[2] <= 0.0) { const double f = 0.001 - start[2] / dirn[2]; for (int q = 0; q < 3; q++) start[q] += dirn[q] * f; }
-    const double A[2] = {start[0] / start[2], start[1] / start[2]}, B[2] = {end[0] / end[2], end[1] / end[2]};
-    double al[2] = {A[0] - B[0], A[1] - B[1]};
-    double aa = al[0] * al[0]; aa += al[1] * al[1];
-    if (aa < 0.00000001) continue;
-    { const double nrm = sqrt(aa); al[0] /= nrm; al[1] /= nrm; }
-    const double nrml[2] = {al[1], -al[0]};
-    double dNormDist = A[0] * nrml[0]; dNormDist += A[1] * nrml[1];
-    if (fabs(dNormDist) > cam.largestRadius) continue;
-    double aA = al[0] * A[0]; aA += al[1] * A[1];
-    double aB = al[0] * B[0]; aB += al[1] * B[1];
-    double dMinLen = std::min(aA, aB) - 0.05, dMaxLen = std::max(aA, aB) + 0.05;
-    if (dMinLen < -2.0) dMinLen = -2.0;
-    if (dMaxLen < -2.0) dMaxLen = -2.0;
-    if (dMinLen > 2.0) dMinLen = 2.0;
-    if (dMaxLen > 2.0) dMaxLen = 2.0;
-    C.nx = nrml[0]; C.ny = nrml[1]; C.ax = al[0]; C.ay = al[1]; C.normDist = dNormDist; C.minLen = dMinLen; C.maxLen = dMaxLen; C.maxDistSq = dMaxDistSq; C.valid = 1;
-  }
+  // The ray of every candidate through the camera model on the host (ATANCamera::UnProject calls libm's tan, like the imUnProj table above);
+  // the line geometry of jni/MapMaker.cc:543-591 -- rotations, depth range, clipping, the line's normal form -- runs on the device
+  // (k_epipolar_geometry, one thread per candidate, the reference's operations in the reference's order).
   if (n == 0) return VSLAM_OK;
-  EpiCand* cd = nullptr; int* oi = nullptr; double* op = nullptr;
-  cudaError_t e = cudaMalloc(&cd, sizeof(EpiCand) * n);
-  if (e == cudaSuccess) e = cudaMalloc(&oi, sizeof(int) * 3 * n);
-  if (e == cudaSuccess) e = cudaMalloc(&op, sizeof(double) * 2 * n);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(cd, cands.data(), sizeof(EpiCand) * n, cudaMemcpyHostToDevice, ctx->stream);
-  if (e == cudaSuccess) { rc = vs_launch_epipolar(ctx, stream, src_kf, level, n, cd, ctx->unproj_lut, 10, oi, op); if (rc) { cudaFree(cd); cudaFree(oi); cudaFree(op); return rc; } }
+  std::vector<double> rays(2 * (size_t)n);
+  for (int k = 0; k < n; k++) {
+    const double root0 = ((double)cand_xy[2 * k] + 0.5) * nLevelScale - 0.5, root1 = ((double)cand_xy[2 * k + 1] + 0.5) * nLevelScale - 0.5;   // LevelZeroPos
+    host_unproject(cam, root0, root1, &rays[2 * (size_t)k]);
+  }
+  // one scratch allocation of the context, grown on demand: [EpiCand n][rays 2n f64][pos 2n f64][xy 2n i32][out 3n i32]
+  const size_t need = sizeof(EpiCand) * n + sizeof(double) * 4 * n + sizeof(int) * 5 * n + 64;
+  if (need > ctx->epi_cap) {
+    VS_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->epi_buf); ctx->epi_buf = nullptr; ctx->epi_cap = 0;
+    VS_CUDA(cudaMalloc(&ctx->epi_buf, need * 2));
+    ctx->epi_cap = need * 2;
+  }
+  EpiCand* cd = (EpiCand*)ctx->epi_buf;
+  double* rays_d = (double*)(cd + n); double* op = rays_d + 2 * (size_t)n;
+  int* xy_d = (int*)(op + 2 * (size_t)n); int* oi = xy_d + 2 * (size_t)n;
+  VS_CUDA(cudaMemcpyAsync(rays_d, rays.data(), sizeof(double) * 2 * n, cudaMemcpyHostToDevice, ctx->stream));
+  VS_CUDA(cudaMemcpyAsync(xy_d, cand_xy, sizeof(int) * 2 * n, cudaMemcpyHostToDevice, ctx->stream));
+  EpiGeom G;
+  for (int q = 0; q < 12; q++) { G.src_pose[q] = src_pose[q]; G.tgt_pose[q] = tgt_pose[q]; }
+  G.start_depth = std::max(wiggle_scale, depth_mean - depth_sigma); G.end_depth = std::min(40 * wiggle_scale, depth_mean + depth_sigma);
+  G.max_dist_sq = dMaxDistSq; G.largest_radius = cam.largestRadius;
+  if ((rc = vs_launch_epipolar_geometry(ctx, n, G, rays_d, xy_d, cd))) return rc;
+  if ((rc = vs_launch_epipolar(ctx, stream, src_kf, level, n, cd, ctx->unproj_lut, 10, oi, op))) return rc;
   std::vector<int> hi(3 * (size_t)n);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(hi.data(), oi, sizeof(int) * 3 * n, cudaMemcpyDeviceToHost, ctx->stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(pos2, op, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, ctx->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  cudaFree(cd); cudaFree(oi); cudaFree(op);
-  if (e != cudaSuccess) { ctx->err = std::string("vslam_epipolar_search: ") + cudaGetErrorString(e); return VSLAM_E_CUDA; }
+  VS_CUDA(cudaMemcpyAsync(hi.data(), oi, sizeof(int) * 3 * n, cudaMemcpyDeviceToHost, ctx->stream));
+  VS_CUDA(cudaMemcpyAsync(pos2, op, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, ctx->stream));
+  VS_CUDA(cudaStreamSynchronize(ctx->stream));
   for (int k = 0; k < n; k++) { found[k] = hi[3 * k]; if (best_corner) best_corner[k] = hi[3 * k + 1]; if (best_zmssd) best_zmssd[k] = hi[3 * k + 2]; }
   return VSLAM_OK;
 }
@@ -1080,8 +1061,12 @@ int vslam_track_frame_async(vslam_ctx* ctx, const uint8_t* gray, int stride, siz
 }
 
 int vslam_wait_step(vslam_ctx* ctx, int step) {
-  if (!ctx || !ctx->pipe_ready || step < 0 || step >= ctx->step) { if (ctx) ctx->err = "unknown step id"; return VSLAM_E_INVALID; }
-  if (ctx->step - step > 2) return VSLAM_OK;   // older steps completed before their slot was reused
+  if (!ctx || !ctx->pipe_ready || step < 0 || step > 0x3fffffff) { if (ctx) ctx->err = "unknown step id"; return VSLAM_E_INVALID; }
+  // ids count modulo 2^30: `age` = how many steps were issued since `step` (1 = the latest); an id that was never handed out shows up as
+  // a huge age and is treated like any long-finished step
+  const long long age = (ctx->step - (long long)step) & 0x3fffffff;
+  if (age == 0) { ctx->err = "unknown step id"; return VSLAM_E_INVALID; }     // = the id the NEXT step will get
+  if (age > 2) return VSLAM_OK;   // older steps completed before their slot was reused
   VS_CUDA(cudaEventSynchronize(ctx->ev_done[step & 1]));
   if (ctx->status_pin[4 * (step & 1)]) {       // corner-capacity overflow seen by that step (the flag is sticky until vslam_sync)
     ctx->err = "corner list capacity exceeded (raise vslam_config.max_corner_frac)";

@@ -1015,6 +1015,63 @@ static int debug_atan(const double* x_host, double* y_host, int n, int dd_only) 
   return e == cudaSuccess ? VSLAM_OK : VSLAM_E_CUDA;
 }
 
+// The line geometry of MapMaker::AddPointEpipolar (jni/MapMaker.cc:543-591), one thread per candidate: the candidate's viewing ray (z = 1
+// plane coordinates `rays`, from ATANCamera::UnProject on the host) rotated into the target camera, the depth range cut to the part in front
+// of the camera, the projected segment A-B in normal form.  The reference's operations in the reference's order (no contraction: -fmad=false).
+namespace {
+__global__ void k_epipolar_geometry(int n, EpiGeom G, const double* __restrict__ rays, const int* __restrict__ xy, EpiCand* __restrict__ out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  EpiCand C;
+  C.nx = C.ny = C.ax = C.ay = C.normDist = C.minLen = C.maxLen = C.maxDistSq = 0.0; C.valid = 0; C.pad = 0;
+  C.x = xy[2 * k]; C.y = xy[2 * k + 1];
+  // v3CamCenter_TC = kTarget.se3CfromW * kSrc.se3CfromW.inverse().get_translation()
+  const double* S = G.src_pose; const double* T = G.tgt_pose;
+  const double ts[3] = {S[3], S[7], S[11]};
+  double rts[3];
+  for (int i = 0; i < 3; i++) { double a = S[i] * ts[0]; a += S[4 + i] * ts[1]; a += S[8 + i] * ts[2]; rts[i] = a; }      // R_s^T t_s
+  const double sinv_t[3] = {-rts[0], -rts[1], -rts[2]};
+  double center[3]; rot_apply(T, sinv_t, center); center[0] = center[0] + T[3]; center[1] = center[1] + T[7]; center[2] = center[2] + T[11];
+  double ray[3] = {rays[2 * k], rays[2 * k + 1], 1.0};
+  { double nn = ray[0] * ray[0]; nn += ray[1] * ray[1]; nn += ray[2] * ray[2]; const double nrm = sqrt(nn); ray[0] /= nrm; ray[1] /= nrm; ray[2] /= nrm; }
+  double tmp[3], dirn[3];
+  for (int i = 0; i < 3; i++) { double a = S[i] * ray[0]; a += S[4 + i] * ray[1]; a += S[8 + i] * ray[2]; tmp[i] = a; }     // R_s^T ray
+  rot_apply(T, tmp, dirn);
+  double start[3], end[3];
+  for (int q = 0; q < 3; q++) { start[q] = center[q] + G.start_depth * dirn[q]; end[q] = center[q] + G.end_depth * dirn[q]; }
+  bool ok = !(end[2] <= start[2]) && !(end[2] <= 0.0);
+  if (ok) {
+    if (start[2] <= 0.0) { const double f = 0.001 - start[2] / dirn[2]; for (int q = 0; q < 3; q++) start[q] += dirn[q] * f; }
+    const double A[2] = {start[0] / start[2], start[1] / start[2]}, B[2] = {end[0] / end[2], end[1] / end[2]};
+    double al[2] = {A[0] - B[0], A[1] - B[1]};
+    double aa = al[0] * al[0]; aa += al[1] * al[1];
+    if (!(aa < 0.00000001)) {
+      { const double nrm = sqrt(aa); al[0] /= nrm; al[1] /= nrm; }
+      const double nrml[2] = {al[1], -al[0]};
+      double dNormDist = A[0] * nrml[0]; dNormDist += A[1] * nrml[1];
+      if (!(fabs(dNormDist) > G.largest_radius)) {
+        double aA = al[0] * A[0]; aA += al[1] * A[1];
+        double aB = al[0] * B[0]; aB += al[1] * B[1];
+        double dMinLen = fmin(aA, aB) - 0.05, dMaxLen = fmax(aA, aB) + 0.05;
+        if (dMinLen < -2.0) dMinLen = -2.0;
+        if (dMaxLen < -2.0) dMaxLen = -2.0;
+        if (dMinLen > 2.0) dMinLen = 2.0;
+        if (dMaxLen > 2.0) dMaxLen = 2.0;
+        C.nx = nrml[0]; C.ny = nrml[1]; C.ax = al[0]; C.ay = al[1]; C.normDist = dNormDist; C.minLen = dMinLen; C.maxLen = dMaxLen; C.maxDistSq = G.max_dist_sq; C.valid = 1;
+      }
+    }
+  }
+  out[k] = C;
+}
+}  // namespace
+int vs_launch_epipolar_geometry(vslam_ctx* ctx, int n, const EpiGeom& G, const double* rays_dev, const int* xy_dev, EpiCand* cand_dev) {
+  if (n <= 0) return VSLAM_OK;
+  k_epipolar_geometry<<<(n + 127) / 128, 128, 0, ctx->stream>>>(n, G, rays_dev, xy_dev, cand_dev);
+  VS_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return VSLAM_OK;
+}
+
 int vs_launch_epipolar(vslam_ctx* ctx, int stream, int src_kf, int level, int n, const EpiCand* cand_dev, const double* unproj_dev, int subpix_its, int* out_int_dev, double* out_pos_dev) {
   if (n <= 0) return VSLAM_OK;
   k_epipolar<<<(n + kSearchWarps - 1) / kSearchWarps, kSearchWarps * 32, 0, ctx->stream>>>(make_dev(ctx), stream, src_kf, level, n, cand_dev, unproj_dev, subpix_its, out_int_dev, out_pos_dev);

@@ -75,6 +75,9 @@ struct EpiCand {
   int x, y, valid, pad;         // candidate position in the source level; valid = 0: rejected before the search
 };
 
+// Inputs of the epipolar line geometry shared by all candidates of one vslam_epipolar_search call
+struct EpiGeom { double src_pose[12], tgt_pose[12]; double start_depth, end_depth, max_dist_sq, largest_radius; };
+
 // Per-stream tracker scalars (Tracker members)
 struct StreamState {
   double pose[12], start_pose[12];
@@ -134,6 +137,7 @@ struct vslam_ctx {
   // keyframe policy (vslam_set_keyframe_policy): the MapMaker heuristics the tracker consults, over the registered keyframes' poses
   bool kf_policy; double kf_wiggle, kf_wiggle_dn, kf_mult; int kf_min_frames;
   int* kf_req;                   // [S] device: compact mirror of StreamState::kf_request (one small D2H copy per poll)
+  void* epi_buf; size_t epi_cap;    // scratch of vslam_epipolar_search (candidates, rays, results), grown on demand
   double* unproj_lut; bool unproj_ok;   // [H][W][2] ATANCamera::UnProject of every integer level-0 pixel (MapMaker::AddPointEpipolar's imUnProj), built on the host
   // on-device SmallBlurryImage (vslam_enable_sbi)
   bool sbi_on; float sbi_taps[9]; CamDev sbi_cam; double sbi_orig[2][3]; float* sbi_tmpl; float* sbi_scratch; float* sbi_jac; uint8_t* sbi_small; int* sbi_have;
@@ -180,6 +184,7 @@ int vs_launch_project_and_derivs(vslam_ctx* ctx, int only_found);
 int vs_launch_calc_jacobians(vslam_ctx* ctx);
 int vs_launch_sbi(vslam_ctx* ctx);          // + k_relocalise when relocaliser keyframes are registered
 int vs_launch_reloc_make(vslam_ctx* ctx, const int* src_ids_dev);
+int vs_launch_epipolar_geometry(vslam_ctx* ctx, int n, const EpiGeom& G, const double* rays_dev, const int* xy_dev, EpiCand* cand_dev);
 int vs_launch_epipolar(vslam_ctx* ctx, int stream, int src_kf, int level, int n, const EpiCand* cand_dev, const double* unproj_dev, int subpix_its, int* out_int_dev, double* out_pos_dev);
 int vs_keyframe_rest(vslam_ctx* ctx, int stream);
 int vs_minipatch_sample(vslam_ctx* ctx, int stream, int which, const int* xy_dev, int n, uint8_t* patches_dev);
