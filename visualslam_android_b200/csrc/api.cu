@@ -132,6 +132,8 @@ int vslam_create(const vslam_config* cfg, vslam_ctx** out) {
     L.cap = (int)((double)w * h * frac); if (L.cap < 64) L.cap = 64;
     L.strip_rows = vs_strip_rows(l, w, L.pitch);
     L.n_strips = (h + L.strip_rows - 1) / L.strip_rows;
+    { auto mg = [](int d) { return d <= 1 ? 0u : 0xffffffffu / (uint32_t)d + 1u; };
+      L.mg_strips = mg(L.n_strips); L.mg_cpr = mg((w + 15) / 16); L.mg_wpr = mg((w + 31) / 32); L.mg_hw = mg(w / 2); L.mg_w = mg(w); }
     CK(dalloc(&L.img, (size_t)S * h * L.pitch));
     CK(dalloc(&L.corners, (size_t)S * L.cap));
     CK(dalloc(&L.lut, (size_t)S * (h + 1)));

@@ -14,12 +14,18 @@
 //      running row offsets ARE the row look-up table of jni/KeyFrame.cc:41-49.
 // Integer / byte arithmetic only; results are bit-exact against the oracle.
 #include "vslam_internal.cuh"
+#include <cstdio>
+#include <cstdlib>
+
+#ifndef VS_PYR_REGS
+#define VS_PYR_REGS 40   // registers per thread of the two FAST kernels (five 320-thread CTAs per SM)
+#endif
 
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kWarps = kThreads / 32;
-constexpr int kQueue = 288;  // per-warp candidate queue: up to 31 carried over + 256 of one work item (2 rows x 128 pixels)
+constexpr int kMaxThreads = 320;           // ten warps: a 16-row VGA strip is exactly ten work items (32 lanes x 16 pixels x 2 rows)
+constexpr int kMaxWarps = kMaxThreads / 32;
+constexpr int kQueue = 288;                // per-warp candidate queue: up to 31 carried over + up to 255 of one work item (denser items bypass the queue)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -48,22 +54,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ uint32_t bytes_gt(uint32_t x, uint32_t k /* (127 - t) * 0x01010101 */) { return ((x & 0x7f7f7f7fu) + k) | x; }
 
 // Exact FAST-10 segment test of one candidate (queue entry = smem row << 16 | x); sets its bit in the strip's corner bitmask.
+// One IMAD per ring pixel yields both polarities: with kc = ((c - t - 1 + 2^15) << 16) + (2^15 - c - t - 1),
+//   z = v * (1 - 2^16) + kc   has   bit 15 = (v - c - t - 1 >= 0) = brighter,   bit 31 = (c - t - 1 - v >= 0) = darker
+// (both 16-bit fields stay inside [2^15 - 266, 2^15 + 254]: no borrow between them).
 __device__ __forceinline__ void ring_test(uint32_t e, const uint8_t* img, int stride, int thr, uint32_t* bitmask, int words_per_row, int row_bias) {
   const int ry = e >> 16, x = e & 0xffff;
-  const uint8_t* p = img + (size_t)ry * stride + x;
-  const int cb = (int)p[0] + thr, c_b = (int)p[0] - thr;
-  const int s1 = stride, s2 = 2 * stride, s3 = 3 * stride;
-  uint32_t br = 0, dk = 0;
-  // sign bit of (cb - v) <=> v > cb ; sign bit of (v - c_b) <=> v < c_b : shifted into the masks with funnel shifts
-#define RING(off)                                                       \
+  const uint8_t* p0 = img + ry * stride + x;
+  const uint8_t *pp1 = p0 + stride, *pp2 = pp1 + stride, *pp3 = pp2 + stride, *pm1 = p0 - stride, *pm2 = pm1 - stride, *pm3 = pm2 - stride;
+  const uint32_t c = p0[0];
+  const uint32_t kc = ((c + (0x8000u - 1u - (uint32_t)thr)) << 16) + ((0x8000u - 1u - (uint32_t)thr) - c);
+  uint32_t a0 = 0, a1 = 0;   // ring positions 0..7 / 8..15: brighter flags end up in bits 8..15, darker flags in bits 24..31
+#define RING(acc, ptr, off)                                             \
   {                                                                     \
-    const int v = (int)p[(off)];                                        \
-    br = __funnelshift_l((uint32_t)(cb - v), br, 1);                    \
-    dk = __funnelshift_l((uint32_t)(v - c_b), dk, 1);                   \
+    const uint32_t z = (uint32_t)(ptr)[(off)] * 0xFFFF0001u + kc;       \
+    acc = (acc >> 1) | (z & 0x80008000u);                               \
   }
-  RING(s3) RING(1 + s3) RING(2 + s2) RING(3 + s1) RING(3) RING(3 - s1) RING(2 - s2) RING(1 - s3)
-  RING(-s3) RING(-1 - s3) RING(-2 - s2) RING(-3 - s1) RING(-3) RING(-3 + s1) RING(-2 + s2) RING(-1 + s3)
+  RING(a0, pp3, 0) RING(a0, pp3, 1) RING(a0, pp2, 2) RING(a0, pp1, 3) RING(a0, p0, 3) RING(a0, pm1, 3) RING(a0, pm2, 2) RING(a0, pm3, 1)
+  RING(a1, pm3, 0) RING(a1, pm3, -1) RING(a1, pm2, -2) RING(a1, pm1, -3) RING(a1, p0, -3) RING(a1, pp1, -3) RING(a1, pp2, -2) RING(a1, pp3, -1)
 #undef RING
+  uint32_t br = ((a0 >> 8) & 0xffu) | (a1 & 0xff00u), dk = (a0 >> 24) | ((a1 >> 16) & 0xff00u);
   br |= br << 16; dk |= dk << 16;
   uint32_t b1 = br & (br >> 1), d1 = dk & (dk >> 1);
   uint32_t b2 = b1 & (b1 >> 2), d2 = d1 & (d1 >> 2);
@@ -72,37 +81,55 @@ __device__ __forceinline__ void ring_test(uint32_t e, const uint8_t* img, int st
   if ((b2 | d2) & 0xffffu) atomicOr(&bitmask[(ry + row_bias) * words_per_row + (x >> 5)], 1u << (x & 31));
 }
 
+// Rejection test of 16 pixels of one row (centre words c, staged row pointer r = &row[x0]): a 10-arc of the 16-ring contains at
+// least one pixel of each opposite pair, so both (0,8) [rows -3 / +3] and (4,12) [columns -3 / +3] must hold a pixel differing
+// from the centre by more than t.  Returns bit i = pixel x0 + i survives.
+__device__ __forceinline__ uint32_t reject16(const uint8_t* r, int stride, const uint4 c, uint32_t kcmp) {
+  const uint4 up = *(const uint4*)(r - 3 * stride), dn = *(const uint4*)(r + 3 * stride);
+  const uint32_t cw[6] = {*(const uint32_t*)(r - 4), c.x, c.y, c.z, c.w, *(const uint32_t*)(r + 16)};
+  const uint32_t uw[4] = {up.x, up.y, up.z, up.w}, dw[4] = {dn.x, dn.y, dn.z, dn.w};
+  uint32_t bits = 0;
+#pragma unroll
+  for (int j = 3; j >= 0; j--) {
+    const uint32_t cc = cw[j + 1];
+    const uint32_t lf = __byte_perm(cw[j], cc, 0x4321), rt = __byte_perm(cc, cw[j + 2], 0x6543);
+    const uint32_t m1 = bytes_gt(__vabsdiffu4(uw[j], cc), kcmp) | bytes_gt(__vabsdiffu4(dw[j], cc), kcmp);
+    const uint32_t m2 = bytes_gt(__vabsdiffu4(lf, cc), kcmp) | bytes_gt(__vabsdiffu4(rt, cc), kcmp);
+    // bit 7 of every byte -> the top nibble of the product (no two partial products meet), pushed into `bits` by a funnel shift
+    bits = __funnelshift_l((m1 & m2 & 0x80808080u) * 0x00204081u, bits, 4);
+  }
+  return bits;
+}
+
 constexpr unsigned long long kFlagAgg = 1ull << 32, kFlagInc = 2ull << 32;
 
 struct StripShared {
   uint64_t bar;
   int ticket, base;
-  int qcnt[kWarps];   // level 0: fill level of every warp's candidate queue
-  int rowcnt[VS_MAX_STRIP_ROWS], rowoff[VS_MAX_STRIP_ROWS + 1];
+  int wsum[2][kMaxWarps];   // per-warp corner counts (double buffered across the chunks of the write-out scan)
 };
 
-// n / d for small n (n * d < 2^32) with m = magic_div(d): one IMAD.HI instead of an integer division
-__device__ __forceinline__ uint32_t magic_div(uint32_t d) { return 0xffffffffu / d + 1u; }
+// n / d for small n (n * d < 2^32) with the reciprocal m = 0xffffffff / d + 1 from the host (LevelDesc::mg_*; m == 0 stands for d == 1):
+// one IMAD.HI instead of an integer division
+__device__ __forceinline__ int div_small(int n, uint32_t m) { return m == 0u ? n : (int)__umulhi((uint32_t)n, m); }
 
-// Levels 2 and 3 of a strip from its level-1 rows kept in shared memory (l1s: rows1 rows of w1 bytes, rows1 % 4 == 0 or
+// Levels 2 and 3 of a strip from its level-1 rows kept in shared memory (l1s: rows1 rows, w1 bytes apart, rows1 % 4 == 0 or
 // rows1 == 4): cv::resize 2:1 once / twice more, every intermediate pixel rounded as the level-by-level computation
 // rounds it, (a+b+c+d+2)>>2 (jni/KeyFrame.cc:20-23).  Threads t of nt.
 __device__ __forceinline__ void emit_levels_2_3(const uint8_t* l1s, int w1, int rows1, const LevelDesc& L2, const LevelDesc& L3, int s, int y0, int t, int nt) {
   uint8_t* d2 = L2.img + ((size_t)s * L2.h + (y0 >> 2)) * L2.pitch;
   uint8_t* d3 = L3.img + ((size_t)s * L3.h + (y0 >> 3)) * L3.pitch;
   const int p2 = L2.w >> 1, n2 = (rows1 >> 1) * p2;       // level 2: two pixels per step
-  const uint32_t m2 = magic_div((uint32_t)p2);
   for (int i = t; i < n2; i += nt) {
-    const int r = (int)__umulhi((uint32_t)i, m2), xp = i - r * p2;
+    const int r = div_small(i, L2.mg_hw), xp = i - r * p2;
     const uint32_t c0 = *(const uint32_t*)(l1s + (2 * r) * w1 + 4 * xp), c1 = *(const uint32_t*)(l1s + (2 * r + 1) * w1 + 4 * xp);
     const unsigned o0 = __dp4a(c0, 0x00000101u, __dp4a(c1, 0x00000101u, 2u)) >> 2;
     const unsigned o1 = __dp4a(c0, 0x01010000u, __dp4a(c1, 0x01010000u, 2u)) >> 2;
     *(uint16_t*)(d2 + (size_t)r * L2.pitch + 2 * xp) = (uint16_t)(o0 | (o1 << 8));
   }
   const int w3 = L3.w, n3 = (rows1 >> 2) * w3;            // level 3: one pixel (a 4x4 block of level 1) per step
-  const uint32_t m3 = magic_div((uint32_t)w3);
   for (int i = t; i < n3; i += nt) {
-    const int r = (int)__umulhi((uint32_t)i, m3), x = i - r * w3;
+    const int r = div_small(i, L3.mg_w), x = i - r * w3;
     const uint8_t* p = l1s + (4 * r) * w1 + 4 * x;
     const uint32_t q0 = *(const uint32_t*)p, q1 = *(const uint32_t*)(p + w1), q2 = *(const uint32_t*)(p + 2 * w1), q3 = *(const uint32_t*)(p + 3 * w1);
     const unsigned a = __dp4a(q0, 0x00000101u, __dp4a(q1, 0x00000101u, 2u)) >> 2, b = __dp4a(q0, 0x01010000u, __dp4a(q1, 0x01010000u, 2u)) >> 2;
@@ -111,11 +138,19 @@ __device__ __forceinline__ void emit_levels_2_3(const uint8_t* l1s, int w1, int 
   }
 }
 
+// four level-1 pixels from two words of row y and two words of row y + 1: (a+b+c+d+2)>>2 each
+__device__ __forceinline__ uint32_t half4(uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b1) {
+  const uint32_t o0 = __dp4a(a0, 0x00000101u, __dp4a(b0, 0x00000101u, 2u)), o1 = __dp4a(a0, 0x01010000u, __dp4a(b0, 0x01010000u, 2u));
+  const uint32_t o2 = __dp4a(a1, 0x00000101u, __dp4a(b1, 0x00000101u, 2u)), o3 = __dp4a(a1, 0x01010000u, __dp4a(b1, 0x01010000u, 2u));
+  const uint32_t lo = ((o0 + (o1 << 16)) >> 2) & 0x00ff00ffu, hi = ((o2 + (o3 << 16)) >> 2) & 0x00ff00ffu;   // sums < 1024: the 16-bit halves do not meet
+  return __byte_perm(lo, hi, 0x6420);
+}
+
 // One strip (rows [strip*R, +R) of level L of stream s): stage, [level 0: write levels 1..3], FAST-10, raster-ordered append.
 template <bool kLevel0>
 __device__ __forceinline__ void fast_strip(const LevelDesc& L, const uint8_t* __restrict__ src, const int stride, const int s, const int strip, const int thr,
                                            const LevelDesc* Lchild /* [3] levels 1..3, level 0 only */, int* __restrict__ status, StripShared& sh, uint8_t* smem) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, nw = nthreads >> 5;
   const int W = L.w, H = L.h, R = L.strip_rows;
   const int y0 = strip * R, y1 = min(y0 + R, H);
   const int ya = max(y0 - 3, 0), yb = min(y1 + 3, H);
@@ -129,108 +164,98 @@ __device__ __forceinline__ void fast_strip(const LevelDesc& L, const uint8_t* __
     mbar_expect_tx(&sh.bar, bytes);
     bulk_g2s(img, src + (size_t)ya * stride, bytes, &sh.bar);
   }
-  for (int i = tid; i < R * words_per_row; i += kThreads) bitmask[i] = 0;
-  if (tid < kWarps) sh.qcnt[tid] = 0;
+  for (int i = tid; i < (R * words_per_row) >> 2; i += nthreads) ((uint4*)bitmask)[i] = make_uint4(0u, 0u, 0u, 0u);   // R % 4 == 0
   __syncthreads();
   mbar_wait(&sh.bar, 0);
 
+  // ---- dense pass: a lane slot = 16 pixels x 2 rows (one 128-bit shared-memory load per row), slots of the strip in raster order,
+  //      32 per work item
   const uint32_t kcmp = (uint32_t)(127 - thr) * 0x01010101u;
   const int n_pairs = (y1 - y0 + 1) >> 1;
-  const int wq = W >> 2, n_slots = n_pairs * wq;      // a lane slot = 4 pixels x 2 rows; slots of the strip in raster order, 32 per work item
-  const uint32_t mq = magic_div((uint32_t)wq);
+  const int cpr = (W + 15) >> 4, n_slots = n_pairs * cpr;
   uint8_t* next_img = nullptr; int next_pitch = 0;
-  uint8_t* l1s = (uint8_t*)(bitmask + R * words_per_row + kWarps * kQueue);   // level 0 only: the strip's level-1 rows, W/2 bytes apart
+  const int l1p = ((W >> 1) + 7) & ~7;                                      // level 0 only: pitch of the strip's level-1 rows in shared memory
+  uint8_t* l1s = (uint8_t*)(bitmask + R * words_per_row + kMaxWarps * kQueue);
   if (kLevel0) { next_pitch = Lchild[0].pitch; next_img = Lchild[0].img + ((size_t)s * Lchild[0].h + (y0 >> 1)) * next_pitch; }   // level-1 row of y0
 
   int qn = 0;   // candidates waiting in this warp's queue (warp-uniform)
-  for (int item = warp; item * 32 < n_slots; item += kWarps) {
+  for (int item = warp; item * 32 < n_slots; item += nw) {
     const int slot = item * 32 + lane;
-    const int pr = (int)__umulhi((uint32_t)slot, mq);
+    const int pr = div_small(slot, L.mg_cpr);
     const int y = y0 + 2 * pr;           // rows y and y+1
-    const int x0 = (slot - pr * wq) << 2;
-    const bool active = slot < n_slots;
-    uint32_t cand[2] = {0u, 0u};
-    if (active) {
-      const uint8_t* r0 = img + (size_t)(y - ya) * stride + x0;
-      const uint32_t c0 = *(const uint32_t*)r0;
+    const int x0 = (slot - pr * cpr) << 4;
+    uint32_t mask = 0;                   // bit 16 k + i: pixel (x0 + i, y + k) survives the rejection test
+    if (slot < n_slots) {
+      const uint8_t* r0 = img + (y - ya) * stride + x0;
+      const uint4 c0 = *(const uint4*)r0;
       const bool have1 = (y + 1) < y1;
-      const uint32_t c1 = have1 ? *(const uint32_t*)(r0 + stride) : 0u;
-      if (kLevel0 && have1) {   // half-sample: two pixels of level 1 per lane
-        const unsigned o0 = __dp4a(c0, 0x00000101u, __dp4a(c1, 0x00000101u, 2u)) >> 2;
-        const unsigned o1 = __dp4a(c0, 0x01010000u, __dp4a(c1, 0x01010000u, 2u)) >> 2;
-        const uint16_t o = (uint16_t)(o0 | (o1 << 8));
-        *(uint16_t*)(next_img + (uint32_t)(pr * next_pitch + (x0 >> 1))) = o;
-        *(uint16_t*)(l1s + pr * (W >> 1) + (x0 >> 1)) = o;
+      const uint4 c1 = have1 ? *(const uint4*)(r0 + stride) : make_uint4(0u, 0u, 0u, 0u);
+      if (kLevel0 && have1) {   // half-sample: eight pixels of level 1 per lane (columns past W/2 land in the row padding)
+        const uint2 o = make_uint2(half4(c0.x, c0.y, c1.x, c1.y), half4(c0.z, c0.w, c1.z, c1.w));
+        *(uint2*)(next_img + (uint32_t)(pr * next_pitch + (x0 >> 1))) = o;
+        *(uint2*)(l1s + pr * l1p + (x0 >> 1)) = o;
       }
       // x in [3, W-4] only (jni/vision/cvfast.cpp:6115-6119)
-      uint32_t vmask = 0x80808080u;
-      if (x0 == 0) vmask = 0x80000000u;
-      if (x0 == W - 4) vmask &= 0x00000080u;
-#pragma unroll
-      for (int k = 0; k < 2; k++) {
-        const int yy = y + k;
-        if (yy < 3 || yy >= H - 3 || yy >= y1) continue;
-        const uint8_t* r = r0 + k * stride;
-        const uint32_t c = k ? c1 : c0;
-        const uint32_t up = *(const uint32_t*)(r - 3 * stride), dn = *(const uint32_t*)(r + 3 * stride);
-        const uint32_t m1 = bytes_gt(__vabsdiffu4(up, c), kcmp) | bytes_gt(__vabsdiffu4(dn, c), kcmp);
-        // unconditional: at x0 == 0 / W-4 the neighbour word lies in the adjacent staged row (rows < 3 and >= H-3 are never
-        // tested, so it is inside the buffer) and only feeds the pixels x < 3 / x > W-4 that vmask clears
-        const uint32_t lw = *(const uint32_t*)(r - 4), rw = *(const uint32_t*)(r + 4);
-        const uint32_t lf = __byte_perm(lw, c, 0x4321), rt = __byte_perm(c, rw, 0x6543);
-        const uint32_t m2 = bytes_gt(__vabsdiffu4(lf, c), kcmp) | bytes_gt(__vabsdiffu4(rt, c), kcmp);
-        cand[k] = m1 & m2 & vmask;
-      }
+      const int n_valid = W - 3 - x0;
+      uint32_t vm = n_valid >= 16 ? 0xffffu : ((1u << n_valid) - 1u);
+      if (x0 == 0) vm &= ~7u;
+      // rows < 3 and >= H-3 are never tested, so the words left of x0 == 0 / right of the last chunk lie inside the staged rows
+      // and only feed pixels that vm clears
+      if (y >= 3 && y < H - 3) mask = reject16(r0, stride, c0, kcmp) & vm;
+      if (have1 && y + 1 >= 3 && y + 1 < H - 3) mask |= (reject16(r0 + stride, stride, c1, kcmp) & vm) << 16;
     }
-    // append the candidates of this work item to the warp's queue (order is irrelevant: corners land in a bitmask)
-    const int mine = __popc(cand[0]) + __popc(cand[1]);
-    int pos;
-    if (kLevel0) {   // sparse candidates (about one lane in three has any): one shared-memory atomic per such lane beats the 5-step scan
-      pos = 0;
-      if (mine) pos = atomicAdd(&sh.qcnt[warp], mine);
+    // ---- survivors -> exact ring test, 32 per pass
+    const int mine = __popc(mask);
+    int incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    const uint32_t ebase = ((uint32_t)(y - ya) << 16) | (uint32_t)x0;     // bit b -> ebase + (b & 15) + ((b >> 4) << 16)
+    if (total > 255) {   // dense levels: every lane tests its own survivors (lanes are about equally loaded), no queue traffic
+      while (mask) {
+        const int b = 31 - __clz(mask); mask ^= 1u << b;
+        ring_test(ebase + (uint32_t)b + (uint32_t)(b & 16) * 4095u, img, stride, thr, bitmask, words_per_row, ya - y0);
+      }
+    } else if (total) {
+      int pos = qn + incl - mine;
+      while (mask) {
+        const int b = 31 - __clz(mask); mask ^= 1u << b;
+        queue[pos++] = ebase + (uint32_t)b + (uint32_t)(b & 16) * 4095u;
+      }
+      qn += total;
       __syncwarp();
-      qn = *(volatile int*)&sh.qcnt[warp];
-    } else {
-      int incl = mine;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
-      pos = qn + incl - mine;
-      qn += __shfl_sync(0xffffffffu, incl, 31);
-    }
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-      uint32_t m = cand[k];
-      const uint32_t ebase = ((uint32_t)(y + k - ya) << 16) | (uint32_t)x0;
-      while (m) {
-        const int b = __ffs(m) - 1; m &= m - 1;
-        queue[pos++] = ebase + (uint32_t)(b >> 3);
-      }
-    }
-    __syncwarp();
-    // exact ring test on full groups of 32 queued candidates; the remainder waits for the next work item
-    if (qn >= 32) {
       while (qn >= 32) { qn -= 32; ring_test(queue[qn + lane], img, stride, thr, bitmask, words_per_row, ya - y0); }
-      if (kLevel0 && lane == 0) sh.qcnt[warp] = qn;
+      __syncwarp();
     }
-    __syncwarp();
   }
   if (lane < qn) ring_test(queue[lane], img, stride, thr, bitmask, words_per_row, ya - y0);
   __syncthreads();
 
-  // per-row corner counts
-  const int rows = y1 - y0;
-  for (int r = warp; r < rows; r += kWarps) {
-    int c = 0;
-    for (int w = lane; w < words_per_row; w += 32) c += __popc(bitmask[r * words_per_row + w]);
+  // ---- corners of the strip in raster order: the bitmask words ARE in raster order, so an exclusive scan of their popcounts gives
+  //      every corner's position, every row's LUT entry and every 32-pixel bucket's column-index entry
+  const int rows = y1 - y0, n_words = rows * words_per_row;
+  int* pre = (int*)(bitmask + R * words_per_row);          // [n_words] exclusive prefix of every word (the candidate queues are done with)
+  int run = 0;
+  {
+    int buf = 0;
+    for (int w0 = 0; w0 < n_words; w0 += nthreads, buf ^= 1) {
+      const int w = w0 + tid;
+      const int mine = (w < n_words) ? __popc(bitmask[w]) : 0;
+      int incl = mine;
 #pragma unroll
-    for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
-    if (lane == 0) sh.rowcnt[r] = c;
+      for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+      if (lane == 31) sh.wsum[buf][warp] = incl;
+      __syncthreads();
+      int ws = (lane < nw) ? sh.wsum[buf][lane] : 0, wi = ws;      // scan of the (at most ten) warp totals, by every warp for itself
+#pragma unroll
+      for (int d = 1; d < 16; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi += v; }
+      const int before = __shfl_sync(0xffffffffu, wi - ws, warp), chunk = __shfl_sync(0xffffffffu, wi, 15);
+      if (w < n_words) pre[w] = run + before + incl - mine;
+      run += chunk;
+    }
   }
-  __syncthreads();
   if (tid == 0) {
-    int acc = 0;
-    for (int r = 0; r < rows; r++) { sh.rowoff[r] = acc; acc += sh.rowcnt[r]; }
-    sh.rowoff[rows] = acc;
+    const int acc = run;
     // decoupled look-back over the strips of this image (predecessors hold lower tickets, hence are resident or done)
     unsigned long long* st = L.strip_state + (size_t)s * L.n_strips;
     unsigned long long excl = 0;
@@ -240,7 +265,7 @@ __device__ __forceinline__ void fast_strip(const LevelDesc& L, const uint8_t* __
       atomicExch(&st[strip], kFlagAgg | (unsigned)acc);
       for (int j = strip - 1; j >= 0; j--) {
         unsigned long long v;
-        do { v = *(volatile unsigned long long*)&st[j]; } while ((v >> 32) == 0);
+        while (((v = *(volatile unsigned long long*)&st[j]) >> 32) == 0) __nanosleep(40);
         excl += (unsigned)v;
         if ((v >> 32) == 2) break;
       }
@@ -250,40 +275,39 @@ __device__ __forceinline__ void fast_strip(const LevelDesc& L, const uint8_t* __
     if ((long long)excl + acc > L.cap) atomicExch(&status[0], 1);
   }
   if (kLevel0 && warp > 0)   // levels 2 and 3 of this strip while thread 0 looks back
-    emit_levels_2_3(l1s, W >> 1, (y1 - y0) >> 1, Lchild[1], Lchild[2], s, y0, tid - 32, kThreads - 32);
+    emit_levels_2_3(l1s, l1p, (y1 - y0) >> 1, Lchild[1], Lchild[2], s, y0, tid - 32, nthreads - 32);
   __syncthreads();
+  // (positions are clamped to the capacity: on overflow -- reported through status[0] -- the readers of the LUT must not index past the list)
   const int base = sh.base;
   int* lut = L.lut + (size_t)s * (H + 1);
-  // (clamped to the capacity: on overflow -- reported through status[0] -- the readers of the LUT must not index past the list)
-  if (tid < rows) lut[y0 + tid] = min(base + sh.rowoff[tid], L.cap);
-  if (tid == 0 && y1 == H) lut[H] = min(base + sh.rowoff[rows], L.cap);
+  int* xlut = L.xlut + ((size_t)s * H + y0) * L.xw;
   uint32_t* out = L.corners + (size_t)s * L.cap;
-  for (int r = warp; r < rows; r += kWarps) {
-    int run = base + sh.rowoff[r];
-    const uint32_t yy = (uint32_t)(y0 + r) << 16;
-    int* xl = L.xlut + ((size_t)s * H + (y0 + r)) * L.xw;   // column index of the row (32-pixel buckets): the running positions below ARE its entries
-    for (int w0 = 0; w0 < words_per_row; w0 += 32) {
-      const int w = w0 + lane;
-      uint32_t m = (w < words_per_row) ? bitmask[r * words_per_row + w] : 0u;
-      const int mine = __popc(m);
-      int incl = mine;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
-      int pos = run + incl - mine;
-      if (w < words_per_row) xl[w] = min(pos, L.cap);
-      while (m) {
-        const int b = __ffs(m) - 1; m &= m - 1;
-        if (pos < L.cap) out[pos] = yy | (uint32_t)((w << 5) + b);
-        pos++;
-      }
-      run += __shfl_sync(0xffffffffu, incl, 31);
+  for (int w = tid; w < n_words; w += nthreads) {
+    uint32_t m = bitmask[w];
+    int pos = base + pre[w];
+    const int r = div_small(w, L.mg_wpr), col = w - r * words_per_row;
+    const int cpos = min(pos, L.cap);
+    xlut[r * L.xw + col] = cpos;                                  // column index of the row (32-pixel buckets)
+    if (col == 0) {
+      lut[y0 + r] = cpos;                                          // the row LUT of jni/KeyFrame.cc:41-49
+      if (r > 0) xlut[(r - 1) * L.xw + words_per_row] = cpos;      // end of the previous row
     }
-    if (lane == 0) xl[words_per_row] = min(run, L.cap);
+    const uint32_t yy = (uint32_t)(y0 + r) << 16, xb = (uint32_t)col << 5;
+    while (m) {
+      const int b = __ffs(m) - 1; m &= m - 1;
+      if (pos < L.cap) out[pos] = yy | (xb + (uint32_t)b);
+      pos++;
+    }
+  }
+  if (tid == 0) {
+    const int cend = min(base + run, L.cap);
+    xlut[(rows - 1) * L.xw + words_per_row] = cend;
+    if (y1 == H) lut[H] = cend;
   }
 }
 
 // Level 0 of every stream: pyramid levels 1..3 + FAST-10 of level 0.
-__global__ void __launch_bounds__(kThreads, 6)   // 40 registers / 6 CTAs per SM measured faster than 32 / 8 (and than 48 / 5: registers are granted in blocks of 8)
+__global__ void __maxnreg__(VS_PYR_REGS)
 k_pyramid_fast(LevelDesc L, LevelDesc L1, LevelDesc L2, LevelDesc L3, const uint8_t* const* __restrict__ l0_ptr, const int* __restrict__ l0_stride,
                int first_stream, int thr, unsigned* __restrict__ ticket, int* __restrict__ status) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -292,12 +316,12 @@ k_pyramid_fast(LevelDesc L, LevelDesc L1, LevelDesc L2, LevelDesc L3, const uint
   if (threadIdx.x == 0) { sh.ticket = (int)atomicAdd(ticket, 1u); mbar_init(&sh.bar, 1); child[0] = L1; child[1] = L2; child[2] = L3; }
   __syncthreads();
   const int t = sh.ticket;
-  const int s = first_stream + t / L.n_strips, strip = t % L.n_strips;
+  const int q = div_small(t, L.mg_strips), s = first_stream + q, strip = t - q * L.n_strips;
   fast_strip<true>(L, l0_ptr[s], l0_stride[s], s, strip, thr, child, status, sh, smem);
 }
 
 // FAST-10 of levels 1..3 of every stream in one launch: tickets run over level 1's strips, then level 2's, then level 3's.
-__global__ void __launch_bounds__(kThreads, 8)
+__global__ void __maxnreg__(VS_PYR_REGS)
 k_fast_levels(LevelDesc L1, LevelDesc L2, LevelDesc L3, int first_stream, int count, int thr1, int thr2, int thr3, unsigned* __restrict__ ticket,
               int* __restrict__ status) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -308,7 +332,7 @@ k_fast_levels(LevelDesc L1, LevelDesc L2, LevelDesc L3, int first_stream, int co
   const int n1 = count * L1.n_strips, n2 = count * L2.n_strips;
   LevelDesc L = L1;
   if (t >= n1) { t -= n1; L = L2; thr = thr2; if (t >= n2) { t -= n2; L = L3; thr = thr3; } }
-  const int s = first_stream + t / L.n_strips, strip = t % L.n_strips;
+  const int q = div_small(t, L.mg_strips), s = first_stream + q, strip = t - q * L.n_strips;
   fast_strip<false>(L, L.img + (size_t)s * L.h * L.pitch, L.pitch, s, strip, thr, nullptr, status, sh, smem);
 }
 
@@ -321,8 +345,18 @@ __global__ void k_half_sample(const uint8_t* __restrict__ src, int sw, int sh, i
 }
 
 size_t pyrfast_smem_bytes(int stride, int w, int rows, bool level0) {
-  const int words_per_row = (w + 31) >> 5;
-  return (size_t)(rows + 6) * stride + (size_t)rows * words_per_row * 4 + (size_t)kWarps * kQueue * 4 + (level0 ? (size_t)(rows / 2) * (w / 2) : 0);
+  const int words_per_row = (w + 31) >> 5, l1p = ((w >> 1) + 7) & ~7;
+  return (size_t)(rows + 6) * stride + (size_t)rows * words_per_row * 4 + (size_t)kMaxWarps * kQueue * 4 + (level0 ? (size_t)(rows / 2) * l1p : 0);
+}
+
+// Threads per CTA for strips of `rows` rows of a w-pixel level: as many warps as the strip has work items (32 lanes x 16 pixels x 2
+// rows), or an even share of them when there are more than ten; at least four (the write-out scan and the level 2-3 rows use every thread).
+int pyrfast_threads(int w, int rows) {
+  const int items = (((rows + 1) / 2) * ((w + 15) / 16) + 31) / 32;
+  const int rounds = (items + kMaxWarps - 1) / kMaxWarps;
+  int warps = (items + rounds - 1) / rounds;
+  warps = warps < 4 ? 4 : warps;
+  return 32 * warps;
 }
 
 }  // namespace
@@ -333,6 +367,13 @@ int vs_strip_rows(int level, int w, int pitch) {
   // wide images (1080p, 4K): 16 rows of level 0 no longer leave room for several CTAs per SM (4K: 116 KB per CTA, one CTA per SM,
   // measured 3.6 % of the HBM peak against 5.8 % at VGA); 8-row strips keep 3-5 CTAs resident.  8 is the floor at level 0: a strip
   // must cover whole rows of level 3.
+  if (const char* e = getenv("VSLAM_STRIP_ROWS")) {     // tuning experiments only: "r0,r1,r2,r3" (r0 a multiple of 8, the others even, <= VS_MAX_STRIP_ROWS)
+    int r[VS_LEVELS] = {0, 0, 0, 0};
+    if (sscanf(e, "%d,%d,%d,%d", &r[0], &r[1], &r[2], &r[3]) == 4 && r[level] >= 2 && r[level] <= VS_MAX_STRIP_ROWS && r[level] % (level == 0 ? 8 : 2) == 0 &&
+        pyrfast_smem_bytes(pitch, w, r[level], level == 0) <= 200 * 1024 && r[level] * ((w + 31) / 32) <= kMaxWarps * kQueue)
+      return r[level];
+  }
+  if (level == 0 && pyrfast_smem_bytes(pitch, w, 32, true) <= 44 * 1024) return 32;   // five CTAs per SM still fit
   if (pyrfast_smem_bytes(pitch, w, 16, level == 0) > 48 * 1024) return 8;
   return 16;
 }
@@ -359,7 +400,7 @@ int vs_launch_pyramid_l0(vslam_ctx* ctx, int first_stream, int count) {
   if (smem > 227 * 1024) { ctx->err = "pyramid_fast: strip does not fit in shared memory (row stride too large)"; return VSLAM_E_INVALID; }
   VS_CUDA(cudaFuncSetAttribute(k_pyramid_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   vs_time_begin(ctx, VS_ST_PYR0);
-  k_pyramid_fast<<<count * L.n_strips, kThreads, smem, ctx->stream>>>(L, ctx->lev[1], ctx->lev[2], ctx->lev[3], ctx->l0_ptr, ctx->l0_stride, first_stream, kFastThr[0],
+  k_pyramid_fast<<<count * L.n_strips, pyrfast_threads(L.w, L.strip_rows), smem, ctx->stream>>>(L, ctx->lev[1], ctx->lev[2], ctx->lev[3], ctx->l0_ptr, ctx->l0_stride, first_stream, kFastThr[0],
                                                                      tickets, ctx->status);
   vs_time_end(ctx);
   VS_CUDA(cudaGetLastError());
@@ -369,17 +410,19 @@ int vs_launch_pyramid_l0(vslam_ctx* ctx, int first_stream, int count) {
 
 // Levels 1..3: FAST-10 (one launch).  Needs the level images written by vs_launch_pyramid_l0.
 int vs_launch_fast_levels(vslam_ctx* ctx, int first_stream, int count) {
-  size_t smem = 0; int blocks = 0;
+  size_t smem = 0; int blocks = 0, threads = 0;
   for (int l = 1; l < VS_LEVELS; l++) {
     const LevelDesc& L = ctx->lev[l];
     const size_t b = pyrfast_smem_bytes(L.pitch, L.w, L.strip_rows, false);
     smem = b > smem ? b : smem;
     blocks += count * L.n_strips;
+    const int t = pyrfast_threads(L.w, L.strip_rows);
+    threads = t > threads ? t : threads;
   }
   if (smem > 227 * 1024) { ctx->err = "fast_levels: strip does not fit in shared memory"; return VSLAM_E_INVALID; }
   VS_CUDA(cudaFuncSetAttribute(k_fast_levels, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   vs_time_begin(ctx, VS_ST_PYR1);
-  k_fast_levels<<<blocks, kThreads, smem, ctx->stream>>>(ctx->lev[1], ctx->lev[2], ctx->lev[3], first_stream, count, kFastThr[1], kFastThr[2], kFastThr[3],
+  k_fast_levels<<<blocks, threads, smem, ctx->stream>>>(ctx->lev[1], ctx->lev[2], ctx->lev[3], first_stream, count, kFastThr[1], kFastThr[2], kFastThr[3],
                                                         ctx->tickets + 2 * ctx->cur_group + 1, ctx->status);
   vs_time_end(ctx);
   VS_CUDA(cudaGetLastError());

@@ -21,6 +21,8 @@ struct LevelDesc {
   int cap;                    // corner capacity per stream
   int strip_rows;             // rows of this level handled by one CTA of the pyramid / FAST kernels (vs_strip_rows)
   int n_strips;               // ceil(h / strip_rows)
+  // 32-bit reciprocals (0xffffffff / d + 1; 0 when d == 1) for the small divisions of the FAST kernels: d = n_strips, ceil(w / 16), ceil(w / 32), w / 2, w
+  uint32_t mg_strips, mg_cpr, mg_wpr, mg_hw, mg_w;
   uint8_t* img;               // [S][h][pitch]      (level 0: only used by the host-input path, see l0_ptr)
   uint32_t* corners;          // [S][cap]           packed (y << 16 | x), raster order
   int* lut;                   // [S][h + 1]         lut[y] = #corners with row < y ; lut[h] = total
