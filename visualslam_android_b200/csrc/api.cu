@@ -139,14 +139,15 @@ int vslam_create(const vslam_config* cfg, vslam_ctx** out) {
     CK(dalloc(&L.lut, (size_t)S * (h + 1)));
     L.xw = (w + 31) / 32 + 1;
     CK(dalloc(&L.xlut, (size_t)S * h * L.xw));
-    strip_words += (size_t)S * L.n_strips;
+    strip_words += ((size_t)S * h * ((w + 31) / 32) + 1) / 2;      // corner bitmask words (32 bit) of this level, in 64-bit units
     ctx->src.w[l] = w; ctx->src.h[l] = h; ctx->src.pitch[l] = L.pitch;
     CK(dalloc(&ctx->src.img[l], (size_t)ctx->n_src * h * L.pitch));
     w /= 2; h /= 2;
   }
-  // one allocation for the look-back words of all levels and the tickets, so that a whole-context frame clears them with one memset
+  // one allocation for the corner bitmasks of all levels and the tickets, so that a whole-context frame clears them with one memset
   CK(dalloc(&ctx->sync_words, strip_words + VS_MAX_GROUPS)); ctx->sync_words_n = strip_words + VS_MAX_GROUPS;
-  { size_t off = 0; for (int l = 0; l < VS_LEVELS; l++) { ctx->lev[l].strip_state = ctx->sync_words + off; off += (size_t)S * ctx->lev[l].n_strips; }
+  { size_t off = 0;
+    for (int l = 0; l < VS_LEVELS; l++) { LevelDesc& L = ctx->lev[l]; L.cbits = (uint32_t*)(ctx->sync_words + off); off += ((size_t)S * L.h * ((L.w + 31) / 32) + 1) / 2; }
     ctx->tickets = (unsigned*)(ctx->sync_words + off); }
   CK(dalloc(&ctx->l0_ptr, (size_t)S)); CK(dalloc(&ctx->l0_stride, (size_t)S));
   ctx->l0_ptr_host = new const uint8_t*[S]; ctx->l0_stride_host = new int[S];

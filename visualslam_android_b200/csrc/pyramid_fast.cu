@@ -1,17 +1,20 @@
 // KeyFrame::MakeKeyFrame_Lite on the GPU (reference: jni/KeyFrame.cc:5-51).
 //
-// Two launches, batched over all streams.  k_pyramid_fast handles level 0 (and writes levels 1..3), k_fast_levels
-// handles levels 1..3.  A CTA owns a strip of LevelDesc::strip_rows rows of one level of one stream.  It
+// Three launches, batched over all streams.  k_pyramid_fast handles level 0 (and writes the images of levels 1..3), k_fast_levels
+// handles levels 1..3, k_corner_lists turns the corner bitmasks of all four levels into the corner lists and row tables.
+// A CTA of the first two owns a strip of LevelDesc::strip_rows rows of one level of one stream.  It
 //   1. stages the strip plus a 3-row halo into shared memory with ONE bulk async copy (cp.async.bulk, TMA engine);
 //   2. (level 0) writes the matching rows of level 1:  (a+b+c+d+2)>>2  (cv::resize 2:1, jni/KeyFrame.cc:20-23; SURVEY.md
 //      F2), and, from the same staged rows, the matching rows of levels 2 and 3;
-//   3. runs FAST-10 (jni/vision/cvfast.cpp:6088-9241 == segment test):
-//        a byte-SIMD rejection test on 4 pixels per lane (VABSDIFF4 + SWAR compares): a 10-arc contains at least one
-//        pixel of every opposite ring pair, so both (0,8) and (4,12) must hold a pixel differing by more than t;
-//        survivors are compacted into a per-warp queue and get the exact 16-pixel ring test, one lane per candidate;
-//   4. appends its corners to the stream's list in raster order: per-row popcounts of a shared-memory corner bitmask,
-//      a decoupled look-back across the strips of the image (tickets guarantee predecessors are resident), and the
-//      running row offsets ARE the row look-up table of jni/KeyFrame.cc:41-49.
+//   3. runs FAST-10 (jni/vision/cvfast.cpp:6088-9241 == segment test), 16 pixels x 2 rows per lane:
+//        a byte-SIMD rejection test (VABSDIFF4 + SWAR compares): a 10-arc contains at least one pixel of every opposite ring pair,
+//        so both (0,8) and (4,12) must hold a pixel differing by more than t;
+//        survivors are compacted into a per-warp queue and, 32 at a time, get the test on the eight even ring positions (five
+//        consecutive of one polarity are necessary) and then the exact 16-pixel ring test, one lane per candidate;
+//   4. sets the bit of every corner in the level's corner bitmask in global memory (one word per 32 pixels, cleared per frame)
+//      and exits: no barrier after the staging, no inter-CTA dependency.
+// k_corner_lists (one CTA per level image): popcounts + one block scan give every corner its raster-order position; the running
+// positions at the row starts ARE the row look-up table of jni/KeyFrame.cc:41-49, those at the word starts the column index.
 // Integer / byte arithmetic only; results are bit-exact against the oracle.
 #include "vslam_internal.cuh"
 #include <cstdio>
@@ -53,11 +56,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // per-byte (x > t) for 4 packed bytes, t < 128: flag in bit 7 of every byte (other bits are garbage)
 __device__ __forceinline__ uint32_t bytes_gt(uint32_t x, uint32_t k /* (127 - t) * 0x01010101 */) { return ((x & 0x7f7f7f7fu) + k) | x; }
 
-// Exact FAST-10 segment test of one candidate (queue entry = smem row << 16 | x); sets its bit in the strip's corner bitmask.
+// Exact FAST-10 segment test of one candidate (queue entry = smem row << 16 | x); sets its bit in the level's corner bitmask.
 // One IMAD per ring pixel yields both polarities: with kc = ((c - t - 1 + 2^15) << 16) + (2^15 - c - t - 1),
 //   z = v * (1 - 2^16) + kc   has   bit 15 = (v - c - t - 1 >= 0) = brighter,   bit 31 = (c - t - 1 - v >= 0) = darker
 // (both 16-bit fields stay inside [2^15 - 266, 2^15 + 254]: no borrow between them).
-__device__ __forceinline__ void ring_test(uint32_t e, const uint8_t* img, int stride, int thr, uint32_t* bitmask, int words_per_row, int row_bias) {
+__device__ __forceinline__ void ring_test(uint32_t e, const uint8_t* img, int stride, int thr, uint32_t* gbits /* word of (staged row 0, x = 0) */, int words_per_row) {
   const int ry = e >> 16, x = e & 0xffff;
   const uint8_t* p0 = img + ry * stride + x;
   const uint8_t *pp1 = p0 + stride, *pp2 = pp1 + stride, *pp3 = pp2 + stride, *pm1 = p0 - stride, *pm2 = pm1 - stride, *pm3 = pm2 - stride;
@@ -78,7 +81,29 @@ __device__ __forceinline__ void ring_test(uint32_t e, const uint8_t* img, int st
   uint32_t b2 = b1 & (b1 >> 2), d2 = d1 & (d1 >> 2);
   b2 &= b2 >> 4; d2 &= d2 >> 4;
   b2 &= b1 >> 8; d2 &= d1 >> 8;
-  if ((b2 | d2) & 0xffffu) atomicOr(&bitmask[(ry + row_bias) * words_per_row + (x >> 5)], 1u << (x & 31));
+  if ((b2 | d2) & 0xffffu) atomicOr(&gbits[ry * words_per_row + (x >> 5)], 1u << (x & 31));   // result unused: a RED
+}
+
+// First stage of the exact test, on the eight even ring positions only: a 10-arc of the 16-ring covers five consecutive even positions,
+// so a corner has five consecutive (circular, of eight) even-position pixels all brighter or all darker.  About one in five survivors
+// of reject16 passes (level 0); only those get the full ring test.
+__device__ __forceinline__ bool ring_even(uint32_t e, const uint8_t* img, int stride, int thr) {
+  const int ry = e >> 16, x = e & 0xffff;
+  const uint8_t* p0 = img + ry * stride + x;
+  const uint8_t *pp2 = p0 + 2 * stride, *pp3 = pp2 + stride, *pm2 = p0 - 2 * stride, *pm3 = pm2 - stride;
+  const uint32_t c = p0[0];
+  const uint32_t kc = ((c + (0x8000u - 1u - (uint32_t)thr)) << 16) + ((0x8000u - 1u - (uint32_t)thr) - c);
+  uint32_t a = 0;   // after eight steps: brighter flags of positions 0,2,..,14 in bits 8..15, darker flags in bits 24..31
+#define RING(ptr, off)                                                  \
+  {                                                                     \
+    const uint32_t z = (uint32_t)(ptr)[(off)] * 0xFFFF0001u + kc;       \
+    a = (a >> 1) | (z & 0x80008000u);                                   \
+  }
+  RING(pp3, 0) RING(pp2, 2) RING(p0, 3) RING(pm2, 2) RING(pm3, 0) RING(pm2, -2) RING(p0, -3) RING(pp2, -2)
+#undef RING
+  const uint32_t v = a | (a >> 8);            // each byte doubled: bits 0..15 brighter (circular), 16..31 darker; starts k = 0..7 read bits k..k+4 <= 11 only
+  const uint32_t r2 = v & (v >> 1), r4 = r2 & (r2 >> 2);
+  return (r4 & (v >> 4) & 0x00ff00ffu) != 0u;
 }
 
 // Rejection test of 16 pixels of one row (centre words c, staged row pointer r = &row[x0]): a 10-arc of the 16-ring contains at
@@ -101,12 +126,10 @@ __device__ __forceinline__ uint32_t reject16(const uint8_t* r, int stride, const
   return bits;
 }
 
-constexpr unsigned long long kFlagAgg = 1ull << 32, kFlagInc = 2ull << 32;
 
 struct StripShared {
   uint64_t bar;
-  int ticket, base;
-  int wsum[2][kMaxWarps];   // per-warp corner counts (double buffered across the chunks of the write-out scan)
+  int ticket, next_item;
 };
 
 // n / d for small n (n * d < 2^32) with the reciprocal m = 0xffffffff / d + 1 from the host (LevelDesc::mg_*; m == 0 stands for d == 1):
@@ -146,26 +169,25 @@ __device__ __forceinline__ uint32_t half4(uint32_t a0, uint32_t a1, uint32_t b0,
   return __byte_perm(lo, hi, 0x6420);
 }
 
-// One strip (rows [strip*R, +R) of level L of stream s): stage, [level 0: write levels 1..3], FAST-10, raster-ordered append.
+// One strip (rows [strip*R, +R) of level L of stream s): stage, [level 0: write levels 1..3], FAST-10 into the corner bitmask.
 template <bool kLevel0>
 __device__ __forceinline__ void fast_strip(const LevelDesc& L, const uint8_t* __restrict__ src, const int stride, const int s, const int strip, const int thr,
-                                           const LevelDesc* Lchild /* [3] levels 1..3, level 0 only */, int* __restrict__ status, StripShared& sh, uint8_t* smem) {
+                                           const LevelDesc* Lchild /* [3] levels 1..3, level 0 only */, StripShared& sh, uint8_t* smem) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, nw = nthreads >> 5;
   const int W = L.w, H = L.h, R = L.strip_rows;
   const int y0 = strip * R, y1 = min(y0 + R, H);
   const int ya = max(y0 - 3, 0), yb = min(y1 + 3, H);
   const int words_per_row = (W + 31) >> 5;
   uint8_t* img = smem;                                                  // rows ya..yb-1, `stride` bytes apart
-  uint32_t* bitmask = (uint32_t*)(smem + (size_t)(R + 6) * stride);     // [R][words_per_row]
-  uint32_t* queue = bitmask + R * words_per_row + warp * kQueue;
+  uint32_t* qbase = (uint32_t*)(smem + (size_t)(R + 6) * stride);
+  uint32_t* queue = qbase + warp * kQueue;
+  uint32_t* gbits = L.cbits + ((size_t)s * H + ya) * words_per_row;     // corner bitmask word of (row ya, x = 0)
 
   if (tid == 0) {
     const uint32_t bytes = (uint32_t)(yb - ya) * (uint32_t)stride;
     mbar_expect_tx(&sh.bar, bytes);
     bulk_g2s(img, src + (size_t)ya * stride, bytes, &sh.bar);
   }
-  for (int i = tid; i < (R * words_per_row) >> 2; i += nthreads) ((uint4*)bitmask)[i] = make_uint4(0u, 0u, 0u, 0u);   // R % 4 == 0
-  __syncthreads();
   mbar_wait(&sh.bar, 0);
 
   // ---- dense pass: a lane slot = 16 pixels x 2 rows (one 128-bit shared-memory load per row), slots of the strip in raster order,
@@ -175,11 +197,28 @@ __device__ __forceinline__ void fast_strip(const LevelDesc& L, const uint8_t* __
   const int cpr = (W + 15) >> 4, n_slots = n_pairs * cpr;
   uint8_t* next_img = nullptr; int next_pitch = 0;
   const int l1p = ((W >> 1) + 7) & ~7;                                      // level 0 only: pitch of the strip's level-1 rows in shared memory
-  uint8_t* l1s = (uint8_t*)(bitmask + R * words_per_row + kMaxWarps * kQueue);
+  uint8_t* l1s = (uint8_t*)(qbase + nw * (kQueue + 64));
   if (kLevel0) { next_pitch = Lchild[0].pitch; next_img = Lchild[0].img + ((size_t)s * Lchild[0].h + (y0 >> 1)) * next_pitch; }   // level-1 row of y0
 
-  int qn = 0;   // candidates waiting in this warp's queue (warp-uniform)
-  for (int item = warp; item * 32 < n_slots; item += nw) {
+  // Candidates go through two stages, each 32 at a time: queue -> ring_even -> queue2 -> ring_test.
+  uint32_t* queue2 = qbase + nw * kQueue + warp * 64;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  int qn = 0, q2n = 0;   // entries waiting in this warp's two queues (warp-uniform)
+  auto two_stage = [&](uint32_t e, bool have) {
+    const bool pass = have && ring_even(e, img, stride, thr);
+    const uint32_t bal = __ballot_sync(0xffffffffu, pass);
+    if (pass) queue2[q2n + __popc(bal & lt_mask)] = e;
+    q2n += __popc(bal);
+    __syncwarp();
+    if (q2n >= 32) {
+      q2n -= 32;
+      const uint32_t e2 = queue2[q2n + lane];
+      __syncwarp();
+      ring_test(e2, img, stride, thr, gbits, words_per_row);
+    }
+  };
+  const int n_items = (n_slots + 31) >> 5;
+  for (int item = warp; item < n_items;) {     // the first nw items are dealt out statically, the rest to whichever warp is free
     const int slot = item * 32 + lane;
     const int pr = div_small(slot, L.mg_cpr);
     const int y = y0 + 2 * pr;           // rows y and y+1
@@ -204,17 +243,18 @@ __device__ __forceinline__ void fast_strip(const LevelDesc& L, const uint8_t* __
       if (y >= 3 && y < H - 3) mask = reject16(r0, stride, c0, kcmp) & vm;
       if (have1 && y + 1 >= 3 && y + 1 < H - 3) mask |= (reject16(r0 + stride, stride, c1, kcmp) & vm) << 16;
     }
-    // ---- survivors -> exact ring test, 32 per pass
     const int mine = __popc(mask);
     int incl = mine;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
     const int total = __shfl_sync(0xffffffffu, incl, 31);
     const uint32_t ebase = ((uint32_t)(y - ya) << 16) | (uint32_t)x0;     // bit b -> ebase + (b & 15) + ((b >> 4) << 16)
-    if (total > 255) {   // dense levels: every lane tests its own survivors (lanes are about equally loaded), no queue traffic
-      while (mask) {
-        const int b = 31 - __clz(mask); mask ^= 1u << b;
-        ring_test(ebase + (uint32_t)b + (uint32_t)(b & 16) * 4095u, img, stride, thr, bitmask, words_per_row, ya - y0);
+    if (total > 255) {   // dense levels: every lane feeds its own survivors (lanes are about equally loaded), no first queue
+      while (__any_sync(0xffffffffu, mask != 0u)) {
+        const bool have = mask != 0u;
+        const int b = have ? 31 - __clz(mask) : 0;
+        mask &= ~(1u << b);
+        two_stage(ebase + (uint32_t)b + (uint32_t)(b & 16) * 4095u, have);
       }
     } else if (total) {
       int pos = qn + incl - mine;
@@ -224,116 +264,112 @@ __device__ __forceinline__ void fast_strip(const LevelDesc& L, const uint8_t* __
       }
       qn += total;
       __syncwarp();
-      while (qn >= 32) { qn -= 32; ring_test(queue[qn + lane], img, stride, thr, bitmask, words_per_row, ya - y0); }
+      while (qn >= 32) {
+        qn -= 32;
+        const uint32_t e = queue[qn + lane];
+        two_stage(e, true);
+      }
       __syncwarp();
     }
+    if (lane == 0) item = atomicAdd(&sh.next_item, 1);
+    item = __shfl_sync(0xffffffffu, item, 0);
   }
-  if (lane < qn) ring_test(queue[lane], img, stride, thr, bitmask, words_per_row, ya - y0);
-  __syncthreads();
+  { const uint32_t e = lane < qn ? queue[lane] : 0u; two_stage(e, lane < qn); }
+  if (lane < q2n) ring_test(queue2[lane], img, stride, thr, gbits, words_per_row);
 
-  // ---- corners of the strip in raster order: the bitmask words ARE in raster order, so an exclusive scan of their popcounts gives
-  //      every corner's position, every row's LUT entry and every 32-pixel bucket's column-index entry
-  const int rows = y1 - y0, n_words = rows * words_per_row;
-  int* pre = (int*)(bitmask + R * words_per_row);          // [n_words] exclusive prefix of every word (the candidate queues are done with)
-  int run = 0;
-  {
-    int buf = 0;
-    for (int w0 = 0; w0 < n_words; w0 += nthreads, buf ^= 1) {
-      const int w = w0 + tid;
-      const int mine = (w < n_words) ? __popc(bitmask[w]) : 0;
-      int incl = mine;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
-      if (lane == 31) sh.wsum[buf][warp] = incl;
-      __syncthreads();
-      int ws = (lane < nw) ? sh.wsum[buf][lane] : 0, wi = ws;      // scan of the (at most ten) warp totals, by every warp for itself
-#pragma unroll
-      for (int d = 1; d < 16; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi += v; }
-      const int before = __shfl_sync(0xffffffffu, wi - ws, warp), chunk = __shfl_sync(0xffffffffu, wi, 15);
-      if (w < n_words) pre[w] = run + before + incl - mine;
-      run += chunk;
-    }
+  if (kLevel0) {   // levels 2 and 3 of this strip from its level-1 rows
+    __syncthreads();
+    emit_levels_2_3(l1s, l1p, (y1 - y0) >> 1, Lchild[1], Lchild[2], s, y0, tid, nthreads);
   }
-  if (tid == 0) {
-    const int acc = run;
-    // decoupled look-back over the strips of this image (predecessors hold lower tickets, hence are resident or done)
-    unsigned long long* st = L.strip_state + (size_t)s * L.n_strips;
-    unsigned long long excl = 0;
-    if (strip == 0) {
-      atomicExch(&st[0], kFlagInc | (unsigned)acc);
-    } else {
-      atomicExch(&st[strip], kFlagAgg | (unsigned)acc);
-      for (int j = strip - 1; j >= 0; j--) {
-        unsigned long long v;
-        while (((v = *(volatile unsigned long long*)&st[j]) >> 32) == 0) __nanosleep(40);
-        excl += (unsigned)v;
-        if ((v >> 32) == 2) break;
-      }
-      atomicExch(&st[strip], kFlagInc | (unsigned)(excl + acc));
-    }
-    sh.base = (int)excl;
-    if ((long long)excl + acc > L.cap) atomicExch(&status[0], 1);
-  }
-  if (kLevel0 && warp > 0)   // levels 2 and 3 of this strip while thread 0 looks back
-    emit_levels_2_3(l1s, l1p, (y1 - y0) >> 1, Lchild[1], Lchild[2], s, y0, tid - 32, nthreads - 32);
+}
+
+// Corner lists of one level image from its corner bitmask (k_pyramid_fast / k_fast_levels set the bits): every warp owns a contiguous run
+// of bitmask words; popcounts + one scan of the warp totals give every word its raster-order position.  The position at a row's first word is the
+// row's LUT entry (jni/KeyFrame.cc:41-49), the positions at the word starts are the column index (32-pixel buckets) of search_fast.cu.
+// Positions are clamped to the capacity: on overflow -- reported through status[0] -- the readers of the LUT must not index past the list.
+__global__ void __launch_bounds__(kMaxThreads)
+k_corner_lists(LevelDesc L0, LevelDesc L1, LevelDesc L2, LevelDesc L3, int first_stream, int count, int first_level, int* __restrict__ status) {
+  __shared__ int wsum[kMaxWarps];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, nw = nthreads >> 5;
+  const int q = blockIdx.x / count, level = first_level + q, s = first_stream + (blockIdx.x - q * count);     // all images of the largest level first
+  const LevelDesc& L = level == 0 ? L0 : level == 1 ? L1 : level == 2 ? L2 : L3;
+  const int H = L.h, wpr = (L.w + 31) >> 5, n_words = H * wpr;
+  const uint32_t* bits = L.cbits + (size_t)s * n_words;
+  // a warp owns a contiguous run of words (a multiple of 32, so that every pass reads whole 128-byte lines) and walks it 32 words at a time
+  const int per_warp = ((n_words + nw - 1) / nw + 31) & ~31;
+  const int wb = min(warp * per_warp, n_words), we = min(wb + per_warp, n_words);
+  int c = 0;
+  for (int w = wb + lane; w < we; w += 32) c += __popc(bits[w]);
+  c = __reduce_add_sync(0xffffffffu, c);
+  if (lane == 0) wsum[warp] = c;
   __syncthreads();
-  // (positions are clamped to the capacity: on overflow -- reported through status[0] -- the readers of the LUT must not index past the list)
-  const int base = sh.base;
+  int ws = (lane < nw) ? wsum[lane] : 0, wi = ws;
+#pragma unroll
+  for (int d = 1; d < 16; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi += v; }
+  const int total = __shfl_sync(0xffffffffu, wi, 15);
+  int run = __shfl_sync(0xffffffffu, wi - ws, warp);          // corners before this warp's run
   int* lut = L.lut + (size_t)s * (H + 1);
-  int* xlut = L.xlut + ((size_t)s * H + y0) * L.xw;
+  int* xlut = L.xlut + (size_t)s * H * L.xw;
   uint32_t* out = L.corners + (size_t)s * L.cap;
-  for (int w = tid; w < n_words; w += nthreads) {
-    uint32_t m = bitmask[w];
-    int pos = base + pre[w];
-    const int r = div_small(w, L.mg_wpr), col = w - r * words_per_row;
-    const int cpos = min(pos, L.cap);
-    xlut[r * L.xw + col] = cpos;                                  // column index of the row (32-pixel buckets)
-    if (col == 0) {
-      lut[y0 + r] = cpos;                                          // the row LUT of jni/KeyFrame.cc:41-49
-      if (r > 0) xlut[(r - 1) * L.xw + words_per_row] = cpos;      // end of the previous row
-    }
-    const uint32_t yy = (uint32_t)(y0 + r) << 16, xb = (uint32_t)col << 5;
-    while (m) {
-      const int b = __ffs(m) - 1; m &= m - 1;
-      if (pos < L.cap) out[pos] = yy | (xb + (uint32_t)b);
-      pos++;
+  uint32_t m_next = (wb + lane < we) ? bits[wb + lane] : 0u;
+  for (int w0 = wb; w0 < we; w0 += 32) {
+    const int w = w0 + lane;
+    uint32_t m = m_next;
+    m_next = (w + 32 < we) ? bits[w + 32] : 0u;                // the next 32 words are on their way while these are scanned
+    const int mine = __popc(m);
+    int incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+    int pos = run + incl - mine;
+    run += __shfl_sync(0xffffffffu, incl, 31);
+    if (w < we) {
+      const int r = div_small(w, L.mg_wpr), col = w - r * wpr;
+      const int cpos = min(pos, L.cap);
+      xlut[r * L.xw + col] = cpos;
+      if (col == 0) lut[r] = cpos;
+      if (col == wpr - 1) xlut[r * L.xw + wpr] = min(pos + mine, L.cap);     // end of the row
+      const uint32_t cw0 = ((uint32_t)r << 16) | ((uint32_t)col << 5);
+      if (pos + mine <= L.cap) {             // (always, unless the list overflows) highest bit first, written from the back: one FLO per corner
+        uint32_t* o = out + pos + mine;
+        while (m) { const int b = 31 - __clz(m); m ^= 1u << b; *--o = cw0 + (uint32_t)b; }
+      } else {
+        while (m) { const int b = __ffs(m) - 1; m &= m - 1; if (pos < L.cap) out[pos] = cw0 + (uint32_t)b; pos++; }
+      }
     }
   }
   if (tid == 0) {
-    const int cend = min(base + run, L.cap);
-    xlut[(rows - 1) * L.xw + words_per_row] = cend;
-    if (y1 == H) lut[H] = cend;
+    lut[H] = min(total, L.cap);
+    if (total > L.cap) atomicExch(&status[0], 1);
   }
 }
 
 // Level 0 of every stream: pyramid levels 1..3 + FAST-10 of level 0.
 __global__ void __maxnreg__(VS_PYR_REGS)
 k_pyramid_fast(LevelDesc L, LevelDesc L1, LevelDesc L2, LevelDesc L3, const uint8_t* const* __restrict__ l0_ptr, const int* __restrict__ l0_stride,
-               int first_stream, int thr, unsigned* __restrict__ ticket, int* __restrict__ status) {
+               int first_stream, int thr, unsigned* __restrict__ ticket) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ StripShared sh;
   __shared__ LevelDesc child[3];
-  if (threadIdx.x == 0) { sh.ticket = (int)atomicAdd(ticket, 1u); mbar_init(&sh.bar, 1); child[0] = L1; child[1] = L2; child[2] = L3; }
+  if (threadIdx.x == 0) { sh.ticket = (int)atomicAdd(ticket, 1u); sh.next_item = (int)(blockDim.x >> 5); mbar_init(&sh.bar, 1); child[0] = L1; child[1] = L2; child[2] = L3; }
   __syncthreads();
   const int t = sh.ticket;
   const int q = div_small(t, L.mg_strips), s = first_stream + q, strip = t - q * L.n_strips;
-  fast_strip<true>(L, l0_ptr[s], l0_stride[s], s, strip, thr, child, status, sh, smem);
+  fast_strip<true>(L, l0_ptr[s], l0_stride[s], s, strip, thr, child, sh, smem);
 }
 
 // FAST-10 of levels 1..3 of every stream in one launch: tickets run over level 1's strips, then level 2's, then level 3's.
 __global__ void __maxnreg__(VS_PYR_REGS)
-k_fast_levels(LevelDesc L1, LevelDesc L2, LevelDesc L3, int first_stream, int count, int thr1, int thr2, int thr3, unsigned* __restrict__ ticket,
-              int* __restrict__ status) {
+k_fast_levels(LevelDesc L1, LevelDesc L2, LevelDesc L3, int first_stream, int count, int thr1, int thr2, int thr3, unsigned* __restrict__ ticket) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ StripShared sh;
-  if (threadIdx.x == 0) { sh.ticket = (int)atomicAdd(ticket, 1u); mbar_init(&sh.bar, 1); }
+  if (threadIdx.x == 0) { sh.ticket = (int)atomicAdd(ticket, 1u); sh.next_item = (int)(blockDim.x >> 5); mbar_init(&sh.bar, 1); }
   __syncthreads();
   int t = sh.ticket, thr = thr1;
   const int n1 = count * L1.n_strips, n2 = count * L2.n_strips;
   LevelDesc L = L1;
   if (t >= n1) { t -= n1; L = L2; thr = thr2; if (t >= n2) { t -= n2; L = L3; thr = thr3; } }
   const int q = div_small(t, L.mg_strips), s = first_stream + q, strip = t - q * L.n_strips;
-  fast_strip<false>(L, L.img + (size_t)s * L.h * L.pitch, L.pitch, s, strip, thr, nullptr, status, sh, smem);
+  fast_strip<false>(L, L.img + (size_t)s * L.h * L.pitch, L.pitch, s, strip, thr, nullptr, sh, smem);
 }
 
 // plain 2:1 half-sample for the (rare) source-keyframe uploads
@@ -344,9 +380,9 @@ __global__ void k_half_sample(const uint8_t* __restrict__ src, int sw, int sh, i
   dst[(size_t)y * dpitch + x] = (uint8_t)((a[0] + a[1] + a[spitch] + a[spitch + 1] + 2) >> 2);
 }
 
-size_t pyrfast_smem_bytes(int stride, int w, int rows, bool level0) {
-  const int words_per_row = (w + 31) >> 5, l1p = ((w >> 1) + 7) & ~7;
-  return (size_t)(rows + 6) * stride + (size_t)rows * words_per_row * 4 + (size_t)kMaxWarps * kQueue * 4 + (level0 ? (size_t)(rows / 2) * l1p : 0);
+size_t pyrfast_smem_bytes(int stride, int w, int rows, bool level0, int warps = kMaxWarps) {
+  const int l1p = ((w >> 1) + 7) & ~7;
+  return (size_t)(rows + 6) * stride + (size_t)warps * (kQueue + 64) * 4 + (level0 ? (size_t)(rows / 2) * l1p : 0);
 }
 
 // Threads per CTA for strips of `rows` rows of a w-pixel level: as many warps as the strip has work items (32 lanes x 16 pixels x 2
@@ -370,7 +406,7 @@ int vs_strip_rows(int level, int w, int pitch) {
   if (const char* e = getenv("VSLAM_STRIP_ROWS")) {     // tuning experiments only: "r0,r1,r2,r3" (r0 a multiple of 8, the others even, <= VS_MAX_STRIP_ROWS)
     int r[VS_LEVELS] = {0, 0, 0, 0};
     if (sscanf(e, "%d,%d,%d,%d", &r[0], &r[1], &r[2], &r[3]) == 4 && r[level] >= 2 && r[level] <= VS_MAX_STRIP_ROWS && r[level] % (level == 0 ? 8 : 2) == 0 &&
-        pyrfast_smem_bytes(pitch, w, r[level], level == 0) <= 200 * 1024 && r[level] * ((w + 31) / 32) <= kMaxWarps * kQueue)
+        pyrfast_smem_bytes(pitch, w, r[level], level == 0) <= 200 * 1024)
       return r[level];
   }
   if (level == 0 && pyrfast_smem_bytes(pitch, w, 32, true) <= 44 * 1024) return 32;   // five CTAs per SM still fit
@@ -385,48 +421,58 @@ static const int kFastThr[VS_LEVELS] = {10, 15, 15, 10};
 int vs_launch_pyramid_l0(vslam_ctx* ctx, int first_stream, int count) {
   unsigned* tickets = ctx->tickets + 2 * ctx->cur_group;   // [0]: level-0 launch, [1]: levels 1-3 launch; one pair per stream group
   if (first_stream == 0 && count == ctx->S && ctx->cur_group == 0) {
-    VS_CUDA(cudaMemsetAsync(ctx->sync_words, 0, sizeof(unsigned long long) * ctx->sync_words_n, ctx->stream));   // all look-back words + tickets at once
+    VS_CUDA(cudaMemsetAsync(ctx->sync_words, 0, sizeof(unsigned long long) * ctx->sync_words_n, ctx->stream));   // the corner bitmasks of all levels + the tickets at once
   } else {
     VS_CUDA(cudaMemsetAsync(tickets, 0, sizeof(unsigned) * 2, ctx->stream));
     for (int l = 0; l < VS_LEVELS; l++) {
       LevelDesc& L = ctx->lev[l];
-      VS_CUDA(cudaMemsetAsync(L.strip_state + (size_t)first_stream * L.n_strips, 0, sizeof(unsigned long long) * (size_t)count * L.n_strips, ctx->stream));
+      const size_t per_stream = (size_t)L.h * ((L.w + 31) / 32);
+      VS_CUDA(cudaMemsetAsync(L.cbits + (size_t)first_stream * per_stream, 0, sizeof(uint32_t) * (size_t)count * per_stream, ctx->stream));
     }
   }
   LevelDesc& L = ctx->lev[0];
   int stride = 0;
   for (int s = first_stream; s < first_stream + count; s++) stride = ctx->l0_stride_host[s] > stride ? ctx->l0_stride_host[s] : stride;
-  const size_t smem = pyrfast_smem_bytes(stride, L.w, L.strip_rows, true);
+  const int threads = pyrfast_threads(L.w, L.strip_rows);
+  const size_t smem = pyrfast_smem_bytes(stride, L.w, L.strip_rows, true, threads / 32);
   if (smem > 227 * 1024) { ctx->err = "pyramid_fast: strip does not fit in shared memory (row stride too large)"; return VSLAM_E_INVALID; }
   VS_CUDA(cudaFuncSetAttribute(k_pyramid_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   vs_time_begin(ctx, VS_ST_PYR0);
-  k_pyramid_fast<<<count * L.n_strips, pyrfast_threads(L.w, L.strip_rows), smem, ctx->stream>>>(L, ctx->lev[1], ctx->lev[2], ctx->lev[3], ctx->l0_ptr, ctx->l0_stride, first_stream, kFastThr[0],
-                                                                     tickets, ctx->status);
+  k_pyramid_fast<<<count * L.n_strips, threads, smem, ctx->stream>>>(L, ctx->lev[1], ctx->lev[2], ctx->lev[3], ctx->l0_ptr, ctx->l0_stride, first_stream, kFastThr[0],
+                                                                     tickets);
   vs_time_end(ctx);
   VS_CUDA(cudaGetLastError());
   ctx->launches++;
   return VSLAM_OK;
 }
 
-// Levels 1..3: FAST-10 (one launch).  Needs the level images written by vs_launch_pyramid_l0.
+// Levels 1..3: FAST-10 (one launch), then the corner lists / row tables of all four levels (one launch).  Needs the level images and the
+// level-0 corner bits written by vs_launch_pyramid_l0.
 int vs_launch_fast_levels(vslam_ctx* ctx, int first_stream, int count) {
   size_t smem = 0; int blocks = 0, threads = 0;
   for (int l = 1; l < VS_LEVELS; l++) {
     const LevelDesc& L = ctx->lev[l];
-    const size_t b = pyrfast_smem_bytes(L.pitch, L.w, L.strip_rows, false);
-    smem = b > smem ? b : smem;
     blocks += count * L.n_strips;
     const int t = pyrfast_threads(L.w, L.strip_rows);
     threads = t > threads ? t : threads;
+  }
+  for (int l = 1; l < VS_LEVELS; l++) {
+    const LevelDesc& L = ctx->lev[l];
+    const size_t b = pyrfast_smem_bytes(L.pitch, L.w, L.strip_rows, false, threads / 32);
+    smem = b > smem ? b : smem;
   }
   if (smem > 227 * 1024) { ctx->err = "fast_levels: strip does not fit in shared memory"; return VSLAM_E_INVALID; }
   VS_CUDA(cudaFuncSetAttribute(k_fast_levels, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   vs_time_begin(ctx, VS_ST_PYR1);
   k_fast_levels<<<blocks, threads, smem, ctx->stream>>>(ctx->lev[1], ctx->lev[2], ctx->lev[3], first_stream, count, kFastThr[1], kFastThr[2], kFastThr[3],
-                                                        ctx->tickets + 2 * ctx->cur_group + 1, ctx->status);
+                                                        ctx->tickets + 2 * ctx->cur_group + 1);
   vs_time_end(ctx);
   VS_CUDA(cudaGetLastError());
-  ctx->launches++;
+  vs_time_begin(ctx, VS_ST_PYR2);
+  k_corner_lists<<<count * VS_LEVELS, kMaxThreads, 0, ctx->stream>>>(ctx->lev[0], ctx->lev[1], ctx->lev[2], ctx->lev[3], first_stream, count, 0, ctx->status);
+  vs_time_end(ctx);
+  VS_CUDA(cudaGetLastError());
+  ctx->launches += 2;
   return VSLAM_OK;
 }
 

@@ -27,7 +27,7 @@ struct LevelDesc {
   uint32_t* corners;          // [S][cap]           packed (y << 16 | x), raster order
   int* lut;                   // [S][h + 1]         lut[y] = #corners with row < y ; lut[h] = total
   int* xlut; int xw;          // [S][h][xw]         xw = ceil(w / 32) + 1: xlut[y][b] = #corners before (row y, column 32 b) in raster order; xlut[y][xw - 1] = end of row y
-  unsigned long long* strip_state;  // [S][n_strips] decoupled look-back words
+  uint32_t* cbits;            // [S][h][ceil(w / 32)] corner bitmask of the frame being processed (bit x & 31 of word x >> 5; cleared per frame, inside ctx->sync_words)
 };
 
 struct CamDev { double fx, fy, cx, cy, W, Winv, twoTan, oneOver2Tan, distEnabled, largestRadius, maxR, width, height; };
@@ -113,7 +113,7 @@ struct vslam_ctx {
   // projection run beside the FAST pass of levels 1..3
   cudaStream_t group_stream[VS_MAX_GROUPS], side_stream[VS_MAX_GROUPS]; cudaEvent_t ev_fork[VS_MAX_GROUPS], ev_join[VS_MAX_GROUPS], ev_end[VS_MAX_GROUPS], ev_begin;
   int cur_s0, cur_cnt, cur_group;   // stream range / group the launchers act on (0, S, 0 outside vs_launch_frame)
-  unsigned long long* sync_words; size_t sync_words_n;   // strip_state of levels 0..3, then the tickets: one allocation, one memset per frame
+  unsigned long long* sync_words; size_t sync_words_n;   // corner bitmasks (LevelDesc::cbits) of levels 0..3, then the tickets: one allocation, one memset per frame
   unsigned* tickets;             // [2 * VS_MAX_GROUPS] device (inside sync_words)
   int* status;                   // [4] device: [0] capacity overflow flag
   CamDev cam;
