@@ -137,8 +137,6 @@ int vslam_create(const vslam_config* cfg, vslam_ctx** out) {
     CK(dalloc(&L.img, (size_t)S * h * L.pitch));
     CK(dalloc(&L.corners, (size_t)S * L.cap));
     CK(dalloc(&L.lut, (size_t)S * (h + 1)));
-    L.xw = (w + 31) / 32 + 1;
-    CK(dalloc(&L.xlut, (size_t)S * h * L.xw));
     strip_words += ((size_t)S * h * ((w + 31) / 32) + 1) / 2;      // corner bitmask words (32 bit) of this level, in 64-bit units
     ctx->src.w[l] = w; ctx->src.h[l] = h; ctx->src.pitch[l] = L.pitch;
     CK(dalloc(&ctx->src.img[l], (size_t)ctx->n_src * h * L.pitch));
@@ -196,7 +194,7 @@ void vslam_destroy(vslam_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->cfg.device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  for (int l = 0; l < VS_LEVELS; l++) { cudaFree(ctx->lev[l].img); cudaFree(ctx->lev[l].corners); cudaFree(ctx->lev[l].lut); cudaFree(ctx->lev[l].xlut); cudaFree(ctx->src.img[l]); }
+  for (int l = 0; l < VS_LEVELS; l++) { cudaFree(ctx->lev[l].img); cudaFree(ctx->lev[l].corners); cudaFree(ctx->lev[l].lut); cudaFree(ctx->src.img[l]); }
   cudaFree(ctx->epi_buf); cudaFree(ctx->l0_ptr); cudaFree(ctx->l0_stride); cudaFree(ctx->sync_words); cudaFree(ctx->status); cudaFree(ctx->evals);
   cudaFree(ctx->map.world); cudaFree(ctx->map.right); cudaFree(ctx->map.down); cudaFree(ctx->map.ircenter); cudaFree(ctx->map.srclevel); cudaFree(ctx->map.srckf);
   PointState& ps = ctx->ps;
@@ -477,6 +475,7 @@ int vslam_get_level(vslam_ctx* ctx, int s, int l, uint8_t* out, int out_stride) 
 int vslam_get_num_corners(vslam_ctx* ctx, int s, int l, int* n) {
   int rc = check_stream(ctx, s); if (rc) return rc;
   if (l < 0 || l >= VS_LEVELS || !n) return VSLAM_E_INVALID;
+  if ((rc = vs_ensure_lists(ctx))) return rc;
   if ((rc = vslam_sync(ctx))) return rc;
   const LevelDesc& L = ctx->lev[l];
   VS_CUDA(cudaMemcpy(n, L.lut + (size_t)s * (L.h + 1) + L.h, sizeof(int), cudaMemcpyDeviceToHost));
@@ -496,6 +495,7 @@ int vslam_get_corners(vslam_ctx* ctx, int s, int l, int32_t* xy, int cap) {
 int vslam_get_row_lut(vslam_ctx* ctx, int s, int l, int32_t* lut) {
   int rc = check_stream(ctx, s); if (rc) return rc;
   if (l < 0 || l >= VS_LEVELS || !lut) return VSLAM_E_INVALID;
+  if ((rc = vs_ensure_lists(ctx))) return rc;
   if ((rc = vslam_sync(ctx))) return rc;
   const LevelDesc& L = ctx->lev[l];
   VS_CUDA(cudaMemcpy(lut, L.lut + (size_t)s * (L.h + 1), sizeof(int) * L.h, cudaMemcpyDeviceToHost));
@@ -528,6 +528,7 @@ int vslam_get_candidates(vslam_ctx* ctx, int s, int l, int32_t* xy, double* scor
 
 int vslam_snapshot_keyframe(vslam_ctx* ctx, int s) {
   int rc = check_stream(ctx, s); if (rc) return rc;
+  if ((rc = vs_ensure_lists(ctx))) return rc;
   const LevelDesc& L = ctx->lev[0];
   if (!ctx->snap_img) {
     VS_CUDA(dalloc(&ctx->snap_img, (size_t)ctx->S * L.h * L.pitch)); VS_CUDA(dalloc(&ctx->snap_corners, (size_t)ctx->S * L.cap));

@@ -150,6 +150,7 @@ __global__ void k_minipatch_find(const uint8_t* img, int stride, int W, int H, c
 
 // Scratch for one stream's MakeKeyFrame_Rest results (allocated on first use).
 int vs_keyframe_rest(vslam_ctx* ctx, int s) {
+  { const int rc_ = vs_ensure_lists(ctx); if (rc_) return rc_; }
   if (!ctx->rest_scores) {
     size_t tot = 0; for (int l = 0; l < VS_LEVELS; l++) tot += ctx->lev[l].cap;
     VS_CUDA(cudaMalloc(&ctx->rest_scores, tot * sizeof(int)));
@@ -189,6 +190,7 @@ int vs_minipatch_sample(vslam_ctx* ctx, int s, int which, const int* xy_dev, int
 }
 
 int vs_minipatch_find(vslam_ctx* ctx, int s, int which, const uint8_t* patches_dev, int n, double* pos_dev, int* found_dev, int* best_dev, int range, int max_ssd) {
+  { const int rc_ = vs_ensure_lists(ctx); if (rc_) return rc_; }
   const LevelDesc& L = ctx->lev[0];
   const uint8_t* img = which ? ctx->snap_img + (size_t)s * L.h * L.pitch : ctx->l0_ptr_host[s];
   const int stride = which ? L.pitch : ctx->l0_stride_host[s];

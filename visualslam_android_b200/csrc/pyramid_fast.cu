@@ -14,7 +14,7 @@
 //   4. sets the bit of every corner in the level's corner bitmask in global memory (one word per 32 pixels, cleared per frame)
 //      and exits: no barrier after the staging, no inter-CTA dependency.
 // k_corner_lists (one CTA per level image): popcounts + one block scan give every corner its raster-order position; the running
-// positions at the row starts ARE the row look-up table of jni/KeyFrame.cc:41-49, those at the word starts the column index.
+// positions at the row starts ARE the row look-up table of jni/KeyFrame.cc:41-49.  (The tracker's patch search reads the bitmasks.)
 // Integer / byte arithmetic only; results are bit-exact against the oracle.
 #include "vslam_internal.cuh"
 #include <cstdio>
@@ -285,7 +285,7 @@ __device__ __forceinline__ void fast_strip(const LevelDesc& L, const uint8_t* __
 
 // Corner lists of one level image from its corner bitmask (k_pyramid_fast / k_fast_levels set the bits): every warp owns a contiguous run
 // of bitmask words; popcounts + one scan of the warp totals give every word its raster-order position.  The position at a row's first word is the
-// row's LUT entry (jni/KeyFrame.cc:41-49), the positions at the word starts are the column index (32-pixel buckets) of search_fast.cu.
+// row's LUT entry (jni/KeyFrame.cc:41-49).
 // Positions are clamped to the capacity: on overflow -- reported through status[0] -- the readers of the LUT must not index past the list.
 __global__ void __launch_bounds__(kMaxThreads)
 k_corner_lists(LevelDesc L0, LevelDesc L1, LevelDesc L2, LevelDesc L3, int first_stream, int count, int first_level, int* __restrict__ status) {
@@ -309,7 +309,6 @@ k_corner_lists(LevelDesc L0, LevelDesc L1, LevelDesc L2, LevelDesc L3, int first
   const int total = __shfl_sync(0xffffffffu, wi, 15);
   int run = __shfl_sync(0xffffffffu, wi - ws, warp);          // corners before this warp's run
   int* lut = L.lut + (size_t)s * (H + 1);
-  int* xlut = L.xlut + (size_t)s * H * L.xw;
   uint32_t* out = L.corners + (size_t)s * L.cap;
   uint32_t m_next = (wb + lane < we) ? bits[wb + lane] : 0u;
   for (int w0 = wb; w0 < we; w0 += 32) {
@@ -324,10 +323,7 @@ k_corner_lists(LevelDesc L0, LevelDesc L1, LevelDesc L2, LevelDesc L3, int first
     run += __shfl_sync(0xffffffffu, incl, 31);
     if (w < we) {
       const int r = div_small(w, L.mg_wpr), col = w - r * wpr;
-      const int cpos = min(pos, L.cap);
-      xlut[r * L.xw + col] = cpos;
-      if (col == 0) lut[r] = cpos;
-      if (col == wpr - 1) xlut[r * L.xw + wpr] = min(pos + mine, L.cap);     // end of the row
+      if (col == 0) lut[r] = min(pos, L.cap);
       const uint32_t cw0 = ((uint32_t)r << 16) | ((uint32_t)col << 5);
       if (pos + mine <= L.cap) {             // (always, unless the list overflows) highest bit first, written from the back: one FLO per corner
         uint32_t* o = out + pos + mine;
@@ -446,8 +442,7 @@ int vs_launch_pyramid_l0(vslam_ctx* ctx, int first_stream, int count) {
   return VSLAM_OK;
 }
 
-// Levels 1..3: FAST-10 (one launch), then the corner lists / row tables of all four levels (one launch).  Needs the level images and the
-// level-0 corner bits written by vs_launch_pyramid_l0.
+// Levels 1..3: FAST-10 (one launch).  Needs the level images written by vs_launch_pyramid_l0.
 int vs_launch_fast_levels(vslam_ctx* ctx, int first_stream, int count) {
   size_t smem = 0; int blocks = 0, threads = 0;
   for (int l = 1; l < VS_LEVELS; l++) {
@@ -468,17 +463,31 @@ int vs_launch_fast_levels(vslam_ctx* ctx, int first_stream, int count) {
                                                         ctx->tickets + 2 * ctx->cur_group + 1);
   vs_time_end(ctx);
   VS_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return VSLAM_OK;
+}
+
+// Corner lists and row LUTs of all four levels from the corner bitmasks (one launch).  The patch search of the tracker
+// (search_fast.cu) reads the bitmasks themselves, so a tracked frame leaves this to whoever asks for the lists next (vs_ensure_lists).
+int vs_launch_corner_lists(vslam_ctx* ctx, int first_stream, int count) {
   vs_time_begin(ctx, VS_ST_PYR2);
   k_corner_lists<<<count * VS_LEVELS, kMaxThreads, 0, ctx->stream>>>(ctx->lev[0], ctx->lev[1], ctx->lev[2], ctx->lev[3], first_stream, count, 0, ctx->status);
   vs_time_end(ctx);
   VS_CUDA(cudaGetLastError());
-  ctx->launches += 2;
+  ctx->launches++;
   return VSLAM_OK;
 }
 
+int vs_ensure_lists(vslam_ctx* ctx) {
+  if (!ctx->lists_stale) return VSLAM_OK;
+  ctx->lists_stale = false;
+  return vs_launch_corner_lists(ctx, 0, ctx->S);
+}
+
 int vs_launch_pyramid_fast(vslam_ctx* ctx, int first_stream, int count) {
-  const int rc = vs_launch_pyramid_l0(ctx, first_stream, count);
-  return rc ? rc : vs_launch_fast_levels(ctx, first_stream, count);
+  int rc = vs_launch_pyramid_l0(ctx, first_stream, count);
+  if (!rc) rc = vs_launch_fast_levels(ctx, first_stream, count);
+  return rc ? rc : vs_launch_corner_lists(ctx, first_stream, count);
 }
 
 int vs_launch_source_pyramid(vslam_ctx* ctx, int kf) {

@@ -31,16 +31,13 @@ constexpr int kQ = 48;            // candidate queue per entry
 #define VS_SEARCH_NB 4
 #endif
 constexpr int kNB = VS_SEARCH_NB; // template rows whose image words are requested together by the ZMSSD (registers: 4 per row)
-constexpr int kR = 3;             // window rows per lane and block
-constexpr int kRows = kGL * kR;   // window rows per block (a 21 x 21 window has 22)
 
 struct FastWarp {
   union {
-    struct { uint32_t cw[kGW][kQ]; int idx[kGW][kQ]; } q;      // candidates waiting for their ZMSSD: corner word, corner index
+    struct { uint32_t cw[kGW][kQ]; } q;                        // candidates waiting for their ZMSSD: corner word (y << 16 | x)
     double pos[VS_MAXP * VS_MAXP * 2];                         // template regeneration: sample positions
   };
   uint32_t tmpl[kGW][VS_TMPL_BYTES / 4];                       // the entries' templates, rows of 3 zero-padded words (the dp4a operand layout)
-  int rows[kGW][2][kRows];                                     // the current block of window rows: first item and first corner index of every row
 };
 
 struct Plan { int first, count, range, subpix_all, n_top, subpix_top; };
@@ -191,75 +188,48 @@ __global__ void __launch_bounds__(kFW * 32, VS_SEARCH_MINB) k_search_fast(Dev D,
   const int nLeft = ix - nRange, nRight = ix + nRange;
   const double r2 = (double)(nRange * nRange);
   unsigned long long best = ((unsigned long long)(unsigned)(maxSSD + 1) << 32) | 0xffffffffull;
-  uint32_t bestcw = 0u;                                         // the corner word of `best` (saves the dependent re-read of the corner list at the end)
   flags |= F_SEARCHED;
   if (nTop < 0) nTop = 0;
-  const uint32_t* corners = L.corners + (size_t)s * L.cap;
-  // The window's corners through the column index of the row LUT (LevelDesc::xlut, 32-pixel buckets, written by the FAST kernels):
-  // rows [nTop, nBot), buckets [wl, wr1) -- a superset of the x range of jni/PatchFinder.cc:214-215, which is then applied exactly.
+  // The window's corners straight from the level's corner bitmask (LevelDesc::cbits, one word per 32 pixels, written by the FAST kernels):
+  // lane j of the entry walks rows nTop + j, nTop + j + 8, ... and, per row, the words that hold columns [nLeft, nRight] clipped to the image
+  // (the x range of jni/PatchFinder.cc:214-215, exact); a set bit IS a corner position, so neither the corner list nor the row LUT is read.
   const int nBot = nBottomPlusOne < lh ? nBottomPlusOne : lh;
   const bool x_empty = nRight < 0 || nLeft > lw - 1;
-  const int wl = (nLeft > 0 ? nLeft : 0) >> 5, wr1 = ((nRight < lw - 1 ? nRight : lw - 1) >> 5) + 1;
-  const int* xl = L.xlut + (size_t)s * lh * L.xw;
-  const int xw = L.xw;
-  bool rows_left = alive && !x_empty && nTop < nBot;   // (nTop >= rows or nBottomPlusOne <= 0: nothing to search, jni/PatchFinder.cc:189-195)
-  int blk = 0, T = 0, t0 = 0;
-  int* const rs = W.rows[g][0]; int* const rl = W.rows[g][1];
+  const int xl0 = nLeft > 0 ? nLeft : 0, xr0 = nRight < lw - 1 ? nRight : lw - 1;
+  const int wl = xl0 >> 5, wr = xr0 >> 5, cwpr = (lw + 31) >> 5;
+  const uint32_t* cb = L.cbits + (size_t)s * lh * cwpr;
+  bool more = alive && !x_empty && nTop < nBot;   // (nTop >= rows or nBottomPlusOne <= 0: nothing to search, jni/PatchFinder.cc:189-195)
+  int yrow = nTop + j - kGL, wi = wr;               // "before the first word": the first advance moves to (row nTop + j, word wl)
+  uint32_t m = 0u;                                  // corner bits of the current word still to be looked at
   const int b = P / 2, nwords = (P + 3) >> 2;
   const uint32_t lastmask = (P & 3) ? ((1u << (8 * (P & 3))) - 1u) : 0xffffffffu;
   int nevals = 0, qn = 0;
   while (true) {
     // -- scan: until the warp's entries have run out of corners or one of the queues could overflow in the next step
-    while (!__any_sync(0xffffffffu, qn > kQ - 2 * kGL)) {
-      if (!__any_sync(0xffffffffu, t0 < T)) {
-        if (!__any_sync(0xffffffffu, rows_left)) break;
-        // next block of kRows rows per entry: lane j takes rows j * kR .. j * kR + kR - 1 of the block; corner ranges from the column index
-        int lo[kR], cnt[kR], mine = 0;
-#pragma unroll
-        for (int r = 0; r < kR; r++) {
-          const int y = nTop + blk * kRows + j * kR + r;
-          lo[r] = 0; cnt[r] = 0;
-          if (rows_left && y < nBot) { const int* row = xl + (size_t)y * xw; lo[r] = __ldg(row + wl); cnt[r] = __ldg(row + wr1) - lo[r]; }
-          mine += cnt[r];
+    while (!__any_sync(0xffffffffu, qn > kQ - kGL)) {
+      if (!__any_sync(0xffffffffu, m != 0u)) {
+        if (!__any_sync(0xffffffffu, more)) break;
+        if (more) {
+          if (wi == wr) { yrow += kGL; wi = wl; } else wi++;
+          if (yrow >= nBot) more = false;
+          else {
+            uint32_t v = __ldg(cb + (size_t)yrow * cwpr + wi);
+            if (wi == wl) v &= 0xffffffffu << (xl0 & 31);
+            if (wi == wr) v &= 0xffffffffu >> (31 - (xr0 & 31));
+            m = v;
+          }
         }
-        int incl = mine;
-#pragma unroll
-        for (int d = 1; d < kGL; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d, kGL); if (j >= d) incl += v; }
-        int start = incl - mine;
-        __syncwarp();
-#pragma unroll
-        for (int r = 0; r < kR; r++) { rs[j * kR + r] = start; rl[j * kR + r] = lo[r]; start += cnt[r]; }
-        T = __shfl_sync(0xffffffffu, incl, kGL - 1, kGL); t0 = 0;
-        blk++;
-        rows_left = rows_left && (nTop + blk * kRows < nBot);
-        __syncwarp();
         continue;
       }
-      // two steps of eight corners per entry: item t of the block's concatenated row ranges -> (row q, offset) by binary search over the row starts
-      uint32_t cwv[2]; int civ[2]; bool hv[2];
-#pragma unroll
-      for (int u = 0; u < 2; u++) {
-        const int t = t0 + u * kGL + j;
-        hv[u] = t < T;
-        int q = 0;
-#pragma unroll
-        for (int step = 16; step; step >>= 1) { const int q2 = q + step; if (q2 < kRows && rs[q2] <= t) q = q2; }
-        civ[u] = rl[q] + (t - rs[q]);
-        cwv[u] = hv[u] ? __ldg(corners + civ[u]) : 0u;
-      }
-#pragma unroll
-      for (int u = 0; u < 2; u++) {
-        bool pass = false;
-        if (hv[u]) {
-          const int cx = cwv[u] & 0xffff, cy = cwv[u] >> 16;
-          pass = !(cx < nLeft || cx > nRight);                      // (the reference compares as doubles: same result for integers)
-          if (pass) { const double dx = ix - (double)cx, dy = iy - (double)cy; double d2 = 0; d2 += dx * dx; d2 += dy * dy; pass = !(d2 > r2); }
-        }
-        const unsigned gb = (__ballot_sync(0xffffffffu, pass) >> (kGL * g)) & ((1u << kGL) - 1u);
-        if (pass) { const int slot = qn + __popc(gb & ((1u << j) - 1u)); W.q.cw[g][slot] = cwv[u]; W.q.idx[g][slot] = civ[u]; }
-        qn += __popc(gb);
-      }
-      t0 += 2 * kGL;
+      // one corner per lane and step: the circle test of jni/PatchFinder.cc:216-219, survivors to the entry's queue
+      bool pass = m != 0u;
+      const int bit = pass ? __ffs(m) - 1 : 0;
+      m &= m - 1u;
+      const int cx = (wi << 5) + bit, cy = yrow;
+      if (pass) { const double dx = ix - (double)cx, dy = iy - (double)cy; double d2 = 0; d2 += dx * dx; d2 += dy * dy; pass = !(d2 > r2); }
+      const unsigned gb = (__ballot_sync(0xffffffffu, pass) >> (kGL * g)) & ((1u << kGL) - 1u);
+      if (pass) W.q.cw[g][qn + __popc(gb & ((1u << j) - 1u))] = ((uint32_t)cy << 16) | (uint32_t)cx;
+      qn += __popc(gb);
     }
     if (!__any_sync(0xffffffffu, qn > 0)) break;
     __syncwarp();
@@ -267,7 +237,6 @@ __global__ void __launch_bounds__(kFW * 32, VS_SEARCH_MINB) k_search_fast(Dev D,
     for (int q0 = 0; __any_sync(0xffffffffu, q0 < qn); q0 += kGL) {
       const bool have = q0 + j < qn;
       const uint32_t cw = W.q.cw[g][have ? q0 + j : 0];
-      const int cidx = W.q.idx[g][have ? q0 + j : 0];
       const int cx = cw & 0xffff, cy = cw >> 16;
       const bool inb = have && (cx >= b && cy >= b && cx < lw - b && cy < lh - b);
       int ssd = maxSSD + 1;
@@ -331,8 +300,8 @@ __global__ void __launch_bounds__(kFW * 32, VS_SEARCH_MINB) k_search_fast(Dev D,
         ssd = ((2 * SA * SB - SA * SA - SB * SB) / PP + (int)sumsq + tsumsq - 2 * (int)cross);
       }
       if (have) {
-        const unsigned long long key = ((unsigned long long)(unsigned)ssd << 32) | (unsigned)cidx;   // ssd >= 0; ties -> lowest corner index
-        if (key < best) { best = key; bestcw = cw; }
+        const unsigned long long key = ((unsigned long long)(unsigned)ssd << 32) | cw;   // ssd >= 0; ties -> first corner in raster order (y << 16 | x)
+        if (key < best) best = key;
       }
       __syncwarp();
     }
@@ -341,8 +310,8 @@ __global__ void __launch_bounds__(kFW * 32, VS_SEARCH_MINB) k_search_fast(Dev D,
   }
 #pragma unroll
   for (int d = kGL / 2; d; d >>= 1) {
-    const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, d); const uint32_t oc = __shfl_xor_sync(0xffffffffu, bestcw, d);
-    if (o < best) { best = o; bestcw = oc; }
+    const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, d);
+    if (o < best) best = o;
   }
   if (!alive) return;
   if (j == 0 && nevals) atomicAdd(D.evals, (unsigned long long)nevals);
@@ -352,7 +321,7 @@ __global__ void __launch_bounds__(kFW * 32, VS_SEARCH_MINB) k_search_fast(Dev D,
     return;
   }
   if (j == 0) {
-    const uint32_t bc = bestcw;
+    const uint32_t bc = (uint32_t)best;
     const double coarse0 = ((double)(bc & 0xffff) + 0.5) * nLevelScale - 0.5, coarse1 = ((double)(bc >> 16) + 0.5) * nLevelScale - 0.5;  // LevelZeroPos
     flags |= F_FOUND;
     D.ps.coarse[gi] = coarse0; D.ps.coarse[SN + gi] = coarse1;

@@ -891,6 +891,7 @@ int vs_launch_project_all(vslam_ctx* ctx, int mode) {
 
 int vs_launch_search(vslam_ctx* ctx, int which, int range, int subpix, int sflags) {
   if (ctx->params.search_kernel == 0) return vs_launch_search_fast(ctx, which, range, subpix, sflags);
+  { const int rc_ = vs_ensure_lists(ctx); if (rc_) return rc_; }
   const Dev D = make_dev(ctx);
   const int max_entries = which == 1 ? (int)(2 * ctx->params.coarse_max) : ctx->list_cap;
   if (max_entries <= 0) return VSLAM_OK;   // nCoarseMax == 0: the reference skips the coarse stage (jni/Tracker.cc:425)
@@ -953,7 +954,7 @@ int vs_launch_track_map(vslam_ctx* ctx, int with_motion_model) {
 // Tracker::TrackFrame for all streams (jni/Tracker.cc:68-160, map-good branch).
 // Launch graph of one stream group: the level images exist once the level-0 launch is done, so SmallBlurryImage + relocaliser +
 // motion model + projection (side stream; one CTA per stream, latency-bound) run beside the FAST pass of levels 1..3 (main stream)
-// and join before the first patch search, which needs the corner lists.
+// and join before the first patch search, which needs the corner bitmasks of all levels.
 static int launch_frame_group(vslam_ctx* ctx, int g, bool fork) {
   int rc;
   cudaStream_t main_stream = ctx->stream;
@@ -969,6 +970,11 @@ static int launch_frame_group(vslam_ctx* ctx, int g, bool fork) {
   if (fork) VS_CUDA(cudaEventRecord(ctx->ev_join[g], ctx->side_stream[g]));
   if (rc) return rc;
   if ((rc = vs_launch_fast_levels(ctx, ctx->cur_s0, ctx->cur_cnt))) return rc;
+  // The corner lists / row LUTs (k_corner_lists) are for the API and for the kernels that walk lists (k_search of round 1, MapMaker's
+  // epipolar search, MiniPatch, MakeKeyFrame_Rest): k_search_fast reads the corner bitmasks.  With it a tracked frame does not build the
+  // lists at all; whoever needs them next builds them from the bitmasks first (vs_ensure_lists).
+  if (ctx->params.search_kernel == 0) ctx->lists_stale = true;
+  else if ((rc = vs_launch_corner_lists(ctx, ctx->cur_s0, ctx->cur_cnt))) return rc;
   if (fork) VS_CUDA(cudaStreamWaitEvent(main_stream, ctx->ev_join[g], 0));
   return vs_launch_track_map_rest(ctx, 1);
 }
@@ -1074,6 +1080,7 @@ int vs_launch_epipolar_geometry(vslam_ctx* ctx, int n, const EpiGeom& G, const d
 
 int vs_launch_epipolar(vslam_ctx* ctx, int stream, int src_kf, int level, int n, const EpiCand* cand_dev, const double* unproj_dev, int subpix_its, int* out_int_dev, double* out_pos_dev) {
   if (n <= 0) return VSLAM_OK;
+  { const int rc_ = vs_ensure_lists(ctx); if (rc_) return rc_; }
   k_epipolar<<<(n + kSearchWarps - 1) / kSearchWarps, kSearchWarps * 32, 0, ctx->stream>>>(make_dev(ctx), stream, src_kf, level, n, cand_dev, unproj_dev, subpix_its, out_int_dev, out_pos_dev);
   VS_CUDA(cudaGetLastError());
   ctx->launches++;

@@ -26,7 +26,6 @@ struct LevelDesc {
   uint8_t* img;               // [S][h][pitch]      (level 0: only used by the host-input path, see l0_ptr)
   uint32_t* corners;          // [S][cap]           packed (y << 16 | x), raster order
   int* lut;                   // [S][h + 1]         lut[y] = #corners with row < y ; lut[h] = total
-  int* xlut; int xw;          // [S][h][xw]         xw = ceil(w / 32) + 1: xlut[y][b] = #corners before (row y, column 32 b) in raster order; xlut[y][xw - 1] = end of row y
   uint32_t* cbits;            // [S][h][ceil(w / 32)] corner bitmask of the frame being processed (bit x & 31 of word x >> 5; cleared per frame, inside ctx->sync_words)
 };
 
@@ -146,6 +145,7 @@ struct vslam_ctx {
   // optional per-kernel timing with CUDA events on ctx->stream (vslam_set_timing)
   bool timing; std::vector<cudaEvent_t> ev_pool; std::vector<int> ev_stage; size_t ev_used;
   size_t smem_attr[4] = {0, 0, 0, 0};   // dynamic shared memory already opted into, per kernel (cudaFuncSetAttribute once, not per frame)
+  bool lists_stale = false;      // the last tracked frame left corner bitmasks only: corner lists / row LUTs are built on demand (vs_ensure_lists)
   std::string err;
 };
 
@@ -170,9 +170,11 @@ inline void vs_time_end(vslam_ctx* ctx) { if (ctx->timing) cudaEventRecord(ctx->
 
 // kernels/launchers implemented in the .cu files
 int vs_strip_rows(int level, int w, int pitch);
-int vs_launch_pyramid_fast(vslam_ctx* ctx, int first_stream, int count);   // = vs_launch_pyramid_l0 + vs_launch_fast_levels
+int vs_launch_pyramid_fast(vslam_ctx* ctx, int first_stream, int count);   // = vs_launch_pyramid_l0 + vs_launch_fast_levels + vs_launch_corner_lists
 int vs_launch_pyramid_l0(vslam_ctx* ctx, int first_stream, int count);
 int vs_launch_fast_levels(vslam_ctx* ctx, int first_stream, int count);
+int vs_launch_corner_lists(vslam_ctx* ctx, int first_stream, int count);   // corner lists + row LUT of all levels from the corner bitmasks
+int vs_ensure_lists(vslam_ctx* ctx);                                       // ... of every stream, if the last tracked frame skipped them
 int vs_launch_source_pyramid(vslam_ctx* ctx, int kf_id);
 int vs_launch_project_all(vslam_ctx* ctx, int build_lists);
 int vs_launch_search(vslam_ctx* ctx, int which /*0 explicit list,1 coarse A,2 fine B*/, int range, int subpix, int sflags /*1: ReFind_Common variant*/);
