@@ -11,7 +11,7 @@ each; UpdateMotionModel; AssessTrackingQuality).  Streams never exchange data: N
   value  tracked frames/s with the frames already resident in HBM (vslam_track_frame_dev), CUDA-event timed
   e2e    the same through the host-buffer C-ABI call (vslam_track_frame: pinned host frames copied in every step) plus a
          device->host read of every stream's pose, every step
-  roofline      pyramid+FAST stage (k_pyramid_fast, 4 launches per step): algorithmic bytes / event-timed duration
+  roofline      KeyFrame::MakeKeyFrame_Lite (k_pyramid_fast + k_fast_levels + k_corner_lists): algorithmic bytes / event-timed duration
   cpu_baseline  the reference's own sources (oracle/_ref) — or the oracle port when that library is absent — tracking the
                 same kind of sequence on the host cores, one process per core
 
@@ -744,38 +744,70 @@ def main():
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    pyr_ms = sum(stage[f"pyrfast_l{l}"][0] for l in range(4))
     stage_sum_ms = sum(v[0] for v in stage.values()) / Ks
     lut_bytes = 4 * sum((H >> l) for l in range(4))
     alg_bytes_step = S * (1.328125 * W * H + lut_bytes) + 4.0 * corners_per_step            # whole stage, per step
-    achieved = alg_bytes_step * Ks / (pyr_ms * 1e-3) / 1e9
-    # level-0 launch alone (75 % of the FAST pixels): reads level 0, writes levels 1-3 + level 0's corner list + LUT
-    l0_corners = sum(int(ctx.corners(s, 0).shape[0]) for s in probe) * (S / len(probe))
-    l0_bytes = S * (1.328125 * W * H + 4 * (H + 1)) + 4.0 * l0_corners
-    l0_ms = stage["pyrfast_l0"][0] / Ks
+    # (a) the COMPLETE KeyFrame::MakeKeyFrame_Lite -- pyramid, FAST-10 of four levels, raster-ordered corner lists and row LUTs: the three
+    #     launches of vslam_make_keyframe_lite_dev -- timed live here with CUDA events over the resident frame pool (a different frame set
+    #     every launch, > L2 in between), stage timing on so that every launch is also timed alone
+    Kr = max(8, min(K, 30))
+    for k in range(3):
+        ctx.make_keyframe_lite_ptr(frames_dev[tri(step_no + k)].data_ptr(), S, W, fs, device=True)
+    ctx.sync()
+    ctx.set_timing(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for k in range(Kr):
+        ctx.make_keyframe_lite_ptr(frames_dev[tri(step_no + 3 + k)].data_ptr(), S, W, fs, device=True)
+    e1.record(stream)
+    barrier()
+    mk_ms = max_over_ranks(e0.elapsed_time(e1)) / Kr
+    mk_stage = ctx.stage_times()
+    ctx.set_timing(False)
+    mk_l = [mk_stage[f"pyrfast_l{l}"][0] / Kr for l in range(3)]       # level-0 launch, levels 1-3 launch, corner-list launch
+    pyr_ms_sum = sum(mk_l)
+    achieved = alg_bytes_step / (pyr_ms_sum * 1e-3) / 1e9
+    # (b) what a tracked frame runs of it: the two FAST launches (the corner bitmasks are what k_search_fast reads; lists are built on demand)
+    in_step_ms = (stage["pyrfast_l0"][0] + stage["pyrfast_l1"][0]) / Ks
+    in_step_bytes = S * 1.328125 * W * H * (1.0 + 1.0 / 8.0)                               # frames in, level 1-3 images + one corner bit per pixel out
+    # level-0 launch alone (75 % of the FAST pixels): reads level 0, writes the images of levels 1-3 + level 0's corner bits
+    l0_bytes = S * (1.328125 * W * H + W * H / 8.0)
+    l0_ms = mk_l[0]
     # DRAM bytes and executed warp-instructions of that launch: read from the committed ncu --set full capture of the CURRENT kernels
-    # (profiles/r02_ncu_counters.json, written by scratch/mkprofiles from the .ncu-rep of `bench.py --steps 2`; a property of the workload, not of
-    # the run).  null when the capture does not cover this configuration.
-    l0_traffic = l0_inst = None; counters_src = None
+    # (profiles/r02_ncu_counters.json, written by profiles/tools/ncu_extract.py from the .ncu-rep of `bench.py --steps 2`; a property of the
+    # workload, not of the run).  null when the capture does not cover this configuration.
+    l0_traffic = l0_inst = None; counters_src = None; traffic_stage = None
     cpath = os.path.join(ROOT, "profiles", "r02_ncu_counters.json")
     if os.path.exists(cpath):
         cj = json.load(open(cpath))
-        kk = cj.get("kernels", {}).get("k_pyramid_fast")
-        if kk and cj.get("streams") == S and cj.get("frame") == [W, H]:
-            l0_traffic = kk["dram_bytes_read"] + kk["dram_bytes_write"]; l0_inst = kk["warp_instructions"]; counters_src = "profiles/r02_ncu_counters.json"
+        kk = cj.get("kernels", {})
+        if "k_pyramid_fast" in kk and cj.get("streams") == S and cj.get("frame") == [W, H]:
+            dram = lambda n: (kk[n].get("dram_bytes_read") or 0.0) + (kk[n].get("dram_bytes_write") or 0.0)
+            l0_traffic = dram("k_pyramid_fast"); l0_inst = kk["k_pyramid_fast"]["warp_instructions"]; counters_src = "profiles/r02_ncu_counters.json"
+            if all(n in kk for n in ("k_fast_levels", "k_corner_lists")):
+                traffic_stage = l0_traffic + dram("k_fast_levels") + dram("k_corner_lists")
     sm_clock_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
     issue = None
     if l0_inst:
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
         issue = {"bound": "instruction issue", "warp_instructions_per_launch": l0_inst, "achieved": l0_inst / (l0_ms * 1e-3) / 1e9,
                  "peak": sms * 4 * sm_clock_hz / 1e9, "unit": "G warp-instr/s", "frac": l0_inst / (l0_ms * 1e-3) / (sms * 4 * sm_clock_hz)}
-    roofline = {"kernel": "k_pyramid_fast + k_fast_levels (pyramid + FAST-10 + raster compaction + row LUT; 2 launches per step: level 0 (+ level 1-3 images), levels 1-3)", "bound": "hbm",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": l0_traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_step": alg_bytes_step, "ms_per_step": pyr_ms / Ks, "share_of_step": (pyr_ms / Ks) / stage_sum_ms,
+    roofline = {"kernel": "k_pyramid_fast + k_fast_levels + k_corner_lists = KeyFrame::MakeKeyFrame_Lite (pyramid + FAST-10 + raster-ordered corner lists + row LUT; 3 launches: "
+                          "level 0 (+ level 1-3 images), levels 1-3, lists)", "bound": "hbm",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic_stage if traffic_stage is not None else l0_traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_step": alg_bytes_step, "ms_per_step": pyr_ms_sum, "ms_per_launch": {"level0": mk_l[0], "levels1_3": mk_l[1], "corner_lists": mk_l[2]},
+                "ms_per_step_back_to_back": mk_ms,
+                "how": f"{Kr} calls of vslam_make_keyframe_lite_dev on {S} resident frames each (a different set of the pool per call), CUDA events around every launch on the library's stream; "
+                       "ms_per_step = sum of the three launches' own times, ms_per_step_back_to_back = one event pair around all calls",
+                "in_tracked_frame": {"what": "the two FAST launches a tracked frame runs (corner bitmasks out; k_search_fast reads them, lists are built on demand)",
+                                     "ms": in_step_ms, "algorithmic_bytes": in_step_bytes, "achieved": in_step_bytes / (in_step_ms * 1e-3) / 1e9,
+                                     "frac": in_step_bytes / (in_step_ms * 1e-3) / 1e9 / peak, "share_of_step": in_step_ms / stage_sum_ms},
+                "share_of_step": in_step_ms / stage_sum_ms,
                 "level0_launch": {"algorithmic_bytes": l0_bytes, "ms": l0_ms, "achieved": l0_bytes / (l0_ms * 1e-3) / 1e9,
                                   "frac": l0_bytes / (l0_ms * 1e-3) / 1e9 / peak, "traffic": l0_traffic, "issue_roofline": issue},
                 "counters_source": counters_src,
-                "note": "traffic is the level-0 launch's dram read+write bytes (ncu --set full); the stage is instruction-issue bound, not HBM bound: DESIGN.md §4.1 and profiles/"}
+                "note": "traffic = dram read+write bytes of the three launches (level0_launch.traffic: of the level-0 launch) from the committed ncu --set full capture; "
+                        "the stage is instruction-issue bound, not HBM bound: DESIGN.md section 4.1 and profiles/"}
     # ZMSSD: 3*P^2 integer MACs per scored candidate over the time of the two search kernels, against a measured dp4a peak
     evals_timed = evals1 - evals0
     search_ms = stage["search_fine"][0] + stage["search_coarse"][0]
