@@ -235,6 +235,28 @@ int vslam_set_point_projection(vslam_ctx* ctx, int stream, const double* v2image
 int vslam_set_lists(vslam_ctx* ctx, const int32_t* idx, const int32_t* n, int idx_stride);
 int vslam_clear_counters(vslam_ctx* ctx);
 int vslam_search_for_points(vslam_ctx* ctx, int range, int subpix_its);
+/* ---- PatchFinder, one object at a time: the per-object methods of jni/PatchFinder.h:45-121 that the batched calls fuse away.  A "PatchFinder
+ * object" is the finder state kept per (stream, map point): template, sums, search level (vslam_get_point_states / _point_template).  Slow
+ * path: one small launch and a synchronous read-back per call; include/vslam_b200_shell.hpp's class PatchFinder is written on these. */
+/* MakeTemplateCoarseCont(p) (jni/PatchFinder.cc:79-125) with the warp of the last projection, re-use rule included */
+int vslam_pf_make_template(vslam_ctx* ctx, int stream, int point, int* template_bad);
+/* MakeTemplateCoarseNoWarp(KeyFrame&, nLevel, x, y) (:130-143): P x P pixels of level `level` of source keyframe `src_kf` around (x, y); sets
+ * the point's search level to `level`.  src_kf < 0: MakeTemplateCoarseNoWarp(MapPoint&) (:146-149), the point's own source keyframe, level and
+ * irCenter (level, x, y are ignored). */
+int vslam_pf_make_template_nowarp(vslam_ctx* ctx, int stream, int point, int src_kf, int level, int x, int y, int* template_bad);
+/* ZMSSDAtPoint(img, icol, irow) (:352-380) at n positions (x, y) of level `level` of the stream's current keyframe; mnMaxSSD + 1 outside the border */
+int vslam_pf_zmssd_at(vslam_ctx* ctx, int stream, int point, int level, int n, const int32_t* xy, int32_t* ssd);
+/* MakeSubPixTemplate's JtJ^-1 (:242-267) and up to max_its x IterateSubPix (:290-350) on the point's search level, from pos2 = mv2SubPixPos
+ * (level-zero pixels, in/out) and *mean_diff = mdMeanDiff (in/out).  max_its = 1: one IterateSubPix, *last_update_sq = its return value
+ * (negative: off the image).  max_its = n: IterateSubPixToConvergence(kf, n) (:272-285), *converged = its return value. */
+int vslam_pf_subpix(vslam_ctx* ctx, int stream, int point, int max_its, double* pos2, double* mean_diff, int* converged, double* last_update_sq);
+
+/* The user event of the reference's shell: SystemPTAM::onTouchScreen -> Tracker::mbUserPressedSpacebar (jni/jni_part.cpp:49-51, 125-129),
+ * consumed by Tracker::TrackForInitialMap (jni/Tracker.cc:232-253).  vslam_take_user_event returns the pending events of a stream and clears them. */
+#define VSLAM_EVENT_SPACEBAR 1
+int vslam_user_event(vslam_ctx* ctx, int stream, int event);
+int vslam_take_user_event(vslam_ctx* ctx, int stream, int* pending);
+
 /* MapMaker::ReFind_Common (jni/MapMaker.cc:967-1036), batched: every stream stands for one keyframe (its current keyframe image and
  * pose), its list (vslam_set_lists) for the map points to re-find in it.  Per pair: projection and in-image tests, a cold-finder
  * MakeTemplateCoarse (always regenerated; the reference's static PatchFinder does the same whenever consecutive calls name different

@@ -16,7 +16,11 @@
 //            TrailTracking_Advance                        (jni/Tracker.cc:203-346); InitFromStereo is MapMaker's: a hook
 //   KeyFrame::MakeKeyFrame_Rest()                         vslam_make_keyframe_rest                   (jni/KeyFrame.cc:53-95)
 //   MiniPatch::SampleFromImage / FindPatch                vslam_minipatch_sample / _find, one patch   (jni/MiniPatch.cc:6-83)
-//   PatchFinder (per-object, slow path)                   stage calls on a one-entry list            (jni/PatchFinder.h:45-121)
+//   PatchFinder (per-object, slow path)                   stage calls on a one-entry list + vslam_pf_* (jni/PatchFinder.h:45-121): CalcSearchLevelAndWarpMatrix,
+//                                                         MakeTemplateCoarse / Cont / NoWarp, FindPatchCoarse, ZMSSDAtPoint, MakeSubPixTemplate,
+//                                                         IterateSubPix, IterateSubPixToConvergence, Get / SetSubPixPos
+//   Tracker(width, height, camera, map, mapmaker)         vslam_b200::TrackerOnReferenceTypes         (jni/Tracker.h:43, jni/jni_part.cpp:27-46)
+//   SystemPTAM::onTouchScreen                             Tracker::mbUserPressedSpacebar / vslam_user_event (jni/jni_part.cpp:49-51)
 //   MapMaker::ReFindInSingleKeyFrame / ReFind_Common,     vslam_b200::MapSearch (vslam_refind, vslam_epipolar_search)
 //            the search of AddPointEpipolar               (jni/MapMaker.cc:525-640, 967-1056)
 //   Relocaliser (inside Tracker::TrackFrame when lost)    Tracker::SetRelocKeyFrames                 (jni/Relocaliser.cc:17-58)
@@ -177,8 +181,9 @@ class Tracker {
     check(ctx_.get(), vslam_reset_stream(ctx_.get(), stream_));
     mbUserPressedSpacebar = false; mnInitialStage = TRAIL_TRACKING_NOT_STARTED; mlTrails.clear(); mnFrame = 0; mnLastKeyFrameDropped = -20; mbMapGood = false;
   }
-  // jni/Tracker.cc:349-353 (the reference's GUI handler sets the flag)
+  // jni/Tracker.cc:349-353 (the reference's GUI handler sets the flag; SystemPTAM::onTouchScreen writes the member directly, jni/jni_part.cpp:49-51)
   void PressSpacebar() { mbUserPressedSpacebar = true; }
+  bool mbUserPressedSpacebar = false;
 
   // jni/Tracker.cc:76-146.  Good map: MakeKeyFrame_Lite, SmallBlurryImage, motion model, TrackMap, quality — one call, all on the
   // device.  No map yet: MakeKeyFrame_Lite + TrackForInitialMap.  With several streams per context use vslam_track_frame
@@ -187,6 +192,7 @@ class Tracker {
     vslam_ctx* c = ctx_.get();
     msg_.str("");
     mnFrame++;
+    { int ev = 0; check(c, vslam_take_user_event(c, stream_, &ev)); if (ev & VSLAM_EVENT_SPACEBAR) mbUserPressedSpacebar = true; }   // events posted through the C-ABI
     if (!mbMapGood) {
       check(c, vslam_make_keyframe_lite(c, stream_, 1, imFrame.data, (int)imFrame.step, 0));
       TrackForInitialMap();
@@ -377,7 +383,8 @@ class Tracker {
     n[stream_] = (int32_t)vTD.size();
     check(c, vslam_set_lists(c, &idx[0], &n[0], stride));
   }
-  Context& ctx_; int stream_; int mnFrame = 0; bool mbUserPressedSpacebar = false; bool mbMapGood = false; std::ostringstream msg_;
+ protected:
+  Context& ctx_; int stream_; int mnFrame = 0; bool mbMapGood = false; std::ostringstream msg_;
 };
 
 // jni/PatchFinder.h:45-121, per object, for one map point of one stream at a time: the slow path (every call moves the whole
@@ -405,13 +412,50 @@ class PatchFinder {
   // TrackerData::v2Image of the point at that pose (what the reference's callers pass to FindPatchCoarse), and any point's level
   Eigen::Vector2d GetProjection() { return Eigen::Vector2d(dbl_[32 * (size_t)point_], dbl_[32 * (size_t)point_ + 1]); }
   int LevelOf(int point) { return ints_[8 * (size_t)point + 1]; }
-  // The template is (re)generated on the device by the next FindPatchCoarse under the reference's reuse rule (jni/PatchFinder.cc:91-102)
-  void MakeTemplateCoarseCont(int point) { point_ = point; }
+  // jni/PatchFinder.cc:79-125, for `point` with the warp CalcSearchLevelAndWarpMatrix left on the device; the re-use rule (:91-102) applies
+  void MakeTemplateCoarseCont(int point) {
+    point_ = point;
+    int bad = 0; check(ctx_.get(), vslam_pf_make_template(ctx_.get(), stream_, point_, &bad));
+    mbTemplateBad = bad != 0;
+  }
+  // jni/PatchFinder.cc:72-76.  (The reference also takes the camera derivatives at the projection; the device recomputes them.)
+  void MakeTemplateCoarse(int point, const SE3& se3CFromW) { if (CalcSearchLevelAndWarpMatrix(point, se3CFromW) >= 0) MakeTemplateCoarseCont(point); }
+  // jni/PatchFinder.cc:146-149: un-warped pixels of the point's own source keyframe, level and irCenter
+  void MakeTemplateCoarseNoWarp(int point) { NoWarp(point, -1, 0, 0, 0); }
+  // jni/PatchFinder.cc:130-143 with the keyframe named by its source-keyframe slot (Tracker::SetSourceKeyFrame)
+  void MakeTemplateCoarseNoWarp(int point, int src_kf_id, int nLevel, int irLevelPos0, int irLevelPos1) { NoWarp(point, src_kf_id, nLevel, irLevelPos0, irLevelPos1); }
   bool TemplateBad() { return mbTemplateBad; }
+  // jni/PatchFinder.cc:352-380.  img must be a level image of the stream's current keyframe (kf.aLevels[l].im): it names the level, the
+  // pixels that are compared are the device's copy of that level.
+  int ZMSSDAtPoint(cv::Mat& img, int icol, int irow) {
+    vslam_ctx* c = ctx_.get();
+    int level = -1;
+    for (int l = 0; l < LEVELS && level < 0; l++) { int w, h; check(c, vslam_level_dims(c, l, &w, &h)); if (w == img.cols && h == img.rows) level = l; }
+    if (level < 0) throw std::runtime_error("vslam_b200: ZMSSDAtPoint: the image is not a level of the stream's keyframe");
+    const int32_t xy[2] = {icol, irow}; int32_t ssd = 0;
+    check(c, vslam_pf_zmssd_at(c, stream_, point_, level, 1, xy, &ssd));
+    return ssd;
+  }
   // Search around v2Pos (level-0 pixels) in the stream's current keyframe (kf must be that keyframe)
   bool FindPatchCoarse(const Eigen::Vector2d& v2Pos, KeyFrame& /*kf*/, unsigned int nRange) { return Search(v2Pos, (int)nRange, 0); }
   Eigen::Vector2d GetCoarsePosAsVector() { return mv2CoarsePos; }
-  void MakeSubPixTemplate() {}
+  // jni/PatchFinder.cc:242-267: start of the refinement (the inverse of JtJ is rebuilt from the template by every device call)
+  void MakeSubPixTemplate() { mv2SubPixPos = mv2CoarsePos; mdMeanDiff = 0.0; }
+  // jni/PatchFinder.cc:272-285
+  bool IterateSubPixToConvergence(KeyFrame& /*kf*/, int nMaxIts) {
+    double pos[2] = {mv2SubPixPos(0), mv2SubPixPos(1)}; int conv = 0;
+    check(ctx_.get(), vslam_pf_subpix(ctx_.get(), stream_, point_, nMaxIts, pos, &mdMeanDiff, &conv, 0));
+    mv2SubPixPos = Eigen::Vector2d(pos[0], pos[1]);
+    return conv != 0;
+  }
+  // jni/PatchFinder.cc:290-350: one iteration; returns the squared pixel update, negative when the patch left the image
+  double IterateSubPix(KeyFrame& /*kf*/) {
+    double pos[2] = {mv2SubPixPos(0), mv2SubPixPos(1)}, upd = -1.0;
+    check(ctx_.get(), vslam_pf_subpix(ctx_.get(), stream_, point_, 1, pos, &mdMeanDiff, 0, &upd));
+    mv2SubPixPos = Eigen::Vector2d(pos[0], pos[1]);
+    return upd;
+  }
+  void SetSubPixPos(const Eigen::Vector2d& v2) { mv2SubPixPos = v2; }
   // Coarse search + inverse-compositional refinement in one device call (the reference splits them; the result is the same)
   bool FindPatchCoarseAndSubPix(const Eigen::Vector2d& v2Pos, KeyFrame& /*kf*/, unsigned int nRange, int nMaxIts) { return Search(v2Pos, (int)nRange, nMaxIts); }
   Eigen::Vector2d GetSubPixPos() { return mv2SubPixPos; }
@@ -423,6 +467,12 @@ class PatchFinder {
     const int n = ctx_.MapSize();
     ints_.resize(8 * (size_t)n); dbl_.resize(32 * (size_t)n);
     check(c, vslam_get_point_states(c, stream_, &ints_[0], &dbl_[0]));
+  }
+  void NoWarp(int point, int kf, int level, int x, int y) {
+    point_ = point;
+    int bad = 0; check(ctx_.get(), vslam_pf_make_template_nowarp(ctx_.get(), stream_, point_, kf, level, x, y, &bad));
+    mbTemplateBad = bad != 0;
+    Pull(); mnSearchLevel = ints_[8 * (size_t)point_ + 1];
   }
   bool Search(const Eigen::Vector2d& v2Pos, int nRange, int nSubPix) {
     vslam_ctx* c = ctx_.get();
@@ -446,8 +496,58 @@ class PatchFinder {
     return mbFound;
   }
   Context& ctx_; int stream_, point_, mnSearchLevel; bool mbFound, mbTemplateBad;
-  Eigen::Matrix2d mm2WarpInverse; Eigen::Vector2d mv2CoarsePos, mv2SubPixPos;
+  Eigen::Matrix2d mm2WarpInverse; Eigen::Vector2d mv2CoarsePos, mv2SubPixPos; double mdMeanDiff = 0.0;
   std::vector<int32_t> ints_; std::vector<double> dbl_;
+};
+
+// The reference's own constructor shape (jni/Tracker.h:43; jni/jni_part.cpp:27-46 builds `new Tracker(800, 480, *mpCamera, *mpMap,
+// *mpMapMaker)`), on the reference's own types -- or anything shaped like them:
+//   ATANCameraT  mvDefaultParams: the five camera parameters (jni/ATANCamera.h:97; the port reads no others)
+//   MapT         vpPoints (MapPoint*: v3WorldPos, v3PixelRight_W, v3PixelDown_W, irCenter, nSourceLevel, pPatchSourceKF), vpKeyFrames
+//                (KeyFrame*: aLevels[0].im), IsGood()                                             (jni/Map.h:29-45, jni/MapPoint.h:33-54)
+//   MapMakerT    kept by reference only (its thread is switched off in the reference)
+// The tracker owns a one-stream context.  Every TrackFrame first brings the device's flat copy of the map up to date: new keyframes are
+// uploaded to source slots (slot = index in vpKeyFrames), new points appended (the reference reads Map::vpPoints live, jni/Tracker.cc:372).
+struct OwnedContext { explicit OwnedContext(Context* c) : own_(c) {} ~OwnedContext() { delete own_; } Context* own_; };
+template <class ATANCameraT, class MapT, class MapMakerT>
+class TrackerOnReferenceTypes : private OwnedContext, public Tracker {
+ public:
+  // bAsShippedRadius: reproduce the int-temporary bug of jni/ATANCamera.cc:70-82 (largest radius 0: no map point is ever in view)
+  TrackerOnReferenceTypes(int width, int height, const ATANCameraT& c, MapT& m, MapMakerT& mm, int max_points = 8192, int max_keyframes = 16, int device = 0, bool bAsShippedRadius = false)
+      : OwnedContext(new Context(width, height, 1, max_points, 11, device, max_keyframes)), Tracker(*own_, 0, Cam13(c, width, height, bAsShippedRadius).v), mMap(m), mMapMaker(mm),
+        mnPointsOnDevice(0), mnKeyFramesOnDevice(0) {
+    if (height % 16 == 0) EnableSBI(Cam13(c, width / 16, height / 16, bAsShippedRadius).v);   // SmallBlurryImage, as the reference's TrackFrame always does
+  }
+  void TrackFrame(cv::Mat& imFrame, cv::Mat& imageColor, bool bDraw) { SyncMap(); Tracker::TrackFrame(imFrame, imageColor, bDraw); }
+  // Flatten what is new in Map::vpKeyFrames / Map::vpPoints onto the device
+  void SyncMap() {
+    vslam_ctx* c = ctx_.get();
+    for (; mnKeyFramesOnDevice < (int)mMap.vpKeyFrames.size(); mnKeyFramesOnDevice++) {
+      cv::Mat& im = mMap.vpKeyFrames[mnKeyFramesOnDevice]->aLevels[0].im;
+      check(c, vslam_upload_source_keyframe(c, mnKeyFramesOnDevice, im.data, (int)im.step));
+    }
+    const int n = (int)mMap.vpPoints.size();
+    if (n > mnPointsOnDevice) {
+      const int k0 = mnPointsOnDevice, m = n - k0;
+      std::vector<double> w(3 * (size_t)m), r(3 * (size_t)m), d(3 * (size_t)m); std::vector<int32_t> irc(2 * (size_t)m), lvl(m), kf(m);
+      for (int k = 0; k < m; k++) {
+        const auto& p = *mMap.vpPoints[k0 + k];
+        for (int q = 0; q < 3; q++) { w[3 * k + q] = p.v3WorldPos(q); r[3 * k + q] = p.v3PixelRight_W(q); d[3 * k + q] = p.v3PixelDown_W(q); }
+        irc[2 * k] = (int32_t)p.irCenter(0); irc[2 * k + 1] = (int32_t)p.irCenter(1); lvl[k] = p.nSourceLevel;
+        int id = 0; while (id < (int)mMap.vpKeyFrames.size() && mMap.vpKeyFrames[id] != p.pPatchSourceKF) id++;
+        if (id == (int)mMap.vpKeyFrames.size()) throw std::runtime_error("vslam_b200: a map point's source keyframe is not in Map::vpKeyFrames");
+        kf[k] = id;
+      }
+      if (k0 == 0) check(c, vslam_set_map(c, m, &w[0], &r[0], &d[0], &irc[0], &lvl[0], &kf[0]));
+      else check(c, vslam_append_map_points(c, m, &w[0], &r[0], &d[0], &irc[0], &lvl[0], &kf[0]));
+      mnPointsOnDevice = n; ctx_.SetMapSize(n);
+    }
+    mbMapGood = mMap.IsGood() && mnPointsOnDevice > 0;
+  }
+  MapT& mMap; MapMakerT& mMapMaker;
+ private:
+  struct Cam13 { double v[13]; Cam13(const ATANCameraT& c, int w, int h, bool shipped) { double p5[5]; for (int k = 0; k < 5; k++) p5[k] = c.mvDefaultParams(k); vslam_camera_from_params(p5, w, h, shipped ? 1 : 0, v); } };
+  int mnPointsOnDevice, mnKeyFramesOnDevice;
 };
 
 // jni/KeyFrame.h:45-50

@@ -133,3 +133,9 @@ def render_sequence(cam, poses, tex_size=2048):
     except ImportError:
         pass
     return np.stack([synth.render_frame(texture(tex_size), cam, p) for p in poses])
+
+
+def map_slice(smap, lo, hi):
+    """Points [lo, hi) of a SyntheticMap as a map of their own."""
+    names = ("world", "pix_right_w", "pix_down_w", "ir_center", "src_level", "center_nc", "one_right_nc", "one_down_nc")
+    return synth.SyntheticMap(**{k: getattr(smap, k)[lo:hi] for k in names})

@@ -1,6 +1,6 @@
 // Test driver for include/vslam_b200_shell.hpp: runs the reference-shaped C++ API (KeyFrame, Tracker, MiniPatch, PatchFinder) on a
 // scene file written by tests/test_gpu_shell.py and prints the results as text; the Python side compares them with the oracle.
-//   shell_driver <scene.bin> trails|track|handoff|stages|mapsearch [map file to write, mapsearch only]
+//   shell_driver <scene.bin> trails|track|reftypes|handoff|stages|mapsearch [map file to write, mapsearch only]
 // scene.bin: int32 W,H,N,F; double params5[5]; u8 src[W*H]; double world[3N], right[3N], down[3N]; int32 irCenter[2N]; int32 level[N];
 //            double pose0[12]; u8 frames[F][W*H]
 #include <cstdio>
@@ -10,6 +10,16 @@
 #include "vslam_b200_shell.hpp"
 
 using namespace vslam_b200;
+
+// Types shaped like the reference's (jni/ATANCamera.h, jni/MapPoint.h, jni/KeyFrame.h, jni/Map.h, jni/MapMaker.h), as far as the tracker reads
+// them: what jni/jni_part.cpp:27-46 hands to `new Tracker(width, height, *mpCamera, *mpMap, *mpMapMaker)`.
+namespace ref_like {
+struct ATANCamera { explicit ATANCamera(const std::string&) : mvDefaultParams(5) {} Eigen::VectorXd mvDefaultParams; };
+struct KeyFrame { Level aLevels[LEVELS]; };
+struct MapPoint { Eigen::Vector3d v3WorldPos, v3PixelDown_W, v3PixelRight_W; Eigen::Vector2d irCenter; int nSourceLevel; KeyFrame* pPatchSourceKF; bool bBad; };
+struct Map { Map() : bGood(false) {} bool IsGood() { return bGood; } std::vector<MapPoint*> vpPoints; std::vector<KeyFrame*> vpKeyFrames; bool bGood; };
+struct MapMaker { MapMaker(Map& m, const ATANCamera&) : mMap(m) {} Map& mMap; };
+}  // namespace ref_like
 
 template <class T> static void rd(std::ifstream& f, T* p, size_t n) { f.read((char*)p, sizeof(T) * n); if (!f) { fprintf(stderr, "short scene file\n"); exit(2); } }
 
@@ -31,6 +41,51 @@ int main(int argc, char** argv) {
   vslam_camera_from_params(p5, W / 16, H / 16, 0, cam_sbi);
   cv::Mat colour(1, 1, CV_8UC4);
   try {
+    if (mode == "reftypes") {   // the reference's constructor shape on reference-shaped types, map read from Map::vpPoints (jni/jni_part.cpp:27-46)
+      ref_like::ATANCamera* mpCamera = new ref_like::ATANCamera("Camera");
+      for (int k = 0; k < 5; k++) mpCamera->mvDefaultParams(k) = p5[k];
+      ref_like::Map* mpMap = new ref_like::Map;
+      ref_like::MapMaker* mpMapMaker = new ref_like::MapMaker(*mpMap, *mpCamera);
+      typedef TrackerOnReferenceTypes<ref_like::ATANCamera, ref_like::Map, ref_like::MapMaker> RefTracker;
+      RefTracker* mpTracker = new RefTracker(W, H, *mpCamera, *mpMap, *mpMapMaker, N > 0 ? N : 1, 4);
+      ref_like::KeyFrame* kf = new ref_like::KeyFrame;
+      kf->aLevels[0].im = cv::Mat(H, W, CV_8UC1, &src[0]);
+      mpMap->vpKeyFrames.push_back(kf);
+      const int n_first = N - N / 4;                      // the last quarter of the map arrives later, like points a map maker adds while tracking
+      for (int k = 0; k < N; k++) {
+        ref_like::MapPoint* p = new ref_like::MapPoint;
+        p->v3WorldPos = Eigen::Vector3d(world[3 * k], world[3 * k + 1], world[3 * k + 2]);
+        p->v3PixelRight_W = Eigen::Vector3d(right[3 * k], right[3 * k + 1], right[3 * k + 2]);
+        p->v3PixelDown_W = Eigen::Vector3d(down[3 * k], down[3 * k + 1], down[3 * k + 2]);
+        p->irCenter = Eigen::Vector2d(irc[2 * k], irc[2 * k + 1]); p->nSourceLevel = lvl[k]; p->pPatchSourceKF = kf; p->bBad = false;
+        if (k < n_first) mpMap->vpPoints.push_back(p); else delete p;
+      }
+      mpMap->bGood = true;
+      SE3 start0; for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) start0.R(i, j) = pose0[4 * i + j]; start0.t(i) = pose0[4 * i + 3]; }
+      mpTracker->SyncMap();
+      mpTracker->SetCurrentPose(start0);
+      for (int k = 0; k < F; k++) {
+        if (k == F / 2) for (int q = n_first; q < N; q++) {
+          ref_like::MapPoint* p = new ref_like::MapPoint;
+          p->v3WorldPos = Eigen::Vector3d(world[3 * q], world[3 * q + 1], world[3 * q + 2]);
+          p->v3PixelRight_W = Eigen::Vector3d(right[3 * q], right[3 * q + 1], right[3 * q + 2]);
+          p->v3PixelDown_W = Eigen::Vector3d(down[3 * q], down[3 * q + 1], down[3 * q + 2]);
+          p->irCenter = Eigen::Vector2d(irc[2 * q], irc[2 * q + 1]); p->nSourceLevel = lvl[q]; p->pPatchSourceKF = kf; p->bBad = false;
+          mpMap->vpPoints.push_back(p);
+        }
+        cv::Mat g(H, W, CV_8UC1, &frames[k][0]);
+        mpTracker->TrackFrame(g, colour, false);
+        const SE3 p = mpTracker->GetCurrentPose();
+        printf("pose");
+        for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) printf(" %.17g", p.R(i, j)); printf(" %.17g", p.t(i)); }
+        printf("\nmsg %s\n", mpTracker->GetMessageForUser().c_str());
+      }
+      // SystemPTAM::onTouchScreen (jni/jni_part.cpp:49-51) writes the member; a C-ABI binding posts the event instead
+      mpTracker->mbUserPressedSpacebar = true;
+      printf("spacebar %d\n", mpTracker->mbUserPressedSpacebar ? 1 : 0);
+      delete mpTracker;
+      return 0;
+    }
     Context ctx(W, H, 1, N > 0 ? N : 1, 11, 0, 4);
     Tracker tracker(ctx, 0, cam);
     SE3 start; for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) start.R(i, j) = pose0[4 * i + j]; start.t(i) = pose0[4 * i + 3]; }
@@ -138,6 +193,19 @@ int main(int argc, char** argv) {
           const bool found = finder.FindPatchCoarseAndSubPix(v2, tracker.mCurrentKF, 10, 8);
           const Eigen::Vector2d c = finder.GetCoarsePosAsVector(), sp = finder.GetSubPixPos();
           printf(" bad %d found %d coarse %.17g %.17g subpix %.17g %.17g", finder.TemplateBad() ? 1 : 0, found ? 1 : 0, c(0), c(1), sp(0), sp(1));
+          if (found) {   // the same in the reference's separate steps: ZMSSDAtPoint at the coarse hit, MakeSubPixTemplate, IterateSubPix x n == IterateSubPixToConvergence
+            cv::Mat& lim = tracker.mCurrentKF.aLevels[level].im;
+            const int cx = (int)((c(0) + 0.5) / (1 << level) - 0.5 + 0.5), cy = (int)((c(1) + 0.5) / (1 << level) - 0.5 + 0.5);
+            const int z = finder.ZMSSDAtPoint(lim, cx, cy);
+            finder.MakeSubPixTemplate();
+            const bool conv = finder.IterateSubPixToConvergence(tracker.mCurrentKF, 8);
+            const Eigen::Vector2d a = finder.GetSubPixPos();
+            finder.SetSubPixPos(c); finder.MakeSubPixTemplate();
+            int its = 0; double u = 1.0;
+            for (; its < 8; its++) { u = finder.IterateSubPix(tracker.mCurrentKF); if (u < 0 || u < 0.03 * 0.03) break; }
+            const Eigen::Vector2d b2 = finder.GetSubPixPos();
+            printf(" zmssd %d maxssd %d conv %d steps %.17g %.17g same %d", z, finder.mnMaxSSD, conv ? 1 : 0, a(0), a(1), (a(0) == b2(0) && a(1) == b2(1)) ? 1 : 0);
+          }
         }
         printf("\n");
       }

@@ -1252,3 +1252,76 @@ def test_track_map_config_switches_no_truncation_and_other_seed():
     ctx1.make_keyframe_lite(f1); ctx1.set_pose(0, synth.IDENTITY_POSE); ctx1.set_motion(0, np.zeros(6), 0.05); ctx1.track_map()
     assert not np.array_equal(ctx1.point_states(0)[0][:, 2], ctx.point_states(0)[0][:, 2])
     ctx.close(); ctx1.close()
+
+
+@pytest.mark.parametrize("P", [11, 8])
+def test_patchfinder_per_object_methods_match_the_oracle(P):
+    """jni/PatchFinder.h:45-121 one object at a time (vslam_pf_*): MakeTemplateCoarseCont alone, ZMSSDAtPoint at chosen positions,
+    MakeSubPixTemplate + IterateSubPix / IterateSubPixToConvergence from a set start, MakeTemplateCoarseNoWarp."""
+    from oracle import oraclebind
+    OL = oraclebind.lib()
+    cam, f0, smap = common.scene()
+    ctx, ow = _ctx(cam, f0, smap, patch_size=P), _orc(cam, f0, smap, P=P)
+    f1, _ = common.frame_at(cam, np.array(synth.CONFIG1_TWIST) * 0.6)
+    start = synth.se3_exp(np.array(synth.CONFIG1_TWIST) * 0.45)
+    okf = ow.make_current_kf(f1); ctx.make_keyframe_lite(f1)
+    ctx.set_pose(0, start); ow.set_pose(start)
+    ctx.project_all(); ow.L.orc_tracker_project_all(ow.tracker)
+    oi, od = ow.point_states()
+    ctx.set_point_projection(0, od[:, 0:2], od[:, 11:15], oi[:, 1])
+    idx = np.nonzero(oi[:, 1] >= 0)[0].astype(np.int32)
+    # the oracle's templates / coarse positions of all points (one batched search on its side only)
+    ow.L.orc_tracker_search_for_points(ow.tracker, idx, len(idx), 10, 0)
+    oi, od = ow.point_states()
+    fnd = idx[oi[idx][:, 3] == 1]
+    assert len(fnd) > 100
+    rng = np.random.default_rng(5)
+    for k in [int(v) for v in rng.choice(fnd, 12, replace=False)]:
+        level = int(oi[k, 1])
+        # (1) MakeTemplateCoarseCont by itself: template pixels and sums
+        assert ctx.pf_make_template(0, k) is False
+        gt, gs, gq = ctx.point_template(0, k); ot, os_, oq = ow.point_template(k)
+        assert np.array_equal(gt, ot) and (gs, gq) == (os_, oq), f"template of point {k}"
+        # (2) ZMSSDAtPoint at positions around the coarse hit, inside and outside the border
+        lw, lh = ctx.level_dims(level)
+        cx, cy = [int((v + 0.5) / (1 << level) - 0.5 + 0.5) for v in od[k, 30:32]]
+        xy = np.array([[cx + dx, cy + dy] for dx in (-3, 0, 2) for dy in (-2, 0, 3)] + [[1, 1], [lw - 1, lh - 1], [P // 2, P // 2], [lw - 1 - P // 2, lh - 1 - P // 2]], dtype=np.int32)
+        tm = np.ascontiguousarray(ot.reshape(-1))
+        want = np.array([OL.orc_zmssd(okf.h, level, tm, P, int(x), int(y)) for x, y in xy], dtype=np.int32)
+        assert np.array_equal(ctx.pf_zmssd_at(0, k, level, xy), want), f"ZMSSD of point {k}"
+        assert want[9] == P * P * 500 + 1 and want[10] == P * P * 500 + 1
+        # (3) IterateSubPixToConvergence from the coarse position, and the same in single IterateSubPix steps
+        coarse = np.ascontiguousarray(od[k, 30:32])
+        opos = np.zeros(2)
+        ok = OL.orc_subpix(okf.h, level, tm, P, coarse, 8, opos, None)
+        gpos, md, conv, last = ctx.pf_subpix(0, k, 8, coarse)
+        assert conv == bool(ok)
+        assert np.abs(gpos - opos).max() <= 1e-9, (k, gpos, opos)
+        pos, md1, n_it = coarse.copy(), 0.0, 0
+        for _ in range(8):
+            pos, md1, c1, last1 = ctx.pf_subpix(0, k, 1, pos, md1); n_it += 1
+            if last1 < 0 or c1:
+                break
+        assert np.array_equal(pos, gpos) and md1 == md and c1 == conv, "single steps == run to convergence"
+    # off the image: IterateSubPix returns a negative value
+    _, _, conv, last = ctx.pf_subpix(0, int(fnd[0]), 3, np.array([-50.0, -50.0]))
+    assert conv is False and last < 0
+    # (4) MakeTemplateCoarseNoWarp: the P x P pixels of the source keyframe level, border rule P / 2 + 1
+    k = int(fnd[1])
+    for level, (x, y) in ((0, (100, 77)), (2, (31, 40)), (1, (P // 2 + 1, P // 2 + 1)), (1, (P // 2, 50))):
+        src = ow.src_kf.pixels(level)
+        bad = ctx.pf_make_template_nowarp(0, k, 0, level, x, y)
+        h, w = src.shape
+        b = P // 2 + 1
+        assert bad == (not (x >= b and y >= b and x < w - b and y < h - b))
+        if not bad:
+            gt, gs, gq = ctx.point_template(0, k)
+            want_t = src[y - P // 2:y - P // 2 + P, x - P // 2:x - P // 2 + P]
+            assert np.array_equal(gt, want_t) and gs == int(want_t.astype(np.int64).sum()) and gq == int((want_t.astype(np.int64) ** 2).sum())
+            gi, _ = ctx.point_states(0)
+            assert gi[k, 1] == level
+    # user events (jni/jni_part.cpp:49-51)
+    assert ctx.take_user_event(0) == 0
+    ctx.user_event(0); ctx.user_event(0)
+    assert ctx.take_user_event(0) == 1 and ctx.take_user_event(0) == 0
+    ctx.close()

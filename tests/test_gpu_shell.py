@@ -151,7 +151,7 @@ def test_shell_stage_functions_and_patchfinder_match_the_oracle(driver, tmp_path
     ow.make_current_kf(f1)
     ow.L.orc_tracker_project_all(ow.tracker)
     ints, dbl = ow.point_states()
-    n_pf = 0
+    n_pf = n_steps = 0
     for l in out:
         w = l.split()
         if w[0] != "pf":
@@ -172,8 +172,14 @@ def test_shell_stage_functions_and_patchfinder_match_the_oracle(driver, tmp_path
             if found:
                 coarse = np.array([float(w[k + 5]), float(w[k + 6])]); sub = np.array([float(w[k + 8]), float(w[k + 9])])
                 assert np.array_equal(coarse, d2[pt, 30:32]) and np.abs(sub - d2[pt, 2:4]).max() <= 1e-6
+                # the reference's separate steps (ZMSSDAtPoint, MakeSubPixTemplate, IterateSubPix / IterateSubPixToConvergence, SetSubPixPos)
+                z = w.index("zmssd")
+                assert 0 <= int(w[z + 1]) < int(w[z + 3]) and int(w[z + 5]) == 1 and int(w[z + 10]) == 1, l
+                steps = np.array([float(w[z + 7]), float(w[z + 8])])
+                assert np.abs(steps - sub).max() <= 1e-9, (steps, sub)
+                n_steps += 1
             n_pf += 1
-    assert n_pf >= 8
+    assert n_pf >= 8 and n_steps >= 4
     # SearchForPoints / CalcPoseUpdate on every third point with a valid level
     ow2 = oraclebind.OrcWorld(cam, f0, smap)
     ow2.set_pose(start)
@@ -250,3 +256,31 @@ def test_shell_mapmaker_searches_match_the_oracle(driver, tmp_path):
     assert [int(v) for v in mf[1:]] == [smap.n, 1, 0, smap.n]
     back = common.mapfile_unpack((tmp_path / "shell.vsmap").read_bytes())
     assert np.array_equal(back["keyframes"][0][2], f0) and np.array_equal(back["points"]["world"], smap.world)
+
+
+def test_shell_reference_shaped_tracker_reads_the_map_like_the_reference(driver, tmp_path):
+    """`new Tracker(width, height, *mpCamera, *mpMap, *mpMapMaker)` as jni/jni_part.cpp:27-46 writes it, on reference-shaped types: the adapter
+    flattens Map::vpPoints / vpKeyFrames itself, picks up the points a map maker pushes while tracking, and tracks like the oracle."""
+    from oracle import oraclebind
+    cam, f0, smap = common.scene(n_points=600)
+    frames = [synth.render_frame(common.texture(), cam, synth.stream_pose(5 * k, 3)) for k in range(1, 7)]
+    scene = str(tmp_path / "reftypes.bin")
+    _write_scene(scene, cam, f0, smap, synth.IDENTITY_POSE, frames)
+    out = _run(driver, scene, "reftypes")
+    poses = [np.array([float(x) for x in l.split()[1:]]).reshape(3, 4) for l in out if l.startswith("pose")]
+    msgs = [l[4:] for l in out if l.startswith("msg ")]
+    n_first = smap.n - smap.n // 4
+    first, rest = common.map_slice(smap, 0, n_first), common.map_slice(smap, n_first, smap.n)
+    ow = oraclebind.OrcWorld(cam, f0, first)
+    ow.set_pose(synth.IDENTITY_POSE)
+    ow.L.orc_tracker_enable_sbi(ow.tracker, synth.Camera(cam.width // 16, cam.height // 16).scalars())
+    n_map = n_first
+    for k, fr in enumerate(frames):
+        if k == len(frames) // 2:
+            ow.append_points(rest); n_map = smap.n
+        ow.L.orc_tracker_track_frame(ow.tracker, np.ascontiguousarray(fr), cam.width, cam.height, cam.width)
+        assert np.abs(poses[k] - ow.get_pose()).max() <= 1e-8, k
+        a, f, q, lost, dc = ow.counters()
+        exp = "Tracking Map, quality " + {2: "good.", 1: "poor.", 0: "bad."}[q] + " Found:" + "".join(f" {f[l]}/{a[l]}" for l in range(4)) + f" Map: {n_map}P"
+        assert msgs[k] == exp, (msgs[k], exp)
+    assert out[-1] == "spacebar 1"

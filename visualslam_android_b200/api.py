@@ -53,6 +53,7 @@ ABI_SYMBOLS = [
     "vslam_project_all", "vslam_set_point_projection", "vslam_set_lists", "vslam_clear_counters", "vslam_search_for_points", "vslam_refind", "vslam_get_refind_results", "vslam_epipolar_search", "vslam_project_and_derivs", "vslam_calc_jacobians",
     "vslam_calc_pose_update", "vslam_track_map", "vslam_track_frame", "vslam_track_frame_dev", "vslam_track_frame_async", "vslam_wait_step", "vslam_debug_atan", "vslam_debug_atan_dd", "vslam_debug_dp4a_peak", "vslam_kernel_launches", "vslam_set_timing", "vslam_get_stage_times",
     "vslam_get_search_stats", "vslam_make_keyframe_from_source", "vslam_append_map_points", "vslam_set_keyframe_policy", "vslam_get_keyframe_requests", "vslam_add_keyframe_from_stream", "vslam_epipolar_make_points", "vslam_map_file_info", "vslam_save_map_file", "vslam_load_map_file", "vslam_export_map_text",
+    "vslam_pf_make_template", "vslam_pf_make_template_nowarp", "vslam_pf_zmssd_at", "vslam_pf_subpix", "vslam_user_event", "vslam_take_user_event",
 ]
 
 _lib = None
@@ -144,6 +145,12 @@ def load():
     sig("vslam_clear_counters", i, vp)
     sig("vslam_search_for_points", i, vp, i, i)
     sig("vslam_refind", i, vp, i, i)
+    sig("vslam_pf_make_template", i, vp, i, i, pi)
+    sig("vslam_pf_make_template_nowarp", i, vp, i, i, i, i, i, i, pi)
+    sig("vslam_pf_zmssd_at", i, vp, i, i, i, i, vp, vp)
+    sig("vslam_pf_subpix", i, vp, i, i, i, vp, pd, pi, pd)
+    sig("vslam_user_event", i, vp, i, i)
+    sig("vslam_take_user_event", i, vp, i, pi)
     sig("vslam_epipolar_search", i, vp, i, i, i, i, vp, vp, vp, d, d, d, vp, vp, vp, vp)
     sig("vslam_get_refind_results", i, vp, i, vp, vp, i, pi)
     sig("vslam_project_and_derivs", i, vp, i)
@@ -510,6 +517,41 @@ class Context:
 
     def search_for_points(self, rng, subpix_its):
         self._ck(self.L.vslam_search_for_points(self.h, rng, subpix_its))
+
+    # ---- PatchFinder, one object at a time (jni/PatchFinder.h:45-121; the slow path)
+    def pf_make_template(self, s, point):
+        """MakeTemplateCoarseCont of one point with the warp of the last projection; returns mbTemplateBad."""
+        bad = C.c_int()
+        self._ck(self.L.vslam_pf_make_template(self.h, s, point, C.byref(bad)))
+        return bool(bad.value)
+
+    def pf_make_template_nowarp(self, s, point, src_kf, level, x, y):
+        """MakeTemplateCoarseNoWarp(KeyFrame&, nLevel, x, y); returns mbTemplateBad."""
+        bad = C.c_int()
+        self._ck(self.L.vslam_pf_make_template_nowarp(self.h, s, point, src_kf, level, int(x), int(y), C.byref(bad)))
+        return bool(bad.value)
+
+    def pf_zmssd_at(self, s, point, level, xy):
+        """ZMSSDAtPoint of the point's template at the (x, y) rows of `xy` on `level` of the stream's current keyframe."""
+        xy = np.ascontiguousarray(xy, dtype=np.int32).reshape(-1, 2)
+        out = np.empty(len(xy), dtype=np.int32)
+        self._ck(self.L.vslam_pf_zmssd_at(self.h, s, point, level, len(xy), xy.ctypes.data, out.ctypes.data))
+        return out
+
+    def pf_subpix(self, s, point, max_its, pos, mean_diff=0.0):
+        """MakeSubPixTemplate's inverse + up to max_its IterateSubPix from `pos` (level-zero pixels); returns (pos, mean_diff, converged, last_update_sq)."""
+        p = np.array(pos, dtype=np.float64)
+        md, conv, last = C.c_double(mean_diff), C.c_int(), C.c_double()
+        self._ck(self.L.vslam_pf_subpix(self.h, s, point, max_its, p.ctypes.data, C.byref(md), C.byref(conv), C.byref(last)))
+        return p, md.value, bool(conv.value), last.value
+
+    def user_event(self, s, event=1):
+        self._ck(self.L.vslam_user_event(self.h, s, event))
+
+    def take_user_event(self, s):
+        v = C.c_int()
+        self._ck(self.L.vslam_take_user_event(self.h, s, C.byref(v)))
+        return v.value
 
     def refind(self, rng=4, subpix_its=8):
         """MapMaker::ReFind_Common for every (stream, listed point) pair (set_lists first)."""

@@ -10,10 +10,10 @@ if [ -f "$OUT" ] && [ "$OUT" -nt "$newest" ]; then echo "build: libvslam_b200.so
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=false -Xcompiler -fPIC -I$HERE/../../include -I$HERE ${VSLAM_NVCC_EXTRA:-}"
 mkdir -p "$HERE/_build"
 pids=()
-for f in pyramid_fast track pose_fast search_fast keyframe_rest sbi mapfile api; do
+for f in pyramid_fast track pose_fast search_fast patchfinder_ops keyframe_rest sbi mapfile api; do
   $NVCC $FLAGS -c "$HERE/$f.cu" -o "$HERE/_build/$f.o" &
   pids+=($!)
 done
 for p in "${pids[@]}"; do wait "$p"; done
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT" "$HERE/_build/pyramid_fast.o" "$HERE/_build/track.o" "$HERE/_build/pose_fast.o" "$HERE/_build/search_fast.o" "$HERE/_build/keyframe_rest.o" "$HERE/_build/sbi.o" "$HERE/_build/mapfile.o" "$HERE/_build/api.o"
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT" "$HERE/_build/pyramid_fast.o" "$HERE/_build/track.o" "$HERE/_build/pose_fast.o" "$HERE/_build/search_fast.o" "$HERE/_build/patchfinder_ops.o" "$HERE/_build/keyframe_rest.o" "$HERE/_build/sbi.o" "$HERE/_build/mapfile.o" "$HERE/_build/api.o"
 echo "build: wrote $OUT"

@@ -56,6 +56,7 @@ __device__ __forceinline__ bool search_plan(const Dev& D, const StreamState* st,
 __device__ __forceinline__ uint32_t ldg_ordered(const uint32_t* p) { uint32_t v; asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
 
 constexpr int kSearchRefindF = 1;   // sflags: MapMaker::ReFind_Common's variant (jni/MapMaker.cc:967-1036), see k_search
+constexpr int kSearchTemplateOnlyF = 2;   // sflags: stop after MakeTemplateCoarseCont (vslam_pf_make_template, the per-object PatchFinder path)
 
 template <int PT>
 __global__ void __launch_bounds__(kFW * 32, VS_SEARCH_MINB) k_search_fast(Dev D, int mode, int range_arg, int subpix_arg, int sflags) {
@@ -165,6 +166,7 @@ __global__ void __launch_bounds__(kFW * 32, VS_SEARCH_MINB) k_search_fast(Dev D,
     }
     __syncwarp();
   }
+  if (sflags & kSearchTemplateOnlyF) { if (alive && j == 0) D.ps.flags[gi] = flags; return; }
   if (alive && (flags & F_TBAD)) {   // jni/Tracker.cc:637-640
     if (j == 0) D.ps.flags[gi] = flags & ~(F_INIMAGE | F_FOUND);
     alive = false;
@@ -474,7 +476,7 @@ int vs_launch_search_fast(vslam_ctx* ctx, int which, int range, int subpix, int 
   ctx->launches++;
   // sub-pixel refinement: every entry of the coarse stage / of an explicit list with subpix > 0, the top-level entries of the fine stage
   const bool any_subpix = which == 0 ? subpix > 0 : (which == 1 ? ctx->params.coarse_subpix_its > 0 : ctx->params.fine_subpix_its_top_level > 0);
-  if (any_subpix) {
+  if (any_subpix && !(sflags & 2)) {
     dim3 g2(std::min((max_entries + kFW * kGW - 1) / (kFW * kGW), 16), ctx->cur_cnt);
     k_subpix<<<g2, kFW * 32, 0, ctx->stream>>>(D, which, range, subpix, sflags);
     ctx->launches++;

@@ -145,6 +145,8 @@ struct vslam_ctx {
   // optional per-kernel timing with CUDA events on ctx->stream (vslam_set_timing)
   bool timing; std::vector<cudaEvent_t> ev_pool; std::vector<int> ev_stage; size_t ev_used;
   size_t smem_attr[4] = {0, 0, 0, 0};   // dynamic shared memory already opted into, per kernel (cudaFuncSetAttribute once, not per frame)
+  void* pf_buf = nullptr; size_t pf_cap = 0;   // scratch of the per-object PatchFinder calls (patchfinder_ops.cu)
+  std::vector<int> user_events;                // [S] pending user events (vslam_user_event)
   bool lists_stale = false;      // the last tracked frame left corner bitmasks only: corner lists / row LUTs are built on demand (vs_ensure_lists)
   std::string err;
 };
