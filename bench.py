@@ -136,11 +136,8 @@ def short_leg(name, size, stream_ids, K, Wm, device, stream, frame_step=None, po
             frames[k - 1, s0:s0 + rb] = render_frames_torch(tex_t, cam, poses[s0:s0 + rb, k], dev)
     ctx = api.Context(w, h, n_streams=S, max_points=smap.n, device=device, cuda_stream=stream.cuda_stream)
     ctx.set_camera(cam.scalars())
-    sbi = (h % 16 == 0)
-    if sbi:
-        ctx.enable_sbi(synth.Camera(w // 16, h // 16).scalars())
-    else:
-        ctx.set_params(use_sbi=0)
+    sbi = True                   # (heights that are not a multiple of 16 -- 1080p -- take cv::resize's general bilinear path for the thumbnail)
+    ctx.enable_sbi(synth.Camera(w // 16, h // 16).scalars())
     ctx.upload_source_keyframe(f0)
     ctx.set_map(smap.world, smap.pix_right_w, smap.pix_down_w, smap.ir_center, smap.src_level)
     step = 0
@@ -497,7 +494,7 @@ def main():
     ap.add_argument("--host-alloc", default="pinned", choices=["pinned", "wc"], help="how the e2e leg's host frame pool is allocated")
     ap.add_argument("--groups", type=int, default=0, help="vslam_params.stream_groups (0 = library default)")
     ap.add_argument("--frame", default="vga", choices=["vga"] + sorted(FRAME_CONFIGS), help="frame size of the whole-TrackFrame workload: vga (the headline "
-                    "config), 1080p (5000 map points, 148 streams per GPU; no SmallBlurryImage: 1080 is not a multiple of 16) or 4k (20000 points, 148 streams)")
+                    "config), 1080p (5000 map points, 148 streams per GPU) or 4k (20000 points, 148 streams)")
     ap.add_argument("--sweep", action="store_true", help="SURVEY §8(d) config 5: 4K frames, batch-size sweep of pyramid+FAST and points x range sweep of the patch search (one GPU)")
     ap.add_argument("--cpu-stages", action="store_true", help="SURVEY §8(d)(i): per-stage CPU times of config 1 (reference build and oracle port), no GPU work")
     args = ap.parse_args()
@@ -513,7 +510,7 @@ def main():
         POOL = int(max(4, min(24, 6e9 // (args.streams * W * H))))      # keep the resident pool (and its pinned host copy) under ~6 GB
         args.scaling = "weak"; args.no_extra_legs = True
         WORKLOAD = (f"{args.frame}: {args.streams} independent synthetic {W}x{H} camera streams per GPU, {N_POINTS} map points, full TrackFrame-equivalent per frame "
-                    f"(MaxPatchesPerFrame = 1000 as in the reference{'' if H % 16 == 0 else '; SmallBlurryImage off: the height is not a multiple of 16'}), P=11")
+                    f"(MaxPatchesPerFrame = 1000 as in the reference), P=11")
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -616,13 +613,10 @@ def main():
     prm = {}
     if args.groups:
         prm["stream_groups"] = args.groups
-    if H % 16:
-        prm["use_sbi"] = 0                                         # 1080p: cv::resize of level 3 is not an exact 2:1, the motion model runs without the SBI rotation
     if prm:
         ctx.set_params(**prm)
     ctx.set_camera(cam.scalars())
-    if H % 16 == 0:
-        ctx.enable_sbi(synth.Camera(W // 16, H // 16).scalars())   # SmallBlurryImage + CalcSBIRotation on the device, like the reference's TrackFrame
+    ctx.enable_sbi(synth.Camera(W // 16, H // 16).scalars())       # SmallBlurryImage + CalcSBIRotation on the device, like the reference's TrackFrame
     ctx.upload_source_keyframe(f0)
     ctx.set_map(smap.world, smap.pix_right_w, smap.pix_down_w, smap.ir_center, smap.src_level)
 

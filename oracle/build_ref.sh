@@ -22,7 +22,8 @@ if [ ! -d "$REF" ]; then
   echo "build_ref: $REF not present; keeping prebuilt $OUT/libvslam_ref.so (if any)"; exit 0
 fi
 if [ "$OUT/libvslam_ref.so" -nt "$HERE/ref_harness.cc" ] && [ "$OUT/libvslam_ref.so" -nt "$HERE/shim/Eigen/Dense" ] \
-   && [ "$OUT/libvslam_ref.so" -nt "$HERE/shim/opencv2/core/core.hpp" ] && [ "$OUT/libvslam_ref.so" -nt "$HERE/build_ref.sh" ]; then
+   && [ "$OUT/libvslam_ref.so" -nt "$HERE/shim/opencv2/core/core.hpp" ] && [ "$OUT/libvslam_ref.so" -nt "$HERE/build_ref.sh" ] \
+   && [ "$OUT/libvslam_ref.so" -nt "$HERE/shim/cv_resize_linear_u8.h" ]; then
   echo "build_ref: up to date"; exit 0
 fi
 TMP="$(mktemp -d "${TMPDIR:-/tmp}/vslam_ref.XXXXXX")"

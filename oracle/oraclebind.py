@@ -62,6 +62,7 @@ def lib():
     sig("orc_se3_ln", None, _f64p, _f64p)
     sig("orc_se3_mul", None, _f64p, _f64p, _f64p)
     sig("orc_se3_inverse", None, _f64p, _f64p)
+    sig("orc_resize_linear_u8", None, _u8p, i, i, _u8p, i, i)
     sig("orc_make_template", i, vp, i, _i32p, i, _f64p, _u8p, pi, pi)
     sig("orc_zmssd", i, vp, i, _u8p, i, i, i)
     sig("orc_find_patch_coarse", i, vp, i, _u8p, i, d, d, u, _f64p, pi, C.POINTER(C.c_long))

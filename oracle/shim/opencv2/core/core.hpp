@@ -3,15 +3,16 @@
 // the reference's tracking front-end.  TEST INFRASTRUCTURE
 // ONLY — lets the unmodified reference sources compile into oracle/_ref/ in an
 // image without OpenCV headers.  Third-party arithmetic restated here:
-//   cv::resize      exact 2:1 only: (a+b+c+d+2)>>2  (what OpenCV's INTER_LINEAR
-//                   gives for an exact half-size u8 image; probed against
-//                   cv2 4.13 in tests/test_oracle_cpu.py).  Anything else aborts.
+//   cv::resize      INTER_LINEAR on CV_8UC1, restated in cv_resize_linear_u8.h; exact 2:1: (a+b+c+d+2)>>2  (what OpenCV's INTER_LINEAR
+//                   gives for an exact half-size u8 image); other sizes: OpenCV's fixed-point bilinear.  Pinned against
+//                   cv2 4.13 in tests/test_oracle_golden.py.
 //   cv::cvtColor    CV_RGB2BGR on 3/4-channel u8 -> 3-channel.
 //   cv::GaussianBlur float, separable, BORDER_REPLICATE, OpenCV's
 //                   getGaussianKernel weights (only the SmallBlurryImage path).
 #ifndef VSLAM_ORACLE_CV_SHIM_CORE
 #define VSLAM_ORACLE_CV_SHIM_CORE
 
+#include "../../cv_resize_linear_u8.h"
 #include <cassert>
 #include <cmath>
 #include <cstdio>
@@ -110,23 +111,11 @@ class Mat {
   std::shared_ptr<std::vector<unsigned char> > buf_;
 };
 
-inline void resize(const Mat& src, Mat& dst, Size dsize) {
-  if (src.type() != CV_8UC1 || dsize.width * 2 > src.cols || dsize.height * 2 > src.rows ||
-      dsize.width != src.cols / 2 || dsize.height != src.rows / 2) {
-    fprintf(stderr, "cv shim: resize supports only exact 2:1 u8 (got %dx%d -> %dx%d)\n", src.cols, src.rows, dsize.width, dsize.height);
-    abort();
-  }
-  if ((src.cols & 1) || (src.rows & 1)) {
-    fprintf(stderr, "cv shim: resize of odd-sized %dx%d is a true bilinear resample in OpenCV; not restated\n", src.cols, src.rows);
-    abort();
-  }
-  dst.create(dsize.height, dsize.width, CV_8UC1);
-  for (int y = 0; y < dsize.height; y++) {
-    const unsigned char* a = src.data + (size_t)(2 * y) * src.step;
-    const unsigned char* b = a + src.step;
-    unsigned char* d = dst.data + (size_t)y * dst.step;
-    for (int x = 0; x < dsize.width; x++) d[x] = (unsigned char)((a[2 * x] + a[2 * x + 1] + b[2 * x] + b[2 * x + 1] + 2) >> 2);
-  }
+inline void resize(const Mat& src, Mat& dst, Size dsize) {   // INTER_LINEAR, CV_8UC1: cv_resize_linear_u8.h
+  if (src.type() != CV_8UC1) { fprintf(stderr, "cv shim: resize supports CV_8UC1 only\n"); abort(); }
+  Mat out; out.create(dsize.height, dsize.width, CV_8UC1);
+  cv_restated::resize_linear_u8(src.data, src.cols, src.rows, src.step, out.data, dsize.width, dsize.height, out.step);
+  dst = out;
 }
 
 inline void cvtColor(const Mat& src, Mat& dst, int code) {

@@ -11,6 +11,7 @@
 // Every function cites the reference file:line it follows.  Floating-point expressions keep the
 // reference's evaluation order (left to right as written; no FMA: build with -ffp-contract=off).
 // No Eigen, no OpenCV: POD arrays only.  Poses are row-major 3x4 [R|t] (camera-from-world).
+#include "shim/cv_resize_linear_u8.h"
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
@@ -707,8 +708,10 @@ void gaussian_blur(std::vector<float>& im, int W, int H, int n /* taps: 9 or 17 
 void sbi_make(SBI& s, const OKeyFrame& kf, double dBlur) {
   const Image& l3 = kf.lev[3].im;
   s.w = l3.w / 2; s.h = l3.h / 2; s.madeJacs = false;
-  Image sm; half_sample(l3, sm);   // cv::resize to exactly half: (a+b+c+d+2)>>2 (requires even level-3 dimensions)
-  s.small = sm.px;
+  // cv::resize(level 3, mimSmall, (cols / 2, rows / 2)), INTER_LINEAR (jni/SmallBlurryImage.cc:22-30): exactly half = (a+b+c+d+2)>>2, odd level-3
+  // sizes (1080p: 240 x 135 -> 120 x 67) = OpenCV's fixed-point bilinear; restated in shim/cv_resize_linear_u8.h
+  s.small.assign((size_t)s.w * s.h, 0);
+  cv_restated::resize_linear_u8(&l3.px[0], l3.w, l3.h, (size_t)l3.w, &s.small[0], s.w, s.h, (size_t)s.w);
   unsigned nSum = 0; for (size_t i = 0; i < s.small.size(); i++) nSum += s.small[i];
   const float fMean = ((float)nSum) / (s.h * s.w);
   s.tmpl.resize((size_t)s.w * s.h);
@@ -1395,6 +1398,7 @@ void orc_tracker_set_lost(void* t_, int lost_frames, int quality) { OTracker* t 
 void orc_tracker_enable_sbi(void* t_, const double* sbi_cam13) { OTracker* t = (OTracker*)t_; t->computeSBI = true; t->useSBI = true; t->sbiCam = cam_from13(sbi_cam13); }
 void orc_tracker_get_sbi_rot(void* t_, double* v6) { memcpy(v6, ((OTracker*)t_)->sbiRot, sizeof(double) * 6); }
 // stand-alone SBI pieces for the tests
+void orc_resize_linear_u8(const uint8_t* src, int sw, int sh, uint8_t* dst, int dw, int dh) { cv_restated::resize_linear_u8(src, sw, sh, (size_t)sw, dst, dw, dh, (size_t)dw); }
 void* orc_sbi_create(void* kf, double blur) { SBI* s = new SBI(); sbi_make(*s, *(OKeyFrame*)kf, blur); return s; }
 void orc_sbi_destroy(void* s) { delete (SBI*)s; }
 void orc_sbi_dims(void* s, int* w, int* h) { *w = ((SBI*)s)->w; *h = ((SBI*)s)->h; }

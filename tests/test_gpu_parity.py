@@ -546,10 +546,13 @@ def test_long_sequence_stays_consistent_with_oracle():
     ctx.close()
 
 
-def test_track_frame_with_on_device_sbi():
+@pytest.mark.parametrize("size", [(640, 480), (640, 360), (320, 200)])
+def test_track_frame_with_on_device_sbi(size):
     """f1: SmallBlurryImage + CalcSBIRotation on the device: vslam_track_frame is then the reference's whole TrackFrame (good-map
-    branch).  The oracle side is the restatement that tests/test_oracle_vs_ref.py pins bit-for-bit to the unmodified TrackFrame."""
-    cam, f0, smap = common.scene()
+    branch).  The oracle side is the restatement that tests/test_oracle_vs_ref.py pins bit-for-bit to the unmodified TrackFrame.
+    640 x 360 and 320 x 200 have odd level-3 heights (45, 25): cv::resize to (cols / 2, rows / 2) is then OpenCV's general fixed-point
+    bilinear, not the exact half-sample -- the 1080p case (240 x 135 -> 120 x 67)."""
+    cam, f0, smap = common.scene(width=size[0], height=size[1], n_points=1000 if size[0] == 640 else 400)
     S, K = 3, 6
     sbi_cam = synth.Camera(cam.width // 16, cam.height // 16)
     ctx = _ctx(cam, f0, smap, n_streams=S)

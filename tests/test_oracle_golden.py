@@ -210,3 +210,26 @@ def test_fast10_is_the_segment_test():
     lut = kf.row_lut(0)
     ys = kf.corners(0)[:, 1]
     assert np.array_equal(lut, np.searchsorted(ys, np.arange(Hh), side="left"))   # LUT[y] = #corners with row < y
+
+
+def test_restated_cv_resize_linear_matches_opencv_golden_vectors():
+    """oracle/shim/cv_resize_linear_u8.h (the cv::resize of SmallBlurryImage::MakeFromKF, jni/SmallBlurryImage.cc:22-30, for level-3 sizes that
+    are not even, e.g. 1080p) against vectors made by the real OpenCV (tests/golden/make_resize_golden.py), and live against cv2 when present."""
+    import os
+    from oracle import oraclebind
+    L = oraclebind.lib()
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "resize_linear.npz"))
+    for k, (sw, sh, dw, dh) in enumerate(g["sizes"]):
+        got = np.zeros((dh, dw), dtype=np.uint8)
+        L.orc_resize_linear_u8(np.ascontiguousarray(g[f"src{k}"]), int(sw), int(sh), got, int(dw), int(dh))
+        assert np.array_equal(got, g[f"dst{k}"]), (sw, sh, dw, dh)
+    try:
+        import cv2
+    except ImportError:
+        return
+    rng = np.random.default_rng(3)
+    for sw, sh, dw, dh in [(240, 135, 120, 67), (17, 9, 8, 4), (30, 16, 45, 24), (240, 135, 120, 68), (160, 120, 80, 60)]:
+        src = rng.integers(0, 256, (sh, sw), dtype=np.uint8)
+        got = np.zeros((dh, dw), dtype=np.uint8)
+        L.orc_resize_linear_u8(src, sw, sh, got, dw, dh)
+        assert np.array_equal(got, cv2.resize(src, (dw, dh))), (sw, sh, dw, dh)

@@ -460,9 +460,12 @@ def test_gaussian_blur_stand_in_is_close_to_opencv():
     assert np.abs(want - ot).max() < 2e-4, np.abs(want - ot).max()
 
 
-def test_track_frame_with_sbi_is_the_reference_trackframe():
-    """The unmodified Tracker::TrackFrame (SmallBlurryImage included) against the restatement with its on-board SBI."""
-    cam, f0, smap, rw, ow = _worlds()
+@pytest.mark.parametrize("size", [(640, 480), (640, 360)])
+def test_track_frame_with_sbi_is_the_reference_trackframe(size):
+    """The unmodified Tracker::TrackFrame (SmallBlurryImage included) against the restatement with its on-board SBI.  640 x 360: level 3 is
+    80 x 45, so SmallBlurryImage::MakeFromKF's cv::resize is the general bilinear one (the stand-in OpenCV and the restatement share
+    oracle/shim/cv_resize_linear_u8.h, which tests/test_oracle_golden.py pins to the real cv2)."""
+    cam, f0, smap, rw, ow = _worlds(width=size[0], height=size[1])
     rw.L.ref_sbi_reset_size()
     rw.L.ref_srand(1)
     ow.L.orc_tracker_enable_sbi(ow.tracker, synth.Camera(cam.width // 16, cam.height // 16).scalars())

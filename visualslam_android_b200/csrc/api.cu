@@ -208,7 +208,7 @@ void vslam_destroy(vslam_ctx* ctx) {
   cudaFree(ctx->l0_alt);
   cudaFree(ctx->rest_scores); cudaFree(ctx->rest_max); cudaFree(ctx->rest_cand); cudaFree(ctx->rest_cand_score); cudaFree(ctx->rest_counts);
   cudaFree(ctx->snap_img); cudaFree(ctx->snap_corners); cudaFree(ctx->snap_lut);
-  cudaFree(ctx->sbi_tmpl); cudaFree(ctx->sbi_scratch); cudaFree(ctx->sbi_jac); cudaFree(ctx->sbi_small); cudaFree(ctx->sbi_have);
+  cudaFree(ctx->sbi_resize_tab); cudaFree(ctx->sbi_tmpl); cudaFree(ctx->sbi_scratch); cudaFree(ctx->sbi_jac); cudaFree(ctx->sbi_small); cudaFree(ctx->sbi_have);
   if (ctx->status_pin) cudaFreeHost(ctx->status_pin);
   delete[] ctx->l0_ptr_host; delete[] ctx->l0_stride_host;
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -263,7 +263,28 @@ int vslam_set_params(vslam_ctx* ctx, const vslam_params* p) {
 int vslam_enable_sbi(vslam_ctx* ctx, const double* c) {
   if (!ctx || !c) return VSLAM_E_INVALID;
   const LevelDesc& L3 = ctx->lev[3];
-  if ((L3.w & 1) || (L3.h & 1)) { ctx->err = "SmallBlurryImage needs even level-3 dimensions (cv::resize to exactly half); height % 16 != 0 here"; return VSLAM_E_INVALID; }
+  {   // cv::resize(level 3, (cols / 2, rows / 2)) (jni/SmallBlurryImage.cc:22-30): exactly half unless a level-3 dimension is odd (1080p: 240 x 135 ->
+      // 120 x 67), then OpenCV's fixed-point INTER_LINEAR.  Coefficient tables as resizeGeneric_ builds them (float sample positions, cvRound to 11 bits).
+    const int sw = L3.w, sh = L3.h, dw = sw / 2, dh = sh / 2;
+    if (dw < 1 || dh < 1) { ctx->err = "image too small for a SmallBlurryImage"; return VSLAM_E_INVALID; }
+    const double scale_x = 1. / ((double)dw / sw), scale_y = 1. / ((double)dh / sh);
+    ctx->sbi_exact_half = (sw == 2 * dw && sh == 2 * dh) ? 1 : 0;
+    std::vector<int> tab((size_t)3 * dw + 3 * dh);
+    int* xofs = tab.data(); int* alpha = xofs + dw; int* yofs = alpha + 2 * dw; int* beta = yofs + dh;
+    auto q11 = [](float v) { long r = lrintf(v); return (int)(r < -32768 ? -32768 : (r > 32767 ? 32767 : r)); };
+    for (int dx = 0; dx < dw; dx++) {
+      float fx = (float)((dx + 0.5) * scale_x - 0.5); int sx = (int)floorf(fx); fx -= sx;
+      if (sx < 0) { fx = 0; sx = 0; }
+      if (sx >= sw - 1) { fx = 0; sx = sw - 1; }
+      xofs[dx] = sx; alpha[2 * dx] = q11((1.f - fx) * 2048); alpha[2 * dx + 1] = q11(fx * 2048);
+    }
+    for (int dy = 0; dy < dh; dy++) {
+      float fy = (float)((dy + 0.5) * scale_y - 0.5); const int sy = (int)floorf(fy); fy -= sy;
+      yofs[dy] = sy; beta[2 * dy] = q11((1.f - fy) * 2048); beta[2 * dy + 1] = q11(fy * 2048);
+    }
+    if (!ctx->sbi_resize_tab) VS_CUDA(dalloc(&ctx->sbi_resize_tab, tab.size()));
+    VS_CUDA(cudaMemcpy(ctx->sbi_resize_tab, tab.data(), sizeof(int) * tab.size(), cudaMemcpyHostToDevice));
+  }
   CamDev& d = ctx->sbi_cam;
   d.fx = c[0]; d.fy = c[1]; d.cx = c[2]; d.cy = c[3]; d.W = c[4]; d.Winv = c[5]; d.twoTan = c[6]; d.oneOver2Tan = c[7]; d.distEnabled = c[8];
   d.largestRadius = c[9]; d.maxR = c[10]; d.width = c[11]; d.height = c[12];

@@ -12,7 +12,13 @@ namespace {
 
 constexpr int kT = 256;
 
+// cv::resize(level 3 -> SmallBlurryImage size), INTER_LINEAR on u8 (OpenCV's fixed-point bilinear; the third-party algorithm is restated
+// and pinned against cv2 in oracle/shim/cv_resize_linear_u8.h): exactly half in both directions = OpenCV's fast area path (a+b+c+d+2)>>2,
+// otherwise per output column / row a source index and two 11-bit weights, built on the host by vslam_enable_sbi
+struct ResizeTab { int exact_half; int l3w; const int* tab; };   // tab: xofs[w], alpha[2 w], yofs[h], beta[2 h]
+
 struct SbiDev {
+  ResizeTab rs;
   int w, h;                 // SBI size = level 3 / 2
   int l3w, l3h, l3pitch; const uint8_t* l3;   // [S][l3h][l3pitch]
   float taps[9];            // getGaussianKernel(9, 0.75) in float, computed on the host
@@ -27,6 +33,7 @@ struct SbiDev {
 };
 
 struct RelocDev {
+  ResizeTab rs;
   int n_kf, w, h, l3h, l3pitch;
   const uint8_t* src_l3;    // level 3 of the source keyframes [K_src][l3h][l3pitch]
   float taps17[17];         // getGaussianKernel(17, 2.5) in float
@@ -86,14 +93,27 @@ struct SbiShared {
 
 // SmallBlurryImage::MakeFromKF (jni/SmallBlurryImage.cc:20-55): level 3 halved, mean removed, separable float Gaussian (ntaps = 9 for
 // dBlur <= 2, else 17), BORDER_REPLICATE.  `out` receives the template; `small` the u8 thumbnail; `tmp` is scratch.
-__device__ void sbi_make(const uint8_t* __restrict__ l3, int l3pitch, int W, int H, const float* taps, int ntaps, uint8_t* small, float* tmp, float* out, SbiShared& sh) {
+__device__ void sbi_make(const uint8_t* __restrict__ l3, int l3pitch, int l3h, const ResizeTab& rs, int W, int H, const float* taps, int ntaps, uint8_t* small, float* tmp, float* out, SbiShared& sh) {
   const int tid = threadIdx.x, n = W * H, half = ntaps / 2;
   double isum = 0;
-  for (int i = tid; i < n; i += kT) {
-    const int y = i / W, x = i - y * W;
-    const uint8_t* a = l3 + (size_t)(2 * y) * l3pitch + 2 * x;
-    const int v = (a[0] + a[1] + a[l3pitch] + a[l3pitch + 1] + 2) >> 2;
-    small[i] = (uint8_t)v; isum += v;
+  if (rs.exact_half) {
+    for (int i = tid; i < n; i += kT) {
+      const int y = i / W, x = i - y * W;
+      const uint8_t* a = l3 + (size_t)(2 * y) * l3pitch + 2 * x;
+      const int v = (a[0] + a[1] + a[l3pitch] + a[l3pitch + 1] + 2) >> 2;
+      small[i] = (uint8_t)v; isum += v;
+    }
+  } else {
+    const int* xofs = rs.tab; const int* alpha = xofs + W; const int* yofs = alpha + 2 * W; const int* beta = yofs + H;
+    for (int i = tid; i < n; i += kT) {
+      const int y = i / W, x = i - y * W;
+      const int sy = yofs[y], sy0 = sy < 0 ? 0 : (sy < l3h ? sy : l3h - 1), sy1 = sy + 1 < 0 ? 0 : (sy + 1 < l3h ? sy + 1 : l3h - 1);
+      const int sx = xofs[x], sx1 = sx + 1 < rs.l3w ? sx + 1 : rs.l3w - 1, a0 = alpha[2 * x], a1 = alpha[2 * x + 1], b0 = beta[2 * y], b1 = beta[2 * y + 1];
+      const uint8_t* S0 = l3 + (size_t)sy0 * l3pitch; const uint8_t* S1 = l3 + (size_t)sy1 * l3pitch;
+      const int r0 = S0[sx] * a0 + S0[sx1] * a1, r1 = S1[sx] * a0 + S1[sx1] * a1;
+      const int v = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
+      small[i] = (uint8_t)v; isum += v;
+    }
   }
   isum = block_sum(isum, sh.red);            // integer valued: exact
   const float fMean = ((float)(unsigned)isum) / (H * W);
@@ -262,7 +282,7 @@ __global__ void __launch_bounds__(kT) k_sbi(SbiDev D) {
   float* tmp = D.scratch + (size_t)s * 3 * n;
   float* warped = tmp + n;
   if (tid == 0) st->recovered = 0;      // set again by k_relocalise if this frame relocalises the stream
-  sbi_make(D.l3 + (size_t)s * D.l3h * D.l3pitch, D.l3pitch, W, H, D.taps, 9, D.small + (size_t)s * n, tmp, cur, sh);
+  sbi_make(D.l3 + (size_t)s * D.l3h * D.l3pitch, D.l3pitch, D.l3h, D.rs, W, H, D.taps, 9, D.small + (size_t)s * n, tmp, cur, sh);
   const bool first = !D.have[s];
   if (first) { for (int i = tid; i < n; i += kT) last[i] = cur[i]; }   // first frame: both SBIs come from the same keyframe (jni/Tracker.cc:90-93)
   __syncthreads();
@@ -286,7 +306,7 @@ __global__ void __launch_bounds__(kT) k_reloc_make(RelocDev Rd, const int* __res
   const int k = blockIdx.x, n = Rd.w * Rd.h;
   const uint8_t* l3 = Rd.src_l3 + (size_t)src_ids[k] * Rd.l3h * Rd.l3pitch;
   float* out = Rd.kf_tmpl + (size_t)k * n;
-  sbi_make(l3, Rd.l3pitch, Rd.w, Rd.h, Rd.taps17, 17, Rd.kf_small + (size_t)k * n, Rd.kf_tmp + (size_t)k * n, out, sh);
+  sbi_make(l3, Rd.l3pitch, Rd.l3h, Rd.rs, Rd.w, Rd.h, Rd.taps17, 17, Rd.kf_small + (size_t)k * n, Rd.kf_tmp + (size_t)k * n, out, sh);
   sbi_make_jacs(out, Rd.kf_jac + (size_t)k * 2 * n, Rd.w, Rd.h);
 }
 
@@ -304,7 +324,7 @@ __global__ void __launch_bounds__(kT) k_relocalise(SbiDev D, RelocDev Rd) {
   float* tmp = D.scratch + (size_t)s * 3 * n;
   float* warped = tmp + n;
   float* cur = tmp + 2 * n;
-  sbi_make(D.l3 + (size_t)s * D.l3h * D.l3pitch, D.l3pitch, W, H, Rd.taps17, 17, D.small + (size_t)s * n, tmp, cur, sh);
+  sbi_make(D.l3 + (size_t)s * D.l3h * D.l3pitch, D.l3pitch, D.l3h, D.rs, W, H, Rd.taps17, 17, D.small + (size_t)s * n, tmp, cur, sh);
   // ScoreKFs: SmallBlurryImage::ZMSSD (jni/SmallBlurryImage.cc:82-94), serial sum in the reference's order (x outer, y inner), one thread per keyframe
   double* scores = Rd.scores + (size_t)s * Rd.n_kf;
   for (int k = tid; k < Rd.n_kf; k += kT) {
@@ -342,6 +362,7 @@ static SbiDev make_sbi_dev(vslam_ctx* ctx) {
   SbiDev D;
   const LevelDesc& L3 = ctx->lev[3];
   D.w = L3.w / 2; D.h = L3.h / 2; D.l3w = L3.w; D.l3h = L3.h; D.l3pitch = L3.pitch; D.l3 = L3.img;
+  D.rs.exact_half = ctx->sbi_exact_half; D.rs.l3w = L3.w; D.rs.tab = ctx->sbi_resize_tab;
   for (int k = 0; k < 9; k++) D.taps[k] = ctx->sbi_taps[k];
   D.cam = ctx->sbi_cam; memcpy(D.orig, ctx->sbi_orig, sizeof(D.orig));
   D.tmpl = ctx->sbi_tmpl; D.scratch = ctx->sbi_scratch; D.jac = ctx->sbi_jac; D.small = ctx->sbi_small; D.ss = ctx->ss; D.have = ctx->sbi_have; D.parity = ctx->sbi_have + ctx->S;
@@ -352,6 +373,7 @@ static RelocDev make_reloc_dev(vslam_ctx* ctx) {
   RelocDev R;
   const LevelDesc& L3 = ctx->lev[3];
   R.n_kf = ctx->reloc_n; R.w = L3.w / 2; R.h = L3.h / 2; R.l3h = ctx->src.h[3]; R.l3pitch = ctx->src.pitch[3]; R.src_l3 = ctx->src.img[3];
+  R.rs.exact_half = ctx->sbi_exact_half; R.rs.l3w = L3.w; R.rs.tab = ctx->sbi_resize_tab;
   for (int k = 0; k < 17; k++) R.taps17[k] = ctx->reloc_taps[k];
   R.kf_tmpl = ctx->reloc_tmpl; R.kf_jac = ctx->reloc_jac; R.kf_tmp = ctx->reloc_tmp; R.kf_small = ctx->reloc_small; R.kf_pose = ctx->reloc_pose; R.scores = ctx->reloc_scores;
   return R;

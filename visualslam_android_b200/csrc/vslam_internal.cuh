@@ -141,6 +141,7 @@ struct vslam_ctx {
   void* epi_buf; size_t epi_cap;    // scratch of vslam_epipolar_search (candidates, rays, results), grown on demand
   double* unproj_lut; bool unproj_ok;   // [H][W][2] ATANCamera::UnProject of every integer level-0 pixel (MapMaker::AddPointEpipolar's imUnProj), built on the host
   // on-device SmallBlurryImage (vslam_enable_sbi)
+  int sbi_exact_half = 1; int* sbi_resize_tab = nullptr;   // cv::resize of level 3 to the SmallBlurryImage size: see sbi.cu ResizeTab
   bool sbi_on; float sbi_taps[9]; CamDev sbi_cam; double sbi_orig[2][3]; float* sbi_tmpl; float* sbi_scratch; float* sbi_jac; uint8_t* sbi_small; int* sbi_have;
   // optional per-kernel timing with CUDA events on ctx->stream (vslam_set_timing)
   bool timing; std::vector<cudaEvent_t> ev_pool; std::vector<int> ev_stage; size_t ev_used;
