@@ -25,7 +25,7 @@ constexpr int kGL = 8;            // lanes per list entry
 constexpr int kGW = 32 / kGL;     // entries per warp
 constexpr int kQ = 48;            // candidate queue per entry
 #ifndef VS_SEARCH_MINB
-#define VS_SEARCH_MINB 5
+#define VS_SEARCH_MINB 8
 #endif
 #ifndef VS_SEARCH_NB
 #define VS_SEARCH_NB 4
@@ -339,11 +339,14 @@ __global__ void __launch_bounds__(kFW * 32, VS_SEARCH_MINB) k_search_fast(Dev D,
 // iteration are added in pixel order like the reference's serial loop, 81 dependent additions each, by three lanes -- so what a warp can
 // do is run four such chains side by side; the bilinear samples and products of an iteration are spread over the entry's eight lanes.
 // The template gradients are recomputed from the template bytes where they are needed (exact: multiples of 0.5).
-struct SubpixEntry { double prod[3][(VS_MAXP - 2) * (VS_MAXP - 2)]; uint32_t tmpl_w[VS_TMPL_BYTES / 4]; };   // dDiff*gx, dDiff*gy, dDiff per interior pixel; the template
+constexpr int kSL = 8;            // k_subpix: lanes per entry
+constexpr int kSW = 32 / kSL;     // k_subpix: entries per warp
+constexpr int kWin = VS_MAXP + 5;   // image window staged per entry: the P - 1 pixels an iteration samples per axis + 3 pixels of travel either way
+struct SubpixEntry { double prod[3][(VS_MAXP - 2) * (VS_MAXP - 2)]; uint32_t tmpl_w[VS_TMPL_BYTES / 4]; uint8_t win[kWin * kWin]; };   // dDiff*gx, dDiff*gy, dDiff per interior pixel; the template; the window
 
 __global__ void __launch_bounds__(kFW * 32) k_subpix(Dev D, int mode, int range_arg, int subpix_arg, int sflags) {
-  __shared__ SubpixEntry sm_all[kFW][kGW];
-  const int s = blockIdx.y + D.s0, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane / kGL, j = lane % kGL;
+  __shared__ SubpixEntry sm_all[kFW][kSW];
+  const int s = blockIdx.y + D.s0, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane / kSL, j = lane % kSL;
   StreamState* st = D.ss + s;
   Plan pl;
   if (!search_plan(D, st, mode, range_arg, subpix_arg, pl)) return;
@@ -351,9 +354,10 @@ __global__ void __launch_bounds__(kFW * 32) k_subpix(Dev D, int mode, int range_
   const bool refind = (sflags & kSearchRefindF) != 0;
   const size_t SN = (size_t)D.S * D.N;
   const int P = D.P, Q = P - 2, QQ = Q * Q;
+  const int rq = (65536 + Q - 1) / Q;                            // k / Q == (k * rq) >> 16 for k < Q * Q <= 81
   SubpixEntry& E = sm_all[warp][g];
   const uint8_t* const tmpl = (const uint8_t*)E.tmpl_w;
-  for (int e0 = (blockIdx.x * kFW + warp) * kGW; e0 < n_sub; e0 += gridDim.x * kFW * kGW) {   // (the grid is a few CTAs per stream: the fine stage refines only its top-level entries)
+  for (int e0 = (blockIdx.x * kFW + warp) * kSW; e0 < n_sub; e0 += gridDim.x * kFW * kSW) {   // (the grid is a few CTAs per stream: the fine stage refines only its top-level entries)
     const int e = e0 + g;
     bool active = e < n_sub;
     const int i = D.lists[(size_t)s * D.list_cap + pl.first + (active ? e : e0)];
@@ -366,7 +370,7 @@ __global__ void __launch_bounds__(kFW * 32) k_subpix(Dev D, int mode, int range_
     const int lv = active ? level : 0;
     const uint32_t* tmpl_g = (const uint32_t*)(D.ps.tmpl + gi * VS_TMPL_BYTES);
 #pragma unroll
-    for (int q = 0; q < 5; q++) if (j + kGL * q < VS_TMPL_BYTES / 4) E.tmpl_w[j + kGL * q] = tmpl_g[j + kGL * q];
+    for (int q = 0; q < 5; q++) if (j + kSL * q < VS_TMPL_BYTES / 4) E.tmpl_w[j + kSL * q] = tmpl_g[j + kSL * q];
     const double coarse0 = D.ps.coarse[gi], coarse1 = D.ps.coarse[SN + gi];
     const LevelDesc& L = D.lev[lv];
     const uint8_t* img; int pitch;
@@ -378,14 +382,14 @@ __global__ void __launch_bounds__(kFW * 32) k_subpix(Dev D, int mode, int range_
     if (entry && j == 0) atomicAdd(D.evals + 3, 1ull);
     // ---- MakeSubPixTemplate (jni/PatchFinder.cc:242-267): JtJ of (gx, gy, 1); sums of multiples of 0.25 below 2^53 are exact in any order
     double hxx = 0, hxy = 0, hyy = 0, hx = 0, hy = 0;
-    for (int k = j; k < QQ; k += kGL) {
-      const int x = k / Q + 1, y = k - (x - 1) * Q + 1;
+    for (int k = j; k < QQ; k += kSL) {
+      const int x = ((k * rq) >> 16) + 1, y = k - (x - 1) * Q + 1;
       const double gx = 0.5 * (tmpl[y * 12 + x + 1] - tmpl[y * 12 + x - 1]), gy = 0.5 * (tmpl[(y + 1) * 12 + x] - tmpl[(y - 1) * 12 + x]);
       hxx += gx * gx; hxy += gx * gy; hyy += gy * gy; hx += gx; hy += gy;
     }
     __syncwarp();
 #pragma unroll
-    for (int d = kGL / 2; d; d >>= 1) {
+    for (int d = kSL / 2; d; d >>= 1) {
       hxx += __shfl_xor_sync(0xffffffffu, hxx, d); hxy += __shfl_xor_sync(0xffffffffu, hxy, d); hyy += __shfl_xor_sync(0xffffffffu, hyy, d);
       hx += __shfl_xor_sync(0xffffffffu, hx, d); hy += __shfl_xor_sync(0xffffffffu, hy, d);
     }
@@ -398,6 +402,20 @@ __global__ void __launch_bounds__(kFW * 32) k_subpix(Dev D, int mode, int range_
       hinv[1] = (H[2] * H[7] - H[1] * H[8]) * invdet; hinv[4] = (H[0] * H[8] - H[2] * H[6]) * invdet; hinv[7] = (H[1] * H[6] - H[0] * H[7]) * invdet;
       hinv[2] = (H[1] * H[5] - H[2] * H[4]) * invdet; hinv[5] = (H[2] * H[3] - H[0] * H[5]) * invdet; hinv[8] = (H[0] * H[4] - H[1] * H[3]) * invdet;
     }
+    // The iterations sample the image around a position that moves by fractions of a pixel: the kWin x kWin pixels around the coarse hit are
+    // staged in shared memory once (32 independent loads per lane) instead of four dependent global loads per pixel and iteration.
+    int wx0 = 0, wy0 = 0;
+    if (active) {
+      const double c0 = (coarse0 + 0.5) * invScale - 0.5, c1 = (coarse1 + 0.5) * invScale - 0.5;
+      wx0 = (int)(c0 - (double)(P / 2)) - 2; wy0 = (int)(c1 - (double)(P / 2)) - 2;
+      for (int k = j; k < kWin * kWin; k += kSL) {
+        const int r = k / kWin, c = k - r * kWin;
+        int yy = wy0 + r, xx = wx0 + c;
+        yy = yy < 0 ? 0 : (yy >= lh ? lh - 1 : yy); xx = xx < 0 ? 0 : (xx >= lw ? lw - 1 : xx);   // (clamped pixels are never sampled: the border test below)
+        E.win[k] = img[(size_t)yy * pitch + xx];
+      }
+    }
+    __syncwarp();
     double sp0 = coarse0, sp1 = coarse1, meanDiff = 0.0;
     int ok = 0, it = 0;
     // ---- IterateSubPixToConvergence / IterateSubPix (jni/PatchFinder.cc:272-350); the four entries of the warp iterate in step
@@ -416,10 +434,14 @@ __global__ void __launch_bounds__(kFW * 32) k_subpix(Dev D, int mode, int range_
         }
       }
       if (active) {
-        for (int k = j; k < QQ; k += kGL) {   // k = (y-1)*Q + (x-1): the reference's loop order
-          const int y = k / Q + 1, x = k - (y - 1) * Q + 1;
-          const uint8_t* tl = img + (size_t)((int)b1 + y) * pitch + ((int)b0 + x);
-          const float fPixel = fTL * tl[0] + fTR * tl[1] + fBL * tl[pitch] + fBR * tl[pitch + 1];
+        const int ox = (int)b0 - wx0, oy = (int)b1 - wy0;             // samples: columns ox + 1 .. ox + P - 1 of the window, rows likewise
+        const bool inwin = ox >= -1 && oy >= -1 && ox + P - 1 < kWin && oy + P - 1 < kWin;
+        const uint8_t* base = inwin ? E.win + oy * kWin + ox : img + (size_t)(int)b1 * pitch + (int)b0;
+        const int bp = inwin ? kWin : pitch;
+        for (int k = j; k < QQ; k += kSL) {   // k = (y-1)*Q + (x-1): the reference's loop order
+          const int y = ((k * rq) >> 16) + 1, x = k - (y - 1) * Q + 1;
+          const uint8_t* tl = base + y * bp + x;
+          const float fPixel = fTL * tl[0] + fTR * tl[1] + fBL * tl[bp] + fBR * tl[bp + 1];
           const double dDiff = fPixel - tmpl[y * 12 + x] + meanDiff;
           const double gx = 0.5 * (tmpl[y * 12 + x + 1] - tmpl[y * 12 + x - 1]), gy = 0.5 * (tmpl[(y + 1) * 12 + x] - tmpl[(y - 1) * 12 + x]);
           E.prod[0][k] = dDiff * gx; E.prod[1][k] = dDiff * gy; E.prod[2][k] = dDiff;
@@ -440,7 +462,7 @@ __global__ void __launch_bounds__(kFW * 32) k_subpix(Dev D, int mode, int range_
         for (; k < QQ; k++) acc += p[k];
       }
       __syncwarp();
-      const double a0 = __shfl_sync(0xffffffffu, acc, 0, kGL), a1 = __shfl_sync(0xffffffffu, acc, 1, kGL), a2 = __shfl_sync(0xffffffffu, acc, 2, kGL);
+      const double a0 = __shfl_sync(0xffffffffu, acc, 0, kSL), a1 = __shfl_sync(0xffffffffu, acc, 1, kSL), a2 = __shfl_sync(0xffffffffu, acc, 2, kSL);
       if (active) {
         double upd[3];
 #pragma unroll
@@ -477,7 +499,7 @@ int vs_launch_search_fast(vslam_ctx* ctx, int which, int range, int subpix, int 
   // sub-pixel refinement: every entry of the coarse stage / of an explicit list with subpix > 0, the top-level entries of the fine stage
   const bool any_subpix = which == 0 ? subpix > 0 : (which == 1 ? ctx->params.coarse_subpix_its > 0 : ctx->params.fine_subpix_its_top_level > 0);
   if (any_subpix && !(sflags & 2)) {
-    dim3 g2(std::min((max_entries + kFW * kGW - 1) / (kFW * kGW), 16), ctx->cur_cnt);
+    dim3 g2(std::min((max_entries + kFW * kSW - 1) / (kFW * kSW), 16), ctx->cur_cnt);
     k_subpix<<<g2, kFW * 32, 0, ctx->stream>>>(D, which, range, subpix, sflags);
     ctx->launches++;
   }
