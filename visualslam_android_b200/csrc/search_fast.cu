@@ -25,7 +25,7 @@ constexpr int kGL = 8;            // lanes per list entry
 constexpr int kGW = 32 / kGL;     // entries per warp
 constexpr int kQ = 48;            // candidate queue per entry
 #ifndef VS_SEARCH_MINB
-#define VS_SEARCH_MINB 8
+#define VS_SEARCH_MINB 6
 #endif
 #ifndef VS_SEARCH_NB
 #define VS_SEARCH_NB 4
@@ -206,28 +206,60 @@ __global__ void __launch_bounds__(kFW * 32, VS_SEARCH_MINB) k_search_fast(Dev D,
   const int b = P / 2, nwords = (P + 3) >> 2;
   const uint32_t lastmask = (P & 3) ? ((1u << (8 * (P & 3))) - 1u) : 0xffffffffu;
   int nevals = 0, qn = 0;
+  // Usual case -- a window of at most 24 rows and 32 columns (ranges up to 11 pixels of the search level: the tracker's 10, MapMaker's 4) for
+  // all four entries of the warp: a lane's three rows are fetched at once (six independent loads, one round trip) and cut down to one 32-bit
+  // mask per row whose bit k stands for column xl0 + k.  Wider windows walk their words one at a time (below).
+  const bool fits = !more || ((nBot - nTop) <= 3 * kGL && (xr0 - xl0) < 32);
+  const bool fastwin = __all_sync(0xffffffffu, fits);
+  uint32_t rm0 = 0u, rm1 = 0u, rm2 = 0u;
+  if (fastwin) {
+    uint32_t lo[3], hi[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      const int y = nTop + j + kGL * r;
+      lo[r] = 0u; hi[r] = 0u;
+      if (more && y < nBot) { const uint32_t* row = cb + (size_t)y * cwpr; lo[r] = __ldg(row + wl); if (wr > wl) hi[r] = __ldg(row + wr); }
+    }
+    const int width = xr0 - xl0 + 1;
+    const uint32_t wmask = width >= 32 ? 0xffffffffu : ((1u << width) - 1u);
+    rm0 = __funnelshift_r(lo[0], hi[0], xl0 & 31) & wmask; rm1 = __funnelshift_r(lo[1], hi[1], xl0 & 31) & wmask; rm2 = __funnelshift_r(lo[2], hi[2], xl0 & 31) & wmask;
+    more = false;
+  }
   while (true) {
     // -- scan: until the warp's entries have run out of corners or one of the queues could overflow in the next step
     while (!__any_sync(0xffffffffu, qn > kQ - kGL)) {
-      if (!__any_sync(0xffffffffu, m != 0u)) {
-        if (!__any_sync(0xffffffffu, more)) break;
-        if (more) {
-          if (wi == wr) { yrow += kGL; wi = wl; } else wi++;
-          if (yrow >= nBot) more = false;
-          else {
-            uint32_t v = __ldg(cb + (size_t)yrow * cwpr + wi);
-            if (wi == wl) v &= 0xffffffffu << (xl0 & 31);
-            if (wi == wr) v &= 0xffffffffu >> (31 - (xr0 & 31));
-            m = v;
+      bool pass; int cx, cy;
+      if (fastwin) {
+        const uint32_t left = rm0 | rm1 | rm2;
+        if (!__any_sync(0xffffffffu, left != 0u)) break;
+        // one corner per lane and step, from the first of the lane's rows that still has one
+        pass = left != 0u;
+        const int r = rm0 ? 0 : (rm1 ? 1 : 2);
+        const uint32_t mm = rm0 ? rm0 : (rm1 ? rm1 : rm2);
+        const int bit = pass ? __ffs(mm) - 1 : 0;
+        if (rm0) rm0 &= rm0 - 1u; else if (rm1) rm1 &= rm1 - 1u; else rm2 &= rm2 - 1u;
+        cx = xl0 + bit; cy = nTop + j + kGL * r;
+      } else {
+        if (!__any_sync(0xffffffffu, m != 0u)) {
+          if (!__any_sync(0xffffffffu, more)) break;
+          if (more) {
+            if (wi == wr) { yrow += kGL; wi = wl; } else wi++;
+            if (yrow >= nBot) more = false;
+            else {
+              uint32_t v = __ldg(cb + (size_t)yrow * cwpr + wi);
+              if (wi == wl) v &= 0xffffffffu << (xl0 & 31);
+              if (wi == wr) v &= 0xffffffffu >> (31 - (xr0 & 31));
+              m = v;
+            }
           }
+          continue;
         }
-        continue;
+        pass = m != 0u;
+        const int bit = pass ? __ffs(m) - 1 : 0;
+        m &= m - 1u;
+        cx = (wi << 5) + bit; cy = yrow;
       }
-      // one corner per lane and step: the circle test of jni/PatchFinder.cc:216-219, survivors to the entry's queue
-      bool pass = m != 0u;
-      const int bit = pass ? __ffs(m) - 1 : 0;
-      m &= m - 1u;
-      const int cx = (wi << 5) + bit, cy = yrow;
+      // the circle test of jni/PatchFinder.cc:216-219, survivors to the entry's queue
       if (pass) { const double dx = ix - (double)cx, dy = iy - (double)cy; double d2 = 0; d2 += dx * dx; d2 += dy * dy; pass = !(d2 > r2); }
       const unsigned gb = (__ballot_sync(0xffffffffu, pass) >> (kGL * g)) & ((1u << kGL) - 1u);
       if (pass) W.q.cw[g][qn + __popc(gb & ((1u << j) - 1u))] = ((uint32_t)cy << 16) | (uint32_t)cx;
