@@ -74,6 +74,16 @@ def main():
         nf += len(sel)
     assert nf > 20, nf
     ctx.project_all(); ctx.clear_counters(); ctx.search_for_points(8, 4); ctx.project_and_derivs(); ctx.calc_jacobians(); ctx.calc_pose_update(0.0, True, True)
+    # PatchFinder one object at a time (patchfinder_ops.cu) and a search range wide enough for the word-by-word window walk of k_search_fast
+    ints, dbl = ctx.point_states(0)
+    pt = int(np.nonzero(ints[:, 3] == 1)[0][0])
+    assert ctx.pf_make_template(0, pt) is False
+    lvl = int(ints[pt, 1]); lw, lh = ctx.level_dims(lvl)
+    z = ctx.pf_zmssd_at(0, pt, lvl, np.array([[lw // 2, lh // 2], [0, 0], [lw - 1, lh - 1]], dtype=np.int32))
+    assert z[1] == z[2] == 11 * 11 * 500 + 1 and 0 <= z[0]
+    ctx.pf_subpix(0, pt, 8, dbl[pt, 30:32])
+    ctx.pf_make_template_nowarp(0, pt, -1, 0, 0, 0); ctx.pf_make_template_nowarp(0, pt, 1, 3, 1, 1)
+    ctx.project_all(); ctx.search_for_points(40, 2)
     ctx.track_map()
     with tempfile.TemporaryDirectory() as d:
         ctx.save_map_file(os.path.join(d, "m.vsmap"))
