@@ -42,6 +42,9 @@ struct RelocDev {
   double* scores;           // [S][n_kf]
 };
 
+// i / W for 0 <= i < W * H (a few thousand) with the 32-bit reciprocal rw = 0xffffffff / W + 1: one IMAD.HI instead of an integer division
+__device__ __forceinline__ int div_w(int i, uint32_t rw) { return (int)__umulhi((uint32_t)i, rw); }
+
 __device__ inline double block_sum(double v, double* red) {
 #pragma unroll
   for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
@@ -95,10 +98,11 @@ struct SbiShared {
 // dBlur <= 2, else 17), BORDER_REPLICATE.  `out` receives the template; `small` the u8 thumbnail; `tmp` is scratch.
 __device__ void sbi_make(const uint8_t* __restrict__ l3, int l3pitch, int l3h, const ResizeTab& rs, int W, int H, const float* taps, int ntaps, uint8_t* small, float* tmp, float* out, SbiShared& sh) {
   const int tid = threadIdx.x, n = W * H, half = ntaps / 2;
+  const uint32_t rw = 0xffffffffu / (uint32_t)W + 1u;      // W >= 2
   double isum = 0;
   if (rs.exact_half) {
     for (int i = tid; i < n; i += kT) {
-      const int y = i / W, x = i - y * W;
+      const int y = div_w(i, rw), x = i - y * W;
       const uint8_t* a = l3 + (size_t)(2 * y) * l3pitch + 2 * x;
       const int v = (a[0] + a[1] + a[l3pitch] + a[l3pitch + 1] + 2) >> 2;
       small[i] = (uint8_t)v; isum += v;
@@ -106,7 +110,7 @@ __device__ void sbi_make(const uint8_t* __restrict__ l3, int l3pitch, int l3h, c
   } else {
     const int* xofs = rs.tab; const int* alpha = xofs + W; const int* yofs = alpha + 2 * W; const int* beta = yofs + H;
     for (int i = tid; i < n; i += kT) {
-      const int y = i / W, x = i - y * W;
+      const int y = div_w(i, rw), x = i - y * W;
       const int sy = yofs[y], sy0 = sy < 0 ? 0 : (sy < l3h ? sy : l3h - 1), sy1 = sy + 1 < 0 ? 0 : (sy + 1 < l3h ? sy + 1 : l3h - 1);
       const int sx = xofs[x], sx1 = sx + 1 < rs.l3w ? sx + 1 : rs.l3w - 1, a0 = alpha[2 * x], a1 = alpha[2 * x + 1], b0 = beta[2 * y], b1 = beta[2 * y + 1];
       const uint8_t* S0 = l3 + (size_t)sy0 * l3pitch; const uint8_t* S1 = l3 + (size_t)sy1 * l3pitch;
@@ -120,13 +124,13 @@ __device__ void sbi_make(const uint8_t* __restrict__ l3, int l3pitch, int l3h, c
   for (int i = tid; i < n; i += kT) out[i] = (float)small[i] - fMean;
   __syncthreads();
   for (int i = tid; i < n; i += kT) {    // row pass
-    const int y = i / W, x = i - y * W; float acc = 0;
+    const int y = div_w(i, rw), x = i - y * W; float acc = 0;
     for (int k = 0; k < ntaps; k++) { int xx = x + k - half; xx = xx < 0 ? 0 : (xx >= W ? W - 1 : xx); acc += taps[k] * out[y * W + xx]; }
     tmp[i] = acc;
   }
   __syncthreads();
   for (int i = tid; i < n; i += kT) {    // column pass
-    const int y = i / W, x = i - y * W; float acc = 0;
+    const int y = div_w(i, rw), x = i - y * W; float acc = 0;
     for (int k = 0; k < ntaps; k++) { int yy = y + k - half; yy = yy < 0 ? 0 : (yy >= H ? H - 1 : yy); acc += taps[k] * tmp[yy * W + x]; }
     out[i] = acc;
   }
@@ -136,8 +140,9 @@ __device__ void sbi_make(const uint8_t* __restrict__ l3, int l3pitch, int l3h, c
 // SmallBlurryImage::MakeJacs (jni/SmallBlurryImage.cc:58-79)
 __device__ void sbi_make_jacs(const float* __restrict__ t, float* jac, int W, int H) {
   const int n = W * H;
+  const uint32_t rw = 0xffffffffu / (uint32_t)W + 1u;
   for (int i = threadIdx.x; i < n; i += kT) {
-    const int y = i / W, x = i - y * W;
+    const int y = div_w(i, rw), x = i - y * W;
     float gx = 0.f, gy = 0.f;
     if (x >= 1 && y >= 1 && x < W - 1 && y < H - 1) { gx = t[i + 1] - t[i - 1]; gy = t[i + W] - t[i - W]; }
     jac[2 * i] = gx; jac[2 * i + 1] = gy;
@@ -160,6 +165,7 @@ __device__ __forceinline__ void sbi_esm_transform(SbiShared& sh, double cx, doub
 // (gradient image `jac`).  Leaves the SE2 in sh.CtoC and the final score (sum of squared differences of the last iteration) in sh.score.
 __device__ void sbi_esm(const float* __restrict__ cur, const float* __restrict__ last, const float* __restrict__ jac, float* warped, int W, int H, int its, SbiShared& sh) {
   const int tid = threadIdx.x, n = W * H;
+  const uint32_t rw = 0xffffffffu / (uint32_t)W + 1u;
   const double cx = W / 2.0, cy = H / 2.0;
   __syncthreads();
   if (tid == 0) { sh.CtoC[0] = 1; sh.CtoC[1] = 0; sh.CtoC[2] = 0; sh.CtoC[3] = 1; sh.CtoC[4] = 0; sh.CtoC[5] = 0; sh.mean = 0.0; sh.score = 0.0; sbi_esm_transform(sh, cx, cy); }
@@ -170,7 +176,7 @@ __device__ void sbi_esm(const float* __restrict__ cur, const float* __restrict__
       const double p00 = sh.X[4], p01 = sh.X[5];   // outOrig = 0  =>  p0 = inOrig
       const float xb = W - 1, yb = H - 1;
       for (int i = tid; i < n; i += kT) {
-        const int r = i / W, c = i - r * W;
+        const int r = div_w(i, rw), c = i - r * W;
         double x = p00 + r * d0 + c * a0, y = p01 + r * d1 + c * a1;
         float v = -9e20f;
         if (0 <= x && 0 <= y && x < xb && y < yb) {
@@ -188,7 +194,7 @@ __device__ void sbi_esm(const float* __restrict__ cur, const float* __restrict__
     for (int k = 0; k < 15; k++) acc[k] = 0;
     const double mean = sh.mean;
     for (int i = tid; i < n; i += kT) {
-      const int y = i / W, x = i - y * W;
+      const int y = div_w(i, rw), x = i - y * W;
       if (!(x >= 1 && y >= 1 && x < W - 1 && y < H - 1)) continue;
       const float l = warped[i - 1], r = warped[i + 1], u = warped[i - W], d = warped[i + W], here = warped[i];
       if (l + r + u + d + here < -9999.9) continue;
