@@ -196,7 +196,7 @@ void vslam_destroy(vslam_ctx* ctx) {
   cudaSetDevice(ctx->cfg.device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (int l = 0; l < VS_LEVELS; l++) { cudaFree(ctx->lev[l].img); cudaFree(ctx->lev[l].corners); cudaFree(ctx->lev[l].lut); cudaFree(ctx->src.img[l]); }
-  cudaFree(ctx->epi_buf); cudaFree(ctx->pf_buf); cudaFree(ctx->l0_ptr); cudaFree(ctx->l0_stride); cudaFree(ctx->sync_words); cudaFree(ctx->status); cudaFree(ctx->evals);
+  cudaFree(ctx->epi_buf); cudaFree(ctx->pf_buf); cudaFree(ctx->list_counts); cudaFree(ctx->l0_ptr); cudaFree(ctx->l0_stride); cudaFree(ctx->sync_words); cudaFree(ctx->status); cudaFree(ctx->evals);
   cudaFree(ctx->map.world); cudaFree(ctx->map.right); cudaFree(ctx->map.down); cudaFree(ctx->map.ircenter); cudaFree(ctx->map.srclevel); cudaFree(ctx->map.srckf);
   PointState& ps = ctx->ps;
   cudaFree(ps.v3cam); cudaFree(ps.v2image); cudaFree(ps.derivs); cudaFree(ps.warpinv); cudaFree(ps.m2); cudaFree(ps.lastwarp); cudaFree(ps.v2found); cudaFree(ps.coarse);

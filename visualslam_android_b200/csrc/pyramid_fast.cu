@@ -1,7 +1,7 @@
 // KeyFrame::MakeKeyFrame_Lite on the GPU (reference: jni/KeyFrame.cc:5-51).
 //
-// Three launches, batched over all streams.  k_pyramid_fast handles level 0 (and writes the images of levels 1..3), k_fast_levels
-// handles levels 1..3, k_corner_lists turns the corner bitmasks of all four levels into the corner lists and row tables.
+// Batched over all streams: k_pyramid_fast handles level 0 (and writes the images of levels 1..3), k_fast_levels handles levels 1..3,
+// k_corner_count + k_corner_lists turn the corner bitmasks of all four levels into the corner lists and row tables.
 // A CTA of the first two owns a strip of LevelDesc::strip_rows rows of one level of one stream.  It
 //   1. stages the strip plus a 3-row halo into shared memory with ONE bulk async copy (cp.async.bulk, TMA engine);
 //   2. (level 0) writes the matching rows of level 1:  (a+b+c+d+2)>>2  (cv::resize 2:1, jni/KeyFrame.cc:20-23; SURVEY.md
@@ -13,7 +13,7 @@
 //        consecutive of one polarity are necessary) and then the exact 16-pixel ring test, one lane per candidate;
 //   4. sets the bit of every corner in the level's corner bitmask in global memory (one word per 32 pixels, cleared per frame)
 //      and exits: no barrier after the staging, no inter-CTA dependency.
-// k_corner_lists (one CTA per level image): popcounts + one block scan give every corner its raster-order position; the running
+// k_corner_lists (one CTA per chunk of at most 4096 bitmask words): popcounts + one block scan give every corner its raster-order position; the running
 // positions at the row starts ARE the row look-up table of jni/KeyFrame.cc:41-49.  (The tracker's patch search reads the bitmasks.)
 // Integer / byte arithmetic only; results are bit-exact against the oracle.
 #include "vslam_internal.cuh"
@@ -283,21 +283,75 @@ __device__ __forceinline__ void fast_strip(const LevelDesc& L, const uint8_t* __
   }
 }
 
-// Corner lists of one level image from its corner bitmask (k_pyramid_fast / k_fast_levels set the bits): every warp owns a contiguous run
-// of bitmask words; popcounts + one scan of the warp totals give every word its raster-order position.  The position at a row's first word is the
-// row's LUT entry (jni/KeyFrame.cc:41-49).
+// Corner lists of the level images from their corner bitmasks (k_pyramid_fast / k_fast_levels set the bits).  An image is cut evenly into chunks of
+// at most kListChunk bitmask words (a VGA level 0 is three chunks, a 4K level 0 sixty-four), one CTA per chunk: k_corner_count leaves every chunk's
+// corner count, k_corner_lists adds up the counts of the chunks before its own (at most a few dozen) and then gives every word its
+// raster-order position -- every warp owns a contiguous run of words, popcounts + one scan of the warp totals.  The position at a row's
+// first word is the row's LUT entry (jni/KeyFrame.cc:41-49).
 // Positions are clamped to the capacity: on overflow -- reported through status[0] -- the readers of the LUT must not index past the list.
+constexpr int kListChunk = 4096;    // target chunk size; an image is split EVENLY into ceil(words / kListChunk) chunks
+__host__ __device__ __forceinline__ int list_chunks(int n_words) { return (n_words + kListChunk - 1) / kListChunk; }
+__host__ __device__ __forceinline__ int list_chunk_words(int n_words) { const int nc = list_chunks(n_words); return (((n_words + nc - 1) / nc) + 31) & ~31; }
+
+struct ListJob { int level, s, chunk, n_chunks, w_begin, w_end; };
+// block -> (level, stream, chunk): all chunks of the largest level first.  (The four descriptors stay kernel parameters -- constant bank --
+// selected by compile-time index after unrolling; an array of them would be copied to local memory by every thread.)
+__device__ __forceinline__ ListJob list_job(const LevelDesc& L0, const LevelDesc& L1, const LevelDesc& L2, const LevelDesc& L3, int first_stream, int count, int first_level) {
+  int blk = blockIdx.x;
+  ListJob J; J.level = VS_LEVELS - 1; J.s = first_stream; J.chunk = 0; J.n_chunks = 1; J.w_begin = 0; J.w_end = 0;
+  bool done = false;
+#pragma unroll
+  for (int l = 0; l < VS_LEVELS; l++) {
+    const LevelDesc& L = l == 0 ? L0 : l == 1 ? L1 : l == 2 ? L2 : L3;
+    const int n_words = L.h * ((L.w + 31) >> 5), nc = list_chunks(n_words), cw = list_chunk_words(n_words);
+    if (!done && l >= first_level) {
+      if (blk < count * nc || l == VS_LEVELS - 1) {
+        const int si = blk / nc;
+        J.level = l; J.n_chunks = nc; J.s = first_stream + si; J.chunk = blk - si * nc;
+        J.w_begin = min(J.chunk * cw, n_words); J.w_end = min(J.w_begin + cw, n_words);
+        done = true;
+      } else blk -= count * nc;
+    }
+  }
+  return J;
+}
+
 __global__ void __launch_bounds__(kMaxThreads)
-k_corner_lists(LevelDesc L0, LevelDesc L1, LevelDesc L2, LevelDesc L3, int first_stream, int count, int first_level, int* __restrict__ status) {
+k_corner_count(LevelDesc L0, LevelDesc L1, LevelDesc L2, LevelDesc L3, int first_stream, int count, int first_level, int* __restrict__ chunk_counts) {
   __shared__ int wsum[kMaxWarps];
+  const ListJob J = list_job(L0, L1, L2, L3, first_stream, count, first_level);
+#define PICK(f) (J.level == 0 ? L0.f : J.level == 1 ? L1.f : J.level == 2 ? L2.f : L3.f)   /* a select among kernel parameters: no local copy of a descriptor */
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const uint32_t* bits = PICK(cbits) + (size_t)J.s * PICK(h) * ((PICK(w) + 31) >> 5);
+  int c = 0;
+  for (int w = J.w_begin + tid; w < J.w_end; w += blockDim.x) c += __popc(bits[w]);
+  c = __reduce_add_sync(0xffffffffu, c);
+  if (lane == 0) wsum[warp] = c;
+  __syncthreads();
+  if (tid == 0) { int t = 0; for (int i = 0; i < nw; i++) t += wsum[i]; chunk_counts[blockIdx.x] = t; }
+}
+
+__global__ void __launch_bounds__(kMaxThreads)
+k_corner_lists(LevelDesc L0, LevelDesc L1, LevelDesc L2, LevelDesc L3, int first_stream, int count, int first_level, const int* __restrict__ chunk_counts,
+               int* __restrict__ status) {
+  __shared__ int wsum[kMaxWarps];
+  __shared__ int s_base;
+  const ListJob J = list_job(L0, L1, L2, L3, first_stream, count, first_level);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, nw = nthreads >> 5;
-  const int q = blockIdx.x / count, level = first_level + q, s = first_stream + (blockIdx.x - q * count);     // all images of the largest level first
-  const LevelDesc& L = level == 0 ? L0 : level == 1 ? L1 : level == 2 ? L2 : L3;
-  const int H = L.h, wpr = (L.w + 31) >> 5, n_words = H * wpr;
-  const uint32_t* bits = L.cbits + (size_t)s * n_words;
+  const int s = J.s, H = PICK(h), wpr = (PICK(w) + 31) >> 5, cap = PICK(cap);
+  const uint32_t mg_wpr = PICK(mg_wpr);
+  const uint32_t* bits = PICK(cbits) + (size_t)s * H * wpr;
+  if (warp == 0) {   // corners of this image before this chunk, and (last chunk) the image's total
+    int c = 0;
+    const int* cc = chunk_counts + (blockIdx.x - J.chunk);
+    for (int k = lane; k < J.chunk; k += 32) c += cc[k];
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (lane == 0) s_base = c;
+  }
   // a warp owns a contiguous run of words (a multiple of 32, so that every pass reads whole 128-byte lines) and walks it 32 words at a time
+  const int n_words = J.w_end - J.w_begin;
   const int per_warp = ((n_words + nw - 1) / nw + 31) & ~31;
-  const int wb = min(warp * per_warp, n_words), we = min(wb + per_warp, n_words);
+  const int wb = J.w_begin + min(warp * per_warp, n_words), we = min(wb + per_warp, J.w_end);
   int c = 0;
   for (int w = wb + lane; w < we; w += 32) c += __popc(bits[w]);
   c = __reduce_add_sync(0xffffffffu, c);
@@ -306,10 +360,10 @@ k_corner_lists(LevelDesc L0, LevelDesc L1, LevelDesc L2, LevelDesc L3, int first
   int ws = (lane < nw) ? wsum[lane] : 0, wi = ws;
 #pragma unroll
   for (int d = 1; d < 16; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi += v; }
-  const int total = __shfl_sync(0xffffffffu, wi, 15);
-  int run = __shfl_sync(0xffffffffu, wi - ws, warp);          // corners before this warp's run
-  int* lut = L.lut + (size_t)s * (H + 1);
-  uint32_t* out = L.corners + (size_t)s * L.cap;
+  const int total = s_base + __shfl_sync(0xffffffffu, wi, 15);       // corners up to the end of this chunk
+  int run = s_base + __shfl_sync(0xffffffffu, wi - ws, warp);        // corners before this warp's run
+  int* lut = PICK(lut) + (size_t)s * (H + 1);
+  uint32_t* out = PICK(corners) + (size_t)s * cap;
   uint32_t m_next = (wb + lane < we) ? bits[wb + lane] : 0u;
   for (int w0 = wb; w0 < we; w0 += 32) {
     const int w = w0 + lane;
@@ -322,21 +376,22 @@ k_corner_lists(LevelDesc L0, LevelDesc L1, LevelDesc L2, LevelDesc L3, int first
     int pos = run + incl - mine;
     run += __shfl_sync(0xffffffffu, incl, 31);
     if (w < we) {
-      const int r = div_small(w, L.mg_wpr), col = w - r * wpr;
-      if (col == 0) lut[r] = min(pos, L.cap);
+      const int r = div_small(w, mg_wpr), col = w - r * wpr;
+      if (col == 0) lut[r] = min(pos, cap);
       const uint32_t cw0 = ((uint32_t)r << 16) | ((uint32_t)col << 5);
-      if (pos + mine <= L.cap) {             // (always, unless the list overflows) highest bit first, written from the back: one FLO per corner
+      if (pos + mine <= cap) {               // (always, unless the list overflows) highest bit first, written from the back: one FLO per corner
         uint32_t* o = out + pos + mine;
         while (m) { const int b = 31 - __clz(m); m ^= 1u << b; *--o = cw0 + (uint32_t)b; }
       } else {
-        while (m) { const int b = __ffs(m) - 1; m &= m - 1; if (pos < L.cap) out[pos] = cw0 + (uint32_t)b; pos++; }
+        while (m) { const int b = __ffs(m) - 1; m &= m - 1; if (pos < cap) out[pos] = cw0 + (uint32_t)b; pos++; }
       }
     }
   }
-  if (tid == 0) {
-    lut[H] = min(total, L.cap);
-    if (total > L.cap) atomicExch(&status[0], 1);
+  if (tid == 0 && J.chunk == J.n_chunks - 1) {
+    lut[H] = min(total, cap);
+    if (total > cap) atomicExch(&status[0], 1);
   }
+#undef PICK
 }
 
 // Level 0 of every stream: pyramid levels 1..3 + FAST-10 of level 0.
@@ -470,11 +525,20 @@ int vs_launch_fast_levels(vslam_ctx* ctx, int first_stream, int count) {
 // Corner lists and row LUTs of all four levels from the corner bitmasks (one launch).  The patch search of the tracker
 // (search_fast.cu) reads the bitmasks themselves, so a tracked frame leaves this to whoever asks for the lists next (vs_ensure_lists).
 int vs_launch_corner_lists(vslam_ctx* ctx, int first_stream, int count) {
+  int blocks = 0;
+  for (int l = 0; l < VS_LEVELS; l++) { const LevelDesc& L = ctx->lev[l]; blocks += count * list_chunks(L.h * ((L.w + 31) / 32)); }
+  if ((size_t)blocks > ctx->list_counts_cap) {
+    if (ctx->list_counts) cudaFree(ctx->list_counts);
+    ctx->list_counts = nullptr; ctx->list_counts_cap = 0;
+    VS_CUDA(cudaMalloc(&ctx->list_counts, sizeof(int) * (size_t)blocks));
+    ctx->list_counts_cap = (size_t)blocks;
+  }
   vs_time_begin(ctx, VS_ST_PYR2);
-  k_corner_lists<<<count * VS_LEVELS, kMaxThreads, 0, ctx->stream>>>(ctx->lev[0], ctx->lev[1], ctx->lev[2], ctx->lev[3], first_stream, count, 0, ctx->status);
+  k_corner_count<<<blocks, kMaxThreads, 0, ctx->stream>>>(ctx->lev[0], ctx->lev[1], ctx->lev[2], ctx->lev[3], first_stream, count, 0, ctx->list_counts);
+  k_corner_lists<<<blocks, kMaxThreads, 0, ctx->stream>>>(ctx->lev[0], ctx->lev[1], ctx->lev[2], ctx->lev[3], first_stream, count, 0, ctx->list_counts, ctx->status);
   vs_time_end(ctx);
   VS_CUDA(cudaGetLastError());
-  ctx->launches++;
+  ctx->launches += 2;
   return VSLAM_OK;
 }
 

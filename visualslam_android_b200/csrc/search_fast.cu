@@ -193,73 +193,55 @@ __global__ void __launch_bounds__(kFW * 32, VS_SEARCH_MINB) k_search_fast(Dev D,
   flags |= F_SEARCHED;
   if (nTop < 0) nTop = 0;
   // The window's corners straight from the level's corner bitmask (LevelDesc::cbits, one word per 32 pixels, written by the FAST kernels):
-  // lane j of the entry walks rows nTop + j, nTop + j + 8, ... and, per row, the words that hold columns [nLeft, nRight] clipped to the image
-  // (the x range of jni/PatchFinder.cc:214-215, exact); a set bit IS a corner position, so neither the corner list nor the row LUT is read.
+  // rows [nTop, nBot), columns [nLeft, nRight] clipped to the image (the x range of jni/PatchFinder.cc:214-215, exact); a set bit IS a
+  // corner position, so neither the corner list nor the row LUT is read.
   const int nBot = nBottomPlusOne < lh ? nBottomPlusOne : lh;
   const bool x_empty = nRight < 0 || nLeft > lw - 1;
   const int xl0 = nLeft > 0 ? nLeft : 0, xr0 = nRight < lw - 1 ? nRight : lw - 1;
-  const int wl = xl0 >> 5, wr = xr0 >> 5, cwpr = (lw + 31) >> 5;
+  const int wr = xr0 >> 5, cwpr = (lw + 31) >> 5;
   const uint32_t* cb = L.cbits + (size_t)s * lh * cwpr;
-  bool more = alive && !x_empty && nTop < nBot;   // (nTop >= rows or nBottomPlusOne <= 0: nothing to search, jni/PatchFinder.cc:189-195)
-  int yrow = nTop + j - kGL, wi = wr;               // "before the first word": the first advance moves to (row nTop + j, word wl)
-  uint32_t m = 0u;                                  // corner bits of the current word still to be looked at
+  const bool more = alive && !x_empty && nTop < nBot;   // (nTop >= rows or nBottomPlusOne <= 0: nothing to search, jni/PatchFinder.cc:189-195)
   const int b = P / 2, nwords = (P + 3) >> 2;
   const uint32_t lastmask = (P & 3) ? ((1u << (8 * (P & 3))) - 1u) : 0xffffffffu;
   int nevals = 0, qn = 0;
-  // Usual case -- a window of at most 24 rows and 32 columns (ranges up to 11 pixels of the search level: the tracker's 10, MapMaker's 4) for
-  // all four entries of the warp: a lane's three rows are fetched at once (six independent loads, one round trip) and cut down to one 32-bit
-  // mask per row whose bit k stands for column xl0 + k.  Wider windows walk their words one at a time (below).
-  const bool fits = !more || ((nBot - nTop) <= 3 * kGL && (xr0 - xl0) < 32);
-  const bool fastwin = __all_sync(0xffffffffu, fits);
+  // The window is walked in batches of 24 rows x 32 columns: lane j fetches rows j, j + 8, j + 16 of the batch at once (six independent
+  // loads, one round trip) and cuts each down to a 32-bit mask whose bit k stands for column x0b + k.  The tracker's windows (ranges up to
+  // 11 pixels of the search level) and MapMaker's (4) are ONE batch; wide windows (the roofline sweep: range 40 = 81 x 81) take a few.
+  const int ncb = more ? ((xr0 - xl0) >> 5) + 1 : 0;                                    // column blocks of 32
+  const int nb = more ? ((nBot - nTop + 3 * kGL - 1) / (3 * kGL)) * ncb : 0;            // batches of this entry
+  int bi = 0, x0b = 0, y0b = 0;
   uint32_t rm0 = 0u, rm1 = 0u, rm2 = 0u;
-  if (fastwin) {
-    uint32_t lo[3], hi[3];
-#pragma unroll
-    for (int r = 0; r < 3; r++) {
-      const int y = nTop + j + kGL * r;
-      lo[r] = 0u; hi[r] = 0u;
-      if (more && y < nBot) { const uint32_t* row = cb + (size_t)y * cwpr; lo[r] = __ldg(row + wl); if (wr > wl) hi[r] = __ldg(row + wr); }
-    }
-    const int width = xr0 - xl0 + 1;
-    const uint32_t wmask = width >= 32 ? 0xffffffffu : ((1u << width) - 1u);
-    rm0 = __funnelshift_r(lo[0], hi[0], xl0 & 31) & wmask; rm1 = __funnelshift_r(lo[1], hi[1], xl0 & 31) & wmask; rm2 = __funnelshift_r(lo[2], hi[2], xl0 & 31) & wmask;
-    more = false;
-  }
   while (true) {
     // -- scan: until the warp's entries have run out of corners or one of the queues could overflow in the next step
     while (!__any_sync(0xffffffffu, qn > kQ - kGL)) {
-      bool pass; int cx, cy;
-      if (fastwin) {
-        const uint32_t left = rm0 | rm1 | rm2;
-        if (!__any_sync(0xffffffffu, left != 0u)) break;
-        // one corner per lane and step, from the first of the lane's rows that still has one
-        pass = left != 0u;
-        const int r = rm0 ? 0 : (rm1 ? 1 : 2);
-        const uint32_t mm = rm0 ? rm0 : (rm1 ? rm1 : rm2);
-        const int bit = pass ? __ffs(mm) - 1 : 0;
-        if (rm0) rm0 &= rm0 - 1u; else if (rm1) rm1 &= rm1 - 1u; else rm2 &= rm2 - 1u;
-        cx = xl0 + bit; cy = nTop + j + kGL * r;
-      } else {
-        if (!__any_sync(0xffffffffu, m != 0u)) {
-          if (!__any_sync(0xffffffffu, more)) break;
-          if (more) {
-            if (wi == wr) { yrow += kGL; wi = wl; } else wi++;
-            if (yrow >= nBot) more = false;
-            else {
-              uint32_t v = __ldg(cb + (size_t)yrow * cwpr + wi);
-              if (wi == wl) v &= 0xffffffffu << (xl0 & 31);
-              if (wi == wr) v &= 0xffffffffu >> (31 - (xr0 & 31));
-              m = v;
-            }
+      const uint32_t left = rm0 | rm1 | rm2;
+      if (!__any_sync(0xffffffffu, left != 0u)) {
+        if (!__any_sync(0xffffffffu, bi < nb)) break;
+        if (bi < nb) {
+          const int rb = bi / ncb, cbk = bi - rb * ncb;
+          y0b = nTop + 3 * kGL * rb; x0b = xl0 + 32 * cbk;
+          const int w0 = x0b >> 5, width = xr0 - x0b + 1;
+          uint32_t lo[3], hi[3];
+#pragma unroll
+          for (int r = 0; r < 3; r++) {
+            const int y = y0b + j + kGL * r;
+            lo[r] = 0u; hi[r] = 0u;
+            if (y < nBot) { const uint32_t* row = cb + (size_t)y * cwpr; lo[r] = __ldg(row + w0); if (w0 < wr) hi[r] = __ldg(row + w0 + 1); }
           }
-          continue;
+          const uint32_t wmask = width >= 32 ? 0xffffffffu : ((1u << width) - 1u);
+          rm0 = __funnelshift_r(lo[0], hi[0], x0b & 31) & wmask; rm1 = __funnelshift_r(lo[1], hi[1], x0b & 31) & wmask; rm2 = __funnelshift_r(lo[2], hi[2], x0b & 31) & wmask;
+          bi++;
         }
-        pass = m != 0u;
-        const int bit = pass ? __ffs(m) - 1 : 0;
-        m &= m - 1u;
-        cx = (wi << 5) + bit; cy = yrow;
+        continue;
       }
-      // the circle test of jni/PatchFinder.cc:216-219, survivors to the entry's queue
+      // one corner per lane and step, from the first of the lane's rows that still has one: the circle test of jni/PatchFinder.cc:216-219,
+      // survivors to the entry's queue
+      bool pass = left != 0u;
+      const int r = rm0 ? 0 : (rm1 ? 1 : 2);
+      const uint32_t mm = rm0 ? rm0 : (rm1 ? rm1 : rm2);
+      const int bit = pass ? __ffs(mm) - 1 : 0;
+      if (rm0) rm0 &= rm0 - 1u; else if (rm1) rm1 &= rm1 - 1u; else rm2 &= rm2 - 1u;
+      const int cx = x0b + bit, cy = y0b + j + kGL * r;
       if (pass) { const double dx = ix - (double)cx, dy = iy - (double)cy; double d2 = 0; d2 += dx * dx; d2 += dy * dy; pass = !(d2 > r2); }
       const unsigned gb = (__ballot_sync(0xffffffffu, pass) >> (kGL * g)) & ((1u << kGL) - 1u);
       if (pass) W.q.cw[g][qn + __popc(gb & ((1u << j) - 1u))] = ((uint32_t)cy << 16) | (uint32_t)cx;

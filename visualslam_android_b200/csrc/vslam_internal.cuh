@@ -148,6 +148,7 @@ struct vslam_ctx {
   size_t smem_attr[4] = {0, 0, 0, 0};   // dynamic shared memory already opted into, per kernel (cudaFuncSetAttribute once, not per frame)
   void* pf_buf = nullptr; size_t pf_cap = 0;   // scratch of the per-object PatchFinder calls (patchfinder_ops.cu)
   std::vector<int> user_events;                // [S] pending user events (vslam_user_event)
+  int* list_counts = nullptr; size_t list_counts_cap = 0;   // per-chunk corner counts of k_corner_count / k_corner_lists
   bool lists_stale = false;      // the last tracked frame left corner bitmasks only: corner lists / row LUTs are built on demand (vs_ensure_lists)
   std::string err;
 };
