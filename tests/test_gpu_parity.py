@@ -1328,3 +1328,29 @@ def test_patchfinder_per_object_methods_match_the_oracle(P):
     ctx.user_event(0); ctx.user_event(0)
     assert ctx.take_user_event(0) == 1 and ctx.take_user_event(0) == 0
     ctx.close()
+
+
+def test_corner_lists_are_built_on_demand_after_tracked_frames():
+    """A tracked frame leaves only the corner bitmasks behind (k_search_fast reads them); the first call that needs the reference's containers --
+    Level::vCorners / vCornerRowLUT (jni/KeyFrame.h:52-58) -- builds them from the bitmasks (vs_ensure_lists).  After every frame the lists of
+    every stream and level must be that frame's, bit for bit, also when they were not asked for after the frame before, and the list consumers
+    (MakeKeyFrame_Rest here) must see them too."""
+    from oracle import oraclebind
+    cam, f0, smap = common.scene(n_points=300)
+    S = 2
+    ctx = _ctx(cam, f0, smap, n_streams=S)
+    ctx.enable_sbi(synth.Camera(cam.width // 16, cam.height // 16).scalars())
+    for k in range(1, 5):
+        frames = np.stack([synth.render_frame(common.texture(), cam, synth.stream_pose(4 * k, s + 1)) for s in range(S)])
+        ctx.track_frame(frames)
+        if k == 2:
+            continue                                   # nobody asks for the lists of frame 2
+        for s in range(S):
+            okf = oraclebind.OrcKeyFrame().make_lite(frames[s])
+            if k == 3 and s == 1:                      # a list consumer comes first: Shi-Tomasi candidates of the frame's corners
+                okf.make_rest(); ctx.make_keyframe_rest(s)
+                for l in range(4):
+                    gxy, gsc = ctx.candidates(s, l); oxy, osc = okf.candidates(l)
+                    assert np.array_equal(gxy, oxy) and np.array_equal(gsc, osc), (k, s, l)
+            _check_keyframe(ctx, s, okf)
+    ctx.close()

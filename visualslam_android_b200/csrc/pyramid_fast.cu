@@ -448,19 +448,19 @@ int pyrfast_threads(int w, int rows) {
 
 }  // namespace
 
-// Rows per CTA for level l.  16 by default: at level 0 the level-1..3 rows a CTA emits stay whole (16 -> 8, 4, 2), and at
-// the small levels taller strips (32 / 64 rows) measured slower on B200 (fewer CTAs to balance, longer look-back chain).
+// Rows per CTA for level l.  Level 0: 32 where four to five CTAs still fit on an SM (the fixed cost per thread -- set-up, level 2-3 rows -- is
+// spread over twice the pixels: 0.121 vs 0.140 ms for 256 VGA frames), else 16; the level-1..3 rows a CTA emits stay whole (32 -> 16, 8, 4).
+// Levels 1-3: 16 (8 and 32 / 64 rows measured slower on B200).
 int vs_strip_rows(int level, int w, int pitch) {
-  // wide images (1080p, 4K): 16 rows of level 0 no longer leave room for several CTAs per SM (4K: 116 KB per CTA, one CTA per SM,
-  // measured 3.6 % of the HBM peak against 5.8 % at VGA); 8-row strips keep 3-5 CTAs resident.  8 is the floor at level 0: a strip
-  // must cover whole rows of level 3.
+  // wide images (1080p, 4K): 16 rows of level 0 no longer leave room for several CTAs per SM (4K: over 100 KB per CTA, one CTA per SM);
+  // 8-row strips keep 3-5 CTAs resident.  8 is the floor at level 0: a strip must cover whole rows of level 3.
   if (const char* e = getenv("VSLAM_STRIP_ROWS")) {     // tuning experiments only: "r0,r1,r2,r3" (r0 a multiple of 8, the others even, <= VS_MAX_STRIP_ROWS)
     int r[VS_LEVELS] = {0, 0, 0, 0};
     if (sscanf(e, "%d,%d,%d,%d", &r[0], &r[1], &r[2], &r[3]) == 4 && r[level] >= 2 && r[level] <= VS_MAX_STRIP_ROWS && r[level] % (level == 0 ? 8 : 2) == 0 &&
         pyrfast_smem_bytes(pitch, w, r[level], level == 0) <= 200 * 1024)
       return r[level];
   }
-  if (level == 0 && pyrfast_smem_bytes(pitch, w, 32, true) <= 44 * 1024) return 32;   // five CTAs per SM still fit
+  if (level == 0 && pyrfast_smem_bytes(pitch, w, 32, true) <= 44 * 1024) return 32;   // (VGA: 43.5 KB; four CTAs of 48 registers per SM)
   if (pyrfast_smem_bytes(pitch, w, 16, level == 0) > 48 * 1024) return 8;
   return 16;
 }

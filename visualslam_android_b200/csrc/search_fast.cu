@@ -5,15 +5,16 @@
 // 32 lanes for one point, and the kernel is bound by instruction issue (71 % of the issue slots).  Here a point gets a quarter warp:
 //   * per-point state, the re-use test of MakeTemplateCoarseCont (jni/PatchFinder.cc:79-125) and the search window (:170-209) cost one
 //     instruction stream per FOUR points;
-//   * the FAST corners of the window's rows are scanned eight at a time per point (x range first, as integers; the FP64 circle test of
-//     :216-219 only for the ~3 % that pass it), survivors go to a per-point queue in shared memory;
+//   * the FAST corners of the window come straight from the level's corner bitmask (LevelDesc::cbits), in batches of 24 rows x 32 columns: a
+//     lane fetches its three rows of a batch at once and cuts each down to a 32-bit mask; a set bit is a corner position (no corner list, no
+//     row LUT); one corner per lane and step goes through the FP64 circle test of :216-219, survivors to a per-point queue in shared memory;
 //   * ZMSSD (jni/PatchFinder.cc:352-380): ONE LANE PER CANDIDATE walks all P rows -- unaligned P-byte rows through aligned 32-bit loads
 //     and a funnel shift, dp4a for sum I, sum I^2, sum I.T -- so the three sums stay in registers (no cross-lane reduction), and a round of up to
 //     eight candidates per point costs one instruction stream for four points;
-//   * argmin over the 64-bit key (ssd << 32 | corner index) = "first in raster order wins ties" (:223-226) by three shuffle steps.
+//   * argmin over the 64-bit key (ssd << 32 | y << 16 | x) = "first in raster order wins ties" (:223-226) by three shuffle steps.
 // A template that has to be regenerated (rare: the 0.07 re-use test keeps > 99 % of them at tracking speed) is produced by the whole warp
 // for that point, exactly like k_search does it (serial position accumulation of transform_image, jni/vision/ImageHandler.cpp:21-113).
-// The sub-pixel refinement (jni/PatchFinder.cc:242-350) of the entries that ask for it runs in a second kernel, k_subpix, one warp per
+// The sub-pixel refinement (jni/PatchFinder.cc:242-350) of the entries that ask for it runs in a second kernel, k_subpix, eight lanes per
 // entry, on the coarse result this kernel leaves behind.
 #include "search_common.cuh"
 #include <algorithm>
