@@ -172,6 +172,11 @@ def test_project_all_matches_oracle():
     vis = oi[:, 0] == 1
     rel = np.abs(gd[vis][:, :2] - od[vis][:, :2]) / np.maximum(np.abs(od[vis][:, :2]), 1.0)
     assert rel.max() <= 1e-12, rel.max()      # SURVEY.md §8 contract for the projected pixel
+    # ... and for the warp matrix (mm2WarpInverse) and the camera derivatives it is built from: 1e-12 relative to the matrix's largest entry
+    for cols, name in (((11, 12, 13, 14), "warpInverse"), ((4, 5, 6, 7), "derivs")):
+        a, b = gd[vis][:, cols], od[vis][:, cols]
+        relm = np.abs(a - b).max(axis=1) / np.maximum(np.abs(b).max(axis=1), 1e-300)
+        assert relm.max() <= 1e-12, (name, relm.max())
     # with the correctly-rounded device atan the whole projection is bit-identical for (almost) every point
     ident = (gd[vis][:, [0, 1, 4, 5, 6, 7, 11, 12, 13, 14]] == od[vis][:, [0, 1, 4, 5, 6, 7, 11, 12, 13, 14]]).all(1)
     assert ident.mean() >= 0.99, ident.mean()
