@@ -1359,3 +1359,35 @@ def test_corner_lists_are_built_on_demand_after_tracked_frames():
                     assert np.array_equal(gxy, oxy) and np.array_equal(gsc, osc), (k, s, l)
             _check_keyframe(ctx, s, okf)
     ctx.close()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_make_keyframe_lite_randomised_images(seed):
+    """Pyramid + FAST-10 + lists on random content: noise of varying contrast (every rejection / even-ring / full-ring path, dense and sparse
+    levels, work items with more than 255 survivors), blocks (long corner-free runs, corners clustered on edges) and a smooth field; several
+    streams per launch with different images, sizes whose last 16-pixel chunk is partial at the small levels."""
+    from oracle import oraclebind
+    rs = np.random.RandomState(100 + seed)
+    W, H = [(96, 64), (160, 120), (352, 272), (640, 480), (224, 8 * 13), (1280, 72)][seed]
+    S = 3
+    imgs = []
+    for s in range(S):
+        kind = (seed + s) % 3
+        if kind == 0:
+            amp = [255, 60, 24][s % 3]
+            im = rs.randint(0, amp + 1, size=(H, W)) + rs.randint(0, 256 - amp)
+        elif kind == 1:
+            bs = [5, 9, 17][s % 3]
+            blocks = rs.randint(0, 256, size=((H + bs - 1) // bs, (W + bs - 1) // bs))
+            im = np.kron(blocks, np.ones((bs, bs), dtype=np.int64))[:H, :W] + rs.randint(0, 12, size=(H, W))
+        else:
+            yy, xx = np.mgrid[0:H, 0:W]
+            im = 128 + 90 * np.sin(xx / 7.0 + s) * np.cos(yy / 5.0) + rs.randint(0, 20, size=(H, W))
+        imgs.append(np.clip(im, 0, 255).astype(np.uint8))
+    frames = np.stack(imgs)
+    from visualslam_android_b200 import api
+    ctx = api.Context(W, H, n_streams=S, max_points=8, max_corner_frac=1.0)
+    ctx.make_keyframe_lite(frames)
+    for s in range(S):
+        _check_keyframe(ctx, s, oraclebind.OrcKeyFrame().make_lite(frames[s]))
+    ctx.close()
