@@ -5,6 +5,7 @@
 #include <new>
 #include <vector>
 #include "vslam_internal.cuh"
+#include <cstdlib>
 
 static std::string g_create_error;
 
@@ -125,6 +126,7 @@ int vslam_create(const vslam_config* cfg, vslam_ctx** out) {
   CK(cudaEventCreateWithFlags(&ctx->ev_begin, cudaEventDisableTiming));
   const int S = ctx->S, N = ctx->N;
   ctx->user_events.assign(S, 0);
+  { const char* e = getenv("VSLAM_PDL"); ctx->pdl = e ? atoi(e) != 0 : true; }    // programmatic dependent launch of a frame's kernels (VSLAM_PDL=0: ordinary launches, for A/B runs)
   int w = cfg->width, h = cfg->height;
   size_t strip_words = 0;
   for (int l = 0; l < VS_LEVELS; l++) {

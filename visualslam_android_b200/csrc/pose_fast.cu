@@ -294,6 +294,7 @@ __device__ __forceinline__ double radix_select(FastSmem& sm, const double (&key)
 
 // mode 1: coarse stage, 2: fine stage (+ scene depth; + motion model / quality if tail)
 __global__ void __launch_bounds__(kFT, 2) k_pose_fast(Dev D, int mode, int tail, int serial) {
+  cudaGridDependencySynchronize(); cudaTriggerProgrammaticLaunchCompletion();   // programmatic dependent launch (vs_launch_pdl); no-ops otherwise
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FastSmem& sm = *reinterpret_cast<FastSmem*>(smem_raw);
   const int s = blockIdx.x + D.s0, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -678,7 +679,7 @@ int vs_launch_pose_fast(vslam_ctx* ctx, int mode) {
     }
   }
   vs_time_begin(ctx, (mode & 3) == 2 ? VS_ST_POSE_FINE : VS_ST_POSE_COARSE);
-  k_pose_fast<<<ctx->cur_cnt, kFT, smem, ctx->stream>>>(D, mode & 3, (mode >> 2) & 1, ctx->params.serial_normal_equations);
+  VS_CUDA(vs_launch_pdl(k_pose_fast, dim3(ctx->cur_cnt), dim3(kFT), smem, ctx->stream, ctx->pdl && !ctx->timing, D, mode & 3, (mode >> 2) & 1, ctx->params.serial_normal_equations));
   vs_time_end(ctx);
   VS_CUDA(cudaGetLastError());
   ctx->launches++;

@@ -188,6 +188,12 @@ __device__ __forceinline__ void fast_strip(const LevelDesc& L, const uint8_t* __
     mbar_expect_tx(&sh.bar, bytes);
     bulk_g2s(img, src + (size_t)ya * stride, bytes, &sh.bar);
   }
+  // the strip's rows of the corner bitmask are set by this CTA alone: it clears them itself (no per-frame memset), behind the bulk copy
+  {
+    uint32_t* own = L.cbits + ((size_t)s * H + y0) * words_per_row;
+    for (int i = tid; i < (y1 - y0) * words_per_row; i += nthreads) own[i] = 0u;
+  }
+  __syncthreads();     // ... before any warp of the CTA sets a bit
   mbar_wait(&sh.bar, 0);
 
   // ---- dense pass: a lane slot = 16 pixels x 2 rows (one 128-bit shared-memory load per row), slots of the strip in raster order,
@@ -401,7 +407,12 @@ k_pyramid_fast(LevelDesc L, LevelDesc L1, LevelDesc L2, LevelDesc L3, const uint
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ StripShared sh;
   __shared__ LevelDesc child[3];
-  if (threadIdx.x == 0) { sh.ticket = (int)atomicAdd(ticket, 1u); sh.next_item = (int)(blockDim.x >> 5); mbar_init(&sh.bar, 1); child[0] = L1; child[1] = L2; child[2] = L3; }
+  cudaGridDependencySynchronize(); cudaTriggerProgrammaticLaunchCompletion();   // programmatic dependent launch (vs_launch_pdl); no-ops otherwise
+  if (threadIdx.x == 0) {
+    const unsigned tk = atomicAdd(ticket, 1u);
+    if (tk == gridDim.x - 1) *ticket = 0u;        // every ticket of this launch has been drawn: the counter is ready for the next frame (no memset)
+    sh.ticket = (int)tk; sh.next_item = (int)(blockDim.x >> 5); mbar_init(&sh.bar, 1); child[0] = L1; child[1] = L2; child[2] = L3;
+  }
   __syncthreads();
   const int t = sh.ticket;
   const int q = div_small(t, L.mg_strips), s = first_stream + q, strip = t - q * L.n_strips;
@@ -413,7 +424,12 @@ __global__ void __maxnreg__(VS_PYR_REGS)
 k_fast_levels(LevelDesc L1, LevelDesc L2, LevelDesc L3, int first_stream, int count, int thr1, int thr2, int thr3, unsigned* __restrict__ ticket) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ StripShared sh;
-  if (threadIdx.x == 0) { sh.ticket = (int)atomicAdd(ticket, 1u); sh.next_item = (int)(blockDim.x >> 5); mbar_init(&sh.bar, 1); }
+  cudaGridDependencySynchronize(); cudaTriggerProgrammaticLaunchCompletion();   // programmatic dependent launch (vs_launch_pdl); no-ops otherwise
+  if (threadIdx.x == 0) {
+    const unsigned tk = atomicAdd(ticket, 1u);
+    if (tk == gridDim.x - 1) *ticket = 0u;
+    sh.ticket = (int)tk; sh.next_item = (int)(blockDim.x >> 5); mbar_init(&sh.bar, 1);
+  }
   __syncthreads();
   int t = sh.ticket, thr = thr1;
   const int n1 = count * L1.n_strips, n2 = count * L2.n_strips;
@@ -470,17 +486,9 @@ static const int kFastThr[VS_LEVELS] = {10, 15, 15, 10};
 
 // Level 0: pyramid levels 1..3 + FAST-10 of level 0 (one launch).
 int vs_launch_pyramid_l0(vslam_ctx* ctx, int first_stream, int count) {
-  unsigned* tickets = ctx->tickets + 2 * ctx->cur_group;   // [0]: level-0 launch, [1]: levels 1-3 launch; one pair per stream group
-  if (first_stream == 0 && count == ctx->S && ctx->cur_group == 0) {
-    VS_CUDA(cudaMemsetAsync(ctx->sync_words, 0, sizeof(unsigned long long) * ctx->sync_words_n, ctx->stream));   // the corner bitmasks of all levels + the tickets at once
-  } else {
-    VS_CUDA(cudaMemsetAsync(tickets, 0, sizeof(unsigned) * 2, ctx->stream));
-    for (int l = 0; l < VS_LEVELS; l++) {
-      LevelDesc& L = ctx->lev[l];
-      const size_t per_stream = (size_t)L.h * ((L.w + 31) / 32);
-      VS_CUDA(cudaMemsetAsync(L.cbits + (size_t)first_stream * per_stream, 0, sizeof(uint32_t) * (size_t)count * per_stream, ctx->stream));
-    }
-  }
+  // [0]: level-0 launch, [1]: levels 1-3 launch; one pair per stream group.  Zero at creation; the CTA that draws a launch's last ticket
+  // zeroes the counter again, and every CTA clears its own rows of the corner bitmask: nothing to memset per frame.
+  unsigned* tickets = ctx->tickets + 2 * ctx->cur_group;
   LevelDesc& L = ctx->lev[0];
   int stride = 0;
   for (int s = first_stream; s < first_stream + count; s++) stride = ctx->l0_stride_host[s] > stride ? ctx->l0_stride_host[s] : stride;
@@ -489,8 +497,8 @@ int vs_launch_pyramid_l0(vslam_ctx* ctx, int first_stream, int count) {
   if (smem > 227 * 1024) { ctx->err = "pyramid_fast: strip does not fit in shared memory (row stride too large)"; return VSLAM_E_INVALID; }
   VS_CUDA(cudaFuncSetAttribute(k_pyramid_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   vs_time_begin(ctx, VS_ST_PYR0);
-  k_pyramid_fast<<<count * L.n_strips, threads, smem, ctx->stream>>>(L, ctx->lev[1], ctx->lev[2], ctx->lev[3], ctx->l0_ptr, ctx->l0_stride, first_stream, kFastThr[0],
-                                                                     tickets);
+  VS_CUDA(vs_launch_pdl(k_pyramid_fast, dim3(count * L.n_strips), dim3(threads), smem, ctx->stream, ctx->pdl && !ctx->timing, L, ctx->lev[1], ctx->lev[2], ctx->lev[3],
+                        (const uint8_t* const*)ctx->l0_ptr, (const int*)ctx->l0_stride, first_stream, kFastThr[0], tickets));
   vs_time_end(ctx);
   VS_CUDA(cudaGetLastError());
   ctx->launches++;
@@ -514,8 +522,8 @@ int vs_launch_fast_levels(vslam_ctx* ctx, int first_stream, int count) {
   if (smem > 227 * 1024) { ctx->err = "fast_levels: strip does not fit in shared memory"; return VSLAM_E_INVALID; }
   VS_CUDA(cudaFuncSetAttribute(k_fast_levels, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   vs_time_begin(ctx, VS_ST_PYR1);
-  k_fast_levels<<<blocks, threads, smem, ctx->stream>>>(ctx->lev[1], ctx->lev[2], ctx->lev[3], first_stream, count, kFastThr[1], kFastThr[2], kFastThr[3],
-                                                        ctx->tickets + 2 * ctx->cur_group + 1);
+  VS_CUDA(vs_launch_pdl(k_fast_levels, dim3(blocks), dim3(threads), smem, ctx->stream, ctx->pdl && !ctx->timing, ctx->lev[1], ctx->lev[2], ctx->lev[3], first_stream, count,
+                        kFastThr[1], kFastThr[2], kFastThr[3], ctx->tickets + 2 * ctx->cur_group + 1));
   vs_time_end(ctx);
   VS_CUDA(cudaGetLastError());
   ctx->launches++;

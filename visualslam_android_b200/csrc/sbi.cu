@@ -278,6 +278,7 @@ __device__ void sbi_se3_from_se2(const double* CtoC, const CamDev& cam, const do
 
 // Per frame and stream: the tracker's SmallBlurryImage pair (blur 0.75) and Tracker::CalcSBIRotation (jni/Tracker.cc:86-97,885-893)
 __global__ void __launch_bounds__(kT) k_sbi(SbiDev D) {
+  cudaGridDependencySynchronize(); cudaTriggerProgrammaticLaunchCompletion();   // programmatic dependent launch (vs_launch_pdl); no-ops otherwise
   __shared__ SbiShared sh;
   const int s = blockIdx.x + D.s0, tid = threadIdx.x;
   const int W = D.w, H = D.h, n = W * H;
@@ -322,6 +323,7 @@ __global__ void __launch_bounds__(kT) k_reloc_make(RelocDev Rd, const int* __res
 // (jni/Tracker.cc:167-180: pose = start pose = best, velocity zero, coarse stage forced).  TrackMap + AssessTrackingQuality follow in
 // the usual kernels, which treat a stream with `recovered` set as alive (no motion model before, no UpdateMotionModel after).
 __global__ void __launch_bounds__(kT) k_relocalise(SbiDev D, RelocDev Rd) {
+  cudaGridDependencySynchronize(); cudaTriggerProgrammaticLaunchCompletion();
   __shared__ SbiShared sh;
   const int s = blockIdx.x + D.s0, tid = threadIdx.x;
   StreamState* st = D.ss + s;
@@ -389,13 +391,13 @@ int vs_launch_sbi(vslam_ctx* ctx) {
   if (!ctx->sbi_on) return VSLAM_OK;
   const SbiDev D = make_sbi_dev(ctx);
   vs_time_begin(ctx, VS_ST_OTHER);
-  k_sbi<<<ctx->cur_cnt, kT, 0, ctx->stream>>>(D);
+  VS_CUDA(vs_launch_pdl(k_sbi, dim3(ctx->cur_cnt), dim3(kT), 0, ctx->stream, ctx->pdl && !ctx->timing, D));
   vs_time_end(ctx);
   VS_CUDA(cudaGetLastError());
   ctx->launches++;
   if (ctx->reloc_n > 0) {   // lost streams try to relocalise; CTAs of streams that are not lost return at once
     vs_time_begin(ctx, VS_ST_OTHER);
-    k_relocalise<<<ctx->cur_cnt, kT, 0, ctx->stream>>>(D, make_reloc_dev(ctx));
+    VS_CUDA(vs_launch_pdl(k_relocalise, dim3(ctx->cur_cnt), dim3(kT), 0, ctx->stream, ctx->pdl && !ctx->timing, D, make_reloc_dev(ctx)));
     vs_time_end(ctx);
     VS_CUDA(cudaGetLastError());
     ctx->launches++;

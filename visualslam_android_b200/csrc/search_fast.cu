@@ -61,6 +61,7 @@ constexpr int kSearchTemplateOnlyF = 2;   // sflags: stop after MakeTemplateCoar
 
 template <int PT>
 __global__ void __launch_bounds__(kFW * 32, VS_SEARCH_MINB) k_search_fast(Dev D, int mode, int range_arg, int subpix_arg, int sflags) {
+  cudaGridDependencySynchronize(); cudaTriggerProgrammaticLaunchCompletion();   // programmatic dependent launch (vs_launch_pdl); no-ops otherwise
   __shared__ FastWarp sm_all[kFW];
   const int s = blockIdx.y + D.s0, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane / kGL, j = lane % kGL;
   StreamState* st = D.ss + s;
@@ -360,6 +361,7 @@ constexpr int kWin = VS_MAXP + 5;   // image window staged per entry: the P - 1 
 struct SubpixEntry { double prod[3][(VS_MAXP - 2) * (VS_MAXP - 2)]; uint32_t tmpl_w[VS_TMPL_BYTES / 4]; uint8_t win[kWin * kWin]; };   // dDiff*gx, dDiff*gy, dDiff per interior pixel; the template; the window
 
 __global__ void __launch_bounds__(kFW * 32) k_subpix(Dev D, int mode, int range_arg, int subpix_arg, int sflags) {
+  cudaGridDependencySynchronize(); cudaTriggerProgrammaticLaunchCompletion();
   __shared__ SubpixEntry sm_all[kFW][kSW];
   const int s = blockIdx.y + D.s0, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane / kSL, j = lane % kSL;
   StreamState* st = D.ss + s;
@@ -507,15 +509,16 @@ int vs_launch_search_fast(vslam_ctx* ctx, int which, int range, int subpix, int 
   const int per_cta = kFW * kGW;
   dim3 grid((max_entries + per_cta - 1) / per_cta, ctx->cur_cnt);
   vs_time_begin(ctx, which == 2 ? VS_ST_SEARCH_FINE : VS_ST_SEARCH_COARSE);
-  if (ctx->P == 11) k_search_fast<11><<<grid, kFW * 32, 0, ctx->stream>>>(D, which, range, subpix, sflags);
-  else if (ctx->P == 8) k_search_fast<8><<<grid, kFW * 32, 0, ctx->stream>>>(D, which, range, subpix, sflags);
-  else k_search_fast<0><<<grid, kFW * 32, 0, ctx->stream>>>(D, which, range, subpix, sflags);
+  const bool pdl = ctx->pdl && !ctx->timing;
+  if (ctx->P == 11) VS_CUDA(vs_launch_pdl(k_search_fast<11>, grid, dim3(kFW * 32), 0, ctx->stream, pdl, D, which, range, subpix, sflags));
+  else if (ctx->P == 8) VS_CUDA(vs_launch_pdl(k_search_fast<8>, grid, dim3(kFW * 32), 0, ctx->stream, pdl, D, which, range, subpix, sflags));
+  else VS_CUDA(vs_launch_pdl(k_search_fast<0>, grid, dim3(kFW * 32), 0, ctx->stream, pdl, D, which, range, subpix, sflags));
   ctx->launches++;
   // sub-pixel refinement: every entry of the coarse stage / of an explicit list with subpix > 0, the top-level entries of the fine stage
   const bool any_subpix = which == 0 ? subpix > 0 : (which == 1 ? ctx->params.coarse_subpix_its > 0 : ctx->params.fine_subpix_its_top_level > 0);
   if (any_subpix && !(sflags & 2)) {
     dim3 g2(std::min((max_entries + kFW * kSW - 1) / (kFW * kSW), 16), ctx->cur_cnt);
-    k_subpix<<<g2, kFW * 32, 0, ctx->stream>>>(D, which, range, subpix, sflags);
+    VS_CUDA(vs_launch_pdl(k_subpix, g2, dim3(kFW * 32), 0, ctx->stream, pdl, D, which, range, subpix, sflags));
     ctx->launches++;
   }
   vs_time_end(ctx);

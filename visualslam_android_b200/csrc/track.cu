@@ -31,6 +31,7 @@ __device__ __forceinline__ void shuffle_swaps(int* v, const int* jv, int n) {
 }
 
 __global__ void __launch_bounds__(kPT) k_project_lists(Dev D, int mode, int apply_motion, int use_smem) {
+  cudaGridDependencySynchronize(); cudaTriggerProgrammaticLaunchCompletion();   // programmatic dependent launch (vs_launch_pdl); no-ops otherwise
   extern __shared__ int sh_i[];          // [N] packed level lists (L3|L2|L1|L0), [N] random draws
   __shared__ double s_pose[12];
   __shared__ int s_cnt[kPT / 32][VS_LEVELS], s_run[VS_LEVELS], s_off[VS_LEVELS + 1];
@@ -846,6 +847,7 @@ __global__ void __launch_bounds__(kPT, 2) k_pose(Dev D, int mode, double sigma_a
 // `found` yet, so only the projection is refreshed; when the coarse stage did not run the pose is unchanged and the
 // projection of k_project_lists is still exact, so the CTA returns at once.
 __global__ void __launch_bounds__(kPT) k_reproject_fine(Dev D) {
+  cudaGridDependencySynchronize(); cudaTriggerProgrammaticLaunchCompletion();   // programmatic dependent launch (vs_launch_pdl); no-ops otherwise
   const int s = blockIdx.x + D.s0;
   StreamState* st = D.ss + s;
   if ((st->lost_frames >= 3 && !st->recovered) || !st->did_coarse) return;
@@ -882,7 +884,7 @@ int vs_launch_project_all(vslam_ctx* ctx, int mode) {
   if (!use_smem) smem = 0;
   if (smem > ctx->smem_attr[0]) { VS_CUDA(cudaFuncSetAttribute(k_project_lists, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); ctx->smem_attr[0] = smem; }
   vs_time_begin(ctx, VS_ST_PROJECT);
-  k_project_lists<<<ctx->cur_cnt, kPT, smem, ctx->stream>>>(D, mode & 1, (mode >> 1) & 1, use_smem);
+  VS_CUDA(vs_launch_pdl(k_project_lists, dim3(ctx->cur_cnt), dim3(kPT), smem, ctx->stream, ctx->pdl && !ctx->timing, D, mode & 1, (mode >> 1) & 1, use_smem));
   vs_time_end(ctx);
   VS_CUDA(cudaGetLastError());
   ctx->launches++;
@@ -938,7 +940,7 @@ int vs_launch_track_map_rest(vslam_ctx* ctx, int with_motion_model) {
   if ((rc = vs_launch_search(ctx, 1, 0, 0, 0))) return rc;
   if ((rc = vs_launch_pose(ctx, 1, 0.0, 0, 0))) return rc;
   vs_time_begin(ctx, VS_ST_OTHER);
-  k_reproject_fine<<<ctx->cur_cnt, kPT, 0, ctx->stream>>>(make_dev(ctx));
+  VS_CUDA(vs_launch_pdl(k_reproject_fine, dim3(ctx->cur_cnt), dim3(kPT), 0, ctx->stream, ctx->pdl && !ctx->timing, make_dev(ctx)));
   vs_time_end(ctx);
   VS_CUDA(cudaGetLastError());
   ctx->launches++;

@@ -149,6 +149,7 @@ struct vslam_ctx {
   void* pf_buf = nullptr; size_t pf_cap = 0;   // scratch of the per-object PatchFinder calls (patchfinder_ops.cu)
   std::vector<int> user_events;                // [S] pending user events (vslam_user_event)
   int* list_counts = nullptr; size_t list_counts_cap = 0;   // per-chunk corner counts of k_corner_count / k_corner_lists
+  bool pdl = true;               // programmatic dependent launch of a frame's kernels (vs_launch_pdl); VSLAM_PDL=0 turns it off
   bool lists_stale = false;      // the last tracked frame left corner bitmasks only: corner lists / row LUTs are built on demand (vs_ensure_lists)
   std::string err;
 };
@@ -171,6 +172,19 @@ inline void vs_time_begin(vslam_ctx* ctx, int stage) {
   cudaEventRecord(ctx->ev_pool[ctx->ev_used++], ctx->stream);
 }
 inline void vs_time_end(vslam_ctx* ctx) { if (ctx->timing) cudaEventRecord(ctx->ev_pool[ctx->ev_used++], ctx->stream); }
+
+// Launch with programmatic dependent launch (sm_90+): the kernel's CTAs may be scheduled while the previous kernel of the stream drains -- its
+// launch latency and ramp-up hide behind that kernel's tail -- and the kernel itself waits for the previous kernel's completion and memory
+// (cudaGridDependencySynchronize() as its FIRST statement; a no-op in an ordinary launch).  pdl = false: an ordinary launch.
+template <class... KArgs, class... Args>
+inline cudaError_t vs_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 // kernels/launchers implemented in the .cu files
 int vs_strip_rows(int level, int w, int pitch);
