@@ -126,7 +126,10 @@ int vslam_create(const vslam_config* cfg, vslam_ctx** out) {
   CK(cudaEventCreateWithFlags(&ctx->ev_begin, cudaEventDisableTiming));
   const int S = ctx->S, N = ctx->N;
   ctx->user_events.assign(S, 0);
-  { const char* e = getenv("VSLAM_PDL"); ctx->pdl = e ? atoi(e) != 0 : true; }    // programmatic dependent launch of a frame's kernels (VSLAM_PDL=0: ordinary launches, for A/B runs)
+  // programmatic dependent launch of a frame's kernels: on by default up to 1080p frames (measured: VGA 0.7509 -> 0.7318 ms per step, 1080p neutral,
+  // 4K 7.15 -> 7.51 ms: there every kernel runs for many waves and the parked CTAs of its successor only take registers and shared memory away);
+  // VSLAM_PDL=0 / 1 overrides (A/B runs)
+  { const char* e = getenv("VSLAM_PDL"); ctx->pdl = e ? atoi(e) != 0 : ((long long)cfg->width * cfg->height <= 1920ll * 1080ll); }
   int w = cfg->width, h = cfg->height;
   size_t strip_words = 0;
   for (int l = 0; l < VS_LEVELS; l++) {
