@@ -101,6 +101,11 @@ typedef struct vslam_params {
                                additions per iteration (measured cost: DESIGN.md section 4.4) */
   int pose_kernel;          /* execution only: 0 (default) = k_pose_fast (found points resident on the SM), 1 = k_pose (the round-1 kernel) */
   int search_kernel;        /* execution only: 0 (default) = k_search_fast + k_subpix (eight lanes per map point), 1 = k_search (one warp per point, round 1) */
+  int frame_lookahead;      /* execution only, no effect on results: 1 = vslam_track_frame* keep two sets of level images / corner bitmasks and run the
+                               pose-independent front end of a frame (pyramid, FAST, SmallBlurryImage rotation) on a second CUDA stream, beside the
+                               previous frame's projection / patch search / pose iterations, whenever the caller has issued that frame before the
+                               previous one finished (the calls are asynchronous); 0 = off; -1 (default) = the library decides from the workload
+                                */
 } vslam_params;
 
 void vslam_default_config(vslam_config* cfg);

@@ -769,6 +769,83 @@ def test_track_frame_relocalises_lost_streams():
     ctx.close()
 
 
+@pytest.mark.parametrize("entry", ["device", "host", "async"])
+def test_frame_lookahead_changes_no_result(entry):
+    """vslam_params.frame_lookahead (two frame sets; the pyramid / FAST / SmallBlurryImage front end of frame k + 1 on a second CUDA stream
+    beside the projection / search / pose back end of frame k) is execution only: the same frames issued back to back WITHOUT any
+    synchronisation give bit-identical poses, counters, update twists and per-point state with it and without it -- through all three
+    vslam_track_frame* entry points, with streams that lose track (noise frames), relocalise against registered keyframes and carry on,
+    and with other calls (getters, a keyframe build) in between, after which the look-ahead has to fall back to a full barrier."""
+    import torch
+    cam, f0, smap = common.scene()
+    sbi_cam = synth.Camera(cam.width // 16, cam.height // 16).scalars()
+    kf_twists = [np.zeros(6), np.array([0.10, 0.02, 0.01, 0.01, -0.04, 0.05])]
+    kf_frames, kf_poses = zip(*[common.frame_at(cam, tw) for tw in kf_twists])
+    S, K = 6, 14
+    rs = np.random.RandomState(11)
+    seq = np.empty((K, S) + f0.shape, dtype=np.uint8)
+    for k in range(K):
+        for s in range(S):
+            if s in (1, 4) and 2 + (s == 4) <= k < 6 + (s == 4):
+                seq[k, s] = rs.randint(0, 255, f0.shape).astype(np.uint8)                 # four frames of noise: the stream gets lost ...
+            elif s in (1, 4) and k >= 6 + (s == 4):
+                seq[k, s] = common.frame_at(cam, kf_twists[1] + 0.002 * (k - 5) * np.array([1.0, -0.5, 0.5, 2.0, 1.5, -2.0]))[0]   # ... and relocalises near keyframe 1
+            else:
+                seq[k, s] = synth.render_frame(common.texture(), cam, synth.stream_pose(3 * (k + 1), s))
+
+    def run(lookahead):
+        ctx = _ctx(cam, f0, smap, n_streams=S, max_source_keyframes=2)
+        ctx.set_params(frame_lookahead=lookahead)
+        ctx.enable_sbi(sbi_cam)
+        ctx.upload_source_keyframe(kf_frames[1], 1)
+        ctx.set_reloc_keyframes([0, 1], np.stack(kf_poses))
+        W, H = cam.width, cam.height
+        mid = {}
+        if entry == "device":
+            dev = torch.from_numpy(seq).cuda()
+            for k in range(K):
+                ctx.track_frame_ptr(dev[k].data_ptr(), W, W * H, device=True)
+                if k == 8:      # other work between two frames: getters (synchronising) and a keyframe build on the current frame set (kernel launches)
+                    mid["poses"] = ctx.get_poses().copy()
+                    mid["corners"] = [ctx.corners(0, l).copy() for l in range(4)]
+                    mid["level"] = ctx.level(2, 1).copy()
+                    ctx.make_keyframe_lite(seq[k])
+        elif entry == "host":
+            for k in range(K):
+                ctx.track_frame(seq[k])
+        else:
+            pin = torch.from_numpy(seq).pin_memory()
+            poses = torch.zeros((K, S, 12), dtype=torch.float64).pin_memory()
+            ids = [ctx.track_frame_async(pin[k].data_ptr(), W, W * H, poses[k].data_ptr()) for k in range(K)]
+            for sid in ids:
+                ctx.wait_step(sid)
+            mid["poses_per_step"] = poses.numpy().copy()
+        out = dict(poses=ctx.get_poses().copy(), counters=[ctx.counters(s) for s in range(S)], updates=[ctx.updates(s) for s in range(S)],
+                   states=[ctx.point_states(s) for s in range(S)], reloc=[ctx.reloc_info(s) for s in range(S)], sbi=[ctx.get_sbi_rotation(s) for s in range(S)],
+                   levels=[ctx.level(s, l).copy() for s in (0, S - 1) for l in range(4)], mid=mid)
+        ctx.close()
+        return out
+
+    a, b = run(0), run(1)
+
+    def same(x, y, what):
+        if isinstance(x, dict):
+            assert x.keys() == y.keys(), what
+            for k in x:
+                same(x[k], y[k], f"{what}.{k}")
+        elif isinstance(x, (list, tuple)):
+            assert len(x) == len(y), what
+            for i, (u, v) in enumerate(zip(x, y)):
+                same(u, v, f"{what}[{i}]")
+        elif isinstance(x, np.ndarray):
+            assert np.array_equal(x, y), what
+        else:
+            assert x == y, (what, x, y)
+    same(a, b, "result")
+    assert sum(r[2] for r in a["reloc"]) >= 2, a["reloc"]                  # the two noisy streams did relocalise
+    assert all(c[2] == 2 for c in a["counters"]), a["counters"]            # and every stream ends with quality GOOD
+
+
 @pytest.mark.parametrize("n_points", [1, 3, 25])
 def test_track_frame_tiny_maps_and_blank_frames(n_points):
     """Edge cases of the whole TrackFrame: maps of 1 / 3 / 25 points (Tukey's `n*2-6` wraps or divides by zero, jni/MEstimator.h:73;

@@ -39,7 +39,7 @@ class Params(C.Structure):
     _fields_ = [("coarse_min", C.c_uint), ("coarse_max", C.c_uint), ("coarse_range", C.c_uint), ("coarse_subpix_its", C.c_int),
                 ("coarse_min_vel", C.c_double), ("fine_range", C.c_int), ("fine_range_after_coarse", C.c_int),
                 ("fine_subpix_its_top_level", C.c_int), ("max_patches_per_frame", C.c_int), ("use_sbi", C.c_int), ("stream_groups", C.c_int),
-                ("serial_normal_equations", C.c_int), ("pose_kernel", C.c_int), ("search_kernel", C.c_int)]
+                ("serial_normal_equations", C.c_int), ("pose_kernel", C.c_int), ("search_kernel", C.c_int), ("frame_lookahead", C.c_int)]
 
 
 # every symbol include/vslam_b200.h declares (tests/test_abi_cpu.py checks the library exports all of them)

@@ -13,9 +13,14 @@ namespace {
 
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
+// cudaMemset / cudaMemset2D run on the legacy default stream and may return before the device has done them; the context's streams are
+// non-blocking and do not wait for that stream, so every clear made from the host is followed by a wait for it.
+cudaError_t memset_sync(void* p, int v, size_t n) { const cudaError_t e = cudaMemset(p, v, n); return e == cudaSuccess ? cudaStreamSynchronize(cudaStreamLegacy) : e; }
+cudaError_t memset2d_sync(void* p, size_t pitch, int v, size_t w, size_t h) { const cudaError_t e = cudaMemset2D(p, pitch, v, w, h); return e == cudaSuccess ? cudaStreamSynchronize(cudaStreamLegacy) : e; }
+
 template <class T> cudaError_t dalloc(T** p, size_t count) {
   cudaError_t e = cudaMalloc((void**)p, count * sizeof(T) + 256);   // +256: aligned word reads may touch the tail
-  if (e == cudaSuccess) e = cudaMemset(*p, 0, count * sizeof(T) + 256);
+  if (e == cudaSuccess) e = memset_sync(*p, 0, count * sizeof(T) + 256);
   return e;
 }
 
@@ -69,7 +74,7 @@ void vslam_default_config(vslam_config* c) {
 
 void vslam_default_params(vslam_params* p) {   // jni/Tracker.cc:405-410,495-497,518
   p->coarse_min = 20; p->coarse_max = 60; p->coarse_range = 30; p->coarse_subpix_its = 8; p->coarse_min_vel = 0.006;
-  p->fine_range = 10; p->fine_range_after_coarse = 5; p->fine_subpix_its_top_level = 8; p->max_patches_per_frame = 1000; p->use_sbi = 1; p->stream_groups = 1; p->serial_normal_equations = 0; p->pose_kernel = 0; p->search_kernel = 0;
+  p->fine_range = 10; p->fine_range_after_coarse = 5; p->fine_subpix_its_top_level = 8; p->max_patches_per_frame = 1000; p->use_sbi = 1; p->stream_groups = 1; p->serial_normal_equations = 0; p->pose_kernel = 0; p->search_kernel = 0; p->frame_lookahead = -1;
 }
 
 const char* vslam_last_error(const vslam_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
@@ -90,6 +95,63 @@ void vslam_camera_from_params(const double* p, int width, int height, int as_shi
   c[10] = 1.5 * c[9];
   c[11] = width; c[12] = height;
 }
+
+// ---------------------------------------------------------------------------------------------- frame sets (frame look-ahead)
+static void use_set(vslam_ctx* ctx, int p) {
+  const FrameSet& F = ctx->sets[p];
+  for (int l = 0; l < VS_LEVELS; l++) { ctx->lev[l].img = F.img[l]; ctx->lev[l].cbits = F.cbits[l]; }
+  ctx->l0_ptr = F.l0_ptr; ctx->l0_stride = F.l0_stride; ctx->l0_ptr_host = F.l0_ptr_host; ctx->l0_stride_host = F.l0_stride_host;
+  ctx->cur_set = p;
+}
+// Second frame set + the front-end streams and events, on the first look-ahead frame.
+static int alloc_set1(vslam_ctx* ctx) {
+  if (ctx->have_set1) return VSLAM_OK;
+  FrameSet& F = ctx->sets[1];
+  const int S = ctx->S;
+  size_t words = 0;
+  for (int l = 0; l < VS_LEVELS; l++) words += ((size_t)S * ctx->lev[l].h * ((ctx->lev[l].w + 31) / 32) + 1) / 2;
+  VS_CUDA(dalloc(&F.cbits_block, words));
+  { size_t off = 0; for (int l = 0; l < VS_LEVELS; l++) { F.cbits[l] = (uint32_t*)(F.cbits_block + off); off += ((size_t)S * ctx->lev[l].h * ((ctx->lev[l].w + 31) / 32) + 1) / 2; } }
+  F.img[0] = ctx->l0_alt;               // (null until a host-input path needs it: vs_ensure_own_l0)
+  for (int l = 1; l < VS_LEVELS; l++) VS_CUDA(dalloc(&F.img[l], (size_t)S * ctx->lev[l].h * ctx->lev[l].pitch));
+  VS_CUDA(dalloc(&F.l0_ptr, (size_t)S)); VS_CUDA(dalloc(&F.l0_stride, (size_t)S));
+  F.l0_ptr_host = new const uint8_t*[S]; F.l0_stride_host = new int[S];
+  for (int s = 0; s < S; s++) { F.l0_ptr_host[s] = nullptr; F.l0_stride_host[s] = 0; }   // no level 0 yet: the first frame of this set uploads its table
+  VS_CUDA(cudaStreamCreateWithFlags(&ctx->front_stream, cudaStreamNonBlocking)); VS_CUDA(cudaStreamCreateWithFlags(&ctx->front_side, cudaStreamNonBlocking));
+  for (cudaEvent_t* e : {&ctx->ev_front_done, &ctx->ev_barrier, &ctx->ev_back_done[0], &ctx->ev_back_done[1], &ctx->ev_la_fork, &ctx->ev_la_join}) VS_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  ctx->have_set1 = true;
+  return VSLAM_OK;
+}
+static int vs_ensure_own_l0(vslam_ctx* ctx) {
+  if (ctx->lev[0].img) return VSLAM_OK;     // (only set 1 starts without one)
+  if (!ctx->l0_alt) { VS_CUDA(dalloc(&ctx->l0_alt, (size_t)ctx->S * ctx->lev[0].h * ctx->lev[0].pitch)); }
+  ctx->sets[1].img[0] = ctx->l0_alt;
+  if (ctx->cur_set == 1) ctx->lev[0].img = ctx->l0_alt;
+  return VSLAM_OK;
+}
+// Start of every vslam_track_frame*.  With look-ahead the frame gets the OTHER frame set, and its input and front end go to front_stream, which
+// waits only for the back end that last read that set (two frames ago) -- so they run beside the previous frame's back end, still in flight on
+// ctx->stream.  That shortcut is taken only when nothing but frames was launched since the last look-ahead frame (ctx->launches unchanged);
+// otherwise front_stream waits for everything enqueued on ctx->stream so far.
+static bool lookahead_default(const vslam_ctx* ctx) {
+  const char* e = getenv("VSLAM_LOOKAHEAD");
+  if (e) return atoi(e) != 0;
+  return (long long)ctx->S * ctx->lev[0].w * ctx->lev[0].h <= 160ll * 640 * 480;
+}
+static int vs_begin_frame(vslam_ctx* ctx) {
+  int la = ctx->params.frame_lookahead < 0 ? (lookahead_default(ctx) ? 1 : 0) : ctx->params.frame_lookahead;
+  if (ctx->timing || ctx->params.stream_groups > 1) la = 0;      // per-stage timing serialises everything on ctx->stream; stream groups have their own streams
+  ctx->la_frame = la != 0; ctx->front = ctx->stream;
+  if (!la) return VSLAM_OK;
+  int rc = alloc_set1(ctx); if (rc) { ctx->la_frame = false; return rc; }
+  const bool chained = ctx->launches == ctx->launches_after_frame;
+  use_set(ctx, ctx->cur_set ^ 1);
+  if (chained) VS_CUDA(cudaStreamWaitEvent(ctx->front_stream, ctx->ev_back_done[ctx->cur_set], 0));
+  else { VS_CUDA(cudaEventRecord(ctx->ev_barrier, ctx->stream)); VS_CUDA(cudaStreamWaitEvent(ctx->front_stream, ctx->ev_barrier, 0)); }
+  ctx->front = ctx->front_stream;
+  return VSLAM_OK;
+}
+static int end_frame(vslam_ctx* ctx, int rc) { ctx->front = nullptr; ctx->la_frame = false; return rc; }
 
 int vslam_create(const vslam_config* cfg, vslam_ctx** out) {
   if (!cfg || !out) { g_create_error = "null argument"; return VSLAM_E_INVALID; }
@@ -158,6 +220,9 @@ int vslam_create(const vslam_config* cfg, vslam_ctx** out) {
   for (int s = 0; s < S; s++) { ctx->l0_ptr_host[s] = ctx->lev[0].img + (size_t)s * ctx->lev[0].h * ctx->lev[0].pitch; ctx->l0_stride_host[s] = ctx->lev[0].pitch; }
   CK(cudaMemcpy(ctx->l0_ptr, ctx->l0_ptr_host, sizeof(uint8_t*) * S, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(ctx->l0_stride, ctx->l0_stride_host, sizeof(int) * S, cudaMemcpyHostToDevice));
+  { FrameSet& F = ctx->sets[0];   // the one frame set every context has (a second one comes with frame look-ahead: alloc_set1)
+    for (int l = 0; l < VS_LEVELS; l++) { F.img[l] = ctx->lev[l].img; F.cbits[l] = ctx->lev[l].cbits; }
+    F.cbits_block = nullptr; F.l0_ptr = ctx->l0_ptr; F.l0_stride = ctx->l0_stride; F.l0_ptr_host = ctx->l0_ptr_host; F.l0_stride_host = ctx->l0_stride_host; }
   CK(dalloc(&ctx->status, (size_t)4)); CK(dalloc(&ctx->evals, (size_t)4));   // [0] ZMSSD candidates scored, [1] unused, [2] templates generated, [3] sub-pixel refinements
   // map
   ctx->map.n = 0;
@@ -200,6 +265,17 @@ void vslam_destroy(vslam_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->cfg.device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->front_stream) cudaStreamSynchronize(ctx->front_stream);
+  use_set(ctx, 0);                      // the aliases freed below are set 0's; set 1 owns the rest (its level 0 is l0_alt)
+  if (ctx->have_set1) {
+    FrameSet& F = ctx->sets[1];
+    for (int l = 1; l < VS_LEVELS; l++) cudaFree(F.img[l]);
+    cudaFree(F.cbits_block); cudaFree(F.l0_ptr); cudaFree(F.l0_stride); delete[] F.l0_ptr_host; delete[] F.l0_stride_host;
+  }
+  if (ctx->front_stream) cudaStreamDestroy(ctx->front_stream);
+  if (ctx->front_side) cudaStreamDestroy(ctx->front_side);
+  for (cudaEvent_t e : {ctx->ev_front_done, ctx->ev_barrier, ctx->ev_back_done[0], ctx->ev_back_done[1], ctx->ev_la_fork, ctx->ev_la_join}) if (e) cudaEventDestroy(e);
+  cudaFree(ctx->sbi_rot_buf); cudaFree(ctx->reloc_frame_scratch); cudaFree(ctx->reloc_frame_small);
   for (int l = 0; l < VS_LEVELS; l++) { cudaFree(ctx->lev[l].img); cudaFree(ctx->lev[l].corners); cudaFree(ctx->lev[l].lut); cudaFree(ctx->src.img[l]); }
   cudaFree(ctx->epi_buf); cudaFree(ctx->pf_buf); cudaFree(ctx->list_counts); cudaFree(ctx->l0_ptr); cudaFree(ctx->l0_stride); cudaFree(ctx->sync_words); cudaFree(ctx->status); cudaFree(ctx->evals);
   cudaFree(ctx->map.world); cudaFree(ctx->map.right); cudaFree(ctx->map.down); cudaFree(ctx->map.ircenter); cudaFree(ctx->map.srclevel); cudaFree(ctx->map.srckf);
@@ -260,6 +336,7 @@ int vslam_set_params(vslam_ctx* ctx, const vslam_params* p) {
   if (2 * p->coarse_max > (unsigned)ctx->list_cap) { ctx->err = "coarse_max too large"; return VSLAM_E_INVALID; }
   if (p->stream_groups < 0 || p->stream_groups > VS_MAX_GROUPS) { ctx->err = "stream_groups must be 0 (default) .. 4"; return VSLAM_E_INVALID; }
   if (p->max_patches_per_frame < 0) { ctx->err = "max_patches_per_frame must be >= 0"; return VSLAM_E_INVALID; }
+  if (p->frame_lookahead < -1 || p->frame_lookahead > 1) { ctx->err = "frame_lookahead must be -1 (library default), 0 or 1"; return VSLAM_E_INVALID; }
   ctx->params = *p;
   return VSLAM_OK;
 }
@@ -310,6 +387,7 @@ int vslam_enable_sbi(vslam_ctx* ctx, const double* c) {
   if (!ctx->sbi_tmpl) {
     VS_CUDA(dalloc(&ctx->sbi_tmpl, (size_t)ctx->S * 2 * n)); VS_CUDA(dalloc(&ctx->sbi_scratch, (size_t)ctx->S * 3 * n));
     VS_CUDA(dalloc(&ctx->sbi_jac, (size_t)ctx->S * 2 * n)); VS_CUDA(dalloc(&ctx->sbi_small, (size_t)ctx->S * n)); VS_CUDA(dalloc(&ctx->sbi_have, (size_t)2 * ctx->S));
+    VS_CUDA(dalloc(&ctx->sbi_rot_buf, (size_t)2 * ctx->S * 6)); VS_CUDA(dalloc(&ctx->reloc_frame_scratch, (size_t)ctx->S * 3 * n)); VS_CUDA(dalloc(&ctx->reloc_frame_small, (size_t)ctx->S * n));
   }
   ctx->sbi_on = true;
   return VSLAM_OK;
@@ -325,7 +403,10 @@ int vslam_set_reloc_keyframes(vslam_ctx* ctx, int n, const int32_t* src_kf_ids, 
   cudaFree(ctx->reloc_tmpl); cudaFree(ctx->reloc_jac); cudaFree(ctx->reloc_tmp); cudaFree(ctx->reloc_small); cudaFree(ctx->reloc_pose); cudaFree(ctx->reloc_scores);
   ctx->reloc_tmpl = nullptr; ctx->reloc_jac = nullptr; ctx->reloc_tmp = nullptr; ctx->reloc_small = nullptr; ctx->reloc_pose = nullptr; ctx->reloc_scores = nullptr;
   ctx->reloc_n = 0; ctx->reloc_ids.clear(); ctx->reloc_poses_host.clear();
-  if (n == 0) return VSLAM_OK;
+  if (n == 0) {   // no relocaliser, no k_relocalise to reset the per-frame `recovered` mark
+    VS_CUDA(memset2d_sync((char*)ctx->ss + offsetof(StreamState, recovered), sizeof(StreamState), 0, sizeof(int), ctx->S));
+    return VSLAM_OK;
+  }
   const size_t px = (size_t)(ctx->lev[3].w / 2) * (ctx->lev[3].h / 2);
   {   // cv::getGaussianKernel(17, 2.5, CV_32F) as the stand-in computes it (host exp, float taps)
     const double sigma = 2.5, scale2x = -0.5 / (sigma * sigma); double sum = 0;
@@ -377,11 +458,11 @@ int vslam_set_map(vslam_ctx* ctx, int n, const double* world, const double* righ
   VS_CUDA(cudaMemcpy(ctx->map.ircenter, irc, sizeof(int) * 2 * n, cudaMemcpyHostToDevice));
   VS_CUDA(cudaMemcpy(ctx->map.srclevel, lvl, sizeof(int) * n, cudaMemcpyHostToDevice));
   if (kf) VS_CUDA(cudaMemcpy(ctx->map.srckf, kf, sizeof(int) * n, cudaMemcpyHostToDevice));
-  else VS_CUDA(cudaMemset(ctx->map.srckf, 0, sizeof(int) * n));
+  else VS_CUDA(memset_sync(ctx->map.srckf, 0, sizeof(int) * n));
   // a new map invalidates every per-point tracker state (TrackerData is created lazily per MapPoint, jni/Tracker.cc:372)
   const size_t SN = (size_t)ctx->S * ctx->N;
-  VS_CUDA(cudaMemset(ctx->ps.flags, 0, SN * sizeof(int)));
-  VS_CUDA(cudaMemset(ctx->ps.counts, 0, 2 * SN * sizeof(int)));
+  VS_CUDA(memset_sync(ctx->ps.flags, 0, SN * sizeof(int)));
+  VS_CUDA(memset_sync(ctx->ps.counts, 0, 2 * SN * sizeof(int)));
   ctx->map.n = n;
   return VSLAM_OK;
 }
@@ -402,23 +483,24 @@ int vslam_append_map_points(vslam_ctx* ctx, int n_new, const double* world, cons
   VS_CUDA(cudaMemcpy(ctx->map.ircenter + 2 * (size_t)n0, irc, sizeof(int) * 2 * n_new, cudaMemcpyHostToDevice));
   VS_CUDA(cudaMemcpy(ctx->map.srclevel + n0, lvl, sizeof(int) * n_new, cudaMemcpyHostToDevice));
   if (kf) VS_CUDA(cudaMemcpy(ctx->map.srckf + n0, kf, sizeof(int) * n_new, cudaMemcpyHostToDevice));
-  else VS_CUDA(cudaMemset(ctx->map.srckf + n0, 0, sizeof(int) * n_new));
+  else VS_CUDA(memset_sync(ctx->map.srckf + n0, 0, sizeof(int) * n_new));
   // per-stream state of the new points only: rows of [S][N] (flags) and [2][S][N] (counters)
-  VS_CUDA(cudaMemset2D(ctx->ps.flags + n0, sizeof(int) * ctx->N, 0, sizeof(int) * n_new, ctx->S));
-  VS_CUDA(cudaMemset2D(ctx->ps.counts + n0, sizeof(int) * ctx->N, 0, sizeof(int) * n_new, 2 * (size_t)ctx->S));
+  VS_CUDA(memset2d_sync(ctx->ps.flags + n0, sizeof(int) * ctx->N, 0, sizeof(int) * n_new, ctx->S));
+  VS_CUDA(memset2d_sync(ctx->ps.counts + n0, sizeof(int) * ctx->N, 0, sizeof(int) * n_new, 2 * (size_t)ctx->S));
   ctx->map.n = n0 + n_new;
   return VSLAM_OK;
 }
 
 // ---------------------------------------------------------------------------------------------- MakeKeyFrame_Lite
 static int adopt_l0(vslam_ctx* ctx, int first, int count, const uint8_t* base, int stride, size_t frame_stride, bool own) {
+  if (own) { const int rc = vs_ensure_own_l0(ctx); if (rc) return rc; }
   for (int k = 0; k < count; k++) {
     const int s = first + k;
     ctx->l0_ptr_host[s] = own ? ctx->lev[0].img + (size_t)s * ctx->lev[0].h * ctx->lev[0].pitch : base + (size_t)k * frame_stride;
     ctx->l0_stride_host[s] = own ? ctx->lev[0].pitch : stride;
   }
-  VS_CUDA(cudaMemcpyAsync(ctx->l0_ptr + first, ctx->l0_ptr_host + first, sizeof(uint8_t*) * count, cudaMemcpyHostToDevice, ctx->stream));
-  VS_CUDA(cudaMemcpyAsync(ctx->l0_stride + first, ctx->l0_stride_host + first, sizeof(int) * count, cudaMemcpyHostToDevice, ctx->stream));
+  VS_CUDA(cudaMemcpyAsync(ctx->l0_ptr + first, ctx->l0_ptr_host + first, sizeof(uint8_t*) * count, cudaMemcpyHostToDevice, vs_in_stream(ctx)));
+  VS_CUDA(cudaMemcpyAsync(ctx->l0_stride + first, ctx->l0_stride_host + first, sizeof(int) * count, cudaMemcpyHostToDevice, vs_in_stream(ctx)));
   return VSLAM_OK;
 }
 
@@ -435,7 +517,7 @@ static int upload_frames_to(vslam_ctx* ctx, uint8_t* base, cudaStream_t st, int 
 }
 static int upload_frames(vslam_ctx* ctx, int first, int count, const uint8_t* gray, int stride, size_t frame_stride) {
   vs_time_begin(ctx, VS_ST_H2D);
-  int rc = upload_frames_to(ctx, ctx->lev[0].img, ctx->stream, first, count, gray, stride, frame_stride);
+  int rc = upload_frames_to(ctx, ctx->lev[0].img, vs_in_stream(ctx), first, count, gray, stride, frame_stride);
   vs_time_end(ctx);
   return rc;
 }
@@ -449,6 +531,7 @@ static int check_range(vslam_ctx* ctx, int first, int count, const void* p, int 
 // Host frames: copy into the ctx-owned level-0 images (re-adopting them if a device buffer had been adopted).
 static int stage_host_frames(vslam_ctx* ctx, int first, int count, const uint8_t* gray, int stride, size_t frame_stride) {
   int rc = check_range(ctx, first, count, gray, stride); if (rc) return rc;
+  if ((rc = vs_ensure_own_l0(ctx))) return rc;
   bool was_adopted = false;
   for (int s = first; s < first + count; s++) was_adopted |= ctx->l0_stride_host[s] != ctx->lev[0].pitch || ctx->l0_ptr_host[s] != ctx->lev[0].img + (size_t)s * ctx->lev[0].h * ctx->lev[0].pitch;
   if (was_adopted && (rc = adopt_l0(ctx, first, count, nullptr, 0, 0, true))) return rc;
@@ -709,7 +792,7 @@ int vslam_add_keyframe_from_stream(vslam_ctx* ctx, int s, int kf_id) {
   if ((rc = vslam_set_reloc_keyframes(ctx, (int)ids.size(), ids.data(), poses.data()))) return rc;
   if ((rc = read_ss(ctx, s, &st))) return rc;
   st.last_kf_dropped = st.frame_no; st.kf_request = 0;
-  VS_CUDA(cudaMemset(ctx->kf_req + s, 0, sizeof(int)));
+  VS_CUDA(memset_sync(ctx->kf_req + s, 0, sizeof(int)));
   return write_ss(ctx, s, &st);
 }
 
@@ -1050,15 +1133,15 @@ int vslam_track_map(vslam_ctx* ctx) { if (!ctx) return VSLAM_E_INVALID; return v
 
 int vslam_track_frame(vslam_ctx* ctx, const uint8_t* gray, int stride, size_t frame_stride) {
   if (!ctx) return VSLAM_E_INVALID;
-  const int rc = stage_host_frames(ctx, 0, ctx->S, gray, stride, frame_stride);
-  return rc ? rc : vs_launch_frame(ctx);
+  int rc = vs_begin_frame(ctx);
+  if (!rc) rc = stage_host_frames(ctx, 0, ctx->S, gray, stride, frame_stride);
+  return end_frame(ctx, rc ? rc : vs_launch_frame(ctx));
 }
 // Pipelined host-input path: the copy of step k (copy stream, level-0 buffer k&1) overlaps the kernels of step k-1.
 int vslam_track_frame_async(vslam_ctx* ctx, const uint8_t* gray, int stride, size_t frame_stride, double* poses_out) {
   int rc = check_range(ctx, 0, ctx ? ctx->S : 0, gray, stride); if (rc) return rc;
   const LevelDesc& L = ctx->lev[0];
   if (!ctx->pipe_ready) {
-    VS_CUDA(dalloc(&ctx->l0_alt, (size_t)ctx->S * L.h * L.pitch));
     VS_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     VS_CUDA(cudaHostAlloc((void**)&ctx->status_pin, sizeof(int) * 8, cudaHostAllocDefault));
     memset(ctx->status_pin, 0, sizeof(int) * 8);
@@ -1071,16 +1154,20 @@ int vslam_track_frame_async(vslam_ctx* ctx, const uint8_t* gray, int stride, siz
   }
   const int slot = (int)(ctx->step & 1);
   VS_CUDA(cudaEventSynchronize(ctx->ev_done[slot]));                       // at most two steps in flight
-  uint8_t* buf = slot ? ctx->l0_alt : L.img;
-  VS_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_computed[slot], 0));   // the kernels that last read this buffer are done
-  if ((rc = upload_frames_to(ctx, buf, ctx->copy_stream, 0, ctx->S, gray, stride, frame_stride))) return rc;
-  VS_CUDA(cudaEventRecord(ctx->ev_copied[slot], ctx->copy_stream));
-  VS_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[slot], 0));
+  if ((rc = vs_begin_frame(ctx))) return end_frame(ctx, rc);
+  // level-0 buffer of this step: with look-ahead the frame set's own one, else the two buffers in turn (b = which of the two: the events of the copy belong to the buffer)
+  const int b = ctx->la_frame ? ctx->cur_set : slot;
+  if (b == 1 && !ctx->l0_alt) { VS_CUDA(dalloc(&ctx->l0_alt, (size_t)ctx->S * L.h * L.pitch)); ctx->sets[1].img[0] = ctx->l0_alt; if (ctx->cur_set == 1) ctx->lev[0].img = ctx->l0_alt; }
+  uint8_t* buf = b ? ctx->l0_alt : ctx->sets[0].img[0];
+  VS_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_computed[b], 0));   // the kernels that last read this buffer are done
+  if ((rc = upload_frames_to(ctx, buf, ctx->copy_stream, 0, ctx->S, gray, stride, frame_stride))) return end_frame(ctx, rc);
+  VS_CUDA(cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
+  VS_CUDA(cudaStreamWaitEvent(vs_in_stream(ctx), ctx->ev_copied[b], 0));
   bool same = true;
   for (int s = 0; s < ctx->S; s++) same &= ctx->l0_ptr_host[s] == buf + (size_t)s * L.h * L.pitch && ctx->l0_stride_host[s] == L.pitch;
-  if (!same && (rc = adopt_l0(ctx, 0, ctx->S, buf, L.pitch, (size_t)L.h * L.pitch, false))) return rc;
-  if ((rc = vs_launch_frame(ctx))) return rc;
-  VS_CUDA(cudaEventRecord(ctx->ev_computed[slot], ctx->stream));
+  if (!same && (rc = adopt_l0(ctx, 0, ctx->S, buf, L.pitch, (size_t)L.h * L.pitch, false))) return end_frame(ctx, rc);
+  if ((rc = end_frame(ctx, vs_launch_frame(ctx)))) return rc;
+  VS_CUDA(cudaEventRecord(ctx->ev_computed[b], ctx->stream));
   if (poses_out)
     VS_CUDA(cudaMemcpy2DAsync(poses_out, sizeof(double) * 12, (char*)ctx->ss + offsetof(StreamState, pose), sizeof(StreamState), sizeof(double) * 12, ctx->S,
                               cudaMemcpyDeviceToHost, ctx->stream));
@@ -1108,8 +1195,9 @@ int vslam_wait_step(vslam_ctx* ctx, int step) {
 
 int vslam_track_frame_dev(vslam_ctx* ctx, const uint8_t* gray, int stride, size_t frame_stride) {
   if (!ctx) return VSLAM_E_INVALID;
-  const int rc = adopt_device_frames(ctx, 0, ctx->S, gray, stride, frame_stride);
-  return rc ? rc : vs_launch_frame(ctx);
+  int rc = vs_begin_frame(ctx);
+  if (!rc) rc = adopt_device_frames(ctx, 0, ctx->S, gray, stride, frame_stride);
+  return end_frame(ctx, rc ? rc : vs_launch_frame(ctx));
 }
 
 }  // extern "C"

@@ -29,6 +29,8 @@ struct SbiDev {
   float* jac;               // [S][2n]    gradient image of the last template
   uint8_t* small;           // [S][n]
   StreamState* ss; int* have; int* parity;   // per stream
+  double* rot_out;          // [S][6] Tracker::mv6SBIRot of this frame (the frame set's slot of ctx->sbi_rot_buf); k_project_lists hands it to StreamState::sbi_rot
+  float* reloc_scratch; uint8_t* reloc_small;   // k_relocalise's own scratch [S][3n] / [S][n]
   int use_sbi, s0;
 };
 
@@ -282,19 +284,19 @@ __global__ void __launch_bounds__(kT) k_sbi(SbiDev D) {
   __shared__ SbiShared sh;
   const int s = blockIdx.x + D.s0, tid = threadIdx.x;
   const int W = D.w, H = D.h, n = W * H;
-  StreamState* st = D.ss + s;
   const int par = D.parity[s];
   float* cur = D.tmpl + ((size_t)s * 2 + par) * n;
   float* last = D.tmpl + ((size_t)s * 2 + (par ^ 1)) * n;
   float* tmp = D.scratch + (size_t)s * 3 * n;
   float* warped = tmp + n;
-  if (tid == 0) st->recovered = 0;      // set again by k_relocalise if this frame relocalises the stream
   sbi_make(D.l3 + (size_t)s * D.l3h * D.l3pitch, D.l3pitch, D.l3h, D.rs, W, H, D.taps, 9, D.small + (size_t)s * n, tmp, cur, sh);
   const bool first = !D.have[s];
   if (first) { for (int i = tid; i < n; i += kT) last[i] = cur[i]; }   // first frame: both SBIs come from the same keyframe (jni/Tracker.cc:90-93)
   __syncthreads();
   if (tid == 0) { D.have[s] = 1; D.parity[s] = par ^ 1; }               // next frame: `cur` becomes `last`
-  if (!D.use_sbi || st->lost_frames >= 3) return;
+  // (The kernel reads no tracker state: it belongs to the pose-independent front end of a frame and may run before the previous frame's pose
+  // is known.  A lost stream's rotation estimate is computed and never used: k_project_lists returns before the motion model.)
+  if (!D.use_sbi) return;
   float* jac = D.jac + (size_t)s * 2 * n;
   sbi_make_jacs(last, jac, W, H);
   sbi_esm(cur, last, jac, warped, W, H, 6, sh);
@@ -302,7 +304,7 @@ __global__ void __launch_bounds__(kT) k_sbi(SbiDev D) {
     double R[9]; sbi_se3_from_se2(sh.CtoC, D.cam, D.orig, W, H, R);
     double P[12]; for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) P[4 * i + j] = R[3 * i + j]; P[4 * i + 3] = 0.0; }
     double v6[6]; se3_ln(P, v6);
-    for (int k = 0; k < 6; k++) st->sbi_rot[k] = v6[k];
+    for (int k = 0; k < 6; k++) D.rot_out[6 * (size_t)s + k] = v6[k];
   }
 }
 
@@ -327,12 +329,13 @@ __global__ void __launch_bounds__(kT) k_relocalise(SbiDev D, RelocDev Rd) {
   __shared__ SbiShared sh;
   const int s = blockIdx.x + D.s0, tid = threadIdx.x;
   StreamState* st = D.ss + s;
+  if (tid == 0) st->recovered = 0;      // set again below if this frame relocalises the stream
   if (st->lost_frames < 3 || Rd.n_kf <= 0) return;
   const int W = D.w, H = D.h, n = W * H;
-  float* tmp = D.scratch + (size_t)s * 3 * n;
+  float* tmp = D.reloc_scratch + (size_t)s * 3 * n;      // (not k_sbi's scratch: with frame look-ahead the next frame's k_sbi may be running)
   float* warped = tmp + n;
   float* cur = tmp + 2 * n;
-  sbi_make(D.l3 + (size_t)s * D.l3h * D.l3pitch, D.l3pitch, D.l3h, D.rs, W, H, Rd.taps17, 17, D.small + (size_t)s * n, tmp, cur, sh);
+  sbi_make(D.l3 + (size_t)s * D.l3h * D.l3pitch, D.l3pitch, D.l3h, D.rs, W, H, Rd.taps17, 17, D.reloc_small + (size_t)s * n, tmp, cur, sh);
   // ScoreKFs: SmallBlurryImage::ZMSSD (jni/SmallBlurryImage.cc:82-94), serial sum in the reference's order (x outer, y inner), one thread per keyframe
   double* scores = Rd.scores + (size_t)s * Rd.n_kf;
   for (int k = tid; k < Rd.n_kf; k += kT) {
@@ -375,6 +378,7 @@ static SbiDev make_sbi_dev(vslam_ctx* ctx) {
   D.cam = ctx->sbi_cam; memcpy(D.orig, ctx->sbi_orig, sizeof(D.orig));
   D.tmpl = ctx->sbi_tmpl; D.scratch = ctx->sbi_scratch; D.jac = ctx->sbi_jac; D.small = ctx->sbi_small; D.ss = ctx->ss; D.have = ctx->sbi_have; D.parity = ctx->sbi_have + ctx->S;
   D.use_sbi = ctx->params.use_sbi; D.s0 = ctx->cur_s0;
+  D.rot_out = ctx->sbi_rot_buf + (size_t)ctx->cur_set * ctx->S * 6; D.reloc_scratch = ctx->reloc_frame_scratch; D.reloc_small = ctx->reloc_frame_small;
   return D;
 }
 static RelocDev make_reloc_dev(vslam_ctx* ctx) {
@@ -395,6 +399,13 @@ int vs_launch_sbi(vslam_ctx* ctx) {
   vs_time_end(ctx);
   VS_CUDA(cudaGetLastError());
   ctx->launches++;
+  return VSLAM_OK;
+}
+
+// The lost branch of Tracker::TrackFrame: needs the lost state the previous frame left, i.e. it opens the back end of a frame
+int vs_launch_relocalise(vslam_ctx* ctx) {
+  if (!ctx->sbi_on) return VSLAM_OK;
+  const SbiDev D = make_sbi_dev(ctx);
   if (ctx->reloc_n > 0) {   // lost streams try to relocalise; CTAs of streams that are not lost return at once
     vs_time_begin(ctx, VS_ST_OTHER);
     VS_CUDA(vs_launch_pdl(k_relocalise, dim3(ctx->cur_cnt), dim3(kT), 0, ctx->stream, ctx->pdl && !ctx->timing, D, make_reloc_dev(ctx)));

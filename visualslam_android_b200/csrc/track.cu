@@ -30,7 +30,7 @@ __device__ __forceinline__ void shuffle_swaps(int* v, const int* jv, int n) {
   }
 }
 
-__global__ void __launch_bounds__(kPT) k_project_lists(Dev D, int mode, int apply_motion, int use_smem) {
+__global__ void __launch_bounds__(kPT) k_project_lists(Dev D, int mode, int apply_motion, int use_smem, const double* __restrict__ sbi_rot_in) {
   cudaGridDependencySynchronize(); cudaTriggerProgrammaticLaunchCompletion();   // programmatic dependent launch (vs_launch_pdl); no-ops otherwise
   extern __shared__ int sh_i[];          // [N] packed level lists (L3|L2|L1|L0), [N] random draws
   __shared__ double s_pose[12];
@@ -45,7 +45,10 @@ __global__ void __launch_bounds__(kPT) k_project_lists(Dev D, int mode, int appl
   if (tid == 0 && apply_motion && !st->recovered) {   // Tracker::ApplyMotionModel (jni/Tracker.cc:781-798); a relocalised stream starts from the recovered pose
     double v[6]; for (int k = 0; k < 6; k++) v[k] = st->velocity[k];
     for (int k = 0; k < 12; k++) st->start_pose[k] = st->pose[k];
-    if (D.prm.use_sbi) { v[0] = 0.0; v[1] = 0.0; v[3] = st->sbi_rot[3]; v[4] = st->sbi_rot[4]; v[5] = st->sbi_rot[5]; }
+    if (D.prm.use_sbi) {
+      if (sbi_rot_in) for (int k = 0; k < 6; k++) st->sbi_rot[k] = sbi_rot_in[6 * (size_t)s + k];   // Tracker::mv6SBIRot of THIS frame (k_sbi, front end of the frame)
+      v[0] = 0.0; v[1] = 0.0; v[3] = st->sbi_rot[3]; v[4] = st->sbi_rot[4]; v[5] = st->sbi_rot[5];
+    }
     double e[12], np[12]; se3_exp(v, e); se3_mul(e, st->start_pose, np);
     for (int k = 0; k < 12; k++) st->pose[k] = np[k];
   }
@@ -884,7 +887,7 @@ int vs_launch_project_all(vslam_ctx* ctx, int mode) {
   if (!use_smem) smem = 0;
   if (smem > ctx->smem_attr[0]) { VS_CUDA(cudaFuncSetAttribute(k_project_lists, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); ctx->smem_attr[0] = smem; }
   vs_time_begin(ctx, VS_ST_PROJECT);
-  VS_CUDA(vs_launch_pdl(k_project_lists, dim3(ctx->cur_cnt), dim3(kPT), smem, ctx->stream, ctx->pdl && !ctx->timing, D, mode & 1, (mode >> 1) & 1, use_smem));
+  VS_CUDA(vs_launch_pdl(k_project_lists, dim3(ctx->cur_cnt), dim3(kPT), smem, ctx->stream, ctx->pdl && !ctx->timing, D, mode & 1, (mode >> 1) & 1, use_smem, ctx->cur_sbi_rot));
   vs_time_end(ctx);
   VS_CUDA(cudaGetLastError());
   ctx->launches++;
@@ -960,6 +963,9 @@ int vs_launch_track_map(vslam_ctx* ctx, int with_motion_model) {
 static int launch_frame_group(vslam_ctx* ctx, int g, bool fork) {
   int rc;
   cudaStream_t main_stream = ctx->stream;
+  // k_project_lists takes this frame's SmallBlurryImage rotation from the frame set's slot of sbi_rot_buf (null: StreamState::sbi_rot as the host set it)
+  struct RotGuard { vslam_ctx* c; ~RotGuard() { c->cur_sbi_rot = nullptr; } } rot_guard{ctx};
+  ctx->cur_sbi_rot = (ctx->sbi_on && ctx->params.use_sbi) ? ctx->sbi_rot_buf + (size_t)ctx->cur_set * ctx->S * 6 : nullptr;
   if ((rc = vs_launch_pyramid_l0(ctx, ctx->cur_s0, ctx->cur_cnt))) return rc;
   if (fork) {
     VS_CUDA(cudaEventRecord(ctx->ev_fork[g], main_stream));
@@ -967,6 +973,7 @@ static int launch_frame_group(vslam_ctx* ctx, int g, bool fork) {
     ctx->stream = ctx->side_stream[g];
   }
   rc = vs_launch_sbi(ctx);
+  if (!rc) rc = vs_launch_relocalise(ctx);
   if (!rc) rc = vs_launch_project_all(ctx, 3);
   ctx->stream = main_stream;
   if (fork) VS_CUDA(cudaEventRecord(ctx->ev_join[g], ctx->side_stream[g]));
@@ -985,7 +992,44 @@ static int launch_frame_group(vslam_ctx* ctx, int g, bool fork) {
 // B200 (256 VGA streams): 2-4 groups are 5 % slower than one (smaller grids, more tails; the hoped-for overlap of one group's
 // latency-bound k_pose with another group's k_search does not materialise because k_pose CTAs hold half an SM's registers each),
 // hence the default of 1.  With per-stage timing on (vslam_set_timing) everything is serialised on ctx->stream.
+// Frame look-ahead (vs_begin_frame chose it: ctx->la_frame, ctx->front == ctx->front_stream, the frame's set is current): the front end
+//   front_stream: k_pyramid_fast -> fork { front_side: k_sbi } || k_fast_levels -> join
+// depends on the frame alone and runs beside the previous frame's back end, which is still in flight on ctx->stream; the back end
+//   ctx->stream:  (front end done) -> k_relocalise -> k_project_lists -> searches and pose iterations
+// follows in stream order.  ev_back_done[set] tells the front end of the frame after next that this set may be overwritten.
+static int launch_frame_lookahead(vslam_ctx* ctx) {
+  int rc;
+  cudaStream_t main_stream = ctx->stream, F = ctx->front_stream;
+  struct Guard { vslam_ctx* c; cudaStream_t m; ~Guard() { c->stream = m; c->cur_sbi_rot = nullptr; } } guard{ctx, main_stream};
+  ctx->cur_sbi_rot = (ctx->sbi_on && ctx->params.use_sbi) ? ctx->sbi_rot_buf + (size_t)ctx->cur_set * ctx->S * 6 : nullptr;
+  ctx->stream = F;
+  if ((rc = vs_launch_pyramid_l0(ctx, 0, ctx->S))) return rc;
+  if (ctx->sbi_on) {
+    VS_CUDA(cudaEventRecord(ctx->ev_la_fork, F));
+    VS_CUDA(cudaStreamWaitEvent(ctx->front_side, ctx->ev_la_fork, 0));
+    ctx->stream = ctx->front_side;
+    rc = vs_launch_sbi(ctx);
+    ctx->stream = F;
+    VS_CUDA(cudaEventRecord(ctx->ev_la_join, ctx->front_side));
+    if (rc) return rc;
+  }
+  if ((rc = vs_launch_fast_levels(ctx, 0, ctx->S))) return rc;
+  if (ctx->sbi_on) VS_CUDA(cudaStreamWaitEvent(F, ctx->ev_la_join, 0));
+  VS_CUDA(cudaEventRecord(ctx->ev_front_done, F));
+  ctx->stream = main_stream;
+  VS_CUDA(cudaStreamWaitEvent(main_stream, ctx->ev_front_done, 0));
+  if (ctx->params.search_kernel == 0) ctx->lists_stale = true;
+  else if ((rc = vs_launch_corner_lists(ctx, 0, ctx->S))) return rc;
+  if ((rc = vs_launch_relocalise(ctx))) return rc;
+  if ((rc = vs_launch_project_all(ctx, 3))) return rc;
+  if ((rc = vs_launch_track_map_rest(ctx, 1))) return rc;
+  VS_CUDA(cudaEventRecord(ctx->ev_back_done[ctx->cur_set], main_stream));
+  ctx->launches_after_frame = ctx->launches;
+  return VSLAM_OK;
+}
+
 int vs_launch_frame(vslam_ctx* ctx) {
+  if (ctx->la_frame) { ctx->cur_s0 = 0; ctx->cur_cnt = ctx->S; ctx->cur_group = 0; return launch_frame_lookahead(ctx); }
   int G = ctx->params.stream_groups;
   if (G < 1) G = 1;
   if (G > VS_MAX_GROUPS) G = VS_MAX_GROUPS;

@@ -96,6 +96,16 @@ struct StreamState {
   int frame_no, last_kf_dropped, kf_request, kf_closest; double kf_dist;
 };
 
+// The buffers one frame's pose-independent front end (pyramid, FAST) writes and its pose-dependent back end (projection, patch search) reads.
+// A context has one set, or two when frame look-ahead is on (vs_begin_frame): frame k lives in set k & 1, so that the front end of frame
+// k + 1 can run beside the back end of frame k.  ctx->lev[l].img / .cbits, ctx->l0_ptr / l0_stride (+ host mirrors) always alias the CURRENT set.
+struct FrameSet {
+  uint8_t* img[VS_LEVELS];          // level images ([0]: the ctx-owned level-0 buffer of the host-input paths; may be null in set 1 until needed)
+  uint32_t* cbits[VS_LEVELS];       // corner bitmasks
+  unsigned long long* cbits_block;  // their allocation (set 1 only; set 0's live in ctx->sync_words)
+  const uint8_t** l0_ptr; int* l0_stride; const uint8_t** l0_ptr_host; int* l0_stride_host;
+};
+
 struct vslam_ctx {
   vslam_config cfg;
   vslam_params params;
@@ -149,6 +159,14 @@ struct vslam_ctx {
   void* pf_buf = nullptr; size_t pf_cap = 0;   // scratch of the per-object PatchFinder calls (patchfinder_ops.cu)
   std::vector<int> user_events;                // [S] pending user events (vslam_user_event)
   int* list_counts = nullptr; size_t list_counts_cap = 0;   // per-chunk corner counts of k_corner_count / k_corner_lists
+  // frame look-ahead (vslam_params.frame_lookahead, vs_begin_frame / vs_launch_frame): two frame sets, the front end of a frame on front_stream
+  FrameSet sets[2] = {}; int cur_set = 0; bool have_set1 = false;
+  cudaStream_t front_stream = nullptr, front_side = nullptr; cudaEvent_t ev_front_done = nullptr, ev_barrier = nullptr, ev_back_done[2] = {nullptr, nullptr}, ev_la_fork = nullptr, ev_la_join = nullptr;
+  cudaStream_t front = nullptr;  // inside a vslam_track_frame* call: the stream the frame's input and front end are enqueued on (front_stream or ctx->stream)
+  bool la_frame = false;         // the frame being enqueued runs with look-ahead
+  unsigned long long launches_after_frame = ~0ull;   // ctx->launches when the last look-ahead frame had been enqueued: any kernel launched since forces a full barrier
+  double* sbi_rot_buf = nullptr; const double* cur_sbi_rot = nullptr;   // [2][S][6] k_sbi's result per frame set; what k_project_lists of this frame reads (null: StreamState::sbi_rot as set by the host)
+  float* reloc_frame_scratch = nullptr; uint8_t* reloc_frame_small = nullptr;      // k_relocalise's own scratch ([S][3n] / [S][n]): it may run beside the next frame's k_sbi
   bool pdl = true;               // programmatic dependent launch of a frame's kernels (vs_launch_pdl); VSLAM_PDL=0 turns it off
   bool lists_stale = false;      // the last tracked frame left corner bitmasks only: corner lists / row LUTs are built on demand (vs_ensure_lists)
   std::string err;
@@ -204,7 +222,9 @@ int vs_launch_track_map_rest(vslam_ctx* ctx, int with_motion_model);   // everyt
 int vs_launch_frame(vslam_ctx* ctx);                                   // pyramid + FAST, SmallBlurryImage, TrackMap of all streams
 int vs_launch_project_and_derivs(vslam_ctx* ctx, int only_found);
 int vs_launch_calc_jacobians(vslam_ctx* ctx);
-int vs_launch_sbi(vslam_ctx* ctx);          // + k_relocalise when relocaliser keyframes are registered
+int vs_launch_sbi(vslam_ctx* ctx);          // SmallBlurryImage pair + CalcSBIRotation of the frame (pose independent: part of the front end)
+int vs_launch_relocalise(vslam_ctx* ctx);   // k_relocalise when relocaliser keyframes are registered (back end: needs the stream's lost state)
+inline cudaStream_t vs_in_stream(vslam_ctx* ctx) { return ctx->front ? ctx->front : ctx->stream; }   // where a frame's input (copies, pointer tables) is enqueued
 int vs_launch_reloc_make(vslam_ctx* ctx, const int* src_ids_dev);
 int vs_launch_epipolar_geometry(vslam_ctx* ctx, int n, const EpiGeom& G, const double* rays_dev, const int* xy_dev, EpiCand* cand_dev);
 int vs_launch_epipolar(vslam_ctx* ctx, int stream, int src_kf, int level, int n, const EpiCand* cand_dev, const double* unproj_dev, int subpix_its, int* out_int_dev, double* out_pos_dev);
