@@ -322,6 +322,9 @@ int vslam_debug_dp4a_peak(double* tmacs_per_s);
 
 /* Number of kernels this library has launched on the context since creation (bench.py's gpu_launches). */
 unsigned long long vslam_kernel_launches(const vslam_ctx* ctx);
+/* 1 if the next vslam_track_frame* call would run with frame look-ahead (vslam_params.frame_lookahead resolved against the workload, per-stage
+   timing and stream groups), else 0.  Execution only: results do not depend on it. */
+int vslam_frame_lookahead_active(const vslam_ctx* ctx);
 
 #ifdef __cplusplus
 }

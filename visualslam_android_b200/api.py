@@ -51,7 +51,7 @@ ABI_SYMBOLS = [
     "vslam_set_pose", "vslam_get_pose", "vslam_get_poses", "vslam_set_motion", "vslam_get_motion", "vslam_reset_stream", "vslam_set_sbi_rotation", "vslam_enable_sbi", "vslam_get_sbi_rotation", "vslam_set_reloc_keyframes", "vslam_get_reloc_info", "vslam_set_lost", "vslam_get_counters",
     "vslam_get_point_states", "vslam_get_point_template", "vslam_get_point_counts", "vslam_get_updates", "vslam_get_zmssd_evals",
     "vslam_project_all", "vslam_set_point_projection", "vslam_set_lists", "vslam_clear_counters", "vslam_search_for_points", "vslam_refind", "vslam_get_refind_results", "vslam_epipolar_search", "vslam_project_and_derivs", "vslam_calc_jacobians",
-    "vslam_calc_pose_update", "vslam_track_map", "vslam_track_frame", "vslam_track_frame_dev", "vslam_track_frame_async", "vslam_wait_step", "vslam_debug_atan", "vslam_debug_atan_dd", "vslam_debug_dp4a_peak", "vslam_kernel_launches", "vslam_set_timing", "vslam_get_stage_times",
+    "vslam_calc_pose_update", "vslam_track_map", "vslam_track_frame", "vslam_track_frame_dev", "vslam_track_frame_async", "vslam_wait_step", "vslam_debug_atan", "vslam_debug_atan_dd", "vslam_debug_dp4a_peak", "vslam_kernel_launches", "vslam_frame_lookahead_active", "vslam_set_timing", "vslam_get_stage_times",
     "vslam_get_search_stats", "vslam_make_keyframe_from_source", "vslam_append_map_points", "vslam_set_keyframe_policy", "vslam_get_keyframe_requests", "vslam_add_keyframe_from_stream", "vslam_epipolar_make_points", "vslam_map_file_info", "vslam_save_map_file", "vslam_load_map_file", "vslam_export_map_text",
     "vslam_pf_make_template", "vslam_pf_make_template_nowarp", "vslam_pf_zmssd_at", "vslam_pf_subpix", "vslam_user_event", "vslam_take_user_event",
 ]
@@ -160,6 +160,7 @@ def load():
     sig("vslam_track_frame", i, vp, vp, i, C.c_size_t)
     sig("vslam_track_frame_dev", i, vp, vp, i, C.c_size_t)
     sig("vslam_kernel_launches", C.c_ulonglong, vp)
+    sig("vslam_frame_lookahead_active", i, vp)
     sig("vslam_track_frame_async", i, vp, vp, i, C.c_size_t, vp)
     sig("vslam_wait_step", i, vp, i)
     sig("vslam_debug_atan", i, vp, vp, i)
@@ -634,3 +635,7 @@ class Context:
 
     def kernel_launches(self):
         return int(self.L.vslam_kernel_launches(self.h))
+
+    def frame_lookahead_active(self):
+        """Whether the next track_frame* call runs with frame look-ahead (execution only)."""
+        return bool(self.L.vslam_frame_lookahead_active(self.h))

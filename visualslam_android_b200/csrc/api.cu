@@ -117,8 +117,11 @@ static int alloc_set1(vslam_ctx* ctx) {
   VS_CUDA(dalloc(&F.l0_ptr, (size_t)S)); VS_CUDA(dalloc(&F.l0_stride, (size_t)S));
   F.l0_ptr_host = new const uint8_t*[S]; F.l0_stride_host = new int[S];
   for (int s = 0; s < S; s++) { F.l0_ptr_host[s] = nullptr; F.l0_stride_host[s] = 0; }   // no level 0 yet: the first frame of this set uploads its table
-  VS_CUDA(cudaStreamCreateWithFlags(&ctx->front_stream, cudaStreamNonBlocking)); VS_CUDA(cudaStreamCreateWithFlags(&ctx->front_side, cudaStreamNonBlocking));
-  for (cudaEvent_t* e : {&ctx->ev_front_done, &ctx->ev_barrier, &ctx->ev_back_done[0], &ctx->ev_back_done[1], &ctx->ev_la_fork, &ctx->ev_la_join}) VS_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  // the back end is the latency chain a frame's result waits for: its kernels get the CTA slots first, the front end of the next frame fills in
+  int prio_least = 0, prio_greatest = 0; VS_CUDA(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+  VS_CUDA(cudaStreamCreateWithPriority(&ctx->front_stream, cudaStreamNonBlocking, prio_least)); VS_CUDA(cudaStreamCreateWithPriority(&ctx->front_side, cudaStreamNonBlocking, prio_least));
+  VS_CUDA(cudaStreamCreateWithPriority(&ctx->back_stream, cudaStreamNonBlocking, prio_greatest));
+  for (cudaEvent_t* e : {&ctx->ev_user, &ctx->ev_front_done, &ctx->ev_barrier, &ctx->ev_back_done[0], &ctx->ev_back_done[1], &ctx->ev_la_fork, &ctx->ev_la_join}) VS_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   ctx->have_set1 = true;
   return VSLAM_OK;
 }
@@ -136,11 +139,18 @@ static int vs_ensure_own_l0(vslam_ctx* ctx) {
 static bool lookahead_default(const vslam_ctx* ctx) {
   const char* e = getenv("VSLAM_LOOKAHEAD");
   if (e) return atoi(e) != 0;
-  return (long long)ctx->S * ctx->lev[0].w * ctx->lev[0].h <= 160ll * 640 * 480;
+  // Measured (B200, ms per step without / with): VGA 32 streams 0.315 / 0.253, 64: 0.390 / 0.319, 128: 0.495 / 0.412, 256: 0.726 / 0.745; 1080p x 148: 1.80 / 1.76;
+  // 4K x 148: 7.15 / 6.89.  What decides is whether the one-CTA-per-stream kernels of the back end leave room on the SMs (up to about one stream per SM)
+  return ctx->S <= 160;
 }
-static int vs_begin_frame(vslam_ctx* ctx) {
+static int lookahead_resolved(const vslam_ctx* ctx) {
   int la = ctx->params.frame_lookahead < 0 ? (lookahead_default(ctx) ? 1 : 0) : ctx->params.frame_lookahead;
   if (ctx->timing || ctx->params.stream_groups > 1) la = 0;      // per-stage timing serialises everything on ctx->stream; stream groups have their own streams
+  return la;
+}
+int vslam_frame_lookahead_active(const vslam_ctx* ctx) { return ctx ? lookahead_resolved(ctx) : 0; }
+static int vs_begin_frame(vslam_ctx* ctx) {
+  const int la = lookahead_resolved(ctx);
   ctx->la_frame = la != 0; ctx->front = ctx->stream;
   if (!la) return VSLAM_OK;
   int rc = alloc_set1(ctx); if (rc) { ctx->la_frame = false; return rc; }
@@ -274,7 +284,8 @@ void vslam_destroy(vslam_ctx* ctx) {
   }
   if (ctx->front_stream) cudaStreamDestroy(ctx->front_stream);
   if (ctx->front_side) cudaStreamDestroy(ctx->front_side);
-  for (cudaEvent_t e : {ctx->ev_front_done, ctx->ev_barrier, ctx->ev_back_done[0], ctx->ev_back_done[1], ctx->ev_la_fork, ctx->ev_la_join}) if (e) cudaEventDestroy(e);
+  if (ctx->back_stream) { cudaStreamSynchronize(ctx->back_stream); cudaStreamDestroy(ctx->back_stream); }
+  for (cudaEvent_t e : {ctx->ev_user, ctx->ev_front_done, ctx->ev_barrier, ctx->ev_back_done[0], ctx->ev_back_done[1], ctx->ev_la_fork, ctx->ev_la_join}) if (e) cudaEventDestroy(e);
   cudaFree(ctx->sbi_rot_buf); cudaFree(ctx->reloc_frame_scratch); cudaFree(ctx->reloc_frame_small);
   for (int l = 0; l < VS_LEVELS; l++) { cudaFree(ctx->lev[l].img); cudaFree(ctx->lev[l].corners); cudaFree(ctx->lev[l].lut); cudaFree(ctx->src.img[l]); }
   cudaFree(ctx->epi_buf); cudaFree(ctx->pf_buf); cudaFree(ctx->list_counts); cudaFree(ctx->l0_ptr); cudaFree(ctx->l0_stride); cudaFree(ctx->sync_words); cudaFree(ctx->status); cudaFree(ctx->evals);

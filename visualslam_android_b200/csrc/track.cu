@@ -1016,14 +1016,21 @@ static int launch_frame_lookahead(vslam_ctx* ctx) {
   if ((rc = vs_launch_fast_levels(ctx, 0, ctx->S))) return rc;
   if (ctx->sbi_on) VS_CUDA(cudaStreamWaitEvent(F, ctx->ev_la_join, 0));
   VS_CUDA(cudaEventRecord(ctx->ev_front_done, F));
-  ctx->stream = main_stream;
-  VS_CUDA(cudaStreamWaitEvent(main_stream, ctx->ev_front_done, 0));
+  // back end on the library's high-priority stream: after whatever the caller has enqueued on ctx->stream so far (that includes the previous
+  // frame's join below) and after this frame's front end; ctx->stream then waits for it, so the caller sees ordinary stream order
+  cudaStream_t B = ctx->back_stream;
+  VS_CUDA(cudaEventRecord(ctx->ev_user, main_stream));
+  VS_CUDA(cudaStreamWaitEvent(B, ctx->ev_user, 0));
+  VS_CUDA(cudaStreamWaitEvent(B, ctx->ev_front_done, 0));
+  ctx->stream = B;
   if (ctx->params.search_kernel == 0) ctx->lists_stale = true;
   else if ((rc = vs_launch_corner_lists(ctx, 0, ctx->S))) return rc;
   if ((rc = vs_launch_relocalise(ctx))) return rc;
   if ((rc = vs_launch_project_all(ctx, 3))) return rc;
   if ((rc = vs_launch_track_map_rest(ctx, 1))) return rc;
-  VS_CUDA(cudaEventRecord(ctx->ev_back_done[ctx->cur_set], main_stream));
+  VS_CUDA(cudaEventRecord(ctx->ev_back_done[ctx->cur_set], B));
+  ctx->stream = main_stream;
+  VS_CUDA(cudaStreamWaitEvent(main_stream, ctx->ev_back_done[ctx->cur_set], 0));
   ctx->launches_after_frame = ctx->launches;
   return VSLAM_OK;
 }

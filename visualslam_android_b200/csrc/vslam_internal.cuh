@@ -161,6 +161,8 @@ struct vslam_ctx {
   int* list_counts = nullptr; size_t list_counts_cap = 0;   // per-chunk corner counts of k_corner_count / k_corner_lists
   // frame look-ahead (vslam_params.frame_lookahead, vs_begin_frame / vs_launch_frame): two frame sets, the front end of a frame on front_stream
   FrameSet sets[2] = {}; int cur_set = 0; bool have_set1 = false;
+  cudaStream_t back_stream = nullptr;   // the back end of a look-ahead frame: a high-priority stream of the library's own (the front-end streams have the lowest priority), joined to ctx->stream
+  cudaEvent_t ev_user = nullptr;
   cudaStream_t front_stream = nullptr, front_side = nullptr; cudaEvent_t ev_front_done = nullptr, ev_barrier = nullptr, ev_back_done[2] = {nullptr, nullptr}, ev_la_fork = nullptr, ev_la_join = nullptr;
   cudaStream_t front = nullptr;  // inside a vslam_track_frame* call: the stream the frame's input and front end are enqueued on (front_stream or ctx->stream)
   bool la_frame = false;         // the frame being enqueued runs with look-ahead
