@@ -697,23 +697,25 @@ def main():
         prev = sid
     ctx.wait_step(prev)
     barrier()
-    acc = 0.0
-    prev = None
-    t0 = time.perf_counter()
-    for k in range(K):
-        sid = ctx.track_frame_async(frames_host[tri(step_no)].data_ptr(), W, fs, poses_pin[k & 1].data_ptr()); step_no += 1
-        if prev is not None:
-            ctx.wait_step(prev)
-            acc += float(poses_pin[(k - 1) & 1, :, 3].sum())      # the result of step k-1 is consumed on the host
-        prev = sid
-    ctx.wait_step(prev)
-    acc += float(poses_pin[(K - 1) & 1, :, 3].sum())
-    barrier()
-    wall_ms = (time.perf_counter() - t0) * 1e3
+
+    def e2e_leg(first_step):
+        step, acc, prev = first_step, 0.0, None
+        t0 = time.perf_counter()
+        for k in range(K):
+            sid = ctx.track_frame_async(frames_host[tri(step)].data_ptr(), W, fs, poses_pin[k & 1].data_ptr()); step += 1
+            if prev is not None:
+                ctx.wait_step(prev)
+                acc += float(poses_pin[(k - 1) & 1, :, 3].sum())      # the result of step k-1 is consumed on the host
+            prev = sid
+        ctx.wait_step(prev)
+        acc += float(poses_pin[(K - 1) & 1, :, 3].sum())
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        assert np.isfinite(acc)
+        return step, max_over_ranks(wall_ms)
+
+    step_no, e2e_ms = e2e_leg(step_no)
     clocks = sampler.stop()
-    e2e_ms = max_over_ranks(wall_ms)
-    e2e_value = streams_total * K / (e2e_ms * 1e-3)
-    assert np.isfinite(acc)
 
     # ---- what bounds e2e: the host-to-device copy of a step's frames.  Peak of this box, measured here: pinned cudaMemcpyAsync of the same
     # frame sets on the library's copy path alone (no kernels), all ranks copying at the same time.
@@ -731,6 +733,14 @@ def main():
     barrier()
     h2d_ms = max_over_ranks(e0.elapsed_time(e1)) / nh
     h2d_peak = h2d_bytes / (h2d_ms * 1e-3) / 1e9                       # GB/s per GPU with all ranks copying
+    # the e2e leg is timed on the host's clock over K short steps: a step time more than twice both of its bounds (the kernels of the `value`
+    # leg, the copy just measured) means the host stalled inside the region (seen once: 0.76 ms per step where 0.29 is the rule, 32 streams);
+    # such a leg is re-measured once, and the line says so -- the policy of the `value` leg
+    e2e_remeasured = None
+    if max_over_ranks(1.0 if e2e_ms / K > 2.0 * max(dev_ms / K, h2d_ms) else 0.0) > 0:      # same decision on every rank
+        e2e_remeasured = e2e_ms / K
+        step_no, e2e_ms = e2e_leg(step_no)
+    e2e_value = streams_total * K / (e2e_ms * 1e-3)
     h2d_achieved = h2d_bytes / (e2e_ms / K * 1e-3) / 1e9
     h2d_roofline = {"bound": "host-to-device copy (PCIe / host memory)", "achieved": h2d_achieved, "peak": h2d_peak, "unit": "GB/s per GPU", "frac": h2d_achieved / h2d_peak,
                     "aggregate_peak_gbs": h2d_peak * world, "bytes_per_step_per_gpu": h2d_bytes,
@@ -843,7 +853,8 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": dev_ms / K, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "u8/i32 (pyramid, FAST, ZMSSD) + f64 (projection, WLS)", "data": "synthetic", "config": config,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": S * H * W * world, "d2h_bytes_per_step": S * 12 * 8 * world, "ms_per_step": e2e_ms / K,
-                    "limiter": "host-to-device copy" if h2d_achieved > 0.8 * h2d_peak else "kernels (copy overlapped)"},
+                    "limiter": "host-to-device copy" if h2d_achieved > 0.8 * h2d_peak else "kernels (copy overlapped)",
+                    **({"remeasured_after_stall_ms_per_step": e2e_remeasured} if e2e_remeasured else {})},
             "h2d_roofline": h2d_roofline,
             "gpu_launches": int(launches), "clocks": clocks, **({"remeasured_after_stall_ms_per_step": remeasured} if remeasured else {}), "roofline": roofline, "zmssd_roofline": zmssd, "stages_ms_per_step": stages_ms, "stage_rates": stage_rates,
             "tracking": {"found_per_frame_mean": float(found.mean()), "quality_good_frac": float((quality == 2).mean()),

@@ -443,7 +443,8 @@ __global__ void __launch_bounds__(kFT, kMinB) k_pose_fast(Dev D, int mode, int t
             double a0 = sm.J[0][slot] * v6[0], a1 = sm.J[6][slot] * v6[0];
 #pragma unroll
             for (int q = 1; q < 6; q++) { a0 += sm.J[q][slot] * v6[q]; a1 += sm.J[6 + q][slot] * v6[q]; }
-            const double sc = 1.0 / P[p].si;
+            // 1 / si, si = 2^-level: the reciprocal of a power of two is the power of two with the mirrored exponent (exact, no division)
+            const double sc = __longlong_as_double((long long)(2046ull - (((unsigned long long)__double_as_longlong(P[p].si) >> 52) & 0x7ffull)) << 52);
             P[p].im0 += a0 * sc; P[p].im1 += a1 * sc;
             D.ps.v2image[gi] = P[p].im0; D.ps.v2image[SN + gi] = P[p].im1;
             const double e0 = (P[p].f0 - P[p].im0) * P[p].si, e1 = (P[p].f1 - P[p].im1) * P[p].si;
@@ -488,12 +489,15 @@ __global__ void __launch_bounds__(kFT, kMinB) k_pose_fast(Dev D, int mode, int t
         double acc[27];
 #pragma unroll
         for (int k = 0; k < 27; k++) acc[k] = 0.0;
+        // the Tukey weights of the thread's points first: kPP independent divisions in flight instead of one per point between its rows
+        double wt[kPP];
+#pragma unroll
+        for (int p = 0; p < kPP; p++) { const double sq = (e2[p] > sig2) ? 0.0 : 1.0 - (e2[p] / sig2); wt[p] = sq * sq; }
 #pragma unroll
         for (int p = 0; p < kPP; p++) {
           const int slot = tid + p * kFT;
           if (slot < nres) {
-            const double sq = (e2[p] > sig2) ? 0.0 : 1.0 - (e2[p] / sig2);
-            const double w = sq * sq;
+            const double w = wt[p];
             if (w == 0.0) { if (mark) D.ps.counts[so + P[p].idx]++; }
             else {
               if (mark) D.ps.counts[SN + so + P[p].idx]++;

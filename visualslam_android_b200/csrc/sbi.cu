@@ -7,6 +7,7 @@
 // Deviations from the serial reference, both below 1e-12 relative on the result: the warp positions are evaluated in closed
 // form (p0 + i*down + j*across) instead of by running sums, and the 15 ESM sums are reduced in a fixed tree, not serially.
 #include "geometry.cuh"
+#include <cstdio>
 
 namespace {
 
@@ -32,6 +33,7 @@ struct SbiDev {
   double* rot_out;          // [S][6] Tracker::mv6SBIRot of this frame (the frame set's slot of ctx->sbi_rot_buf); k_project_lists hands it to StreamState::sbi_rot
   float* reloc_scratch; uint8_t* reloc_small;   // k_relocalise's own scratch [S][3n] / [S][n]
   int use_sbi, s0;
+  int smem_floats;          // k_sbi: 3n when this frame's template and the two scratch images fit in dynamic shared memory, else 0 (they stay in global memory)
 };
 
 struct RelocDev {
@@ -58,24 +60,54 @@ __device__ inline double block_sum(double v, double* red) {
   return r;
 }
 
-// 4x4 inverse by partial-pivot LU (same routine as the oracle's inverse_lu), then inv * b
+// 4x4 inverse by partial-pivot LU (same routine as the oracle's inverse_lu), then inv * b.  Every loop is unrolled and the row swap is a chain
+// of selects, so that the matrix stays in registers (a run-time row index would put it in local memory); the arithmetic and its order are those
+// of the plain loops.
 __device__ inline void solve4(const double* m, const double* b, double* x4) {
-  double a[16], inv[16], x[4]; int piv[4];
+  double a[16], inv[16]; int piv[4];
+#pragma unroll
   for (int i = 0; i < 16; i++) a[i] = m[i];
+#pragma unroll
   for (int i = 0; i < 4; i++) piv[i] = i;
+#pragma unroll
   for (int k = 0; k < 4; k++) {
     int p = k; double best = fabs(a[k * 4 + k]);
+#pragma unroll
     for (int i = k + 1; i < 4; i++) if (fabs(a[i * 4 + k]) > best) { best = fabs(a[i * 4 + k]); p = i; }
-    if (p != k) { for (int j = 0; j < 4; j++) { const double t = a[k * 4 + j]; a[k * 4 + j] = a[p * 4 + j]; a[p * 4 + j] = t; } const int t = piv[k]; piv[k] = piv[p]; piv[p] = t; }
-    for (int i = k + 1; i < 4; i++) { a[i * 4 + k] /= a[k * 4 + k]; for (int j = k + 1; j < 4; j++) a[i * 4 + j] -= a[i * 4 + k] * a[k * 4 + j]; }
+#pragma unroll
+    for (int i = k + 1; i < 4; i++) {
+      const bool sw = p == i;
+#pragma unroll
+      for (int j = 0; j < 4; j++) { const double u = a[k * 4 + j], v = a[i * 4 + j]; a[k * 4 + j] = sw ? v : u; a[i * 4 + j] = sw ? u : v; }
+      const int u = piv[k], v = piv[i]; piv[k] = sw ? v : u; piv[i] = sw ? u : v;
+    }
+#pragma unroll
+    for (int i = k + 1; i < 4; i++) {
+      a[i * 4 + k] /= a[k * 4 + k];
+#pragma unroll
+      for (int j = k + 1; j < 4; j++) a[i * 4 + j] -= a[i * 4 + k] * a[k * 4 + j];
+    }
   }
+#pragma unroll
   for (int c = 0; c < 4; c++) {
+    double x[4];
+#pragma unroll
     for (int i = 0; i < 4; i++) x[i] = (piv[i] == c) ? 1.0 : 0.0;
-    for (int i = 0; i < 4; i++) for (int j = 0; j < i; j++) x[i] -= a[i * 4 + j] * x[j];
-    for (int i = 3; i >= 0; i--) { for (int j = i + 1; j < 4; j++) x[i] -= a[i * 4 + j] * x[j]; x[i] /= a[i * 4 + i]; }
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < i; j++) x[i] -= a[i * 4 + j] * x[j];
+#pragma unroll
+    for (int i = 3; i >= 0; i--) {
+#pragma unroll
+      for (int j = i + 1; j < 4; j++) x[i] -= a[i * 4 + j] * x[j];
+      x[i] /= a[i * 4 + i];
+    }
+#pragma unroll
     for (int i = 0; i < 4; i++) inv[i * 4 + c] = x[i];
   }
-  for (int i = 0; i < 4; i++) { double s = inv[4 * i] * b[0]; for (int k = 1; k < 4; k++) s += inv[4 * i + k] * b[k]; x4[i] = s; }
+#pragma unroll
+  for (int i = 0; i < 4; i++) { double sacc = inv[4 * i] * b[0]; for (int k = 1; k < 4; k++) sacc += inv[4 * i + k] * b[k]; x4[i] = sacc; }
 }
 
 __device__ inline void inverse3(const double* m, double* r) {
@@ -87,7 +119,16 @@ __device__ inline void inverse3(const double* m, double* r) {
 }
 
 // ---- building blocks (called by every thread of a kT-thread CTA) -----------------------------------------------------------------
+#ifdef VS_SBI_TIMING   // instrumented build (scratch experiments): cycles per phase of one CTA, printed by stream 7
+#define SBI_MARK(k) do { __syncthreads(); if (threadIdx.x == 0) { const long long t_ = clock64(); sh.tacc[k] += t_ - sh.tlast; sh.tlast = t_; } } while (0)
+#else
+#define SBI_MARK(k) do { } while (0)
+#endif
+
 struct SbiShared {
+#ifdef VS_SBI_TIMING
+  long long tacc[12], tlast;
+#endif
   double red[kT / 32];
   double red15[kT / 32][15];
   double X[6];        // current warp: R (4, row-major) and t (2)
@@ -191,6 +232,7 @@ __device__ void sbi_esm(const float* __restrict__ cur, const float* __restrict__
       }
     }
     __syncthreads();
+    SBI_MARK(3);
     double acc[15];
 #pragma unroll
     for (int k = 0; k < 15; k++) acc[k] = 0;
@@ -208,20 +250,33 @@ __device__ void sbi_esm(const float* __restrict__ cur, const float* __restrict__
       acc[4] += J0 * J0; acc[5] += J1 * J0; acc[6] += J1 * J1; acc[7] += J2 * J0; acc[8] += J2 * J1; acc[9] += J2 * J2;
       acc[10] += J0; acc[11] += J1; acc[12] += J2; acc[13] += 1.0; acc[14] += dd * dd;
     }
-    // one fixed-shape reduction for all 15 sums: warp shuffles, then 8 partials per sum through shared memory
+    // one fixed-shape reduction for all 15 sums: a transposing butterfly (each step halves what a lane holds: 8 + 4 + 2 + 1 + 1 = 16 shuffles of
+    // doubles instead of 15 x 5; every sum still pairs lanes at distance 16, 8, 4, 2, 1 in that order, so the values are those of the plain
+    // butterfly), then 8 partials per sum through shared memory
+    {
+      const int lane = tid & 31;
+      const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2, b0 = lane & 1;
+      double v8[8], v4[4], v2[2];
 #pragma unroll
-    for (int k = 0; k < 15; k++) {
+      for (int i = 0; i < 8; i++) { const double hi = (8 + i < 15) ? acc[(8 + i < 15) ? 8 + i : 0] : 0.0; const double keep = b4 ? hi : acc[i], give = b4 ? acc[i] : hi; v8[i] = keep + __shfl_xor_sync(0xffffffffu, give, 16); }
 #pragma unroll
-      for (int d = 16; d; d >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], d);
+      for (int i = 0; i < 4; i++) { const double keep = b3 ? v8[4 + i] : v8[i], give = b3 ? v8[i] : v8[4 + i]; v4[i] = keep + __shfl_xor_sync(0xffffffffu, give, 8); }
+#pragma unroll
+      for (int i = 0; i < 2; i++) { const double keep = b2 ? v4[2 + i] : v4[i], give = b2 ? v4[i] : v4[2 + i]; v2[i] = keep + __shfl_xor_sync(0xffffffffu, give, 4); }
+      const double keep1 = b1 ? v2[1] : v2[0], give1 = b1 ? v2[0] : v2[1];
+      const double v1 = keep1 + __shfl_xor_sync(0xffffffffu, give1, 2);
+      const double r = v1 + __shfl_xor_sync(0xffffffffu, v1, 1);         // both lanes of a pair end with the sum
+      const int q = (b4 ? 8 : 0) + (b3 ? 4 : 0) + (b2 ? 2 : 0) + (b1 ? 1 : 0);   // the sum this lane pair holds (15 = the padding)
+      __syncthreads();
+      if (!b0 && q < 15) sh.red15[tid >> 5][q] = r;
     }
-    __syncthreads();
-    if ((tid & 31) == 0) { for (int k = 0; k < 15; k++) sh.red15[tid >> 5][k] = acc[k]; }
     __syncthreads();
     if (tid < 15) {   // lane k adds the eight partials of sum k (same order as a serial loop), lane 0 collects them
       double r = 0; for (int w = 0; w < kT / 32; w++) r += sh.red15[w][tid];
       sh.red15[0][tid] = r;
     }
     if (tid < 32) __syncwarp();
+    SBI_MARK(4);
     if (tid == 0) {
       for (int k = 0; k < 15; k++) acc[k] = sh.red15[0][k];
       sh.score = acc[14];
@@ -240,6 +295,7 @@ __device__ void sbi_esm(const float* __restrict__ cur, const float* __restrict__
       if (it + 1 < its) sbi_esm_transform(sh, cx, cy);   // for the next iteration, in the same single-thread section (one barrier less per iteration)
     }
     __syncthreads();
+    SBI_MARK(5);
   }
 }
 
@@ -285,12 +341,24 @@ __global__ void __launch_bounds__(kT) k_sbi(SbiDev D) {
   const int s = blockIdx.x + D.s0, tid = threadIdx.x;
   const int W = D.w, H = D.h, n = W * H;
   const int par = D.parity[s];
-  float* cur = D.tmpl + ((size_t)s * 2 + par) * n;
+  float* cur_g = D.tmpl + ((size_t)s * 2 + par) * n;
   float* last = D.tmpl + ((size_t)s * 2 + (par ^ 1)) * n;
-  float* tmp = D.scratch + (size_t)s * 3 * n;
+  // This frame's template and the two scratch images (blur row pass / warped image) are written and re-read by the whole CTA between barriers
+  // a dozen times: in shared memory when they fit (VGA 14 KB, 1080p 94 KB), so that those hand-overs do not go through L2
+  extern __shared__ float sbi_dyn[];
+  const bool in_smem = D.smem_floats > 0;
+  float* tmp = in_smem ? sbi_dyn : D.scratch + (size_t)s * 3 * n;
   float* warped = tmp + n;
+  float* cur = in_smem ? sbi_dyn + 2 * n : cur_g;
+#ifdef VS_SBI_TIMING
+  if (tid < 12) sh.tacc[tid] = 0;
+  if (tid == 0) sh.tlast = clock64();
+  __syncthreads();
+#endif
   sbi_make(D.l3 + (size_t)s * D.l3h * D.l3pitch, D.l3pitch, D.l3h, D.rs, W, H, D.taps, 9, D.small + (size_t)s * n, tmp, cur, sh);
+  SBI_MARK(0);
   const bool first = !D.have[s];
+  if (in_smem) { for (int i = tid; i < n; i += kT) cur_g[i] = cur[i]; }   // the next frame's `last`
   if (first) { for (int i = tid; i < n; i += kT) last[i] = cur[i]; }   // first frame: both SBIs come from the same keyframe (jni/Tracker.cc:90-93)
   __syncthreads();
   if (tid == 0) { D.have[s] = 1; D.parity[s] = par ^ 1; }               // next frame: `cur` becomes `last`
@@ -299,13 +367,19 @@ __global__ void __launch_bounds__(kT) k_sbi(SbiDev D) {
   if (!D.use_sbi) return;
   float* jac = D.jac + (size_t)s * 2 * n;
   sbi_make_jacs(last, jac, W, H);
+  SBI_MARK(1);
   sbi_esm(cur, last, jac, warped, W, H, 6, sh);
+  SBI_MARK(2);
   if (tid == 0) {   // SE3fromSE2 and ln() -> Tracker::mv6SBIRot
     double R[9]; sbi_se3_from_se2(sh.CtoC, D.cam, D.orig, W, H, R);
     double P[12]; for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) P[4 * i + j] = R[3 * i + j]; P[4 * i + 3] = 0.0; }
     double v6[6]; se3_ln(P, v6);
     for (int k = 0; k < 6; k++) D.rot_out[6 * (size_t)s + k] = v6[k];
   }
+#ifdef VS_SBI_TIMING
+  SBI_MARK(6);
+  if (tid == 0 && s == 7) printf("k_sbi cycles: make %lld jacs %lld esm_rest %lld | esm transform %lld accumulate %lld solve %lld | se3fromse2 %lld\n", sh.tacc[0], sh.tacc[1], sh.tacc[2], sh.tacc[3], sh.tacc[4], sh.tacc[5], sh.tacc[6]);
+#endif
 }
 
 // Relocaliser keyframe k: SmallBlurryImage(kf) with the default blur 2.5 (jni/KeyFrame.cc:98) + MakeJacs, from the level-3 image of a
@@ -378,6 +452,7 @@ static SbiDev make_sbi_dev(vslam_ctx* ctx) {
   D.cam = ctx->sbi_cam; memcpy(D.orig, ctx->sbi_orig, sizeof(D.orig));
   D.tmpl = ctx->sbi_tmpl; D.scratch = ctx->sbi_scratch; D.jac = ctx->sbi_jac; D.small = ctx->sbi_small; D.ss = ctx->ss; D.have = ctx->sbi_have; D.parity = ctx->sbi_have + ctx->S;
   D.use_sbi = ctx->params.use_sbi; D.s0 = ctx->cur_s0;
+  { const size_t fl = 3 * (size_t)D.w * D.h; D.smem_floats = fl * sizeof(float) <= 200 * 1024 ? (int)fl : 0; }
   D.rot_out = ctx->sbi_rot_buf + (size_t)ctx->cur_set * ctx->S * 6; D.reloc_scratch = ctx->reloc_frame_scratch; D.reloc_small = ctx->reloc_frame_small;
   return D;
 }
@@ -395,7 +470,10 @@ int vs_launch_sbi(vslam_ctx* ctx) {
   if (!ctx->sbi_on) return VSLAM_OK;
   const SbiDev D = make_sbi_dev(ctx);
   vs_time_begin(ctx, VS_ST_OTHER);
-  VS_CUDA(vs_launch_pdl(k_sbi, dim3(ctx->cur_cnt), dim3(kT), 0, ctx->stream, ctx->pdl && !ctx->timing, D));
+  const size_t smem = (size_t)D.smem_floats * sizeof(float);
+  static size_t smem_opted = 48 * 1024;
+  if (smem > smem_opted) { VS_CUDA(cudaFuncSetAttribute(k_sbi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_opted = smem; }
+  VS_CUDA(vs_launch_pdl(k_sbi, dim3(ctx->cur_cnt), dim3(kT), smem, ctx->stream, ctx->pdl && !ctx->timing, D));
   vs_time_end(ctx);
   VS_CUDA(cudaGetLastError());
   ctx->launches++;
