@@ -51,6 +51,21 @@ def test_default_params_are_the_reference_constants():
     # jni/Tracker.cc:405-410, 495-497, 518
     assert (p.coarse_min, p.coarse_max, p.coarse_range, p.coarse_subpix_its, p.coarse_min_vel) == (20, 60, 30, 8, 0.006)
     assert (p.fine_range, p.fine_range_after_coarse, p.fine_subpix_its_top_level, p.max_patches_per_frame, p.use_sbi) == (10, 5, 8, 1000, 1)
+    # execution-only knobs: one stream group, parallel normal-equation sums, the round-2 kernels, frame look-ahead left to the library
+    assert (p.stream_groups, p.serial_normal_equations, p.pose_kernel, p.search_kernel, p.frame_lookahead) == (1, 0, 0, 0, -1)
+
+
+def test_params_struct_matches_the_header(tmp_path):
+    """The ctypes mirror of vslam_params has the C struct's size (a field added to the header but not to api.Params would let
+    vslam_default_params write past the Python object)."""
+    import subprocess
+    src = tmp_path / "sz.c"
+    src.write_text('#include "vslam_b200.h"\n#include <stdio.h>\nint main(void) { printf("%zu %zu\\n", sizeof(vslam_params), sizeof(vslam_config)); return 0; }\n')
+    exe = tmp_path / "sz"
+    r = subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    sp, sc = map(int, subprocess.run([str(exe)], capture_output=True, text=True).stdout.split())
+    assert sp == C.sizeof(api.Params) and sc == C.sizeof(api.Config)
 
 
 @pytest.mark.parametrize("size", [(640, 480), (1920, 1080), (3840, 2160)])
