@@ -104,8 +104,22 @@ static void use_set(vslam_ctx* ctx, int p) {
   ctx->cur_set = p;
 }
 // Second frame set + the front-end streams and events, on the first look-ahead frame.
+static int alloc_set1_impl(vslam_ctx* ctx);
 static int alloc_set1(vslam_ctx* ctx) {
   if (ctx->have_set1) return VSLAM_OK;
+  const int rc = alloc_set1_impl(ctx);
+  if (rc) {   // out of memory half-way: give back what was taken, the context carries on with one frame set
+    FrameSet& F = ctx->sets[1];
+    for (int l = 1; l < VS_LEVELS; l++) { cudaFree(F.img[l]); F.img[l] = nullptr; }
+    cudaFree(F.cbits_block); F.cbits_block = nullptr; cudaFree(F.l0_ptr); F.l0_ptr = nullptr; cudaFree(F.l0_stride); F.l0_stride = nullptr;
+    delete[] F.l0_ptr_host; F.l0_ptr_host = nullptr; delete[] F.l0_stride_host; F.l0_stride_host = nullptr;
+    for (cudaStream_t* st : {&ctx->front_stream, &ctx->front_side, &ctx->back_stream}) if (*st) { cudaStreamDestroy(*st); *st = nullptr; }
+    for (cudaEvent_t* e : {&ctx->ev_user, &ctx->ev_front_done, &ctx->ev_barrier, &ctx->ev_back_done[0], &ctx->ev_back_done[1], &ctx->ev_la_fork, &ctx->ev_la_join}) if (*e) { cudaEventDestroy(*e); *e = nullptr; }
+    cudaGetLastError();
+  }
+  return rc;
+}
+static int alloc_set1_impl(vslam_ctx* ctx) {
   FrameSet& F = ctx->sets[1];
   const int S = ctx->S;
   size_t words = 0;
@@ -145,7 +159,7 @@ static bool lookahead_default(const vslam_ctx* ctx) {
 }
 static int lookahead_resolved(const vslam_ctx* ctx) {
   int la = ctx->params.frame_lookahead < 0 ? (lookahead_default(ctx) ? 1 : 0) : ctx->params.frame_lookahead;
-  if (ctx->timing || ctx->params.stream_groups > 1) la = 0;      // per-stage timing serialises everything on ctx->stream; stream groups have their own streams
+  if (ctx->timing || ctx->params.stream_groups > 1 || ctx->la_unavailable) la = 0;      // per-stage timing serialises everything on ctx->stream; stream groups have their own streams
   return la;
 }
 int vslam_frame_lookahead_active(const vslam_ctx* ctx) { return ctx ? lookahead_resolved(ctx) : 0; }
@@ -153,7 +167,10 @@ static int vs_begin_frame(vslam_ctx* ctx) {
   const int la = lookahead_resolved(ctx);
   ctx->la_frame = la != 0; ctx->front = ctx->stream;
   if (!la) return VSLAM_OK;
-  int rc = alloc_set1(ctx); if (rc) { ctx->la_frame = false; return rc; }
+  if (alloc_set1(ctx)) {   // no memory for a second frame set: this context runs without look-ahead from here on
+    ctx->la_unavailable = true; ctx->la_frame = false; ctx->err.clear();
+    return VSLAM_OK;
+  }
   const bool chained = ctx->launches == ctx->launches_after_frame;
   use_set(ctx, ctx->cur_set ^ 1);
   if (chained) VS_CUDA(cudaStreamWaitEvent(ctx->front_stream, ctx->ev_back_done[ctx->cur_set], 0));

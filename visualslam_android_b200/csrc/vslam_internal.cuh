@@ -166,6 +166,7 @@ struct vslam_ctx {
   cudaStream_t front_stream = nullptr, front_side = nullptr; cudaEvent_t ev_front_done = nullptr, ev_barrier = nullptr, ev_back_done[2] = {nullptr, nullptr}, ev_la_fork = nullptr, ev_la_join = nullptr;
   cudaStream_t front = nullptr;  // inside a vslam_track_frame* call: the stream the frame's input and front end are enqueued on (front_stream or ctx->stream)
   bool la_frame = false;         // the frame being enqueued runs with look-ahead
+  bool la_unavailable = false;   // the second frame set could not be allocated
   unsigned long long launches_after_frame = ~0ull;   // ctx->launches when the last look-ahead frame had been enqueued: any kernel launched since forces a full barrier
   double* sbi_rot_buf = nullptr; const double* cur_sbi_rot = nullptr;   // [2][S][6] k_sbi's result per frame set; what k_project_lists of this frame reads (null: StreamState::sbi_rot as set by the host)
   float* reloc_frame_scratch = nullptr; uint8_t* reloc_frame_small = nullptr;      // k_relocalise's own scratch ([S][3n] / [S][n]): it may run beside the next frame's k_sbi
