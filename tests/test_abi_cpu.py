@@ -52,7 +52,7 @@ def test_default_params_are_the_reference_constants():
     assert (p.coarse_min, p.coarse_max, p.coarse_range, p.coarse_subpix_its, p.coarse_min_vel) == (20, 60, 30, 8, 0.006)
     assert (p.fine_range, p.fine_range_after_coarse, p.fine_subpix_its_top_level, p.max_patches_per_frame, p.use_sbi) == (10, 5, 8, 1000, 1)
     # execution-only knobs: one stream group, parallel normal-equation sums, the round-2 kernels, frame look-ahead left to the library
-    assert (p.stream_groups, p.serial_normal_equations, p.pose_kernel, p.search_kernel, p.frame_lookahead) == (1, 0, 0, 0, -1)
+    assert (p.stream_groups, p.serial_normal_equations, p.pose_kernel, p.search_kernel, p.frame_lookahead, p.coarse_chain) == (1, 0, 0, 0, -1, -1)
 
 
 def test_params_struct_matches_the_header(tmp_path):

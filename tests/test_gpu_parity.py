@@ -793,9 +793,9 @@ def test_frame_lookahead_changes_no_result(entry):
             else:
                 seq[k, s] = synth.render_frame(common.texture(), cam, synth.stream_pose(3 * (k + 1), s))
 
-    def run(lookahead):
+    def run(lookahead, coarse_chain=0):
         ctx = _ctx(cam, f0, smap, n_streams=S, max_source_keyframes=2)
-        ctx.set_params(frame_lookahead=lookahead)
+        ctx.set_params(frame_lookahead=lookahead, coarse_chain=coarse_chain)
         ctx.enable_sbi(sbi_cam)
         ctx.upload_source_keyframe(kf_frames[1], 1)
         ctx.set_reloc_keyframes([0, 1], np.stack(kf_poses))
@@ -842,6 +842,11 @@ def test_frame_lookahead_changes_no_result(entry):
         else:
             assert x == y, (what, x, y)
     same(a, b, "result")
+    # vslam_params.coarse_chain (the coarse-stage streams of a frame on a launch chain of their own beside the fine-only streams) is execution
+    # only as well: forced on without and with look-ahead, and left to the library (-1: the layout follows an unsynchronised hint)
+    same(a, run(0, 1), "coarse_chain=1")
+    same(a, run(1, 1), "coarse_chain=1 with look-ahead")
+    same(a, run(1, -1), "coarse_chain=-1 with look-ahead")
     assert sum(r[2] for r in a["reloc"]) >= 2, a["reloc"]                  # the two noisy streams did relocalise
     assert all(c[2] == 2 for c in a["counters"]), a["counters"]            # and every stream ends with quality GOOD
 

@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libvslam_b200.so")
+LIB_PATH = os.environ.get("VSLAM_LIB") or os.path.join(HERE, "libvslam_b200.so")   # VSLAM_LIB: A/B runs of an experimental build of the same library
 LEVELS = 4
 
 OK, E_INVALID, E_CUDA, E_CAPACITY, E_NO_DEVICE, E_IO = 0, -1, -2, -3, -4, -5
@@ -39,7 +39,7 @@ class Params(C.Structure):
     _fields_ = [("coarse_min", C.c_uint), ("coarse_max", C.c_uint), ("coarse_range", C.c_uint), ("coarse_subpix_its", C.c_int),
                 ("coarse_min_vel", C.c_double), ("fine_range", C.c_int), ("fine_range_after_coarse", C.c_int),
                 ("fine_subpix_its_top_level", C.c_int), ("max_patches_per_frame", C.c_int), ("use_sbi", C.c_int), ("stream_groups", C.c_int),
-                ("serial_normal_equations", C.c_int), ("pose_kernel", C.c_int), ("search_kernel", C.c_int), ("frame_lookahead", C.c_int)]
+                ("serial_normal_equations", C.c_int), ("pose_kernel", C.c_int), ("search_kernel", C.c_int), ("frame_lookahead", C.c_int), ("coarse_chain", C.c_int)]
 
 
 # every symbol include/vslam_b200.h declares (tests/test_abi_cpu.py checks the library exports all of them)

@@ -74,7 +74,7 @@ void vslam_default_config(vslam_config* c) {
 
 void vslam_default_params(vslam_params* p) {   // jni/Tracker.cc:405-410,495-497,518
   p->coarse_min = 20; p->coarse_max = 60; p->coarse_range = 30; p->coarse_subpix_its = 8; p->coarse_min_vel = 0.006;
-  p->fine_range = 10; p->fine_range_after_coarse = 5; p->fine_subpix_its_top_level = 8; p->max_patches_per_frame = 1000; p->use_sbi = 1; p->stream_groups = 1; p->serial_normal_equations = 0; p->pose_kernel = 0; p->search_kernel = 0; p->frame_lookahead = -1;
+  p->fine_range = 10; p->fine_range_after_coarse = 5; p->fine_subpix_its_top_level = 8; p->max_patches_per_frame = 1000; p->use_sbi = 1; p->stream_groups = 1; p->serial_normal_equations = 0; p->pose_kernel = 0; p->search_kernel = 0; p->frame_lookahead = -1; p->coarse_chain = -1;
 }
 
 const char* vslam_last_error(const vslam_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
@@ -265,6 +265,8 @@ int vslam_create(const vslam_config* cfg, vslam_ctx** out) {
   { std::vector<int> lv(SN, -1); CK(cudaMemcpy(ps.level, lv.data(), SN * sizeof(int), cudaMemcpyHostToDevice)); }
   // per-stream state
   CK(dalloc(&ctx->ss, (size_t)S)); CK(dalloc(&ctx->kf_req, (size_t)S));
+  CK(cudaHostAlloc((void**)&ctx->coarse_hint_host, sizeof(int) * (size_t)S, cudaHostAllocMapped)); memset(ctx->coarse_hint_host, 0, sizeof(int) * (size_t)S);
+  CK(cudaHostGetDevicePointer((void**)&ctx->coarse_hint_dev, ctx->coarse_hint_host, 0));
   {
     std::vector<StreamState> h(S);
     memset(h.data(), 0, sizeof(StreamState) * S);
@@ -319,6 +321,7 @@ void vslam_destroy(vslam_ctx* ctx) {
   cudaFree(ctx->snap_img); cudaFree(ctx->snap_corners); cudaFree(ctx->snap_lut);
   cudaFree(ctx->sbi_resize_tab); cudaFree(ctx->sbi_tmpl); cudaFree(ctx->sbi_scratch); cudaFree(ctx->sbi_jac); cudaFree(ctx->sbi_small); cudaFree(ctx->sbi_have);
   if (ctx->status_pin) cudaFreeHost(ctx->status_pin);
+  if (ctx->coarse_hint_host) cudaFreeHost(ctx->coarse_hint_host);
   delete[] ctx->l0_ptr_host; delete[] ctx->l0_stride_host;
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   cudaFree(ctx->unproj_lut); cudaFree(ctx->reloc_tmpl); cudaFree(ctx->reloc_jac); cudaFree(ctx->reloc_tmp); cudaFree(ctx->reloc_small); cudaFree(ctx->reloc_pose); cudaFree(ctx->reloc_scores);
@@ -328,7 +331,11 @@ void vslam_destroy(vslam_ctx* ctx) {
     if (ctx->ev_fork[g]) cudaEventDestroy(ctx->ev_fork[g]);
     if (ctx->ev_join[g]) cudaEventDestroy(ctx->ev_join[g]);
     if (ctx->ev_end[g]) cudaEventDestroy(ctx->ev_end[g]);
+    if (ctx->chain_stream[g]) cudaStreamDestroy(ctx->chain_stream[g]);
+    if (ctx->ev_chain_fork[g]) cudaEventDestroy(ctx->ev_chain_fork[g]);
+    if (ctx->ev_chain_join[g]) cudaEventDestroy(ctx->ev_chain_join[g]);
   }
+  if (ctx->chain_stream_hi) cudaStreamDestroy(ctx->chain_stream_hi);
   if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
   delete ctx;
 }
@@ -364,6 +371,7 @@ int vslam_set_params(vslam_ctx* ctx, const vslam_params* p) {
   if (2 * p->coarse_max > (unsigned)ctx->list_cap) { ctx->err = "coarse_max too large"; return VSLAM_E_INVALID; }
   if (p->stream_groups < 0 || p->stream_groups > VS_MAX_GROUPS) { ctx->err = "stream_groups must be 0 (default) .. 4"; return VSLAM_E_INVALID; }
   if (p->max_patches_per_frame < 0) { ctx->err = "max_patches_per_frame must be >= 0"; return VSLAM_E_INVALID; }
+  if (p->coarse_chain < -1 || p->coarse_chain > 1) { ctx->err = "coarse_chain must be -1 (library default), 0 or 1"; return VSLAM_E_INVALID; }
   if (p->frame_lookahead < -1 || p->frame_lookahead > 1) { ctx->err = "frame_lookahead must be -1 (library default), 0 or 1"; return VSLAM_E_INVALID; }
   ctx->params = *p;
   return VSLAM_OK;

@@ -283,6 +283,7 @@ __global__ void __launch_bounds__(kFT, kMinB) k_pose_fast(Dev D, int mode, int t
   StreamState* st = D.ss + s;
   if (st->lost_frames >= 3 && !st->recovered) return;
   if (mode == 1 && !st->try_coarse) return;
+  if (other_chain(D, st)) return;
   const size_t SN = (size_t)D.S * D.N, so = (size_t)s * D.N;
   const int* list = D.lists + (size_t)s * D.list_cap;
   const int nlist = (mode == 2) ? st->nA + st->nB : st->nA;

@@ -45,6 +45,7 @@ struct Plan { int first, count, range, subpix_all, n_top, subpix_top; };
 // which entries a launch covers and with what range / sub-pixel iterations (jni/Tracker.cc:464-532); false: nothing to do for this stream
 __device__ __forceinline__ bool search_plan(const Dev& D, const StreamState* st, int mode, int range_arg, int subpix_arg, Plan& p) {
   if (mode != 0 && st->lost_frames >= 3 && !st->recovered) return false;
+  if (mode != 0 && other_chain(D, st)) return false;
   p.n_top = 0; p.subpix_top = 0;
   if (mode == 0) { p.first = 0; p.count = st->nA; p.range = range_arg; p.subpix_all = subpix_arg; }
   else if (mode == 1) { if (!st->try_coarse) return false; p.first = 0; p.count = st->nA; p.range = st->coarse_range; p.subpix_all = D.prm.coarse_subpix_its; }

@@ -30,7 +30,48 @@ __device__ __forceinline__ void shuffle_swaps(int* v, const int* jv, int n) {
   }
 }
 
-__global__ void __launch_bounds__(kPT) k_project_lists(Dev D, int mode, int apply_motion, int use_smem, const double* __restrict__ sbi_rot_in) {
+// Tracker::ApplyMotionModel (jni/Tracker.cc:781-798): the pose a frame starts from.  sbi (6 doubles or null): Tracker::mv6SBIRot of THIS frame.
+__device__ __forceinline__ void motion_model_pose(const Dev& D, const double* velocity, const double* pose, const double* sbi, double* np) {
+  double v[6]; for (int k = 0; k < 6; k++) v[k] = velocity[k];
+  if (D.prm.use_sbi) { v[0] = 0.0; v[1] = 0.0; v[3] = sbi[3]; v[4] = sbi[4]; v[5] = sbi[5]; }
+  double e[12]; se3_exp(v, e); se3_mul(e, pose, np);
+}
+
+// Large maps (vs_launch_project_all: more than kSplitProjectN points): the per-point half of k_project_lists -- TrackerData::Project, GetDerivsUnsafe,
+// CalcSearchLevelAndWarpMatrix -- on a grid of (point chunks, streams) instead of one CTA per stream walking the whole map (4K, 20000 points: 79 rounds of
+// 256 points with three barriers each).  Every CTA derives the frame's start pose from the stream's state with the arithmetic of ApplyMotionModel and
+// writes none of it: k_project_lists, launched behind it with pre_projected = 1, installs the same pose (same operations, same bits) and builds the lists
+// from the flags / levels left here.
+__global__ void __launch_bounds__(kPT) k_project_points(Dev D, int apply_motion, const double* __restrict__ sbi_rot_in) {
+  cudaGridDependencySynchronize(); cudaTriggerProgrammaticLaunchCompletion();
+  __shared__ double s_pose[12];
+  const int s = blockIdx.y + D.s0, tid = threadIdx.x;
+  const StreamState* st = D.ss + s;
+  if (st->lost_frames >= 3 && !st->recovered) return;
+  if (tid == 0) {
+    if (apply_motion && !st->recovered) {
+      double np[12]; motion_model_pose(D, st->velocity, st->pose, sbi_rot_in ? sbi_rot_in + 6 * (size_t)s : st->sbi_rot, np);
+      for (int k = 0; k < 12; k++) s_pose[k] = np[k];
+    } else for (int k = 0; k < 12; k++) s_pose[k] = st->pose[k];
+  }
+  __syncthreads();
+  const int i = blockIdx.x * kPT + tid;
+  if (i >= D.map.n) return;
+  const size_t SN = (size_t)D.S * D.N, gi = (size_t)s * D.N + i;
+  int flags = D.ps.flags[gi] | F_HASTD;
+  CamCache cc;
+  td_project(D, s_pose, i, gi, SN, cc, flags);
+  if (flags & F_INIMAGE) {
+    double dv[4]; cam_derivs(D.cam, cc, dv);
+    for (int k = 0; k < 4; k++) D.ps.derivs[k * SN + gi] = dv[k];
+    const int level = calc_level_warp(D, s_pose, i, gi, SN, dv, flags);
+    D.ps.level[gi] = level;
+    if (level >= 0) flags &= ~(F_SEARCHED | F_FOUND);
+  }
+  D.ps.flags[gi] = flags;
+}
+
+__global__ void __launch_bounds__(kPT) k_project_lists(Dev D, int mode, int apply_motion, int use_smem, const double* __restrict__ sbi_rot_in, int pre_projected) {
   cudaGridDependencySynchronize(); cudaTriggerProgrammaticLaunchCompletion();   // programmatic dependent launch (vs_launch_pdl); no-ops otherwise
   extern __shared__ int sh_i[];          // [N] packed level lists (L3|L2|L1|L0), [N] random draws
   __shared__ double s_pose[12];
@@ -41,15 +82,11 @@ __global__ void __launch_bounds__(kPT) k_project_lists(Dev D, int mode, int appl
   const size_t SN = (size_t)D.S * D.N;
   StreamState* st = D.ss + s;
   if (tid == 0 && apply_motion) { st->frame_no++; st->kf_request = 0; D.kf_req[s] = 0; }   // mnFrame++ (jni/Tracker.cc:100): every TrackFrame, lost or not
-  if (mode == 1 && st->lost_frames >= 3 && !st->recovered) return;   // lost and not relocalised this frame (k_relocalise): nothing to do, jni/Tracker.cc:104,134-140
+  if (mode == 1 && st->lost_frames >= 3 && !st->recovered) { if (tid == 0) D.coarse_hint[s] = 0; return; }   // lost and not relocalised this frame (k_relocalise): nothing to do, jni/Tracker.cc:104,134-140
   if (tid == 0 && apply_motion && !st->recovered) {   // Tracker::ApplyMotionModel (jni/Tracker.cc:781-798); a relocalised stream starts from the recovered pose
-    double v[6]; for (int k = 0; k < 6; k++) v[k] = st->velocity[k];
     for (int k = 0; k < 12; k++) st->start_pose[k] = st->pose[k];
-    if (D.prm.use_sbi) {
-      if (sbi_rot_in) for (int k = 0; k < 6; k++) st->sbi_rot[k] = sbi_rot_in[6 * (size_t)s + k];   // Tracker::mv6SBIRot of THIS frame (k_sbi, front end of the frame)
-      v[0] = 0.0; v[1] = 0.0; v[3] = st->sbi_rot[3]; v[4] = st->sbi_rot[4]; v[5] = st->sbi_rot[5];
-    }
-    double e[12], np[12]; se3_exp(v, e); se3_mul(e, st->start_pose, np);
+    if (D.prm.use_sbi && sbi_rot_in) for (int k = 0; k < 6; k++) st->sbi_rot[k] = sbi_rot_in[6 * (size_t)s + k];   // Tracker::mv6SBIRot of THIS frame (k_sbi, front end of the frame)
+    double np[12]; motion_model_pose(D, st->velocity, st->start_pose, st->sbi_rot, np);
     for (int k = 0; k < 12; k++) st->pose[k] = np[k];
   }
   __syncthreads();
@@ -62,7 +99,10 @@ __global__ void __launch_bounds__(kPT) k_project_lists(Dev D, int mode, int appl
   for (int base = 0; base < N; base += kPT) {
     const int i = base + tid;
     int level = -1; bool pv = false;
-    if (i < N) {
+    if (i < N && pre_projected) {   // k_project_points has been here: a point is potentially visible if it is in the image and its warp was accepted
+      const size_t gi = (size_t)s * D.N + i;
+      if (D.ps.flags[gi] & F_INIMAGE) { level = D.ps.level[gi]; pv = level >= 0; }
+    } else if (i < N) {
       const size_t gi = (size_t)s * D.N + i;
       int flags = D.ps.flags[gi] | F_HASTD;
       if (mode == 0) { flags &= ~(F_SEARCHED | F_FOUND | F_SUBPIX); }
@@ -145,6 +185,7 @@ __global__ void __launch_bounds__(kPT) k_project_lists(Dev D, int mode, int appl
       }
     } else tryCoarse = false;
     st->try_coarse = tryCoarse ? 1 : 0; st->coarse_range = (int)nCoarseRange; st->did_coarse = 0;
+    D.coarse_hint[s] = tryCoarse ? 1 : 0;
     const int nFine = total - f0;
     int use = D.prm.max_patches_per_frame - ((a1 - a0) + (t1 - t0));
     if (use < 0) use = 0;
@@ -853,7 +894,7 @@ __global__ void __launch_bounds__(kPT) k_reproject_fine(Dev D) {
   cudaGridDependencySynchronize(); cudaTriggerProgrammaticLaunchCompletion();   // programmatic dependent launch (vs_launch_pdl); no-ops otherwise
   const int s = blockIdx.x + D.s0;
   StreamState* st = D.ss + s;
-  if ((st->lost_frames >= 3 && !st->recovered) || !st->did_coarse) return;
+  if ((st->lost_frames >= 3 && !st->recovered) || !st->did_coarse || other_chain(D, st)) return;
   const size_t SN = (size_t)D.S * D.N;
   const int* list = D.lists + (size_t)s * D.list_cap + st->nA;
   for (int k = threadIdx.x; k < st->nB; k += kPT) {
@@ -879,6 +920,7 @@ __global__ void k_atan(const double* x, double* y, int n, int dd_only) { const i
 
 }  // namespace
 
+constexpr int kSplitProjectN = 2048;   // maps above this many points project on a (point chunks, streams) grid (k_project_points)
 int vs_launch_project_all(vslam_ctx* ctx, int mode) {
   const Dev D = make_dev(ctx);
   // packed level lists + random draws: 2 x N ints of shared memory when that fits beside the static part, the stream's global scratch otherwise
@@ -886,8 +928,13 @@ int vs_launch_project_all(vslam_ctx* ctx, int mode) {
   const int use_smem = smem <= 200 * 1024;
   if (!use_smem) smem = 0;
   if (smem > ctx->smem_attr[0]) { VS_CUDA(cudaFuncSetAttribute(k_project_lists, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); ctx->smem_attr[0] = smem; }
+  // large maps: the per-point projection on its own grid (k_project_points), the list building behind it
+  static const int split_env = getenv("VSLAM_SPLIT_PROJECT") ? atoi(getenv("VSLAM_SPLIT_PROJECT")) : -1;
+  const int pre = (mode & 1) && (split_env >= 0 ? split_env != 0 : ctx->map.n > kSplitProjectN);
+  const bool pdl = ctx->pdl && !ctx->timing;
   vs_time_begin(ctx, VS_ST_PROJECT);
-  VS_CUDA(vs_launch_pdl(k_project_lists, dim3(ctx->cur_cnt), dim3(kPT), smem, ctx->stream, ctx->pdl && !ctx->timing, D, mode & 1, (mode >> 1) & 1, use_smem, ctx->cur_sbi_rot));
+  if (pre) { VS_CUDA(vs_launch_pdl(k_project_points, dim3((ctx->map.n + kPT - 1) / kPT, ctx->cur_cnt), dim3(kPT), 0, ctx->stream, pdl, D, (mode >> 1) & 1, ctx->cur_sbi_rot)); ctx->launches++; }
+  VS_CUDA(vs_launch_pdl(k_project_lists, dim3(ctx->cur_cnt), dim3(kPT), smem, ctx->stream, pdl, D, mode & 1, (mode >> 1) & 1, use_smem, ctx->cur_sbi_rot, pre));
   vs_time_end(ctx);
   VS_CUDA(cudaGetLastError());
   ctx->launches++;
@@ -938,7 +985,50 @@ int vs_launch_calc_jacobians(vslam_ctx* ctx) {
 }
 
 // Tracker::TrackMap for all streams: 6 launches, no host synchronisation in between.
+// Two launch chains.  Whether a stream runs the coarse stage is decided on the device (k_project_lists: StreamState::try_coarse), so the host
+// launches it for every frame: three searches / pose kernels and the re-projection that do nothing at ordinary camera speed, each waiting for
+// the one before -- 0.018 ms of a frame's latency (32 streams: 7 % of the step).  Instead the frame forks: the streams that try the coarse stage
+// take the whole chain (coarse search, coarse pose, re-projection, fine search, fine pose) on a stream of its own, the others the fine stage alone
+// on the calling stream (Dev::chain tells a kernel which streams are its own); the chains join at the end.  A chain without streams is a row of
+// empty kernels BESIDE the other chain's work instead of in front of it.  Streams are independent: no result depends on the split.
+static int track_map_rest_chain(vslam_ctx* ctx, int with_motion_model);
+constexpr int kDualChainMaxList = 2048;
 int vs_launch_track_map_rest(vslam_ctx* ctx, int with_motion_model) {
+  static const int env = getenv("VSLAM_COARSE_CHAIN") ? atoi(getenv("VSLAM_COARSE_CHAIN")) : -1;   // A/B runs: overrides vslam_params.coarse_chain
+  const int want = env >= 0 ? env : ctx->params.coarse_chain;
+  bool dual = want != 0 && !ctx->timing && ctx->params.search_kernel == 0 && ctx->params.pose_kernel == 0;
+  if (dual && want < 0) {
+    // Worth it only while the coarse chain is empty and its empty kernels are small: with a fast camera the work would merely move to the
+    // other stream and pay the fork / join (measured: + 2 %), and the empty fine search of a 20000-point map is 185 k CTAs (4K: + 1.2 %).  Which
+    // streams tried the coarse stage in their latest frame is a HINT read without synchronisation (k_project_lists writes it to mapped host
+    // memory): it chooses the layout, never the result -- both layouts run every stream through the stages it asks for.
+    if (ctx->list_cap > kDualChainMaxList) dual = false;
+    else { const volatile int* h = ctx->coarse_hint_host; for (int s = ctx->cur_s0; s < ctx->cur_s0 + ctx->cur_cnt && dual; s++) if (h[s]) dual = false; }
+  }
+  if (!dual) return track_map_rest_chain(ctx, with_motion_model);
+  const int g = ctx->cur_group;
+  const bool hi = ctx->back_stream && ctx->stream == ctx->back_stream;     // look-ahead back end: keep its priority
+  cudaStream_t* slot = hi ? &ctx->chain_stream_hi : &ctx->chain_stream[g];
+  if (!*slot) {
+    int lo_p = 0, hi_p = 0; VS_CUDA(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
+    VS_CUDA(cudaStreamCreateWithPriority(slot, cudaStreamNonBlocking, hi ? hi_p : 0));
+  }
+  if (!ctx->ev_chain_fork[g]) { VS_CUDA(cudaEventCreateWithFlags(&ctx->ev_chain_fork[g], cudaEventDisableTiming)); VS_CUDA(cudaEventCreateWithFlags(&ctx->ev_chain_join[g], cudaEventDisableTiming)); }
+  cudaStream_t main_stream = ctx->stream, side = *slot;
+  struct Guard { vslam_ctx* c; cudaStream_t m; ~Guard() { c->stream = m; c->cur_chain = -1; } } guard{ctx, main_stream};
+  VS_CUDA(cudaEventRecord(ctx->ev_chain_fork[g], main_stream));
+  VS_CUDA(cudaStreamWaitEvent(side, ctx->ev_chain_fork[g], 0));
+  int rc;
+  ctx->stream = side; ctx->cur_chain = 1;
+  if ((rc = track_map_rest_chain(ctx, with_motion_model))) return rc;
+  VS_CUDA(cudaEventRecord(ctx->ev_chain_join[g], side));
+  ctx->stream = main_stream; ctx->cur_chain = 0;
+  if ((rc = vs_launch_search(ctx, 2, 0, 0, 0))) return rc;
+  if ((rc = vs_launch_pose(ctx, 2 | (with_motion_model ? 4 : 0), 0.0, 0, 0))) return rc;
+  VS_CUDA(cudaStreamWaitEvent(main_stream, ctx->ev_chain_join[g], 0));
+  return VSLAM_OK;
+}
+static int track_map_rest_chain(vslam_ctx* ctx, int with_motion_model) {
   int rc;
   if ((rc = vs_launch_search(ctx, 1, 0, 0, 0))) return rc;
   if ((rc = vs_launch_pose(ctx, 1, 0.0, 0, 0))) return rc;

@@ -16,12 +16,16 @@ struct Dev {   // everything the kernels need, passed by value
   unsigned long long* evals;
   int S, N, P, truncate;
   int s0;                  // first stream of this launch (stream groups of vs_launch_frame; 0 otherwise)
+  int* coarse_hint;        // [S] host-visible: did the stream try the coarse stage in this frame (vs_launch_track_map_rest reads it as a layout hint)
+  int chain;               // vs_launch_track_map_rest's two launch chains: -1 every stream, 1 only the streams that try the coarse stage this frame, 0 only the others
   vslam_params prm;
   // keyframe policy: poses of the map's keyframes (the relocaliser registration), 0 keyframes = policy off
   const double* kf_pose; int kf_n, kf_min_frames; double kf_excess_dist, kf_need_dist; int* kf_req;
 };
 
 __device__ __forceinline__ int LevelScale(int l) { return 1 << l; }
+// true: this stream belongs to the other launch chain of the frame (Dev::chain)
+__device__ __forceinline__ bool other_chain(const Dev& D, const StreamState* st) { return D.chain >= 0 && (st->try_coarse != 0) != (D.chain != 0); }
 
 // ------------------------------------------------------------------------------------------------
 // TrackerData::Project (jni/TrackerData.h:69-86).  Returns true if Cam.Project was reached (cache valid).
@@ -79,7 +83,7 @@ inline Dev make_dev(const vslam_ctx* ctx) {
   D.l0_ptr = ctx->l0_ptr; D.l0_stride = ctx->l0_stride;
   D.cam = ctx->cam; D.map = ctx->map; D.src = ctx->src; D.ps = ctx->ps; D.ss = ctx->ss; D.lists = ctx->lists; D.list_cap = ctx->list_cap;
   D.pvs = ctx->pvs; D.sort_scratch = ctx->sort_scratch; D.sort_cap = ctx->sort_cap; D.evals = ctx->evals;
-  D.S = ctx->S; D.N = ctx->N; D.P = ctx->P; D.truncate = ctx->cfg.truncate_error; D.prm = ctx->params; D.s0 = ctx->cur_s0;
+  D.S = ctx->S; D.N = ctx->N; D.P = ctx->P; D.truncate = ctx->cfg.truncate_error; D.prm = ctx->params; D.s0 = ctx->cur_s0; D.chain = ctx->cur_chain; D.coarse_hint = ctx->coarse_hint_dev;
   const bool kf = ctx->kf_policy && ctx->reloc_n > 0;
   D.kf_pose = ctx->reloc_pose; D.kf_n = kf ? ctx->reloc_n : 0; D.kf_min_frames = ctx->kf_min_frames;
   D.kf_excess_dist = ctx->kf_wiggle * 10.0; D.kf_need_dist = ctx->kf_mult * ctx->kf_wiggle_dn; D.kf_req = ctx->kf_req;
