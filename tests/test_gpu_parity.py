@@ -298,10 +298,11 @@ def test_calc_pose_update_degenerate_sets():
     ctx.close()
 
 
-def _track_map_case(scale_start, scale_frame, velocity=None, P=11, n_points=1000):
-    cam, f0, smap = common.scene(n_points=n_points)
+def _track_map_case(scale_start, scale_frame, velocity=None, P=11, n_points=1000, size=(640, 480), tex=2048):
+    cam, f0, smap = common.scene(size[0], size[1], n_points, tex)
+    assert smap.n == n_points
     ctx, ow = _ctx(cam, f0, smap, patch_size=P), _orc(cam, f0, smap, P=P)
-    f1, _ = common.frame_at(cam, np.array(synth.CONFIG1_TWIST) * scale_frame)
+    f1, _ = common.frame_at(cam, np.array(synth.CONFIG1_TWIST) * scale_frame, tex)
     start = synth.se3_exp(np.array(synth.CONFIG1_TWIST) * scale_start)
     ctx.make_keyframe_lite(f1); ow.make_current_kf(f1)
     ctx.set_pose(0, start); ow.set_pose(start)
@@ -352,6 +353,21 @@ def test_track_map_more_points_than_the_patch_cap():
     ctx, ow = _track_map_case(0.0, 0.6, n_points=2500)
     a = ow.counters()[0]
     assert a.sum() <= 1000 and a.sum() > 900
+    _check_track_map(ctx, ow)
+    ctx.close()
+
+
+@pytest.mark.parametrize("size,n_points,velocity", [((640, 480), 5000, None), ((1920, 1080), 12000, None), ((1920, 1080), 12000, 0.05)])
+def test_track_map_large_maps_shuffle_without_the_swap_chain(size, n_points, velocity):
+    """Maps of 5000 / 12000 points: the four level shuffles and the fifth one over ~N fine candidates (jni/Tracker.cc:396-397,518-527) run as
+    shuffle_parallel -- scratch in shared memory at 5000 points, in the stream's global scratch at 12000 -- and the projection on its own grid
+    (k_project_points).  Which points are searched (flags per point, counters per level) is the permutation's fingerprint: a wrong element
+    among the first MaxPatchesPerFrame of the shuffled list, or among the coarse set's share of the level-3 / level-2 lists, changes it."""
+    ctx, ow = _track_map_case(0.0, 0.6, velocity=velocity, n_points=n_points, size=size, tex=2048 if size[0] == 640 else 4096)
+    a = ow.counters()[0]
+    assert a.sum() > 900        # (at 12000 points the level-3 list alone exceeds MaxPatchesPerFrame and is searched in full, jni/Tracker.cc:499-527)
+    if velocity:
+        assert ow.counters()[4] == 1, "coarse stage must have run in this case"
     _check_track_map(ctx, ow)
     ctx.close()
 

@@ -29,6 +29,118 @@ __device__ __forceinline__ void shuffle_swaps(int* v, const int* jv, int n) {
     v[k] = vj; v[j] = vk;
   }
 }
+// (Measured and dropped: requesting the partner value of step k + 1 before the stores of step k and patching it from registers when step k wrote that
+// position -- the index of the partner then becomes the chain, and the patch costs what the overlap saves: 43-47 cycles per step either way.)
+
+// glibc_rand_fill (geometry.cuh) by many threads.  The generator is linear over Z / 2^32: 31 draws map the (rotated) ring r to T r, and kRandJumpBlocks
+// such blocks to M r with M = T^kRandJumpBlocks -- a 31 x 31 matrix the host computes once (g_rand_jump, row-major, rows padded to 32).  Warp 0
+// steps the ring from chunk to chunk of kRandChunk draws (31 multiply-adds per lane and chunk, operands by shuffle) and parks every chunk's start
+// ring where that chunk's draws will go; then thread c produces chunk c from registers, exactly like the serial routine.  Same draws, same final
+// ring / indices as n calls of rand().
+constexpr int kRandJumpBlocks = 8, kRandChunk = 31 * kRandJumpBlocks;
+__device__ uint32_t g_rand_jump[31 * 32];
+__device__ void glibc_rand_fill_parallel(int* ring, int& f, int& b, int* out, int n) {
+  __shared__ uint32_t s_tail[31];                                   // start ring of a last chunk shorter than 31 draws
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (n <= 0) return;                                               // (uniform)
+  const int b0 = b, C = (n + kRandChunk - 1) / kRandChunk;
+  if (tid < 32) {
+    uint32_t m[31];
+#pragma unroll
+    for (int j = 0; j < 31; j++) m[j] = lane < 31 ? g_rand_jump[lane * 32 + j] : 0u;
+    int q = b0 + lane; if (q >= 31) q -= 31;
+    uint32_t sv = lane < 31 ? (uint32_t)ring[q] : 0u;
+    for (int c = 0; c < C; c++) {
+      if (lane < 31) { if (c * kRandChunk + 31 <= n) out[c * kRandChunk + lane] = (int)sv; else s_tail[lane] = sv; }
+      if (c + 1 < C) {
+        uint32_t acc = 0u;
+#pragma unroll
+        for (int j = 0; j < 31; j++) acc += m[j] * __shfl_sync(0xffffffffu, sv, j);
+        sv = acc;
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += kPT) {
+    const int base = c * kRandChunk, cnt = min(kRandChunk, n - base);
+    uint32_t r[31];
+#pragma unroll
+    for (int j = 0; j < 31; j++) r[j] = base + 31 <= n ? (uint32_t)out[base + j] : s_tail[j];
+    int k = 0;
+    for (; cnt - k >= 31; k += 31) {
+#pragma unroll
+      for (int j = 0; j < 31; j++) { r[(j + 3) % 31] += r[j]; out[base + k + j] = (int)(r[(j + 3) % 31] >> 1); }
+    }
+    const int rem = cnt - k;
+#pragma unroll
+    for (int j = 0; j < 31; j++) if (j < rem) { r[(j + 3) % 31] += r[j]; out[base + k + j] = (int)(r[(j + 3) % 31] >> 1); }
+    if (c == C - 1) {
+#pragma unroll
+      for (int j = 0; j < 31; j++) { int q = b0 + j; if (q >= 31) q -= 31; ring[q] = (int)r[j]; }
+      b = (b0 + n) % 31; f = (b + 3) % 31;
+    }
+  }
+  __syncthreads();
+}
+
+// The same swaps WITHOUT the chain.  Step k (k = 1..n-1, in order) swaps v[k] with v[t_k], t_k <= k; position k is untouched before step k.  Hence
+//   * a step with t_k = q < k leaves v0[k] (the original element k) at q: position q ends up holding v0[k*], k* = the LAST step that targets q;
+//   * what step k moves INTO position k -- W_k, the value at q = t_k at that time -- is v0[k'] with k' = the last step BEFORE k that targets q, or, if
+//     there is none, what q's own step left there: W_q (W_q = v0[q] for t_q = q and for a position without a step);
+//   * a position no later step targets keeps W_p.
+// So: bucket the steps by target (counting sort, buckets unordered -- a bucket holds ~ln(n / q) steps, scanned linearly), give every step either its
+// source element or a link to an earlier step's W (res), and every wanted output position p < m follows at most a few links (a link goes to a uniformly
+// drawn earlier position that was not targeted again: ~1 on average).  All threads of the CTA; any number of independent segments at once (a segment's
+// first element has t = itself).  tgt (n), ptr (n + 1), ent (n), res (n): scratch, shared or global; tgt is consumed.  Result: v[0..m).
+__device__ void shuffle_parallel(int* v, int* tgt, int n, int m, int* ptr, int* ent, int* res) {
+  __shared__ int s_part[kPT / 32], s_base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (n <= 1 || m <= 0) return;                                   // (uniform)
+  for (int q = tid; q <= n; q += kPT) ptr[q] = 0;
+  __syncthreads();
+  for (int k = tid; k < n; k += kPT) { const int q = tgt[k]; if (q != k) atomicAdd(&ptr[q], 1); }
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int b = 0; b <= n; b += kPT) {                             // inclusive prefix sums: ptr[q] = end of bucket q; ptr[n] = number of real steps
+    const int q = b + tid;
+    const int c = q <= n ? ptr[q] : 0;
+    int inc = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+    if (lane == 31) s_part[warp] = inc;
+    __syncthreads();
+    int off = s_base;
+    for (int w = 0; w < warp; w++) off += s_part[w];
+    if (q <= n) ptr[q] = off + inc;
+    __syncthreads();
+    if (tid == kPT - 1) s_base = off + inc;
+  }
+  __syncthreads();
+  for (int k = tid; k < n; k += kPT) { const int q = tgt[k]; if (q != k) ent[atomicSub(&ptr[q], 1) - 1] = k; }   // afterwards ptr[q] = start of bucket q, ptr[q + 1] its end
+  __syncthreads();
+  for (int k = tid; k < n; k += kPT) {
+    const int q = tgt[k];
+    int r = k;                                                     // t_k = k (or no step): W_k = v0[k]
+    if (q != k) {
+      int best = -1;
+      for (int e = ptr[q], e1 = ptr[q + 1]; e < e1; e++) { const int x = ent[e]; if (x < k && x > best) best = x; }
+      r = best >= 0 ? best : -(q + 1);                             // the last earlier step onto q, else a link to W_q
+    }
+    res[k] = r;
+    int last = -1;                                                 // the last step that targets position k
+    for (int e = ptr[k], e1 = ptr[k + 1]; e < e1; e++) { const int x = ent[e]; if (x > last) last = x; }
+    tgt[k] = last;                                                 // (tgt[k] was read by this thread alone)
+  }
+  __syncthreads();
+  for (int p = tid; p < m; p += kPT) {
+    int r = tgt[p];
+    if (r < 0) { r = res[p]; while (r < 0) r = res[-(r + 1)]; }
+    ent[p] = v[r];                                                 // (ent is free: the buckets are not needed any more)
+  }
+  __syncthreads();
+  for (int p = tid; p < m; p += kPT) v[p] = ent[p];
+  __syncthreads();
+}
 
 // Tracker::ApplyMotionModel (jni/Tracker.cc:781-798): the pose a frame starts from.  sbi (6 doubles or null): Tracker::mv6SBIRot of THIS frame.
 __device__ __forceinline__ void motion_model_pose(const Dev& D, const double* velocity, const double* pose, const double* sbi, double* np) {
@@ -71,9 +183,17 @@ __global__ void __launch_bounds__(kPT) k_project_points(Dev D, int apply_motion,
   D.ps.flags[gi] = flags;
 }
 
-__global__ void __launch_bounds__(kPT) k_project_lists(Dev D, int mode, int apply_motion, int use_smem, const double* __restrict__ sbi_rot_in, int pre_projected) {
+// par_shuffle: 0 = the shuffles as serial swap chains; 1 = shuffle_parallel with its scratch behind the two shared-memory arrays (6 N + 1 ints in all);
+// 2 = ... with its scratch in the stream's global scratch (sort scratch + the PVS lists, which are free by then); needs use_smem
+__global__ void __launch_bounds__(kPT) k_project_lists(Dev D, int mode, int apply_motion, int use_smem, const double* __restrict__ sbi_rot_in, int pre_projected, int par_shuffle) {
   cudaGridDependencySynchronize(); cudaTriggerProgrammaticLaunchCompletion();   // programmatic dependent launch (vs_launch_pdl); no-ops otherwise
   extern __shared__ int sh_i[];          // [N] packed level lists (L3|L2|L1|L0), [N] random draws
+#ifdef VS_PROJ_TIMING   // instrumented build (scratch experiments): cycles per phase of one CTA, printed by stream 7
+  long long tm_[12]; int tn_ = 0;
+#define PJ_MARK() do { __syncthreads(); if (tn_ < 12) tm_[tn_++] = clock64(); } while (0)
+#else
+#define PJ_MARK() do { } while (0)
+#endif
   __shared__ double s_pose[12];
   __shared__ int s_cnt[kPT / 32][VS_LEVELS], s_run[VS_LEVELS], s_off[VS_LEVELS + 1];
   __shared__ int s_seg[8];
@@ -82,7 +202,7 @@ __global__ void __launch_bounds__(kPT) k_project_lists(Dev D, int mode, int appl
   const size_t SN = (size_t)D.S * D.N;
   StreamState* st = D.ss + s;
   if (tid == 0 && apply_motion) { st->frame_no++; st->kf_request = 0; D.kf_req[s] = 0; }   // mnFrame++ (jni/Tracker.cc:100): every TrackFrame, lost or not
-  if (mode == 1 && st->lost_frames >= 3 && !st->recovered) { if (tid == 0) D.coarse_hint[s] = 0; return; }   // lost and not relocalised this frame (k_relocalise): nothing to do, jni/Tracker.cc:104,134-140
+  if (mode == 1 && st->lost_frames >= 3 && !st->recovered) return;   // lost and not relocalised this frame (k_relocalise): nothing to do, jni/Tracker.cc:104,134-140
   if (tid == 0 && apply_motion && !st->recovered) {   // Tracker::ApplyMotionModel (jni/Tracker.cc:781-798); a relocalised stream starts from the recovered pose
     for (int k = 0; k < 12; k++) st->start_pose[k] = st->pose[k];
     if (D.prm.use_sbi && sbi_rot_in) for (int k = 0; k < 6; k++) st->sbi_rot[k] = sbi_rot_in[6 * (size_t)s + k];   // Tracker::mv6SBIRot of THIS frame (k_sbi, front end of the frame)
@@ -95,14 +215,54 @@ __global__ void __launch_bounds__(kPT) k_project_lists(Dev D, int mode, int appl
   if (mode == 1 && tid < VS_LEVELS) { st->attempted[tid] = 0; st->found[tid] = 0; }
   __syncthreads();
   int* pvs = D.pvs + (size_t)s * VS_LEVELS * D.N;
+  PJ_MARK();   // 0: motion model done
 
-  for (int base = 0; base < N; base += kPT) {
+  if (pre_projected) {
+    // k_project_points has been here: a point is potentially visible if it is in the image and its warp was accepted.  Ordered append to the
+    // per-level PVS lists (jni/Tracker.cc:391) without a barrier per 256 points: every warp owns a contiguous range of the map, counts its points
+    // per level, and -- once the counts of the warps before it are known -- writes them in index order.
+    const int C = ((N + kPT - 1) / kPT) * 32, w0 = warp * C, w1 = min(N, w0 + C);
+    // (a warp requests the flags / levels of kPvsBatch x 32 points before it looks at any of them: one round trip to L2 per batch, not two per 32 points)
+    constexpr int kPvsBatch = 8;
+    int cnt[VS_LEVELS] = {0, 0, 0, 0};
+    for (int i0 = w0; i0 < w1; i0 += 32 * kPvsBatch) {
+      int fl[kPvsBatch], lv[kPvsBatch];
+#pragma unroll
+      for (int u = 0; u < kPvsBatch; u++) { const int i = i0 + 32 * u + lane; const size_t gi = (size_t)s * D.N + (i < w1 ? i : w0); fl[u] = D.ps.flags[gi]; lv[u] = D.ps.level[gi]; }
+#pragma unroll
+      for (int u = 0; u < kPvsBatch; u++) {
+        const int i = i0 + 32 * u + lane; const int l_ = (i < w1 && (fl[u] & F_INIMAGE)) ? lv[u] : -1;
+#pragma unroll
+        for (int l = 0; l < VS_LEVELS; l++) cnt[l] += __popc(__ballot_sync(0xffffffffu, l_ == l));
+      }
+    }
+    if (lane == 0) for (int l = 0; l < VS_LEVELS; l++) s_cnt[warp][l] = cnt[l];
+    __syncthreads();
+    int off[VS_LEVELS];
+#pragma unroll
+    for (int l = 0; l < VS_LEVELS; l++) { off[l] = 0; for (int w = 0; w < warp; w++) off[l] += s_cnt[w][l]; }
+    for (int i0 = w0; i0 < w1; i0 += 32 * kPvsBatch) {
+      int fl[kPvsBatch], lv[kPvsBatch];
+#pragma unroll
+      for (int u = 0; u < kPvsBatch; u++) { const int i = i0 + 32 * u + lane; const size_t gi = (size_t)s * D.N + (i < w1 ? i : w0); fl[u] = D.ps.flags[gi]; lv[u] = D.ps.level[gi]; }
+#pragma unroll
+      for (int u = 0; u < kPvsBatch; u++) {
+        const int i = i0 + 32 * u + lane; const int l_ = (i < w1 && (fl[u] & F_INIMAGE)) ? lv[u] : -1;
+#pragma unroll
+        for (int l = 0; l < VS_LEVELS; l++) {
+          const unsigned bal = __ballot_sync(0xffffffffu, l_ == l);
+          if (l_ == l) pvs[l * D.N + off[l] + __popc(bal & ((1u << lane) - 1u))] = i;
+          off[l] += __popc(bal);
+        }
+      }
+    }
+    if (tid < VS_LEVELS) { int a = 0; for (int w = 0; w < kPT / 32; w++) a += s_cnt[w][tid]; s_run[tid] = a; }
+    __syncthreads();
+  }
+  for (int base = 0; base < N && !pre_projected; base += kPT) {
     const int i = base + tid;
     int level = -1; bool pv = false;
-    if (i < N && pre_projected) {   // k_project_points has been here: a point is potentially visible if it is in the image and its warp was accepted
-      const size_t gi = (size_t)s * D.N + i;
-      if (D.ps.flags[gi] & F_INIMAGE) { level = D.ps.level[gi]; pv = level >= 0; }
-    } else if (i < N) {
+    if (i < N) {
       const size_t gi = (size_t)s * D.N + i;
       int flags = D.ps.flags[gi] | F_HASTD;
       if (mode == 0) { flags &= ~(F_SEARCHED | F_FOUND | F_SUBPIX); }
@@ -134,6 +294,7 @@ __global__ void __launch_bounds__(kPT) k_project_lists(Dev D, int mode, int appl
     }
   }
   if (mode == 0) return;
+  PJ_MARK();   // 1: projection / PVS rounds
 
   // packed layout in shared memory: [L3][L2][L1][L0]
   if (tid == 0) { s_off[0] = 0; s_off[1] = s_run[3]; s_off[2] = s_off[1] + s_run[2]; s_off[3] = s_off[2] + s_run[1]; s_off[4] = s_off[3] + s_run[0]; }
@@ -149,8 +310,11 @@ __global__ void __launch_bounds__(kPT) k_project_lists(Dev D, int mode, int appl
   int n_draws = 0;
 #pragma unroll
   for (int l = 0; l < VS_LEVELS; l++) n_draws += max(s_run[l] - 1, 0);
-  if (tid == 0) glibc_rand_fill(st->rng_ring, st->rng_f, st->rng_b, rnd, n_draws);
+  PJ_MARK();   // 2: packed copy
+  if (par_shuffle) glibc_rand_fill_parallel(st->rng_ring, st->rng_f, st->rng_b, rnd, n_draws);
+  else if (tid == 0) glibc_rand_fill(st->rng_ring, st->rng_f, st->rng_b, rnd, n_draws);
   __syncthreads();
+  PJ_MARK();   // 3: rand fill
   // draw -> swap partner of std::random_shuffle (libstdc++ bits/stl_algo.h:4581-4597: i-th element swaps with rand() % (i+1)), all threads
   for (int d = tid; d < n_draws; d += kPT) {
     int k = d;
@@ -159,6 +323,23 @@ __global__ void __launch_bounds__(kPT) k_project_lists(Dev D, int mode, int appl
     rnd[d] = rnd[d] % (k + 2);
   }
   __syncthreads();
+  PJ_MARK();   // 4: modulo
+  int* const sc_tgt = par_shuffle == 1 ? sh_i + 2 * D.N : (int*)(D.sort_scratch + (size_t)s * D.sort_cap);
+  int* const sc_ptr = par_shuffle == 1 ? sc_tgt + D.N : pvs;       // (the PVS lists have been copied into `list`)
+  int* const sc_ent = sc_ptr + D.N + 1; int* const sc_res = sc_ent + D.N;
+  if (par_shuffle == 1) {
+    // the four level shuffles as ONE shuffle_parallel problem over the packed list: the partner of packed position pos = s_off[q] + k (level 3 - q,
+    // k >= 1) is s_off[q] + rnd[draws of the lower levels + k - 1]; a level's first element has no step.  Only with the scratch in shared memory
+    // (5000 points: 60 k cycles against 96 k for the longest level's chain; 1000 points: 14 k against 19.5 k); with the scratch in global memory the
+    // dozen passes over all levels wait for L2 and lose against the chains (20000 points: 642 k against 392 k).
+    for (int pos = tid; pos < total; pos += kPT) {
+      const int q = pos >= s_off[3] ? 3 : (pos >= s_off[2] ? 2 : (pos >= s_off[1] ? 1 : 0)), l = 3 - q, k = pos - s_off[q];
+      int roff = 0; for (int u = 0; u < l; u++) roff += max(s_run[u] - 1, 0);
+      sc_tgt[pos] = k == 0 ? pos : s_off[q] + rnd[roff + k - 1];
+    }
+    __syncthreads();
+    shuffle_parallel(list, sc_tgt, total, total, sc_ptr, sc_ent, sc_res);
+  } else
   if (lane == 0 && warp < VS_LEVELS) {   // the swaps of level `warp`, in order
     const int l = warp, n = s_run[l];
     int roff = 0; for (int k = 0; k < l; k++) roff += max(s_run[k] - 1, 0);
@@ -167,6 +348,7 @@ __global__ void __launch_bounds__(kPT) k_project_lists(Dev D, int mode, int appl
     shuffle_swaps(v, jv, n);
   }
   __syncthreads();
+  PJ_MARK();   // 5: level swaps
   if (tid == 0) {   // coarse / fine selection (jni/Tracker.cc:399-527)
     const int n3 = s_run[3], n2 = s_run[2];
     unsigned nCoarseMax = D.prm.coarse_max, nCoarseRange = D.prm.coarse_range;
@@ -185,7 +367,6 @@ __global__ void __launch_bounds__(kPT) k_project_lists(Dev D, int mode, int appl
       }
     } else tryCoarse = false;
     st->try_coarse = tryCoarse ? 1 : 0; st->coarse_range = (int)nCoarseRange; st->did_coarse = 0;
-    D.coarse_hint[s] = tryCoarse ? 1 : 0;
     const int nFine = total - f0;
     int use = D.prm.max_patches_per_frame - ((a1 - a0) + (t1 - t0));
     if (use < 0) use = 0;
@@ -198,12 +379,22 @@ __global__ void __launch_bounds__(kPT) k_project_lists(Dev D, int mode, int appl
     // truncation (jni/Tracker.cc:518-527).  Same three steps as the level shuffles: draws in bulk (one thread, ring in registers),
     // `% (k+1)` by all threads, then the swap chain -- the only serial part -- with the next partner fetched ahead.
     const int nF = s_seg[5];
-    if (tid == 0) glibc_rand_fill(st->rng_ring, st->rng_f, st->rng_b, rnd, nF - 1);
+    PJ_MARK();   // 6: selection
+    if (par_shuffle) glibc_rand_fill_parallel(st->rng_ring, st->rng_f, st->rng_b, rnd, nF - 1);
+    else if (tid == 0) glibc_rand_fill(st->rng_ring, st->rng_f, st->rng_b, rnd, nF - 1);
     __syncthreads();
-    for (int d = tid; d < nF - 1; d += kPT) rnd[d] = rnd[d] % (d + 2);
+    PJ_MARK();   // 7: fifth rand fill
+    if (par_shuffle) {   // only the first `use` positions of the shuffled fine list are kept
+      for (int k = tid; k < nF; k += kPT) sc_tgt[k] = k == 0 ? 0 : rnd[k - 1] % (k + 1);
+      __syncthreads();
+      shuffle_parallel(list + s_seg[4], sc_tgt, nF, min(nF, s_seg[7]), sc_ptr, sc_ent, sc_res);
+    } else {
+      for (int d = tid; d < nF - 1; d += kPT) rnd[d] = rnd[d] % (d + 2);
+      __syncthreads();
+      if (tid == 0) shuffle_swaps(list + s_seg[4], rnd - 1, nF);
+    }
     __syncthreads();
-    if (tid == 0) shuffle_swaps(list + s_seg[4], rnd - 1, nF);
-    __syncthreads();
+    PJ_MARK();   // 8: fifth modulo + swaps
   }
   if (tid == 0) {
     const int nFine = s_seg[6] ? s_seg[7] : s_seg[5];
@@ -218,6 +409,10 @@ __global__ void __launch_bounds__(kPT) k_project_lists(Dev D, int mode, int appl
     for (int k = tid; k < n; k += kPT) out[dst + k] = list[src0 + k];
     dst += n;
   }
+#ifdef VS_PROJ_TIMING
+  PJ_MARK();
+  if (tid == 0 && s == 7) { printf("k_project_lists cycles (N=%d total=%d):", N, total); for (int q = 1; q < tn_; q++) printf(" %lld", tm_[q] - tm_[q - 1]); printf("\n"); }
+#endif
 }
 
 // mode 0: explicit list [0,nA) with (range, subpix) arguments; 1: coarse set A; 2: fine set B
@@ -894,7 +1089,12 @@ __global__ void __launch_bounds__(kPT) k_reproject_fine(Dev D) {
   cudaGridDependencySynchronize(); cudaTriggerProgrammaticLaunchCompletion();   // programmatic dependent launch (vs_launch_pdl); no-ops otherwise
   const int s = blockIdx.x + D.s0;
   StreamState* st = D.ss + s;
-  if ((st->lost_frames >= 3 && !st->recovered) || !st->did_coarse || other_chain(D, st)) return;
+  // The layout hint of vs_launch_track_map_rest: did this stream try the coarse stage in this frame?  Written to mapped HOST memory, from here because
+  // this kernel is off the critical path whenever the answer matters (in the two-chain layout it belongs to the coarse chain, which is empty while the
+  // hint reads 0): a kernel that has written to system memory completes ~3 us later (measured in k_project_lists: 0.0375 -> 0.0412 ms at 32 streams).
+  const bool lost = st->lost_frames >= 3 && !st->recovered;
+  if (threadIdx.x == 0) D.coarse_hint[s] = lost ? 0 : st->try_coarse;
+  if (lost || !st->did_coarse || other_chain(D, st)) return;
   const size_t SN = (size_t)D.S * D.N;
   const int* list = D.lists + (size_t)s * D.list_cap + st->nA;
   for (int k = threadIdx.x; k < st->nB; k += kPT) {
@@ -920,6 +1120,21 @@ __global__ void k_atan(const double* x, double* y, int n, int dd_only) { const i
 
 }  // namespace
 
+// M = T^kRandJumpBlocks of glibc_rand_fill_parallel: column j = the ring after kRandJumpBlocks blocks of 31 draws started from the unit vector e_j
+static int upload_rand_jump(vslam_ctx* ctx) {
+  static const std::vector<uint32_t> M = [] {
+    std::vector<uint32_t> m(31 * 32, 0u);
+    for (int j = 0; j < 31; j++) {
+      uint32_t r[31] = {}; r[j] = 1u;
+      for (int blk = 0; blk < kRandJumpBlocks; blk++) for (int q = 0; q < 31; q++) r[(q + 3) % 31] += r[q];
+      for (int i = 0; i < 31; i++) m[i * 32 + j] = r[i];
+    }
+    return m;
+  }();
+  VS_CUDA(cudaMemcpyToSymbolAsync(g_rand_jump, M.data(), M.size() * sizeof(uint32_t), 0, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->rand_jump_ready = true;
+  return VSLAM_OK;
+}
 constexpr int kSplitProjectN = 2048;   // maps above this many points project on a (point chunks, streams) grid (k_project_points)
 int vs_launch_project_all(vslam_ctx* ctx, int mode) {
   const Dev D = make_dev(ctx);
@@ -927,6 +1142,15 @@ int vs_launch_project_all(vslam_ctx* ctx, int mode) {
   size_t smem = (size_t)2 * ctx->N * sizeof(int);
   const int use_smem = smem <= 200 * 1024;
   if (!use_smem) smem = 0;
+  // std::random_shuffle without the swap chain (shuffle_parallel): scratch behind the two arrays when 6 N + 1 ints fit, else in the stream's global
+  // scratch; maps too large for the two arrays in shared memory keep the serial chains
+  static const int par_env = getenv("VSLAM_PAR_SHUFFLE") ? atoi(getenv("VSLAM_PAR_SHUFFLE")) : -1;
+  int par_shuffle = 0;
+  if (!ctx->rand_jump_ready) { const int rc_ = upload_rand_jump(ctx); if (rc_) return rc_; }
+  if (use_smem && par_env != 0) {
+    const size_t smem6 = ((size_t)6 * ctx->N + 1) * sizeof(int);
+    if (smem6 <= 200 * 1024 && par_env != 2) { par_shuffle = 1; smem = smem6; } else par_shuffle = 2;
+  }
   if (smem > ctx->smem_attr[0]) { VS_CUDA(cudaFuncSetAttribute(k_project_lists, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); ctx->smem_attr[0] = smem; }
   // large maps: the per-point projection on its own grid (k_project_points), the list building behind it
   static const int split_env = getenv("VSLAM_SPLIT_PROJECT") ? atoi(getenv("VSLAM_SPLIT_PROJECT")) : -1;
@@ -934,7 +1158,7 @@ int vs_launch_project_all(vslam_ctx* ctx, int mode) {
   const bool pdl = ctx->pdl && !ctx->timing;
   vs_time_begin(ctx, VS_ST_PROJECT);
   if (pre) { VS_CUDA(vs_launch_pdl(k_project_points, dim3((ctx->map.n + kPT - 1) / kPT, ctx->cur_cnt), dim3(kPT), 0, ctx->stream, pdl, D, (mode >> 1) & 1, ctx->cur_sbi_rot)); ctx->launches++; }
-  VS_CUDA(vs_launch_pdl(k_project_lists, dim3(ctx->cur_cnt), dim3(kPT), smem, ctx->stream, pdl, D, mode & 1, (mode >> 1) & 1, use_smem, ctx->cur_sbi_rot, pre));
+  VS_CUDA(vs_launch_pdl(k_project_lists, dim3(ctx->cur_cnt), dim3(kPT), smem, ctx->stream, pdl, D, mode & 1, (mode >> 1) & 1, use_smem, ctx->cur_sbi_rot, pre, par_shuffle));
   vs_time_end(ctx);
   VS_CUDA(cudaGetLastError());
   ctx->launches++;

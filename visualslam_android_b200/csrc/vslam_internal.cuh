@@ -172,6 +172,7 @@ struct vslam_ctx {
   float* reloc_frame_scratch = nullptr; uint8_t* reloc_frame_small = nullptr;      // k_relocalise's own scratch ([S][3n] / [S][n]): it may run beside the next frame's k_sbi
   // vs_launch_track_map_rest: the coarse-stage chain of a frame (streams that try the coarse stage) runs on a stream of its own beside the fine-only chain
   int* coarse_hint_host = nullptr; int* coarse_hint_dev = nullptr;   // [S] mapped pinned memory: k_project_lists leaves each stream's try_coarse of its latest frame here; read by the host WITHOUT synchronisation, as a hint for the launch layout only
+  bool rand_jump_ready = false;  // g_rand_jump (track.cu) has been uploaded to this context's device
   int cur_chain = -1; cudaStream_t chain_stream[VS_MAX_GROUPS] = {}, chain_stream_hi = nullptr; cudaEvent_t ev_chain_fork[VS_MAX_GROUPS] = {}, ev_chain_join[VS_MAX_GROUPS] = {};
   bool pdl = true;               // programmatic dependent launch of a frame's kernels (vs_launch_pdl); VSLAM_PDL=0 turns it off
   bool lists_stale = false;      // the last tracked frame left corner bitmasks only: corner lists / row LUTs are built on demand (vs_ensure_lists)
