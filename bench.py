@@ -624,6 +624,8 @@ def main():
     ctx.set_map(smap.world, smap.pix_right_w, smap.pix_down_w, smap.ir_center, smap.src_level)
     config["frame_lookahead"] = ("on: pyramid + FAST + SmallBlurryImage of frame k+1 on a second stream beside projection / search / pose of frame k (two frame sets)"
                                  if ctx.frame_lookahead_active() else "off")
+    config["coarse_chain"] = ("library default: while no stream tried TrackMap's coarse stage in its latest frame (and the map has at most 2040 points) the "
+                              "coarse stage's kernels run as a launch chain of their own beside the fine stage instead of in front of it")
 
     def barrier():
         torch.cuda.synchronize()

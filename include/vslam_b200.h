@@ -110,8 +110,8 @@ typedef struct vslam_params {
                                kernels are launched for every frame and, at ordinary camera speed, find nothing to do -- each still waiting for the one
                                before.  1 = a frame's back end forks into two launch chains, coarse stage + fine stage for the streams that try the coarse
                                stage and the fine stage alone for the others, so that an empty chain runs BESIDE the other one instead of in front of it;
-                               0 = one chain; -1 (default) = two chains while no stream of the context tried the coarse stage in its latest frame and the
-                               map has at most 2040 points */
+                               0 = one chain; -1 (default) = two chains while no stream of the context tried the coarse stage in its latest frame, for contexts
+                               of at least 48 streams (fewer: the host's launch rate decides) and maps of at most 2040 points */
 } vslam_params;
 
 void vslam_default_config(vslam_config* cfg);

@@ -1216,7 +1216,7 @@ int vs_launch_calc_jacobians(vslam_ctx* ctx) {
 // on the calling stream (Dev::chain tells a kernel which streams are its own); the chains join at the end.  A chain without streams is a row of
 // empty kernels BESIDE the other chain's work instead of in front of it.  Streams are independent: no result depends on the split.
 static int track_map_rest_chain(vslam_ctx* ctx, int with_motion_model);
-constexpr int kDualChainMaxList = 2048;
+constexpr int kDualChainMaxList = 2048, kDualChainMinStreams = 48;
 int vs_launch_track_map_rest(vslam_ctx* ctx, int with_motion_model) {
   static const int env = getenv("VSLAM_COARSE_CHAIN") ? atoi(getenv("VSLAM_COARSE_CHAIN")) : -1;   // A/B runs: overrides vslam_params.coarse_chain
   const int want = env >= 0 ? env : ctx->params.coarse_chain;
@@ -1226,7 +1226,10 @@ int vs_launch_track_map_rest(vslam_ctx* ctx, int with_motion_model) {
     // other stream and pay the fork / join (measured: + 2 %), and the empty fine search of a 20000-point map is 185 k CTAs (4K: + 1.2 %).  Which
     // streams tried the coarse stage in their latest frame is a HINT read without synchronisation (k_project_lists writes it to mapped host
     // memory): it chooses the layout, never the result -- both layouts run every stream through the stages it asks for.
-    if (ctx->list_cap > kDualChainMaxList) dual = false;
+    // ... and while the host keeps up: the second chain costs three more launches and two event pairs per frame, and a context of a few streams finishes a
+    // frame in the time the host needs to enqueue one (32 streams per GPU: 0.250 -> 0.245 ms with one process driving one GPU, but 0.248 -> 0.257 ms
+    // with eight processes driving eight GPUs of one host)
+    if (ctx->list_cap > kDualChainMaxList || ctx->S < kDualChainMinStreams) dual = false;
     else { const volatile int* h = ctx->coarse_hint_host; for (int s = ctx->cur_s0; s < ctx->cur_s0 + ctx->cur_cnt && dual; s++) if (h[s]) dual = false; }
   }
   if (!dual) return track_map_rest_chain(ctx, with_motion_model);
