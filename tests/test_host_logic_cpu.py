@@ -109,3 +109,105 @@ def test_reference_arm_runs_on_the_gpu_arms_workload():
     assert line["impl"] == "reference" and line["value"] > 0 and line["e2e"]["value"] == line["value"]
     assert line["cpu_baseline"]["kind"] == ("reference" if refbind.available() else "port")
     assert line["tracking"]["found_per_frame_mean"] > 900
+
+
+def _shuffle_without_the_chain(v0, tgt, m):
+    """The rules of shuffle_parallel (visualslam_android_b200/csrc/track.cu) restated with numpy: buckets of steps by target, every step either
+    names its source element or links to an earlier step, every output position follows the links.  No sequential state anywhere."""
+    n = len(v0)
+    buckets = [[] for _ in range(n)]
+    for k in range(n):
+        if tgt[k] != k:
+            buckets[tgt[k]].append(k)                       # (unordered in the kernel: filled by atomics)
+    res = np.empty(n, dtype=np.int64)
+    last = np.full(n, -1, dtype=np.int64)
+    for k in range(n):
+        q = tgt[k]
+        if q == k:
+            res[k] = k
+        else:
+            earlier = [x for x in buckets[q] if x < k]
+            res[k] = max(earlier) if earlier else -(q + 1)
+        if buckets[k]:
+            last[k] = max(buckets[k])
+    out = np.empty(m, dtype=v0.dtype)
+    for p in range(m):
+        r = last[p]
+        if r < 0:
+            r = res[p]
+            while r < 0:
+                r = res[-(r + 1)]
+        out[p] = v0[r]
+    return out
+
+
+def test_shuffle_without_the_swap_chain_equals_std_random_shuffle():
+    """std::random_shuffle is `for k in 1..n-1: swap(v[k], v[rand() % (k+1)])` (libstdc++ bits/stl_algo.h:4581-4597).  The kernel that builds the
+    tracker's search lists replaces that chain by a data-parallel evaluation; this is its rule set against the chain, on
+    single shuffles, on truncated ones (TrackMap keeps the first MaxPatchesPerFrame elements of the fifth shuffle) and on several independent
+    segments handled as one problem (the four level lists).  The CUDA code itself is held to the oracle's shuffle by the GPU parity tests."""
+    rs = np.random.RandomState(5)
+    for n in [1, 2, 3, 7, 64, 257, 1500]:
+        for _ in range(6):
+            v0 = rs.permutation(10 * n + 3)[:n]
+            tgt = np.array([0] + [rs.randint(0, k + 1) for k in range(1, n)], dtype=np.int64)
+            if n > 3 and rs.rand() < 0.5:
+                tgt[rs.randint(1, n, size=n // 3)] = rs.randint(0, 2)           # crowd the low positions: long buckets, links to links
+                tgt = np.minimum(tgt, np.arange(n))
+            v = v0.copy()
+            for k in range(1, n):
+                j = tgt[k]
+                v[k], v[j] = v[j], v[k]
+            for m in sorted({n, min(n, 5), n // 2}):
+                assert np.array_equal(_shuffle_without_the_chain(v0, tgt, m), v[:m]), (n, m)
+    # four segments at once: a segment's first element has no step (target = itself), targets are positions of the packed array
+    sizes = [300, 0, 1, 450]
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    v0 = rs.permutation(offs[-1])
+    tgt = np.arange(offs[-1])
+    v = v0.copy()
+    for q, nseg in enumerate(sizes):
+        for k in range(1, nseg):
+            j = rs.randint(0, k + 1)
+            tgt[offs[q] + k] = offs[q] + j
+            a, b = offs[q] + k, offs[q] + j
+            v[a], v[b] = v[b], v[a]
+    assert np.array_equal(_shuffle_without_the_chain(v0, tgt, len(v0)), v)
+
+
+def test_glibc_rand_jump_matrix_reproduces_the_serial_generator():
+    """glibc's TYPE_3 rand() is r[i] = r[i-3] + r[i-31] (mod 2^32), output r[i] >> 1: linear, so 31 * B draws are one 31 x 31 matrix applied to the
+    ring.  k_project_lists draws a frame's random numbers in chunks of 248 started from M^c * ring (glibc_rand_fill_parallel, M = T^8 computed by
+    upload_rand_jump the way it is computed here); this checks chunk starts and draws against the generator run serially."""
+    rs = np.random.RandomState(9)
+    B = 8
+
+    def block(r, out=None):
+        for q in range(31):
+            r[(q + 3) % 31] = (r[(q + 3) % 31] + r[q]) & 0xffffffff
+            if out is not None:
+                out.append(r[(q + 3) % 31] >> 1)
+
+    M = np.zeros((31, 31), dtype=object)
+    for j in range(31):
+        r = [0] * 31
+        r[j] = 1
+        for _ in range(B):
+            block(r)
+        for i in range(31):
+            M[i, j] = r[i]
+    ring0 = [int(x) for x in rs.randint(0, 2 ** 32, 31, dtype=np.uint64)]
+    n = 1000                                                  # a VGA frame's draws: 4 full chunks + 8 draws
+    serial, r = [], list(ring0)
+    while len(serial) < n + 31:
+        block(r, serial)
+    serial = serial[:n]
+    chunked, start = [], list(ring0)
+    for c in range((n + 31 * B - 1) // (31 * B)):
+        r, out = list(start), []
+        for _ in range(B):
+            block(r, out)
+        chunked += out
+        start = [int(sum(M[i, j] * start[j] for j in range(31)) & 0xffffffff) for i in range(31)]
+        assert start == r                                      # the jump lands where the serial generator is
+    assert chunked[:n] == serial
