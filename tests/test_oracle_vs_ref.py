@@ -153,6 +153,7 @@ def test_patchfinder_p8_object_level():
 
 @pytest.mark.parametrize("start,frame,vel,n_points", [(0.0, 1.0, None, 1000), (0.0, 1.0, 0.05, 1000), (0.2, 0.5, None, 1000), (0.5, 0.5, 0.02, 1000),
                                                       (0.0, 0.6, None, 2500), (0.0, 0.6, 0.05, 2500),    # 2500: beyond the 1000-patch cap (jni/Tracker.cc:518-527)
+                                                      (0.0, 0.6, None, 5000),                            # 5000: the GPU's large-map shuffle test runs against the oracle at this size
                                                       (0.0, 0.6, 0.05, 150), (0.0, 0.6, 0.05, 300), (0.0, 0.6, 0.05, 90)])   # small maps: the coarse-set branches of :425-462, incl. the vNextToSearch overwrite
 def test_track_map_whole(start, frame, vel, n_points):
     cam, f0, smap, rw, ow = _worlds(n_points=n_points)
@@ -174,6 +175,31 @@ def test_track_map_whole(start, frame, vel, n_points):
     assert np.array_equal(ri[srch][:, 5], oi[srch][:, 5])
     if n_points > 1000:
         assert srch.sum() == 1000 and pvs.sum() > 1000       # the cap was hit
+    fnd = oi[:, 3] == 1
+    assert np.array_equal(rd[fnd][:, :4], od[fnd][:, :4])
+
+
+@pytest.mark.parametrize("vel", [None, 0.05])
+def test_track_map_whole_1080p_12000_points(vel):
+    """1920 x 1080 with 12000 map points: the level-3 list alone (1200 points) exceeds MaxPatchesPerFrame, so every one of its points is searched and the
+    fifth shuffle's result is thrown away whole (jni/Tracker.cc:499-527) -- the branch the GPU's large-map test
+    (tests/test_gpu_parity.py::test_track_map_large_maps_shuffle_without_the_swap_chain) holds against the restatement, here held against the reference."""
+    cam, f0, smap, rw, ow = _worlds(width=1920, height=1080, n_points=12000, tex_size=4096)
+    assert smap.n == 12000
+    f1, _ = common.frame_at(cam, np.array(synth.CONFIG1_TWIST) * 0.6, 4096)
+    rw.make_current_kf(f1); ow.make_current_kf(f1)
+    rw.set_pose(synth.IDENTITY_POSE); ow.set_pose(synth.IDENTITY_POSE)
+    if vel is not None:
+        rw.L.ref_tracker_set_velocity(rw.tracker, np.zeros(6), vel); ow.L.orc_tracker_set_velocity(ow.tracker, np.zeros(6), vel)
+    rw.L.ref_srand(1)
+    rw.L.ref_tracker_track_map(rw.tracker); ow.L.orc_tracker_track_map(ow.tracker)
+    assert np.array_equal(rw.get_pose(), ow.get_pose())
+    ra, rf, _, _, rdc = rw.counters(); oa, of, _, _, odc = ow.counters()
+    assert np.array_equal(ra, oa) and np.array_equal(rf, of) and rdc == odc and rdc == (1 if vel else 0)
+    assert oa[3] >= 1000 and oa[:3].sum() <= (120 if vel else 0)       # level 3 in full; the lower levels only through the coarse set
+    ri, rd = rw.point_states(); oi, od = ow.point_states()
+    pvs = oi[:, 1] >= 0
+    assert np.array_equal(ri[pvs][:, [0, 1, 2, 3]], oi[pvs][:, [0, 1, 2, 3]])
     fnd = oi[:, 3] == 1
     assert np.array_equal(rd[fnd][:, :4], od[fnd][:, :4])
 
