@@ -39,6 +39,20 @@ def test_make_keyframe_lite(kind):
         assert np.array_equal(rk.row_lut(l), ok.row_lut(l))
 
 
+@pytest.mark.parametrize("size", [(1920, 1080), (3840, 2160), (640, 360), (352, 272)])
+def test_make_keyframe_lite_at_the_other_frame_sizes(size):
+    """BASELINE's 1080p and 4K frames (and two sizes whose levels have odd or ragged dimensions) through the reference's own MakeKeyFrame_Lite:
+    the GPU parity tests at those sizes compare with the restatement, which is therefore held to the reference there as well."""
+    W, H = size
+    cam = synth.Camera(W, H)
+    im = synth.render_frame(common.texture(4096 if W > 640 else 2048), cam, synth.se3_exp(np.array(synth.CONFIG1_TWIST) * 0.3))
+    rk, ok = refbind.RefKeyFrame().make_lite(im), oraclebind.OrcKeyFrame().make_lite(im)
+    for l in range(4):
+        assert np.array_equal(rk.pixels(l), ok.pixels(l))
+        assert np.array_equal(rk.corners(l), ok.corners(l)) and len(rk.corners(l)) > 0
+        assert np.array_equal(rk.row_lut(l), ok.row_lut(l))
+
+
 def test_make_keyframe_rest_nonmax_and_shi_tomasi():
     cam, f0, _ = common.scene()
     im, _ = common.frame_at(cam, np.array(synth.CONFIG1_TWIST) * 0.7)
