@@ -867,6 +867,47 @@ def test_frame_lookahead_changes_no_result(entry):
     assert all(c[2] == 2 for c in a["counters"]), a["counters"]            # and every stream ends with quality GOOD
 
 
+def test_coarse_chain_layout_follows_the_hint_and_changes_no_result():
+    """48 streams (the smallest context whose default is two launch chains, vslam_params.coarse_chain = -1): half of them speed up for a few frames --
+    they enter TrackMap's coarse stage, the layout hint flips, the library falls back to one chain -- and slow down again.  Poses, counters, update twists
+    and per-point state are bit-identical to a run with one chain throughout, frame by frame; the fast streams did run the coarse stage, the slow ones
+    never did.  (No synchronisation is needed for the hint: it is read after each frame's getters here, and unsynchronised in the bench.)"""
+    cam, f0, smap = common.scene()
+    S, K, D = 48, 12, 6                                       # D distinct renderings, each tracked by S / D streams
+    steps = [[2] * K if d % 2 == 0 else [2, 2, 12, 12, 12, 12, 2, 2, 2, 2, 2, 2] for d in range(D)]
+    seq = np.empty((K, S) + f0.shape, dtype=np.uint8)
+    for d in range(D):
+        p = 0
+        for k in range(K):
+            p += steps[d][k]
+            seq[k, d::D] = synth.render_frame(common.texture(), cam, synth.stream_pose(p, d))
+
+    def run(coarse_chain):
+        ctx = _ctx(cam, f0, smap, n_streams=S)
+        ctx.set_params(coarse_chain=coarse_chain)
+        per_frame = []
+        for k in range(K):
+            ctx.track_frame(seq[k])
+            per_frame.append((ctx.get_poses().copy(), [ctx.counters(s) for s in range(D)]))
+        out = dict(per_frame=per_frame, updates=[ctx.updates(s) for s in range(S)], states=[ctx.point_states(s) for s in range(0, S, 7)])
+        ctx.close()
+        return out
+
+    a, b = run(0), run(-1)
+    for k in range(K):
+        assert np.array_equal(a["per_frame"][k][0], b["per_frame"][k][0]), k
+        for d in range(D):
+            for u, v in zip(a["per_frame"][k][1][d], b["per_frame"][k][1][d]):
+                assert np.array_equal(u, v), (k, d)
+    for u, v in zip(a["updates"], b["updates"]):
+        assert np.array_equal(u[0], v[0]) and np.array_equal(u[1], v[1])
+    for u, v in zip(a["states"], b["states"]):
+        assert np.array_equal(u[0], v[0]) and np.array_equal(u[1], v[1])
+    did = np.array([[a["per_frame"][k][1][d][4] for d in range(D)] for k in range(K)])          # mbDidCoarse per frame and rendering
+    assert did[:, 0::2].sum() == 0 and np.all(did[:, 1::2].sum(axis=0) >= 2) and np.all(did[-1] == 0), did
+    assert all(c[2] == 2 for c in a["per_frame"][-1][1])                                          # every stream ends with quality GOOD
+
+
 @pytest.mark.parametrize("n_points", [1, 3, 25])
 def test_track_frame_tiny_maps_and_blank_frames(n_points):
     """Edge cases of the whole TrackFrame: maps of 1 / 3 / 25 points (Tukey's `n*2-6` wraps or divides by zero, jni/MEstimator.h:73;
